@@ -1,0 +1,116 @@
+"""ctypes binding of liber_b200.so (the C ABI declared in include/er_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call
+fails, an exception is raised.  The oracle under /oracle is test infrastructure
+and is never imported from here.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'liber_b200.so')
+
+c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t
+
+# er_slot_t (include/er_b200.h), 48 bytes
+SLOT_DTYPE = np.dtype(
+    [('num_buckets', '<i8'), ('row_offset', '<i8'), ('seg_begin', '<i4'),
+     ('n_seg', '<i4'), ('bucket_mode', '<i4'), ('combiner', '<i4'),
+     ('out_buf', '<i4'), ('out_stride', '<i4'), ('out_col', '<i4'),
+     ('shard_n', '<i4')],
+    align=True)
+assert SLOT_DTYPE.itemsize == 48
+
+BUCKET_FARM_DECIMAL, BUCKET_MOD, BUCKET_IDENTITY, BUCKET_NONE = 0, 1, 2, 3
+COMBINER_SUM, COMBINER_MEAN, COMBINER_SQRTN = 0, 1, 2
+OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM, OPT_ADAM_ROWS = 0, 1, 2, 3
+MAX_BUFS = 8
+
+
+class ErOpt(ctypes.Structure):
+  """er_opt_t."""
+  _fields_ = [('kind', c_i32), ('lr', c_f32), ('beta1', c_f32),
+              ('beta2', c_f32), ('eps', c_f32), ('beta1_power', c_f32),
+              ('beta2_power', c_f32), ('grad_scale', c_f32)]
+
+
+# name -> (restype, argtypes); must list every symbol include/er_b200.h declares
+SIGNATURES = {
+    'er_abi_version': (c_i32, []),
+    'er_last_error': (ctypes.c_char_p, []),
+    'er_csr_workspace_bytes': (c_sz, [c_i64]),
+    'er_csr_from_lens': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz,
+                                 c_vp]),
+    'er_bucketize': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32,
+                             c_vp, c_vp, c_vp]),
+    'er_fingerprint64_host': (ctypes.c_uint64, [ctypes.c_char_p, c_sz]),
+    'er_embedding_fwd': (c_i32, [
+        c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,
+        c_i32, ctypes.POINTER(c_vp), c_i32, c_vp, c_vp
+    ]),
+    'er_embedding_bwd_workspace_bytes': (c_sz, [c_i64]),
+    'er_embedding_bwd': (c_i32, [
+        c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64,
+        c_i64, c_vp, c_i32, ctypes.POINTER(c_vp), c_i32, c_vp,
+        ctypes.POINTER(ErOpt), c_vp, c_vp, c_vp, c_vp, c_sz, c_vp
+    ]),
+    'er_sparse_apply': (c_i32, [
+        c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
+        ctypes.POINTER(ErOpt), c_vp
+    ]),
+    'er_adam_dense_sweep': (c_i32, [
+        c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp,
+        ctypes.POINTER(ErOpt), c_vp
+    ]),
+    'er_mark_rows': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp]),
+    'er_sort_workspace_bytes': (c_sz, [c_i64]),
+    'er_sort_rows': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz,
+                             c_vp]),
+    'er_fm_fwd': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'er_fm_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i32,
+                          c_i32, c_vp]),
+    'er_sigmoid_ce_fwd_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp,
+                                      c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class ErError(RuntimeError):
+  pass
+
+
+def load():
+  """Load liber_b200.so once; raise if it is absent (no CPU fallback exists)."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise ErError(
+        'liber_b200.so not found at %s: build it with '
+        '`python -c "import __graft_entry__ as g; g.build()"` or '
+        '`make -C easyrec_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+  lib = ctypes.CDLL(LIB_PATH)
+  for name, (res, args) in SIGNATURES.items():
+    fn = getattr(lib, name)  # AttributeError if the symbol is missing
+    fn.restype = res
+    fn.argtypes = args
+  _lib = lib
+  return lib
+
+
+def check(status, what):
+  if status != 0:
+    msg = load().er_last_error()
+    raise ErError('%s failed (status %d): %s' %
+                  (what, status, msg.decode() if msg else ''))
+
+
+def fingerprint64(data):
+  """Fingerprint64 of a bytes/str object (host side)."""
+  if isinstance(data, str):
+    data = data.encode('utf-8')
+  return int(load().er_fingerprint64_host(data, len(data)))

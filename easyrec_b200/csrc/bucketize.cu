@@ -1,0 +1,128 @@
+// K0: lens -> CSR (row_ptr, seg_ids);  K1: raw int64 ids -> arena rows.
+//
+// Reference ops replaced:
+//   cumsum(lens) + searchsorted        compat/feature_column/feature_column.py:264-266
+//   as_string + string_to_hash_bucket_fast   feature_column_v2.py:3915-3921
+//   vals % num_buckets                 input/parquet_input.py:221
+//   identity column with default 0     feature_column_v2.py:4268-4292
+//   uniq % N / int64(recv / N)         compat/feature_column/feature_column.py:296,317
+// Both kernels are pure streaming integer work: 8 B in + 8 B out per lookup.
+#include "common.cuh"
+#include "hash.cuh"
+#include "scan.cuh"
+
+namespace er {
+
+struct LensIn {
+  const int32_t* lens;
+  __device__ int operator()(int64_t j) const { return lens[j]; }
+};
+struct RowPtrOut {
+  int32_t* row_ptr;
+  int64_t n;
+  __device__ void operator()(int64_t j, int ex, int v) const {
+    row_ptr[j] = ex;
+    if (j == n - 1) row_ptr[n] = ex + v;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+    expand_seg_ids_kernel(const int32_t* __restrict__ row_ptr, int64_t n_seg, int64_t cap,
+                          int32_t* __restrict__ seg_ids) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_seg;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = row_ptr[s], e = row_ptr[s + 1];
+    if (e > cap) e = cap;
+    for (int64_t j = b; j < e; ++j) seg_ids[j] = (int32_t)s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    bucketize_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ seg_ids,
+                     const int32_t* __restrict__ row_ptr, int64_t n_seg, int64_t cap,
+                     const er_slot_t* __restrict__ slots, int n_slots,
+                     int64_t* __restrict__ rows, int32_t* __restrict__ owner) {
+  extern __shared__ int32_t s_seg_begin[];
+  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_seg_begin[i] = slots[i].seg_begin;
+  __syncthreads();
+  int64_t n = cap;
+  if (row_ptr) {
+    int64_t t = row_ptr[n_seg];
+    n = t < cap ? t : cap;
+  }
+  for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n;
+       l += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s = seg_ids ? seg_ids[l] : (int32_t)l;
+    const int f = find_slot(s_seg_begin, n_slots, s);
+    const int64_t nb = slots[f].num_buckets;
+    const int64_t off = slots[f].row_offset;
+    const int mode = slots[f].bucket_mode;
+    const int shard_n = slots[f].shard_n;
+    const int64_t v = ids[l];
+    int64_t r;
+    bool drop = false;
+    if (mode == ER_BUCKET_FARM_DECIMAL) {
+      farm::Dec d = farm::to_decimal(v);
+      uint64_t h = farm::fingerprint64_dec(d);
+      r = (int64_t)(h % (uint64_t)nb);
+    } else if (mode == ER_BUCKET_MOD) {
+      int64_t m = v % nb;
+      r = m < 0 ? m + nb : m;
+    } else if (mode == ER_BUCKET_IDENTITY) {
+      drop = (v == -1);
+      r = (v < 0 || v >= nb) ? 0 : v;
+    } else {
+      drop = (v < 0);
+      r = v;
+    }
+    int32_t own = 0;
+    if (shard_n > 1) {
+      own = (int32_t)(r % shard_n);
+      r = r / shard_n;
+    }
+    rows[l] = drop ? -1 : (off + r);
+    if (owner) owner[l] = drop ? -1 : own;
+  }
+}
+
+}  // namespace er
+
+extern "C" size_t er_csr_workspace_bytes(int64_t n_seg) {
+  return er::scan::workspace_bytes(n_seg);
+}
+
+extern "C" int er_csr_from_lens(const int32_t* lens, int64_t n_seg, int32_t* row_ptr,
+                                int32_t* seg_ids, int64_t n_lookups_cap, void* ws,
+                                size_t ws_bytes, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(lens && row_ptr, "lens and row_ptr must be non-null");
+  ER_REQUIRE(n_seg > 0 && n_seg < (1LL << 31), "n_seg out of range");
+  ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31), "n_lookups_cap out of range");
+  if (ws_bytes < scan::workspace_bytes(n_seg) || !ws)
+    return fail(ER_ERR_WORKSPACE, "er_csr_from_lens: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  scan::exclusive_scan(LensIn{lens}, RowPtrOut{row_ptr, n_seg}, n_seg, nullptr, ws, st);
+  if (seg_ids && n_lookups_cap > 0) {
+    expand_seg_ids_kernel<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(row_ptr, n_seg, n_lookups_cap,
+                                                                    seg_ids);
+  }
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_bucketize(const int64_t* ids, const int32_t* seg_ids, const int32_t* row_ptr,
+                            int64_t n_seg, int64_t n_lookups_cap, const er_slot_t* slots,
+                            int32_t n_slots, int64_t* rows, int32_t* owner,
+                            er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(ids && rows && slots, "ids, rows and slots must be non-null");
+  ER_REQUIRE(n_slots > 0 && n_slots <= 8192, "n_slots must be in [1, 8192]");
+  ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31), "n_lookups_cap out of range");
+  ER_REQUIRE(seg_ids || !row_ptr || true, "");
+  if (n_lookups_cap == 0) return ER_OK;
+  cudaStream_t st = as_stream(stream);
+  bucketize_kernel<<<grid_for(n_lookups_cap, 256, 8), 256, n_slots * sizeof(int32_t), st>>>(
+      ids, seg_ids, row_ptr, n_seg, n_lookups_cap, slots, n_slots, rows, owner);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}

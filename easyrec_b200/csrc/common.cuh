@@ -1,0 +1,79 @@
+// Shared helpers for liber_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "er_b200.h"
+
+namespace er {
+
+void set_error(const std::string& msg);
+
+inline int fail(int code, const std::string& msg) {
+  set_error(msg);
+  return code;
+}
+
+#define ER_REQUIRE(cond, msg)                                              \
+  do {                                                                     \
+    if (!(cond)) return ::er::fail(ER_ERR_INVALID_ARG, std::string(__func__) + ": " + (msg)); \
+  } while (0)
+
+#define ER_CUDA_LAUNCH_CHECK()                                             \
+  do {                                                                     \
+    cudaError_t e__ = cudaPeekAtLastError();                               \
+    if (e__ != cudaSuccess) {                                              \
+      cudaGetLastError();                                                  \
+      return ::er::fail(ER_ERR_CUDA, std::string(__func__) + ": " + cudaGetErrorString(e__)); \
+    }                                                                      \
+  } while (0)
+
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+inline cudaStream_t as_stream(er_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Cap a 1-D grid: enough CTAs to cover `work_items` at `per_cta`, rounded so
+// large problems run as whole waves of the 148 SMs (grid-stride loops inside).
+inline int grid_for(int64_t work_items, int per_cta, int ctas_per_sm) {
+  int64_t need = ceil_div(work_items, per_cta);
+  int64_t wave = (int64_t)kSmCount * ctas_per_sm;
+  if (need <= 0) return 1;
+  if (need <= wave) return (int)need;
+  return (int)wave;
+}
+
+// 16-byte streaming load / store that do not allocate in L1 (rows are touched
+// once per launch; L2 keeps the hot Zipf head).
+__device__ __forceinline__ float4 ld_row_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// slot of a segment: largest f with slots[f].seg_begin <= s (slots sorted by seg_begin).
+__device__ __forceinline__ int find_slot(const int32_t* __restrict__ seg_begins, int n_slots,
+                                         int32_t s) {
+  int lo = 0, hi = n_slots;  // invariant: seg_begins[lo] <= s < seg_begins[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_begins[mid] <= s)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+}  // namespace er

@@ -1,0 +1,553 @@
+// K7: backward of the gather+pool = gradient dedup + per-row segment sum + fused
+// optimizer row update, in one pipeline with no host sync:
+//
+//   rows[L] --stable radix sort--> (row, lookup) runs --one lane group per run-->
+//   G_row = sum over the run, in ascending lookup order, of coef_l * dL/d(pooled[seg(l)])
+//   row, state <- optimizer(row, state, G_row * grad_scale)          (same kernel)
+//
+// Reference ops replaced: the IndexedSlices gradient of embedding_lookup_sparse,
+// TF Optimizer._deduplicate_indexed_slices (Unique + UnsortedSegmentSum) and the
+// sparse apply: lazy Adam compat/adam_s.py:185-213, TF SparseApplyAdagrad
+// (acc += g^2; w -= lr*g*rsqrt(acc); acc0 = 0.1, protos/optimizer.proto:79),
+// EP gradient scaling compat/optimizers.py:315-316.
+//
+// Summation order inside a run is the lookup order (the sort is stable), which is
+// the order a sequential CPU segment-sum uses; runs longer than kLongRun (hot ids
+// under Zipf) are handed to a second kernel that splits them over a whole CTA and
+// combines partials in a fixed tree, so results stay deterministic.
+//
+// HBM traffic per launch (algorithmic): L*(4+4) sorted pairs + L*R gathered upstream
+// gradient rows + U*(k*R) row/state read-modify-write, R = 4*dim, k = 2 (sgd),
+// 4 (adagrad), 6 (adam).
+#include "common.cuh"
+#include "scan.cuh"
+#include "sort.cuh"
+
+namespace er {
+
+struct CBufs {
+  const float* p[ER_MAX_BUFS];
+};
+
+constexpr int kLongRun = 64;      // runs longer than this go to the CTA-wide kernel
+constexpr int kBatch = 4;         // lookups fetched per step of the run loop
+
+struct BwdArgs {
+  float* table;
+  float* state0;
+  float* state1;
+  int dim;
+  int row_stride;
+  uint32_t sentinel;  // == n_rows
+  const uint32_t* keys;
+  const uint32_t* vals;
+  int64_t n;  // sorted pairs (== n_lookups_cap)
+  const float* weights;
+  const int32_t* seg_ids;
+  const er_slot_t* slots;
+  int n_slots;
+  CBufs gbufs;
+  const float* seg_scale;
+  er_opt_t opt;
+  float lr_t;  // adam: lr*sqrt(1-b2^t)/(1-b1^t)
+  int64_t* uniq_rows;
+  float* uniq_grads;
+  const int32_t* head_rank;  // exclusive count of run heads before each position (emit mode)
+  int32_t* long_count;
+  int32_t* long_list;
+};
+
+// gradient row pointer and coefficient of sorted entry with lookup position l
+__device__ __forceinline__ const float* grad_src(const BwdArgs& a, const int32_t* s_seg_begin,
+                                                 uint32_t l, float* coef) {
+  const int32_t s = a.seg_ids ? a.seg_ids[l] : (int32_t)l;
+  const int f = find_slot(s_seg_begin, a.n_slots, s);
+  const er_slot_t sl = a.slots[f];
+  float c = a.weights ? a.weights[l] : 1.0f;
+  if (a.seg_scale) c = __fmul_rn(c, a.seg_scale[s]);
+  *coef = c;
+  return a.gbufs.p[sl.out_buf] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
+}
+
+__device__ __forceinline__ float upd_one(const BwdArgs& a, float g, float& w, float& s0, float& s1) {
+  // returns nothing meaningful; updates w, s0, s1 in registers
+  switch (a.opt.kind) {
+    case ER_OPT_ADAGRAD: {
+      s0 = __fadd_rn(s0, __fmul_rn(g, g));
+      w = __fsub_rn(w, __fmul_rn(__fmul_rn(a.opt.lr, g), __frsqrt_rn(s0)));
+      break;
+    }
+    case ER_OPT_LAZY_ADAM:
+    case ER_OPT_ADAM_ROWS: {
+      // m_part = g*(1-b1) + m*b1 ; v_part = g*g*(1-b2) + v*b2 ; w += -lr_t*m_part/(sqrt(v_part)+eps)
+      s0 = __fadd_rn(__fmul_rn(g, 1.0f - a.opt.beta1), __fmul_rn(s0, a.opt.beta1));
+      s1 = __fadd_rn(__fmul_rn(__fmul_rn(g, g), 1.0f - a.opt.beta2), __fmul_rn(s1, a.opt.beta2));
+      w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-a.lr_t, s0), __fadd_rn(sqrtf(s1), a.opt.eps)));
+      break;
+    }
+    default:  // SGD
+      w = __fsub_rn(w, __fmul_rn(a.opt.lr, g));
+  }
+  return w;
+}
+
+template <int LANES>
+__device__ __forceinline__ void apply_row_vec(const BwdArgs& a, uint32_t row, int lane, float4 g,
+                                              int64_t head_pos) {
+  g.x = __fmul_rn(g.x, a.opt.grad_scale);
+  g.y = __fmul_rn(g.y, a.opt.grad_scale);
+  g.z = __fmul_rn(g.z, a.opt.grad_scale);
+  g.w = __fmul_rn(g.w, a.opt.grad_scale);
+  if (a.uniq_rows) {
+    const int32_t u = a.head_rank[head_pos];
+    if (lane == 0) a.uniq_rows[u] = (int64_t)row;
+    reinterpret_cast<float4*>(a.uniq_grads + (int64_t)u * a.dim)[lane] = g;
+  }
+  if (!a.table) return;
+  const int64_t off = (int64_t)row * a.row_stride;
+  float4* wp = reinterpret_cast<float4*>(a.table + off) + lane;
+  float4 w = *wp;
+  float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
+  float4* s0p = a.state0 ? reinterpret_cast<float4*>(a.state0 + off) + lane : nullptr;
+  float4* s1p = a.state1 ? reinterpret_cast<float4*>(a.state1 + off) + lane : nullptr;
+  if (s0p) s0 = *s0p;
+  if (s1p) s1 = *s1p;
+  upd_one(a, g.x, w.x, s0.x, s1.x);
+  upd_one(a, g.y, w.y, s0.y, s1.y);
+  upd_one(a, g.z, w.z, s0.z, s1.z);
+  upd_one(a, g.w, w.w, s0.w, s1.w);
+  *wp = w;
+  if (s0p) *s0p = s0;
+  if (s1p) *s1p = s1;
+}
+
+// One LANES-wide group per sorted position; only run heads do work.
+template <int LANES>
+__global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ int32_t s_seg_begin[];
+  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
+  __syncthreads();
+  const int lane = threadIdx.x % LANES;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
+  if (i >= a.n) return;
+  const uint32_t key = a.keys[i];
+  if (key >= a.sentinel) return;
+  if (i > 0 && a.keys[i - 1] == key) return;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t j = i;
+  int cnt = 0;
+  while (true) {
+    uint32_t l[kBatch];
+    int m = 0;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const bool in = (j + u < a.n);
+      const uint32_t k = in ? a.keys[j + u] : a.sentinel;
+      l[u] = in ? a.vals[j + u] : 0u;
+      if (m == u && k == key) m = u + 1;
+    }
+    float4 gv[kBatch];
+    float c[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (u < m) {
+        const float* src = grad_src(a, s_seg_begin, l[u], &c[u]);
+        gv[u] = reinterpret_cast<const float4*>(src)[lane];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (u < m) {
+        g.x = __fadd_rn(g.x, __fmul_rn(gv[u].x, c[u]));
+        g.y = __fadd_rn(g.y, __fmul_rn(gv[u].y, c[u]));
+        g.z = __fadd_rn(g.z, __fmul_rn(gv[u].z, c[u]));
+        g.w = __fadd_rn(g.w, __fmul_rn(gv[u].w, c[u]));
+      }
+    }
+    j += m;
+    cnt += m;
+    if (m < kBatch) break;
+    if (cnt >= kLongRun) {
+      if (j < a.n && a.keys[j] == key) {  // hot row: hand the whole run to the CTA-wide kernel
+        if (lane == 0) {
+          int slot = atomicAdd(a.long_count, 1);
+          a.long_list[slot] = (int32_t)i;
+        }
+        return;
+      }
+      break;
+    }
+  }
+  apply_row_vec<LANES>(a, key, lane, g, i);
+}
+
+// Hot rows: one CTA per run, 256/LANES groups each sum a contiguous chunk in lookup
+// order, then a fixed-order tree in shared memory.
+template <int LANES>
+__global__ void __launch_bounds__(256) bwd_long_vec_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ int32_t s_dyn[];
+  int32_t* s_seg_begin = s_dyn;
+  float4* s_part = reinterpret_cast<float4*>(s_dyn + ((a.n_slots + 3) & ~3));
+  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
+  __syncthreads();
+  constexpr int G = 256 / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int grp = threadIdx.x / LANES;
+  const int n_long = *a.long_count;
+  for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
+    const int64_t i = a.long_list[q];
+    const uint32_t key = a.keys[i];
+    // upper bound of key in keys[i, n)
+    int64_t lo = i, hi = a.n;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (a.keys[mid] <= key)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    const int64_t len = lo - i;
+    const int64_t chunk = ceil_div(len, G);
+    int64_t b = i + grp * chunk, e = b + chunk;
+    if (e > i + len) e = i + len;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t j = b; j < e; j += kBatch) {
+      float4 gv[kBatch];
+      float c[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (j + u < e) {
+          const float* src = grad_src(a, s_seg_begin, a.vals[j + u], &c[u]);
+          gv[u] = reinterpret_cast<const float4*>(src)[lane];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (j + u < e) {
+          g.x = __fadd_rn(g.x, __fmul_rn(gv[u].x, c[u]));
+          g.y = __fadd_rn(g.y, __fmul_rn(gv[u].y, c[u]));
+          g.z = __fadd_rn(g.z, __fmul_rn(gv[u].z, c[u]));
+          g.w = __fadd_rn(g.w, __fmul_rn(gv[u].w, c[u]));
+        }
+      }
+    }
+    s_part[grp * LANES + lane] = g;
+    __syncthreads();
+    for (int stride = G / 2; stride >= 1; stride >>= 1) {
+      if (grp < stride) {
+        float4 x = s_part[grp * LANES + lane], y = s_part[(grp + stride) * LANES + lane];
+        x.x = __fadd_rn(x.x, y.x);
+        x.y = __fadd_rn(x.y, y.y);
+        x.z = __fadd_rn(x.z, y.z);
+        x.w = __fadd_rn(x.w, y.w);
+        s_part[grp * LANES + lane] = x;
+      }
+      __syncthreads();
+    }
+    if (grp == 0) apply_row_vec<LANES>(a, key, lane, s_part[lane], i);
+    __syncthreads();
+  }
+}
+
+// Scalar path (wide dim=1 tables, odd dims): one thread per (sorted position, column).
+__global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ int32_t s_seg_begin[];
+  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / a.dim;
+  const int c = (int)(t - i * a.dim);
+  if (i >= a.n) return;
+  const uint32_t key = a.keys[i];
+  if (key >= a.sentinel) return;
+  if (i > 0 && a.keys[i - 1] == key) return;
+  float g = 0.f;
+  for (int64_t j = i; j < a.n && a.keys[j] == key; ++j) {
+    float coef;
+    const float* src = grad_src(a, s_seg_begin, a.vals[j], &coef);
+    g = __fadd_rn(g, __fmul_rn(src[c], coef));
+  }
+  g = __fmul_rn(g, a.opt.grad_scale);
+  if (a.uniq_rows) {
+    const int32_t u = a.head_rank[i];
+    if (c == 0) a.uniq_rows[u] = (int64_t)key;
+    a.uniq_grads[(int64_t)u * a.dim + c] = g;
+  }
+  if (!a.table) return;
+  const int64_t off = (int64_t)key * a.row_stride + c;
+  float w = a.table[off];
+  float s0 = a.state0 ? a.state0[off] : 0.f;
+  float s1 = a.state1 ? a.state1[off] : 0.f;
+  upd_one(a, g, w, s0, s1);
+  a.table[off] = w;
+  if (a.state0) a.state0[off] = s0;
+  if (a.state1) a.state1[off] = s1;
+}
+
+struct HeadIn {
+  const uint32_t* keys;
+  uint32_t sentinel;
+  __device__ int operator()(int64_t j) const {
+    uint32_t k = keys[j];
+    return (k < sentinel && (j == 0 || keys[j - 1] != k)) ? 1 : 0;
+  }
+};
+struct HeadOut {
+  int32_t* rank;
+  __device__ void operator()(int64_t j, int ex, int) const { rank[j] = ex; }
+};
+
+__global__ void zero_i32_kernel(int32_t* p) { *p = 0; }
+
+inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct BwdWs {
+  uint32_t* keys;
+  uint32_t* vals;
+  int32_t* head_rank;
+  int32_t* long_list;
+  int32_t* long_count;
+  void* sort_ws;
+  void* scan_ws;
+};
+
+inline size_t bwd_ws_bytes(int64_t n) {
+  return a256((size_t)n * 4) * 4 + 256 + a256(rsort::workspace_bytes(n)) +
+         a256(scan::workspace_bytes(n)) + 512;
+}
+inline BwdWs bwd_carve(void* ws, int64_t n) {
+  char* p = reinterpret_cast<char*>(a256(reinterpret_cast<size_t>(ws)));
+  BwdWs w;
+  w.keys = reinterpret_cast<uint32_t*>(p); p += a256((size_t)n * 4);
+  w.vals = reinterpret_cast<uint32_t*>(p); p += a256((size_t)n * 4);
+  w.head_rank = reinterpret_cast<int32_t*>(p); p += a256((size_t)n * 4);
+  w.long_list = reinterpret_cast<int32_t*>(p); p += a256((size_t)n * 4);
+  w.long_count = reinterpret_cast<int32_t*>(p); p += 256;
+  w.sort_ws = p; p += a256(rsort::workspace_bytes(n));
+  w.scan_ws = p;
+  return w;
+}
+
+static float adam_lr_t(const er_opt_t& o) {
+  // lr * sqrt(1 - beta2_power) / (1 - beta1_power), fp32 like the TF graph (adam_s.py:193)
+  return o.lr * sqrtf(1.0f - o.beta2_power) / (1.0f - o.beta1_power);
+}
+
+template <int LANES>
+static void launch_vec(const BwdArgs& a, cudaStream_t st) {
+  const int groups = 256 / LANES;
+  const size_t smem = (size_t)a.n_slots * sizeof(int32_t);
+  bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, groups), 256, smem, st>>>(a);
+  const size_t smem_long = (size_t)((a.n_slots + 3) & ~3) * sizeof(int32_t) + 256 * sizeof(float4);
+  bwd_long_vec_kernel<LANES><<<kSmCount, 256, smem_long, st>>>(a);
+}
+
+}  // namespace er
+
+extern "C" size_t er_sort_workspace_bytes(int64_t n) { return er::rsort::workspace_bytes(n); }
+
+extern "C" int er_sort_rows(const int64_t* rows, int64_t n, const int32_t* n_dev, int64_t max_row,
+                            uint32_t* keys_out, uint32_t* vals_out, void* ws, size_t ws_bytes,
+                            er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(rows && keys_out && vals_out, "null argument");
+  ER_REQUIRE(n > 0 && n < (1LL << 31), "n out of range");
+  ER_REQUIRE(max_row > 0 && max_row < 0xFFFFFFFFLL, "max_row must be in (0, 2^32-1)");
+  if (!ws || ws_bytes < rsort::workspace_bytes(n))
+    return fail(ER_ERR_WORKSPACE, "er_sort_rows: workspace too small");
+  rsort::sort_rows(rows, n, n_dev, max_row, keys_out, vals_out, ws, as_stream(stream));
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap) {
+  return er::bwd_ws_bytes(n_lookups_cap > 0 ? n_lookups_cap : 1);
+}
+
+extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int64_t n_rows,
+                                int32_t dim, int32_t row_stride, const int64_t* rows,
+                                const float* weights, const int32_t* seg_ids,
+                                const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                                const er_slot_t* slots, int32_t n_slots,
+                                const float* const* grad_bufs, int32_t n_bufs,
+                                const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
+                                float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
+                                er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(rows && slots && grad_bufs && opt, "null argument");
+  ER_REQUIRE(table || uniq_rows, "nothing to do: table and uniq_rows are both NULL");
+  ER_REQUIRE((uniq_rows == nullptr) == (uniq_grads == nullptr) &&
+                 (uniq_rows == nullptr) == (n_uniq == nullptr),
+             "uniq_rows, uniq_grads and n_uniq go together");
+  ER_REQUIRE(dim > 0 && row_stride >= dim, "bad dim / row_stride");
+  ER_REQUIRE(n_rows > 0 && n_rows < 0xFFFFFFFFLL, "n_rows must be in (0, 2^32-1)");
+  ER_REQUIRE(n_slots > 0 && n_slots <= 8192, "n_slots must be in [1, 8192]");
+  ER_REQUIRE(n_bufs > 0 && n_bufs <= ER_MAX_BUFS, "n_bufs must be in [1, ER_MAX_BUFS]");
+  ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31), "n_lookups_cap out of range");
+  ER_REQUIRE(row_ptr || n_lookups_cap == n_seg, "row_ptr == NULL requires n_lookups_cap == n_seg");
+  ER_REQUIRE(!row_ptr || seg_ids, "CSR input needs seg_ids (er_csr_from_lens)");
+  if (table) {
+    const int k = opt->kind;
+    ER_REQUIRE(k == ER_OPT_SGD || k == ER_OPT_ADAGRAD || k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS,
+               "unknown optimizer kind");
+    ER_REQUIRE(k == ER_OPT_SGD || state0, "optimizer state0 missing");
+    ER_REQUIRE((k != ER_OPT_LAZY_ADAM && k != ER_OPT_ADAM_ROWS) || state1, "adam needs state1 (v)");
+  }
+  if (n_lookups_cap == 0) return ER_OK;
+  if (!ws || ws_bytes < bwd_ws_bytes(n_lookups_cap))
+    return fail(ER_ERR_WORKSPACE, "er_embedding_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  BwdWs w = bwd_carve(ws, n_lookups_cap);
+  // number of live lookups: row_ptr[n_seg] when CSR (device side), else the capacity
+  const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
+  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, st);
+
+  BwdArgs a;
+  a.table = table;
+  a.state0 = state0;
+  a.state1 = state1;
+  a.dim = dim;
+  a.row_stride = row_stride;
+  a.sentinel = (uint32_t)n_rows;
+  a.keys = w.keys;
+  a.vals = w.vals;
+  a.n = n_lookups_cap;
+  a.weights = weights;
+  a.seg_ids = seg_ids;
+  a.slots = slots;
+  a.n_slots = n_slots;
+  bool aligned = true;
+  for (int i = 0; i < ER_MAX_BUFS; ++i) {
+    a.gbufs.p[i] = i < n_bufs ? grad_bufs[i] : nullptr;
+    if (i < n_bufs) {
+      ER_REQUIRE(grad_bufs[i] != nullptr, "null gradient buffer");
+      aligned = aligned && (reinterpret_cast<uintptr_t>(grad_bufs[i]) % 16 == 0);
+    }
+  }
+  a.seg_scale = seg_scale;
+  a.opt = *opt;
+  a.lr_t = (opt->kind == ER_OPT_LAZY_ADAM || opt->kind == ER_OPT_ADAM_ROWS) ? adam_lr_t(*opt) : opt->lr;
+  a.uniq_rows = uniq_rows;
+  a.uniq_grads = uniq_grads;
+  a.head_rank = nullptr;
+  a.long_count = w.long_count;
+  a.long_list = w.long_list;
+  if (uniq_rows) {
+    scan::exclusive_scan(HeadIn{w.keys, a.sentinel}, HeadOut{w.head_rank}, n_lookups_cap, n_uniq,
+                         w.scan_ws, st);
+    a.head_rank = w.head_rank;
+  }
+  zero_i32_kernel<<<1, 1, 0, st>>>(w.long_count);
+  if (table) {
+    aligned = aligned && reinterpret_cast<uintptr_t>(table) % 16 == 0 && row_stride % 4 == 0 &&
+              (!state0 || reinterpret_cast<uintptr_t>(state0) % 16 == 0) &&
+              (!state1 || reinterpret_cast<uintptr_t>(state1) % 16 == 0);
+  }
+  if (uniq_grads) aligned = aligned && reinterpret_cast<uintptr_t>(uniq_grads) % 16 == 0;
+  const bool vec_dim = (dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128);
+  if (vec_dim && aligned) {
+    switch (dim / 4) {
+      case 1: launch_vec<1>(a, st); break;
+      case 2: launch_vec<2>(a, st); break;
+      case 4: launch_vec<4>(a, st); break;
+      case 8: launch_vec<8>(a, st); break;
+      case 16: launch_vec<16>(a, st); break;
+      default: launch_vec<32>(a, st); break;
+    }
+  } else {
+    bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256,
+                             (size_t)n_slots * sizeof(int32_t), st>>>(a);
+  }
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+namespace er {
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    sparse_apply_kernel(const __grid_constant__ BwdArgs a, const int64_t* __restrict__ uniq_rows,
+                        const float* __restrict__ uniq_grads, const int32_t* __restrict__ n_uniq,
+                        int64_t n_cap) {
+  const int64_t n = n_uniq ? (int64_t)(*n_uniq < n_cap ? *n_uniq : n_cap) : n_cap;
+  const int per_row = a.dim / VEC;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * per_row;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = t / per_row;
+    const int c = (int)(t - u * per_row) * VEC;
+    const int64_t row = uniq_rows[u];
+    if (row < 0) continue;
+    const int64_t off = row * a.row_stride + c;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float g = __fmul_rn(uniq_grads[u * a.dim + c + k], a.opt.grad_scale);
+      float w = a.table[off + k];
+      float s0 = a.state0 ? a.state0[off + k] : 0.f;
+      float s1 = a.state1 ? a.state1[off + k] : 0.f;
+      upd_one(a, g, w, s0, s1);
+      a.table[off + k] = w;
+      if (a.state0) a.state0[off + k] = s0;
+      if (a.state1) a.state1[off + k] = s1;
+    }
+  }
+}
+
+template <int UNUSED>
+__global__ void __launch_bounds__(256)
+    adam_sweep_kernel(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v,
+                      int64_t n_rows, int dim, int row_stride, const uint8_t* __restrict__ touched,
+                      float beta1, float beta2, float eps, float lr_t) {
+  const int64_t total = n_rows * dim;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / dim;
+    const int c = (int)(t - r * dim);
+    if (touched && touched[r]) continue;
+    const int64_t off = r * row_stride + c;
+    float mm = __fmul_rn(m[off], beta1);
+    float vv = __fmul_rn(v[off], beta2);
+    m[off] = mm;
+    v[off] = vv;
+    table[off] = __fsub_rn(table[off], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(sqrtf(vv), eps)));
+  }
+}
+
+}  // namespace er
+
+extern "C" int er_sparse_apply(float* table, float* state0, float* state1, int32_t dim,
+                               int32_t row_stride, const int64_t* uniq_rows,
+                               const float* uniq_grads, const int32_t* n_uniq, int64_t n_cap,
+                               const er_opt_t* opt, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(table && uniq_rows && uniq_grads && opt, "null argument");
+  ER_REQUIRE(dim > 0 && row_stride >= dim, "bad dim / row_stride");
+  const int k = opt->kind;
+  ER_REQUIRE(k == ER_OPT_SGD || state0, "optimizer state0 missing");
+  ER_REQUIRE((k != ER_OPT_LAZY_ADAM && k != ER_OPT_ADAM_ROWS) || state1, "adam needs state1 (v)");
+  if (n_cap <= 0) return ER_OK;
+  BwdArgs a = {};
+  a.table = table;
+  a.state0 = state0;
+  a.state1 = state1;
+  a.dim = dim;
+  a.row_stride = row_stride;
+  a.opt = *opt;
+  a.lr_t = (k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS) ? adam_lr_t(*opt) : opt->lr;
+  sparse_apply_kernel<1><<<grid_for(n_cap * dim, 256, 8), 256, 0, as_stream(stream)>>>(
+      a, uniq_rows, uniq_grads, n_uniq, n_cap);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_adam_dense_sweep(float* table, float* m, float* v, int64_t n_rows, int32_t dim,
+                                   int32_t row_stride, const uint8_t* touched,
+                                   const er_opt_t* opt, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(table && m && v && opt, "null argument");
+  ER_REQUIRE(dim > 0 && row_stride >= dim && n_rows > 0, "bad shape");
+  adam_sweep_kernel<0><<<grid_for(n_rows * dim, 256, 8), 256, 0, as_stream(stream)>>>(
+      table, m, v, n_rows, dim, row_stride, touched, opt->beta1, opt->beta2, opt->eps,
+      adam_lr_t(*opt));
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}

@@ -1,0 +1,227 @@
+"""Thin torch shim over the C ABI: tensors in, `data_ptr()`s + current stream out.
+
+torch is plumbing here (device memory, streams); every function below is one
+call into liber_b200.so.  Shapes/dtypes are checked on the host; nothing falls
+back to a torch implementation.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from easyrec_b200 import _lib
+from easyrec_b200._lib import ErOpt, SLOT_DTYPE, c_vp
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+  return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+  if t is None:
+    return
+  if not t.is_cuda:
+    raise _lib.ErError('%s must be a CUDA tensor (no CPU fallback)' % name)
+  if t.dtype != dtype:
+    raise _lib.ErError('%s must be %s, got %s' % (name, dtype, t.dtype))
+  if not t.is_contiguous():
+    raise _lib.ErError('%s must be contiguous' % name)
+
+
+def _buf_array(bufs):
+  arr = (c_vp * len(bufs))()
+  for i, b in enumerate(bufs):
+    arr[i] = b.data_ptr()
+  return arr
+
+
+def make_slots(records):
+  """records: list of dicts with er_slot_t field names -> numpy structured array."""
+  arr = np.zeros(len(records), dtype=SLOT_DTYPE)
+  for i, r in enumerate(records):
+    for k, v in r.items():
+      arr[i][k] = v
+    if arr[i]['shard_n'] == 0:
+      arr[i]['shard_n'] = 1
+  order = np.argsort(arr['seg_begin'], kind='stable')
+  if not np.array_equal(order, np.arange(len(records))):
+    raise _lib.ErError('slots must be ordered by seg_begin')
+  return arr
+
+
+def slots_to_device(slots_np, device):
+  raw = torch.from_numpy(slots_np.view(np.uint8).reshape(-1).copy())
+  return raw.to(device)
+
+
+def csr_from_lens(lens, n_lookups_cap, want_seg_ids=True):
+  """lens int32 [n_seg] -> (row_ptr int32 [n_seg+1], seg_ids int32 [cap] | None)."""
+  lib = _lib.load()
+  _chk(lens, torch.int32, 'lens')
+  n_seg = lens.numel()
+  row_ptr = torch.empty(n_seg + 1, dtype=torch.int32, device=lens.device)
+  seg_ids = (torch.empty(max(n_lookups_cap, 1), dtype=torch.int32, device=lens.device)
+             if want_seg_ids else None)
+  ws_bytes = lib.er_csr_workspace_bytes(n_seg)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lens.device)
+  _lib.check(
+      lib.er_csr_from_lens(_p(lens), n_seg, _p(row_ptr), _p(seg_ids), n_lookups_cap, _p(ws),
+                           ws_bytes, _stream()), 'er_csr_from_lens')
+  return row_ptr, seg_ids
+
+
+def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=None,
+              owner=None):
+  lib = _lib.load()
+  _chk(ids, torch.int64, 'ids')
+  _chk(seg_ids, torch.int32, 'seg_ids')
+  _chk(row_ptr, torch.int32, 'row_ptr')
+  _chk(owner, torch.int32, 'owner')
+  if rows is None:
+    rows = torch.empty_like(ids)
+  _chk(rows, torch.int64, 'rows')
+  _lib.check(
+      lib.er_bucketize(_p(ids), _p(seg_ids), _p(row_ptr), n_seg, ids.numel(), _p(slots_dev),
+                       n_slots, _p(rows), _p(owner), _stream()), 'er_bucketize')
+  return rows
+
+
+def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, out_bufs, weights=None,
+                  row_ptr=None, seg_scale=None, row_stride=None):
+  lib = _lib.load()
+  _chk(table, torch.float32, 'table')
+  _chk(rows, torch.int64, 'rows')
+  _chk(weights, torch.float32, 'weights')
+  _chk(row_ptr, torch.int32, 'row_ptr')
+  _chk(seg_scale, torch.float32, 'seg_scale')
+  for i, b in enumerate(out_bufs):
+    _chk(b, torch.float32, 'out_bufs[%d]' % i)
+  row_stride = row_stride or dim
+  n_rows = table.numel() // row_stride
+  _lib.check(
+      lib.er_embedding_fwd(_p(table), n_rows, dim, row_stride, _p(rows), _p(weights), _p(row_ptr),
+                           n_seg, rows.numel(), _p(slots_dev), n_slots, _buf_array(out_bufs),
+                           len(out_bufs), _p(seg_scale), _stream()), 'er_embedding_fwd')
+
+
+def bwd_workspace(n_lookups_cap, device):
+  lib = _lib.load()
+  return torch.empty(lib.er_embedding_bwd_workspace_bytes(n_lookups_cap), dtype=torch.uint8,
+                     device=device)
+
+
+def make_opt(kind, lr, beta1=0.9, beta2=0.999, eps=1e-8, beta1_power=0.9, beta2_power=0.999,
+             grad_scale=1.0):
+  return ErOpt(kind, lr, beta1, beta2, eps, beta1_power, beta2_power, grad_scale)
+
+
+def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt,
+                  ws, weights=None, seg_ids=None, row_ptr=None, seg_scale=None, row_stride=None,
+                  uniq_rows=None, uniq_grads=None, n_uniq=None, n_rows=None):
+  lib = _lib.load()
+  _chk(table, torch.float32, 'table')
+  _chk(state0, torch.float32, 'state0')
+  _chk(state1, torch.float32, 'state1')
+  _chk(rows, torch.int64, 'rows')
+  _chk(weights, torch.float32, 'weights')
+  _chk(seg_ids, torch.int32, 'seg_ids')
+  _chk(row_ptr, torch.int32, 'row_ptr')
+  _chk(seg_scale, torch.float32, 'seg_scale')
+  _chk(uniq_rows, torch.int64, 'uniq_rows')
+  _chk(uniq_grads, torch.float32, 'uniq_grads')
+  _chk(n_uniq, torch.int32, 'n_uniq')
+  for i, b in enumerate(grad_bufs):
+    _chk(b, torch.float32, 'grad_bufs[%d]' % i)
+  row_stride = row_stride or dim
+  if n_rows is None:
+    n_rows = table.numel() // row_stride
+  _lib.check(
+      lib.er_embedding_bwd(_p(table), _p(state0), _p(state1), n_rows, dim, row_stride, _p(rows),
+                           _p(weights), _p(seg_ids), _p(row_ptr), n_seg, rows.numel(),
+                           _p(slots_dev), n_slots, _buf_array(grad_bufs), len(grad_bufs),
+                           _p(seg_scale), ctypes.byref(opt), _p(uniq_rows), _p(uniq_grads),
+                           _p(n_uniq), _p(ws), ws.numel(), _stream()), 'er_embedding_bwd')
+
+
+def sparse_apply(table, state0, state1, dim, uniq_rows, uniq_grads, n_uniq, opt, row_stride=None):
+  lib = _lib.load()
+  row_stride = row_stride or dim
+  _lib.check(
+      lib.er_sparse_apply(_p(table), _p(state0), _p(state1), dim, row_stride, _p(uniq_rows),
+                          _p(uniq_grads), _p(n_uniq), uniq_rows.numel(), ctypes.byref(opt),
+                          _stream()), 'er_sparse_apply')
+
+
+def adam_dense_sweep(table, m, v, dim, touched, opt, row_stride=None):
+  lib = _lib.load()
+  row_stride = row_stride or dim
+  _lib.check(
+      lib.er_adam_dense_sweep(_p(table), _p(m), _p(v), table.numel() // row_stride, dim,
+                              row_stride, _p(touched), ctypes.byref(opt), _stream()),
+      'er_adam_dense_sweep')
+
+
+def mark_rows(rows, n_rows, touched, value, n_dev=None):
+  lib = _lib.load()
+  _lib.check(
+      lib.er_mark_rows(_p(rows), rows.numel(), _p(n_dev), n_rows, _p(touched), value, _stream()),
+      'er_mark_rows')
+
+
+def sort_rows(rows, max_row, n_dev=None):
+  lib = _lib.load()
+  _chk(rows, torch.int64, 'rows')
+  n = rows.numel()
+  keys = torch.empty(n, dtype=torch.int32, device=rows.device)
+  vals = torch.empty(n, dtype=torch.int32, device=rows.device)
+  ws_bytes = lib.er_sort_workspace_bytes(n)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=rows.device)
+  _lib.check(
+      lib.er_sort_rows(_p(rows), n, _p(n_dev), max_row, _p(keys), _p(vals), _p(ws), ws_bytes,
+                       _stream()), 'er_sort_rows')
+  return keys, vals
+
+
+def fm_fwd(x, n_field, dim, y=None):
+  lib = _lib.load()
+  _chk(x, torch.float32, 'x')
+  batch = x.shape[0]
+  if y is None:
+    y = torch.empty(batch, dim, dtype=torch.float32, device=x.device)
+  _lib.check(lib.er_fm_fwd(_p(x), batch, n_field, dim, x.stride(0), _p(y), _stream()), 'er_fm_fwd')
+  return y
+
+
+def fm_bwd(x, gy, n_field, dim, gx=None, accumulate=False):
+  lib = _lib.load()
+  _chk(x, torch.float32, 'x')
+  _chk(gy, torch.float32, 'gy')
+  batch = x.shape[0]
+  if gx is None:
+    gx = torch.empty(batch, n_field * dim, dtype=torch.float32, device=x.device)
+    accumulate = False
+  _lib.check(
+      lib.er_fm_bwd(_p(x), _p(gy), batch, n_field, dim, x.stride(0), _p(gx), gx.stride(0),
+                    1 if accumulate else 0, _stream()), 'er_fm_bwd')
+  return gx
+
+
+def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
+  """returns (loss [1], probs [B], g_logits [B])."""
+  lib = _lib.load()
+  _chk(logits, torch.float32, 'logits')
+  _chk(labels, torch.float32, 'labels')
+  batch = logits.numel()
+  if inv_count is None:
+    inv_count = 1.0 / batch
+  loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+  probs = torch.empty(batch, dtype=torch.float32, device=logits.device)
+  g = torch.empty(batch, dtype=torch.float32, device=logits.device) if want_grad else None
+  _lib.check(
+      lib.er_sigmoid_ce_fwd_bwd(_p(logits), _p(labels), _p(weights), batch, inv_count, _p(loss),
+                                _p(probs), _p(g), _stream()), 'er_sigmoid_ce_fwd_bwd')
+  return loss, probs, g

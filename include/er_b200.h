@@ -1,0 +1,225 @@
+/*
+ * er_b200.h -- C ABI of liber_b200.so: the sm_100a kernels behind EasyRec's
+ * sparse-embedding + feature-interaction training path.
+ *
+ * The reference (alibaba/EasyRec) has NO native ABI on this path: the path is a
+ * TensorFlow graph assembled in Python.  Every entry
+ * point below therefore cites the reference *Python* call it replaces; the
+ * ctypes binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented "host"; nothing here allocates or frees device
+ *     memory, and there is no hidden global state;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns immediately; it is CUDA-graph capturable;
+ *   - return value: 0 = ER_OK, anything else is an er_status; the message for
+ *     the calling thread's last failure is er_last_error();
+ *   - "rows" are int64 row numbers inside one embedding ARENA (all tables with
+ *     the same embedding_dim packed back to back); -1 marks a dropped lookup;
+ *   - segments are the (slot, sample) cells of the reference's packed CSR
+ *     layout (feature-major, easy_rec/python/input/load_parquet.py:81-90).
+ */
+#ifndef ER_B200_H_
+#define ER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ER_B200_ABI_VERSION 1
+
+typedef void* er_stream_t; /* cudaStream_t */
+
+typedef enum er_status {
+  ER_OK = 0,
+  ER_ERR_INVALID_ARG = 1,
+  ER_ERR_WORKSPACE = 2,
+  ER_ERR_CUDA = 3,
+  ER_ERR_UNSUPPORTED = 4
+} er_status;
+
+/* raw value -> table row rule */
+typedef enum er_bucket_mode {
+  /* row = Fingerprint64(as_string(v)) mod hash_bucket_size
+   * (feature_column_v2.py:3915-3921, input/input.py:356-376,541-543) */
+  ER_BUCKET_FARM_DECIMAL = 0,
+  /* row = v floormod num_buckets (input/parquet_input.py:221) */
+  ER_BUCKET_MOD = 1,
+  /* v == -1 dropped (feature_column_v2.py:2566-2585); v < 0 or v >= num_buckets
+   * -> default 0 (feature_column_v2.py:4268-4292, feature_column.py:293-294) */
+  ER_BUCKET_IDENTITY = 2,
+  /* already a table-local row (e.g. RawFeature projection ids 0..k-1,
+   * input/input.py:648-673); v < 0 dropped */
+  ER_BUCKET_NONE = 3
+} er_bucket_mode;
+
+/* safe_embedding_lookup_sparse combiners (compat/embedding_ops.py:37-162,
+ * compat/feature_column/feature_column.py:202-244) */
+typedef enum er_combiner {
+  ER_COMBINER_SUM = 0,
+  ER_COMBINER_MEAN = 1,
+  ER_COMBINER_SQRTN = 2
+} er_combiner;
+
+/* One embedding slot = one (feature column, output position) pair; the
+ * host-side table plan (FeatureColumnParser equivalent) fills an array of
+ * these once and uploads it. 48 bytes, no pointers. */
+typedef struct er_slot {
+  int64_t num_buckets; /* hash_bucket_size | num_buckets of the column        */
+  int64_t row_offset;  /* first arena row of the column's table               */
+  int32_t seg_begin;   /* first segment (global numbering) of this slot       */
+  int32_t n_seg;       /* segments of this slot: B, or B*T for sequence slots */
+  int32_t bucket_mode; /* er_bucket_mode                                      */
+  int32_t combiner;    /* er_combiner                                         */
+  int32_t out_buf;     /* index into the out_bufs[] / grad_bufs[] argument    */
+  int32_t out_stride;  /* row stride of that buffer, in floats                */
+  int32_t out_col;     /* first column of this slot inside a buffer row       */
+  int32_t shard_n;     /* >1: rows are mod-sharded over shard_n ranks
+                          (feature_column.py:296,317,461-463)                 */
+} er_slot_t;
+
+#define ER_MAX_BUFS 8
+
+typedef enum er_opt_kind {
+  ER_OPT_SGD = 0,
+  ER_OPT_ADAGRAD = 1,   /* tf.train.AdagradOptimizer sparse apply            */
+  ER_OPT_LAZY_ADAM = 2, /* compat/adam_s.py:185-213                          */
+  ER_OPT_ADAM_ROWS = 3  /* TF Adam restricted to touched rows == lazy rule;
+                           the dense decay sweep is er_adam_dense_sweep       */
+} er_opt_kind;
+
+typedef struct er_opt {
+  int32_t kind;      /* er_opt_kind */
+  float lr;          /* learning rate of this step (host-side schedule)       */
+  float beta1;
+  float beta2;
+  float eps;
+  float beta1_power; /* beta1^t BEFORE this step's _finish (adam_s.py:233-245) */
+  float beta2_power;
+  float grad_scale;  /* multiplies the summed gradient: 1/N for sharded tables
+                        (compat/optimizers.py:315-316) times
+                        embedding_learning_rate_multiplier                    */
+} er_opt_t;
+
+/* ---- library ---------------------------------------------------------- */
+int er_abi_version(void);
+const char* er_last_error(void);
+
+/* ---- K0: lens -> CSR --------------------------------------------------
+ * row_ptr[0]=0, row_ptr[s+1]=row_ptr[s]+lens[s]; seg_ids[l]=s for the lookups
+ * of segment s.  Replaces cumsum(segment_lens) + searchsorted
+ * (compat/feature_column/feature_column.py:264-266).
+ * ws: er_csr_workspace_bytes(n_seg) bytes. */
+size_t er_csr_workspace_bytes(int64_t n_seg);
+int er_csr_from_lens(const int32_t* lens, int64_t n_seg, int32_t* row_ptr,
+                     int32_t* seg_ids, int64_t n_lookups_cap, void* ws,
+                     size_t ws_bytes, er_stream_t stream);
+
+/* ---- K1: raw ids -> arena rows ---------------------------------------
+ * rows[l] = slot.row_offset + bucket(ids[l]) per the slot's er_bucket_mode,
+ * or -1 when the lookup is dropped.  With shard_n > 1 the result is the
+ * owner-local row and owner[l] (may be NULL) receives id mod shard_n.
+ * seg_ids == NULL means lookup l belongs to segment l (single-valued slots);
+ * row_ptr == NULL means exactly n_lookups_cap lookups, else row_ptr[n_seg]. */
+int er_bucketize(const int64_t* ids, const int32_t* seg_ids,
+                 const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                 const er_slot_t* slots, int32_t n_slots, int64_t* rows,
+                 int32_t* owner, er_stream_t stream);
+
+/* Scalar helpers used by tests and by host-side plan code (host pointers). */
+uint64_t er_fingerprint64_host(const char* s, size_t len);
+
+/* ---- K2: multi-slot gather + pool ------------------------------------
+ * For every segment s of every slot: out = combine_l w_l * table[rows[l]]
+ * with safe_embedding_lookup_sparse pruning (rows<0 dropped; w<=0 dropped
+ * unless combiner is sum; empty -> zeros).  Writes
+ *   out_bufs[slot.out_buf][(s-slot.seg_begin)*out_stride + out_col + 0..dim)
+ * i.e. the per-group concat of feature_column.input_layer
+ * (compat/feature_column/feature_column.py:384-414) is fused into the store.
+ * seg_scale (n_seg floats, may be NULL when every slot is sum) receives the
+ * mean/sqrtn denominators' reciprocal for the backward pass.
+ * out_bufs is a HOST array of n_bufs (<= ER_MAX_BUFS) device pointers. */
+int er_embedding_fwd(const float* table, int64_t n_rows, int32_t dim,
+                     int32_t row_stride, const int64_t* rows,
+                     const float* weights, const int32_t* row_ptr,
+                     int64_t n_seg, int64_t n_lookups_cap,
+                     const er_slot_t* slots, int32_t n_slots,
+                     float* const* out_bufs, int32_t n_bufs, float* seg_scale,
+                     er_stream_t stream);
+
+/* ---- K7: backward = dedup + segment-sum + fused optimizer row update ---
+ * The IndexedSlices gradient of K2 (one row per lookup:
+ * coef_l * grad_bufs[..][segment of l]) is summed per distinct row in
+ * ascending lookup order (stable radix sort on the row number, the
+ * deterministic equivalent of TF's _deduplicate_indexed_slices), multiplied
+ * by opt.grad_scale, and applied to the row and its optimizer state in the
+ * same kernel.  state0/state1: adagrad accumulator | adam m, v (same layout
+ * and stride as table; unused ones NULL).
+ * When uniq_rows/uniq_grads are non-NULL the deduplicated gradient is ALSO
+ * written there (compact, sorted by row; *n_uniq receives the count); pass
+ * table == NULL to only emit it. */
+size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap);
+int er_embedding_bwd(float* table, float* state0, float* state1,
+                     int64_t n_rows, int32_t dim, int32_t row_stride,
+                     const int64_t* rows, const float* weights,
+                     const int32_t* seg_ids, const int32_t* row_ptr,
+                     int64_t n_seg, int64_t n_lookups_cap,
+                     const er_slot_t* slots, int32_t n_slots,
+                     const float* const* grad_bufs, int32_t n_bufs,
+                     const float* seg_scale, const er_opt_t* opt,
+                     int64_t* uniq_rows, float* uniq_grads, int32_t* n_uniq,
+                     void* ws, size_t ws_bytes, er_stream_t stream);
+
+/* Apply an already deduplicated sparse gradient (rows distinct). */
+int er_sparse_apply(float* table, float* state0, float* state1, int32_t dim,
+                    int32_t row_stride, const int64_t* uniq_rows,
+                    const float* uniq_grads, const int32_t* n_uniq,
+                    int64_t n_cap, const er_opt_t* opt, er_stream_t stream);
+
+/* TF AdamOptimizer's dense part for rows NOT touched this step
+ * (documented at compat/adam_s.py:74-81): m*=b1, v*=b2, w-=lr_t*m/(sqrt(v)+eps)
+ * streamed over the whole table; touched[] (n_rows bytes) masks rows already
+ * updated by er_embedding_bwd. */
+int er_adam_dense_sweep(float* table, float* m, float* v, int64_t n_rows,
+                        int32_t dim, int32_t row_stride,
+                        const uint8_t* touched, const er_opt_t* opt,
+                        er_stream_t stream);
+
+/* touched[rows[l]] = value for every live lookup (mask for er_adam_dense_sweep). */
+int er_mark_rows(const int64_t* rows, int64_t n_lookups_cap, const int32_t* n_dev,
+                 int64_t n_rows, uint8_t* touched, int32_t value,
+                 er_stream_t stream);
+
+/* ---- stable radix sort / unique (exposed for the sharded path) -------- */
+size_t er_sort_workspace_bytes(int64_t n);
+/* keys_out sorted ascending, vals_out = original positions (stable). */
+int er_sort_rows(const int64_t* rows, int64_t n, const int32_t* n_dev,
+                 int64_t max_row, uint32_t* keys_out, uint32_t* vals_out,
+                 void* ws, size_t ws_bytes, er_stream_t stream);
+
+/* ---- K3: FM second order ----------------------------------------------
+ * y[b,:] = 0.5*((sum_f x[b,f,:])^2 - sum_f x[b,f,:]^2)   (layers/fm.py:20-26)
+ * x is [B, F*D] with row stride x_stride. */
+int er_fm_fwd(const float* x, int64_t batch, int32_t n_field, int32_t dim,
+              int32_t x_stride, float* y, er_stream_t stream);
+/* gx[b,f,:] (+)= gy[b,:] * (sum_f' x[b,f',:] - x[b,f,:]) */
+int er_fm_bwd(const float* x, const float* gy, int64_t batch, int32_t n_field,
+              int32_t dim, int32_t x_stride, float* gx, int32_t gx_stride,
+              int32_t accumulate, er_stream_t stream);
+
+/* sigmoid cross entropy (tf.losses.sigmoid_cross_entropy,
+ * builders/loss_builder.py:36-39): loss_sum += sum_b w*(max(x,0)-x*z+log1p(exp(-|x|)))
+ * g_logits[b] = w*(sigmoid(x)-z)*inv_count  (inv_count applied by caller=host scalar) */
+int er_sigmoid_ce_fwd_bwd(const float* logits, const float* labels,
+                          const float* weights, int64_t batch, float inv_count,
+                          float* loss_out, float* probs, float* g_logits,
+                          er_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ER_B200_H_ */

@@ -1,0 +1,185 @@
+"""CPU: pin the oracle against every known answer available for the hot path."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_kats.json')))
+
+
+def test_fingerprint64_tensorflow_frozen_vectors():
+  for s, want in KATS['fingerprint64']['vectors'].items():
+    assert O.fingerprint64(s) == int(want), s
+  assert O.fingerprint64('') == 0x9ae16a3b2f90404f  # k2 for the empty string
+
+
+def test_string_to_hash_bucket_fast_examples():
+  for case in KATS['fingerprint64']['hash_bucket_fast']:
+    got = [O.fingerprint64(s) % case['num_buckets'] for s in case['inputs']]
+    assert got == case['expected']
+
+
+def test_product_host_hash_equals_oracle_all_lengths():
+  # two independently written implementations (oracle C bytes-wise, product C++ memcpy-wise)
+  from easyrec_b200 import _lib
+  rnd = random.Random(7)
+  for n in list(range(0, 200)) + [255, 256, 257, 1000, 4097]:
+    for _ in range(3):
+      s = bytes(rnd.getrandbits(8) for _ in range(n))
+      assert _lib.fingerprint64(s) == O.fingerprint64(s), n
+
+
+def test_embed_test_raw_known_answer():
+  k = KATS['embed_test_raw']
+  row_ptr, _ = O.csr_from_lens(k['lens'])
+  out, _ = O.embedding_fwd(np.array(k['table'], np.float32), k['ids'], row_ptr, 0,
+                           weights=np.array(k['weights'], np.float32))
+  assert np.abs(out - np.array(k['expected'], np.float32)).max() < k['tolerance']
+
+
+def test_embed_test_seq_multi_known_answer():
+  k = KATS['embed_test_seq_multi']
+  row_ptr, _ = O.csr_from_lens(k['lens'])
+  out, _ = O.embedding_fwd(np.array(k['table'], np.float32), k['ids'], row_ptr, 1)
+  for seg, want in list(k['expected_asserted'].items()) + list(k['expected_derived'].items()):
+    assert np.abs(out[int(seg)] - np.array(want, np.float32)).max() < k['tolerance'], seg
+
+
+def test_bucketize_rules():
+  ids = np.array([0, 1, -1, -7, 12, 5, 2**62, -2**63], np.int64)
+  # floored mod (python semantics), input/parquet_input.py:221
+  rows, _ = O.bucketize(ids, 1, 5, 100)
+  assert rows.tolist() == [100 + (int(v) % 5) for v in ids]
+  # identity: -1 dropped, out of range -> 0
+  rows, _ = O.bucketize(ids, 2, 10, 0)
+  assert rows.tolist() == [0, 1, -1, 0, 0, 5, 0, 0]
+  # hash of decimal text, negative numbers keep their sign
+  rows, _ = O.bucketize(ids, 0, 1000003, 7)
+  want = [7 + O.fingerprint64(str(int(v))) % 1000003 for v in ids]
+  assert rows.tolist() == want
+  # mod-sharding: owner = r % N, local = r // N (feature_column.py:296,317)
+  rows, owner = O.bucketize(np.arange(20), 1, 1000, 0, shard_n=8)
+  assert owner.tolist() == [i % 8 for i in range(20)]
+  assert rows.tolist() == [i // 8 for i in range(20)]
+
+
+def test_safe_lookup_pruning_and_combiners():
+  table = np.arange(20, dtype=np.float32).reshape(10, 2) + 1
+  ids = np.array([1, -1, 2, 3, 4, 5, 6], np.int64)
+  w = np.array([1.0, 1.0, 0.0, 2.0, -1.0, 3.0, 4.0], np.float32)
+  lens = [3, 0, 2, 2]
+  row_ptr, _ = O.csr_from_lens(lens)
+  s, _ = O.embedding_fwd(table, ids, row_ptr, 0, weights=w)
+  np.testing.assert_allclose(s[0], 1 * table[1] + 0 * table[2])  # id<0 dropped, w=0 kept for sum
+  np.testing.assert_allclose(s[1], 0)
+  np.testing.assert_allclose(s[2], 2 * table[3] - table[4])
+  m, sc = O.embedding_fwd(table, ids, row_ptr, 1, weights=w)
+  np.testing.assert_allclose(m[0], table[1])  # w<=0 pruned for mean
+  np.testing.assert_allclose(m[2], table[3])  # negative weight pruned
+  np.testing.assert_allclose(m[3], (3 * table[5] + 4 * table[6]) / 7, rtol=1e-6)
+  q, _ = O.embedding_fwd(table, ids, row_ptr, 2, weights=w)
+  np.testing.assert_allclose(q[3], (3 * table[5] + 4 * table[6]) / 5, rtol=1e-6)
+
+
+@pytest.mark.parametrize('kind', [O.OPT_SGD, O.OPT_ADAGRAD, O.OPT_LAZY_ADAM])
+def test_optimizer_rules_against_formulas(kind):
+  rng = np.random.default_rng(3)
+  V, D, L = 50, 4, 200
+  table = rng.normal(size=(V, D)).astype(np.float32)
+  s0 = np.full((V, D), 0.1, np.float32) if kind == O.OPT_ADAGRAD else np.zeros((V, D), np.float32)
+  s1 = np.zeros((V, D), np.float32)
+  rows = rng.integers(0, V, L)
+  rows[::17] = -1
+  gseg = rng.normal(size=(L, D)).astype(np.float32)
+  t0, a0, b0 = table.copy(), s0.copy(), s1.copy()
+  n, ur, ug = O.embedding_bwd(table, s0, s1, rows, None, gseg, kind, 0.05, beta1_power=0.9**3,
+                              beta2_power=0.999**3, want_uniq=True)
+  G = np.zeros((V, D), np.float64)
+  for l, r in enumerate(rows):
+    if r >= 0:
+      G[r] += gseg[l]
+  touched = np.unique(rows[rows >= 0])
+  assert n == touched.size and ur.tolist() == touched.tolist()
+  np.testing.assert_allclose(ug, G[touched], rtol=1e-5, atol=1e-6)
+  lr = 0.05
+  if kind == O.OPT_SGD:
+    want = t0 - lr * G
+  elif kind == O.OPT_ADAGRAD:
+    acc = a0 + G**2
+    want = np.where(G != 0, t0 - lr * G / np.sqrt(acc), t0)
+    np.testing.assert_allclose(s0[touched], acc[touched], rtol=1e-5)
+  else:
+    lr_t = lr * np.sqrt(1 - 0.999**3) / (1 - 0.9**3)
+    # (1 - beta) is evaluated in fp32 by the TF graph (adam_s.py:196,202)
+    m = float(np.float32(1) - np.float32(0.9)) * G
+    v = float(np.float32(1) - np.float32(0.999)) * G**2
+    want = t0 - lr_t * m / (np.sqrt(v) + 1e-8)
+    np.testing.assert_allclose(s0[touched], m[touched], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(s1[touched], v[touched], rtol=1e-5, atol=1e-9)
+  np.testing.assert_allclose(table[touched], want[touched], rtol=1e-5, atol=1e-6)
+  untouched = np.setdiff1d(np.arange(V), touched)
+  assert np.array_equal(table[untouched], t0[untouched])
+
+
+def test_dense_oracle_matches_torch_autograd_cpu():
+  """The numpy DNN/DeepFM backward is hand written: verify it with torch CPU autograd."""
+  import torch
+  rng = np.random.default_rng(0)
+  B, F, D = 64, 5, 4
+
+  def mk(i, o, bn=True):
+    L = {'W': rng.normal(0, 0.3, (i, o)).astype(np.float32), 'b': rng.normal(0, 0.1, o).astype(np.float32)}
+    if bn:
+      L.update(gamma=rng.uniform(0.5, 1.5, o).astype(np.float32), beta=rng.normal(0, 0.1, o).astype(np.float32))
+    return L
+
+  params = {'dnn': [mk(F * D, 16), mk(16, 8)], 'final': [mk(1 + D + 8, 8), mk(8, 4)],
+            'out_W': rng.normal(0, 0.3, (4, 1)).astype(np.float32), 'out_b': np.zeros(1, np.float32)}
+  wide = rng.normal(size=(B, F)).astype(np.float32)
+  deep = rng.normal(size=(B, F * D)).astype(np.float32)
+  labels = (rng.uniform(size=B) < 0.3).astype(np.float32)
+  logits, cache = O.deepfm_forward(wide, deep, F, D, params)
+  loss, _, g_logits = O.sigmoid_ce(logits, labels)
+  g_wide, g_deep, grads = O.deepfm_backward(g_logits, wide, deep, F, D, params, cache)
+
+  tw = torch.tensor(wide, requires_grad=True)
+  td = torch.tensor(deep, requires_grad=True)
+  tp = {}
+
+  def tdnn(x, layers, tag):
+    for i, L in enumerate(layers):
+      W = torch.tensor(L['W'], requires_grad=True)
+      b = torch.tensor(L['b'], requires_grad=True)
+      ga = torch.tensor(L['gamma'], requires_grad=True)
+      be = torch.tensor(L['beta'], requires_grad=True)
+      tp[(tag, i)] = (W, b, ga, be)
+      z = x @ W + b
+      mu = z.mean(0)
+      var = ((z - mu)**2).mean(0)
+      x = torch.relu((z - mu) / torch.sqrt(var + O.BN_EPS) * ga + be)
+    return x
+
+  v = td.reshape(B, F, D)
+  fm = 0.5 * (v.sum(1)**2 - (v**2).sum(1))
+  deep_fea = tdnn(td, params['dnn'], 'dnn')
+  allf = torch.cat([tw.sum(1, keepdim=True), fm, deep_fea], 1)
+  fin = tdnn(allf, params['final'], 'final')
+  oW = torch.tensor(params['out_W'], requires_grad=True)
+  tl = (fin @ oW)[:, 0]
+  tloss = torch.nn.functional.binary_cross_entropy_with_logits(tl, torch.tensor(labels))
+  tloss.backward()
+  np.testing.assert_allclose(logits, tl.detach().numpy(), rtol=1e-4, atol=1e-5)
+  assert abs(loss - float(tloss)) < 1e-5
+  np.testing.assert_allclose(g_wide, tw.grad.numpy(), rtol=1e-3, atol=1e-6)
+  np.testing.assert_allclose(g_deep, td.grad.numpy(), rtol=1e-3, atol=1e-6)
+  for tag in ('dnn', 'final'):
+    for i in range(2):
+      W, b, ga, be = tp[(tag, i)]
+      np.testing.assert_allclose(grads[tag][i]['W'], W.grad.numpy(), rtol=1e-3, atol=1e-6)
+      np.testing.assert_allclose(grads[tag][i]['gamma'], ga.grad.numpy(), rtol=1e-3, atol=1e-6)
+      np.testing.assert_allclose(grads[tag][i]['beta'], be.grad.numpy(), rtol=1e-3, atol=1e-6)
+  np.testing.assert_allclose(grads['out_W'], oW.grad.numpy(), rtol=1e-3, atol=1e-6)
