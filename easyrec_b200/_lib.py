@@ -41,6 +41,7 @@ class ErOpt(ctypes.Structure):
 SIGNATURES = {
     'er_abi_version': (c_i32, []),
     'er_last_error': (ctypes.c_char_p, []),
+    'er_launch_count': (ctypes.c_uint64, []),
     'er_csr_workspace_bytes': (c_sz, [c_i64]),
     'er_csr_from_lens': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz,
                                  c_vp]),

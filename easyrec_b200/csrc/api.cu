@@ -2,15 +2,21 @@
 // and the host-side Fingerprint64 for arbitrary byte strings.
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "hash.cuh"
 
 namespace er {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n); }
 }  // namespace er
 
 extern "C" int er_abi_version(void) { return ER_B200_ABI_VERSION; }
+
+extern "C" uint64_t er_launch_count(void) { return er::g_launches.load(); }
 
 extern "C" const char* er_last_error(void) { return er::g_last_error.c_str(); }
 

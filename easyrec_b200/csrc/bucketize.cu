@@ -102,9 +102,11 @@ extern "C" int er_csr_from_lens(const int32_t* lens, int64_t n_seg, int32_t* row
     return fail(ER_ERR_WORKSPACE, "er_csr_from_lens: workspace too small");
   cudaStream_t st = as_stream(stream);
   scan::exclusive_scan(LensIn{lens}, RowPtrOut{row_ptr, n_seg}, n_seg, nullptr, ws, st);
+  count_launches(3);
   if (seg_ids && n_lookups_cap > 0) {
     expand_seg_ids_kernel<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(row_ptr, n_seg, n_lookups_cap,
                                                                     seg_ids);
+    count_launches(1);
   }
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -123,6 +125,7 @@ extern "C" int er_bucketize(const int64_t* ids, const int32_t* seg_ids, const in
   cudaStream_t st = as_stream(stream);
   bucketize_kernel<<<grid_for(n_lookups_cap, 256, 8), 256, n_slots * sizeof(int32_t), st>>>(
       ids, seg_ids, row_ptr, n_seg, n_lookups_cap, slots, n_slots, rows, owner);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

@@ -11,6 +11,7 @@
 namespace er {
 
 void set_error(const std::string& msg);
+void count_launches(int n);  // kernels enqueued by this library (er_launch_count)
 
 inline int fail(int code, const std::string& msg) {
   set_error(msg);

@@ -340,6 +340,7 @@ static void launch_vec(const BwdArgs& a, cudaStream_t st) {
   bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, groups), 256, smem, st>>>(a);
   const size_t smem_long = (size_t)((a.n_slots + 3) & ~3) * sizeof(int32_t) + 256 * sizeof(float4);
   bwd_long_vec_kernel<LANES><<<kSmCount, 256, smem_long, st>>>(a);
+  count_launches(2);
 }
 
 }  // namespace er
@@ -436,8 +437,10 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
     scan::exclusive_scan(HeadIn{w.keys, a.sentinel}, HeadOut{w.head_rank}, n_lookups_cap, n_uniq,
                          w.scan_ws, st);
     a.head_rank = w.head_rank;
+    count_launches(3);
   }
   zero_i32_kernel<<<1, 1, 0, st>>>(w.long_count);
+  count_launches(1);
   if (table) {
     aligned = aligned && reinterpret_cast<uintptr_t>(table) % 16 == 0 && row_stride % 4 == 0 &&
               (!state0 || reinterpret_cast<uintptr_t>(state0) % 16 == 0) &&
@@ -457,6 +460,7 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
   } else {
     bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256,
                              (size_t)n_slots * sizeof(int32_t), st>>>(a);
+    count_launches(1);
   }
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -535,6 +539,7 @@ extern "C" int er_sparse_apply(float* table, float* state0, float* state1, int32
   a.lr_t = (k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS) ? adam_lr_t(*opt) : opt->lr;
   sparse_apply_kernel<1><<<grid_for(n_cap * dim, 256, 8), 256, 0, as_stream(stream)>>>(
       a, uniq_rows, uniq_grads, n_uniq, n_cap);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
@@ -548,6 +553,7 @@ extern "C" int er_adam_dense_sweep(float* table, float* m, float* v, int64_t n_r
   adam_sweep_kernel<0><<<grid_for(n_rows * dim, 256, 8), 256, 0, as_stream(stream)>>>(
       table, m, v, n_rows, dim, row_stride, touched, opt->beta1, opt->beta2, opt->eps,
       adam_lr_t(*opt));
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

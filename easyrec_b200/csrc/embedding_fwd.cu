@@ -271,6 +271,7 @@ extern "C" int er_embedding_fwd(const float* table, int64_t n_rows, int32_t dim,
         table, dim, row_stride, rows, weights, row_ptr, n_seg, n_lookups_cap, slots, n_slots, bufs,
         seg_scale);
   }
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

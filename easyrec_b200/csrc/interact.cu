@@ -139,6 +139,7 @@ extern "C" int er_fm_fwd(const float* x, int64_t batch, int32_t n_field, int32_t
   else
     fm_fwd_scalar_kernel<<<grid_for(batch * dim, 256, 8), 256, 0, st>>>(x, batch, n_field, dim,
                                                                        x_stride, y);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
@@ -159,6 +160,7 @@ extern "C" int er_fm_bwd(const float* x, const float* gy, int64_t batch, int32_t
   else
     fm_bwd_kernel<1><<<grid_for(batch * dim, 256, 8), 256, 0, st>>>(
         x, gy, batch, n_field, dim, x_stride, gx, gx_stride, accumulate);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
@@ -172,6 +174,7 @@ extern "C" int er_sigmoid_ce_fwd_bwd(const float* logits, const float* labels,
   ER_REQUIRE(batch > 0, "batch must be positive");
   sigmoid_ce_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, labels, weights, batch, inv_count,
                                                       loss_out, probs, g_logits);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
@@ -184,6 +187,7 @@ extern "C" int er_mark_rows(const int64_t* rows, int64_t n_lookups_cap, const in
   if (n_lookups_cap <= 0) return ER_OK;
   mark_rows_kernel<<<grid_for(n_lookups_cap, 256, 8), 256, 0, as_stream(stream)>>>(
       rows, n_lookups_cap, n_dev, n_rows, touched, (uint8_t)value);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

@@ -163,11 +163,13 @@ inline void sort_rows(const int64_t* rows, int64_t cap, const int32_t* n_dev, in
   uint32_t* kb = (passes % 2 == 0) ? w.keys_tmp : keys_out;
   uint32_t* vb = (passes % 2 == 0) ? w.vals_tmp : vals_out;
   init_pairs_kernel<<<grid_for(cap, 256, 8), 256, 0, st>>>(rows, cap, n_dev, (uint32_t)n_rows, ka, va);
+  count_launches(1);
   for (int p = 0; p < passes; ++p) {
     const int shift = p * kRadixBits;
     hist_kernel<<<(unsigned)nt, kThreads, 0, st>>>(ka, cap, shift, w.hist, nt);
     scan::exclusive_scan(HistIn{w.hist}, HistOut{w.hist}, (int64_t)kRadix * nt, nullptr, w.scan_ws, st);
     scatter_kernel<<<(unsigned)nt, kThreads, 0, st>>>(ka, va, kb, vb, cap, shift, w.hist, nt);
+    count_launches(5);
     uint32_t* t = ka; ka = kb; kb = t;
     t = va; va = vb; vb = t;
   }

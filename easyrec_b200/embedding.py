@@ -1,0 +1,227 @@
+"""Embedding arenas and the fused lookup / backward-update engine.
+
+B200-first data layout (DESIGN.md "HBM layout"):
+  * every table with the same embedding_dim lives back to back in ONE fp32 arena
+    [n_rows, dim] (row = dim*4 bytes, 64 B at dim 16), so a whole feature group -- all
+    slots, all tables -- is one gather launch and one dedup+update pipeline;
+  * optimizer state (adagrad accumulator | adam m, v) are arenas of the same shape;
+  * lookups of a batch are the reference's packed CSR (feature-major segments,
+    easy_rec/python/input/load_parquet.py:81-90); `rows` are arena row numbers.
+
+This is the host-side counterpart of `feature_column.input_layer` +
+`embedding_parallel_lookup` (compat/feature_column/feature_column.py:248-357, 384-414,
+643-715): same role, none of its graph.
+"""
+import math
+
+import numpy as np
+import torch
+
+from easyrec_b200 import _lib
+from easyrec_b200 import kernels as K
+
+
+class Slot(object):
+  """One (feature column -> output position) pair of an arena."""
+
+  def __init__(self, name, table, bucket_mode, num_buckets, combiner=_lib.COMBINER_SUM,
+               out_buf=0, n_seg_per_sample=1):
+    self.name = name
+    self.table = table            # table name inside the arena (shared embeddings share it)
+    self.bucket_mode = bucket_mode
+    self.num_buckets = int(num_buckets)
+    self.combiner = combiner
+    self.out_buf = out_buf        # which output matrix of the arena call
+    self.n_seg_per_sample = n_seg_per_sample  # T for sequence slots (un-pooled [B,T,D])
+
+
+class Arena(object):
+  """All tables of one embedding_dim, plus optimizer state, on one device."""
+
+  def __init__(self, dim, device, shard_n=1, shard_rank=0):
+    self.dim = dim
+    self.device = device
+    self.shard_n = shard_n
+    self.shard_rank = shard_rank
+    self.tables = {}   # name -> (row_offset, n_rows_local, n_rows_global)
+    self.n_rows = 0
+    self.weight = None
+    self.state0 = None
+    self.state1 = None
+
+  def add_table(self, name, n_rows_global):
+    if name in self.tables:
+      assert self.tables[name][2] == n_rows_global, 'shared table %s: size mismatch' % name
+      return
+    # per-worker rows (V + N - 1) // N  (feature_column.py:461-463)
+    local = (n_rows_global + self.shard_n - 1) // self.shard_n
+    self.tables[name] = (self.n_rows, local, n_rows_global)
+    self.n_rows += local
+
+  def materialize(self, opt_kind, init_fn=None, adagrad_init=0.1, generator=None):
+    """Allocate the arena.  Default init: truncated_normal(0, 0.01/sqrt(dim))
+    (feature_column_v2.py:910-912)."""
+    assert self.n_rows > 0
+    w = torch.empty(self.n_rows, self.dim, dtype=torch.float32, device=self.device)
+    if init_fn is not None:
+      init_fn(w)
+    else:
+      std = 0.01 / math.sqrt(self.dim)
+      torch.nn.init.trunc_normal_(w, mean=0.0, std=std, a=-2 * std, b=2 * std,
+                                  generator=generator)
+    self.weight = w
+    self.opt_kind = opt_kind
+    if opt_kind == _lib.OPT_ADAGRAD:
+      self.state0 = torch.full_like(w, adagrad_init)
+    elif opt_kind in (_lib.OPT_LAZY_ADAM, _lib.OPT_ADAM_ROWS):
+      self.state0 = torch.zeros_like(w)
+      self.state1 = torch.zeros_like(w)
+
+  def table_view(self, name):
+    off, n, _ = self.tables[name]
+    return self.weight[off:off + n]
+
+
+class ArenaCall(object):
+  """The static plan of one fused lookup over an arena for a fixed batch size:
+  slot descriptors on the device, output matrices, backward workspace."""
+
+  def __init__(self, arena, slots, batch_size, out_widths, single_valued, max_lookups=None):
+    self.arena = arena
+    self.slots = slots
+    self.batch_size = batch_size
+    dim = arena.dim
+    recs = []
+    seg = 0
+    cols = [0] * len(out_widths)
+    # row stride of each output matrix: padded to 4 floats so 16 B vector stores stay aligned
+    self.out_strides = [((w + 3) // 4) * 4 if dim % 4 == 0 else w for w in out_widths]
+    self.out_widths = out_widths
+    self.slot_cols = []
+    for s in slots:
+      off, _, _ = arena.tables[s.table]
+      n_seg = batch_size * s.n_seg_per_sample
+      if s.n_seg_per_sample == 1:
+        col = cols[s.out_buf]
+        cols[s.out_buf] += dim
+        stride = self.out_strides[s.out_buf]
+      else:  # sequence slot: its own [B*T, dim] matrix
+        col = 0
+        stride = self.out_strides[s.out_buf]
+      self.slot_cols.append(col)
+      recs.append(dict(num_buckets=s.num_buckets, row_offset=off, seg_begin=seg, n_seg=n_seg,
+                       bucket_mode=s.bucket_mode, combiner=s.combiner, out_buf=s.out_buf,
+                       out_stride=stride, out_col=col, shard_n=arena.shard_n))
+      seg += n_seg
+    self.n_seg = seg
+    self.slots_np = K.make_slots(recs)
+    self.slots_dev = K.slots_to_device(self.slots_np, arena.device)
+    self.n_slots = len(recs)
+    self.single_valued = single_valued
+    self.max_lookups = self.n_seg if single_valued else int(max_lookups)
+    self.needs_scale = any(s.combiner != _lib.COMBINER_SUM for s in slots)
+    self.ws = K.bwd_workspace(self.max_lookups, arena.device)
+    self.seg_scale = (torch.empty(self.n_seg, dtype=torch.float32, device=arena.device)
+                      if self.needs_scale else None)
+
+  def out_rows(self, buf):
+    for s in self.slots:
+      if s.out_buf == buf:
+        return self.batch_size * s.n_seg_per_sample
+    raise KeyError(buf)
+
+  def alloc_outputs(self):
+    return [torch.empty(self.out_rows(i), st, dtype=torch.float32, device=self.arena.device)
+            for i, st in enumerate(self.out_strides)]
+
+
+class _FusedLookup(torch.autograd.Function):
+  """forward = K2 gather+pool; backward = K7 dedup + fused optimizer row update.
+
+  The table is not a torch Parameter: its gradient never materialises as a tensor, the
+  row update happens inside backward (reference: IndexedSlices -> apply_gradients,
+  compat/optimizers.py:413-416)."""
+
+  @staticmethod
+  def forward(ctx, anchor, call, rows, weights, row_ptr, seg_ids, opt_holder, outs):
+    a = call.arena
+    K.embedding_fwd(a.weight, a.dim, rows, call.slots_dev, call.n_slots, call.n_seg, outs,
+                    weights=weights, row_ptr=row_ptr, seg_scale=call.seg_scale)
+    ctx.call = call
+    ctx.opt_holder = opt_holder
+    ctx.save_for_backward(rows, weights, row_ptr, seg_ids)
+    ctx.mark_non_differentiable()
+    return tuple(outs)
+
+  @staticmethod
+  def backward(ctx, *grads):
+    call = ctx.call
+    a = call.arena
+    rows, weights, row_ptr, seg_ids = ctx.saved_tensors
+    gbufs = []
+    for i, g in enumerate(grads):
+      if g is None:
+        g = torch.zeros(call.out_rows(i), call.out_strides[i], dtype=torch.float32,
+                        device=a.device)
+      gbufs.append(g.contiguous())
+    K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, rows, call.slots_dev, call.n_slots,
+                    call.n_seg, gbufs, ctx.opt_holder['opt'], call.ws, weights=weights,
+                    seg_ids=seg_ids, row_ptr=row_ptr, seg_scale=call.seg_scale)
+    return (None,) * 8
+
+
+def fused_lookup(call, rows, opt_holder, weights=None, row_ptr=None, seg_ids=None, outs=None,
+                 anchor=None):
+  """Returns the output matrices of `call` (list of [B(*T), stride] tensors).
+
+  `anchor` is any tensor that requires grad; it only makes autograd call backward."""
+  if outs is None:
+    outs = call.alloc_outputs()
+  if anchor is None:
+    anchor = torch.zeros((), device=call.arena.device, requires_grad=True)
+  return list(_FusedLookup.apply(anchor, call, rows, weights, row_ptr, seg_ids, opt_holder, outs))
+
+
+class _FM(torch.autograd.Function):
+  """K3: layers/fm.py:20-26 on the [B, F*D] group matrix."""
+
+  @staticmethod
+  def forward(ctx, x, n_field, dim):
+    ctx.n_field, ctx.dim = n_field, dim
+    ctx.save_for_backward(x)
+    return K.fm_fwd(x, n_field, dim)
+
+  @staticmethod
+  def backward(ctx, gy):
+    (x,) = ctx.saved_tensors
+    gx = torch.empty(x.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
+    if x.shape[1] > ctx.n_field * ctx.dim:
+      gx.zero_()
+    K.fm_bwd(x, gy.contiguous(), ctx.n_field, ctx.dim, gx=gx)
+    return gx, None, None
+
+
+def fm(x, n_field, dim):
+  return _FM.apply(x, n_field, dim)
+
+
+class _SigmoidCE(torch.autograd.Function):
+  """tf.losses.sigmoid_cross_entropy (builders/loss_builder.py:36-39), mean over nonzero weights."""
+
+  @staticmethod
+  def forward(ctx, logits, labels, weights, inv_count):
+    loss, probs, g = K.sigmoid_ce(logits.contiguous(), labels, weights, inv_count)
+    ctx.save_for_backward(g)
+    ctx.mark_non_differentiable(probs)
+    return loss[0], probs
+
+  @staticmethod
+  def backward(ctx, gl, _gp):
+    (g,) = ctx.saved_tensors
+    return g * gl, None, None, None
+
+
+def sigmoid_cross_entropy(logits, labels, weights=None, inv_count=None):
+  if inv_count is None:
+    inv_count = 1.0 / logits.numel()
+  return _SigmoidCE.apply(logits, labels, weights, inv_count)

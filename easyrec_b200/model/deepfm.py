@@ -1,0 +1,69 @@
+"""DeepFM on the fused path (reference: easy_rec/python/model/deepfm.py:24-109).
+
+wide  = sum_f wide_f                      [B,1]   (deepfm.py:62-63)
+fm    = 0.5((sum_f v)^2 - sum_f v^2)      [B,D]   (layers/fm.py:20-26) over the deep group's features
+deep  = DNN(deep concat)                          (deepfm.py:70-72)
+with final_dnn: logits = dense(final_dnn(concat[wide, fm, deep]))   (deepfm.py:75-88)
+without:        logits = wide + sum_d fm + dense(deep)             (deepfm.py:89-105)
+"""
+import torch
+from torch import nn
+
+from easyrec_b200 import embedding as E
+from easyrec_b200 import layers as L
+
+
+class DeepFM(nn.Module):
+
+  def __init__(self, input_layer, dnn_units, final_units, l2_reg=0.0, embedding_reg=0.0,
+               generator=None):
+    super().__init__()
+    self.input_layer = input_layer
+    deep_layout = input_layer.group_layout['deep']
+    self.n_field = len(deep_layout)
+    self.dim = deep_layout[0][2]
+    assert all(e[2] == self.dim and e[1] == 'emb' for e in deep_layout), \
+        'FM needs every deep feature embedded with the same dim'
+    self.deep_width = self.n_field * self.dim
+    self.dnn = L.DNN(self.deep_width, dnn_units, generator=generator)
+    self.has_final = len(final_units) > 0
+    if self.has_final:
+      self.final_dnn = L.DNN(1 + self.dim + self.dnn.out_dim, final_units, generator=generator)
+      self.output = L.Dense(self.final_dnn.out_dim, 1, generator)
+    else:
+      self.output = L.Dense(self.dnn.out_dim, 1, generator)
+    self.l2_reg = l2_reg
+    self.embedding_reg = embedding_reg
+
+  def forward(self, features):
+    g = self.input_layer.lookup(features)
+    wide, _ = g['wide']
+    deep, _ = g['deep']
+    wide_fea = wide.sum(dim=1, keepdim=True)
+    fm_fea = E.fm(deep, self.n_field, self.dim)
+    deep_fea = self.dnn(deep[:, :self.deep_width] if deep.shape[1] != self.deep_width else deep)
+    if self.has_final:
+      all_fea = torch.cat([wide_fea, fm_fea, deep_fea], dim=1)
+      logits = self.output(self.final_dnn(all_fea))
+    else:
+      logits = wide_fea + fm_fea.sum(dim=1, keepdim=True) + self.output(deep_fea)
+    self._emb_outputs = (wide, deep)
+    return logits[:, 0]
+
+  def regularization_loss(self):
+    """l2_regularizer(scale)(w) = scale * sum(w^2)/2 (compat/regularizers.py) on dense kernels
+    (layers/dnn.py:57-62) and on the *looked-up* embedding outputs (layers/input_layer.py:369-375)."""
+    reg = 0.0
+    if self.l2_reg > 0:
+      ks = self.dnn.kernels() + [self.output.kernel]
+      if self.has_final:
+        ks += self.final_dnn.kernels()
+      reg = reg + self.l2_reg * 0.5 * sum((k * k).sum() for k in ks)
+    if self.embedding_reg > 0:
+      wide, deep = self._emb_outputs
+      reg = reg + self.embedding_reg * 0.5 * ((wide * wide).sum() + (deep * deep).sum())
+    return reg
+
+  def loss(self, logits, labels):
+    ce, probs = E.sigmoid_cross_entropy(logits, labels)
+    return ce + self.regularization_loss(), probs

@@ -108,6 +108,8 @@ typedef struct er_opt {
 /* ---- library ---------------------------------------------------------- */
 int er_abi_version(void);
 const char* er_last_error(void);
+/* kernels this library has enqueued since load (bench.py's gpu_launches) */
+uint64_t er_launch_count(void);
 
 /* ---- K0: lens -> CSR --------------------------------------------------
  * row_ptr[0]=0, row_ptr[s+1]=row_ptr[s]+lens[s]; seg_ids[l]=s for the lookups
