@@ -135,51 +135,35 @@ class ArenaCall(object):
             for i, st in enumerate(self.out_strides)]
 
 
-class _FusedLookup(torch.autograd.Function):
-  """forward = K2 gather+pool; backward = K7 dedup + fused optimizer row update.
-
-  The table is not a torch Parameter: its gradient never materialises as a tensor, the
-  row update happens inside backward (reference: IndexedSlices -> apply_gradients,
+def fused_lookup(call, rows, weights=None, row_ptr=None, outs=None):
+  """K2 over one arena.  Returns the call's output matrices as autograd LEAVES
+  (requires_grad=True): after loss.backward() their .grad is dL/d(pooled), which
+  `fused_backward_update` hands to K7.  The table itself is never a torch Parameter and its
+  gradient never materialises as a tensor (reference: IndexedSlices -> apply_gradients,
   compat/optimizers.py:413-416)."""
-
-  @staticmethod
-  def forward(ctx, anchor, call, rows, weights, row_ptr, seg_ids, opt_holder, outs):
-    a = call.arena
-    K.embedding_fwd(a.weight, a.dim, rows, call.slots_dev, call.n_slots, call.n_seg, outs,
-                    weights=weights, row_ptr=row_ptr, seg_scale=call.seg_scale)
-    ctx.call = call
-    ctx.opt_holder = opt_holder
-    ctx.save_for_backward(rows, weights, row_ptr, seg_ids)
-    ctx.mark_non_differentiable()
-    return tuple(outs)
-
-  @staticmethod
-  def backward(ctx, *grads):
-    call = ctx.call
-    a = call.arena
-    rows, weights, row_ptr, seg_ids = ctx.saved_tensors
-    gbufs = []
-    for i, g in enumerate(grads):
-      if g is None:
-        g = torch.zeros(call.out_rows(i), call.out_strides[i], dtype=torch.float32,
-                        device=a.device)
-      gbufs.append(g.contiguous())
-    K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, rows, call.slots_dev, call.n_slots,
-                    call.n_seg, gbufs, ctx.opt_holder['opt'], call.ws, weights=weights,
-                    seg_ids=seg_ids, row_ptr=row_ptr, seg_scale=call.seg_scale)
-    return (None,) * 8
-
-
-def fused_lookup(call, rows, opt_holder, weights=None, row_ptr=None, seg_ids=None, outs=None,
-                 anchor=None):
-  """Returns the output matrices of `call` (list of [B(*T), stride] tensors).
-
-  `anchor` is any tensor that requires grad; it only makes autograd call backward."""
+  a = call.arena
   if outs is None:
     outs = call.alloc_outputs()
-  if anchor is None:
-    anchor = torch.zeros((), device=call.arena.device, requires_grad=True)
-  return list(_FusedLookup.apply(anchor, call, rows, weights, row_ptr, seg_ids, opt_holder, outs))
+  K.embedding_fwd(a.weight, a.dim, rows, call.slots_dev, call.n_slots, call.n_seg, outs,
+                  weights=weights, row_ptr=row_ptr, seg_scale=call.seg_scale)
+  for o in outs:
+    o.requires_grad_(True)
+  return outs
+
+
+def fused_backward_update(call, rows, outs, opt, weights=None, row_ptr=None, seg_ids=None):
+  """K7: dedup + segment-sum + optimizer row update from the leaves' gradients.  Runs on the
+  caller's thread and stream (not inside the autograd engine), so it is CUDA-graph capturable."""
+  a = call.arena
+  gbufs = []
+  for i, o in enumerate(outs):
+    g = o.grad
+    if g is None:
+      g = torch.zeros_like(o)
+    gbufs.append(g.contiguous())
+  K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, rows, call.slots_dev, call.n_slots,
+                  call.n_seg, gbufs, opt, call.ws, weights=weights, seg_ids=seg_ids,
+                  row_ptr=row_ptr, seg_scale=call.seg_scale)
 
 
 class _FM(torch.autograd.Function):

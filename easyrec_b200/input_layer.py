@@ -146,7 +146,7 @@ class InputLayer(object):
     self.raw_sub = torch.tensor(np.where(rng > 0, np.array(mn, np.float32), 0.0),
                                 dtype=torch.float32, device=device)
     self.opt_holder = {'opt': K.make_opt(embedding_optimizer, 0.01)}
-    self._anchor = torch.zeros((), device=device, requires_grad=True)
+    self._pending = []
     self._rows_cache = {}
     self._gather_plan = {}
 
@@ -157,6 +157,14 @@ class InputLayer(object):
     kind = next(iter(self.arenas.values())).opt_kind
     self.opt_holder['opt'] = K.make_opt(kind, lr, beta1, beta2, eps, beta1**(step + 1),
                                         beta2**(step + 1), grad_scale)
+
+  def backward_update(self):
+    """After loss.backward(): K7 for every arena looked up since the last call (dedup, segment
+    sum and the fused optimizer row update).  The reference's counterpart is
+    opt.apply_gradients on the tables' IndexedSlices (compat/optimizers.py:413-416)."""
+    for call, rows, w, outs in self._pending:
+      E.fused_backward_update(call, rows, outs, self.opt_holder['opt'], weights=w)
+    self._pending = []
 
   def normalize_dense(self, dense):
     if not self.raw_has_range:
@@ -215,6 +223,7 @@ class InputLayer(object):
     dense_norm = self.normalize_dense(dense) if dense is not None else None
     results = {}
     self._rows_cache = {}
+    self._pending = []
     for dim, call in self.calls.items():
       # arenas whose slots read the same features with the same bucket rules and row offsets
       # (e.g. DeepFM's wide and deep groups) share one gather + one K1 launch
@@ -227,8 +236,9 @@ class InputLayer(object):
         self._rows_cache[key] = (rows, w)
       else:
         rows, w = hit
-      outs = E.fused_lookup(call, rows, self.opt_holder, weights=w, anchor=self._anchor)
+      outs = E.fused_lookup(call, rows, weights=w)
       results[dim] = outs
+      self._pending.append((call, rows, w, outs))
     out = {}
     for gname, layout in self.group_layout.items():
       mats = {}

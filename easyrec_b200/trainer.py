@@ -115,6 +115,7 @@ class Trainer(object):
     logits = self.model(features)
     loss, probs = self.model.loss(logits, labels)
     loss.backward()
+    self.input_layer.backward_update()   # K7: dedup + fused row update, on this thread/stream
     self.dense_opt.step()
     return loss.detach(), probs
 
