@@ -11,14 +11,17 @@
 // (acc += g^2; w -= lr*g*rsqrt(acc); acc0 = 0.1, protos/optimizer.proto:79),
 // EP gradient scaling compat/optimizers.py:315-316.
 //
-// Summation order inside a run is the lookup order (the sort is stable), which is
-// the order a sequential CPU segment-sum uses; runs longer than kLongRun (hot ids
-// under Zipf) are handed to a second kernel that splits them over a whole CTA and
-// combines partials in a fixed tree, so results stay deterministic.
+// Launches per call: P+1 sort launches (sort.cuh) + runs kernel + hot-row kernel.
+//  * runs kernel: a warp scans 32 sorted positions, ballots the run heads and deals them
+//    to its dim/4-lane groups; a group prefetches the row and its optimizer state, sums
+//    the run in lookup order (the sort is stable => the order a sequential CPU
+//    segment-sum uses), applies the optimizer, stores.
+//  * runs longer than kLongRun (Zipf-hot ids, 1-row RawFeature tables: run length = B)
+//    are queued with their length and summed by a whole CTA, one lookup per thread,
+//    then a fixed-order shared-memory tree: deterministic, no atomics on floats.
 //
-// HBM traffic per launch (algorithmic): L*(4+4) sorted pairs + L*R gathered upstream
-// gradient rows + U*(k*R) row/state read-modify-write, R = 4*dim, k = 2 (sgd),
-// 4 (adagrad), 6 (adam).
+// HBM traffic per call (algorithmic): L*8 sorted pairs + L*R gathered upstream gradient
+// rows + U*k*R row/state read-modify-write, R = 4*dim, k = 2 (sgd), 4 (adagrad), 6 (adam).
 #include "common.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
@@ -29,8 +32,8 @@ struct CBufs {
   const float* p[ER_MAX_BUFS];
 };
 
-constexpr int kLongRun = 64;      // runs longer than this go to the CTA-wide kernel
-constexpr int kBatch = 4;         // lookups fetched per step of the run loop
+constexpr int kLongRun = 64;  // runs longer than this go to the CTA-wide kernel
+constexpr int kBatch = 4;     // lookups fetched per step of the run loop
 
 struct BwdArgs {
   float* table;
@@ -54,7 +57,7 @@ struct BwdArgs {
   float* uniq_grads;
   const int32_t* head_rank;  // exclusive count of run heads before each position (emit mode)
   int32_t* long_count;
-  int32_t* long_list;
+  int2* long_list;  // (start, length) of each hot run
 };
 
 // gradient row pointer and coefficient of sorted entry with lookup position l
@@ -62,15 +65,15 @@ __device__ __forceinline__ const float* grad_src(const BwdArgs& a, const int32_t
                                                  uint32_t l, float* coef) {
   const int32_t s = a.seg_ids ? a.seg_ids[l] : (int32_t)l;
   const int f = find_slot(s_seg_begin, a.n_slots, s);
-  const er_slot_t sl = a.slots[f];
+  const er_slot_t* sl = a.slots + f;
+  const int seg_begin = sl->seg_begin, stride = sl->out_stride, col = sl->out_col, buf = sl->out_buf;
   float c = a.weights ? a.weights[l] : 1.0f;
   if (a.seg_scale) c = __fmul_rn(c, a.seg_scale[s]);
   *coef = c;
-  return a.gbufs.p[sl.out_buf] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
+  return a.gbufs.p[buf] + (int64_t)(s - seg_begin) * stride + col;
 }
 
-__device__ __forceinline__ float upd_one(const BwdArgs& a, float g, float& w, float& s0, float& s1) {
-  // returns nothing meaningful; updates w, s0, s1 in registers
+__device__ __forceinline__ void upd_one(const BwdArgs& a, float g, float& w, float& s0, float& s1) {
   switch (a.opt.kind) {
     case ER_OPT_ADAGRAD: {
       s0 = __fadd_rn(s0, __fmul_rn(g, g));
@@ -88,12 +91,38 @@ __device__ __forceinline__ float upd_one(const BwdArgs& a, float g, float& w, fl
     default:  // SGD
       w = __fsub_rn(w, __fmul_rn(a.opt.lr, g));
   }
-  return w;
 }
 
-template <int LANES>
+__device__ __forceinline__ void f4_fma_sep(float4& g, const float4& v, float c) {
+  g.x = __fadd_rn(g.x, __fmul_rn(v.x, c));
+  g.y = __fadd_rn(g.y, __fmul_rn(v.y, c));
+  g.z = __fadd_rn(g.z, __fmul_rn(v.z, c));
+  g.w = __fadd_rn(g.w, __fmul_rn(v.w, c));
+}
+__device__ __forceinline__ void f4_acc(float4& g, const float4& v) {
+  g.x = __fadd_rn(g.x, v.x);
+  g.y = __fadd_rn(g.y, v.y);
+  g.z = __fadd_rn(g.z, v.z);
+  g.w = __fadd_rn(g.w, v.w);
+}
+
+struct RowRegs {
+  float4 w, s0, s1;
+};
+
+__device__ __forceinline__ RowRegs load_row(const BwdArgs& a, uint32_t row, int lane) {
+  RowRegs r;
+  r.w = r.s0 = r.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!a.table) return r;
+  const int64_t off = (int64_t)row * a.row_stride;
+  r.w = reinterpret_cast<const float4*>(a.table + off)[lane];
+  if (a.state0) r.s0 = reinterpret_cast<const float4*>(a.state0 + off)[lane];
+  if (a.state1) r.s1 = reinterpret_cast<const float4*>(a.state1 + off)[lane];
+  return r;
+}
+
 __device__ __forceinline__ void apply_row_vec(const BwdArgs& a, uint32_t row, int lane, float4 g,
-                                              int64_t head_pos) {
+                                              int64_t head_pos, RowRegs r) {
   g.x = __fmul_rn(g.x, a.opt.grad_scale);
   g.y = __fmul_rn(g.y, a.opt.grad_scale);
   g.z = __fmul_rn(g.z, a.opt.grad_scale);
@@ -104,172 +133,165 @@ __device__ __forceinline__ void apply_row_vec(const BwdArgs& a, uint32_t row, in
     reinterpret_cast<float4*>(a.uniq_grads + (int64_t)u * a.dim)[lane] = g;
   }
   if (!a.table) return;
+  upd_one(a, g.x, r.w.x, r.s0.x, r.s1.x);
+  upd_one(a, g.y, r.w.y, r.s0.y, r.s1.y);
+  upd_one(a, g.z, r.w.z, r.s0.z, r.s1.z);
+  upd_one(a, g.w, r.w.w, r.s0.w, r.s1.w);
   const int64_t off = (int64_t)row * a.row_stride;
-  float4* wp = reinterpret_cast<float4*>(a.table + off) + lane;
-  float4 w = *wp;
-  float4 s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
-  float4* s0p = a.state0 ? reinterpret_cast<float4*>(a.state0 + off) + lane : nullptr;
-  float4* s1p = a.state1 ? reinterpret_cast<float4*>(a.state1 + off) + lane : nullptr;
-  if (s0p) s0 = *s0p;
-  if (s1p) s1 = *s1p;
-  upd_one(a, g.x, w.x, s0.x, s1.x);
-  upd_one(a, g.y, w.y, s0.y, s1.y);
-  upd_one(a, g.z, w.z, s0.z, s1.z);
-  upd_one(a, g.w, w.w, s0.w, s1.w);
-  *wp = w;
-  if (s0p) *s0p = s0;
-  if (s1p) *s1p = s1;
+  reinterpret_cast<float4*>(a.table + off)[lane] = r.w;
+  if (a.state0) reinterpret_cast<float4*>(a.state0 + off)[lane] = r.s0;
+  if (a.state1) reinterpret_cast<float4*>(a.state1 + off)[lane] = r.s1;
 }
 
-// One LANES-wide group per sorted position; only run heads do work.
+// upper bound of `key` in keys[lo, n)
+__device__ __forceinline__ int64_t run_end(const uint32_t* __restrict__ keys, int64_t lo, int64_t n,
+                                           uint32_t key) {
+  int64_t hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] <= key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// ---- runs, vector rows (dim = 4*LANES) ---------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ int32_t s_seg_begin[];
   for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
   __syncthreads();
-  const int lane = threadIdx.x % LANES;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
-  if (i >= a.n) return;
-  const uint32_t key = a.keys[i];
-  if (key >= a.sentinel) return;
-  if (i > 0 && a.keys[i - 1] == key) return;
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  int64_t j = i;
-  int cnt = 0;
-  while (true) {
-    uint32_t l[kBatch];
-    int m = 0;
+  constexpr int GROUPS = 32 / LANES;
+  const int lane32 = threadIdx.x & 31;
+  const int lane = lane32 % LANES;
+  const int grp = lane32 / LANES;
+  const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (base >= a.n) return;
+  const int64_t pos = base + lane32;
+  const uint32_t k = pos < a.n ? a.keys[pos] : a.sentinel;
+  uint32_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+  if (lane32 == 0) kprev = (base > 0) ? a.keys[base - 1] : ~k;
+  const bool is_head = pos < a.n && k < a.sentinel && (pos == 0 || kprev != k);
+  const unsigned heads = __ballot_sync(0xffffffffu, is_head);
+  const int n_heads = __popc(heads);
+  for (int h = grp; h < n_heads; h += GROUPS) {
+    const int p = __fns(heads, 0, h + 1);
+    const int64_t i = base + p;
+    const uint32_t key = a.keys[i];
+    RowRegs row = load_row(a, key, lane);  // in flight while the run is summed
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t j = i;
+    int cnt = 0;
+    bool queued = false;
+    while (true) {
+      uint32_t l[kBatch];
+      int m = 0;
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const bool in = (j + u < a.n);
-      const uint32_t k = in ? a.keys[j + u] : a.sentinel;
-      l[u] = in ? a.vals[j + u] : 0u;
-      if (m == u && k == key) m = u + 1;
-    }
-    float4 gv[kBatch];
-    float c[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      if (u < m) {
-        const float* src = grad_src(a, s_seg_begin, l[u], &c[u]);
-        gv[u] = reinterpret_cast<const float4*>(src)[lane];
+      for (int u = 0; u < kBatch; ++u) {
+        const bool in = (j + u < a.n);
+        const uint32_t kk = in ? a.keys[j + u] : a.sentinel;
+        l[u] = in ? a.vals[j + u] : 0u;
+        if (m == u && kk == key) m = u + 1;
       }
-    }
+      float4 gv[kBatch];
+      float c[kBatch];
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      if (u < m) {
-        g.x = __fadd_rn(g.x, __fmul_rn(gv[u].x, c[u]));
-        g.y = __fadd_rn(g.y, __fmul_rn(gv[u].y, c[u]));
-        g.z = __fadd_rn(g.z, __fmul_rn(gv[u].z, c[u]));
-        g.w = __fadd_rn(g.w, __fmul_rn(gv[u].w, c[u]));
-      }
-    }
-    j += m;
-    cnt += m;
-    if (m < kBatch) break;
-    if (cnt >= kLongRun) {
-      if (j < a.n && a.keys[j] == key) {  // hot row: hand the whole run to the CTA-wide kernel
-        if (lane == 0) {
-          int slot = atomicAdd(a.long_count, 1);
-          a.long_list[slot] = (int32_t)i;
+      for (int u = 0; u < kBatch; ++u) {
+        if (u < m) {
+          const float* src = grad_src(a, s_seg_begin, l[u], &c[u]);
+          gv[u] = reinterpret_cast<const float4*>(src)[lane];
         }
-        return;
       }
-      break;
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+        if (u < m) f4_fma_sep(g, gv[u], c[u]);
+      j += m;
+      cnt += m;
+      if (m < kBatch) break;
+      if (cnt >= kLongRun) {
+        if (j < a.n && a.keys[j] == key) {  // hot row: hand the whole run to the CTA-wide kernel
+          if (lane == 0) {
+            const int64_t e = run_end(a.keys, j, a.n, key);
+            const int slot = atomicAdd(a.long_count, 1);
+            a.long_list[slot] = make_int2((int)i, (int)(e - i));
+          }
+          queued = true;
+        }
+        break;
+      }
     }
+    if (!queued) apply_row_vec(a, key, lane, g, i, row);
   }
-  apply_row_vec<LANES>(a, key, lane, g, i);
 }
 
-// Hot rows: one CTA per run, 256/LANES groups each sum a contiguous chunk in lookup
-// order, then a fixed-order tree in shared memory.
-template <int LANES>
+// ---- hot rows, vector: one CTA per run; TPE threads share one lookup (TPE = 1 for dim <= 32:
+// a thread moves a whole 4*LANES-float gradient row), then a fixed shared-memory tree -----------
+template <int LANES, int TPE>
 __global__ void __launch_bounds__(256) bwd_long_vec_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ int32_t s_dyn[];
   int32_t* s_seg_begin = s_dyn;
   float4* s_part = reinterpret_cast<float4*>(s_dyn + ((a.n_slots + 3) & ~3));
   for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
   __syncthreads();
-  constexpr int G = 256 / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int grp = threadIdx.x / LANES;
+  constexpr int CH = LANES / TPE;   // float4 chunks per thread
+  constexpr int G = 256 / TPE;      // lookups in flight per CTA step
+  const int sub = threadIdx.x % TPE;
+  const int grp = threadIdx.x / TPE;
   const int n_long = *a.long_count;
   for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
-    const int64_t i = a.long_list[q];
+    const int2 rl = a.long_list[q];
+    const int64_t i = rl.x, len = rl.y;
     const uint32_t key = a.keys[i];
-    // upper bound of key in keys[i, n)
-    int64_t lo = i, hi = a.n;
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (a.keys[mid] <= key)
-        lo = mid + 1;
-      else
-        hi = mid;
-    }
-    const int64_t len = lo - i;
-    const int64_t chunk = ceil_div(len, G);
-    int64_t b = i + grp * chunk, e = b + chunk;
-    if (e > i + len) e = i + len;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t j = b; j < e; j += kBatch) {
-      float4 gv[kBatch];
-      float c[kBatch];
+    float4 g[CH];
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        if (j + u < e) {
-          const float* src = grad_src(a, s_seg_begin, a.vals[j + u], &c[u]);
-          gv[u] = reinterpret_cast<const float4*>(src)[lane];
-        }
+    for (int c = 0; c < CH; ++c) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t e = grp; e < len; e += 2 * G) {
+      const bool two = (e + G < len);
+      float c0, c1 = 0.f;
+      const float* s0 = grad_src(a, s_seg_begin, a.vals[i + e], &c0);
+      const float* s1 = two ? grad_src(a, s_seg_begin, a.vals[i + e + G], &c1) : s0;
+      float4 v0[CH], v1[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        v0[c] = reinterpret_cast<const float4*>(s0)[sub * CH + c];
+        v1[c] = reinterpret_cast<const float4*>(s1)[sub * CH + c];
       }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        if (j + u < e) {
-          g.x = __fadd_rn(g.x, __fmul_rn(gv[u].x, c[u]));
-          g.y = __fadd_rn(g.y, __fmul_rn(gv[u].y, c[u]));
-          g.z = __fadd_rn(g.z, __fmul_rn(gv[u].z, c[u]));
-          g.w = __fadd_rn(g.w, __fmul_rn(gv[u].w, c[u]));
-        }
+      for (int c = 0; c < CH; ++c) {
+        f4_fma_sep(g[c], v0[c], c0);
+        if (two) f4_fma_sep(g[c], v1[c], c1);
       }
     }
-    s_part[grp * LANES + lane] = g;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s_part[grp * LANES + sub * CH + c] = g[c];
     __syncthreads();
     for (int stride = G / 2; stride >= 1; stride >>= 1) {
       if (grp < stride) {
-        float4 x = s_part[grp * LANES + lane], y = s_part[(grp + stride) * LANES + lane];
-        x.x = __fadd_rn(x.x, y.x);
-        x.y = __fadd_rn(x.y, y.y);
-        x.z = __fadd_rn(x.z, y.z);
-        x.w = __fadd_rn(x.w, y.w);
-        s_part[grp * LANES + lane] = x;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          float4 x = s_part[grp * LANES + sub * CH + c];
+          f4_acc(x, s_part[(grp + stride) * LANES + sub * CH + c]);
+          s_part[grp * LANES + sub * CH + c] = x;
+        }
       }
       __syncthreads();
     }
-    if (grp == 0) apply_row_vec<LANES>(a, key, lane, s_part[lane], i);
+    if (threadIdx.x < LANES) {
+      RowRegs row = load_row(a, key, threadIdx.x);
+      apply_row_vec(a, key, threadIdx.x, s_part[threadIdx.x], i, row);
+    }
     __syncthreads();
   }
 }
 
-// Scalar path (wide dim=1 tables, odd dims): one thread per (sorted position, column).
-__global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
-  __syncthreads();
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = t / a.dim;
-  const int c = (int)(t - i * a.dim);
-  if (i >= a.n) return;
-  const uint32_t key = a.keys[i];
-  if (key >= a.sentinel) return;
-  if (i > 0 && a.keys[i - 1] == key) return;
-  float g = 0.f;
-  for (int64_t j = i; j < a.n && a.keys[j] == key; ++j) {
-    float coef;
-    const float* src = grad_src(a, s_seg_begin, a.vals[j], &coef);
-    g = __fadd_rn(g, __fmul_rn(src[c], coef));
-  }
+// ---- scalar rows (wide dim=1 tables, odd dims): one thread per (sorted position, column) ----
+__device__ __forceinline__ void apply_scalar(const BwdArgs& a, uint32_t key, int c, float g,
+                                             int64_t head_pos) {
   g = __fmul_rn(g, a.opt.grad_scale);
   if (a.uniq_rows) {
-    const int32_t u = a.head_rank[i];
+    const int32_t u = a.head_rank[head_pos];
     if (c == 0) a.uniq_rows[u] = (int64_t)key;
     a.uniq_grads[(int64_t)u * a.dim + c] = g;
   }
@@ -282,6 +304,66 @@ __global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_const
   a.table[off] = w;
   if (a.state0) a.state0[off] = s0;
   if (a.state1) a.state1[off] = s1;
+}
+
+__global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ int32_t s_seg_begin[];
+  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / a.dim;
+  const int c = (int)(t - i * a.dim);
+  if (i >= a.n) return;
+  const uint32_t key = a.keys[i];
+  if (key >= a.sentinel) return;
+  if (i > 0 && a.keys[i - 1] == key) return;
+  float g = 0.f;
+  int64_t j = i;
+  for (; j < a.n && a.keys[j] == key; ++j) {
+    if (j - i >= kLongRun) {  // hot row
+      if (c == 0) {
+        const int64_t e = run_end(a.keys, j, a.n, key);
+        const int slot = atomicAdd(a.long_count, 1);
+        a.long_list[slot] = make_int2((int)i, (int)(e - i));
+      }
+      return;
+    }
+    float coef;
+    const float* src = grad_src(a, s_seg_begin, a.vals[j], &coef);
+    g = __fadd_rn(g, __fmul_rn(src[c], coef));
+  }
+  apply_scalar(a, key, c, g, i);
+}
+
+__global__ void __launch_bounds__(256) bwd_long_scalar_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ int32_t s_dyn[];
+  int32_t* s_seg_begin = s_dyn;
+  float* s_part = reinterpret_cast<float*>(s_dyn + ((a.n_slots + 3) & ~3));
+  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
+  __syncthreads();
+  const int n_long = *a.long_count;
+  for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
+    const int2 rl = a.long_list[q];
+    const int64_t i = rl.x, len = rl.y;
+    const uint32_t key = a.keys[i];
+    for (int c = 0; c < a.dim; ++c) {
+      float g = 0.f;
+      for (int64_t e = threadIdx.x; e < len; e += 256) {
+        float coef;
+        const float* src = grad_src(a, s_seg_begin, a.vals[i + e], &coef);
+        g = __fadd_rn(g, __fmul_rn(src[c], coef));
+      }
+      s_part[threadIdx.x] = g;
+      __syncthreads();
+      for (int stride = 128; stride >= 1; stride >>= 1) {
+        if ((int)threadIdx.x < stride)
+          s_part[threadIdx.x] = __fadd_rn(s_part[threadIdx.x], s_part[threadIdx.x + stride]);
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) apply_scalar(a, key, c, s_part[0], i);
+      __syncthreads();
+    }
+  }
 }
 
 struct HeadIn {
@@ -297,23 +379,22 @@ struct HeadOut {
   __device__ void operator()(int64_t j, int ex, int) const { rank[j] = ex; }
 };
 
-__global__ void zero_i32_kernel(int32_t* p) { *p = 0; }
-
 inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BwdWs {
   uint32_t* keys;
   uint32_t* vals;
   int32_t* head_rank;
-  int32_t* long_list;
+  int2* long_list;
   int32_t* long_count;
   void* sort_ws;
   void* scan_ws;
 };
 
 inline size_t bwd_ws_bytes(int64_t n) {
-  return a256((size_t)n * 4) * 4 + 256 + a256(rsort::workspace_bytes(n)) +
-         a256(scan::workspace_bytes(n)) + 512;
+  // keys, vals, head_rank (4 B each), long list (one int2 per kLongRun lookups at most)
+  return a256((size_t)n * 4) * 3 + a256((size_t)(n / kLongRun + 1) * 8) + 256 +
+         a256(rsort::workspace_bytes(n)) + a256(scan::workspace_bytes(n)) + 512;
 }
 inline BwdWs bwd_carve(void* ws, int64_t n) {
   char* p = reinterpret_cast<char*>(a256(reinterpret_cast<size_t>(ws)));
@@ -321,7 +402,7 @@ inline BwdWs bwd_carve(void* ws, int64_t n) {
   w.keys = reinterpret_cast<uint32_t*>(p); p += a256((size_t)n * 4);
   w.vals = reinterpret_cast<uint32_t*>(p); p += a256((size_t)n * 4);
   w.head_rank = reinterpret_cast<int32_t*>(p); p += a256((size_t)n * 4);
-  w.long_list = reinterpret_cast<int32_t*>(p); p += a256((size_t)n * 4);
+  w.long_list = reinterpret_cast<int2*>(p); p += a256((size_t)(n / kLongRun + 1) * 8);
   w.long_count = reinterpret_cast<int32_t*>(p); p += 256;
   w.sort_ws = p; p += a256(rsort::workspace_bytes(n));
   w.scan_ws = p;
@@ -335,17 +416,19 @@ static float adam_lr_t(const er_opt_t& o) {
 
 template <int LANES>
 static void launch_vec(const BwdArgs& a, cudaStream_t st) {
-  const int groups = 256 / LANES;
   const size_t smem = (size_t)a.n_slots * sizeof(int32_t);
-  bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, groups), 256, smem, st>>>(a);
-  const size_t smem_long = (size_t)((a.n_slots + 3) & ~3) * sizeof(int32_t) + 256 * sizeof(float4);
-  bwd_long_vec_kernel<LANES><<<kSmCount, 256, smem_long, st>>>(a);
+  // one warp per 32 sorted positions, 8 warps per CTA
+  bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
+  constexpr int TPE = (LANES <= 8) ? 1 : LANES;
+  const size_t smem_long =
+      (size_t)((a.n_slots + 3) & ~3) * sizeof(int32_t) + (size_t)(256 / TPE) * LANES * sizeof(float4);
+  bwd_long_vec_kernel<LANES, TPE><<<2 * kSmCount, 256, smem_long, st>>>(a);
   count_launches(2);
 }
 
 }  // namespace er
 
-extern "C" size_t er_sort_workspace_bytes(int64_t n) { return er::rsort::workspace_bytes(n); }
+extern "C" size_t er_sort_workspace_bytes(int64_t n) { return er::rsort::workspace_bytes(n > 0 ? n : 1); }
 
 extern "C" int er_sort_rows(const int64_t* rows, int64_t n, const int32_t* n_dev, int64_t max_row,
                             uint32_t* keys_out, uint32_t* vals_out, void* ws, size_t ws_bytes,
@@ -356,7 +439,7 @@ extern "C" int er_sort_rows(const int64_t* rows, int64_t n, const int32_t* n_dev
   ER_REQUIRE(max_row > 0 && max_row < 0xFFFFFFFFLL, "max_row must be in (0, 2^32-1)");
   if (!ws || ws_bytes < rsort::workspace_bytes(n))
     return fail(ER_ERR_WORKSPACE, "er_sort_rows: workspace too small");
-  rsort::sort_rows(rows, n, n_dev, max_row, keys_out, vals_out, ws, as_stream(stream));
+  rsort::sort_rows(rows, n, n_dev, max_row, keys_out, vals_out, ws, nullptr, as_stream(stream));
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
@@ -401,7 +484,7 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
   BwdWs w = bwd_carve(ws, n_lookups_cap);
   // number of live lookups: row_ptr[n_seg] when CSR (device side), else the capacity
   const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
-  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, st);
+  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.long_count, st);
 
   BwdArgs a;
   a.table = table;
@@ -439,8 +522,6 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
     a.head_rank = w.head_rank;
     count_launches(3);
   }
-  zero_i32_kernel<<<1, 1, 0, st>>>(w.long_count);
-  count_launches(1);
   if (table) {
     aligned = aligned && reinterpret_cast<uintptr_t>(table) % 16 == 0 && row_stride % 4 == 0 &&
               (!state0 || reinterpret_cast<uintptr_t>(state0) % 16 == 0) &&
@@ -458,9 +539,11 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
       default: launch_vec<32>(a, st); break;
     }
   } else {
-    bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256,
-                             (size_t)n_slots * sizeof(int32_t), st>>>(a);
-    count_launches(1);
+    const size_t smem = (size_t)n_slots * sizeof(int32_t);
+    bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256, smem, st>>>(a);
+    const size_t smem_long = (size_t)((n_slots + 3) & ~3) * sizeof(int32_t) + 256 * sizeof(float);
+    bwd_long_scalar_kernel<<<2 * kSmCount, 256, smem_long, st>>>(a);
+    count_launches(2);
   }
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -468,35 +551,29 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
 
 namespace er {
 
-template <int VEC>
 __global__ void __launch_bounds__(256)
     sparse_apply_kernel(const __grid_constant__ BwdArgs a, const int64_t* __restrict__ uniq_rows,
                         const float* __restrict__ uniq_grads, const int32_t* __restrict__ n_uniq,
                         int64_t n_cap) {
   const int64_t n = n_uniq ? (int64_t)(*n_uniq < n_cap ? *n_uniq : n_cap) : n_cap;
-  const int per_row = a.dim / VEC;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * per_row;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * a.dim;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t u = t / per_row;
-    const int c = (int)(t - u * per_row) * VEC;
+    const int64_t u = t / a.dim;
+    const int c = (int)(t - u * a.dim);
     const int64_t row = uniq_rows[u];
     if (row < 0) continue;
     const int64_t off = row * a.row_stride + c;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float g = __fmul_rn(uniq_grads[u * a.dim + c + k], a.opt.grad_scale);
-      float w = a.table[off + k];
-      float s0 = a.state0 ? a.state0[off + k] : 0.f;
-      float s1 = a.state1 ? a.state1[off + k] : 0.f;
-      upd_one(a, g, w, s0, s1);
-      a.table[off + k] = w;
-      if (a.state0) a.state0[off + k] = s0;
-      if (a.state1) a.state1[off + k] = s1;
-    }
+    float g = __fmul_rn(uniq_grads[u * a.dim + c], a.opt.grad_scale);
+    float w = a.table[off];
+    float s0 = a.state0 ? a.state0[off] : 0.f;
+    float s1 = a.state1 ? a.state1[off] : 0.f;
+    upd_one(a, g, w, s0, s1);
+    a.table[off] = w;
+    if (a.state0) a.state0[off] = s0;
+    if (a.state1) a.state1[off] = s1;
   }
 }
 
-template <int UNUSED>
 __global__ void __launch_bounds__(256)
     adam_sweep_kernel(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v,
                       int64_t n_rows, int dim, int row_stride, const uint8_t* __restrict__ touched,
@@ -537,7 +614,7 @@ extern "C" int er_sparse_apply(float* table, float* state0, float* state1, int32
   a.row_stride = row_stride;
   a.opt = *opt;
   a.lr_t = (k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS) ? adam_lr_t(*opt) : opt->lr;
-  sparse_apply_kernel<1><<<grid_for(n_cap * dim, 256, 8), 256, 0, as_stream(stream)>>>(
+  sparse_apply_kernel<<<grid_for(n_cap * dim, 256, 8), 256, 0, as_stream(stream)>>>(
       a, uniq_rows, uniq_grads, n_uniq, n_cap);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
@@ -550,7 +627,7 @@ extern "C" int er_adam_dense_sweep(float* table, float* m, float* v, int64_t n_r
   using namespace er;
   ER_REQUIRE(table && m && v && opt, "null argument");
   ER_REQUIRE(dim > 0 && row_stride >= dim && n_rows > 0, "bad shape");
-  adam_sweep_kernel<0><<<grid_for(n_rows * dim, 256, 8), 256, 0, as_stream(stream)>>>(
+  adam_sweep_kernel<<<grid_for(n_rows * dim, 256, 8), 256, 0, as_stream(stream)>>>(
       table, m, v, n_rows, dim, row_stride, touched, opt->beta1, opt->beta2, opt->eps,
       adam_lr_t(*opt));
   count_launches(1);

@@ -4,12 +4,22 @@
 // every TF sparse apply; and array_ops.unique at
 // compat/feature_column/feature_column.py:263).
 //
-// Keys are arena rows (< 2^32 per GPU: 180 GB / 16 B minimum row), values the
-// lookup positions; dropped lookups (row < 0) get the sentinel key `n_rows`
-// and therefore sort behind every valid row.  8-bit digits; only
-// ceil(bits(n_rows)/8) passes are run (3 for a 10M-row arena).  Working set at
-// the benchmark shapes (<= 1M pairs x 8 B x 2 buffers) is L2 resident on B200,
-// so the passes are latency-, not HBM-bound; each pass is hist -> scan -> scatter.
+// Keys are arena rows (< 2^32 per GPU), values the lookup positions; dropped
+// lookups (row < 0) get the sentinel key `n_rows` and sort behind every valid
+// row.  8-bit digits, ceil(bits(n_rows)/8) passes (3 for a 10M-row arena).
+//
+// Launch structure (P passes -> P + 1 launches, no separate scan kernels):
+//   init_hist_kernel : rows -> (key, pos) pairs + per-tile histogram of digit 0;
+//                      zeroes the histograms of the later passes
+//   scatter_kernel x P: each CTA derives its tile's global offsets by summing the
+//                      per-tile histograms of the tiles before it (tiles are large,
+//                      so there are <= ~128 of them: one coalesced column sum per
+//                      thread), ranks its keys stably with warp match_any, scatters,
+//                      and counts the NEXT pass's per-tile histogram at the
+//                      destination with global atomics (counts are order-free, so
+//                      determinism is kept).
+// Working set at the benchmark shapes (<= 1M pairs x 8 B x 2 buffers) is L2
+// resident on B200: the passes are latency-, not HBM-bound.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -21,27 +31,32 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = 4;
-constexpr int kTile = kThreads * kItems;  // 1024 pairs per CTA
+constexpr int kMaxPasses = 4;
 
-inline int64_t num_tiles(int64_t n) { return n > 0 ? ceil_div(n, kTile) : 1; }
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// items per thread: smallest of {4, 8, 16} that keeps the tile count <= 128
+inline int items_for(int64_t n) {
+  if (ceil_div(n, (int64_t)kThreads * 4) <= 128) return 4;
+  if (ceil_div(n, (int64_t)kThreads * 8) <= 128) return 8;
+  return 16;
+}
+inline int64_t num_tiles(int64_t n) {
+  return n > 0 ? ceil_div(n, (int64_t)kThreads * items_for(n)) : 1;
+}
 
 struct Workspace {
   uint32_t* keys_tmp;
   uint32_t* vals_tmp;
-  int32_t* hist;   // [kRadix][n_tiles], scanned in place
-  void* scan_ws;
+  int32_t* hist;  // [kMaxPasses][n_tiles][kRadix]
 };
 
 inline size_t workspace_bytes(int64_t n) {
   const int64_t nt = num_tiles(n);
-  return align256((size_t)n * 4) * 2 + align256((size_t)kRadix * nt * 4) +
-         align256(scan::workspace_bytes((int64_t)kRadix * nt)) + 256;
+  return align256((size_t)n * 4) * 2 + align256((size_t)kMaxPasses * kRadix * nt * 4) + 512;
 }
 
 inline Workspace carve(void* ws, int64_t n) {
-  const int64_t nt = num_tiles(n);
   char* p = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(ws)));
   Workspace w;
   w.keys_tmp = reinterpret_cast<uint32_t*>(p);
@@ -49,8 +64,6 @@ inline Workspace carve(void* ws, int64_t n) {
   w.vals_tmp = reinterpret_cast<uint32_t*>(p);
   p += align256((size_t)n * 4);
   w.hist = reinterpret_cast<int32_t*>(p);
-  p += align256((size_t)kRadix * nt * 4);
-  w.scan_ws = p;
   return w;
 }
 
@@ -60,61 +73,80 @@ inline int num_passes(int64_t n_rows) {
   return (bits + kRadixBits - 1) / kRadixBits;
 }
 
-static __global__ void __launch_bounds__(256)
-    init_pairs_kernel(const int64_t* __restrict__ rows, int64_t cap, const int32_t* __restrict__ n_dev,
-                      uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const int64_t n = n_dev ? (int64_t)(*n_dev < cap ? *n_dev : cap) : cap;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = (i < n) ? rows[i] : -1;
-    keys[i] = (r < 0 || r >= (int64_t)sentinel) ? sentinel : (uint32_t)r;
-    vals[i] = (uint32_t)i;
-  }
-}
-
+// One CTA per tile.  zero_me (optional) is cleared by CTA 0 (the backward's hot-row counter).
+template <int ITEMS>
 static __global__ void __launch_bounds__(kThreads)
-    hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int32_t* __restrict__ hist,
-                int64_t n_tiles) {
+    init_hist_kernel(const int64_t* __restrict__ rows, int64_t cap, const int32_t* __restrict__ n_dev,
+                     uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                     int32_t* __restrict__ hist, int passes, int32_t* __restrict__ zero_me) {
   __shared__ int s_hist[kRadix];
+  const int64_t n_tiles = gridDim.x;
   s_hist[threadIdx.x] = 0;
+  for (int p = 1; p < passes; ++p)
+    hist[((int64_t)p * n_tiles + blockIdx.x) * kRadix + threadIdx.x] = 0;
+  if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kTile;
+  const int64_t n = n_dev ? (int64_t)(*n_dev < cap ? *n_dev : cap) : cap;
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * ITEMS);
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    int64_t idx = base + i * kThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&s_hist[(keys[idx] >> shift) & (kRadix - 1)], 1);
+  for (int i = 0; i < ITEMS; ++i) {
+    const int64_t idx = base + i * kThreads + threadIdx.x;
+    if (idx < cap) {
+      const int64_t r = (idx < n) ? rows[idx] : -1;
+      const uint32_t k = (r < 0 || r >= (int64_t)sentinel) ? sentinel : (uint32_t)r;
+      keys[idx] = k;
+      vals[idx] = (uint32_t)idx;
+      atomicAdd(&s_hist[k & (kRadix - 1)], 1);
+    }
   }
   __syncthreads();
-  hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = s_hist[threadIdx.x];
+  hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = s_hist[threadIdx.x];
 }
 
-struct HistIn {
-  const int32_t* h;
-  __device__ int operator()(int64_t j) const { return h[j]; }
-};
-struct HistOut {
-  int32_t* h;
-  __device__ void operator()(int64_t j, int ex, int) const { h[j] = ex; }
-};
-
+template <int ITEMS>
 static __global__ void __launch_bounds__(kThreads)
     scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
-                   int shift, const int32_t* __restrict__ offsets, int64_t n_tiles) {
+                   int shift, const int32_t* __restrict__ hist_cur, int32_t* __restrict__ hist_next) {
   __shared__ int s_warp_hist[kWarps][kRadix];
+  const int64_t n_tiles = gridDim.x;
   for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&s_warp_hist[0][0])[i] = 0;
-  __syncthreads();
+  // ---- this tile's global offsets: digit threadIdx.x, sum over all tiles / the tiles before ----
+  int before = 0, total = 0;
+  {
+    const int32_t* col = hist_cur + threadIdx.x;
+    int64_t t = 0;
+    for (; t + 8 <= n_tiles; t += 8) {
+      int h[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h[u] = col[(t + u) * kRadix];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (t + u == blockIdx.x) before = total;
+        total += h[u];
+      }
+    }
+    for (; t < n_tiles; ++t) {
+      if (t == blockIdx.x) before = total;
+      total += col[t * kRadix];
+    }
+  }
+  const int digit_base = scan::block_excl_scan(total, nullptr) + before;  // includes __syncthreads
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)w * (32 * kItems);
-  uint32_t key[kItems], val[kItems];
-  int rank[kItems];
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * ITEMS) + (int64_t)w * (32 * ITEMS);
+  uint32_t key[ITEMS], val[ITEMS];
+  int rank[ITEMS];
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
+    const int64_t idx = base + i * 32 + lane;
+    key[i] = (idx < n) ? keys_in[idx] : 0u;
+    val[i] = (idx < n) ? vals_in[idx] : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = base + i * 32 + lane;
     const bool valid = idx < n;
-    key[i] = valid ? keys_in[idx] : 0u;
-    val[i] = valid ? vals_in[idx] : 0u;
     const int d = (int)((key[i] >> shift) & (kRadix - 1));
     // lanes past the end never match a real digit
     const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (kRadix + lane));
@@ -128,8 +160,7 @@ static __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
   {
-    // digit threadIdx.x: exclusive prefix over warps + this tile's global offset
-    int run = offsets[(int64_t)threadIdx.x * n_tiles + blockIdx.x];
+    int run = digit_base;
 #pragma unroll
     for (int ww = 0; ww < kWarps; ++ww) {
       int t = s_warp_hist[ww][threadIdx.x];
@@ -139,22 +170,25 @@ static __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = base + i * 32 + lane;
     if (idx < n) {
       const int d = (int)((key[i] >> shift) & (kRadix - 1));
       const int pos = s_warp_hist[w][d] + rank[i];
       keys_out[pos] = key[i];
       vals_out[pos] = val[i];
+      if (hist_next) {
+        const int d2 = (int)((key[i] >> (shift + kRadixBits)) & (kRadix - 1));
+        atomicAdd(&hist_next[(int64_t)(pos / (kThreads * ITEMS)) * kRadix + d2], 1);
+      }
     }
   }
 }
 
-// Sort `cap` pairs; result lands in keys_out / vals_out.  hist_kernel reads tiles in a
-// strided (coalesced) order, scatter_kernel in a warp-blocked order: both cover the same
-// [tile*kTile, (tile+1)*kTile) range, so the per-tile digit counts agree.
-inline void sort_rows(const int64_t* rows, int64_t cap, const int32_t* n_dev, int64_t n_rows,
-                      uint32_t* keys_out, uint32_t* vals_out, void* ws, cudaStream_t st) {
+template <int ITEMS>
+inline void sort_rows_t(const int64_t* rows, int64_t cap, const int32_t* n_dev, int64_t n_rows,
+                        uint32_t* keys_out, uint32_t* vals_out, void* ws, int32_t* zero_me,
+                        cudaStream_t st) {
   Workspace w = carve(ws, cap);
   const int passes = num_passes(n_rows);
   const int64_t nt = num_tiles(cap);
@@ -162,16 +196,26 @@ inline void sort_rows(const int64_t* rows, int64_t cap, const int32_t* n_dev, in
   uint32_t* va = (passes % 2 == 0) ? vals_out : w.vals_tmp;
   uint32_t* kb = (passes % 2 == 0) ? w.keys_tmp : keys_out;
   uint32_t* vb = (passes % 2 == 0) ? w.vals_tmp : vals_out;
-  init_pairs_kernel<<<grid_for(cap, 256, 8), 256, 0, st>>>(rows, cap, n_dev, (uint32_t)n_rows, ka, va);
-  count_launches(1);
+  init_hist_kernel<ITEMS><<<(unsigned)nt, kThreads, 0, st>>>(rows, cap, n_dev, (uint32_t)n_rows, ka, va,
+                                                             w.hist, passes, zero_me);
   for (int p = 0; p < passes; ++p) {
-    const int shift = p * kRadixBits;
-    hist_kernel<<<(unsigned)nt, kThreads, 0, st>>>(ka, cap, shift, w.hist, nt);
-    scan::exclusive_scan(HistIn{w.hist}, HistOut{w.hist}, (int64_t)kRadix * nt, nullptr, w.scan_ws, st);
-    scatter_kernel<<<(unsigned)nt, kThreads, 0, st>>>(ka, va, kb, vb, cap, shift, w.hist, nt);
-    count_launches(5);
+    const int32_t* hc = w.hist + (int64_t)p * nt * kRadix;
+    int32_t* hn = (p + 1 < passes) ? w.hist + (int64_t)(p + 1) * nt * kRadix : nullptr;
+    scatter_kernel<ITEMS><<<(unsigned)nt, kThreads, 0, st>>>(ka, va, kb, vb, cap, p * kRadixBits, hc, hn);
     uint32_t* t = ka; ka = kb; kb = t;
     t = va; va = vb; vb = t;
+  }
+  count_launches(1 + passes);
+}
+
+// Sort `cap` pairs; result lands in keys_out / vals_out.
+inline void sort_rows(const int64_t* rows, int64_t cap, const int32_t* n_dev, int64_t n_rows,
+                      uint32_t* keys_out, uint32_t* vals_out, void* ws, int32_t* zero_me,
+                      cudaStream_t st) {
+  switch (items_for(cap)) {
+    case 4: sort_rows_t<4>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;
+    case 8: sort_rows_t<8>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;
+    default: sort_rows_t<16>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;
   }
 }
 
