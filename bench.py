@@ -229,7 +229,7 @@ def main():
   lib = _lib.load()
 
   il, model = workloads.build_deepfm_criteo(B, args.vocab, dev, seed=20240)
-  trainer = Trainer(model, il, 'adagrad', lr=0.01, use_cuda_graph=not args.no_graph)
+  trainer = Trainer(model, il, 'adagrad', lr=0.01, use_cuda_graph=not args.no_graph, world_size=world)
   n_rot = 16
   host = [workloads.criteo_batch(B, 20240 + rank * 1000 + i, uniform=args.uniform_ids) for i in range(n_rot)]
   pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(), torch.from_numpy(c).pin_memory())

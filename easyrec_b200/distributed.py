@@ -1,0 +1,99 @@
+"""Data-parallel training over NCCL, one process per GPU (torchrun).
+
+Replicated-table DP = what the reference gets from `HorovodStrategy`
+(compat/optimizers.py:285-293): every gradient is averaged over the replicas; the sparse ones
+(IndexedSlices) travel as an all-gather of (indices, values).  Here the all-gather moves the
+*inputs* of K7 -- each rank's arena rows, per-lookup weights and upstream gradient matrix -- and
+every rank then runs the same deterministic dedup + fused row update over the global batch, so
+replicas stay bit-identical without a broadcast.  Dense gradients: one flat all-reduce
+(`hvd.allreduce(g, Average)`, compat/optimizers.py:289-292).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from easyrec_b200 import kernels as K
+
+
+class GlobalCall(object):
+  """Slot plan of one arena call replicated for `world` ranks' gathered lookups."""
+
+  def __init__(self, call, world):
+    self.call = call
+    self.world = world
+    recs = []
+    base = call.slots_np
+    for r in range(world):
+      for i in range(call.n_slots):
+        s = base[i]
+        rows_of_buf = call.out_rows(int(s['out_buf']))
+        recs.append(dict(num_buckets=int(s['num_buckets']), row_offset=int(s['row_offset']),
+                         seg_begin=int(s['seg_begin']) + r * call.n_seg, n_seg=int(s['n_seg']),
+                         bucket_mode=int(s['bucket_mode']), combiner=int(s['combiner']),
+                         out_buf=int(s['out_buf']), out_stride=int(s['out_stride']),
+                         out_col=int(s['out_col']) + r * rows_of_buf * int(s['out_stride']),
+                         shard_n=1))
+    assert max(r['out_col'] for r in recs) < 2**31
+    self.slots_np = K.make_slots(recs)
+    dev = call.arena.device
+    self.slots_dev = K.slots_to_device(self.slots_np, dev)
+    self.n_slots = len(recs)
+    self.n_seg = call.n_seg * world
+    self.max_lookups = call.max_lookups * world
+    self.ws = K.bwd_workspace(self.max_lookups, dev)
+    self.rows = torch.empty(self.max_lookups, dtype=torch.int64, device=dev)
+    self.weights = torch.empty(self.max_lookups, dtype=torch.float32, device=dev)
+    self.seg_scale = None
+    self.grads = [torch.empty(world * call.out_rows(i), st, dtype=torch.float32, device=dev)
+                  for i, st in enumerate(call.out_strides)]
+
+
+class DataParallel(object):
+
+  def __init__(self, input_layer, dense_params, world):
+    self.input_layer = input_layer
+    self.world = world
+    self.params = list(dense_params)
+    self.sizes = [p.numel() for p in self.params]
+    self.flat = torch.empty(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
+    self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+    self.gcalls = {id(c): GlobalCall(c, world) for c in input_layer.calls.values()}
+
+  def sync_dense_grads(self):
+    """mean over replicas, one bucket (compat/optimizers.py:289-292)."""
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+    torch._foreach_copy_(self.views, grads)
+    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+    self.flat.mul_(1.0 / self.world)
+    for p, v in zip(self.params, self.views):
+      p.grad = v
+
+  def gather_sparse(self, call, rows, w, outs):
+    """all-gather one arena call's K7 inputs (rows, weights, segment scales, upstream gradients)
+    into the GlobalCall buffers; returns the GlobalCall."""
+    g = self.gcalls[id(call)]
+    dist.all_gather_into_tensor(g.rows, rows)
+    if w is not None:
+      dist.all_gather_into_tensor(g.weights, w)
+    if call.seg_scale is not None:
+      if g.seg_scale is None:
+        g.seg_scale = torch.empty(g.n_seg, dtype=torch.float32, device=rows.device)
+      dist.all_gather_into_tensor(g.seg_scale, call.seg_scale)
+    for i, o in enumerate(outs):
+      grad = o.grad if o.grad is not None else torch.zeros_like(o)
+      dist.all_gather_into_tensor(g.grads[i], grad.contiguous())
+    return g
+
+  def sparse_backward_update(self, opt):
+    """all-gather K7's inputs, then the same fused dedup+update on every rank; gradients are
+    scaled by 1/world (mean over replicas)."""
+    il = self.input_layer
+    opt.grad_scale = opt.grad_scale / self.world
+    for call, rows, w, outs in il._pending:
+      g = self.gather_sparse(call, rows, w, outs)
+      a = call.arena
+      K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, g.rows, g.slots_dev, g.n_slots, g.n_seg,
+                      g.grads, opt, g.ws, weights=g.weights if w is not None else None,
+                      seg_scale=g.seg_scale)
+    il._pending = []
+    opt.grad_scale = opt.grad_scale * self.world

@@ -82,7 +82,7 @@ class TFAdam(torch.optim.Optimizer):
 class Trainer(object):
 
   def __init__(self, model, input_layer, dense_optimizer='adagrad', lr=0.01, lr_fn=None,
-               use_cuda_graph=False):
+               use_cuda_graph=False, world_size=1):
     self.model = model
     self.input_layer = input_layer
     self.lr = lr
@@ -94,6 +94,10 @@ class Trainer(object):
       self.dense_opt = TFAdam(params, lr)
     else:
       raise ValueError(dense_optimizer)
+    self.dp = None
+    if world_size > 1:
+      from easyrec_b200.distributed import DataParallel
+      self.dp = DataParallel(input_layer, params, world_size)
     self.step = 0
     self.use_cuda_graph = use_cuda_graph
     self._graph = None
@@ -115,7 +119,11 @@ class Trainer(object):
     logits = self.model(features)
     loss, probs = self.model.loss(logits, labels)
     loss.backward()
-    self.input_layer.backward_update()   # K7: dedup + fused row update, on this thread/stream
+    if self.dp is not None:
+      self.dp.sync_dense_grads()                                       # flat all-reduce (mean)
+      self.dp.sparse_backward_update(self.input_layer.opt_holder['opt'])  # all-gather + K7
+    else:
+      self.input_layer.backward_update()   # K7: dedup + fused row update, on this thread/stream
     self.dense_opt.step()
     return loss.detach(), probs
 
