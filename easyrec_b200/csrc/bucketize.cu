@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "hash.cuh"
 #include "scan.cuh"
+#include "slots.cuh"
 
 namespace er {
 
@@ -37,14 +38,38 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+struct BucketRule {  // 32 bytes, staged in shared memory per CTA
+  int64_t num_buckets;
+  int64_t row_offset;
+  int32_t seg_begin;
+  int32_t mode;
+  int32_t shard_n;
+  int32_t pad;
+};
+
 __global__ void __launch_bounds__(256)
     bucketize_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ seg_ids,
                      const int32_t* __restrict__ row_ptr, int64_t n_seg, int64_t cap,
                      const er_slot_t* __restrict__ slots, int n_slots,
                      int64_t* __restrict__ rows, int32_t* __restrict__ owner) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_seg_begin[i] = slots[i].seg_begin;
-  __syncthreads();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  BucketRule* tab = reinterpret_cast<BucketRule*>(s_raw);
+  const int nseg0 = slots[0].n_seg;
+  int ok = 1;
+  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+    const er_slot_t s = slots[i];
+    BucketRule r;
+    r.num_buckets = s.num_buckets;
+    r.row_offset = s.row_offset;
+    r.seg_begin = s.seg_begin;
+    r.mode = s.bucket_mode;
+    r.shard_n = s.shard_n;
+    r.pad = 0;
+    tab[i] = r;
+    if (s.n_seg != nseg0 || s.seg_begin != i * nseg0) ok = 0;
+  }
+  const int uniform = __syncthreads_and(ok);
+  const FastDiv div = make_fastdiv((uint32_t)(nseg0 > 0 ? nseg0 : 1));
   int64_t n = cap;
   if (row_ptr) {
     int64_t t = row_ptr[n_seg];
@@ -53,11 +78,24 @@ __global__ void __launch_bounds__(256)
   for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n;
        l += (int64_t)gridDim.x * blockDim.x) {
     const int32_t s = seg_ids ? seg_ids[l] : (int32_t)l;
-    const int f = find_slot(s_seg_begin, n_slots, s);
-    const int64_t nb = slots[f].num_buckets;
-    const int64_t off = slots[f].row_offset;
-    const int mode = slots[f].bucket_mode;
-    const int shard_n = slots[f].shard_n;
+    int f;
+    if (uniform) {
+      f = (int)fastdiv((uint32_t)s, div);
+    } else {
+      int lo = 0, hi = n_slots;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid].seg_begin <= s)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      f = lo;
+    }
+    const int64_t nb = tab[f].num_buckets;
+    const int64_t off = tab[f].row_offset;
+    const int mode = tab[f].mode;
+    const int shard_n = tab[f].shard_n;
     const int64_t v = ids[l];
     int64_t r;
     bool drop = false;
@@ -118,12 +156,11 @@ extern "C" int er_bucketize(const int64_t* ids, const int32_t* seg_ids, const in
                             er_stream_t stream) {
   using namespace er;
   ER_REQUIRE(ids && rows && slots, "ids, rows and slots must be non-null");
-  ER_REQUIRE(n_slots > 0 && n_slots <= 8192, "n_slots must be in [1, 8192]");
+  ER_REQUIRE(n_slots > 0 && n_slots <= 1024, "n_slots must be in [1, 1024]");
   ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31), "n_lookups_cap out of range");
-  ER_REQUIRE(seg_ids || !row_ptr || true, "");
   if (n_lookups_cap == 0) return ER_OK;
   cudaStream_t st = as_stream(stream);
-  bucketize_kernel<<<grid_for(n_lookups_cap, 256, 8), 256, n_slots * sizeof(int32_t), st>>>(
+  bucketize_kernel<<<grid_for(n_lookups_cap, 256, 8), 256, (size_t)n_slots * sizeof(BucketRule), st>>>(
       ids, seg_ids, row_ptr, n_seg, n_lookups_cap, slots, n_slots, rows, owner);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();

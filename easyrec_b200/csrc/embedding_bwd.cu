@@ -12,18 +12,21 @@
 // EP gradient scaling compat/optimizers.py:315-316.
 //
 // Launches per call: P+1 sort launches (sort.cuh) + runs kernel + hot-row kernel.
-//  * runs kernel: a warp scans 32 sorted positions, ballots the run heads and deals them
-//    to its dim/4-lane groups; a group prefetches the row and its optimizer state, sums
-//    the run in lookup order (the sort is stable => the order a sequential CPU
+//  * runs kernel: a warp scans 32 sorted positions, ballots the run heads and deals the
+//    positions to its dim/4-lane groups; a group prefetches the row and its optimizer state,
+//    sums the run in lookup order (the sort is stable => the order a sequential CPU
 //    segment-sum uses), applies the optimizer, stores.
-//  * runs longer than kLongRun (Zipf-hot ids, 1-row RawFeature tables: run length = B)
-//    are queued with their length and summed by a whole CTA, one lookup per thread,
-//    then a fixed-order shared-memory tree: deterministic, no atomics on floats.
+//  * runs longer than kLongRun (Zipf-hot ids, 1-row RawFeature tables: run length = B) are
+//    queued as kChunk-lookup work items; the hot-row kernel sums one chunk per CTA (one
+//    lookup per thread, warp shuffles + a fixed-order shared-memory combine), and the CTA that
+//    finishes a run last adds the chunk partials in chunk order and applies the optimizer:
+//    deterministic, no float atomics.
 //
 // HBM traffic per call (algorithmic): L*8 sorted pairs + L*R gathered upstream gradient
 // rows + U*k*R row/state read-modify-write, R = 4*dim, k = 2 (sgd), 4 (adagrad), 6 (adam).
 #include "common.cuh"
 #include "scan.cuh"
+#include "slots.cuh"
 #include "sort.cuh"
 
 namespace er {
@@ -32,8 +35,9 @@ struct CBufs {
   const float* p[ER_MAX_BUFS];
 };
 
-constexpr int kLongRun = 64;  // runs longer than this go to the CTA-wide kernel
+constexpr int kLongRun = 64;  // runs longer than this go to the chunked CTA-wide kernel
 constexpr int kBatch = 4;     // lookups fetched per step of the run loop
+constexpr int kChunk = 512;   // lookups per hot-row work item (2 per thread)
 
 struct BwdArgs {
   float* table;
@@ -56,21 +60,22 @@ struct BwdArgs {
   int64_t* uniq_rows;
   float* uniq_grads;
   const int32_t* head_rank;  // exclusive count of run heads before each position (emit mode)
-  int32_t* long_count;
-  int2* long_list;  // (start, length) of each hot run
+  int32_t* counters;         // [0] hot runs, [1] chunks (zeroed by the sort's init kernel)
+  int4* long_list;           // per hot run: (start, length, first chunk, n_chunks)
+  int32_t* run_done;         // per hot run: chunks finished
+  int2* chunk_list;          // per chunk: (run, chunk index)
+  float* partials;           // [chunk][dim]
 };
 
 // gradient row pointer and coefficient of sorted entry with lookup position l
-__device__ __forceinline__ const float* grad_src(const BwdArgs& a, const int32_t* s_seg_begin,
-                                                 uint32_t l, float* coef) {
+__device__ __forceinline__ const float* grad_src(const BwdArgs& a, const SlotView& sv, uint32_t l,
+                                                 float* coef) {
   const int32_t s = a.seg_ids ? a.seg_ids[l] : (int32_t)l;
-  const int f = find_slot(s_seg_begin, a.n_slots, s);
-  const er_slot_t* sl = a.slots + f;
-  const int seg_begin = sl->seg_begin, stride = sl->out_stride, col = sl->out_col, buf = sl->out_buf;
+  const SlotLite sl = slot_lite(sv, slot_of(sv, s));
   float c = a.weights ? a.weights[l] : 1.0f;
   if (a.seg_scale) c = __fmul_rn(c, a.seg_scale[s]);
   *coef = c;
-  return a.gbufs.p[buf] + (int64_t)(s - seg_begin) * stride + col;
+  return a.gbufs.p[sl.misc & 0xff] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
 }
 
 __device__ __forceinline__ void upd_one(const BwdArgs& a, float g, float& w, float& s0, float& s1) {
@@ -143,6 +148,25 @@ __device__ __forceinline__ void apply_row_vec(const BwdArgs& a, uint32_t row, in
   if (a.state1) reinterpret_cast<float4*>(a.state1 + off)[lane] = r.s1;
 }
 
+__device__ __forceinline__ void apply_scalar(const BwdArgs& a, uint32_t key, int c, float g,
+                                             int64_t head_pos) {
+  g = __fmul_rn(g, a.opt.grad_scale);
+  if (a.uniq_rows) {
+    const int32_t u = a.head_rank[head_pos];
+    if (c == 0) a.uniq_rows[u] = (int64_t)key;
+    a.uniq_grads[(int64_t)u * a.dim + c] = g;
+  }
+  if (!a.table) return;
+  const int64_t off = (int64_t)key * a.row_stride + c;
+  float w = a.table[off];
+  float s0 = a.state0 ? a.state0[off] : 0.f;
+  float s1 = a.state1 ? a.state1[off] : 0.f;
+  upd_one(a, g, w, s0, s1);
+  a.table[off] = w;
+  if (a.state0) a.state0[off] = s0;
+  if (a.state1) a.state1[off] = s1;
+}
+
 // upper bound of `key` in keys[lo, n)
 __device__ __forceinline__ int64_t run_end(const uint32_t* __restrict__ keys, int64_t lo, int64_t n,
                                            uint32_t key) {
@@ -157,12 +181,23 @@ __device__ __forceinline__ int64_t run_end(const uint32_t* __restrict__ keys, in
   return lo;
 }
 
+// One thread registers a hot run and its chunks.
+__device__ __forceinline__ void enqueue_long(const BwdArgs& a, int64_t start, int64_t j, uint32_t key) {
+  const int64_t e = run_end(a.keys, j, a.n, key);
+  const int len = (int)(e - start);
+  const int nch = (len + kChunk - 1) / kChunk;
+  const int q = atomicAdd(&a.counters[0], 1);
+  const int c0 = atomicAdd(&a.counters[1], nch);
+  a.long_list[q] = make_int4((int)start, len, c0, nch);
+  a.run_done[q] = 0;
+  for (int c = 0; c < nch; ++c) a.chunk_list[c0 + c] = make_int2(q, c);
+}
+
 // ---- runs, vector rows (dim = 4*LANES) ---------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
-  __syncthreads();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
   constexpr int GROUPS = 32 / LANES;
   const int lane32 = threadIdx.x & 31;
   const int lane = lane32 % LANES;
@@ -175,9 +210,10 @@ __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant
   if (lane32 == 0) kprev = (base > 0) ? a.keys[base - 1] : ~k;
   const bool is_head = pos < a.n && k < a.sentinel && (pos == 0 || kprev != k);
   const unsigned heads = __ballot_sync(0xffffffffu, is_head);
-  const int n_heads = __popc(heads);
-  for (int h = grp; h < n_heads; h += GROUPS) {
-    const int p = __fns(heads, 0, h + 1);
+#pragma unroll 1
+  for (int t = 0; t < LANES; ++t) {
+    const int p = grp + t * GROUPS;
+    if (!((heads >> p) & 1u)) continue;
     const int64_t i = base + p;
     const uint32_t key = a.keys[i];
     RowRegs row = load_row(a, key, lane);  // in flight while the run is summed
@@ -200,7 +236,7 @@ __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         if (u < m) {
-          const float* src = grad_src(a, s_seg_begin, l[u], &c[u]);
+          const float* src = grad_src(a, sv, l[u], &c[u]);
           gv[u] = reinterpret_cast<const float4*>(src)[lane];
         }
       }
@@ -211,12 +247,8 @@ __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant
       cnt += m;
       if (m < kBatch) break;
       if (cnt >= kLongRun) {
-        if (j < a.n && a.keys[j] == key) {  // hot row: hand the whole run to the CTA-wide kernel
-          if (lane == 0) {
-            const int64_t e = run_end(a.keys, j, a.n, key);
-            const int slot = atomicAdd(a.long_count, 1);
-            a.long_list[slot] = make_int2((int)i, (int)(e - i));
-          }
+        if (j < a.n && a.keys[j] == key) {  // hot row: hand the whole run to the chunked kernel
+          if (lane == 0) enqueue_long(a, i, j, key);
           queued = true;
         }
         break;
@@ -226,90 +258,99 @@ __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant
   }
 }
 
-// ---- hot rows, vector: one CTA per run; TPE threads share one lookup (TPE = 1 for dim <= 32:
-// a thread moves a whole 4*LANES-float gradient row), then a fixed shared-memory tree -----------
+// ---- hot rows, vector: one CTA per chunk of a run; TPE threads share one lookup (TPE = 1 for
+// dim <= 32: a thread moves a whole gradient row) -----------------------------------------------
 template <int LANES, int TPE>
 __global__ void __launch_bounds__(256) bwd_long_vec_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ int32_t s_dyn[];
-  int32_t* s_seg_begin = s_dyn;
-  float4* s_part = reinterpret_cast<float4*>(s_dyn + ((a.n_slots + 3) & ~3));
-  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
-  __syncthreads();
-  constexpr int CH = LANES / TPE;   // float4 chunks per thread
-  constexpr int G = 256 / TPE;      // lookups in flight per CTA step
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  float4* s_part = reinterpret_cast<float4*>(s_raw + ((slot_smem_bytes(a.n_slots) + 15) & ~(size_t)15));
+  __shared__ int s_last;
+  constexpr int CH = LANES / TPE;  // float4 chunks per thread
+  constexpr int G = 256 / TPE;     // lookups in flight per CTA step
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = threadIdx.x % TPE;
   const int grp = threadIdx.x / TPE;
-  const int n_long = *a.long_count;
-  for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
-    const int2 rl = a.long_list[q];
-    const int64_t i = rl.x, len = rl.y;
+  const int n_chunks = a.counters[1];
+  for (int x = blockIdx.x; x < n_chunks; x += gridDim.x) {
+    const int2 qc = a.chunk_list[x];
+    const int4 run = a.long_list[qc.x];
+    const int64_t i = run.x;
+    const int len = run.y, c0 = run.z, nch = run.w;
     const uint32_t key = a.keys[i];
+    const int e0 = qc.y * kChunk, e1 = min(len, e0 + kChunk);
     float4 g[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t e = grp; e < len; e += 2 * G) {
-      const bool two = (e + G < len);
-      float c0, c1 = 0.f;
-      const float* s0 = grad_src(a, s_seg_begin, a.vals[i + e], &c0);
-      const float* s1 = two ? grad_src(a, s_seg_begin, a.vals[i + e + G], &c1) : s0;
+    for (int e = e0 + grp; e < e1; e += 2 * G) {
+      const bool two = (e + G < e1);
+      float w0, w1 = 0.f;
+      const float* p0 = grad_src(a, sv, a.vals[i + e], &w0);
+      const float* p1 = two ? grad_src(a, sv, a.vals[i + e + G], &w1) : p0;
       float4 v0[CH], v1[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        v0[c] = reinterpret_cast<const float4*>(s0)[sub * CH + c];
-        v1[c] = reinterpret_cast<const float4*>(s1)[sub * CH + c];
+        v0[c] = reinterpret_cast<const float4*>(p0)[sub * CH + c];
+        v1[c] = reinterpret_cast<const float4*>(p1)[sub * CH + c];
       }
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        f4_fma_sep(g[c], v0[c], c0);
-        if (two) f4_fma_sep(g[c], v1[c], c1);
+        f4_fma_sep(g[c], v0[c], w0);
+        if (two) f4_fma_sep(g[c], v1[c], w1);
       }
     }
+    // lanes that hold the same columns: xor-shuffle tree inside the warp ...
 #pragma unroll
-    for (int c = 0; c < CH; ++c) s_part[grp * LANES + sub * CH + c] = g[c];
+    for (int o = 16; o >= TPE; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float4 y;
+        y.x = __shfl_xor_sync(0xffffffffu, g[c].x, o);
+        y.y = __shfl_xor_sync(0xffffffffu, g[c].y, o);
+        y.z = __shfl_xor_sync(0xffffffffu, g[c].z, o);
+        y.w = __shfl_xor_sync(0xffffffffu, g[c].w, o);
+        f4_acc(g[c], y);
+      }
+    }
+    // ... then the 8 warps in a fixed order through shared memory
+    if (lane32 < TPE) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) s_part[warp * LANES + lane32 * CH + c] = g[c];
+    }
     __syncthreads();
-    for (int stride = G / 2; stride >= 1; stride >>= 1) {
-      if (grp < stride) {
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          float4 x = s_part[grp * LANES + sub * CH + c];
-          f4_acc(x, s_part[(grp + stride) * LANES + sub * CH + c]);
-          s_part[grp * LANES + sub * CH + c] = x;
-        }
-      }
-      __syncthreads();
-    }
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x < LANES) {
+      for (int ww = 0; ww < 8; ++ww) f4_acc(tot, s_part[ww * LANES + threadIdx.x]);
+    }
+    bool finish = (nch == 1);
+    if (nch > 1) {
+      if (threadIdx.x < LANES)
+        __stcg(reinterpret_cast<float4*>(a.partials + (int64_t)(c0 + qc.y) * a.dim) + threadIdx.x, tot);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(&a.run_done[qc.x], 1) == nch - 1);
+      __syncthreads();
+      finish = s_last != 0;
+      if (finish && threadIdx.x < LANES) {
+        __threadfence();
+        tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < nch; ++c)
+          f4_acc(tot, __ldcg(reinterpret_cast<const float4*>(a.partials + (int64_t)(c0 + c) * a.dim) +
+                             threadIdx.x));
+      }
+    }
+    if (finish && threadIdx.x < LANES) {
       RowRegs row = load_row(a, key, threadIdx.x);
-      apply_row_vec(a, key, threadIdx.x, s_part[threadIdx.x], i, row);
+      apply_row_vec(a, key, threadIdx.x, tot, i, row);
     }
     __syncthreads();
   }
 }
 
 // ---- scalar rows (wide dim=1 tables, odd dims): one thread per (sorted position, column) ----
-__device__ __forceinline__ void apply_scalar(const BwdArgs& a, uint32_t key, int c, float g,
-                                             int64_t head_pos) {
-  g = __fmul_rn(g, a.opt.grad_scale);
-  if (a.uniq_rows) {
-    const int32_t u = a.head_rank[head_pos];
-    if (c == 0) a.uniq_rows[u] = (int64_t)key;
-    a.uniq_grads[(int64_t)u * a.dim + c] = g;
-  }
-  if (!a.table) return;
-  const int64_t off = (int64_t)key * a.row_stride + c;
-  float w = a.table[off];
-  float s0 = a.state0 ? a.state0[off] : 0.f;
-  float s1 = a.state1 ? a.state1[off] : 0.f;
-  upd_one(a, g, w, s0, s1);
-  a.table[off] = w;
-  if (a.state0) a.state0[off] = s0;
-  if (a.state1) a.state1[off] = s1;
-}
-
 __global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
-  __syncthreads();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = t / a.dim;
   const int c = (int)(t - i * a.dim);
@@ -321,46 +362,63 @@ __global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_const
   int64_t j = i;
   for (; j < a.n && a.keys[j] == key; ++j) {
     if (j - i >= kLongRun) {  // hot row
-      if (c == 0) {
-        const int64_t e = run_end(a.keys, j, a.n, key);
-        const int slot = atomicAdd(a.long_count, 1);
-        a.long_list[slot] = make_int2((int)i, (int)(e - i));
-      }
+      if (c == 0) enqueue_long(a, i, j, key);
       return;
     }
     float coef;
-    const float* src = grad_src(a, s_seg_begin, a.vals[j], &coef);
+    const float* src = grad_src(a, sv, a.vals[j], &coef);
     g = __fadd_rn(g, __fmul_rn(src[c], coef));
   }
   apply_scalar(a, key, c, g, i);
 }
 
 __global__ void __launch_bounds__(256) bwd_long_scalar_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ int32_t s_dyn[];
-  int32_t* s_seg_begin = s_dyn;
-  float* s_part = reinterpret_cast<float*>(s_dyn + ((a.n_slots + 3) & ~3));
-  for (int i = threadIdx.x; i < a.n_slots; i += blockDim.x) s_seg_begin[i] = a.slots[i].seg_begin;
-  __syncthreads();
-  const int n_long = *a.long_count;
-  for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
-    const int2 rl = a.long_list[q];
-    const int64_t i = rl.x, len = rl.y;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  __shared__ float s_w[8];
+  __shared__ int s_last;
+  const int lane32 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chunks = a.counters[1];
+  for (int x = blockIdx.x; x < n_chunks; x += gridDim.x) {
+    const int2 qc = a.chunk_list[x];
+    const int4 run = a.long_list[qc.x];
+    const int64_t i = run.x;
+    const int len = run.y, c0 = run.z, nch = run.w;
     const uint32_t key = a.keys[i];
+    const int e0 = qc.y * kChunk, e1 = min(len, e0 + kChunk);
     for (int c = 0; c < a.dim; ++c) {
       float g = 0.f;
-      for (int64_t e = threadIdx.x; e < len; e += 256) {
+      for (int e = e0 + threadIdx.x; e < e1; e += 256) {
         float coef;
-        const float* src = grad_src(a, s_seg_begin, a.vals[i + e], &coef);
+        const float* src = grad_src(a, sv, a.vals[i + e], &coef);
         g = __fadd_rn(g, __fmul_rn(src[c], coef));
       }
-      s_part[threadIdx.x] = g;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) g = __fadd_rn(g, __shfl_xor_sync(0xffffffffu, g, o));
+      if (lane32 == 0) s_w[warp] = g;
       __syncthreads();
-      for (int stride = 128; stride >= 1; stride >>= 1) {
-        if ((int)threadIdx.x < stride)
-          s_part[threadIdx.x] = __fadd_rn(s_part[threadIdx.x], s_part[threadIdx.x + stride]);
-        __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int ww = 0; ww < 8; ++ww) tot = __fadd_rn(tot, s_w[ww]);
+        if (nch == 1)
+          apply_scalar(a, key, c, tot, i);
+        else
+          __stcg(a.partials + (int64_t)(c0 + qc.y) * a.dim + c, tot);
       }
-      if (threadIdx.x == 0) apply_scalar(a, key, c, s_part[0], i);
+      __syncthreads();
+    }
+    if (nch > 1) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(&a.run_done[qc.x], 1) == nch - 1);
+      __syncthreads();
+      if (s_last && (int)threadIdx.x < a.dim) {
+        __threadfence();
+        float tot = 0.f;
+        for (int c = 0; c < nch; ++c)
+          tot = __fadd_rn(tot, __ldcg(a.partials + (int64_t)(c0 + c) * a.dim + threadIdx.x));
+        apply_scalar(a, key, (int)threadIdx.x, tot, i);
+      }
       __syncthreads();
     }
   }
@@ -385,25 +443,34 @@ struct BwdWs {
   uint32_t* keys;
   uint32_t* vals;
   int32_t* head_rank;
-  int2* long_list;
-  int32_t* long_count;
+  int4* long_list;
+  int32_t* run_done;
+  int2* chunk_list;
+  float* partials;
+  int32_t* counters;
   void* sort_ws;
   void* scan_ws;
 };
 
-inline size_t bwd_ws_bytes(int64_t n) {
-  // keys, vals, head_rank (4 B each), long list (one int2 per kLongRun lookups at most)
-  return a256((size_t)n * 4) * 3 + a256((size_t)(n / kLongRun + 1) * 8) + 256 +
+inline int64_t max_long_runs(int64_t n) { return n / kLongRun + 1; }
+inline int64_t max_chunks(int64_t n) { return n / kChunk + max_long_runs(n) + 1; }
+
+inline size_t bwd_ws_bytes(int64_t n, int dim) {
+  return a256((size_t)n * 4) * 3 + a256((size_t)max_long_runs(n) * 16) + a256((size_t)max_long_runs(n) * 4) +
+         a256((size_t)max_chunks(n) * 8) + a256((size_t)max_chunks(n) * dim * 4) + 256 +
          a256(rsort::workspace_bytes(n)) + a256(scan::workspace_bytes(n)) + 512;
 }
-inline BwdWs bwd_carve(void* ws, int64_t n) {
+inline BwdWs bwd_carve(void* ws, int64_t n, int dim) {
   char* p = reinterpret_cast<char*>(a256(reinterpret_cast<size_t>(ws)));
   BwdWs w;
   w.keys = reinterpret_cast<uint32_t*>(p); p += a256((size_t)n * 4);
   w.vals = reinterpret_cast<uint32_t*>(p); p += a256((size_t)n * 4);
   w.head_rank = reinterpret_cast<int32_t*>(p); p += a256((size_t)n * 4);
-  w.long_list = reinterpret_cast<int2*>(p); p += a256((size_t)(n / kLongRun + 1) * 8);
-  w.long_count = reinterpret_cast<int32_t*>(p); p += 256;
+  w.long_list = reinterpret_cast<int4*>(p); p += a256((size_t)max_long_runs(n) * 16);
+  w.run_done = reinterpret_cast<int32_t*>(p); p += a256((size_t)max_long_runs(n) * 4);
+  w.chunk_list = reinterpret_cast<int2*>(p); p += a256((size_t)max_chunks(n) * 8);
+  w.partials = reinterpret_cast<float*>(p); p += a256((size_t)max_chunks(n) * dim * 4);
+  w.counters = reinterpret_cast<int32_t*>(p); p += 256;
   w.sort_ws = p; p += a256(rsort::workspace_bytes(n));
   w.scan_ws = p;
   return w;
@@ -416,13 +483,12 @@ static float adam_lr_t(const er_opt_t& o) {
 
 template <int LANES>
 static void launch_vec(const BwdArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)a.n_slots * sizeof(int32_t);
+  const size_t smem = slot_smem_bytes(a.n_slots);
   // one warp per 32 sorted positions, 8 warps per CTA
   bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
   constexpr int TPE = (LANES <= 8) ? 1 : LANES;
-  const size_t smem_long =
-      (size_t)((a.n_slots + 3) & ~3) * sizeof(int32_t) + (size_t)(256 / TPE) * LANES * sizeof(float4);
-  bwd_long_vec_kernel<LANES, TPE><<<2 * kSmCount, 256, smem_long, st>>>(a);
+  const size_t smem_long = ((smem + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
+  bwd_long_vec_kernel<LANES, TPE><<<4 * kSmCount, 256, smem_long, st>>>(a);
   count_launches(2);
 }
 
@@ -444,8 +510,8 @@ extern "C" int er_sort_rows(const int64_t* rows, int64_t n, const int32_t* n_dev
   return ER_OK;
 }
 
-extern "C" size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap) {
-  return er::bwd_ws_bytes(n_lookups_cap > 0 ? n_lookups_cap : 1);
+extern "C" size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap, int32_t dim) {
+  return er::bwd_ws_bytes(n_lookups_cap > 0 ? n_lookups_cap : 1, dim > 0 ? dim : 1);
 }
 
 extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int64_t n_rows,
@@ -465,7 +531,7 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
              "uniq_rows, uniq_grads and n_uniq go together");
   ER_REQUIRE(dim > 0 && row_stride >= dim, "bad dim / row_stride");
   ER_REQUIRE(n_rows > 0 && n_rows < 0xFFFFFFFFLL, "n_rows must be in (0, 2^32-1)");
-  ER_REQUIRE(n_slots > 0 && n_slots <= 8192, "n_slots must be in [1, 8192]");
+  ER_REQUIRE(n_slots > 0 && n_slots <= 2048, "n_slots must be in [1, 2048]");
   ER_REQUIRE(n_bufs > 0 && n_bufs <= ER_MAX_BUFS, "n_bufs must be in [1, ER_MAX_BUFS]");
   ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31), "n_lookups_cap out of range");
   ER_REQUIRE(row_ptr || n_lookups_cap == n_seg, "row_ptr == NULL requires n_lookups_cap == n_seg");
@@ -478,13 +544,13 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
     ER_REQUIRE((k != ER_OPT_LAZY_ADAM && k != ER_OPT_ADAM_ROWS) || state1, "adam needs state1 (v)");
   }
   if (n_lookups_cap == 0) return ER_OK;
-  if (!ws || ws_bytes < bwd_ws_bytes(n_lookups_cap))
+  if (!ws || ws_bytes < bwd_ws_bytes(n_lookups_cap, dim))
     return fail(ER_ERR_WORKSPACE, "er_embedding_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
-  BwdWs w = bwd_carve(ws, n_lookups_cap);
+  BwdWs w = bwd_carve(ws, n_lookups_cap, dim);
   // number of live lookups: row_ptr[n_seg] when CSR (device side), else the capacity
   const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
-  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.long_count, st);
+  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, st);
 
   BwdArgs a;
   a.table = table;
@@ -514,8 +580,11 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
   a.uniq_rows = uniq_rows;
   a.uniq_grads = uniq_grads;
   a.head_rank = nullptr;
-  a.long_count = w.long_count;
+  a.counters = w.counters;
   a.long_list = w.long_list;
+  a.run_done = w.run_done;
+  a.chunk_list = w.chunk_list;
+  a.partials = w.partials;
   if (uniq_rows) {
     scan::exclusive_scan(HeadIn{w.keys, a.sentinel}, HeadOut{w.head_rank}, n_lookups_cap, n_uniq,
                          w.scan_ws, st);
@@ -539,10 +608,9 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
       default: launch_vec<32>(a, st); break;
     }
   } else {
-    const size_t smem = (size_t)n_slots * sizeof(int32_t);
+    const size_t smem = slot_smem_bytes(n_slots);
     bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256, smem, st>>>(a);
-    const size_t smem_long = (size_t)((n_slots + 3) & ~3) * sizeof(int32_t) + 256 * sizeof(float);
-    bwd_long_scalar_kernel<<<2 * kSmCount, 256, smem_long, st>>>(a);
+    bwd_long_scalar_kernel<<<4 * kSmCount, 256, smem, st>>>(a);
     count_launches(2);
   }
   ER_CUDA_LAUNCH_CHECK();

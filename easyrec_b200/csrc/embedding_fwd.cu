@@ -11,9 +11,11 @@
 // with one 16 B non-allocating load per lane; kUnroll independent segments per
 // group are in flight before the first use so that each SM keeps >32 KB of row
 // reads outstanding (Little's law at ~6.5 TB/s x ~600 ns needs ~26 KB/SM).
-// Accumulation inside a segment is sequential in lookup order with separate
-// multiply and add (no FMA contraction), i.e. the CPU reference's order.
+// Segment -> slot goes through the shared-memory SlotView (slots.cuh): one multiply-shift
+// and one LDS.128 per segment.  Accumulation inside a segment is sequential in lookup
+// order with separate multiply and add (no FMA contraction), i.e. the CPU reference's order.
 #include "common.cuh"
+#include "slots.cuh"
 
 namespace er {
 
@@ -38,11 +40,10 @@ template <int LANES, int UNROLL>
 __global__ void __launch_bounds__(256)
     fwd_single_kernel(const float* __restrict__ table, int row_stride,
                       const int64_t* __restrict__ rows, const float* __restrict__ weights,
-                      int64_t n_seg, const er_slot_t* __restrict__ slots, int n_slots, const __grid_constant__ Bufs bufs,
-                      float* __restrict__ seg_scale) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_seg_begin[i] = slots[i].seg_begin;
-  __syncthreads();
+                      int64_t n_seg, const er_slot_t* __restrict__ slots, int n_slots,
+                      const __grid_constant__ Bufs bufs, float* __restrict__ seg_scale) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, slots, n_slots);
   const int lane = threadIdx.x % LANES;
   const int64_t n_groups = (int64_t)gridDim.x * (blockDim.x / LANES);
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
@@ -66,25 +67,24 @@ __global__ void __launch_bounds__(256)
     for (int u = 0; u < UNROLL; ++u) {
       const int64_t s = base + (int64_t)u * n_groups + g;
       if (s >= n_seg) continue;
-      const int f = find_slot(s_seg_begin, n_slots, (int32_t)s);
-      const er_slot_t sl = slots[f];
+      const SlotLite sl = slot_lite(sv, slot_of(sv, (int32_t)s));
+      const int comb = sl.misc >> 8;
       float4 o = f4_zero();
       float scale = 0.f;
-      const bool keep = r[u] >= 0 && (sl.combiner == ER_COMBINER_SUM || w[u] > 0.f);
+      const bool keep = r[u] >= 0 && (comb == ER_COMBINER_SUM || w[u] > 0.f);
       if (keep) {
         o = weights ? f4_scale(v[u], w[u]) : v[u];
-        if (sl.combiner == ER_COMBINER_MEAN) {
+        scale = 1.f;
+        if (comb == ER_COMBINER_MEAN) {
           o = f4_div(o, w[u]);
           scale = __fdiv_rn(1.f, w[u]);
-        } else if (sl.combiner == ER_COMBINER_SQRTN) {
-          float d = sqrtf(__fmul_rn(w[u], w[u]));
+        } else if (comb == ER_COMBINER_SQRTN) {
+          const float d = sqrtf(__fmul_rn(w[u], w[u]));
           o = f4_div(o, d);
           scale = __fdiv_rn(1.f, d);
-        } else {
-          scale = 1.f;
         }
       }
-      float* dst = bufs.p[sl.out_buf] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
+      float* dst = bufs.p[sl.misc & 0xff] + (int64_t)((int32_t)s - sl.seg_begin) * sl.out_stride + sl.out_col;
       reinterpret_cast<float4*>(dst)[lane] = o;
       if (seg_scale && lane == 0) seg_scale[s] = scale;
     }
@@ -97,23 +97,22 @@ __global__ void __launch_bounds__(256)
     fwd_csr_kernel(const float* __restrict__ table, int row_stride,
                    const int64_t* __restrict__ rows, const float* __restrict__ weights,
                    const int32_t* __restrict__ row_ptr, int64_t n_seg, int64_t cap,
-                   const er_slot_t* __restrict__ slots, int n_slots, const __grid_constant__ Bufs bufs,
-                   float* __restrict__ seg_scale) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_seg_begin[i] = slots[i].seg_begin;
-  __syncthreads();
+                   const er_slot_t* __restrict__ slots, int n_slots,
+                   const __grid_constant__ Bufs bufs, float* __restrict__ seg_scale) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, slots, n_slots);
   const int lane = threadIdx.x % LANES;
   const int64_t n_groups = (int64_t)gridDim.x * (blockDim.x / LANES);
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
   constexpr int U = 4;
   for (int64_t s = g; s < n_seg; s += n_groups) {
-    const int f = find_slot(s_seg_begin, n_slots, (int32_t)s);
-    const er_slot_t sl = slots[f];
+    const SlotLite sl = slot_lite(sv, slot_of(sv, (int32_t)s));
+    const int comb = sl.misc >> 8;
     int64_t b = row_ptr[s], e = row_ptr[s + 1];
     if (e > cap) e = cap;
     float4 acc = f4_zero();
     float wsum = 0.f, w2sum = 0.f;
-    const bool is_sum = sl.combiner == ER_COMBINER_SUM;
+    const bool is_sum = comb == ER_COMBINER_SUM;
     for (int64_t j = b; j < e; j += U) {
       int64_t r[U];
       float w[U];
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(256)
       }
     }
     float scale = 1.f;
-    if (sl.combiner == ER_COMBINER_MEAN) {
+    if (comb == ER_COMBINER_MEAN) {
       if (wsum != 0.f) {
         acc = f4_div(acc, wsum);
         scale = __fdiv_rn(1.f, wsum);
@@ -147,8 +146,8 @@ __global__ void __launch_bounds__(256)
         acc = f4_zero();
         scale = 0.f;
       }
-    } else if (sl.combiner == ER_COMBINER_SQRTN) {
-      float d = sqrtf(w2sum);
+    } else if (comb == ER_COMBINER_SQRTN) {
+      const float d = sqrtf(w2sum);
       if (d != 0.f) {
         acc = f4_div(acc, d);
         scale = __fdiv_rn(1.f, d);
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(256)
         scale = 0.f;
       }
     }
-    float* dst = bufs.p[sl.out_buf] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
+    float* dst = bufs.p[sl.misc & 0xff] + (int64_t)((int32_t)s - sl.seg_begin) * sl.out_stride + sl.out_col;
     reinterpret_cast<float4*>(dst)[lane] = acc;
     if (seg_scale && lane == 0) seg_scale[s] = scale;
   }
@@ -168,21 +167,21 @@ __global__ void __launch_bounds__(256)
     fwd_scalar_kernel(const float* __restrict__ table, int dim, int row_stride,
                       const int64_t* __restrict__ rows, const float* __restrict__ weights,
                       const int32_t* __restrict__ row_ptr, int64_t n_seg, int64_t cap,
-                      const er_slot_t* __restrict__ slots, int n_slots, const __grid_constant__ Bufs bufs,
-                      float* __restrict__ seg_scale) {
-  extern __shared__ int32_t s_seg_begin[];
-  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) s_seg_begin[i] = slots[i].seg_begin;
-  __syncthreads();
+                      const er_slot_t* __restrict__ slots, int n_slots,
+                      const __grid_constant__ Bufs bufs, float* __restrict__ seg_scale) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, slots, n_slots);
+  const FastDiv ddiv = make_fastdiv((uint32_t)dim);
   const int64_t total = n_seg * dim;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = t / dim;
+    const int64_t s = (total < (1LL << 32)) ? (int64_t)fastdiv((uint32_t)t, ddiv) : t / dim;
     const int c = (int)(t - s * dim);
-    const int f = find_slot(s_seg_begin, n_slots, (int32_t)s);
-    const er_slot_t sl = slots[f];
+    const SlotLite sl = slot_lite(sv, slot_of(sv, (int32_t)s));
+    const int comb = sl.misc >> 8;
     int64_t b = row_ptr ? row_ptr[s] : s, e = row_ptr ? row_ptr[s + 1] : s + 1;
     if (e > cap) e = cap;
-    const bool is_sum = sl.combiner == ER_COMBINER_SUM;
+    const bool is_sum = comb == ER_COMBINER_SUM;
     float acc = 0.f, wsum = 0.f, w2sum = 0.f;
     for (int64_t j = b; j < e; ++j) {
       const int64_t r = rows[j];
@@ -194,15 +193,15 @@ __global__ void __launch_bounds__(256)
       w2sum = __fadd_rn(w2sum, __fmul_rn(w, w));
     }
     float scale = 1.f;
-    if (sl.combiner == ER_COMBINER_MEAN) {
+    if (comb == ER_COMBINER_MEAN) {
       scale = wsum != 0.f ? __fdiv_rn(1.f, wsum) : 0.f;
       acc = wsum != 0.f ? __fdiv_rn(acc, wsum) : 0.f;
-    } else if (sl.combiner == ER_COMBINER_SQRTN) {
-      float d = sqrtf(w2sum);
+    } else if (comb == ER_COMBINER_SQRTN) {
+      const float d = sqrtf(w2sum);
       scale = d != 0.f ? __fdiv_rn(1.f, d) : 0.f;
       acc = d != 0.f ? __fdiv_rn(acc, d) : 0.f;
     }
-    bufs.p[sl.out_buf][(int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col + c] = acc;
+    bufs.p[sl.misc & 0xff][(int64_t)((int32_t)s - sl.seg_begin) * sl.out_stride + sl.out_col + c] = acc;
     if (seg_scale && c == 0) seg_scale[s] = scale;
   }
 }
@@ -212,7 +211,7 @@ static void launch_vec(const float* table, int row_stride, const int64_t* rows,
                        const float* weights, const int32_t* row_ptr, int64_t n_seg, int64_t cap,
                        const er_slot_t* slots, int n_slots, const Bufs& bufs, float* seg_scale,
                        cudaStream_t st) {
-  const size_t smem = (size_t)n_slots * sizeof(int32_t);
+  const size_t smem = slot_smem_bytes(n_slots);
   const int groups_per_cta = 256 / LANES;
   if (!row_ptr) {
     constexpr int UNROLL = 4;
@@ -237,7 +236,7 @@ extern "C" int er_embedding_fwd(const float* table, int64_t n_rows, int32_t dim,
   ER_REQUIRE(table && rows && slots && out_bufs, "null argument");
   ER_REQUIRE(dim > 0 && row_stride >= dim, "bad dim / row_stride");
   ER_REQUIRE(n_rows > 0, "n_rows must be positive");
-  ER_REQUIRE(n_slots > 0 && n_slots <= 8192, "n_slots must be in [1, 8192]");
+  ER_REQUIRE(n_slots > 0 && n_slots <= 2048, "n_slots must be in [1, 2048]");
   ER_REQUIRE(n_bufs > 0 && n_bufs <= ER_MAX_BUFS, "n_bufs must be in [1, ER_MAX_BUFS]");
   ER_REQUIRE(n_seg >= 0 && n_seg < (1LL << 31), "n_seg out of range");
   ER_REQUIRE(row_ptr || n_lookups_cap == n_seg,
@@ -267,7 +266,7 @@ extern "C" int er_embedding_fwd(const float* table, int64_t n_rows, int32_t dim,
     }
   } else {
     int grid = grid_for(n_seg * (int64_t)dim, 256, 8);
-    fwd_scalar_kernel<<<grid, 256, (size_t)n_slots * sizeof(int32_t), st>>>(
+    fwd_scalar_kernel<<<grid, 256, slot_smem_bytes(n_slots), st>>>(
         table, dim, row_stride, rows, weights, row_ptr, n_seg, n_lookups_cap, slots, n_slots, bufs,
         seg_scale);
   }

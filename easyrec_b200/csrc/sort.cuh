@@ -8,37 +8,38 @@
 // lookups (row < 0) get the sentinel key `n_rows` and sort behind every valid
 // row.  8-bit digits, ceil(bits(n_rows)/8) passes (3 for a 10M-row arena).
 //
-// Launch structure (P passes -> P + 1 launches, no separate scan kernels):
+// Shape of the launches: the batch is cut into ~one tile per SM (<= 160 tiles of
+// 1024 threads x {2,4,8,16} items), so every launch is a single wave of the 148 SMs.
+// P passes -> P + 1 launches, no separate scan kernels:
 //   init_hist_kernel : rows -> (key, pos) pairs + per-tile histogram of digit 0;
 //                      zeroes the histograms of the later passes
-//   scatter_kernel x P: each CTA derives its tile's global offsets by summing the
-//                      per-tile histograms of the tiles before it (tiles are large,
-//                      so there are <= ~128 of them: one coalesced column sum per
-//                      thread), ranks its keys stably with warp match_any, scatters,
-//                      and counts the NEXT pass's per-tile histogram at the
-//                      destination with global atomics (counts are order-free, so
+//   scatter_kernel x P: a CTA derives its tile's global offsets by summing the per-tile
+//                      histograms over the tiles (4 threads per digit, coalesced column
+//                      reads of <= 160 values), ranks its keys stably with warp
+//                      match_any, scatters, and counts the NEXT pass's per-tile histogram
+//                      at the destination with global atomics (counts are order-free, so
 //                      determinism is kept).
 // Working set at the benchmark shapes (<= 1M pairs x 8 B x 2 buffers) is L2
 // resident on B200: the passes are latency-, not HBM-bound.
 #pragma once
 #include "common.cuh"
-#include "scan.cuh"
 
 namespace er {
 namespace rsort {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxPasses = 4;
+constexpr int kMaxTiles = 160;
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// items per thread: smallest of {4, 8, 16} that keeps the tile count <= 128
+// items per thread: smallest of {2, 4, 8, 16} that keeps the tile count <= kMaxTiles
 inline int items_for(int64_t n) {
-  if (ceil_div(n, (int64_t)kThreads * 4) <= 128) return 4;
-  if (ceil_div(n, (int64_t)kThreads * 8) <= 128) return 8;
+  for (int it = 2; it < 16; it *= 2)
+    if (ceil_div(n, (int64_t)kThreads * it) <= kMaxTiles) return it;
   return 16;
 }
 inline int64_t num_tiles(int64_t n) {
@@ -81,10 +82,12 @@ static __global__ void __launch_bounds__(kThreads)
                      int32_t* __restrict__ hist, int passes, int32_t* __restrict__ zero_me) {
   __shared__ int s_hist[kRadix];
   const int64_t n_tiles = gridDim.x;
-  s_hist[threadIdx.x] = 0;
-  for (int p = 1; p < passes; ++p)
-    hist[((int64_t)p * n_tiles + blockIdx.x) * kRadix + threadIdx.x] = 0;
-  if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0;
+  if (threadIdx.x < kRadix) {
+    s_hist[threadIdx.x] = 0;
+    for (int p = 1; p < passes; ++p)
+      hist[((int64_t)p * n_tiles + blockIdx.x) * kRadix + threadIdx.x] = 0;
+  }
+  if (zero_me && blockIdx.x == 0 && threadIdx.x < 2) zero_me[threadIdx.x] = 0;  // two counters
   __syncthreads();
   const int64_t n = n_dev ? (int64_t)(*n_dev < cap ? *n_dev : cap) : cap;
   const int64_t base = (int64_t)blockIdx.x * (kThreads * ITEMS);
@@ -100,7 +103,7 @@ static __global__ void __launch_bounds__(kThreads)
     }
   }
   __syncthreads();
-  hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = s_hist[threadIdx.x];
+  if (threadIdx.x < kRadix) hist[(int64_t)blockIdx.x * kRadix + threadIdx.x] = s_hist[threadIdx.x];
 }
 
 template <int ITEMS>
@@ -108,32 +111,14 @@ static __global__ void __launch_bounds__(kThreads)
     scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
                    int shift, const int32_t* __restrict__ hist_cur, int32_t* __restrict__ hist_next) {
-  __shared__ int s_warp_hist[kWarps][kRadix];
-  const int64_t n_tiles = gridDim.x;
-  for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&s_warp_hist[0][0])[i] = 0;
-  // ---- this tile's global offsets: digit threadIdx.x, sum over all tiles / the tiles before ----
-  int before = 0, total = 0;
-  {
-    const int32_t* col = hist_cur + threadIdx.x;
-    int64_t t = 0;
-    for (; t + 8 <= n_tiles; t += 8) {
-      int h[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) h[u] = col[(t + u) * kRadix];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (t + u == blockIdx.x) before = total;
-        total += h[u];
-      }
-    }
-    for (; t < n_tiles; ++t) {
-      if (t == blockIdx.x) before = total;
-      total += col[t * kRadix];
-    }
-  }
-  const int digit_base = scan::block_excl_scan(total, nullptr) + before;  // includes __syncthreads
+  __shared__ int s_warp_hist[kWarps][kRadix];  // 32 KB
+  __shared__ int s_tot[4][kRadix];
+  __shared__ int s_bef[4][kRadix];
+  __shared__ int s_wsum[kRadix / 32];
+  const int n_tiles = gridDim.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&s_warp_hist[0][0])[i] = 0;
+  // keys first: their loads overlap the histogram column sums below
   const int64_t base = (int64_t)blockIdx.x * (kThreads * ITEMS) + (int64_t)w * (32 * ITEMS);
   uint32_t key[ITEMS], val[ITEMS];
   int rank[ITEMS];
@@ -143,6 +128,56 @@ static __global__ void __launch_bounds__(kThreads)
     key[i] = (idx < n) ? keys_in[idx] : 0u;
     val[i] = (idx < n) ? vals_in[idx] : 0u;
   }
+  // ---- this tile's global offsets: 4 threads per digit each sum a quarter of the tiles ----
+  {
+    const int d = threadIdx.x & (kRadix - 1), part = threadIdx.x >> kRadixBits;
+    const int per = (n_tiles + 3) >> 2;
+    const int t0 = part * per, t1 = min(n_tiles, t0 + per);
+    int total = 0, before = 0;
+    const int32_t* col = hist_cur + d;
+    int t = t0;
+    for (; t + 8 <= t1; t += 8) {
+      int h[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h[u] = col[(int64_t)(t + u) * kRadix];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        before += (t + u < (int)blockIdx.x) ? h[u] : 0;
+        total += h[u];
+      }
+    }
+    for (; t < t1; ++t) {
+      const int h = col[(int64_t)t * kRadix];
+      before += (t < (int)blockIdx.x) ? h : 0;
+      total += h;
+    }
+    s_tot[part][d] = total;
+    s_bef[part][d] = before;
+  }
+  __syncthreads();
+  int digit_base = 0;
+  if (threadIdx.x < kRadix) {
+    const int d = threadIdx.x;
+    const int total = s_tot[0][d] + s_tot[1][d] + s_tot[2][d] + s_tot[3][d];
+    const int before = s_bef[0][d] + s_bef[1][d] + s_bef[2][d] + s_bef[3][d];
+    // exclusive scan of `total` over the 256 digits (8 warps)
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[w] = incl;
+    digit_base = incl - total + before;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRadix) {
+    int off = 0;
+    for (int ww = 0; ww < w; ++ww) off += s_wsum[ww];
+    digit_base += off;
+  }
+  // ---- stable rank of every key inside the tile ----
+  const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = base + i * 32 + lane;
@@ -159,9 +194,9 @@ static __global__ void __launch_bounds__(kThreads)
     rank[i] = prev + r;
   }
   __syncthreads();
-  {
+  if (threadIdx.x < kRadix) {
     int run = digit_base;
-#pragma unroll
+#pragma unroll 8
     for (int ww = 0; ww < kWarps; ++ww) {
       int t = s_warp_hist[ww][threadIdx.x];
       s_warp_hist[ww][threadIdx.x] = run;
@@ -213,6 +248,7 @@ inline void sort_rows(const int64_t* rows, int64_t cap, const int32_t* n_dev, in
                       uint32_t* keys_out, uint32_t* vals_out, void* ws, int32_t* zero_me,
                       cudaStream_t st) {
   switch (items_for(cap)) {
+    case 2: sort_rows_t<2>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;
     case 4: sort_rows_t<4>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;
     case 8: sort_rows_t<8>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;
     default: sort_rows_t<16>(rows, cap, n_dev, n_rows, keys_out, vals_out, ws, zero_me, st); break;

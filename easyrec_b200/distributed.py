@@ -40,7 +40,7 @@ class GlobalCall(object):
     self.n_slots = len(recs)
     self.n_seg = call.n_seg * world
     self.max_lookups = call.max_lookups * world
-    self.ws = K.bwd_workspace(self.max_lookups, dev)
+    self.ws = K.bwd_workspace(self.max_lookups, dev, call.arena.dim)
     self.rows = torch.empty(self.max_lookups, dtype=torch.int64, device=dev)
     self.weights = torch.empty(self.max_lookups, dtype=torch.float32, device=dev)
     self.seg_scale = None

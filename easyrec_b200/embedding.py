@@ -120,7 +120,7 @@ class ArenaCall(object):
     self.single_valued = single_valued
     self.max_lookups = self.n_seg if single_valued else int(max_lookups)
     self.needs_scale = any(s.combiner != _lib.COMBINER_SUM for s in slots)
-    self.ws = K.bwd_workspace(self.max_lookups, arena.device)
+    self.ws = K.bwd_workspace(self.max_lookups, arena.device, arena.dim)
     self.seg_scale = (torch.empty(self.n_seg, dtype=torch.float32, device=arena.device)
                       if self.needs_scale else None)
 

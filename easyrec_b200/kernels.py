@@ -108,9 +108,9 @@ def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, out_bufs, weights
                            len(out_bufs), _p(seg_scale), _stream()), 'er_embedding_fwd')
 
 
-def bwd_workspace(n_lookups_cap, device):
+def bwd_workspace(n_lookups_cap, device, dim):
   lib = _lib.load()
-  return torch.empty(lib.er_embedding_bwd_workspace_bytes(n_lookups_cap), dtype=torch.uint8,
+  return torch.empty(lib.er_embedding_bwd_workspace_bytes(n_lookups_cap, dim), dtype=torch.uint8,
                      device=device)
 
 

@@ -164,7 +164,7 @@ int er_embedding_fwd(const float* table, int64_t n_rows, int32_t dim,
  * When uniq_rows/uniq_grads are non-NULL the deduplicated gradient is ALSO
  * written there (compact, sorted by row; *n_uniq receives the count); pass
  * table == NULL to only emit it. */
-size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap);
+size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap, int32_t dim);
 int er_embedding_bwd(float* table, float* state0, float* state1,
                      int64_t n_rows, int32_t dim, int32_t row_stride,
                      const int64_t* rows, const float* weights,

@@ -224,7 +224,7 @@ def _run_bwd(kind, dim, rng, V, B, F, with_csr, hot):
     out = torch.empty(B, stride, device=DEV)
     K.embedding_fwd(d_table, dim, d_rows, sd, F, B * F, [out], weights=t(w), row_ptr=row_ptr, seg_scale=scale)
   opt = K.make_opt(kind, 0.05, beta1_power=0.9**4, beta2_power=0.999**4, grad_scale=0.5)
-  ws = K.bwd_workspace(L, DEV)
+  ws = K.bwd_workspace(L, DEV, dim)
   ur = torch.empty(L, dtype=torch.int64, device=DEV)
   ug = torch.empty(L, dim, device=DEV)
   nu = torch.zeros(1, dtype=torch.int32, device=DEV)
@@ -285,7 +285,7 @@ def test_bwd_ten_steps_adagrad_tracks_oracle():
   recs = [dict(num_buckets=V, row_offset=0, seg_begin=f * B, n_seg=B, bucket_mode=3, combiner=0, out_buf=0,
                out_stride=stride, out_col=f * dim) for f in range(F)]
   sd = K.slots_to_device(K.make_slots(recs), DEV)
-  ws = K.bwd_workspace(B * F, DEV)
+  ws = K.bwd_workspace(B * F, DEV, dim)
   for step in range(10):
     rows = (rng.zipf(1.3, B * F) % V).astype(np.int64)
     gout = rng.normal(0, 0.1, (B, stride)).astype(np.float32)
@@ -354,7 +354,7 @@ def test_full_size_c2_properties():
   ur = torch.empty(B * F, dtype=torch.int64, device=DEV)
   ug = torch.empty(B * F, D, device=DEV)
   nu = torch.zeros(1, dtype=torch.int32, device=DEV)
-  ws = K.bwd_workspace(B * F, DEV)
+  ws = K.bwd_workspace(B * F, DEV, D)
   acc = torch.full((V, D), 0.1, device=DEV)
   t0 = table.clone()
   K.embedding_bwd(table, acc, None, D, rows, sd, F, B * F, [gout], K.make_opt(_lib.OPT_ADAGRAD, 0.01), ws,
