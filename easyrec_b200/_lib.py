@@ -75,6 +75,13 @@ SIGNATURES = {
                           c_i32, c_vp]),
     'er_sigmoid_ce_fwd_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp,
                                       c_vp, c_vp, c_vp]),
+    'er_dense_workspace_bytes': (c_sz, [c_i64, c_i32]),
+    'er_bias_bn_act_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                   c_i32, c_f32, c_f32, c_i32, c_i32, c_vp,
+                                   c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'er_bias_bn_act_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                   c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_sz, c_vp]),
 }
 
 _lib = None

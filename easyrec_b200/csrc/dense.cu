@@ -1,0 +1,306 @@
+// K6 epilogues: the non-GEMM part of EasyRec's DNN layer (layers/dnn.py:56-79)
+//     z = x W + b ;  h = batch_norm(z) ;  y = relu(h)
+// fused into two launches forward and two backward, fp32, deterministic.
+//   tf.layers.batch_normalization defaults: momentum 0.99, epsilon 1e-3, batch statistics in
+//   training with the BIASED variance for both the normalisation and the moving average.
+// The GEMMs themselves stay plain library SGEMMs (cuBLAS, TF32 off).
+//
+// Decomposition: 32-column tiles x R row chunks (grid ~ 2 waves of the 148 SMs).  Pass 1 writes
+// per-chunk partial statistics (Welford count/mean/M2, merged with Chan's formula in a fixed order
+// -- no atomics, no E[x^2]-E[x]^2 cancellation); pass 2 re-derives the column statistics from the
+// R partials (R*32 L2 reads per CTA) and streams the tile.  Traffic: fwd 2 reads + 1 write of
+// [B,U]; bwd 3 reads (z, y, gy) twice + 1 write.
+#include "common.cuh"
+
+namespace er {
+
+constexpr int kColTile = 32;
+constexpr int kRowLanes = 8;  // 256 threads = 32 columns x 8 row lanes
+
+struct Welford {
+  float n, mean, m2;
+};
+__device__ __forceinline__ void wf_merge(Welford& a, const Welford& b) {
+  if (b.n == 0.f) return;
+  const float n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  a.mean += d * (b.n / n);
+  a.m2 += b.m2 + d * d * (a.n * b.n / n);
+  a.n = n;
+}
+
+struct DenseShape {
+  int64_t batch;
+  int units;
+  int rows_per_chunk;
+  int n_chunks;
+};
+
+inline DenseShape dense_shape(int64_t batch, int units) {
+  DenseShape s;
+  s.batch = batch;
+  s.units = units;
+  const int col_tiles = (units + kColTile - 1) / kColTile;
+  int r = (2 * kSmCount + col_tiles - 1) / col_tiles;
+  if (r < 1) r = 1;
+  int64_t rpc = ceil_div(batch, (int64_t)r);
+  rpc = ceil_div(rpc, (int64_t)kRowLanes) * kRowLanes;
+  if (rpc < kRowLanes) rpc = kRowLanes;
+  s.rows_per_chunk = (int)rpc;
+  s.n_chunks = (int)ceil_div(batch, rpc);
+  return s;
+}
+
+// ---- forward pass 1: partial statistics of z + b ----
+__global__ void __launch_bounds__(256)
+    bn_stats_kernel(const float* __restrict__ z, const float* __restrict__ bias, DenseShape s,
+                    float* __restrict__ part /* [n_chunks][units][3] */) {
+  __shared__ Welford s_w[kRowLanes][kColTile];
+  const int c = blockIdx.x * kColTile + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * s.rows_per_chunk;
+  const int64_t r1 = min(s.batch, r0 + s.rows_per_chunk);
+  Welford w = {0.f, 0.f, 0.f};
+  if (c < s.units && r0 + rl < r1) {
+    // shifted sums (shift = first value of the lane) -> (n, mean, M2): no per-element division,
+    // and no E[x^2]-E[x]^2 cancellation because the shift sits next to the mean
+    const float b = bias ? bias[c] : 0.f;
+    const float shift = z[(r0 + rl) * s.units + c] + b;
+    float n = 0.f, sm = 0.f, sq = 0.f;
+    for (int64_t r = r0 + rl; r < r1; r += kRowLanes) {
+      const float d = (z[r * s.units + c] + b) - shift;
+      n += 1.f;
+      sm += d;
+      sq += d * d;
+    }
+    w.n = n;
+    w.mean = shift + sm / n;
+    w.m2 = sq - sm * sm / n;
+  }
+  s_w[rl][threadIdx.x & 31] = w;
+  __syncthreads();
+  if (rl == 0 && c < s.units) {
+    Welford t = s_w[0][threadIdx.x];
+    for (int k = 1; k < kRowLanes; ++k) wf_merge(t, s_w[k][threadIdx.x]);
+    float* p = part + ((int64_t)blockIdx.y * s.units + c) * 3;
+    p[0] = t.n;
+    p[1] = t.mean;
+    p[2] = t.m2;
+  }
+}
+
+// ---- forward pass 2: merge partials, normalise, activation ----
+__global__ void __launch_bounds__(256)
+    bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ moving_mean, float* __restrict__ moving_var, DenseShape s,
+                    float eps, float momentum, int training, int relu, const float* __restrict__ part,
+                    float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  __shared__ float s_mean[kColTile], s_rstd[kColTile];
+  const int c = blockIdx.x * kColTile + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  if (rl == 0 && c < s.units) {
+    float mean, var;
+    if (training) {
+      Welford t = {0.f, 0.f, 0.f};
+      for (int k = 0; k < s.n_chunks; ++k) {
+        const float* p = part + ((int64_t)k * s.units + c) * 3;
+        Welford q = {p[0], p[1], p[2]};
+        wf_merge(t, q);
+      }
+      mean = t.mean;
+      var = t.m2 / t.n;  // biased
+      if (blockIdx.y == 0) {
+        moving_mean[c] = moving_mean[c] * momentum + mean * (1.f - momentum);
+        moving_var[c] = moving_var[c] * momentum + var * (1.f - momentum);
+      }
+    } else {
+      mean = moving_mean[c];
+      var = moving_var[c];
+    }
+    const float rstd = 1.0f / sqrtf(var + eps);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+    if (blockIdx.y == 0 && save_mean) {
+      save_mean[c] = mean;
+      save_rstd[c] = rstd;
+    }
+  }
+  __syncthreads();
+  if (c >= s.units) return;
+  const float b = bias ? bias[c] : 0.f;
+  const float mean = s_mean[threadIdx.x & 31], rstd = s_rstd[threadIdx.x & 31];
+  const float ga = gamma[c], be = beta[c];
+  const int64_t r0 = (int64_t)blockIdx.y * s.rows_per_chunk;
+  const int64_t r1 = min(s.batch, r0 + s.rows_per_chunk);
+  for (int64_t r = r0 + rl; r < r1; r += kRowLanes) {
+    const float h = ((z[r * s.units + c] + b) - mean) * rstd * ga + be;
+    y[r * s.units + c] = relu ? fmaxf(h, 0.f) : h;
+  }
+}
+
+// no batch norm: y = act(z + b)
+__global__ void __launch_bounds__(256)
+    bias_act_kernel(const float* __restrict__ z, const float* __restrict__ bias, int64_t total, int units,
+                    int relu, float* __restrict__ y) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const float h = z[t] + (bias ? bias[t % units] : 0.f);
+    y[t] = relu ? fmaxf(h, 0.f) : h;
+  }
+}
+
+// ---- backward pass 1: partial column sums of g and g*xhat (BN) or of g (no BN) ----
+__global__ void __launch_bounds__(256)
+    bn_bwd_stats_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                        const float* __restrict__ y, const float* __restrict__ gy,
+                        const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                        DenseShape s, int relu, int use_bn, float* __restrict__ part /* [n_chunks][units][2] */) {
+  __shared__ float s_a[kRowLanes][kColTile], s_b[kRowLanes][kColTile];
+  const int c = blockIdx.x * kColTile + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * s.rows_per_chunk;
+  const int64_t r1 = min(s.batch, r0 + s.rows_per_chunk);
+  float sg = 0.f, sgx = 0.f;
+  if (c < s.units) {
+    const float b = bias ? bias[c] : 0.f;
+    const float mean = use_bn ? save_mean[c] : 0.f, rstd = use_bn ? save_rstd[c] : 0.f;
+    for (int64_t r = r0 + rl; r < r1; r += kRowLanes) {
+      const int64_t i = r * s.units + c;
+      float g = gy[i];
+      if (relu && !(y[i] > 0.f)) g = 0.f;
+      sg += g;
+      if (use_bn) sgx += g * (((z[i] + b) - mean) * rstd);
+    }
+  }
+  s_a[rl][threadIdx.x & 31] = sg;
+  s_b[rl][threadIdx.x & 31] = sgx;
+  __syncthreads();
+  if (rl == 0 && c < s.units) {
+    float a = s_a[0][threadIdx.x], bb = s_b[0][threadIdx.x];
+    for (int k = 1; k < kRowLanes; ++k) {
+      a += s_a[k][threadIdx.x];
+      bb += s_b[k][threadIdx.x];
+    }
+    float* p = part + ((int64_t)blockIdx.y * s.units + c) * 2;
+    p[0] = a;
+    p[1] = bb;
+  }
+}
+
+// ---- backward pass 2: gz = gamma*rstd*(g - dbeta/B - xhat*dgamma/B)  (BN)   |   gz = g ----
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                        const float* __restrict__ gamma, const float* __restrict__ y,
+                        const float* __restrict__ gy, const float* __restrict__ save_mean,
+                        const float* __restrict__ save_rstd, DenseShape s, int relu, int use_bn,
+                        const float* __restrict__ part, float* __restrict__ gz,
+                        float* __restrict__ gbias, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  __shared__ float s_dg[kColTile], s_db[kColTile];
+  const int c = blockIdx.x * kColTile + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  if (rl == 0 && c < s.units) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < s.n_chunks; ++k) {
+      const float* p = part + ((int64_t)k * s.units + c) * 2;
+      a += p[0];
+      b += p[1];
+    }
+    s_db[threadIdx.x] = a;  // sum g
+    s_dg[threadIdx.x] = b;  // sum g*xhat
+    if (blockIdx.y == 0) {
+      if (use_bn) {
+        if (ggamma) ggamma[c] = b;
+        if (gbeta) gbeta[c] = a;
+        // d/dbias of a batch-normalised pre-activation is identically zero (BN removes the mean);
+        // TF evaluates it as rounding noise ~1e-9.
+        if (gbias) gbias[c] = 0.f;
+      } else if (gbias) {
+        gbias[c] = a;
+      }
+    }
+  }
+  __syncthreads();
+  if (c >= s.units) return;
+  const float bsum = s_db[threadIdx.x & 31], gsum = s_dg[threadIdx.x & 31];
+  const float bv = bias ? bias[c] : 0.f;
+  const float mean = use_bn ? save_mean[c] : 0.f, rstd = use_bn ? save_rstd[c] : 0.f;
+  const float ga = use_bn ? gamma[c] : 1.f;
+  const float inv_b = 1.0f / (float)s.batch;
+  const int64_t r0 = (int64_t)blockIdx.y * s.rows_per_chunk;
+  const int64_t r1 = min(s.batch, r0 + s.rows_per_chunk);
+  for (int64_t r = r0 + rl; r < r1; r += kRowLanes) {
+    const int64_t i = r * s.units + c;
+    float g = gy[i];
+    if (relu && !(y[i] > 0.f)) g = 0.f;
+    if (use_bn) {
+      const float xhat = ((z[i] + bv) - mean) * rstd;
+      g = ga * rstd * (g - bsum * inv_b - xhat * gsum * inv_b);
+    }
+    gz[i] = g;
+  }
+}
+
+}  // namespace er
+
+extern "C" size_t er_dense_workspace_bytes(int64_t batch, int32_t units) {
+  er::DenseShape s = er::dense_shape(batch > 0 ? batch : 1, units > 0 ? units : 1);
+  return (size_t)s.n_chunks * s.units * 3 * sizeof(float) + 256;
+}
+
+extern "C" int er_bias_bn_act_fwd(const float* z, const float* bias, const float* gamma,
+                                  const float* beta, float* moving_mean, float* moving_var,
+                                  int64_t batch, int32_t units, float eps, float momentum,
+                                  int32_t training, int32_t relu, float* y, float* save_mean,
+                                  float* save_rstd, void* ws, size_t ws_bytes, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(z && y, "null argument");
+  ER_REQUIRE(batch > 0 && units > 0, "bad shape");
+  cudaStream_t st = as_stream(stream);
+  if (!gamma) {
+    bias_act_kernel<<<grid_for(batch * units, 256, 8), 256, 0, st>>>(z, bias, batch * units, units, relu, y);
+    count_launches(1);
+    ER_CUDA_LAUNCH_CHECK();
+    return ER_OK;
+  }
+  ER_REQUIRE(beta && moving_mean && moving_var, "batch norm needs beta and moving statistics");
+  DenseShape s = dense_shape(batch, units);
+  dim3 grid((units + kColTile - 1) / kColTile, s.n_chunks);
+  if (training) {
+    ER_REQUIRE(save_mean && save_rstd, "training needs save_mean / save_rstd");
+    if (!ws || ws_bytes < er_dense_workspace_bytes(batch, units))
+      return fail(ER_ERR_WORKSPACE, "er_bias_bn_act_fwd: workspace too small");
+    bn_stats_kernel<<<grid, 256, 0, st>>>(z, bias, s, reinterpret_cast<float*>(ws));
+    count_launches(1);
+  }
+  bn_apply_kernel<<<grid, 256, 0, st>>>(z, bias, gamma, beta, moving_mean, moving_var, s, eps, momentum,
+                                        training, relu, reinterpret_cast<const float*>(ws), y, save_mean,
+                                        save_rstd);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float* gamma,
+                                  const float* y, const float* gy, const float* save_mean,
+                                  const float* save_rstd, int64_t batch, int32_t units,
+                                  int32_t relu, float* gz, float* gbias, float* ggamma,
+                                  float* gbeta, void* ws, size_t ws_bytes, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(z && y && gy && gz, "null argument");
+  ER_REQUIRE(batch > 0 && units > 0, "bad shape");
+  const int use_bn = gamma != nullptr;
+  ER_REQUIRE(!use_bn || (save_mean && save_rstd), "batch norm backward needs the saved statistics");
+  if (!ws || ws_bytes < er_dense_workspace_bytes(batch, units))
+    return fail(ER_ERR_WORKSPACE, "er_bias_bn_act_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  DenseShape s = dense_shape(batch, units);
+  dim3 grid((units + kColTile - 1) / kColTile, s.n_chunks);
+  float* part = reinterpret_cast<float*>(ws);
+  bn_bwd_stats_kernel<<<grid, 256, 0, st>>>(z, bias, y, gy, save_mean, save_rstd, s, relu, use_bn, part);
+  bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(z, bias, gamma, y, gy, save_mean, save_rstd, s, relu, use_bn,
+                                            part, gz, gbias, ggamma, gbeta);
+  count_launches(2);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}

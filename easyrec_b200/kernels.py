@@ -32,6 +32,16 @@ def _chk(t, dtype, name):
     raise _lib.ErError('%s must be contiguous' % name)
 
 
+def _chk_rows(t, name):
+  """table / optimizer-state matrix [n_rows, dim]: fp32, unit inner stride; the row stride may
+  exceed dim (interleaved [w | state] rows).  Returns (n_rows, row_stride)."""
+  if t is None:
+    return None
+  if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+    raise _lib.ErError('%s must be a CUDA fp32 [rows, dim] matrix with unit inner stride' % name)
+  return t.shape[0], t.stride(0)
+
+
 def _buf_array(bufs):
   arr = (c_vp * len(bufs))()
   for i, b in enumerate(bufs):
@@ -93,15 +103,13 @@ def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=N
 def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, out_bufs, weights=None,
                   row_ptr=None, seg_scale=None, row_stride=None):
   lib = _lib.load()
-  _chk(table, torch.float32, 'table')
+  n_rows, row_stride = _chk_rows(table, 'table')
   _chk(rows, torch.int64, 'rows')
   _chk(weights, torch.float32, 'weights')
   _chk(row_ptr, torch.int32, 'row_ptr')
   _chk(seg_scale, torch.float32, 'seg_scale')
   for i, b in enumerate(out_bufs):
     _chk(b, torch.float32, 'out_bufs[%d]' % i)
-  row_stride = row_stride or dim
-  n_rows = table.numel() // row_stride
   _lib.check(
       lib.er_embedding_fwd(_p(table), n_rows, dim, row_stride, _p(rows), _p(weights), _p(row_ptr),
                            n_seg, rows.numel(), _p(slots_dev), n_slots, _buf_array(out_bufs),
@@ -123,9 +131,13 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
                   ws, weights=None, seg_ids=None, row_ptr=None, seg_scale=None, row_stride=None,
                   uniq_rows=None, uniq_grads=None, n_uniq=None, n_rows=None):
   lib = _lib.load()
-  _chk(table, torch.float32, 'table')
-  _chk(state0, torch.float32, 'state0')
-  _chk(state1, torch.float32, 'state1')
+  row_stride = dim
+  if table is not None:
+    n_rows_t, row_stride = _chk_rows(table, 'table')
+    n_rows = n_rows if n_rows is not None else n_rows_t
+    for st, nm in ((state0, 'state0'), (state1, 'state1')):
+      if st is not None and _chk_rows(st, nm)[1] != row_stride:
+        raise _lib.ErError('%s must share the table row stride' % nm)
   _chk(rows, torch.int64, 'rows')
   _chk(weights, torch.float32, 'weights')
   _chk(seg_ids, torch.int32, 'seg_ids')
@@ -136,9 +148,6 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
   _chk(n_uniq, torch.int32, 'n_uniq')
   for i, b in enumerate(grad_bufs):
     _chk(b, torch.float32, 'grad_bufs[%d]' % i)
-  row_stride = row_stride or dim
-  if n_rows is None:
-    n_rows = table.numel() // row_stride
   _lib.check(
       lib.er_embedding_bwd(_p(table), _p(state0), _p(state1), n_rows, dim, row_stride, _p(rows),
                            _p(weights), _p(seg_ids), _p(row_ptr), n_seg, rows.numel(),
@@ -149,7 +158,7 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
 
 def sparse_apply(table, state0, state1, dim, uniq_rows, uniq_grads, n_uniq, opt, row_stride=None):
   lib = _lib.load()
-  row_stride = row_stride or dim
+  _, row_stride = _chk_rows(table, 'table')
   _lib.check(
       lib.er_sparse_apply(_p(table), _p(state0), _p(state1), dim, row_stride, _p(uniq_rows),
                           _p(uniq_grads), _p(n_uniq), uniq_rows.numel(), ctypes.byref(opt),
@@ -158,9 +167,9 @@ def sparse_apply(table, state0, state1, dim, uniq_rows, uniq_grads, n_uniq, opt,
 
 def adam_dense_sweep(table, m, v, dim, touched, opt, row_stride=None):
   lib = _lib.load()
-  row_stride = row_stride or dim
+  n_rows_t, row_stride = _chk_rows(table, 'table')
   _lib.check(
-      lib.er_adam_dense_sweep(_p(table), _p(m), _p(v), table.numel() // row_stride, dim,
+      lib.er_adam_dense_sweep(_p(table), _p(m), _p(v), n_rows_t, dim,
                               row_stride, _p(touched), ctypes.byref(opt), _stream()),
       'er_adam_dense_sweep')
 
@@ -225,3 +234,43 @@ def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
       lib.er_sigmoid_ce_fwd_bwd(_p(logits), _p(labels), _p(weights), batch, inv_count, _p(loss),
                                 _p(probs), _p(g), _stream()), 'er_sigmoid_ce_fwd_bwd')
   return loss, probs, g
+
+
+def dense_workspace(batch, units, device):
+  lib = _lib.load()
+  return torch.empty(lib.er_dense_workspace_bytes(batch, units), dtype=torch.uint8, device=device)
+
+
+def bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, eps, momentum, training, relu,
+                    ws, y=None, save_mean=None, save_rstd=None):
+  """y = act(bn(z + bias)) (gamma None: no batch norm). Returns (y, save_mean, save_rstd)."""
+  lib = _lib.load()
+  _chk(z, torch.float32, 'z')
+  batch, units = z.shape
+  if y is None:
+    y = torch.empty_like(z)
+  if gamma is not None and training and save_mean is None:
+    save_mean = torch.empty(units, dtype=torch.float32, device=z.device)
+    save_rstd = torch.empty(units, dtype=torch.float32, device=z.device)
+  _lib.check(
+      lib.er_bias_bn_act_fwd(_p(z), _p(bias), _p(gamma), _p(beta), _p(moving_mean), _p(moving_var),
+                             batch, units, eps, momentum, 1 if training else 0, 1 if relu else 0,
+                             _p(y), _p(save_mean), _p(save_rstd), _p(ws), ws.numel(), _stream()),
+      'er_bias_bn_act_fwd')
+  return y, save_mean, save_rstd
+
+
+def bias_bn_act_bwd(z, bias, gamma, y, gy, save_mean, save_rstd, relu, ws):
+  """Returns (gz, gbias, ggamma, gbeta)."""
+  lib = _lib.load()
+  _chk(gy, torch.float32, 'gy')
+  batch, units = z.shape
+  gz = torch.empty_like(z)
+  gbias = torch.empty(units, dtype=torch.float32, device=z.device)
+  ggamma = torch.empty(units, dtype=torch.float32, device=z.device) if gamma is not None else None
+  gbeta = torch.empty(units, dtype=torch.float32, device=z.device) if gamma is not None else None
+  _lib.check(
+      lib.er_bias_bn_act_bwd(_p(z), _p(bias), _p(gamma), _p(y), _p(gy), _p(save_mean), _p(save_rstd),
+                             batch, units, 1 if relu else 0, _p(gz), _p(gbias), _p(ggamma), _p(gbeta),
+                             _p(ws), ws.numel(), _stream()), 'er_bias_bn_act_bwd')
+  return gz, gbias, ggamma, gbeta

@@ -5,77 +5,108 @@
         training, *biased* variance for both the normalisation and the moving average (2-D
         inputs take TF's non-fused path)
 
-The GEMMs are plain library matmuls (cuBLAS SGEMM through torch, TF32 disabled so logits stay
-within 1e-4 of an fp32 CPU run); everything sparse around them is liber_b200.so.
+Per layer: one library SGEMM (cuBLAS through torch.mm, TF32 disabled so logits stay within 1e-4 of
+an fp32 CPU run) + liber_b200's fused bias/batch-norm/ReLU epilogue (2 launches forward, 2
+backward, deterministic statistics).  There is no torch fallback for the epilogue.
 """
 import math
 
 import torch
 from torch import nn
 
+from easyrec_b200 import kernels as K
+
 BN_EPS = 1e-3
 BN_MOMENTUM = 0.99
 
 
-class TFBatchNorm(nn.Module):
+class _DenseBNAct(torch.autograd.Function):
 
-  def __init__(self, units):
-    super().__init__()
-    self.gamma = nn.Parameter(torch.ones(units))
-    self.beta = nn.Parameter(torch.zeros(units))
-    self.register_buffer('moving_mean', torch.zeros(units))
-    self.register_buffer('moving_var', torch.ones(units))
+  @staticmethod
+  def forward(ctx, x, kernel, bias, gamma, beta, moving_mean, moving_var, training, relu, ws):
+    z = torch.mm(x, kernel)
+    y, mean, rstd = K.bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, BN_EPS,
+                                      BN_MOMENTUM, training, relu, ws)
+    ctx.relu = relu
+    ctx.ws = ws
+    ctx.has_bn = gamma is not None
+    ctx.save_for_backward(x, kernel, bias, gamma, z, y, mean, rstd)
+    return y
 
-  def forward(self, x):
-    if self.training:
-      mu = x.mean(0)
-      var = ((x - mu)**2).mean(0)
-      with torch.no_grad():
-        self.moving_mean.mul_(BN_MOMENTUM).add_(mu.detach(), alpha=1 - BN_MOMENTUM)
-        self.moving_var.mul_(BN_MOMENTUM).add_(var.detach(), alpha=1 - BN_MOMENTUM)
-    else:
-      mu, var = self.moving_mean, self.moving_var
-    return (x - mu) * torch.rsqrt(var + BN_EPS) * self.gamma + self.beta
+  @staticmethod
+  def backward(ctx, gy):
+    x, kernel, bias, gamma, z, y, mean, rstd = ctx.saved_tensors
+    gz, gbias, ggamma, gbeta = K.bias_bn_act_bwd(z, bias, gamma, y, gy.contiguous(), mean, rstd,
+                                                 ctx.relu, ctx.ws)
+    gk = torch.mm(x.t(), gz)
+    gx = torch.mm(gz, kernel.t()) if ctx.needs_input_grad[0] else None
+    return gx, gk, gbias, ggamma, gbeta, None, None, None, None, None
 
 
-class Dense(nn.Module):
-  """tf.layers.dense: kernel [in, out] glorot-uniform, bias zeros."""
+class DenseLayer(nn.Module):
+  """tf.layers.dense (kernel [in, out] glorot-uniform, bias zeros) [+ batch_norm] [+ relu]."""
 
-  def __init__(self, n_in, n_out, generator=None):
+  def __init__(self, n_in, n_out, use_bn, relu, generator=None):
     super().__init__()
     limit = math.sqrt(6.0 / (n_in + n_out))
     w = torch.empty(n_in, n_out)
     w.uniform_(-limit, limit, generator=generator)
     self.kernel = nn.Parameter(w)
     self.bias = nn.Parameter(torch.zeros(n_out))
+    self.use_bn = use_bn
+    self.relu = relu
+    if use_bn:
+      self.gamma = nn.Parameter(torch.ones(n_out))
+      self.beta = nn.Parameter(torch.zeros(n_out))
+      self.register_buffer('moving_mean', torch.zeros(n_out))
+      self.register_buffer('moving_var', torch.ones(n_out))
+    self.n_out = n_out
+    self._ws = None
+    self._ws_batch = -1
 
   def forward(self, x):
-    return torch.addmm(self.bias, x, self.kernel)
+    if self._ws is None or self._ws_batch != x.shape[0] or self._ws.device != x.device:
+      self._ws = K.dense_workspace(x.shape[0], self.n_out, x.device)
+      self._ws_batch = x.shape[0]
+    if self.use_bn:
+      return _DenseBNAct.apply(x, self.kernel, self.bias, self.gamma, self.beta, self.moving_mean,
+                               self.moving_var, self.training, self.relu, self._ws)
+    return _DenseBNAct.apply(x, self.kernel, self.bias, None, None, None, None, self.training,
+                             self.relu, self._ws)
+
+
+class Dense(DenseLayer):
+  """plain tf.layers.dense: no batch norm, no activation (logit heads)."""
+
+  def __init__(self, n_in, n_out, generator=None):
+    super().__init__(n_in, n_out, use_bn=False, relu=False, generator=generator)
 
 
 class DNN(nn.Module):
+  """layers/dnn.py:50-87.  Inputs of rank 3 ([B, T, d], DIN attention) are flattened to rows, which
+  is exactly what tf.layers.batch_normalization does on the last axis."""
 
   def __init__(self, n_in, hidden_units, use_bn=True, last_layer_no_activation=False,
                last_layer_no_batch_norm=False, generator=None):
     super().__init__()
-    self.dense = nn.ModuleList()
-    self.bn = nn.ModuleList()
-    self.act = []
+    self.layers = nn.ModuleList()
     n = len(hidden_units)
     for i, u in enumerate(hidden_units):
-      self.dense.append(Dense(n_in, u, generator))
       bn = use_bn and (i + 1 < n or not last_layer_no_batch_norm)
-      self.bn.append(TFBatchNorm(u) if bn else nn.Identity())
-      self.act.append(i + 1 < n or not last_layer_no_activation)
+      act = i + 1 < n or not last_layer_no_activation
+      self.layers.append(DenseLayer(n_in, u, bn, act, generator))
       n_in = u
     self.out_dim = n_in
 
   def forward(self, x):
-    for d, b, a in zip(self.dense, self.bn, self.act):
-      x = b(d(x))
-      if a:
-        x = torch.relu(x)
+    shape = x.shape
+    if x.dim() == 3:
+      x = x.reshape(-1, shape[-1])
+    for layer in self.layers:
+      x = layer(x)
+    if len(shape) == 3:
+      x = x.reshape(shape[0], shape[1], -1)
     return x
 
   def kernels(self):
-    return [d.kernel for d in self.dense]
+    return [layer.kernel for layer in self.layers]

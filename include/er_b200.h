@@ -213,6 +213,27 @@ int er_fm_bwd(const float* x, const float* gy, int64_t batch, int32_t n_field,
               int32_t dim, int32_t x_stride, float* gx, int32_t gx_stride,
               int32_t accumulate, er_stream_t stream);
 
+/* ---- K6 epilogues: dense bias + batch-norm + relu (layers/dnn.py:56-79) ------
+ * z is the SGEMM output x W (no bias).  Training: batch statistics (biased
+ * variance, tf.layers.batch_normalization defaults) are computed deterministically
+ * in two launches; moving_mean / moving_var are updated with `momentum`.
+ * gamma == NULL means "no batch norm": y = act(z + bias).
+ * ws: er_dense_workspace_bytes(batch, units). */
+size_t er_dense_workspace_bytes(int64_t batch, int32_t units);
+int er_bias_bn_act_fwd(const float* z, const float* bias, const float* gamma,
+                       const float* beta, float* moving_mean, float* moving_var,
+                       int64_t batch, int32_t units, float eps, float momentum,
+                       int32_t training, int32_t relu, float* y, float* save_mean,
+                       float* save_rstd, void* ws, size_t ws_bytes,
+                       er_stream_t stream);
+/* gz = dL/dz; ggamma/gbeta = batch-norm parameter gradients; gbias = column sum
+ * of gz (identically zero under batch norm). */
+int er_bias_bn_act_bwd(const float* z, const float* bias, const float* gamma,
+                       const float* y, const float* gy, const float* save_mean,
+                       const float* save_rstd, int64_t batch, int32_t units,
+                       int32_t relu, float* gz, float* gbias, float* ggamma,
+                       float* gbeta, void* ws, size_t ws_bytes, er_stream_t stream);
+
 /* sigmoid cross entropy (tf.losses.sigmoid_cross_entropy,
  * builders/loss_builder.py:36-39): loss_sum += sum_b w*(max(x,0)-x*z+log1p(exp(-|x|)))
  * g_logits[b] = w*(sigmoid(x)-z)*inv_count  (inv_count applied by caller=host scalar) */
