@@ -23,6 +23,9 @@ SLOT_DTYPE = np.dtype(
      ('shard_n', '<i4')],
     align=True)
 assert SLOT_DTYPE.itemsize == 48
+# er_dense_seg_t, 24 bytes
+DENSE_SEG_DTYPE = np.dtype([('offset', '<i8'), ('n', '<i8'), ('l2', '<f4'), ('lr_mult', '<f4')], align=True)
+assert DENSE_SEG_DTYPE.itemsize == 24
 
 BUCKET_FARM_DECIMAL, BUCKET_MOD, BUCKET_IDENTITY, BUCKET_NONE = 0, 1, 2, 3
 COMBINER_SUM, COMBINER_MEAN, COMBINER_SQRTN = 0, 1, 2
@@ -76,6 +79,8 @@ SIGNATURES = {
     'er_sigmoid_ce_fwd_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp,
                                       c_vp, c_vp, c_vp]),
     'er_dense_workspace_bytes': (c_sz, [c_i64, c_i32]),
+    'er_dense_apply': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, ctypes.POINTER(ErOpt), c_vp,
+                               c_vp, c_vp]),
     'er_bias_bn_act_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                    c_i32, c_f32, c_f32, c_i32, c_i32, c_vp,
                                    c_vp, c_vp, c_vp, c_sz, c_vp]),

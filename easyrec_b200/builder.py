@@ -1,0 +1,93 @@
+"""pipeline config -> (feature specs, feature groups, InputLayer, model).
+
+Host-side counterpart of `FeatureColumnParser` (feature_column/feature_column.py:44-203,259-656)
+and of `EasyRecModel.create_class(model_class)` (model/easy_rec_model.py:44-49, main.py:137).
+"""
+import collections
+
+from easyrec_b200 import _lib
+from easyrec_b200 import input_layer as IL
+from easyrec_b200.config import config_util
+
+_OPT_KIND = {'adagrad_optimizer': _lib.OPT_ADAGRAD, 'lazy_adam_optimizer': _lib.OPT_LAZY_ADAM,
+             'adam_optimizer': _lib.OPT_ADAM_ROWS, 'momentum_optimizer': _lib.OPT_SGD}
+
+
+def feature_specs(pipeline_config, packed_mod=False):
+  """FeatureConfig protos -> FeatureSpec list (config order = packed feature order)."""
+  specs = []
+  for fc in config_util.get_feature_configs(pipeline_config):
+    name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+    ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
+    if ftype == 'IdFeature':
+      specs.append(IL.id_feature(name, fc.embedding_dim, hash_bucket_size=fc.hash_bucket_size,
+                                 num_buckets=fc.num_buckets, combiner=fc.combiner,
+                                 embedding_name=fc.embedding_name, packed_mod=packed_mod))
+    elif ftype == 'RawFeature':
+      if len(fc.boundaries) > 0:
+        raise NotImplementedError('RawFeature boundaries (bucketized column) for %s' % name)
+      specs.append(IL.raw_feature(name, fc.embedding_dim, fc.min_val, fc.max_val, fc.raw_input_dim))
+    elif ftype in ('TagFeature', 'SequenceFeature'):
+      specs.append(IL.multi_feature(name, 'tag' if ftype == 'TagFeature' else 'seq', fc.embedding_dim,
+                                    hash_bucket_size=fc.hash_bucket_size, num_buckets=fc.num_buckets,
+                                    combiner=fc.combiner, embedding_name=fc.embedding_name,
+                                    seq_len=fc.sequence_length if ftype == 'SequenceFeature' else 1,
+                                    packed_mod=packed_mod))
+    else:
+      raise NotImplementedError('feature_type %s (feature %s) is outside the hot-path scope' % (ftype, name))
+  return specs
+
+
+def feature_groups(model_config):
+  groups = collections.OrderedDict()
+  for g in model_config.feature_groups:
+    wd = g.DESCRIPTOR.fields_by_name['wide_deep'].enum_type.values_by_number[g.wide_deep].name
+    groups[g.group_name] = dict(features=list(g.feature_names), wide=(wd == 'WIDE'))
+  return groups
+
+
+def optimizer_settings(pipeline_config):
+  """builders/optimizer_builder.py:28-144: kind + constant / exponential-decay schedule."""
+  tc = pipeline_config.train_config
+  if len(tc.optimizer_config) == 0:
+    return dict(kind='adagrad_optimizer', lr_fn=lambda step: 0.01, beta1=0.9, beta2=0.999, acc0=0.1)
+  oc = tc.optimizer_config[0]
+  kind = oc.WhichOneof('optimizer')
+  o = getattr(oc, kind)
+  lr = o.learning_rate
+  which = lr.WhichOneof('learning_rate')
+  if which == 'exponential_decay_learning_rate':
+    e = lr.exponential_decay_learning_rate
+
+    def lr_fn(step, e=e):
+      # core/learning_schedules.py:30-75 exponential_decay_with_burnin
+      p = step / float(e.decay_steps)
+      if e.staircase:
+        p = float(int(p))
+      v = e.initial_learning_rate * (e.decay_factor**p)
+      if e.burnin_steps > 0 and step < e.burnin_steps:
+        v = e.burnin_learning_rate
+      return max(v, e.min_learning_rate)
+  else:
+    c = lr.constant_learning_rate.learning_rate if which == 'constant_learning_rate' else 0.002
+    lr_fn = lambda step, c=c: c  # noqa: E731
+  return dict(kind=kind, lr_fn=lr_fn, beta1=getattr(o, 'beta1', 0.9), beta2=getattr(o, 'beta2', 0.999),
+              acc0=getattr(o, 'initial_accumulator_value', 0.1),
+              emb_lr_mult=oc.embedding_learning_rate_multiplier
+              if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
+
+
+def build_model(pipeline_config, batch_size, device, generator=None, cpu_generator=None, world=1, rank=0):
+  """Returns (input_layer, model, optimizer settings) for the config's model_class."""
+  from easyrec_b200 import model as model_pkg
+  mc = pipeline_config.model_config
+  specs = feature_specs(pipeline_config)
+  groups = feature_groups(mc)
+  opt = optimizer_settings(pipeline_config)
+  cls = model_pkg.get_model_class(mc.model_class)
+  wide_dim = cls.wide_output_dim(mc)
+  il = IL.InputLayer(specs, groups, batch_size, device, wide_output_dim=wide_dim,
+                     embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
+                     adagrad_init=opt['acc0'])
+  model = cls.from_config(mc, il, generator=cpu_generator).to(device)
+  return il, model, opt

@@ -97,17 +97,26 @@ __global__ void __launch_bounds__(256)
                     float eps, float momentum, int training, int relu, const float* __restrict__ part,
                     float* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
   __shared__ float s_mean[kColTile], s_rstd[kColTile];
+  __shared__ Welford s_m[kRowLanes][kColTile];
   const int c = blockIdx.x * kColTile + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
-  if (rl == 0 && c < s.units) {
-    float mean, var;
-    if (training) {
-      Welford t = {0.f, 0.f, 0.f};
-      for (int k = 0; k < s.n_chunks; ++k) {
+  if (training) {  // the 8 row lanes merge the chunk partials in parallel, then lane 0 merges the 8
+    Welford t = {0.f, 0.f, 0.f};
+    if (c < s.units) {
+      for (int k = rl; k < s.n_chunks; k += kRowLanes) {
         const float* p = part + ((int64_t)k * s.units + c) * 3;
         Welford q = {p[0], p[1], p[2]};
         wf_merge(t, q);
       }
+    }
+    s_m[rl][threadIdx.x & 31] = t;
+    __syncthreads();
+  }
+  if (rl == 0 && c < s.units) {
+    float mean, var;
+    if (training) {
+      Welford t = s_m[0][threadIdx.x];
+      for (int k = 1; k < kRowLanes; ++k) wf_merge(t, s_m[k][threadIdx.x]);
       mean = t.mean;
       var = t.m2 / t.n;  // biased
       if (blockIdx.y == 0) {
@@ -197,14 +206,27 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ part, float* __restrict__ gz,
                         float* __restrict__ gbias, float* __restrict__ ggamma, float* __restrict__ gbeta) {
   __shared__ float s_dg[kColTile], s_db[kColTile];
+  __shared__ float s_pa[kRowLanes][kColTile], s_pb[kRowLanes][kColTile];
   const int c = blockIdx.x * kColTile + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
+  {  // the 8 row lanes add the chunk partials in parallel (fixed order), lane 0 adds the 8
+    float a = 0.f, b = 0.f;
+    if (c < s.units) {
+      for (int k = rl; k < s.n_chunks; k += kRowLanes) {
+        const float* p = part + ((int64_t)k * s.units + c) * 2;
+        a += p[0];
+        b += p[1];
+      }
+    }
+    s_pa[rl][threadIdx.x & 31] = a;
+    s_pb[rl][threadIdx.x & 31] = b;
+    __syncthreads();
+  }
   if (rl == 0 && c < s.units) {
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < s.n_chunks; ++k) {
-      const float* p = part + ((int64_t)k * s.units + c) * 2;
-      a += p[0];
-      b += p[1];
+    for (int k = 0; k < kRowLanes; ++k) {
+      a += s_pa[k][threadIdx.x];
+      b += s_pb[k][threadIdx.x];
     }
     s_db[threadIdx.x] = a;  // sum g
     s_dg[threadIdx.x] = b;  // sum g*xhat
@@ -301,6 +323,72 @@ extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float
   bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(z, bias, gamma, y, gy, save_mean, save_rstd, s, relu, use_bn,
                                             part, gz, gbias, ggamma, gbeta);
   count_launches(2);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+// ---- dense optimizer: every dense parameter lives in ONE flat fp32 buffer (params, grads and
+// optimizer state are flat arrays with the same segment table), so the whole dense update of
+// optimize_loss -> opt.apply_gradients (compat/optimizers.py:413-416) is one launch:
+//   g = grad + l2 * w          (kernel_regularizer = l2_regularizer(scale), layers/dnn.py:57-62)
+//   adagrad: acc += g^2 ; w -= lr * g * rsqrt(acc)            (tf.train.AdagradOptimizer)
+//   adam   : m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; w -= lr_t * m / (sqrt(v) + eps)
+// reg_loss_out (optional) accumulates sum l2/2 * w^2 of the pre-update weights (reporting only).
+namespace er {
+
+__global__ void __launch_bounds__(256)
+    dense_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
+                       float* __restrict__ s1, const er_dense_seg_t* __restrict__ segs, er_opt_t opt,
+                       const float* __restrict__ lr_dev, float* __restrict__ reg_loss_out) {
+  const er_dense_seg_t seg = segs[blockIdx.y];
+  const float lr = (lr_dev ? *lr_dev : opt.lr) * seg.lr_mult;
+  float reg = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < seg.n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = seg.offset + i;
+    float w = p[j];
+    float gr = g[j] * opt.grad_scale;
+    if (seg.l2 != 0.f) {
+      reg += 0.5f * seg.l2 * w * w;
+      gr += seg.l2 * w;
+    }
+    if (opt.kind == ER_OPT_ADAGRAD) {
+      const float a = s0[j] + gr * gr;
+      s0[j] = a;
+      w -= lr * gr * __frsqrt_rn(a);
+    } else if (opt.kind == ER_OPT_LAZY_ADAM || opt.kind == ER_OPT_ADAM_ROWS) {
+      const float m = opt.beta1 * s0[j] + (1.0f - opt.beta1) * gr;
+      const float v = opt.beta2 * s1[j] + (1.0f - opt.beta2) * gr * gr;
+      s0[j] = m;
+      s1[j] = v;
+      w -= lr * m / (sqrtf(v) + opt.eps);
+    } else {
+      w -= lr * gr;
+    }
+    p[j] = w;
+  }
+  if (reg_loss_out) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) reg += __shfl_xor_sync(0xffffffffu, reg, o);
+    if ((threadIdx.x & 31) == 0 && reg != 0.f) atomicAdd(reg_loss_out, reg);
+  }
+}
+
+}  // namespace er
+
+extern "C" int er_dense_apply(float* params, const float* grads, float* state0, float* state1,
+                              const er_dense_seg_t* segs, int32_t n_segs, int64_t max_seg_n,
+                              const er_opt_t* opt, const float* lr_dev, float* reg_loss_out,
+                              er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(params && grads && segs && opt, "null argument");
+  ER_REQUIRE(n_segs > 0 && n_segs <= 65535 && max_seg_n > 0, "bad segment table");
+  ER_REQUIRE(opt->kind == ER_OPT_SGD || state0, "optimizer state0 missing");
+  ER_REQUIRE((opt->kind != ER_OPT_LAZY_ADAM && opt->kind != ER_OPT_ADAM_ROWS) || state1, "adam needs state1");
+  dim3 grid((unsigned)min((int64_t)64, ceil_div(max_seg_n, (int64_t)1024)), n_segs);
+  dense_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(params, grads, state0, state1, segs, *opt, lr_dev,
+                                                          reg_loss_out);
+  count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

@@ -258,6 +258,163 @@ __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant
   }
 }
 
+// ---- runs, lane-per-lookup segmented scan (dim <= 32) ------------------------------------------
+// A warp owns 32 consecutive sorted positions.  Each LANE takes one lookup: it resolves its
+// gradient source once (no redundant address math across a lane group) and issues its whole
+// 4*LANES-float gradient row at once, so 32 x LANES 16-byte loads are in flight per warp.  Equal
+// keys are adjacent, so the per-row sums are a segmented inclusive scan over the lanes (5 shuffle
+// steps); the last lane of a segment stages its sum in shared memory and LANES-lane groups then
+// apply the optimizer with the row/state loads that were issued before the gradient loads.
+// A run that starts in this window and continues past it is finished by this warp (it belongs to
+// the warp that holds its head); leading lanes that continue an earlier warp's run are skipped.
+// The order of additions is the fixed scan tree (deterministic; differs from sequential order in
+// the last ulp).
+template <int LANES>
+__global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  constexpr int D4 = LANES;            // float4 per row
+  constexpr int GROUPS = 32 / LANES;
+  float4* s_stage = reinterpret_cast<float4*>(s_raw + ((slot_smem_bytes(a.n_slots) + 15) & ~(size_t)15));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* my_stage = s_stage + (size_t)warp * 32 * D4;
+  __shared__ int s_tail_lane[8][32];
+  __shared__ int s_tail_head[8][32];
+  const int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32;
+  if (base >= a.n) return;
+  const int64_t pos = base + lane;
+  const bool in = pos < a.n;
+  const uint32_t k = in ? a.keys[pos] : a.sentinel;
+  const uint32_t l = in ? a.vals[pos] : 0u;
+  const bool valid = in && k < a.sentinel;
+  uint32_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+  if (lane == 0) kprev = (base > 0) ? a.keys[base - 1] : ~k;
+  uint32_t knext = __shfl_down_sync(0xffffffffu, k, 1);
+  if (lane == 31) knext = (base + 32 < a.n) ? a.keys[base + 32] : ~k;
+  const bool is_head = valid && (pos == 0 || kprev != k);
+  // lanes that continue a run begun in an earlier window are summed by that window's warp
+  const uint32_t k0 = __shfl_sync(0xffffffffu, k, 0);
+  const int head0 = __shfl_sync(0xffffffffu, (int)is_head, 0);
+  const bool owned = valid && (head0 || k != k0);
+  bool is_tail = owned && (knext != k);   // lane 31 with a continuing run is fixed up below
+  const int cont = __shfl_sync(0xffffffffu, (int)(owned && knext == k), 31);  // last run continues
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // ---- tails of this window and the row prefetch -------------------------------------------
+  const unsigned tails0 = __ballot_sync(0xffffffffu, is_tail || (lane == 31 && cont));
+  if (is_tail || (lane == 31 && cont)) s_tail_lane[warp][__popc(tails0 & lt_mask)] = lane;
+  __syncwarp();
+  const int n_tails = __popc(tails0);
+  const int glane = lane % LANES, grp = lane / LANES;
+  RowRegs row0;
+  uint32_t row0_key = a.sentinel;
+  if (grp < n_tails) {
+    const int tl = s_tail_lane[warp][grp];
+    row0_key = a.keys[base + tl];
+    row0 = load_row(a, row0_key, glane);
+  }
+  // ---- this lane's gradient row ------------------------------------------------------------
+  float4 g[D4];
+#pragma unroll
+  for (int c = 0; c < D4; ++c) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (owned) {
+    float coef;
+    const float4* src = reinterpret_cast<const float4*>(grad_src(a, sv, l, &coef));
+    float4 v[D4];
+#pragma unroll
+    for (int c = 0; c < D4; ++c) v[c] = src[c];
+#pragma unroll
+    for (int c = 0; c < D4; ++c) f4_fma_sep(g[c], v[c], coef);
+  }
+  // ---- segmented inclusive scan over equal keys ----------------------------------------------
+  int cnt = owned ? 1 : 0;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t kk = __shfl_up_sync(0xffffffffu, k, off);
+    const int oo = __shfl_up_sync(0xffffffffu, (int)owned, off);
+    const int cc = __shfl_up_sync(0xffffffffu, cnt, off);
+    const bool take = lane >= off && owned && oo && kk == k;
+#pragma unroll
+    for (int c = 0; c < D4; ++c) {
+      float4 y;
+      y.x = __shfl_up_sync(0xffffffffu, g[c].x, off);
+      y.y = __shfl_up_sync(0xffffffffu, g[c].y, off);
+      y.z = __shfl_up_sync(0xffffffffu, g[c].z, off);
+      y.w = __shfl_up_sync(0xffffffffu, g[c].w, off);
+      if (take) f4_acc(g[c], y);
+    }
+    if (take) cnt += cc;
+  }
+  // ---- a run that leaves the window: finish it here (or hand it to the hot-row kernel) -----------
+  int handed_off = 0;
+  if (cont) {
+    const uint32_t key = __shfl_sync(0xffffffffu, k, 31);
+    int total = __shfl_sync(0xffffffffu, cnt, 31);
+    const int64_t start = base + 32 - total;
+    int64_t j = base + 32;
+    while (true) {
+      const int64_t p = j + lane;
+      const bool m = p < a.n && a.keys[p] == key;
+      const unsigned mm = __ballot_sync(0xffffffffu, m);
+      float4 x[D4];
+#pragma unroll
+      for (int c = 0; c < D4; ++c) x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m) {
+        float coef;
+        const float4* src = reinterpret_cast<const float4*>(grad_src(a, sv, a.vals[p], &coef));
+#pragma unroll
+        for (int c = 0; c < D4; ++c) f4_fma_sep(x[c], src[c], coef);
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < D4; ++c) {
+          float4 y;
+          y.x = __shfl_xor_sync(0xffffffffu, x[c].x, o);
+          y.y = __shfl_xor_sync(0xffffffffu, x[c].y, o);
+          y.z = __shfl_xor_sync(0xffffffffu, x[c].z, o);
+          y.w = __shfl_xor_sync(0xffffffffu, x[c].w, o);
+          f4_acc(x[c], y);
+        }
+      }
+      if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < D4; ++c) f4_acc(g[c], x[c]);
+      }
+      const int got = __popc(mm);
+      total += got;
+      j += got;
+      if (mm != 0xffffffffu) break;
+      if (total >= kLongRun) {
+        if (j < a.n && a.keys[j] == key) {
+          if (lane == 0) enqueue_long(a, start, j, key);
+          handed_off = 1;
+        }
+        break;
+      }
+    }
+  }
+  // ---- stage the sums of the runs that END in this warp, then apply -------------------------
+  const bool finish = (is_tail || (lane == 31 && cont && !handed_off));
+  if (finish) {
+#pragma unroll
+    for (int c = 0; c < D4; ++c) my_stage[lane * D4 + c] = g[c];
+  }
+  if (is_tail || (lane == 31 && cont))  // window part of the run length; -1: handed to the hot-row kernel
+    s_tail_head[warp][__popc(tails0 & lt_mask)] = (lane == 31 && cont && handed_off) ? -1 : cnt;
+  __syncwarp();
+  for (int r = grp; r < n_tails; r += GROUPS) {
+    const int tl = s_tail_lane[warp][r];
+    const int run_cnt = s_tail_head[warp][r];
+    if (run_cnt < 0) continue;  // handed to the hot-row kernel
+    const uint32_t key = (r == grp) ? row0_key : a.keys[base + tl];
+    RowRegs row = (r == grp) ? row0 : load_row(a, key, glane);
+    // head of the run = tail lane - (entries of the run inside this window) + 1; for a run finished
+    // by the continuation loop the tail lane is 31 and the count is its window part
+    const int64_t head_pos = base + tl - (run_cnt - 1);
+    apply_row_vec(a, key, glane, my_stage[tl * D4 + glane], head_pos, row);
+  }
+}
+
 // ---- hot rows, vector: one CTA per chunk of a run; TPE threads share one lookup (TPE = 1 for
 // dim <= 32: a thread moves a whole gradient row) -----------------------------------------------
 template <int LANES, int TPE>
@@ -485,7 +642,12 @@ template <int LANES>
 static void launch_vec(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = slot_smem_bytes(a.n_slots);
   // one warp per 32 sorted positions, 8 warps per CTA
-  bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
+  if constexpr (LANES <= 8) {
+    const size_t smem_scan = ((smem + 15) & ~(size_t)15) + (size_t)8 * 32 * LANES * sizeof(float4);
+    bwd_scan_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem_scan, st>>>(a);
+  } else {
+    bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
+  }
   constexpr int TPE = (LANES <= 8) ? 1 : LANES;
   const size_t smem_long = ((smem + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
   bwd_long_vec_kernel<LANES, TPE><<<4 * kSmCount, 256, smem_long, st>>>(a);

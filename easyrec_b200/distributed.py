@@ -50,23 +50,18 @@ class GlobalCall(object):
 
 class DataParallel(object):
 
-  def __init__(self, input_layer, dense_params, world):
+  def __init__(self, input_layer, dense_opt, world):
+    """dense_opt: trainer.FlatDenseOptimizer -- its flat gradient buffer is the all-reduce bucket."""
     self.input_layer = input_layer
     self.world = world
-    self.params = list(dense_params)
-    self.sizes = [p.numel() for p in self.params]
-    self.flat = torch.empty(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
-    self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+    self.dense_opt = dense_opt
+    dense_opt.grad_scale = 1.0 / world  # mean over replicas, applied inside er_dense_apply
     self.gcalls = {id(c): GlobalCall(c, world) for c in input_layer.calls.values()}
 
   def sync_dense_grads(self):
-    """mean over replicas, one bucket (compat/optimizers.py:289-292)."""
-    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-    torch._foreach_copy_(self.views, grads)
-    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-    self.flat.mul_(1.0 / self.world)
-    for p, v in zip(self.params, self.views):
-      p.grad = v
+    """sum over replicas in one bucket; the 1/world of hvd.allreduce(Average)
+    (compat/optimizers.py:289-292) is folded into the dense apply's grad_scale."""
+    dist.all_reduce(self.dense_opt.flat_g, op=dist.ReduceOp.SUM)
 
   def gather_sparse(self, call, rows, w, outs):
     """all-gather one arena call's K7 inputs (rows, weights, segment scales, upstream gradients)

@@ -50,15 +50,18 @@ class DeepFM(nn.Module):
     self._emb_outputs = (wide, deep)
     return logits[:, 0]
 
+  def l2_of(self, name, param):
+    """kernel_regularizer = l2_regularizer(l2_regularization) on every dense kernel
+    (layers/dnn.py:57-62, model/deepfm.py:83-87); biases and batch-norm parameters are not
+    regularised."""
+    return self.l2_reg if name.endswith('kernel') else 0.0
+
   def regularization_loss(self):
     """l2_regularizer(scale)(w) = scale * sum(w^2)/2 (compat/regularizers.py) on dense kernels
     (layers/dnn.py:57-62) and on the *looked-up* embedding outputs (layers/input_layer.py:369-375)."""
     reg = 0.0
-    if self.l2_reg > 0:
-      ks = self.dnn.kernels() + [self.output.kernel]
-      if self.has_final:
-        ks += self.final_dnn.kernels()
-      reg = reg + self.l2_reg * 0.5 * sum((k * k).sum() for k in ks)
+    # dense kernel l2 is applied (and its loss term evaluated) inside the fused dense optimizer
+    # launch: see l2_of() and trainer.FlatDenseOptimizer
     if self.embedding_reg > 0:
       wide, deep = self._emb_outputs
       reg = reg + self.embedding_reg * 0.5 * ((wide * wide).sum() + (deep * deep).sum())

@@ -3,101 +3,116 @@
 and optimize_loss, compat/optimizers.py:89-450).
 
 One step = K1 bucketize -> K2 gather+pool -> interaction + dense MLP -> loss -> backward ->
-K7 dedup + fused row update (inside backward) -> dense optimizer.  The whole step is
-shape-static, so it can be captured once into a CUDA graph and replayed (launch latency, not
-HBM, bounds a batch-8192 step: SURVEY.md section 8d).
+K7 dedup + fused row update -> one fused dense-optimizer launch.  The whole step is shape-static,
+so it is captured once into a CUDA graph and replayed (launch latency, not HBM, bounds a
+batch-8192 step: SURVEY.md section 8d); the learning rate lives in device memory so a schedule
+does not need a re-capture.
 """
+import ctypes
+
+import numpy as np
 import torch
 
 from easyrec_b200 import _lib
+from easyrec_b200 import kernels as K
 
 
-class TFAdagrad(torch.optim.Optimizer):
-  """tf.train.AdagradOptimizer (dense apply): acc += g^2; w -= lr * g * rsqrt(acc); acc0 = 0.1
-  (protos/optimizer.proto:79).  foreach implementation, capturable (lr lives on the device)."""
+class FlatDenseOptimizer(object):
+  """All dense parameters as views of one flat fp32 buffer; gradients are gathered into a flat
+  buffer (one multi-tensor copy) and applied by ONE er_dense_apply launch.
 
-  def __init__(self, params, lr, initial_accumulator_value=0.1):
-    super().__init__(params, dict(lr=lr))
-    self.params = [p for g in self.param_groups for p in g['params']]
-    self.acc = [torch.full_like(p, initial_accumulator_value) for p in self.params]
+  kind 'adagrad': tf.train.AdagradOptimizer (acc0 = 0.1, protos/optimizer.proto:79)
+  kind 'adam' / 'lazy_adam': tf.train.AdamOptimizer dense rule, lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+  l2 per tensor: kernel_regularizer l2_regularizer(scale) applied as g += scale * w."""
+
+  def __init__(self, named_params, kind, lr, l2_of=None, beta1=0.9, beta2=0.999, eps=1e-8,
+               adagrad_init=0.1):
+    self.names = [n for n, _ in named_params]
+    self.params = [p for _, p in named_params]
     dev = self.params[0].device
-    self.lr_t = torch.tensor(float(lr), device=dev)
-
-  def set_lr(self, lr):
-    self.lr_t.fill_(float(lr))
-
-  @torch.no_grad()
-  def step(self):
-    ps = [p for p in self.params if p.grad is not None]
-    if not ps:
-      return
-    accs = [a for p, a in zip(self.params, self.acc) if p.grad is not None]
-    gs = [p.grad for p in ps]
-    torch._foreach_addcmul_(accs, gs, gs, value=1.0)
-    upd = torch._foreach_div(gs, torch._foreach_sqrt(accs))
-    torch._foreach_mul_(upd, self.lr_t)
-    torch._foreach_sub_(ps, upd)
-
-
-class TFAdam(torch.optim.Optimizer):
-  """tf.train.AdamOptimizer (dense apply): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
-  m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; w -= lr_t * m / (sqrt(v) + eps)."""
-
-  def __init__(self, params, lr, beta1=0.9, beta2=0.999, eps=1e-8):
-    super().__init__(params, dict(lr=lr))
-    self.params = [p for g in self.param_groups for p in g['params']]
-    self.m = [torch.zeros_like(p) for p in self.params]
-    self.v = [torch.zeros_like(p) for p in self.params]
-    dev = self.params[0].device
+    sizes = [p.numel() for p in self.params]
+    self.sizes = sizes
+    total = sum(sizes)
+    self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+    self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+    off = 0
+    segs = np.zeros(len(sizes), dtype=_lib.DENSE_SEG_DTYPE)
+    self.grad_views = []
+    for i, (n, p) in enumerate(named_params):
+      v = self.flat_p[off:off + sizes[i]].view_as(p)
+      v.copy_(p.data)
+      p.data = v
+      self.grad_views.append(self.flat_g[off:off + sizes[i]].view_as(p))
+      segs[i]['offset'] = off
+      segs[i]['n'] = sizes[i]
+      segs[i]['l2'] = float(l2_of(n, p)) if l2_of else 0.0
+      segs[i]['lr_mult'] = 1.0
+      off += sizes[i]
+    self.segs_dev = torch.from_numpy(segs.view(np.uint8).reshape(-1).copy()).to(dev)
+    self.n_segs = len(sizes)
+    self.max_n = max(sizes)
+    self.kind = {'adagrad': _lib.OPT_ADAGRAD, 'adam': _lib.OPT_ADAM_ROWS, 'lazy_adam': _lib.OPT_ADAM_ROWS,
+                 'sgd': _lib.OPT_SGD}[kind]
+    self.s0 = self.s1 = None
+    if self.kind == _lib.OPT_ADAGRAD:
+      self.s0 = torch.full((total,), adagrad_init, dtype=torch.float32, device=dev)
+    elif self.kind == _lib.OPT_ADAM_ROWS:
+      self.s0 = torch.zeros(total, dtype=torch.float32, device=dev)
+      self.s1 = torch.zeros(total, dtype=torch.float32, device=dev)
     self.b1, self.b2, self.eps = beta1, beta2, eps
-    self.lr_t = torch.tensor(float(lr), device=dev)   # already bias-corrected by set_lr
-    self.t = 0
-    self.base_lr = lr
-    self.set_lr(lr, 0)
+    self.lr_dev = torch.tensor([float(lr)], dtype=torch.float32, device=dev)
+    self.reg_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    self.grad_scale = 1.0
 
   def set_lr(self, lr, step):
-    t = step + 1
-    self.lr_t.fill_(float(lr) * (1 - self.b2**t)**0.5 / (1 - self.b1**t))
+    if self.kind == _lib.OPT_ADAM_ROWS:
+      t = step + 1
+      lr = float(lr) * (1 - self.b2**t)**0.5 / (1 - self.b1**t)
+    self.lr_dev.fill_(float(lr))
 
-  @torch.no_grad()
-  def step(self):
-    idx = [i for i, p in enumerate(self.params) if p.grad is not None]
-    if not idx:
-      return
-    ps = [self.params[i] for i in idx]
-    gs = [p.grad for p in ps]
-    ms = [self.m[i] for i in idx]
-    vs = [self.v[i] for i in idx]
-    torch._foreach_mul_(ms, self.b1)
-    torch._foreach_add_(ms, gs, alpha=1 - self.b1)
-    torch._foreach_mul_(vs, self.b2)
-    torch._foreach_addcmul_(vs, gs, gs, value=1 - self.b2)
-    den = torch._foreach_sqrt(vs)
-    torch._foreach_add_(den, self.eps)
-    upd = torch._foreach_div(ms, den)
-    torch._foreach_mul_(upd, self.lr_t)
-    torch._foreach_sub_(ps, upd)
+  def zero_grad(self):
+    for p in self.params:
+      p.grad = None
+
+  def gather_grads(self):
+    """p.grad (fresh autograd tensors) -> the flat gradient buffer (one multi-tensor copy)."""
+    srcs, dsts = [], []
+    for p, v in zip(self.params, self.grad_views):
+      if p.grad is None:
+        v.zero_()
+      else:
+        srcs.append(p.grad)
+        dsts.append(v)
+    torch._foreach_copy_(dsts, srcs)
+
+  def apply(self):
+    lib = _lib.load()
+    opt = K.make_opt(self.kind, 0.0, self.b1, self.b2, self.eps, grad_scale=self.grad_scale)
+    self.reg_loss.zero_()
+    _lib.check(
+        lib.er_dense_apply(self.flat_p.data_ptr(), self.flat_g.data_ptr(), K._p(self.s0), K._p(self.s1),
+                           self.segs_dev.data_ptr(), self.n_segs, self.max_n, ctypes.byref(opt),
+                           self.lr_dev.data_ptr(), self.reg_loss.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream), 'er_dense_apply')
 
 
 class Trainer(object):
 
   def __init__(self, model, input_layer, dense_optimizer='adagrad', lr=0.01, lr_fn=None,
-               use_cuda_graph=False, world_size=1):
+               use_cuda_graph=False, world_size=1, beta1=0.9, beta2=0.999, adagrad_init=0.1):
     self.model = model
     self.input_layer = input_layer
     self.lr = lr
     self.lr_fn = lr_fn or (lambda step: lr)
-    params = [p for p in model.parameters() if p.requires_grad]
-    if dense_optimizer == 'adagrad':
-      self.dense_opt = TFAdagrad(params, lr)
-    elif dense_optimizer in ('adam', 'lazy_adam'):
-      self.dense_opt = TFAdam(params, lr)
-    else:
-      raise ValueError(dense_optimizer)
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    l2 = getattr(model, 'l2_of', None)
+    self.dense_opt = FlatDenseOptimizer(named, dense_optimizer, lr, l2_of=l2, beta1=beta1, beta2=beta2,
+                                        adagrad_init=adagrad_init)
+    self.world = world_size
     self.dp = None
     if world_size > 1:
       from easyrec_b200.distributed import DataParallel
-      self.dp = DataParallel(input_layer, params, world_size)
+      self.dp = DataParallel(input_layer, self.dense_opt, world_size)
     self.step = 0
     self.use_cuda_graph = use_cuda_graph
     self._graph = None
@@ -108,24 +123,22 @@ class Trainer(object):
   def _set_hyper(self):
     lr = self.lr_fn(self.step)
     self.input_layer.set_optimizer_step(lr, self.step)
-    if isinstance(self.dense_opt, TFAdam):
-      self.dense_opt.set_lr(lr, self.step)
-    else:
-      self.dense_opt.set_lr(lr)
+    self.dense_opt.set_lr(lr, self.step)
 
   def _step_body(self, features, labels):
-    for p in self.dense_opt.params:
-      p.grad = None
+    self.dense_opt.zero_grad()
     logits = self.model(features)
     loss, probs = self.model.loss(logits, labels)
     loss.backward()
+    self.dense_opt.gather_grads()
     if self.dp is not None:
-      self.dp.sync_dense_grads()                                       # flat all-reduce (mean)
+      self.dp.sync_dense_grads()                                          # flat all-reduce (mean)
       self.dp.sparse_backward_update(self.input_layer.opt_holder['opt'])  # all-gather + K7
     else:
       self.input_layer.backward_update()   # K7: dedup + fused row update, on this thread/stream
-    self.dense_opt.step()
-    return loss.detach(), probs
+    self.dense_opt.apply()                 # one launch: l2 + adagrad/adam over the flat buffer
+    # reported loss = data loss + embedding regularisation (autograd) + dense l2 (from the apply)
+    return loss.detach() + self.dense_opt.reg_loss[0], probs
 
   def train_step(self, features, labels):
     """features/labels: device tensors.  Returns (loss [scalar tensor], probs [B])."""
@@ -147,7 +160,8 @@ class Trainer(object):
 
   def _capture(self, features, labels):
     # The fused row update reads its hyper-parameters from kernel arguments, which a CUDA graph
-    # freezes; graphs are therefore only used with a constant learning rate and adagrad/sgd rows.
+    # freezes; graphs are therefore only used with a constant learning rate and adagrad/sgd rows
+    # (the dense optimizer reads lr from device memory and follows any schedule).
     kind = next(iter(self.input_layer.arenas.values())).opt_kind
     if kind not in (_lib.OPT_ADAGRAD, _lib.OPT_SGD):
       raise _lib.ErError('CUDA-graph capture needs step-invariant row-update arguments '

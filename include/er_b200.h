@@ -234,6 +234,22 @@ int er_bias_bn_act_bwd(const float* z, const float* bias, const float* gamma,
                        int32_t relu, float* gz, float* gbias, float* ggamma,
                        float* gbeta, void* ws, size_t ws_bytes, er_stream_t stream);
 
+/* Dense optimizer over ONE flat parameter buffer (dense apply_gradients,
+ * compat/optimizers.py:413-416): g = grad*grad_scale + l2*w, then the adagrad / adam / sgd rule.
+ * segs: DEVICE array describing the tensors inside the flat buffers; lr_dev (optional device
+ * scalar) overrides opt->lr so a captured CUDA graph can follow a schedule; reg_loss_out
+ * (optional) += sum l2/2*w^2. */
+typedef struct er_dense_seg {
+  int64_t offset;
+  int64_t n;
+  float l2;
+  float lr_mult;
+} er_dense_seg_t;
+int er_dense_apply(float* params, const float* grads, float* state0, float* state1,
+                   const er_dense_seg_t* segs, int32_t n_segs, int64_t max_seg_n,
+                   const er_opt_t* opt, const float* lr_dev, float* reg_loss_out,
+                   er_stream_t stream);
+
 /* sigmoid cross entropy (tf.losses.sigmoid_cross_entropy,
  * builders/loss_builder.py:36-39): loss_sum += sum_b w*(max(x,0)-x*z+log1p(exp(-|x|)))
  * g_logits[b] = w*(sigmoid(x)-z)*inv_count  (inv_count applied by caller=host scalar) */

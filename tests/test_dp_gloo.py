@@ -56,15 +56,20 @@ def _worker(rank, port, ret):
     calls = {D: call}
     _pending = []
 
+  from easyrec_b200.trainer import FlatDenseOptimizer
   w1 = torch.nn.Parameter(torch.ones(5, 3) * (rank + 1))
   w2 = torch.nn.Parameter(torch.ones(7) * (rank + 2))
-  dp = DataParallel(FakeIL, [w1, w2], WORLD)
-  # ---- dense: mean over replicas ----
+  dopt = FlatDenseOptimizer([('w1', w1), ('w2', w2)], 'adagrad', 0.01)
+  assert w1.data_ptr() == dopt.flat_p.data_ptr()  # parameters are views of the flat buffer
+  dp = DataParallel(FakeIL, dopt, WORLD)
+  # ---- dense: mean over replicas = all-reduce(sum) x grad_scale ----
   w1.grad = torch.full((5, 3), float(rank + 1))
   w2.grad = torch.full((7,), float(10 * (rank + 1)))
+  dopt.gather_grads()
   dp.sync_dense_grads()
-  assert torch.allclose(w1.grad, torch.full((5, 3), 1.5))
-  assert torch.allclose(w2.grad, torch.full((7,), 15.0))
+  mean = dopt.flat_g * dopt.grad_scale
+  assert torch.allclose(mean[:15], torch.full((15,), 1.5))
+  assert torch.allclose(mean[15:], torch.full((7,), 15.0))
   # ---- sparse: gathered inputs through the replicated slot plan == global batch ----
   rng = np.random.default_rng(100 + rank)
   offs = np.repeat(np.array([0, 30, 0]), B)

@@ -1,0 +1,133 @@
+"""GPU: end-to-end DeepFM parity against the CPU oracle on identical inputs and identical initial weights.
+
+BASELINE.md parity gates: bucket ids bit-exact; pooled embeddings <= 1e-6 abs; logits and loss <= 1e-4 abs
+(fp32); post-step touched rows <= 1e-6 abs after 1 and after 10 steps.
+"""
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import _lib, workloads
+from easyrec_b200.trainer import Trainer
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+B, V, F, D = 512, 100003, 39, 16
+LR, L2, EMB_REG = 0.01, 1e-5, 1e-5
+
+
+def _oracle_params(model):
+  def grab(dnn):
+    out = []
+    for lay in dnn.layers:
+      d = {'W': lay.kernel.detach().cpu().numpy().copy(), 'b': lay.bias.detach().cpu().numpy().copy()}
+      if lay.use_bn:
+        d['gamma'] = lay.gamma.detach().cpu().numpy().copy()
+        d['beta'] = lay.beta.detach().cpu().numpy().copy()
+      out.append(d)
+    return out
+
+  return {'dnn': grab(model.dnn), 'final': grab(model.final_dnn),
+          'out_W': model.output.kernel.detach().cpu().numpy().copy(),
+          'out_b': model.output.bias.detach().cpu().numpy().copy()}
+
+
+def _oracle_inputs(ids, dense):
+  rows_id, _ = O.bucketize(ids, 0, V, 13)
+  rows = np.concatenate([np.repeat(np.arange(13, dtype=np.int64), B), rows_id])
+  mn = np.array(workloads.CRITEO_MIN, np.float32)
+  mx = np.array(workloads.CRITEO_MAX, np.float32)
+  dn = ((dense - mn) / (mx - mn)).astype(np.float32)
+  w = np.concatenate([dn.T.reshape(-1), np.ones(26 * B, np.float32)])
+  return rows, w
+
+
+def _oracle_step(st, ids, dense, labels):
+  rows, w = _oracle_inputs(ids, dense)
+  rp = np.arange(F * B + 1, dtype=np.int32)
+  deep_seg, _ = O.embedding_fwd(st['t16'], rows, rp, 0, weights=w)
+  wide_seg, _ = O.embedding_fwd(st['t1'], rows, rp, 0, weights=w)
+  deep = np.ascontiguousarray(deep_seg.reshape(F, B, D).transpose(1, 0, 2).reshape(B, F * D))
+  wide = np.ascontiguousarray(wide_seg.reshape(F, B).T)
+  logits, cache = O.deepfm_forward(wide, deep, F, D, st['params'])
+  ce, probs, g_logits = O.sigmoid_ce(logits, labels)
+  reg = 0.0
+  for tag in ('dnn', 'final'):
+    for lay in st['params'][tag]:
+      reg += L2 * 0.5 * float((lay['W'].astype(np.float64)**2).sum())
+  reg += L2 * 0.5 * float((st['params']['out_W'].astype(np.float64)**2).sum())
+  reg += EMB_REG * 0.5 * float((deep.astype(np.float64)**2).sum() + (wide.astype(np.float64)**2).sum())
+  g_wide, g_deep, grads = O.deepfm_backward(g_logits, wide, deep, F, D, st['params'], cache)
+  g_deep = (g_deep + np.float32(EMB_REG) * deep).astype(np.float32)
+  g_wide = (g_wide + np.float32(EMB_REG) * wide).astype(np.float32)
+  gd = np.ascontiguousarray(g_deep.reshape(B, F, D).transpose(1, 0, 2).reshape(F * B, D))
+  gw = np.ascontiguousarray(g_wide.T.reshape(F * B, 1))
+  O.embedding_bwd(st['t16'], st['a16'], None, rows, None, gd, O.OPT_ADAGRAD, LR, weights=w)
+  O.embedding_bwd(st['t1'], st['a1'], None, rows, None, gw, O.OPT_ADAGRAD, LR, weights=w)
+
+  def adagrad(p, g, key):
+    acc = st['acc'].setdefault(key, np.full_like(p, 0.1))
+    acc += g * g
+    p -= (np.float32(LR) * g / np.sqrt(acc)).astype(np.float32)
+
+  for tag in ('dnn', 'final'):
+    for i, (lay, gr) in enumerate(zip(st['params'][tag], grads[tag])):
+      adagrad(lay['W'], gr['W'] + np.float32(L2) * lay['W'], (tag, i, 'W'))
+      for k in ('gamma', 'beta'):
+        adagrad(lay[k], gr[k], (tag, i, k))
+      # bias gradient under batch norm is identically zero
+  adagrad(st['params']['out_W'], grads['out_W'] + np.float32(L2) * st['params']['out_W'], 'oW')
+  adagrad(st['params']['out_b'], grads['out_b'].astype(np.float32), 'ob')
+  return logits, ce + reg, deep
+
+
+def test_deepfm_logits_loss_and_ten_training_steps_match_oracle():
+  torch.backends.cuda.matmul.allow_tf32 = False
+  il, model = workloads.build_deepfm_criteo(B, V, DEV, dnn=(64, 32), final=(32, 16), l2_reg=L2, emb_reg=EMB_REG)
+  tr = Trainer(model, il, 'adagrad', lr=LR)
+  a16, a1 = il.arenas[16], il.arenas[1]
+  st = {'t16': a16.weight.cpu().numpy().copy(), 'a16': a16.state0.cpu().numpy().copy(),
+        't1': a1.weight.cpu().numpy().copy(), 'a1': a1.state0.cpu().numpy().copy(),
+        'params': _oracle_params(model), 'acc': {}}
+  for step in range(10):
+    ids, dense, labels = workloads.criteo_batch(B, 50 + step)
+    feats = {'sparse_fea': torch.from_numpy(ids).to(DEV), 'dense_fea': torch.from_numpy(dense).to(DEV)}
+    lab = torch.from_numpy(labels).to(DEV)
+    if step == 0:  # integer stage: arena rows bit exact
+      call = il.calls[16]
+      dn = il.normalize_dense(feats['dense_fea'])
+      cids, w = il._gather_inputs(16, feats['sparse_fea'], dn)
+      from easyrec_b200 import kernels as K
+      rows = K.bucketize(cids, call.slots_dev, call.n_slots, call.n_seg).cpu().numpy()
+      want_rows, want_w = _oracle_inputs(ids, dense)
+      assert np.array_equal(rows, want_rows)
+      np.testing.assert_allclose(w.cpu().numpy(), want_w, rtol=0, atol=1e-7)
+    # forward of THIS step on the pre-step weights: logits/loss from train_step are pre-update
+    model.train()
+    with torch.no_grad():
+      pass
+    loss, probs = tr.train_step(feats, lab)
+    o_logits, o_loss, o_deep = _oracle_step(st, ids, dense, labels)
+    got_probs = probs.detach().cpu().numpy()
+    want_probs = 1.0 / (1.0 + np.exp(-o_logits.astype(np.float64)))
+    # logits within 1e-4  <=>  probabilities within 2.5e-5 (|d sigmoid| <= 1/4)
+    got_logits = np.log(got_probs.astype(np.float64) / (1 - got_probs.astype(np.float64)))
+    assert np.abs(got_logits - o_logits).max() < 1e-4, (step, np.abs(got_logits - o_logits).max())
+    assert np.abs(got_probs - want_probs).max() < 2.5e-5
+    assert abs(float(loss) - o_loss) < 1e-4, (step, float(loss), o_loss)
+    if step in (0, 9):
+      touched = np.unique(_oracle_inputs(ids, dense)[0])
+      np.testing.assert_allclose(a16.weight.cpu().numpy()[touched], st['t16'][touched], rtol=0, atol=1e-6)
+      np.testing.assert_allclose(a16.state0.cpu().numpy()[touched], st['a16'][touched], rtol=1e-5, atol=1e-6)
+      np.testing.assert_allclose(a1.weight.cpu().numpy()[touched], st['t1'][touched], rtol=0, atol=1e-6)
+  # after ten steps the whole arenas still agree (untouched rows are bit identical)
+  np.testing.assert_allclose(a16.weight.cpu().numpy(), st['t16'], rtol=0, atol=2e-6)
+  np.testing.assert_allclose(a1.weight.cpu().numpy(), st['t1'], rtol=0, atol=2e-6)
+  # dense weights after ten adagrad steps
+  got = _oracle_params(model)
+  for tag in ('dnn', 'final'):
+    for a, b in zip(got[tag], st['params'][tag]):
+      np.testing.assert_allclose(a['W'], b['W'], rtol=0, atol=5e-5)
+      np.testing.assert_allclose(a['gamma'], b['gamma'], rtol=0, atol=5e-5)
+  np.testing.assert_allclose(got['out_W'], st['params']['out_W'], rtol=0, atol=5e-5)

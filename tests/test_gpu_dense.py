@@ -81,7 +81,15 @@ def test_fused_dnn_matches_torch_and_oracle(B, dims, last_plain):
   yo, cache = O.dnn_forward(x.detach().cpu().numpy(), ol, True, last_no_act=last_plain, last_no_bn=last_plain)
   np.testing.assert_allclose(y.detach().cpu().numpy(), yo, rtol=2e-4, atol=2e-5)
   gxo, _ = O.dnn_backward(gy.cpu().numpy(), ol, cache)
-  np.testing.assert_allclose(x.grad.cpu().numpy(), gxo, rtol=2e-4, atol=2e-5)
+  # ReLU is discontinuous in its derivative: a pre-activation within fp32 noise of 0 may flip the mask in one
+  # implementation and not the other, which changes that sample's whole input gradient.  Compare the samples
+  # whose activations all stay clear of zero (the others are a ~1e-4 fraction).
+  safe = np.ones(B, bool)
+  for c in cache:
+    if c['act']:
+      safe &= (np.abs(c['h']) > 1e-4).all(axis=1)
+  assert safe.mean() > 0.9
+  np.testing.assert_allclose(x.grad.cpu().numpy()[safe], gxo[safe], rtol=2e-4, atol=2e-5)
 
 
 def test_moving_statistics_and_inference_mode():

@@ -260,7 +260,8 @@ def test_embedding_bwd_dedup_update_parity(kind, dim, with_csr, hot):
   np.testing.assert_allclose(r['ug'][:r['n']], r['oug'], rtol=2e-5, atol=2e-5)
   short = np.ones(r['n'], bool)
   short[np.isin(r['our'], [5, 9])] = False
-  assert np.array_equal(r['ug'][:r['n']][short], r['oug'][short])
+  # (dim <= 32 sums a run with a fixed shuffle-scan tree: last-ulp differences vs sequential order)
+  np.testing.assert_allclose(r['ug'][:r['n']][short], r['oug'][short], rtol=2e-6, atol=2e-6)
   # post-step rows and optimizer state: <= 1e-6 abs (BASELINE.md parity gate) for every row whose
   # gradient was summed in the oracle's order; the two hot rows (fixed-tree sum of ~500 N(0,1)
   # gradients, |G| ~ 30) get the same bound relative to their magnitude
