@@ -87,6 +87,19 @@ SIGNATURES = {
     'er_bias_bn_act_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_sz, c_vp]),
+    'er_din_concat_fwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    'er_din_concat_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    'er_din_pool_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'er_din_pool_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    'er_cross_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    'er_cross_workspace_bytes': (c_sz, [c_i64, c_i32]),
+    'er_cross_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32,
+                             c_vp, c_sz, c_vp]),
+    'er_mmoe_mix_fwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'er_mmoe_mix_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    'er_l2norm_fwd': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    'er_l2norm_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'er_inbatch_softmax_ce': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -194,26 +194,64 @@ static __global__ void __launch_bounds__(kThreads)
     rank[i] = prev + r;
   }
   __syncthreads();
+  // ---- local (in-tile) sorted position of every key; delta[d] = global - local offset of digit d ----
+  int tile_cnt = 0;
   if (threadIdx.x < kRadix) {
-    int run = digit_base;
+    int run = 0;
 #pragma unroll 8
     for (int ww = 0; ww < kWarps; ++ww) {
       int t = s_warp_hist[ww][threadIdx.x];
-      s_warp_hist[ww][threadIdx.x] = run;
+      s_warp_hist[ww][threadIdx.x] = run;  // entries of this digit in earlier warps of the tile
       run += t;
     }
+    tile_cnt = run;
+    int incl = tile_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[w] = incl;
+    s_tot[0][threadIdx.x] = incl - tile_cnt;  // exclusive within the warp of digits
   }
   __syncthreads();
+  if (threadIdx.x < kRadix) {
+    int off = 0;
+    for (int ww = 0; ww < w; ++ww) off += s_wsum[ww];
+    const int lstart = s_tot[0][threadIdx.x] + off;  // first in-tile slot of this digit
+    s_tot[1][threadIdx.x] = lstart;
+    s_bef[0][threadIdx.x] = digit_base - lstart;     // delta: global position = local + delta
+  }
+  __syncthreads();
+  // ---- stage the tile in digit order in shared memory, then write runs of equal digits to
+  //      consecutive global addresses (coalesced sectors instead of 4-byte scattered stores) ----
+  extern __shared__ uint32_t s_stage[];
+  uint32_t* s_k = s_stage;
+  uint32_t* s_v = s_stage + kThreads * ITEMS;
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = base + i * 32 + lane;
     if (idx < n) {
       const int d = (int)((key[i] >> shift) & (kRadix - 1));
-      const int pos = s_warp_hist[w][d] + rank[i];
-      keys_out[pos] = key[i];
-      vals_out[pos] = val[i];
+      const int lp = s_tot[1][d] + s_warp_hist[w][d] + rank[i];
+      s_k[lp] = key[i];
+      s_v[lp] = val[i];
+    }
+  }
+  __syncthreads();
+  const int64_t tile_base = (int64_t)blockIdx.x * (kThreads * ITEMS);
+  const int tile_n = (int)min((int64_t)(kThreads * ITEMS), n - tile_base);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int lp = i * kThreads + threadIdx.x;
+    if (lp < tile_n) {
+      const uint32_t kk = s_k[lp];
+      const int d = (int)((kk >> shift) & (kRadix - 1));
+      const int pos = lp + s_bef[0][d];
+      keys_out[pos] = kk;
+      vals_out[pos] = s_v[lp];
       if (hist_next) {
-        const int d2 = (int)((key[i] >> (shift + kRadixBits)) & (kRadix - 1));
+        const int d2 = (int)((kk >> (shift + kRadixBits)) & (kRadix - 1));
         atomicAdd(&hist_next[(int64_t)(pos / (kThreads * ITEMS)) * kRadix + d2], 1);
       }
     }
@@ -231,12 +269,20 @@ inline void sort_rows_t(const int64_t* rows, int64_t cap, const int32_t* n_dev, 
   uint32_t* va = (passes % 2 == 0) ? vals_out : w.vals_tmp;
   uint32_t* kb = (passes % 2 == 0) ? w.keys_tmp : keys_out;
   uint32_t* vb = (passes % 2 == 0) ? w.vals_tmp : vals_out;
+  // staging buffer of the scatter kernel: (key, val) per tile element; with the 40 KB of static
+  // shared memory this exceeds the 48 KB default, so opt in once per instantiation
+  constexpr size_t stage_bytes = (size_t)kThreads * ITEMS * 2 * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(scatter_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    attr_set = true;
+  }
   init_hist_kernel<ITEMS><<<(unsigned)nt, kThreads, 0, st>>>(rows, cap, n_dev, (uint32_t)n_rows, ka, va,
                                                              w.hist, passes, zero_me);
   for (int p = 0; p < passes; ++p) {
     const int32_t* hc = w.hist + (int64_t)p * nt * kRadix;
     int32_t* hn = (p + 1 < passes) ? w.hist + (int64_t)(p + 1) * nt * kRadix : nullptr;
-    scatter_kernel<ITEMS><<<(unsigned)nt, kThreads, 0, st>>>(ka, va, kb, vb, cap, p * kRadixBits, hc, hn);
+    scatter_kernel<ITEMS><<<(unsigned)nt, kThreads, stage_bytes, st>>>(ka, va, kb, vb, cap, p * kRadixBits, hc, hn);
     uint32_t* t = ka; ka = kb; kb = t;
     t = va; va = vb; vb = t;
   }

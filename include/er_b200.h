@@ -258,6 +258,58 @@ int er_sigmoid_ce_fwd_bwd(const float* logits, const float* labels,
                           float* loss_out, float* probs, float* g_logits,
                           er_stream_t stream);
 
+/* ---- K4: DIN target attention (layers/sequence_feature_layer.py:150-189,
+ * model/multi_tower_din.py:62-97).  The attention MLP is a library SGEMM chain; these are the
+ * fused pieces around it:
+ *  concat: din_in[b,t,:] = [q, k, q-k, q*k]  ([B*T, 4D]) and its backward
+ *  pool  : scores[B,T] masked at t >= len with -2^32+1, softmax over T,
+ *          out[b,:] = sum_t p[b,t]*keys[b,t,:]; backward routes no gradient to padded scores */
+int er_din_concat_fwd(const float* query, const float* keys, int64_t batch,
+                      int32_t seq_len, int32_t dim, float* din_in, er_stream_t stream);
+int er_din_concat_bwd(const float* query, const float* keys, const float* g_din_in,
+                      int64_t batch, int32_t seq_len, int32_t dim, float* g_query,
+                      float* g_keys, int32_t accumulate_gkeys, er_stream_t stream);
+int er_din_pool_fwd(const float* scores, const float* keys, const int32_t* lens,
+                    int64_t batch, int32_t seq_len, int32_t dim, float* probs,
+                    float* out, er_stream_t stream);
+int er_din_pool_bwd(const float* probs, const float* keys, const float* gout,
+                    const int32_t* lens, int64_t batch, int32_t seq_len, int32_t dim,
+                    float* g_scores, float* g_keys, int32_t accumulate_gkeys,
+                    er_stream_t stream);
+
+/* ---- K5: DCN cross layer (model/dcn.py:32-45): out = x0*(xl.w) + b + xl; xw_out[b] = xl.w.
+ * bwd: gxl = gout + w*s, gx0 (+)= gout*xw, gw = sum_b s_b*xl[b,:], gb = sum_b gout[b,:]
+ * with s_b = gout[b,:].x0[b,:] (deterministic two-stage column sums).
+ * ws: er_cross_workspace_bytes(batch, dim). */
+int er_cross_fwd(const float* x0, const float* xl, const float* w, const float* b,
+                 int64_t batch, int32_t dim, float* out, float* xw_out,
+                 er_stream_t stream);
+size_t er_cross_workspace_bytes(int64_t batch, int32_t dim);
+int er_cross_bwd(const float* x0, const float* xl, const float* w, const float* xw,
+                 const float* gout, int64_t batch, int32_t dim, float* gx0, float* gxl,
+                 float* gw, float* gb, int32_t accumulate_gx0, void* ws, size_t ws_bytes,
+                 er_stream_t stream);
+
+/* ---- MMoE mixture (layers/mmoe.py:73-83): out[b,:] = sum_e softmax(gate[b,:])[e]*experts[b,e,:] */
+int er_mmoe_mix_fwd(const float* gate_logits, const float* experts, int64_t batch,
+                    int32_t n_expert, int32_t dim, float* probs, float* out,
+                    er_stream_t stream);
+int er_mmoe_mix_bwd(const float* probs, const float* experts, const float* gout,
+                    int64_t batch, int32_t n_expert, int32_t dim, float* g_gate_logits,
+                    float* g_experts, int32_t accumulate_gexperts, er_stream_t stream);
+
+/* ---- DSSM (model/dssm.py:64-71, model/match_model.py:50-69,213-234) ----
+ * l2norm: tf.nn.l2_normalize rows.  inbatch_softmax_ce: rows of sim [B, n_cols >= B], the
+ * positive of row b is column b, in-batch duplicates of its item id are masked with -1e32,
+ * loss_rows[b] = -log(p_bb + 1e-12)*w_b*inv_wsum (sum them for the loss), g_sim = dloss/dsim. */
+int er_l2norm_fwd(const float* x, int64_t batch, int32_t dim, float* y, float* inv_norm,
+                  er_stream_t stream);
+int er_l2norm_bwd(const float* y, const float* inv_norm, const float* gy, int64_t batch,
+                  int32_t dim, float* gx, er_stream_t stream);
+int er_inbatch_softmax_ce(const float* sim, const int64_t* item_ids, const float* weights,
+                          int64_t batch, int32_t n_cols, float inv_wsum, float* loss_rows,
+                          float* probs_diag, float* g_sim, er_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,7 +89,7 @@ def test_fused_dnn_matches_torch_and_oracle(B, dims, last_plain):
     if c['act']:
       safe &= (np.abs(c['h']) > 1e-4).all(axis=1)
   assert safe.mean() > 0.9
-  np.testing.assert_allclose(x.grad.cpu().numpy()[safe], gxo[safe], rtol=2e-4, atol=2e-5)
+  np.testing.assert_allclose(x.grad.cpu().numpy()[safe], gxo[safe], rtol=5e-4, atol=2e-4)
 
 
 def test_moving_statistics_and_inference_mode():
