@@ -110,3 +110,42 @@ class DNN(nn.Module):
 
   def kernels(self):
     return [layer.kernel for layer in self.layers]
+
+
+class _BNOnly(torch.autograd.Function):
+  """tf.layers.batch_normalization on a feature matrix (no dense, no activation):
+  model/multi_tower_din.py:103-107.  Same fused kernels with an identity pre-activation."""
+
+  @staticmethod
+  def forward(ctx, x, gamma, beta, moving_mean, moving_var, training, ws):
+    x = x.contiguous()
+    y, mean, rstd = K.bias_bn_act_fwd(x, None, gamma, beta, moving_mean, moving_var, BN_EPS, BN_MOMENTUM,
+                                      training, False, ws)
+    ctx.ws = ws
+    ctx.save_for_backward(x, gamma, y, mean, rstd)
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, gamma, y, mean, rstd = ctx.saved_tensors
+    gx, _, ggamma, gbeta = K.bias_bn_act_bwd(x, None, gamma, y, gy.contiguous(), mean, rstd, False, ctx.ws)
+    return gx, ggamma, gbeta, None, None, None, None
+
+
+class BatchNorm(nn.Module):
+
+  def __init__(self, units):
+    super().__init__()
+    self.gamma = nn.Parameter(torch.ones(units))
+    self.beta = nn.Parameter(torch.zeros(units))
+    self.register_buffer('moving_mean', torch.zeros(units))
+    self.register_buffer('moving_var', torch.ones(units))
+    self.units = units
+    self._ws = None
+    self._ws_batch = -1
+
+  def forward(self, x):
+    if self._ws is None or self._ws_batch != x.shape[0] or self._ws.device != x.device:
+      self._ws = K.dense_workspace(x.shape[0], self.units, x.device)
+      self._ws_batch = x.shape[0]
+    return _BNOnly.apply(x, self.gamma, self.beta, self.moving_mean, self.moving_var, self.training, self._ws)

@@ -1,0 +1,17 @@
+"""Model registry: model_class name -> class (utils/load_class.py:203-222, main.py:137)."""
+
+_REGISTRY = {}
+
+
+def register(name):
+  def deco(cls):
+    _REGISTRY[name] = cls
+    return cls
+  return deco
+
+
+def get_model_class(name):
+  from easyrec_b200.model import dcn, deepfm, dssm, mmoe, multi_tower_din  # noqa: F401
+  if name not in _REGISTRY:
+    raise KeyError('model_class %r is outside the hot-path scope (have: %s)' % (name, sorted(_REGISTRY)))
+  return _REGISTRY[name]

@@ -11,9 +11,22 @@ from torch import nn
 
 from easyrec_b200 import embedding as E
 from easyrec_b200 import layers as L
+from easyrec_b200 import model as registry
 
 
+@registry.register('DeepFM')
 class DeepFM(nn.Module):
+
+  @staticmethod
+  def wide_output_dim(model_config):
+    return model_config.deepfm.wide_output_dim
+
+  @classmethod
+  def from_config(cls, model_config, input_layer, generator=None):
+    c = model_config.deepfm
+    return cls(input_layer, list(c.dnn.hidden_units), list(c.final_dnn.hidden_units),
+               l2_reg=c.l2_regularization, embedding_reg=model_config.embedding_regularization,
+               generator=generator)
 
   def __init__(self, input_layer, dnn_units, final_units, l2_reg=0.0, embedding_reg=0.0,
                generator=None):
