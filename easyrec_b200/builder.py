@@ -13,7 +13,7 @@ _OPT_KIND = {'adagrad_optimizer': _lib.OPT_ADAGRAD, 'lazy_adam_optimizer': _lib.
              'adam_optimizer': _lib.OPT_ADAM_ROWS, 'momentum_optimizer': _lib.OPT_SGD}
 
 
-def feature_specs(pipeline_config, packed_mod=False):
+def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
   """FeatureConfig protos -> FeatureSpec list (config order = packed feature order)."""
   specs = []
   for fc in config_util.get_feature_configs(pipeline_config):
@@ -31,7 +31,8 @@ def feature_specs(pipeline_config, packed_mod=False):
       specs.append(IL.multi_feature(name, 'tag' if ftype == 'TagFeature' else 'seq', fc.embedding_dim,
                                     hash_bucket_size=fc.hash_bucket_size, num_buckets=fc.num_buckets,
                                     combiner=fc.combiner, embedding_name=fc.embedding_name,
-                                    seq_len=fc.sequence_length if ftype == 'SequenceFeature' else 1,
+                                    seq_len=((fc.max_seq_len if fc.HasField('max_seq_len') else default_seq_len)
+                                             if ftype == 'SequenceFeature' else 1),
                                     packed_mod=packed_mod))
     else:
       raise NotImplementedError('feature_type %s (feature %s) is outside the hot-path scope' % (ftype, name))
@@ -44,6 +45,14 @@ def feature_groups(model_config):
     wd = g.DESCRIPTOR.fields_by_name['wide_deep'].enum_type.values_by_number[g.wide_deep].name
     groups[g.group_name] = dict(features=list(g.feature_names), wide=(wd == 'WIDE'))
   return groups
+
+
+def seq_att_groups(model_config):
+  """EasyRecModel.seq_att_groups -> {group: [(keys, hist_seqs), ...]} (layers/seq_input_layer.py:63-101)."""
+  out = collections.OrderedDict()
+  for g in model_config.seq_att_groups:
+    out[g.group_name] = [(list(m.key), list(m.hist_seq)) for m in g.seq_att_map]
+  return out
 
 
 def optimizer_settings(pipeline_config):
@@ -77,17 +86,18 @@ def optimizer_settings(pipeline_config):
               if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
 
 
-def build_model(pipeline_config, batch_size, device, generator=None, cpu_generator=None, world=1, rank=0):
+def build_model(pipeline_config, batch_size, device, generator=None, cpu_generator=None, world=1, rank=0,
+                default_seq_len=50):
   """Returns (input_layer, model, optimizer settings) for the config's model_class."""
   from easyrec_b200 import model as model_pkg
   mc = pipeline_config.model_config
-  specs = feature_specs(pipeline_config)
+  specs = feature_specs(pipeline_config, default_seq_len=default_seq_len)
   groups = feature_groups(mc)
   opt = optimizer_settings(pipeline_config)
   cls = model_pkg.get_model_class(mc.model_class)
   wide_dim = cls.wide_output_dim(mc)
   il = IL.InputLayer(specs, groups, batch_size, device, wide_output_dim=wide_dim,
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
-                     adagrad_init=opt['acc0'])
+                     adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc))
   model = cls.from_config(mc, il, generator=cpu_generator).to(device)
   return il, model, opt

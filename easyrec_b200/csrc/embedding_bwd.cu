@@ -696,7 +696,8 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
   ER_REQUIRE(n_slots > 0 && n_slots <= 2048, "n_slots must be in [1, 2048]");
   ER_REQUIRE(n_bufs > 0 && n_bufs <= ER_MAX_BUFS, "n_bufs must be in [1, ER_MAX_BUFS]");
   ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31), "n_lookups_cap out of range");
-  ER_REQUIRE(row_ptr || n_lookups_cap == n_seg, "row_ptr == NULL requires n_lookups_cap == n_seg");
+  ER_REQUIRE(row_ptr || seg_ids || n_lookups_cap == n_seg,
+             "without row_ptr / seg_ids every segment must hold exactly one lookup");
   ER_REQUIRE(!row_ptr || seg_ids, "CSR input needs seg_ids (er_csr_from_lens)");
   if (table) {
     const int k = opt->kind;

@@ -56,7 +56,8 @@ class DataParallel(object):
     self.world = world
     self.dense_opt = dense_opt
     dense_opt.grad_scale = 1.0 / world  # mean over replicas, applied inside er_dense_apply
-    self.gcalls = {id(c): GlobalCall(c, world) for c in input_layer.calls.values()}
+    plans = getattr(input_layer, 'merged', None) or input_layer.calls
+    self.gcalls = {id(c): GlobalCall(c, world) for c in plans.values()}
 
   def sync_dense_grads(self):
     """sum over replicas in one bucket; the 1/world of hvd.allreduce(Average)
@@ -79,16 +80,32 @@ class DataParallel(object):
       dist.all_gather_into_tensor(g.grads[i], grad.contiguous())
     return g
 
-  def sparse_backward_update(self, opt):
-    """all-gather K7's inputs, then the same fused dedup+update on every rank; gradients are
-    scaled by 1/world (mean over replicas)."""
-    il = self.input_layer
+  def exchange(self, pending):
+    """The collectives of one step (eager NCCL calls, kept OUTSIDE CUDA-graph capture): dense flat
+    all-reduce + all-gather of every arena's K7 inputs."""
+    self.sync_dense_grads()
+    for call, rows, w, outs, seg_ids in pending:
+      if seg_ids is not None:
+        raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
+      self.gather_sparse(call, rows, w, outs)
+
+  def apply_sparse(self, pending, opt):
+    """The same fused dedup + row update on every rank over the gathered global batch; gradients
+    are scaled by 1/world (mean over replicas).  No collectives: CUDA-graph capturable."""
     opt.grad_scale = opt.grad_scale / self.world
-    for call, rows, w, outs in il._pending:
-      g = self.gather_sparse(call, rows, w, outs)
+    for call, rows, w, outs, seg_ids in pending:
+      g = self.gcalls[id(call)]
       a = call.arena
       K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, g.rows, g.slots_dev, g.n_slots, g.n_seg,
                       g.grads, opt, g.ws, weights=g.weights if w is not None else None,
                       seg_scale=g.seg_scale)
-    il._pending = []
     opt.grad_scale = opt.grad_scale * self.world
+
+  def sparse_backward_update(self, opt):
+    il = self.input_layer
+    for call, rows, w, outs, seg_ids in il._pending:
+      if seg_ids is not None:
+        raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
+      self.gather_sparse(call, rows, w, outs)
+    self.apply_sparse(il._pending, opt)
+    il._pending = []

@@ -1,17 +1,24 @@
 """InputLayer: feature groups -> dense tensors, on the fused sm_100a lookup path.
 
 Mirrors the reference surface
-  InputLayer(feature_configs, feature_groups, ..., wide_output_dim)      layers/input_layer.py:33-69
-  input_layer(features, group_name) -> (concat [B, sum D], [per-feature])  layers/input_layer.py:245-278
+  InputLayer(feature_configs, feature_groups, ..., wide_output_dim)       layers/input_layer.py:33-69
+  input_layer(features, group_name) -> (concat [B, sum D], [per-feature])   layers/input_layer.py:245-278
+  SeqInputLayer(...)(features, seq_group) -> {key, hist_seq_emb, hist_seq_len}  layers/seq_input_layer.py:34-124
 with `FeatureColumnParser` (feature_column/feature_column.py:44-203, 259-656) collapsed into a
 static *table plan*: which table each feature reads (shared `embedding_name` groups), its bucket
 rule, combiner and output column -- fixed at construction, uploaded once as er_slot_t records.
 
-Input contract (the reference's packed form, input/parquet_input.py:201-239):
-  features['sparse_fea'] = ids int64 [n_sparse*B] feature-major (single-valued), or
-                           (ids int64 [L], lens int32 [n_sparse*B]) for multi-valued features
+Input contract (the reference's packed form, input/parquet_input.py:201-239, plus sequences):
+  features['sparse_fea'] = ids int64 [n_id*B], feature-major, for the single-valued IdFeatures
   features['dense_fea']  = float32 [B, sum raw_input_dim] in raw-feature config order
+  features['seq_fea'][name] = (ids int64 [B, T], lens int32 [B])        SequenceFeature
+  features['tag_fea'][name] = (ids int64 [L], lens int32 [B], weights fp32 [L] | None)  TagFeature
 Outputs keep feature_group CONFIG order (compat/feature_column/feature_column.py:388-414).
+
+Per arena (= embedding_dim) the lookups run as up to three uniform launches -- single-valued slots,
+sequence slots (one segment per (sample, position), un-pooled [B,T,D]), CSR tag slots -- and the
+backward is ONE dedup + fused row update over all of them, so a table shared by several slots
+(key + history of the same id space) gets one optimizer step from the summed gradient, as in TF.
 """
 import collections
 
@@ -29,17 +36,20 @@ FeatureSpec = collections.namedtuple(
      'min_val', 'max_val', 'raw_input_dim', 'seq_len'])
 
 
+def _bucket_rule(hash_bucket_size, num_buckets, packed_mod):
+  if hash_bucket_size > 0:
+    return _lib.BUCKET_FARM_DECIMAL, hash_bucket_size
+  if packed_mod:
+    return _lib.BUCKET_MOD, num_buckets
+  return _lib.BUCKET_IDENTITY, num_buckets
+
+
 def id_feature(name, embedding_dim, hash_bucket_size=0, num_buckets=0, combiner='sum',
                embedding_name='', packed_mod=False):
   """IdFeature: hash_bucket_size -> Fingerprint64(as_string) % size; num_buckets -> identity
   (feature_column/feature_column.py:259-300).  packed_mod: the Parquet packed rule
   `vals % num_buckets` (input/parquet_input.py:221)."""
-  if hash_bucket_size > 0:
-    mode, nb = _lib.BUCKET_FARM_DECIMAL, hash_bucket_size
-  elif packed_mod:
-    mode, nb = _lib.BUCKET_MOD, num_buckets
-  else:
-    mode, nb = _lib.BUCKET_IDENTITY, num_buckets
+  mode, nb = _bucket_rule(hash_bucket_size, num_buckets, packed_mod)
   return FeatureSpec(name, 'id', embedding_dim, mode, nb, combiner, embedding_name, 0., 0., 1, 1)
 
 
@@ -50,25 +60,100 @@ def raw_feature(name, embedding_dim=0, min_val=0.0, max_val=0.0, raw_input_dim=1
                      float(min_val), float(max_val), raw_input_dim, 1)
 
 
+def multi_feature(name, kind, embedding_dim, hash_bucket_size=0, num_buckets=0, combiner='sum',
+                  embedding_name='', seq_len=1, packed_mod=False):
+  """TagFeature (kind 'tag': multi-valued, pooled by `combiner`, optional kv weights;
+  feature_column/feature_column.py:301-360) or SequenceFeature (kind 'seq': un-pooled [B,T,D];
+  feature_column_v2.py:4988-5002)."""
+  assert kind in ('tag', 'seq')
+  mode, nb = _bucket_rule(hash_bucket_size, num_buckets, packed_mod)
+  return FeatureSpec(name, kind, embedding_dim, mode, nb, combiner, embedding_name, 0., 0., 1,
+                     max(int(seq_len), 1))
+
+
 _COMBINER = {'sum': _lib.COMBINER_SUM, 'mean': _lib.COMBINER_MEAN, 'sqrtn': _lib.COMBINER_SQRTN}
+
+
+class _SubCall(object):
+  """One uniform launch over an arena: a list of slots that all have the same segment count."""
+
+  def __init__(self, kind, n_seg_per_slot):
+    self.kind = kind               # 'single' | 'seq' | 'tag'
+    self.n_seg_per_slot = n_seg_per_slot
+    self.items = []                # (out_key, feature name, Slot, source)
+    self.call = None               # E.ArenaCall
+
+
+class MergedCall(object):
+  """The arena-wide slot plan used by K7: every sub-call's slots back to back (segments
+  renumbered), all output matrices as grad buffers."""
+
+  def __init__(self, arena, subcalls):
+    self.arena = arena
+    recs = []
+    self.buf_of = []   # (subcall index, local out_buf) per merged buffer
+    seg = 0
+    lookups = 0
+    self.sub_lookup_off = []
+    self.sub_seg_off = []
+    for si, sc in enumerate(subcalls):
+      c = sc.call
+      base_buf = len(self.buf_of)
+      for b in range(len(c.out_strides)):
+        self.buf_of.append((si, b))
+      self.sub_seg_off.append(seg)
+      self.sub_lookup_off.append(lookups)
+      for r in c.slots_np:
+        recs.append(dict(num_buckets=int(r['num_buckets']), row_offset=int(r['row_offset']),
+                         seg_begin=int(r['seg_begin']) + seg, n_seg=int(r['n_seg']),
+                         bucket_mode=int(r['bucket_mode']), combiner=int(r['combiner']),
+                         out_buf=int(r['out_buf']) + base_buf, out_stride=int(r['out_stride']),
+                         out_col=int(r['out_col']), shard_n=int(r['shard_n'])))
+      seg += c.n_seg
+      lookups += c.max_lookups
+    assert len(self.buf_of) <= _lib.MAX_BUFS, 'too many output matrices on one arena'
+    self.slots_np = K.make_slots(recs)
+    self.slots_dev = K.slots_to_device(self.slots_np, arena.device)
+    self.n_slots = len(recs)
+    self.n_seg = seg
+    self.max_lookups = lookups
+    self.out_strides = [subcalls[si].call.out_strides[b] for si, b in self.buf_of]
+    self._out_rows = [subcalls[si].call.out_rows(b) for si, b in self.buf_of]
+    self.ws = K.bwd_workspace(lookups, arena.device, arena.dim)
+    self.has_csr = any(sc.kind == 'tag' for sc in subcalls)
+    self.needs_scale = any(sc.call.needs_scale for sc in subcalls)
+    dev = arena.device
+    self.rows = torch.empty(lookups, dtype=torch.int64, device=dev) if len(subcalls) > 1 else None
+    self.weights = None
+    self.seg_ids = torch.empty(lookups, dtype=torch.int32, device=dev) if self.has_csr else None
+    if len(subcalls) == 1:
+      self.seg_scale = subcalls[0].call.seg_scale   # written in place by K2
+    else:
+      self.seg_scale = torch.ones(seg, dtype=torch.float32, device=dev) if self.needs_scale else None
+
+  def out_rows(self, buf):
+    return self._out_rows[buf]
 
 
 class InputLayer(object):
   """Builds arenas + fused calls for a set of feature groups and evaluates them.
 
   groups: OrderedDict group_name -> dict(features=[names...], wide=bool)
+  seq_att_groups: OrderedDict name -> list of (key feature names, hist_seq feature names)
+      (SeqAttGroupConfig.seq_att_map, protos/feature_config.proto; layers/seq_input_layer.py)
   A group marked wide uses `wide_output_dim` columns per feature with combiner sum
   (feature_column/feature_column.py:616-622)."""
 
   def __init__(self, features, groups, batch_size, device, wide_output_dim=1,
                embedding_optimizer=_lib.OPT_ADAGRAD, shard_n=1, shard_rank=0, generator=None,
-               adagrad_init=0.1):
+               adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None):
     self.features = collections.OrderedDict((f.name, f) for f in features)
     self.groups = groups
+    self.seq_att_groups = seq_att_groups or collections.OrderedDict()
     self.batch_size = batch_size
     self.device = device
     self.wide_output_dim = wide_output_dim
-    self.sparse_names = [f.name for f in features if f.kind != 'raw']
+    self.sparse_names = [f.name for f in features if f.kind == 'id']
     self.raw_names = [f.name for f in features if f.kind == 'raw']
     self.raw_cols = {}
     c = 0
@@ -76,70 +161,127 @@ class InputLayer(object):
       self.raw_cols[n] = (c, c + self.features[n].raw_input_dim)
       c += self.features[n].raw_input_dim
     self.n_dense = c
-    # ---- table plan: one arena per embedding dim --------------------------------------
-    self.arenas = collections.OrderedDict()
-    plan = collections.OrderedDict()  # dim -> list of (group, feature, Slot)
-    self.group_layout = {}            # group -> list of (feature, kind, dim, arena_dim, buf, col)
-    self.group_bufs = collections.OrderedDict()   # (dim, group) -> buf index within arena call
+    B = batch_size
+    # ---- table plan -------------------------------------------------------------------
+    self.arenas = collections.OrderedDict()          # dim -> Arena
+    self.subcalls = collections.OrderedDict()        # dim -> OrderedDict(key -> _SubCall)
+    self.group_layout = {}    # group -> list of (feature, kind, width, dim, out_key, col)
+    self.seq_layout = {}      # seq group -> dict(key=[(feature, dim, out_key, col)], hist=[...], T=..)
+
+    def add_slot(dim, out_key, fname, table, kind, wide=False, pooled_seq=False):
+      f = self.features[fname]
+      arena = self.arenas.setdefault(dim, E.Arena(dim, device, shard_n, shard_rank))
+      arena.add_table(table, f.num_buckets)
+      if kind == 'seq':
+        sk, nseg = ('seq', f.seq_len), B * f.seq_len
+      elif kind == 'tag':
+        sk, nseg = ('tag',), B
+      else:
+        sk, nseg = ('single',), B
+      subs = self.subcalls.setdefault(dim, collections.OrderedDict())
+      sc = subs.setdefault(sk, _SubCall(sk[0], nseg))
+      comb = _lib.COMBINER_SUM if (wide or f.kind == 'raw' or kind == 'seq') else _COMBINER[f.combiner]
+      slot = E.Slot(out_key + '/' + fname, table, f.bucket_mode, f.num_buckets, comb, out_buf=out_key,
+                    n_seg_per_sample=f.seq_len if kind == 'seq' else 1)
+      if f.kind == 'raw':
+        src = ('raw', self.raw_cols[fname][0])
+      elif kind == 'seq':
+        src = ('seq', fname)
+      elif kind == 'tag':
+        src = ('tag', fname)
+      else:
+        src = ('id', self.sparse_names.index(fname))
+      sc.items.append((out_key, fname, slot, src))
+
     for gname, g in groups.items():
       layout = []
+      wide = bool(g.get('wide'))
       for fname in g['features']:
         f = self.features[fname]
-        wide = bool(g.get('wide'))
         dim = wide_output_dim if wide else f.embedding_dim
         if f.kind == 'raw' and dim == 0:
           layout.append((fname, 'dense', f.raw_input_dim, None, None, None))
           continue
+        if f.kind == 'seq':
+          raise NotImplementedError('SequenceFeature %s in a plain group needs a sequence_combiner; '
+                                    'put it in seq_att_groups (DIN)' % fname)
         table = (f.embedding_name or fname + '_embedding') + ('_wide' if wide else '')
-        arena = self.arenas.setdefault(dim, E.Arena(dim, device, shard_n, shard_rank))
-        arena.add_table(table, f.num_buckets)
-        key = (dim, gname)
-        if key not in self.group_bufs:
-          self.group_bufs[key] = sum(1 for k in self.group_bufs if k[0] == dim)
-        comb = _lib.COMBINER_SUM if (wide or f.kind == 'raw') else _COMBINER[f.combiner]
-        slot = E.Slot(gname + '/' + fname, table, f.bucket_mode, f.num_buckets, comb,
-                      out_buf=self.group_bufs[key])
-        plan.setdefault(dim, []).append((gname, fname, slot))
-        layout.append((fname, 'emb', dim, dim, self.group_bufs[key], None))
+        kind = 'tag' if f.kind == 'tag' else 'single'
+        add_slot(dim, gname, fname, table, kind, wide=wide)
+        layout.append([fname, 'emb', dim, dim, gname, None])
       self.group_layout[gname] = layout
+    for sname, maps in self.seq_att_groups.items():
+      lay = dict(key=[], hist=[], T=None)
+      for keys, hists in maps:
+        for k in keys:
+          f = self.features[k]
+          # the key column lives in the sequence group's own variable scope
+          # (layers/seq_input_layer.py:56-75): a table separate from the plain group's
+          table = f.embedding_name or '%s/%s_embedding' % (sname, k)
+          add_slot(f.embedding_dim, sname + '/key', k, table, 'single')
+          lay['key'].append([k, f.embedding_dim, sname + '/key', None])
+        for h in hists:
+          f = self.features[h]
+          assert f.kind == 'seq', '%s must be a SequenceFeature' % h
+          assert lay['T'] in (None, f.seq_len), 'hist_seq features of one group must share seq_len'
+          lay['T'] = f.seq_len
+          table = f.embedding_name or '%s/%s_embedding' % (sname, h)
+          add_slot(f.embedding_dim, sname + '/hist', h, table, 'seq')
+          lay['hist'].append([h, f.embedding_dim, sname + '/hist', None])
+      self.seq_layout[sname] = lay
     for a in self.arenas.values():
       a.materialize(embedding_optimizer, generator=generator, adagrad_init=adagrad_init)
-    # ---- fused calls (all slots single-valued here; CSR inputs go through lookup_csr) ----
-    self.calls = collections.OrderedDict()
-    self.call_feature_idx = {}
+    # ---- launches ---------------------------------------------------------------------
+    self.calls = collections.OrderedDict()     # dim -> the single-valued ArenaCall (bench/tests)
+    self.merged = collections.OrderedDict()    # dim -> MergedCall
+    self._gather_plan = {}
     self.static_ids = {}
     self.static_w = {}
-    B = batch_size
-    for dim, items in plan.items():
-      n_bufs = sum(1 for k in self.group_bufs if k[0] == dim)
-      widths = [0] * n_bufs
-      for gname, fname, slot in items:
-        widths[slot.out_buf] += dim
-      call = E.ArenaCall(self.arenas[dim], [s for _, _, s in items], B, widths, single_valued=True)
-      self.calls[dim] = call
-      for i, (gname, fname, slot) in enumerate(items):
-        lay = self.group_layout[gname]
-        for j, e in enumerate(lay):
-          if e[0] == fname and e[1] == 'emb' and e[5] is None:
-            lay[j] = e[:5] + (call.slot_cols[i],)
-            break
-      # where each slot's ids / weights come from
-      sparse_idx = {n: i for i, n in enumerate(self.sparse_names)}
-      src = []
-      for gname, fname, slot in items:
-        f = self.features[fname]
-        src.append(('raw', self.raw_cols[fname][0]) if f.kind == 'raw' else ('id', sparse_idx[fname]))
-      self.call_feature_idx[dim] = src
-      self.static_ids[dim] = torch.zeros(call.n_seg, dtype=torch.int64, device=device)
-      has_raw = any(k == 'raw' for k, _ in src)
-      self.static_w[dim] = (torch.ones(call.n_seg, dtype=torch.float32, device=device)
-                            if has_raw else None)
-      identity = [k for k, _ in src] == ['id'] * len(src) and [i for _, i in src] == list(
-          range(len(self.sparse_names)))
-      call.identity_ids = identity
+    self.out_index = {}                        # (dim, out_key) -> (subcall key, local buf index)
+    for dim, subs in self.subcalls.items():
+      for sk, sc in subs.items():
+        keys = []
+        for out_key, _, _, _ in sc.items:
+          if out_key not in keys:
+            keys.append(out_key)
+        widths = [0] * len(keys)
+        slots = []
+        for out_key, fname, slot, src in sc.items:
+          slot.out_buf = keys.index(out_key)
+          widths[slot.out_buf] += dim
+          slots.append(slot)
+        if sc.kind == 'tag':
+          cap = max_tag_lookups or 8 * B * len(slots)
+          sc.call = E.ArenaCall(self.arenas[dim], slots, B, widths, single_valued=False, max_lookups=cap)
+        else:
+          sc.call = E.ArenaCall(self.arenas[dim], slots, B, widths, single_valued=True)
+        for i, (out_key, fname, slot, src) in enumerate(sc.items):
+          col = sc.call.slot_cols[i]
+          for lay in list(self.group_layout.values()):
+            for e in lay:
+              if e[1] == 'emb' and e[0] == fname and e[4] == out_key and e[5] is None:
+                e[5] = col
+          for lay in self.seq_layout.values():
+            for part in ('key', 'hist'):
+              for e in lay[part]:
+                if e[0] == fname and e[2] == out_key and e[3] is None:
+                  e[3] = col
+        for j, k in enumerate(keys):
+          self.out_index[(dim, k)] = (sk, j)
+        if sc.kind == 'single':
+          self.calls[dim] = sc.call
+          src = [s for _, _, _, s in sc.items]
+          self.static_ids[dim] = torch.zeros(sc.call.n_seg, dtype=torch.int64, device=device)
+          has_raw = any(k == 'raw' for k, _ in src)
+          self.static_w[dim] = (torch.ones(sc.call.n_seg, dtype=torch.float32, device=device)
+                                if has_raw else None)
+          sc.call.identity_ids = ([k for k, _ in src] == ['id'] * len(src) and
+                                  [i for _, i in src] == list(range(len(self.sparse_names))))
+          sc.call.sources = src
+      self.merged[dim] = MergedCall(self.arenas[dim], list(subs.values()))
+    self.call_feature_idx = {d: c.sources for d, c in self.calls.items()}
     mn = [self.features[n].min_val for n in self.raw_names for _ in range(self.features[n].raw_input_dim)]
     mx = [self.features[n].max_val for n in self.raw_names for _ in range(self.features[n].raw_input_dim)]
-    self.raw_min = torch.tensor(mn, dtype=torch.float32, device=device)
     rng = np.array(mx, np.float32) - np.array(mn, np.float32)
     self.raw_has_range = bool((rng > 0).any())
     self.raw_range = torch.tensor(np.where(rng > 0, rng, 1.0), dtype=torch.float32, device=device)
@@ -148,7 +290,7 @@ class InputLayer(object):
     self.opt_holder = {'opt': K.make_opt(embedding_optimizer, 0.01)}
     self._pending = []
     self._rows_cache = {}
-    self._gather_plan = {}
+    self._pos = {}
 
   # ------------------------------------------------------------------
   def set_optimizer_step(self, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
@@ -162,8 +304,8 @@ class InputLayer(object):
     """After loss.backward(): K7 for every arena looked up since the last call (dedup, segment
     sum and the fused optimizer row update).  The reference's counterpart is
     opt.apply_gradients on the tables' IndexedSlices (compat/optimizers.py:413-416)."""
-    for call, rows, w, outs in self._pending:
-      E.fused_backward_update(call, rows, outs, self.opt_holder['opt'], weights=w)
+    for m, rows, w, outs, seg_ids in self._pending:
+      E.fused_backward_update(m, rows, outs, self.opt_holder['opt'], weights=w, seg_ids=seg_ids)
     self._pending = []
 
   def normalize_dense(self, dense):
@@ -172,7 +314,7 @@ class InputLayer(object):
     return (dense - self.raw_sub) / self.raw_range  # (x - min) / (max - min), input/input.py:638-640
 
   def _gather_inputs(self, dim, ids, dense_norm):
-    """ids int64 [n_sparse*B] feature-major -> (ids, weights) in this call's slot order.
+    """ids int64 [n_id*B] feature-major -> (ids, weights) in the single-valued call's slot order.
 
     Two strided copies per arena (ids of the id slots, normalised values of the raw slots);
     slots that are already in packed order are used in place."""
@@ -185,7 +327,7 @@ class InputLayer(object):
     out_w = self.static_w[dim]
     plan = self._gather_plan.get(dim)
     if plan is None:
-      src = self.call_feature_idx[dim]
+      src = call.sources
       id_pos = [i for i, (k, _) in enumerate(src) if k == 'id']
       id_src = [j for k, j in src if k == 'id']
       raw_pos = [i for i, (k, _) in enumerate(src) if k == 'raw']
@@ -201,12 +343,13 @@ class InputLayer(object):
                   raw_pos_t=torch.tensor(raw_pos, dtype=torch.int64, device=self.device),
                   raw_src_t=torch.tensor(raw_src, dtype=torch.int64, device=self.device))
       self._gather_plan[dim] = plan
-    ids2 = ids.view(len(self.sparse_names), B)
     o2 = out_ids.view(S, B)
-    if plan['id_pos'] and plan['id_src']:
-      o2[plan['id_pos'][0]:plan['id_pos'][1]].copy_(ids2[plan['id_src'][0]:plan['id_src'][1]])
-    elif plan['id_pos_t'].numel():
-      o2.index_copy_(0, plan['id_pos_t'], ids2.index_select(0, plan['id_src_t']))
+    if plan['id_pos_t'].numel():
+      ids2 = ids.view(len(self.sparse_names), B)
+      if plan['id_pos'] and plan['id_src']:
+        o2[plan['id_pos'][0]:plan['id_pos'][1]].copy_(ids2[plan['id_src'][0]:plan['id_src'][1]])
+      else:
+        o2.index_copy_(0, plan['id_pos_t'], ids2.index_select(0, plan['id_src_t']))
     if out_w is not None and plan['raw_pos_t'].numel():
       w2 = out_w.view(S, B)
       dt = dense_norm.t()
@@ -216,49 +359,147 @@ class InputLayer(object):
         w2.index_copy_(0, plan['raw_pos_t'], dt.index_select(0, plan['raw_src_t']))
     return out_ids, out_w
 
-  def lookup(self, features):
-    """Runs K1 + K2 for every arena; returns {group: (concat, [per-feature views])}."""
-    ids = features['sparse_fea']
-    dense = features.get('dense_fea')
-    dense_norm = self.normalize_dense(dense) if dense is not None else None
-    results = {}
-    self._rows_cache = {}
-    self._pending = []
-    for dim, call in self.calls.items():
-      # arenas whose slots read the same features with the same bucket rules and row offsets
-      # (e.g. DeepFM's wide and deep groups) share one gather + one K1 launch
+  # ------------------------------------------------------------------
+  def _run_subcall(self, dim, sk, sc, features, dense_norm):
+    """K1 + K2 of one uniform launch; returns (rows, weights, row_ptr, seg_ids, outs)."""
+    call = sc.call
+    B = self.batch_size
+    if sc.kind == 'single':
       key = (call.slots_np[['num_buckets', 'row_offset', 'seg_begin', 'bucket_mode']].tobytes(),
-             tuple(self.call_feature_idx[dim]))
+             tuple(call.sources))
       hit = self._rows_cache.get(key)
       if hit is None:
-        cids, w = self._gather_inputs(dim, ids, dense_norm)
+        cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
         rows = K.bucketize(cids, call.slots_dev, call.n_slots, call.n_seg)
         self._rows_cache[key] = (rows, w)
       else:
         rows, w = hit
       outs = E.fused_lookup(call, rows, weights=w)
-      results[dim] = outs
-      self._pending.append((call, rows, w, outs))
+      return rows, w, None, None, outs
+    if sc.kind == 'seq':
+      T = sc.n_seg_per_slot // B
+      ids_list, pad_list = [], []
+      for _, fname, _, _ in sc.items:
+        ids, lens = features['seq_fea'][fname]
+        ids_list.append(ids.reshape(-1))
+        pos = self._pos.get(T)
+        if pos is None:
+          pos = torch.arange(T, device=self.device, dtype=torch.int32)[None, :]
+          self._pos[T] = pos
+        pad_list.append((pos >= lens[:, None]).reshape(-1))
+      ids = ids_list[0] if len(ids_list) == 1 else torch.cat(ids_list)
+      pad = pad_list[0] if len(pad_list) == 1 else torch.cat(pad_list)
+      rows = K.bucketize(ids.contiguous(), call.slots_dev, call.n_slots, call.n_seg)
+      rows.masked_fill_(pad, -1)   # positions >= seq_len: empty segment -> zero vector
+      outs = E.fused_lookup(call, rows)
+      return rows, None, None, None, outs
+    # tag: CSR
+    ids_list, lens_list, w_list = [], [], []
+    any_w = False
+    for _, fname, _, _ in sc.items:
+      ids, lens, w = features['tag_fea'][fname]
+      ids_list.append(ids)
+      lens_list.append(lens)
+      w_list.append(w)
+      any_w = any_w or (w is not None)
+    ids = torch.cat(ids_list) if len(ids_list) > 1 else ids_list[0]
+    lens = torch.cat(lens_list) if len(lens_list) > 1 else lens_list[0]
+    L = ids.numel()
+    cap = call.max_lookups
+    assert L <= cap, 'tag lookups %d exceed max_tag_lookups %d' % (L, cap)
+    weights = None
+    if any_w:
+      weights = torch.ones(cap, dtype=torch.float32, device=self.device)
+      off = 0
+      for i_, w in zip(ids_list, w_list):
+        if w is not None:
+          weights[off:off + i_.numel()].copy_(w)
+        off += i_.numel()
+    ids_cap = torch.zeros(cap, dtype=torch.int64, device=self.device)
+    ids_cap[:L].copy_(ids)
+    row_ptr, seg_ids = K.csr_from_lens(lens.contiguous(), cap)
+    rows = torch.full((cap,), -1, dtype=torch.int64, device=self.device)
+    K.bucketize(ids_cap, call.slots_dev, call.n_slots, call.n_seg, seg_ids=seg_ids, row_ptr=row_ptr,
+                rows=rows)
+    outs = E.fused_lookup(call, rows, weights=weights, row_ptr=row_ptr)
+    return rows, weights, row_ptr, seg_ids, outs
+
+  def lookup(self, features):
+    """Runs K1 + K2 for every arena; returns {group: (concat, [per-feature views])} and fills
+    self.seq_outputs {seq group: {key, hist_seq_emb, hist_seq_len}}."""
+    dense = features.get('dense_fea')
+    dense_norm = self.normalize_dense(dense) if dense is not None else None
+    self._rows_cache = {}
+    self._pending = []
+    outs_by_key = {}
+    for dim, subs in self.subcalls.items():
+      m = self.merged[dim]
+      parts = []
+      for sk, sc in subs.items():
+        rows, w, row_ptr, seg_ids, outs = self._run_subcall(dim, sk, sc, features, dense_norm)
+        parts.append((sc, rows, w, seg_ids, outs))
+        for (d, k), (skk, j) in self.out_index.items():
+          if d == dim and skk == sk:
+            outs_by_key[(dim, k)] = outs[j]
+      if len(parts) == 1:
+        sc, rows, w, seg_ids, outs = parts[0]
+        self._pending.append((m, rows, w, outs, seg_ids))
+      else:
+        all_outs = []
+        any_w = any(p[2] is not None for p in parts)
+        if any_w and m.weights is None:
+          m.weights = torch.ones(m.max_lookups, dtype=torch.float32, device=self.device)
+        for si, (sc, rows, w, seg_ids, outs) in enumerate(parts):
+          lo = m.sub_lookup_off[si]
+          n = rows.numel()
+          m.rows[lo:lo + n].copy_(rows)
+          if any_w:
+            if w is not None:
+              m.weights[lo:lo + n].copy_(w)
+            else:
+              m.weights[lo:lo + n].fill_(1.0)
+          if m.has_csr:
+            if seg_ids is not None:
+              m.seg_ids[lo:lo + n].copy_(seg_ids[:n] + m.sub_seg_off[si])
+            else:
+              m.seg_ids[lo:lo + n].copy_(
+                  torch.arange(m.sub_seg_off[si], m.sub_seg_off[si] + n, device=self.device,
+                               dtype=torch.int32))
+          if m.needs_scale:
+            so = m.sub_seg_off[si]
+            if sc.call.seg_scale is not None:
+              m.seg_scale[so:so + sc.call.n_seg].copy_(sc.call.seg_scale)
+          all_outs.extend(outs)
+        self._pending.append((m, m.rows, m.weights if any_w else None, all_outs,
+                              m.seg_ids if m.has_csr else None))
     out = {}
     for gname, layout in self.group_layout.items():
-      mats = {}
-      per_feature = []
-      pieces = []
-      for (fname, kind, width, adim, buf, col) in layout:
+      per_feature, mats, kinds = [], {}, []
+      for (fname, kind, width, dim, out_key, col) in layout:
         if kind == 'dense':
           c0, c1 = self.raw_cols[fname]
           v = dense_norm[:, c0:c1]
         else:
-          m = results[adim][buf]
-          mats[(adim, buf)] = m
-          v = m[:, col:col + width]
+          mat = outs_by_key[(dim, out_key)]
+          mats[(dim, out_key)] = mat
+          v = mat[:, col:col + width]
         per_feature.append(v)
-        pieces.append((kind, adim, buf))
-      if len(mats) == 1 and all(k == 'emb' for k, _, _ in pieces):
-        (adim, buf), m = next(iter(mats.items()))
-        w = self.calls[adim].out_widths[buf]
-        concat = m if m.shape[1] == w else m[:, :w]
+        kinds.append(kind)
+      if len(mats) == 1 and all(k == 'emb' for k in kinds):
+        (dim, out_key), mat = next(iter(mats.items()))
+        width = sum(e[2] for e in layout)
+        concat = mat if mat.shape[1] == width else mat[:, :width]
       else:
         concat = torch.cat(per_feature, dim=1)
       out[gname] = (concat, per_feature)
+    self.seq_outputs = {}
+    B = self.batch_size
+    for sname, lay in self.seq_layout.items():
+      keys = [outs_by_key[(d, ok)][:, c:c + d] for (_, d, ok, c) in lay['key']]
+      hists = [outs_by_key[(d, ok)][:, c:c + d].reshape(B, lay['T'], d) for (_, d, ok, c) in lay['hist']]
+      lens = features['seq_fea'][lay['hist'][0][0]][1]
+      self.seq_outputs[sname] = dict(
+          key=keys[0] if len(keys) == 1 else torch.cat(keys, dim=-1),
+          hist_seq_emb=hists[0] if len(hists) == 1 else torch.cat(hists, dim=-1),
+          hist_seq_len=lens)
     return out

@@ -1,0 +1,33 @@
+"""Shared pieces of the rank models (reference: model/rank_model.py:57-151, 213-335;
+builders/loss_builder.py:36-55; layers/input_layer.py:369-375 embedding regularisation)."""
+import torch
+from torch import nn
+
+from easyrec_b200 import embedding as E
+
+
+class RankModel(nn.Module):
+  """num_class == 1 CLASSIFICATION head: logits -> sigmoid, tf.losses.sigmoid_cross_entropy."""
+
+  l2_reg = 0.0
+  embedding_reg = 0.0
+
+  @staticmethod
+  def wide_output_dim(model_config):
+    return 1
+
+  def l2_of(self, name, param):
+    """kernel_regularizer = l2_regularizer(l2_regularization) on dense kernels (layers/dnn.py:57-62);
+    biases, batch-norm and cross-layer vectors are not regularised."""
+    return self.l2_reg if name.endswith('kernel') else 0.0
+
+  def embedding_reg_loss(self, tensors):
+    """l2_regularizer(embedding_regularization) over the LOOKED-UP group outputs
+    (layers/input_layer.py:369-375, compat/regularizers.py): scale * sum(x^2) / 2."""
+    if self.embedding_reg <= 0 or not tensors:
+      return 0.0
+    return self.embedding_reg * 0.5 * sum((t * t).sum() for t in tensors)
+
+  def loss(self, logits, labels):
+    ce, probs = E.sigmoid_cross_entropy(logits, labels)
+    return ce + self.embedding_reg_loss(getattr(self, '_emb_outputs', ())), probs

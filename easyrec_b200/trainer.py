@@ -116,6 +116,8 @@ class Trainer(object):
     self.step = 0
     self.use_cuda_graph = use_cuda_graph
     self._graph = None
+    self._graph2 = None
+    self._step_pending = []
     self._static = None
     self._loss = None
     self._probs = None
@@ -125,20 +127,36 @@ class Trainer(object):
     self.input_layer.set_optimizer_step(lr, self.step)
     self.dense_opt.set_lr(lr, self.step)
 
-  def _step_body(self, features, labels):
+  # The step is three segments; only the middle one talks to other ranks, so with world > 1 the
+  # CUDA graph is captured as two graphs around eager NCCL calls.
+  def _segment_compute(self, features, labels):
+    """lookup -> model -> loss -> backward -> dense grads into the flat buffer."""
     self.dense_opt.zero_grad()
     logits = self.model(features)
     loss, probs = self.model.loss(logits, labels)
     loss.backward()
     self.dense_opt.gather_grads()
+    self._step_pending = list(self.input_layer._pending)
+    return loss.detach(), probs
+
+  def _segment_exchange(self):
     if self.dp is not None:
-      self.dp.sync_dense_grads()                                          # flat all-reduce (mean)
-      self.dp.sparse_backward_update(self.input_layer.opt_holder['opt'])  # all-gather + K7
+      self.dp.exchange(self._step_pending)   # flat all-reduce + all-gather of K7 inputs
+
+  def _segment_update(self, loss):
+    if self.dp is not None:
+      self.dp.apply_sparse(self._step_pending, self.input_layer.opt_holder['opt'])
+      self.input_layer._pending = []
     else:
       self.input_layer.backward_update()   # K7: dedup + fused row update, on this thread/stream
     self.dense_opt.apply()                 # one launch: l2 + adagrad/adam over the flat buffer
     # reported loss = data loss + embedding regularisation (autograd) + dense l2 (from the apply)
-    return loss.detach() + self.dense_opt.reg_loss[0], probs
+    return loss + self.dense_opt.reg_loss[0]
+
+  def _step_body(self, features, labels):
+    loss, probs = self._segment_compute(features, labels)
+    self._segment_exchange()
+    return self._segment_update(loss), probs
 
   def train_step(self, features, labels):
     """features/labels: device tensors.  Returns (loss [scalar tensor], probs [B])."""
@@ -155,6 +173,9 @@ class Trainer(object):
         self._static[k].copy_(v, non_blocking=True)
       self._static['__labels'].copy_(labels, non_blocking=True)
     self._graph.replay()
+    if self._graph2 is not None:   # world > 1: collectives between the two captured segments
+      self._segment_exchange()
+      self._graph2.replay()
     self.step += 1
     return self._loss, self._probs
 
@@ -177,7 +198,15 @@ class Trainer(object):
     torch.cuda.current_stream().wait_stream(s)
     self._graph = torch.cuda.CUDAGraph()
     n0 = _lib.load().er_launch_count()
-    with torch.cuda.graph(self._graph):
-      self._loss, self._probs = self._step_body(feats, self._static['__labels'])
-    # kernels of liber_b200.so inside one replay of the graph
+    if self.dp is None:
+      with torch.cuda.graph(self._graph):
+        self._loss, self._probs = self._step_body(feats, self._static['__labels'])
+    else:
+      with torch.cuda.graph(self._graph):
+        loss, self._probs = self._segment_compute(feats, self._static['__labels'])
+      self._segment_exchange()   # eager: NCCL stays out of the capture
+      self._graph2 = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self._graph2, pool=self._graph.pool()):
+        self._loss = self._segment_update(loss)
+    # kernels of liber_b200.so inside one replay of the graph(s)
     self.launches_per_step = int(_lib.load().er_launch_count() - n0)

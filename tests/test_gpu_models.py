@@ -1,0 +1,157 @@
+"""GPU: the BASELINE model families built from EasyRec-format pipeline configs (text_format, subset schema),
+trained a few steps on the fused path; MultiTowerDIN's forward is additionally checked against a plain
+PyTorch restatement of the reference graph on the same tables/weights (logits within 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import builder
+from easyrec_b200.config import config_util
+from easyrec_b200.trainer import Trainer
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+B = 256
+
+HEAD = '''
+model_dir: "/tmp/x"
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } }
+data_config { batch_size: 256 input_type: DummyInput label_fields: "clk" }
+'''
+
+FEATS = '''
+feature_config {
+  features { input_names: "user_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 1000 }
+  features { input_names: "age" feature_type: IdFeature embedding_dim: 16 num_buckets: 10 }
+  features { input_names: "item_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 5000 }
+  features { input_names: "cate" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 200 }
+  features { input_names: "price" feature_type: RawFeature embedding_dim: 16 min_val: 0 max_val: 100 }
+  features { input_names: "hist_items" feature_type: SequenceFeature embedding_dim: 16 hash_bucket_size: 5000 max_seq_len: 20 }
+}
+'''
+
+DCN_CFG = HEAD + FEATS + '''
+model_config { model_class: "DCN"
+  feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
+  dcn { deep_tower { input: "all" dnn { hidden_units: [64, 32] } } cross_tower { input: "all" cross_num: 3 }
+        final_dnn { hidden_units: [32, 16] } l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
+DIN_CFG = HEAD + FEATS + '''
+model_config { model_class: "MultiTowerDIN"
+  feature_groups { group_name: "user" feature_names: ["user_id", "age"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate", "price"] wide_deep: DEEP }
+  seq_att_groups { group_name: "din" seq_att_map { key: "item_id" hist_seq: "hist_items" } }
+  multi_tower { towers { input: "user" dnn { hidden_units: [32, 16] } } towers { input: "item" dnn { hidden_units: [32, 16] } }
+                din_towers { input: "din" dnn { hidden_units: [32, 16, 1] } } final_dnn { hidden_units: [32, 16] }
+                l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
+MMOE_CFG = HEAD.replace('label_fields: "clk"', 'label_fields: "clk" label_fields: "buy"') + FEATS + '''
+model_config { model_class: "MMoE"
+  feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
+  mmoe { expert_dnn { hidden_units: [32, 16] } num_expert: 4
+         task_towers { tower_name: "ctr" label_name: "clk" dnn { hidden_units: [16, 8] } loss_type: CLASSIFICATION weight: 1.0 }
+         task_towers { tower_name: "cvr" label_name: "buy" dnn { hidden_units: [16, 8] } loss_type: CLASSIFICATION weight: 0.5 }
+         l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
+DSSM_CFG = HEAD + FEATS + '''
+model_config { model_class: "DSSM"
+  feature_groups { group_name: "user" feature_names: ["user_id", "age"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate", "price"] wide_deep: DEEP }
+  dssm { user_tower { id: "user_id" dnn { hidden_units: [64, 32, 16] } } item_tower { id: "item_id" dnn { hidden_units: [64, 32, 16] } }
+         simi_func: COSINE temperature: 0.1 scale_simi: true l2_regularization: 1e-5 }
+  loss_type: SOFTMAX_CROSS_ENTROPY embedding_regularization: 1e-5 }
+'''
+
+
+def make_batch(seed, n_task=1):
+  rng = np.random.default_rng(seed)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B),
+                  rng.integers(0, 500, B)]).astype(np.int64)  # feature-major: user_id, age, item_id, cate
+  dense = rng.uniform(0, 100, (B, 1)).astype(np.float32)
+  T = 20
+  hist = rng.integers(0, 10**6, (B, T)).astype(np.int64)
+  lens = rng.integers(0, T + 1, B).astype(np.int32)
+  labels = (rng.uniform(size=(B, n_task)) < 0.3).astype(np.float32)
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1)).to(DEV), 'dense_fea': torch.from_numpy(dense).to(DEV),
+           'seq_fea': {'hist_items': (torch.from_numpy(hist).to(DEV), torch.from_numpy(lens).to(DEV))},
+           'item_ids': torch.from_numpy(ids[2]).to(DEV)}
+  lab = torch.from_numpy(labels if n_task > 1 else labels[:, 0]).to(DEV)
+  return feats, lab, (ids, dense, hist, lens)
+
+
+@pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1)])
+def test_models_from_pipeline_config_train(cfg_text, n_task):
+  torch.backends.cuda.matmul.allow_tf32 = False
+  cfg = config_util.get_configs_from_pipeline_file(cfg_text.encode())
+  il, model, opt = builder.build_model(cfg, B, DEV, generator=torch.Generator(device=DEV).manual_seed(1),
+                                       cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  tr = Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  feats, lab, _ = make_batch(3, n_task)
+  losses = [float(tr.train_step(feats, lab)[0]) for _ in range(25)]
+  assert all(np.isfinite(losses))
+  assert losses[-1] < losses[0] - 0.02, losses  # the same batch is being fitted
+  # a different batch still runs through the same static plan
+  feats2, lab2, _ = make_batch(4, n_task)
+  assert np.isfinite(float(tr.train_step(feats2, lab2)[0]))
+
+
+def test_din_forward_matches_plain_torch_restatement():
+  torch.backends.cuda.matmul.allow_tf32 = False
+  cfg = config_util.get_configs_from_pipeline_file(DIN_CFG.encode())
+  il, model, _ = builder.build_model(cfg, B, DEV, generator=torch.Generator(device=DEV).manual_seed(1),
+                                     cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  model.train()
+  feats, lab, (ids, dense, hist, lens) = make_batch(5)
+  logits = model(feats).detach()
+  arena = il.arenas[16]
+  W = arena.weight.detach()
+
+  def table(name):
+    off, n, _ = arena.tables[name]
+    return W[off:off + n]
+
+  def hashed(v, nb):
+    rows, _ = O.bucketize(v.reshape(-1), 0, nb, 0)
+    return torch.from_numpy(rows.reshape(v.shape)).to(DEV)
+
+  def bn(x):
+    mu, var = x.mean(0), ((x - x.mean(0))**2).mean(0)
+    return (x - mu) / torch.sqrt(var + 1e-3)
+
+  def dnn(mod, x, last_plain=False):
+    n = len(mod.layers)
+    for i, lay in enumerate(mod.layers):
+      x = x @ lay.kernel + lay.bias
+      if lay.use_bn:
+        x = bn(x) * lay.gamma + lay.beta
+      if lay.relu:
+        x = torch.relu(x)
+    return x
+
+  age = torch.from_numpy(np.where((ids[1] < 0) | (ids[1] >= 10), 0, ids[1])).to(DEV)
+  user = torch.cat([table('user_id_embedding')[hashed(ids[0], 1000)], table('age_embedding')[age]], 1)
+  pn = torch.from_numpy(dense / 100.0).to(DEV)
+  item = torch.cat([table('item_id_embedding')[hashed(ids[2], 5000)], table('cate_embedding')[hashed(ids[3], 200)],
+                    pn * table('price_embedding')[0][None, :]], 1)
+  key = table('din/item_id_embedding')[hashed(ids[2], 5000)]
+  he = table('din/hist_items_embedding')[hashed(hist, 5000)]
+  T = hist.shape[1]
+  mask = torch.arange(T, device=DEV)[None, :] < torch.from_numpy(lens).to(DEV)[:, None]
+  he = he * mask[:, :, None]
+  cur = key[:, None, :].expand(-1, T, -1)
+  din_in = torch.cat([cur, he, cur - he, cur * he], -1).reshape(B * T, -1)
+  scores = dnn(model.din_dnn[0], din_in).reshape(B, 1, T)
+  scores = torch.where(mask[:, None, :], scores, torch.full_like(scores, -2.0**32 + 1))
+  att = (torch.softmax(scores, -1) @ he).reshape(B, -1)
+  feas = [dnn(model.tower_dnn[0], bn(user) * model.tower_bn[0].gamma + model.tower_bn[0].beta),
+          dnn(model.tower_dnn[1], bn(item) * model.tower_bn[1].gamma + model.tower_bn[1].beta),
+          torch.cat([att, key], 1)]
+  ref = (dnn(model.final_dnn, torch.cat(feas, 1)) @ model.output.kernel + model.output.bias)[:, 0]
+  assert float((logits - ref).abs().max()) < 1e-4
