@@ -1,0 +1,152 @@
+"""EasyRecEstimator on the fused path: same constructor and train/evaluate/predict surface as the
+reference (`model/easy_rec_estimator.py:62-153`, `main.py:102-163,296-400`), body replaced by the
+torch/liber_b200 training loop.  tf.estimator plumbing (hooks, Scaffold, SavedModel export, PS/worker)
+is out of scope.
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+
+from easyrec_b200 import builder
+from easyrec_b200.config import config_util
+from easyrec_b200.input import readers
+from easyrec_b200.trainer import Trainer
+
+_DENSE_KIND = {'adagrad_optimizer': 'adagrad', 'adam_optimizer': 'adam', 'lazy_adam_optimizer': 'lazy_adam',
+               'momentum_optimizer': 'sgd'}
+
+
+def auc(labels, scores):
+  """Exact ROC AUC (Mann-Whitney); the reference's tf.metrics.auc is a 200-threshold approximation of it."""
+  labels = np.asarray(labels).astype(np.float64)
+  scores = np.asarray(scores).astype(np.float64)
+  order = np.argsort(scores, kind='mergesort')
+  ranks = np.empty(len(scores), np.float64)
+  s = scores[order]
+  i = 0
+  r = np.arange(1, len(s) + 1, dtype=np.float64)
+  while i < len(s):  # average ranks over ties
+    j = i
+    while j + 1 < len(s) and s[j + 1] == s[i]:
+      j += 1
+    r[i:j + 1] = 0.5 * (i + j) + 1
+    i = j + 1
+  ranks[order] = r
+  n_pos = labels.sum()
+  n_neg = len(labels) - n_pos
+  if n_pos == 0 or n_neg == 0:
+    return float('nan')
+  return float((ranks[labels > 0].sum() - n_pos * (n_pos + 1) / 2) / (n_pos * n_neg))
+
+
+class EasyRecEstimator(object):
+
+  def __init__(self, pipeline_config, model_cls=None, run_config=None, params=None, device='cuda:0',
+               batch_size=None, use_cuda_graph=False, world_size=1, seed=20240, default_seq_len=50):
+    if isinstance(pipeline_config, (str, bytes)):
+      pipeline_config = config_util.get_configs_from_pipeline_file(pipeline_config)
+    self._pipeline_config = pipeline_config
+    self._device = device
+    self._batch_size = batch_size or pipeline_config.data_config.batch_size
+    gen = torch.Generator(device=device).manual_seed(seed) if str(device).startswith('cuda') else None
+    self.input_layer, self.model, self._opt = builder.build_model(
+        pipeline_config, self._batch_size, device, generator=gen,
+        cpu_generator=torch.Generator().manual_seed(seed), default_seq_len=default_seq_len)
+    self.trainer = Trainer(self.model, self.input_layer, _DENSE_KIND[self._opt['kind']], lr_fn=self._opt['lr_fn'],
+                           use_cuda_graph=use_cuda_graph, world_size=world_size, beta1=self._opt['beta1'],
+                           beta2=self._opt['beta2'], adagrad_init=self._opt['acc0'])
+    self.global_step = 0
+
+  # -- properties of the reference estimator (easy_rec_estimator.py:97-153) --
+  @property
+  def feature_configs(self):
+    return config_util.get_feature_configs(self._pipeline_config)
+
+  @property
+  def model_config(self):
+    return self._pipeline_config.model_config
+
+  @property
+  def train_config(self):
+    return self._pipeline_config.train_config
+
+  @property
+  def eval_config(self):
+    return self._pipeline_config.eval_config
+
+  def train(self, input_fn, hooks=None, steps=None, max_steps=None, saving_listeners=None):
+    """input_fn() -> iterable of (features, labels) host batches.  Logs step/loss/steps-per-sec every
+    log_step_count_steps like LoggingTensorHook + StepCounterHook (easy_rec_estimator.py:384-396,455-458)."""
+    limit = steps if steps is not None else (max_steps or self.train_config.num_steps or None)
+    every = max(int(self.train_config.log_step_count_steps), 1)
+    t0, n0 = time.time(), self.global_step
+    loss = None
+    for feats, labels in input_fn():
+      feats, labels = readers.to_device(feats, labels, self._device)
+      loss, _ = self.trainer.train_step(feats, labels)
+      self.global_step += 1
+      if self.global_step % every == 0:
+        dt = time.time() - t0
+        logging.info('global_step = %d, loss = %.6f, global_step/sec = %.2f', self.global_step, float(loss),
+                     (self.global_step - n0) / max(dt, 1e-9))
+      if limit is not None and self.global_step - n0 >= limit:
+        break
+    return None if loss is None else float(loss)
+
+  @torch.no_grad()
+  def _forward_eval(self, feats):
+    self.model.eval()
+    logits = self.model(feats)
+    self.input_layer._pending = []
+    return logits
+
+  def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
+    labels_all, probs_all = [], []
+    n = 0
+    for feats, labels in input_fn():
+      feats, labels = readers.to_device(feats, labels, self._device)
+      logits = self._forward_eval(feats)
+      if logits.dim() == 1:
+        probs_all.append(torch.sigmoid(logits).cpu().numpy())
+        labels_all.append(labels.cpu().numpy())
+      n += 1
+      if steps is not None and n >= steps:
+        break
+    out = {'global_step': self.global_step}
+    if probs_all:
+      out['auc'] = auc(np.concatenate(labels_all), np.concatenate(probs_all))
+    return out
+
+  def predict(self, input_fn, predict_keys=None, hooks=None, checkpoint_path=None, yield_single_examples=True):
+    for feats, labels in input_fn():
+      feats, _ = readers.to_device(feats, labels, self._device)
+      logits = self._forward_eval(feats)
+      yield {'logits': logits.cpu().numpy(), 'probs': torch.sigmoid(logits).cpu().numpy()}
+
+  def save(self, model_dir=None):
+    """dense parameters + arenas (weights and optimizer state) as one torch checkpoint."""
+    model_dir = model_dir or self._pipeline_config.model_dir
+    os.makedirs(model_dir, exist_ok=True)
+    path = os.path.join(model_dir, 'model.ckpt-%d.pt' % self.global_step)
+    torch.save({'model': self.model.state_dict(),
+                'arenas': {d: a.storage for d, a in self.input_layer.arenas.items()},
+                'tables': {d: a.tables for d, a in self.input_layer.arenas.items()},
+                'global_step': self.global_step}, path)
+    return path
+
+
+def train_and_evaluate(pipeline_config_path, train_input_fn=None, eval_input_fn=None, device='cuda:0', **kw):
+  """main._train_and_evaluate_impl (main.py:296-400) for the supported model families."""
+  est = EasyRecEstimator(pipeline_config_path, device=device, **kw)
+  cfg = est._pipeline_config
+  if train_input_fn is None:
+    path = cfg.train_input_path
+    train_input_fn = lambda: readers.CSVInput(cfg, est.input_layer, path)  # noqa: E731
+  est.train(train_input_fn)
+  if eval_input_fn is None and cfg.eval_input_path:
+    epath = cfg.eval_input_path
+    eval_input_fn = lambda: readers.CSVInput(cfg, est.input_layer, epath)  # noqa: E731
+  return est, (est.evaluate(eval_input_fn) if eval_input_fn else {})

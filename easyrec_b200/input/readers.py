@@ -1,0 +1,163 @@
+"""Host-side inputs: EasyRec data_config -> packed batches for InputLayer.
+
+Counterpart of input/input.py:806-939 (`_preprocess`) + input/csv_input.py:78-175 restricted to the
+feature types of the hot path.  A batch is the reference's packed form (input/parquet_input.py:201-239):
+  sparse_fea int64 [n_id*B] feature-major | dense_fea fp32 [B, sum raw_dim] | seq_fea | tag_fea | labels.
+
+String-typed id fields are fingerprinted on the host with the library's Fingerprint64
+(er_fingerprint64_host == StringToHashBucketFast's hash, feature_column_v2.py:3915-3921); integer fields
+go to the device untouched and are hashed there from their decimal text (input/input.py:541-543).
+"""
+import numpy as np
+import torch
+
+from easyrec_b200 import _lib
+from easyrec_b200.config import config_util
+
+
+class DummyInput(object):
+  """input/dummy_input.py:13-58: a constant in-memory batch, for pipeline-free throughput runs and tests."""
+
+  def __init__(self, input_layer, n_labels=1, seed=0):
+    self.il = input_layer
+    self.n_labels = n_labels
+    self.seed = seed
+
+  def batch(self, step=0):
+    il = self.il
+    B = il.batch_size
+    rng = np.random.default_rng(self.seed + step)
+    feats = {}
+    if il.sparse_names:
+      ids = rng.integers(0, 2**40, len(il.sparse_names) * B, dtype=np.int64)
+      feats['sparse_fea'] = torch.from_numpy(ids)
+    if il.n_dense:
+      feats['dense_fea'] = torch.from_numpy(rng.uniform(0, 1, (B, il.n_dense)).astype(np.float32))
+    seq, tag = {}, {}
+    for f in il.features.values():
+      if f.kind == 'seq':
+        lens = rng.integers(1, f.seq_len + 1, B).astype(np.int32)
+        seq[f.name] = (torch.from_numpy(rng.integers(0, 2**40, (B, f.seq_len), dtype=np.int64)),
+                       torch.from_numpy(lens))
+      elif f.kind == 'tag':
+        lens = rng.integers(0, 5, B).astype(np.int32)
+        tag[f.name] = (torch.from_numpy(rng.integers(0, 2**40, int(lens.sum()), dtype=np.int64)),
+                       torch.from_numpy(lens), None)
+    if seq:
+      feats['seq_fea'] = seq
+    if tag:
+      feats['tag_fea'] = tag
+    labels = (rng.uniform(size=(B, self.n_labels)) < 0.25).astype(np.float32)
+    labels = torch.from_numpy(labels if self.n_labels > 1 else labels[:, 0])
+    return feats, labels
+
+  def __iter__(self):
+    step = 0
+    while True:
+      yield self.batch(step)
+      step += 1
+
+
+class CSVInput(object):
+  """CSVInput (input/csv_input.py): delimiter-separated text, one sample per line, columns in
+  data_config.input_fields order; labels from label_fields.  Only Id / Raw / Sequence / Tag features."""
+
+  def __init__(self, pipeline_config, input_layer, path, batch_size=None, seq_sep='|'):
+    self.cfg = pipeline_config
+    self.il = input_layer
+    self.path = path
+    dc = pipeline_config.data_config
+    self.sep = dc.separator or ','
+    self.fields = [f.input_name for f in dc.input_fields]
+    self.ftypes = {f.input_name: dc.DESCRIPTOR.nested_types_by_name['Field'].fields_by_name['input_type']
+                   .enum_type.values_by_number[f.input_type].name for f in dc.input_fields}
+    self.defaults = {f.input_name: f.default_val for f in dc.input_fields}
+    self.labels = list(dc.label_fields)
+    self.batch_size = batch_size or input_layer.batch_size
+    self.feature_inputs = {}
+    for fc in config_util.get_feature_configs(pipeline_config):
+      name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+      self.feature_inputs[name] = (fc.input_names[0], fc.separator or seq_sep)
+
+  def _id_column(self, col, ftype, default):
+    """int fields -> int64 as is (device hashes the decimal text); string fields -> host Fingerprint64."""
+    if ftype in ('INT32', 'INT64'):
+      return np.array([int(x) if x != '' else int(default or 0) for x in col], np.int64), False
+    return np.array([_lib.fingerprint64(x if x != '' else (default or '')) for x in col],
+                    np.uint64).view(np.int64), True
+
+  def batches(self):
+    il = self.il
+    B = self.batch_size
+    buf = []
+    with open(self.path, 'rb') as f:
+      for line in f:
+        buf.append(line.rstrip(b'\r\n').decode('utf-8', errors='surrogateescape').split(self.sep))
+        if len(buf) == B:
+          yield self._pack(buf)
+          buf = []
+    # the reference drops nothing; a ragged last batch does not fit the static plan, so it is skipped
+
+  def _pack(self, rows):
+    il = self.il
+    cols = {name: [r[i] if i < len(r) else '' for r in rows] for i, name in enumerate(self.fields)}
+    feats = {}
+    ids = []
+    for n in il.sparse_names:
+      src, _ = self.feature_inputs[n]
+      arr, hashed = self._id_column(cols[src], self.ftypes[src], self.defaults.get(src))
+      if hashed and il.features[n].bucket_mode == _lib.BUCKET_FARM_DECIMAL:
+        raise NotImplementedError('string-typed hashed id field %s: use an integer field or pre-hash' % src)
+      ids.append(arr)
+    if ids:
+      feats['sparse_fea'] = torch.from_numpy(np.concatenate(ids))
+    if il.raw_names:
+      dense = np.zeros((len(rows), il.n_dense), np.float32)
+      for n in il.raw_names:
+        src, sep = self.feature_inputs[n]
+        c0, c1 = il.raw_cols[n]
+        for i, x in enumerate(cols[src]):
+          x = x if x != '' else (self.defaults.get(src) or '0')
+          vals = x.split(sep) if c1 - c0 > 1 else [x]
+          dense[i, c0:c0 + len(vals)] = [float(v) for v in vals[:c1 - c0]]
+      feats['dense_fea'] = torch.from_numpy(dense)
+    seq, tag = {}, {}
+    for f in il.features.values():
+      if f.kind not in ('seq', 'tag'):
+        continue
+      src, sep = self.feature_inputs[f.name]
+      toks = [[t for t in x.split(sep) if t != ''] for x in cols[src]]
+      if f.kind == 'seq':
+        T = f.seq_len
+        arr = np.zeros((len(rows), T), np.int64)
+        lens = np.zeros(len(rows), np.int32)
+        for i, ts in enumerate(toks):
+          ts = ts[:T]  # keep the FIRST max_seq_len steps (utils/shape_utils.py:393-410)
+          lens[i] = len(ts)
+          arr[i, :len(ts)] = [int(t) for t in ts]
+        seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(lens))
+      else:
+        lens = np.array([len(ts) for ts in toks], np.int32)
+        flat = np.array([int(t) for ts in toks for t in ts], np.int64)
+        tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), None)
+    if seq:
+      feats['seq_fea'] = seq
+    if tag:
+      feats['tag_fea'] = tag
+    lab = np.stack([np.array([float(x or 0) for x in cols[l]], np.float32) for l in self.labels], 1)
+    labels = torch.from_numpy(lab if lab.shape[1] > 1 else lab[:, 0])
+    return feats, labels
+
+  def __iter__(self):
+    return self.batches()
+
+
+def to_device(feats, labels, device):
+  out = {}
+  for k, v in feats.items():
+    if isinstance(v, dict):
+      out[k] = {n: tuple(None if t is None else t.to(device, non_blocking=True) for t in tup)
+                for n, tup in v.items()}
+    else:
+      out[k] = v.to(device, non_blocking=True)
+  return out, labels.to(device, non_blocking=True)
