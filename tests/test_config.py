@@ -1,0 +1,92 @@
+"""CPU: pipeline-config loading (runtime proto2 schema, text_format) and config -> model plan.
+
+When the reference checkout is mounted (/root/reference, build container only) the subset schema is
+cross-checked field by field against the reference's protos and every reference sample config is parsed;
+on the GPU box those cases skip and the in-repo config texts below still run."""
+import glob
+import os
+
+import pytest
+import torch
+
+from easyrec_b200 import builder
+from easyrec_b200.config import config_util, proto_loader
+
+REF = '/root/reference'
+HAVE_REF = os.path.isdir(os.path.join(REF, 'easy_rec/python/protos'))
+
+MINI = b'''
+model_dir: "/tmp/m"
+train_config { num_steps: 7 optimizer_config { adam_optimizer { learning_rate { exponential_decay_learning_rate {
+  initial_learning_rate: 0.001 decay_steps: 1000 decay_factor: 0.5 min_learning_rate: 0.00001 } } } } }
+data_config { batch_size: 32 input_type: CSVInput separator: "\\t" label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "F1" input_type: FLOAT }
+  input_fields { input_name: "C1" input_type: INT64 } }
+feature_config {
+  features { input_names: "F1" feature_type: RawFeature embedding_dim: 16 min_val: 0.0 max_val: 10.0 }
+  features { input_names: "C1" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 1000 unknown_future_field: 3 }
+}
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: "F1" feature_names: "C1" wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: "F1" feature_names: "C1" wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [32, 16] } final_dnn { hidden_units: [16] } l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
+
+def test_subset_schema_parses_config_and_skips_unknown_fields():
+  cfg = config_util.get_configs_from_pipeline_file(MINI)
+  assert cfg.model_config.model_class == 'DeepFM'
+  assert cfg.data_config.separator == '\t'
+  assert [f.input_names[0] for f in config_util.get_feature_configs(cfg)] == ['F1', 'C1']
+  assert cfg.model_config.deepfm.wide_output_dim == 1  # proto default
+  assert list(cfg.model_config.deepfm.dnn.hidden_units) == [32, 16]
+  cfg = config_util.edit_config(cfg, {'train_config.num_steps': 11, 'data_config.batch_size': 64,
+                                      'model_config.deepfm.dnn.hidden_units[0]': 48})
+  assert cfg.train_config.num_steps == 11 and cfg.data_config.batch_size == 64
+  assert cfg.model_config.deepfm.dnn.hidden_units[0] == 48
+
+
+def test_config_to_table_plan_and_schedule():
+  cfg = config_util.get_configs_from_pipeline_file(MINI)
+  il, model, opt = builder.build_model(cfg, 32, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert set(il.arenas) == {16, 1}
+  assert il.arenas[16].n_rows == 1 + 1000  # raw projection row + hashed table
+  assert [e[0] for e in il.group_layout['deep']] == ['F1', 'C1']  # config order
+  assert opt['kind'] == 'adam_optimizer'
+  lr = opt['lr_fn']
+  assert abs(lr(0) - 0.001) < 1e-9 and abs(lr(999) - 0.001) < 1e-9   # staircase (proto floats are fp32)
+  assert abs(lr(1000) - 0.0005) < 1e-9 and lr(10**7) == pytest.approx(0.00001)
+  assert model.l2_of('dnn.layers.0.kernel', None) == pytest.approx(1e-5)
+  assert model.l2_of('dnn.layers.0.bias', None) == 0.0
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+def test_subset_schema_is_consistent_with_reference_protos():
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+  import check_subset_schema
+  assert check_subset_schema.check(os.path.join(REF, 'easy_rec/python/protos')) == []
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+def test_every_reference_sample_config_parses():
+  full = proto_loader.load_schema(sorted(glob.glob(os.path.join(REF, 'easy_rec/python/protos/*.proto'))),
+                                  virtual_name='full_ref.proto')
+  paths = sorted(glob.glob(os.path.join(REF, 'samples/model_config/*.config'))) + \
+      sorted(glob.glob(os.path.join(REF, 'examples/configs/*.config')))
+  assert len(paths) > 200
+  for p in paths:
+    config_util.get_configs_from_pipeline_file(p, schema=full)  # strict: complete schema
+    config_util.get_configs_from_pipeline_file(p)               # subset schema, unknown fields skipped
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+@pytest.mark.parametrize('rel', ['examples/configs/deepfm_on_criteo.config', 'samples/model_config/din_on_taobao.config',
+                                 'samples/model_config/dcn_on_taobao.config', 'samples/model_config/dssm_on_taobao.config',
+                                 'samples/model_config/mmoe_on_taobao.config'])
+def test_baseline_model_families_build_from_unmodified_reference_configs(rel):
+  cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, rel))
+  il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert sum(p.numel() for p in model.parameters()) > 1000
+  assert all(a.n_rows > 0 for a in il.arenas.values())
