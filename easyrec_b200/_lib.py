@@ -56,6 +56,11 @@ SIGNATURES = {
         c_i32, ctypes.POINTER(c_vp), c_i32, c_vp, c_vp
     ]),
     'er_embedding_bwd_workspace_bytes': (c_sz, [c_i64, c_i32]),
+    'er_embedding_bwd_reuse_sort': (c_i32, [
+        c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
+        c_i64, c_vp, c_i32, ctypes.POINTER(c_vp), c_i32, c_vp,
+        ctypes.POINTER(ErOpt), c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz, c_i32, c_vp
+    ]),
     'er_embedding_bwd': (c_i32, [
         c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64,
         c_i64, c_vp, c_i32, ctypes.POINTER(c_vp), c_i32, c_vp,
@@ -81,6 +86,13 @@ SIGNATURES = {
     'er_dense_workspace_bytes': (c_sz, [c_i64, c_i32]),
     'er_dense_apply': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, ctypes.POINTER(ErOpt), c_vp,
                                c_vp, c_vp]),
+    'er_fm_block_workspace_bytes': (c_sz, [c_i64]),
+    'er_fm_block_fwd': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'er_fm_block_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32,
+                                c_vp]),
+    'er_gemm_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64]),
+    'er_gemm': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
+                        c_vp, c_sz, c_vp]),
     'er_bias_bn_act_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                    c_i32, c_f32, c_f32, c_i32, c_i32, c_vp,
                                    c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -581,6 +581,83 @@ __global__ void __launch_bounds__(256) bwd_long_scalar_kernel(const __grid_const
   }
 }
 
+// ---- dim == 1 (wide tables): lane-per-lookup segmented scan, the run's last lane applies --------
+// Same window protocol as bwd_scan_vec_kernel; a "row" is one float (+ its optimizer slots, which the
+// interleaved arena keeps in the same 32-byte sector), so every tail lane does its own RMW.
+__global__ void __launch_bounds__(256) bwd_scan_d1_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32;
+  if (base >= a.n) return;
+  const int64_t pos = base + lane;
+  const bool in = pos < a.n;
+  const uint32_t k = in ? a.keys[pos] : a.sentinel;
+  const uint32_t l = in ? a.vals[pos] : 0u;
+  const bool valid = in && k < a.sentinel;
+  uint32_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+  if (lane == 0) kprev = (base > 0) ? a.keys[base - 1] : ~k;
+  uint32_t knext = __shfl_down_sync(0xffffffffu, k, 1);
+  if (lane == 31) knext = (base + 32 < a.n) ? a.keys[base + 32] : ~k;
+  const bool is_head = valid && (pos == 0 || kprev != k);
+  const uint32_t k0 = __shfl_sync(0xffffffffu, k, 0);
+  const int head0 = __shfl_sync(0xffffffffu, (int)is_head, 0);
+  const bool owned = valid && (head0 || k != k0);
+  const bool is_tail = owned && (knext != k);
+  const int cont = __shfl_sync(0xffffffffu, (int)(owned && knext == k), 31);
+  float g = 0.f;
+  if (owned) {
+    float coef;
+    const float* src = grad_src(a, sv, l, &coef);
+    g = __fmul_rn(src[0], coef);
+  }
+  int cnt = owned ? 1 : 0;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t kk = __shfl_up_sync(0xffffffffu, k, off);
+    const int oo = __shfl_up_sync(0xffffffffu, (int)owned, off);
+    const int cc = __shfl_up_sync(0xffffffffu, cnt, off);
+    const float y = __shfl_up_sync(0xffffffffu, g, off);
+    if (lane >= off && owned && oo && kk == k) {
+      g = __fadd_rn(g, y);
+      cnt += cc;
+    }
+  }
+  int handed_off = 0;
+  if (cont) {
+    const uint32_t key = __shfl_sync(0xffffffffu, k, 31);
+    int total = __shfl_sync(0xffffffffu, cnt, 31);
+    const int64_t start = base + 32 - total;
+    int64_t j = base + 32;
+    while (true) {
+      const int64_t p = j + lane;
+      const bool m = p < a.n && a.keys[p] == key;
+      const unsigned mm = __ballot_sync(0xffffffffu, m);
+      float x = 0.f;
+      if (m) {
+        float coef;
+        const float* src = grad_src(a, sv, a.vals[p], &coef);
+        x = __fmul_rn(src[0], coef);
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+      if (lane == 31) g = __fadd_rn(g, x);
+      const int got = __popc(mm);
+      total += got;
+      j += got;
+      if (mm != 0xffffffffu) break;
+      if (total >= kLongRun) {
+        if (j < a.n && a.keys[j] == key) {
+          if (lane == 0) enqueue_long(a, start, j, key);
+          handed_off = 1;
+        }
+        break;
+      }
+    }
+  }
+  if (is_tail || (lane == 31 && cont && !handed_off)) apply_scalar(a, k, 0, g, pos - (cnt - 1));
+}
+
 struct HeadIn {
   const uint32_t* keys;
   uint32_t sentinel;
@@ -676,17 +753,18 @@ extern "C" size_t er_embedding_bwd_workspace_bytes(int64_t n_lookups_cap, int32_
   return er::bwd_ws_bytes(n_lookups_cap > 0 ? n_lookups_cap : 1, dim > 0 ? dim : 1);
 }
 
-extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int64_t n_rows,
-                                int32_t dim, int32_t row_stride, const int64_t* rows,
-                                const float* weights, const int32_t* seg_ids,
-                                const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
-                                const er_slot_t* slots, int32_t n_slots,
-                                const float* const* grad_bufs, int32_t n_bufs,
-                                const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
-                                float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
-                                er_stream_t stream) {
+static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_t n_rows,
+                              int32_t dim, int32_t row_stride, const int64_t* rows,
+                              const float* weights, const int32_t* seg_ids,
+                              const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                              const er_slot_t* slots, int32_t n_slots,
+                              const float* const* grad_bufs, int32_t n_bufs,
+                              const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
+                              float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
+                              const void* sorted_ws, size_t sorted_ws_bytes, int32_t sorted_dim,
+                              er_stream_t stream) {
   using namespace er;
-  ER_REQUIRE(rows && slots && grad_bufs && opt, "null argument");
+  ER_REQUIRE((rows || sorted_ws) && slots && grad_bufs && opt, "null argument");
   ER_REQUIRE(table || uniq_rows, "nothing to do: table and uniq_rows are both NULL");
   ER_REQUIRE((uniq_rows == nullptr) == (uniq_grads == nullptr) &&
                  (uniq_rows == nullptr) == (n_uniq == nullptr),
@@ -713,7 +791,17 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
   BwdWs w = bwd_carve(ws, n_lookups_cap, dim);
   // number of live lookups: row_ptr[n_seg] when CSR (device side), else the capacity
   const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
-  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, st);
+  if (sorted_ws) {
+    // the same lookups were sorted by an earlier call on this stream (a table with the same row plan)
+    if (sorted_ws_bytes < bwd_ws_bytes(n_lookups_cap, sorted_dim))
+      return fail(ER_ERR_WORKSPACE, "er_embedding_bwd_reuse_sort: source workspace too small");
+    const BwdWs src = bwd_carve(const_cast<void*>(sorted_ws), n_lookups_cap, sorted_dim);
+    w.keys = src.keys;
+    w.vals = src.vals;
+    cudaMemsetAsync(w.counters, 0, 2 * sizeof(int32_t), st);
+  } else {
+    rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, st);
+  }
 
   BwdArgs a;
   a.table = table;
@@ -772,12 +860,45 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
     }
   } else {
     const size_t smem = slot_smem_bytes(n_slots);
-    bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256, smem, st>>>(a);
+    if (dim == 1)
+      bwd_scan_d1_kernel<<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
+    else
+      bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256, smem, st>>>(a);
     bwd_long_scalar_kernel<<<4 * kSmCount, 256, smem, st>>>(a);
     count_launches(2);
   }
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
+}
+
+extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int64_t n_rows,
+                                int32_t dim, int32_t row_stride, const int64_t* rows,
+                                const float* weights, const int32_t* seg_ids,
+                                const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                                const er_slot_t* slots, int32_t n_slots,
+                                const float* const* grad_bufs, int32_t n_bufs,
+                                const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
+                                float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
+                                er_stream_t stream) {
+  return embedding_bwd_impl(table, state0, state1, n_rows, dim, row_stride, rows, weights, seg_ids, row_ptr,
+                            n_seg, n_lookups_cap, slots, n_slots, grad_bufs, n_bufs, seg_scale, opt,
+                            uniq_rows, uniq_grads, n_uniq, ws, ws_bytes, nullptr, 0, 0, stream);
+}
+
+extern "C" int er_embedding_bwd_reuse_sort(float* table, float* state0, float* state1, int64_t n_rows,
+                                           int32_t dim, int32_t row_stride, const float* weights,
+                                           const int32_t* seg_ids, const int32_t* row_ptr, int64_t n_seg,
+                                           int64_t n_lookups_cap, const er_slot_t* slots, int32_t n_slots,
+                                           const float* const* grad_bufs, int32_t n_bufs,
+                                           const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
+                                           float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
+                                           const void* sorted_ws, size_t sorted_ws_bytes,
+                                           int32_t sorted_dim, er_stream_t stream) {
+  if (!sorted_ws) return er::fail(ER_ERR_INVALID_ARG, "er_embedding_bwd_reuse_sort: sorted_ws is NULL");
+  return embedding_bwd_impl(table, state0, state1, n_rows, dim, row_stride, nullptr, weights, seg_ids,
+                            row_ptr, n_seg, n_lookups_cap, slots, n_slots, grad_bufs, n_bufs, seg_scale,
+                            opt, uniq_rows, uniq_grads, n_uniq, ws, ws_bytes, sorted_ws, sorted_ws_bytes,
+                            sorted_dim, stream);
 }
 
 namespace er {

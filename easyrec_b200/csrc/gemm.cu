@@ -1,0 +1,454 @@
+// Dense-layer GEMM of the interaction stage on the 5th-gen tensor cores (tcgen05 + TMEM), fp32 in /
+// fp32 out with "3xTF32" operand splitting so logits stay within the 1e-4 budget of an fp32 CPU run:
+//
+//     x = hi + lo,  hi = tf32-rounded x,  lo = x - hi  (exact in fp32)
+//     A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi      (three tcgen05.mma.kind::tf32 per k-step, fp32 accumulate)
+//
+// Replaces the library SGEMMs of layers/dnn.py:50-87 (tf.layers.dense forward) and of its gradient
+// (dX = dY.W^T, dW = X^T.dY) with one kernel that reads the operands *as they lie* in HBM:
+//   - an operand whose K index is contiguous (activations in forward/dX, W[in,out] in dX) is staged as a
+//     K-major SWIZZLE_128B tile: 128 rows (M or N) x 32 k
+//   - an operand whose M/N index is contiguous (W[in,out] in forward, X and dY in dW) is staged as an
+//     MN-major SWIZZLE_128B_BASE32B tile (the only MN-major form of 32-bit operands): 4 atoms x 32 k-rows
+//     x 32 elements
+//   both are "128 segments of 128 B", so the producer code and the shared-memory offsets are the same and
+//   no transposed copy of any matrix is ever made.
+//
+// CTA = 128x128 output tile (one k-slice of it under split-K): 8 producer warps (global -> registers ->
+// hi/lo split -> swizzled st.shared, 3-stage ring), 1 MMA warp (one lane issues tcgen05.mma, tcgen05.commit
+// frees the stage), accumulators 128 lanes x 2 x 128 columns of TMEM (main product / cross terms); the producer warps then become the
+// epilogue (tcgen05.ld -> optional bias -> global).  Split-K partials are reduced by a second kernel in a
+// fixed order, so results are run-to-run deterministic.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace er {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int kStages = 3;
+constexpr int kPrefetch = 3;      // k-blocks of global loads in flight per producer thread
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 32;
+constexpr int kTileBytes = 128 * 128;          // 128 segments x 128 B
+constexpr int kStageBytes = 4 * kTileBytes;    // A hi, A lo, B hi, B lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* align slack */ + 256 /* barriers */;
+constexpr uint32_t kTmemCols = 256;   // [0,128): hi.hi accumulator, [128,256): the two cross terms
+
+struct Args {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  float* partials;
+  long long lda, ldb, ldc;
+  int M, N, K;
+  int a_mn, b_mn;      // 1: the M (resp. N) index is the contiguous one in memory
+  int k_per_slice;     // multiple of BK
+  int n_slices;
+  int dbg;             // ER_GEMM_DEBUG timing experiments (results invalid when != 0)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor (tcgen05); segments are 128 B apart in both modes.
+//   K-major : SWIZZLE_128B (16 B chunk ^= row % 8), 8-row groups 1024 B apart (SBO), LBO unused.
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (32 B chunk ^= k-row % 4): atoms of
+//             4 k-rows x 32 elements, SBO = 512 B between k-atoms, LBO = 4096 B between M/N atoms.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int mn_major) {
+  const uint32_t lbo = mn_major ? 4096u : 16u, sbo = mn_major ? 512u : 1024u;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)(mn_major ? 1 : 2) << 61;     // SWIZZLE_128B_BASE32B : SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;  // round-to-nearest onto 10 mantissa bits
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
+// One operand's 128 B segment `seg` (0..127), 16 B chunk `c` (0..7) of the k-block starting at k0.
+//   mn_major == 0: segment = M/N row (mn0+seg), chunk = k0+4c .. +3
+//   mn_major == 1: segment = (atom j = seg/32, k-row k0 + seg%32), chunk = mn0 + 32j + 4c .. +3
+// The load is only ISSUED here (predicated, destination pre-zeroed); elements past the K / MN edge are
+// cleared by mask_chunk at consume time, so nothing touches the registers while the load is in flight.
+__device__ __forceinline__ int chunk_nvalid(int mn_major, int mn0, int mn_end, int k0, int k_end, int seg, int c) {
+  return mn_major ? mn_end - (mn0 + 32 * (seg >> 5) + 4 * c) : k_end - (k0 + 4 * c);
+}
+__device__ __forceinline__ float4 load_chunk(const float* __restrict__ P, long long ld, int mn_major,
+                                             int mn0, int mn_end, int k0, int k_end, int seg, int c) {
+  int row, col, row_end;
+  if (!mn_major) {
+    row = mn0 + seg; row_end = mn_end; col = k0 + 4 * c;
+  } else {
+    row = k0 + (seg & 31); row_end = k_end; col = mn0 + 32 * (seg >> 5) + 4 * c;
+  }
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < row_end && chunk_nvalid(mn_major, mn0, mn_end, k0, k_end, seg, c) > 0)
+    v = __ldg(reinterpret_cast<const float4*>(P + (long long)row * ld + col));   // pitch % 4 == 0: in bounds
+  return v;
+}
+__device__ __forceinline__ float4 mask_chunk(float4 v, int nvalid) {
+  if (nvalid < 4) {
+    if (nvalid < 1) v.x = 0.f;
+    if (nvalid < 2) v.y = 0.f;
+    if (nvalid < 3) v.z = 0.f;
+    v.w = 0.f;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1024 B aligned
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barriers: full[s] at +8s, empty[s] at +8(kStages+s), accum at +8*2*kStages, tmem ptr after
+  const uint32_t accum_bar = bar_base + 8 * 2 * kStages;
+  const uint32_t tmem_slot = accum_bar + 8;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int k_begin = blockIdx.z * a.k_per_slice;
+  const int k_end = min(a.K, k_begin + a.k_per_slice);
+  const int n_kb = (k_end - k_begin + BK - 1) / BK;
+  // MMA N: the live columns of this tile rounded up to the instruction granularity
+  const int n_eff = min(BN, ((a.N - n0 + 15) >> 4) << 4);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_base + 8 * s, kProducerThreads / 32);
+      mbar_init(bar_base + 8 * (kStages + s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerThreads / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp < kProducerThreads / 32) {
+    // ===== producers: HBM/L2 -> registers -> hi/lo -> swizzled smem =====
+    const int c = tid & 7, srow = tid >> 3;   // 32 segment rows x 8 chunks per pass, 4 passes
+    const uint32_t off_k = (uint32_t)srow * 128u + (uint32_t)((c ^ (srow & 7)) << 4);
+    const uint32_t off_mn = (uint32_t)srow * 128u + (uint32_t)((c ^ ((srow & 3) << 1)) << 4);
+    const uint32_t off_a = a.a_mn ? off_mn : off_k, off_b = a.b_mn ? off_mn : off_k;
+    // kPrefetch k-blocks of global loads stay in flight per thread (register ring) so the ~1 us HBM/L2
+    // latency is paid once per tile, not once per k-block.
+    float4 va[kPrefetch][4], vb[kPrefetch][4];
+    auto issue = [&](int kb, float4 (&xa)[4], float4 (&xb)[4]) {
+      const int k0 = k_begin + kb * BK;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        xa[j] = (a.dbg & 2) ? make_float4(1.f, 1.f, 1.f, 1.f) : load_chunk(a.A, a.lda, a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // segments wholly outside the MMA's N range are never read by the tensor core
+        const bool live = a.b_mn ? (32 * j < n_eff) : (32 * j + srow < n_eff);
+        xb[j] = (live && !(a.dbg & 2)) ? load_chunk(a.B, a.ldb, a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto stage_out = [&](int kb, const float4 (&xa)[4], const float4 (&xb)[4]) {
+      const int s = kb % kStages;
+      const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+      mbar_wait(bar_base + 8 * (kStages + s), ph ^ 1u);   // stage free (first lap passes at once)
+      const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a.dbg & 4) break;
+        const int k0 = k_begin + kb * BK;
+        const float4 xaj = mask_chunk(xa[j], chunk_nvalid(a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c));
+        const float4 xbj = mask_chunk(xb[j], chunk_nvalid(a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c));
+        float4 hi, lo;
+        split_tf32(xaj.x, hi.x, lo.x); split_tf32(xaj.y, hi.y, lo.y);
+        split_tf32(xaj.z, hi.z, lo.z); split_tf32(xaj.w, hi.w, lo.w);
+        const uint32_t o = st + off_a + (uint32_t)j * 4096u;
+        const uint32_t ob = st + off_b + (uint32_t)j * 4096u;
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(o + kTileBytes), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        split_tf32(xbj.x, hi.x, lo.x); split_tf32(xbj.y, hi.y, lo.y);
+        split_tf32(xbj.z, hi.z, lo.z); split_tf32(xbj.w, hi.w, lo.w);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ob + 2 * kTileBytes), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ob + 3 * kTileBytes), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * s);                   // one arrival per producer warp
+    };
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+      if (u < n_kb) issue(u, va[u], vb[u]);
+    for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
+#pragma unroll
+      for (int u = 0; u < kPrefetch; ++u) {
+        const int kb = kb0 + u;
+        if (kb < n_kb) {
+          stage_out(kb, va[u], vb[u]);
+          if (kb + kPrefetch < n_kb) issue(kb + kPrefetch, va[u], vb[u]);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer (one thread) =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a.a_mn << 15) |
+                           ((uint32_t)a.b_mn << 16) | ((uint32_t)(n_eff >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_kstep = a.a_mn ? 1024u : 32u, b_kstep = a.b_mn ? 1024u : 32u;   // 8 k per MMA
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+      mbar_wait(bar_base + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
+#pragma unroll
+      for (int kk = 0; kk < BK / 8; ++kk) {
+        if (a.dbg & 1) break;
+        const uint64_t ahi = make_desc(st + kk * a_kstep, a.a_mn);
+        const uint64_t alo = make_desc(st + kTileBytes + kk * a_kstep, a.a_mn);
+        const uint64_t bhi = make_desc(st + 2 * kTileBytes + kk * b_kstep, a.b_mn);
+        const uint64_t blo = make_desc(st + 3 * kTileBytes + kk * b_kstep, a.b_mn);
+        // The tensor core truncates (not rounds) the fp32 accumulator on every accumulate, a bias of
+        // ~2^-25 of the accumulator per MMA.  The small cross terms go to their own accumulator, so the
+        // main sum sees one accumulate per 8 k instead of three (measured: error 3e-6 -> ~1e-6, the level
+        // of an fp32 SGEMM).
+        umma_tf32(tmem_d + BN, alo, bhi, idesc, (kb | kk) != 0);
+        umma_tf32(tmem_d + BN, ahi, blo, idesc, 1u);
+        umma_tf32(tmem_d, ahi, bhi, idesc, (kb | kk) != 0);
+      }
+      umma_commit(bar_base + 8 * (kStages + s));   // stage reusable once these MMAs have read it
+    }
+    umma_commit(accum_bar);
+  }
+
+  if (warp < kProducerThreads / 32) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(accum_bar, 0u);
+    tc_fence_after();
+    const int q = warp & 3, h = warp >> 2;            // TMEM lane quarter (fixed by warp id % 4), column half
+    float* out = a.n_slices > 1 ? a.partials + (long long)blockIdx.z * a.M * a.N : a.C;
+    const long long ldo = a.n_slices > 1 ? (long long)a.N : a.ldc;
+    const bool vec_ok = (ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int col0 = h * 64 + cb * 32;
+      if (col0 >= n_eff) break;                        // warp-uniform
+      uint32_t r[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+            "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+            "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+            "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      {
+        uint32_t r2[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]),
+              "=r"(r2[7]), "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]),
+              "=r"(r2[14]), "=r"(r2[15]), "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]),
+              "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]), "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]),
+              "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
+            : "r"(taddr + (uint32_t)BN)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
+      // A thread owns one row x 32 columns; stores straight from here would put 32 different rows in every
+      // warp store.  Transpose through this warp's 4 KB of the (now idle) stage-0 buffer - 16 B units,
+      // unit ^= row % 8, conflict-free both ways - so each warp store covers 4 rows x 128 contiguous bytes.
+      const uint32_t wbuf = smem_base + (uint32_t)warp * 4096u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t o = wbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(o), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                     "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                     : "memory");
+      }
+      __syncwarp();
+      const bool add_bias = a.bias != nullptr && a.n_slices == 1;
+      const int u = lane & 7;                          // 16 B unit of the 128 B row segment
+      const int col = n0 + col0 + 4 * u;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_bias) {
+        if (col < a.N) bv.x = a.bias[col];
+        if (col + 1 < a.N) bv.y = a.bias[col + 1];
+        if (col + 2 < a.N) bv.z = a.bias[col + 2];
+        if (col + 3 < a.N) bv.w = a.bias[col + 3];
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);           // row of this warp's 32
+        const uint32_t o = wbuf + (uint32_t)rr * 128u + (uint32_t)((u ^ (rr & 7)) << 4);
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(o));
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        const int grow = m0 + 32 * q + rr;
+        if (grow < a.M) {
+          float* orow = out + (long long)grow * ldo;
+          if (vec_ok && col + 3 < a.N) {
+            *reinterpret_cast<float4*>(orow + col) = v;
+          } else {
+            if (col < a.N) orow[col] = v.x;
+            if (col + 1 < a.N) orow[col + 1] = v.y;
+            if (col + 2 < a.N) orow[col + 2] = v.z;
+            if (col + 3 < a.N) orow[col + 3] = v.w;
+          }
+        }
+      }
+      __syncwarp();                                    // wbuf is reused by the next 32-column block
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerThreads / 32) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// C[m,n] = sum_s partials[s][m][n] (+ bias[n]), fixed order.
+__global__ void splitk_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ bias,
+                                     float* __restrict__ C, long long ldc, int M, int N, int n_slices) {
+  const long long total = (long long)M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i % N);
+    float acc = partials[i];
+    for (int s = 1; s < n_slices; ++s) acc += partials[(long long)s * total + i];
+    if (bias) acc += bias[n];
+    C[(long long)m * ldc + n] = acc;
+  }
+}
+
+// Split K when the output has too few tiles to occupy the 148 SMs (the dW GEMMs: K = batch).
+static void plan(int64_t M, int64_t N, int64_t K, int* n_slices, int* k_per_slice) {
+  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int64_t kblocks = ceil_div(K, BK);
+  int64_t s = 1;
+  if (tiles * 2 <= kSmCount && kblocks >= 16) {
+    s = kSmCount / tiles;
+    s = std::min<int64_t>(s, kblocks / 8);   // at least 8 k-blocks (256 k) per slice
+    s = std::max<int64_t>(s, 1);
+  }
+  const int64_t per = ceil_div(kblocks, s);
+  *k_per_slice = (int)(per * BK);
+  *n_slices = (int)ceil_div(kblocks, per);
+}
+
+}  // namespace gemm
+}  // namespace er
+
+extern "C" size_t er_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  int s, kp;
+  er::gemm::plan(M, N, K, &s, &kp);
+  return s > 1 ? (size_t)s * (size_t)M * (size_t)N * sizeof(float) : 0;
+}
+
+extern "C" int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+                       int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
+                       int64_t K, void* ws, size_t ws_bytes, er_stream_t stream) {
+  using namespace er::gemm;
+  ER_REQUIRE(A && B && C, "null operand");
+  ER_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "bad shape");
+  ER_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "operand pitch must be a multiple of 4 floats");
+  ER_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             "operands must be 16-byte aligned");
+  ER_REQUIRE(lda >= (a_mn_major ? M : K) - 3 && ldb >= (b_mn_major ? N : K) - 3, "pitch smaller than row");
+  ER_REQUIRE(ldc >= N, "ldc < N");
+  Args a;
+  a.A = A; a.B = B; a.C = C; a.bias = bias;
+  a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+  a.M = (int)M; a.N = (int)N; a.K = (int)K;
+  a.a_mn = a_mn_major ? 1 : 0; a.b_mn = b_mn_major ? 1 : 0;
+  plan(M, N, K, &a.n_slices, &a.k_per_slice);
+  {
+    const char* e = getenv("ER_GEMM_DEBUG");
+    a.dbg = e ? atoi(e) : 0;
+  }
+  a.partials = nullptr;
+  if (a.n_slices > 1) {
+    ER_REQUIRE(ws && ws_bytes >= er_gemm_workspace_bytes(M, N, K), "workspace too small");
+    a.partials = static_cast<float*>(ws);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBytes);
+    if (e != cudaSuccess) return er::fail(ER_ERR_CUDA, std::string("er_gemm: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaStream_t st = er::as_stream(stream);
+  dim3 grid((unsigned)er::ceil_div(N, BN), (unsigned)er::ceil_div(M, BM), (unsigned)a.n_slices);
+  gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+  int launches = 1;
+  if (a.n_slices > 1) {
+    const long long total = (long long)M * N;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 4LL * er::kSmCount);
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(a.partials, bias, C, ldc, (int)M, (int)N, a.n_slices);
+    ++launches;
+  }
+  er::count_launches(launches);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}

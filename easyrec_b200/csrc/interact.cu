@@ -3,6 +3,8 @@
 //   loss: builders/loss_builder.py:36-39 tf.losses.sigmoid_cross_entropy
 // Elementwise / small-reduction kernels: HBM- (in practice L2-) bound streaming
 // reads of the [B, F*D] group matrix that K2 just wrote.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace er {
@@ -84,13 +86,14 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// one CTA-wide reduction of the loss; per-sample probs and dL/dlogit
-__global__ void __launch_bounds__(256)
+// one CTA-wide reduction of the loss (1024 threads; fixed shuffle + shared-memory tree: deterministic);
+// per-sample probs and dL/dlogit
+__global__ void __launch_bounds__(1024)
     sigmoid_ce_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                       const float* __restrict__ weights, int64_t batch, float inv_count,
                       float* __restrict__ loss_out, float* __restrict__ probs,
                       float* __restrict__ g_logits) {
-  __shared__ float s_red[256];
+  __shared__ float s_red[32];
   float acc = 0.f;
   for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) {
     const float x = logits[b], z = labels[b];
@@ -102,13 +105,14 @@ __global__ void __launch_bounds__(256)
     if (probs) probs[b] = p;
     if (g_logits) g_logits[b] = w * (p - z) * inv_count;
   }
-  s_red[threadIdx.x] = acc;
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  for (int s = 128; s >= 1; s >>= 1) {
-    if ((int)threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
-    __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = s_red[threadIdx.x];
+    for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0 && loss_out) *loss_out = t * inv_count;
   }
-  if (threadIdx.x == 0 && loss_out) *loss_out = s_red[0] * inv_count;
 }
 
 __global__ void __launch_bounds__(256)
@@ -120,6 +124,144 @@ __global__ void __launch_bounds__(256)
     const int64_t r = rows[i];
     if (r >= 0 && r < n_rows) touched[r] = value;
   }
+}
+
+// ---- FM block, one warp per sample row --------------------------------------------------------
+// The [F*D] row is read once, coalesced (lane + 32 j float4s), and stays in registers.  32 % (D/4) == 0,
+// so every float4 a lane holds belongs to the same 4-column chunk (lane % (D/4)) and the per-chunk
+// field sums are an xor-shuffle tree over the lanes of equal residue (fixed order: deterministic).
+//   fwd: y = 0.5((sum_f x)^2 - sum_f x^2);  sumsq = sum_{b,f,d} x^2 (the embedding-regulariser term of
+//        layers/input_layer.py:369-375, free here because FM needs sum_f x^2 anyway)
+//   bwd: gx = g_pass + gy*(S - x) + coef*x   -- the three gradients that reach the group matrix (deep
+//        tower input, FM, regulariser) in ONE pass instead of three kernels + two autograd adds.
+template <int J>
+__device__ __forceinline__ void fm_row_load(const float4* __restrict__ row, int n4, int lane, float4 (&v)[J]) {
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = i < n4 ? row[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ float4 f4_xor_add(float4 v, int o) {
+  v.x = __fadd_rn(v.x, __shfl_xor_sync(0xffffffffu, v.x, o));
+  v.y = __fadd_rn(v.y, __shfl_xor_sync(0xffffffffu, v.y, o));
+  v.z = __fadd_rn(v.z, __shfl_xor_sync(0xffffffffu, v.z, o));
+  v.w = __fadd_rn(v.w, __shfl_xor_sync(0xffffffffu, v.w, o));
+  return v;
+}
+
+template <int J>
+__global__ void __launch_bounds__(256)
+    fm_block_fwd_kernel(const float* __restrict__ x, int64_t batch, int n_field, int dim, int x_stride,
+                        float* __restrict__ y, float* __restrict__ partials, unsigned int* counter,
+                        float* __restrict__ sumsq_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = dim >> 2, n4 = n_field * d4;
+  __shared__ float s_w[8];
+  __shared__ int s_last;
+  float warp_sq = 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < batch; b += (int64_t)gridDim.x * 8) {
+    float4 v[J];
+    fm_row_load<J>(reinterpret_cast<const float4*>(x + b * x_stride), n4, lane, v);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      s.x = __fadd_rn(s.x, v[j].x); s.y = __fadd_rn(s.y, v[j].y);
+      s.z = __fadd_rn(s.z, v[j].z); s.w = __fadd_rn(s.w, v[j].w);
+      q.x = __fadd_rn(q.x, __fmul_rn(v[j].x, v[j].x)); q.y = __fadd_rn(q.y, __fmul_rn(v[j].y, v[j].y));
+      q.z = __fadd_rn(q.z, __fmul_rn(v[j].z, v[j].z)); q.w = __fadd_rn(q.w, __fmul_rn(v[j].w, v[j].w));
+    }
+    for (int o = 16; o >= d4; o >>= 1) {
+      s = f4_xor_add(s, o);
+      q = f4_xor_add(q, o);
+    }
+    if (lane < d4) {
+      float4 o4;
+      o4.x = __fmul_rn(0.5f, __fsub_rn(__fmul_rn(s.x, s.x), q.x));
+      o4.y = __fmul_rn(0.5f, __fsub_rn(__fmul_rn(s.y, s.y), q.y));
+      o4.z = __fmul_rn(0.5f, __fsub_rn(__fmul_rn(s.z, s.z), q.z));
+      o4.w = __fmul_rn(0.5f, __fsub_rn(__fmul_rn(s.w, s.w), q.w));
+      reinterpret_cast<float4*>(y + b * dim)[lane] = o4;
+    }
+    if (partials) {
+      float t = (lane < d4) ? __fadd_rn(__fadd_rn(q.x, q.y), __fadd_rn(q.z, q.w)) : 0.f;
+      for (int o = 16; o >= 1; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+      warp_sq = __fadd_rn(warp_sq, t);
+    }
+  }
+  if (!partials) return;
+  if (lane == 0) s_w[warp] = warp_sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t = __fadd_rn(t, s_w[w]);
+    __stcg(partials + blockIdx.x, t);
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {   // last CTA: fixed-order sum of the CTA partials; leaves the counter at 0 for the next call
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t = __fadd_rn(t, __ldcg(partials + i));
+    for (int o = 16; o >= 1; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+    __syncthreads();
+    if (lane == 0) s_w[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot = __fadd_rn(tot, s_w[w]);
+      *sumsq_out = tot;
+      *counter = 0u;
+    }
+  }
+}
+
+template <int J>
+__global__ void __launch_bounds__(256)
+    fm_block_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                        const float* __restrict__ g_pass, const float* __restrict__ coef_dev, float coef_mul,
+                        int64_t batch, int n_field, int dim, int x_stride, int gp_stride,
+                        float* __restrict__ gx, int gx_stride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d4 = dim >> 2, n4 = n_field * d4;
+  const float coef = coef_dev ? __fmul_rn(*coef_dev, coef_mul) : 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < batch; b += (int64_t)gridDim.x * 8) {
+    float4 v[J], gp[J];
+    fm_row_load<J>(reinterpret_cast<const float4*>(x + b * x_stride), n4, lane, v);
+    if (g_pass) fm_row_load<J>(reinterpret_cast<const float4*>(g_pass + b * gp_stride), n4, lane, gp);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy) g = reinterpret_cast<const float4*>(gy + b * dim)[lane % d4];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      s.x = __fadd_rn(s.x, v[j].x); s.y = __fadd_rn(s.y, v[j].y);
+      s.z = __fadd_rn(s.z, v[j].z); s.w = __fadd_rn(s.w, v[j].w);
+    }
+    for (int o = 16; o >= d4; o >>= 1) s = f4_xor_add(s, o);
+    float4* orow = reinterpret_cast<float4*>(gx + b * gx_stride);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int i = lane + 32 * j;
+      if (i < n4) {
+        float4 r;
+        r.x = __fadd_rn(__fmul_rn(g.x, __fsub_rn(s.x, v[j].x)), __fmul_rn(coef, v[j].x));
+        r.y = __fadd_rn(__fmul_rn(g.y, __fsub_rn(s.y, v[j].y)), __fmul_rn(coef, v[j].y));
+        r.z = __fadd_rn(__fmul_rn(g.z, __fsub_rn(s.z, v[j].z)), __fmul_rn(coef, v[j].z));
+        r.w = __fadd_rn(__fmul_rn(g.w, __fsub_rn(s.w, v[j].w)), __fmul_rn(coef, v[j].w));
+        if (g_pass) {
+          r.x = __fadd_rn(r.x, gp[j].x); r.y = __fadd_rn(r.y, gp[j].y);
+          r.z = __fadd_rn(r.z, gp[j].z); r.w = __fadd_rn(r.w, gp[j].w);
+        }
+        orow[i] = r;
+      }
+    }
+  }
+}
+
+static bool fm_block_shape_ok(int n_field, int dim) {
+  const int d4 = dim / 4;
+  return dim % 4 == 0 && d4 >= 1 && d4 <= 32 && (d4 & (d4 - 1)) == 0 && (int64_t)n_field * d4 <= 32 * 8;
 }
 
 }  // namespace er
@@ -172,7 +314,7 @@ extern "C" int er_sigmoid_ce_fwd_bwd(const float* logits, const float* labels,
   using namespace er;
   ER_REQUIRE(logits && labels, "null argument");
   ER_REQUIRE(batch > 0, "batch must be positive");
-  sigmoid_ce_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, labels, weights, batch, inv_count,
+  sigmoid_ce_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, labels, weights, batch, inv_count,
                                                       loss_out, probs, g_logits);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
@@ -187,6 +329,71 @@ extern "C" int er_mark_rows(const int64_t* rows, int64_t n_lookups_cap, const in
   if (n_lookups_cap <= 0) return ER_OK;
   mark_rows_kernel<<<grid_for(n_lookups_cap, 256, 8), 256, 0, as_stream(stream)>>>(
       rows, n_lookups_cap, n_dev, n_rows, touched, (uint8_t)value);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" size_t er_fm_block_workspace_bytes(int64_t batch) {
+  (void)batch;
+  return 16 + sizeof(float) * 4 * er::kSmCount * 2;
+}
+
+// ws must be zero-filled once by the caller (the kernel leaves its counter at zero).
+extern "C" int er_fm_block_fwd(const float* x, int64_t batch, int32_t n_field, int32_t dim,
+                               int32_t x_stride, float* y, float* sumsq_out, void* ws, size_t ws_bytes,
+                               er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && y, "null argument");
+  ER_REQUIRE(batch > 0 && n_field > 0 && x_stride >= n_field * dim, "bad shape");
+  ER_REQUIRE(fm_block_shape_ok(n_field, dim), "dim must be 4*2^k (<= 128) and n_field*dim <= 1024");
+  ER_REQUIRE(x_stride % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(y) % 16 == 0, "x / y must be 16-byte aligned rows");
+  const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), 4 * kSmCount);
+  float* partials = nullptr;
+  unsigned int* counter = nullptr;
+  if (sumsq_out) {
+    ER_REQUIRE(ws && ws_bytes >= er_fm_block_workspace_bytes(batch), "workspace too small");
+    counter = reinterpret_cast<unsigned int*>(ws);
+    partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 16);
+  }
+  const int J = (int)ceil_div((int64_t)n_field * (dim / 4), 32);
+  cudaStream_t st = as_stream(stream);
+#define ER_FM_FWD(JJ) fm_block_fwd_kernel<JJ><<<grid, 256, 0, st>>>(x, batch, n_field, dim, x_stride, y, partials, counter, sumsq_out)
+  switch (J) {
+    case 1: ER_FM_FWD(1); break; case 2: ER_FM_FWD(2); break; case 3: ER_FM_FWD(3); break;
+    case 4: ER_FM_FWD(4); break; case 5: ER_FM_FWD(5); break; case 6: ER_FM_FWD(6); break;
+    case 7: ER_FM_FWD(7); break; default: ER_FM_FWD(8); break;
+  }
+#undef ER_FM_FWD
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_fm_block_bwd(const float* x, const float* gy, const float* g_pass,
+                               const float* coef_dev, float coef_mul, int64_t batch, int32_t n_field,
+                               int32_t dim, int32_t x_stride, int32_t g_pass_stride, float* gx,
+                               int32_t gx_stride, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && gx, "null argument");
+  ER_REQUIRE(batch > 0 && n_field > 0 && x_stride >= n_field * dim && gx_stride >= n_field * dim, "bad shape");
+  ER_REQUIRE(!g_pass || g_pass_stride >= n_field * dim, "bad g_pass stride");
+  ER_REQUIRE(fm_block_shape_ok(n_field, dim), "dim must be 4*2^k (<= 128) and n_field*dim <= 1024");
+  ER_REQUIRE(x_stride % 4 == 0 && gx_stride % 4 == 0 && (!g_pass || g_pass_stride % 4 == 0) &&
+                 reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(gx) % 16 == 0 &&
+                 (!g_pass || reinterpret_cast<uintptr_t>(g_pass) % 16 == 0) &&
+                 (!gy || reinterpret_cast<uintptr_t>(gy) % 16 == 0), "operands must be 16-byte aligned rows");
+  const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), 8 * kSmCount);
+  const int J = (int)ceil_div((int64_t)n_field * (dim / 4), 32);
+  cudaStream_t st = as_stream(stream);
+#define ER_FM_BWD(JJ) fm_block_bwd_kernel<JJ><<<grid, 256, 0, st>>>(x, gy, g_pass, coef_dev, coef_mul, batch, n_field, dim, x_stride, g_pass_stride, gx, gx_stride)
+  switch (J) {
+    case 1: ER_FM_BWD(1); break; case 2: ER_FM_BWD(2); break; case 3: ER_FM_BWD(3); break;
+    case 4: ER_FM_BWD(4); break; case 5: ER_FM_BWD(5); break; case 6: ER_FM_BWD(6); break;
+    case 7: ER_FM_BWD(7); break; default: ER_FM_BWD(8); break;
+  }
+#undef ER_FM_BWD
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;

@@ -172,7 +172,7 @@ def fused_lookup(call, rows, weights=None, row_ptr=None, outs=None):
   return outs
 
 
-def fused_backward_update(call, rows, outs, opt, weights=None, row_ptr=None, seg_ids=None):
+def fused_backward_update(call, rows, outs, opt, weights=None, row_ptr=None, seg_ids=None, sorted_from=None):
   """K7: dedup + segment-sum + optimizer row update from the leaves' gradients.  Runs on the
   caller's thread and stream (not inside the autograd engine), so it is CUDA-graph capturable."""
   a = call.arena
@@ -184,7 +184,7 @@ def fused_backward_update(call, rows, outs, opt, weights=None, row_ptr=None, seg
     gbufs.append(g.contiguous())
   K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, rows, call.slots_dev, call.n_slots,
                   call.n_seg, gbufs, opt, call.ws, weights=weights, seg_ids=seg_ids,
-                  row_ptr=row_ptr, seg_scale=call.seg_scale)
+                  row_ptr=row_ptr, seg_scale=call.seg_scale, sorted_from=sorted_from)
 
 
 class _FM(torch.autograd.Function):
@@ -208,6 +208,33 @@ class _FM(torch.autograd.Function):
 
 def fm(x, n_field, dim):
   return _FM.apply(x, n_field, dim)
+
+
+class _FMBlock(torch.autograd.Function):
+  """DeepFM's three consumers of the deep group matrix behind one autograd node: FM (layers/fm.py:20-26),
+  the deep tower input (returned as a pass-through view) and the embedding regulariser's sum of squares
+  (layers/input_layer.py:369-375).  Backward merges the three incoming gradients in one kernel pass, so the
+  group matrix (an autograd leaf) receives a single gradient and autograd never runs an accumulation add."""
+
+  @staticmethod
+  def forward(ctx, x, n_field, dim):
+    ctx.n_field, ctx.dim = n_field, dim
+    y, sumsq = K.fm_block_fwd(x, n_field, dim, want_sumsq=True)
+    ctx.save_for_backward(x)
+    return y, x.view_as(x), sumsq
+
+  @staticmethod
+  def backward(ctx, gy, g_pass, g_sumsq):
+    (x,) = ctx.saved_tensors
+    # d(sumsq)/dx = 2x; g_sumsq stays on the device (no host sync: CUDA-graph capturable)
+    gx = K.fm_block_bwd(x, None if gy is None else gy.contiguous(), g_pass,
+                        None if g_sumsq is None else g_sumsq.contiguous(), 2.0, ctx.n_field, ctx.dim)
+    return gx, None, None
+
+
+def fm_block(x, n_field, dim):
+  """returns (fm [B, dim], x pass-through, sum(x^2) [1])."""
+  return _FMBlock.apply(x, n_field, dim)
 
 
 class _SigmoidCE(torch.autograd.Function):

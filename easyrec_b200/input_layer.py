@@ -304,8 +304,15 @@ class InputLayer(object):
     """After loss.backward(): K7 for every arena looked up since the last call (dedup, segment
     sum and the fused optimizer row update).  The reference's counterpart is
     opt.apply_gradients on the tables' IndexedSlices (compat/optimizers.py:413-416)."""
+    sorted_by = {}   # id(rows tensor) -> (workspace, dim, n_rows) of the call that sorted it
     for m, rows, w, outs, seg_ids in self._pending:
-      E.fused_backward_update(m, rows, outs, self.opt_holder['opt'], weights=w, seg_ids=seg_ids)
+      # arenas with the same row plan (DeepFM / Wide&Deep: the wide dim-1 and the deep tables) look up the
+      # same rows tensor: the second K7 reuses the first one's radix sort.
+      hit = sorted_by.get(id(rows))
+      src = (hit[0], hit[1]) if hit is not None and hit[2] == m.arena.n_rows else None
+      E.fused_backward_update(m, rows, outs, self.opt_holder['opt'], weights=w, seg_ids=seg_ids, sorted_from=src)
+      if hit is None:
+        sorted_by[id(rows)] = (m.ws, m.arena.dim, m.arena.n_rows)
     self._pending = []
 
   def normalize_dense(self, dense):

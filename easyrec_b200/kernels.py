@@ -129,7 +129,9 @@ def make_opt(kind, lr, beta1=0.9, beta2=0.999, eps=1e-8, beta1_power=0.9, beta2_
 
 def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt,
                   ws, weights=None, seg_ids=None, row_ptr=None, seg_scale=None, row_stride=None,
-                  uniq_rows=None, uniq_grads=None, n_uniq=None, n_rows=None):
+                  uniq_rows=None, uniq_grads=None, n_uniq=None, n_rows=None, sorted_from=None):
+  """sorted_from = (ws, dim) of an earlier embedding_bwd on this stream over the SAME rows tensor and a
+  table with the same n_rows: its radix sort is reused (er_embedding_bwd_reuse_sort)."""
   lib = _lib.load()
   row_stride = dim
   if table is not None:
@@ -148,6 +150,16 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
   _chk(n_uniq, torch.int32, 'n_uniq')
   for i, b in enumerate(grad_bufs):
     _chk(b, torch.float32, 'grad_bufs[%d]' % i)
+  if sorted_from is not None:
+    src_ws, src_dim = sorted_from
+    _lib.check(
+        lib.er_embedding_bwd_reuse_sort(_p(table), _p(state0), _p(state1), n_rows, dim, row_stride,
+                                        _p(weights), _p(seg_ids), _p(row_ptr), n_seg, rows.numel(),
+                                        _p(slots_dev), n_slots, _buf_array(grad_bufs), len(grad_bufs),
+                                        _p(seg_scale), ctypes.byref(opt), _p(uniq_rows), _p(uniq_grads),
+                                        _p(n_uniq), _p(ws), ws.numel(), _p(src_ws), src_ws.numel(), src_dim,
+                                        _stream()), 'er_embedding_bwd_reuse_sort')
+    return
   _lib.check(
       lib.er_embedding_bwd(_p(table), _p(state0), _p(state1), n_rows, dim, row_stride, _p(rows),
                            _p(weights), _p(seg_ids), _p(row_ptr), n_seg, rows.numel(),
@@ -219,6 +231,46 @@ def fm_bwd(x, gy, n_field, dim, gx=None, accumulate=False):
   return gx
 
 
+def fm_block_ok(n_field, dim):
+  d4 = dim // 4
+  return dim % 4 == 0 and 1 <= d4 <= 32 and (d4 & (d4 - 1)) == 0 and n_field * d4 <= 256
+
+
+_fm_ws = {}
+
+
+def fm_block_fwd(x, n_field, dim, want_sumsq=True):
+  """(y [B, dim], sumsq [1] or None): FM second order and sum(x^2) in one pass over the group matrix."""
+  lib = _lib.load()
+  if x.dtype != torch.float32 or x.stride(1) != 1:
+    raise _lib.ErError('x must be float32 with unit column stride')
+  batch = x.shape[0]
+  y = torch.empty(batch, dim, dtype=torch.float32, device=x.device)
+  sumsq = ws = None
+  if want_sumsq:
+    sumsq = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = _fm_ws.get(x.device)
+    if ws is None:
+      ws = torch.zeros(lib.er_fm_block_workspace_bytes(batch), dtype=torch.uint8, device=x.device)
+      _fm_ws[x.device] = ws
+  _lib.check(lib.er_fm_block_fwd(_p(x), batch, n_field, dim, x.stride(0), _p(y), _p(sumsq), _p(ws),
+                                 0 if ws is None else ws.numel(), _stream()), 'er_fm_block_fwd')
+  return y, sumsq
+
+
+def fm_block_bwd(x, gy, g_pass, coef_dev, coef_mul, n_field, dim):
+  """gx [B, F*dim] = g_pass + gy*(S - x) + coef*x (any of the three sources may be None)."""
+  lib = _lib.load()
+  batch = x.shape[0]
+  gx = torch.empty(batch, n_field * dim, dtype=torch.float32, device=x.device)
+  if g_pass is not None and g_pass.stride(1) != 1:
+    g_pass = g_pass.contiguous()
+  _lib.check(lib.er_fm_block_bwd(_p(x), _p(gy), _p(g_pass), _p(coef_dev), coef_mul, batch, n_field, dim,
+                                 x.stride(0), 0 if g_pass is None else g_pass.stride(0), _p(gx), gx.stride(0),
+                                 _stream()), 'er_fm_block_bwd')
+  return gx
+
+
 def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
   """returns (loss [1], probs [B], g_logits [B])."""
   lib = _lib.load()
@@ -234,6 +286,68 @@ def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
       lib.er_sigmoid_ce_fwd_bwd(_p(logits), _p(labels), _p(weights), batch, inv_count, _p(loss),
                                 _p(probs), _p(g), _stream()), 'er_sigmoid_ce_fwd_bwd')
   return loss, probs, g
+
+
+def _gemm_operand(t, name):
+  """2-D fp32 tensor -> (tensor, pitch, contiguous_index) with contiguous_index 1 if dim 1 is the unit-stride one.
+  Copies only when the view cannot be read in place (pitch not a multiple of 4 floats / misaligned)."""
+  if t.dtype != torch.float32 or t.dim() != 2:
+    raise _lib.ErError('%s must be a 2-D float32 tensor' % name)
+  for _ in range(2):
+    if t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0:
+      return t, t.stride(0), 1
+    if t.stride(0) == 1 and t.stride(1) % 4 == 0 and t.stride(1) >= t.shape[0] and t.data_ptr() % 16 == 0:
+      return t, t.stride(1), 0
+    if t.shape[1] % 4:   # pad the pitch: [r, c] -> view of [r, ceil4(c)]
+      buf = torch.zeros(t.shape[0], (t.shape[1] + 3) // 4 * 4, dtype=torch.float32, device=t.device)
+      buf[:, :t.shape[1]].copy_(t)
+      t = buf[:, :t.shape[1]]
+    else:
+      t = t.contiguous() if not t.is_contiguous() else t.clone()   # clone: a 16-byte aligned allocation
+  raise ValueError('%s: cannot be laid out for er_gemm' % name)
+
+
+def gemm_ready(t):
+  """A tensor er_gemm can read in place (and its transpose too): identity for 16-byte aligned rows with a
+  pitch that is a multiple of 4 floats, else one padded copy.  Layers call it once in forward and save the
+  result, so forward, dX and dW all read the same buffer."""
+  return _gemm_operand(t, 'x')[0]
+
+
+_gemm_ws = {}
+
+
+def gemm(a, b, bias=None, out=None):
+  """out[M,N] = a[M,K] @ b[K,N] (+ bias) on the tensor cores (3xTF32).  a / b may be transposed views."""
+  lib = _lib.load()
+  M, Ka = a.shape
+  Kb, N = b.shape
+  assert Ka == Kb, (a.shape, b.shape)
+  if N < 8 or Ka < 8 or M < 8:
+    # vector-sized problems (the [64 -> 1] logit head): library GEMV, a 128x128 tensor-core tile is idle
+    r = torch.mm(a, b)
+    if bias is not None:
+      r += bias
+    if out is not None:
+      out.copy_(r)
+      return out
+    return r
+  a, lda, a_unit = _gemm_operand(a, 'a')      # a_unit == 1: k contiguous -> K-major
+  b, ldb, b_unit = _gemm_operand(b, 'b')      # b_unit == 1: n contiguous -> MN-major
+  if out is None:
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+  assert out.stride(1) == 1
+  nbytes = lib.er_gemm_workspace_bytes(M, N, Ka)
+  ws = None
+  if nbytes:
+    key = (a.device, torch.cuda.current_stream().cuda_stream if a.is_cuda else 0)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+      ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+      _gemm_ws[key] = ws
+  _lib.check(lib.er_gemm(_p(a), lda, 0 if a_unit else 1, _p(b), ldb, 1 if b_unit else 0, _p(bias), _p(out),
+                         out.stride(0), M, N, Ka, _p(ws), 0 if ws is None else ws.numel(), _stream()), 'er_gemm')
+  return out
 
 
 def dense_workspace(batch, units, device):

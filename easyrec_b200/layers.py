@@ -5,9 +5,9 @@
         training, *biased* variance for both the normalisation and the moving average (2-D
         inputs take TF's non-fused path)
 
-Per layer: one library SGEMM (cuBLAS through torch.mm, TF32 disabled so logits stay within 1e-4 of
-an fp32 CPU run) + liber_b200's fused bias/batch-norm/ReLU epilogue (2 launches forward, 2
-backward, deterministic statistics).  There is no torch fallback for the epilogue.
+Per layer: er_gemm (tcgen05 tensor cores, 3xTF32 operand split so logits stay within 1e-4 of an fp32
+CPU run; forward, dX and dW read X / W[in,out] / dY in place) + liber_b200's fused bias/batch-norm/ReLU
+epilogue (2 launches forward, 2 backward, deterministic statistics).  There is no torch fallback.
 """
 import math
 
@@ -24,7 +24,8 @@ class _DenseBNAct(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, kernel, bias, gamma, beta, moving_mean, moving_var, training, relu, ws):
-    z = torch.mm(x, kernel)
+    x = K.gemm_ready(x)
+    z = K.gemm(x, kernel)
     y, mean, rstd = K.bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, BN_EPS,
                                       BN_MOMENTUM, training, relu, ws)
     ctx.relu = relu
@@ -38,8 +39,8 @@ class _DenseBNAct(torch.autograd.Function):
     x, kernel, bias, gamma, z, y, mean, rstd = ctx.saved_tensors
     gz, gbias, ggamma, gbeta = K.bias_bn_act_bwd(z, bias, gamma, y, gy.contiguous(), mean, rstd,
                                                  ctx.relu, ctx.ws)
-    gk = torch.mm(x.t(), gz)
-    gx = torch.mm(gz, kernel.t()) if ctx.needs_input_grad[0] else None
+    gk = K.gemm(x.t(), gz)
+    gx = K.gemm(gz, kernel.t()) if ctx.needs_input_grad[0] else None
     return gx, gk, gbias, ggamma, gbeta, None, None, None, None, None
 
 

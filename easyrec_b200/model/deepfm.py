@@ -10,6 +10,7 @@ import torch
 from torch import nn
 
 from easyrec_b200 import embedding as E
+from easyrec_b200 import kernels as K
 from easyrec_b200 import layers as L
 from easyrec_b200 import model as registry
 
@@ -53,8 +54,14 @@ class DeepFM(nn.Module):
     wide, _ = g['wide']
     deep, _ = g['deep']
     wide_fea = wide.sum(dim=1, keepdim=True)
-    fm_fea = E.fm(deep, self.n_field, self.dim)
-    deep_fea = self.dnn(deep[:, :self.deep_width] if deep.shape[1] != self.deep_width else deep)
+    self._deep_sumsq = None
+    if deep.shape[1] == self.deep_width and K.fm_block_ok(self.n_field, self.dim) and deep.is_cuda:
+      # FM, the tower input and the regulariser's sum of squares from one pass; one merged gradient back
+      fm_fea, deep_in, self._deep_sumsq = E.fm_block(deep, self.n_field, self.dim)
+    else:
+      fm_fea = E.fm(deep, self.n_field, self.dim)
+      deep_in = deep[:, :self.deep_width] if deep.shape[1] != self.deep_width else deep
+    deep_fea = self.dnn(deep_in)
     if self.has_final:
       all_fea = torch.cat([wide_fea, fm_fea, deep_fea], dim=1)
       logits = self.output(self.final_dnn(all_fea))
@@ -77,7 +84,8 @@ class DeepFM(nn.Module):
     # launch: see l2_of() and trainer.FlatDenseOptimizer
     if self.embedding_reg > 0:
       wide, deep = self._emb_outputs
-      reg = reg + self.embedding_reg * 0.5 * ((wide * wide).sum() + (deep * deep).sum())
+      deep_sq = self._deep_sumsq[0] if self._deep_sumsq is not None else (deep * deep).sum()
+      reg = reg + self.embedding_reg * 0.5 * ((wide * wide).sum() + deep_sq)
     return reg
 
   def loss(self, logits, labels):

@@ -32,7 +32,8 @@ class FlatDenseOptimizer(object):
     dev = self.params[0].device
     sizes = [p.numel() for p in self.params]
     self.sizes = sizes
-    total = sum(sizes)
+    # every tensor starts on a 16-byte boundary so er_gemm reads the kernels in place (float4 loads)
+    total = sum((n + 3) // 4 * 4 for n in sizes)
     self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
     self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
     off = 0
@@ -47,7 +48,7 @@ class FlatDenseOptimizer(object):
       segs[i]['n'] = sizes[i]
       segs[i]['l2'] = float(l2_of(n, p)) if l2_of else 0.0
       segs[i]['lr_mult'] = 1.0
-      off += sizes[i]
+      off += (sizes[i] + 3) // 4 * 4
     self.segs_dev = torch.from_numpy(segs.view(np.uint8).reshape(-1).copy()).to(dev)
     self.n_segs = len(sizes)
     self.max_n = max(sizes)

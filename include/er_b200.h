@@ -176,6 +176,21 @@ int er_embedding_bwd(float* table, float* state0, float* state1,
                      int64_t* uniq_rows, float* uniq_grads, int32_t* n_uniq,
                      void* ws, size_t ws_bytes, er_stream_t stream);
 
+/* Same as er_embedding_bwd for a second table that was looked up with the SAME rows array (same
+ * n_rows, e.g. the wide dim-1 table next to the deep table of DeepFM / Wide&Deep): the lookups were
+ * already radix-sorted by an earlier er_embedding_bwd on this stream whose workspace is sorted_ws
+ * (allocated for dimension sorted_dim and left untouched since); only the segment sums and the row
+ * updates run.  `ws` is this call's own workspace (er_embedding_bwd_workspace_bytes(n, dim)). */
+int er_embedding_bwd_reuse_sort(float* table, float* state0, float* state1, int64_t n_rows,
+                                int32_t dim, int32_t row_stride, const float* weights,
+                                const int32_t* seg_ids, const int32_t* row_ptr, int64_t n_seg,
+                                int64_t n_lookups_cap, const er_slot_t* slots, int32_t n_slots,
+                                const float* const* grad_bufs, int32_t n_bufs,
+                                const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
+                                float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
+                                const void* sorted_ws, size_t sorted_ws_bytes, int32_t sorted_dim,
+                                er_stream_t stream);
+
 /* Apply an already deduplicated sparse gradient (rows distinct). */
 int er_sparse_apply(float* table, float* state0, float* state1, int32_t dim,
                     int32_t row_stride, const int64_t* uniq_rows,
@@ -213,6 +228,21 @@ int er_fm_bwd(const float* x, const float* gy, int64_t batch, int32_t n_field,
               int32_t dim, int32_t x_stride, float* gx, int32_t gx_stride,
               int32_t accumulate, er_stream_t stream);
 
+/* FM block of DeepFM in one pass per direction (one warp per sample row, the row stays in registers):
+ *   fwd: y as er_fm_fwd; *sumsq_out = sum_{b,f,d} x^2 - the embedding-regulariser term
+ *        0.5*scale*||e||^2 of layers/input_layer.py:369-375 (NULL: skipped).  Deterministic.
+ *   bwd: gx = g_pass + gy*(sum_f x - x) + (*coef_dev * coef_mul)*x  - the gradients of the deep tower
+ *        input (g_pass, NULL = 0), of FM (gy, NULL = 0) and of the regulariser (coef_dev device scalar,
+ *        NULL = 0) that all land on the same group matrix.
+ * dim = 4*2^k <= 128, n_field*dim <= 1024, rows 16-byte aligned.  ws (er_fm_block_workspace_bytes)
+ * must be zero-filled once by the caller; the kernel leaves it reusable. */
+size_t er_fm_block_workspace_bytes(int64_t batch);
+int er_fm_block_fwd(const float* x, int64_t batch, int32_t n_field, int32_t dim, int32_t x_stride,
+                    float* y, float* sumsq_out, void* ws, size_t ws_bytes, er_stream_t stream);
+int er_fm_block_bwd(const float* x, const float* gy, const float* g_pass, const float* coef_dev,
+                    float coef_mul, int64_t batch, int32_t n_field, int32_t dim, int32_t x_stride,
+                    int32_t g_pass_stride, float* gx, int32_t gx_stride, er_stream_t stream);
+
 /* ---- K6 epilogues: dense bias + batch-norm + relu (layers/dnn.py:56-79) ------
  * z is the SGEMM output x W (no bias).  Training: batch statistics (biased
  * variance, tf.layers.batch_normalization defaults) are computed deterministically
@@ -249,6 +279,21 @@ int er_dense_apply(float* params, const float* grads, float* state0, float* stat
                    const er_dense_seg_t* segs, int32_t n_segs, int64_t max_seg_n,
                    const er_opt_t* opt, const float* lr_dev, float* reg_loss_out,
                    er_stream_t stream);
+
+/* ---- dense-layer GEMM on the tcgen05 tensor cores (layers/dnn.py:50-87 tf.layers.dense and its
+ * gradient): C[M,N] = A(M,K).B(K,N) (+ bias[n]), fp32 in / fp32 accumulate / fp32 out, operands split
+ * hi+lo into three TF32 products ("3xTF32", error ~1e-6 relative - inside the 1e-4 logit budget).
+ * Operands are read where they lie:
+ *   a_mn_major = 0: A is [M, lda] with k contiguous      a_mn_major = 1: A is [K, lda] with m contiguous
+ *   b_mn_major = 0: B is [N, ldb] with k contiguous      b_mn_major = 1: B is [K, ldb] with n contiguous
+ * so forward (X, W[in,out]) = (0,1), dX (dY, W) = (0,0), dW (X, dY) = (1,1) need no transposed copy.
+ * Pitches must be multiples of 4 floats and base pointers 16-byte aligned (K, M, N are free).
+ * Small-output / long-K problems are split along K; partials go to ws (er_gemm_workspace_bytes) and
+ * are summed in a fixed order (deterministic). */
+size_t er_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+            int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
+            int64_t K, void* ws, size_t ws_bytes, er_stream_t stream);
 
 /* sigmoid cross entropy (tf.losses.sigmoid_cross_entropy,
  * builders/loss_builder.py:36-39): loss_sum += sum_b w*(max(x,0)-x*z+log1p(exp(-|x|)))

@@ -67,9 +67,10 @@ def _worker(rank, port, ret):
   w2.grad = torch.full((7,), float(10 * (rank + 1)))
   dopt.gather_grads()
   dp.sync_dense_grads()
-  mean = dopt.flat_g * dopt.grad_scale
-  assert torch.allclose(mean[:15], torch.full((15,), 1.5))
-  assert torch.allclose(mean[15:], torch.full((7,), 15.0))
+  # (each tensor starts on a 16-byte boundary of the flat buffer; the padding stays zero)
+  assert torch.allclose(dopt.grad_views[0] * dopt.grad_scale, torch.full((5, 3), 1.5))
+  assert torch.allclose(dopt.grad_views[1] * dopt.grad_scale, torch.full((7,), 15.0))
+  assert dopt.grad_views[1].data_ptr() % 16 == dopt.flat_g.data_ptr() % 16 and float(dopt.flat_g[15]) == 0.0
   # ---- sparse: gathered inputs through the replicated slot plan == global batch ----
   rng = np.random.default_rng(100 + rank)
   offs = np.repeat(np.array([0, 30, 0]), B)

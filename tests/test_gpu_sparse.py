@@ -317,6 +317,64 @@ def test_fm_and_sigmoid_ce_parity():
   np.testing.assert_allclose(g.cpu().numpy(), wg, atol=1e-8, rtol=1e-5)
 
 
+def test_fm_block_one_pass_matches_oracle():
+  """fused FM + sum-of-squares forward, merged (tower + FM + regulariser) gradient backward."""
+  rng = np.random.default_rng(5)
+  for B, F, D in [(100, 39, 16), (37, 5, 8), (8192, 39, 16), (64, 26, 32), (19, 3, 4)]:
+    x = rng.normal(size=(B, F * D)).astype(np.float32)
+    gy = rng.normal(size=(B, D)).astype(np.float32)
+    gp = rng.normal(size=(B, F * D)).astype(np.float32)
+    coef = np.float32(0.37)
+    y, sumsq = K.fm_block_fwd(t(x), F, D)
+    # shuffle-tree vs sequential summation order: bound each element by the size of the two terms whose
+    # difference it is (0.5*(S^2 - Q) cancels), not by the result
+    x3 = x.astype(np.float64).reshape(B, F, D)
+    s2, qq = x3.sum(1) ** 2, (x3 ** 2).sum(1)
+    assert (np.abs(y.cpu().numpy() - 0.5 * (s2 - qq)) <= 2e-6 * (s2 + qq) + 1e-7).all()
+    assert np.abs(y.cpu().numpy() - O.fm_fwd(x, F, D)).max() <= 1e-5 * max(1.0, float(np.abs(s2 + qq).max()))
+    ref_sq = float((x.astype(np.float64) ** 2).sum())
+    assert abs(float(sumsq.item()) - ref_sq) <= 2e-6 * ref_sq
+    y2, sumsq2 = K.fm_block_fwd(t(x), F, D)
+    assert torch.equal(y, y2) and torch.equal(sumsq, sumsq2)   # deterministic, workspace self-resets
+    gx = K.fm_block_bwd(t(x), t(gy), t(gp), t(np.array([coef])), 2.0, F, D).cpu().numpy()
+    want_gx = O.fm_bwd(x, gy, F, D).astype(np.float64) + gp + 2.0 * float(coef) * x.astype(np.float64)
+    np.testing.assert_allclose(gx, want_gx, rtol=1e-5, atol=1e-5)
+    gx0 = K.fm_block_bwd(t(x), t(gy), None, None, 0.0, F, D).cpu().numpy()
+    np.testing.assert_allclose(gx0, O.fm_bwd(x, gy, F, D), rtol=1e-5, atol=1e-5)
+
+
+def test_bwd_reuse_sort_is_identical_to_a_fresh_sort():
+  """A second table looked up with the same rows (DeepFM's wide dim-1 table) reuses the first K7's sort."""
+  rng = np.random.default_rng(21)
+  V, B, F = 3000, 400, 5
+  rows = (rng.zipf(1.2, B * F) % V).astype(np.int64)
+  rows[rng.integers(0, B * F, 30)] = -1
+  rows[rng.integers(0, B * F, 200)] = 7   # hot row -> chunked path
+  d_rows = t(rows)
+  res = {}
+  for mode in ('fresh', 'reuse'):
+    out = []
+    ws16 = K.bwd_workspace(B * F, DEV, 16)
+    src = None
+    for dim in (16, 1):
+      r2 = np.random.default_rng(dim)
+      table = t(r2.normal(size=(V, dim)).astype(np.float32))
+      acc = t(np.full((V, dim), 0.1, np.float32))
+      stride = (F * dim + 3) // 4 * 4
+      gout = t(r2.normal(size=(B, stride)).astype(np.float32))
+      recs = [dict(num_buckets=V, row_offset=0, seg_begin=f * B, n_seg=B, bucket_mode=3, combiner=0, out_buf=0,
+                   out_stride=stride, out_col=f * dim) for f in range(F)]
+      sd = K.slots_to_device(K.make_slots(recs), DEV)
+      ws = ws16 if dim == 16 else K.bwd_workspace(B * F, DEV, dim)
+      K.embedding_bwd(table, acc, None, dim, d_rows, sd, F, B * F, [gout], K.make_opt(_lib.OPT_ADAGRAD, 0.05), ws,
+                      sorted_from=src if (mode == 'reuse' and dim == 1) else None)
+      src = (ws16, 16)
+      out.append((table.cpu(), acc.cpu()))
+    res[mode] = out
+  for (ta, aa), (tb, ab) in zip(res['fresh'], res['reuse']):
+    assert torch.equal(ta, tb) and torch.equal(aa, ab)
+
+
 def test_full_size_c2_properties():
   """BASELINE config 2 sizes (B=8192, 26+13 slots, V=10M, D=16): size-independent properties."""
   B, F, D, V = 8192, 39, 16, 10_000_013
