@@ -40,6 +40,12 @@ class ErOpt(ctypes.Structure):
               ('beta2_power', c_f32), ('grad_scale', c_f32)]
 
 
+class ErBnStats(ctypes.Structure):
+  """er_bn_stats_t."""
+  _fields_ = [('bias', c_vp), ('save_mean', c_vp), ('save_rstd', c_vp), ('moving_mean', c_vp),
+              ('moving_var', c_vp), ('eps', c_f32), ('momentum', c_f32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/er_b200.h declares
 SIGNATURES = {
     'er_abi_version': (c_i32, []),
@@ -86,6 +92,19 @@ SIGNATURES = {
     'er_dense_workspace_bytes': (c_sz, [c_i64, c_i32]),
     'er_dense_apply': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, ctypes.POINTER(ErOpt), c_vp,
                                c_vp, c_vp]),
+    'er_concat_cols': (c_i32, [ctypes.POINTER(c_vp), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32), c_i32, c_i64,
+                               c_vp, c_i32, c_vp]),
+    'er_split_cols': (c_i32, [c_vp, c_i32, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_i32),
+                              ctypes.POINTER(c_i32), c_i32, c_vp]),
+    'er_rowsum_block_fwd': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'er_rowsum_block_bwd': (c_i32, [c_vp, c_vp, c_vp, c_f32, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp]),
+    'er_dense1_workspace_bytes': (c_sz, [c_i32]),
+    'er_dense1_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    'er_dense1_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'er_gemm_bn_workspace_bytes': (c_sz, [c_i64, c_i64]),
+    'er_gemm_bn': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64,
+                           ctypes.POINTER(ErBnStats), c_vp, c_sz, c_vp]),
+    'er_bn_act_apply': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     'er_fm_block_workspace_bytes': (c_sz, [c_i64]),
     'er_fm_block_fwd': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'er_fm_block_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32,

@@ -10,6 +10,8 @@
 // -- no atomics, no E[x^2]-E[x]^2 cancellation); pass 2 re-derives the column statistics from the
 // R partials (R*32 L2 reads per CTA) and streams the tile.  Traffic: fwd 2 reads + 1 write of
 // [B,U]; bwd 3 reads (z, y, gy) twice + 1 write.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace er {
@@ -148,6 +150,46 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// y = act(bn(z + b)) with known column statistics: one streaming pass, 16 B per thread access
+__global__ void __launch_bounds__(256)
+    bn_act_apply_vec_kernel(const float4* __restrict__ z, const float* __restrict__ bias,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ mean, const float* __restrict__ rstd, int64_t total4,
+                            int units, int relu, float4* __restrict__ y) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((t * 4) % units);
+    const float4 v = z[t];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = *reinterpret_cast<const float4*>(bias + c);
+    float4 h;
+    h.x = ((v.x + b.x) - mu.x) * rs.x * ga.x + be.x;
+    h.y = ((v.y + b.y) - mu.y) * rs.y * ga.y + be.y;
+    h.z = ((v.z + b.z) - mu.z) * rs.z * ga.z + be.z;
+    h.w = ((v.w + b.w) - mu.w) * rs.w * ga.w + be.w;
+    if (relu) {
+      h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f); h.z = fmaxf(h.z, 0.f); h.w = fmaxf(h.w, 0.f);
+    }
+    y[t] = h;
+  }
+}
+__global__ void __launch_bounds__(256)
+    bn_act_apply_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, int64_t total,
+                        int units, int relu, float* __restrict__ y) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % units);
+    const float h = ((z[t] + (bias ? bias[c] : 0.f)) - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    y[t] = relu ? fmaxf(h, 0.f) : h;
+  }
+}
+
 // no batch norm: y = act(z + b)
 __global__ void __launch_bounds__(256)
     bias_act_kernel(const float* __restrict__ z, const float* __restrict__ bias, int64_t total, int units,
@@ -265,9 +307,10 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace er
 
+// Layout: 1024 reserved bytes, then the chunk partials [n_chunks][units][3].
 extern "C" size_t er_dense_workspace_bytes(int64_t batch, int32_t units) {
   er::DenseShape s = er::dense_shape(batch > 0 ? batch : 1, units > 0 ? units : 1);
-  return (size_t)s.n_chunks * s.units * 3 * sizeof(float) + 256;
+  return 1024 + (size_t)s.n_chunks * s.units * 3 * sizeof(float) + 256;
 }
 
 extern "C" int er_bias_bn_act_fwd(const float* z, const float* bias, const float* gamma,
@@ -292,12 +335,35 @@ extern "C" int er_bias_bn_act_fwd(const float* z, const float* bias, const float
     ER_REQUIRE(save_mean && save_rstd, "training needs save_mean / save_rstd");
     if (!ws || ws_bytes < er_dense_workspace_bytes(batch, units))
       return fail(ER_ERR_WORKSPACE, "er_bias_bn_act_fwd: workspace too small");
-    bn_stats_kernel<<<grid, 256, 0, st>>>(z, bias, s, reinterpret_cast<float*>(ws));
+    bn_stats_kernel<<<grid, 256, 0, st>>>(z, bias, s, reinterpret_cast<float*>(static_cast<char*>(ws) + 1024));
     count_launches(1);
   }
   bn_apply_kernel<<<grid, 256, 0, st>>>(z, bias, gamma, beta, moving_mean, moving_var, s, eps, momentum,
-                                        training, relu, reinterpret_cast<const float*>(ws), y, save_mean,
+                                        training, relu,
+                                        ws ? reinterpret_cast<const float*>(static_cast<char*>(ws) + 1024) : nullptr, y, save_mean,
                                         save_rstd);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_bn_act_apply(const float* z, const float* bias, const float* gamma, const float* beta,
+                               const float* mean, const float* rstd, int64_t batch, int32_t units,
+                               int32_t relu, float* y, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(z && gamma && beta && mean && rstd && y, "null argument");
+  ER_REQUIRE(batch > 0 && units > 0, "bad shape");
+  cudaStream_t st = as_stream(stream);
+  auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const int64_t total = batch * units;
+  if (units % 4 == 0 && al(z) && al(y) && al(gamma) && al(beta) && al(mean) && al(rstd) && (!bias || al(bias))) {
+    bn_act_apply_vec_kernel<<<grid_for(total / 4, 256, 8), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(z), bias, gamma, beta, mean, rstd, total / 4, units, relu,
+        reinterpret_cast<float4*>(y));
+  } else {
+    bn_act_apply_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(z, bias, gamma, beta, mean, rstd, total, units,
+                                                                 relu, y);
+  }
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -318,7 +384,7 @@ extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float
   cudaStream_t st = as_stream(stream);
   DenseShape s = dense_shape(batch, units);
   dim3 grid((units + kColTile - 1) / kColTile, s.n_chunks);
-  float* part = reinterpret_cast<float*>(ws);
+  float* part = reinterpret_cast<float*>(static_cast<char*>(ws) + 1024);
   bn_bwd_stats_kernel<<<grid, 256, 0, st>>>(z, bias, y, gy, save_mean, save_rstd, s, relu, use_bn, part);
   bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(z, bias, gamma, y, gy, save_mean, save_rstd, s, relu, use_bn,
                                             part, gz, gbias, ggamma, gbeta);
@@ -336,15 +402,39 @@ extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float
 // reg_loss_out (optional) accumulates sum l2/2 * w^2 of the pre-update weights (reporting only).
 namespace er {
 
+// Work items are 256-element chunks of the segments, numbered across all segments (prefix of chunk
+// counts built per CTA in shared memory, binary search per chunk): one wave covers every tensor, however
+// small, without a grid dimension per tensor.
 __global__ void __launch_bounds__(256)
     dense_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
-                       float* __restrict__ s1, const er_dense_seg_t* __restrict__ segs, er_opt_t opt,
+                       float* __restrict__ s1, const er_dense_seg_t* __restrict__ segs, int n_segs, er_opt_t opt,
                        const float* __restrict__ lr_dev, float* __restrict__ reg_loss_out) {
-  const er_dense_seg_t seg = segs[blockIdx.y];
-  const float lr = (lr_dev ? *lr_dev : opt.lr) * seg.lr_mult;
+  extern __shared__ int s_first[];   // [n_segs + 1] first chunk of every segment
+  for (int i = threadIdx.x; i < n_segs; i += blockDim.x) s_first[i + 1] = (int)((segs[i].n + 255) >> 8);
+  __syncthreads();
+  if (threadIdx.x == 0) {   // exclusive prefix in shared memory (the loads above were issued in parallel)
+    int acc = 0;
+    for (int i = 0; i < n_segs; ++i) {
+      const int c = s_first[i + 1];
+      s_first[i] = acc;
+      acc += c;
+    }
+    s_first[n_segs] = acc;
+  }
+  __syncthreads();
+  const int n_chunks = s_first[n_segs];
+  const float lr0 = lr_dev ? *lr_dev : opt.lr;
   float reg = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < seg.n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    int lo = 0, hi = n_segs;   // s_first[lo] <= ch < s_first[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_first[mid] <= ch) lo = mid; else hi = mid;
+    }
+    const er_dense_seg_t seg = segs[lo];
+    const float lr = lr0 * seg.lr_mult;
+    const int64_t i = (int64_t)(ch - s_first[lo]) * 256 + threadIdx.x;
+    if (i >= seg.n) continue;
     const int64_t j = seg.offset + i;
     float w = p[j];
     float gr = g[j] * opt.grad_scale;
@@ -382,12 +472,13 @@ extern "C" int er_dense_apply(float* params, const float* grads, float* state0, 
                               er_stream_t stream) {
   using namespace er;
   ER_REQUIRE(params && grads && segs && opt, "null argument");
-  ER_REQUIRE(n_segs > 0 && n_segs <= 65535 && max_seg_n > 0, "bad segment table");
+  ER_REQUIRE(n_segs > 0 && n_segs <= 8192 && max_seg_n > 0, "bad segment table");
   ER_REQUIRE(opt->kind == ER_OPT_SGD || state0, "optimizer state0 missing");
   ER_REQUIRE((opt->kind != ER_OPT_LAZY_ADAM && opt->kind != ER_OPT_ADAM_ROWS) || state1, "adam needs state1");
-  dim3 grid((unsigned)min((int64_t)64, ceil_div(max_seg_n, (int64_t)1024)), n_segs);
-  dense_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(params, grads, state0, state1, segs, *opt, lr_dev,
-                                                          reg_loss_out);
+  // enough CTAs for the biggest tensor's chunks plus one per small tensor, capped at 8 waves
+  const int grid = (int)min((int64_t)8 * kSmCount, ceil_div(max_seg_n, (int64_t)256) + n_segs);
+  dense_apply_kernel<<<grid, 256, (size_t)(n_segs + 1) * sizeof(int), as_stream(stream)>>>(
+      params, grads, state0, state1, segs, n_segs, *opt, lr_dev, reg_loss_out);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;

@@ -34,7 +34,8 @@ constexpr int kProducerThreads = 256;
 constexpr int kThreads = kProducerThreads + 32;
 constexpr int kTileBytes = 128 * 128;          // 128 segments x 128 B
 constexpr int kStageBytes = 4 * kTileBytes;    // A hi, A lo, B hi, B lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* align slack */ + 256 /* barriers */;
+constexpr int kStatBytes = 4 * 128 * 3 * 4;   // per row-quarter Welford partials of the tile's columns
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* align slack */ + 256 /* barriers */ + kStatBytes;
 constexpr uint32_t kTmemCols = 256;   // [0,128): hi.hi accumulator, [128,256): the two cross terms
 
 struct Args {
@@ -49,6 +50,10 @@ struct Args {
   int k_per_slice;     // multiple of BK
   int n_slices;
   int dbg;             // ER_GEMM_DEBUG timing experiments (results invalid when != 0)
+  // batch-norm statistics of the output columns (training forward of a dense+BN layer), optional
+  float* bn_part;            // [m_tiles][N][3] Welford (n, mean, M2) per 128-row tile
+  unsigned int* bn_counter;  // [n_tiles], zero on entry, left zero
+  er_bn_stats_t bn;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -140,6 +145,18 @@ __device__ __forceinline__ float4 mask_chunk(float4 v, int nvalid) {
   return v;
 }
 
+struct Welford {
+  float n, mean, m2;
+};
+__device__ __forceinline__ void wf_merge(Welford& a, const Welford& b) {   // Chan et al., fixed order
+  if (b.n == 0.f) return;
+  const float n = a.n + b.n;
+  const float d = b.mean - a.mean;
+  a.mean += d * (b.n / n);
+  a.m2 += b.m2 + d * d * (a.n * b.n / n);
+  a.n = n;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1024 B aligned
@@ -149,6 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
   const uint32_t tmem_slot = accum_bar + 8;
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  int* s_flag = reinterpret_cast<int*>(tmem_slot_ptr + 1);
+  float* s_stats = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -272,18 +291,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
   }
 
   if (warp < kProducerThreads / 32) {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> shared (transpose) -> global =====
     mbar_wait(accum_bar, 0u);
     tc_fence_after();
     const int q = warp & 3, h = warp >> 2;            // TMEM lane quarter (fixed by warp id % 4), column half
     float* out = a.n_slices > 1 ? a.partials + (long long)blockIdx.z * a.M * a.N : a.C;
     const long long ldo = a.n_slices > 1 ? (long long)a.N : a.ldc;
     const bool vec_ok = (ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    // A thread owns one row x 32 columns of a block; stores straight from registers would put 32 different
+    // rows in every warp store.  Each warp transposes its two 32x32 blocks through 8 KB of the (now idle)
+    // stage-0 buffer - 16 B units, unit ^= row % 8, conflict-free both ways - so a warp store covers 4 rows
+    // x 128 contiguous bytes.
+    const uint32_t wbuf0 = smem_base + (uint32_t)warp * 8192u;
+    const int nv = min(32, a.M - (m0 + 32 * q));     // valid rows of this warp (<= 0: none)
+    // ---- phase 1: accumulators -> shared; column statistics of the staged blocks ----
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
       const int col0 = h * 64 + cb * 32;
       if (col0 >= n_eff) break;                        // warp-uniform
-      uint32_t r[32];
+      const uint32_t wbuf = wbuf0 + (uint32_t)cb * 4096u;
+      uint32_t r[32], r2[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -296,66 +323,161 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
             "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr)
           : "memory");
-      {
-        uint32_t r2[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]),
-              "=r"(r2[7]), "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]),
-              "=r"(r2[14]), "=r"(r2[15]), "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]),
-              "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]), "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]),
-              "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
-            : "r"(taddr + (uint32_t)BN)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-      }
-      // A thread owns one row x 32 columns; stores straight from here would put 32 different rows in every
-      // warp store.  Transpose through this warp's 4 KB of the (now idle) stage-0 buffer - 16 B units,
-      // unit ^= row % 8, conflict-free both ways - so each warp store covers 4 rows x 128 contiguous bytes.
-      const uint32_t wbuf = smem_base + (uint32_t)warp * 4096u;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]),
+            "=r"(r2[7]), "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]),
+            "=r"(r2[14]), "=r"(r2[15]), "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]),
+            "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]), "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]),
+            "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
+          : "r"(taddr + (uint32_t)BN)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t o = wbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(o), "r"(r[4 * j]), "r"(r[4 * j + 1]),
-                     "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(o),
+                     "f"(__uint_as_float(r[4 * j]) + __uint_as_float(r2[4 * j])),
+                     "f"(__uint_as_float(r[4 * j + 1]) + __uint_as_float(r2[4 * j + 1])),
+                     "f"(__uint_as_float(r[4 * j + 2]) + __uint_as_float(r2[4 * j + 2])),
+                     "f"(__uint_as_float(r[4 * j + 3]) + __uint_as_float(r2[4 * j + 3]))
                      : "memory");
       }
       __syncwarp();
+      if (a.bn_part) {
+        // column statistics of this warp's 32 rows: lane l walks column l of the staged block (one full row
+        // per ld.shared: conflict-free); two passes (mean, then squared deviations) - no cancellation
+        // one pass of shifted sums (shift = the column's first value, so no E[x^2]-E[x]^2 cancellation)
+        const int sw = lane >> 2, wi = lane & 3;
+        const float* wb = reinterpret_cast<const float*>(smem_raw + (wbuf - smem_u32(smem_raw)));
+        const float shift = wb[(sw << 2) + wi];            // row 0 (unit ^ 0)
+        float sd0 = 0.f, sd1 = 0.f, sq0 = 0.f, sq1 = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; rr += 2) {
+          const float v0 = wb[rr * 32 + ((sw ^ (rr & 7)) << 2) + wi] - shift;
+          const float v1 = wb[(rr + 1) * 32 + ((sw ^ ((rr + 1) & 7)) << 2) + wi] - shift;
+          if (rr < nv) { sd0 += v0; sq0 += v0 * v0; }
+          if (rr + 1 < nv) { sd1 += v1; sq1 += v1 * v1; }
+        }
+        const float fn = (float)max(nv, 1);
+        const float sd = sd0 + sd1;
+        const float mean = shift + sd / fn;
+        const float m20 = (sq0 + sq1) - sd * sd / fn, m21 = 0.f;
+        float* sst = s_stats + ((q * BN) + col0 + lane) * 3;
+        sst[0] = (float)max(nv, 0);
+        sst[1] = mean;
+        sst[2] = fmaxf(m20 + m21, 0.f);
+      }
+    }
+    // ---- batch-norm statistics: publish this tile's partials and take a ticket BEFORE the big stores, so
+    // the fence only has to cover 1.5 KB of partials ----
+    const int m_tiles = gridDim.y;
+    if (a.bn_part) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps (the MMA warp is not here)
+      if (tid < n_eff && n0 + tid < a.N) {
+        Welford t = {s_stats[tid * 3], s_stats[tid * 3 + 1], s_stats[tid * 3 + 2]};
+        for (int qq = 1; qq < 4; ++qq) {
+          const float* p = s_stats + ((qq * BN) + tid) * 3;
+          wf_merge(t, Welford{p[0], p[1], p[2]});
+        }
+        float* gp = a.bn_part + ((long long)blockIdx.y * a.N + n0 + tid) * 3;
+        __stcg(gp, t.n); __stcg(gp + 1, t.mean); __stcg(gp + 2, t.m2);
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) *s_flag = (atomicAdd(a.bn_counter + blockIdx.x, 1u) == (unsigned)(m_tiles - 1));
+    }
+    // ---- phase 2: shared -> global, coalesced ----
+    {
       const bool add_bias = a.bias != nullptr && a.n_slices == 1;
       const int u = lane & 7;                          // 16 B unit of the 128 B row segment
-      const int col = n0 + col0 + 4 * u;
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (add_bias) {
-        if (col < a.N) bv.x = a.bias[col];
-        if (col + 1 < a.N) bv.y = a.bias[col + 1];
-        if (col + 2 < a.N) bv.z = a.bias[col + 2];
-        if (col + 3 < a.N) bv.w = a.bias[col + 3];
-      }
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        const int col0 = h * 64 + cb * 32;
+        if (col0 >= n_eff) break;
+        const uint32_t wbuf = wbuf0 + (uint32_t)cb * 4096u;
+        const int col = n0 + col0 + 4 * u;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_bias) {
+          if (col < a.N) bv.x = a.bias[col];
+          if (col + 1 < a.N) bv.y = a.bias[col + 1];
+          if (col + 2 < a.N) bv.z = a.bias[col + 2];
+          if (col + 3 < a.N) bv.w = a.bias[col + 3];
+        }
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + (lane >> 3);           // row of this warp's 32
-        const uint32_t o = wbuf + (uint32_t)rr * 128u + (uint32_t)((u ^ (rr & 7)) << 4);
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(o));
-        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-        const int grow = m0 + 32 * q + rr;
-        if (grow < a.M) {
-          float* orow = out + (long long)grow * ldo;
-          if (vec_ok && col + 3 < a.N) {
-            *reinterpret_cast<float4*>(orow + col) = v;
-          } else {
-            if (col < a.N) orow[col] = v.x;
-            if (col + 1 < a.N) orow[col + 1] = v.y;
-            if (col + 2 < a.N) orow[col + 2] = v.z;
-            if (col + 3 < a.N) orow[col + 3] = v.w;
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);         // row of this warp's 32
+          const uint32_t o = wbuf + (uint32_t)rr * 128u + (uint32_t)((u ^ (rr & 7)) << 4);
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(o));
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          const int grow = m0 + 32 * q + rr;
+          if (grow < a.M) {
+            float* orow = out + (long long)grow * ldo;
+            if (vec_ok && col + 3 < a.N) {
+              *reinterpret_cast<float4*>(orow + col) = v;
+            } else {
+              if (col < a.N) orow[col] = v.x;
+              if (col + 1 < a.N) orow[col + 1] = v.y;
+              if (col + 2 < a.N) orow[col + 2] = v.z;
+              if (col + 3 < a.N) orow[col + 3] = v.w;
+            }
           }
         }
       }
-      __syncwarp();                                    // wbuf is reused by the next 32-column block
+    }
+    if (a.bn_part) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (*s_flag) {
+        // Last row-tile of this column tile: combine the per-tile (n, mean, M2) of its 128 columns.  Two
+        // threads per column (even / odd tiles), two passes (global mean, then M2 about it) whose loads are
+        // independent - the whole merge costs a few L2 round trips instead of one per tile - fixed order.
+        __threadfence();
+        const int cl2 = tid & 127, half = tid >> 7;
+        const int col = n0 + cl2;
+        const bool live = cl2 < n_eff && col < a.N;
+        float* s_red = s_stats;                           // reuse: [2][128] floats per pass
+        float cnt = 0.f, wsum = 0.f;
+        if (live) {
+#pragma unroll 16
+          for (int mt = half; mt < m_tiles; mt += 2) {
+            const float* gp = a.bn_part + ((long long)mt * a.N + col) * 3;
+            const float n = __ldcg(gp), mu = __ldcg(gp + 1);
+            cnt += n;
+            wsum += n * mu;
+          }
+        }
+        s_red[half * 128 + cl2] = cnt;
+        s_red[256 + half * 128 + cl2] = wsum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float n_tot = s_red[cl2] + s_red[128 + cl2];
+        const float mean_z = (s_red[256 + cl2] + s_red[384 + cl2]) / fmaxf(n_tot, 1.f);
+        float m2 = 0.f;
+        if (live) {
+#pragma unroll 16
+          for (int mt = half; mt < m_tiles; mt += 2) {
+            const float* gp = a.bn_part + ((long long)mt * a.N + col) * 3;
+            const float n = __ldcg(gp), mu = __ldcg(gp + 1), q2 = __ldcg(gp + 2);
+            const float d = mu - mean_z;
+            m2 += q2 + n * d * d;
+          }
+        }
+        s_red[512 + half * 128 + cl2] = m2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (live && half == 0) {
+          const float mean = mean_z + (a.bn.bias ? a.bn.bias[col] : 0.f);
+          const float var = (s_red[512 + cl2] + s_red[640 + cl2]) / n_tot;   // biased (tf.layers.batch_normalization)
+          a.bn.save_mean[col] = mean;
+          a.bn.save_rstd[col] = 1.0f / sqrtf(var + a.bn.eps);
+          if (a.bn.moving_mean) {
+            a.bn.moving_mean[col] = a.bn.moving_mean[col] * a.bn.momentum + mean * (1.f - a.bn.momentum);
+            a.bn.moving_var[col] = a.bn.moving_var[col] * a.bn.momentum + var * (1.f - a.bn.momentum);
+          }
+        }
+        if (tid == 0) a.bn_counter[blockIdx.x] = 0u;
+      }
     }
   }
   tc_fence_before();
@@ -405,9 +527,11 @@ extern "C" size_t er_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   return s > 1 ? (size_t)s * (size_t)M * (size_t)N * sizeof(float) : 0;
 }
 
-extern "C" int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
-                       int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
-                       int64_t K, void* ws, size_t ws_bytes, er_stream_t stream) {
+extern "C" size_t er_gemm_bn_workspace_bytes(int64_t M, int64_t N);
+
+static int gemm_impl(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+                     int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
+                     int64_t K, const er_bn_stats_t* bn, void* ws, size_t ws_bytes, er_stream_t stream) {
   using namespace er::gemm;
   ER_REQUIRE(A && B && C, "null operand");
   ER_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "bad shape");
@@ -427,9 +551,20 @@ extern "C" int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const fl
     a.dbg = e ? atoi(e) : 0;
   }
   a.partials = nullptr;
+  a.bn_part = nullptr;
+  a.bn_counter = nullptr;
   if (a.n_slices > 1) {
+    ER_REQUIRE(!bn, "batch-norm statistics need an unsplit K (er_gemm_workspace_bytes(M,N,K) == 0)");
     ER_REQUIRE(ws && ws_bytes >= er_gemm_workspace_bytes(M, N, K), "workspace too small");
     a.partials = static_cast<float*>(ws);
+  }
+  if (bn) {
+    ER_REQUIRE(bn->save_mean && bn->save_rstd, "bn: save_mean / save_rstd missing");
+    ER_REQUIRE((bn->moving_mean == nullptr) == (bn->moving_var == nullptr), "bn: moving_mean and moving_var go together");
+    ER_REQUIRE(ws && ws_bytes >= er_gemm_bn_workspace_bytes(M, N), "bn workspace too small");
+    a.bn = *bn;
+    a.bn_counter = static_cast<unsigned int*>(ws);
+    a.bn_part = reinterpret_cast<float*>(static_cast<char*>(ws) + 1024);
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -451,4 +586,22 @@ extern "C" int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const fl
   er::count_launches(launches);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
+}
+
+extern "C" int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+                       int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
+                       int64_t K, void* ws, size_t ws_bytes, er_stream_t stream) {
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, bias, C, ldc, M, N, K, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" size_t er_gemm_bn_workspace_bytes(int64_t M, int64_t N) {
+  return 1024 + (size_t)er::ceil_div(M, er::gemm::BM) * (size_t)N * 3 * sizeof(float);
+}
+
+extern "C" int er_gemm_bn(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+                          int32_t b_mn_major, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                          const er_bn_stats_t* bn, void* ws, size_t ws_bytes, er_stream_t stream) {
+  if (!bn) return er::fail(ER_ERR_INVALID_ARG, "er_gemm_bn: bn is NULL");
+  if (er::ceil_div(N, er::gemm::BN) > 256) return er::fail(ER_ERR_INVALID_ARG, "er_gemm_bn: N too large");
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, nullptr, C, ldc, M, N, K, bn, ws, ws_bytes, stream);
 }

@@ -259,6 +259,194 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- wide block: y[b] = sum_f x[b,f] (model/deepfm.py:62-63 reduce_sum over the wide group) and
+// sumsq = sum x^2 (embedding regulariser), one warp per sample row; bwd: gx[b,f] = gy[b] + coef*x[b,f].
+__global__ void __launch_bounds__(256)
+    rowsum_block_fwd_kernel(const float* __restrict__ x, int64_t batch, int width, int x_stride,
+                            float* __restrict__ y, float* __restrict__ partials, unsigned int* counter,
+                            float* __restrict__ sumsq_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float s_w[8];
+  __shared__ int s_last;
+  float warp_sq = 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < batch; b += (int64_t)gridDim.x * 8) {
+    float sv = 0.f, q = 0.f;
+    for (int f = lane; f < width; f += 32) {
+      const float v = x[b * x_stride + f];
+      sv = __fadd_rn(sv, v);
+      q = __fadd_rn(q, __fmul_rn(v, v));
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+      sv = __fadd_rn(sv, __shfl_xor_sync(0xffffffffu, sv, o));
+      q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, o));
+    }
+    if (lane == 0) y[b] = sv;
+    warp_sq = __fadd_rn(warp_sq, q);
+  }
+  if (!partials) return;
+  if (lane == 0) s_w[warp] = warp_sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t = __fadd_rn(t, s_w[w]);
+    __stcg(partials + blockIdx.x, t);
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t = __fadd_rn(t, __ldcg(partials + i));
+    for (int o = 16; o >= 1; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+    __syncthreads();
+    if (lane == 0) s_w[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot = __fadd_rn(tot, s_w[w]);
+      *sumsq_out = tot;
+      *counter = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    rowsum_block_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                            const float* __restrict__ coef_dev, float coef_mul, int64_t batch, int width,
+                            int x_stride, float* __restrict__ gx, int gx_stride) {
+  const float coef = coef_dev ? __fmul_rn(*coef_dev, coef_mul) : 0.f;
+  const int64_t total = batch * width;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / width;
+    const int f = (int)(t - b * width);
+    gx[b * gx_stride + f] = __fadd_rn(gy ? gy[b] : 0.f, __fmul_rn(coef, x[b * x_stride + f]));
+  }
+}
+
+// ---- single-unit dense head (the logit layer, tf.layers.dense(units=1)): a GEMV, one warp per row ----
+__global__ void __launch_bounds__(256)
+    dense1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      int64_t batch, int width, int x_stride, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < batch; b += (int64_t)gridDim.x * 8) {
+    float acc = 0.f;
+    for (int f = lane; f < width; f += 32) acc = fmaf(x[b * x_stride + f], w[f], acc);
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[b] = acc + b0;
+  }
+}
+// gx[b,f] = g[b]*w[f];  gw[f] = sum_b g[b]*x[b,f], gb = sum_b g[b].  Warps stride over the rows with the
+// column sums in registers (lane owns columns lane, lane+32, ...), the 8 warps of a CTA and then the CTAs are
+// combined in index order (per-CTA partials, last CTA finishes): deterministic, no float atomics.
+template <int JW>
+__global__ void __launch_bounds__(256)
+    dense1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g,
+                      int64_t batch, int width, int x_stride, float* __restrict__ gx, int gx_stride,
+                      float* __restrict__ partials /* [grid][width+1] */, unsigned int* counter,
+                      float* __restrict__ gw, float* __restrict__ gb) {
+  extern __shared__ float s_col[];   // [8][width+1], later [256] for the final combine
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wp = width + 1;
+  float wv[JW], acc[JW];
+#pragma unroll
+  for (int j = 0; j < JW; ++j) {
+    const int f = lane + 32 * j;
+    wv[j] = f < width ? w[f] : 0.f;
+    acc[j] = 0.f;
+  }
+  float accg = 0.f;
+  const int64_t total_warps = (int64_t)gridDim.x * 8;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < batch; b += total_warps) {
+    const float gb_ = g[b];
+    accg += gb_;
+#pragma unroll
+    for (int j = 0; j < JW; ++j) {
+      const int f = lane + 32 * j;
+      if (f < width) {
+        acc[j] = fmaf(gb_, x[b * x_stride + f], acc[j]);
+        if (gx) gx[b * gx_stride + f] = gb_ * wv[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < JW; ++j) {
+    const int f = lane + 32 * j;
+    if (f < width) s_col[warp * wp + f] = acc[j];
+  }
+  if (lane == 0) s_col[warp * wp + width] = accg;
+  __syncthreads();
+  for (int f = threadIdx.x; f < wp; f += 256) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += s_col[k * wp + f];
+    __stcg(partials + (int64_t)blockIdx.x * wp + f, t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // P threads per column split the CTA partials (interleaved), then combine in order
+  const int P = max(1, 256 / wp);
+  const int f = threadIdx.x % wp, part = threadIdx.x / wp;
+  float t = 0.f;
+  if (part < P) {
+#pragma unroll 8
+    for (int k = part; k < (int)gridDim.x; k += P) t += __ldcg(partials + (int64_t)k * wp + f);
+  }
+  __syncthreads();
+  if (part < P) s_col[part * wp + f] = t;
+  __syncthreads();
+  if (part == 0) {
+    for (int k = 1; k < P; ++k) t += s_col[k * wp + f];
+    if (f < width) gw[f] = t;
+    else if (gb) gb[0] = t;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// ---- column concat into a pitched buffer / split back (tf.concat(axis=1) of model/deepfm.py:76 and its
+// gradient): one launch each way; the destination pitch is a multiple of 4 floats so the next dense layer's
+// GEMM reads it in place, padding columns are written as zeros.
+struct CatArgs {
+  float* p[ER_MAX_CAT];        // source (concat) / destination (split) matrices [B, width_i]
+  int width[ER_MAX_CAT];
+  int stride[ER_MAX_CAT];
+  int first[ER_MAX_CAT + 1];   // first column of each piece inside the wide matrix
+  int n;
+};
+__global__ void __launch_bounds__(256)
+    concat_cols_kernel(CatArgs a, int64_t batch, float* __restrict__ dst, int dst_stride) {
+  const int64_t total = batch * dst_stride;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / dst_stride;
+    const int c = (int)(t - b * dst_stride);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < ER_MAX_CAT; ++i)
+      if (i < a.n && c >= a.first[i] && c < a.first[i + 1]) v = a.p[i][b * a.stride[i] + (c - a.first[i])];
+    dst[t] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+    split_cols_kernel(CatArgs a, int64_t batch, const float* __restrict__ src, int src_stride, int total_w) {
+  const int64_t total = batch * total_w;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / total_w;
+    const int c = (int)(t - b * total_w);
+    const float v = src[b * src_stride + c];
+#pragma unroll
+    for (int i = 0; i < ER_MAX_CAT; ++i)
+      if (i < a.n && c >= a.first[i] && c < a.first[i + 1]) a.p[i][b * a.stride[i] + (c - a.first[i])] = v;
+  }
+}
+
 static bool fm_block_shape_ok(int n_field, int dim) {
   const int d4 = dim / 4;
   return dim % 4 == 0 && d4 >= 1 && d4 <= 32 && (d4 & (d4 - 1)) == 0 && (int64_t)n_field * d4 <= 32 * 8;
@@ -394,6 +582,131 @@ extern "C" int er_fm_block_bwd(const float* x, const float* gy, const float* g_p
     case 7: ER_FM_BWD(7); break; default: ER_FM_BWD(8); break;
   }
 #undef ER_FM_BWD
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_rowsum_block_fwd(const float* x, int64_t batch, int32_t width, int32_t x_stride, float* y,
+                                   float* sumsq_out, void* ws, size_t ws_bytes, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && y, "null argument");
+  ER_REQUIRE(batch > 0 && width > 0 && x_stride >= width, "bad shape");
+  const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), 4 * kSmCount);
+  float* partials = nullptr;
+  unsigned int* counter = nullptr;
+  if (sumsq_out) {
+    ER_REQUIRE(ws && ws_bytes >= er_fm_block_workspace_bytes(batch), "workspace too small");
+    counter = reinterpret_cast<unsigned int*>(ws);
+    partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 16);
+  }
+  rowsum_block_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, batch, width, x_stride, y, partials, counter,
+                                                               sumsq_out);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_rowsum_block_bwd(const float* x, const float* gy, const float* coef_dev, float coef_mul,
+                                   int64_t batch, int32_t width, int32_t x_stride, float* gx,
+                                   int32_t gx_stride, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && gx, "null argument");
+  ER_REQUIRE(batch > 0 && width > 0 && x_stride >= width && gx_stride >= width, "bad shape");
+  rowsum_block_bwd_kernel<<<grid_for(batch * width, 256, 8), 256, 0, as_stream(stream)>>>(
+      x, gy, coef_dev, coef_mul, batch, width, x_stride, gx, gx_stride);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" size_t er_dense1_workspace_bytes(int32_t width) {
+  return 16 + (size_t)er::kSmCount * ((size_t)width + 1) * sizeof(float);
+}
+
+extern "C" int er_dense1_fwd(const float* x, const float* w, const float* bias, int64_t batch, int32_t width,
+                             int32_t x_stride, float* y, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && w && y, "null argument");
+  ER_REQUIRE(batch > 0 && width > 0 && x_stride >= width, "bad shape");
+  const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), 4 * kSmCount);
+  dense1_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, batch, width, x_stride, y);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+// ws: er_dense1_workspace_bytes(width), first 16 bytes zero on first use (left zero).
+extern "C" int er_dense1_bwd(const float* x, const float* w, const float* g, int64_t batch, int32_t width,
+                             int32_t x_stride, float* gx, int32_t gx_stride, float* gw, float* gb, void* ws,
+                             size_t ws_bytes, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && w && g && gw, "null argument");
+  ER_REQUIRE(batch > 0 && width > 0 && width <= 255 && x_stride >= width && (!gx || gx_stride >= width), "bad shape (width <= 255)");
+  ER_REQUIRE(ws && ws_bytes >= er_dense1_workspace_bytes(width), "workspace too small");
+  const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), kSmCount);
+  const size_t smem = (size_t)std::max(8 * (width + 1), 256) * sizeof(float);
+  float* part = reinterpret_cast<float*>(static_cast<char*>(ws) + 16);
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(ws);
+  cudaStream_t st = as_stream(stream);
+#define ER_D1(JJ) dense1_bwd_kernel<JJ><<<grid, 256, smem, st>>>(x, w, g, batch, width, x_stride, gx, gx_stride, part, cnt, gw, gb)
+  switch ((width + 31) / 32) {
+    case 1: ER_D1(1); break; case 2: ER_D1(2); break; case 3: ER_D1(3); break; case 4: ER_D1(4); break;
+    case 5: ER_D1(5); break; case 6: ER_D1(6); break; case 7: ER_D1(7); break; default: ER_D1(8); break;
+  }
+#undef ER_D1
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+static int cat_args(er::CatArgs* a, float* const* mats, const int32_t* widths, const int32_t* strides,
+                    int32_t n) {
+  using namespace er;
+  ER_REQUIRE(mats && widths && strides, "null argument");
+  ER_REQUIRE(n > 0 && n <= ER_MAX_CAT, "1..ER_MAX_CAT pieces");
+  a->n = n;
+  int col = 0;
+  for (int i = 0; i < ER_MAX_CAT; ++i) {
+    a->first[i] = col;
+    if (i < n) {
+      ER_REQUIRE(mats[i] && widths[i] > 0 && strides[i] >= widths[i], "bad piece");
+      a->p[i] = mats[i];
+      a->width[i] = widths[i];
+      a->stride[i] = strides[i];
+      col += widths[i];
+    } else {
+      a->p[i] = nullptr;
+      a->width[i] = a->stride[i] = 0;
+    }
+  }
+  a->first[ER_MAX_CAT] = col;
+  for (int i = n; i <= ER_MAX_CAT; ++i) a->first[i] = col;
+  return ER_OK;
+}
+
+extern "C" int er_concat_cols(const float* const* srcs, const int32_t* widths, const int32_t* strides,
+                              int32_t n, int64_t batch, float* dst, int32_t dst_stride, er_stream_t stream) {
+  using namespace er;
+  CatArgs a;
+  int rc = cat_args(&a, const_cast<float* const*>(srcs), widths, strides, n);
+  if (rc != ER_OK) return rc;
+  ER_REQUIRE(dst && batch > 0 && dst_stride >= a.first[ER_MAX_CAT], "bad destination");
+  concat_cols_kernel<<<grid_for(batch * dst_stride, 256, 8), 256, 0, as_stream(stream)>>>(a, batch, dst, dst_stride);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_split_cols(const float* src, int32_t src_stride, int64_t batch, float* const* dsts,
+                             const int32_t* widths, const int32_t* strides, int32_t n, er_stream_t stream) {
+  using namespace er;
+  CatArgs a;
+  int rc = cat_args(&a, dsts, widths, strides, n);
+  if (rc != ER_OK) return rc;
+  ER_REQUIRE(src && batch > 0 && src_stride >= a.first[ER_MAX_CAT], "bad source");
+  split_cols_kernel<<<grid_for(batch * a.first[ER_MAX_CAT], 256, 8), 256, 0, as_stream(stream)>>>(
+      a, batch, src, src_stride, a.first[ER_MAX_CAT]);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;

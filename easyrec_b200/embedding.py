@@ -237,6 +237,49 @@ def fm_block(x, n_field, dim):
   return _FMBlock.apply(x, n_field, dim)
 
 
+class _RowsumBlock(torch.autograd.Function):
+  """The wide group's two consumers behind one node: reduce_sum over the features (model/deepfm.py:62-63)
+  and the embedding regulariser's sum of squares; backward merges both gradients in one pass."""
+
+  @staticmethod
+  def forward(ctx, x):
+    y, sumsq = K.rowsum_block_fwd(x, want_sumsq=True)
+    ctx.save_for_backward(x)
+    return y.unsqueeze(1), sumsq
+
+  @staticmethod
+  def backward(ctx, gy, g_sumsq):
+    (x,) = ctx.saved_tensors
+    gx = K.rowsum_block_bwd(x, None if gy is None else gy.contiguous().view(-1),
+                            None if g_sumsq is None else g_sumsq.contiguous(), 2.0)
+    return gx
+
+
+def rowsum_block(x):
+  """returns (row sums [B, 1], sum(x^2) [1])."""
+  return _RowsumBlock.apply(x)
+
+
+class _ConcatCols(torch.autograd.Function):
+  """tf.concat(axis=1) into a buffer whose pitch the next dense layer's GEMM reads in place; the gradient is
+  split back into contiguous pieces by one launch."""
+
+  @staticmethod
+  def forward(ctx, *mats):
+    ctx.widths = [m.shape[1] for m in mats]
+    return K.concat_cols(list(mats))
+
+  @staticmethod
+  def backward(ctx, g):
+    return tuple(K.split_cols(g, ctx.widths))
+
+
+def concat_cols(mats):
+  if len(mats) > 8 or not mats[0].is_cuda:
+    return torch.cat(mats, dim=1)
+  return _ConcatCols.apply(*mats)
+
+
 class _SigmoidCE(torch.autograd.Function):
   """tf.losses.sigmoid_cross_entropy (builders/loss_builder.py:36-39), mean over nonzero weights."""
 

@@ -372,8 +372,11 @@ class InputLayer(object):
     call = sc.call
     B = self.batch_size
     if sc.kind == 'single':
-      key = (call.slots_np[['num_buckets', 'row_offset', 'seg_begin', 'bucket_mode']].tobytes(),
-             tuple(call.sources))
+      key = getattr(sc, 'rows_key', None)
+      if key is None:   # arenas with the same row plan (wide dim-1 next to the deep tables) share K1's rows
+        key = (tuple((int(r['num_buckets']), int(r['row_offset']), int(r['seg_begin']), int(r['n_seg']),
+                      int(r['bucket_mode']), int(r['shard_n'])) for r in call.slots_np), tuple(call.sources))
+        sc.rows_key = key
       hit = self._rows_cache.get(key)
       if hit is None:
         cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)

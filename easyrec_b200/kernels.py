@@ -271,6 +271,93 @@ def fm_block_bwd(x, gy, g_pass, coef_dev, coef_mul, n_field, dim):
   return gx
 
 
+_blk_ws = {}
+
+
+def _zero_ws(key, nbytes, device):
+  ws = _blk_ws.get((key, device))
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)   # tickets start at zero, kernels leave them zero
+    _blk_ws[(key, device)] = ws
+  return ws
+
+
+def rowsum_block_fwd(x, want_sumsq=True):
+  """(y [B], sumsq [1] or None): row sums of a [B, F] matrix and sum(x^2) in one pass."""
+  lib = _lib.load()
+  batch, width = x.shape
+  y = torch.empty(batch, dtype=torch.float32, device=x.device)
+  sumsq = ws = None
+  if want_sumsq:
+    sumsq = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = _zero_ws('rowsum', lib.er_fm_block_workspace_bytes(batch), x.device)
+  _lib.check(lib.er_rowsum_block_fwd(_p(x), batch, width, x.stride(0), _p(y), _p(sumsq), _p(ws),
+                                     0 if ws is None else ws.numel(), _stream()), 'er_rowsum_block_fwd')
+  return y, sumsq
+
+
+def rowsum_block_bwd(x, gy, coef_dev, coef_mul):
+  lib = _lib.load()
+  batch, width = x.shape
+  gx = torch.empty(batch, width, dtype=torch.float32, device=x.device)
+  _lib.check(lib.er_rowsum_block_bwd(_p(x), _p(gy), _p(coef_dev), coef_mul, batch, width, x.stride(0), _p(gx),
+                                     gx.stride(0), _stream()), 'er_rowsum_block_bwd')
+  return gx
+
+
+def dense1_fwd(x, w, bias):
+  lib = _lib.load()
+  batch, width = x.shape
+  y = torch.empty(batch, 1, dtype=torch.float32, device=x.device)
+  _lib.check(lib.er_dense1_fwd(_p(x), _p(w), _p(bias), batch, width, x.stride(0), _p(y), _stream()), 'er_dense1_fwd')
+  return y
+
+
+def dense1_bwd(x, w, g, need_gx=True):
+  lib = _lib.load()
+  batch, width = x.shape
+  gx = torch.empty(batch, width, dtype=torch.float32, device=x.device) if need_gx else None
+  gw = torch.empty(width, 1, dtype=torch.float32, device=x.device)
+  gb = torch.empty(1, dtype=torch.float32, device=x.device)
+  ws = _zero_ws('dense1', lib.er_dense1_workspace_bytes(width), x.device)
+  _lib.check(lib.er_dense1_bwd(_p(x), _p(w), _p(g), batch, width, x.stride(0), _p(gx), width, _p(gw), _p(gb),
+                               _p(ws), ws.numel(), _stream()), 'er_dense1_bwd')
+  return gx, gw, gb
+
+
+def _cat_arrays(mats):
+  n = len(mats)
+  ptrs = (c_vp * n)(*[m.data_ptr() for m in mats])
+  widths = (ctypes.c_int32 * n)(*[m.shape[1] for m in mats])
+  strides = (ctypes.c_int32 * n)(*[m.stride(0) for m in mats])
+  return ptrs, widths, strides, n
+
+
+def concat_cols(mats, pitch_multiple=4):
+  """[B, w_i] matrices -> view [B, sum w] of a pitched buffer [B, ceil_k(sum w)] (padding written as zeros)."""
+  lib = _lib.load()
+  mats = [m if m.stride(1) == 1 else m.contiguous() for m in mats]
+  batch = mats[0].shape[0]
+  total = sum(m.shape[1] for m in mats)
+  pitch = (total + pitch_multiple - 1) // pitch_multiple * pitch_multiple
+  dst = torch.empty(batch, pitch, dtype=torch.float32, device=mats[0].device)
+  ptrs, widths, strides, n = _cat_arrays(mats)
+  _lib.check(lib.er_concat_cols(ptrs, widths, strides, n, batch, _p(dst), pitch, _stream()), 'er_concat_cols')
+  return dst[:, :total]
+
+
+def split_cols(src, widths):
+  """inverse of concat_cols: contiguous [B, w_i] pieces of the columns of src."""
+  lib = _lib.load()
+  if src.stride(1) != 1:
+    src = src.contiguous()
+  batch = src.shape[0]
+  outs = [torch.empty(batch, w, dtype=torch.float32, device=src.device) for w in widths]
+  ptrs, warr, strides, n = _cat_arrays(outs)
+  _lib.check(lib.er_split_cols(_p(src), src.stride(0), batch, ptrs, warr, strides, n, _stream()), 'er_split_cols')
+  return outs
+
+
 def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
   """returns (loss [1], probs [B], g_logits [B])."""
   lib = _lib.load()
@@ -350,9 +437,50 @@ def gemm(a, b, bias=None, out=None):
   return out
 
 
+_gemm_bn_ws = {}
+
+
+def gemm_bn(a, b, bias, moving_mean, moving_var, eps, momentum):
+  """z = a @ b on the tensor cores, with the batch-norm statistics of z + bias from the GEMM epilogue.
+  Returns (z, save_mean, save_rstd), or None when the problem would be split along K (caller falls back)."""
+  lib = _lib.load()
+  M, Ka = a.shape
+  Kb, N = b.shape
+  assert Ka == Kb, (a.shape, b.shape)
+  if N < 8 or Ka < 8 or M < 8 or lib.er_gemm_workspace_bytes(M, N, Ka) != 0:
+    return None
+  a, lda, a_unit = _gemm_operand(a, 'a')
+  b, ldb, b_unit = _gemm_operand(b, 'b')
+  z = torch.empty(M, N, dtype=torch.float32, device=a.device)
+  mean = torch.empty(N, dtype=torch.float32, device=a.device)
+  rstd = torch.empty(N, dtype=torch.float32, device=a.device)
+  nbytes = lib.er_gemm_bn_workspace_bytes(M, N)
+  key = (a.device, torch.cuda.current_stream().cuda_stream if a.is_cuda else 0)
+  ws = _gemm_bn_ws.get(key)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=a.device)   # counters must start at zero
+    _gemm_bn_ws[key] = ws
+  bn = _lib.ErBnStats(_p(bias), _p(mean), _p(rstd), _p(moving_mean), _p(moving_var), eps, momentum)
+  _lib.check(lib.er_gemm_bn(_p(a), lda, 0 if a_unit else 1, _p(b), ldb, 1 if b_unit else 0, _p(z), z.stride(0),
+                            M, N, Ka, ctypes.byref(bn), _p(ws), ws.numel(), _stream()), 'er_gemm_bn')
+  return z, mean, rstd
+
+
+def bn_act_apply(z, bias, gamma, beta, mean, rstd, relu, y=None):
+  lib = _lib.load()
+  _chk(z, torch.float32, 'z')
+  batch, units = z.shape
+  if y is None:
+    y = torch.empty_like(z)
+  _lib.check(lib.er_bn_act_apply(_p(z), _p(bias), _p(gamma), _p(beta), _p(mean), _p(rstd), batch, units,
+                                 1 if relu else 0, _p(y), _stream()), 'er_bn_act_apply')
+  return y
+
+
 def dense_workspace(batch, units, device):
   lib = _lib.load()
-  return torch.empty(lib.er_dense_workspace_bytes(batch, units), dtype=torch.uint8, device=device)
+  # zero-filled: the head of the workspace holds the backward's CTA tickets (self-resetting)
+  return torch.zeros(lib.er_dense_workspace_bytes(batch, units), dtype=torch.uint8, device=device)
 
 
 def bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, eps, momentum, training, relu,

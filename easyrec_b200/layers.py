@@ -10,6 +10,7 @@ CPU run; forward, dX and dW read X / W[in,out] / dY in place) + liber_b200's fus
 epilogue (2 launches forward, 2 backward, deterministic statistics).  There is no torch fallback.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -18,6 +19,16 @@ from easyrec_b200 import kernels as K
 
 BN_EPS = 1e-3
 BN_MOMENTUM = 0.99
+_OVERLAP_DW_DX = os.environ.get('ER_OVERLAP_DW_DX', '1') == '1'
+_side = {}
+
+
+def _side_stream(device):
+  s = _side.get(device)
+  if s is None:
+    s = torch.cuda.Stream(device=device)
+    _side[device] = s
+  return s
 
 
 class _DenseBNAct(torch.autograd.Function):
@@ -25,9 +36,20 @@ class _DenseBNAct(torch.autograd.Function):
   @staticmethod
   def forward(ctx, x, kernel, bias, gamma, beta, moving_mean, moving_var, training, relu, ws):
     x = K.gemm_ready(x)
-    z = K.gemm(x, kernel)
-    y, mean, rstd = K.bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, BN_EPS,
-                                      BN_MOMENTUM, training, relu, ws)
+    ctx.kernel_param = kernel
+    if hasattr(kernel, '_er_uses'):
+      kernel._er_uses += 1
+    fused = None
+    if gamma is not None and training:
+      # batch statistics come out of the GEMM epilogue; one elementwise pass normalises + activates
+      fused = K.gemm_bn(x, kernel, bias, moving_mean, moving_var, BN_EPS, BN_MOMENTUM)
+    if fused is not None:
+      z, mean, rstd = fused
+      y = K.bn_act_apply(z, bias, gamma, beta, mean, rstd, relu)
+    else:
+      z = K.gemm(x, kernel)
+      y, mean, rstd = K.bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, BN_EPS,
+                                        BN_MOMENTUM, training, relu, ws)
     ctx.relu = relu
     ctx.ws = ws
     ctx.has_bn = gamma is not None
@@ -39,9 +61,46 @@ class _DenseBNAct(torch.autograd.Function):
     x, kernel, bias, gamma, z, y, mean, rstd = ctx.saved_tensors
     gz, gbias, ggamma, gbeta = K.bias_bn_act_bwd(z, bias, gamma, y, gy.contiguous(), mean, rstd,
                                                  ctx.relu, ctx.ws)
-    gk = K.gemm(x.t(), gz)
-    gx = K.gemm(gz, kernel.t()) if ctx.needs_input_grad[0] else None
+    # dW goes straight into the optimizer's flat gradient buffer when this kernel is applied once per step
+    # (a fresh view object, so AccumulateGrad adopts it instead of cloning)
+    kp = ctx.kernel_param
+    dst = getattr(kp, '_er_grad_out', None)
+    if dst is not None and getattr(kp, '_er_uses', 2) == 1 and kp.grad is None:
+      gk = dst.view_as(dst)
+    else:
+      gk = torch.empty(x.shape[1], gz.shape[1], dtype=torch.float32, device=x.device)
+    if ctx.needs_input_grad[0] and x.is_cuda and _OVERLAP_DW_DX:
+      # dW (split-K, few tiles) and dX (many tiles) are independent: fork dW onto a side stream so the two
+      # fill the 148 SMs together (captured as a fork/join inside the step's CUDA graph).  Outputs are
+      # allocated on the main stream; the side stream only launches.
+      cur = torch.cuda.current_stream()
+      side = _side_stream(x.device)
+      side.wait_stream(cur)
+      with torch.cuda.stream(side):
+        K.gemm(x.t(), gz, out=gk)
+      gx = K.gemm(gz, kernel.t())
+      cur.wait_stream(side)
+    else:
+      K.gemm(x.t(), gz, out=gk)
+      gx = K.gemm(gz, kernel.t()) if ctx.needs_input_grad[0] else None
     return gx, gk, gbias, ggamma, gbeta, None, None, None, None, None
+
+
+class _Dense1(torch.autograd.Function):
+  """tf.layers.dense(units=1): the logit head as a GEMV (one warp per row) instead of a 128-wide GEMM tile."""
+
+  @staticmethod
+  def forward(ctx, x, kernel, bias):
+    if x.stride(1) != 1:
+      x = x.contiguous()
+    ctx.save_for_backward(x, kernel)
+    return K.dense1_fwd(x, kernel, bias)
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, kernel = ctx.saved_tensors
+    gx, gw, gb = K.dense1_bwd(x, kernel, gy.contiguous().view(-1), need_gx=ctx.needs_input_grad[0])
+    return gx, gw, gb
 
 
 class DenseLayer(nn.Module):
@@ -72,6 +131,8 @@ class DenseLayer(nn.Module):
     if self.use_bn:
       return _DenseBNAct.apply(x, self.kernel, self.bias, self.gamma, self.beta, self.moving_mean,
                                self.moving_var, self.training, self.relu, self._ws)
+    if self.n_out == 1 and not self.relu and x.is_cuda and self.kernel.shape[0] <= 255:
+      return _Dense1.apply(x, self.kernel, self.bias)
     return _DenseBNAct.apply(x, self.kernel, self.bias, None, None, None, None, self.training,
                              self.relu, self._ws)
 

@@ -53,7 +53,11 @@ class DeepFM(nn.Module):
     g = self.input_layer.lookup(features)
     wide, _ = g['wide']
     deep, _ = g['deep']
-    wide_fea = wide.sum(dim=1, keepdim=True)
+    self._wide_sumsq = None
+    if wide.is_cuda:
+      wide_fea, self._wide_sumsq = E.rowsum_block(wide)
+    else:
+      wide_fea = wide.sum(dim=1, keepdim=True)
     self._deep_sumsq = None
     if deep.shape[1] == self.deep_width and K.fm_block_ok(self.n_field, self.dim) and deep.is_cuda:
       # FM, the tower input and the regulariser's sum of squares from one pass; one merged gradient back
@@ -63,7 +67,7 @@ class DeepFM(nn.Module):
       deep_in = deep[:, :self.deep_width] if deep.shape[1] != self.deep_width else deep
     deep_fea = self.dnn(deep_in)
     if self.has_final:
-      all_fea = torch.cat([wide_fea, fm_fea, deep_fea], dim=1)
+      all_fea = E.concat_cols([wide_fea, fm_fea, deep_fea])
       logits = self.output(self.final_dnn(all_fea))
     else:
       logits = wide_fea + fm_fea.sum(dim=1, keepdim=True) + self.output(deep_fea)
@@ -85,7 +89,8 @@ class DeepFM(nn.Module):
     if self.embedding_reg > 0:
       wide, deep = self._emb_outputs
       deep_sq = self._deep_sumsq[0] if self._deep_sumsq is not None else (deep * deep).sum()
-      reg = reg + self.embedding_reg * 0.5 * ((wide * wide).sum() + deep_sq)
+      wide_sq = self._wide_sumsq[0] if self._wide_sumsq is not None else (wide * wide).sum()
+      reg = reg + self.embedding_reg * 0.5 * (wide_sq + deep_sq)
     return reg
 
   def loss(self, logits, labels):

@@ -44,6 +44,10 @@ class FlatDenseOptimizer(object):
       v.copy_(p.data)
       p.data = v
       self.grad_views.append(self.flat_g[off:off + sizes[i]].view_as(p))
+      # dense layers write dW straight into this slice (layers._DenseBNAct.backward) when the kernel is
+      # used once per step, so the big gradients skip the gather copy
+      p._er_grad_out = self.grad_views[-1] if p.dim() == 2 else None
+      p._er_uses = 0
       segs[i]['offset'] = off
       segs[i]['n'] = sizes[i]
       segs[i]['l2'] = float(l2_of(n, p)) if l2_of else 0.0
@@ -74,6 +78,7 @@ class FlatDenseOptimizer(object):
   def zero_grad(self):
     for p in self.params:
       p.grad = None
+      p._er_uses = 0
 
   def gather_grads(self):
     """p.grad (fresh autograd tensors) -> the flat gradient buffer (one multi-tensor copy)."""
@@ -81,10 +86,11 @@ class FlatDenseOptimizer(object):
     for p, v in zip(self.params, self.grad_views):
       if p.grad is None:
         v.zero_()
-      else:
+      elif p.grad.data_ptr() != v.data_ptr():   # else: already produced in place
         srcs.append(p.grad)
         dsts.append(v)
-    torch._foreach_copy_(dsts, srcs)
+    if srcs:
+      torch._foreach_copy_(dsts, srcs)
 
   def apply(self):
     lib = _lib.load()

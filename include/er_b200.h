@@ -243,6 +243,35 @@ int er_fm_block_bwd(const float* x, const float* gy, const float* g_pass, const 
                     float coef_mul, int64_t batch, int32_t n_field, int32_t dim, int32_t x_stride,
                     int32_t g_pass_stride, float* gx, int32_t gx_stride, er_stream_t stream);
 
+/* Column concat into a pitched matrix and its gradient (tf.concat(axis=1), model/deepfm.py:76):
+ * dst[b, first_i + c] = srcs[i][b, c]; columns past the last piece up to dst_stride are written as 0.
+ * er_split_cols scatters the columns of src back into the pieces. */
+#define ER_MAX_CAT 8
+int er_concat_cols(const float* const* srcs, const int32_t* widths, const int32_t* strides, int32_t n,
+                   int64_t batch, float* dst, int32_t dst_stride, er_stream_t stream);
+int er_split_cols(const float* src, int32_t src_stride, int64_t batch, float* const* dsts,
+                  const int32_t* widths, const int32_t* strides, int32_t n, er_stream_t stream);
+
+/* Wide block (model/deepfm.py:62-63 and the regulariser of layers/input_layer.py:369-375):
+ *   fwd: y[b] = sum_f x[b,f]; *sumsq_out = sum x^2 (NULL: skipped; ws as er_fm_block_fwd)
+ *   bwd: gx[b,f] = gy[b] + (*coef_dev * coef_mul) * x[b,f] */
+int er_rowsum_block_fwd(const float* x, int64_t batch, int32_t width, int32_t x_stride, float* y,
+                        float* sumsq_out, void* ws, size_t ws_bytes, er_stream_t stream);
+int er_rowsum_block_bwd(const float* x, const float* gy, const float* coef_dev, float coef_mul,
+                        int64_t batch, int32_t width, int32_t x_stride, float* gx, int32_t gx_stride,
+                        er_stream_t stream);
+
+/* Single-unit dense head (the logit layer tf.layers.dense(units=1), model/deepfm.py:75-105,
+ * rank_model.py:57-74): y[b] = x[b,:].w + bias;  gx[b,f] = g[b]*w[f] (gx NULL: skipped),
+ * gw[f] = sum_b g[b]*x[b,f], gb = sum_b g[b] (deterministic).  ws: er_dense1_workspace_bytes(width),
+ * first 16 bytes zero on first use (left zero). */
+size_t er_dense1_workspace_bytes(int32_t width);
+int er_dense1_fwd(const float* x, const float* w, const float* bias, int64_t batch, int32_t width,
+                  int32_t x_stride, float* y, er_stream_t stream);
+int er_dense1_bwd(const float* x, const float* w, const float* g, int64_t batch, int32_t width,
+                  int32_t x_stride, float* gx, int32_t gx_stride, float* gw, float* gb, void* ws,
+                  size_t ws_bytes, er_stream_t stream);
+
 /* ---- K6 epilogues: dense bias + batch-norm + relu (layers/dnn.py:56-79) ------
  * z is the SGEMM output x W (no bias).  Training: batch statistics (biased
  * variance, tf.layers.batch_normalization defaults) are computed deterministically
@@ -294,6 +323,31 @@ size_t er_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
             int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
             int64_t K, void* ws, size_t ws_bytes, er_stream_t stream);
+
+/* Dense + batch-norm training forward: the GEMM also produces the batch statistics of its output
+ * columns (per-tile Welford partials merged in tile order by the last CTA of each column tile:
+ * deterministic, no extra pass over z).  On return (stream order) save_mean[n] = mean(z[:,n]) + bias[n],
+ * save_rstd[n] = 1/sqrt(biased var + eps) and, when given, the moving statistics are updated with
+ * `momentum` (tf.layers.batch_normalization, layers/dnn.py:64-72).  z itself is stored WITHOUT the bias;
+ * er_bn_act_apply adds it.  Needs an unsplit K (er_gemm_workspace_bytes(M,N,K) == 0) and a workspace of
+ * er_gemm_bn_workspace_bytes(M,N) whose first 1024 bytes are zero on first use (left zero afterwards). */
+typedef struct {
+  const float* bias;      /* [N] or NULL */
+  float* save_mean;       /* [N] out */
+  float* save_rstd;       /* [N] out */
+  float* moving_mean;     /* [N] in/out or NULL */
+  float* moving_var;      /* [N] in/out or NULL */
+  float eps;
+  float momentum;
+} er_bn_stats_t;
+size_t er_gemm_bn_workspace_bytes(int64_t M, int64_t N);
+int er_gemm_bn(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+               int32_t b_mn_major, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+               const er_bn_stats_t* bn, void* ws, size_t ws_bytes, er_stream_t stream);
+/* y = act((z + bias - mean) * rstd * gamma + beta) with given statistics (one elementwise pass). */
+int er_bn_act_apply(const float* z, const float* bias, const float* gamma, const float* beta,
+                    const float* mean, const float* rstd, int64_t batch, int32_t units, int32_t relu,
+                    float* y, er_stream_t stream);
 
 /* sigmoid cross entropy (tf.losses.sigmoid_cross_entropy,
  * builders/loss_builder.py:36-39): loss_sum += sum_b w*(max(x,0)-x*z+log1p(exp(-|x|)))
