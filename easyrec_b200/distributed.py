@@ -58,6 +58,7 @@ class DataParallel(object):
     dense_opt.grad_scale = 1.0 / world  # mean over replicas, applied inside er_dense_apply
     plans = getattr(input_layer, 'merged', None) or input_layer.calls
     self.gcalls = {id(c): GlobalCall(c, world) for c in plans.values()}
+    self._rows_owner = {}
 
   def sync_dense_grads(self):
     """sum over replicas in one bucket; the 1/world of hvd.allreduce(Average)
@@ -68,9 +69,17 @@ class DataParallel(object):
     """all-gather one arena call's K7 inputs (rows, weights, segment scales, upstream gradients)
     into the GlobalCall buffers; returns the GlobalCall."""
     g = self.gcalls[id(call)]
-    dist.all_gather_into_tensor(g.rows, rows)
-    if w is not None:
-      dist.all_gather_into_tensor(g.weights, w)
+    # arenas with the same row plan (wide dim-1 next to the deep tables) were looked up with the SAME rows /
+    # weights tensors: gather those once and let the later call alias the first one's buffers (and its sort)
+    first = self._rows_owner.get(id(rows))
+    if first is not None and first is not g and first.call.arena.n_rows == call.arena.n_rows:
+      g.rows_src = first
+    else:
+      g.rows_src = None
+      self._rows_owner[id(rows)] = g
+      dist.all_gather_into_tensor(g.rows, rows)
+      if w is not None:
+        dist.all_gather_into_tensor(g.weights, w)
     if call.seg_scale is not None:
       if g.seg_scale is None:
         g.seg_scale = torch.empty(g.n_seg, dtype=torch.float32, device=rows.device)
@@ -84,6 +93,7 @@ class DataParallel(object):
     """The collectives of one step (eager NCCL calls, kept OUTSIDE CUDA-graph capture): dense flat
     all-reduce + all-gather of every arena's K7 inputs."""
     self.sync_dense_grads()
+    self._rows_owner = {}
     for call, rows, w, outs, seg_ids in pending:
       if seg_ids is not None:
         raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
@@ -96,13 +106,17 @@ class DataParallel(object):
     for call, rows, w, outs, seg_ids in pending:
       g = self.gcalls[id(call)]
       a = call.arena
-      K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, g.rows, g.slots_dev, g.n_slots, g.n_seg,
-                      g.grads, opt, g.ws, weights=g.weights if w is not None else None,
-                      seg_scale=g.seg_scale)
+      src = getattr(g, 'rows_src', None)
+      owner = src if src is not None else g
+      K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, owner.rows, g.slots_dev, g.n_slots, g.n_seg,
+                      g.grads, opt, g.ws, weights=owner.weights if w is not None else None,
+                      seg_scale=g.seg_scale,
+                      sorted_from=(src.ws, src.call.arena.dim) if src is not None else None)
     opt.grad_scale = opt.grad_scale * self.world
 
   def sparse_backward_update(self, opt):
     il = self.input_layer
+    self._rows_owner = {}
     for call, rows, w, outs, seg_ids in il._pending:
       if seg_ids is not None:
         raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
