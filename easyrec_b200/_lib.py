@@ -62,6 +62,7 @@ SIGNATURES = {
         c_i32, ctypes.POINTER(c_vp), c_i32, c_vp, c_vp
     ]),
     'er_embedding_bwd_workspace_bytes': (c_sz, [c_i64, c_i32]),
+    'er_embedding_bwd_presort': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_sz, c_vp]),
     'er_embedding_bwd_reuse_sort': (c_i32, [
         c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
         c_i64, c_vp, c_i32, ctypes.POINTER(c_vp), c_i32, c_vp,

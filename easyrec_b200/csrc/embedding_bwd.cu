@@ -885,6 +885,23 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
                             uniq_rows, uniq_grads, n_uniq, ws, ws_bytes, nullptr, 0, 0, stream);
 }
 
+extern "C" int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, const int32_t* row_ptr,
+                                        int64_t n_seg, int64_t n_lookups_cap, int32_t dim, void* ws,
+                                        size_t ws_bytes, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(rows, "null argument");
+  ER_REQUIRE(n_rows > 0 && n_rows < 0xFFFFFFFFLL, "n_rows must be in (0, 2^32-1)");
+  ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31) && dim > 0, "bad shape");
+  if (n_lookups_cap == 0) return ER_OK;
+  if (!ws || ws_bytes < bwd_ws_bytes(n_lookups_cap, dim))
+    return fail(ER_ERR_WORKSPACE, "er_embedding_bwd_presort: workspace too small");
+  BwdWs w = bwd_carve(ws, n_lookups_cap, dim);
+  const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
+  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, as_stream(stream));
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
 extern "C" int er_embedding_bwd_reuse_sort(float* table, float* state0, float* state1, int64_t n_rows,
                                            int32_t dim, int32_t row_stride, const float* weights,
                                            const int32_t* seg_ids, const int32_t* row_ptr, int64_t n_seg,

@@ -54,6 +54,7 @@ class DataParallel(object):
     """dense_opt: trainer.FlatDenseOptimizer -- its flat gradient buffer is the all-reduce bucket."""
     self.input_layer = input_layer
     self.world = world
+    input_layer.presort_enabled = False   # K7 runs on the gathered global batch, sorted after the exchange
     self.dense_opt = dense_opt
     dense_opt.grad_scale = 1.0 / world  # mean over replicas, applied inside er_dense_apply
     plans = getattr(input_layer, 'merged', None) or input_layer.calls

@@ -101,6 +101,7 @@ class EasyRecEstimator(object):
     self.model.eval()
     logits = self.model(feats)
     self.input_layer._pending = []
+    self.input_layer._presorted = {}
     return logits
 
   def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):

@@ -290,6 +290,9 @@ class InputLayer(object):
     self.opt_holder = {'opt': K.make_opt(embedding_optimizer, 0.01)}
     self._pending = []
     self._rows_cache = {}
+    self._presorted = {}
+    self._side = None
+    self.presort_enabled = True
     self._pos = {}
 
   # ------------------------------------------------------------------
@@ -304,7 +307,10 @@ class InputLayer(object):
     """After loss.backward(): K7 for every arena looked up since the last call (dedup, segment
     sum and the fused optimizer row update).  The reference's counterpart is
     opt.apply_gradients on the tables' IndexedSlices (compat/optimizers.py:413-416)."""
-    sorted_by = {}   # id(rows tensor) -> (workspace, dim, n_rows) of the call that sorted it
+    sorted_by = dict(self._presorted)   # id(rows tensor) -> (workspace, dim, n_rows) of the call that sorted it
+    if self._presorted:
+      torch.cuda.current_stream().wait_stream(self._side)   # join the early sorts
+      self._presorted = {}
     for m, rows, w, outs, seg_ids in self._pending:
       # arenas with the same row plan (DeepFM / Wide&Deep: the wide dim-1 and the deep tables) look up the
       # same rows tensor: the second K7 reuses the first one's radix sort.
@@ -314,6 +320,26 @@ class InputLayer(object):
       if hit is None:
         sorted_by[id(rows)] = (m.ws, m.arena.dim, m.arena.n_rows)
     self._pending = []
+
+  def _presort(self):
+    """K7's radix sort needs only the looked-up rows: start it now on a side stream so it runs under the
+    dense forward/backward instead of after it (joined in backward_update; captured as a fork/join)."""
+    self._presorted = {}
+    if not (self.presort_enabled and torch.is_grad_enabled() and str(self.device).startswith('cuda')):
+      return
+    todo = []
+    for m, rows, w, outs, seg_ids in self._pending:
+      if id(rows) not in self._presorted:
+        self._presorted[id(rows)] = (m.ws, m.arena.dim, m.arena.n_rows)
+        todo.append((m, rows))
+    if not todo:
+      return
+    if self._side is None:
+      self._side = torch.cuda.Stream(device=self.device)
+    self._side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(self._side):
+      for m, rows in todo:
+        K.embedding_bwd_presort(rows, m.arena.n_rows, m.arena.dim, m.ws)
 
   def normalize_dense(self, dense):
     if not self.raw_has_range:
@@ -482,6 +508,7 @@ class InputLayer(object):
           all_outs.extend(outs)
         self._pending.append((m, m.rows, m.weights if any_w else None, all_outs,
                               m.seg_ids if m.has_csr else None))
+    self._presort()
     out = {}
     for gname, layout in self.group_layout.items():
       per_feature, mats, kinds = [], {}, []

@@ -168,6 +168,14 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
                            _p(n_uniq), _p(ws), ws.numel(), _stream()), 'er_embedding_bwd')
 
 
+def embedding_bwd_presort(rows, n_rows, dim, ws, row_ptr=None, n_seg=0):
+  """K7's dedup sort alone (needs only the rows): finish with embedding_bwd(..., sorted_from=(ws, dim))."""
+  lib = _lib.load()
+  _chk(rows, torch.int64, 'rows')
+  _lib.check(lib.er_embedding_bwd_presort(_p(rows), n_rows, _p(row_ptr), n_seg, rows.numel(), dim, _p(ws),
+                                          ws.numel(), _stream()), 'er_embedding_bwd_presort')
+
+
 def sparse_apply(table, state0, state1, dim, uniq_rows, uniq_grads, n_uniq, opt, row_stride=None):
   lib = _lib.load()
   _, row_stride = _chk_rows(table, 'table')

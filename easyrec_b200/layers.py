@@ -21,6 +21,27 @@ BN_EPS = 1e-3
 BN_MOMENTUM = 0.99
 _OVERLAP_DW_DX = os.environ.get('ER_OVERLAP_DW_DX', '1') == '1'
 _side = {}
+_defer = {'on': False, 'dirty': set()}
+
+
+class defer_dw_join(object):
+  """Inside this context the side stream that computes the kernel gradients is NOT joined after every layer:
+  the dW GEMMs (which nothing in the backward pass consumes) queue up on the side stream while the main
+  stream runs the dX / batch-norm chain, and everything is joined once on exit.  The trainer wraps
+  loss.backward() in it; code that reads .grad right after a layer's backward must not."""
+
+  def __enter__(self):
+    self.prev = _defer['on']
+    _defer['on'] = True
+    return self
+
+  def __exit__(self, *exc):
+    _defer['on'] = self.prev
+    if not self.prev:
+      for dev in list(_defer['dirty']):
+        torch.cuda.current_stream(dev).wait_stream(_side[dev])
+      _defer['dirty'].clear()
+    return False
 
 
 def _side_stream(device):
@@ -79,7 +100,13 @@ class _DenseBNAct(torch.autograd.Function):
       with torch.cuda.stream(side):
         K.gemm(x.t(), gz, out=gk)
       gx = K.gemm(gz, kernel.t())
-      cur.wait_stream(side)
+      if _defer['on']:
+        # joined by defer_dw_join.__exit__; the operands must outlive this function on the side stream
+        gz.record_stream(side)
+        x.record_stream(side)
+        _defer['dirty'].add(x.device)
+      else:
+        cur.wait_stream(side)
     else:
       K.gemm(x.t(), gz, out=gk)
       gx = K.gemm(gz, kernel.t()) if ctx.needs_input_grad[0] else None

@@ -15,6 +15,7 @@ import torch
 
 from easyrec_b200 import _lib
 from easyrec_b200 import kernels as K
+from easyrec_b200 import layers as L
 
 
 class FlatDenseOptimizer(object):
@@ -141,7 +142,8 @@ class Trainer(object):
     self.dense_opt.zero_grad()
     logits = self.model(features)
     loss, probs = self.model.loss(logits, labels)
-    loss.backward()
+    with L.defer_dw_join():   # kernel-gradient GEMMs overlap the rest of the backward chain
+      loss.backward()
     self.dense_opt.gather_grads()
     self._step_pending = list(self.input_layer._pending)
     return loss.detach(), probs

@@ -176,6 +176,14 @@ int er_embedding_bwd(float* table, float* state0, float* state1,
                      int64_t* uniq_rows, float* uniq_grads, int32_t* n_uniq,
                      void* ws, size_t ws_bytes, er_stream_t stream);
 
+/* The dedup sort of er_embedding_bwd alone: it depends only on the looked-up rows, not on any gradient,
+ * so it can run as soon as er_bucketize has produced them (e.g. on a side stream under the dense
+ * forward/backward).  Leaves the sorted (row, lookup) pairs in `ws`; finish with
+ * er_embedding_bwd_reuse_sort(..., sorted_ws = ws, sorted_dim = dim). */
+int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, const int32_t* row_ptr, int64_t n_seg,
+                             int64_t n_lookups_cap, int32_t dim, void* ws, size_t ws_bytes,
+                             er_stream_t stream);
+
 /* Same as er_embedding_bwd for a second table that was looked up with the SAME rows array (same
  * n_rows, e.g. the wide dim-1 table next to the deep table of DeepFM / Wide&Deep): the lookups were
  * already radix-sorted by an earlier er_embedding_bwd on this stream whose workspace is sorted_ws
