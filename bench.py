@@ -385,7 +385,11 @@ def main():
     k['frac'] = k['achieved'] / peak
   dom = k_bwd if bwd_ms >= fwd_ms else k_fwd
   roofline = {'bound': 'hbm', 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s', 'frac': dom['frac'],
-              'traffic': None, 'kernel': dom['kernel'], 'peak_source': peak_src,
+              # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the pipeline's largest launch
+              # (bwd_scan_vec_kernel<4>: 37.03 MB read + 0.07 MB written during the launch; the updated rows are
+              # written back from L2 after it) -- profiles/r01_ncu_bwd_scan_vec.txt; fwd_single_kernel: 23.4 MB
+              'traffic': 37.1e6 if dom is k_bwd else 23.5e6, 'traffic_source': 'profiles/r01_ncu_*.txt',
+              'kernel': dom['kernel'], 'peak_source': peak_src,
               'kernels': [k_fwd, k_bwd, k_gemm],
               'random_64B_row_ceiling_gbs': 1000.0,
               'ceiling_note': 'tools/microbench_gather.cu: independent random 64 B row reads reach 15.6 Grows/s '

@@ -305,12 +305,164 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- vector backward (units % 4 == 0): the same two passes with 16-byte accesses --------------------
+// CTA = 128 columns (32 float4 lanes) x 8 row lanes over one row chunk; one wave of CTAs.  Pass 1 writes one
+// (sum g, sum g*xhat) partial per (chunk, column); pass 2's CTAs each re-add the chunk partials of their
+// 128 columns (8 row lanes in parallel, fixed order: deterministic, no tickets, no atomics) and stream.
+constexpr int kVecCols = 128;
+
+struct VecShape {
+  int64_t batch;
+  int units;
+  int rows_per_chunk;
+  int n_chunks;
+};
+inline VecShape vec_shape(int64_t batch, int units) {
+  VecShape s;
+  s.batch = batch;
+  s.units = units;
+  const int col_tiles = (units + kVecCols - 1) / kVecCols;
+  const int r = std::max(1, (kSmCount + col_tiles - 1) / col_tiles);
+  int64_t rpc = ceil_div(batch, (int64_t)r);
+  rpc = std::max<int64_t>(ceil_div(rpc, (int64_t)kRowLanes) * kRowLanes, 2 * kRowLanes);
+  s.rows_per_chunk = (int)rpc;
+  s.n_chunks = (int)ceil_div(batch, rpc);
+  return s;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void relu_mask4(float4& g, const float4& yy) {
+  if (!(yy.x > 0.f)) g.x = 0.f;
+  if (!(yy.y > 0.f)) g.y = 0.f;
+  if (!(yy.z > 0.f)) g.z = 0.f;
+  if (!(yy.w > 0.f)) g.w = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+    bn_bwd_stats_vec_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                            const float* __restrict__ y, const float* __restrict__ gy,
+                            const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                            VecShape s, int relu, int use_bn, float* __restrict__ part /* [n_chunks][units][2] */) {
+  __shared__ float4 s_a[kRowLanes][32], s_b[kRowLanes][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * kVecCols + 4 * cl;
+  const int64_t r0 = (int64_t)blockIdx.y * s.rows_per_chunk;
+  const int64_t r1 = min(s.batch, r0 + s.rows_per_chunk);
+  float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sx = sg;
+  if (c < s.units) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), mu = b, rs = b;
+    if (bias) b = ld4(bias + c);
+    if (use_bn) {
+      mu = ld4(save_mean + c);
+      rs = ld4(save_rstd + c);
+    }
+#pragma unroll 4
+    for (int64_t r = r0 + rl; r < r1; r += kRowLanes) {
+      const int64_t i = r * s.units + c;
+      float4 g = ld4(gy + i);
+      if (relu) relu_mask4(g, ld4(y + i));
+      sg.x += g.x; sg.y += g.y; sg.z += g.z; sg.w += g.w;
+      if (use_bn) {
+        const float4 zz = ld4(z + i);
+        sx.x += g.x * (((zz.x + b.x) - mu.x) * rs.x);
+        sx.y += g.y * (((zz.y + b.y) - mu.y) * rs.y);
+        sx.z += g.z * (((zz.z + b.z) - mu.z) * rs.z);
+        sx.w += g.w * (((zz.w + b.w) - mu.w) * rs.w);
+      }
+    }
+  }
+  s_a[rl][cl] = sg;
+  s_b[rl][cl] = sx;
+  __syncthreads();
+  if (rl == 0 && c < s.units) {
+    float4 a = s_a[0][cl], bb = s_b[0][cl];
+    for (int k = 1; k < kRowLanes; ++k) {
+      const float4 p = s_a[k][cl], q = s_b[k][cl];
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+      bb.x += q.x; bb.y += q.y; bb.z += q.z; bb.w += q.w;
+    }
+    float4* p = reinterpret_cast<float4*>(part + ((int64_t)blockIdx.y * s.units + c) * 2);
+    p[0] = a;    // sum g   of columns c..c+3
+    p[1] = bb;   // sum g*xhat
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_vec_kernel(const float* __restrict__ z, const float* __restrict__ bias,
+                            const float* __restrict__ gamma, const float* __restrict__ y,
+                            const float* __restrict__ gy, const float* __restrict__ save_mean,
+                            const float* __restrict__ save_rstd, VecShape s, int relu, int use_bn,
+                            const float* __restrict__ part, float* __restrict__ gz,
+                            float* __restrict__ gbias, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  __shared__ float4 s_a[kRowLanes][32], s_b[kRowLanes][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * kVecCols + 4 * cl;
+  {  // the 8 row lanes add the chunk partials in parallel (chunks rl, rl+8, ...), lane 0 adds the 8
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c < s.units) {
+#pragma unroll 4
+      for (int k = rl; k < s.n_chunks; k += kRowLanes) {
+        const float4* p = reinterpret_cast<const float4*>(part + ((int64_t)k * s.units + c) * 2);
+        const float4 pa = p[0], pb = p[1];
+        a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+        b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+      }
+    }
+    s_a[rl][cl] = a;
+    s_b[rl][cl] = b;
+    __syncthreads();
+  }
+  float4 sg = s_a[0][cl], sx = s_b[0][cl];
+  for (int k = 1; k < kRowLanes; ++k) {
+    const float4 p = s_a[k][cl], q = s_b[k][cl];
+    sg.x += p.x; sg.y += p.y; sg.z += p.z; sg.w += p.w;
+    sx.x += q.x; sx.y += q.y; sx.z += q.z; sx.w += q.w;
+  }
+  if (c >= s.units) return;
+  if (blockIdx.y == 0 && rl == 0) {
+    if (use_bn) {
+      if (ggamma) *reinterpret_cast<float4*>(ggamma + c) = sx;
+      if (gbeta) *reinterpret_cast<float4*>(gbeta + c) = sg;
+      if (gbias) *reinterpret_cast<float4*>(gbias + c) = make_float4(0.f, 0.f, 0.f, 0.f);   // see scalar kernel
+    } else if (gbias) {
+      *reinterpret_cast<float4*>(gbias + c) = sg;
+    }
+  }
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f), mu = b, rs = b, ga = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (bias) b = ld4(bias + c);
+  if (use_bn) {
+    mu = ld4(save_mean + c);
+    rs = ld4(save_rstd + c);
+    ga = ld4(gamma + c);
+  }
+  const float inv_b = 1.0f / (float)s.batch;
+  const int64_t r0 = (int64_t)blockIdx.y * s.rows_per_chunk;
+  const int64_t r1 = min(s.batch, r0 + s.rows_per_chunk);
+#pragma unroll 4
+  for (int64_t r = r0 + rl; r < r1; r += kRowLanes) {
+    const int64_t i = r * s.units + c;
+    float4 g = ld4(gy + i);
+    if (relu) relu_mask4(g, ld4(y + i));
+    if (use_bn) {
+      const float4 zz = ld4(z + i);
+      g.x = ga.x * rs.x * (g.x - sg.x * inv_b - (((zz.x + b.x) - mu.x) * rs.x) * sx.x * inv_b);
+      g.y = ga.y * rs.y * (g.y - sg.y * inv_b - (((zz.y + b.y) - mu.y) * rs.y) * sx.y * inv_b);
+      g.z = ga.z * rs.z * (g.z - sg.z * inv_b - (((zz.z + b.z) - mu.z) * rs.z) * sx.z * inv_b);
+      g.w = ga.w * rs.w * (g.w - sg.w * inv_b - (((zz.w + b.w) - mu.w) * rs.w) * sx.w * inv_b);
+    }
+    *reinterpret_cast<float4*>(gz + i) = g;
+  }
+}
+
 }  // namespace er
 
 // Layout: 1024 reserved bytes, then the chunk partials [n_chunks][units][3].
 extern "C" size_t er_dense_workspace_bytes(int64_t batch, int32_t units) {
   er::DenseShape s = er::dense_shape(batch > 0 ? batch : 1, units > 0 ? units : 1);
-  return 1024 + (size_t)s.n_chunks * s.units * 3 * sizeof(float) + 256;
+  er::VecShape v = er::vec_shape(batch > 0 ? batch : 1, units > 0 ? units : 1);
+  const size_t scalar = (size_t)s.n_chunks * s.units * 3 * sizeof(float);
+  const size_t vec = (size_t)v.n_chunks * (((size_t)v.units + 3) / 4 * 4) * 2 * sizeof(float);
+  return 1024 + std::max(scalar, vec) + 256;
 }
 
 extern "C" int er_bias_bn_act_fwd(const float* z, const float* bias, const float* gamma,
@@ -385,6 +537,18 @@ extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float
   DenseShape s = dense_shape(batch, units);
   dim3 grid((units + kColTile - 1) / kColTile, s.n_chunks);
   float* part = reinterpret_cast<float*>(static_cast<char*>(ws) + 1024);
+  auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (units % 4 == 0 && al(z) && al(y) && al(gy) && al(gz) && (!bias || al(bias)) && (!gbias || al(gbias)) &&
+      (!use_bn || (al(gamma) && al(save_mean) && al(save_rstd) && (!ggamma || al(ggamma)) && (!gbeta || al(gbeta))))) {
+    VecShape v = vec_shape(batch, units);
+    dim3 vgrid((units + kVecCols - 1) / kVecCols, v.n_chunks);
+    bn_bwd_stats_vec_kernel<<<vgrid, 256, 0, st>>>(z, bias, y, gy, save_mean, save_rstd, v, relu, use_bn, part);
+    bn_bwd_apply_vec_kernel<<<vgrid, 256, 0, st>>>(z, bias, gamma, y, gy, save_mean, save_rstd, v, relu, use_bn,
+                                                    part, gz, gbias, ggamma, gbeta);
+    count_launches(2);
+    ER_CUDA_LAUNCH_CHECK();
+    return ER_OK;
+  }
   bn_bwd_stats_kernel<<<grid, 256, 0, st>>>(z, bias, y, gy, save_mean, save_rstd, s, relu, use_bn, part);
   bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(z, bias, gamma, y, gy, save_mean, save_rstd, s, relu, use_bn,
                                             part, gz, gbias, ggamma, gbeta);

@@ -305,12 +305,17 @@ __global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant
   __syncwarp();
   const int n_tails = __popc(tails0);
   const int glane = lane % LANES, grp = lane / LANES;
-  RowRegs row0;
-  uint32_t row0_key = a.sentinel;
+  RowRegs row0, row1;   // the first two rows this lane group will update: loads in flight under the gradient sums
+  uint32_t row0_key = a.sentinel, row1_key = a.sentinel;
   if (grp < n_tails) {
     const int tl = s_tail_lane[warp][grp];
     row0_key = a.keys[base + tl];
     row0 = load_row(a, row0_key, glane);
+  }
+  if (grp + GROUPS < n_tails) {
+    const int tl = s_tail_lane[warp][grp + GROUPS];
+    row1_key = a.keys[base + tl];
+    row1 = load_row(a, row1_key, glane);
   }
   // ---- this lane's gradient row ------------------------------------------------------------
   float4 g[D4];
@@ -406,8 +411,8 @@ __global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant
     const int tl = s_tail_lane[warp][r];
     const int run_cnt = s_tail_head[warp][r];
     if (run_cnt < 0) continue;  // handed to the hot-row kernel
-    const uint32_t key = (r == grp) ? row0_key : a.keys[base + tl];
-    RowRegs row = (r == grp) ? row0 : load_row(a, key, glane);
+    const uint32_t key = (r == grp) ? row0_key : (r == grp + GROUPS) ? row1_key : a.keys[base + tl];
+    RowRegs row = (r == grp) ? row0 : (r == grp + GROUPS) ? row1 : load_row(a, key, glane);
     // head of the run = tail lane - (entries of the run inside this window) + 1; for a run finished
     // by the continuation loop the tail lane is 31 and the count is its window part
     const int64_t head_pos = base + tl - (run_cnt - 1);

@@ -177,6 +177,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
   // MMA N: the live columns of this tile rounded up to the instruction granularity
   const int n_eff = min(BN, ((a.N - n0 + 15) >> 4) << 4);
 
+  const int c = tid & 7, srow = tid >> 3;   // 32 segment rows x 8 chunks per pass, 4 passes
+  const uint32_t off_k = (uint32_t)srow * 128u + (uint32_t)((c ^ (srow & 7)) << 4);
+  const uint32_t off_mn = (uint32_t)srow * 128u + (uint32_t)((c ^ ((srow & 3) << 1)) << 4);
+  const uint32_t off_a = a.a_mn ? off_mn : off_k, off_b = a.b_mn ? off_mn : off_k;
+  // kPrefetch k-blocks of global loads stay in flight per thread (register ring) so the ~1 us HBM/L2
+  // latency is paid once per tile, not once per k-block.
+  float4 va[kPrefetch][4], vb[kPrefetch][4];
+  auto issue = [&](int kb, float4 (&xa)[4], float4 (&xb)[4]) {
+    const int k0 = k_begin + kb * BK;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      xa[j] = (a.dbg & 2) ? make_float4(1.f, 1.f, 1.f, 1.f) : load_chunk(a.A, a.lda, a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // segments wholly outside the MMA's N range are never read by the tensor core
+      const bool live = a.b_mn ? (32 * j < n_eff) : (32 * j + srow < n_eff);
+      xb[j] = (live && !(a.dbg & 2)) ? load_chunk(a.B, a.ldb, a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // The first k-blocks' global loads are issued before the barrier / TMEM set-up below, so their latency
+  // overlaps the prologue.
+  if (warp < kProducerThreads / 32) {
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+      if (u < n_kb) issue(u, va[u], vb[u]);
+  }
+
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_base + 8 * s, kProducerThreads / 32);
@@ -198,26 +226,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
 
   if (warp < kProducerThreads / 32) {
     // ===== producers: HBM/L2 -> registers -> hi/lo -> swizzled smem =====
-    const int c = tid & 7, srow = tid >> 3;   // 32 segment rows x 8 chunks per pass, 4 passes
-    const uint32_t off_k = (uint32_t)srow * 128u + (uint32_t)((c ^ (srow & 7)) << 4);
-    const uint32_t off_mn = (uint32_t)srow * 128u + (uint32_t)((c ^ ((srow & 3) << 1)) << 4);
-    const uint32_t off_a = a.a_mn ? off_mn : off_k, off_b = a.b_mn ? off_mn : off_k;
-    // kPrefetch k-blocks of global loads stay in flight per thread (register ring) so the ~1 us HBM/L2
-    // latency is paid once per tile, not once per k-block.
-    float4 va[kPrefetch][4], vb[kPrefetch][4];
-    auto issue = [&](int kb, float4 (&xa)[4], float4 (&xb)[4]) {
-      const int k0 = k_begin + kb * BK;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        xa[j] = (a.dbg & 2) ? make_float4(1.f, 1.f, 1.f, 1.f) : load_chunk(a.A, a.lda, a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // segments wholly outside the MMA's N range are never read by the tensor core
-        const bool live = a.b_mn ? (32 * j < n_eff) : (32 * j + srow < n_eff);
-        xb[j] = (live && !(a.dbg & 2)) ? load_chunk(a.B, a.ldb, a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
     auto stage_out = [&](int kb, const float4 (&xa)[4], const float4 (&xb)[4]) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -245,9 +253,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_base + 8 * s);                   // one arrival per producer warp
     };
-#pragma unroll
-    for (int u = 0; u < kPrefetch; ++u)
-      if (u < n_kb) issue(u, va[u], vb[u]);
     for (int kb0 = 0; kb0 < n_kb; kb0 += kPrefetch) {
 #pragma unroll
       for (int u = 0; u < kPrefetch; ++u) {

@@ -145,9 +145,9 @@ def train_and_evaluate(pipeline_config_path, train_input_fn=None, eval_input_fn=
   cfg = est._pipeline_config
   if train_input_fn is None:
     path = cfg.train_input_path
-    train_input_fn = lambda: readers.CSVInput(cfg, est.input_layer, path)  # noqa: E731
+    train_input_fn = lambda: readers.make_input(cfg, est.input_layer, path)  # noqa: E731
   est.train(train_input_fn)
   if eval_input_fn is None and cfg.eval_input_path:
     epath = cfg.eval_input_path
-    eval_input_fn = lambda: readers.CSVInput(cfg, est.input_layer, epath)  # noqa: E731
+    eval_input_fn = lambda: readers.make_input(cfg, est.input_layer, epath)  # noqa: E731
   return est, (est.evaluate(eval_input_fn) if eval_input_fn else {})

@@ -1,7 +1,7 @@
 """Host-side inputs: EasyRec data_config -> packed batches for InputLayer.
 
-Counterpart of input/input.py:806-939 (`_preprocess`) + input/csv_input.py:78-175 restricted to the
-feature types of the hot path.  A batch is the reference's packed form (input/parquet_input.py:201-239):
+Counterpart of input/input.py:806-939 (`_preprocess`) + input/csv_input.py:78-175 +
+input/parquet_input.py:201-239 restricted to the feature types of the hot path.  A batch is the reference's packed form (input/parquet_input.py:201-239):
   sparse_fea int64 [n_id*B] feature-major | dense_fea fp32 [B, sum raw_dim] | seq_fea | tag_fea | labels.
 
 String-typed id fields are fingerprinted on the host with the library's Fingerprint64
@@ -150,6 +150,121 @@ class CSVInput(object):
 
   def __iter__(self):
     return self.batches()
+
+
+class ParquetInput(object):
+  """ParquetInput (input/parquet_input.py:201-239 + input/load_parquet.py:81-99): columnar file, one column per
+  input field; the batch is the reference's packed form - ids of all sparse features feature-major
+  (`sparse_fea`), dense features as one fp32 matrix (`dense_fea`), labels.  Sparse columns may be scalars or
+  lists (the reference stores lists, load_parquet.py:139-205); a single-valued feature takes the first id of
+  a list (empty list -> -1 = missing, dropped by K1), Tag / Sequence features keep the whole list.  Like the
+  reference's packed path the ids go to the device untouched and are bucketed there (`vals % num_buckets`,
+  parquet_input.py:221, or the feature's hash rule)."""
+
+  def __init__(self, pipeline_config, input_layer, path, batch_size=None):
+    import pyarrow.parquet as pq   # optional dependency of this reader only
+    self._pq = pq
+    self.cfg = pipeline_config
+    self.il = input_layer
+    self.paths = [path] if isinstance(path, str) else list(path)
+    self.labels = list(pipeline_config.data_config.label_fields)
+    self.batch_size = batch_size or input_layer.batch_size
+    self.feature_inputs = {}
+    for fc in config_util.get_feature_configs(pipeline_config):
+      name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+      self.feature_inputs[name] = fc.input_names[0]
+
+  @staticmethod
+  def _column(col):
+    """arrow column -> (values, lens or None): lens is None for scalar columns."""
+    import pyarrow as pa
+    col = col.combine_chunks() if hasattr(col, 'combine_chunks') else col
+    if pa.types.is_list(col.type) or pa.types.is_large_list(col.type):
+      offs = col.offsets.to_numpy()
+      vals = col.values.to_numpy(zero_copy_only=False)
+      return vals[offs[0]:offs[-1]], np.diff(offs).astype(np.int32)
+    return col.to_numpy(zero_copy_only=False), None
+
+  def _pack(self, table):
+    il = self.il
+    n = table.num_rows
+    feats = {}
+    ids = []
+    for name in il.sparse_names:
+      vals, lens = self._column(table.column(self.feature_inputs[name]))
+      if lens is None:
+        ids.append(np.asarray(vals, np.int64))
+      else:   # first id of every list, -1 where the list is empty
+        first = np.cumsum(lens) - lens
+        out = np.full(n, -1, np.int64)
+        has = lens > 0
+        out[has] = np.asarray(vals, np.int64)[first[has]]
+        ids.append(out)
+    if ids:
+      feats['sparse_fea'] = torch.from_numpy(np.concatenate(ids))
+    if il.raw_names:
+      dense = np.zeros((n, il.n_dense), np.float32)
+      for name in il.raw_names:
+        c0, c1 = il.raw_cols[name]
+        vals, lens = self._column(table.column(self.feature_inputs[name]))
+        dense[:, c0:c1] = np.asarray(vals, np.float32).reshape(n, c1 - c0)
+      feats['dense_fea'] = torch.from_numpy(dense)
+    seq, tag = {}, {}
+    for f in il.features.values():
+      if f.kind not in ('seq', 'tag'):
+        continue
+      vals, lens = self._column(table.column(self.feature_inputs[f.name]))
+      vals = np.asarray(vals, np.int64)
+      if lens is None:
+        lens = np.ones(n, np.int32)
+      if f.kind == 'seq':
+        T = f.seq_len
+        arr = np.zeros((n, T), np.int64)
+        start = np.cumsum(lens) - lens
+        keep = np.minimum(lens, T)   # the FIRST max_seq_len steps (utils/shape_utils.py:393-410)
+        for i in range(n):
+          arr[i, :keep[i]] = vals[start[i]:start[i] + keep[i]]
+        seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(keep.astype(np.int32)))
+      else:
+        tag[f.name] = (torch.from_numpy(vals), torch.from_numpy(lens), None)
+    if seq:
+      feats['seq_fea'] = seq
+    if tag:
+      feats['tag_fea'] = tag
+    lab = np.stack([np.asarray(table.column(l).to_numpy(zero_copy_only=False), np.float32) for l in self.labels], 1)
+    labels = torch.from_numpy(lab if lab.shape[1] > 1 else lab[:, 0].copy())
+    return feats, labels
+
+  def batches(self):
+    import pyarrow as pa
+    B = self.batch_size
+    pending, have = [], 0
+    for path in self.paths:
+      pf = self._pq.ParquetFile(path)
+      for rb in pf.iter_batches(batch_size=B):   # record batches stop at row-group boundaries: re-chunk
+        pending.append(rb)
+        have += rb.num_rows
+        while have >= B:
+          tab = pa.Table.from_batches(pending)
+          yield self._pack(tab.slice(0, B))
+          rest = tab.slice(B)
+          pending = rest.to_batches() if rest.num_rows else []
+          have = rest.num_rows
+    # the static plan holds exactly batch_size samples; a ragged tail is skipped
+
+  def __iter__(self):
+    return self.batches()
+
+
+def make_input(pipeline_config, input_layer, path):
+  """reader for data_config.input_type (CSVInput / ParquetInput / DummyInput)."""
+  dc = pipeline_config.data_config
+  kind = dc.DESCRIPTOR.fields_by_name['input_type'].enum_type.values_by_number[dc.input_type].name
+  if kind.startswith('Parquet'):
+    return ParquetInput(pipeline_config, input_layer, path)
+  if kind == 'DummyInput':
+    return DummyInput(input_layer, n_labels=max(1, len(dc.label_fields)))
+  return CSVInput(pipeline_config, input_layer, path)
 
 
 def to_device(feats, labels, device):

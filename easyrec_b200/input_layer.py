@@ -311,14 +311,26 @@ class InputLayer(object):
     if self._presorted:
       torch.cuda.current_stream().wait_stream(self._side)   # join the early sorts
       self._presorted = {}
-    for m, rows, w, outs, seg_ids in self._pending:
+    cur = torch.cuda.current_stream() if str(self.device).startswith('cuda') else None
+    forked = False
+    for idx, (m, rows, w, outs, seg_ids) in enumerate(self._pending):
       # arenas with the same row plan (DeepFM / Wide&Deep: the wide dim-1 and the deep tables) look up the
       # same rows tensor: the second K7 reuses the first one's radix sort.
       hit = sorted_by.get(id(rows))
       src = (hit[0], hit[1]) if hit is not None and hit[2] == m.arena.n_rows else None
-      E.fused_backward_update(m, rows, outs, self.opt_holder['opt'], weights=w, seg_ids=seg_ids, sorted_from=src)
+      if idx > 0 and src is not None and self._side is not None and cur is not None:
+        # different arenas, sort already done: this update runs beside the first one on the side stream
+        if not forked:
+          self._side.wait_stream(cur)
+          forked = True
+        with torch.cuda.stream(self._side):
+          E.fused_backward_update(m, rows, outs, self.opt_holder['opt'], weights=w, seg_ids=seg_ids, sorted_from=src)
+      else:
+        E.fused_backward_update(m, rows, outs, self.opt_holder['opt'], weights=w, seg_ids=seg_ids, sorted_from=src)
       if hit is None:
         sorted_by[id(rows)] = (m.ws, m.arena.dim, m.arena.n_rows)
+    if forked:
+      cur.wait_stream(self._side)
     self._pending = []
 
   def _presort(self):

@@ -90,3 +90,31 @@ def test_baseline_model_families_build_from_unmodified_reference_configs(rel):
   il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
   assert sum(p.numel() for p in model.parameters()) > 1000
   assert all(a.n_rows > 0 for a in il.arenas.values())
+
+
+def test_parquet_and_csv_inputs_pack_the_same_batches(tmp_path):
+  """ParquetInput (scalar and list columns) and CSVInput yield the reference's packed batch form."""
+  import numpy as np
+  import pyarrow as pa
+  import pyarrow.parquet as pq
+  from easyrec_b200.input import readers
+  cfg = config_util.get_configs_from_pipeline_file(MINI)
+  il, model, _ = builder.build_model(cfg, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  rng = np.random.default_rng(0)
+  n = 9
+  lab = (rng.uniform(size=n) < 0.5).astype(np.float32)
+  f1 = rng.uniform(0, 10, n).astype(np.float32)
+  c1 = rng.integers(0, 2**40, n).astype(np.int64)
+  pq.write_table(pa.table({'label': lab, 'F1': f1, 'C1': pa.array([[int(v)] for v in c1], pa.list_(pa.int64()))}),
+                 str(tmp_path / 'a.parquet'), row_group_size=5)
+  with open(tmp_path / 'a.csv', 'w') as f:
+    for i in range(n):
+      f.write('%g\t%r\t%d\n' % (lab[i], float(f1[i]), c1[i]))
+  pb = list(readers.ParquetInput(cfg, il, str(tmp_path / 'a.parquet')))
+  cb = list(readers.CSVInput(cfg, il, str(tmp_path / 'a.csv')))
+  assert len(pb) == len(cb) == 2   # 9 rows -> two full batches of 4, ragged tail skipped
+  for (pf, pl), (cf, cl) in zip(pb, cb):
+    assert torch.equal(pf['sparse_fea'], cf['sparse_fea']) and pf['sparse_fea'].dtype == torch.int64
+    assert torch.allclose(pf['dense_fea'], cf['dense_fea'])
+    assert torch.equal(pl, cl)
+  assert torch.equal(pb[0][0]['sparse_fea'], torch.from_numpy(c1[:4]))
