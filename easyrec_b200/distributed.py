@@ -8,6 +8,8 @@ every rank then runs the same deterministic dedup + fused row update over the gl
 replicas stay bit-identical without a broadcast.  Dense gradients: one flat all-reduce
 (`hvd.allreduce(g, Average)`, compat/optimizers.py:289-292).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -60,6 +62,39 @@ class DataParallel(object):
     plans = getattr(input_layer, 'merged', None) or input_layer.calls
     self.gcalls = {id(c): GlobalCall(c, world) for c in plans.values()}
     self._rows_owner = {}
+    self._pre = {}
+    self._side = None
+    self.prephase = os.environ.get('ER_DP_PREPHASE', '1') == '1' and str(getattr(input_layer, 'device', 'cpu')).startswith('cuda')
+
+  def pre_exchange(self, features):
+    """Ahead of the step (eager, outside CUDA-graph capture): K1 on this rank's batch, all-gather of the rows
+    and per-lookup weights, and the global dedup sort started on a side stream - it needs no gradient, so
+    it runs under the dense forward/backward (with N ranks it is N times the single-GPU sort)."""
+    if not self.prephase:
+      return
+    il = self.input_layer
+    self._pre = {}
+    owners = {}
+    todo = []
+    for dim, m, rows, w in il.precompute_rows(features):
+      g = self.gcalls[id(m)]
+      first = owners.get(id(rows))
+      if first is not None and first.call.arena.n_rows == m.arena.n_rows:
+        self._pre[id(m)] = (first, False)
+        continue
+      owners[id(rows)] = g
+      dist.all_gather_into_tensor(g.rows, rows)
+      if w is not None:
+        dist.all_gather_into_tensor(g.weights, w)
+      self._pre[id(m)] = (g, True)
+      todo.append(g)
+    if todo:
+      if self._side is None:
+        self._side = torch.cuda.Stream(device=todo[0].rows.device)
+      self._side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self._side):
+        for g in todo:
+          K.embedding_bwd_presort(g.rows, g.call.arena.n_rows, g.call.arena.dim, g.ws)
 
   def sync_dense_grads(self):
     """sum over replicas in one bucket; the 1/world of hvd.allreduce(Average)
@@ -70,6 +105,14 @@ class DataParallel(object):
     """all-gather one arena call's K7 inputs (rows, weights, segment scales, upstream gradients)
     into the GlobalCall buffers; returns the GlobalCall."""
     g = self.gcalls[id(call)]
+    pre = self._pre.get(id(call))
+    if pre is not None:   # rows / weights were gathered (and their sort started) before the step
+      owner, is_owner = pre
+      g.rows_src = None if is_owner else owner
+      g.presorted = True
+      self._gather_grads(g, call, outs)
+      return g
+    g.presorted = False
     # arenas with the same row plan (wide dim-1 next to the deep tables) were looked up with the SAME rows /
     # weights tensors: gather those once and let the later call alias the first one's buffers (and its sort)
     first = self._rows_owner.get(id(rows))
@@ -81,14 +124,17 @@ class DataParallel(object):
       dist.all_gather_into_tensor(g.rows, rows)
       if w is not None:
         dist.all_gather_into_tensor(g.weights, w)
+    self._gather_grads(g, call, outs)
+    return g
+
+  def _gather_grads(self, g, call, outs):
     if call.seg_scale is not None:
       if g.seg_scale is None:
-        g.seg_scale = torch.empty(g.n_seg, dtype=torch.float32, device=rows.device)
+        g.seg_scale = torch.empty(g.n_seg, dtype=torch.float32, device=outs[0].device)
       dist.all_gather_into_tensor(g.seg_scale, call.seg_scale)
     for i, o in enumerate(outs):
       grad = o.grad if o.grad is not None else torch.zeros_like(o)
       dist.all_gather_into_tensor(g.grads[i], grad.contiguous())
-    return g
 
   def exchange(self, pending):
     """The collectives of one step (eager NCCL calls, kept OUTSIDE CUDA-graph capture): dense flat
@@ -100,6 +146,11 @@ class DataParallel(object):
         raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
       self.gather_sparse(call, rows, w, outs)
 
+  def join_presort(self):
+    """main stream waits for the early global sorts (call before apply_sparse / its graph replay)."""
+    if self._pre and self._side is not None:
+      torch.cuda.current_stream().wait_stream(self._side)
+
   def apply_sparse(self, pending, opt):
     """The same fused dedup + row update on every rank over the gathered global batch; gradients
     are scaled by 1/world (mean over replicas).  No collectives: CUDA-graph capturable."""
@@ -109,10 +160,12 @@ class DataParallel(object):
       a = call.arena
       src = getattr(g, 'rows_src', None)
       owner = src if src is not None else g
+      sorted_from = None
+      if src is not None or getattr(g, 'presorted', False):
+        sorted_from = (owner.ws, owner.call.arena.dim)
       K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, owner.rows, g.slots_dev, g.n_slots, g.n_seg,
                       g.grads, opt, g.ws, weights=owner.weights if w is not None else None,
-                      seg_scale=g.seg_scale,
-                      sorted_from=(src.ws, src.call.arena.dim) if src is not None else None)
+                      seg_scale=g.seg_scale, sorted_from=sorted_from)
     opt.grad_scale = opt.grad_scale * self.world
 
   def sparse_backward_update(self, opt):

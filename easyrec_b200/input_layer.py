@@ -293,6 +293,8 @@ class InputLayer(object):
     self._presorted = {}
     self._side = None
     self.presort_enabled = True
+    self._preset_rows = {}
+    self._rows_bufs = {}
     self._pos = {}
 
   # ------------------------------------------------------------------
@@ -332,6 +334,41 @@ class InputLayer(object):
     if forked:
       cur.wait_stream(self._side)
     self._pending = []
+
+  def _rows_buf(self, key, call):
+    """persistent output buffer of K1 per row plan (stable address: CUDA graphs, early exchange)."""
+    buf = self._rows_bufs.get(key)
+    if buf is None:
+      buf = torch.empty(call.n_seg, dtype=torch.int64, device=self.device)
+      self._rows_bufs[key] = buf
+    return buf
+
+  def precompute_rows(self, features):
+    """K1 (index hashing / bucketing) of the single-valued slots ahead of the step, outside any CUDA-graph
+    capture: data-parallel training all-gathers the rows and starts the global dedup sort while the dense
+    forward/backward runs.  Returns [(arena dim, ArenaCall, rows, weights)]; the next lookup() reuses them."""
+    dense = features.get('dense_fea')
+    dense_norm = self.normalize_dense(dense) if dense is not None else None
+    out = []
+    self._preset_rows = {}
+    for dim, subs in self.subcalls.items():
+      for sk, sc in subs.items():
+        if sc.kind != 'single' or len(subs) != 1:
+          continue
+        call = sc.call
+        key = getattr(sc, 'rows_key', None)
+        if key is None:
+          key = (tuple((int(r['num_buckets']), int(r['row_offset']), int(r['seg_begin']), int(r['n_seg']),
+                        int(r['bucket_mode']), int(r['shard_n'])) for r in call.slots_np), tuple(call.sources))
+          sc.rows_key = key
+        hit = self._preset_rows.get(key)
+        if hit is None:
+          cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
+          rows = K.bucketize(cids, call.slots_dev, call.n_slots, call.n_seg, rows=self._rows_buf(key, call))
+          hit = (rows, w)
+          self._preset_rows[key] = hit
+        out.append((dim, self.merged[dim], hit[0], hit[1]))
+    return out
 
   def _presort(self):
     """K7's radix sort needs only the looked-up rows: start it now on a side stream so it runs under the
@@ -418,7 +455,7 @@ class InputLayer(object):
       hit = self._rows_cache.get(key)
       if hit is None:
         cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
-        rows = K.bucketize(cids, call.slots_dev, call.n_slots, call.n_seg)
+        rows = K.bucketize(cids, call.slots_dev, call.n_slots, call.n_seg, rows=self._rows_buf(key, call))
         self._rows_cache[key] = (rows, w)
       else:
         rows, w = hit
@@ -477,7 +514,8 @@ class InputLayer(object):
     self.seq_outputs {seq group: {key, hist_seq_emb, hist_seq_len}}."""
     dense = features.get('dense_fea')
     dense_norm = self.normalize_dense(dense) if dense is not None else None
-    self._rows_cache = {}
+    self._rows_cache = dict(self._preset_rows)   # K1 results computed ahead of the step (precompute_rows)
+    self._preset_rows = {}
     self._pending = []
     outs_by_key = {}
     for dim, subs in self.subcalls.items():

@@ -151,6 +151,7 @@ class Trainer(object):
   def _segment_exchange(self):
     if self.dp is not None:
       self.dp.exchange(self._step_pending)   # flat all-reduce + all-gather of K7 inputs
+      self.dp.join_presort()
 
   def _segment_update(self, loss):
     if self.dp is not None:
@@ -162,7 +163,12 @@ class Trainer(object):
     # reported loss = data loss + embedding regularisation (autograd) + dense l2 (from the apply)
     return loss + self.dense_opt.reg_loss[0]
 
+  def _segment_pre(self, features):
+    if self.dp is not None:
+      self.dp.pre_exchange(features)   # eager: K1 + all-gather of rows + global dedup sort on a side stream
+
   def _step_body(self, features, labels):
+    self._segment_pre(features)
     loss, probs = self._segment_compute(features, labels)
     self._segment_exchange()
     return self._segment_update(loss), probs
@@ -181,6 +187,8 @@ class Trainer(object):
       for k, v in features.items():
         self._static[k].copy_(v, non_blocking=True)
       self._static['__labels'].copy_(labels, non_blocking=True)
+    if self._graph2 is not None:
+      self._segment_pre(self._static_feats)
     self._graph.replay()
     if self._graph2 is not None:   # world > 1: collectives between the two captured segments
       self._segment_exchange()
@@ -199,6 +207,7 @@ class Trainer(object):
     self._static = {k: v.clone() for k, v in features.items()}
     self._static['__labels'] = labels.clone()
     feats = {k: self._static[k] for k in features}
+    self._static_feats = feats
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -211,6 +220,7 @@ class Trainer(object):
       with torch.cuda.graph(self._graph):
         self._loss, self._probs = self._step_body(feats, self._static['__labels'])
     else:
+      self._segment_pre(feats)   # eager, before the capture: the captured lookup reuses these rows
       with torch.cuda.graph(self._graph):
         loss, self._probs = self._segment_compute(feats, self._static['__labels'])
       self._segment_exchange()   # eager: NCCL stays out of the capture
