@@ -38,8 +38,8 @@ N_SPARSE, N_DENSE, DIM = 26, 13, 16
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=200)
-  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=2000)
+  ap.add_argument('--warmup', type=int, default=50)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--vocab', type=int, default=10_000_000)
   ap.add_argument('--batch', type=int, default=BATCH)
@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
-           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+           '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       for line in self.proc.stdout:
         self.rows.append([x.strip() for x in line.split(',')])
         if self.stop_flag:

@@ -20,7 +20,6 @@
 // epilogue (tcgen05.ld -> optional bias -> global).  Split-K partials are reduced by a second kernel in a
 // fixed order, so results are run-to-run deterministic.
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -49,7 +48,6 @@ struct Args {
   int a_mn, b_mn;      // 1: the M (resp. N) index is the contiguous one in memory
   int k_per_slice;     // multiple of BK
   int n_slices;
-  int dbg;             // ER_GEMM_DEBUG timing experiments (results invalid when != 0)
   // batch-norm statistics of the output columns (training forward of a dense+BN layer), optional
   float* bn_part;            // [m_tiles][N][3] Welford (n, mean, M2) per 128-row tile
   unsigned int* bn_counter;  // [n_tiles], zero on entry, left zero
@@ -188,12 +186,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
     const int k0 = k_begin + kb * BK;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      xa[j] = (a.dbg & 2) ? make_float4(1.f, 1.f, 1.f, 1.f) : load_chunk(a.A, a.lda, a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c);
+      xa[j] = load_chunk(a.A, a.lda, a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // segments wholly outside the MMA's N range are never read by the tensor core
       const bool live = a.b_mn ? (32 * j < n_eff) : (32 * j + srow < n_eff);
-      xb[j] = (live && !(a.dbg & 2)) ? load_chunk(a.B, a.ldb, a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c)
+      xb[j] = live ? load_chunk(a.B, a.ldb, a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c)
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
@@ -233,7 +231,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
       const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (a.dbg & 4) break;
         const int k0 = k_begin + kb * BK;
         const float4 xaj = mask_chunk(xa[j], chunk_nvalid(a.a_mn, m0, a.M, k0, k_end, srow + 32 * j, c));
         const float4 xbj = mask_chunk(xb[j], chunk_nvalid(a.b_mn, n0, a.N, k0, k_end, srow + 32 * j, c));
@@ -277,7 +274,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
       const uint32_t st = smem_base + (uint32_t)s * kStageBytes;
 #pragma unroll
       for (int kk = 0; kk < BK / 8; ++kk) {
-        if (a.dbg & 1) break;
         const uint64_t ahi = make_desc(st + kk * a_kstep, a.a_mn);
         const uint64_t alo = make_desc(st + kTileBytes + kk * a_kstep, a.a_mn);
         const uint64_t bhi = make_desc(st + 2 * kTileBytes + kk * b_kstep, a.b_mn);
@@ -551,10 +547,6 @@ static int gemm_impl(const float* A, int64_t lda, int32_t a_mn_major, const floa
   a.M = (int)M; a.N = (int)N; a.K = (int)K;
   a.a_mn = a_mn_major ? 1 : 0; a.b_mn = b_mn_major ? 1 : 0;
   plan(M, N, K, &a.n_slices, &a.k_per_slice);
-  {
-    const char* e = getenv("ER_GEMM_DEBUG");
-    a.dbg = e ? atoi(e) : 0;
-  }
   a.partials = nullptr;
   a.bn_part = nullptr;
   a.bn_counter = nullptr;
