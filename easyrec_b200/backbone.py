@@ -1,0 +1,391 @@
+"""Configurable backbone network (reference: easy_rec/python/layers/backbone.py:215-348, 420-510):
+a DAG of named blocks over feature groups, each block a Keras-style layer, a lambda, a recurrent or a
+repeat wrapper; `concat_blocks` / `output_blocks` select the outputs, `top_mlp` finishes.
+
+The wiring is host-side (done once); the layers run on liber_b200: `MLP` = layers.DenseLayer stack (tcgen05
+GEMM + fused batch-norm/activation, layers/keras/blocks.py:33-129), `Cross` = DCN-v2 cross
+`x0 * (W x + b) + x` (layers/keras/interaction.py:249-286), `FM` = the FM kernels
+(layers/keras/interaction.py:24-44), `MMoE` = expert MLPs + the softmax mixture kernel
+(layers/keras/multi_task.py:47-67).  Like the reference, `input_fn` / `input_slice` / `lambda.expression`
+are Python source strings evaluated on tensors (backbone.py:240,255,259,274,424-426) -- configs are trusted
+input there and here; a small `tf` namespace maps the TensorFlow calls that appear in the sample configs
+onto torch.
+"""
+import math
+
+import torch
+from torch import nn
+
+from easyrec_b200 import embedding as E
+from easyrec_b200 import interactions as I
+from easyrec_b200 import layers as L
+
+
+class _TF(object):
+  """the handful of tf.* calls used by `input_fn` / `lambda` strings in samples/model_config/*.config"""
+  float32 = torch.float32
+
+  @staticmethod
+  def concat(values, axis=-1):
+    return torch.cat(list(values), dim=axis)
+
+  @staticmethod
+  def stack(values, axis=0):
+    return torch.stack(list(values), dim=axis)
+
+  @staticmethod
+  def reduce_sum(x, axis=None, keepdims=False):
+    return x.sum() if axis is None else x.sum(dim=axis, keepdim=keepdims)
+
+  @staticmethod
+  def reduce_mean(x, axis=None, keepdims=False):
+    return x.mean() if axis is None else x.mean(dim=axis, keepdim=keepdims)
+
+  @staticmethod
+  def expand_dims(x, axis):
+    return x.unsqueeze(axis)
+
+  @staticmethod
+  def squeeze(x, axis=None):
+    return x.squeeze() if axis is None else x.squeeze(axis)
+
+  @staticmethod
+  def reshape(x, shape):
+    return x.reshape(*shape)
+
+  @staticmethod
+  def multiply(a, b):
+    return a * b
+
+  @staticmethod
+  def add(a, b):
+    return a + b
+
+
+_EVAL_ENV = {'tf': _TF, 'torch': torch, '__builtins__': {'len': len, 'range': range, 'list': list, 'sum': sum,
+                                                          'int': int, 'float': float, 'tuple': tuple}}
+
+
+def _eval(src):
+  return eval(src, dict(_EVAL_ENV))  # noqa: S307 -- same trust model as the reference (backbone.py:240)
+
+
+class MLP(nn.Module):
+  """layers/keras/blocks.py:33-129: Dense -> BatchNorm -> activation per layer (bias off by default,
+  he_uniform kernels); the last layer uses use_final_bn / final_activation / use_final_bias."""
+
+  def __init__(self, n_in, conf, generator=None):
+    super().__init__()
+    units = list(conf.hidden_units)
+    assert units, 'MLP takes at least one hidden unit'
+    if conf.use_bn_after_activation:
+      raise NotImplementedError('MLP.use_bn_after_activation')
+    for act in (conf.activation, conf.final_activation):
+      if act not in ('relu', '', 'linear', 'None'):
+        raise NotImplementedError('MLP activation %r' % act)
+    self.layers = nn.ModuleList()
+    n = len(units)
+    for i, u in enumerate(units):
+      last = i + 1 == n
+      bn = conf.use_final_bn if last else conf.use_bn
+      act = conf.final_activation if last else conf.activation
+      lay = L.DenseLayer(n_in, u, bn, act == 'relu', generator)
+      lim = math.sqrt(6.0 / n_in)   # he_uniform
+      with torch.no_grad():
+        lay.kernel.uniform_(-lim, lim, generator=generator)
+      use_bias = conf.use_final_bias if last else conf.use_bias
+      if not use_bias:
+        lay.bias.requires_grad_(False)   # stays zero: tf Dense(use_bias=False)
+      self.layers.append(lay)
+      n_in = u
+    self.out_dim = n_in
+
+  def forward(self, x):
+    if isinstance(x, (list, tuple)):
+      x = torch.cat(list(x), dim=-1)
+    for lay in self.layers:
+      x = lay(x)
+    return x
+
+
+class Cross(nn.Module):
+  """DCN-v2 cross (layers/keras/interaction.py:249-286): x0 * (W x + b [+ diag_scale x]) + x, full-rank W
+  (kernel_initializer truncated_normal, bias zeros)."""
+
+  def __init__(self, dim, params, generator=None):
+    super().__init__()
+    if params.get('projection_dim'):
+      raise NotImplementedError('Cross.projection_dim (low-rank variant)')
+    self.diag_scale = float(params.get('diag_scale', 0.0))
+    self.dense = L.Dense(dim, dim, generator)
+    with torch.no_grad():
+      nn.init.trunc_normal_(self.dense.kernel, std=0.05, a=-0.1, b=0.1, generator=generator)
+    if params.get('use_bias', True) is False:
+      self.dense.bias.requires_grad_(False)
+    self.out_dim = dim
+
+  def forward(self, inputs):
+    x0, x = inputs if isinstance(inputs, (list, tuple)) else (inputs, inputs)
+    prod = self.dense(x.contiguous())
+    if self.diag_scale:
+      prod = prod + self.diag_scale * x
+    return x0 * prod + x
+
+
+class FM(nn.Module):
+  """layers/keras/interaction.py:24-44: list of [B, D] (or [B, F, D]) -> 0.5((sum v)^2 - sum v^2);
+  use_variant keeps [B, D], else reduce_sum -> [B, 1]."""
+
+  def __init__(self, conf):
+    super().__init__()
+    self.use_variant = bool(conf.use_variant) if conf is not None else False
+
+  def forward(self, inputs):
+    if isinstance(inputs, (list, tuple)):
+      n_field, dim = len(inputs), inputs[0].shape[-1]
+      x = torch.cat(list(inputs), dim=-1)
+    else:
+      n_field, dim = inputs.shape[1], inputs.shape[2]
+      x = inputs.reshape(inputs.shape[0], n_field * dim)
+    y = E.fm(x.contiguous(), n_field, dim)
+    return y if self.use_variant else y.sum(dim=1, keepdim=True)
+
+
+class DotInteraction(nn.Module):
+  """DLRM dot interaction (layers/keras/interaction.py:47-128): features [B, F, D] -> all pairwise dot products
+  of the lower triangle (with the diagonal when self_interaction), [B, F(F-1)/2] (or [B, F*F] with the upper
+  triangle zeroed when skip_gather).  One batched F x D x F product per sample: a library bmm (fp32)."""
+
+  def __init__(self, params):
+    super().__init__()
+    self.self_interaction = bool(params.get('self_interaction', False))
+    self.skip_gather = bool(params.get('skip_gather', False))
+    self._idx = {}
+
+  def out_dim(self, n):
+    if self.skip_gather:
+      return n * n
+    return n * (n + 1) // 2 if self.self_interaction else n * (n - 1) // 2
+
+  def forward(self, inputs):
+    x = torch.stack(list(inputs), dim=1) if isinstance(inputs, (list, tuple)) else inputs
+    n = x.shape[1]
+    xa = torch.bmm(x, x.transpose(1, 2)).reshape(x.shape[0], n * n)
+    key = (n, x.device)
+    if key not in self._idx:   # static gather indices (row-major lower triangle): no boolean-mask host sync
+      keep = torch.tril(torch.ones(n, n, dtype=torch.bool), diagonal=0 if self.self_interaction else -1)
+      self._idx[key] = (keep.reshape(-1).nonzero()[:, 0].to(x.device), keep.reshape(1, -1).to(x.device, x.dtype))
+    idx, mask = self._idx[key]
+    if self.skip_gather:
+      return xa * mask
+    return xa.index_select(1, idx)
+
+
+class MMoE(nn.Module):
+  """layers/keras/multi_task.py:47-67: num_expert expert MLPs on the same input, one softmax gate per task,
+  task output = sum_e gate_e * expert_e (the mixture runs in er_mmoe_mix)."""
+
+  def __init__(self, n_in, conf, generator=None):
+    super().__init__()
+    self.experts = nn.ModuleList([MLP(n_in, conf.expert_mlp, generator) for _ in range(conf.num_expert)])
+    self.gates = nn.ModuleList([L.Dense(n_in, conf.num_expert, generator) for _ in range(conf.num_task)])
+    self.out_dim = self.experts[0].out_dim
+
+  def forward(self, x):
+    ex = torch.stack([e(x) for e in self.experts], dim=1).contiguous()
+    return [I.mmoe_mix(g(x), ex) for g in self.gates]
+
+
+def _shape_of(x):
+  if isinstance(x, (list, tuple)):
+    return [_shape_of(t) for t in x]
+  return tuple(x.shape)
+
+
+class Backbone(nn.Module):
+  """Backbone.__call__ + Package.call (backbone.py:215-348,482-510).  Layers are instantiated by a shape-only
+  dry run on `meta` tensors, so construction needs no GPU and the optimizer sees every parameter."""
+
+  def __init__(self, config, input_layer, batch_size, generator=None):
+    super().__init__()
+    self.config = config
+    self.input_layer = input_layer
+    self.blocks = list(config.blocks)
+    if config.packages:
+      raise NotImplementedError('backbone packages')
+    self.mods = nn.ModuleDict()
+    self._gen = generator
+    outs = self._run(None, batch_size, build=True)
+    self.out_dim = outs.shape[-1]
+
+  # -- inputs -----------------------------------------------------------------------------------------
+  def _block_input(self, block, outputs, groups):
+    ins = []
+    for inp in block.inputs:
+      which = inp.WhichOneof('name')
+      if which == 'feature_group_name':
+        v = groups(inp.feature_group_name)
+      elif which == 'block_name':
+        v = outputs[inp.block_name]
+      else:
+        raise NotImplementedError('backbone input %s' % which)
+      if inp.HasField('input_fn'):
+        v = _eval(inp.input_fn)(v)
+      if inp.HasField('input_slice'):
+        v = _eval('lambda x: x' + inp.input_slice.strip())(v)
+      ins.append(v)
+    if block.merge_inputs_into_list:
+      out = ins
+    elif len(ins) == 1:
+      out = ins[0]
+    else:   # merge_inputs: lists are extended, tensors concatenated on input_concat_axis
+      if any(isinstance(v, (list, tuple)) for v in ins):
+        out = [t for v in ins for t in (v if isinstance(v, (list, tuple)) else [v])]
+      else:
+        out = torch.cat(ins, dim=block.input_concat_axis)
+    if block.HasField('extra_input_fn'):
+      out = _eval(block.extra_input_fn)(out)
+    return out
+
+  # -- layers -----------------------------------------------------------------------------------------
+  def _keras(self, name, conf, x, build):
+    if build and name not in self.mods:
+      cls = conf.class_name
+      d = (x[0] if isinstance(x, (list, tuple)) else x).shape[-1]
+      if cls == 'MLP':
+        n_in = sum(t.shape[-1] for t in x) if isinstance(x, (list, tuple)) else d
+        self.mods[name] = MLP(n_in, conf.mlp, self._gen)
+      elif cls == 'Cross':
+        params = {}
+        if conf.HasField('st_params'):
+          params = {k: (v.number_value if v.HasField('number_value') else v.bool_value if v.HasField('bool_value')
+                        else v.string_value) for k, v in conf.st_params.fields.items()}
+        self.mods[name] = Cross(d, params, self._gen)
+      elif cls == 'FM':
+        self.mods[name] = FM(conf.fm if conf.HasField('fm') else None)
+      elif cls == 'MMoE':
+        self.mods[name] = MMoE(d, conf.mmoe, self._gen)
+      elif cls == 'DotInteraction':
+        params = {}
+        if conf.HasField('st_params'):
+          params = {k: (v.bool_value if v.HasField('bool_value') else v.number_value)
+                    for k, v in conf.st_params.fields.items()}
+        self.mods[name] = DotInteraction(params)
+      else:
+        raise NotImplementedError('backbone keras_layer %s' % cls)
+    mod = self.mods[name]
+    if build:   # shape-only: no kernels
+      first = x[0] if isinstance(x, (list, tuple)) else x
+      lead = tuple(first.shape[:-1])
+      if isinstance(mod, MLP):
+        return torch.empty(lead + (mod.out_dim,), device='meta')
+      if isinstance(mod, Cross):
+        return torch.empty(tuple(first.shape), device='meta')
+      if isinstance(mod, FM):
+        dim = first.shape[-1]
+        return torch.empty((first.shape[0], dim if mod.use_variant else 1), device='meta')
+      if isinstance(mod, MMoE):
+        return [torch.empty(lead + (mod.out_dim,), device='meta') for _ in mod.gates]
+      if isinstance(mod, DotInteraction):
+        n = len(x) if isinstance(x, (list, tuple)) else first.shape[1]
+        return torch.empty((first.shape[0], mod.out_dim(n)), device='meta')
+    return mod(x)
+
+  def _layer(self, name, conf, x, build):
+    which = conf.WhichOneof('layer')
+    if which == 'keras_layer':
+      return self._keras(name, conf.keras_layer, x, build)
+    if which == 'lambda':
+      return _eval(getattr(conf, 'lambda').expression)(x)
+    if which == 'recurrent':
+      rc = conf.recurrent
+      fixed = rc.fixed_input_index if rc.HasField('fixed_input_index') else -1
+      out = list(x) if fixed >= 0 else x
+      for i in range(rc.num_steps):
+        o = self._keras('%s_%d' % (name, i), rc.keras_layer, out, build)
+        if fixed >= 0:
+          j = 0
+          for idx in range(len(out)):
+            if idx == fixed:
+              continue
+            out[idx] = o[j] if isinstance(o, (list, tuple)) else o
+            j += 1
+        else:
+          out = o
+      if fixed >= 0:
+        out = [t for idx, t in enumerate(out) if idx != fixed]
+        return out[0] if len(out) == 1 else out
+      return out
+    if which == 'repeat':
+      rp = conf.repeat
+      outs = []
+      for i in range(rp.num_repeat):
+        xi = x
+        if rp.HasField('input_slice'):
+          xi = _eval('lambda x, i: x' + rp.input_slice.strip())(xi, i)
+        if rp.HasField('input_fn'):
+          xi = _eval(rp.input_fn)(xi, i)
+        outs.append(self._keras('%s_%d' % (name, i), rp.keras_layer, xi, build))
+      if len(outs) == 1:
+        return outs[0]
+      if rp.HasField('output_concat_axis'):
+        return torch.cat(outs, dim=rp.output_concat_axis)
+      return outs
+    raise NotImplementedError('backbone layer %s' % which)
+
+  # -- execution --------------------------------------------------------------------------------------
+  def _run(self, group_tensors, batch_size, build=False):
+    il = self.input_layer
+
+    def groups(name, as_list=False):
+      if build:
+        if as_list:
+          return [torch.empty(batch_size, e[2], device='meta') for e in il.group_layout[name]]
+        width = sum(e[2] for e in il.group_layout[name])
+        return torch.empty(batch_size, width, device='meta')
+      return list(group_tensors[name][1]) if as_list else group_tensors[name][0]
+
+    outputs = {}
+    for block in self.blocks:
+      which = block.WhichOneof('layer')
+      as_list = which == 'input_layer' and block.input_layer.only_output_feature_list
+      x = self._block_input(block, outputs, (lambda n: groups(n, True)) if as_list else groups)
+      if which == 'input_layer':
+        conf = block.input_layer
+        if conf.output_2d_tensor_and_feature_list or conf.only_output_3d_tensor:
+          raise NotImplementedError('input_layer block: 2d+list / 3d outputs')
+        out = x
+      elif which in ('keras_layer', 'lambda', 'recurrent', 'repeat'):
+        out = self._layer(block.name, block, x, build)
+      elif which is None:   # sequential `layers` or a pure input-merging block
+        out = x
+        for i, ly in enumerate(block.layers):
+          out = self._layer('%s_l%d' % (block.name, i), ly, out, build)
+      else:
+        raise NotImplementedError('backbone block type %s' % which)
+      outputs[block.name] = out
+    names = list(self.config.output_blocks) or list(self.config.concat_blocks)
+    if not names:   # leaves of the DAG (backbone.py:196-206)
+      used = {inp.block_name for b in self.blocks for inp in b.inputs if inp.WhichOneof('name') == 'block_name'}
+      names = [b.name for b in self.blocks if b.name not in used]
+    outs = []
+    for n in names:
+      o = outputs[n]
+      outs.extend(o if isinstance(o, (list, tuple)) else [o])
+    if self.config.output_blocks and not self.config.HasField('top_mlp'):
+      result = outs[0] if len(outs) == 1 else outs
+    else:
+      result = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+    if self.config.HasField('top_mlp'):
+      if isinstance(result, (list, tuple)):
+        result = torch.cat(list(result), dim=-1)
+      if build:
+        if 'backbone_top_mlp' not in self.mods:
+          self.mods['backbone_top_mlp'] = MLP(result.shape[-1], self.config.top_mlp, self._gen)
+        return torch.empty(tuple(result.shape[:-1]) + (self.mods['backbone_top_mlp'].out_dim,), device='meta')
+      result = self.mods['backbone_top_mlp'](result)
+    return result
+
+  def forward(self, group_tensors):
+    """group_tensors: InputLayer.lookup() result {group: (concat, per-feature list)}."""
+    return self._run(group_tensors, self.input_layer.batch_size, build=False)

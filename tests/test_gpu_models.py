@@ -50,6 +50,37 @@ model_config { model_class: "MultiTowerDIN"
   embedding_regularization: 1e-5 }
 '''
 
+BACKBONE_DCN_CFG = HEAD + FEATS + '''
+model_config { model_class: "RankModel"
+  feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "deep" inputs { feature_group_name: "all" } keras_layer { class_name: "MLP" mlp { hidden_units: [64, 32] } } }
+    blocks { name: "cross" inputs { feature_group_name: "all" input_fn: "lambda x: [x, x]" }
+             recurrent { num_steps: 3 fixed_input_index: 0 keras_layer { class_name: "Cross" } } }
+    concat_blocks: ["deep", "cross"]
+    top_mlp { hidden_units: [32, 16] }
+  }
+  model_params { l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
+BACKBONE_DLRM_CFG = HEAD + FEATS + '''
+model_config { model_class: "RankModel"
+  feature_groups { group_name: "sparse" feature_names: ["user_id", "age", "item_id", "cate"] wide_deep: DEEP }
+  feature_groups { group_name: "dense" feature_names: ["price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "bottom" inputs { feature_group_name: "dense" } keras_layer { class_name: "MLP" mlp { hidden_units: [32, 16] } } }
+    blocks { name: "sparse" inputs { feature_group_name: "sparse" } input_layer { only_output_feature_list: true } }
+    blocks { name: "dot" inputs { block_name: "bottom" input_fn: "lambda x: [x]" } inputs { block_name: "sparse" }
+             keras_layer { class_name: "DotInteraction" } }
+    blocks { name: "top" inputs { block_name: "bottom" } inputs { block_name: "dot" } input_concat_axis: 1
+             keras_layer { class_name: "MLP" mlp { hidden_units: [32, 16] } } }
+    concat_blocks: ["top"]
+  }
+  model_params { l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
 MMOE_CFG = HEAD.replace('label_fields: "clk"', 'label_fields: "clk" label_fields: "buy"') + FEATS + '''
 model_config { model_class: "MMoE"
   feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
@@ -86,7 +117,8 @@ def make_batch(seed, n_task=1):
   return feats, lab, (ids, dense, hist, lens)
 
 
-@pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1)])
+@pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1),
+                                             (BACKBONE_DCN_CFG, 1), (BACKBONE_DLRM_CFG, 1)])
 def test_models_from_pipeline_config_train(cfg_text, n_task):
   torch.backends.cuda.matmul.allow_tf32 = False
   cfg = config_util.get_configs_from_pipeline_file(cfg_text.encode())
@@ -155,3 +187,26 @@ def test_din_forward_matches_plain_torch_restatement():
           torch.cat([att, key], 1)]
   ref = (dnn(model.final_dnn, torch.cat(feas, 1)) @ model.output.kernel + model.output.bias)[:, 0]
   assert float((logits - ref).abs().max()) < 1e-4
+
+
+def test_backbone_layers_match_reference_formulas():
+  """keras Cross (DCN v2) and DotInteraction of the backbone against their TF formulas in float64."""
+  from easyrec_b200 import backbone as BB
+  g = torch.Generator(device=DEV).manual_seed(2)
+  x0 = torch.randn(300, 48, device=DEV, generator=g)
+  x = torch.randn(300, 48, device=DEV, generator=g)
+  cross = BB.Cross(48, {'diag_scale': 0.1}, torch.Generator().manual_seed(0)).to(DEV)
+  with torch.no_grad():
+    cross.dense.bias.copy_(torch.randn(48, device=DEV, generator=g) * 0.1)
+  got = cross([x0, x])
+  W, b = cross.dense.kernel.double(), cross.dense.bias.double()
+  want = x0.double() * (x.double() @ W + b + 0.1 * x.double()) + x.double()
+  assert float((got.double() - want).abs().max()) < 1e-5
+  feats = [torch.randn(64, 16, device=DEV, generator=g) for _ in range(5)]
+  for self_int in (False, True):
+    got = BB.DotInteraction({'self_interaction': self_int})(feats)
+    f = torch.stack(feats, 1).double()
+    xa = f @ f.transpose(1, 2)
+    pairs = [(i, j) for i in range(5) for j in range(5) if (j <= i if self_int else j < i)]
+    want = torch.stack([xa[:, i, j] for i, j in pairs], 1)   # boolean_mask order: row-major lower triangle
+    assert got.shape == want.shape and float((got.double() - want).abs().max()) < 1e-5
