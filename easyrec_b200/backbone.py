@@ -181,6 +181,40 @@ class DotInteraction(nn.Module):
     return xa.index_select(1, idx)
 
 
+class SENet(nn.Module):
+  """FiBiNet SENet (layers/keras/fibinet.py:14-96): per field, per squeeze group -> (max, mean); two dense layers
+  (relu, linear) produce one weight per embedding element; re-weight, skip connection, layer norm."""
+
+  def __init__(self, dims, conf, generator=None):
+    super().__init__()
+    self.g = conf.num_squeeze_group
+    assert all(d >= self.g and d % self.g == 0 for d in dims), 'field dims must be divisible by num_squeeze_group'
+    emb = sum(dims)
+    red = max(1, len(dims) * self.g * 2 // conf.reduction_ratio)
+    self.reduce = L.DenseLayer(len(dims) * self.g * 2, red, False, True, generator)
+    self.excite = L.Dense(red, emb, generator)
+    with torch.no_grad():
+      nn.init.kaiming_normal_(self.reduce.kernel.t(), generator=generator)           # he_normal (fan_in)
+      nn.init.xavier_normal_(self.excite.kernel, generator=generator)                # glorot_normal
+    self.skip = conf.use_skip_connection
+    self.ln = nn.LayerNorm(emb, eps=1e-3) if conf.use_output_layer_norm else None   # keras default epsilon
+    self.out_dim = emb
+
+  def forward(self, inputs):
+    sq = []
+    for e in inputs:
+      ge = e.reshape(e.shape[0], self.g, e.shape[1] // self.g)
+      sq.append(ge.max(dim=-1).values)
+      sq.append(ge.mean(dim=-1))
+    z = torch.cat(sq, dim=1).contiguous()
+    w = self.excite(self.reduce(z))
+    x = torch.cat(list(inputs), dim=-1)
+    out = x * w
+    if self.skip:
+      out = out + x
+    return self.ln(out) if self.ln is not None else out
+
+
 class MMoE(nn.Module):
   """layers/keras/multi_task.py:47-67: num_expert expert MLPs on the same input, one softmax gate per task,
   task output = sum_e gate_e * expert_e (the mixture runs in er_mmoe_mix)."""
@@ -216,7 +250,14 @@ class Backbone(nn.Module):
     self.mods = nn.ModuleDict()
     self._gen = generator
     outs = self._run(None, batch_size, build=True)
-    self.out_dim = outs.shape[-1]
+    if isinstance(outs, (list, tuple)):   # one tensor per task (multi-task models)
+      self.n_outputs = len(outs)
+      self.out_dims = [o.shape[-1] for o in outs]
+      self.out_dim = sum(self.out_dims)
+    else:
+      self.n_outputs = 1
+      self.out_dims = [outs.shape[-1]]
+      self.out_dim = outs.shape[-1]
 
   # -- inputs -----------------------------------------------------------------------------------------
   def _block_input(self, block, outputs, groups):
@@ -265,6 +306,9 @@ class Backbone(nn.Module):
         self.mods[name] = FM(conf.fm if conf.HasField('fm') else None)
       elif cls == 'MMoE':
         self.mods[name] = MMoE(d, conf.mmoe, self._gen)
+      elif cls == 'SENet':
+        assert isinstance(x, (list, tuple)), 'SENet takes the feature list (input_layer.only_output_feature_list)'
+        self.mods[name] = SENet([t.shape[-1] for t in x], conf.senet, self._gen)
       elif cls == 'DotInteraction':
         params = {}
         if conf.HasField('st_params'):
@@ -286,6 +330,8 @@ class Backbone(nn.Module):
         return torch.empty((first.shape[0], dim if mod.use_variant else 1), device='meta')
       if isinstance(mod, MMoE):
         return [torch.empty(lead + (mod.out_dim,), device='meta') for _ in mod.gates]
+      if isinstance(mod, SENet):
+        return torch.empty((first.shape[0], mod.out_dim), device='meta')
       if isinstance(mod, DotInteraction):
         n = len(x) if isinstance(x, (list, tuple)) else first.shape[1]
         return torch.empty((first.shape[0], mod.out_dim(n)), device='meta')
@@ -372,10 +418,10 @@ class Backbone(nn.Module):
     for n in names:
       o = outputs[n]
       outs.extend(o if isinstance(o, (list, tuple)) else [o])
-    if self.config.output_blocks and not self.config.HasField('top_mlp'):
-      result = outs[0] if len(outs) == 1 else outs
-    else:
+    if self.config.concat_blocks and not self.config.output_blocks:
       result = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+    else:   # output_blocks / DAG leaves: tensors are handed on as a list (backbone.py:330-348)
+      result = outs[0] if len(outs) == 1 else outs
     if self.config.HasField('top_mlp'):
       if isinstance(result, (list, tuple)):
         result = torch.cat(list(result), dim=-1)

@@ -87,7 +87,11 @@ def test_every_reference_sample_config_parses():
                                  'samples/model_config/mmoe_on_taobao.config',
                                  'samples/model_config/dcn_backbone_on_taobao.config',
                                  'samples/model_config/dlrm_backbone_on_taobao.config',
-                                 'samples/model_config/multi_tower_backbone_on_taobao.config'])
+                                 'samples/model_config/multi_tower_backbone_on_taobao.config',
+                                 'samples/model_config/mmoe_backbone_on_taobao.config',
+                                 'samples/model_config/simple_multi_task_backbone_on_taobao.config',
+                                 'samples/model_config/dssm_on_taobao_backbone.config',
+                                 'samples/model_config/dssm_senet_on_taobao_backbone.config'])
 def test_baseline_model_families_build_from_unmodified_reference_configs(rel):
   cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, rel))
   il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))

@@ -81,6 +81,40 @@ model_config { model_class: "RankModel"
   embedding_regularization: 1e-5 }
 '''
 
+BACKBONE_MTL_CFG = HEAD.replace('label_fields: "clk"', 'label_fields: "clk" label_fields: "buy"') + FEATS + '''
+model_config { model_class: "MultiTaskModel"
+  feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "all" inputs { feature_group_name: "all" } input_layer { only_output_feature_list: true } }
+    blocks { name: "senet" inputs { block_name: "all" } keras_layer { class_name: "SENet" senet { reduction_ratio: 4 } } }
+    blocks { name: "mmoe" inputs { block_name: "senet" }
+             keras_layer { class_name: "MMoE" mmoe { num_task: 2 num_expert: 3 expert_mlp { hidden_units: [32, 16] } } } }
+  }
+  model_params {
+    task_towers { tower_name: "ctr" label_name: "clk" dnn { hidden_units: [16, 8] } weight: 1.0 }
+    task_towers { tower_name: "cvr" label_name: "buy" dnn { hidden_units: [16, 8] } weight: 0.5 }
+    l2_regularization: 1e-6 }
+  embedding_regularization: 1e-5 }
+'''
+
+BACKBONE_MATCH_CFG = HEAD + FEATS + '''
+model_config { model_class: "MatchModel"
+  feature_groups { group_name: "user" feature_names: ["user_id", "age"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate", "price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "user" inputs { feature_group_name: "user" } input_layer { } }
+    blocks { name: "item" inputs { feature_group_name: "item" } input_layer { } }
+    blocks { name: "user_tower" inputs { block_name: "user" }
+             keras_layer { class_name: "MLP" mlp { hidden_units: [32, 16] use_final_bn: false final_activation: "linear" } } }
+    blocks { name: "item_tower" inputs { block_name: "item" }
+             keras_layer { class_name: "MLP" mlp { hidden_units: [32, 16] use_final_bn: false final_activation: "linear" } } }
+    output_blocks: ["user_tower", "item_tower"]
+  }
+  model_params { l2_regularization: 1e-6 temperature: 0.05 }
+  loss_type: SOFTMAX_CROSS_ENTROPY
+  embedding_regularization: 1e-5 }
+'''
+
 MMOE_CFG = HEAD.replace('label_fields: "clk"', 'label_fields: "clk" label_fields: "buy"') + FEATS + '''
 model_config { model_class: "MMoE"
   feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
@@ -118,7 +152,8 @@ def make_batch(seed, n_task=1):
 
 
 @pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1),
-                                             (BACKBONE_DCN_CFG, 1), (BACKBONE_DLRM_CFG, 1)])
+                                             (BACKBONE_DCN_CFG, 1), (BACKBONE_DLRM_CFG, 1), (BACKBONE_MTL_CFG, 2),
+                                             (BACKBONE_MATCH_CFG, 1)])
 def test_models_from_pipeline_config_train(cfg_text, n_task):
   torch.backends.cuda.matmul.allow_tf32 = False
   cfg = config_util.get_configs_from_pipeline_file(cfg_text.encode())
