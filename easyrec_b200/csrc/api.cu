@@ -1,5 +1,6 @@
 // Library-level entry points of liber_b200.so: version, per-thread error text,
 // and the host-side Fingerprint64 for arbitrary byte strings.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -12,6 +13,13 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ER_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace er
 
 extern "C" int er_abi_version(void) { return ER_B200_ABI_VERSION; }

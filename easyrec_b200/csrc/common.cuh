@@ -63,6 +63,34 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// The step is a chain of short kernels.  Launched with the programmatic-stream-serialization attribute, a
+// kernel's CTAs may be scheduled while its predecessor is still draining: they run their prologue (barrier /
+// TMEM set-up, index math) and block in er_pdl_wait() until the predecessor has completed and its writes are
+// visible - so correctness is exactly stream order, only launch latency and ramp-up overlap.  Every kernel
+// launched through launch_pdl() calls er_pdl_wait() before its first global access and then lets its own
+// successor start launching.  ER_PDL=0 in the environment turns the attribute off (plain launches).
+__device__ __forceinline__ void er_pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();   // api.cu
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // slot of a segment: largest f with slots[f].seg_begin <= s (slots sorted by seg_begin).
 __device__ __forceinline__ int find_slot(const int32_t* __restrict__ seg_begins, int n_slots,
                                          int32_t s) {

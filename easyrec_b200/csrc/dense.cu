@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(256)
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             const float* __restrict__ mean, const float* __restrict__ rstd, int64_t total4,
                             int units, int relu, float4* __restrict__ y) {
+  er_pdl_wait();
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)((t * 4) % units);
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(256)
                             const float* __restrict__ y, const float* __restrict__ gy,
                             const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                             VecShape s, int relu, int use_bn, float* __restrict__ part /* [n_chunks][units][2] */) {
+  er_pdl_wait();
   __shared__ float4 s_a[kRowLanes][32], s_b[kRowLanes][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * kVecCols + 4 * cl;
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(256)
                             const float* __restrict__ save_rstd, VecShape s, int relu, int use_bn,
                             const float* __restrict__ part, float* __restrict__ gz,
                             float* __restrict__ gbias, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  er_pdl_wait();
   __shared__ float4 s_a[kRowLanes][32], s_b[kRowLanes][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * kVecCols + 4 * cl;
@@ -509,9 +512,9 @@ extern "C" int er_bn_act_apply(const float* z, const float* bias, const float* g
   auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   const int64_t total = batch * units;
   if (units % 4 == 0 && al(z) && al(y) && al(gamma) && al(beta) && al(mean) && al(rstd) && (!bias || al(bias))) {
-    bn_act_apply_vec_kernel<<<grid_for(total / 4, 256, 8), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(z), bias, gamma, beta, mean, rstd, total / 4, units, relu,
-        reinterpret_cast<float4*>(y));
+    launch_pdl(bn_act_apply_vec_kernel, dim3(grid_for(total / 4, 256, 8)), dim3(256), 0, st,
+               reinterpret_cast<const float4*>(z), bias, gamma, beta, mean, rstd, total / 4, (int)units, (int)relu,
+               reinterpret_cast<float4*>(y));
   } else {
     bn_act_apply_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(z, bias, gamma, beta, mean, rstd, total, units,
                                                                  relu, y);
@@ -542,9 +545,10 @@ extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float
       (!use_bn || (al(gamma) && al(save_mean) && al(save_rstd) && (!ggamma || al(ggamma)) && (!gbeta || al(gbeta))))) {
     VecShape v = vec_shape(batch, units);
     dim3 vgrid((units + kVecCols - 1) / kVecCols, v.n_chunks);
-    bn_bwd_stats_vec_kernel<<<vgrid, 256, 0, st>>>(z, bias, y, gy, save_mean, save_rstd, v, relu, use_bn, part);
-    bn_bwd_apply_vec_kernel<<<vgrid, 256, 0, st>>>(z, bias, gamma, y, gy, save_mean, save_rstd, v, relu, use_bn,
-                                                    part, gz, gbias, ggamma, gbeta);
+    launch_pdl(bn_bwd_stats_vec_kernel, vgrid, dim3(256), 0, st, z, bias, y, gy, save_mean, save_rstd, v, (int)relu,
+               use_bn, part);
+    launch_pdl(bn_bwd_apply_vec_kernel, vgrid, dim3(256), 0, st, z, bias, gamma, y, gy, save_mean, save_rstd, v,
+               (int)relu, use_bn, (const float*)part, gz, gbias, ggamma, gbeta);
     count_launches(2);
     ER_CUDA_LAUNCH_CHECK();
     return ER_OK;
@@ -573,6 +577,7 @@ __global__ void __launch_bounds__(256)
     dense_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
                        float* __restrict__ s1, const er_dense_seg_t* __restrict__ segs, int n_segs, er_opt_t opt,
                        const float* __restrict__ lr_dev, float* __restrict__ reg_loss_out) {
+  er_pdl_wait();
   extern __shared__ int s_first[];   // [n_segs + 1] first chunk of every segment
   for (int i = threadIdx.x; i < n_segs; i += blockDim.x) s_first[i + 1] = (int)((segs[i].n + 255) >> 8);
   __syncthreads();
@@ -641,8 +646,8 @@ extern "C" int er_dense_apply(float* params, const float* grads, float* state0, 
   ER_REQUIRE((opt->kind != ER_OPT_LAZY_ADAM && opt->kind != ER_OPT_ADAM_ROWS) || state1, "adam needs state1");
   // enough CTAs for the biggest tensor's chunks plus one per small tensor, capped at 8 waves
   const int grid = (int)min((int64_t)8 * kSmCount, ceil_div(max_seg_n, (int64_t)256) + n_segs);
-  dense_apply_kernel<<<grid, 256, (size_t)(n_segs + 1) * sizeof(int), as_stream(stream)>>>(
-      params, grads, state0, state1, segs, n_segs, *opt, lr_dev, reg_loss_out);
+  launch_pdl(dense_apply_kernel, dim3(grid), dim3(256), (size_t)(n_segs + 1) * sizeof(int), as_stream(stream), params,
+             grads, state0, state1, segs, (int)n_segs, *opt, lr_dev, reg_loss_out);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;

@@ -195,14 +195,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  // The first k-blocks' global loads are issued before the barrier / TMEM set-up below, so their latency
-  // overlaps the prologue.
-  if (warp < kProducerThreads / 32) {
-#pragma unroll
-    for (int u = 0; u < kPrefetch; ++u)
-      if (u < n_kb) issue(u, va[u], vb[u]);
-  }
-
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_base + 8 * s, kProducerThreads / 32);
@@ -216,6 +208,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
                  "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // Everything above touches only this CTA's shared / tensor memory and can run while the previous kernel
+  // of the stream drains (programmatic dependent launch); operands are read only after the wait.  The first
+  // k-blocks' loads are issued before the CTA-wide sync so their latency overlaps it.
+  er_pdl_wait();
+  if (warp < kProducerThreads / 32) {
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+      if (u < n_kb) issue(u, va[u], vb[u]);
   }
   tc_fence_before();
   __syncthreads();
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(Args a) {
 // C[m,n] = sum_s partials[s][m][n] (+ bias[n]), fixed order.
 __global__ void splitk_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ bias,
                                      float* __restrict__ C, long long ldc, int M, int N, int n_slices) {
+  er_pdl_wait();
   const long long total = (long long)M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -572,12 +574,13 @@ static int gemm_impl(const float* A, int64_t lda, int32_t a_mn_major, const floa
   }
   cudaStream_t st = er::as_stream(stream);
   dim3 grid((unsigned)er::ceil_div(N, BN), (unsigned)er::ceil_div(M, BM), (unsigned)a.n_slices);
-  gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+  er::launch_pdl(gemm_tf32x3_kernel, grid, dim3(kThreads), (size_t)kSmemBytes, st, a);
   int launches = 1;
   if (a.n_slices > 1) {
     const long long total = (long long)M * N;
     int blocks = (int)std::min<long long>((total + 255) / 256, 4LL * er::kSmCount);
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(a.partials, bias, C, ldc, (int)M, (int)N, a.n_slices);
+    er::launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float*)a.partials, bias, C,
+                   (long long)ldc, (int)M, (int)N, a.n_slices);
     ++launches;
   }
   er::count_launches(launches);

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(1024)
                       const float* __restrict__ weights, int64_t batch, float inv_count,
                       float* __restrict__ loss_out, float* __restrict__ probs,
                       float* __restrict__ g_logits) {
+  er_pdl_wait();
   __shared__ float s_red[32];
   float acc = 0.f;
   for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) {
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256)
     fm_block_fwd_kernel(const float* __restrict__ x, int64_t batch, int n_field, int dim, int x_stride,
                         float* __restrict__ y, float* __restrict__ partials, unsigned int* counter,
                         float* __restrict__ sumsq_out) {
+  er_pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = dim >> 2, n4 = n_field * d4;
   __shared__ float s_w[8];
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ g_pass, const float* __restrict__ coef_dev, float coef_mul,
                         int64_t batch, int n_field, int dim, int x_stride, int gp_stride,
                         float* __restrict__ gx, int gx_stride) {
+  er_pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d4 = dim >> 2, n4 = n_field * d4;
   const float coef = coef_dev ? __fmul_rn(*coef_dev, coef_mul) : 0.f;
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(256)
     rowsum_block_fwd_kernel(const float* __restrict__ x, int64_t batch, int width, int x_stride,
                             float* __restrict__ y, float* __restrict__ partials, unsigned int* counter,
                             float* __restrict__ sumsq_out) {
+  er_pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ float s_w[8];
   __shared__ int s_last;
@@ -315,6 +319,7 @@ __global__ void __launch_bounds__(256)
     rowsum_block_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy,
                             const float* __restrict__ coef_dev, float coef_mul, int64_t batch, int width,
                             int x_stride, float* __restrict__ gx, int gx_stride) {
+  er_pdl_wait();
   const float coef = coef_dev ? __fmul_rn(*coef_dev, coef_mul) : 0.f;
   const int64_t total = batch * width;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -329,6 +334,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     dense1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       int64_t batch, int width, int x_stride, float* __restrict__ y) {
+  er_pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float b0 = bias ? bias[0] : 0.f;
   for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < batch; b += (int64_t)gridDim.x * 8) {
@@ -347,6 +353,7 @@ __global__ void __launch_bounds__(256)
                       int64_t batch, int width, int x_stride, float* __restrict__ gx, int gx_stride,
                       float* __restrict__ partials /* [grid][width+1] */, unsigned int* counter,
                       float* __restrict__ gw, float* __restrict__ gb) {
+  er_pdl_wait();
   extern __shared__ float s_col[];   // [8][width+1], later [256] for the final combine
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -421,6 +428,7 @@ struct CatArgs {
 };
 __global__ void __launch_bounds__(256)
     concat_cols_kernel(CatArgs a, int64_t batch, float* __restrict__ dst, int dst_stride) {
+  er_pdl_wait();
   const int64_t total = batch * dst_stride;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -435,6 +443,7 @@ __global__ void __launch_bounds__(256)
 }
 __global__ void __launch_bounds__(256)
     split_cols_kernel(CatArgs a, int64_t batch, const float* __restrict__ src, int src_stride, int total_w) {
+  er_pdl_wait();
   const int64_t total = batch * total_w;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -502,8 +511,8 @@ extern "C" int er_sigmoid_ce_fwd_bwd(const float* logits, const float* labels,
   using namespace er;
   ER_REQUIRE(logits && labels, "null argument");
   ER_REQUIRE(batch > 0, "batch must be positive");
-  sigmoid_ce_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, labels, weights, batch, inv_count,
-                                                      loss_out, probs, g_logits);
+  launch_pdl(sigmoid_ce_kernel, dim3(1), dim3(1024), 0, as_stream(stream), logits, labels, weights, batch, inv_count,
+             loss_out, probs, g_logits);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -547,7 +556,7 @@ extern "C" int er_fm_block_fwd(const float* x, int64_t batch, int32_t n_field, i
   }
   const int J = (int)ceil_div((int64_t)n_field * (dim / 4), 32);
   cudaStream_t st = as_stream(stream);
-#define ER_FM_FWD(JJ) fm_block_fwd_kernel<JJ><<<grid, 256, 0, st>>>(x, batch, n_field, dim, x_stride, y, partials, counter, sumsq_out)
+#define ER_FM_FWD(JJ) launch_pdl(fm_block_fwd_kernel<JJ>, dim3(grid), dim3(256), 0, st, x, batch, (int)n_field, (int)dim, (int)x_stride, y, partials, counter, sumsq_out)
   switch (J) {
     case 1: ER_FM_FWD(1); break; case 2: ER_FM_FWD(2); break; case 3: ER_FM_FWD(3); break;
     case 4: ER_FM_FWD(4); break; case 5: ER_FM_FWD(5); break; case 6: ER_FM_FWD(6); break;
@@ -575,7 +584,7 @@ extern "C" int er_fm_block_bwd(const float* x, const float* gy, const float* g_p
   const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), 8 * kSmCount);
   const int J = (int)ceil_div((int64_t)n_field * (dim / 4), 32);
   cudaStream_t st = as_stream(stream);
-#define ER_FM_BWD(JJ) fm_block_bwd_kernel<JJ><<<grid, 256, 0, st>>>(x, gy, g_pass, coef_dev, coef_mul, batch, n_field, dim, x_stride, g_pass_stride, gx, gx_stride)
+#define ER_FM_BWD(JJ) launch_pdl(fm_block_bwd_kernel<JJ>, dim3(grid), dim3(256), 0, st, x, gy, g_pass, coef_dev, coef_mul, batch, (int)n_field, (int)dim, (int)x_stride, (int)g_pass_stride, gx, (int)gx_stride)
   switch (J) {
     case 1: ER_FM_BWD(1); break; case 2: ER_FM_BWD(2); break; case 3: ER_FM_BWD(3); break;
     case 4: ER_FM_BWD(4); break; case 5: ER_FM_BWD(5); break; case 6: ER_FM_BWD(6); break;
@@ -600,8 +609,8 @@ extern "C" int er_rowsum_block_fwd(const float* x, int64_t batch, int32_t width,
     counter = reinterpret_cast<unsigned int*>(ws);
     partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 16);
   }
-  rowsum_block_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, batch, width, x_stride, y, partials, counter,
-                                                               sumsq_out);
+  launch_pdl(rowsum_block_fwd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), x, batch, (int)width, (int)x_stride, y,
+             partials, counter, sumsq_out);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -613,8 +622,8 @@ extern "C" int er_rowsum_block_bwd(const float* x, const float* gy, const float*
   using namespace er;
   ER_REQUIRE(x && gx, "null argument");
   ER_REQUIRE(batch > 0 && width > 0 && x_stride >= width && gx_stride >= width, "bad shape");
-  rowsum_block_bwd_kernel<<<grid_for(batch * width, 256, 8), 256, 0, as_stream(stream)>>>(
-      x, gy, coef_dev, coef_mul, batch, width, x_stride, gx, gx_stride);
+  launch_pdl(rowsum_block_bwd_kernel, dim3(grid_for(batch * width, 256, 8)), dim3(256), 0, as_stream(stream), x, gy,
+             coef_dev, coef_mul, batch, (int)width, (int)x_stride, gx, (int)gx_stride);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -630,7 +639,7 @@ extern "C" int er_dense1_fwd(const float* x, const float* w, const float* bias, 
   ER_REQUIRE(x && w && y, "null argument");
   ER_REQUIRE(batch > 0 && width > 0 && x_stride >= width, "bad shape");
   const int grid = (int)std::min<int64_t>(ceil_div(batch, 8), 4 * kSmCount);
-  dense1_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, batch, width, x_stride, y);
+  launch_pdl(dense1_fwd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), x, w, bias, batch, (int)width, (int)x_stride, y);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -649,7 +658,7 @@ extern "C" int er_dense1_bwd(const float* x, const float* w, const float* g, int
   float* part = reinterpret_cast<float*>(static_cast<char*>(ws) + 16);
   unsigned int* cnt = reinterpret_cast<unsigned int*>(ws);
   cudaStream_t st = as_stream(stream);
-#define ER_D1(JJ) dense1_bwd_kernel<JJ><<<grid, 256, smem, st>>>(x, w, g, batch, width, x_stride, gx, gx_stride, part, cnt, gw, gb)
+#define ER_D1(JJ) launch_pdl(dense1_bwd_kernel<JJ>, dim3(grid), dim3(256), smem, st, x, w, g, batch, (int)width, (int)x_stride, gx, (int)gx_stride, part, cnt, gw, gb)
   switch ((width + 31) / 32) {
     case 1: ER_D1(1); break; case 2: ER_D1(2); break; case 3: ER_D1(3); break; case 4: ER_D1(4); break;
     case 5: ER_D1(5); break; case 6: ER_D1(6); break; case 7: ER_D1(7); break; default: ER_D1(8); break;
@@ -692,7 +701,8 @@ extern "C" int er_concat_cols(const float* const* srcs, const int32_t* widths, c
   int rc = cat_args(&a, const_cast<float* const*>(srcs), widths, strides, n);
   if (rc != ER_OK) return rc;
   ER_REQUIRE(dst && batch > 0 && dst_stride >= a.first[ER_MAX_CAT], "bad destination");
-  concat_cols_kernel<<<grid_for(batch * dst_stride, 256, 8), 256, 0, as_stream(stream)>>>(a, batch, dst, dst_stride);
+  launch_pdl(concat_cols_kernel, dim3(grid_for(batch * dst_stride, 256, 8)), dim3(256), 0, as_stream(stream), a, batch, dst,
+             (int)dst_stride);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
@@ -705,8 +715,8 @@ extern "C" int er_split_cols(const float* src, int32_t src_stride, int64_t batch
   int rc = cat_args(&a, dsts, widths, strides, n);
   if (rc != ER_OK) return rc;
   ER_REQUIRE(src && batch > 0 && src_stride >= a.first[ER_MAX_CAT], "bad source");
-  split_cols_kernel<<<grid_for(batch * a.first[ER_MAX_CAT], 256, 8), 256, 0, as_stream(stream)>>>(
-      a, batch, src, src_stride, a.first[ER_MAX_CAT]);
+  launch_pdl(split_cols_kernel, dim3(grid_for(batch * a.first[ER_MAX_CAT], 256, 8)), dim3(256), 0, as_stream(stream), a,
+             batch, src, (int)src_stride, a.first[ER_MAX_CAT]);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
