@@ -7,7 +7,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
     --log-file gpurun_out/r01_launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 python tools/summarize_launches.py gpurun_out/r01_launches.csv 70 > gpurun_out/r01_launches_summary.txt
 for k in gemm_tf32x3_kernel bwd_scan_vec_kernel fwd_single_kernel scatter_kernel; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 20 -c 2 \
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 2 \
       -o gpurun_out/r01_$k $B > gpurun_out/ncu_$k.log 2>&1
 done
 ls -la gpurun_out/*.ncu-rep
