@@ -382,3 +382,12 @@ int oracle_num_threads(void) {
   return 1;
 #endif
 }
+
+/* thread count of the OpenMP loops above (bench.py picks the fastest setting on the box) */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

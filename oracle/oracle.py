@@ -53,6 +53,10 @@ def num_threads():
   return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n):
+  lib().oracle_set_num_threads(int(n))
+
+
 def fingerprint64(data):
   if isinstance(data, str):
     data = data.encode('utf-8')
