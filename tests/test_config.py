@@ -125,3 +125,36 @@ def test_parquet_and_csv_inputs_pack_the_same_batches(tmp_path):
     assert torch.allclose(pf['dense_fea'], cf['dense_fea'])
     assert torch.equal(pl, cl)
   assert torch.equal(pb[0][0]['sparse_fea'], torch.from_numpy(c1[:4]))
+
+
+BACKBONE_WIRING = MINI.replace(b'model_class: "DeepFM"', b'model_class: "RankModel"').replace(
+    b'deepfm { dnn { hidden_units: [32, 16] } final_dnn { hidden_units: [16] } l2_regularization: 1e-5 }',
+    b'''backbone {
+      blocks { name: "feats" inputs { feature_group_name: "deep" } input_layer { only_output_feature_list: true } }
+      blocks { name: "halves" inputs { feature_group_name: "deep" }
+               repeat { num_repeat: 2 input_fn: "lambda x, i: x[:, i * 16:(i + 1) * 16]" output_concat_axis: 1
+                        keras_layer { class_name: "MLP" mlp { hidden_units: [8] } } } }
+      blocks { name: "scaled" inputs { block_name: "halves" input_slice: "[:, :8]" } lambda { expression: "lambda x: x * 2.0" } }
+      blocks { name: "fm" inputs { block_name: "feats" } keras_layer { class_name: "FM" fm { use_variant: true } } }
+      blocks { name: "cross" inputs { feature_group_name: "deep" input_fn: "lambda x: [x, x]" }
+               recurrent { num_steps: 2 fixed_input_index: 0 keras_layer { class_name: "Cross" } } }
+      concat_blocks: ["halves", "scaled", "fm", "cross"]
+      top_mlp { hidden_units: [12] }
+    }
+    model_params { l2_regularization: 1e-5 }''')
+
+
+def test_backbone_wiring_shapes_and_parameters_without_a_gpu():
+  """block inputs / input_fn / input_slice / lambda / repeat / recurrent / concat_blocks / top_mlp are resolved by a
+  shape-only dry run (meta tensors): widths and parameter shapes must follow layers/backbone.py semantics."""
+  cfg = config_util.get_configs_from_pipeline_file(BACKBONE_WIRING)
+  il, model, opt = builder.build_model(cfg, 32, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  bb = model.backbone
+  # halves: 2 x MLP(16 -> 8) concatenated = 16; scaled: 8; fm (use_variant): 16; cross: 32 -> concat 72 -> top_mlp 12
+  assert bb.out_dim == 12 and model.output is not None
+  shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
+  assert shapes['backbone.mods.halves_0.layers.0.kernel'] == (16, 8)
+  assert shapes['backbone.mods.halves_1.layers.0.kernel'] == (16, 8)
+  assert shapes['backbone.mods.cross_0.dense.kernel'] == (32, 32) and 'backbone.mods.cross_1.dense.kernel' in shapes
+  assert shapes['backbone.mods.backbone_top_mlp.layers.0.kernel'] == (72, 12)
+  assert model.l2_of('backbone.mods.cross_0.dense.kernel', None) == pytest.approx(1e-5)

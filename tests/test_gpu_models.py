@@ -115,6 +115,23 @@ model_config { model_class: "MatchModel"
   embedding_regularization: 1e-5 }
 '''
 
+BACKBONE_WIRING_CFG = HEAD + FEATS + '''
+model_config { model_class: "RankModel"
+  feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "feats" inputs { feature_group_name: "all" } input_layer { only_output_feature_list: true } }
+    blocks { name: "parts" inputs { feature_group_name: "all" }
+             repeat { num_repeat: 2 input_fn: "lambda x, i: x[:, i * 40:(i + 1) * 40]" output_concat_axis: 1
+                      keras_layer { class_name: "MLP" mlp { hidden_units: [16] } } } }
+    blocks { name: "scaled" inputs { block_name: "parts" input_slice: "[:, :16]" } lambda { expression: "lambda x: x * 2.0" } }
+    blocks { name: "fm" inputs { block_name: "feats" } keras_layer { class_name: "FM" fm { use_variant: true } } }
+    concat_blocks: ["parts", "scaled", "fm"]
+    top_mlp { hidden_units: [16] }
+  }
+  model_params { l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
 MMOE_CFG = HEAD.replace('label_fields: "clk"', 'label_fields: "clk" label_fields: "buy"') + FEATS + '''
 model_config { model_class: "MMoE"
   feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
@@ -153,7 +170,7 @@ def make_batch(seed, n_task=1):
 
 @pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1),
                                              (BACKBONE_DCN_CFG, 1), (BACKBONE_DLRM_CFG, 1), (BACKBONE_MTL_CFG, 2),
-                                             (BACKBONE_MATCH_CFG, 1)])
+                                             (BACKBONE_MATCH_CFG, 1), (BACKBONE_WIRING_CFG, 1)])
 def test_models_from_pipeline_config_train(cfg_text, n_task):
   torch.backends.cuda.matmul.allow_tf32 = False
   cfg = config_util.get_configs_from_pipeline_file(cfg_text.encode())
