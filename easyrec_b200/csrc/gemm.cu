@@ -14,11 +14,20 @@
 //   both are "128 segments of 128 B", so the producer code and the shared-memory offsets are the same and
 //   no transposed copy of any matrix is ever made.
 //
-// CTA = 128x128 output tile (one k-slice of it under split-K): 8 producer warps (global -> registers ->
-// hi/lo split -> swizzled st.shared, 3-stage ring), 1 MMA warp (one lane issues tcgen05.mma, tcgen05.commit
-// frees the stage), accumulators 128 lanes x 2 x 128 columns of TMEM (main product / cross terms); the producer warps then become the
-// epilogue (tcgen05.ld -> optional bias -> global).  Split-K partials are reduced by a second kernel in a
-// fixed order, so results are run-to-run deterministic.
+// CTA = 128x128 output tile (one k-slice of it under split-K):
+//   - 8 producer warps: global -> registers -> hi/lo split -> swizzled st.shared into a 3-stage mbarrier ring,
+//     with kPrefetch k-blocks of loads in flight per thread (the first ones are issued before the CTA-wide
+//     set-up sync);
+//   - 1 MMA warp: one lane issues the tcgen05.mma's, tcgen05.commit hands the stage back;
+//   - accumulators in TMEM: 128 lanes x 128 columns for Ahi.Bhi and another 128 columns for the two cross
+//     terms (the tensor core truncates the fp32 accumulator on every accumulate: keeping the small terms
+//     apart brings the error down to an fp32 SGEMM's);
+//   - epilogue (the producer warps): tcgen05.ld both accumulators -> add -> transpose through shared memory ->
+//     4 x 128 B coalesced stores (+ bias); optionally the batch-norm statistics of the output columns
+//     (per-warp shifted sums -> per-tile Welford -> the last CTA of a column tile merges the tiles in order).
+// Split-K partials are reduced by a second kernel in a fixed order: results are run-to-run deterministic.
+// The kernel is launched with programmatic dependent launch: everything before er_pdl_wait() (barrier init,
+// TMEM allocation) overlaps the previous kernel's drain.
 #include <algorithm>
 
 #include "common.cuh"
