@@ -183,3 +183,32 @@ def test_dense_oracle_matches_torch_autograd_cpu():
       np.testing.assert_allclose(grads[tag][i]['gamma'], ga.grad.numpy(), rtol=1e-3, atol=1e-6)
       np.testing.assert_allclose(grads[tag][i]['beta'], be.grad.numpy(), rtol=1e-3, atol=1e-6)
   np.testing.assert_allclose(grads['out_W'], oW.grad.numpy(), rtol=1e-3, atol=1e-6)
+
+
+FORMULAS = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_formulas.json')))
+
+
+def test_fm_oracle_matches_the_reference_code_output():
+  """golden = layers/fm.py FM.__call__ executed on a numpy shim of its tf ops (make_formula_golden.py)."""
+  c = FORMULAS['cases']['fm']
+  x = np.asarray(c['x'], np.float32)          # [B, F, D]
+  B, F, D = x.shape
+  got = O.fm_fwd(x.reshape(B, F * D), F, D)
+  np.testing.assert_allclose(got, np.asarray(c['y'], np.float32), rtol=1e-6, atol=1e-6)
+
+
+def test_formula_golden_file_matches_its_generator_when_the_reference_is_mounted():
+  if not os.path.isdir('/root/reference/easy_rec/python'):
+    pytest.skip('reference checkout not mounted')
+  import subprocess
+  import sys
+  import tempfile
+  gen = os.path.join(os.path.dirname(__file__), 'golden', 'make_formula_golden.py')
+  src = open(gen).read()
+  with tempfile.TemporaryDirectory() as d:
+    alt = os.path.join(d, 'gen.py')
+    open(alt, 'w').write(src.replace("OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_formulas.json')",
+                                     "OUT = %r" % os.path.join(d, 'out.json')))
+    subprocess.check_call([sys.executable, alt], stdout=subprocess.DEVNULL)
+    fresh = json.load(open(os.path.join(d, 'out.json')))
+  assert fresh['cases'] == FORMULAS['cases']
