@@ -109,24 +109,38 @@ class MLP(nn.Module):
 
 
 class Cross(nn.Module):
-  """DCN-v2 cross (layers/keras/interaction.py:249-286): x0 * (W x + b [+ diag_scale x]) + x, full-rank W
+  """DCN-v2 cross (layers/keras/interaction.py:249-286): x0 * (W x + b [+ diag_scale x]) + x with a full-rank
+  W, or W = U V (projection_dim: U [d, p] without bias, V [p, d] with the bias) for the low-rank variant
   (kernel_initializer truncated_normal, bias zeros)."""
 
   def __init__(self, dim, params, generator=None):
     super().__init__()
-    if params.get('projection_dim'):
-      raise NotImplementedError('Cross.projection_dim (low-rank variant)')
     self.diag_scale = float(params.get('diag_scale', 0.0))
-    self.dense = L.Dense(dim, dim, generator)
+    if self.diag_scale < 0:
+      raise ValueError('`diag_scale` should be non-negative. Got `diag_scale` = %r' % self.diag_scale)
+    proj = params.get('projection_dim')
+    self.dense_u = None
+    if proj:
+      self.dense_u = L.Dense(dim, int(proj), generator)
+      self.dense_u.bias.requires_grad_(False)        # Dense(use_bias=False): the zero bias never moves
+      self.dense = L.Dense(int(proj), dim, generator)
+    else:
+      self.dense = L.Dense(dim, dim, generator)
     with torch.no_grad():
-      nn.init.trunc_normal_(self.dense.kernel, std=0.05, a=-0.1, b=0.1, generator=generator)
+      for d in (self.dense_u, self.dense):
+        if d is not None:
+          nn.init.trunc_normal_(d.kernel, std=0.05, a=-0.1, b=0.1, generator=generator)
     if params.get('use_bias', True) is False:
       self.dense.bias.requires_grad_(False)
     self.out_dim = dim
 
   def forward(self, inputs):
     x0, x = inputs if isinstance(inputs, (list, tuple)) else (inputs, inputs)
-    prod = self.dense(x.contiguous())
+    if x0.shape[-1] != x.shape[-1]:
+      raise ValueError('`x0` and `x` dimension mismatch! Got `x0` dimension %d, and x dimension %d. This case is '
+                       'not supported yet.' % (x0.shape[-1], x.shape[-1]))
+    x = x.contiguous()
+    prod = self.dense(x) if self.dense_u is None else self.dense(self.dense_u(x))
     if self.diag_scale:
       prod = prod + self.diag_scale * x
     return x0 * prod + x

@@ -5,6 +5,8 @@ and of `EasyRecModel.create_class(model_class)` (model/easy_rec_model.py:44-49, 
 """
 import collections
 
+import numpy as np
+
 from easyrec_b200 import _lib
 from easyrec_b200 import input_layer as IL
 from easyrec_b200.config import config_util
@@ -69,17 +71,30 @@ def optimizer_settings(pipeline_config):
     e = lr.exponential_decay_learning_rate
 
     def lr_fn(step, e=e):
-      # core/learning_schedules.py:30-75 exponential_decay_with_burnin
-      p = step / float(e.decay_steps)
-      if e.staircase:
-        p = float(int(p))
-      v = e.initial_learning_rate * (e.decay_factor**p)
-      if e.burnin_steps > 0 and step < e.burnin_steps:
-        v = e.burnin_learning_rate
-      return max(v, e.min_learning_rate)
-  else:
-    c = lr.constant_learning_rate.learning_rate if which == 'constant_learning_rate' else 0.002
+      # core/learning_schedules.py:30-75 exponential_decay_with_burnin, in fp32 like the TF graph it builds:
+      # burn-in ramps linearly from burnin_learning_rate to the base rate (or holds the base rate when
+      # burnin_learning_rate is 0); the decay clock starts after the burn-in steps.
+      f32 = np.float32
+      base = f32(e.initial_learning_rate)
+      if step < e.burnin_steps:
+        if e.burnin_learning_rate == 0:
+          v = base
+        else:
+          slope = (e.initial_learning_rate - e.burnin_learning_rate) / e.burnin_steps
+          v = f32(slope) * f32(step) + f32(e.burnin_learning_rate)
+      else:
+        p = f32(step - e.burnin_steps) / f32(e.decay_steps)
+        if e.staircase:
+          p = np.floor(p)
+        v = base * np.power(f32(e.decay_factor), p, dtype=f32)
+      return float(max(f32(v), f32(e.min_learning_rate)))
+  elif which == 'constant_learning_rate':
+    c = lr.constant_learning_rate.learning_rate
     lr_fn = lambda step, c=c: c  # noqa: E731
+  else:
+    # builders/optimizer_builder.py:145-215 also knows manual_step / cosine / poly / transformer schedules;
+    # they are outside the hot-path scope: refuse instead of training with a made-up rate.
+    raise ValueError('unsupported learning_rate schedule: %r' % which)
   return dict(kind=kind, lr_fn=lr_fn, beta1=getattr(o, 'beta1', 0.9), beta2=getattr(o, 'beta2', 0.999),
               acc0=getattr(o, 'initial_accumulator_value', 0.1),
               emb_lr_mult=oc.embedding_learning_rate_multiplier

@@ -158,3 +158,15 @@ def test_backbone_wiring_shapes_and_parameters_without_a_gpu():
   assert shapes['backbone.mods.cross_0.dense.kernel'] == (32, 32) and 'backbone.mods.cross_1.dense.kernel' in shapes
   assert shapes['backbone.mods.backbone_top_mlp.layers.0.kernel'] == (72, 12)
   assert model.l2_of('backbone.mods.cross_0.dense.kernel', None) == pytest.approx(1e-5)
+
+
+def test_cross_layer_variants_have_the_keras_parameter_shapes():
+  """layers/keras/interaction.py:213-245: full-rank W [d, d] + bias, or U [d, p] (no bias) and V [p, d] + bias."""
+  from easyrec_b200 import backbone as BB
+  full = BB.Cross(12, {'diag_scale': 0.1})
+  assert tuple(full.dense.kernel.shape) == (12, 12) and full.dense_u is None
+  low = BB.Cross(12, {'projection_dim': 3.0})     # st_params numbers arrive as floats
+  assert tuple(low.dense_u.kernel.shape) == (12, 3) and tuple(low.dense.kernel.shape) == (3, 12)
+  assert not low.dense_u.bias.requires_grad and low.dense.bias.requires_grad
+  with pytest.raises(ValueError):
+    BB.Cross(12, {'diag_scale': -1.0})

@@ -212,3 +212,42 @@ def test_formula_golden_file_matches_its_generator_when_the_reference_is_mounted
     subprocess.check_call([sys.executable, alt], stdout=subprocess.DEVNULL)
     fresh = json.load(open(os.path.join(d, 'out.json')))
   assert fresh['cases'] == FORMULAS['cases']
+
+
+def test_lazy_adam_oracle_matches_adam_s_sparse_apply():
+  """golden = compat/adam_s.py _apply_sparse_shared executed for three steps (unique rows, summed grads)."""
+  c = FORMULAS['cases']['lazy_adam_sparse']
+  w = np.array(c['w0'], np.float32)
+  m, v = np.zeros_like(w), np.zeros_like(w)
+  p1, p2 = c['beta1'], c['beta2']
+  for st in c['steps']:
+    rows = np.array(st['indices'], np.int64)
+    g = np.array(st['grad'], np.float32)
+    O.embedding_bwd(w, m, v, rows, np.arange(rows.size, dtype=np.int32), g, O.OPT_LAZY_ADAM, c['lr'],
+                    beta1=c['beta1'], beta2=c['beta2'], eps=c['epsilon'], beta1_power=p1, beta2_power=p2)
+    p1, p2 = p1 * c['beta1'], p2 * c['beta2']
+    np.testing.assert_allclose(m, np.array(st['m'], np.float32), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(v, np.array(st['v'], np.float32), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(w, np.array(st['w'], np.float32), rtol=2e-6, atol=1e-8)
+  untouched = np.setdiff1d(np.arange(w.shape[0]), np.concatenate([s['indices'] for s in c['steps']]))
+  assert untouched.size and np.array_equal(w[untouched], np.array(c['w0'], np.float32)[untouched])
+
+
+def test_learning_rate_schedule_matches_exponential_decay_with_burnin():
+  """golden = core/learning_schedules.py exponential_decay_with_burnin executed in fp32 (burn-in ramp, decay
+  clock starting after the burn-in, staircase, floor)."""
+  from easyrec_b200 import builder
+  from easyrec_b200.config import config_util
+  tmpl = ('train_config { optimizer_config { adagrad_optimizer { learning_rate { exponential_decay_learning_rate { '
+          'initial_learning_rate: %r decay_steps: %d decay_factor: %r burnin_learning_rate: %r burnin_steps: %d '
+          'min_learning_rate: %r staircase: %s } } } } }')
+  for s in FORMULAS['cases']['lr_exponential_decay_with_burnin']['schedules']:
+    cfg = config_util.get_configs_from_pipeline_file((tmpl % (
+        s['initial_learning_rate'], s['decay_steps'], s['decay_factor'], s['burnin_learning_rate'], s['burnin_steps'],
+        s['min_learning_rate'], 'true' if s['staircase'] else 'false')).encode())
+    lr_fn = builder.optimizer_settings(cfg)['lr_fn']
+    got = [lr_fn(st) for st in s['steps']]
+    np.testing.assert_allclose(got, s['lr'], rtol=3e-6, atol=0)
+  with pytest.raises(ValueError):
+    builder.optimizer_settings(config_util.get_configs_from_pipeline_file(
+        b'train_config { optimizer_config { adagrad_optimizer { } } }'))
