@@ -57,6 +57,11 @@ def seq_att_groups(model_config):
   return out
 
 
+def input_type_name(pipeline_config):
+  dc = pipeline_config.data_config
+  return dc.DESCRIPTOR.fields_by_name['input_type'].enum_type.values_by_number[dc.input_type].name
+
+
 def optimizer_settings(pipeline_config):
   """builders/optimizer_builder.py:28-144: kind + constant / exponential-decay schedule."""
   tc = pipeline_config.train_config
@@ -106,7 +111,10 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   """Returns (input_layer, model, optimizer settings) for the config's model_class."""
   from easyrec_b200 import model as model_pkg
   mc = pipeline_config.model_config
-  specs = feature_specs(pipeline_config, default_seq_len=default_seq_len)
+  # the Parquet inputs bucket ids as `vals % num_buckets` (input/parquet_input.py:221,
+  # input/parquet_input_v2.py:96-100) where the feature-column path maps out-of-range ids to 0
+  specs = feature_specs(pipeline_config, packed_mod=input_type_name(pipeline_config).startswith('Parquet'),
+                        default_seq_len=default_seq_len)
   groups = feature_groups(mc)
   opt = optimizer_settings(pipeline_config)
   cls = model_pkg.get_model_class(mc.model_class)

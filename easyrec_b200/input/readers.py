@@ -156,8 +156,9 @@ class ParquetInput(object):
   """ParquetInput (input/parquet_input.py:201-239 + input/load_parquet.py:81-99): columnar file, one column per
   input field; the batch is the reference's packed form - ids of all sparse features feature-major
   (`sparse_fea`), dense features as one fp32 matrix (`dense_fea`), labels.  Sparse columns may be scalars or
-  lists (the reference stores lists, load_parquet.py:139-205); a single-valued feature takes the first id of
-  a list (empty list -> -1 = missing, dropped by K1), Tag / Sequence features keep the whole list.  Like the
+  lists (the reference stores lists, load_parquet.py:139-205); an IdFeature needs exactly one id per cell (ragged
+  cells belong to a TagFeature), Tag / Sequence features keep the whole list; a list-valued dense cell
+  holds raw_input_dim values (the reference reads x[0] of a list cell, load_parquet.py:108-114, i.e. dim 1).  Like the
   reference's packed path the ids go to the device untouched and are bucketed there (`vals % num_buckets`,
   parquet_input.py:221, or the feature's hash rule)."""
 
@@ -194,12 +195,13 @@ class ParquetInput(object):
       vals, lens = self._column(table.column(self.feature_inputs[name]))
       if lens is None:
         ids.append(np.asarray(vals, np.int64))
-      else:   # first id of every list, -1 where the list is empty
-        first = np.cumsum(lens) - lens
-        out = np.full(n, -1, np.int64)
-        has = lens > 0
-        out[has] = np.asarray(vals, np.int64)[first[has]]
-        ids.append(out)
+      else:
+        # list column on a single-valued slot: exactly one id per sample.  The packed path pools whatever the
+        # list holds (empty -> zero vector, several -> combined); that is the Tag slot's CSR lookup here.
+        if not (lens == 1).all():
+          raise ValueError('IdFeature %r has empty or multi-valued cells in %r: declare it as a TagFeature (combiner '
+                           '"sum") so that the ragged lists are pooled' % (name, self.feature_inputs[name]))
+        ids.append(np.asarray(vals, np.int64))
     if ids:
       feats['sparse_fea'] = torch.from_numpy(np.concatenate(ids))
     if il.raw_names:
@@ -214,7 +216,7 @@ class ParquetInput(object):
       if f.kind not in ('seq', 'tag'):
         continue
       vals, lens = self._column(table.column(self.feature_inputs[f.name]))
-      vals = np.asarray(vals, np.int64)
+      vals = np.array(vals, np.int64)   # owned, writable copy (arrow buffers are read-only)
       if lens is None:
         lens = np.ones(n, np.int32)
       if f.kind == 'seq':
@@ -236,30 +238,85 @@ class ParquetInput(object):
     return feats, labels
 
   def batches(self):
+    """Batch order of the reference loader with one reader process (load_parquet.py:166-301): every file
+    yields its own full batches first; its last `rows % batch_size` rows are appended to the rows carried over
+    from earlier files, and a batch is cut from that carry as soon as it holds batch_size rows."""
     import pyarrow as pa
     B = self.batch_size
-    pending, have = [], 0
+    carry = None
     for path in self.paths:
       pf = self._pq.ParquetFile(path)
+      n_full = pf.metadata.num_rows // B * B
+      pending, have, done = [], 0, 0
       for rb in pf.iter_batches(batch_size=B):   # record batches stop at row-group boundaries: re-chunk
         pending.append(rb)
         have += rb.num_rows
-        while have >= B:
+        while have >= B and done < n_full:
           tab = pa.Table.from_batches(pending)
           yield self._pack(tab.slice(0, B))
+          done += B
           rest = tab.slice(B)
           pending = rest.to_batches() if rest.num_rows else []
           have = rest.num_rows
-    # the static plan holds exactly batch_size samples; a ragged tail is skipped
+      if have:
+        tail = pa.Table.from_batches(pending)
+        carry = tail if carry is None else pa.concat_tables([carry, tail])
+        if carry.num_rows >= B:
+          yield self._pack(carry.slice(0, B).combine_chunks())
+          carry = carry.slice(B) if carry.num_rows > B else None
+    # the static plan holds exactly batch_size samples: the last partial batch (emitted by the reference unless
+    # data_config.drop_remainder) is skipped
 
   def __iter__(self):
     return self.batches()
 
 
+def from_reference_packed(input_layer, fea_dict, sparse_fea_names):
+  """The reference's packed feature dict (ParquetInput._to_fea_dict, input/parquet_input.py:201-239) -> the
+  InputLayer's batch form.  fea_dict['sparse_fea'] = (vals int64 [L], lens int32 [n_feat * B]) with the lens
+  feature-major in `sparse_fea_names` order (load_parquet.py:81-90); 'dense_fea' fp32 [B, sum raw_dim].
+  Raw (un-bucketed) ids are expected: the bucket rule runs on the device."""
+  il = input_layer
+  B = il.batch_size
+  vals, lens = fea_dict['sparse_fea']
+  vals = np.asarray(vals, np.int64)
+  lens = np.asarray(lens, np.int32)
+  if lens.size != len(sparse_fea_names) * B:
+    raise ValueError('sparse_fea lens has %d entries, expected %d features x batch %d' %
+                     (lens.size, len(sparse_fea_names), B))
+  counts = lens.reshape(len(sparse_fea_names), B).sum(axis=1)
+  ends = np.cumsum(counts)
+  if ends[-1] != vals.size:
+    raise ValueError('len(all_vals)=%d np.sum(all_lens)=%d' % (vals.size, ends[-1]))
+  per = {}
+  for i, name in enumerate(sparse_fea_names):
+    per[name] = (vals[ends[i] - counts[i]:ends[i]], lens[i * B:(i + 1) * B])
+  feats, ids, tag = {}, [], {}
+  for name in il.sparse_names:
+    v, l = per[name]
+    if not (l == 1).all():
+      raise ValueError('IdFeature %r has empty or multi-valued cells: declare it as a TagFeature (combiner "sum")' % name)
+    ids.append(v)
+  if ids:
+    feats['sparse_fea'] = torch.from_numpy(np.concatenate(ids))
+  for f in il.features.values():
+    if f.kind == 'tag':
+      v, l = per[f.name]
+      tag[f.name] = (torch.from_numpy(v.copy()), torch.from_numpy(l.copy()), None)
+    elif f.kind == 'seq':
+      raise ValueError('SequenceFeature %r has no packed form in the reference (Id / Tag / Raw only)' % f.name)
+  if tag:
+    feats['tag_fea'] = tag
+  if 'dense_fea' in fea_dict:
+    feats['dense_fea'] = torch.from_numpy(np.ascontiguousarray(fea_dict['dense_fea'], np.float32))
+  return feats
+
+
 def make_input(pipeline_config, input_layer, path):
   """reader for data_config.input_type (CSVInput / ParquetInput / DummyInput)."""
+  from easyrec_b200 import builder
   dc = pipeline_config.data_config
-  kind = dc.DESCRIPTOR.fields_by_name['input_type'].enum_type.values_by_number[dc.input_type].name
+  kind = builder.input_type_name(pipeline_config)
   if kind.startswith('Parquet'):
     return ParquetInput(pipeline_config, input_layer, path)
   if kind == 'DummyInput':
