@@ -251,3 +251,55 @@ def test_learning_rate_schedule_matches_exponential_decay_with_burnin():
   with pytest.raises(ValueError):
     builder.optimizer_settings(config_util.get_configs_from_pipeline_file(
         b'train_config { optimizer_config { adagrad_optimizer { } } }'))
+
+
+LOOKUP = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_lookup.json')))['cases']
+
+
+@pytest.mark.parametrize('k', [0, 1, 2])
+def test_pooling_oracle_matches_embedding_lookup_ragged(k):
+  """golden = compat/feature_column/feature_column.py embedding_lookup_ragged executed (unique -> gather ->
+  sparse segment sum / mean / sqrtn; empty bags -> zeros)."""
+  c = LOOKUP['embedding_lookup_ragged']
+  case = c['outputs'][k]
+  comb = {'sum': 0, 'mean': 1, 'sqrtn': 2}[case['combiner']]
+  row_ptr, _ = O.csr_from_lens(np.array(c['lens'], np.int32))
+  got, _ = O.embedding_fwd(np.array(c['table'], np.float32), np.array(c['ids'], np.int64), row_ptr, comb)
+  np.testing.assert_allclose(got, np.array(case['y'], np.float32), rtol=1e-6, atol=1e-6)
+  assert 0 in c['lens'] and not got[c['lens'].index(0)].any()
+
+
+def test_shard_rule_oracle_matches_embedding_parallel_lookup_on_two_ranks():
+  """golden = embedding_parallel_lookup executed by two threads whose hvd.alltoall really exchanges buffers
+  (owner = id % N, local row = int64(id / N), sum combiner, [B, n_feat * D] output).  The oracle's bucketize
+  with shard_n = N must address the same shard rows; gathering from the shards reproduces each rank's output."""
+  from easyrec_b200 import _lib
+  c = LOOKUP['embedding_parallel_lookup']
+  N, B, F = c['world'], c['batch_size'], c['n_feature']
+  full = np.array(c['table'], np.float32)
+  V, D = full.shape
+  assert c['shard_rows'] == (V + N - 1) // N
+  shards = [full[r::N] for r in range(N)]
+  for rank in c['ranks']:
+    ids, lens = np.array(rank['ids'], np.int64), np.array(rank['lens'], np.int32)
+    local, owner = O.bucketize(ids, _lib.BUCKET_IDENTITY, V, 0, shard_n=N)
+    assert np.array_equal(owner, ids % N) and np.array_equal(local, (ids / N).astype(np.int64))
+    rows = np.stack([shards[o][l] for o, l in zip(owner, local)]) if ids.size else np.zeros((0, D), np.float32)
+    seg = np.repeat(np.arange(F * B), lens)
+    pooled = np.zeros((F * B, D), np.float32)
+    np.add.at(pooled, seg, rows)
+    got = pooled.reshape(F, B, D).transpose(1, 0, 2).reshape(B, F * D)
+    np.testing.assert_allclose(got, np.array(rank['y'], np.float32), rtol=1e-6, atol=1e-6)
+
+
+def test_lookup_golden_file_matches_its_generator_when_the_reference_is_mounted(tmp_path):
+  if not os.path.isdir('/root/reference/easy_rec/python'):
+    pytest.skip('reference checkout not mounted')
+  import importlib.util
+  spec = importlib.util.spec_from_file_location(
+      'make_lookup_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_lookup_golden.py'))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)
+  gen.OUT = str(tmp_path / 'out.json')
+  gen.main()
+  assert json.load(open(gen.OUT))['cases'] == LOOKUP
