@@ -57,6 +57,7 @@ SIGNATURES = {
     'er_bucketize': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32,
                              c_vp, c_vp, c_vp]),
     'er_fingerprint64_host': (ctypes.c_uint64, [ctypes.c_char_p, c_sz]),
+    'er_load_embed': (c_i32, [ctypes.c_char_p, ctypes.c_char_p, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp]),
     'er_embedding_fwd': (c_i32, [
         c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,
         c_i32, ctypes.POINTER(c_vp), c_i32, c_vp, c_vp

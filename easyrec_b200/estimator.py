@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-from easyrec_b200 import builder
+from easyrec_b200 import builder, checkpoint
 from easyrec_b200.config import config_util
 from easyrec_b200.input import readers
 from easyrec_b200.trainer import Trainer
@@ -127,8 +127,11 @@ class EasyRecEstimator(object):
       logits = self._forward_eval(feats)
       yield {'logits': logits.cpu().numpy(), 'probs': torch.sigmoid(logits).cpu().numpy()}
 
-  def save(self, model_dir=None):
-    """dense parameters + arenas (weights and optimizer state) as one torch checkpoint."""
+  def save(self, model_dir=None, embedding_parts=False):
+    """dense parameters + arenas (weights and optimizer state) as one torch checkpoint.  embedding_parts=True
+    also writes every table and optimizer slot in the reference's row-sharded layout
+    `model.ckpt-<step>-embedding/embed-<var>-part-<rank>.bin` (compat/embedding_parallel_saver.py:99-123),
+    which `restore` can read back on a different number of workers."""
     model_dir = model_dir or self._pipeline_config.model_dir
     os.makedirs(model_dir, exist_ok=True)
     path = os.path.join(model_dir, 'model.ckpt-%d.pt' % self.global_step)
@@ -136,7 +139,25 @@ class EasyRecEstimator(object):
                 'arenas': {d: a.storage for d, a in self.input_layer.arenas.items()},
                 'tables': {d: a.tables for d, a in self.input_layer.arenas.items()},
                 'global_step': self.global_step}, path)
+    if embedding_parts:
+      for a in self.input_layer.arenas.values():
+        checkpoint.save_arena(a, path[:-3])
     return path
+
+  def restore(self, path):
+    """`path` as returned by save().  Tables come from the part files next to it when they exist (re-sharded for
+    this job's worker count by er_load_embed), else from the arenas stored in the torch checkpoint."""
+    ck = torch.load(path, map_location='cpu')
+    self.model.load_state_dict(ck['model'])
+    self.global_step = int(ck['global_step'])
+    parts = os.path.isdir(path[:-3] + '-embedding')
+    for d, a in self.input_layer.arenas.items():
+      if parts:
+        checkpoint.restore_arena(a, path[:-3])
+      else:
+        assert ck['tables'][d] == a.tables, 'checkpoint was written with another table plan'
+        a.storage.copy_(ck['arenas'][d])
+    return self
 
 
 def train_and_evaluate(pipeline_config_path, train_input_fn=None, eval_input_fn=None, device='cuda:0', **kw):

@@ -417,6 +417,19 @@ int er_inbatch_softmax_ce(const float* sim, const int64_t* item_ids, const float
                           int64_t batch, int32_t n_cols, float inv_wsum, float* loss_rows,
                           float* probs_diag, float* g_sim, er_stream_t stream);
 
+/* ---- sharded-table restore: the LoadEmbed custom op (ops/src/load_dense_embed.cc:28-156;
+ * python fallback compat/embedding_parallel_saver.py:141-173) ----
+ * HOST function, HOST pointers (the op is a CPU kernel in the reference as well).  Reads every
+ * `<ckpt_path>-embedding/<var_name>-part-<p>.bin` (raw fp32 [rows_p, embed_dim]; row j of old part p
+ * is global row j * P + p, P = number of part files), and fills this worker's shard
+ * vals[embed_part_size, embed_dim]: global rows g with g % task_num == task_index and
+ * g < embed_part_size * task_num land on local row g / task_num; rows no file provides stay 0.
+ * var_name is the file stem the saver used ("embed-" + variable name with '/' -> "__").
+ * *rows_loaded (optional) receives the number of rows copied; like the op, anything but
+ * embed_part_size or embed_part_size - 1 is an error (ER_ERR_INVALID_ARG). */
+int er_load_embed(const char* ckpt_path, const char* var_name, int32_t task_index, int32_t task_num,
+                  int32_t embed_dim, int64_t embed_part_size, float* vals, int64_t* rows_loaded);
+
 #ifdef __cplusplus
 }
 #endif

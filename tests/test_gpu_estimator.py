@@ -62,6 +62,13 @@ def _run(tmp_path, kind, path):
   assert preds['probs'].shape == (256,) and np.all((preds['probs'] >= 0) & (preds['probs'] <= 1))
   ckpt = est.save()
   assert ckpt.endswith('model.ckpt-120.pt')
+  # tables + Adagrad slots through the reference's part-file layout and back (native re-shard loader)
+  arena = est.input_layer.arenas[16]
+  w, acc = arena.weight.clone(), arena.state0.clone()
+  assert est.save(embedding_parts=True) == ckpt
+  arena.storage.zero_()
+  est.restore(ckpt)
+  assert torch.equal(arena.weight, w) and torch.equal(arena.state0, acc) and est.global_step == 120
   return ev['auc'], {k: v.detach().clone() for k, v in est.model.state_dict().items()}, est.input_layer.arenas[16].weight.clone()
 
 
