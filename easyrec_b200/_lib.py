@@ -46,6 +46,16 @@ class ErBnStats(ctypes.Structure):
               ('moving_var', c_vp), ('eps', c_f32), ('momentum', c_f32)]
 
 
+class ErCsvCol(ctypes.Structure):
+  """er_csv_col_t."""
+  _fields_ = [('kind', c_i32), ('width', c_i32), ('inner_sep', ctypes.c_char), ('pad_', ctypes.c_char * 7),
+              ('default_i64', c_i64), ('default_f32', c_f32), ('pad2_', c_i32), ('default_str', ctypes.c_char_p),
+              ('out', c_vp), ('lens', c_vp), ('list_cap', c_i64), ('n_vals', c_i64)]
+
+
+ER_OK, ER_ERR_INVALID_ARG, ER_ERR_WORKSPACE, ER_ERR_CUDA, ER_ERR_UNSUPPORTED = range(5)
+CSV_SKIP, CSV_I64, CSV_F32, CSV_HASH, CSV_I64_LIST, CSV_F32_VEC = range(6)
+
 # name -> (restype, argtypes); must list every symbol include/er_b200.h declares
 SIGNATURES = {
     'er_abi_version': (c_i32, []),
@@ -57,6 +67,8 @@ SIGNATURES = {
     'er_bucketize': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32,
                              c_vp, c_vp, c_vp]),
     'er_fingerprint64_host': (ctypes.c_uint64, [ctypes.c_char_p, c_sz]),
+    'er_csv_parse': (c_i32, [c_vp, c_sz, ctypes.c_char, ctypes.POINTER(ErCsvCol), c_i32, c_i64, c_i32,
+                             ctypes.POINTER(c_i64), ctypes.POINTER(c_sz)]),
     'er_load_embed': (c_i32, [ctypes.c_char_p, ctypes.c_char_p, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp]),
     'er_embedding_fwd': (c_i32, [
         c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,

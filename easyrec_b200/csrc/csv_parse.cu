@@ -1,0 +1,305 @@
+// Host-side text reader for the CSV input path (input/csv_input.py:78-175 -> tf.decode_csv with per-field
+// record_defaults; input/input.py:537-675 for what the fields become): one pass over a byte buffer of
+// delimiter-separated lines straight into the column arrays the packed batch is made of -- int64 ids,
+// Fingerprint64 of string ids, fp32 dense values / fixed-width vectors, CSR lists for Tag / Sequence fields.
+// No CUDA: the result is what the trainer copies to the device.  Lines are split across std::threads.
+#include <cerrno>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+extern "C" uint64_t er_fingerprint64_host(const char* s, size_t len);
+
+namespace er {
+namespace {
+
+struct Span {
+  const char* p;
+  size_t n;
+};
+
+// decimal int64 with optional sign; surrounding blanks allowed (tf.decode_csv strips them for numbers)
+inline bool parse_i64(Span s, int64_t* out) {
+  const char* p = s.p;
+  const char* e = s.p + s.n;
+  while (p < e && (*p == ' ' || *p == '\t')) ++p;
+  while (e > p && (e[-1] == ' ' || e[-1] == '\t')) --e;
+  if (p == e) return false;
+  bool neg = false;
+  if (*p == '-' || *p == '+') {
+    neg = *p == '-';
+    ++p;
+  }
+  if (p == e) return false;
+  uint64_t v = 0;
+  for (; p < e; ++p) {
+    const unsigned d = (unsigned)(*p - '0');
+    if (d > 9) return false;
+    v = v * 10 + d;
+  }
+  *out = neg ? (int64_t)(0 - v) : (int64_t)v;
+  return true;
+}
+
+// Correctly rounded decimal -> float.  Fast path (Clinger): at most 7-8 significant digits (mantissa < 2^24)
+// and a power of ten that is exact in binary32 (10^0..10^10): one exact int->float conversion and ONE rounded
+// multiply or divide, i.e. the same value strtof returns.  Everything else (long mantissas, big exponents,
+// inf / nan spellings, hex floats) goes to strtof itself.
+inline bool parse_f32(Span s, float* out) {
+  static const float kPow10[11] = {1e0f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+  const char* p = s.p;
+  const char* e = s.p + s.n;
+  while (p < e && (*p == ' ' || *p == '\t')) ++p;
+  while (e > p && (e[-1] == ' ' || e[-1] == '\t')) --e;
+  if (p == e) return false;
+  const char* q = p;
+  bool neg = false;
+  if (*q == '-' || *q == '+') {
+    neg = *q == '-';
+    ++q;
+  }
+  uint32_t m = 0;
+  int digits = 0, exp10 = 0;
+  bool ok = q < e, seen = false;
+  for (; q < e && (unsigned)(*q - '0') <= 9; ++q) {
+    seen = true;
+    if (m || *q != '0') {
+      if (++digits > 7) ok = false;
+      m = m * 10 + (unsigned)(*q - '0');
+    }
+  }
+  if (q < e && *q == '.') {
+    for (++q; q < e && (unsigned)(*q - '0') <= 9; ++q) {
+      seen = true;
+      --exp10;
+      if (m || *q != '0') {
+        if (++digits > 7) ok = false;
+      }
+      if (ok) m = m * 10 + (unsigned)(*q - '0');
+    }
+  }
+  if (ok && seen && q < e && (*q == 'e' || *q == 'E')) {
+    ++q;
+    bool eneg = false;
+    if (q < e && (*q == '-' || *q == '+')) {
+      eneg = *q == '-';
+      ++q;
+    }
+    int ex = 0, nd = 0;
+    for (; q < e && (unsigned)(*q - '0') <= 9 && nd < 4; ++q, ++nd) ex = ex * 10 + (*q - '0');
+    if (nd == 0 || nd == 4) ok = false;
+    exp10 += eneg ? -ex : ex;
+  }
+  if (ok && seen && q == e && exp10 >= -10 && exp10 <= 10) {
+    float v = (float)m;                       // exact: m < 10^7 < 2^24
+    v = exp10 < 0 ? v / kPow10[-exp10] : v * kPow10[exp10];
+    *out = neg ? -v : v;
+    return true;
+  }
+  char tmp[64];
+  const size_t n = (size_t)(e - p);
+  if (n >= sizeof(tmp)) return false;
+  std::memcpy(tmp, p, n);
+  tmp[n] = 0;
+  char* end = nullptr;
+  const float v = std::strtof(tmp, &end);
+  if (end == tmp || *end != 0) return false;
+  *out = v;
+  return true;
+}
+
+struct LineErr {
+  int64_t row = -1;
+  int col = 0;
+};
+
+}  // namespace
+}  // namespace er
+
+extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
+                            int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed) {
+  using namespace er;
+  ER_REQUIRE(buf && cols && n_rows && consumed, "null argument");
+  ER_REQUIRE(n_cols > 0 && max_rows >= 0, "bad n_cols / max_rows");
+  for (int c = 0; c < n_cols; ++c) {
+    const er_csv_col_t& k = cols[c];
+    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_F32_VEC, "unknown column kind");
+    ER_REQUIRE(k.kind == ER_CSV_SKIP || k.out, "column without an output array");
+    ER_REQUIRE(k.kind != ER_CSV_I64_LIST || (k.lens && k.list_cap >= 0), "list column needs lens and list_cap");
+    ER_REQUIRE(k.kind != ER_CSV_F32_VEC || k.width > 0, "vector column needs width");
+    cols[c].n_vals = 0;
+  }
+  // ---- complete lines in the buffer (the tail without '\n' is left to the caller) ----
+  std::vector<size_t> starts;
+  starts.reserve((size_t)std::min<int64_t>(max_rows, 1 << 20) + 1);
+  size_t pos = 0;
+  while ((int64_t)starts.size() < max_rows && pos < len) {
+    const char* nl = (const char*)std::memchr(buf + pos, '\n', len - pos);
+    if (!nl) break;
+    starts.push_back(pos);
+    pos = (size_t)(nl - buf) + 1;
+  }
+  const int64_t rows = (int64_t)starts.size();
+  starts.push_back(pos);
+  *n_rows = rows;
+  *consumed = pos;
+  if (rows == 0) return ER_OK;
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : 1, (rows + 255) / 256));
+  std::vector<LineErr> errs(T);
+
+  // field c of line r; missing trailing fields read as empty (-> the column default)
+  auto for_rows = [&](auto&& body) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) {
+      const int64_t r0 = rows * t / T, r1 = rows * (t + 1) / T;
+      th.emplace_back([&, t, r0, r1] {
+        std::vector<Span> f((size_t)n_cols);
+        for (int64_t r = r0; r < r1 && errs[t].row < 0; ++r) {
+          const char* p = buf + starts[r];
+          const char* e = buf + starts[r + 1] - 1;          // the '\n'
+          if (e > p && e[-1] == '\r') --e;
+          int c = 0;
+          while (c < n_cols) {
+            const char* q = (const char*)std::memchr(p, sep, (size_t)(e - p));
+            const char* fe = q ? q : e;
+            f[c++] = Span{p, (size_t)(fe - p)};
+            if (!q) break;
+            p = q + 1;
+          }
+          for (; c < n_cols; ++c) f[c] = Span{e, 0};
+          const int bad = body(r, f.data());
+          if (bad >= 0) {
+            errs[t].row = r;
+            errs[t].col = bad;
+          }
+        }
+      });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; ++t)
+      if (errs[t].row >= 0) return t;
+    return -1;
+  };
+  auto report = [&](int t) {
+    const er_csv_col_t& k = cols[errs[t].col];
+    return fail(ER_ERR_INVALID_ARG, "er_csv_parse: line " + std::to_string(errs[t].row + 1) + ", field " +
+                                        std::to_string(errs[t].col + 1) + " is not a valid " +
+                                        (k.kind == ER_CSV_F32 || k.kind == ER_CSV_F32_VEC ? "float" : "integer"));
+  };
+
+  // ---- pass 1: scalar kinds, and the list lengths ----
+  bool any_list = false;
+  for (int c = 0; c < n_cols; ++c) any_list |= cols[c].kind == ER_CSV_I64_LIST;
+  int bad = for_rows([&](int64_t r, const Span* f) -> int {
+    for (int c = 0; c < n_cols; ++c) {
+      const er_csv_col_t& k = cols[c];
+      const Span s = f[c];
+      switch (k.kind) {
+        case ER_CSV_I64: {
+          int64_t v = k.default_i64;
+          if (s.n && !parse_i64(s, &v)) return c;
+          ((int64_t*)k.out)[r] = v;
+          break;
+        }
+        case ER_CSV_F32: {
+          float v = k.default_f32;
+          if (s.n && !parse_f32(s, &v)) return c;
+          ((float*)k.out)[r] = v;
+          break;
+        }
+        case ER_CSV_HASH: {
+          const char* p = s.p;
+          size_t n = s.n;
+          if (!n && k.default_str) {
+            p = k.default_str;
+            n = std::strlen(k.default_str);
+          }
+          ((int64_t*)k.out)[r] = (int64_t)er_fingerprint64_host(p, n);
+          break;
+        }
+        case ER_CSV_F32_VEC: {
+          float* o = (float*)k.out + r * k.width;
+          for (int j = 0; j < k.width; ++j) o[j] = 0.f;
+          const char* p = s.p;
+          const char* e = s.p + s.n;
+          for (int j = 0; j < k.width && p <= e && s.n; ++j) {
+            const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
+            const char* fe = q ? q : e;
+            float v = k.default_f32;
+            if (fe > p && !parse_f32(Span{p, (size_t)(fe - p)}, &v)) return c;
+            o[j] = v;
+            if (!q) break;
+            p = q + 1;
+          }
+          if (!s.n) o[0] = k.default_f32;
+          break;
+        }
+        case ER_CSV_I64_LIST: {   // count the non-empty tokens
+          int32_t cnt = 0;
+          const char* p = s.p;
+          const char* e = s.p + s.n;
+          while (p < e) {
+            const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
+            const char* fe = q ? q : e;
+            cnt += fe > p;
+            p = fe + 1;
+          }
+          if (k.width > 0 && cnt > k.width) cnt = k.width;   // keep the FIRST width tokens
+          k.lens[r] = cnt;
+          break;
+        }
+        default:
+          break;
+      }
+    }
+    return -1;
+  });
+  if (bad >= 0) return report(bad);
+  if (!any_list) return ER_OK;
+
+  // ---- pass 2: list values at their CSR offsets ----
+  std::vector<std::vector<int64_t>> offs((size_t)n_cols);
+  for (int c = 0; c < n_cols; ++c) {
+    er_csv_col_t& k = cols[c];
+    if (k.kind != ER_CSV_I64_LIST) continue;
+    offs[c].resize((size_t)rows + 1);
+    int64_t acc = 0;
+    for (int64_t r = 0; r < rows; ++r) {
+      offs[c][r] = acc;
+      acc += k.lens[r];
+    }
+    offs[c][rows] = acc;
+    k.n_vals = acc;
+    if (acc > k.list_cap)
+      return fail(ER_ERR_WORKSPACE, "er_csv_parse: list column " + std::to_string(c + 1) + " holds " +
+                                        std::to_string(acc) + " values, capacity " + std::to_string(k.list_cap));
+  }
+  bad = for_rows([&](int64_t r, const Span* f) -> int {
+    for (int c = 0; c < n_cols; ++c) {
+      const er_csv_col_t& k = cols[c];
+      if (k.kind != ER_CSV_I64_LIST) continue;
+      int64_t* o = (int64_t*)k.out + offs[c][r];
+      int32_t left = k.lens[r];
+      const char* p = f[c].p;
+      const char* e = p + f[c].n;
+      while (p < e && left > 0) {
+        const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
+        const char* fe = q ? q : e;
+        if (fe > p) {
+          if (!parse_i64(Span{p, (size_t)(fe - p)}, o)) return c;
+          ++o;
+          --left;
+        }
+        p = fe + 1;
+      }
+    }
+    return -1;
+  });
+  if (bad >= 0) return report(bad);
+  return ER_OK;
+}

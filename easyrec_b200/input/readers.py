@@ -8,6 +8,9 @@ String-typed id fields are fingerprinted on the host with the library's Fingerpr
 (er_fingerprint64_host == StringToHashBucketFast's hash, feature_column_v2.py:3915-3921); integer fields
 go to the device untouched and are hashed there from their decimal text (input/input.py:541-543).
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
@@ -60,12 +63,16 @@ class DummyInput(object):
 
 class CSVInput(object):
   """CSVInput (input/csv_input.py): delimiter-separated text, one sample per line, columns in
-  data_config.input_fields order; labels from label_fields.  Only Id / Raw / Sequence / Tag features."""
+  data_config.input_fields order; labels from label_fields.  Only Id / Raw / Sequence / Tag features.
+  The file bytes go through the library's native parser (er_csv_parse) straight into the batch arrays."""
 
-  def __init__(self, pipeline_config, input_layer, path, batch_size=None, seq_sep='|'):
+  def __init__(self, pipeline_config, input_layer, path, batch_size=None, seq_sep='|', engine='native', n_threads=None):
     self.cfg = pipeline_config
     self.il = input_layer
     self.path = path
+    assert engine in ('native', 'python')
+    self.engine = engine
+    self.n_threads = n_threads or min(8, os.cpu_count() or 1)
     dc = pipeline_config.data_config
     self.sep = dc.separator or ','
     self.fields = [f.input_name for f in dc.input_fields]
@@ -87,6 +94,142 @@ class CSVInput(object):
                     np.uint64).view(np.int64), True
 
   def batches(self):
+    return self._batches_native() if self.engine == 'native' else self._batches_python()
+
+  # ---- native path: er_csv_parse fills the batch's column arrays straight from the file bytes ----
+  def _column_plan(self):
+    """per input field: (kind, width, inner_sep, default) -- what er_csv_parse extracts from it."""
+    il = self.il
+    plan = {}
+
+    def want(field, spec):
+      if plan.setdefault(field, spec) != spec:
+        raise ValueError('input field %r is used by features that need different parsings' % field)
+    for l in self.labels:
+      want(l, (_lib.CSV_F32, 0, b',', 0.0))
+    for n in il.sparse_names:
+      src, _ = self.feature_inputs[n]
+      if self.ftypes[src] in ('INT32', 'INT64'):
+        want(src, (_lib.CSV_I64, 0, b',', int(self.defaults.get(src) or 0)))
+      else:
+        if il.features[n].bucket_mode == _lib.BUCKET_FARM_DECIMAL:
+          raise NotImplementedError('string-typed hashed id field %s: use an integer field or pre-hash' % src)
+        want(src, (_lib.CSV_HASH, 0, b',', (self.defaults.get(src) or '')))
+    for n in il.raw_names:
+      src, sep = self.feature_inputs[n]
+      c0, c1 = il.raw_cols[n]
+      d = float(self.defaults.get(src) or 0)
+      want(src, (_lib.CSV_F32, 0, b',', d) if c1 - c0 == 1 else (_lib.CSV_F32_VEC, c1 - c0, sep.encode(), d))
+    for f in il.features.values():
+      if f.kind in ('seq', 'tag'):
+        src, sep = self.feature_inputs[f.name]
+        want(src, (_lib.CSV_I64_LIST, f.seq_len if f.kind == 'seq' else 0, sep.encode(), 0))
+    return plan
+
+  def _parse(self, data, size, plan, list_cap):
+    """one er_csv_parse call on `size` bytes at `data` (address or bytes) for up to batch_size lines
+    -> (n_rows, consumed, {field: arrays}), or None when a list column needs a larger array."""
+    B = self.batch_size
+    cols = (_lib.ErCsvCol * len(self.fields))()
+    out = {}
+    for i, name in enumerate(self.fields):
+      kind, width, sep, default = plan.get(name, (_lib.CSV_SKIP, 0, b',', 0))
+      c = cols[i]
+      c.kind, c.width, c.inner_sep = kind, width, sep
+      if kind == _lib.CSV_I64:
+        c.default_i64 = default
+        out[name] = (np.empty(B, np.int64),)
+      elif kind == _lib.CSV_HASH:
+        c.default_str = default.encode()
+        out[name] = (np.empty(B, np.int64),)
+      elif kind == _lib.CSV_F32:
+        c.default_f32 = default
+        out[name] = (np.empty(B, np.float32),)
+      elif kind == _lib.CSV_F32_VEC:
+        c.default_f32 = default
+        out[name] = (np.empty((B, width), np.float32),)
+      elif kind == _lib.CSV_I64_LIST:
+        cap = B * width if width else list_cap
+        out[name] = (np.empty(cap, np.int64), np.empty(B, np.int32))
+        c.lens = out[name][1].ctypes.data
+        c.list_cap = cap
+      if kind != _lib.CSV_SKIP:
+        c.out = out[name][0].ctypes.data
+    n_rows, consumed = ctypes.c_int64(0), ctypes.c_size_t(0)
+    st = _lib.load().er_csv_parse(data, size, self.sep.encode(), cols, len(self.fields), B, self.n_threads,
+                                  ctypes.byref(n_rows), ctypes.byref(consumed))
+    if st == _lib.ER_ERR_WORKSPACE:
+      return None
+    _lib.check(st, 'er_csv_parse')
+    for i, name in enumerate(self.fields):
+      if cols[i].kind == _lib.CSV_I64_LIST:
+        out[name] = (out[name][0][:cols[i].n_vals], out[name][1])
+    return n_rows.value, consumed.value, out
+
+  def _batches_native(self):
+    """the file is memory-mapped and parsed in place, batch_size lines per call."""
+    import mmap
+    B = self.batch_size
+    plan = self._column_plan()
+    list_cap = 16 * B
+    if os.path.getsize(self.path) == 0:
+      return
+    with open(self.path, 'rb') as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+      view = np.frombuffer(mm, np.uint8)
+      try:
+        base, size, off = view.ctypes.data, view.size, 0
+        while True:
+          res = self._parse(base + off, size - off, plan, list_cap)
+          if res is None:          # a list column outgrew its array
+            list_cap *= 4
+            continue
+          n_rows, consumed, cols = res
+          if n_rows < B:           # end of file; a last line without '\n' still counts
+            tail = bytes(mm[off:])
+            if tail and not tail.endswith(b'\n'):
+              res = self._parse(tail + b'\n', len(tail) + 1, plan, max(list_cap, len(tail)))
+              if res is not None and res[0] == B:
+                yield self._pack_columns(res[2])
+            return                 # a ragged last batch does not fit the static plan: skipped
+          off += consumed
+          yield self._pack_columns(cols)
+      finally:
+        del view
+
+  def _pack_columns(self, cols):
+    il = self.il
+    B = self.batch_size
+    feats = {}
+    if il.sparse_names:
+      feats['sparse_fea'] = torch.from_numpy(np.concatenate([cols[self.feature_inputs[n][0]][0] for n in il.sparse_names]))
+    if il.raw_names:
+      dense = np.empty((B, il.n_dense), np.float32)
+      for n in il.raw_names:
+        c0, c1 = il.raw_cols[n]
+        dense[:, c0:c1] = cols[self.feature_inputs[n][0]][0].reshape(B, c1 - c0)
+      feats['dense_fea'] = torch.from_numpy(dense)
+    seq, tag = {}, {}
+    for f in il.features.values():
+      if f.kind not in ('seq', 'tag'):
+        continue
+      vals, lens = cols[self.feature_inputs[f.name][0]]
+      if f.kind == 'seq':
+        arr = np.zeros((B, f.seq_len), np.int64)
+        starts = np.cumsum(lens) - lens
+        arr[np.repeat(np.arange(B), lens), np.arange(vals.size) - np.repeat(starts, lens)] = vals
+        seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(lens))
+      else:
+        tag[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens), None)
+    if seq:
+      feats['seq_fea'] = seq
+    if tag:
+      feats['tag_fea'] = tag
+    lab = np.stack([cols[l][0] for l in self.labels], 1)
+    return feats, torch.from_numpy(lab if lab.shape[1] > 1 else lab[:, 0].copy())
+
+  # ---- pure-python parsing of the same format (engine='python'): the readable restatement the native parser is
+  # tested against ----
+  def _batches_python(self):
     il = self.il
     B = self.batch_size
     buf = []

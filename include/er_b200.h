@@ -417,6 +417,38 @@ int er_inbatch_softmax_ce(const float* sim, const int64_t* item_ids, const float
                           int64_t batch, int32_t n_cols, float inv_wsum, float* loss_rows,
                           float* probs_diag, float* g_sim, er_stream_t stream);
 
+/* ---- CSV input: text lines -> the column arrays of the packed batch (HOST function, HOST pointers) ----
+ * Replaces tf.decode_csv + the per-field parsing of the CSV input path (input/csv_input.py:78-175,
+ * input/input.py:537-675: ids stay int64 / string ids are fingerprinted, raw values become fp32, Tag /
+ * Sequence fields are split on their inner separator).  Empty or missing fields take the column default
+ * (record_defaults).  No quoting.  Parses the complete lines of buf[0, len) up to max_rows; *consumed is
+ * the offset of the first unparsed byte (an unterminated last line stays with the caller). */
+enum {
+  ER_CSV_SKIP = 0,
+  ER_CSV_I64 = 1,      /* out int64[max_rows]: decimal integer */
+  ER_CSV_F32 = 2,      /* out float[max_rows] */
+  ER_CSV_HASH = 3,     /* out int64[max_rows]: Fingerprint64 of the field bytes (string-typed id field) */
+  ER_CSV_I64_LIST = 4, /* out int64[list_cap] + lens int32[max_rows]: inner_sep-separated integers, empty
+                          tokens dropped, at most `width` per line when width > 0 (the first ones) */
+  ER_CSV_F32_VEC = 5   /* out float[max_rows * width]: inner_sep-separated floats, zero padded */
+};
+typedef struct {
+  int32_t kind;
+  int32_t width;
+  char inner_sep;
+  char pad_[7];
+  int64_t default_i64;
+  float default_f32;
+  int32_t pad2_;
+  const char* default_str; /* ER_CSV_HASH: hashed instead of an empty field (NULL = "") */
+  void* out;
+  int32_t* lens;
+  int64_t list_cap;
+  int64_t n_vals;          /* written by the call: values stored for an ER_CSV_I64_LIST column */
+} er_csv_col_t;
+int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
+                 int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed);
+
 /* ---- sharded-table restore: the LoadEmbed custom op (ops/src/load_dense_embed.cc:28-156;
  * python fallback compat/embedding_parallel_saver.py:141-173) ----
  * HOST function, HOST pointers (the op is a CPU kernel in the reference as well).  Reads every

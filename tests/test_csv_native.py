@@ -1,0 +1,110 @@
+"""CPU: the native CSV parser (er_csv_parse, through the C ABI) against the pure-python restatement of the same
+format, on files with every field kind of the hot path: integer ids (negative, 19 digits), string ids
+(Fingerprint64), floats in assorted spellings, empty fields -> defaults, missing trailing fields, \\r\\n line
+ends, a sequence field (truncated to max_seq_len), a tag field with empty tokens, a 3-wide raw vector, and a
+last line without a newline.  Results must be bit-identical."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import _lib, builder
+from easyrec_b200.config import config_util
+from easyrec_b200.input import readers
+
+CFG = b'''
+data_config { batch_size: 64 input_type: CSVInput separator: "\\t" label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT }
+  input_fields { input_name: "F1" input_type: FLOAT default_val: "2.5" }
+  input_fields { input_name: "V3" input_type: STRING }
+  input_fields { input_name: "C1" input_type: INT64 default_val: "7" }
+  input_fields { input_name: "S1" input_type: STRING }
+  input_fields { input_name: "unused" input_type: STRING }
+  input_fields { input_name: "H1" input_type: STRING }
+  input_fields { input_name: "T1" input_type: STRING } }
+feature_config {
+  features { input_names: "F1" feature_type: RawFeature embedding_dim: 8 }
+  features { input_names: "V3" feature_type: RawFeature embedding_dim: 8 raw_input_dim: 3 separator: "," }
+  features { input_names: "C1" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 1000 }
+  features { input_names: "S1" feature_type: IdFeature embedding_dim: 8 num_buckets: 1000 }
+  features { input_names: "H1" feature_type: SequenceFeature embedding_dim: 8 num_buckets: 500 max_seq_len: 4 separator: "|" }
+  features { input_names: "T1" feature_type: TagFeature embedding_dim: 8 num_buckets: 500 separator: "|" combiner: "mean" }
+}
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["F1", "V3", "C1", "S1", "T1"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["C1", "S1"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } } }
+'''
+
+
+def _file(path, n, rng, crlf=False, last_newline=True):
+  lines = []
+  for i in range(n):
+    f1 = ['', '3', '-0.5', '1e-3', '7.25E+1', '.5'][rng.integers(0, 6)]
+    v3 = ','.join('%g' % v for v in rng.normal(size=rng.integers(1, 4)))
+    c1 = ['', str(rng.integers(-2**62, 2**62)), '-9223372036854775808', '9223372036854775807', '0'][rng.integers(0, 5)]
+    s1 = ['', 'abc', 'user_%d' % rng.integers(0, 50), 'x' * 40][rng.integers(0, 4)]
+    h1 = '|'.join(str(v) for v in rng.integers(0, 10**6, rng.integers(0, 7)))
+    t1 = ['', '5', '5||6|', '|'.join(str(v) for v in rng.integers(-50, 10**9, rng.integers(1, 6)))][rng.integers(0, 4)]
+    fields = ['%d' % rng.integers(0, 2), f1, v3, c1, s1, 'junk', h1, t1]
+    if i % 11 == 3:
+      fields = fields[:6]          # trailing fields missing altogether
+    lines.append('\t'.join(fields))
+  text = ('\r\n' if crlf else '\n').join(lines) + (('\r\n' if crlf else '\n') if last_newline else '')
+  open(path, 'w', newline='').write(text)
+
+
+def _same(a, b):
+  (fa, la), (fb, lb) = a, b
+  assert torch.equal(la, lb) and la.dtype == lb.dtype
+  assert sorted(fa) == sorted(fb)
+  for k in fa:
+    if isinstance(fa[k], dict):
+      for n in fa[k]:
+        for x, y in zip(fa[k][n], fb[k][n]):
+          assert (x is None and y is None) or (torch.equal(x, y) and x.dtype == y.dtype), (k, n)
+    else:
+      assert torch.equal(fa[k], fb[k]) and fa[k].dtype == fb[k].dtype, k
+
+
+@pytest.mark.parametrize('crlf,last_newline,threads', [(False, True, 1), (True, False, 4), (False, False, 8)])
+def test_native_csv_batches_equal_the_python_restatement(tmp_path, crlf, last_newline, threads):
+  cfg = config_util.get_configs_from_pipeline_file(CFG)
+  il, _, _ = builder.build_model(cfg, 64, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  path = str(tmp_path / 'd.csv')
+  _file(path, 64 * 5 + 17, np.random.default_rng(5), crlf=crlf, last_newline=last_newline)
+  native = list(readers.CSVInput(cfg, il, path, n_threads=threads))
+  python = list(readers.CSVInput(cfg, il, path, engine='python'))
+  assert len(native) == len(python) == 5
+  for a, b in zip(native, python):
+    _same(a, b)
+  feats, _ = native[0]
+  assert feats['seq_fea']['H1'][0].shape == (64, 4) and int(feats['seq_fea']['H1'][1].max()) == 4
+  assert feats['dense_fea'].shape == (64, 4)
+
+
+def test_native_csv_reports_the_offending_line(tmp_path):
+  cfg = config_util.get_configs_from_pipeline_file(CFG)
+  il, _, _ = builder.build_model(cfg, 64, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  path = str(tmp_path / 'bad.csv')
+  rows = ['1\t2.0\t1,2,3\t%d\ta\tj\t1|2\t3' % i for i in range(64)]
+  rows[41] = rows[41].replace('\t41\t', '\t4x1\t')
+  open(path, 'w').write('\n'.join(rows) + '\n')
+  with pytest.raises(_lib.ErError, match='line 42, field 4 is not a valid integer'):
+    list(readers.CSVInput(cfg, il, path))
+
+
+def test_er_csv_parse_stops_at_max_rows_and_leaves_the_unterminated_tail():
+  lib = _lib.load()
+  data = b'1,2.5\n3,\n5,7'                     # third line has no newline yet
+  ids, vals = np.zeros(2, np.int64), np.zeros(2, np.float32)
+  cols = (_lib.ErCsvCol * 2)()
+  cols[0].kind, cols[0].out = _lib.CSV_I64, ids.ctypes.data
+  cols[1].kind, cols[1].out, cols[1].default_f32 = _lib.CSV_F32, vals.ctypes.data, -1.0
+  n, used = ctypes.c_int64(0), ctypes.c_size_t(0)
+  assert lib.er_csv_parse(data, len(data), b',', cols, 2, 2, 1, ctypes.byref(n), ctypes.byref(used)) == 0
+  assert n.value == 2 and used.value == 9 and ids.tolist() == [1, 3] and vals.tolist() == [2.5, -1.0]
+  assert lib.er_csv_parse(data, len(data), b',', cols, 2, 1, 1, ctypes.byref(n), ctypes.byref(used)) == 0
+  assert n.value == 1 and used.value == 6
