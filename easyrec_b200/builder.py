@@ -18,13 +18,17 @@ _OPT_KIND = {'adagrad_optimizer': _lib.OPT_ADAGRAD, 'lazy_adam_optimizer': _lib.
 def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
   """FeatureConfig protos -> FeatureSpec list (config order = packed feature order)."""
   specs = []
+  field_types = input_field_types(pipeline_config)
   for fc in config_util.get_feature_configs(pipeline_config):
     name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+    # a STRING field is hashed where its bytes are, by the reader (Fingerprint64 % hash_bucket_size); integer
+    # fields go to the device as int64 and are hashed there from their decimal text (input/input.py:541-543)
+    host_hashed = fc.hash_bucket_size > 0 and field_types.get(fc.input_names[0]) == 'STRING'
     ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
     if ftype == 'IdFeature':
       specs.append(IL.id_feature(name, fc.embedding_dim, hash_bucket_size=fc.hash_bucket_size,
                                  num_buckets=fc.num_buckets, combiner=fc.combiner,
-                                 embedding_name=fc.embedding_name, packed_mod=packed_mod))
+                                 embedding_name=fc.embedding_name, packed_mod=packed_mod, host_hashed=host_hashed))
     elif ftype == 'RawFeature':
       if len(fc.boundaries) > 0:
         raise NotImplementedError('RawFeature boundaries (bucketized column) for %s' % name)
@@ -35,7 +39,7 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
                                     combiner=fc.combiner, embedding_name=fc.embedding_name,
                                     seq_len=((fc.max_seq_len if fc.HasField('max_seq_len') else default_seq_len)
                                              if ftype == 'SequenceFeature' else 1),
-                                    packed_mod=packed_mod))
+                                    packed_mod=packed_mod, host_hashed=host_hashed))
     else:
       raise NotImplementedError('feature_type %s (feature %s) is outside the hot-path scope' % (ftype, name))
   return specs
@@ -55,6 +59,13 @@ def seq_att_groups(model_config):
   for g in model_config.seq_att_groups:
     out[g.group_name] = [(list(m.key), list(m.hist_seq)) for m in g.seq_att_map]
   return out
+
+
+def input_field_types(pipeline_config):
+  """input field name -> 'INT32' | 'INT64' | 'STRING' | 'FLOAT' | 'DOUBLE' | ... (data_config.input_fields)."""
+  dc = pipeline_config.data_config
+  enum = dc.DESCRIPTOR.nested_types_by_name['Field'].fields_by_name['input_type'].enum_type
+  return {f.input_name: enum.values_by_number[f.input_type].name for f in dc.input_fields}
 
 
 def input_type_name(pipeline_config):

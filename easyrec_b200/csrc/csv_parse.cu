@@ -18,6 +18,8 @@ extern "C" uint64_t er_fingerprint64_host(const char* s, size_t len);
 namespace er {
 namespace {
 
+inline bool is_list(int kind) { return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST; }
+
 struct Span {
   const char* p;
   size_t n;
@@ -113,6 +115,16 @@ inline bool parse_f32(Span s, float* out) {
   return true;
 }
 
+// Fingerprint64 of a string id; with hash_mod the hash bucket (uint64 mod, StringToHashBucketFast) and an
+// empty string -> -1, the "no value" id the lookup drops (feature_column_v2.py:2566-2585 ignores '').
+inline int64_t hashed(const er_csv_col_t& k, const char* p, size_t n) {
+  if (k.hash_mod) {
+    if (!n) return -1;
+    return (int64_t)(er_fingerprint64_host(p, n) % k.hash_mod);
+  }
+  return (int64_t)er_fingerprint64_host(p, n);
+}
+
 struct LineErr {
   int64_t row = -1;
   int col = 0;
@@ -128,9 +140,9 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
   ER_REQUIRE(n_cols > 0 && max_rows >= 0, "bad n_cols / max_rows");
   for (int c = 0; c < n_cols; ++c) {
     const er_csv_col_t& k = cols[c];
-    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_F32_VEC, "unknown column kind");
+    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_HASH_LIST, "unknown column kind");
     ER_REQUIRE(k.kind == ER_CSV_SKIP || k.out, "column without an output array");
-    ER_REQUIRE(k.kind != ER_CSV_I64_LIST || (k.lens && k.list_cap >= 0), "list column needs lens and list_cap");
+    ER_REQUIRE(!is_list(k.kind) || (k.lens && k.list_cap >= 0), "list column needs lens and list_cap");
     ER_REQUIRE(k.kind != ER_CSV_F32_VEC || k.width > 0, "vector column needs width");
     cols[c].n_vals = 0;
   }
@@ -194,7 +206,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
 
   // ---- pass 1: scalar kinds, and the list lengths ----
   bool any_list = false;
-  for (int c = 0; c < n_cols; ++c) any_list |= cols[c].kind == ER_CSV_I64_LIST;
+  for (int c = 0; c < n_cols; ++c) any_list |= is_list(cols[c].kind);
   int bad = for_rows([&](int64_t r, const Span* f) -> int {
     for (int c = 0; c < n_cols; ++c) {
       const er_csv_col_t& k = cols[c];
@@ -219,7 +231,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
             p = k.default_str;
             n = std::strlen(k.default_str);
           }
-          ((int64_t*)k.out)[r] = (int64_t)er_fingerprint64_host(p, n);
+          ((int64_t*)k.out)[r] = hashed(k, p, n);
           break;
         }
         case ER_CSV_F32_VEC: {
@@ -239,6 +251,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
           if (!s.n) o[0] = k.default_f32;
           break;
         }
+        case ER_CSV_HASH_LIST:
         case ER_CSV_I64_LIST: {   // count the non-empty tokens
           int32_t cnt = 0;
           const char* p = s.p;
@@ -266,7 +279,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
   std::vector<std::vector<int64_t>> offs((size_t)n_cols);
   for (int c = 0; c < n_cols; ++c) {
     er_csv_col_t& k = cols[c];
-    if (k.kind != ER_CSV_I64_LIST) continue;
+    if (!is_list(k.kind)) continue;
     offs[c].resize((size_t)rows + 1);
     int64_t acc = 0;
     for (int64_t r = 0; r < rows; ++r) {
@@ -282,7 +295,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
   bad = for_rows([&](int64_t r, const Span* f) -> int {
     for (int c = 0; c < n_cols; ++c) {
       const er_csv_col_t& k = cols[c];
-      if (k.kind != ER_CSV_I64_LIST) continue;
+      if (!is_list(k.kind)) continue;
       int64_t* o = (int64_t*)k.out + offs[c][r];
       int32_t left = k.lens[r];
       const char* p = f[c].p;
@@ -291,7 +304,10 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
         const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
         const char* fe = q ? q : e;
         if (fe > p) {
-          if (!parse_i64(Span{p, (size_t)(fe - p)}, o)) return c;
+          if (k.kind == ER_CSV_HASH_LIST)
+            *o = hashed(k, p, (size_t)(fe - p));
+          else if (!parse_i64(Span{p, (size_t)(fe - p)}, o))
+            return c;
           ++o;
           --left;
         }

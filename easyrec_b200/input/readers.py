@@ -4,9 +4,10 @@ Counterpart of input/input.py:806-939 (`_preprocess`) + input/csv_input.py:78-17
 input/parquet_input.py:201-239 restricted to the feature types of the hot path.  A batch is the reference's packed form (input/parquet_input.py:201-239):
   sparse_fea int64 [n_id*B] feature-major | dense_fea fp32 [B, sum raw_dim] | seq_fea | tag_fea | labels.
 
-String-typed id fields are fingerprinted on the host with the library's Fingerprint64
-(er_fingerprint64_host == StringToHashBucketFast's hash, feature_column_v2.py:3915-3921); integer fields
-go to the device untouched and are hashed there from their decimal text (input/input.py:541-543).
+String-typed id fields with a hash_bucket_size are bucketed where their bytes are, on the host, by the native
+parser: Fingerprint64(bytes) % hash_bucket_size (StringToHashBucketFast, feature_column_v2.py:3915-3921), '' -> -1
+(the ignored value of string columns, :2566-2585), and the table plan takes those buckets unchanged; integer
+fields go to the device untouched and are hashed there from their decimal text (input/input.py:541-543).
 """
 import ctypes
 import os
@@ -82,16 +83,27 @@ class CSVInput(object):
     self.labels = list(dc.label_fields)
     self.batch_size = batch_size or input_layer.batch_size
     self.feature_inputs = {}
+    self.hash_buckets = {}     # feature -> hash_bucket_size when its STRING field is hashed here, on the host
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = (fc.input_names[0], fc.separator or seq_sep)
+      if fc.hash_bucket_size > 0 and self.ftypes.get(fc.input_names[0]) == 'STRING' and name in input_layer.features:
+        assert input_layer.features[name].bucket_mode in (_lib.BUCKET_IDENTITY, _lib.BUCKET_MOD), \
+            'feature %s: the table plan must take host-hashed buckets (builder.feature_specs)' % name
+        self.hash_buckets[name] = fc.hash_bucket_size
 
-  def _id_column(self, col, ftype, default):
-    """int fields -> int64 as is (device hashes the decimal text); string fields -> host Fingerprint64."""
-    if ftype in ('INT32', 'INT64'):
-      return np.array([int(x) if x != '' else int(default or 0) for x in col], np.int64), False
-    return np.array([_lib.fingerprint64(x if x != '' else (default or '')) for x in col],
-                    np.uint64).view(np.int64), True
+  def _token(self, x, feature):
+    """one id token -> int64: Fingerprint64 % hash_bucket_size for a host-hashed STRING field ('' -> -1, the
+    ignored value of string columns, feature_column_v2.py:2566-2585), else the integer it spells
+    (input/input.py:544-555 string_to_number)."""
+    nb = self.hash_buckets.get(feature)
+    if nb:
+      return _lib.fingerprint64(x) % nb if x != '' else -1
+    return int(x)
+
+  def _id_column(self, col, feature, default):
+    return np.array([self._token(x if x != '' else (default or ('' if feature in self.hash_buckets else '0')), feature)
+                     for x in col], np.int64)
 
   def batches(self):
     return self._batches_native() if self.engine == 'native' else self._batches_python()
@@ -106,24 +118,23 @@ class CSVInput(object):
       if plan.setdefault(field, spec) != spec:
         raise ValueError('input field %r is used by features that need different parsings' % field)
     for l in self.labels:
-      want(l, (_lib.CSV_F32, 0, b',', 0.0))
+      want(l, (_lib.CSV_F32, 0, b',', 0.0, 0))
     for n in il.sparse_names:
       src, _ = self.feature_inputs[n]
-      if self.ftypes[src] in ('INT32', 'INT64'):
-        want(src, (_lib.CSV_I64, 0, b',', int(self.defaults.get(src) or 0)))
+      if n in self.hash_buckets:
+        want(src, (_lib.CSV_HASH, 0, b',', self.defaults.get(src) or '', self.hash_buckets[n]))
       else:
-        if il.features[n].bucket_mode == _lib.BUCKET_FARM_DECIMAL:
-          raise NotImplementedError('string-typed hashed id field %s: use an integer field or pre-hash' % src)
-        want(src, (_lib.CSV_HASH, 0, b',', (self.defaults.get(src) or '')))
+        want(src, (_lib.CSV_I64, 0, b',', int(self.defaults.get(src) or 0), 0))
     for n in il.raw_names:
       src, sep = self.feature_inputs[n]
       c0, c1 = il.raw_cols[n]
       d = float(self.defaults.get(src) or 0)
-      want(src, (_lib.CSV_F32, 0, b',', d) if c1 - c0 == 1 else (_lib.CSV_F32_VEC, c1 - c0, sep.encode(), d))
+      want(src, (_lib.CSV_F32, 0, b',', d, 0) if c1 - c0 == 1 else (_lib.CSV_F32_VEC, c1 - c0, sep.encode(), d, 0))
     for f in il.features.values():
       if f.kind in ('seq', 'tag'):
         src, sep = self.feature_inputs[f.name]
-        want(src, (_lib.CSV_I64_LIST, f.seq_len if f.kind == 'seq' else 0, sep.encode(), 0))
+        nb = self.hash_buckets.get(f.name, 0)
+        want(src, (_lib.CSV_HASH_LIST if nb else _lib.CSV_I64_LIST, f.seq_len if f.kind == 'seq' else 0, sep.encode(), 0, nb))
     return plan
 
   def _parse(self, data, size, plan, list_cap):
@@ -131,16 +142,17 @@ class CSVInput(object):
     -> (n_rows, consumed, {field: arrays}), or None when a list column needs a larger array."""
     B = self.batch_size
     cols = (_lib.ErCsvCol * len(self.fields))()
-    out = {}
+    out, keep = {}, []
     for i, name in enumerate(self.fields):
-      kind, width, sep, default = plan.get(name, (_lib.CSV_SKIP, 0, b',', 0))
+      kind, width, sep, default, hash_mod = plan.get(name, (_lib.CSV_SKIP, 0, b',', 0, 0))
       c = cols[i]
-      c.kind, c.width, c.inner_sep = kind, width, sep
+      c.kind, c.width, c.inner_sep, c.hash_mod = kind, width, sep, hash_mod
       if kind == _lib.CSV_I64:
         c.default_i64 = default
         out[name] = (np.empty(B, np.int64),)
       elif kind == _lib.CSV_HASH:
-        c.default_str = default.encode()
+        keep.append(default.encode())
+        c.default_str = keep[-1]
         out[name] = (np.empty(B, np.int64),)
       elif kind == _lib.CSV_F32:
         c.default_f32 = default
@@ -148,7 +160,7 @@ class CSVInput(object):
       elif kind == _lib.CSV_F32_VEC:
         c.default_f32 = default
         out[name] = (np.empty((B, width), np.float32),)
-      elif kind == _lib.CSV_I64_LIST:
+      elif kind in (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST):
         cap = B * width if width else list_cap
         out[name] = (np.empty(cap, np.int64), np.empty(B, np.int32))
         c.lens = out[name][1].ctypes.data
@@ -162,7 +174,7 @@ class CSVInput(object):
       return None
     _lib.check(st, 'er_csv_parse')
     for i, name in enumerate(self.fields):
-      if cols[i].kind == _lib.CSV_I64_LIST:
+      if cols[i].kind in (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST):
         out[name] = (out[name][0][:cols[i].n_vals], out[name][1])
     return n_rows.value, consumed.value, out
 
@@ -248,10 +260,7 @@ class CSVInput(object):
     ids = []
     for n in il.sparse_names:
       src, _ = self.feature_inputs[n]
-      arr, hashed = self._id_column(cols[src], self.ftypes[src], self.defaults.get(src))
-      if hashed and il.features[n].bucket_mode == _lib.BUCKET_FARM_DECIMAL:
-        raise NotImplementedError('string-typed hashed id field %s: use an integer field or pre-hash' % src)
-      ids.append(arr)
+      ids.append(self._id_column(cols[src], n, self.defaults.get(src)))
     if ids:
       feats['sparse_fea'] = torch.from_numpy(np.concatenate(ids))
     if il.raw_names:
@@ -277,11 +286,11 @@ class CSVInput(object):
         for i, ts in enumerate(toks):
           ts = ts[:T]  # keep the FIRST max_seq_len steps (utils/shape_utils.py:393-410)
           lens[i] = len(ts)
-          arr[i, :len(ts)] = [int(t) for t in ts]
+          arr[i, :len(ts)] = [self._token(t, f.name) for t in ts]
         seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(lens))
       else:
         lens = np.array([len(ts) for ts in toks], np.int32)
-        flat = np.array([int(t) for ts in toks for t in ts], np.int64)
+        flat = np.array([self._token(t, f.name) for ts in toks for t in ts], np.int64)
         tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), None)
     if seq:
       feats['seq_fea'] = seq

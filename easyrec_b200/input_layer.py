@@ -36,8 +36,12 @@ FeatureSpec = collections.namedtuple(
      'min_val', 'max_val', 'raw_input_dim', 'seq_len'])
 
 
-def _bucket_rule(hash_bucket_size, num_buckets, packed_mod):
+def _bucket_rule(hash_bucket_size, num_buckets, packed_mod, host_hashed=False):
   if hash_bucket_size > 0:
+    if host_hashed:
+      # string-typed field: the reader already computed Fingerprint64(bytes) % hash_bucket_size (er_csv_parse),
+      # the device takes the bucket as it is (-1 = empty string = no value)
+      return _lib.BUCKET_IDENTITY, hash_bucket_size
     return _lib.BUCKET_FARM_DECIMAL, hash_bucket_size
   if packed_mod:
     return _lib.BUCKET_MOD, num_buckets
@@ -45,11 +49,11 @@ def _bucket_rule(hash_bucket_size, num_buckets, packed_mod):
 
 
 def id_feature(name, embedding_dim, hash_bucket_size=0, num_buckets=0, combiner='sum',
-               embedding_name='', packed_mod=False):
+               embedding_name='', packed_mod=False, host_hashed=False):
   """IdFeature: hash_bucket_size -> Fingerprint64(as_string) % size; num_buckets -> identity
   (feature_column/feature_column.py:259-300).  packed_mod: the Parquet packed rule
   `vals % num_buckets` (input/parquet_input.py:221)."""
-  mode, nb = _bucket_rule(hash_bucket_size, num_buckets, packed_mod)
+  mode, nb = _bucket_rule(hash_bucket_size, num_buckets, packed_mod, host_hashed)
   return FeatureSpec(name, 'id', embedding_dim, mode, nb, combiner, embedding_name, 0., 0., 1, 1)
 
 
@@ -61,12 +65,12 @@ def raw_feature(name, embedding_dim=0, min_val=0.0, max_val=0.0, raw_input_dim=1
 
 
 def multi_feature(name, kind, embedding_dim, hash_bucket_size=0, num_buckets=0, combiner='sum',
-                  embedding_name='', seq_len=1, packed_mod=False):
+                  embedding_name='', seq_len=1, packed_mod=False, host_hashed=False):
   """TagFeature (kind 'tag': multi-valued, pooled by `combiner`, optional kv weights;
   feature_column/feature_column.py:301-360) or SequenceFeature (kind 'seq': un-pooled [B,T,D];
   feature_column_v2.py:4988-5002)."""
   assert kind in ('tag', 'seq')
-  mode, nb = _bucket_rule(hash_bucket_size, num_buckets, packed_mod)
+  mode, nb = _bucket_rule(hash_bucket_size, num_buckets, packed_mod, host_hashed)
   return FeatureSpec(name, kind, embedding_dim, mode, nb, combiner, embedding_name, 0., 0., 1,
                      max(int(seq_len), 1))
 

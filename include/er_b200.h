@@ -427,10 +427,13 @@ enum {
   ER_CSV_SKIP = 0,
   ER_CSV_I64 = 1,      /* out int64[max_rows]: decimal integer */
   ER_CSV_F32 = 2,      /* out float[max_rows] */
-  ER_CSV_HASH = 3,     /* out int64[max_rows]: Fingerprint64 of the field bytes (string-typed id field) */
+  ER_CSV_HASH = 3,     /* out int64[max_rows]: Fingerprint64 of the field bytes (string-typed id field);
+                          with hash_mod: Fingerprint64 % hash_mod as uint64 (string_to_hash_bucket_fast,
+                          feature_column_v2.py:3915-3921) and -1 for an empty string (dropped by the lookup) */
   ER_CSV_I64_LIST = 4, /* out int64[list_cap] + lens int32[max_rows]: inner_sep-separated integers, empty
                           tokens dropped, at most `width` per line when width > 0 (the first ones) */
-  ER_CSV_F32_VEC = 5   /* out float[max_rows * width]: inner_sep-separated floats, zero padded */
+  ER_CSV_F32_VEC = 5,  /* out float[max_rows * width]: inner_sep-separated floats, zero padded */
+  ER_CSV_HASH_LIST = 6 /* like ER_CSV_I64_LIST, every token fingerprinted (string Tag / Sequence tokens) */
 };
 typedef struct {
   int32_t kind;
@@ -444,7 +447,8 @@ typedef struct {
   void* out;
   int32_t* lens;
   int64_t list_cap;
-  int64_t n_vals;          /* written by the call: values stored for an ER_CSV_I64_LIST column */
+  int64_t n_vals;          /* written by the call: values stored for a list column */
+  uint64_t hash_mod;       /* ER_CSV_HASH / ER_CSV_HASH_LIST: 0 = raw fingerprints, else the hash_bucket_size */
 } er_csv_col_t;
 int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
                  int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed);

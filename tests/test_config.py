@@ -170,3 +170,42 @@ def test_cross_layer_variants_have_the_keras_parameter_shapes():
   assert not low.dense_u.bias.requires_grad and low.dense.bias.requires_grad
   with pytest.raises(ValueError):
     BB.Cross(12, {'diag_scale': -1.0})
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+def test_reference_criteo_config_reads_kaggle_format_lines(tmp_path):
+  """examples/configs/deepfm_on_criteo.config as it is (STRING categorical fields with hash_bucket_size, FLOAT
+  integer counts, empty cells) over lines in the Criteo Kaggle layout (examples/data/criteo/process_criteo_kaggle.py):
+  the categorical tokens are hashed on the host - Fingerprint64(bytes) % hash_bucket_size - and an empty cell is
+  the dropped id -1; the table plan takes those buckets unchanged."""
+  import numpy as np
+  from easyrec_b200 import _lib
+  from easyrec_b200.input import readers
+  from oracle import oracle as O
+  cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, 'examples/configs/deepfm_on_criteo.config'))
+  cfg = config_util.edit_config(cfg, {'data_config.batch_size': 8})
+  il, model, _ = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  rng = np.random.default_rng(3)
+  rows = []
+  for i in range(8):
+    ints = ['' if rng.uniform() < 0.3 else str(rng.integers(0, 5000)) for _ in range(13)]
+    cats = ['' if rng.uniform() < 0.2 else '%08x' % rng.integers(0, 2**32) for _ in range(26)]
+    rows.append([str(i % 2)] + ints + cats)
+  open(tmp_path / 'criteo_train_data', 'w').write(''.join('\t'.join(r) + '\n' for r in rows))
+  (feats, labels), = list(readers.make_input(cfg, il, str(tmp_path / 'criteo_train_data')))
+  assert labels.tolist() == [float(i % 2) for i in range(8)]
+  names = il.sparse_names
+  assert len(names) == 26 and all(il.features[n].bucket_mode == _lib.BUCKET_IDENTITY for n in names)
+  ids = feats['sparse_fea'].reshape(26, 8).numpy()
+  fields = [f.input_name for f in cfg.data_config.input_fields]
+  hbs = {(fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]): (fc.input_names[0], fc.hash_bucket_size)
+         for fc in config_util.get_feature_configs(cfg)}
+  for k, n in enumerate(names):
+    col = fields.index(hbs[n][0])
+    want = [O.fingerprint64(r[col]) % hbs[n][1] if r[col] != '' else -1 for r in rows]
+    assert ids[k].tolist() == want, n
+  assert (ids == -1).any()
+  dense = feats['dense_fea'].numpy()
+  for k, n in enumerate(il.raw_names):
+    col = fields.index(hbs[n][0])
+    assert dense[:, il.raw_cols[n][0]].tolist() == [float(r[col] or 0) for r in rows]

@@ -1,7 +1,7 @@
 """CPU: the native CSV parser (er_csv_parse, through the C ABI) against the pure-python restatement of the same
 format, on files with every field kind of the hot path: integer ids (negative, 19 digits), string ids
 (Fingerprint64), floats in assorted spellings, empty fields -> defaults, missing trailing fields, \\r\\n line
-ends, a sequence field (truncated to max_seq_len), a tag field with empty tokens, a 3-wide raw vector, and a
+ends, a sequence field (truncated to max_seq_len), a string tag field (tokens hashed on the host) with empty tokens, a 3-wide raw vector, and a
 last line without a newline.  Results must be bit-identical."""
 import ctypes
 import os
@@ -28,9 +28,9 @@ feature_config {
   features { input_names: "F1" feature_type: RawFeature embedding_dim: 8 }
   features { input_names: "V3" feature_type: RawFeature embedding_dim: 8 raw_input_dim: 3 separator: "," }
   features { input_names: "C1" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 1000 }
-  features { input_names: "S1" feature_type: IdFeature embedding_dim: 8 num_buckets: 1000 }
+  features { input_names: "S1" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 1000 }
   features { input_names: "H1" feature_type: SequenceFeature embedding_dim: 8 num_buckets: 500 max_seq_len: 4 separator: "|" }
-  features { input_names: "T1" feature_type: TagFeature embedding_dim: 8 num_buckets: 500 separator: "|" combiner: "mean" }
+  features { input_names: "T1" feature_type: TagFeature embedding_dim: 8 hash_bucket_size: 500 separator: "|" combiner: "mean" }
 }
 model_config { model_class: "DeepFM"
   feature_groups { group_name: "deep" feature_names: ["F1", "V3", "C1", "S1", "T1"] wide_deep: DEEP }
@@ -81,6 +81,16 @@ def test_native_csv_batches_equal_the_python_restatement(tmp_path, crlf, last_ne
   for a, b in zip(native, python):
     _same(a, b)
   feats, _ = native[0]
+  # string-typed hashed fields: bucket = Fingerprint64(bytes) % hash_bucket_size on the host (oracle's hash), '' -> -1,
+  # and the table plan takes those buckets as they are
+  from oracle import oracle as O
+  first = [l.rstrip('\r\n').split('\t') for l in open(path, newline='').read().splitlines()[:64]]
+  want = [O.fingerprint64(r[4]) % 1000 if len(r) > 4 and r[4] != '' else -1 for r in first]
+  s1 = feats['sparse_fea'].reshape(2, 64)[il.sparse_names.index('S1')]
+  assert s1.tolist() == want and -1 in want
+  assert il.features['S1'].bucket_mode == _lib.BUCKET_IDENTITY and il.features['C1'].bucket_mode == _lib.BUCKET_FARM_DECIMAL
+  toks = [t for r in first for t in (r[7].split('|') if len(r) > 7 else []) if t != '']
+  assert feats['tag_fea']['T1'][0].tolist() == [O.fingerprint64(t) % 500 for t in toks]
   assert feats['seq_fea']['H1'][0].shape == (64, 4) and int(feats['seq_fea']['H1'][1].max()) == 4
   assert feats['dense_fea'].shape == (64, 4)
 
