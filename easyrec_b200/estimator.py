@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-from easyrec_b200 import builder, checkpoint
+from easyrec_b200 import builder, checkpoint, metrics
 from easyrec_b200.config import config_util
 from easyrec_b200.input import readers
 from easyrec_b200.trainer import Trainer
@@ -19,27 +19,7 @@ _DENSE_KIND = {'adagrad_optimizer': 'adagrad', 'adam_optimizer': 'adam', 'lazy_a
                'momentum_optimizer': 'sgd'}
 
 
-def auc(labels, scores):
-  """Exact ROC AUC (Mann-Whitney); the reference's tf.metrics.auc is a 200-threshold approximation of it."""
-  labels = np.asarray(labels).astype(np.float64)
-  scores = np.asarray(scores).astype(np.float64)
-  order = np.argsort(scores, kind='mergesort')
-  ranks = np.empty(len(scores), np.float64)
-  s = scores[order]
-  i = 0
-  r = np.arange(1, len(s) + 1, dtype=np.float64)
-  while i < len(s):  # average ranks over ties
-    j = i
-    while j + 1 < len(s) and s[j + 1] == s[i]:
-      j += 1
-    r[i:j + 1] = 0.5 * (i + j) + 1
-    i = j + 1
-  ranks[order] = r
-  n_pos = labels.sum()
-  n_neg = len(labels) - n_pos
-  if n_pos == 0 or n_neg == 0:
-    return float('nan')
-  return float((ranks[labels > 0].sum() - n_pos * (n_pos + 1) / 2) / (n_pos * n_neg))
+auc = metrics.auc   # exact ROC AUC; the reference's tf.metrics.auc is a 200-threshold approximation of it
 
 
 class EasyRecEstimator(object):
@@ -104,10 +84,34 @@ class EasyRecEstimator(object):
     self.input_layer._presorted = {}
     return logits
 
+  def _group_fields(self):
+    """eval_config.metrics_set gauc / session_auc -> [(metric name, position of the key feature in the packed
+    single-valued ids, reduction)]  (model/rank_model.py:375-421: keys = features[uid_field])."""
+    out = []
+    by_input = {}
+    for fc in self.feature_configs:
+      name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+      by_input.setdefault(fc.input_names[0], name)
+    for m in self.eval_config.metrics_set:
+      which = m.WhichOneof('metric')
+      if which in ('gauc', 'session_auc'):
+        conf = getattr(m, which)
+        field = conf.uid_field if which == 'gauc' else conf.session_id_field
+        feat = by_input.get(field, field)
+        if feat not in self.input_layer.sparse_names:
+          raise ValueError('%s: key field %r is not a single-valued id feature of this model' % (which, field))
+        out.append((which, self.input_layer.sparse_names.index(feat), conf.reduction))
+    return out
+
   def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
     labels_all, probs_all = [], []
+    groups = self._group_fields()
+    keys_all = [[] for _ in groups]
+    B = self.input_layer.batch_size
     n = 0
     for feats, labels in input_fn():
+      for k, (_, pos, _) in enumerate(groups):
+        keys_all[k].append(feats['sparse_fea'][pos * B:(pos + 1) * B].cpu().numpy())
       feats, labels = readers.to_device(feats, labels, self._device)
       logits = self._forward_eval(feats)
       if logits.dim() == 1:
@@ -118,7 +122,10 @@ class EasyRecEstimator(object):
         break
     out = {'global_step': self.global_step}
     if probs_all:
-      out['auc'] = auc(np.concatenate(labels_all), np.concatenate(probs_all))
+      lab, prob = np.concatenate(labels_all), np.concatenate(probs_all)
+      out['auc'] = metrics.auc(lab, prob)
+      for (which, _, reduction), keys in zip(groups, keys_all):
+        out[which] = float(metrics.gauc(lab, prob, np.concatenate(keys), reduction))
     return out
 
   def predict(self, input_fn, predict_keys=None, hooks=None, checkpoint_path=None, yield_single_examples=True):
