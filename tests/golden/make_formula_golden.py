@@ -16,6 +16,7 @@ are (ast), and they run against `_tf`, a numpy implementation of exactly those o
   model/match_model.py:50-69,71-126,213-234  MatchModel._mask_in_batch / _list_wise_sim / _build_list_wise_loss_graph
   core/learning_schedules.py:30-75           exponential_decay_with_burnin
   compat/adam_s.py:185-213                   AdamOptimizerS._apply_sparse_shared (lazy Adam row rule)
+  model/deepfm.py:53-109                     DeepFM.build_predict_graph (wide sum | FM | deep DNN -> final DNN -> logit)
 
 Run in the build container (reference mounted):  python tests/golden/make_formula_golden.py
 -> tests/golden/reference_formulas.json (inputs + outputs, small shapes), replayed by
@@ -49,7 +50,7 @@ def _make_tf(variables):
   tf.stack = lambda xs, axis=0: np.stack([np.asarray(x, np.float32) for x in xs], axis=axis)
   tf.concat = lambda xs, axis: np.concatenate(xs, axis=axis)
   tf.square = lambda x: np.square(x, dtype=np.float32)
-  tf.reduce_sum = lambda x, axis=None, keepdims=False: np.sum(x, axis=axis, keepdims=keepdims, dtype=np.float32)
+  tf.reduce_sum = lambda x, axis=None, keepdims=False, name=None: np.sum(x, axis=axis, keepdims=keepdims, dtype=np.float32)
   tf.subtract = lambda a, b: (a - b).astype(np.float32)
   tf.matmul = lambda a, b, transpose_b=False: np.matmul(a, np.swapaxes(b, -1, -2) if transpose_b else b).astype(np.float32)
   tf.shape = lambda x: x.shape
@@ -334,6 +335,42 @@ def more_cases(rng, out):
     steps.append({'indices': idx.tolist(), 'grad': g.tolist(), 'w': var.a.tolist(), 'm': m.a.tolist(), 'v': v.a.tolist()})
   out['cases']['lazy_adam_sparse'] = {'ref': 'compat/adam_s.py:%d' % line, 'lr': lr, 'beta1': b1, 'beta2': b2,
                                       'epsilon': eps, 'w0': w0.tolist(), 'steps': steps}
+  # ---- DeepFM.build_predict_graph: the head wiring, with and without final_dnn ----
+  B, F, D = 6, 5, 4
+  wide = rng.normal(size=(B, F)).astype(f32)
+  fm_feas = [rng.normal(size=(B, D)).astype(f32) for _ in range(F)]
+  deep = np.concatenate(fm_feas, axis=1)
+
+  class Cfg(dict):
+    hidden_units = ()
+  fm_code, _ = _function('layers/fm.py', 'FM', '__call__')
+  fm_ns = {'tf': _make_tf({})}
+  exec(fm_code, fm_ns)
+
+  class RefFM(object):
+    def __init__(self, name='fm'):
+      self._name = name
+    __call__ = fm_ns['__call__']
+  for final in (True, False):
+    deep_mlp = _mlp(rng, [F * D, 8, 6])
+    final_mlp = _mlp(rng, [1 + D + 6, 7]) if final else []
+    variables = {}
+    for nm, d_in in ((('output', 7),) if final else (('deep_logits', 6),)):
+      variables[nm + '/kernel'] = rng.normal(0, 0.4, (d_in, 1)).astype(f32)
+      variables[nm + '/bias'] = rng.normal(0, 0.1, 1).astype(f32)
+    dnn_cfg, final_cfg = Cfg(deep_feature=deep_mlp), Cfg(final_dnn=final_mlp)
+    final_cfg.hidden_units = (7,) if final else ()
+    got = {}
+    me = types.SimpleNamespace(_num_class=1, _wide_output_dim=1, _wide_features=wide, _fm_features=fm_feas,
+                               _deep_features=deep, _l2_reg=None, _is_training=True, _prediction_dict={},
+                               _model_config=types.SimpleNamespace(dnn=dnn_cfg, final_dnn=final_cfg),
+                               _add_to_prediction_dict=lambda o: got.update(logits=o))
+    _, line = run('model/deepfm.py', 'DeepFM', 'build_predict_graph', _make_tf(variables), me,
+                  fm=types.SimpleNamespace(FM=RefFM), dnn=types.SimpleNamespace(DNN=_NumpyDNN))
+    out['cases']['deepfm_head_final' if final else 'deepfm_head_plain'] = {
+        'ref': 'model/deepfm.py:%d' % line, 'wide': wide.tolist(), 'deep': deep.tolist(), 'n_field': F, 'dim': D,
+        'dnn': _mlp_json(deep_mlp), 'final_dnn': _mlp_json(final_mlp),
+        'head': {k: v.tolist() for k, v in variables.items()}, 'logits': np.asarray(got['logits'], f32).tolist()}
 
 
 if __name__ == '__main__':

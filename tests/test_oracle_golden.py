@@ -303,3 +303,24 @@ def test_lookup_golden_file_matches_its_generator_when_the_reference_is_mounted(
   gen.OUT = str(tmp_path / 'out.json')
   gen.main()
   assert json.load(open(gen.OUT))['cases'] == LOOKUP
+
+
+def _layers(js):
+  return [dict(W=np.array(l['w'], np.float32), b=np.array(l['b'], np.float32)) for l in js]
+
+
+def test_deepfm_head_oracle_matches_build_predict_graph():
+  """golden = model/deepfm.py DeepFM.build_predict_graph executed (reference FM class, dense stacks without BN):
+  logits = dense(final_dnn(concat[sum(wide), fm, dnn(deep)]))."""
+  c = FORMULAS['cases']['deepfm_head_final']
+  params = dict(dnn=_layers(c['dnn']), final=_layers(c['final_dnn']),
+                out_W=np.array(c['head']['output/kernel'], np.float32), out_b=np.array(c['head']['output/bias'], np.float32))
+  logits, _ = O.deepfm_forward(np.array(c['wide'], np.float32), np.array(c['deep'], np.float32), c['n_field'], c['dim'], params)
+  np.testing.assert_allclose(logits, np.array(c['logits'], np.float32)[:, 0], rtol=1e-5, atol=1e-5)
+  # without final_dnn: wide + sum(fm) + dense(dnn(deep))  (model/deepfm.py:92-105)
+  c = FORMULAS['cases']['deepfm_head_plain']
+  wide, deep = np.array(c['wide'], np.float32), np.array(c['deep'], np.float32)
+  h, _ = O.dnn_forward(deep, _layers(c['dnn']))
+  want = wide.sum(1, keepdims=True) + O.fm_fwd(deep, c['n_field'], c['dim']).sum(1, keepdims=True) + \
+      h @ np.array(c['head']['deep_logits/kernel'], np.float32) + np.array(c['head']['deep_logits/bias'], np.float32)
+  np.testing.assert_allclose(want, np.array(c['logits'], np.float32), rtol=1e-5, atol=1e-5)
