@@ -61,6 +61,25 @@ class _TF(object):
   def add(a, b):
     return a + b
 
+  @staticmethod
+  def subtract(a, b):
+    return a - b
+
+  @staticmethod
+  def square(x):
+    return x * x
+
+  @staticmethod
+  def add_n(inputs):
+    out = inputs[0]
+    for t in inputs[1:]:
+      out = out + t
+    return out
+
+  @staticmethod
+  def unstack(value, num=None, axis=0):
+    return list(torch.unbind(value, dim=axis))
+
 
 _EVAL_ENV = {'tf': _TF, 'torch': torch, '__builtins__': {'len': len, 'range': range, 'list': list, 'sum': sum,
                                                           'int': int, 'float': float, 'tuple': tuple}}
@@ -244,6 +263,22 @@ class MMoE(nn.Module):
     return [I.mmoe_mix(g(x), ex) for g in self.gates]
 
 
+_KERAS_MERGE = {'Add': lambda xs: _TF.add_n(list(xs)), 'Concatenate': lambda xs: torch.cat(list(xs), dim=-1),
+                'Multiply': lambda xs: __import__('functools').reduce(lambda a, b: a * b, xs)}
+
+
+class _Merge(nn.Module):
+  """tf.keras.layers.Add / Concatenate / Multiply on a list of tensors (layers/keras/__init__.py falls back to
+  tf.keras.layers for class names it does not define itself, utils/load_class.py)."""
+
+  def __init__(self, kind):
+    super().__init__()
+    self.kind = kind
+
+  def forward(self, inputs):
+    return _KERAS_MERGE[self.kind](inputs)
+
+
 def _shape_of(x):
   if isinstance(x, (list, tuple)):
     return [_shape_of(t) for t in x]
@@ -323,6 +358,8 @@ class Backbone(nn.Module):
       elif cls == 'SENet':
         assert isinstance(x, (list, tuple)), 'SENet takes the feature list (input_layer.only_output_feature_list)'
         self.mods[name] = SENet([t.shape[-1] for t in x], conf.senet, self._gen)
+      elif cls in _KERAS_MERGE:       # stock tf.keras.layers merge layers: no parameters
+        self.mods[name] = _Merge(cls)
       elif cls == 'DotInteraction':
         params = {}
         if conf.HasField('st_params'):
@@ -408,12 +445,23 @@ class Backbone(nn.Module):
     outputs = {}
     for block in self.blocks:
       which = block.WhichOneof('layer')
-      as_list = which == 'input_layer' and block.input_layer.only_output_feature_list
-      x = self._block_input(block, outputs, (lambda n: groups(n, True)) if as_list else groups)
+      # EnhancedInputLayer.call (layers/common_layers.py:142-190): the group as one matrix, as its feature list,
+      # as a [B, F, D] stack, or as the (matrix, list) pair that later blocks pick apart with input_slice
+      ilc = block.input_layer if which == 'input_layer' else None
+      mode = 'list' if ilc and ilc.only_output_feature_list else '3d' if ilc and ilc.only_output_3d_tensor else \
+          'both' if ilc and ilc.output_2d_tensor_and_feature_list else '2d'
+      if mode == '2d':
+        getter = groups
+      elif mode == 'list':
+        getter = lambda n: groups(n, True)  # noqa: E731
+      elif mode == '3d':
+        getter = lambda n: torch.stack(groups(n, True), dim=1)  # noqa: E731
+      else:
+        getter = lambda n: (groups(n), groups(n, True))  # noqa: E731
+      x = self._block_input(block, outputs, getter)
       if which == 'input_layer':
-        conf = block.input_layer
-        if conf.output_2d_tensor_and_feature_list or conf.only_output_3d_tensor:
-          raise NotImplementedError('input_layer block: 2d+list / 3d outputs')
+        if any(0.0 < r < 1.0 for r in (ilc.dropout_rate, ilc.feature_dropout_rate)) or ilc.do_batch_norm or ilc.do_layer_norm:
+          raise NotImplementedError('input_layer block %s: dropout / feature dropout / normalisation' % block.name)
         out = x
       elif which in ('keras_layer', 'lambda', 'recurrent', 'repeat'):
         out = self._layer(block.name, block, x, build)

@@ -80,6 +80,10 @@ def optimizer_settings(pipeline_config):
     return dict(kind='adagrad_optimizer', lr_fn=lambda step: 0.01, beta1=0.9, beta2=0.999, acc0=0.1)
   oc = tc.optimizer_config[0]
   kind = oc.WhichOneof('optimizer')
+  if kind is None:
+    # builders/optimizer_builder.py:28-144 knows more optimizers (adam_async, ftrl, adamw, ...); only the ones with a
+    # fused row rule on this path are accepted
+    raise ValueError('unsupported optimizer in train_config.optimizer_config (have: %s)' % sorted(_OPT_KIND))
   o = getattr(oc, kind)
   lr = o.learning_rate
   which = lr.WhichOneof('learning_rate')

@@ -91,7 +91,11 @@ def test_every_reference_sample_config_parses():
                                  'samples/model_config/mmoe_backbone_on_taobao.config',
                                  'samples/model_config/simple_multi_task_backbone_on_taobao.config',
                                  'samples/model_config/dssm_on_taobao_backbone.config',
-                                 'samples/model_config/dssm_senet_on_taobao_backbone.config'])
+                                 'samples/model_config/dssm_senet_on_taobao_backbone.config',
+                                 'examples/configs/deepfm_backbone_on_criteo.config',
+                                 'examples/configs/dlrm_backbone_on_criteo.config',
+                                 'examples/configs/dlrm_senet_on_criteo.config',
+                                 'examples/configs/wide_and_deep_backbone_on_movielens.config'])
 def test_baseline_model_families_build_from_unmodified_reference_configs(rel):
   cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, rel))
   il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
@@ -138,7 +142,11 @@ BACKBONE_WIRING = MINI.replace(b'model_class: "DeepFM"', b'model_class: "RankMod
       blocks { name: "fm" inputs { block_name: "feats" } keras_layer { class_name: "FM" fm { use_variant: true } } }
       blocks { name: "cross" inputs { feature_group_name: "deep" input_fn: "lambda x: [x, x]" }
                recurrent { num_steps: 2 fixed_input_index: 0 keras_layer { class_name: "Cross" } } }
-      concat_blocks: ["halves", "scaled", "fm", "cross"]
+      blocks { name: "cube" inputs { feature_group_name: "deep" } input_layer { only_output_3d_tensor: true } }
+      blocks { name: "cube_sum" inputs { block_name: "cube" } lambda { expression: "lambda x: tf.reduce_sum(x, axis=1)" } }
+      blocks { name: "pair" inputs { feature_group_name: "deep" } input_layer { output_2d_tensor_and_feature_list: true } }
+      blocks { name: "pair_first" inputs { block_name: "pair" input_slice: "[1]" } lambda { expression: "lambda x: x[0]" } }
+      concat_blocks: ["halves", "scaled", "fm", "cross", "cube_sum", "pair_first"]
       top_mlp { hidden_units: [12] }
     }
     model_params { l2_regularization: 1e-5 }''')
@@ -150,13 +158,14 @@ def test_backbone_wiring_shapes_and_parameters_without_a_gpu():
   cfg = config_util.get_configs_from_pipeline_file(BACKBONE_WIRING)
   il, model, opt = builder.build_model(cfg, 32, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
   bb = model.backbone
-  # halves: 2 x MLP(16 -> 8) concatenated = 16; scaled: 8; fm (use_variant): 16; cross: 32 -> concat 72 -> top_mlp 12
+  # halves: 2 x MLP(16 -> 8) concatenated = 16; scaled: 8; fm (use_variant): 16; cross: 32; cube_sum ([B,2,16] summed
+  # over the features): 16; pair_first (first tensor of the pair's feature list): 16 -> concat 104 -> top_mlp 12
   assert bb.out_dim == 12 and model.output is not None
   shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
   assert shapes['backbone.mods.halves_0.layers.0.kernel'] == (16, 8)
   assert shapes['backbone.mods.halves_1.layers.0.kernel'] == (16, 8)
   assert shapes['backbone.mods.cross_0.dense.kernel'] == (32, 32) and 'backbone.mods.cross_1.dense.kernel' in shapes
-  assert shapes['backbone.mods.backbone_top_mlp.layers.0.kernel'] == (72, 12)
+  assert shapes['backbone.mods.backbone_top_mlp.layers.0.kernel'] == (104, 12)
   assert model.l2_of('backbone.mods.cross_0.dense.kernel', None) == pytest.approx(1e-5)
 
 
