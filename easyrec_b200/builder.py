@@ -29,9 +29,14 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
       specs.append(IL.id_feature(name, fc.embedding_dim, hash_bucket_size=fc.hash_bucket_size,
                                  num_buckets=fc.num_buckets, combiner=fc.combiner,
                                  embedding_name=fc.embedding_name, packed_mod=packed_mod, host_hashed=host_hashed))
+    elif ftype == 'RawFeature' and raw_boundaries(fc) is not None:
+      # bucketized column (feature_column/feature_column.py:364-386): the reader turns the value into its bucket
+      # (readers.bucketize_raw), from there on it is an id feature over len(boundaries) + 1 rows
+      if fc.raw_input_dim != 1:
+        raise NotImplementedError('bucketized RawFeature %s with raw_input_dim %d' % (name, fc.raw_input_dim))
+      specs.append(IL.id_feature(name, fc.embedding_dim, num_buckets=len(raw_boundaries(fc)) + 1, combiner=fc.combiner,
+                                 embedding_name=fc.embedding_name))
     elif ftype == 'RawFeature':
-      if len(fc.boundaries) > 0:
-        raise NotImplementedError('RawFeature boundaries (bucketized column) for %s' % name)
       specs.append(IL.raw_feature(name, fc.embedding_dim, fc.min_val, fc.max_val, fc.raw_input_dim))
     elif ftype in ('TagFeature', 'SequenceFeature'):
       specs.append(IL.multi_feature(name, 'tag' if ftype == 'TagFeature' else 'seq', fc.embedding_dim,
@@ -43,6 +48,17 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     else:
       raise NotImplementedError('feature_type %s (feature %s) is outside the hot-path scope' % (ftype, name))
   return specs
+
+
+def raw_boundaries(fc):
+  """sorted bucket boundaries of a RawFeature, or None: explicit `boundaries`, or - num_buckets > 1 with a
+  min/max range - equal-width cuts i / num_buckets on the normalised value
+  (feature_column/feature_column.py:364-376)."""
+  if len(fc.boundaries) > 0:
+    return sorted(fc.boundaries)
+  if fc.num_buckets > 1 and fc.max_val > fc.min_val:
+    return [x / float(fc.num_buckets) for x in range(0, fc.num_buckets)]
+  return None
 
 
 def feature_groups(model_config):

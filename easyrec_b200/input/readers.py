@@ -19,6 +19,30 @@ from easyrec_b200 import _lib
 from easyrec_b200.config import config_util
 
 
+def bucketize_raw(x, fc):
+  """RawFeature with boundaries: float32 value -> bucket id, as the reference graph computes it:
+  (x - min) / (max - min) when max > min (input/input.py:638-640, float32), then the number of boundaries <= x
+  (bucketized_column, feature_column_v2.py:2866-2870)."""
+  from easyrec_b200 import builder
+  x = np.asarray(x, np.float32)
+  if fc.max_val > fc.min_val:
+    x = (x - np.float32(fc.min_val)) / np.float32(fc.max_val - fc.min_val)
+  bounds = np.asarray(builder.raw_boundaries(fc), np.float32)
+  return np.searchsorted(bounds, x, side='right').astype(np.int64)
+
+
+def _bucketized_features(pipeline_config, input_layer):
+  """feature name -> FeatureConfig for the RawFeatures the plan treats as bucket ids."""
+  from easyrec_b200 import builder
+  out = {}
+  for fc in config_util.get_feature_configs(pipeline_config):
+    name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+    ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
+    if ftype == 'RawFeature' and builder.raw_boundaries(fc) is not None and name in input_layer.sparse_names:
+      out[name] = fc
+  return out
+
+
 class DummyInput(object):
   """input/dummy_input.py:13-58: a constant in-memory batch, for pipeline-free throughput runs and tests."""
 
@@ -84,6 +108,7 @@ class CSVInput(object):
     self.batch_size = batch_size or input_layer.batch_size
     self.feature_inputs = {}
     self.hash_buckets = {}     # feature -> hash_bucket_size when its STRING field is hashed here, on the host
+    self.bucketized = _bucketized_features(pipeline_config, input_layer)
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = (fc.input_names[0], fc.separator or seq_sep)
@@ -102,6 +127,8 @@ class CSVInput(object):
     return int(x)
 
   def _id_column(self, col, feature, default):
+    if feature in self.bucketized:
+      return bucketize_raw([float(x if x != '' else (default or 0)) for x in col], self.bucketized[feature])
     return np.array([self._token(x if x != '' else (default or ('' if feature in self.hash_buckets else '0')), feature)
                      for x in col], np.int64)
 
@@ -123,6 +150,8 @@ class CSVInput(object):
       src, _ = self.feature_inputs[n]
       if n in self.hash_buckets:
         want(src, (_lib.CSV_HASH, 0, b',', self.defaults.get(src) or '', self.hash_buckets[n]))
+      elif n in self.bucketized:
+        want(src, (_lib.CSV_F32, 0, b',', float(self.defaults.get(src) or 0), 0))
       else:
         want(src, (_lib.CSV_I64, 0, b',', int(self.defaults.get(src) or 0), 0))
     for n in il.raw_names:
@@ -213,7 +242,9 @@ class CSVInput(object):
     B = self.batch_size
     feats = {}
     if il.sparse_names:
-      feats['sparse_fea'] = torch.from_numpy(np.concatenate([cols[self.feature_inputs[n][0]][0] for n in il.sparse_names]))
+      feats['sparse_fea'] = torch.from_numpy(np.concatenate(
+          [bucketize_raw(cols[self.feature_inputs[n][0]][0], self.bucketized[n]) if n in self.bucketized
+           else cols[self.feature_inputs[n][0]][0] for n in il.sparse_names]))
     if il.raw_names:
       dense = np.empty((B, il.n_dense), np.float32)
       for n in il.raw_names:
@@ -326,6 +357,7 @@ class ParquetInput(object):
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = fc.input_names[0]
+    self.bucketized = _bucketized_features(pipeline_config, input_layer)
 
   @staticmethod
   def _column(col):
@@ -345,7 +377,9 @@ class ParquetInput(object):
     ids = []
     for name in il.sparse_names:
       vals, lens = self._column(table.column(self.feature_inputs[name]))
-      if lens is None:
+      if name in self.bucketized:
+        ids.append(bucketize_raw(vals, self.bucketized[name]))
+      elif lens is None:
         ids.append(np.asarray(vals, np.int64))
       else:
         # list column on a single-valued slot: exactly one id per sample.  The packed path pools whatever the

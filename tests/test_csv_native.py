@@ -118,3 +118,45 @@ def test_er_csv_parse_stops_at_max_rows_and_leaves_the_unterminated_tail():
   assert n.value == 2 and used.value == 9 and ids.tolist() == [1, 3] and vals.tolist() == [2.5, -1.0]
   assert lib.er_csv_parse(data, len(data), b',', cols, 2, 1, 1, ctypes.byref(n), ctypes.byref(used)) == 0
   assert n.value == 1 and used.value == 6
+
+
+def test_bucketized_raw_features_become_bucket_ids(tmp_path):
+  """RawFeature + boundaries / num_buckets (bucketized_column, feature_column/feature_column.py:364-386): the
+  readers normalise in float32 and count the boundaries <= x; the table plan sees an id feature with
+  len(boundaries) + 1 rows.  Checked against a direct restatement of the TF graph on edge values."""
+  import pyarrow as pa
+  import pyarrow.parquet as pq
+  cfg_text = b'''
+data_config { batch_size: 8 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT }
+  input_fields { input_name: "hour" input_type: INT32 default_val: "3" }
+  input_fields { input_name: "price" input_type: DOUBLE } }
+feature_config {
+  features { input_names: "hour" feature_type: RawFeature embedding_dim: 8 boundaries: [18.0, 6.0, 12.0] }
+  features { input_names: "price" feature_type: RawFeature embedding_dim: 8 min_val: 10.0 max_val: 110.0 num_buckets: 4 }
+}
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["hour", "price"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["hour", "price"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } } }
+'''
+  cfg = config_util.get_configs_from_pipeline_file(cfg_text)
+  il, _, _ = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert il.sparse_names == ['hour', 'price'] and il.raw_names == []
+  assert il.features['hour'].num_buckets == 4 and il.features['price'].num_buckets == 5   # bounds 0, .25, .5, .75
+  assert il.arenas[8].tables['hour_embedding'][2] == 4 and il.arenas[8].tables['price_embedding'][2] == 5
+  hours = ['0', '5', '6', '11', '12', '18', '23', '']
+  prices = ['9.99', '10', '34.9', '35', '60', '85', '109.9', '500']
+  open(tmp_path / 'a.csv', 'w').write(''.join('1,%s,%s\n' % hp for hp in zip(hours, prices)))
+  want_hour = [0, 0, 1, 1, 2, 3, 3, 0]                      # '' -> default 3 -> below 6
+  norm = (np.array([float(p) for p in prices], np.float32) - np.float32(10.0)) / np.float32(100.0)
+  want_price = [int((np.array([0, .25, .5, .75], np.float32) <= v).sum()) for v in norm]
+  assert want_price == [0, 1, 1, 2, 3, 4, 4, 4]
+  for engine in ('native', 'python'):
+    (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 'a.csv'), engine=engine))
+    assert feats['sparse_fea'].reshape(2, 8).tolist() == [want_hour, want_price], engine
+    assert 'dense_fea' not in feats
+  pq.write_table(pa.table({'label': np.ones(8, np.float32), 'hour': np.array([int(h or 3) for h in hours], np.int32),
+                           'price': np.array([float(p) for p in prices], np.float64)}), str(tmp_path / 'a.parquet'))
+  (feats, _), = list(readers.ParquetInput(cfg, il, str(tmp_path / 'a.parquet')))
+  assert feats['sparse_fea'].reshape(2, 8).tolist() == [want_hour, want_price]
