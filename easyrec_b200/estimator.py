@@ -64,7 +64,7 @@ class EasyRecEstimator(object):
     every = max(int(self.train_config.log_step_count_steps), 1)
     t0, n0 = time.time(), self.global_step
     loss = None
-    for feats, labels in input_fn():
+    for feats, labels in readers.Prefetcher(input_fn(), depth=2):   # host parsing runs ahead of the device step
       feats, labels = readers.to_device(feats, labels, self._device)
       loss, _ = self.trainer.train_step(feats, labels)
       self.global_step += 1

@@ -510,6 +510,58 @@ def make_input(pipeline_config, input_layer, path):
   return CSVInput(pipeline_config, input_layer, path)
 
 
+class Prefetcher(object):
+  """Runs a batch source in a background thread, `depth` batches ahead of the consumer, so that parsing the
+  next batches (er_csv_parse / pyarrow release the GIL) overlaps the device step of the current one - the role of
+  `dataset.prefetch(prefetch_size)` in the reference input pipeline (input/input.py:1046-1051).  Order is
+  preserved, an exception in the source is re-raised at the consumer, and abandoning the iterator (a step
+  limit reached) stops the thread."""
+
+  _END = object()
+
+  def __init__(self, source, depth=2):
+    self.source = source
+    self.depth = max(int(depth), 1)
+
+  def __iter__(self):
+    import queue
+    import threading
+    q = queue.Queue(maxsize=self.depth)
+    stop = threading.Event()
+
+    def put(item):
+      while not stop.is_set():
+        try:
+          q.put(item, timeout=0.1)
+          return True
+        except queue.Full:
+          pass
+      return False
+
+    def work():
+      try:
+        for item in self.source:
+          if not put(item):
+            return
+        put(self._END)
+      except BaseException as e:   # handed to the consumer
+        put(e)
+
+    t = threading.Thread(target=work, name='easyrec_b200-prefetch', daemon=True)
+    t.start()
+    try:
+      while True:
+        item = q.get()
+        if item is self._END:
+          return
+        if isinstance(item, BaseException):
+          raise item
+        yield item
+    finally:
+      stop.set()
+      t.join(timeout=5.0)
+
+
 def to_device(feats, labels, device):
   out = {}
   for k, v in feats.items():

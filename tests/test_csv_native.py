@@ -160,3 +160,37 @@ model_config { model_class: "DeepFM"
                            'price': np.array([float(p) for p in prices], np.float64)}), str(tmp_path / 'a.parquet'))
   (feats, _), = list(readers.ParquetInput(cfg, il, str(tmp_path / 'a.parquet')))
   assert feats['sparse_fea'].reshape(2, 8).tolist() == [want_hour, want_price]
+
+
+def test_prefetcher_keeps_order_propagates_errors_and_stops_when_abandoned():
+  import threading
+  import time
+  produced = []
+
+  def source(n, fail_at=None):
+    for i in range(n):
+      if i == fail_at:
+        raise RuntimeError('bad line %d' % i)
+      produced.append(i)
+      yield i
+  assert list(readers.Prefetcher(source(50), depth=3)) == list(range(50))
+  with pytest.raises(RuntimeError, match='bad line 7'):
+    list(readers.Prefetcher(source(20, fail_at=7)))
+  del produced[:]
+  it = iter(readers.Prefetcher(source(10**9), depth=2))
+  assert [next(it) for _ in range(5)] == [0, 1, 2, 3, 4]
+  it.close()                                   # what leaving a `for` loop with `break` does
+  n = len(produced)
+  time.sleep(0.3)
+  assert len(produced) == n and n <= 5 + 2 + 1   # the producer stopped at most depth + 1 items ahead
+  assert not [t for t in threading.enumerate() if t.name == 'easyrec_b200-prefetch' and t.is_alive()]
+  # the source runs ahead of a slow consumer
+  t0 = time.perf_counter()
+
+  def slow(n):
+    for i in range(n):
+      time.sleep(0.05)
+      yield i
+  for _ in readers.Prefetcher(slow(10), depth=2):
+    time.sleep(0.05)
+  assert time.perf_counter() - t0 < 0.85        # overlapped: ~0.55 s, serial would be 1.0 s
