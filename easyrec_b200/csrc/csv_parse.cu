@@ -38,12 +38,15 @@ inline bool parse_i64(Span s, int64_t* out) {
     ++p;
   }
   if (p == e) return false;
+  while (p + 1 < e && *p == '0') ++p;            // leading zeros do not count towards the 19 digits
+  if (e - p > 19) return false;                  // cannot fit int64 (and would wrap the accumulator)
   uint64_t v = 0;
   for (; p < e; ++p) {
     const unsigned d = (unsigned)(*p - '0');
     if (d > 9) return false;
     v = v * 10 + d;
   }
+  if (v > (neg ? (uint64_t)1 << 63 : ((uint64_t)1 << 63) - 1)) return false;   // out of range, like decode_csv
   *out = neg ? (int64_t)(0 - v) : (int64_t)v;
   return true;
 }

@@ -194,3 +194,20 @@ def test_prefetcher_keeps_order_propagates_errors_and_stops_when_abandoned():
   for _ in readers.Prefetcher(slow(10), depth=2):
     time.sleep(0.05)
   assert time.perf_counter() - t0 < 0.85        # overlapped: ~0.55 s, serial would be 1.0 s
+
+
+def test_er_csv_parse_integer_range_and_spellings():
+  lib = _lib.load()
+
+  def parse(tok):
+    out = np.array([-77], np.int64)
+    cols = (_lib.ErCsvCol * 1)()
+    cols[0].kind, cols[0].out, cols[0].default_i64 = _lib.CSV_I64, out.ctypes.data, -77
+    data = (tok + '\n').encode()
+    n, used = ctypes.c_int64(0), ctypes.c_size_t(0)
+    return lib.er_csv_parse(data, len(data), b',', cols, 1, 1, 1, ctypes.byref(n), ctypes.byref(used)), int(out[0])
+  assert parse('9223372036854775807') == (0, 2**63 - 1) and parse('-9223372036854775808') == (0, -2**63)
+  for bad in ('9223372036854775808', '-9223372036854775809', '18446744073709551616', '99999999999999999999', '1.5', '0x10', '--1'):
+    assert parse(bad)[0] == _lib.ER_ERR_INVALID_ARG, bad     # out of int64 range / not an integer: refused like decode_csv
+  assert parse('00000000000000000000012') == (0, 12) and parse('+5') == (0, 5) and parse(' 42 ') == (0, 42)
+  assert parse('') == (0, -77)                                 # empty -> record default
