@@ -18,9 +18,20 @@ def test_fingerprint64_tensorflow_frozen_vectors():
 
 
 def test_string_to_hash_bucket_fast_examples():
+  from easyrec_b200 import _lib
+  assert len(KATS['fingerprint64']['hash_bucket_fast']) >= 6
   for case in KATS['fingerprint64']['hash_bucket_fast']:
     got = [O.fingerprint64(s) % case['num_buckets'] for s in case['inputs']]
     assert got == case['expected']
+    assert [_lib.fingerprint64(s) % case['num_buckets'] for s in case['inputs']] == case['expected']   # product host hash
+
+
+def test_integer_ids_hash_like_tensorflows_hashed_column():
+  """HashedCategoricalColumn over int64 values 101, 201, 301 with 10 buckets -> [3, 7, 5] (TF's frozen test): the
+  oracle's decimal-text rule (the restatement of K1's FARM_DECIMAL mode) must give the same buckets."""
+  from easyrec_b200 import _lib
+  rows, _ = O.bucketize(np.array([101, 201, 301], np.int64), _lib.BUCKET_FARM_DECIMAL, 10, 0)
+  assert rows.tolist() == [3, 7, 5]
 
 
 def test_product_host_hash_equals_oracle_all_lengths():
