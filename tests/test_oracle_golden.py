@@ -335,3 +335,14 @@ def test_deepfm_head_oracle_matches_build_predict_graph():
   want = wide.sum(1, keepdims=True) + O.fm_fwd(deep, c['n_field'], c['dim']).sum(1, keepdims=True) + \
       h @ np.array(c['head']['deep_logits/kernel'], np.float32) + np.array(c['head']['deep_logits/bias'], np.float32)
   np.testing.assert_allclose(want, np.array(c['logits'], np.float32), rtol=1e-5, atol=1e-5)
+
+
+def test_adagrad_row_rule_reproduces_tensorflows_adagrad_test_constants():
+  k = KATS['adagrad_sparse']
+  for c in k['cases']:
+    w = np.array(c['table'], np.float32)
+    acc = np.full_like(w, k['initial_accumulator_value'])
+    for _ in range(k['steps']):
+      O.embedding_bwd(w, acc, None, np.array([c['row']], np.int64), np.zeros(1, np.int32),
+                      np.array([[c['grad']]], np.float32), O.OPT_ADAGRAD, k['lr'])
+    np.testing.assert_allclose(w, np.array(c['expected'], np.float32), rtol=k['tolerance'], atol=k['tolerance'])
