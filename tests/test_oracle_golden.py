@@ -346,3 +346,18 @@ def test_adagrad_row_rule_reproduces_tensorflows_adagrad_test_constants():
       O.embedding_bwd(w, acc, None, np.array([c['row']], np.int64), np.zeros(1, np.int32),
                       np.array([[c['grad']]], np.float32), O.OPT_ADAGRAD, k['lr'])
     np.testing.assert_allclose(w, np.array(c['expected'], np.float32), rtol=k['tolerance'], atol=k['tolerance'])
+
+
+@pytest.mark.parametrize('weighted', [True, False])
+def test_pooling_oracle_follows_tensorflows_safe_lookup_test_cases(weighted):
+  """ids < 0 pruned, weights <= 0 pruned for the mean combiner, empty rows -> zeros, weighted mean otherwise."""
+  k = KATS['safe_embedding_lookup_sparse']
+  e = np.random.default_rng(3).normal(size=(5, 4)).astype(np.float32)
+  n_rows = k['dense_shape'][0]
+  lens = np.bincount([i[0] for i in k['indices']], minlength=n_rows).astype(np.int32)
+  row_ptr, _ = O.csr_from_lens(lens)
+  got, _ = O.embedding_fwd(e, np.array(k['ids'], np.int64), row_ptr, 1,
+                           weights=np.array(k['weights'], np.float32) if weighted else None)
+  for r, spec in enumerate(k['expected_weighted' if weighted else 'expected_no_weights']):
+    want = np.zeros(4, np.float32) if spec is None else sum(w * e[i] for i, w in spec['terms']) / spec['div']
+    np.testing.assert_allclose(got[r], want, rtol=1e-6, atol=1e-6)
