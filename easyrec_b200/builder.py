@@ -101,6 +101,10 @@ def optimizer_settings(pipeline_config):
     # fused row rule on this path are accepted
     raise ValueError('unsupported optimizer in train_config.optimizer_config (have: %s)' % sorted(_OPT_KIND))
   o = getattr(oc, kind)
+  if kind == 'momentum_optimizer' and o.momentum_optimizer_value != 0:
+    # the fused row rule keeps no momentum accumulator: plain SGD is only the same optimizer at momentum 0
+    raise ValueError('momentum_optimizer with momentum_optimizer_value %g is not supported (only 0 = SGD)'
+                     % o.momentum_optimizer_value)
   lr = o.learning_rate
   which = lr.WhichOneof('learning_rate')
   if which == 'exponential_decay_learning_rate':
