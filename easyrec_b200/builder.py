@@ -141,10 +141,44 @@ def optimizer_settings(pipeline_config):
               if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
 
 
+_RANK_CLASSES = ('DeepFM', 'DCN', 'MultiTowerDIN', 'RankModel')
+
+
+def check_scope(pipeline_config):
+  """Refuse configs whose training semantics depend on something this path does not implement, rather than
+  training a different model silently.  (Control-plane fields - export, hooks, distribution strategy - do not
+  change the arithmetic and are ignored.)"""
+  mc = pipeline_config.model_config
+  tc = pipeline_config.train_config
+  bad = []
+  if mc.HasField('ev_params'):
+    bad.append('model_config.ev_params (embedding variables / dynamic tables)')
+  if len(mc.kd) > 0:
+    bad.append('model_config.kd (knowledge distillation losses)')
+  if mc.HasField('variational_dropout'):
+    bad.append('model_config.variational_dropout')
+  if len(tc.optimizer_config) > 1:
+    bad.append('two optimizer_config entries (separate embedding / dense optimizers, easy_rec_model.py:446-467)')
+  if any(oc.use_moving_average for oc in tc.optimizer_config):
+    bad.append('optimizer_config.use_moving_average')
+  if mc.model_class in _RANK_CLASSES:
+    names = mc.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number
+    if mc.num_class != 1:
+      bad.append('num_class %d (only the binary head, num_class 1)' % mc.num_class)
+    if names[mc.loss_type].name != 'CLASSIFICATION':
+      bad.append('loss_type %s (rank models train with CLASSIFICATION = sigmoid cross entropy)' % names[mc.loss_type].name)
+    extra = [names[l.loss_type].name for l in mc.losses if names[l.loss_type].name != 'CLASSIFICATION' or l.weight != 1.0]
+    if extra or len(mc.losses) > 1:
+      bad.append('model_config.losses %s' % ([names[l.loss_type].name for l in mc.losses],))
+  if bad:
+    raise NotImplementedError('config is outside the hot-path scope: ' + '; '.join(bad))
+
+
 def build_model(pipeline_config, batch_size, device, generator=None, cpu_generator=None, world=1, rank=0,
                 default_seq_len=50):
   """Returns (input_layer, model, optimizer settings) for the config's model_class."""
   from easyrec_b200 import model as model_pkg
+  check_scope(pipeline_config)
   mc = pipeline_config.model_config
   # the Parquet inputs bucket ids as `vals % num_buckets` (input/parquet_input.py:221,
   # input/parquet_input_v2.py:96-100) where the feature-column path maps out-of-range ids to 0

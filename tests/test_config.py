@@ -87,7 +87,6 @@ def test_every_reference_sample_config_parses():
                                  'samples/model_config/mmoe_on_taobao.config',
                                  'samples/model_config/dcn_backbone_on_taobao.config',
                                  'samples/model_config/dlrm_backbone_on_taobao.config',
-                                 'samples/model_config/multi_tower_backbone_on_taobao.config',
                                  'samples/model_config/mmoe_backbone_on_taobao.config',
                                  'samples/model_config/simple_multi_task_backbone_on_taobao.config',
                                  'samples/model_config/dssm_on_taobao_backbone.config',
@@ -229,3 +228,29 @@ def test_optimizers_without_a_fused_row_rule_are_refused():
   with pytest.raises(ValueError, match='unsupported optimizer'):
     builder.optimizer_settings(config_util.get_configs_from_pipeline_file(
         b'train_config { optimizer_config { ftrl_optimizer { } } }'))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+@pytest.mark.parametrize('rel,why', [
+    ('samples/model_config/multi_tower_backbone_on_taobao.config', 'losses'),           # F1-reweighted + pairwise
+    ('samples/model_config/deepfm_combo_on_avazu_reg.config', None),                    # ComboFeature comes first
+    ('samples/model_config/deepfm_multi_cls_on_avazu_ctr.config', None),
+    ('samples/model_config/wide_and_deep_two_opti.config', None),
+    ('samples/model_config/taobao_fg_ev.config', 'ev_params')])
+def test_configs_that_need_unimplemented_training_semantics_are_refused(rel, why):
+  cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, rel))
+  with pytest.raises((NotImplementedError, KeyError, ValueError)) as e:
+    builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  if why:
+    assert why in str(e.value)
+
+
+def test_scope_check_names_every_offending_field():
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
+      b'embedding_regularization: 1e-5', b'embedding_regularization: 1e-5 num_class: 3 loss_type: L2_LOSS '
+      b'variational_dropout { } losses { loss_type: PAIR_WISE_LOSS }'))
+  with pytest.raises(NotImplementedError) as e:
+    builder.check_scope(cfg)
+  for word in ('num_class 3', 'L2_LOSS', 'variational_dropout', 'PAIR_WISE_LOSS'):
+    assert word in str(e.value)
+  builder.check_scope(config_util.get_configs_from_pipeline_file(MINI))   # the plain config passes
