@@ -24,6 +24,16 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     # a STRING field is hashed where its bytes are, by the reader (Fingerprint64 % hash_bucket_size); integer
     # fields go to the device as int64 and are hashed there from their decimal text (input/input.py:541-543)
     host_hashed = fc.hash_bucket_size > 0 and field_types.get(fc.input_names[0]) == 'STRING'
+    # per-feature options that change which row / value a sample reads and are not implemented: refuse
+    unsupported = [w for w, on in (
+        ('vocab_file / vocab_list (vocabulary lookup)', fc.HasField('vocab_file') or len(fc.vocab_list) > 0),
+        ('kv_separator (weighted tags)', fc.HasField('kv_separator')),
+        ('seq_multi_sep (multi-valued sequence steps)', fc.HasField('seq_multi_sep')),
+        ('normalizer_fn', fc.HasField('normalizer_fn')),
+        ('shared_names', len(fc.shared_names) > 0),
+        ('sub_feature_type RawFeature', fc.HasField('sub_feature_type') and fc.sub_feature_type != fc.IdFeature)) if on]
+    if unsupported:
+      raise NotImplementedError('feature %s: %s is outside the hot-path scope' % (name, ', '.join(unsupported)))
     ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
     if ftype == 'IdFeature':
       specs.append(IL.id_feature(name, fc.embedding_dim, hash_bucket_size=fc.hash_bucket_size,

@@ -254,3 +254,12 @@ def test_scope_check_names_every_offending_field():
   for word in ('num_class 3', 'L2_LOSS', 'variational_dropout', 'PAIR_WISE_LOSS'):
     assert word in str(e.value)
   builder.check_scope(config_util.get_configs_from_pipeline_file(MINI))   # the plain config passes
+
+
+def test_feature_options_that_change_the_looked_up_rows_are_refused():
+  for extra, word in ((b'vocab_list: ["a", "b"]', 'vocab'), (b'kv_separator: ":"', 'kv_separator'),
+                      (b'normalizer_fn: "tf.math.log1p"', 'normalizer_fn')):
+    cfg = config_util.get_configs_from_pipeline_file(
+        MINI.replace(b'hash_bucket_size: 1000 unknown_future_field: 3', b'hash_bucket_size: 1000 ' + extra))
+    with pytest.raises(NotImplementedError, match=word):
+      builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
