@@ -161,6 +161,9 @@ def check_scope(pipeline_config):
   mc = pipeline_config.model_config
   tc = pipeline_config.train_config
   bad = []
+  dc = pipeline_config.data_config
+  if dc.HasField('sample_weight'):
+    bad.append('data_config.sample_weight (per-sample loss weights)')
   if mc.HasField('ev_params'):
     bad.append('model_config.ev_params (embedding variables / dynamic tables)')
   if len(mc.kd) > 0:

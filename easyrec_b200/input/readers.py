@@ -219,6 +219,8 @@ class CSVInput(object):
       view = np.frombuffer(mm, np.uint8)
       try:
         base, size, off = view.ctypes.data, view.size, 0
+        if self.cfg.data_config.with_header:      # the first line names the columns (csv_input.py:139-145)
+          off = mm.find(b'\n') + 1 or size
         while True:
           res = self._parse(base + off, size - off, plan, list_cap)
           if res is None:          # a list column outgrew its array
@@ -277,6 +279,8 @@ class CSVInput(object):
     B = self.batch_size
     buf = []
     with open(self.path, 'rb') as f:
+      if self.cfg.data_config.with_header:
+        f.readline()
       for line in f:
         buf.append(line.rstrip(b'\r\n').decode('utf-8', errors='surrogateescape').split(self.sep))
         if len(buf) == B:
@@ -502,6 +506,10 @@ def make_input(pipeline_config, input_layer, path):
   """reader for data_config.input_type (CSVInput / ParquetInput / DummyInput)."""
   from easyrec_b200 import builder
   dc = pipeline_config.data_config
+  if dc.WhichOneof('sampler') is not None:
+    # the model itself builds from such a config; its batches (sampled negatives appended to every batch,
+    # input/sampler.py) are not something these readers produce
+    raise NotImplementedError('data_config.%s: negative samplers are outside the hot-path scope' % dc.WhichOneof('sampler'))
   kind = builder.input_type_name(pipeline_config)
   if kind.startswith('Parquet'):
     return ParquetInput(pipeline_config, input_layer, path)

@@ -263,3 +263,21 @@ def test_feature_options_that_change_the_looked_up_rows_are_refused():
         MINI.replace(b'hash_bucket_size: 1000 unknown_future_field: 3', b'hash_bucket_size: 1000 ' + extra))
     with pytest.raises(NotImplementedError, match=word):
       builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+
+
+def test_data_options_that_change_the_batches_or_the_loss_are_refused_and_headers_are_skipped(tmp_path):
+  from easyrec_b200.input import readers
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'label_fields: "label"', b'label_fields: "label" sample_weight: "F1"'))
+  with pytest.raises(NotImplementedError, match='sample_weight'):
+    builder.check_scope(cfg)
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
+      b'label_fields: "label"', b'label_fields: "label" negative_sampler { input_path: "x" num_sample: 4 }'))
+  il, _, _ = builder.build_model(cfg, 2, 'cpu', cpu_generator=torch.Generator().manual_seed(0))   # the model builds
+  with pytest.raises(NotImplementedError, match='negative_sampler'):                                 # its input does not
+    readers.make_input(cfg, il, str(tmp_path / 'x.csv'))
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'batch_size: 32', b'batch_size: 2 with_header: true'))
+  il, _, _ = builder.build_model(cfg, 2, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 'h.csv', 'w').write('label\tF1\tC1\n1\t2.5\t7\n0\t3.5\t8\n')
+  for engine in ('native', 'python'):
+    (feats, labels), = list(readers.CSVInput(cfg, il, str(tmp_path / 'h.csv'), engine=engine))
+    assert labels.tolist() == [1.0, 0.0] and feats['sparse_fea'].tolist() == [7, 8]
