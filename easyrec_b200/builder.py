@@ -154,6 +154,19 @@ def optimizer_settings(pipeline_config):
 _RANK_CLASSES = ('DeepFM', 'DCN', 'MultiTowerDIN', 'RankModel')
 
 
+def _walk_messages(msg, path):
+  """(dotted path, message) for every set sub-message, depth first."""
+  for fd, value in msg.ListFields():
+    if fd.type != fd.TYPE_MESSAGE or fd.message_type.GetOptions().map_entry:
+      continue
+    items = list(value) if fd.label == fd.LABEL_REPEATED else [value]
+    for i, v in enumerate(items):
+      p = '%s.%s%s' % (path, fd.name, '[%d]' % i if fd.label == fd.LABEL_REPEATED else '')
+      yield p, v
+      for sub in _walk_messages(v, p):
+        yield sub
+
+
 def check_scope(pipeline_config):
   """Refuse configs whose training semantics depend on something this path does not implement, rather than
   training a different model silently.  (Control-plane fields - export, hooks, distribution strategy - do not
@@ -183,6 +196,15 @@ def check_scope(pipeline_config):
     extra = [names[l.loss_type].name for l in mc.losses if names[l.loss_type].name != 'CLASSIFICATION' or l.weight != 1.0]
     if extra or len(mc.losses) > 1:
       bad.append('model_config.losses %s' % ([names[l.loss_type].name for l in mc.losses],))
+  for path, m in _walk_messages(mc, 'model_config'):
+    kind = m.DESCRIPTOR.name
+    if kind in ('DNN', 'MLP'):
+      if any(r > 0 for r in m.dropout_ratio):
+        bad.append('%s.dropout_ratio' % path)
+      if kind == 'DNN' and m.activation not in ('tf.nn.relu', 'relu'):
+        bad.append('%s.activation %r' % (path, m.activation))
+      if kind == 'DNN' and not m.use_bn:
+        bad.append('%s.use_bn false' % path)
   if bad:
     raise NotImplementedError('config is outside the hot-path scope: ' + '; '.join(bad))
 

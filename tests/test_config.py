@@ -281,3 +281,12 @@ def test_data_options_that_change_the_batches_or_the_loss_are_refused_and_header
   for engine in ('native', 'python'):
     (feats, labels), = list(readers.CSVInput(cfg, il, str(tmp_path / 'h.csv'), engine=engine))
     assert labels.tolist() == [1.0, 0.0] and feats['sparse_fea'].tolist() == [7, 8]
+
+
+def test_tower_options_that_are_not_implemented_are_refused():
+  for new, word in ((b'dnn { hidden_units: [32, 16] dropout_ratio: [0.1, 0.1] }', 'dropout_ratio'),
+                    (b'dnn { hidden_units: [32, 16] activation: "dice" }', 'activation'),
+                    (b'dnn { hidden_units: [32, 16] use_bn: false }', 'use_bn')):
+    cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'dnn { hidden_units: [32, 16] }', new))
+    with pytest.raises(NotImplementedError, match=word):
+      builder.check_scope(cfg)
