@@ -154,14 +154,22 @@ def optimizer_settings(pipeline_config):
 _RANK_CLASSES = ('DeepFM', 'DCN', 'MultiTowerDIN', 'RankModel')
 
 
+def _is_repeated(fd):
+  rep = getattr(fd, 'is_repeated', None)     # protobuf >= 5.29 (FieldDescriptor.label is deprecated there)
+  if rep is None:
+    return fd.label == fd.LABEL_REPEATED
+  return rep() if callable(rep) else rep
+
+
 def _walk_messages(msg, path):
   """(dotted path, message) for every set sub-message, depth first."""
   for fd, value in msg.ListFields():
     if fd.type != fd.TYPE_MESSAGE or fd.message_type.GetOptions().map_entry:
       continue
-    items = list(value) if fd.label == fd.LABEL_REPEATED else [value]
+    rep = _is_repeated(fd)
+    items = list(value) if rep else [value]
     for i, v in enumerate(items):
-      p = '%s.%s%s' % (path, fd.name, '[%d]' % i if fd.label == fd.LABEL_REPEATED else '')
+      p = '%s.%s%s' % (path, fd.name, '[%d]' % i if rep else '')
       yield p, v
       for sub in _walk_messages(v, p):
         yield sub
