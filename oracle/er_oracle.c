@@ -6,16 +6,23 @@
  * bench.py's cpu_baseline / --impl reference legs as the checker.  Nothing under
  * easyrec_b200/ may import or link it.
  *
- * PINNING STATUS (see DESIGN.md "Oracle"):
- *   - Fingerprint64: pinned by TensorFlow's own known-answer tests
- *     (string_to_hash_bucket_op_test.py: 'a','b','c','d'; fingerprint_test.cc
- *     "IsForeverFrozen": "Hello","World") -- covers the len 1-3 and 4-7 branches;
- *     longer branches follow the published farmhashna code, cross-checked only
- *     against an independently written second implementation: parity unpinned.
- *   - lookup + pooling: pinned by the reference's only numeric tests,
- *     easy_rec/python/test/embed_test.py:23-86 and :88-151 (tests/golden/).
- *   - optimizer rules, losses, sharding: parity unpinned (the reference has no
- *     numeric test for them and TensorFlow cannot be imported here).
+ * PINNING STATUS (the table in DESIGN.md section 4 is authoritative):
+ *   - Fingerprint64: pinned by TensorFlow's own known-answer tests for inputs up to
+ *     16 bytes (string_to_hash_bucket_op_test.py 'a','b','c','d'; fingerprint_test.cc
+ *     "Hello","World"; the hashed feature column test 'omar','stringer','marlo' and the
+ *     int64 path 101,201,301; lookup_ops OOV buckets; docstring examples) --
+ *     tests/golden/reference_kats.json.  Longer inputs follow the published farmhashna
+ *     code, cross-checked only against an independently written second implementation:
+ *     parity unpinned.
+ *   - lookup + pooling: the reference's numeric tests (test/embed_test.py:23-86, :88-151),
+ *     TensorFlow's SafeEmbeddingLookupSparseTest case table, and the reference's
+ *     embedding_lookup_ragged executed on a numpy shim.
+ *   - shard rule (owner = id mod N, local row = id div N): embedding_parallel_lookup
+ *     executed on two ranks (tests/golden/make_lookup_golden.py).
+ *   - sparse Adagrad: the constants of TensorFlow's adagrad_test.py; lazy Adam:
+ *     compat/adam_s.py _apply_sparse_shared executed (tests/golden/make_formula_golden.py).
+ *   - sigmoid cross entropy and the dedup order: parity unpinned (TensorFlow-owned, no
+ *     known-answer vector available offline).
  *
  * Third-party arithmetic restated here (absent from /root/reference):
  *   TensorFlow 1.15.5 / 2.12.0 (docker/Dockerfile:1, docker/Dockerfile_tf212:1):

@@ -5,10 +5,15 @@ legs may import this module; the product package (easyrec_b200/) never does.
 
 The sparse path is the C restatement; the dense model pieces (DNN + batch-norm,
 DeepFM head, DIN attention, DCN cross, MMoE, DSSM, losses) are restated in numpy
-fp32 below, each citing the reference lines it follows.  Parity status: see the
-header of er_oracle.c and DESIGN.md -- everything except Fingerprint64's short-string
-branches and the two embed_test.py known answers is "parity unpinned" (TensorFlow
-cannot be imported in this container).
+fp32 below, each citing the reference lines it follows.  Parity status:
+TensorFlow cannot be imported in this container, so the oracle is pinned piece by piece -- to
+TensorFlow's own frozen test vectors (Fingerprint64 up to 16 bytes, the hashed feature column, the
+sparse Adagrad constants, the safe-lookup case table), to the reference's embed_test.py known
+answers, and to golden vectors obtained by EXECUTING the reference's own function bodies on a numpy
+shim (tests/golden/make_*_golden.py: FM, DCN cross, keras Cross, dot interaction, DIN attention,
+MMoE, list-wise match loss, DeepFM head, lazy Adam, LR schedule, pooling, shard rule, Parquet
+batches, checkpoint layout, GAUC).  Still unpinned: Fingerprint64 beyond 16 bytes, batch-norm /
+dense arithmetic and sigmoid cross entropy (TensorFlow-owned), the dedup order.
 """
 import ctypes
 import os
@@ -245,3 +250,96 @@ def deepfm_backward(g_logits, wide, deep, n_field, dim, params, cache):
                                           params['dnn'], cache['c1'])
   g_deep = (g_deep_mlp + fm_bwd(deep, np.ascontiguousarray(g_fm), n_field, dim)).astype(np.float32)
   return g_wide, g_deep, grads
+
+
+# ---- interaction formulas of the other model families (numpy fp32) ---------------------------------
+
+
+def din_attention(query, keys, lens, mlp_layers):
+  """layers/sequence_feature_layer.py:123-189 (= model/multi_tower_din.py:62-97): target attention.
+
+  query [B, D], keys [B, T, D], lens [B]; mlp_layers as for dnn_forward (last layer linear, no BN).
+  concat[q, k, q-k, q*k] -> DNN -> scores [B, T]; positions >= len get -2**32 + 1; softmax over T;
+  returns the attended history [B, D] (the reference then concatenates the key)."""
+  query, keys = query.astype(np.float32), keys.astype(np.float32)
+  B, T, D = keys.shape
+  q = np.broadcast_to(query[:, None, :], (B, T, D))
+  din = np.concatenate([q, keys, q - keys, q * keys], axis=-1).reshape(B * T, 4 * D)
+  scores, _ = dnn_forward(din, mlp_layers, training=True, last_no_act=True, last_no_bn=True)
+  scores = scores.reshape(B, T)
+  mask = np.arange(T)[None, :] < np.asarray(lens).reshape(B, 1)
+  scores = np.where(mask, scores, np.float32(-2.0**32 + 1)).astype(np.float32)
+  e = np.exp(scores - scores.max(axis=1, keepdims=True), dtype=np.float32)
+  p = (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+  return np.einsum('bt,btd->bd', p, keys).astype(np.float32)
+
+
+def cross_v1(x0, weights, biases):
+  """model/dcn.py:32-45: x <- x0 * (x . w) + b + x, one (w, b) pair per cross layer."""
+  x0 = x0.astype(np.float32)
+  x = x0
+  for w, b in zip(weights, biases):
+    xw = (x * np.asarray(w, np.float32)).sum(axis=1, keepdims=True, dtype=np.float32)
+    x = (x0 * xw + np.asarray(b, np.float32) + x).astype(np.float32)
+  return x
+
+
+def cross_v2(x0, x, kernel, bias, diag_scale=0.0, u=None):
+  """layers/keras/interaction.py:249-286: x0 * (W x + b [+ diag_scale * x]) + x; W = u @ kernel when the
+  low-rank projection `u` [d, p] is given (then kernel is V [p, d])."""
+  x0, x = x0.astype(np.float32), x.astype(np.float32)
+  h = x if u is None else (x @ np.asarray(u, np.float32)).astype(np.float32)
+  prod = (h @ np.asarray(kernel, np.float32) + np.asarray(bias, np.float32)).astype(np.float32)
+  if diag_scale:
+    prod = prod + np.float32(diag_scale) * x
+  return (x0 * prod + x).astype(np.float32)
+
+
+def dot_interaction(x, self_interaction=False, skip_gather=False):
+  """layers/keras/interaction.py:47-128: x [B, F, D] -> pairwise dot products of the lower triangle in
+  row-major order (with the diagonal when self_interaction); skip_gather keeps [B, F*F] with the rest zeroed."""
+  x = x.astype(np.float32)
+  B, F, _ = x.shape
+  xa = np.einsum('bfd,bgd->bfg', x, x).astype(np.float32)
+  keep = np.tril(np.ones((F, F), bool), 0 if self_interaction else -1)
+  if skip_gather:
+    return (xa * keep).reshape(B, F * F).astype(np.float32)
+  return xa[:, keep]
+
+
+def mmoe(x, experts, gates):
+  """layers/mmoe.py:55-83: experts = list of DNN layer lists (relu on every layer), gates = list of (W, b);
+  task output = sum_e softmax(x W + b)[e] * expert_e(x).  Returns one [B, H] array per task."""
+  x = x.astype(np.float32)
+  ex = np.stack([dnn_forward(x, layers)[0] for layers in experts], axis=1)   # [B, E, H]
+  outs = []
+  for w, b in gates:
+    logit = (x @ np.asarray(w, np.float32) + np.asarray(b, np.float32)).astype(np.float32)
+    e = np.exp(logit - logit.max(axis=1, keepdims=True), dtype=np.float32)
+    g = (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    outs.append((ex * g[:, :, None]).sum(axis=1, dtype=np.float32))
+  return outs
+
+
+def l2_normalize(x, eps=1e-12):
+  """tf.nn.l2_normalize over the last axis (model/dssm.py:64-66 via match_model.norm)."""
+  x = x.astype(np.float32)
+  return (x / np.sqrt(np.maximum((x * x).sum(axis=-1, keepdims=True, dtype=np.float32), np.float32(eps)))).astype(np.float32)
+
+
+def inbatch_softmax_ce(sim, item_ids=None, weights=None):
+  """model/match_model.py:50-69 + model/dssm.py:90-93 + match_model.py:213-226: in-batch duplicates of the
+  positive item are pushed to -1e32, softmax over the row, loss = -mean(log(p_bb + 1e-12) * w) / mean(w).
+  sim [B, N >= B].  Returns (loss, probs [B, N])."""
+  sim = sim.astype(np.float32).copy()
+  B = sim.shape[0]
+  if item_ids is not None:
+    ids = np.asarray(item_ids)[:B]
+    dup = (ids[None, :] == ids[:, None]).astype(np.float32) - np.eye(B, dtype=np.float32)
+    sim[:, :B] = sim[:, :B] - dup * np.float32(1e32)
+  e = np.exp(sim - sim.max(axis=1, keepdims=True), dtype=np.float32)
+  probs = (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+  w = np.ones(B, np.float32) if weights is None else np.asarray(weights, np.float32)
+  hit = probs[np.arange(B), np.arange(B)]
+  loss = -np.mean(np.log(hit + np.float32(1e-12)) * w, dtype=np.float32) / np.mean(w, dtype=np.float32)
+  return np.float32(loss), probs

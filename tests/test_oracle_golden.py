@@ -361,3 +361,39 @@ def test_pooling_oracle_follows_tensorflows_safe_lookup_test_cases(weighted):
   for r, spec in enumerate(k['expected_weighted' if weighted else 'expected_no_weights']):
     want = np.zeros(4, np.float32) if spec is None else sum(w * e[i] for i, w in spec['terms']) / spec['div']
     np.testing.assert_allclose(got[r], want, rtol=1e-6, atol=1e-6)
+
+
+def test_interaction_oracles_match_the_reference_code_outputs():
+  """DIN target attention, DCN cross v1, keras Cross (full / low rank), dot interaction, MMoE, list-wise match loss:
+  the numpy restatements in oracle/oracle.py against the golden vectors produced by executing the reference."""
+  c = FORMULAS['cases']
+  f32 = np.float32
+
+  def A(x):
+    return np.array(x, f32)
+  d = c['din_target_attention']
+  att = O.din_attention(A(d['key']), A(d['hist']), np.array(d['lens']), _layers(d['mlp']))
+  np.testing.assert_allclose(np.concatenate([att, A(d['key'])], axis=1), A(d['y']), rtol=1e-5, atol=1e-6)
+  d = c['dcn_cross']
+  np.testing.assert_allclose(O.cross_v1(A(d['x']), d['w'], d['b']), A(d['y']), rtol=1e-5, atol=1e-6)
+  d = c['keras_cross_full']
+  np.testing.assert_allclose(O.cross_v2(A(d['x0']), A(d['x']), d['w'], d['b'], d['diag_scale']), A(d['y']), rtol=1e-5, atol=1e-6)
+  d = c['keras_cross_lowrank']
+  np.testing.assert_allclose(O.cross_v2(A(d['x0']), A(d['x']), d['v'], d['b'], u=d['u']), A(d['y']), rtol=1e-5, atol=1e-6)
+  for key in ('dot_interaction_self0', 'dot_interaction_self1'):
+    d = c[key]
+    np.testing.assert_allclose(O.dot_interaction(A(d['x']), d['self_interaction']), A(d['y']), rtol=1e-5, atol=1e-5)
+  d = c['mmoe']
+  got = O.mmoe(A(d['x']), [_layers(e) for e in d['experts']], [(g['w'], g['b']) for g in d['gates']])
+  for a, b in zip(got, d['y']):
+    np.testing.assert_allclose(a, A(b), rtol=1e-5, atol=1e-6)
+  d = c['match_listwise']
+  user, item = O.l2_normalize(A(d['user'])), O.l2_normalize(A(d['item']))
+  np.testing.assert_allclose(user, A(d['user']), rtol=1e-6, atol=1e-6)       # already unit rows
+  sim = (user @ item.T / f32(d['temperature'])).astype(f32)
+  np.testing.assert_allclose(sim, A(d['sim']), rtol=1e-5, atol=1e-5)
+  loss, probs = O.inbatch_softmax_ce(A(d['sim']), d['item_ids'], d['sample_weight'])
+  np.testing.assert_allclose(probs, A(d['probs']), rtol=1e-5, atol=1e-7)
+  assert abs(float(loss) - d['cross_entropy_loss']) < 1e-5
+  reg_pos = np.mean(np.maximum(-(user * item).sum(1), 0) * A(d['sample_weight'])) / np.mean(A(d['sample_weight']))
+  assert abs(float(reg_pos) - d['reg_pos_loss']) < 1e-6
