@@ -397,3 +397,14 @@ def test_interaction_oracles_match_the_reference_code_outputs():
   assert abs(float(loss) - d['cross_entropy_loss']) < 1e-5
   reg_pos = np.mean(np.maximum(-(user * item).sum(1), 0) * A(d['sample_weight'])) / np.mean(A(d['sample_weight']))
   assert abs(float(reg_pos) - d['reg_pos_loss']) < 1e-6
+
+
+def test_sigmoid_cross_entropy_oracle_reproduces_tensorflows_loss_test_values():
+  for c in KATS['sigmoid_cross_entropy']['cases']:
+    loss, _, _ = O.sigmoid_ce(np.array(c['logits'], np.float32), np.array(c['labels'], np.float32))
+    assert round(abs(loss - c['expected']), c['places']) == 0
+  # weights: the sum is divided by the number of NON-ZERO weights, not by their sum or by the batch size
+  x, z, w = np.array([2.0, -1.0, 0.5, 3.0], np.float32), np.array([0, 1, 1, 0], np.float32), np.array([3.0, 0.0, 0.5, 2.0], np.float32)
+  per = np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
+  loss, _, _ = O.sigmoid_ce(x, z, w)
+  assert abs(loss - float((per * w).sum() / 3)) < 1e-6
