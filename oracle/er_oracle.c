@@ -21,7 +21,7 @@
  *     executed on two ranks (tests/golden/make_lookup_golden.py).
  *   - sparse Adagrad: the constants of TensorFlow's adagrad_test.py; lazy Adam:
  *     compat/adam_s.py _apply_sparse_shared executed (tests/golden/make_formula_golden.py).
- *   - sigmoid cross entropy and the dedup order: parity unpinned (TensorFlow-owned, no
+ *   - sigmoid cross entropy and the summation order of duplicated rows: parity unpinned (TensorFlow-owned, no
  *     known-answer vector available offline).
  *
  * Third-party arithmetic restated here (absent from /root/reference):

@@ -13,7 +13,7 @@ answers, and to golden vectors obtained by EXECUTING the reference's own functio
 shim (tests/golden/make_*_golden.py: FM, DCN cross, keras Cross, dot interaction, DIN attention,
 MMoE, list-wise match loss, DeepFM head, lazy Adam, LR schedule, pooling, shard rule, Parquet
 batches, checkpoint layout, GAUC).  Still unpinned: Fingerprint64 beyond 16 bytes, batch-norm /
-dense arithmetic and sigmoid cross entropy (TensorFlow-owned), the dedup order.
+dense arithmetic and sigmoid cross entropy (TensorFlow-owned), the summation order inside duplicated rows.
 """
 import ctypes
 import os
