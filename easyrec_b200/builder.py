@@ -191,6 +191,13 @@ def check_scope(pipeline_config):
     bad.append('model_config.kd (knowledge distillation losses)')
   if mc.HasField('variational_dropout'):
     bad.append('model_config.variational_dropout')
+  if tc.gradient_clipping_by_norm > 0:
+    bad.append('train_config.gradient_clipping_by_norm (global-norm clipping needs every gradient, sparse rows included, '
+               'before any update: not available with the row update fused into the backward pass)')
+  if len(tc.freeze_gradient) > 0:
+    bad.append('train_config.freeze_gradient')
+  if tc.fine_tune_checkpoint:
+    bad.append('train_config.fine_tune_checkpoint (TF checkpoints cannot be read here; use EasyRecEstimator.restore)')
   if len(tc.optimizer_config) > 1:
     bad.append('two optimizer_config entries (separate embedding / dense optimizers, easy_rec_model.py:446-467)')
   if any(oc.use_moving_average for oc in tc.optimizer_config):
