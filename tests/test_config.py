@@ -290,3 +290,23 @@ def test_tower_options_that_are_not_implemented_are_refused():
     cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'dnn { hidden_units: [32, 16] }', new))
     with pytest.raises(NotImplementedError, match=word):
       builder.check_scope(cfg)
+
+
+def test_every_config_embedded_in_the_gpu_tests_builds_without_a_gpu():
+  """the GPU tests cannot run in the build container; at least their configs must pass every host-side check
+  (scope, feature plan, optimizer settings, backbone dry run) here."""
+  import importlib
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  n = 0
+  for mod in ('test_gpu_models', 'test_gpu_estimator'):
+    m = importlib.import_module(mod)
+    for name in dir(m):
+      v = getattr(m, name)
+      if isinstance(v, str) and 'model_config' in v:
+        text = v % dict(dir='/tmp/m', kind='CSVInput') if '%(' in v else v
+        cfg = config_util.get_configs_from_pipeline_file(text.encode())
+        il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+        assert callable(opt['lr_fn']) and sum(p.numel() for p in model.parameters()) > 0, name
+        n += 1
+  assert n >= 10
