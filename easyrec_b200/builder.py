@@ -39,6 +39,15 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
       specs.append(IL.id_feature(name, fc.embedding_dim, hash_bucket_size=fc.hash_bucket_size,
                                  num_buckets=fc.num_buckets, combiner=fc.combiner,
                                  embedding_name=fc.embedding_name, packed_mod=packed_mod, host_hashed=host_hashed))
+    elif ftype == 'ComboFeature':
+      # crossed_column over the inputs' string forms (feature_column/feature_column.py:424-455): the reader computes
+      # FingerprintCat64 over the inputs' fingerprints % hash_bucket_size (readers.cross_hash); an id slot from there on
+      if len(fc.combo_join_sep) > 0 or len(fc.combo_input_seps) > 0:
+        raise NotImplementedError('ComboFeature %s: combo_join_sep / combo_input_seps' % name)
+      if len(fc.input_names) < 2 or fc.hash_bucket_size <= 0:
+        raise ValueError('ComboFeature %s needs at least two input_names and a hash_bucket_size' % name)
+      specs.append(IL.id_feature(name, fc.embedding_dim, hash_bucket_size=fc.hash_bucket_size, combiner=fc.combiner,
+                                 embedding_name=fc.embedding_name, host_hashed=True))
     elif ftype == 'RawFeature' and raw_boundaries(fc) is not None:
       # bucketized column (feature_column/feature_column.py:364-386): the reader turns the value into its bucket
       # (readers.bucketize_raw), from there on it is an id feature over len(boundaries) + 1 rows

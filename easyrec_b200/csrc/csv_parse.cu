@@ -5,6 +5,7 @@
 // No CUDA: the result is what the trainer copies to the device.  Lines are split across std::threads.
 #include <cerrno>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -135,6 +136,17 @@ struct LineErr {
 
 }  // namespace
 }  // namespace er
+
+extern "C" int er_fingerprint64_i64(const int64_t* values, int64_t n, uint64_t* out) {
+  using namespace er;
+  ER_REQUIRE((values && out) || n == 0, "null argument");
+  char buf[32];
+  for (int64_t i = 0; i < n; ++i) {
+    const int len = std::snprintf(buf, sizeof(buf), "%lld", (long long)values[i]);   // tf.as_string of an int64
+    out[i] = er_fingerprint64_host(buf, (size_t)len);
+  }
+  return ER_OK;
+}
 
 extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
                             int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed) {

@@ -31,6 +31,53 @@ def bucketize_raw(x, fc):
   return np.searchsorted(bounds, x, side='right').astype(np.int64)
 
 
+FP_EMPTY = 0x9ae16a3b2f90404f       # Fingerprint64('')
+CROSS_HASH_KEY = 0xDECAFCAFFE       # sparse_ops._DEFAULT_HASH_KEY, what crossed_column(hash_key=None) uses
+
+
+def fingerprint_cat64(fp1, fp2):
+  """tensorflow::FingerprintCat64 on uint64 arrays (platform/fingerprint.h): how the SparseCross kernel folds
+  the next column's feature into the running hash."""
+  k = np.uint64(0xc6a4a7935bd1e995)
+  s47 = np.uint64(47)
+  with np.errstate(over='ignore'):
+    r = fp1 ^ k
+    t = fp2 * k
+    r = r ^ ((t ^ (t >> s47)) * k)
+    r = r * k
+    r = (r ^ (r >> s47)) * k
+    return r ^ (r >> s47)
+
+
+def cross_hash(fingerprints, num_buckets, hash_key=CROSS_HASH_KEY):
+  """crossed_column / sparse_cross_hashed over one value per column: `fingerprints` = list of uint64 arrays (a
+  string input contributes Fingerprint64(bytes), an integer column its value), folded left to right from hash_key,
+  then % num_buckets as uint64 (feature_column_v2.py:4532-4552)."""
+  h = np.full(np.asarray(fingerprints[0]).shape, hash_key, np.uint64)
+  for fp in fingerprints:
+    h = fingerprint_cat64(h, np.asarray(fp).astype(np.uint64))
+  return (h % np.uint64(num_buckets)).astype(np.int64)
+
+
+def fingerprint_i64(values):
+  """Fingerprint64 of the decimal text of int64 values (tf.as_string first, input/input.py:356-376)."""
+  v = np.ascontiguousarray(values, np.int64)
+  out = np.empty(v.shape, np.uint64)
+  _lib.check(_lib.load().er_fingerprint64_i64(v.ctypes.data, v.size, out.ctypes.data), 'er_fingerprint64_i64')
+  return out
+
+
+def _combo_features(pipeline_config, input_layer):
+  """feature name -> (input field names, hash_bucket_size) for the ComboFeatures of the plan."""
+  out = {}
+  for fc in config_util.get_feature_configs(pipeline_config):
+    ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
+    name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+    if ftype == 'ComboFeature' and name in input_layer.sparse_names:
+      out[name] = (list(fc.input_names), fc.hash_bucket_size)
+  return out
+
+
 def _bucketized_features(pipeline_config, input_layer):
   """feature name -> FeatureConfig for the RawFeatures the plan treats as bucket ids."""
   from easyrec_b200 import builder
@@ -109,6 +156,11 @@ class CSVInput(object):
     self.feature_inputs = {}
     self.hash_buckets = {}     # feature -> hash_bucket_size when its STRING field is hashed here, on the host
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
+    self.combos = _combo_features(pipeline_config, input_layer)
+    for n in self.combos:
+      self.hash_buckets.pop(n, None)
+    # fields a cross reads: parsed to raw fingerprints (STRING) or integers (INT), every consumer derives from those
+    self.cross_fields = set(f for fields, _ in self.combos.values() for f in fields)
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = (fc.input_names[0], fc.separator or seq_sep)
@@ -125,6 +177,28 @@ class CSVInput(object):
     if nb:
       return _lib.fingerprint64(x) % nb if x != '' else -1
     return int(x)
+
+  def _combo_column(self, cols, feature):
+    """ComboFeature, one row at a time in python ints (the restatement the vectorised path is tested against)."""
+    fields, nb = self.combos[feature]
+    mask = (1 << 64) - 1
+    k = 0xc6a4a7935bd1e995
+
+    def cat(a, b):
+      r = a ^ k
+      t = (b * k) & mask
+      r ^= ((t ^ (t >> 47)) * k) & mask
+      r = (r * k) & mask
+      r = ((r ^ (r >> 47)) * k) & mask
+      return r ^ (r >> 47)
+    out = []
+    for i in range(len(cols[fields[0]])):
+      h = CROSS_HASH_KEY
+      for f in fields:
+        x = cols[f][i] if cols[f][i] != '' else (self.defaults.get(f) or ('' if self.ftypes[f] == 'STRING' else '0'))
+        h = cat(h, _lib.fingerprint64(x if self.ftypes[f] == 'STRING' else str(int(x))))
+      out.append(h % nb)
+    return np.array(out, np.int64)
 
   def _id_column(self, col, feature, default):
     if feature in self.bucketized:
@@ -146,9 +220,19 @@ class CSVInput(object):
         raise ValueError('input field %r is used by features that need different parsings' % field)
     for l in self.labels:
       want(l, (_lib.CSV_F32, 0, b',', 0.0, 0))
+    def raw_spec(field):
+      """a field read by a cross: raw Fingerprint64 of a STRING field / the integer of an INT field."""
+      if self.ftypes[field] == 'STRING':
+        return (_lib.CSV_HASH, 0, b',', self.defaults.get(field) or '', 0)
+      return (_lib.CSV_I64, 0, b',', int(self.defaults.get(field) or 0), 0)
     for n in il.sparse_names:
       src, _ = self.feature_inputs[n]
-      if n in self.hash_buckets:
+      if n in self.combos:
+        for f in self.combos[n][0]:
+          want(f, raw_spec(f))
+      elif src in self.cross_fields:
+        want(src, raw_spec(src))
+      elif n in self.hash_buckets:
         want(src, (_lib.CSV_HASH, 0, b',', self.defaults.get(src) or '', self.hash_buckets[n]))
       elif n in self.bucketized:
         want(src, (_lib.CSV_F32, 0, b',', float(self.defaults.get(src) or 0), 0))
@@ -239,14 +323,30 @@ class CSVInput(object):
       finally:
         del view
 
+  def _fingerprints(self, field, cols):
+    """uint64 fingerprint of a cross input per sample: the parsed Fingerprint64 of a STRING field, or
+    Fingerprint64(as_string(v)) of an INT field."""
+    arr = cols[field][0]
+    return arr.view(np.uint64) if self.ftypes[field] == 'STRING' else fingerprint_i64(arr)
+
+  def _ids_from_columns(self, n, cols):
+    src = self.feature_inputs[n][0]
+    if n in self.combos:
+      fields, nb = self.combos[n]
+      return cross_hash([self._fingerprints(f, cols) for f in fields], nb)
+    if n in self.bucketized:
+      return bucketize_raw(cols[src][0], self.bucketized[n])
+    if n in self.hash_buckets and src in self.cross_fields:   # the field was parsed to raw fingerprints for a cross
+      fp = cols[src][0].view(np.uint64)
+      return np.where(fp == np.uint64(FP_EMPTY), np.int64(-1), (fp % np.uint64(self.hash_buckets[n])).astype(np.int64))
+    return cols[src][0]
+
   def _pack_columns(self, cols):
     il = self.il
     B = self.batch_size
     feats = {}
     if il.sparse_names:
-      feats['sparse_fea'] = torch.from_numpy(np.concatenate(
-          [bucketize_raw(cols[self.feature_inputs[n][0]][0], self.bucketized[n]) if n in self.bucketized
-           else cols[self.feature_inputs[n][0]][0] for n in il.sparse_names]))
+      feats['sparse_fea'] = torch.from_numpy(np.concatenate([self._ids_from_columns(n, cols) for n in il.sparse_names]))
     if il.raw_names:
       dense = np.empty((B, il.n_dense), np.float32)
       for n in il.raw_names:
@@ -295,7 +395,7 @@ class CSVInput(object):
     ids = []
     for n in il.sparse_names:
       src, _ = self.feature_inputs[n]
-      ids.append(self._id_column(cols[src], n, self.defaults.get(src)))
+      ids.append(self._combo_column(cols, n) if n in self.combos else self._id_column(cols[src], n, self.defaults.get(src)))
     if ids:
       feats['sparse_fea'] = torch.from_numpy(np.concatenate(ids))
     if il.raw_names:
@@ -362,6 +462,7 @@ class ParquetInput(object):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = fc.input_names[0]
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
+    self.combos = _combo_features(pipeline_config, input_layer)
 
   @staticmethod
   def _column(col):
@@ -380,9 +481,27 @@ class ParquetInput(object):
     feats = {}
     ids = []
     for name in il.sparse_names:
+      if name in self.combos:
+        fields, nb = self.combos[name]
+        fps = []
+        for f in fields:
+          vals, lens = self._column(table.column(f))
+          if lens is not None:
+            raise ValueError('ComboFeature %r: input column %r holds lists' % (name, f))
+          fps.append(fingerprint_i64(vals) if np.asarray(vals).dtype.kind in 'iu' else
+                     np.array([_lib.fingerprint64(v if v is not None else '') for v in vals], np.uint64))
+        ids.append(cross_hash(fps, nb))
+        continue
       vals, lens = self._column(table.column(self.feature_inputs[name]))
       if name in self.bucketized:
         ids.append(bucketize_raw(vals, self.bucketized[name]))
+      elif lens is None and np.asarray(vals).dtype.kind in 'OUS':
+        # string column of a hashed feature: bucket on the host like the CSV reader ('' / null -> -1)
+        f = il.features[name]
+        if f.bucket_mode != _lib.BUCKET_IDENTITY:
+          raise ValueError('feature %r: string column %r needs a hash_bucket_size and a STRING input field'
+                           % (name, self.feature_inputs[name]))
+        ids.append(np.array([_lib.fingerprint64(v) % f.num_buckets if v else -1 for v in vals], np.int64))
       elif lens is None:
         ids.append(np.asarray(vals, np.int64))
       else:

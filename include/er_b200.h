@@ -453,6 +453,10 @@ typedef struct {
 int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
                  int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed);
 
+/* Fingerprint64 of the decimal text of each int64 (tf.as_string + the string hash): what an integer input of a
+ * crossed / hashed column contributes (input/input.py:356-376).  HOST pointers. */
+int er_fingerprint64_i64(const int64_t* values, int64_t n, uint64_t* out);
+
 /* ---- sharded-table restore: the LoadEmbed custom op (ops/src/load_dense_embed.cc:28-156;
  * python fallback compat/embedding_parallel_saver.py:141-173) ----
  * HOST function, HOST pointers (the op is a CPU kernel in the reference as well).  Reads every

@@ -310,3 +310,57 @@ def test_every_config_embedded_in_the_gpu_tests_builds_without_a_gpu():
         assert callable(opt['lr_fn']) and sum(p.numel() for p in model.parameters()) > 0, name
         n += 1
   assert n >= 10
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+def test_reference_avazu_combo_config_reads_synthetic_lines(tmp_path):
+  """samples/model_config/deepfm_combo_on_avazu_ctr.config, the DeepFM config of the reference's own train tests
+  (STRING hashed ids, bucketized RawFeatures, a ComboFeature): it builds unmodified and its reader turns text lines
+  into the buckets the TF graph would compute - checked per feature against the scalar restatements."""
+  import numpy as np
+  from easyrec_b200 import _lib
+  from easyrec_b200.input import readers
+  from oracle import oracle as O
+  cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, 'samples/model_config/deepfm_combo_on_avazu_ctr.config'))
+  cfg = config_util.edit_config(cfg, {'data_config.batch_size': 8})
+  il, model, _ = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  types = builder.input_field_types(cfg)
+  fields = [f.input_name for f in cfg.data_config.input_fields]
+  rng = np.random.default_rng(11)
+  rows = []
+  for i in range(8):
+    row = []
+    for f in fields:
+      if f in cfg.data_config.label_fields:
+        row.append(str(i % 2))
+      elif types[f] == 'STRING':
+        row.append('' if rng.uniform() < 0.15 else '%08x' % rng.integers(0, 2**32))
+      elif types[f] in ('INT32', 'INT64'):
+        row.append(str(rng.integers(0, 30)))
+      else:
+        row.append('%.3f' % rng.uniform(0, 30))
+    rows.append(row)
+  sep = cfg.data_config.separator
+  open(tmp_path / 'avazu.csv', 'w').write(''.join(sep.join(r) + '\n' for r in rows))
+  (feats, labels), = list(readers.make_input(cfg, il, str(tmp_path / 'avazu.csv')))
+  ids = feats['sparse_fea'].reshape(len(il.sparse_names), 8).numpy()
+  by_name = {(fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]): fc
+             for fc in config_util.get_feature_configs(cfg)}
+  defaults = {f.input_name: f.default_val for f in cfg.data_config.input_fields}
+  kinds = set()
+  for k, name in enumerate(il.sparse_names):
+    fc = by_name[name]
+    ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
+    cols = [[r[fields.index(f)] or defaults.get(f, '') for r in rows] for f in fc.input_names]
+    if ftype == 'ComboFeature':
+      want = readers.cross_hash([np.array([O.fingerprint64(v) for v in col], np.uint64) for col in cols],
+                                fc.hash_bucket_size).tolist()
+    elif ftype == 'RawFeature':
+      want = readers.bucketize_raw([float(v or 0) for v in cols[0]], fc).tolist()
+    elif types[fc.input_names[0]] == 'STRING':
+      want = [O.fingerprint64(v) % fc.hash_bucket_size if v != '' else -1 for v in cols[0]]
+    else:
+      continue          # integer ids go to the device untouched
+    kinds.add(ftype)
+    assert ids[k].tolist() == want, name
+  assert kinds == {'ComboFeature', 'RawFeature', 'IdFeature'}

@@ -211,3 +211,70 @@ def test_er_csv_parse_integer_range_and_spellings():
     assert parse(bad)[0] == _lib.ER_ERR_INVALID_ARG, bad     # out of int64 range / not an integer: refused like decode_csv
   assert parse('00000000000000000000012') == (0, 12) and parse('+5') == (0, 5) and parse(' 42 ') == (0, 42)
   assert parse('') == (0, -77)                                 # empty -> record default
+
+
+def test_combo_feature_is_tensorflows_crossed_column_hash(tmp_path):
+  """ComboFeature = crossed_column(inputs as strings, hash_bucket_size) (feature_column/feature_column.py:424-455).
+  The cross hash is pinned to TensorFlow's own crossed-column test (feature_column_test.py CrossedColumnTest:
+  bucketized [-1, .5], [.5, 1.] with boundaries (0, 1) x ['cA'], ['cB', 'cC'], hash_key 5, 5 buckets ->
+  (1, 0, 1, 3, 4, 2)); the readers must produce the same buckets from text / Parquet, for STRING and INT inputs,
+  and a field shared with a hashed IdFeature must still yield that feature's own bucket."""
+  import pyarrow as pa
+  import pyarrow.parquet as pq
+  from oracle import oracle as O
+  import json
+  k = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_kats.json')))['crossed_column']
+  b = np.array(k['int_column'], np.uint64)               # bucket + 3 * k for the 2-wide bucketized column
+  c = np.array([O.fingerprint64(s) for s in k['string_column']], np.uint64)
+  assert readers.cross_hash([b, c], k['num_buckets'], hash_key=k['hash_key']).tolist() == k['expected'] == [1, 0, 1, 3, 4, 2]
+  assert (readers.fingerprint_i64(np.array([101, 201, 301])) % 10).tolist() == [3, 7, 5]
+  cfg_text = b'''
+data_config { batch_size: 6 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT }
+  input_fields { input_name: "site_id" input_type: STRING }
+  input_fields { input_name: "app_id" input_type: STRING default_val: "none" }
+  input_fields { input_name: "hour" input_type: INT64 } }
+feature_config {
+  features { input_names: "site_id" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 100 }
+  features { input_names: ["site_id", "app_id"] feature_name: "site_app" feature_type: ComboFeature embedding_dim: 8 hash_bucket_size: 1000 }
+  features { input_names: ["app_id", "hour", "site_id"] feature_name: "app_hour_site" feature_type: ComboFeature embedding_dim: 8 hash_bucket_size: 50 }
+}
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["site_id", "site_app", "app_hour_site"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["site_id", "site_app", "app_hour_site"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } } }
+'''
+  cfg = config_util.get_configs_from_pipeline_file(cfg_text)
+  il, _, _ = builder.build_model(cfg, 6, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert il.sparse_names == ['site_id', 'site_app', 'app_hour_site']
+  assert all(il.features[n].bucket_mode == _lib.BUCKET_IDENTITY for n in il.sparse_names)
+  rows = [('85f751fd', 'ecad2386', '14102100'), ('', 'ecad2386', '-3'), ('1fbe01fe', '', '7'), ('x' * 40, 'y', '0'),
+          ('85f751fd', 'ecad2386', '14102100'), ('', '', '12')]
+  open(tmp_path / 'a.csv', 'w').write(''.join('1,%s,%s,%s\n' % r for r in rows))
+
+  def cat(a, bb):                                         # FingerprintCat64 in python ints
+    m, k = (1 << 64) - 1, 0xc6a4a7935bd1e995
+    r = a ^ k
+    t = (bb * k) & m
+    r ^= ((t ^ (t >> 47)) * k) & m
+    r = (r * k) & m
+    r = ((r ^ (r >> 47)) * k) & m
+    return r ^ (r >> 47)
+
+  def cross(strings, nb):
+    h = 0xDECAFCAFFE
+    for s_ in strings:
+      h = cat(h, O.fingerprint64(s_))
+    return h % nb
+  want_site = [O.fingerprint64(s_) % 100 if s_ else -1 for s_, _, _ in rows]
+  want_sa = [cross([s_, a or 'none'], 1000) for s_, a, _ in rows]
+  want_ahs = [cross([a or 'none', str(int(h)), s_], 50) for s_, a, h in rows]
+  for engine in ('native', 'python'):
+    (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 'a.csv'), engine=engine))
+    assert feats['sparse_fea'].reshape(3, 6).tolist() == [want_site, want_sa, want_ahs], engine
+  assert want_sa[0] == want_sa[4] and -1 in want_site
+  pq.write_table(pa.table({'label': np.ones(6, np.float32), 'site_id': [r[0] for r in rows],
+                           'app_id': [r[1] or 'none' for r in rows], 'hour': np.array([int(r[2]) for r in rows], np.int64)}),
+                 str(tmp_path / 'a.parquet'))
+  (feats, _), = list(readers.ParquetInput(cfg, il, str(tmp_path / 'a.parquet')))
+  assert feats['sparse_fea'].reshape(3, 6).tolist() == [want_site, want_sa, want_ahs]
