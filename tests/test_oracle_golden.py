@@ -408,3 +408,18 @@ def test_sigmoid_cross_entropy_oracle_reproduces_tensorflows_loss_test_values():
   per = np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
   loss, _, _ = O.sigmoid_ce(x, z, w)
   assert abs(loss - float((per * w).sum() / 3)) < 1e-6
+
+
+def test_bucketize_and_mean_pooling_reproduce_tensorflows_feature_column_tests():
+  import types
+  from easyrec_b200.input import readers
+  k = KATS['bucketized_column']
+  fc = types.SimpleNamespace(boundaries=k['boundaries'], num_buckets=0, min_val=0.0, max_val=0.0)
+  got = readers.bucketize_raw(k['x'], fc)
+  assert got.tolist() == k['expected_buckets']
+  n = len(k['boundaries']) + 1                         # a 2-wide column offsets the k-th value by (len + 1) * k
+  assert [int(b) + n * (i % 2) for i, b in enumerate(got)] == k['expected_ids_dim2']
+  k = KATS['embedding_column_mean']
+  row_ptr, _ = O.csr_from_lens(np.array(k['lens'], np.int32))
+  out, _ = O.embedding_fwd(np.array(k['table'], np.float32), np.array(k['ids'], np.int64), row_ptr, 1)
+  np.testing.assert_allclose(out, np.array(k['expected'], np.float32), rtol=1e-6, atol=1e-6)
