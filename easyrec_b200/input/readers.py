@@ -157,13 +157,13 @@ class CSVInput(object):
     self.hash_buckets = {}     # feature -> hash_bucket_size when its STRING field is hashed here, on the host
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
     self.combos = _combo_features(pipeline_config, input_layer)
-    for n in self.combos:
-      self.hash_buckets.pop(n, None)
     # fields a cross reads: parsed to raw fingerprints (STRING) or integers (INT), every consumer derives from those
     self.cross_fields = set(f for fields, _ in self.combos.values() for f in fields)
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = (fc.input_names[0], fc.separator or seq_sep)
+      if name in self.combos:
+        continue
       if fc.hash_bucket_size > 0 and self.ftypes.get(fc.input_names[0]) == 'STRING' and name in input_layer.features:
         assert input_layer.features[name].bucket_mode in (_lib.BUCKET_IDENTITY, _lib.BUCKET_MOD), \
             'feature %s: the table plan must take host-hashed buckets (builder.feature_specs)' % name
@@ -224,6 +224,9 @@ class CSVInput(object):
       """a field read by a cross: raw Fingerprint64 of a STRING field / the integer of an INT field."""
       if self.ftypes[field] == 'STRING':
         return (_lib.CSV_HASH, 0, b',', self.defaults.get(field) or '', 0)
+      if self.ftypes[field] not in ('INT32', 'INT64'):
+        raise NotImplementedError('ComboFeature input %r of type %s (as_string of a float needs its precision)'
+                                  % (field, self.ftypes[field]))
       return (_lib.CSV_I64, 0, b',', int(self.defaults.get(field) or 0), 0)
     for n in il.sparse_names:
       src, _ = self.feature_inputs[n]
