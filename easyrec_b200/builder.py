@@ -51,10 +51,15 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     elif ftype == 'RawFeature' and raw_boundaries(fc) is not None:
       # bucketized column (feature_column/feature_column.py:364-386): the reader turns the value into its bucket
       # (readers.bucketize_raw), from there on it is an id feature over len(boundaries) + 1 rows
-      if fc.raw_input_dim != 1:
-        raise NotImplementedError('bucketized RawFeature %s with raw_input_dim %d' % (name, fc.raw_input_dim))
-      specs.append(IL.id_feature(name, fc.embedding_dim, num_buckets=len(raw_boundaries(fc)) + 1, combiner=fc.combiner,
-                                 embedding_name=fc.embedding_name))
+      n_bucket = len(raw_boundaries(fc)) + 1
+      if fc.raw_input_dim == 1:
+        specs.append(IL.id_feature(name, fc.embedding_dim, num_buckets=n_bucket, combiner=fc.combiner,
+                                   embedding_name=fc.embedding_name))
+      else:
+        # k values per sample -> k ids `bucket + (len(boundaries) + 1) * k_index` (feature_column_v2.py:2849-2870),
+        # pooled by the feature's combiner: a fixed-length tag slot
+        specs.append(IL.multi_feature(name, 'tag', fc.embedding_dim, num_buckets=n_bucket * fc.raw_input_dim,
+                                      combiner=fc.combiner, embedding_name=fc.embedding_name))
     elif ftype == 'RawFeature':
       specs.append(IL.raw_feature(name, fc.embedding_dim, fc.min_val, fc.max_val, fc.raw_input_dim))
     elif ftype in ('TagFeature', 'SequenceFeature'):

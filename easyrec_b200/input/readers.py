@@ -78,6 +78,16 @@ def _combo_features(pipeline_config, input_layer):
   return out
 
 
+def bucketize_raw_multi(x, fc):
+  """[n, k] values of a k-wide bucketized RawFeature -> ids `bucket + (len(boundaries) + 1) * k_index`, row-major
+  (feature_column_v2.py:2849-2870); the matching lens are k per sample."""
+  from easyrec_b200 import builder
+  x = np.asarray(x, np.float32).reshape(-1, fc.raw_input_dim)
+  n_bucket = len(builder.raw_boundaries(fc)) + 1
+  ids = bucketize_raw(x, fc) + n_bucket * np.arange(fc.raw_input_dim, dtype=np.int64)[None, :]
+  return ids.reshape(-1), np.full(x.shape[0], fc.raw_input_dim, np.int32)
+
+
 def _bucketized_features(pipeline_config, input_layer):
   """feature name -> FeatureConfig for the RawFeatures the plan treats as bucket ids."""
   from easyrec_b200 import builder
@@ -85,8 +95,8 @@ def _bucketized_features(pipeline_config, input_layer):
   for fc in config_util.get_feature_configs(pipeline_config):
     name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
     ftype = fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
-    if ftype == 'RawFeature' and builder.raw_boundaries(fc) is not None and name in input_layer.sparse_names:
-      out[name] = fc
+    if ftype == 'RawFeature' and builder.raw_boundaries(fc) is not None and name in input_layer.features:
+      out[name] = fc     # a single-valued id slot (raw_input_dim 1) or a fixed-length tag slot (raw_input_dim k)
   return out
 
 
@@ -247,7 +257,10 @@ class CSVInput(object):
       d = float(self.defaults.get(src) or 0)
       want(src, (_lib.CSV_F32, 0, b',', d, 0) if c1 - c0 == 1 else (_lib.CSV_F32_VEC, c1 - c0, sep.encode(), d, 0))
     for f in il.features.values():
-      if f.kind in ('seq', 'tag'):
+      if f.kind == 'tag' and f.name in self.bucketized:
+        src, sep = self.feature_inputs[f.name]
+        want(src, (_lib.CSV_F32_VEC, self.bucketized[f.name].raw_input_dim, sep.encode(), float(self.defaults.get(src) or 0), 0))
+      elif f.kind in ('seq', 'tag'):
         src, sep = self.feature_inputs[f.name]
         nb = self.hash_buckets.get(f.name, 0)
         want(src, (_lib.CSV_HASH_LIST if nb else _lib.CSV_I64_LIST, f.seq_len if f.kind == 'seq' else 0, sep.encode(), 0, nb))
@@ -360,6 +373,10 @@ class CSVInput(object):
     for f in il.features.values():
       if f.kind not in ('seq', 'tag'):
         continue
+      if f.name in self.bucketized:
+        v, l = bucketize_raw_multi(cols[self.feature_inputs[f.name][0]][0], self.bucketized[f.name])
+        tag[f.name] = (torch.from_numpy(v), torch.from_numpy(l), None)
+        continue
       vals, lens = cols[self.feature_inputs[f.name][0]]
       if f.kind == 'seq':
         arr = np.zeros((B, f.seq_len), np.int64)
@@ -416,6 +433,16 @@ class CSVInput(object):
       if f.kind not in ('seq', 'tag'):
         continue
       src, sep = self.feature_inputs[f.name]
+      if f.name in self.bucketized:
+        k = self.bucketized[f.name].raw_input_dim
+        d = float(self.defaults.get(src) or 0)
+        mat = np.zeros((len(rows), k), np.float32)
+        for i, x in enumerate(cols[src]):
+          vals = x.split(sep) if x != '' else [str(d)]
+          mat[i, :len(vals[:k])] = [float(v) if v != '' else d for v in vals[:k]]
+        v, l = bucketize_raw_multi(mat, self.bucketized[f.name])
+        tag[f.name] = (torch.from_numpy(v), torch.from_numpy(l), None)
+        continue
       toks = [[t for t in x.split(sep) if t != ''] for x in cols[src]]
       if f.kind == 'seq':
         T = f.seq_len
@@ -528,6 +555,10 @@ class ParquetInput(object):
       if f.kind not in ('seq', 'tag'):
         continue
       vals, lens = self._column(table.column(self.feature_inputs[f.name]))
+      if f.name in self.bucketized:
+        v, l = bucketize_raw_multi(vals, self.bucketized[f.name])
+        tag[f.name] = (torch.from_numpy(v), torch.from_numpy(l), None)
+        continue
       vals = np.array(vals, np.int64)   # owned, writable copy (arrow buffers are read-only)
       if lens is None:
         lens = np.ones(n, np.int32)

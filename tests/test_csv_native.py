@@ -278,3 +278,35 @@ model_config { model_class: "DeepFM"
                  str(tmp_path / 'a.parquet'))
   (feats, _), = list(readers.ParquetInput(cfg, il, str(tmp_path / 'a.parquet')))
   assert feats['sparse_fea'].reshape(3, 6).tolist() == [want_site, want_sa, want_ahs]
+
+
+def test_multi_dim_bucketized_raw_feature_reproduces_tensorflows_ids(tmp_path):
+  """BucketizedColumnTest: price shape (2,), boundaries [0, 2, 4, 6], [[-1., 1.], [5., 6.]] -> ids [0, 6, 3, 9]; here
+  the feature becomes a fixed-length tag slot over 5 * 2 rows fed with exactly those ids, from text and Parquet."""
+  import pyarrow as pa
+  import pyarrow.parquet as pq
+  cfg = config_util.get_configs_from_pipeline_file(b'''
+data_config { batch_size: 2 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "price" input_type: STRING }
+  input_fields { input_name: "uid" input_type: INT64 } }
+feature_config {
+  features { input_names: "price" feature_type: RawFeature raw_input_dim: 2 separator: "|" embedding_dim: 8
+             boundaries: [0.0, 2.0, 4.0, 6.0] combiner: "mean" }
+  features { input_names: "uid" feature_type: IdFeature embedding_dim: 8 num_buckets: 10 } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["price", "uid"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["price", "uid"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } } }
+''')
+  il, _, _ = builder.build_model(cfg, 2, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  f = il.features['price']
+  assert f.kind == 'tag' and f.num_buckets == 10 and f.bucket_mode == _lib.BUCKET_IDENTITY
+  open(tmp_path / 'p.csv', 'w').write('1,-1|1,3\n0,5|6,4\n')
+  pq.write_table(pa.table({'label': np.array([1, 0], np.float32), 'uid': np.array([3, 4], np.int64),
+                           'price': pa.array([[-1.0, 1.0], [5.0, 6.0]], pa.list_(pa.float32()))}), str(tmp_path / 'p.parquet'))
+  got = [list(readers.CSVInput(cfg, il, str(tmp_path / 'p.csv'), engine=e)) for e in ('native', 'python')]
+  got.append(list(readers.ParquetInput(cfg, il, str(tmp_path / 'p.parquet'))))
+  for (feats, _), in got:
+    ids, lens, w = feats['tag_fea']['price']
+    assert ids.tolist() == [0, 6, 3, 9] and lens.tolist() == [2, 2] and w is None
+    assert feats['sparse_fea'].tolist() == [3, 4]
