@@ -21,6 +21,15 @@ def check(ref_dir):
       if rv.get(v.name) != v.number:
         problems.append('%s: enum value %s=%d, reference %r' % (where, v.name, v.number, rv.get(v.name)))
 
+  def _attr(fd, attr):
+    if attr != 'label':
+      return getattr(fd, attr)
+    if hasattr(fd, 'is_repeated'):     # protobuf >= 5.29 deprecates FieldDescriptor.label
+      rep, req = fd.is_repeated, fd.is_required
+      rep, req = (rep() if callable(rep) else rep), (req() if callable(req) else req)
+      return 'repeated' if rep else 'required' if req else 'optional'
+    return {fd.LABEL_REPEATED: 'repeated', fd.LABEL_REQUIRED: 'required'}.get(fd.label, 'optional')
+
   def cmp_msg(sd, rd):
     rf = {f.name: f for f in rd.fields}
     for f in sd.fields:
@@ -29,8 +38,9 @@ def check(ref_dir):
         problems.append('%s.%s: not in reference' % (sd.full_name, f.name))
         continue
       for attr in ('number', 'type', 'label'):
-        if getattr(f, attr) != getattr(r, attr):
-          problems.append('%s.%s: %s %r != reference %r' % (sd.full_name, f.name, attr, getattr(f, attr), getattr(r, attr)))
+        a, b = _attr(f, attr), _attr(r, attr)
+        if a != b:
+          problems.append('%s.%s: %s %r != reference %r' % (sd.full_name, f.name, attr, a, b))
       if f.has_default_value != r.has_default_value or (f.has_default_value and f.default_value != r.default_value):
         problems.append('%s.%s: default %r != reference %r' % (sd.full_name, f.name, f.default_value, r.default_value))
       if f.message_type is not None and r.message_type is not None and f.message_type.name != r.message_type.name:
