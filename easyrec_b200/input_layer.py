@@ -211,8 +211,11 @@ class InputLayer(object):
                                     'put it in seq_att_groups (DIN)' % fname)
         table = (f.embedding_name or fname + '_embedding') + ('_wide' if wide else '')
         kind = 'tag' if f.kind == 'tag' else 'single'
-        add_slot(dim, gname, fname, table, kind, wide=wide)
-        layout.append([fname, 'emb', dim, dim, gname, None])
+        # one output matrix per (group, launch kind): the single-valued and the CSR launch of a mixed group
+        # write their own matrices, the group's concat is assembled from both in config order
+        out_key = gname if kind == 'single' else gname + '#tag'
+        add_slot(dim, out_key, fname, table, kind, wide=wide)
+        layout.append([fname, 'emb', dim, dim, out_key, None])
       self.group_layout[gname] = layout
     for sname, maps in self.seq_att_groups.items():
       lay = dict(key=[], hist=[], T=None)

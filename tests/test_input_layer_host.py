@@ -1,0 +1,167 @@
+"""CPU: the glue of InputLayer (table plan, slot descriptors, input gathering, tag CSR path, group layout,
+pending list -> backward update) with the four sparse kernels replaced by doubles whose bodies are the CPU
+oracle.  The kernels themselves are compared with that oracle on the GPU; what runs here is everything around
+them, on a config with every slot flavour: a device-hashed integer id, a weighted-mean TagFeature, a k-wide
+bucketized RawFeature (fixed-length tag slot) and a RawFeature projection, fed by the native CSV reader.
+
+The expectation is built feature by feature straight from the config semantics (table rows by name, bucket
+rules, pooling), independently of the slot plan."""
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import _lib, builder, kernels as K
+from easyrec_b200.config import config_util
+from easyrec_b200.input import readers
+from oracle import oracle as O
+
+CFG = b'''
+data_config { batch_size: 6 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "uid" input_type: INT64 }
+  input_fields { input_name: "tags" input_type: STRING } input_fields { input_name: "price" input_type: STRING }
+  input_fields { input_name: "age" input_type: FLOAT } }
+feature_config {
+  features { input_names: "uid" feature_type: IdFeature embedding_dim: 4 hash_bucket_size: 50 }
+  features { input_names: "tags" feature_type: TagFeature embedding_dim: 4 num_buckets: 20 separator: "|" combiner: "mean" }
+  features { input_names: "price" feature_type: RawFeature raw_input_dim: 2 separator: "|" embedding_dim: 4
+             boundaries: [0.0, 2.0, 4.0, 6.0] combiner: "sum" }
+  features { input_names: "age" feature_type: RawFeature embedding_dim: 4 min_val: 0.0 max_val: 100.0 } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["age", "uid", "price", "tags"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["uid", "tags"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [8] } final_dnn { hidden_units: [4] } } }
+'''
+ROWS = [('1', '7', '3|5|5', '-1|1', '10'), ('0', '-12', '', '5|6', '55.5'), ('1', '7', '19', '2|2', '0'),
+        ('0', '123456789012', '0|1|2|3', '7|-3', '100'), ('1', '0', '4', '0|0', '31'), ('0', '99', '6|6', '3.5|4', '77')]
+
+
+def _slots(slots_dev):
+  return np.frombuffer(slots_dev.numpy().tobytes(), dtype=K.SLOT_DTYPE)
+
+
+def _seg_field(sl, field, n_seg):
+  return np.concatenate([np.full(int(s['n_seg']), s[field]) for s in sl])[:n_seg]
+
+
+@pytest.fixture
+def oracle_kernels(monkeypatch):
+  def csr_from_lens(lens, cap, want_seg_ids=True):
+    row_ptr, seg = O.csr_from_lens(lens.numpy())
+    seg_ids = np.zeros(max(cap, 1), np.int32)
+    seg_ids[:seg.size] = seg
+    return torch.from_numpy(row_ptr), torch.from_numpy(seg_ids)
+
+  def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=None, owner=None):
+    sl = _slots(slots_dev)
+    n = ids.numel()
+    if row_ptr is None:
+      seg_of = np.arange(n)
+      live = np.ones(n, bool)
+    else:
+      total = int(row_ptr[-1])
+      seg_of = seg_ids.numpy()[:n].astype(np.int64)
+      live = np.arange(n) < total
+      seg_of = np.where(live, seg_of, 0)
+    per = lambda f: _seg_field(sl, f, n_seg)[seg_of]   # noqa: E731
+    r, _ = O.bucketize(ids.numpy(), per('bucket_mode'), per('num_buckets'), per('row_offset'))
+    r = np.where(live, r, -1)
+    out = rows if rows is not None else torch.empty_like(ids)
+    out.copy_(torch.from_numpy(r))
+    return out
+
+  def _csr(n_seg, rows, row_ptr):
+    return np.arange(n_seg + 1, dtype=np.int32) if row_ptr is None else row_ptr.numpy()
+
+  def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, outs, weights=None, row_ptr=None, seg_scale=None,
+                    row_stride=None):
+    sl = _slots(slots_dev)
+    rp = _csr(n_seg, rows, row_ptr)
+    pooled, scale = O.embedding_fwd(np.ascontiguousarray(table.numpy()), rows.numpy(), rp, _seg_field(sl, 'combiner', n_seg),
+                                    weights=None if weights is None else weights.numpy())
+    for s in sl:
+      out = outs[int(s['out_buf'])].view(-1)
+      for k in range(int(s['n_seg'])):
+        o = k * int(s['out_stride']) + int(s['out_col'])
+        out[o:o + dim] = torch.from_numpy(pooled[int(s['seg_begin']) + k])
+    if seg_scale is not None:
+      seg_scale.copy_(torch.from_numpy(scale))
+
+  def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt, ws, weights=None,
+                    seg_ids=None, row_ptr=None, seg_scale=None, row_stride=None, uniq_rows=None, uniq_grads=None,
+                    n_uniq=None, n_rows=None, sorted_from=None):
+    sl = _slots(slots_dev)
+    gseg = np.zeros((n_seg, dim), np.float32)
+    for s in sl:
+      buf = grad_bufs[int(s['out_buf'])].reshape(-1).numpy()
+      for k in range(int(s['n_seg'])):
+        o = k * int(s['out_stride']) + int(s['out_col'])
+        gseg[int(s['seg_begin']) + k] = buf[o:o + dim]
+    t, a = np.ascontiguousarray(table.numpy()), np.ascontiguousarray(state0.numpy())
+    O.embedding_bwd(t, a, None, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
+                    O.OPT_ADAGRAD, opt.lr, weights=None if weights is None else weights.numpy(),
+                    seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=opt.grad_scale)
+    table.copy_(torch.from_numpy(t))
+    state0.copy_(torch.from_numpy(a))
+  for name, fn in (('csr_from_lens', csr_from_lens), ('bucketize', bucketize), ('embedding_fwd', embedding_fwd),
+                   ('embedding_bwd', embedding_bwd)):
+    monkeypatch.setattr(K, name, fn)
+
+
+def _expected_deep(il, rows_txt):
+  """[B, 4 features x 4] in feature-group order age, uid, price, tags - straight from the config semantics."""
+  a = il.arenas[4]
+  tab = a.weight.numpy()
+
+  def table(name):
+    off, local, _ = a.tables[name + '_embedding']
+    return tab[off:off + local]
+  out = []
+  for _, uid, tags, price, age in rows_txt:
+    e_age = np.float32(float(age) / 100.0) * table('age')[0]                       # projection: x_norm * E[0]
+    e_uid = table('uid')[O.fingerprint64(str(int(uid))) % 50]                      # as_string -> hash -> mod
+    p = np.array([float(v) for v in price.split('|')], np.float32)
+    ids = np.searchsorted(np.array([0, 2, 4, 6], np.float32), p, side='right') + 5 * np.arange(2)
+    e_price = table('price')[ids].sum(0)                                           # k ids, sum combiner
+    t_ids = [int(v) for v in tags.split('|') if v != '']
+    e_tags = table('tags')[t_ids].mean(0) if t_ids else np.zeros(4, np.float32)    # mean; empty bag -> zeros
+    out.append(np.concatenate([e_age, e_uid, e_price, e_tags]))
+  return np.array(out, np.float32)
+
+
+def test_input_layer_glue_with_oracle_kernels(tmp_path, oracle_kernels):
+  cfg = config_util.get_configs_from_pipeline_file(CFG)
+  il, model, _ = builder.build_model(cfg, 6, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 'd.csv', 'w').write(''.join(','.join(r) + '\n' for r in ROWS))
+  (feats, labels), = list(readers.make_input(cfg, il, str(tmp_path / 'd.csv')))
+  groups = il.lookup(feats)
+  deep, per_feature = groups['deep']
+  want = _expected_deep(il, ROWS)
+  np.testing.assert_allclose(deep.detach().numpy()[:, :16], want, rtol=1e-6, atol=1e-6)
+  assert [tuple(v.shape) for v in per_feature] == [(6, 4)] * 4
+  wide, _ = groups['wide']
+  assert wide.shape[0] == 6 and wide.shape[1] >= 2
+  # ---- backward: every looked-up row moves by the Adagrad rule on the summed gradient ----
+  before = il.arenas[4].weight.clone()
+  g = torch.from_numpy(np.random.default_rng(1).normal(size=tuple(deep.shape)).astype(np.float32))
+  (deep * g).sum().backward()
+  il.set_optimizer_step(0.05, 0)
+  il.backward_update()
+  a = il.arenas[4]
+  tab0, G = before.numpy(), np.zeros_like(before.numpy())
+  gd = g.numpy()
+
+  def off(name):
+    return a.tables[name + '_embedding'][0]
+  for b, (_, uid, tags, price, age) in enumerate(ROWS):
+    G[off('age')] += np.float32(float(age) / 100.0) * gd[b, 0:4]
+    G[off('uid') + O.fingerprint64(str(int(uid))) % 50] += gd[b, 4:8]
+    p = np.array([float(v) for v in price.split('|')], np.float32)
+    for i in np.searchsorted(np.array([0, 2, 4, 6], np.float32), p, side='right') + 5 * np.arange(2):
+      G[off('price') + i] += gd[b, 8:12]
+    t_ids = [int(v) for v in tags.split('|') if v != '']
+    for i in t_ids:
+      G[off('tags') + i] += gd[b, 12:16] / len(t_ids)
+  acc = 0.1 + G * G
+  want_tab = np.where(G != 0, tab0 - 0.05 * G / np.sqrt(acc), tab0)
+  np.testing.assert_allclose(a.weight.numpy(), want_tab, rtol=1e-5, atol=1e-6)
+  assert (G != 0).any(1).sum() >= 10
