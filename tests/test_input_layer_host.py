@@ -188,3 +188,34 @@ def test_input_layer_glue_with_oracle_kernels(tmp_path, oracle_kernels):
     want_b = (e * ww[:, None]).sum(0) / ww.sum() if n else np.zeros(4, np.float32)
     np.testing.assert_allclose(deep2.detach().numpy()[b, 12:16], want_b, rtol=1e-5, atol=1e-6)
     o += n
+
+
+def test_reference_packed_batch_through_input_layer_matches_embedding_parallel_lookup(oracle_kernels):
+  """The reference's own packed batch form and its own lookup result: `embedding_parallel_lookup` executed on the
+  numpy shim (tests/golden/reference_lookup.json; ids, lens feature-major, one shared table, sum combiner,
+  [B, n_feat * D] output) against readers.from_reference_packed -> InputLayer.lookup on the same table."""
+  import json
+  import os
+  c = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_lookup.json')))['cases']['embedding_parallel_lookup']
+  B, F = c['batch_size'], c['n_feature']
+  table = np.array(c['table'], np.float32)
+  V, D = table.shape
+  names = ['f%d' % i for i in range(F)]
+  cfg = config_util.get_configs_from_pipeline_file((
+      'data_config { batch_size: %d input_type: ParquetInput label_fields: "label" '
+      'input_fields { input_name: "label" input_type: FLOAT } %s }\n'
+      'feature_config { %s }\n'
+      'model_config { model_class: "DeepFM" feature_groups { group_name: "deep" %s wide_deep: DEEP } '
+      'feature_groups { group_name: "wide" %s wide_deep: WIDE } deepfm { dnn { hidden_units: [8] } final_dnn { hidden_units: [4] } } }' % (
+          B, ' '.join('input_fields { input_name: "%s" input_type: INT64 }' % n for n in names),
+          ' '.join('features { input_names: "%s" feature_type: TagFeature embedding_dim: %d num_buckets: %d '
+                   'embedding_name: "embedding" combiner: "sum" }' % (n, D, V) for n in names),
+          ' '.join('feature_names: "%s"' % n for n in names), ' '.join('feature_names: "%s"' % n for n in names))).encode())
+  il, _, _ = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  off, local, _ = il.arenas[D].tables['embedding']
+  assert local == V
+  il.arenas[D].weight[off:off + V].copy_(torch.from_numpy(table))
+  for rank in c['ranks']:
+    feats = readers.from_reference_packed(il, {'sparse_fea': (np.array(rank['ids'], np.int64), np.array(rank['lens'], np.int32))}, names)
+    deep, _ = il.lookup(feats)['deep']
+    np.testing.assert_allclose(deep.detach().numpy()[:, :F * D], np.array(rank['y'], np.float32), rtol=1e-6, atol=1e-6)
