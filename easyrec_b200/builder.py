@@ -27,7 +27,9 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     # per-feature options that change which row / value a sample reads and are not implemented: refuse
     unsupported = [w for w, on in (
         ('vocab_file / vocab_list (vocabulary lookup)', fc.HasField('vocab_file') or len(fc.vocab_list) > 0),
-        ('kv_separator (weighted tags)', fc.HasField('kv_separator')),
+        ('kv_separator on a feature that is not a TagFeature', fc.HasField('kv_separator') and ftype_name(fc) != 'TagFeature'),
+        ('a separate weight input (second input_names entry of a TagFeature)',
+         ftype_name(fc) == 'TagFeature' and len(fc.input_names) > 1),
         ('seq_multi_sep (multi-valued sequence steps)', fc.HasField('seq_multi_sep')),
         ('normalizer_fn', fc.HasField('normalizer_fn')),
         ('shared_names', len(fc.shared_names) > 0),
@@ -72,6 +74,10 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     else:
       raise NotImplementedError('feature_type %s (feature %s) is outside the hot-path scope' % (ftype, name))
   return specs
+
+
+def ftype_name(fc):
+  return fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[fc.feature_type].name
 
 
 def raw_boundaries(fc):

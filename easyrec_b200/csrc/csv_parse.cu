@@ -19,7 +19,8 @@ extern "C" uint64_t er_fingerprint64_host(const char* s, size_t len);
 namespace er {
 namespace {
 
-inline bool is_list(int kind) { return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST; }
+inline bool is_kv(int kind) { return kind == ER_CSV_I64_KV_LIST || kind == ER_CSV_HASH_KV_LIST; }
+inline bool is_list(int kind) { return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST || is_kv(kind); }
 
 struct Span {
   const char* p;
@@ -155,9 +156,10 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
   ER_REQUIRE(n_cols > 0 && max_rows >= 0, "bad n_cols / max_rows");
   for (int c = 0; c < n_cols; ++c) {
     const er_csv_col_t& k = cols[c];
-    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_HASH_LIST, "unknown column kind");
+    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_HASH_KV_LIST, "unknown column kind");
     ER_REQUIRE(k.kind == ER_CSV_SKIP || k.out, "column without an output array");
     ER_REQUIRE(!is_list(k.kind) || (k.lens && k.list_cap >= 0), "list column needs lens and list_cap");
+    ER_REQUIRE(!is_kv(k.kind) || (k.weights && k.kv_sep), "key:weight list column needs weights and kv_sep");
     ER_REQUIRE(k.kind != ER_CSV_F32_VEC || k.width > 0, "vector column needs width");
     cols[c].n_vals = 0;
   }
@@ -216,7 +218,9 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
     const er_csv_col_t& k = cols[errs[t].col];
     return fail(ER_ERR_INVALID_ARG, "er_csv_parse: line " + std::to_string(errs[t].row + 1) + ", field " +
                                         std::to_string(errs[t].col + 1) + " is not a valid " +
-                                        (k.kind == ER_CSV_F32 || k.kind == ER_CSV_F32_VEC ? "float" : "integer"));
+                                        (k.kind == ER_CSV_F32 || k.kind == ER_CSV_F32_VEC ? "float"
+                                         : is_kv(k.kind)                                  ? "key:weight list"
+                                                                                          : "integer"));
   };
 
   // ---- pass 1: scalar kinds, and the list lengths ----
@@ -267,6 +271,8 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
           break;
         }
         case ER_CSV_HASH_LIST:
+        case ER_CSV_I64_KV_LIST:
+        case ER_CSV_HASH_KV_LIST:
         case ER_CSV_I64_LIST: {   // count the non-empty tokens
           int32_t cnt = 0;
           const char* p = s.p;
@@ -319,9 +325,16 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
         const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
         const char* fe = q ? q : e;
         if (fe > p) {
-          if (k.kind == ER_CSV_HASH_LIST)
-            *o = hashed(k, p, (size_t)(fe - p));
-          else if (!parse_i64(Span{p, (size_t)(fe - p)}, o))
+          const char* ke = fe;                       // end of the key part of the token
+          if (is_kv(k.kind)) {                       // "key<kv_sep>weight": both parts are mandatory (input.py:447-458)
+            const char* kv = (const char*)std::memchr(p, k.kv_sep, (size_t)(fe - p));
+            float* w = k.weights + (o - (int64_t*)k.out);
+            if (!kv || !parse_f32(Span{kv + 1, (size_t)(fe - kv - 1)}, w)) return c;
+            ke = kv;
+          }
+          if (k.kind == ER_CSV_HASH_LIST || k.kind == ER_CSV_HASH_KV_LIST)
+            *o = hashed(k, p, (size_t)(ke - p));
+          else if (!parse_i64(Span{p, (size_t)(ke - p)}, o))
             return c;
           ++o;
           --left;

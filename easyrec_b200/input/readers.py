@@ -31,6 +31,7 @@ def bucketize_raw(x, fc):
   return np.searchsorted(bounds, x, side='right').astype(np.int64)
 
 
+_LIST_KINDS = (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST, _lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST)
 FP_EMPTY = 0x9ae16a3b2f90404f       # Fingerprint64('')
 CROSS_HASH_KEY = 0xDECAFCAFFE       # sparse_ops._DEFAULT_HASH_KEY, what crossed_column(hash_key=None) uses
 
@@ -167,11 +168,14 @@ class CSVInput(object):
     self.hash_buckets = {}     # feature -> hash_bucket_size when its STRING field is hashed here, on the host
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
     self.combos = _combo_features(pipeline_config, input_layer)
+    self.kv_seps = {}          # TagFeature -> kv_separator: tokens are `id<kv>weight` (input/input.py:447-458)
     # fields a cross reads: parsed to raw fingerprints (STRING) or integers (INT), every consumer derives from those
     self.cross_fields = set(f for fields, _ in self.combos.values() for f in fields)
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = (fc.input_names[0], fc.separator or seq_sep)
+      if fc.HasField('kv_separator'):
+        self.kv_seps[name] = fc.kv_separator
       if name in self.combos:
         continue
       if fc.hash_bucket_size > 0 and self.ftypes.get(fc.input_names[0]) == 'STRING' and name in input_layer.features:
@@ -263,7 +267,11 @@ class CSVInput(object):
       elif f.kind in ('seq', 'tag'):
         src, sep = self.feature_inputs[f.name]
         nb = self.hash_buckets.get(f.name, 0)
-        want(src, (_lib.CSV_HASH_LIST if nb else _lib.CSV_I64_LIST, f.seq_len if f.kind == 'seq' else 0, sep.encode(), 0, nb))
+        if f.name in self.kv_seps:
+          kind = _lib.CSV_HASH_KV_LIST if nb else _lib.CSV_I64_KV_LIST
+        else:
+          kind = _lib.CSV_HASH_LIST if nb else _lib.CSV_I64_LIST
+        want(src, (kind, f.seq_len if f.kind == 'seq' else 0, sep.encode(), self.kv_seps.get(f.name, ''), nb))
     return plan
 
   def _parse(self, data, size, plan, list_cap):
@@ -289,11 +297,15 @@ class CSVInput(object):
       elif kind == _lib.CSV_F32_VEC:
         c.default_f32 = default
         out[name] = (np.empty((B, width), np.float32),)
-      elif kind in (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST):
+      elif kind in _LIST_KINDS:
         cap = B * width if width else list_cap
         out[name] = (np.empty(cap, np.int64), np.empty(B, np.int32))
         c.lens = out[name][1].ctypes.data
         c.list_cap = cap
+        if kind in (_lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST):
+          out[name] += (np.empty(cap, np.float32),)
+          c.weights = out[name][2].ctypes.data
+          c.kv_sep = default.encode()     # the plan's default slot carries the key / weight separator
       if kind != _lib.CSV_SKIP:
         c.out = out[name][0].ctypes.data
     n_rows, consumed = ctypes.c_int64(0), ctypes.c_size_t(0)
@@ -303,8 +315,8 @@ class CSVInput(object):
       return None
     _lib.check(st, 'er_csv_parse')
     for i, name in enumerate(self.fields):
-      if cols[i].kind in (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST):
-        out[name] = (out[name][0][:cols[i].n_vals], out[name][1])
+      if cols[i].kind in _LIST_KINDS:
+        out[name] = (out[name][0][:cols[i].n_vals], out[name][1]) + tuple(w[:cols[i].n_vals] for w in out[name][2:])
     return n_rows.value, consumed.value, out
 
   def _batches_native(self):
@@ -377,14 +389,16 @@ class CSVInput(object):
         v, l = bucketize_raw_multi(cols[self.feature_inputs[f.name][0]][0], self.bucketized[f.name])
         tag[f.name] = (torch.from_numpy(v), torch.from_numpy(l), None)
         continue
-      vals, lens = cols[self.feature_inputs[f.name][0]]
+      got = cols[self.feature_inputs[f.name][0]]
+      vals, lens = got[0], got[1]
       if f.kind == 'seq':
         arr = np.zeros((B, f.seq_len), np.int64)
         starts = np.cumsum(lens) - lens
         arr[np.repeat(np.arange(B), lens), np.arange(vals.size) - np.repeat(starts, lens)] = vals
         seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(lens))
       else:
-        tag[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens), None)
+        tag[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens),
+                       torch.from_numpy(got[2].copy()) if len(got) > 2 else None)
     if seq:
       feats['seq_fea'] = seq
     if tag:
@@ -455,8 +469,16 @@ class CSVInput(object):
         seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(lens))
       else:
         lens = np.array([len(ts) for ts in toks], np.int32)
-        flat = np.array([self._token(t, f.name) for ts in toks for t in ts], np.int64)
-        tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), None)
+        kv = self.kv_seps.get(f.name)
+        w = None
+        if kv:   # `id<kv>weight` tokens: both parts mandatory
+          pairs = [t.split(kv) for ts in toks for t in ts]
+          assert all(len(p_) == 2 for p_ in pairs), 'TagFeature %s: tokens must be key%sweight' % (f.name, kv)
+          flat = np.array([self._token(p_[0], f.name) for p_ in pairs], np.int64)
+          w = torch.from_numpy(np.array([float(p_[1]) for p_ in pairs], np.float32))
+        else:
+          flat = np.array([self._token(t, f.name) for ts in toks for t in ts], np.int64)
+        tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), w)
     if seq:
       feats['seq_fea'] = seq
     if tag:
@@ -491,6 +513,8 @@ class ParquetInput(object):
     for fc in config_util.get_feature_configs(pipeline_config):
       name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
       self.feature_inputs[name] = fc.input_names[0]
+      if fc.HasField('kv_separator'):
+        raise NotImplementedError('feature %s: kv_separator needs text tokens; Parquet columns carry ids only' % name)
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
     self.combos = _combo_features(pipeline_config, input_layer)
 

@@ -433,13 +433,17 @@ enum {
   ER_CSV_I64_LIST = 4, /* out int64[list_cap] + lens int32[max_rows]: inner_sep-separated integers, empty
                           tokens dropped, at most `width` per line when width > 0 (the first ones) */
   ER_CSV_F32_VEC = 5,  /* out float[max_rows * width]: inner_sep-separated floats, zero padded */
-  ER_CSV_HASH_LIST = 6 /* like ER_CSV_I64_LIST, every token fingerprinted (string Tag / Sequence tokens) */
+  ER_CSV_HASH_LIST = 6, /* like ER_CSV_I64_LIST, every token fingerprinted (string Tag / Sequence tokens) */
+  ER_CSV_I64_KV_LIST = 7,  /* tokens `key<kv_sep>weight` (TagFeature kv_separator, input/input.py:447-458): integer
+                              keys to out, fp32 weights to `weights` at the same positions */
+  ER_CSV_HASH_KV_LIST = 8  /* the same with fingerprinted string keys */
 };
 typedef struct {
   int32_t kind;
   int32_t width;
   char inner_sep;
-  char pad_[7];
+  char kv_sep;             /* key / weight separator of the *_KV_LIST kinds */
+  char pad_[6];
   int64_t default_i64;
   float default_f32;
   int32_t pad2_;
@@ -449,6 +453,7 @@ typedef struct {
   int64_t list_cap;
   int64_t n_vals;          /* written by the call: values stored for a list column */
   uint64_t hash_mod;       /* ER_CSV_HASH / ER_CSV_HASH_LIST: 0 = raw fingerprints, else the hash_bucket_size */
+  float* weights;          /* *_KV_LIST: float[list_cap] */
 } er_csv_col_t;
 int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
                  int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed);

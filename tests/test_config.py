@@ -257,7 +257,7 @@ def test_scope_check_names_every_offending_field():
 
 
 def test_feature_options_that_change_the_looked_up_rows_are_refused():
-  for extra, word in ((b'vocab_list: ["a", "b"]', 'vocab'), (b'kv_separator: ":"', 'kv_separator'),
+  for extra, word in ((b'vocab_list: ["a", "b"]', 'vocab'), (b'kv_separator: ":"', 'kv_separator'),   # on an IdFeature
                       (b'normalizer_fn: "tf.math.log1p"', 'normalizer_fn')):
     cfg = config_util.get_configs_from_pipeline_file(
         MINI.replace(b'hash_bucket_size: 1000 unknown_future_field: 3', b'hash_bucket_size: 1000 ' + extra))

@@ -310,3 +310,34 @@ model_config { model_class: "DeepFM"
     ids, lens, w = feats['tag_fea']['price']
     assert ids.tolist() == [0, 6, 3, 9] and lens.tolist() == [2, 2] and w is None
     assert feats['sparse_fea'].tolist() == [3, 4]
+
+
+def test_weighted_tags_with_kv_separator(tmp_path):
+  """TagFeature kv_separator (input/input.py:447-458): tokens `id:weight`; ids and fp32 weights come out in step,
+  integer keys and hashed string keys alike; a token without its weight is an error."""
+  from oracle import oracle as O
+  cfg = config_util.get_configs_from_pipeline_file(b'''
+data_config { batch_size: 3 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "kv" input_type: STRING }
+  input_fields { input_name: "skv" input_type: STRING } }
+feature_config {
+  features { input_names: "kv" feature_type: TagFeature embedding_dim: 8 num_buckets: 100 separator: "|" kv_separator: ":" combiner: "mean" }
+  features { input_names: "skv" feature_type: TagFeature embedding_dim: 8 hash_bucket_size: 30 separator: "|" kv_separator: "=" } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["kv", "skv"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["kv", "skv"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } } }
+''')
+  il, _, _ = builder.build_model(cfg, 3, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 'k.csv', 'w').write('1,3:0.5|7:2,cat=1.5\n0,,dog=0.25|cat=4|\n1,99:1e-1,\n')
+  for engine in ('native', 'python'):
+    (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 'k.csv'), engine=engine))
+    ids, lens, w = feats['tag_fea']['kv']
+    assert ids.tolist() == [3, 7, 99] and lens.tolist() == [2, 0, 1] and w.dtype == torch.float32
+    assert w.tolist() == pytest.approx([0.5, 2.0, 0.1])
+    ids, lens, w = feats['tag_fea']['skv']
+    assert ids.tolist() == [O.fingerprint64(s) % 30 for s in ('cat', 'dog', 'cat')] and lens.tolist() == [1, 2, 0]
+    assert w.tolist() == [1.5, 0.25, 4.0]
+  open(tmp_path / 'bad.csv', 'w').write('1,3:0.5|7,cat=1\n0,,\n1,,\n')
+  with pytest.raises(_lib.ErError, match='line 1, field 2 is not a valid key:weight list'):
+    list(readers.CSVInput(cfg, il, str(tmp_path / 'bad.csv')))
