@@ -319,10 +319,10 @@ class Backbone(nn.Module):
         v = outputs[inp.block_name]
       else:
         raise NotImplementedError('backbone input %s' % which)
+      if inp.HasField('input_slice'):     # slice first, then input_fn (layers/backbone.py:253-259)
+        v = _eval('lambda x: x' + inp.input_slice.strip())(v)
       if inp.HasField('input_fn'):
         v = _eval(inp.input_fn)(v)
-      if inp.HasField('input_slice'):
-        v = _eval('lambda x: x' + inp.input_slice.strip())(v)
       ins.append(v)
     if block.merge_inputs_into_list:
       out = ins

@@ -1,0 +1,143 @@
+"""CPU: whole training steps of config-built models - InputLayer, backbone DAG, dense towers, loss, backward,
+fused row update, flat dense optimizer, learning-rate schedule - with every kernel entry point replaced by a
+double (sparse: the CPU oracle, as in test_input_layer_host.py; dense: plain torch / the oracle's numpy).  The
+kernels are checked against the same references on the GPU; here the HOST wiring runs, including the backbone
+paths no GPU test builds yet (3-D / pair outputs of the input_layer block, low-rank Cross, keras merge layers,
+mixed id + tag groups)."""
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import builder, kernels as K, trainer as T
+from easyrec_b200.config import config_util
+from easyrec_b200.input import readers
+from oracle import oracle as O
+from test_input_layer_host import oracle_kernels  # noqa: F401  (fixture)
+
+BN_EPS, BN_MOM = 1e-3, 0.99
+
+
+@pytest.fixture
+def dense_kernels(monkeypatch, oracle_kernels):  # noqa: F811
+  def gemm(a, b, bias=None, out=None):
+    r = a @ b
+    if bias is not None:
+      r = r + bias
+    if out is not None:
+      out.copy_(r)
+      return out
+    return r
+
+  def bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, eps, momentum, training, relu, ws,
+                      y=None, save_mean=None, save_rstd=None):
+    h = z + bias
+    mean = rstd = None
+    if gamma is not None:
+      if training:
+        mean = h.mean(0)
+        var = ((h - mean) ** 2).mean(0)
+        moving_mean.mul_(momentum).add_(mean * (1 - momentum))
+        moving_var.mul_(momentum).add_(var * (1 - momentum))
+      else:
+        mean, var = moving_mean, moving_var
+      rstd = 1.0 / torch.sqrt(var + eps)
+      h = (h - mean) * rstd * gamma + beta
+    return (torch.relu(h) if relu else h), mean, rstd
+
+  def bias_bn_act_bwd(z, bias, gamma, y, gy, mean, rstd, relu, ws):
+    g = gy * (y > 0) if relu else gy
+    if gamma is None:
+      return g, g.sum(0), None, None
+    xhat = (z + bias - mean) * rstd
+    B = z.shape[0]
+    ggamma, gbeta = (g * xhat).sum(0), g.sum(0)
+    gx = g * gamma
+    gz = rstd / B * (B * gx - gx.sum(0) - xhat * (gx * xhat).sum(0))
+    return gz, gz.sum(0), ggamma, gbeta
+
+  def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
+    loss, probs, g = O.sigmoid_ce(logits.detach().numpy(), labels.numpy())
+    return torch.tensor([loss], dtype=torch.float32), torch.from_numpy(probs), torch.from_numpy(g)
+
+  def fm_fwd(x, n_field, dim, y=None):
+    return torch.from_numpy(O.fm_fwd(np.ascontiguousarray(x.detach().numpy()), n_field, dim))
+
+  def fm_bwd(x, gy, n_field, dim, gx=None, accumulate=False):
+    return torch.from_numpy(O.fm_bwd(np.ascontiguousarray(x.detach().numpy()), np.ascontiguousarray(gy.numpy()), n_field, dim))
+
+  def apply(self):   # FlatDenseOptimizer.apply: l2 + TF Adagrad over the flat buffer
+    assert self.kind == 1, 'this double implements the adagrad rule only'
+    segs = np.frombuffer(self.segs_dev.numpy().tobytes(), dtype=T._lib.DENSE_SEG_DTYPE)
+    self.reg_loss.zero_()
+    lr = float(self.lr_dev[0])
+    for s in segs:
+      o, n = int(s['offset']), int(s['n'])
+      w, g = self.flat_p[o:o + n], self.flat_g[o:o + n] * self.grad_scale
+      if s['l2'] > 0:
+        self.reg_loss += 0.5 * float(s['l2']) * (w * w).sum()
+        g = g + float(s['l2']) * w
+      self.s0[o:o + n] += g * g
+      w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
+  for name, fn in (('gemm', gemm), ('gemm_ready', lambda t: t), ('gemm_bn', lambda *a, **k: None),
+                   ('bias_bn_act_fwd', bias_bn_act_fwd), ('bias_bn_act_bwd', bias_bn_act_bwd),
+                   ('dense_workspace', lambda b, u, d: torch.zeros(1, dtype=torch.uint8)), ('sigmoid_ce', sigmoid_ce),
+                   ('fm_fwd', fm_fwd), ('fm_bwd', fm_bwd)):
+    monkeypatch.setattr(K, name, fn)
+  monkeypatch.setattr(T.FlatDenseOptimizer, 'apply', apply)
+
+
+CFG = b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { exponential_decay_learning_rate {
+  initial_learning_rate: 0.05 decay_steps: 5 decay_factor: 0.5 min_learning_rate: 0.01 } } } } }
+data_config { batch_size: 16 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "uid" input_type: INT64 }
+  input_fields { input_name: "item" input_type: STRING } input_fields { input_name: "tags" input_type: STRING }
+  input_fields { input_name: "price" input_type: FLOAT } }
+feature_config {
+  features { input_names: "uid" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 40 }
+  features { input_names: "item" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 30 }
+  features { input_names: "tags" feature_type: TagFeature embedding_dim: 8 num_buckets: 12 separator: "|" combiner: "mean" }
+  features { input_names: ["uid", "item"] feature_name: "uid_item" feature_type: ComboFeature embedding_dim: 8 hash_bucket_size: 64 }
+  features { input_names: "price" feature_type: RawFeature embedding_dim: 8 boundaries: [1.0, 2.0, 5.0] } }
+model_config { model_class: "RankModel"
+  feature_groups { group_name: "all" feature_names: ["uid", "item", "tags", "uid_item", "price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "mlp" inputs { feature_group_name: "all" } keras_layer { class_name: "MLP" mlp { hidden_units: [16, 8] } } }
+    blocks { name: "cube" inputs { feature_group_name: "all" } input_layer { only_output_3d_tensor: true } }
+    blocks { name: "pooled" inputs { block_name: "cube" } lambda { expression: "lambda x: tf.reduce_sum(x, axis=1)" } }
+    blocks { name: "pair" inputs { feature_group_name: "all" } input_layer { output_2d_tensor_and_feature_list: true } }
+    blocks { name: "fm" inputs { block_name: "pair" input_slice: "[1]" } keras_layer { class_name: "FM" fm { use_variant: true } } }
+    blocks { name: "cross" inputs { block_name: "pair" input_slice: "[0]" input_fn: "lambda x: [x, x]" }
+             keras_layer { class_name: "Cross" st_params { fields { key: "projection_dim" value { number_value: 4 } } } } }
+    blocks { name: "added" inputs { block_name: "pooled" } inputs { block_name: "fm" } merge_inputs_into_list: true
+             keras_layer { class_name: "Add" } }
+    concat_blocks: ["mlp", "added", "cross"]
+    top_mlp { hidden_units: [8] }
+  }
+  model_params { l2_regularization: 1e-4 }
+  embedding_regularization: 1e-5 }
+'''
+
+
+def test_backbone_model_trains_on_the_host_with_kernel_doubles(tmp_path, dense_kernels):
+  cfg = config_util.get_configs_from_pipeline_file(CFG)
+  il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  rng = np.random.default_rng(0)
+  lines = []
+  for i in range(16):
+    uid, item = int(rng.integers(0, 6)), 'i%d' % rng.integers(0, 5)
+    tags = '|'.join(str(v) for v in rng.integers(0, 12, rng.integers(0, 4)))
+    label = int((uid + len(item)) % 2 == 0)
+    lines.append('%d,%d,%s,%s,%.2f\n' % (label, uid, item, tags, rng.uniform(0, 8)))
+  open(tmp_path / 't.csv', 'w').write(''.join(lines))
+  (feats, labels), = list(readers.make_input(cfg, il, str(tmp_path / 't.csv')))
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  table0 = il.arenas[8].weight.clone()
+  losses = [float(tr.train_step(feats, labels)[0]) for _ in range(12)]
+  assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 0.01, losses      # the batch is being fitted
+  assert float(tr.dense_opt.lr_dev[0]) == pytest.approx(opt['lr_fn'](11)) == pytest.approx(0.0125)   # staircase decay reached step 11
+  moved = (il.arenas[8].weight != table0).any(1)
+  assert 5 < int(moved.sum()) < il.arenas[8].n_rows                               # only looked-up rows moved
+  shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
+  assert shapes['backbone.mods.cross.dense_u.kernel'] == (40, 4) and shapes['backbone.mods.cross.dense.kernel'] == (4, 40)
+  assert not model.backbone.mods['cross'].dense_u.bias.requires_grad
