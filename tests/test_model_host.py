@@ -141,3 +141,38 @@ def test_backbone_model_trains_on_the_host_with_kernel_doubles(tmp_path, dense_k
   shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
   assert shapes['backbone.mods.cross.dense_u.kernel'] == (40, 4) and shapes['backbone.mods.cross.dense.kernel'] == (4, 40)
   assert not model.backbone.mods['cross'].dense_u.bias.requires_grad
+
+
+@pytest.mark.parametrize('final', [True, False])
+def test_deepfm_wiring_matches_the_oracle_on_the_host(final, dense_kernels):
+  """DeepFM from config (with and without final_dnn) against oracle.deepfm_forward / the plain-head formula of
+  model/deepfm.py:92-105 on the model's own weights (batch-norm in training mode)."""
+  import sys
+  import os
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  from test_config import MINI
+  text = MINI if final else MINI.replace(b'final_dnn { hidden_units: [16] }', b'')
+  cfg = config_util.get_configs_from_pipeline_file(text.replace(b'batch_size: 32', b'batch_size: 8'))
+  il, model, _ = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(3))
+  rng = np.random.default_rng(0)
+  with torch.no_grad():
+    for p in model.parameters():
+      p.add_(torch.from_numpy(rng.normal(0, 0.05, tuple(p.shape)).astype(np.float32)))
+  feats = {'sparse_fea': torch.from_numpy(rng.integers(0, 2**40, 8)), 'dense_fea': torch.from_numpy(rng.uniform(0, 10, (8, 1)).astype(np.float32))}
+  model.train()
+  logits = model(feats).detach().numpy()
+  g = il.lookup(feats)
+  wide, deep = g['wide'][0].detach().numpy(), g['deep'][0].detach().numpy()[:, :32]
+
+  def layers(dnn):
+    return [dict(W=l.kernel.detach().numpy(), b=l.bias.detach().numpy(), gamma=l.gamma.detach().numpy(),
+                 beta=l.beta.detach().numpy()) for l in dnn.layers]
+  if final:
+    params = dict(dnn=layers(model.dnn), final=layers(model.final_dnn), out_W=model.output.kernel.detach().numpy(),
+                  out_b=model.output.bias.detach().numpy())
+    want, _ = O.deepfm_forward(wide[:, :2], deep, 2, 16, params)
+  else:
+    h, _ = O.dnn_forward(deep, layers(model.dnn))
+    want = (wide[:, :2].sum(1, keepdims=True) + O.fm_fwd(deep, 2, 16).sum(1, keepdims=True) +
+            h @ model.output.kernel.detach().numpy() + model.output.bias.detach().numpy())[:, 0]
+  np.testing.assert_allclose(logits, want, rtol=1e-4, atol=1e-5)
