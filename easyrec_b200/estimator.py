@@ -64,16 +64,27 @@ class EasyRecEstimator(object):
     every = max(int(self.train_config.log_step_count_steps), 1)
     t0, n0 = time.time(), self.global_step
     loss = None
-    for feats, labels in readers.Prefetcher(input_fn(), depth=2):   # host parsing runs ahead of the device step
-      feats, labels = readers.to_device(feats, labels, self._device)
-      loss, _ = self.trainer.train_step(feats, labels)
-      self.global_step += 1
-      if self.global_step % every == 0:
-        dt = time.time() - t0
-        logging.info('global_step = %d, loss = %.6f, global_step/sec = %.2f', self.global_step, float(loss),
-                     (self.global_step - n0) / max(dt, 1e-9))
-      if limit is not None and self.global_step - n0 >= limit:
-        break
+    # data_config.num_epochs: 0 = pass over the data again and again until the step limit (input/input.py:1033-1040
+    # dataset.repeat); without a step limit one pass is made
+    epochs = int(self._pipeline_config.data_config.num_epochs)
+    done = False
+    epoch = 0
+    while not done:
+      seen = self.global_step
+      for feats, labels in readers.Prefetcher(input_fn(), depth=2):   # host parsing runs ahead of the device step
+        feats, labels = readers.to_device(feats, labels, self._device)
+        loss, _ = self.trainer.train_step(feats, labels)
+        self.global_step += 1
+        if self.global_step % every == 0:
+          dt = time.time() - t0
+          logging.info('global_step = %d, loss = %.6f, global_step/sec = %.2f', self.global_step, float(loss),
+                       (self.global_step - n0) / max(dt, 1e-9))
+        if limit is not None and self.global_step - n0 >= limit:
+          done = True
+          break
+      epoch += 1
+      if limit is None or self.global_step == seen or (epochs > 0 and epoch >= epochs):
+        done = True
     return None if loss is None else float(loss)
 
   @torch.no_grad()

@@ -4,6 +4,8 @@ double (sparse: the CPU oracle, as in test_input_layer_host.py; dense: plain tor
 kernels are checked against the same references on the GPU; here the HOST wiring runs, including the backbone
 paths no GPU test builds yet (3-D / pair outputs of the input_layer block, low-rank Cross, keras merge layers,
 mixed id + tag groups)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -176,3 +178,48 @@ def test_deepfm_wiring_matches_the_oracle_on_the_host(final, dense_kernels):
     want = (wide[:, :2].sum(1, keepdims=True) + O.fm_fwd(deep, 2, 16).sum(1, keepdims=True) +
             h @ model.output.kernel.detach().numpy() + model.output.bias.detach().numpy())[:, 0]
   np.testing.assert_allclose(logits, want, rtol=1e-4, atol=1e-5)
+
+
+def test_estimator_flow_on_the_host(tmp_path, dense_kernels):
+  """EasyRecEstimator end to end on CPU with kernel doubles: train over a CSV file through the Prefetcher, evaluate
+  (AUC + GAUC keyed by an input field), predict, save with the reference's part files, restore into a fresh
+  estimator - same predictions."""
+  from easyrec_b200.estimator import EasyRecEstimator
+  text = ('''
+model_dir: "%s"
+train_config { num_steps: 240 log_step_count_steps: 100
+  optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.1 } } } } }
+eval_config { metrics_set { auc {} } metrics_set { gauc { uid_field: "grp" } } }
+data_config { batch_size: 32 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "grp" input_type: INT64 }
+  input_fields { input_name: "c" input_type: STRING } input_fields { input_name: "x" input_type: FLOAT } }
+feature_config {
+  features { input_names: "grp" feature_type: IdFeature embedding_dim: 8 num_buckets: 4 }
+  features { input_names: "c" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 64 }
+  features { input_names: "x" feature_type: RawFeature embedding_dim: 8 min_val: 0.0 max_val: 1.0 } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["grp", "c", "x"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["grp", "c"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } l2_regularization: 1e-6 } }
+''' % str(tmp_path / 'm')).encode()
+  rng = np.random.default_rng(4)
+  with open(tmp_path / 'd.csv', 'w') as f:
+    for _ in range(32 * 12):
+      c = int(rng.integers(0, 10))
+      f.write('%d,%d,tok%d,%.3f\n' % (int(rng.uniform() < (0.85 if c % 2 else 0.15)), rng.integers(0, 4), c, rng.uniform()))
+  est = EasyRecEstimator(text, device='cpu', seed=3)
+  make = lambda e: (lambda: readers.make_input(e._pipeline_config, e.input_layer, str(tmp_path / 'd.csv')))  # noqa: E731
+  loss = est.train(make(est))
+  assert est.global_step == 240 and np.isfinite(loss)          # 20 passes over the 12 batches
+  ev = est.evaluate(make(est))
+  assert ev['auc'] > 0.75 and 0.5 < ev['gauc'] <= 1.0 and ev["global_step"] == 240   # the label follows the token's parity
+  first = next(iter(est.predict(make(est))))['probs']
+  path = est.save(embedding_parts=True)
+  assert sorted(p for p in os.listdir(path[:-3] + '-embedding') if 'c_embedding' in p and 'wide' not in p) == [
+      'embed-input_layer__c_embedding__embedding_weights:0-part-0.bin',
+      'embed-input_layer__c_embedding__embedding_weights__Adagrad:0-part-0.bin']
+  fresh = EasyRecEstimator(text, device='cpu', seed=99)        # different initial weights
+  assert not np.allclose(next(iter(fresh.predict(make(fresh))))['probs'], first)
+  fresh.restore(path)
+  np.testing.assert_allclose(next(iter(fresh.predict(make(fresh))))['probs'], first, rtol=1e-6, atol=1e-7)
+  assert fresh.global_step == 240
