@@ -32,7 +32,7 @@ def dense_kernels(monkeypatch, oracle_kernels):  # noqa: F811
 
   def bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, eps, momentum, training, relu, ws,
                       y=None, save_mean=None, save_rstd=None):
-    h = z + bias
+    h = z if bias is None else z + bias
     mean = rstd = None
     if gamma is not None:
       if training:
@@ -50,7 +50,7 @@ def dense_kernels(monkeypatch, oracle_kernels):  # noqa: F811
     g = gy * (y > 0) if relu else gy
     if gamma is None:
       return g, g.sum(0), None, None
-    xhat = (z + bias - mean) * rstd
+    xhat = ((z if bias is None else z + bias) - mean) * rstd
     B = z.shape[0]
     ggamma, gbeta = (g * xhat).sum(0), g.sum(0)
     gx = g * gamma
@@ -223,3 +223,55 @@ model_config { model_class: "DeepFM"
   fresh.restore(path)
   np.testing.assert_allclose(next(iter(fresh.predict(make(fresh))))['probs'], first, rtol=1e-6, atol=1e-7)
   assert fresh.global_step == 240
+
+
+@pytest.fixture
+def interaction_doubles(monkeypatch, dense_kernels):
+  """torch-native stand-ins for the fused interaction ops (autograd supplies their backward)."""
+  from easyrec_b200 import interactions as I
+
+  def din_attention(query, keys, lens, attention_mlp):
+    B, T, D = keys.shape
+    q = query[:, None, :].expand(B, T, D)
+    scores = attention_mlp(torch.cat([q, keys, q - keys, q * keys], dim=-1)).reshape(B, T)
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    p = torch.softmax(torch.where(mask, scores, torch.full_like(scores, -2.0**32 + 1)), dim=1)
+    return (p[:, :, None] * keys).sum(1)
+
+  def inbatch_softmax_ce(sim, item_ids=None, weights=None):
+    B = sim.shape[0]
+    if item_ids is not None:
+      dup = (item_ids[None, :B] == item_ids[:B, None]).float() - torch.eye(B)
+      sim = torch.cat([sim[:, :B] - dup * 1e32, sim[:, B:]], dim=1)
+    p = torch.softmax(sim, dim=1)
+    diag = p[torch.arange(B), torch.arange(B)]
+    w = torch.ones(B) if weights is None else weights
+    return -(torch.log(diag + 1e-12) * w).mean() / w.mean(), diag.detach()
+  monkeypatch.setattr(I, 'din_attention', din_attention)
+  monkeypatch.setattr(I, 'cross_layer', lambda x0, xl, w, b: x0 * (xl * w).sum(1, keepdim=True) + b + xl)
+  monkeypatch.setattr(I, 'mmoe_mix', lambda g, ex: (torch.softmax(g, dim=1)[:, :, None] * ex).sum(1))
+  monkeypatch.setattr(I, 'l2_normalize', lambda x: x / torch.sqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12)))
+  monkeypatch.setattr(I, 'inbatch_softmax_ce', inbatch_softmax_ce)
+
+
+def _gpu_test_configs():
+  import test_gpu_models as G
+  names = ['DCN_CFG', 'DIN_CFG', 'MMOE_CFG', 'DSSM_CFG', 'BACKBONE_DCN_CFG', 'BACKBONE_DLRM_CFG', 'BACKBONE_MTL_CFG',
+           'BACKBONE_MATCH_CFG', 'BACKBONE_WIRING_CFG']
+  return [(n, getattr(G, n)) for n in names]
+
+
+@pytest.mark.parametrize('name,text', _gpu_test_configs(), ids=[n for n, _ in _gpu_test_configs()])
+def test_every_gpu_test_model_config_trains_on_the_host(name, text, interaction_doubles):
+  """The model configs of tests/test_gpu_models.py, run here with kernel doubles: what the GPU job will execute
+  at the end of the round must at least build, step and fit a batch on the host side of the same code."""
+  cfg = config_util.get_configs_from_pipeline_file(text.encode())
+  B = 32
+  il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  n_labels = max(1, len(cfg.data_config.label_fields))
+  feats, labels = readers.DummyInput(il, n_labels=n_labels, seed=5).batch()
+  if 'sparse_fea' in feats:   # keep the random ids small so that identity slots do not all collapse onto row 0
+    feats['sparse_fea'] = feats['sparse_fea'] % 37
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  losses = [float(tr.train_step(feats, labels)[0]) for _ in range(15)]
+  assert all(np.isfinite(losses)) and losses[-1] < losses[0], (name, losses)
