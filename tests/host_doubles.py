@@ -1,0 +1,196 @@
+"""Kernel doubles for the host-side tests (TEST INFRASTRUCTURE): stand-ins with the signatures of the entry points in
+easyrec_b200.kernels / interactions whose bodies are the CPU oracle (sparse path), plain torch (dense towers,
+interactions) or numpy.  `patch(obj, name, fn)` is pytest's monkeypatch.setattr in fixtures and plain setattr in
+spawned worker processes."""
+import numpy as np
+import torch
+
+from easyrec_b200 import kernels as K, trainer as T
+from oracle import oracle as O
+
+
+def _slots(slots_dev):
+  return np.frombuffer(slots_dev.numpy().tobytes(), dtype=K.SLOT_DTYPE)
+
+
+def _seg_field(sl, field, n_seg):
+  return np.concatenate([np.full(int(s['n_seg']), s[field]) for s in sl])[:n_seg]
+
+
+def install_sparse(patch):
+  """bucketize / csr_from_lens / embedding_fwd / embedding_bwd -> the CPU oracle."""
+  def csr_from_lens(lens, cap, want_seg_ids=True):
+    row_ptr, seg = O.csr_from_lens(lens.numpy())
+    seg_ids = np.zeros(max(cap, 1), np.int32)
+    seg_ids[:seg.size] = seg
+    return torch.from_numpy(row_ptr), torch.from_numpy(seg_ids)
+
+  def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=None, owner=None):
+    sl = _slots(slots_dev)
+    n = ids.numel()
+    if row_ptr is None:
+      seg_of = np.arange(n)
+      live = np.ones(n, bool)
+    else:
+      total = int(row_ptr[-1])
+      seg_of = seg_ids.numpy()[:n].astype(np.int64)
+      live = np.arange(n) < total
+      seg_of = np.where(live, seg_of, 0)
+    per = lambda f: _seg_field(sl, f, n_seg)[seg_of]   # noqa: E731
+    r, _ = O.bucketize(ids.numpy(), per('bucket_mode'), per('num_buckets'), per('row_offset'))
+    r = np.where(live, r, -1)
+    out = rows if rows is not None else torch.empty_like(ids)
+    out.copy_(torch.from_numpy(r))
+    return out
+
+  def _csr(n_seg, rows, row_ptr):
+    return np.arange(n_seg + 1, dtype=np.int32) if row_ptr is None else row_ptr.numpy()
+
+  def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, outs, weights=None, row_ptr=None, seg_scale=None,
+                    row_stride=None):
+    sl = _slots(slots_dev)
+    rp = _csr(n_seg, rows, row_ptr)
+    pooled, scale = O.embedding_fwd(np.ascontiguousarray(table.numpy()), rows.numpy(), rp, _seg_field(sl, 'combiner', n_seg),
+                                    weights=None if weights is None else weights.numpy())
+    for s in sl:
+      out = outs[int(s['out_buf'])].view(-1)
+      for k in range(int(s['n_seg'])):
+        o = k * int(s['out_stride']) + int(s['out_col'])
+        out[o:o + dim] = torch.from_numpy(pooled[int(s['seg_begin']) + k])
+    if seg_scale is not None:
+      seg_scale.copy_(torch.from_numpy(scale))
+
+  def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt, ws, weights=None,
+                    seg_ids=None, row_ptr=None, seg_scale=None, row_stride=None, uniq_rows=None, uniq_grads=None,
+                    n_uniq=None, n_rows=None, sorted_from=None):
+    sl = _slots(slots_dev)
+    gseg = np.zeros((n_seg, dim), np.float32)
+    for s in sl:
+      buf = grad_bufs[int(s['out_buf'])].reshape(-1).numpy()
+      for k in range(int(s['n_seg'])):
+        o = k * int(s['out_stride']) + int(s['out_col'])
+        gseg[int(s['seg_begin']) + k] = buf[o:o + dim]
+    t, a = np.ascontiguousarray(table.numpy()), np.ascontiguousarray(state0.numpy())
+    O.embedding_bwd(t, a, None, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
+                    O.OPT_ADAGRAD, opt.lr, weights=None if weights is None else weights.numpy(),
+                    seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=opt.grad_scale)
+    table.copy_(torch.from_numpy(t))
+    state0.copy_(torch.from_numpy(a))
+  for name, fn in (('csr_from_lens', csr_from_lens), ('bucketize', bucketize), ('embedding_fwd', embedding_fwd),
+                   ('embedding_bwd', embedding_bwd)):
+    patch(K, name, fn)
+
+
+
+def install_dense(patch):
+  """dense towers, loss, FM and the flat dense optimizer -> plain torch / the oracle's numpy."""
+  def gemm(a, b, bias=None, out=None):
+    r = a @ b
+    if bias is not None:
+      r = r + bias
+    if out is not None:
+      out.copy_(r)
+      return out
+    return r
+
+  def bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, eps, momentum, training, relu, ws,
+                      y=None, save_mean=None, save_rstd=None):
+    h = z if bias is None else z + bias
+    mean = rstd = None
+    if gamma is not None:
+      if training:
+        mean = h.mean(0)
+        var = ((h - mean) ** 2).mean(0)
+        moving_mean.mul_(momentum).add_(mean * (1 - momentum))
+        moving_var.mul_(momentum).add_(var * (1 - momentum))
+      else:
+        mean, var = moving_mean, moving_var
+      rstd = 1.0 / torch.sqrt(var + eps)
+      h = (h - mean) * rstd * gamma + beta
+    return (torch.relu(h) if relu else h), mean, rstd
+
+  def bias_bn_act_bwd(z, bias, gamma, y, gy, mean, rstd, relu, ws):
+    g = gy * (y > 0) if relu else gy
+    if gamma is None:
+      return g, g.sum(0), None, None
+    xhat = ((z if bias is None else z + bias) - mean) * rstd
+    B = z.shape[0]
+    ggamma, gbeta = (g * xhat).sum(0), g.sum(0)
+    gx = g * gamma
+    gz = rstd / B * (B * gx - gx.sum(0) - xhat * (gx * xhat).sum(0))
+    return gz, gz.sum(0), ggamma, gbeta
+
+  def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
+    loss, probs, g = O.sigmoid_ce(logits.detach().numpy(), labels.numpy())
+    return torch.tensor([loss], dtype=torch.float32), torch.from_numpy(probs), torch.from_numpy(g)
+
+  def fm_fwd(x, n_field, dim, y=None):
+    return torch.from_numpy(O.fm_fwd(np.ascontiguousarray(x.detach().numpy()[:, :n_field * dim]), n_field, dim))
+
+  def fm_bwd(x, gy, n_field, dim, gx=None, accumulate=False):
+    w = n_field * dim
+    g = torch.from_numpy(O.fm_bwd(np.ascontiguousarray(x.detach().numpy()[:, :w]), np.ascontiguousarray(gy.numpy()), n_field, dim))
+    if gx is None:
+      return g
+    if accumulate:
+      gx[:, :w] += g
+    else:
+      gx[:, :w] = g
+    return gx
+
+  def apply(self):   # FlatDenseOptimizer.apply: l2 + TF Adagrad over the flat buffer
+    assert self.kind == 1, 'this double implements the adagrad rule only'
+    segs = np.frombuffer(self.segs_dev.numpy().tobytes(), dtype=T._lib.DENSE_SEG_DTYPE)
+    self.reg_loss.zero_()
+    lr = float(self.lr_dev[0])
+    for s in segs:
+      o, n = int(s['offset']), int(s['n'])
+      w, g = self.flat_p[o:o + n], self.flat_g[o:o + n] * self.grad_scale
+      if s['l2'] > 0:
+        self.reg_loss += 0.5 * float(s['l2']) * (w * w).sum()
+        g = g + float(s['l2']) * w
+      self.s0[o:o + n] += g * g
+      w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
+  for name, fn in (('gemm', gemm), ('gemm_ready', lambda t: t), ('gemm_bn', lambda *a, **k: None),
+                   ('bias_bn_act_fwd', bias_bn_act_fwd), ('bias_bn_act_bwd', bias_bn_act_bwd),
+                   ('dense_workspace', lambda b, u, d: torch.zeros(1, dtype=torch.uint8)), ('sigmoid_ce', sigmoid_ce),
+                   ('fm_fwd', fm_fwd), ('fm_bwd', fm_bwd)):
+    patch(K, name, fn)
+  patch(T.FlatDenseOptimizer, 'apply', apply)
+
+
+
+def install_interactions(patch):
+  """torch-native stand-ins for the fused interaction ops (autograd supplies their backward)."""
+  from easyrec_b200 import interactions as I
+
+  def din_attention(query, keys, lens, attention_mlp):
+    B, T, D = keys.shape
+    q = query[:, None, :].expand(B, T, D)
+    scores = attention_mlp(torch.cat([q, keys, q - keys, q * keys], dim=-1)).reshape(B, T)
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    p = torch.softmax(torch.where(mask, scores, torch.full_like(scores, -2.0**32 + 1)), dim=1)
+    return (p[:, :, None] * keys).sum(1)
+
+  def inbatch_softmax_ce(sim, item_ids=None, weights=None):
+    B = sim.shape[0]
+    if item_ids is not None:
+      dup = (item_ids[None, :B] == item_ids[:B, None]).float() - torch.eye(B)
+      sim = torch.cat([sim[:, :B] - dup * 1e32, sim[:, B:]], dim=1)
+    p = torch.softmax(sim, dim=1)
+    diag = p[torch.arange(B), torch.arange(B)]
+    w = torch.ones(B) if weights is None else weights
+    return -(torch.log(diag + 1e-12) * w).mean() / w.mean(), diag.detach()
+  patch(I, 'din_attention', din_attention)
+  patch(I, 'cross_layer', lambda x0, xl, w, b: x0 * (xl * w).sum(1, keepdim=True) + b + xl)
+  patch(I, 'mmoe_mix', lambda g, ex: (torch.softmax(g, dim=1)[:, :, None] * ex).sum(1))
+  patch(I, 'l2_normalize', lambda x: x / torch.sqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12)))
+  patch(I, 'inbatch_softmax_ce', inbatch_softmax_ce)
+
+
+
+
+def install_all(patch=setattr):
+  install_sparse(patch)
+  install_dense(patch)
+  install_interactions(patch)

@@ -16,6 +16,8 @@ from easyrec_b200.config import config_util
 from easyrec_b200.input import readers
 from oracle import oracle as O
 
+import host_doubles  # noqa: E402  (tests/ is on sys.path under pytest's rootdir conftest)
+
 CFG = b'''
 data_config { batch_size: 6 input_type: CSVInput separator: "," label_fields: "label"
   input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "uid" input_type: INT64 }
@@ -40,76 +42,17 @@ ROWS = [('1', '7', '3|5|5', '-1|1', '10', '5'), ('0', '-12', '', '5|6', '55.5', 
         ('0', '99', '6|6', '3.5|4', '77', '7|8|9|10')]
 
 
-def _slots(slots_dev):
-  return np.frombuffer(slots_dev.numpy().tobytes(), dtype=K.SLOT_DTYPE)
-
-
-def _seg_field(sl, field, n_seg):
-  return np.concatenate([np.full(int(s['n_seg']), s[field]) for s in sl])[:n_seg]
-
-
 @pytest.fixture
 def oracle_kernels(monkeypatch):
-  def csr_from_lens(lens, cap, want_seg_ids=True):
-    row_ptr, seg = O.csr_from_lens(lens.numpy())
-    seg_ids = np.zeros(max(cap, 1), np.int32)
-    seg_ids[:seg.size] = seg
-    return torch.from_numpy(row_ptr), torch.from_numpy(seg_ids)
-
-  def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=None, owner=None):
-    sl = _slots(slots_dev)
-    n = ids.numel()
-    if row_ptr is None:
-      seg_of = np.arange(n)
-      live = np.ones(n, bool)
-    else:
-      total = int(row_ptr[-1])
-      seg_of = seg_ids.numpy()[:n].astype(np.int64)
-      live = np.arange(n) < total
-      seg_of = np.where(live, seg_of, 0)
-    per = lambda f: _seg_field(sl, f, n_seg)[seg_of]   # noqa: E731
-    r, _ = O.bucketize(ids.numpy(), per('bucket_mode'), per('num_buckets'), per('row_offset'))
-    r = np.where(live, r, -1)
-    out = rows if rows is not None else torch.empty_like(ids)
-    out.copy_(torch.from_numpy(r))
-    return out
-
-  def _csr(n_seg, rows, row_ptr):
-    return np.arange(n_seg + 1, dtype=np.int32) if row_ptr is None else row_ptr.numpy()
-
-  def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, outs, weights=None, row_ptr=None, seg_scale=None,
-                    row_stride=None):
-    sl = _slots(slots_dev)
-    rp = _csr(n_seg, rows, row_ptr)
-    pooled, scale = O.embedding_fwd(np.ascontiguousarray(table.numpy()), rows.numpy(), rp, _seg_field(sl, 'combiner', n_seg),
-                                    weights=None if weights is None else weights.numpy())
-    for s in sl:
-      out = outs[int(s['out_buf'])].view(-1)
-      for k in range(int(s['n_seg'])):
-        o = k * int(s['out_stride']) + int(s['out_col'])
-        out[o:o + dim] = torch.from_numpy(pooled[int(s['seg_begin']) + k])
-    if seg_scale is not None:
-      seg_scale.copy_(torch.from_numpy(scale))
-
-  def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt, ws, weights=None,
-                    seg_ids=None, row_ptr=None, seg_scale=None, row_stride=None, uniq_rows=None, uniq_grads=None,
-                    n_uniq=None, n_rows=None, sorted_from=None):
-    sl = _slots(slots_dev)
-    gseg = np.zeros((n_seg, dim), np.float32)
-    for s in sl:
-      buf = grad_bufs[int(s['out_buf'])].reshape(-1).numpy()
-      for k in range(int(s['n_seg'])):
-        o = k * int(s['out_stride']) + int(s['out_col'])
-        gseg[int(s['seg_begin']) + k] = buf[o:o + dim]
-    t, a = np.ascontiguousarray(table.numpy()), np.ascontiguousarray(state0.numpy())
-    O.embedding_bwd(t, a, None, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
-                    O.OPT_ADAGRAD, opt.lr, weights=None if weights is None else weights.numpy(),
-                    seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=opt.grad_scale)
-    table.copy_(torch.from_numpy(t))
-    state0.copy_(torch.from_numpy(a))
-  for name, fn in (('csr_from_lens', csr_from_lens), ('bucketize', bucketize), ('embedding_fwd', embedding_fwd),
-                   ('embedding_bwd', embedding_bwd)):
-    monkeypatch.setattr(K, name, fn)
+  host_doubles.install_sparse(monkeypatch.setattr)
+  # torch.empty() returns NaN-filled memory while these tests run: host code that consumes a buffer it never wrote
+  # shows up as NaN instead of passing or failing with whatever the allocator left behind
+  was = torch.are_deterministic_algorithms_enabled(), torch.utils.deterministic.fill_uninitialized_memory
+  torch.use_deterministic_algorithms(True)
+  torch.utils.deterministic.fill_uninitialized_memory = True
+  yield
+  torch.use_deterministic_algorithms(was[0])
+  torch.utils.deterministic.fill_uninitialized_memory = was[1]
 
 
 def _expected_deep(il, rows_txt):

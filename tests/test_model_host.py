@@ -14,6 +14,7 @@ from easyrec_b200 import builder, kernels as K, trainer as T
 from easyrec_b200.config import config_util
 from easyrec_b200.input import readers
 from oracle import oracle as O
+import host_doubles
 from test_input_layer_host import oracle_kernels  # noqa: F401  (fixture)
 
 BN_EPS, BN_MOM = 1e-3, 0.99
@@ -21,71 +22,7 @@ BN_EPS, BN_MOM = 1e-3, 0.99
 
 @pytest.fixture
 def dense_kernels(monkeypatch, oracle_kernels):  # noqa: F811
-  def gemm(a, b, bias=None, out=None):
-    r = a @ b
-    if bias is not None:
-      r = r + bias
-    if out is not None:
-      out.copy_(r)
-      return out
-    return r
-
-  def bias_bn_act_fwd(z, bias, gamma, beta, moving_mean, moving_var, eps, momentum, training, relu, ws,
-                      y=None, save_mean=None, save_rstd=None):
-    h = z if bias is None else z + bias
-    mean = rstd = None
-    if gamma is not None:
-      if training:
-        mean = h.mean(0)
-        var = ((h - mean) ** 2).mean(0)
-        moving_mean.mul_(momentum).add_(mean * (1 - momentum))
-        moving_var.mul_(momentum).add_(var * (1 - momentum))
-      else:
-        mean, var = moving_mean, moving_var
-      rstd = 1.0 / torch.sqrt(var + eps)
-      h = (h - mean) * rstd * gamma + beta
-    return (torch.relu(h) if relu else h), mean, rstd
-
-  def bias_bn_act_bwd(z, bias, gamma, y, gy, mean, rstd, relu, ws):
-    g = gy * (y > 0) if relu else gy
-    if gamma is None:
-      return g, g.sum(0), None, None
-    xhat = ((z if bias is None else z + bias) - mean) * rstd
-    B = z.shape[0]
-    ggamma, gbeta = (g * xhat).sum(0), g.sum(0)
-    gx = g * gamma
-    gz = rstd / B * (B * gx - gx.sum(0) - xhat * (gx * xhat).sum(0))
-    return gz, gz.sum(0), ggamma, gbeta
-
-  def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
-    loss, probs, g = O.sigmoid_ce(logits.detach().numpy(), labels.numpy())
-    return torch.tensor([loss], dtype=torch.float32), torch.from_numpy(probs), torch.from_numpy(g)
-
-  def fm_fwd(x, n_field, dim, y=None):
-    return torch.from_numpy(O.fm_fwd(np.ascontiguousarray(x.detach().numpy()), n_field, dim))
-
-  def fm_bwd(x, gy, n_field, dim, gx=None, accumulate=False):
-    return torch.from_numpy(O.fm_bwd(np.ascontiguousarray(x.detach().numpy()), np.ascontiguousarray(gy.numpy()), n_field, dim))
-
-  def apply(self):   # FlatDenseOptimizer.apply: l2 + TF Adagrad over the flat buffer
-    assert self.kind == 1, 'this double implements the adagrad rule only'
-    segs = np.frombuffer(self.segs_dev.numpy().tobytes(), dtype=T._lib.DENSE_SEG_DTYPE)
-    self.reg_loss.zero_()
-    lr = float(self.lr_dev[0])
-    for s in segs:
-      o, n = int(s['offset']), int(s['n'])
-      w, g = self.flat_p[o:o + n], self.flat_g[o:o + n] * self.grad_scale
-      if s['l2'] > 0:
-        self.reg_loss += 0.5 * float(s['l2']) * (w * w).sum()
-        g = g + float(s['l2']) * w
-      self.s0[o:o + n] += g * g
-      w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
-  for name, fn in (('gemm', gemm), ('gemm_ready', lambda t: t), ('gemm_bn', lambda *a, **k: None),
-                   ('bias_bn_act_fwd', bias_bn_act_fwd), ('bias_bn_act_bwd', bias_bn_act_bwd),
-                   ('dense_workspace', lambda b, u, d: torch.zeros(1, dtype=torch.uint8)), ('sigmoid_ce', sigmoid_ce),
-                   ('fm_fwd', fm_fwd), ('fm_bwd', fm_bwd)):
-    monkeypatch.setattr(K, name, fn)
-  monkeypatch.setattr(T.FlatDenseOptimizer, 'apply', apply)
+  host_doubles.install_dense(monkeypatch.setattr)
 
 
 CFG = b'''
@@ -227,31 +164,7 @@ model_config { model_class: "DeepFM"
 
 @pytest.fixture
 def interaction_doubles(monkeypatch, dense_kernels):
-  """torch-native stand-ins for the fused interaction ops (autograd supplies their backward)."""
-  from easyrec_b200 import interactions as I
-
-  def din_attention(query, keys, lens, attention_mlp):
-    B, T, D = keys.shape
-    q = query[:, None, :].expand(B, T, D)
-    scores = attention_mlp(torch.cat([q, keys, q - keys, q * keys], dim=-1)).reshape(B, T)
-    mask = torch.arange(T)[None, :] < lens[:, None]
-    p = torch.softmax(torch.where(mask, scores, torch.full_like(scores, -2.0**32 + 1)), dim=1)
-    return (p[:, :, None] * keys).sum(1)
-
-  def inbatch_softmax_ce(sim, item_ids=None, weights=None):
-    B = sim.shape[0]
-    if item_ids is not None:
-      dup = (item_ids[None, :B] == item_ids[:B, None]).float() - torch.eye(B)
-      sim = torch.cat([sim[:, :B] - dup * 1e32, sim[:, B:]], dim=1)
-    p = torch.softmax(sim, dim=1)
-    diag = p[torch.arange(B), torch.arange(B)]
-    w = torch.ones(B) if weights is None else weights
-    return -(torch.log(diag + 1e-12) * w).mean() / w.mean(), diag.detach()
-  monkeypatch.setattr(I, 'din_attention', din_attention)
-  monkeypatch.setattr(I, 'cross_layer', lambda x0, xl, w, b: x0 * (xl * w).sum(1, keepdim=True) + b + xl)
-  monkeypatch.setattr(I, 'mmoe_mix', lambda g, ex: (torch.softmax(g, dim=1)[:, :, None] * ex).sum(1))
-  monkeypatch.setattr(I, 'l2_normalize', lambda x: x / torch.sqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12)))
-  monkeypatch.setattr(I, 'inbatch_softmax_ce', inbatch_softmax_ce)
+  host_doubles.install_interactions(monkeypatch.setattr)
 
 
 def _gpu_test_configs():
