@@ -258,6 +258,8 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   opt = optimizer_settings(pipeline_config)
   cls = model_pkg.get_model_class(mc.model_class)
   wide_dim = cls.wide_output_dim(mc)
+  if generator is None and not str(device).startswith('cuda'):
+    generator = cpu_generator   # tables initialised from the caller's seed on a host build too
   il = IL.InputLayer(specs, groups, batch_size, device, wide_output_dim=wide_dim,
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc))
