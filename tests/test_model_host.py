@@ -188,3 +188,39 @@ def test_every_gpu_test_model_config_trains_on_the_host(name, text, interaction_
   tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
   losses = [float(tr.train_step(feats, labels)[0]) for _ in range(15)]
   assert all(np.isfinite(losses)) and losses[-1] < losses[0], (name, losses)
+
+
+def test_din_from_csv_sequences_on_the_host(tmp_path, interaction_doubles):
+  """MultiTowerDIN fed by the native CSV reader: `|`-separated history, truncated to max_seq_len, key / history
+  tables of the sequence group, target attention; the attended vector of a row must ignore everything past its length."""
+  cfg = config_util.get_configs_from_pipeline_file(b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } }
+data_config { batch_size: 8 input_type: CSVInput separator: "," label_fields: "clk"
+  input_fields { input_name: "clk" input_type: FLOAT } input_fields { input_name: "user_id" input_type: INT64 }
+  input_fields { input_name: "item_id" input_type: INT64 } input_fields { input_name: "hist" input_type: STRING } }
+feature_config {
+  features { input_names: "user_id" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 50 }
+  features { input_names: "item_id" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 100 }
+  features { input_names: "hist" feature_type: SequenceFeature embedding_dim: 8 hash_bucket_size: 100 max_seq_len: 5 separator: "|" } }
+model_config { model_class: "MultiTowerDIN"
+  feature_groups { group_name: "user" feature_names: ["user_id"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id"] wide_deep: DEEP }
+  seq_att_groups { group_name: "din" seq_att_map { key: "item_id" hist_seq: "hist" } }
+  multi_tower { towers { input: "user" dnn { hidden_units: [16] } } towers { input: "item" dnn { hidden_units: [16] } }
+                din_towers { input: "din" dnn { hidden_units: [16, 1] } } final_dnn { hidden_units: [16] } } }
+''')
+  il, model, opt = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(2))
+  rows = ['1,1,10,10|11|12', '0,2,20,', '1,3,30,1|2|3|4|5|6|7', '0,4,40,40', '1,5,50,9|9', '0,6,60,60|61', '1,7,70,5', '0,8,80,1|2|3']
+  open(tmp_path / 's.csv', 'w').write('\n'.join(rows) + '\n')
+  (feats, labels), = list(readers.make_input(cfg, il, str(tmp_path / 's.csv')))
+  ids, lens = feats['seq_fea']['hist']
+  # a STRING field with a hash_bucket_size: the tokens are bucketed by the reader (Fingerprint64 % 100)
+  assert lens.tolist() == [3, 0, 5, 1, 2, 2, 1, 3] and ids[1].tolist() == [0] * 5
+  assert ids[2].tolist() == [O.fingerprint64(t) % 100 for t in '12345']            # the FIRST max_seq_len steps
+  il.lookup(feats)
+  so = il.seq_outputs['din']
+  assert tuple(so['hist_seq_emb'].shape) == (8, 5, 8) and tuple(so['key'].shape) == (8, 8)
+  assert not so['hist_seq_emb'][1].any() and not so['hist_seq_emb'][0, 3:].any()     # padded steps are zero vectors
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  losses = [float(tr.train_step(feats, labels)[0]) for _ in range(15)]
+  assert all(np.isfinite(losses)) and losses[-1] < losses[0]
