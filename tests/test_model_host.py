@@ -224,3 +224,21 @@ model_config { model_class: "MultiTowerDIN"
   tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
   losses = [float(tr.train_step(feats, labels)[0]) for _ in range(15)]
   assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_deepfm_trains_from_the_reference_loaders_parquet_case_on_the_host(tmp_path, dense_kernels):
+  """the Parquet data set behind tests/golden/reference_parquet_batches.json (floored-mod buckets, ragged tag lists,
+  carry-over across files) through ParquetInput -> InputLayer -> DeepFM for a few optimizer steps."""
+  sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+  import sys
+  sys.path.insert(0, sys_path)
+  import parquet_case as case
+  cfg = config_util.get_configs_from_pipeline_file(case.CONFIG)
+  il, model, opt = builder.build_model(cfg, case.BATCH, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  batches = list(readers.make_input(cfg, il, case.write_files(str(tmp_path))))
+  assert len(batches) == 4
+  tr = T.Trainer(model, il, 'adagrad', lr=0.05)
+  first = [float(tr.train_step(f, l)[0]) for f, l in batches]
+  for _ in range(6):
+    last = [float(tr.train_step(f, l)[0]) for f, l in batches]
+  assert all(np.isfinite(first + last)) and sum(last) < sum(first)
