@@ -242,3 +242,24 @@ def test_deepfm_trains_from_the_reference_loaders_parquet_case_on_the_host(tmp_p
   for _ in range(6):
     last = [float(tr.train_step(f, l)[0]) for f, l in batches]
   assert all(np.isfinite(first + last)) and sum(last) < sum(first)
+
+
+def test_adam_step_hyper_parameters_follow_adam_s():
+  """compat/adam_s.py:117-129,185-192,236-245: at the t-th apply (t = 1, 2, ...) the powers are beta^t and
+  lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t); the trainer's step counter starts at 0."""
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  from test_config import MINI
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'adam_optimizer', b'lazy_adam_optimizer'))
+  il, model, opt = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert opt['kind'] == 'lazy_adam_optimizer' and next(iter(il.arenas.values())).opt_kind == T._lib.OPT_LAZY_ADAM
+  tr = T.Trainer(model, il, 'lazy_adam', lr_fn=opt['lr_fn'], beta1=opt['beta1'], beta2=opt['beta2'])
+  for step in (0, 1, 7):
+    tr.step = step
+    tr._set_hyper()
+    o = il.opt_holder['opt']
+    t = step + 1
+    assert o.kind == T._lib.OPT_LAZY_ADAM and o.lr == pytest.approx(0.001)
+    assert o.beta1_power == pytest.approx(0.9**t) and o.beta2_power == pytest.approx(0.999**t)
+    # (the config's beta2 is the fp32 proto value 0.99900001..., as it is in the TF graph: 1e-5 relative slack)
+    assert float(tr.dense_opt.lr_dev[0]) == pytest.approx(0.001 * (1 - 0.999**t)**0.5 / (1 - 0.9**t), rel=2e-5)
