@@ -205,6 +205,15 @@ def check_scope(pipeline_config):
   dc = pipeline_config.data_config
   if dc.HasField('sample_weight'):
     bad.append('data_config.sample_weight (per-sample loss weights)')
+  for g in mc.feature_groups:
+    if len(g.sequence_features) > 0:
+      bad.append('feature_groups[%s].sequence_features (target attention inside a plain group, '
+                 'layers/sequence_feature_layer.py; use seq_att_groups with MultiTowerDIN)' % g.group_name)
+    if g.negative_sampler:
+      bad.append('feature_groups[%s].negative_sampler' % g.group_name)
+    names = g.DESCRIPTOR.fields_by_name['wide_deep'].enum_type.values_by_number
+    if names[g.wide_deep].name == 'WIDE_AND_DEEP':
+      bad.append('feature_groups[%s].wide_deep WIDE_AND_DEEP' % g.group_name)
   if mc.HasField('ev_params'):
     bad.append('model_config.ev_params (embedding variables / dynamic tables)')
   if len(mc.kd) > 0:

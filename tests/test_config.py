@@ -364,3 +364,13 @@ def test_reference_avazu_combo_config_reads_synthetic_lines(tmp_path):
     kinds.add(ftype)
     assert ids[k].tolist() == want, name
   assert kinds == {'ComboFeature', 'RawFeature', 'IdFeature'}
+
+
+def test_in_group_sequence_features_are_refused():
+  """feature_groups { sequence_features { ... } } asks for target attention inside a plain group
+  (layers/sequence_feature_layer.py); building the model without it would train something else."""
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
+      b'feature_names: "C1" wide_deep: DEEP', b'feature_names: "C1" wide_deep: DEEP sequence_features { group_name: "s" '
+      b'seq_att_map { key: "C1" hist_seq: "C1" } }'))
+  with pytest.raises(NotImplementedError, match='sequence_features'):
+    builder.check_scope(cfg)
