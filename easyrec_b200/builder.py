@@ -242,6 +242,11 @@ def check_scope(pipeline_config):
       bad.append('model_config.losses %s' % ([names[l.loss_type].name for l in mc.losses],))
   for path, m in _walk_messages(mc, 'model_config'):
     kind = m.DESCRIPTOR.name
+    if kind in ('TaskTower', 'BayesTaskTower'):
+      lt = m.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[m.loss_type].name
+      if lt != 'CLASSIFICATION' or m.num_class != 1:
+        bad.append('%s: loss_type %s / num_class %d (task towers train with binary sigmoid cross entropy)'
+                   % (path, lt, m.num_class))
     if kind in ('DNN', 'MLP'):
       if any(r > 0 for r in m.dropout_ratio):
         bad.append('%s.dropout_ratio' % path)

@@ -374,3 +374,13 @@ def test_in_group_sequence_features_are_refused():
       b'seq_att_map { key: "C1" hist_seq: "C1" } }'))
   with pytest.raises(NotImplementedError, match='sequence_features'):
     builder.check_scope(cfg)
+
+
+def test_non_binary_task_towers_are_refused():
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  import test_gpu_models as G
+  cfg = config_util.get_configs_from_pipeline_file(G.MMOE_CFG.replace('loss_type: CLASSIFICATION weight: 0.5', 'loss_type: L2_LOSS weight: 0.5').encode())
+  with pytest.raises(NotImplementedError, match='L2_LOSS'):
+    builder.check_scope(cfg)
+  builder.check_scope(config_util.get_configs_from_pipeline_file(G.MMOE_CFG.encode()))
