@@ -244,6 +244,10 @@ def check_scope(pipeline_config):
     kind = m.DESCRIPTOR.name
     if kind in ('TaskTower', 'BayesTaskTower'):
       lt = m.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[m.loss_type].name
+      if len(m.losses) > 0:
+        bad.append('%s.losses (per-tower loss list)' % path)
+      if m.HasField('task_space_indicator_label'):
+        bad.append('%s.task_space_indicator_label (in / out of task-space sample weights)' % path)
       if lt != 'CLASSIFICATION' or m.num_class != 1:
         bad.append('%s: loss_type %s / num_class %d (task towers train with binary sigmoid cross entropy)'
                    % (path, lt, m.num_class))

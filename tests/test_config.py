@@ -384,3 +384,41 @@ def test_non_binary_task_towers_are_refused():
   with pytest.raises(NotImplementedError, match='L2_LOSS'):
     builder.check_scope(cfg)
   builder.check_scope(config_util.get_configs_from_pipeline_file(G.MMOE_CFG.encode()))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+def test_no_model_or_optimizer_field_is_silently_dropped_for_configs_that_build():
+  """The subset schema skips fields it does not know.  For every reference sample config that BUILDS here, parse it
+  with the reference's full schema as well and diff the set fields: anything under model_config, the optimizer, the
+  label / input-field declarations that the subset dropped would mean training a different model in silence.
+  (Control plane - export, kafka / odps inputs, extra eval metrics - may be dropped.)"""
+  full = proto_loader.load_schema(sorted(glob.glob(os.path.join(REF, 'easy_rec/python/protos/*.proto'))),
+                                  virtual_name='full_ref2.proto')
+
+  def walk(msg, prefix, out):
+    for fd, v in msg.ListFields():
+      p = prefix + '.' + fd.name
+      out.add(p)
+      if fd.type == fd.TYPE_MESSAGE and not fd.message_type.GetOptions().map_entry:
+        for it in (list(v) if builder._is_repeated(fd) else [v]):
+          walk(it, p, out)
+  guarded = ('.model_config', '.train_config.optimizer_config', '.train_config.gradient_clipping_by_norm',
+             '.data_config.input_fields', '.data_config.label_fields', '.data_config.separator', '.data_config.sample_weight')
+  paths = sorted(glob.glob(os.path.join(REF, 'samples/model_config/*.config'))) + \
+      sorted(glob.glob(os.path.join(REF, 'examples/configs/*.config')))
+  built, dropped = 0, {}
+  for p in paths:
+    try:
+      cfg = config_util.get_configs_from_pipeline_file(p)
+      builder.build_model(cfg, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+    except (NotImplementedError, ValueError, KeyError, AssertionError):
+      continue          # refused loudly: fine
+    built += 1
+    a, b = set(), set()
+    walk(config_util.get_configs_from_pipeline_file(p, schema=full), '', a)
+    walk(cfg, '', b)
+    bad = sorted(f for f in a - b if f.startswith(guarded))
+    if bad:
+      dropped[os.path.basename(p)] = bad
+  assert built >= 40
+  assert not dropped, dropped
