@@ -31,13 +31,15 @@ BUCKET_FARM_DECIMAL, BUCKET_MOD, BUCKET_IDENTITY, BUCKET_NONE = 0, 1, 2, 3
 COMBINER_SUM, COMBINER_MEAN, COMBINER_SQRTN = 0, 1, 2
 OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM, OPT_ADAM_ROWS = 0, 1, 2, 3
 MAX_BUFS = 8
+ABI_VERSION = 2
+HYPER_LR, HYPER_BETA1_POWER, HYPER_BETA2_POWER, HYPER_GRAD_SCALE, HYPER_N = 0, 1, 2, 3, 4
 
 
 class ErOpt(ctypes.Structure):
   """er_opt_t."""
   _fields_ = [('kind', c_i32), ('lr', c_f32), ('beta1', c_f32),
               ('beta2', c_f32), ('eps', c_f32), ('beta1_power', c_f32),
-              ('beta2_power', c_f32), ('grad_scale', c_f32)]
+              ('beta2_power', c_f32), ('grad_scale', c_f32), ('hyper_dev', c_vp)]
 
 
 class ErBnStats(ctypes.Structure):
@@ -170,6 +172,9 @@ def load():
     fn = getattr(lib, name)  # AttributeError if the symbol is missing
     fn.restype = res
     fn.argtypes = args
+  if lib.er_abi_version() != ABI_VERSION:
+    raise ErError('liber_b200.so has ABI version %d, this binding needs %d: rebuild it (make -C easyrec_b200/csrc)'
+                  % (lib.er_abi_version(), ABI_VERSION))
   _lib = lib
   return lib
 

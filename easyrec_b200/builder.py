@@ -282,4 +282,25 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc))
   model = cls.from_config(mc, il, generator=cpu_generator).to(device)
+  bind_task_labels(model, list(pipeline_config.data_config.label_fields))
   return il, model, opt
+
+
+def bind_task_labels(model, label_fields):
+  """Multi-task towers read the label their `label_name` names; a tower without one takes the label at its own
+  position (model/multi_task_model.py:114-122).  Sets model.label_cols = column of each tower in the [B, n_label]
+  label matrix the readers build in data_config.label_fields order."""
+  names = getattr(model, 'label_names', None)
+  if names is None:
+    return
+  cols = []
+  for i, n in enumerate(names):
+    if not n:
+      if i >= len(label_fields):
+        raise ValueError('task tower %d has no label_name and there is no label field at its position' % i)
+      cols.append(i)
+    elif n in label_fields:
+      cols.append(label_fields.index(n))
+    else:
+      raise ValueError('task tower label_name %r is not one of data_config.label_fields %r' % (n, label_fields))
+  model.label_cols = cols

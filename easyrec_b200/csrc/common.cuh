@@ -1,6 +1,7 @@
 // Shared helpers for liber_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -89,6 +90,16 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// lr * sqrt(1 - beta2_power) / (1 - beta1_power) in fp32, the order of the TF graph (adam_s.py:193);
+// every operation correctly rounded so the host (adam_lr_t) and device values are the same float
+__host__ __device__ __forceinline__ float adam_lr_t_of(float lr, float b1p, float b2p) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+#else
+  return lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+#endif
 }
 
 // slot of a segment: largest f with slots[f].seg_begin <= s (slots sorted by seg_begin).

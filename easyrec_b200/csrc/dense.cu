@@ -592,7 +592,14 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   const int n_chunks = s_first[n_segs];
-  const float lr0 = lr_dev ? *lr_dev : opt.lr;
+  // step scalars: a device scalar (lr_dev: already the effective rate), or the caller's hyper-parameter block
+  // (opt.hyper_dev: lr and Adam's beta powers, from which lr_t is formed here), or the struct itself
+  float lr0 = lr_dev ? *lr_dev : opt.lr;
+  if (!lr_dev && opt.hyper_dev) {
+    lr0 = __ldg(opt.hyper_dev + ER_HYPER_LR);
+    if (opt.kind == ER_OPT_LAZY_ADAM || opt.kind == ER_OPT_ADAM_ROWS)
+      lr0 = adam_lr_t_of(lr0, __ldg(opt.hyper_dev + ER_HYPER_BETA1_POWER), __ldg(opt.hyper_dev + ER_HYPER_BETA2_POWER));
+  }
   float reg = 0.f;
   for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     int lo = 0, hi = n_segs;   // s_first[lo] <= ch < s_first[hi]

@@ -57,6 +57,7 @@ struct BwdArgs {
   const float* seg_scale;
   er_opt_t opt;
   float lr_t;  // adam: lr*sqrt(1-b2^t)/(1-b1^t)
+  const float* hyper;  // device float[ER_HYPER_N] overriding opt.lr / beta powers / grad_scale (CUDA graphs)
   int64_t* uniq_rows;
   float* uniq_grads;
   const int32_t* head_rank;  // exclusive count of run heads before each position (emit mode)
@@ -78,11 +79,33 @@ __device__ __forceinline__ const float* grad_src(const BwdArgs& a, const SlotVie
   return a.gbufs.p[sl.misc & 0xff] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
 }
 
-__device__ __forceinline__ void upd_one(const BwdArgs& a, float g, float& w, float& s0, float& s1) {
+struct Hyper {
+  float lr, lr_t, grad_scale;
+};
+
+// per-step scalars of the row rule: kernel arguments, or - when the caller keeps them in device memory so that a
+// captured graph follows a schedule - four broadcast loads by the threads that apply an update
+__device__ __forceinline__ Hyper load_hyper(const er_opt_t& o, float lr_t_arg, const float* __restrict__ hyper) {
+  Hyper h;
+  if (hyper) {
+    h.lr = __ldg(hyper + ER_HYPER_LR);
+    h.grad_scale = __ldg(hyper + ER_HYPER_GRAD_SCALE);
+    h.lr_t = h.lr;
+    if (o.kind == ER_OPT_LAZY_ADAM || o.kind == ER_OPT_ADAM_ROWS)
+      h.lr_t = adam_lr_t_of(h.lr, __ldg(hyper + ER_HYPER_BETA1_POWER), __ldg(hyper + ER_HYPER_BETA2_POWER));
+  } else {
+    h.lr = o.lr;
+    h.lr_t = lr_t_arg;
+    h.grad_scale = o.grad_scale;
+  }
+  return h;
+}
+
+__device__ __forceinline__ void upd_one(const BwdArgs& a, const Hyper& h, float g, float& w, float& s0, float& s1) {
   switch (a.opt.kind) {
     case ER_OPT_ADAGRAD: {
       s0 = __fadd_rn(s0, __fmul_rn(g, g));
-      w = __fsub_rn(w, __fmul_rn(__fmul_rn(a.opt.lr, g), __frsqrt_rn(s0)));
+      w = __fsub_rn(w, __fmul_rn(__fmul_rn(h.lr, g), __frsqrt_rn(s0)));
       break;
     }
     case ER_OPT_LAZY_ADAM:
@@ -90,11 +113,11 @@ __device__ __forceinline__ void upd_one(const BwdArgs& a, float g, float& w, flo
       // m_part = g*(1-b1) + m*b1 ; v_part = g*g*(1-b2) + v*b2 ; w += -lr_t*m_part/(sqrt(v_part)+eps)
       s0 = __fadd_rn(__fmul_rn(g, 1.0f - a.opt.beta1), __fmul_rn(s0, a.opt.beta1));
       s1 = __fadd_rn(__fmul_rn(__fmul_rn(g, g), 1.0f - a.opt.beta2), __fmul_rn(s1, a.opt.beta2));
-      w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-a.lr_t, s0), __fadd_rn(sqrtf(s1), a.opt.eps)));
+      w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-h.lr_t, s0), __fadd_rn(__fsqrt_rn(s1), a.opt.eps)));
       break;
     }
     default:  // SGD
-      w = __fsub_rn(w, __fmul_rn(a.opt.lr, g));
+      w = __fsub_rn(w, __fmul_rn(h.lr, g));
   }
 }
 
@@ -128,20 +151,21 @@ __device__ __forceinline__ RowRegs load_row(const BwdArgs& a, uint32_t row, int 
 
 __device__ __forceinline__ void apply_row_vec(const BwdArgs& a, uint32_t row, int lane, float4 g,
                                               int64_t head_pos, RowRegs r) {
-  g.x = __fmul_rn(g.x, a.opt.grad_scale);
-  g.y = __fmul_rn(g.y, a.opt.grad_scale);
-  g.z = __fmul_rn(g.z, a.opt.grad_scale);
-  g.w = __fmul_rn(g.w, a.opt.grad_scale);
+  const Hyper h = load_hyper(a.opt, a.lr_t, a.hyper);
+  g.x = __fmul_rn(g.x, h.grad_scale);
+  g.y = __fmul_rn(g.y, h.grad_scale);
+  g.z = __fmul_rn(g.z, h.grad_scale);
+  g.w = __fmul_rn(g.w, h.grad_scale);
   if (a.uniq_rows) {
     const int32_t u = a.head_rank[head_pos];
     if (lane == 0) a.uniq_rows[u] = (int64_t)row;
     reinterpret_cast<float4*>(a.uniq_grads + (int64_t)u * a.dim)[lane] = g;
   }
   if (!a.table) return;
-  upd_one(a, g.x, r.w.x, r.s0.x, r.s1.x);
-  upd_one(a, g.y, r.w.y, r.s0.y, r.s1.y);
-  upd_one(a, g.z, r.w.z, r.s0.z, r.s1.z);
-  upd_one(a, g.w, r.w.w, r.s0.w, r.s1.w);
+  upd_one(a, h, g.x, r.w.x, r.s0.x, r.s1.x);
+  upd_one(a, h, g.y, r.w.y, r.s0.y, r.s1.y);
+  upd_one(a, h, g.z, r.w.z, r.s0.z, r.s1.z);
+  upd_one(a, h, g.w, r.w.w, r.s0.w, r.s1.w);
   const int64_t off = (int64_t)row * a.row_stride;
   reinterpret_cast<float4*>(a.table + off)[lane] = r.w;
   if (a.state0) reinterpret_cast<float4*>(a.state0 + off)[lane] = r.s0;
@@ -150,7 +174,8 @@ __device__ __forceinline__ void apply_row_vec(const BwdArgs& a, uint32_t row, in
 
 __device__ __forceinline__ void apply_scalar(const BwdArgs& a, uint32_t key, int c, float g,
                                              int64_t head_pos) {
-  g = __fmul_rn(g, a.opt.grad_scale);
+  const Hyper h = load_hyper(a.opt, a.lr_t, a.hyper);
+  g = __fmul_rn(g, h.grad_scale);
   if (a.uniq_rows) {
     const int32_t u = a.head_rank[head_pos];
     if (c == 0) a.uniq_rows[u] = (int64_t)key;
@@ -161,7 +186,7 @@ __device__ __forceinline__ void apply_scalar(const BwdArgs& a, uint32_t key, int
   float w = a.table[off];
   float s0 = a.state0 ? a.state0[off] : 0.f;
   float s1 = a.state1 ? a.state1[off] : 0.f;
-  upd_one(a, g, w, s0, s1);
+  upd_one(a, h, g, w, s0, s1);
   a.table[off] = w;
   if (a.state0) a.state0[off] = s0;
   if (a.state1) a.state1[off] = s1;
@@ -715,10 +740,7 @@ inline BwdWs bwd_carve(void* ws, int64_t n, int dim) {
   return w;
 }
 
-static float adam_lr_t(const er_opt_t& o) {
-  // lr * sqrt(1 - beta2_power) / (1 - beta1_power), fp32 like the TF graph (adam_s.py:193)
-  return o.lr * sqrtf(1.0f - o.beta2_power) / (1.0f - o.beta1_power);
-}
+static float adam_lr_t(const er_opt_t& o) { return adam_lr_t_of(o.lr, o.beta1_power, o.beta2_power); }
 
 template <int LANES>
 static void launch_vec(const BwdArgs& a, cudaStream_t st) {
@@ -833,6 +855,7 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   a.seg_scale = seg_scale;
   a.opt = *opt;
   a.lr_t = (opt->kind == ER_OPT_LAZY_ADAM || opt->kind == ER_OPT_ADAM_ROWS) ? adam_lr_t(*opt) : opt->lr;
+  a.hyper = opt->hyper_dev;
   a.uniq_rows = uniq_rows;
   a.uniq_grads = uniq_grads;
   a.head_rank = nullptr;
@@ -930,6 +953,7 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ uniq_grads, const int32_t* __restrict__ n_uniq,
                         int64_t n_cap) {
   const int64_t n = n_uniq ? (int64_t)(*n_uniq < n_cap ? *n_uniq : n_cap) : n_cap;
+  const Hyper h = load_hyper(a.opt, a.lr_t, a.hyper);
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * a.dim;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t u = t / a.dim;
@@ -937,33 +961,84 @@ __global__ void __launch_bounds__(256)
     const int64_t row = uniq_rows[u];
     if (row < 0) continue;
     const int64_t off = row * a.row_stride + c;
-    float g = __fmul_rn(uniq_grads[u * a.dim + c], a.opt.grad_scale);
+    float g = __fmul_rn(uniq_grads[u * a.dim + c], h.grad_scale);
     float w = a.table[off];
     float s0 = a.state0 ? a.state0[off] : 0.f;
     float s1 = a.state1 ? a.state1[off] : 0.f;
-    upd_one(a, g, w, s0, s1);
+    upd_one(a, h, g, w, s0, s1);
     a.table[off] = w;
     if (a.state0) a.state0[off] = s0;
     if (a.state1) a.state1[off] = s1;
   }
 }
 
-__global__ void __launch_bounds__(256)
-    adam_sweep_kernel(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v,
-                      int64_t n_rows, int dim, int row_stride, const uint8_t* __restrict__ touched,
-                      float beta1, float beta2, float eps, float lr_t) {
-  const int64_t total = n_rows * dim;
+// TF AdamOptimizer on the rows that received no gradient this step: m *= b1, v *= b2,
+// w -= lr_t*m/(sqrt(v)+eps) (the decay half of _apply_sparse_shared in TF's adam.py; behaviour stated at
+// compat/adam_s.py:74-81).  Pure stream over the table: one thread per VEC floats of a row, rows whose
+// moments are all zero are not written back (never-touched rows: the update is exactly 0).
+struct SweepArgs {
+  float* table;
+  float* m;
+  float* v;
+  int64_t n_rows;
+  int dim;
+  int row_stride;
+  const uint8_t* touched;
+  er_opt_t opt;
+  float lr_t;
+  const float* hyper;
+};
+
+__device__ __forceinline__ void sweep_one(float& w, float& m, float& v, float b1, float b2, float eps, float lr_t) {
+  m = __fmul_rn(m, b1);
+  v = __fmul_rn(v, b2);
+  w = __fsub_rn(w, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
+__global__ void __launch_bounds__(256) adam_sweep_vec_kernel(const __grid_constant__ SweepArgs a) {
+  const Hyper h = load_hyper(a.opt, a.lr_t, a.hyper);
+  const int d4 = a.dim >> 2;
+  const int64_t total = a.n_rows * d4;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = t / dim;
-    const int c = (int)(t - r * dim);
-    if (touched && touched[r]) continue;
-    const int64_t off = r * row_stride + c;
-    float mm = __fmul_rn(m[off], beta1);
-    float vv = __fmul_rn(v[off], beta2);
-    m[off] = mm;
-    v[off] = vv;
-    table[off] = __fsub_rn(table[off], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(sqrtf(vv), eps)));
+    const int64_t r = t / d4;
+    const int c = (int)(t - r * d4);
+    if (a.touched && a.touched[r]) continue;
+    const int64_t off = r * a.row_stride;
+    float4* pm = reinterpret_cast<float4*>(a.m + off) + c;
+    float4* pv = reinterpret_cast<float4*>(a.v + off) + c;
+    float4 m = *pm, v = *pv;
+    if (m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f &&
+        v.w == 0.f)
+      continue;
+    float4* pw = reinterpret_cast<float4*>(a.table + off) + c;
+    float4 w = *pw;
+    sweep_one(w.x, m.x, v.x, a.opt.beta1, a.opt.beta2, a.opt.eps, h.lr_t);
+    sweep_one(w.y, m.y, v.y, a.opt.beta1, a.opt.beta2, a.opt.eps, h.lr_t);
+    sweep_one(w.z, m.z, v.z, a.opt.beta1, a.opt.beta2, a.opt.eps, h.lr_t);
+    sweep_one(w.w, m.w, v.w, a.opt.beta1, a.opt.beta2, a.opt.eps, h.lr_t);
+    *pm = m;
+    *pv = v;
+    *pw = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_sweep_kernel(const __grid_constant__ SweepArgs a) {
+  const Hyper h = load_hyper(a.opt, a.lr_t, a.hyper);
+  const int64_t total = a.n_rows * a.dim;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / a.dim;
+    const int c = (int)(t - r * a.dim);
+    if (a.touched && a.touched[r]) continue;
+    const int64_t off = r * a.row_stride + c;
+    float m = a.m[off], v = a.v[off];
+    if (m == 0.f && v == 0.f) continue;
+    float w = a.table[off];
+    sweep_one(w, m, v, a.opt.beta1, a.opt.beta2, a.opt.eps, h.lr_t);
+    a.m[off] = m;
+    a.v[off] = v;
+    a.table[off] = w;
   }
 }
 
@@ -988,6 +1063,7 @@ extern "C" int er_sparse_apply(float* table, float* state0, float* state1, int32
   a.row_stride = row_stride;
   a.opt = *opt;
   a.lr_t = (k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS) ? adam_lr_t(*opt) : opt->lr;
+  a.hyper = opt->hyper_dev;
   sparse_apply_kernel<<<grid_for(n_cap * dim, 256, 8), 256, 0, as_stream(stream)>>>(
       a, uniq_rows, uniq_grads, n_uniq, n_cap);
   count_launches(1);
@@ -1001,9 +1077,24 @@ extern "C" int er_adam_dense_sweep(float* table, float* m, float* v, int64_t n_r
   using namespace er;
   ER_REQUIRE(table && m && v && opt, "null argument");
   ER_REQUIRE(dim > 0 && row_stride >= dim && n_rows > 0, "bad shape");
-  adam_sweep_kernel<<<grid_for(n_rows * dim, 256, 8), 256, 0, as_stream(stream)>>>(
-      table, m, v, n_rows, dim, row_stride, touched, opt->beta1, opt->beta2, opt->eps,
-      adam_lr_t(*opt));
+  SweepArgs a;
+  a.table = table;
+  a.m = m;
+  a.v = v;
+  a.n_rows = n_rows;
+  a.dim = dim;
+  a.row_stride = row_stride;
+  a.touched = touched;
+  a.opt = *opt;
+  a.opt.kind = ER_OPT_ADAM_ROWS;
+  a.lr_t = adam_lr_t(*opt);
+  a.hyper = opt->hyper_dev;
+  const bool vec = dim % 4 == 0 && row_stride % 4 == 0 && reinterpret_cast<uintptr_t>(table) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(m) % 16 == 0 && reinterpret_cast<uintptr_t>(v) % 16 == 0;
+  if (vec)
+    adam_sweep_vec_kernel<<<grid_for(n_rows * (dim / 4), 256, 8), 256, 0, as_stream(stream)>>>(a);
+  else
+    adam_sweep_kernel<<<grid_for(n_rows * dim, 256, 8), 256, 0, as_stream(stream)>>>(a);
   count_launches(1);
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;

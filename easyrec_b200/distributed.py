@@ -14,6 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from easyrec_b200 import embedding as E
 from easyrec_b200 import kernels as K
 
 
@@ -59,6 +60,7 @@ class DataParallel(object):
     input_layer.presort_enabled = False   # K7 runs on the gathered global batch, sorted after the exchange
     self.dense_opt = dense_opt
     dense_opt.grad_scale = 1.0 / world  # mean over replicas, applied inside er_dense_apply
+    input_layer.replica_grad_scale = 1.0 / world   # same for the sparse rows (InputLayer.set_optimizer_step)
     plans = getattr(input_layer, 'merged', None) or input_layer.calls
     self.gcalls = {id(c): GlobalCall(c, world) for c in plans.values()}
     self._rows_owner = {}
@@ -154,7 +156,11 @@ class DataParallel(object):
   def apply_sparse(self, pending, opt):
     """The same fused dedup + row update on every rank over the gathered global batch; gradients
     are scaled by 1/world (mean over replicas).  No collectives: CUDA-graph capturable."""
-    opt.grad_scale = opt.grad_scale / self.world
+    # mean over replicas: a caller that keeps the step scalars in device memory (InputLayer.hyper) has folded
+    # 1/world into them (replica_grad_scale); a plain er_opt_t is scaled here
+    struct_scaled = not opt.hyper_dev
+    if struct_scaled:
+      opt.grad_scale = opt.grad_scale / self.world
     for call, rows, w, outs, seg_ids in pending:
       g = self.gcalls[id(call)]
       a = call.arena
@@ -166,7 +172,9 @@ class DataParallel(object):
       K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, owner.rows, g.slots_dev, g.n_slots, g.n_seg,
                       g.grads, opt, g.ws, weights=owner.weights if w is not None else None,
                       seg_scale=g.seg_scale, sorted_from=sorted_from)
-    opt.grad_scale = opt.grad_scale * self.world
+      E.adam_dense_decay(a, owner.rows, opt)   # tf.train.AdamOptimizer: the rows nobody looked up decay too
+    if struct_scaled:
+      opt.grad_scale = opt.grad_scale * self.world
 
   def sparse_backward_update(self, opt):
     il = self.input_layer

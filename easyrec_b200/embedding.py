@@ -97,6 +97,10 @@ class Arena(object):
     elif opt_kind in (_lib.OPT_LAZY_ADAM, _lib.OPT_ADAM_ROWS):
       self.state0 = state(0, 0.0)
       self.state1 = state(1, 0.0)
+    # tf.train.AdamOptimizer decays m, v and moves w on EVERY row each step; the rows of this step's lookups are
+    # marked here so that the dense sweep skips exactly the rows the fused row update has already written
+    self.touched = (torch.zeros(self.n_rows, dtype=torch.uint8, device=self.device)
+                    if opt_kind == _lib.OPT_ADAM_ROWS else None)
 
   def table_view(self, name):
     off, n, _ = self.tables[name]
@@ -122,13 +126,11 @@ class ArenaCall(object):
     for s in slots:
       off, _, _ = arena.tables[s.table]
       n_seg = batch_size * s.n_seg_per_sample
-      if s.n_seg_per_sample == 1:
-        col = cols[s.out_buf]
-        cols[s.out_buf] += dim
-        stride = self.out_strides[s.out_buf]
-      else:  # sequence slot: its own [B*T, dim] matrix
-        col = 0
-        stride = self.out_strides[s.out_buf]
+      # every slot owns its own column range of its output matrix: [B, sum dim] for pooled slots, [B*T, sum dim]
+      # for the sequence slots of one group (two hist_seq features of a DIN group sit side by side)
+      col = cols[s.out_buf]
+      cols[s.out_buf] += dim
+      stride = self.out_strides[s.out_buf]
       self.slot_cols.append(col)
       recs.append(dict(num_buckets=s.num_buckets, row_offset=off, seg_begin=seg, n_seg=n_seg,
                        bucket_mode=s.bucket_mode, combiner=s.combiner, out_buf=s.out_buf,
@@ -172,6 +174,19 @@ def fused_lookup(call, rows, weights=None, row_ptr=None, outs=None):
   return outs
 
 
+def adam_dense_decay(arena, rows, opt, n_dev=None):
+  """The dense half of tf.train.AdamOptimizer's sparse apply (builders/optimizer_builder.py:61-66; behaviour
+  stated at compat/adam_s.py:74-81): every row WITHOUT a gradient this step still gets m *= b1, v *= b2,
+  w -= lr_t*m/(sqrt(v)+eps).  `rows` are the step's looked-up rows (already updated by K7's row rule)."""
+  if arena.opt_kind != _lib.OPT_ADAM_ROWS:
+    return
+  if rows is not None and rows.numel():
+    K.mark_rows(rows, arena.n_rows, arena.touched, 1, n_dev=n_dev)
+  K.adam_dense_sweep(arena.weight, arena.state0, arena.state1, arena.dim, arena.touched, opt)
+  if rows is not None and rows.numel():
+    K.mark_rows(rows, arena.n_rows, arena.touched, 0, n_dev=n_dev)
+
+
 def fused_backward_update(call, rows, outs, opt, weights=None, row_ptr=None, seg_ids=None, sorted_from=None):
   """K7: dedup + segment-sum + optimizer row update from the leaves' gradients.  Runs on the
   caller's thread and stream (not inside the autograd engine), so it is CUDA-graph capturable."""
@@ -185,6 +200,7 @@ def fused_backward_update(call, rows, outs, opt, weights=None, row_ptr=None, seg
   K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, rows, call.slots_dev, call.n_slots,
                   call.n_seg, gbufs, opt, call.ws, weights=weights, seg_ids=seg_ids,
                   row_ptr=row_ptr, seg_scale=call.seg_scale, sorted_from=sorted_from)
+  adam_dense_decay(a, rows, opt, n_dev=None if row_ptr is None else row_ptr[call.n_seg:])
 
 
 class _FM(torch.autograd.Function):

@@ -38,6 +38,9 @@ class EasyRecEstimator(object):
     self.trainer = Trainer(self.model, self.input_layer, _DENSE_KIND[self._opt['kind']], lr_fn=self._opt['lr_fn'],
                            use_cuda_graph=use_cuda_graph, world_size=world_size, beta1=self._opt['beta1'],
                            beta2=self._opt['beta2'], adagrad_init=self._opt['acc0'])
+    # optimizer_config.embedding_learning_rate_multiplier: gradient multiplier of the embedding tables
+    # (model/easy_rec_estimator.py:308-317)
+    self.input_layer.emb_grad_mult = float(self._opt.get('emb_lr_mult', 1.0))
     self.global_step = 0
 
   # -- properties of the reference estimator (easy_rec_estimator.py:97-153) --
@@ -153,9 +156,15 @@ class EasyRecEstimator(object):
     model_dir = model_dir or self._pipeline_config.model_dir
     os.makedirs(model_dir, exist_ok=True)
     path = os.path.join(model_dir, 'model.ckpt-%d.pt' % self.global_step)
+    do = self.trainer.dense_opt
     torch.save({'model': self.model.state_dict(),
                 'arenas': {d: a.storage for d, a in self.input_layer.arenas.items()},
                 'tables': {d: a.tables for d, a in self.input_layer.arenas.items()},
+                # dense optimizer slots (Adagrad accumulators | Adam m, v), keyed by parameter name: the reference's
+                # Saver stores every slot variable, a resumed run continues from them
+                'dense_slots': {n: [None if st is None else st[o:o + k].clone() for st in (do.s0, do.s1)]
+                                for n, o, k in do.named_ranges()},
+                'trainer_step': self.trainer.step,
                 'global_step': self.global_step}, path)
     if embedding_parts:
       for a in self.input_layer.arenas.values():
@@ -168,6 +177,17 @@ class EasyRecEstimator(object):
     ck = torch.load(path, map_location='cpu')
     self.model.load_state_dict(ck['model'])
     self.global_step = int(ck['global_step'])
+    # the step counter drives the learning-rate schedule and Adam's beta powers; the dense slots continue
+    self.trainer.step = int(ck.get('trainer_step', self.global_step))
+    do = self.trainer.dense_opt
+    slots = ck.get('dense_slots')
+    if slots is not None:
+      for n, o, k in do.named_ranges():
+        if n not in slots:
+          raise KeyError('checkpoint has no optimizer slots for parameter %s' % n)
+        for st, saved in zip((do.s0, do.s1), slots[n]):
+          if st is not None and saved is not None:
+            st[o:o + k].copy_(saved)
     parts = os.path.isdir(path[:-3] + '-embedding')
     for d, a in self.input_layer.arenas.items():
       if parts:

@@ -294,7 +294,15 @@ class InputLayer(object):
     self.raw_range = torch.tensor(np.where(rng > 0, rng, 1.0), dtype=torch.float32, device=device)
     self.raw_sub = torch.tensor(np.where(rng > 0, np.array(mn, np.float32), 0.0),
                                 dtype=torch.float32, device=device)
-    self.opt_holder = {'opt': K.make_opt(embedding_optimizer, 0.01)}
+    # step-varying optimizer scalars live in device memory (K.StepHyper): a captured graph follows the schedule
+    self.hyper = K.StepHyper(device)
+    self.hyper.set(0.01, 0)
+    self.opt_holder = {'opt': self.hyper.opt(embedding_optimizer)}
+    # embedding_learning_rate_multiplier: the reference multiplies the GRADIENT of every `embedding_weights`
+    # variable by it (model/easy_rec_estimator.py:308-317 gradient_multipliers), before the optimizer rule
+    self.emb_grad_mult = 1.0
+    # 1/N of data-parallel replicas or of row-sharded tables (compat/optimizers.py:289-292,315-316)
+    self.replica_grad_scale = 1.0
     self._pending = []
     self._rows_cache = {}
     self._presorted = {}
@@ -309,8 +317,11 @@ class InputLayer(object):
     """Per-step hyper-parameters of the fused row update (host-side schedule,
     core/learning_schedules.py:30-75; beta powers as compat/adam_s.py:233-245)."""
     kind = next(iter(self.arenas.values())).opt_kind
-    self.opt_holder['opt'] = K.make_opt(kind, lr, beta1, beta2, eps, beta1**(step + 1),
-                                        beta2**(step + 1), grad_scale)
+    h = self.hyper
+    if np.float32(beta1) != h.beta1 or np.float32(beta2) != h.beta2:
+      h.beta1, h.beta2, h._pow_step = np.float32(beta1), np.float32(beta2), None
+    h.set(lr, step, grad_scale * self.emb_grad_mult * self.replica_grad_scale)
+    self.opt_holder['opt'] = h.opt(kind, eps)
 
   def backward_update(self):
     """After loss.backward(): K7 for every arena looked up since the last call (dedup, segment

@@ -123,8 +123,55 @@ def bwd_workspace(n_lookups_cap, device, dim):
 
 
 def make_opt(kind, lr, beta1=0.9, beta2=0.999, eps=1e-8, beta1_power=0.9, beta2_power=0.999,
-             grad_scale=1.0):
-  return ErOpt(kind, lr, beta1, beta2, eps, beta1_power, beta2_power, grad_scale)
+             grad_scale=1.0, hyper_dev=None):
+  """er_opt_t.  hyper_dev: device float[HYPER_N] the kernels read lr / beta powers / grad_scale from instead of
+  the struct fields (which the caller keeps equal to it), so a captured graph follows the schedule."""
+  return ErOpt(kind, lr, beta1, beta2, eps, beta1_power, beta2_power, grad_scale, _p(hyper_dev))
+
+
+class StepHyper(object):
+  """The step-varying scalars of the optimizers - learning rate (core/learning_schedules.py:30-75), Adam's
+  beta1^t / beta2^t (fp32 accumulators multiplied once per step like TF's `_finish`, compat/adam_s.py:233-245)
+  and the sparse gradient scale (1/N for sharded tables x embedding_learning_rate_multiplier) - in ONE device
+  float[HYPER_N], refreshed by one 16-byte stream-ordered copy per step (from a fresh pageable host tensor: the
+  driver stages it before returning, so the host may run any number of steps ahead of the device)."""
+
+  def __init__(self, device, beta1=0.9, beta2=0.999):
+    self.device = device
+    self.beta1, self.beta2 = np.float32(beta1), np.float32(beta2)
+    self.dev = torch.zeros(_lib.HYPER_N, dtype=torch.float32, device=device)
+    self._pow_step = None
+    self.b1p = self.b2p = None
+    self.lr = 0.0
+    self.grad_scale = 1.0
+
+  def _powers(self, step):
+    """beta^(step+1) by repeated fp32 multiplication (what the TF variables hold before step `step`)."""
+    if self._pow_step is not None and step == self._pow_step + 1:
+      self.b1p = np.float32(self.b1p * self.beta1)
+      self.b2p = np.float32(self.b2p * self.beta2)
+    elif self._pow_step is None or step != self._pow_step:
+      b1p, b2p = self.beta1, self.beta2
+      for _ in range(int(step)):
+        b1p = np.float32(b1p * self.beta1)
+        b2p = np.float32(b2p * self.beta2)
+      self.b1p, self.b2p = b1p, b2p
+    self._pow_step = step
+
+  def set(self, lr, step, grad_scale=1.0):
+    self._powers(step)
+    self.lr, self.grad_scale = float(np.float32(lr)), float(np.float32(grad_scale))
+    h = [0.0] * _lib.HYPER_N
+    h[_lib.HYPER_LR] = self.lr
+    h[_lib.HYPER_BETA1_POWER] = float(self.b1p)
+    h[_lib.HYPER_BETA2_POWER] = float(self.b2p)
+    h[_lib.HYPER_GRAD_SCALE] = self.grad_scale
+    self.dev.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=True)
+
+  def opt(self, kind, eps=1e-8, grad_scale=None):
+    """er_opt_t for `kind` carrying both the values and the device block."""
+    return make_opt(kind, self.lr, float(self.beta1), float(self.beta2), eps, float(self.b1p), float(self.b2p),
+                    self.grad_scale if grad_scale is None else grad_scale, hyper_dev=self.dev)
 
 
 def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt,

@@ -21,7 +21,7 @@ class MMoE(RankModel):
       experts = [list(c.expert_dnn.hidden_units)] * c.num_expert
     else:
       experts = [list(e.dnn.hidden_units) for e in c.experts]
-    towers = [(t.tower_name, t.label_name, list(t.dnn.hidden_units) if t.HasField('dnn') else [], t.weight)
+    towers = [(t.tower_name, t.label_name if t.HasField('label_name') else None, list(t.dnn.hidden_units) if t.HasField('dnn') else [], t.weight)
               for t in c.task_towers]
     group = model_config.feature_groups[0].group_name
     return cls(input_layer, group, experts, towers, l2_reg=c.l2_regularization,
@@ -62,11 +62,13 @@ class MMoE(RankModel):
     return torch.stack(logits, dim=1)  # [B, n_task]
 
   def loss(self, logits, labels):
-    """labels [B, n_task] (label_fields order); multi_task_model.py:201-280: sum_t w_t * CE_t."""
+    """labels [B, n_label] in data_config.label_fields order; tower t reads column label_cols[t] (its
+    label_name, multi_task_model.py:114-122); multi_task_model.py:201-280: sum_t w_t * CE_t."""
     total = 0.0
     probs = []
+    cols = getattr(self, 'label_cols', None) or list(range(len(self.task_weights)))
     for t, w in enumerate(self.task_weights):
-      ce, p = E.sigmoid_cross_entropy(logits[:, t].contiguous(), labels[:, t].contiguous())
+      ce, p = E.sigmoid_cross_entropy(logits[:, t].contiguous(), labels[:, cols[t]].contiguous())
       total = total + w * ce
       probs.append(p)
     return total + self.embedding_reg_loss(self._emb_outputs), torch.stack(probs, dim=1)

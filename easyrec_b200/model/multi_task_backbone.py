@@ -33,7 +33,7 @@ class MultiTaskBackboneModel(RankModel):
     self.l2_reg = mp.l2_regularization
     self.embedding_reg = model_config.embedding_regularization
     self.tower_names = [t.tower_name for t in towers]
-    self.label_names = [t.label_name for t in towers]
+    self.label_names = [t.label_name if t.HasField('label_name') else None for t in towers]
     self.task_weights = [float(t.weight) for t in towers]
     self.per_task = self.backbone.n_outputs == len(towers) and self.backbone.n_outputs > 1
     d = self.backbone.out_dims[0] if self.per_task else self.backbone.out_dim
@@ -61,8 +61,9 @@ class MultiTaskBackboneModel(RankModel):
   def loss(self, logits, labels):
     total = 0.0
     probs = []
+    cols = getattr(self, 'label_cols', None) or list(range(len(self.task_weights)))
     for t, w in enumerate(self.task_weights):
-      ce, p = E.sigmoid_cross_entropy(logits[:, t].contiguous(), labels[:, t].contiguous())
+      ce, p = E.sigmoid_cross_entropy(logits[:, t].contiguous(), labels[:, cols[t]].contiguous())
       total = total + w * ce
       probs.append(p)
     return total + self.embedding_reg_loss(self._emb_outputs), torch.stack(probs, dim=1)

@@ -114,8 +114,12 @@ class ShardedArena(object):
     recv_g = torch.empty(max(n_recv, 1), D, dtype=torch.float32, device=self.device)
     dist.all_to_all_single(recv_g[:n_recv], send_g, rc, sc)
     if n_recv:
-      opt.grad_scale = opt.grad_scale / N
+      struct_scaled = not opt.hyper_dev   # a device-resident grad_scale already carries the 1/N
+      if struct_scaled:
+        opt.grad_scale = opt.grad_scale / N
       K.embedding_bwd(self.arena.weight, self.arena.state0, self.arena.state1, D, recv_rows, self.owner_slots, 1,
                       n_recv, [recv_g], opt, self.owner_ws, n_rows=self.arena.n_rows)
-      opt.grad_scale = opt.grad_scale * N
+      if struct_scaled:
+        opt.grad_scale = opt.grad_scale * N
+    E.adam_dense_decay(self.arena, recv_rows if n_recv else None, opt)
     self._ctx = None

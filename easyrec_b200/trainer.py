@@ -66,15 +66,27 @@ class FlatDenseOptimizer(object):
       self.s0 = torch.zeros(total, dtype=torch.float32, device=dev)
       self.s1 = torch.zeros(total, dtype=torch.float32, device=dev)
     self.b1, self.b2, self.eps = beta1, beta2, eps
-    self.lr_dev = torch.tensor([float(lr)], dtype=torch.float32, device=dev)
+    # lr and Adam's beta powers of the step: the device block shared with the sparse row update (Trainer points
+    # this at the input layer's), read by the kernel - lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is formed there
+    self.hyper = K.StepHyper(dev, beta1, beta2)
+    self.hyper.set(lr, 0)
     self.reg_loss = torch.zeros(1, dtype=torch.float32, device=dev)
     self.grad_scale = 1.0
 
-  def set_lr(self, lr, step):
+  @property
+  def lr_dev(self):
+    """the effective rate of the current step as a [1] tensor (lr, or Adam's lr_t in fp32 like the TF graph)."""
+    h = self.hyper
+    lr = np.float32(h.lr)
     if self.kind == _lib.OPT_ADAM_ROWS:
-      t = step + 1
-      lr = float(lr) * (1 - self.b2**t)**0.5 / (1 - self.b1**t)
-    self.lr_dev.fill_(float(lr))
+      one = np.float32(1.0)
+      lr = np.float32(np.float32(lr * np.sqrt(one - h.b2p)) / (one - h.b1p))
+    return torch.tensor([float(lr)], dtype=torch.float32)
+
+  def named_ranges(self):
+    """(parameter name, offset, numel) of every tensor inside the flat buffers."""
+    segs = np.frombuffer(self.segs_dev.cpu().numpy().tobytes(), dtype=_lib.DENSE_SEG_DTYPE)
+    return [(n, int(s['offset']), int(s['n'])) for n, s in zip(self.names, segs)]
 
   def zero_grad(self):
     for p in self.params:
@@ -95,12 +107,12 @@ class FlatDenseOptimizer(object):
 
   def apply(self):
     lib = _lib.load()
-    opt = K.make_opt(self.kind, 0.0, self.b1, self.b2, self.eps, grad_scale=self.grad_scale)
+    opt = self.hyper.opt(self.kind, self.eps, grad_scale=self.grad_scale)
     self.reg_loss.zero_()
     _lib.check(
         lib.er_dense_apply(self.flat_p.data_ptr(), self.flat_g.data_ptr(), K._p(self.s0), K._p(self.s1),
                            self.segs_dev.data_ptr(), self.n_segs, self.max_n, ctypes.byref(opt),
-                           self.lr_dev.data_ptr(), self.reg_loss.data_ptr(),
+                           None, self.reg_loss.data_ptr(),
                            torch.cuda.current_stream().cuda_stream), 'er_dense_apply')
 
 
@@ -116,6 +128,8 @@ class Trainer(object):
     l2 = getattr(model, 'l2_of', None)
     self.dense_opt = FlatDenseOptimizer(named, dense_optimizer, lr, l2_of=l2, beta1=beta1, beta2=beta2,
                                         adagrad_init=adagrad_init)
+    self.beta1, self.beta2 = beta1, beta2
+    self.dense_opt.hyper = input_layer.hyper   # one device block for both optimizers: one copy per step
     self.world = world_size
     self.dp = None
     if world_size > 1:
@@ -123,6 +137,11 @@ class Trainer(object):
       self.dp = DataParallel(input_layer, self.dense_opt, world_size)
     self.step = 0
     self.use_cuda_graph = use_cuda_graph
+    # the first steps of a graph-mode run execute eagerly as ordinary training steps (allocator pools, lazily
+    # created workspaces and handles get their final shape); the step after them is captured WITHOUT being
+    # executed and replayed from then on, so every batch is applied exactly once
+    self.graph_warmup_steps = 2
+    self._eager_steps = 0
     self._graph = None
     self._graph2 = None
     self._step_pending = []
@@ -132,8 +151,7 @@ class Trainer(object):
 
   def _set_hyper(self):
     lr = self.lr_fn(self.step)
-    self.input_layer.set_optimizer_step(lr, self.step)
-    self.dense_opt.set_lr(lr, self.step)
+    self.input_layer.set_optimizer_step(lr, self.step, beta1=self.beta1, beta2=self.beta2)
 
   # The step is three segments; only the middle one talks to other ranks, so with world > 1 the
   # CUDA graph is captured as two graphs around eager NCCL calls.
@@ -177,9 +195,10 @@ class Trainer(object):
     """features/labels: device tensors.  Returns (loss [scalar tensor], probs [B])."""
     self.model.train()
     self._set_hyper()
-    if not self.use_cuda_graph:
+    if not self.use_cuda_graph or self._eager_steps < self.graph_warmup_steps:
       out = self._step_body(features, labels)
       self.step += 1
+      self._eager_steps += 1
       return out
     if self._graph is None:
       self._capture(features, labels)
@@ -197,23 +216,15 @@ class Trainer(object):
     return self._loss, self._probs
 
   def _capture(self, features, labels):
-    # The fused row update reads its hyper-parameters from kernel arguments, which a CUDA graph
-    # freezes; graphs are therefore only used with a constant learning rate and adagrad/sgd rows
-    # (the dense optimizer reads lr from device memory and follows any schedule).
-    kind = next(iter(self.input_layer.arenas.values())).opt_kind
-    if kind not in (_lib.OPT_ADAGRAD, _lib.OPT_SGD):
-      raise _lib.ErError('CUDA-graph capture needs step-invariant row-update arguments '
-                         '(adagrad/sgd); adam rows carry beta powers per step')
+    """Record one step into a CUDA graph (nothing executes here; train_step replays it).  Every step-varying
+    scalar of the optimizers - learning rate, Adam's beta powers, gradient scale - is read by the kernels from
+    the device block `input_layer.hyper` that _set_hyper refreshes before each replay, so Adagrad, lazy Adam
+    and tf.train.AdamOptimizer rows and any learning-rate schedule replay the same graph."""
     self._static = {k: v.clone() for k, v in features.items()}
     self._static['__labels'] = labels.clone()
     feats = {k: self._static[k] for k in features}
     self._static_feats = feats
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-      for _ in range(2):  # warm-up on the side stream (allocator, cuBLAS handles)
-        self._step_body(feats, self._static['__labels'])
-    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
     self._graph = torch.cuda.CUDAGraph()
     n0 = _lib.load().er_launch_count()
     if self.dp is None:
@@ -223,7 +234,9 @@ class Trainer(object):
       self._segment_pre(feats)   # eager, before the capture: the captured lookup reuses these rows
       with torch.cuda.graph(self._graph):
         loss, self._probs = self._segment_compute(feats, self._static['__labels'])
-      self._segment_exchange()   # eager: NCCL stays out of the capture
+      # eager and on stale buffers (graph 1 has not run yet): it only fixes which gathered buffers the update
+      # segment reads - every buffer it touches is rewritten by the first replay before it is used
+      self._segment_exchange()
       self._graph2 = torch.cuda.CUDAGraph()
       with torch.cuda.graph(self._graph2, pool=self._graph.pool()):
         self._loss = self._segment_update(loss)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ER_B200_ABI_VERSION 1
+#define ER_B200_ABI_VERSION 2
 
 typedef void* er_stream_t; /* cudaStream_t */
 
@@ -88,9 +88,22 @@ typedef enum er_opt_kind {
   ER_OPT_SGD = 0,
   ER_OPT_ADAGRAD = 1,   /* tf.train.AdagradOptimizer sparse apply            */
   ER_OPT_LAZY_ADAM = 2, /* compat/adam_s.py:185-213                          */
-  ER_OPT_ADAM_ROWS = 3  /* TF Adam restricted to touched rows == lazy rule;
-                           the dense decay sweep is er_adam_dense_sweep       */
+  ER_OPT_ADAM_ROWS = 3  /* tf.train.AdamOptimizer (builders/optimizer_builder.py:61-66):
+                           touched rows take the same row rule as lazy Adam in
+                           er_embedding_bwd; every other row decays in
+                           er_adam_dense_sweep (behaviour documented at
+                           compat/adam_s.py:74-81)                            */
 } er_opt_kind;
+
+/* Step-varying hyper-parameters in DEVICE memory (er_opt_t.hyper_dev): the kernels read them at run
+ * time, so one captured CUDA graph follows a learning-rate schedule and Adam's beta powers. */
+enum {
+  ER_HYPER_LR = 0,          /* learning rate of this step (core/learning_schedules.py:30-75) */
+  ER_HYPER_BETA1_POWER = 1, /* beta1^t before this step's _finish (compat/adam_s.py:233-245) */
+  ER_HYPER_BETA2_POWER = 2,
+  ER_HYPER_GRAD_SCALE = 3,
+  ER_HYPER_N = 4
+};
 
 typedef struct er_opt {
   int32_t kind;      /* er_opt_kind */
@@ -102,7 +115,10 @@ typedef struct er_opt {
   float beta2_power;
   float grad_scale;  /* multiplies the summed gradient: 1/N for sharded tables
                         (compat/optimizers.py:315-316) times
-                        embedding_learning_rate_multiplier                    */
+                        embedding_learning_rate_multiplier
+                        (model/easy_rec_estimator.py:308-317)                 */
+  const float* hyper_dev; /* NULL, or DEVICE float[ER_HYPER_N] that overrides lr,
+                             beta1_power, beta2_power and grad_scale above      */
 } er_opt_t;
 
 /* ---- library ---------------------------------------------------------- */
@@ -208,7 +224,8 @@ int er_sparse_apply(float* table, float* state0, float* state1, int32_t dim,
 /* TF AdamOptimizer's dense part for rows NOT touched this step
  * (documented at compat/adam_s.py:74-81): m*=b1, v*=b2, w-=lr_t*m/(sqrt(v)+eps)
  * streamed over the whole table; touched[] (n_rows bytes) masks rows already
- * updated by er_embedding_bwd. */
+ * updated by er_embedding_bwd.  Rows whose m and v are both zero are left unwritten
+ * (their update is exactly zero), so a mostly-cold table costs one read pass. */
 int er_adam_dense_sweep(float* table, float* m, float* v, int64_t n_rows,
                         int32_t dim, int32_t row_stride,
                         const uint8_t* touched, const er_opt_t* opt,
@@ -303,9 +320,11 @@ int er_bias_bn_act_bwd(const float* z, const float* bias, const float* gamma,
 
 /* Dense optimizer over ONE flat parameter buffer (dense apply_gradients,
  * compat/optimizers.py:413-416): g = grad*grad_scale + l2*w, then the adagrad / adam / sgd rule.
- * segs: DEVICE array describing the tensors inside the flat buffers; lr_dev (optional device
- * scalar) overrides opt->lr so a captured CUDA graph can follow a schedule; reg_loss_out
- * (optional) += sum l2/2*w^2. */
+ * segs: DEVICE array describing the tensors inside the flat buffers; the step's rate comes from lr_dev
+ * (optional device scalar, used as is), else from opt->hyper_dev (lr and Adam's beta powers in device
+ * memory, lr_t = lr*sqrt(1-b2^t)/(1-b1^t) formed in the kernel; grad_scale is NOT taken from it: the dense
+ * and the sparse gradients scale differently), else from opt->lr, so a captured CUDA graph can follow a
+ * schedule; reg_loss_out (optional) += sum l2/2*w^2. */
 typedef struct er_dense_seg {
   int64_t offset;
   int64_t n;

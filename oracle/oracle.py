@@ -137,6 +137,40 @@ def embedding_bwd(table, s0, s1, rows, seg_of, gseg, kind, lr, weights=None, seg
   return int(u), None, None
 
 
+def adam_lr_t(lr, beta1_power, beta2_power):
+  """lr * sqrt(1 - beta2_power) / (1 - beta1_power) in fp32, the order of the TF graph (compat/adam_s.py:193;
+  TensorFlow's adam.py builds the same expression)."""
+  f = np.float32
+  return f(f(f(lr) * np.sqrt(f(1.0) - f(beta2_power))) / (f(1.0) - f(beta1_power)))
+
+
+def embedding_bwd_adam_dense(table, m, v, rows, seg_of, gseg, lr, weights=None, seg_scale=None, beta1=0.9,
+                             beta2=0.999, eps=1e-8, beta1_power=0.9, beta2_power=0.999, grad_scale=1.0):
+  """tf.train.AdamOptimizer._apply_sparse_shared (TensorFlow 1.15 python/training/adam.py; the optimizer
+  builders/optimizer_builder.py:61-66 constructs; its dense behaviour is described at compat/adam_s.py:74-81):
+
+      m <- m*beta1 (ALL rows);  m[indices] += (1-beta1)*g        v likewise with g*g
+      var <- var - lr_t * m / (sqrt(v) + eps)   (ALL rows)
+
+  so a row with a gradient gets exactly the lazy row rule (same operations on the same operands) and every
+  other row decays: m*beta1, v*beta2, var - lr_t*m/(sqrt(v)+eps).  In-place on float32 [V, D] arrays.
+  Parity unpinned against TensorFlow itself (TensorFlow is absent here): restated from the TF source."""
+  f = np.float32
+  n_uniq, ur, _ = embedding_bwd(None, None, None, rows, seg_of, gseg, OPT_SGD, 0.0, weights=weights,
+                                seg_scale=seg_scale, grad_scale=grad_scale, want_uniq=True)
+  embedding_bwd(table, m, v, rows, seg_of, gseg, OPT_LAZY_ADAM, lr, weights=weights, seg_scale=seg_scale, beta1=beta1,
+                beta2=beta2, eps=eps, beta1_power=beta1_power, beta2_power=beta2_power, grad_scale=grad_scale)
+  cold = np.ones(table.shape[0], bool)
+  cold[ur] = False
+  lr_t = adam_lr_t(lr, beta1_power, beta2_power)
+  mc = (m[cold] * f(beta1)).astype(np.float32)
+  vc = (v[cold] * f(beta2)).astype(np.float32)
+  m[cold] = mc
+  v[cold] = vc
+  table[cold] = table[cold] - (lr_t * mc) / (np.sqrt(vc) + f(eps))
+  return n_uniq
+
+
 def fm_fwd(x, n_field, dim):
   x = _c(x, np.float32)
   y = np.empty((x.shape[0], dim), np.float32)

@@ -70,14 +70,39 @@ def install_sparse(patch):
       for k in range(int(s['n_seg'])):
         o = k * int(s['out_stride']) + int(s['out_col'])
         gseg[int(s['seg_begin']) + k] = buf[o:o + dim]
-    t, a = np.ascontiguousarray(table.numpy()), np.ascontiguousarray(state0.numpy())
-    O.embedding_bwd(t, a, None, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
-                    O.OPT_ADAGRAD, opt.lr, weights=None if weights is None else weights.numpy(),
-                    seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=opt.grad_scale)
+    t = np.ascontiguousarray(table.numpy())
+    a = None if state0 is None else np.ascontiguousarray(state0.numpy())
+    b = None if state1 is None else np.ascontiguousarray(state1.numpy())
+    # the row rule of tf.train.AdamOptimizer on touched rows is the lazy rule (kind 3 -> 2); its dense decay is the
+    # adam_dense_sweep double below
+    kind = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_LAZY_ADAM, 3: O.OPT_LAZY_ADAM}[int(opt.kind)]
+    O.embedding_bwd(t, a, b, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
+                    kind, opt.lr, weights=None if weights is None else weights.numpy(),
+                    seg_scale=None if seg_scale is None else seg_scale.numpy(), beta1=opt.beta1, beta2=opt.beta2,
+                    eps=opt.eps, beta1_power=opt.beta1_power, beta2_power=opt.beta2_power, grad_scale=opt.grad_scale)
     table.copy_(torch.from_numpy(t))
-    state0.copy_(torch.from_numpy(a))
+    if state0 is not None:
+      state0.copy_(torch.from_numpy(a))
+    if state1 is not None:
+      state1.copy_(torch.from_numpy(b))
+
+  def mark_rows(rows, n_rows, touched, value, n_dev=None):
+    r = rows.numpy()
+    n = r.size if n_dev is None else min(int(n_dev.reshape(-1)[0]), r.size)
+    r = r[:n]
+    touched[torch.from_numpy(r[(r >= 0) & (r < n_rows)])] = value
+
+  def adam_dense_sweep(table, m, v, dim, touched, opt, row_stride=None):
+    f = np.float32
+    cold = torch.from_numpy(touched.numpy() == 0) if touched is not None else torch.ones(table.shape[0], dtype=torch.bool)
+    lr_t = O.adam_lr_t(opt.lr, opt.beta1_power, opt.beta2_power)
+    mc = (m[cold].numpy() * f(opt.beta1)).astype(np.float32)
+    vc = (v[cold].numpy() * f(opt.beta2)).astype(np.float32)
+    m[cold] = torch.from_numpy(mc)
+    v[cold] = torch.from_numpy(vc)
+    table[cold] = torch.from_numpy(table[cold].numpy() - (lr_t * mc) / (np.sqrt(vc) + f(opt.eps)))
   for name, fn in (('csr_from_lens', csr_from_lens), ('bucketize', bucketize), ('embedding_fwd', embedding_fwd),
-                   ('embedding_bwd', embedding_bwd)):
+                   ('embedding_bwd', embedding_bwd), ('mark_rows', mark_rows), ('adam_dense_sweep', adam_dense_sweep)):
     patch(K, name, fn)
 
 
@@ -138,8 +163,8 @@ def install_dense(patch):
       gx[:, :w] = g
     return gx
 
-  def apply(self):   # FlatDenseOptimizer.apply: l2 + TF Adagrad over the flat buffer
-    assert self.kind == 1, 'this double implements the adagrad rule only'
+  def apply(self):   # FlatDenseOptimizer.apply: l2 + TF Adagrad / Adam over the flat buffer
+    assert self.kind in (1, 3), 'this double implements the adagrad and adam rules'
     segs = np.frombuffer(self.segs_dev.numpy().tobytes(), dtype=T._lib.DENSE_SEG_DTYPE)
     self.reg_loss.zero_()
     lr = float(self.lr_dev[0])
@@ -149,8 +174,13 @@ def install_dense(patch):
       if s['l2'] > 0:
         self.reg_loss += 0.5 * float(s['l2']) * (w * w).sum()
         g = g + float(s['l2']) * w
-      self.s0[o:o + n] += g * g
-      w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
+      if self.kind == 1:
+        self.s0[o:o + n] += g * g
+        w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
+      else:   # ApplyAdam: m, v, var -= lr_t*m/(sqrt(v)+eps)
+        self.s0[o:o + n] = self.b1 * self.s0[o:o + n] + (1 - self.b1) * g
+        self.s1[o:o + n] = self.b2 * self.s1[o:o + n] + (1 - self.b2) * g * g
+        w -= lr * float(s['lr_mult']) * self.s0[o:o + n] / (torch.sqrt(self.s1[o:o + n]) + self.eps)
   for name, fn in (('gemm', gemm), ('gemm_ready', lambda t: t), ('gemm_bn', lambda *a, **k: None),
                    ('bias_bn_act_fwd', bias_bn_act_fwd), ('bias_bn_act_bwd', bias_bn_act_bwd),
                    ('dense_workspace', lambda b, u, d: torch.zeros(1, dtype=torch.uint8)), ('sigmoid_ce', sigmoid_ce),

@@ -25,9 +25,9 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_abi_version_and_struct_layout():
   lib = _lib.load()
-  assert lib.er_abi_version() == 1
+  assert lib.er_abi_version() == _lib.ABI_VERSION == 2
   assert _lib.SLOT_DTYPE.itemsize == 48
-  assert ctypes.sizeof(_lib.ErOpt) == 32
+  assert ctypes.sizeof(_lib.ErOpt) == 40 and _lib.ErOpt.hyper_dev.offset == 32
 
 
 def test_invalid_arguments_fail_loudly_without_gpu():
