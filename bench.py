@@ -389,7 +389,7 @@ def main():
 
   # the two stages of K7 on their own: the dedup sort (L2-resident, latency-bound) and the HBM stage
   def run_sort(it):
-    K.embedding_bwd_presort(rows_list[it % 4], arena.n_rows, DIM, call.ws)
+    K.embedding_bwd_presort(rows_list[it % 4], arena.n_rows, DIM, call.ws, call.slots_dev, call.n_slots)
 
   def run_after_sort(it):
     K.embedding_bwd(arena.weight, arena.state0, None, DIM, rows_list[it % 4], call.slots_dev, call.n_slots,

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'liber_b200.so')
+# ER_LIB_PATH: another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get('ER_LIB_PATH') or os.path.join(_HERE, 'lib', 'liber_b200.so')
 
 c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t
@@ -27,7 +28,7 @@ assert SLOT_DTYPE.itemsize == 48
 DENSE_SEG_DTYPE = np.dtype([('offset', '<i8'), ('n', '<i8'), ('l2', '<f4'), ('lr_mult', '<f4')], align=True)
 assert DENSE_SEG_DTYPE.itemsize == 24
 
-BUCKET_FARM_DECIMAL, BUCKET_MOD, BUCKET_IDENTITY, BUCKET_NONE = 0, 1, 2, 3
+BUCKET_FARM_DECIMAL, BUCKET_MOD, BUCKET_IDENTITY, BUCKET_NONE, BUCKET_ONE_ROW = 0, 1, 2, 3, 4
 COMBINER_SUM, COMBINER_MEAN, COMBINER_SQRTN = 0, 1, 2
 OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM, OPT_ADAM_ROWS = 0, 1, 2, 3
 MAX_BUFS = 8
@@ -78,9 +79,9 @@ SIGNATURES = {
         c_i32, ctypes.POINTER(c_vp), c_i32, c_vp, c_vp
     ]),
     'er_embedding_bwd_workspace_bytes': (c_sz, [c_i64, c_i32]),
-    'er_embedding_bwd_presort': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_sz, c_vp]),
+    'er_embedding_bwd_presort': (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_vp, c_sz, c_vp]),
     'er_embedding_bwd_reuse_sort': (c_i32, [
-        c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
+        c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64,
         c_i64, c_vp, c_i32, ctypes.POINTER(c_vp), c_i32, c_vp,
         ctypes.POINTER(ErOpt), c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_sz, c_i32, c_vp
     ]),

@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(256)
     } else if (mode == ER_BUCKET_IDENTITY) {
       drop = (v == -1);
       r = (v < 0 || v >= nb) ? 0 : v;
+    } else if (mode == ER_BUCKET_ONE_ROW) {
+      drop = (v < 0);
+      r = 0;
     } else {
       drop = (v < 0);
       r = v;

@@ -24,10 +24,14 @@
 //
 // HBM traffic per call (algorithmic): L*8 sorted pairs + L*R gathered upstream gradient
 // rows + U*k*R row/state read-modify-write, R = 4*dim, k = 2 (sgd), 4 (adagrad), 6 (adam).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "scan.cuh"
 #include "slots.cuh"
 #include "sort.cuh"
+#include "bucket_bwd.cuh"
 
 namespace er {
 
@@ -48,6 +52,7 @@ struct BwdArgs {
   uint32_t sentinel;  // == n_rows
   const uint32_t* keys;
   const uint32_t* vals;
+  const uint64_t* pairs;  // bucket mode: (row << 32 | lookup) pairs replace keys / vals
   int64_t n;  // sorted pairs (== n_lookups_cap)
   const float* weights;
   const int32_t* seg_ids;
@@ -132,6 +137,10 @@ __device__ __forceinline__ void f4_acc(float4& g, const float4& v) {
   g.y = __fadd_rn(g.y, v.y);
   g.z = __fadd_rn(g.z, v.z);
   g.w = __fadd_rn(g.w, v.w);
+}
+
+__device__ __forceinline__ float4 f4_scale1(const float4& v, float c) {
+  return make_float4(__fmul_rn(v.x, c), __fmul_rn(v.y, c), __fmul_rn(v.z, c), __fmul_rn(v.w, c));
 }
 
 struct RowRegs {
@@ -445,6 +454,13 @@ __global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant
   }
 }
 
+__device__ __forceinline__ uint32_t key_at(const BwdArgs& a, int64_t i) {
+  return a.pairs ? (uint32_t)(a.pairs[i] >> 32) : a.keys[i];
+}
+__device__ __forceinline__ uint32_t val_at(const BwdArgs& a, int64_t i) {
+  return a.pairs ? (uint32_t)a.pairs[i] : a.vals[i];
+}
+
 // ---- hot rows, vector: one CTA per chunk of a run; TPE threads share one lookup (TPE = 1 for
 // dim <= 32: a thread moves a whole gradient row) -----------------------------------------------
 template <int LANES, int TPE>
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(256) bwd_long_vec_kernel(const __grid_constant
     const int4 run = a.long_list[qc.x];
     const int64_t i = run.x;
     const int len = run.y, c0 = run.z, nch = run.w;
-    const uint32_t key = a.keys[i];
+    const uint32_t key = key_at(a, i);
     const int e0 = qc.y * kChunk, e1 = min(len, e0 + kChunk);
     float4 g[CH];
 #pragma unroll
@@ -472,8 +488,8 @@ __global__ void __launch_bounds__(256) bwd_long_vec_kernel(const __grid_constant
     for (int e = e0 + grp; e < e1; e += 2 * G) {
       const bool two = (e + G < e1);
       float w0, w1 = 0.f;
-      const float* p0 = grad_src(a, sv, a.vals[i + e], &w0);
-      const float* p1 = two ? grad_src(a, sv, a.vals[i + e + G], &w1) : p0;
+      const float* p0 = grad_src(a, sv, val_at(a, i + e), &w0);
+      const float* p1 = two ? grad_src(a, sv, val_at(a, i + e + G), &w1) : p0;
       float4 v0[CH], v1[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -571,13 +587,13 @@ __global__ void __launch_bounds__(256) bwd_long_scalar_kernel(const __grid_const
     const int4 run = a.long_list[qc.x];
     const int64_t i = run.x;
     const int len = run.y, c0 = run.z, nch = run.w;
-    const uint32_t key = a.keys[i];
+    const uint32_t key = key_at(a, i);
     const int e0 = qc.y * kChunk, e1 = min(len, e0 + kChunk);
     for (int c = 0; c < a.dim; ++c) {
       float g = 0.f;
       for (int e = e0 + threadIdx.x; e < e1; e += 256) {
         float coef;
-        const float* src = grad_src(a, sv, a.vals[i + e], &coef);
+        const float* src = grad_src(a, sv, val_at(a, i + e), &coef);
         g = __fadd_rn(g, __fmul_rn(src[c], coef));
       }
 #pragma unroll
@@ -688,6 +704,540 @@ __global__ void __launch_bounds__(256) bwd_scan_d1_kernel(const __grid_constant_
   if (is_tail || (lane == 31 && cont && !handed_off)) apply_scalar(a, k, 0, g, pos - (cnt - 1));
 }
 
+// =====================================================================================================
+// Bucketed K7 (bucket_bwd.cuh): one CTA per bucket sorts its (row, lookup) pairs in shared memory, sums the
+// runs and applies the optimizer.
+// =====================================================================================================
+#ifndef ER_BK_MINB
+#define ER_BK_MINB 5   // resident bucket CTAs per SM the register allocation aims for
+#endif
+
+struct BkArgs {
+  bk::Ws w;
+  int log2_nb;
+};
+
+__device__ __forceinline__ void enqueue_run(const BwdArgs& a, int64_t start, int len) {
+  const int nch = (len + kChunk - 1) / kChunk;
+  const int q = atomicAdd(&a.counters[0], 1);
+  const int c0 = atomicAdd(&a.counters[1], nch);
+  a.long_list[q] = make_int4((int)start, len, c0, nch);
+  a.run_done[q] = 0;
+  for (int c = 0; c < nch; ++c) a.chunk_list[c0 + c] = make_int2(q, c);
+}
+
+// Sum entries [j0, j1) of the sorted pairs `sp` (shared memory) for one row, sequentially in lookup order.
+template <int LANES>
+__device__ __forceinline__ float4 sum_entries(const BwdArgs& a, const SlotView& sv, const uint64_t* sp, int j0, int j1,
+                                              int lane) {
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = j0; j < j1; j += kBatch) {
+    float4 gv[kBatch];
+    float c[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (j + u < j1) {
+        const float* src = grad_src(a, sv, (uint32_t)sp[j + u], &c[u]);
+        gv[u] = reinterpret_cast<const float4*>(src)[lane];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (j + u < j1) f4_fma_sep(g, gv[u], c[u]);
+  }
+  return g;
+}
+
+constexpr int kStageF4 = 1024;   // float4 slots of the gradient staging buffer (16 KB)
+constexpr uint32_t kDonePos = 0xFFFFFFFFu;
+
+template <typename IdxT>
+__device__ __forceinline__ bool run_is_long(const IdxT* s_start, int r) {
+  return (int)s_start[r + 1] - (int)s_start[r] > bk::kCoopRun;
+}
+
+// Runs [0, R) of the sorted window sp[0, s_start[R]).
+//  1. runs longer than kCoopRun: the whole CTA sums them straight from global memory with a fixed two-level tree
+//     (or, queue_base >= 0 and longer than kQueueRun, hands them to the multi-CTA hot-row kernel - their pairs lie
+//     sorted in global memory at queue_base + index); their entries are then marked done;
+//  2. everything else in chunks: ALL threads stage the chunk's gradient rows (already multiplied by their
+//     coefficients) in shared memory - every load of the chunk is in flight at once, no per-row serial chain - then
+//     each lane group walks its runs r = grp, grp + G, ... adding the staged rows in lookup order and applies the
+//     optimizer; the next run's table row is requested before the current update is computed.
+template <int LANES, int THREADS, typename IdxT>
+__device__ __forceinline__ void process_runs_vec(const BwdArgs& a, const SlotView& sv, uint64_t* sp,
+                                                 const IdxT* s_start, int R, float4* s_stage, float4* s_part,
+                                                 int* s_coop, int* s_ncoop, int64_t queue_base) {
+  constexpr int G = THREADS / LANES;
+  constexpr int S_ENT = kStageF4 / LANES;
+  const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  if (threadIdx.x == 0) *s_ncoop = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += THREADS)
+    if (run_is_long(s_start, r)) s_coop[atomicAdd(s_ncoop, 1)] = r;
+  __syncthreads();
+  const int nco = *s_ncoop;
+  for (int c = 0; c < nco; ++c) {
+    const int r = s_coop[c];
+    const int st = s_start[r], en = s_start[r + 1], len = en - st;
+    if (queue_base >= 0 && len > bk::kQueueRun) {
+      if (threadIdx.x == 0) enqueue_run(a, queue_base + st, len);
+    } else {
+      // fixed two-level tree: G consecutive sub-ranges summed in lookup order, then added in sub-range order
+      const int chunk = (len + G - 1) / G;
+      const int j0 = st + grp * chunk, j1 = min(en, j0 + chunk);
+      const float4 g = sum_entries<LANES>(a, sv, sp, j0, j1, lane);
+      s_part[grp * LANES + lane] = g;
+      __syncthreads();
+      if (threadIdx.x < LANES) {
+        const uint32_t key = (uint32_t)(sp[st] >> 32);
+        RowRegs row = load_row(a, key, threadIdx.x);
+        const int used = (len + chunk - 1) / chunk;
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < used; ++q) f4_acc(tot, s_part[q * LANES + threadIdx.x]);
+        apply_row_vec(a, key, threadIdx.x, tot, 0, row);
+      }
+    }
+    __syncthreads();
+    for (int i = st + threadIdx.x; i < en; i += THREADS) sp[i] |= (uint64_t)kDonePos;
+  }
+  __syncthreads();
+  // ---- staged chunks ----
+  const int n = s_start[R];
+  int r = grp;
+  while (r < R && run_is_long(s_start, r)) r += G;
+  RowRegs row;
+  row.w = row.s0 = row.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < R) row = load_row(a, (uint32_t)(sp[s_start[r]] >> 32), lane);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = 0; c0 < n; c0 += S_ENT) {
+    const int c1 = min(n, c0 + S_ENT);
+    for (int q = threadIdx.x; q < (c1 - c0) * LANES; q += THREADS) {
+      const int e = q / LANES;
+      const uint32_t pos = (uint32_t)sp[c0 + e];
+      if (pos != kDonePos) {
+        float coef;
+        const float* src = grad_src(a, sv, pos, &coef);
+        s_stage[q] = f4_scale1(reinterpret_cast<const float4*>(src)[q % LANES], coef);
+      }
+    }
+    __syncthreads();
+    while (r < R && (int)s_start[r] < c1) {
+      const int st = s_start[r], en = s_start[r + 1];
+      const int lo = max(st, c0), hi = min(en, c1);
+      for (int i = lo; i < hi; ++i) f4_acc(acc, s_stage[(i - c0) * LANES + lane]);
+      if (en > c1) break;   // the run continues in the next chunk
+      const uint32_t key = (uint32_t)(sp[st] >> 32);
+      int rn = r + G;
+      while (rn < R && run_is_long(s_start, rn)) rn += G;
+      RowRegs nxt;
+      nxt.w = nxt.s0 = nxt.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rn < R) nxt = load_row(a, (uint32_t)(sp[s_start[rn]] >> 32), lane);
+      apply_row_vec(a, key, lane, acc, 0, row);
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      row = nxt;
+      r = rn;
+    }
+    __syncthreads();
+  }
+}
+
+// any dim: one thread per (run, column), same two phases; the staging buffer holds kStageF4 * 4 floats
+template <int THREADS, typename IdxT>
+__device__ __forceinline__ void process_runs_scalar(const BwdArgs& a, const SlotView& sv, uint64_t* sp,
+                                                    const IdxT* s_start, int R, float* s_stagef, float* s_partf,
+                                                    int* s_coop, int* s_ncoop, int64_t queue_base) {
+  const int dim = a.dim;
+  if (threadIdx.x == 0) *s_ncoop = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += THREADS)
+    if (run_is_long(s_start, r)) s_coop[atomicAdd(s_ncoop, 1)] = r;
+  __syncthreads();
+  const int nco = *s_ncoop;
+  for (int cc = 0; cc < nco; ++cc) {
+    const int r = s_coop[cc];
+    const int st = s_start[r], en = s_start[r + 1], len = en - st;
+    if (queue_base >= 0 && len > bk::kQueueRun) {
+      if (threadIdx.x == 0) enqueue_run(a, queue_base + st, len);
+    } else {
+      const int chunk = (len + THREADS - 1) / THREADS;
+      const int j0 = st + threadIdx.x * chunk, j1 = min(en, j0 + chunk);
+      const int used = (len + chunk - 1) / chunk;
+      for (int c = 0; c < dim; ++c) {
+        float g = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          float coef;
+          const float* src = grad_src(a, sv, (uint32_t)sp[j], &coef);
+          g = __fadd_rn(g, __fmul_rn(src[c], coef));
+        }
+        s_partf[threadIdx.x] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float tot = 0.f;
+          for (int q = 0; q < used; ++q) tot = __fadd_rn(tot, s_partf[q]);
+          apply_scalar(a, (uint32_t)(sp[st] >> 32), c, tot, 0);
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    for (int i = st + threadIdx.x; i < en; i += THREADS) sp[i] |= (uint64_t)kDonePos;
+  }
+  __syncthreads();
+  const int n = s_start[R];
+  const int S_ENT = max(1, (kStageF4 * 4) / dim);
+  const int total = R * dim;
+  int idx = threadIdx.x;
+  float acc = 0.f;
+  for (int c0 = 0; c0 < n; c0 += S_ENT) {
+    const int c1 = min(n, c0 + S_ENT);
+    for (int q = threadIdx.x; q < (c1 - c0) * dim; q += THREADS) {
+      const int e = q / dim;
+      const uint32_t pos = (uint32_t)sp[c0 + e];
+      if (pos != kDonePos) {
+        float coef;
+        const float* src = grad_src(a, sv, pos, &coef);
+        s_stagef[q] = __fmul_rn(src[q - e * dim], coef);
+      }
+    }
+    __syncthreads();
+    while (idx < total) {
+      const int r = idx / dim, c = idx - r * dim;
+      if (run_is_long(s_start, r)) {
+        idx += THREADS;
+        continue;
+      }
+      const int st = s_start[r], en = s_start[r + 1];
+      if (st >= c1) break;
+      const int lo = max(st, c0), hi = min(en, c1);
+      for (int i = lo; i < hi; ++i) acc = __fadd_rn(acc, s_stagef[(i - c0) * dim + c]);
+      if (en > c1) break;
+      apply_scalar(a, (uint32_t)(sp[st] >> 32), c, acc, 0);
+      acc = 0.f;
+      idx += THREADS;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- one-row tables (ER_BUCKET_ONE_ROW slots): weighted column sums -----------------------------------------
+// CTA (slot f, chunk c) sums coef_b * g[b, cols of f] over its kOneRowChunk samples: lane groups take samples
+// g, g + G, ... in order, the groups are added in group order, the chunk partials in chunk order by the slot's
+// last CTA, which then applies the optimizer to the row: deterministic.  CTAs of other slots exit at once.
+struct OneRowArgs {
+  const int64_t* rows;
+  float* partials;   // [n_slots][n_chunks][dim]
+  int32_t* tickets;  // [n_slots], zero between calls
+  int n_chunks;
+};
+
+template <int LANES>
+__device__ __forceinline__ void one_row_cta(const BwdArgs& a, const OneRowArgs& o, int cta, float* s_part /*[1024]*/) {
+  __shared__ int s_last;
+  const int f = cta / o.n_chunks, c = cta - f * o.n_chunks;
+  const er_slot_t sl = a.slots[f];
+  if (sl.bucket_mode != ER_BUCKET_ONE_ROW) return;
+  constexpr int L = LANES > 0 ? LANES : 1;
+  constexpr int G = 256 / L;
+  const int dim = a.dim;
+  const int s0 = c * bk::kOneRowChunk, s1 = min(sl.n_seg, s0 + bk::kOneRowChunk);
+  const int used_chunks = (sl.n_seg + bk::kOneRowChunk - 1) / bk::kOneRowChunk;
+  if (s0 >= sl.n_seg) return;
+  const float* gbuf = a.gbufs.p[sl.out_buf];
+  const uint32_t row = (uint32_t)sl.row_offset;
+  if constexpr (LANES > 0) {
+    const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 4;   // samples of a lane group in flight
+    for (int e = s0 + grp; e < s1; e += G * U) {
+      float4 v[U];
+      float coef[U];
+      bool use[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ee = e + u * G;
+        use[u] = false;
+        if (ee < s1) {
+          const int64_t l = (int64_t)sl.seg_begin + ee;   // single-valued slot: lookup == segment
+          use[u] = o.rows[l] >= 0;                        // a dropped lookup contributes nothing
+          coef[u] = a.weights ? a.weights[l] : 1.0f;
+          if (a.seg_scale) coef[u] = __fmul_rn(coef[u], a.seg_scale[l]);
+          v[u] = reinterpret_cast<const float4*>(gbuf + (int64_t)ee * sl.out_stride + sl.out_col)[lane];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (use[u]) f4_fma_sep(g, v[u], coef[u]);
+    }
+    reinterpret_cast<float4*>(s_part)[grp * LANES + lane] = g;
+    __syncthreads();
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < LANES) {
+      for (int q = 0; q < G; ++q) f4_acc(tot, reinterpret_cast<float4*>(s_part)[q * LANES + threadIdx.x]);
+      __stcg(reinterpret_cast<float4*>(o.partials + ((int64_t)f * o.n_chunks + c) * dim) + threadIdx.x, tot);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&o.tickets[f], 1) == used_chunks - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      // the chunk partials: fetched in parallel, added in chunk order
+      for (int base = 0; base < used_chunks; base += G) {
+        const int q = base + grp;
+        if (q < used_chunks)
+          reinterpret_cast<float4*>(s_part)[grp * LANES + lane] =
+              __ldcg(reinterpret_cast<const float4*>(o.partials + ((int64_t)f * o.n_chunks + q) * dim) + lane);
+        __syncthreads();
+        if (threadIdx.x < LANES) {
+          if (base == 0) tot = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int m = min(G, used_chunks - base);
+          for (int q2 = 0; q2 < m; ++q2) f4_acc(tot, reinterpret_cast<float4*>(s_part)[q2 * LANES + threadIdx.x]);
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < LANES) {
+        RowRegs r = load_row(a, row, threadIdx.x);
+        apply_row_vec(a, row, threadIdx.x, tot, 0, r);
+        if (threadIdx.x == 0) o.tickets[f] = 0;
+      }
+    }
+  } else {
+    for (int col = 0; col < dim; ++col) {
+      float g = 0.f;
+      for (int e = s0 + threadIdx.x; e < s1; e += 256) {
+        const int64_t l = (int64_t)sl.seg_begin + e;
+        if (o.rows[l] < 0) continue;
+        float coef = a.weights ? a.weights[l] : 1.0f;
+        if (a.seg_scale) coef = __fmul_rn(coef, a.seg_scale[l]);
+        g = __fadd_rn(g, __fmul_rn(gbuf[(int64_t)e * sl.out_stride + sl.out_col + col], coef));
+      }
+      s_part[threadIdx.x] = g;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int q = 0; q < 256; ++q) tot = __fadd_rn(tot, s_part[q]);
+        __stcg(o.partials + ((int64_t)f * o.n_chunks + c) * dim + col, tot);
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&o.tickets[f], 1) == used_chunks - 1);
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < dim) {
+      __threadfence();
+      float tot = 0.f;
+      for (int q = 0; q < used_chunks; ++q)
+        tot = __fadd_rn(tot, __ldcg(o.partials + ((int64_t)f * o.n_chunks + q) * dim + threadIdx.x));
+      apply_scalar(a, row, (int)threadIdx.x, tot, 0);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) o.tickets[f] = 0;
+  }
+}
+
+inline size_t bk_reduce_smem(int n_slots, int cap, int threads) {
+  return ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15) + (size_t)cap * 8 + (((size_t)(cap + 1) * 2 + 15) & ~(size_t)15) +
+         (size_t)max(kStageF4, threads) * 16 + (size_t)(cap / bk::kCoopRun + 2) * 4 + 64;
+}
+
+struct BkSmem {
+  uint64_t* pairs;
+  uint16_t* start;
+  float4* stage;
+  float4* part;
+  int* coop;
+  int* ncoop;
+};
+__device__ __forceinline__ BkSmem bk_carve(unsigned char* s_raw, int n_slots, int cap, int threads) {
+  BkSmem m;
+  unsigned char* p = s_raw + ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15);
+  m.pairs = reinterpret_cast<uint64_t*>(p); p += (size_t)cap * 8;
+  m.start = reinterpret_cast<uint16_t*>(p); p += ((size_t)(cap + 1) * 2 + 15) & ~(size_t)15;
+  m.stage = reinterpret_cast<float4*>(p); p += (size_t)max(kStageF4, threads) * 16;
+  m.part = m.stage;   // the tree partials of the long runs are done with before the staging starts
+  m.coop = reinterpret_cast<int*>(p); p += (size_t)(cap / bk::kCoopRun + 1) * 4;
+  m.ncoop = reinterpret_cast<int*>(p);
+  return m;
+}
+
+// normal buckets (<= kCap pairs).  LANES == 0: scalar rows of any dim.
+template <int LANES>
+__global__ void __launch_bounds__(bk::kThreads, ER_BK_MINB) bk_reduce_kernel(const __grid_constant__ BwdArgs a,
+                                                                 const __grid_constant__ BkArgs k,
+                                                                 const __grid_constant__ OneRowArgs o) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_warp[bk::kThreads / 32 + 1];
+  const int b = blockIdx.x;
+  if (b >= (1 << k.log2_nb)) {   // the CTAs behind the buckets: column sums of the one-row slots
+    one_row_cta<LANES>(a, o, b - (1 << k.log2_nb), reinterpret_cast<float*>(s_raw));
+    return;
+  }
+  const int n = k.w.bcnt[b];
+  if (n == 0 || n > bk::kCap) return;   // empty, or one of the big buckets (bk_reduce_big_kernel)
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  const BkSmem m = bk_carve(s_raw, a.n_slots, bk::kCap, bk::kThreads);
+  const int off = k.w.boff[b];
+  int P = 32;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += bk::kThreads) m.pairs[i] = i < n ? k.w.pairs[off + i] : ~0ull;
+  __syncthreads();
+  bk::bitonic_sort<bk::kThreads>(m.pairs, P);
+  const int R = bk::run_starts<bk::kThreads, bk::kCap / bk::kThreads>(m.pairs, n, m.start, s_warp);
+  if constexpr (LANES > 0)
+    process_runs_vec<LANES, bk::kThreads>(a, sv, m.pairs, m.start, R, m.stage, m.part, m.coop, m.ncoop, -1);
+  else
+    process_runs_scalar<bk::kThreads>(a, sv, m.pairs, m.start, R, reinterpret_cast<float*>(m.stage),
+                                      reinterpret_cast<float*>(m.part), m.coop, m.ncoop, -1);
+}
+
+// One pass of a CTA-local stable LSD radix sort through global memory (oversized buckets only).
+// Returns false (and moves nothing) when every element has the same digit.
+__device__ __forceinline__ bool cta_radix_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int n,
+                                               int shift, int* s_wh /*[32][256]*/, int* s_cur /*[256]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int i = threadIdx.x; i < 256; i += bk::kBigThreads) s_cur[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += bk::kBigThreads) atomicAdd(&s_cur[(int)((in[i] >> shift) & 255)], 1);
+  __syncthreads();
+  int single = 0;
+  if (threadIdx.x < 256) single = (s_cur[threadIdx.x] == n);
+  if (__syncthreads_or(single)) return false;
+  if (threadIdx.x < 32) {   // exclusive scan of the 256 digit counts
+    int carry = 0;
+    for (int base = 0; base < 256; base += 32) {
+      const int v = s_cur[base + lane];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      s_cur[base + lane] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncthreads();
+  for (int base = 0; base < n; base += bk::kBigThreads) {
+    for (int i = threadIdx.x; i < 32 * 256; i += bk::kBigThreads) s_wh[i] = 0;
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    const bool valid = i < n;
+    const uint64_t e = valid ? in[i] : 0ull;
+    const int d = (int)((e >> shift) & 255);
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (256 + lane));
+    const int r = __popc(peers & lt_mask);
+    if (valid && r == 0) s_wh[wid * 256 + d] = __popc(peers);
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      int run = s_cur[threadIdx.x];
+      for (int ww = 0; ww < 32; ++ww) {
+        const int t = s_wh[ww * 256 + threadIdx.x];
+        s_wh[ww * 256 + threadIdx.x] = run;
+        run += t;
+      }
+      s_cur[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (valid) out[s_wh[wid * 256 + d] + r] = e;
+    __syncthreads();
+  }
+  return true;
+}
+
+// big buckets: a few CTAs (one per SM, kBigCap pairs of shared memory) walk the list of buckets above kCap
+template <int LANES>
+__global__ void __launch_bounds__(bk::kBigThreads) bk_reduce_big_kernel(const __grid_constant__ BwdArgs a,
+                                                                        const __grid_constant__ BkArgs k) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_warp[bk::kBigThreads / 32 + 1];
+  __shared__ int s_flag;
+  const int n_big = *k.w.n_big;
+  if ((int)blockIdx.x >= n_big) return;
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  const BkSmem m = bk_carve(s_raw, a.n_slots, bk::kBigCap, bk::kBigThreads);
+  for (int x = blockIdx.x; x < n_big; x += gridDim.x) {
+    const int b = k.w.big_list[x];
+    const int n = k.w.bcnt[b];
+    const int64_t off = k.w.boff[b];
+    uint64_t* gp = k.w.pairs + off;
+    bool sorted_in_global = false;
+    if (n > bk::kBigCap) {
+      // more than kBigCap lookups in one bucket (>= thousands of duplicates of one row): stable LSD radix sort of the
+      // 64-bit composites through global memory, digits that do not vary are skipped
+      int* s_wh = reinterpret_cast<int*>(m.pairs);
+      int* s_cur = s_wh + 32 * 256;
+      uint64_t* src = gp;
+      uint64_t* dst = k.w.pairs_tmp + off;
+      for (int shift = 0; shift < 64; shift += 8) {
+        if (cta_radix_pass(src, dst, n, shift, s_wh, s_cur)) {
+          uint64_t* t = src; src = dst; dst = t;
+        }
+        __syncthreads();
+      }
+      if (src != gp) {
+        for (int i = threadIdx.x; i < n; i += bk::kBigThreads) gp[i] = src[i];
+      }
+      __threadfence_block();
+      __syncthreads();
+      sorted_in_global = true;
+    }
+    int p = 0;
+    while (p < n) {
+      const int mwin = min(bk::kBigCap, n - p);
+      if (!sorted_in_global) {
+        int P = 32;
+        while (P < mwin) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += bk::kBigThreads) m.pairs[i] = i < mwin ? gp[i] : ~0ull;
+        __syncthreads();
+        bk::bitonic_sort<bk::kBigThreads>(m.pairs, P);
+      } else {
+        for (int i = threadIdx.x; i < mwin; i += bk::kBigThreads) m.pairs[i] = gp[p + i];
+        __syncthreads();
+      }
+      int R = bk::run_starts<bk::kBigThreads, bk::kBigCap / bk::kBigThreads>(m.pairs, mwin, m.start, s_warp);
+      int advance = mwin;
+      if (sorted_in_global && p + mwin < n &&
+          (uint32_t)(m.pairs[mwin - 1] >> 32) == (uint32_t)(gp[p + mwin] >> 32)) {
+        // the last run of the window continues past it
+        if (R == 1) {   // the window is one run: find its end, queue it (len > kBigCap > kQueueRun)
+          const uint32_t key = (uint32_t)(m.pairs[0] >> 32);
+          int lo = p + mwin, hi = n;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)(gp[mid] >> 32) <= key) lo = mid + 1; else hi = mid;
+          }
+          if (threadIdx.x == 0) enqueue_run(a, off + p, lo - p);
+          p = lo;
+          __syncthreads();
+          continue;
+        }
+        advance = m.start[R - 1];
+        R -= 1;
+      }
+      // does any run of this window go to the hot-row kernel?  then its pairs must lie sorted in global memory
+      if (!sorted_in_global) {
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        for (int r = threadIdx.x; r < R; r += bk::kBigThreads)
+          if (m.start[r + 1] - m.start[r] > bk::kQueueRun) s_flag = 1;
+        __syncthreads();
+        if (s_flag)
+          for (int i = threadIdx.x; i < mwin; i += bk::kBigThreads) gp[i] = m.pairs[i];
+      }
+      if constexpr (LANES > 0)
+        process_runs_vec<LANES, bk::kBigThreads>(a, sv, m.pairs, m.start, R, m.stage, m.part, m.coop, m.ncoop, off + p);
+      else
+        process_runs_scalar<bk::kBigThreads>(a, sv, m.pairs, m.start, R, reinterpret_cast<float*>(m.stage),
+                                             reinterpret_cast<float*>(m.part), m.coop, m.ncoop, off + p);
+      p += advance;
+      __syncthreads();
+    }
+  }
+}
+
 struct HeadIn {
   const uint32_t* keys;
   uint32_t sentinel;
@@ -714,15 +1264,20 @@ struct BwdWs {
   int32_t* counters;
   void* sort_ws;
   void* scan_ws;
+  bk::Ws bk;          // bucketed dedup (bucket_bwd.cuh)
+  int32_t* tickets;   // one-row slots: CTAs finished per slot
+  float* one_row_partials;
 };
 
 inline int64_t max_long_runs(int64_t n) { return n / kLongRun + 1; }
 inline int64_t max_chunks(int64_t n) { return n / kChunk + max_long_runs(n) + 1; }
+inline int64_t max_one_row_parts(int64_t n) { return n / bk::kOneRowChunk + 2048 + 1; }
 
 inline size_t bwd_ws_bytes(int64_t n, int dim) {
   return a256((size_t)n * 4) * 3 + a256((size_t)max_long_runs(n) * 16) + a256((size_t)max_long_runs(n) * 4) +
-         a256((size_t)max_chunks(n) * 8) + a256((size_t)max_chunks(n) * dim * 4) + 256 +
-         a256(rsort::workspace_bytes(n)) + a256(scan::workspace_bytes(n)) + 512;
+         a256((size_t)max_chunks(n) * 8) + a256((size_t)max_chunks(n) * dim * 4) +
+         a256(rsort::workspace_bytes(n)) + a256(scan::workspace_bytes(n)) + bk::ws_bytes(n) +
+         a256((size_t)max_one_row_parts(n) * dim * 4) + 512;
 }
 inline BwdWs bwd_carve(void* ws, int64_t n, int dim) {
   char* p = reinterpret_cast<char*>(a256(reinterpret_cast<size_t>(ws)));
@@ -734,10 +1289,19 @@ inline BwdWs bwd_carve(void* ws, int64_t n, int dim) {
   w.run_done = reinterpret_cast<int32_t*>(p); p += a256((size_t)max_long_runs(n) * 4);
   w.chunk_list = reinterpret_cast<int2*>(p); p += a256((size_t)max_chunks(n) * 8);
   w.partials = reinterpret_cast<float*>(p); p += a256((size_t)max_chunks(n) * dim * 4);
-  w.counters = reinterpret_cast<int32_t*>(p); p += 256;
+  w.bk = bk::carve(p, n, &w.counters, &w.tickets, &p);
+  w.one_row_partials = reinterpret_cast<float*>(p); p += a256((size_t)max_one_row_parts(n) * dim * 4);
   w.sort_ws = p; p += a256(rsort::workspace_bytes(n));
   w.scan_ws = p;
   return w;
+}
+
+static bool k7_radix_forced() {
+  static const bool on = [] {
+    const char* e = getenv("ER_K7");
+    return e && strcmp(e, "radix") == 0;
+  }();
+  return on;
 }
 
 static float adam_lr_t(const er_opt_t& o) { return adam_lr_t_of(o.lr, o.beta1_power, o.beta2_power); }
@@ -756,6 +1320,83 @@ static void launch_vec(const BwdArgs& a, cudaStream_t st) {
   const size_t smem_long = ((smem + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
   bwd_long_vec_kernel<LANES, TPE><<<4 * kSmCount, 256, smem_long, st>>>(a);
   count_launches(2);
+}
+
+// ---- bucketed path: host side ------------------------------------------------------------------------------
+static int log2_of(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// zero the placement state, count, place.  one_row: slots of mode ER_BUCKET_ONE_ROW are left out.
+static void bk_place(const int64_t* rows, int64_t cap, const int32_t* n_dev, int64_t n_rows, const int32_t* seg_ids,
+                     const er_slot_t* slots, int n_slots, bool one_row, const BwdWs& w, bool zero_call_block,
+                     cudaStream_t st) {
+  bk::PlaceArgs pa;
+  pa.rows = rows;
+  pa.cap = cap;
+  pa.n_dev = n_dev;
+  pa.sentinel = (uint32_t)n_rows;
+  pa.seg_ids = seg_ids;
+  pa.slots = one_row ? slots : nullptr;
+  pa.n_slots = n_slots;
+  const int nb = bk::num_buckets(cap);
+  pa.log2_nb = log2_of(nb);
+  pa.w = w.bk;
+  cudaMemsetAsync(w.bk.bcnt, 0, bk::zero_place_bytes() + (zero_call_block ? bk::zero_call_bytes() : 0), st);
+  const size_t smem = bk::place_smem_bytes(n_slots, nb, pa.slots != nullptr);
+  static bool attr = false;
+  if (!attr) {
+    const int mx = (int)bk::place_smem_bytes(2048, bk::kMaxBuckets, true);
+    cudaFuncSetAttribute(bk::bk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(bk::bk_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    attr = true;
+  }
+  const unsigned tiles = (unsigned)ceil_div(cap, (int64_t)bk::kTile);
+  bk::bk_count_kernel<<<tiles, bk::kTileThreads, smem, st>>>(pa);
+  bk::bk_place_kernel<<<tiles, bk::kTileThreads, smem, st>>>(pa);
+  count_launches(2);
+}
+
+template <int LANES>
+static void bk_launch_reduce(const BwdArgs& a, const BwdWs& src, const int64_t* rows, bool one_row,
+                             float* one_row_partials, int32_t* tickets, cudaStream_t st) {
+  BkArgs k;
+  k.w = src.bk;
+  const int nb = bk::num_buckets(a.n);
+  k.log2_nb = log2_of(nb);
+  const size_t smem = bk_reduce_smem(a.n_slots, bk::kCap, bk::kThreads);
+  const size_t smem_big = bk_reduce_smem(a.n_slots, bk::kBigCap, bk::kBigThreads);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(bk_reduce_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)bk_reduce_smem(2048, bk::kCap, bk::kThreads));
+    // ~30 KB per CTA: without this the driver's default carve-out leaves room for two of them per SM
+    cudaFuncSetAttribute(bk_reduce_kernel<LANES>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bk_reduce_big_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)bk_reduce_smem(2048, bk::kBigCap, bk::kBigThreads));
+    attr = true;
+  }
+  OneRowArgs o;
+  o.rows = rows;
+  o.partials = one_row_partials;
+  o.tickets = tickets;
+  // one-row slots are single-valued: their segment count is the batch size, the smallest of the plan
+  o.n_chunks = (int)ceil_div(ceil_div(a.n, (int64_t)a.n_slots), (int64_t)bk::kOneRowChunk);
+  const int extra = one_row ? a.n_slots * o.n_chunks : 0;
+  bk_reduce_kernel<LANES><<<nb + extra, bk::kThreads, smem, st>>>(a, k, o);
+  bk_reduce_big_kernel<LANES><<<kSmCount, bk::kBigThreads, smem_big, st>>>(a, k);
+  const size_t sl = slot_smem_bytes(a.n_slots);
+  if constexpr (LANES > 0) {
+    constexpr int TPE = (LANES <= 8) ? 1 : LANES;
+    const size_t smem_long = ((sl + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
+    bwd_long_vec_kernel<LANES, TPE><<<4 * kSmCount, 256, smem_long, st>>>(a);
+  } else {
+    bwd_long_scalar_kernel<<<4 * kSmCount, 256, sl, st>>>(a);
+  }
+  count_launches(3);
 }
 
 }  // namespace er
@@ -791,7 +1432,7 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
                               const void* sorted_ws, size_t sorted_ws_bytes, int32_t sorted_dim,
                               er_stream_t stream) {
   using namespace er;
-  ER_REQUIRE((rows || sorted_ws) && slots && grad_bufs && opt, "null argument");
+  ER_REQUIRE(rows && slots && grad_bufs && opt, "null argument");
   ER_REQUIRE(table || uniq_rows, "nothing to do: table and uniq_rows are both NULL");
   ER_REQUIRE((uniq_rows == nullptr) == (uniq_grads == nullptr) &&
                  (uniq_rows == nullptr) == (n_uniq == nullptr),
@@ -818,14 +1459,25 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   BwdWs w = bwd_carve(ws, n_lookups_cap, dim);
   // number of live lookups: row_ptr[n_seg] when CSR (device side), else the capacity
   const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
+  // Two dedup engines.  Bucketed (bucket_bwd.cuh) is the product path; the global radix sort + scan is kept for
+  // the calls that also want the deduplicated gradient written out sorted by row (uniq_rows), and as the A/B
+  // reference (ER_K7=radix in the environment).
+  const bool bucketed = (uniq_rows == nullptr) && !k7_radix_forced();
+  // one-row slots (ER_BUCKET_ONE_ROW) bypass the dedup when lookup == segment (no CSR lookups in the call)
+  const bool one_row = bucketed && seg_ids == nullptr;
+  BwdWs src = w;
   if (sorted_ws) {
-    // the same lookups were sorted by an earlier call on this stream (a table with the same row plan)
+    // the same lookups were placed / sorted by an earlier call on this stream (a table with the same row plan)
     if (sorted_ws_bytes < bwd_ws_bytes(n_lookups_cap, sorted_dim))
       return fail(ER_ERR_WORKSPACE, "er_embedding_bwd_reuse_sort: source workspace too small");
-    const BwdWs src = bwd_carve(const_cast<void*>(sorted_ws), n_lookups_cap, sorted_dim);
+    if (!bucketed && !k7_radix_forced())
+      return fail(ER_ERR_UNSUPPORTED, "er_embedding_bwd_reuse_sort: uniq_rows output needs the rows (er_embedding_bwd)");
+    src = bwd_carve(const_cast<void*>(sorted_ws), n_lookups_cap, sorted_dim);
     w.keys = src.keys;
     w.vals = src.vals;
-    cudaMemsetAsync(w.counters, 0, 2 * sizeof(int32_t), st);
+    cudaMemsetAsync(w.counters, 0, bk::zero_call_bytes(), st);
+  } else if (bucketed) {
+    bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, one_row, w, true, st);
   } else {
     rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, st);
   }
@@ -839,6 +1491,7 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   a.sentinel = (uint32_t)n_rows;
   a.keys = w.keys;
   a.vals = w.vals;
+  a.pairs = bucketed ? src.bk.pairs : nullptr;
   a.n = n_lookups_cap;
   a.weights = weights;
   a.seg_ids = seg_ids;
@@ -877,6 +1530,23 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   }
   if (uniq_grads) aligned = aligned && reinterpret_cast<uintptr_t>(uniq_grads) % 16 == 0;
   const bool vec_dim = (dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128);
+  if (bucketed) {
+    ER_REQUIRE(table != nullptr, "the bucketed path updates a table");
+    if (vec_dim && aligned) {
+      switch (dim / 4) {
+        case 1: bk_launch_reduce<1>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
+        case 2: bk_launch_reduce<2>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
+        case 4: bk_launch_reduce<4>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
+        case 8: bk_launch_reduce<8>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
+        case 16: bk_launch_reduce<16>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
+        default: bk_launch_reduce<32>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
+      }
+    } else {
+      bk_launch_reduce<0>(a, src, rows, one_row, w.one_row_partials, w.tickets, st);
+    }
+    ER_CUDA_LAUNCH_CHECK();
+    return ER_OK;
+  }
   if (vec_dim && aligned) {
     switch (dim / 4) {
       case 1: launch_vec<1>(a, st); break;
@@ -913,34 +1583,42 @@ extern "C" int er_embedding_bwd(float* table, float* state0, float* state1, int6
                             uniq_rows, uniq_grads, n_uniq, ws, ws_bytes, nullptr, 0, 0, stream);
 }
 
-extern "C" int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, const int32_t* row_ptr,
-                                        int64_t n_seg, int64_t n_lookups_cap, int32_t dim, void* ws,
+extern "C" int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, const int32_t* seg_ids,
+                                        const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                                        const er_slot_t* slots, int32_t n_slots, int32_t dim, void* ws,
                                         size_t ws_bytes, er_stream_t stream) {
   using namespace er;
-  ER_REQUIRE(rows, "null argument");
+  ER_REQUIRE(rows && slots, "null argument");
   ER_REQUIRE(n_rows > 0 && n_rows < 0xFFFFFFFFLL, "n_rows must be in (0, 2^32-1)");
+  ER_REQUIRE(n_slots > 0 && n_slots <= 2048, "n_slots must be in [1, 2048]");
   ER_REQUIRE(n_lookups_cap >= 0 && n_lookups_cap < (1LL << 31) && dim > 0, "bad shape");
   if (n_lookups_cap == 0) return ER_OK;
   if (!ws || ws_bytes < bwd_ws_bytes(n_lookups_cap, dim))
     return fail(ER_ERR_WORKSPACE, "er_embedding_bwd_presort: workspace too small");
   BwdWs w = bwd_carve(ws, n_lookups_cap, dim);
   const int32_t* n_dev = row_ptr ? row_ptr + n_seg : nullptr;
-  rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, as_stream(stream));
+  if (k7_radix_forced())
+    rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, as_stream(stream));
+  else
+    bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, seg_ids == nullptr, w, false,
+             as_stream(stream));
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
 
 extern "C" int er_embedding_bwd_reuse_sort(float* table, float* state0, float* state1, int64_t n_rows,
-                                           int32_t dim, int32_t row_stride, const float* weights,
-                                           const int32_t* seg_ids, const int32_t* row_ptr, int64_t n_seg,
-                                           int64_t n_lookups_cap, const er_slot_t* slots, int32_t n_slots,
+                                           int32_t dim, int32_t row_stride, const int64_t* rows,
+                                           const float* weights, const int32_t* seg_ids,
+                                           const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                                           const er_slot_t* slots, int32_t n_slots,
                                            const float* const* grad_bufs, int32_t n_bufs,
                                            const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
                                            float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,
                                            const void* sorted_ws, size_t sorted_ws_bytes,
                                            int32_t sorted_dim, er_stream_t stream) {
   if (!sorted_ws) return er::fail(ER_ERR_INVALID_ARG, "er_embedding_bwd_reuse_sort: sorted_ws is NULL");
-  return embedding_bwd_impl(table, state0, state1, n_rows, dim, row_stride, nullptr, weights, seg_ids,
+  if (!rows) return er::fail(ER_ERR_INVALID_ARG, "er_embedding_bwd_reuse_sort: rows is NULL");
+  return embedding_bwd_impl(table, state0, state1, n_rows, dim, row_stride, rows, weights, seg_ids,
                             row_ptr, n_seg, n_lookups_cap, slots, n_slots, grad_bufs, n_bufs, seg_scale,
                             opt, uniq_rows, uniq_grads, n_uniq, ws, ws_bytes, sorted_ws, sorted_ws_bytes,
                             sorted_dim, stream);

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from easyrec_b200 import _lib
 from easyrec_b200 import embedding as E
 from easyrec_b200 import kernels as K
 
@@ -32,7 +33,9 @@ class GlobalCall(object):
         rows_of_buf = call.out_rows(int(s['out_buf']))
         recs.append(dict(num_buckets=int(s['num_buckets']), row_offset=int(s['row_offset']),
                          seg_begin=int(s['seg_begin']) + r * call.n_seg, n_seg=int(s['n_seg']),
-                         bucket_mode=int(s['bucket_mode']), combiner=int(s['combiner']),
+                         # every rank's copy of a one-row slot reads the same table row: ordinary dedup here
+                         bucket_mode=(_lib.BUCKET_NONE if int(s['bucket_mode']) == _lib.BUCKET_ONE_ROW
+                                      else int(s['bucket_mode'])), combiner=int(s['combiner']),
                          out_buf=int(s['out_buf']), out_stride=int(s['out_stride']),
                          out_col=int(s['out_col']) + r * rows_of_buf * int(s['out_stride']),
                          shard_n=1))
@@ -96,7 +99,7 @@ class DataParallel(object):
       self._side.wait_stream(torch.cuda.current_stream())
       with torch.cuda.stream(self._side):
         for g in todo:
-          K.embedding_bwd_presort(g.rows, g.call.arena.n_rows, g.call.arena.dim, g.ws)
+          K.embedding_bwd_presort(g.rows, g.call.arena.n_rows, g.call.arena.dim, g.ws, g.slots_dev, g.n_slots)
 
   def sync_dense_grads(self):
     """sum over replicas in one bucket; the 1/world of hvd.allreduce(Average)

@@ -60,7 +60,10 @@ def id_feature(name, embedding_dim, hash_bucket_size=0, num_buckets=0, combiner=
 def raw_feature(name, embedding_dim=0, min_val=0.0, max_val=0.0, raw_input_dim=1):
   """RawFeature: (x-min)/(max-min) when max>min (input/input.py:638-640); with embedding_dim>0
   it becomes ids 0..k-1 weighted by the values (input/input.py:648-673)."""
-  return FeatureSpec(name, 'raw', embedding_dim, _lib.BUCKET_NONE, raw_input_dim, 'sum', '',
+  # raw_input_dim 1: a ONE-row table that every sample hits with weight x (ids are all 0): its gradient is a weighted
+  # column sum, which er_embedding_bwd computes without sending B duplicates of one row through the dedup
+  mode = _lib.BUCKET_ONE_ROW if raw_input_dim == 1 else _lib.BUCKET_NONE
+  return FeatureSpec(name, 'raw', embedding_dim, mode, raw_input_dim, 'sum', '',
                      float(min_val), float(max_val), raw_input_dim, 1)
 
 
@@ -236,6 +239,14 @@ class InputLayer(object):
           add_slot(f.embedding_dim, sname + '/hist', h, table, 'seq')
           lay['hist'].append([h, f.embedding_dim, sname + '/hist', None])
       self.seq_layout[sname] = lay
+    # ER_BUCKET_ONE_ROW promises that no other slot of the arena reads the table (a raw feature listed in two groups
+    # of the same width breaks that): such slots go through the ordinary dedup
+    for dim, subs in self.subcalls.items():
+      uses = collections.Counter(slot.table for sc in subs.values() for _, _, slot, _ in sc.items)
+      for sc in subs.values():
+        for _, _, slot, _ in sc.items:
+          if slot.bucket_mode == _lib.BUCKET_ONE_ROW and (uses[slot.table] > 1 or sc.kind != 'single'):
+            slot.bucket_mode = _lib.BUCKET_NONE
     for a in self.arenas.values():
       a.materialize(embedding_optimizer, generator=generator, adagrad_init=adagrad_init)
     # ---- launches ---------------------------------------------------------------------
@@ -398,15 +409,15 @@ class InputLayer(object):
     for m, rows, w, outs, seg_ids in self._pending:
       if id(rows) not in self._presorted:
         self._presorted[id(rows)] = (m.ws, m.arena.dim, m.arena.n_rows)
-        todo.append((m, rows))
+        todo.append((m, rows, seg_ids))
     if not todo:
       return
     if self._side is None:
       self._side = torch.cuda.Stream(device=self.device)
     self._side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(self._side):
-      for m, rows in todo:
-        K.embedding_bwd_presort(rows, m.arena.n_rows, m.arena.dim, m.ws)
+      for m, rows, sids in todo:
+        K.embedding_bwd_presort(rows, m.arena.n_rows, m.arena.dim, m.ws, m.slots_dev, m.n_slots, seg_ids=sids)
 
   def normalize_dense(self, dense):
     if not self.raw_has_range:

@@ -200,7 +200,7 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
   if sorted_from is not None:
     src_ws, src_dim = sorted_from
     _lib.check(
-        lib.er_embedding_bwd_reuse_sort(_p(table), _p(state0), _p(state1), n_rows, dim, row_stride,
+        lib.er_embedding_bwd_reuse_sort(_p(table), _p(state0), _p(state1), n_rows, dim, row_stride, _p(rows),
                                         _p(weights), _p(seg_ids), _p(row_ptr), n_seg, rows.numel(),
                                         _p(slots_dev), n_slots, _buf_array(grad_bufs), len(grad_bufs),
                                         _p(seg_scale), ctypes.byref(opt), _p(uniq_rows), _p(uniq_grads),
@@ -215,12 +215,15 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
                            _p(n_uniq), _p(ws), ws.numel(), _stream()), 'er_embedding_bwd')
 
 
-def embedding_bwd_presort(rows, n_rows, dim, ws, row_ptr=None, n_seg=0):
-  """K7's dedup sort alone (needs only the rows): finish with embedding_bwd(..., sorted_from=(ws, dim))."""
+def embedding_bwd_presort(rows, n_rows, dim, ws, slots_dev, n_slots, seg_ids=None, row_ptr=None, n_seg=0):
+  """The row-only half of K7's dedup (hashing the lookups into buckets), with the same rows / seg_ids / slots as the
+  embedding_bwd it prepares: finish with embedding_bwd(..., sorted_from=(ws, dim))."""
   lib = _lib.load()
   _chk(rows, torch.int64, 'rows')
-  _lib.check(lib.er_embedding_bwd_presort(_p(rows), n_rows, _p(row_ptr), n_seg, rows.numel(), dim, _p(ws),
-                                          ws.numel(), _stream()), 'er_embedding_bwd_presort')
+  _chk(seg_ids, torch.int32, 'seg_ids')
+  _lib.check(lib.er_embedding_bwd_presort(_p(rows), n_rows, _p(seg_ids), _p(row_ptr), n_seg, rows.numel(),
+                                          _p(slots_dev), n_slots, dim, _p(ws), ws.numel(), _stream()),
+             'er_embedding_bwd_presort')
 
 
 def sparse_apply(table, state0, state1, dim, uniq_rows, uniq_grads, n_uniq, opt, row_stride=None):

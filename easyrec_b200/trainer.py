@@ -35,7 +35,7 @@ class FlatDenseOptimizer(object):
     self.sizes = sizes
     # every tensor starts on a 16-byte boundary so er_gemm reads the kernels in place (float4 loads)
     total = sum((n + 3) // 4 * 4 for n in sizes)
-    self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+    self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)   # (alignment padding between tensors stays 0)
     self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
     off = 0
     segs = np.zeros(len(sizes), dtype=_lib.DENSE_SEG_DTYPE)

@@ -54,7 +54,12 @@ typedef enum er_bucket_mode {
   ER_BUCKET_IDENTITY = 2,
   /* already a table-local row (e.g. RawFeature projection ids 0..k-1,
    * input/input.py:648-673); v < 0 dropped */
-  ER_BUCKET_NONE = 3
+  ER_BUCKET_NONE = 3,
+  /* the slot's table has exactly ONE row (RawFeature projection with raw_input_dim 1,
+   * input/input.py:648-673: id 0 weighted by the value) and no other slot of the call reads it:
+   * every value >= 0 maps to that row, < 0 is dropped.  er_embedding_bwd does not send these lookups
+   * through the dedup: the row's gradient is the weighted column sum of the slot's gradient block. */
+  ER_BUCKET_ONE_ROW = 4
 } er_bucket_mode;
 
 /* safe_embedding_lookup_sparse combiners (compat/embedding_ops.py:37-162,
@@ -172,10 +177,12 @@ int er_embedding_fwd(const float* table, int64_t n_rows, int32_t dim,
 /* ---- K7: backward = dedup + segment-sum + fused optimizer row update ---
  * The IndexedSlices gradient of K2 (one row per lookup:
  * coef_l * grad_bufs[..][segment of l]) is summed per distinct row in
- * ascending lookup order (stable radix sort on the row number, the
- * deterministic equivalent of TF's _deduplicate_indexed_slices), multiplied
- * by opt.grad_scale, and applied to the row and its optimizer state in the
- * same kernel.  state0/state1: adagrad accumulator | adam m, v (same layout
+ * ascending lookup order (the lookups are hashed into buckets by row and each
+ * bucket is sorted on (row, lookup) in shared memory: the deterministic
+ * equivalent of TF's _deduplicate_indexed_slices), multiplied by
+ * opt.grad_scale, and applied to the row and its optimizer state in the
+ * same kernel.  Slots of mode ER_BUCKET_ONE_ROW take a weighted column sum
+ * instead.  state0/state1: adagrad accumulator | adam m, v (same layout
  * and stride as table; unused ones NULL).
  * When uniq_rows/uniq_grads are non-NULL the deduplicated gradient is ALSO
  * written there (compact, sorted by row; *n_uniq receives the count); pass
@@ -192,23 +199,26 @@ int er_embedding_bwd(float* table, float* state0, float* state1,
                      int64_t* uniq_rows, float* uniq_grads, int32_t* n_uniq,
                      void* ws, size_t ws_bytes, er_stream_t stream);
 
-/* The dedup sort of er_embedding_bwd alone: it depends only on the looked-up rows, not on any gradient,
- * so it can run as soon as er_bucketize has produced them (e.g. on a side stream under the dense
- * forward/backward).  Leaves the sorted (row, lookup) pairs in `ws`; finish with
+/* The row-only half of er_embedding_bwd's dedup (hashing the lookups into buckets): it depends only on the
+ * looked-up rows, not on any gradient, so it can run as soon as er_bucketize has produced them (e.g. on a side
+ * stream under the dense forward/backward).  Takes the same rows / seg_ids / row_ptr / slots as the
+ * er_embedding_bwd it prepares.  Leaves its result in `ws`; finish with
  * er_embedding_bwd_reuse_sort(..., sorted_ws = ws, sorted_dim = dim). */
-int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, const int32_t* row_ptr, int64_t n_seg,
-                             int64_t n_lookups_cap, int32_t dim, void* ws, size_t ws_bytes,
-                             er_stream_t stream);
+int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, const int32_t* seg_ids,
+                             const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                             const er_slot_t* slots, int32_t n_slots, int32_t dim, void* ws,
+                             size_t ws_bytes, er_stream_t stream);
 
-/* Same as er_embedding_bwd for a second table that was looked up with the SAME rows array (same
- * n_rows, e.g. the wide dim-1 table next to the deep table of DeepFM / Wide&Deep): the lookups were
- * already radix-sorted by an earlier er_embedding_bwd on this stream whose workspace is sorted_ws
- * (allocated for dimension sorted_dim and left untouched since); only the segment sums and the row
- * updates run.  `ws` is this call's own workspace (er_embedding_bwd_workspace_bytes(n, dim)). */
+/* Same as er_embedding_bwd when the SAME rows array (same n_rows, same slot rules - e.g. the wide dim-1 table
+ * next to the deep table of DeepFM / Wide&Deep) was already prepared by er_embedding_bwd_presort or
+ * deduplicated by an earlier er_embedding_bwd on this stream whose workspace is sorted_ws (allocated for
+ * dimension sorted_dim and left untouched since): only the per-row sums and the row updates run.  `ws` is this
+ * call's own workspace (er_embedding_bwd_workspace_bytes(n, dim)).  uniq_rows output is not available here. */
 int er_embedding_bwd_reuse_sort(float* table, float* state0, float* state1, int64_t n_rows,
-                                int32_t dim, int32_t row_stride, const float* weights,
-                                const int32_t* seg_ids, const int32_t* row_ptr, int64_t n_seg,
-                                int64_t n_lookups_cap, const er_slot_t* slots, int32_t n_slots,
+                                int32_t dim, int32_t row_stride, const int64_t* rows,
+                                const float* weights, const int32_t* seg_ids,
+                                const int32_t* row_ptr, int64_t n_seg, int64_t n_lookups_cap,
+                                const er_slot_t* slots, int32_t n_slots,
                                 const float* const* grad_bufs, int32_t n_bufs,
                                 const float* seg_scale, const er_opt_t* opt, int64_t* uniq_rows,
                                 float* uniq_grads, int32_t* n_uniq, void* ws, size_t ws_bytes,

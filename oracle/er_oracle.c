@@ -169,6 +169,7 @@ uint64_t oracle_fingerprint64(const uint8_t* s, size_t len) {
 /*  2: identity; -1 dropped (feature_column_v2.py:2566-2585); out of     */
 /*     range -> 0 (feature_column_v2.py:4268-4292)                       */
 /*  3: passthrough, negative dropped                                     */
+/*  4: one-row table: every value >= 0 is row 0 (input/input.py:648-673) */
 /* sharding: owner = r mod N, local = int64(r / N)                       */
 /*     (compat/feature_column/feature_column.py:296,317)                 */
 /* ------------------------------------------------------------------ */
@@ -190,6 +191,9 @@ void oracle_bucketize(const int64_t* ids, int64_t n, const int32_t* mode, const 
     } else if (mode[i] == 2) {
       drop = (v == -1);
       r = (v < 0 || v >= nb[i]) ? 0 : v;
+    } else if (mode[i] == 4) { /* one-row table (RawFeature projection, raw_input_dim 1: id 0) */
+      drop = v < 0;
+      r = 0;
     } else {
       drop = v < 0;
       r = v;

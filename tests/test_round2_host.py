@@ -1,0 +1,265 @@
+"""CPU (kernel doubles, tests/host_doubles.py): the host-side behaviour added after the first review.
+
+  * two hist_seq features of one DIN group own separate columns of the sequence matrix (forward and backward);
+  * `adam_optimizer` = tf.train.AdamOptimizer: rows without a gradient decay as well (builders/optimizer_builder.py:61-66,
+    behaviour stated at compat/adam_s.py:74-81), against the oracle restatement step by step;
+  * multi-task towers read the label their `label_name` names (model/multi_task_model.py:114-122);
+  * a resumed run (save -> restore) continues exactly like an uninterrupted one: dense optimizer slots, the
+    learning-rate clock and Adam's beta powers are part of the checkpoint;
+  * embedding_learning_rate_multiplier multiplies the table gradients (model/easy_rec_estimator.py:308-317);
+  * the optimizer step scalars of the device block (what a captured CUDA graph reads) equal the struct's.
+"""
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import _lib, builder, kernels as K, trainer as T
+from easyrec_b200.config import config_util
+from easyrec_b200.input import readers
+from oracle import oracle as O
+import host_doubles
+from test_input_layer_host import oracle_kernels  # noqa: F401  (fixture)
+from test_model_host import dense_kernels, interaction_doubles  # noqa: F401  (fixtures)
+
+DIN2 = b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } }
+data_config { batch_size: 4 input_type: CSVInput separator: "," label_fields: "clk"
+  input_fields { input_name: "clk" input_type: FLOAT } input_fields { input_name: "item_id" input_type: INT64 }
+  input_fields { input_name: "cate_id" input_type: INT64 }
+  input_fields { input_name: "hist" input_type: STRING } input_fields { input_name: "hist_c" input_type: STRING } }
+feature_config {
+  features { input_names: "item_id" feature_type: IdFeature embedding_dim: 8 num_buckets: 40 }
+  features { input_names: "cate_id" feature_type: IdFeature embedding_dim: 8 num_buckets: 12 }
+  features { input_names: "hist" feature_type: SequenceFeature embedding_dim: 8 num_buckets: 40 max_seq_len: 3 separator: "|" }
+  features { input_names: "hist_c" feature_type: SequenceFeature embedding_dim: 8 num_buckets: 12 max_seq_len: 3 separator: "|" } }
+model_config { model_class: "MultiTowerDIN"
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate_id"] wide_deep: DEEP }
+  seq_att_groups { group_name: "din" seq_att_map { key: "item_id" hist_seq: "hist" } seq_att_map { key: "cate_id" hist_seq: "hist_c" } }
+  multi_tower { towers { input: "item" dnn { hidden_units: [8] } }
+                din_towers { input: "din" dnn { hidden_units: [8, 1] } } final_dnn { hidden_units: [8] } } }
+'''
+
+
+def test_two_hist_seq_features_of_one_group_keep_their_own_columns(tmp_path, interaction_doubles):  # noqa: F811
+  """din_on_taobao.config's shape (tag_brand_list + tag_category_list in group 'din'): each history feature is looked
+  up in its own table and lands in its own half of hist_seq_emb; the backward routes each half to its own table."""
+  cfg = config_util.get_configs_from_pipeline_file(DIN2)
+  il, model, opt = builder.build_model(cfg, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(2))
+  rows = ['1,5,1,7|8|9,2|3|4', '0,6,2,10,5', '1,7,3,,', '0,8,4,11|12,6|7']
+  open(tmp_path / 's.csv', 'w').write('\n'.join(rows) + '\n')
+  (feats, labels), = list(readers.make_input(cfg, il, str(tmp_path / 's.csv')))
+  il.lookup(feats)
+  so = il.seq_outputs['din']
+  emb = so['hist_seq_emb'].detach().numpy()
+  assert emb.shape == (4, 3, 16)
+  a = il.arenas[8]
+  tab = a.weight.numpy()
+
+  def table(name):
+    off, local, _ = a.tables[name]
+    return tab[off:off + local]
+  t_hist, t_cate = table('din/hist_embedding'), table('din/hist_c_embedding')
+  want = np.zeros((4, 3, 16), np.float32)
+  for b, (h, c) in enumerate([([7, 8, 9], [2, 3, 4]), ([10], [5]), ([], []), ([11, 12], [6, 7])]):
+    for t, i in enumerate(h):
+      want[b, t, :8] = t_hist[i]
+    for t, i in enumerate(c):
+      want[b, t, 8:] = t_cate[i]
+  np.testing.assert_array_equal(emb, want)
+  assert not np.array_equal(emb[0, :, :8], emb[0, :, 8:])          # the two halves are different tables
+  key = so['key'].detach().numpy()
+  np.testing.assert_array_equal(key[:, :8], table('din/item_id_embedding')[[5, 6, 7, 8]])
+  np.testing.assert_array_equal(key[:, 8:], table('din/cate_id_embedding')[[1, 2, 3, 4]])
+  # ---- backward: a gradient on the second half only moves rows of the second history table ----
+  before = tab.copy()
+  g = torch.zeros_like(so['hist_seq_emb'])
+  g[:, :, 8:] = 1.0
+  so['hist_seq_emb'].backward(g)
+  il.set_optimizer_step(0.05, 0)
+  il.backward_update()
+  moved = np.flatnonzero((a.weight.numpy() != before).any(1))
+  off_c, _, _ = a.tables['din/hist_c_embedding']
+  assert sorted(moved.tolist()) == sorted(off_c + i for i in (2, 3, 4, 5, 6, 7))
+  # ... and the whole model trains
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  losses = [float(tr.train_step(feats, labels)[0]) for _ in range(12)]
+  assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+ADAM = b'''
+train_config { optimizer_config { adam_optimizer { learning_rate { exponential_decay_learning_rate {
+  initial_learning_rate: 0.01 decay_steps: 2 decay_factor: 0.5 min_learning_rate: 0.0001 } } }
+  embedding_learning_rate_multiplier: 2.0 } }
+data_config { batch_size: 8 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "c" input_type: INT64 }
+  input_fields { input_name: "d" input_type: INT64 } }
+feature_config {
+  features { input_names: "c" feature_type: IdFeature embedding_dim: 4 num_buckets: 30 }
+  features { input_names: "d" feature_type: IdFeature embedding_dim: 4 num_buckets: 10 } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["c", "d"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["c", "d"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [8] } final_dnn { hidden_units: [4] } } }
+'''
+
+
+def test_adam_optimizer_decays_untouched_rows_like_tf_adam(dense_kernels):  # noqa: F811
+  """Five steps of a DeepFM with `adam_optimizer`: after each step the deep arena equals the oracle's
+  tf.train.AdamOptimizer sparse apply on the gradient the step produced - rows looked up in an EARLIER step keep
+  moving (m, v decay, w -= lr_t*m/(sqrt(v)+eps)) although the current batch does not contain them."""
+  from easyrec_b200.estimator import EasyRecEstimator
+  est = EasyRecEstimator(ADAM, device='cpu', seed=1)
+  il, tr = est.input_layer, est.trainer
+  a = il.arenas[4]
+  assert a.opt_kind == _lib.OPT_ADAM_ROWS and a.touched is not None and il.emb_grad_mult == 2.0
+  rng = np.random.default_rng(0)
+  w, m, v = (x.numpy().copy() for x in (a.weight, a.state0, a.state1))
+  seen = set()
+  for step in range(5):
+    ids_c = rng.integers(0, 30, 8) if step < 2 else rng.integers(0, 5, 8)   # later batches miss most early rows
+    ids_d = rng.integers(0, 10, 8)
+    feats = {'sparse_fea': torch.from_numpy(np.concatenate([ids_c, ids_d]).astype(np.int64))}
+    labels = torch.from_numpy((rng.uniform(size=8) < 0.5).astype(np.float32))
+    # the gradient of this step's lookups, captured from the leaves K7 would read
+    captured = {}
+    real_bwd = K.embedding_bwd
+
+    def spy(table, s0, s1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt, ws, **kw):
+      if dim == 4:
+        captured['rows'] = rows.numpy().copy()
+        captured['g'] = grad_bufs[0].numpy().copy()
+        captured['opt'] = (opt.lr, opt.beta1_power, opt.beta2_power, opt.grad_scale)
+      return real_bwd(table, s0, s1, dim, rows, slots_dev, n_slots, n_seg, grad_bufs, opt, ws, **kw)
+    K.embedding_bwd = spy
+    try:
+      tr.train_step(feats, labels)
+    finally:
+      K.embedding_bwd = real_bwd
+    lr, b1p, b2p, gs = captured['opt']
+    t = step + 1
+    assert lr == pytest.approx(est._opt['lr_fn'](step)) and gs == 2.0
+    assert b1p == pytest.approx(0.9**t, rel=1e-6) and b2p == pytest.approx(0.999**t, rel=1e-6)
+    g = captured['g'][:, :8].reshape(8, 2, 4).transpose(1, 0, 2).reshape(16, 4)   # per-lookup rows, feature-major
+    O.embedding_bwd_adam_dense(w, m, v, captured['rows'], None, g, lr, beta1_power=b1p, beta2_power=b2p, grad_scale=gs)
+    np.testing.assert_array_equal(a.weight.numpy(), w)
+    np.testing.assert_array_equal(a.state0.numpy(), m)
+    np.testing.assert_array_equal(a.state1.numpy(), v)
+    if step >= 2:   # rows of the first batches that this batch does not touch still moved
+      cold = sorted(seen - set(captured['rows'].tolist()))
+      assert cold and (np.abs(m[cold]).sum() > 0)
+    seen |= set(captured['rows'].tolist())
+    assert not a.touched.any()                      # the mask is left clean for the next step
+  # the struct and the device block carry the same scalars
+  o = il.opt_holder['opt']
+  dev = il.hyper.dev.numpy()
+  assert (o.lr, o.beta1_power, o.beta2_power, o.grad_scale) == tuple(float(x) for x in dev)
+  assert o.hyper_dev == il.hyper.dev.data_ptr()
+
+
+def test_oracle_adam_dense_equals_dense_adam_with_zero_gradient_on_cold_rows():
+  """compat/adam_s.py:74-81: "the sparse behavior is equivalent to the dense behavior".  The oracle's sparse apply on
+  some rows == TensorFlow's dense ApplyAdam formula (adam_update_numpy of TF's adam_test.py) on a gradient that is
+  zero on every other row."""
+  rng = np.random.default_rng(3)
+  V, D = 20, 4
+  w = rng.normal(size=(V, D)).astype(np.float32)
+  m = (rng.normal(size=(V, D)) * 0.1).astype(np.float32)
+  v = (rng.uniform(size=(V, D)) * 0.01).astype(np.float32)
+  m[15:] = 0
+  v[15:] = 0
+  rows = np.array([3, 7, 3, 11], np.int64)
+  g = rng.normal(size=(4, D)).astype(np.float32)
+  full = np.zeros((V, D), np.float32)
+  for r, gr in zip(rows, g):
+    full[r] = full[r] + gr
+  f = np.float32
+  b1, b2, eps, lr, t = f(0.9), f(0.999), f(1e-8), f(0.01), 4
+  b1p, b2p = f(0.9)**t, f(0.999)**t
+  lr_t = O.adam_lr_t(lr, b1p, b2p)
+  m_t = (full * (f(1) - b1) + m * b1).astype(np.float32)
+  v_t = ((full * full) * (f(1) - b2) + v * b2).astype(np.float32)
+  w_t = w - (lr_t * m_t) / (np.sqrt(v_t) + eps)
+  w2, m2, v2 = w.copy(), m.copy(), v.copy()
+  O.embedding_bwd_adam_dense(w2, m2, v2, rows, None, g, float(lr), beta1_power=float(b1p), beta2_power=float(b2p))
+  np.testing.assert_allclose(m2, m_t, rtol=0, atol=1e-9)
+  np.testing.assert_allclose(v2, v_t, rtol=0, atol=1e-9)
+  np.testing.assert_allclose(w2, w_t, rtol=0, atol=1e-7)
+  np.testing.assert_array_equal(w2[15:], w[15:])         # never-touched rows (m = v = 0) do not move at all
+
+
+MTL = b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.1 } } } } }
+data_config { batch_size: 16 input_type: CSVInput separator: "," label_fields: ["buy", "aux", "clk"]
+  input_fields { input_name: "buy" input_type: FLOAT } input_fields { input_name: "aux" input_type: FLOAT }
+  input_fields { input_name: "clk" input_type: FLOAT } input_fields { input_name: "c" input_type: INT64 } }
+feature_config { features { input_names: "c" feature_type: IdFeature embedding_dim: 4 num_buckets: 16 } }
+model_config { model_class: "MMoE"
+  feature_groups { group_name: "all" feature_names: ["c"] wide_deep: DEEP }
+  mmoe { experts { expert_name: "e0" dnn { hidden_units: [8] } } experts { expert_name: "e1" dnn { hidden_units: [8] } }
+         task_towers { tower_name: "ctr" label_name: "clk" dnn { hidden_units: [4] } }
+         task_towers { tower_name: "cvr" label_name: "buy" dnn { hidden_units: [4] } } } }
+'''
+
+
+def test_task_towers_train_on_the_label_their_label_name_names(interaction_doubles):  # noqa: F811
+  """tower order (ctr, cvr) differs from label_fields order (buy, aux, clk): the towers must read columns 2 and 0."""
+  cfg = config_util.get_configs_from_pipeline_file(MTL)
+  il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert model.label_cols == [2, 0]
+  ids = torch.arange(16, dtype=torch.int64)
+  labels = torch.zeros(16, 3)
+  labels[:, 2] = (ids % 2 == 0).float()      # clk: even ids
+  labels[:, 0] = (ids < 4).float()           # buy: small ids
+  labels[:, 1] = 1.0 - labels[:, 2]          # aux: the opposite of clk (a tower bound by position would learn this one)
+  logits = torch.from_numpy(np.random.default_rng(1).normal(size=(16, 2)).astype(np.float32))
+  model._emb_outputs = ()
+  loss, probs = model.loss(logits, labels)
+  want = (O.sigmoid_ce(logits[:, 0].numpy(), labels[:, 2].numpy())[0] +      # ctr tower <- clk
+          O.sigmoid_ce(logits[:, 1].numpy(), labels[:, 0].numpy())[0])       # cvr tower <- buy
+  by_position = (O.sigmoid_ce(logits[:, 0].numpy(), labels[:, 0].numpy())[0] +
+                 O.sigmoid_ce(logits[:, 1].numpy(), labels[:, 1].numpy())[0])
+  assert float(loss) == pytest.approx(want, rel=1e-6) and abs(want - by_position) > 1e-3
+  bad = config_util.get_configs_from_pipeline_file(MTL.replace(b'label_name: "buy"', b'label_name: "nope"'))
+  with pytest.raises(ValueError, match='label_name'):
+    builder.build_model(bad, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+
+
+def test_resumed_run_equals_the_uninterrupted_one(tmp_path, dense_kernels):  # noqa: F811
+  """train(2N) == train(N) + save + restore + train(N): tables, dense parameters, dense optimizer slots, the decayed
+  learning rate and Adam's beta powers all continue where they stopped."""
+  from easyrec_b200.estimator import EasyRecEstimator
+  text = ADAM.replace(b'train_config {', b'model_dir: "%s" train_config {' % str(tmp_path / 'm').encode())
+  rng = np.random.default_rng(5)
+  batches = []
+  for _ in range(6):
+    ids = np.concatenate([rng.integers(0, 30, 8), rng.integers(0, 10, 8)]).astype(np.int64)
+    batches.append(({'sparse_fea': torch.from_numpy(ids)}, torch.from_numpy((rng.uniform(size=8) < 0.5).astype(np.float32))))
+  full = EasyRecEstimator(text, device='cpu', seed=7)
+  full.train(lambda: iter(batches), steps=6)
+  half = EasyRecEstimator(text, device='cpu', seed=7)
+  half.train(lambda: iter(batches[:3]), steps=3)
+  path = half.save()
+  resumed = EasyRecEstimator(text, device='cpu', seed=123)      # other initial weights: everything comes from the file
+  resumed.restore(path)
+  assert resumed.trainer.step == 3 and resumed.global_step == 3
+  resumed.train(lambda: iter(batches[3:]), steps=3)
+  for d in full.input_layer.arenas:
+    np.testing.assert_array_equal(resumed.input_layer.arenas[d].storage.numpy(), full.input_layer.arenas[d].storage.numpy())
+  np.testing.assert_array_equal(resumed.trainer.dense_opt.flat_p.numpy(), full.trainer.dense_opt.flat_p.numpy())
+  np.testing.assert_array_equal(resumed.trainer.dense_opt.s0.numpy(), full.trainer.dense_opt.s0.numpy())
+  np.testing.assert_array_equal(resumed.trainer.dense_opt.s1.numpy(), full.trainer.dense_opt.s1.numpy())
+  assert resumed.input_layer.opt_holder['opt'].beta1_power == full.input_layer.opt_holder['opt'].beta1_power
+
+
+def test_beta_powers_are_fp32_products_like_the_tf_accumulators():
+  """compat/adam_s.py:233-245 (_finish): beta1_power <- beta1_power * beta1 in fp32, once per step."""
+  h = K.StepHyper('cpu', 0.9, 0.999)
+  b1p, b2p = np.float32(0.9), np.float32(0.999)
+  for step in range(50):
+    h.set(0.001, step)
+    assert h.b1p == b1p and h.b2p == b2p
+    b1p, b2p = np.float32(b1p * np.float32(0.9)), np.float32(b2p * np.float32(0.999))
+  h2 = K.StepHyper('cpu', 0.9, 0.999)
+  h2.set(0.001, 37)                          # a restored run starts in the middle: same accumulators
+  h.set(0.001, 37)
+  assert (h2.b1p, h2.b2p) == (h.b1p, h.b2p)

@@ -38,7 +38,7 @@ def full(it):
 
 
 def presort(it):
-  K.embedding_bwd_presort(rows_l[it % 4], arena.n_rows, DIM, call.ws)
+  K.embedding_bwd_presort(rows_l[it % 4], arena.n_rows, DIM, call.ws, call.slots_dev, call.n_slots)
 
 
 def after_sort(it):
