@@ -1,28 +1,25 @@
-// K7, bucketed form: the gradient dedup WITHOUT a global sort.
+// K7, bucketed dedup: the (row, lookup) pairs are brought into "equal rows adjacent, ascending lookup order"
+// WITHOUT a global sort.
 //
-//   lookups --hash of the row--> NB buckets (two streaming passes over the rows: count, place)
-//   one CTA per bucket: the bucket's (row, lookup) pairs are sorted in SHARED memory (bitonic on the
-//   64-bit composite, so equal rows come out in ascending lookup order), the runs of equal rows are
-//   summed in that order and the optimizer is applied to the row in the same kernel.
+//   lookups --multiplicative hash of the row--> NB buckets (two streaming passes over the rows: count, place)
+//   one WARP per bucket sorts its pairs in registers on the 64-bit composite (row << 32 | lookup) and writes
+//   them out; buckets are laid out back to back, so the result has every run of equal rows contiguous and
+//   internally ordered by lookup position - exactly what the run kernels of embedding_bwd.cu need (they never
+//   required rows to ascend ACROSS runs).
 //
-// Against the 3-pass LSD radix sort + scan of sort.cuh this moves each (row, lookup) pair through global
-// memory once instead of four times, needs 3 dependent launches instead of 6, and the sorted order never
-// leaves the SM.  A bucket is chosen by a multiplicative hash of the row, so clustered ids (identity
-// columns, sequences) spread evenly; only duplicates of one row land together, and those are exactly the
-// entries that must meet.  Determinism: placement inside a bucket uses atomics (any order), but the
-// in-bucket sort is a total order on (row, lookup position), so the order of additions is fixed:
-// sequential in lookup order for runs <= kCoopRun (the order of a sequential CPU segment sum), a fixed
-// two-level tree above that.
+// Against the 3-pass LSD radix sort of sort.cuh (3 x 18 us at the C2 batch, latency bound) this is two cheap
+// streaming kernels plus one register-level sort: ~20 us.  A bucket is chosen by a multiplicative hash of the
+// row, so clustered ids (identity columns, sequences) spread evenly; only duplicates of one row land together,
+// and those are exactly the entries that must meet.  Determinism: placement inside a bucket uses atomics (any
+// order), but the in-bucket sort is a total order on (row, lookup position), so the output is unique.
 //
-// Bucket sizes are exact (pass 1 counts), the pair array is dense.  Three size classes:
-//   n <= kCap (1024)        bk_reduce_kernel, 256 threads, ~8 CTAs per SM
-//   n <= kBigCap (16384)    bk_reduce_big_kernel, 1024 threads, one CTA per SM (128 KB of pairs); runs
-//                           longer than kQueueRun are written back sorted and queued for the chunked
-//                           multi-CTA hot-row kernel
-//   larger                  same kernel, the CTA radix-sorts its range through global memory first
-//                           (slow, correct: needs > 16K lookups of ONE row in a batch)
-// Slots of mode ER_BUCKET_ONE_ROW (a one-row table hit by every sample: RawFeature projections) never
-// enter the buckets: their gradient is a weighted column sum (one_row_kernel).
+// Bucket sizes are exact (pass 1 counts), the pair array is dense.  Size classes:
+//   n <= kWarpCap (128)     bk_sort_kernel: one warp, bitonic network over shuffles, 1/2/4 registers per lane
+//   n <= kBigCap (16384)    bk_sort_big_kernel: one CTA of 1024 threads, bitonic in 128 KB of shared memory
+//   larger                  same kernel, stable LSD radix sort through global memory (slow, correct: needs
+//                           > 16K lookups of ONE row in a batch)
+// Slots of mode ER_BUCKET_ONE_ROW (a one-row table hit by every sample: RawFeature projections) never enter the
+// buckets: their gradient is a weighted column sum (one_row_cta, riding in the sort launch).
 #pragma once
 #include "common.cuh"
 #include "slots.cuh"
@@ -30,20 +27,18 @@
 namespace er {
 namespace bk {
 
-constexpr int kCap = 1024;
-constexpr int kBigCap = 16384;
-constexpr int kThreads = 256;
+constexpr int kWarpCap = 128;     // pairs a warp sorts in registers (4 per lane)
+constexpr int kBigCap = 16384;    // pairs a big-bucket CTA sorts in shared memory (128 KB)
 constexpr int kBigThreads = 1024;
-constexpr int kCoopRun = 48;      // longer runs are summed by the whole CTA
-constexpr int kQueueRun = 4096;   // big buckets: longer runs go to the multi-CTA hot-row kernel
 constexpr int kTile = 2048;       // lookups per CTA of the count / place passes
 constexpr int kTileThreads = 512;
 constexpr int kMaxBuckets = 8192;
 constexpr int kOneRowChunk = 512; // samples per CTA of the one-row column sum
 
+// about 50-80 lookups per bucket: a warp sorts 64 pairs with two registers per lane
 inline int num_buckets(int64_t n) {
   int nb = 64;
-  while (nb < kMaxBuckets && (int64_t)nb * 320 < n) nb <<= 1;
+  while (nb < kMaxBuckets && (int64_t)nb * 80 < n) nb <<= 1;
   return nb;
 }
 
@@ -199,7 +194,7 @@ static __global__ void __launch_bounds__(kTileThreads) bk_place_kernel(const __g
       s_base[b] = ex;
       if (blockIdx.x == 0) {
         a.w.boff[b] = ex;
-        if (loc[u] > kCap) a.w.big_list[atomicAdd(a.w.n_big, 1)] = b;
+        if (loc[u] > kWarpCap) a.w.big_list[atomicAdd(a.w.n_big, 1)] = b;
       }
       ex += loc[u];
     }
@@ -250,43 +245,6 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* s, int P) {
       __syncthreads();
     }
   }
-}
-
-// run starts of the sorted pairs s[0, n): s_start[r] = first index of run r, s_start[R] = n.  Returns R.
-// ITEMS consecutive elements per thread (THREADS * ITEMS >= n).
-template <int THREADS, int ITEMS, typename IdxT>
-__device__ __forceinline__ int run_starts(const uint64_t* s, int n, IdxT* s_start, int* s_warp /*[THREADS/32 + 1]*/) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int i0 = threadIdx.x * ITEMS;
-  unsigned heads = 0;
-  int cnt = 0;
-#pragma unroll
-  for (int u = 0; u < ITEMS; ++u) {
-    const int i = i0 + u;
-    const bool h = i < n && (i == 0 || (uint32_t)(s[i] >> 32) != (uint32_t)(s[i - 1] >> 32));
-    heads |= (h ? 1u : 0u) << u;
-    cnt += h;
-  }
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  int woff = 0, total = 0;
-  for (int ww = 0; ww < THREADS / 32; ++ww) {
-    if (ww < wid) woff += s_warp[ww];
-    total += s_warp[ww];
-  }
-  int r = woff + incl - cnt;
-#pragma unroll
-  for (int u = 0; u < ITEMS; ++u)
-    if ((heads >> u) & 1u) s_start[r++] = (IdxT)(i0 + u);
-  if (threadIdx.x == 0) s_start[total] = (IdxT)n;
-  __syncthreads();
-  return total;
 }
 
 }  // namespace bk

@@ -52,7 +52,6 @@ struct BwdArgs {
   uint32_t sentinel;  // == n_rows
   const uint32_t* keys;
   const uint32_t* vals;
-  const uint64_t* pairs;  // bucket mode: (row << 32 | lookup) pairs replace keys / vals
   int64_t n;  // sorted pairs (== n_lookups_cap)
   const float* weights;
   const int32_t* seg_ids;
@@ -71,6 +70,13 @@ struct BwdArgs {
   int32_t* run_done;         // per hot run: chunks finished
   int2* chunk_list;          // per chunk: (run, chunk index)
   float* partials;           // [chunk][dim]
+  // one-row slots (ER_BUCKET_ONE_ROW): their column sums are computed by the CTAs behind the first main_ctas of the
+  // run kernel's grid (or_chunks == 0: none)
+  const int64_t* or_rows;
+  float* or_partials;        // [n_slots][or_chunks][dim]
+  int32_t* or_tickets;       // [n_slots], zero between calls
+  int or_chunks;
+  int main_ctas;
 };
 
 // gradient row pointer and coefficient of sorted entry with lookup position l
@@ -201,18 +207,25 @@ __device__ __forceinline__ void apply_scalar(const BwdArgs& a, uint32_t key, int
   if (a.state1) a.state1[off] = s1;
 }
 
-// upper bound of `key` in keys[lo, n)
+// first index >= lo whose key differs from `key` (keys[lo] == key).  Equal rows are contiguous, but rows need not
+// ascend across runs (bucket order), so this gallops forward and bisects on equality, not on order.
 __device__ __forceinline__ int64_t run_end(const uint32_t* __restrict__ keys, int64_t lo, int64_t n,
                                            uint32_t key) {
-  int64_t hi = n;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if (keys[mid] <= key)
-      lo = mid + 1;
+  int64_t step = 1, hi = lo + 1;
+  while (hi < n && keys[hi] == key) {
+    lo = hi;
+    step <<= 1;
+    hi = lo + step;
+  }
+  if (hi > n) hi = n;
+  while (hi - lo > 1) {   // keys[lo] == key, keys[hi] != key (or hi == n)
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] == key)
+      lo = mid;
     else
       hi = mid;
   }
-  return lo;
+  return hi;
 }
 
 // One thread registers a hot run and its chunks.
@@ -227,9 +240,124 @@ __device__ __forceinline__ void enqueue_long(const BwdArgs& a, int64_t start, in
   for (int c = 0; c < nch; ++c) a.chunk_list[c0 + c] = make_int2(q, c);
 }
 
+// ---- one-row tables (ER_BUCKET_ONE_ROW slots): weighted column sums -----------------------------------------
+// CTA (slot f, chunk c) sums coef_b * g[b, cols of f] over its kOneRowChunk samples: lane groups take samples
+// g, g + G, ... in order, the groups are added in group order, the chunk partials in chunk order by the slot's
+// last CTA, which then applies the optimizer to the row: deterministic.  CTAs of other slots exit at once.
+template <int LANES>
+__device__ __forceinline__ void one_row_cta(const BwdArgs& a, int cta) {
+  __shared__ __align__(16) float s_part[1024];   // vec: G groups x LANES float4; scalar: 256 floats
+  __shared__ int s_last;
+  const int f = cta / a.or_chunks, c = cta - f * a.or_chunks;
+  const er_slot_t sl = a.slots[f];
+  if (sl.bucket_mode != ER_BUCKET_ONE_ROW) return;
+  constexpr int L = LANES > 0 ? LANES : 1;
+  constexpr int G = 256 / L;
+  const int dim = a.dim;
+  const int s0 = c * bk::kOneRowChunk, s1 = min(sl.n_seg, s0 + bk::kOneRowChunk);
+  const int used_chunks = (sl.n_seg + bk::kOneRowChunk - 1) / bk::kOneRowChunk;
+  if (s0 >= sl.n_seg) return;
+  const float* gbuf = a.gbufs.p[sl.out_buf];
+  const uint32_t row = (uint32_t)sl.row_offset;
+  if constexpr (LANES > 0) {
+    const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 4;   // samples of a lane group in flight
+    for (int e = s0 + grp; e < s1; e += G * U) {
+      float4 v[U];
+      float coef[U];
+      bool use[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ee = e + u * G;
+        use[u] = false;
+        if (ee < s1) {
+          const int64_t l = (int64_t)sl.seg_begin + ee;   // single-valued slot: lookup == segment
+          use[u] = a.or_rows[l] >= 0;                        // a dropped lookup contributes nothing
+          coef[u] = a.weights ? a.weights[l] : 1.0f;
+          if (a.seg_scale) coef[u] = __fmul_rn(coef[u], a.seg_scale[l]);
+          v[u] = reinterpret_cast<const float4*>(gbuf + (int64_t)ee * sl.out_stride + sl.out_col)[lane];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (use[u]) f4_fma_sep(g, v[u], coef[u]);
+    }
+    reinterpret_cast<float4*>(s_part)[grp * LANES + lane] = g;
+    __syncthreads();
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < LANES) {
+      for (int q = 0; q < G; ++q) f4_acc(tot, reinterpret_cast<float4*>(s_part)[q * LANES + threadIdx.x]);
+      __stcg(reinterpret_cast<float4*>(a.or_partials + ((int64_t)f * a.or_chunks + c) * dim) + threadIdx.x, tot);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.or_tickets[f], 1) == used_chunks - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      // the chunk partials: fetched in parallel, added in chunk order
+      for (int base = 0; base < used_chunks; base += G) {
+        const int q = base + grp;
+        if (q < used_chunks)
+          reinterpret_cast<float4*>(s_part)[grp * LANES + lane] =
+              __ldcg(reinterpret_cast<const float4*>(a.or_partials + ((int64_t)f * a.or_chunks + q) * dim) + lane);
+        __syncthreads();
+        if (threadIdx.x < LANES) {
+          if (base == 0) tot = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int m = min(G, used_chunks - base);
+          for (int q2 = 0; q2 < m; ++q2) f4_acc(tot, reinterpret_cast<float4*>(s_part)[q2 * LANES + threadIdx.x]);
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < LANES) {
+        RowRegs r = load_row(a, row, threadIdx.x);
+        apply_row_vec(a, row, threadIdx.x, tot, 0, r);
+        if (threadIdx.x == 0) a.or_tickets[f] = 0;
+      }
+    }
+  } else {
+    for (int col = 0; col < dim; ++col) {
+      float g = 0.f;
+      for (int e = s0 + threadIdx.x; e < s1; e += 256) {
+        const int64_t l = (int64_t)sl.seg_begin + e;
+        if (a.or_rows[l] < 0) continue;
+        float coef = a.weights ? a.weights[l] : 1.0f;
+        if (a.seg_scale) coef = __fmul_rn(coef, a.seg_scale[l]);
+        g = __fadd_rn(g, __fmul_rn(gbuf[(int64_t)e * sl.out_stride + sl.out_col + col], coef));
+      }
+      s_part[threadIdx.x] = g;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int q = 0; q < 256; ++q) tot = __fadd_rn(tot, s_part[q]);
+        __stcg(a.or_partials + ((int64_t)f * a.or_chunks + c) * dim + col, tot);
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.or_tickets[f], 1) == used_chunks - 1);
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < dim) {
+      __threadfence();
+      float tot = 0.f;
+      for (int q = 0; q < used_chunks; ++q)
+        tot = __fadd_rn(tot, __ldcg(a.or_partials + ((int64_t)f * a.or_chunks + q) * dim + threadIdx.x));
+      apply_scalar(a, row, (int)threadIdx.x, tot, 0);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) a.or_tickets[f] = 0;
+  }
+}
+
 // ---- runs, vector rows (dim = 4*LANES) ---------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant__ BwdArgs a) {
+  if (a.or_chunks > 0 && (int)blockIdx.x >= a.main_ctas) {   // CTAs behind the run CTAs: one-row column sums
+    one_row_cta<LANES>(a, (int)blockIdx.x - a.main_ctas);
+    return;
+  }
   extern __shared__ __align__(16) unsigned char s_raw[];
   const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
   constexpr int GROUPS = 32 / LANES;
@@ -305,6 +433,10 @@ __global__ void __launch_bounds__(256) bwd_runs_vec_kernel(const __grid_constant
 // the last ulp).
 template <int LANES>
 __global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant__ BwdArgs a) {
+  if (a.or_chunks > 0 && (int)blockIdx.x >= a.main_ctas) {   // CTAs behind the run CTAs: one-row column sums
+    one_row_cta<LANES>(a, (int)blockIdx.x - a.main_ctas);
+    return;
+  }
   extern __shared__ __align__(16) unsigned char s_raw[];
   const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
   constexpr int D4 = LANES;            // float4 per row
@@ -454,12 +586,8 @@ __global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant
   }
 }
 
-__device__ __forceinline__ uint32_t key_at(const BwdArgs& a, int64_t i) {
-  return a.pairs ? (uint32_t)(a.pairs[i] >> 32) : a.keys[i];
-}
-__device__ __forceinline__ uint32_t val_at(const BwdArgs& a, int64_t i) {
-  return a.pairs ? (uint32_t)a.pairs[i] : a.vals[i];
-}
+__device__ __forceinline__ uint32_t key_at(const BwdArgs& a, int64_t i) { return a.keys[i]; }
+__device__ __forceinline__ uint32_t val_at(const BwdArgs& a, int64_t i) { return a.vals[i]; }
 
 // ---- hot rows, vector: one CTA per chunk of a run; TPE threads share one lookup (TPE = 1 for
 // dim <= 32: a thread moves a whole gradient row) -----------------------------------------------
@@ -552,6 +680,10 @@ __global__ void __launch_bounds__(256) bwd_long_vec_kernel(const __grid_constant
 
 // ---- scalar rows (wide dim=1 tables, odd dims): one thread per (sorted position, column) ----
 __global__ void __launch_bounds__(256) bwd_runs_scalar_kernel(const __grid_constant__ BwdArgs a) {
+  if (a.or_chunks > 0 && (int)blockIdx.x >= a.main_ctas) {   // CTAs behind the run CTAs: one-row column sums
+    one_row_cta<0>(a, (int)blockIdx.x - a.main_ctas);
+    return;
+  }
   extern __shared__ __align__(16) unsigned char s_raw[];
   const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -631,6 +763,10 @@ __global__ void __launch_bounds__(256) bwd_long_scalar_kernel(const __grid_const
 // Same window protocol as bwd_scan_vec_kernel; a "row" is one float (+ its optimizer slots, which the
 // interleaved arena keeps in the same 32-byte sector), so every tail lane does its own RMW.
 __global__ void __launch_bounds__(256) bwd_scan_d1_kernel(const __grid_constant__ BwdArgs a) {
+  if (a.or_chunks > 0 && (int)blockIdx.x >= a.main_ctas) {   // CTAs behind the run CTAs: one-row column sums
+    one_row_cta<0>(a, (int)blockIdx.x - a.main_ctas);
+    return;
+  }
   extern __shared__ __align__(16) unsigned char s_raw[];
   const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -705,391 +841,78 @@ __global__ void __launch_bounds__(256) bwd_scan_d1_kernel(const __grid_constant_
 }
 
 // =====================================================================================================
-// Bucketed K7 (bucket_bwd.cuh): one CTA per bucket sorts its (row, lookup) pairs in shared memory, sums the
-// runs and applies the optimizer.
+// Bucketed dedup sort (bucket_bwd.cuh): the lookups have been hashed into buckets by row; here every bucket is
+// sorted on (row, lookup) and written out, so that the concatenation of the buckets has equal rows adjacent and in
+// ascending lookup order - what the run kernels above consume.  One WARP per bucket sorts in registers (bitonic
+// network over 32-wide shuffles, no shared memory, no block barriers); the rare bigger buckets go to one CTA each.
 // =====================================================================================================
-#ifndef ER_BK_MINB
-#define ER_BK_MINB 5   // resident bucket CTAs per SM the register allocation aims for
-#endif
-
 struct BkArgs {
   bk::Ws w;
   int log2_nb;
+  uint32_t* keys_out;
+  uint32_t* vals_out;
+  int64_t cap;
+  uint32_t sentinel;
 };
 
-__device__ __forceinline__ void enqueue_run(const BwdArgs& a, int64_t start, int len) {
-  const int nch = (len + kChunk - 1) / kChunk;
-  const int q = atomicAdd(&a.counters[0], 1);
-  const int c0 = atomicAdd(&a.counters[1], nch);
-  a.long_list[q] = make_int4((int)start, len, c0, nch);
-  a.run_done[q] = 0;
-  for (int c = 0; c < nch; ++c) a.chunk_list[c0 + c] = make_int2(q, c);
+// compare-exchange of two registers of one lane (indices i < l = i | j of the network)
+__device__ __forceinline__ void cx(uint64_t& lo, uint64_t& hi, bool up) {
+  const uint64_t mn = lo < hi ? lo : hi, mx = lo < hi ? hi : lo;
+  lo = up ? mn : mx;
+  hi = up ? mx : mn;
 }
 
-// Sum entries [j0, j1) of the sorted pairs `sp` (shared memory) for one row, sequentially in lookup order.
-template <int LANES>
-__device__ __forceinline__ float4 sum_entries(const BwdArgs& a, const SlotView& sv, const uint64_t* sp, int j0, int j1,
-                                              int lane) {
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = j0; j < j1; j += kBatch) {
-    float4 gv[kBatch];
-    float c[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      if (j + u < j1) {
-        const float* src = grad_src(a, sv, (uint32_t)sp[j + u], &c[u]);
-        gv[u] = reinterpret_cast<const float4*>(src)[lane];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      if (j + u < j1) f4_fma_sep(g, gv[u], c[u]);
-  }
-  return g;
-}
-
-constexpr int kStageF4 = 1024;   // float4 slots of the gradient staging buffer (16 KB)
-constexpr uint32_t kDonePos = 0xFFFFFFFFu;
-
-template <typename IdxT>
-__device__ __forceinline__ bool run_is_long(const IdxT* s_start, int r) {
-  return (int)s_start[r + 1] - (int)s_start[r] > bk::kCoopRun;
-}
-
-// Runs [0, R) of the sorted window sp[0, s_start[R]).
-//  1. runs longer than kCoopRun: the whole CTA sums them straight from global memory with a fixed two-level tree
-//     (or, queue_base >= 0 and longer than kQueueRun, hands them to the multi-CTA hot-row kernel - their pairs lie
-//     sorted in global memory at queue_base + index); their entries are then marked done;
-//  2. everything else in chunks: ALL threads stage the chunk's gradient rows (already multiplied by their
-//     coefficients) in shared memory - every load of the chunk is in flight at once, no per-row serial chain - then
-//     each lane group walks its runs r = grp, grp + G, ... adding the staged rows in lookup order and applies the
-//     optimizer; the next run's table row is requested before the current update is computed.
-template <int LANES, int THREADS, typename IdxT>
-__device__ __forceinline__ void process_runs_vec(const BwdArgs& a, const SlotView& sv, uint64_t* sp,
-                                                 const IdxT* s_start, int R, float4* s_stage, float4* s_part,
-                                                 int* s_coop, int* s_ncoop, int64_t queue_base) {
-  constexpr int G = THREADS / LANES;
-  constexpr int S_ENT = kStageF4 / LANES;
-  const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
-  if (threadIdx.x == 0) *s_ncoop = 0;
-  __syncthreads();
-  for (int r = threadIdx.x; r < R; r += THREADS)
-    if (run_is_long(s_start, r)) s_coop[atomicAdd(s_ncoop, 1)] = r;
-  __syncthreads();
-  const int nco = *s_ncoop;
-  for (int c = 0; c < nco; ++c) {
-    const int r = s_coop[c];
-    const int st = s_start[r], en = s_start[r + 1], len = en - st;
-    if (queue_base >= 0 && len > bk::kQueueRun) {
-      if (threadIdx.x == 0) enqueue_run(a, queue_base + st, len);
-    } else {
-      // fixed two-level tree: G consecutive sub-ranges summed in lookup order, then added in sub-range order
-      const int chunk = (len + G - 1) / G;
-      const int j0 = st + grp * chunk, j1 = min(en, j0 + chunk);
-      const float4 g = sum_entries<LANES>(a, sv, sp, j0, j1, lane);
-      s_part[grp * LANES + lane] = g;
-      __syncthreads();
-      if (threadIdx.x < LANES) {
-        const uint32_t key = (uint32_t)(sp[st] >> 32);
-        RowRegs row = load_row(a, key, threadIdx.x);
-        const int used = (len + chunk - 1) / chunk;
-        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < used; ++q) f4_acc(tot, s_part[q * LANES + threadIdx.x]);
-        apply_row_vec(a, key, threadIdx.x, tot, 0, row);
-      }
-    }
-    __syncthreads();
-    for (int i = st + threadIdx.x; i < en; i += THREADS) sp[i] |= (uint64_t)kDonePos;
-  }
-  __syncthreads();
-  // ---- staged chunks ----
-  const int n = s_start[R];
-  int r = grp;
-  while (r < R && run_is_long(s_start, r)) r += G;
-  RowRegs row;
-  row.w = row.s0 = row.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < R) row = load_row(a, (uint32_t)(sp[s_start[r]] >> 32), lane);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c0 = 0; c0 < n; c0 += S_ENT) {
-    const int c1 = min(n, c0 + S_ENT);
-    for (int q = threadIdx.x; q < (c1 - c0) * LANES; q += THREADS) {
-      const int e = q / LANES;
-      const uint32_t pos = (uint32_t)sp[c0 + e];
-      if (pos != kDonePos) {
-        float coef;
-        const float* src = grad_src(a, sv, pos, &coef);
-        s_stage[q] = f4_scale1(reinterpret_cast<const float4*>(src)[q % LANES], coef);
-      }
-    }
-    __syncthreads();
-    while (r < R && (int)s_start[r] < c1) {
-      const int st = s_start[r], en = s_start[r + 1];
-      const int lo = max(st, c0), hi = min(en, c1);
-      for (int i = lo; i < hi; ++i) f4_acc(acc, s_stage[(i - c0) * LANES + lane]);
-      if (en > c1) break;   // the run continues in the next chunk
-      const uint32_t key = (uint32_t)(sp[st] >> 32);
-      int rn = r + G;
-      while (rn < R && run_is_long(s_start, rn)) rn += G;
-      RowRegs nxt;
-      nxt.w = nxt.s0 = nxt.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rn < R) nxt = load_row(a, (uint32_t)(sp[s_start[rn]] >> 32), lane);
-      apply_row_vec(a, key, lane, acc, 0, row);
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      row = nxt;
-      r = rn;
-    }
-    __syncthreads();
-  }
-}
-
-// any dim: one thread per (run, column), same two phases; the staging buffer holds kStageF4 * 4 floats
-template <int THREADS, typename IdxT>
-__device__ __forceinline__ void process_runs_scalar(const BwdArgs& a, const SlotView& sv, uint64_t* sp,
-                                                    const IdxT* s_start, int R, float* s_stagef, float* s_partf,
-                                                    int* s_coop, int* s_ncoop, int64_t queue_base) {
-  const int dim = a.dim;
-  if (threadIdx.x == 0) *s_ncoop = 0;
-  __syncthreads();
-  for (int r = threadIdx.x; r < R; r += THREADS)
-    if (run_is_long(s_start, r)) s_coop[atomicAdd(s_ncoop, 1)] = r;
-  __syncthreads();
-  const int nco = *s_ncoop;
-  for (int cc = 0; cc < nco; ++cc) {
-    const int r = s_coop[cc];
-    const int st = s_start[r], en = s_start[r + 1], len = en - st;
-    if (queue_base >= 0 && len > bk::kQueueRun) {
-      if (threadIdx.x == 0) enqueue_run(a, queue_base + st, len);
-    } else {
-      const int chunk = (len + THREADS - 1) / THREADS;
-      const int j0 = st + threadIdx.x * chunk, j1 = min(en, j0 + chunk);
-      const int used = (len + chunk - 1) / chunk;
-      for (int c = 0; c < dim; ++c) {
-        float g = 0.f;
-        for (int j = j0; j < j1; ++j) {
-          float coef;
-          const float* src = grad_src(a, sv, (uint32_t)sp[j], &coef);
-          g = __fadd_rn(g, __fmul_rn(src[c], coef));
-        }
-        s_partf[threadIdx.x] = g;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          float tot = 0.f;
-          for (int q = 0; q < used; ++q) tot = __fadd_rn(tot, s_partf[q]);
-          apply_scalar(a, (uint32_t)(sp[st] >> 32), c, tot, 0);
-        }
-        __syncthreads();
-      }
-    }
-    __syncthreads();
-    for (int i = st + threadIdx.x; i < en; i += THREADS) sp[i] |= (uint64_t)kDonePos;
-  }
-  __syncthreads();
-  const int n = s_start[R];
-  const int S_ENT = max(1, (kStageF4 * 4) / dim);
-  const int total = R * dim;
-  int idx = threadIdx.x;
-  float acc = 0.f;
-  for (int c0 = 0; c0 < n; c0 += S_ENT) {
-    const int c1 = min(n, c0 + S_ENT);
-    for (int q = threadIdx.x; q < (c1 - c0) * dim; q += THREADS) {
-      const int e = q / dim;
-      const uint32_t pos = (uint32_t)sp[c0 + e];
-      if (pos != kDonePos) {
-        float coef;
-        const float* src = grad_src(a, sv, pos, &coef);
-        s_stagef[q] = __fmul_rn(src[q - e * dim], coef);
-      }
-    }
-    __syncthreads();
-    while (idx < total) {
-      const int r = idx / dim, c = idx - r * dim;
-      if (run_is_long(s_start, r)) {
-        idx += THREADS;
-        continue;
-      }
-      const int st = s_start[r], en = s_start[r + 1];
-      if (st >= c1) break;
-      const int lo = max(st, c0), hi = min(en, c1);
-      for (int i = lo; i < hi; ++i) acc = __fadd_rn(acc, s_stagef[(i - c0) * dim + c]);
-      if (en > c1) break;
-      apply_scalar(a, (uint32_t)(sp[st] >> 32), c, acc, 0);
-      acc = 0.f;
-      idx += THREADS;
-    }
-    __syncthreads();
-  }
-}
-
-// ---- one-row tables (ER_BUCKET_ONE_ROW slots): weighted column sums -----------------------------------------
-// CTA (slot f, chunk c) sums coef_b * g[b, cols of f] over its kOneRowChunk samples: lane groups take samples
-// g, g + G, ... in order, the groups are added in group order, the chunk partials in chunk order by the slot's
-// last CTA, which then applies the optimizer to the row: deterministic.  CTAs of other slots exit at once.
-struct OneRowArgs {
-  const int64_t* rows;
-  float* partials;   // [n_slots][n_chunks][dim]
-  int32_t* tickets;  // [n_slots], zero between calls
-  int n_chunks;
-};
-
-template <int LANES>
-__device__ __forceinline__ void one_row_cta(const BwdArgs& a, const OneRowArgs& o, int cta, float* s_part /*[1024]*/) {
-  __shared__ int s_last;
-  const int f = cta / o.n_chunks, c = cta - f * o.n_chunks;
-  const er_slot_t sl = a.slots[f];
-  if (sl.bucket_mode != ER_BUCKET_ONE_ROW) return;
-  constexpr int L = LANES > 0 ? LANES : 1;
-  constexpr int G = 256 / L;
-  const int dim = a.dim;
-  const int s0 = c * bk::kOneRowChunk, s1 = min(sl.n_seg, s0 + bk::kOneRowChunk);
-  const int used_chunks = (sl.n_seg + bk::kOneRowChunk - 1) / bk::kOneRowChunk;
-  if (s0 >= sl.n_seg) return;
-  const float* gbuf = a.gbufs.p[sl.out_buf];
-  const uint32_t row = (uint32_t)sl.row_offset;
-  if constexpr (LANES > 0) {
-    const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int U = 4;   // samples of a lane group in flight
-    for (int e = s0 + grp; e < s1; e += G * U) {
-      float4 v[U];
-      float coef[U];
-      bool use[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ee = e + u * G;
-        use[u] = false;
-        if (ee < s1) {
-          const int64_t l = (int64_t)sl.seg_begin + ee;   // single-valued slot: lookup == segment
-          use[u] = o.rows[l] >= 0;                        // a dropped lookup contributes nothing
-          coef[u] = a.weights ? a.weights[l] : 1.0f;
-          if (a.seg_scale) coef[u] = __fmul_rn(coef[u], a.seg_scale[l]);
-          v[u] = reinterpret_cast<const float4*>(gbuf + (int64_t)ee * sl.out_stride + sl.out_col)[lane];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (use[u]) f4_fma_sep(g, v[u], coef[u]);
-    }
-    reinterpret_cast<float4*>(s_part)[grp * LANES + lane] = g;
-    __syncthreads();
-    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (threadIdx.x < LANES) {
-      for (int q = 0; q < G; ++q) f4_acc(tot, reinterpret_cast<float4*>(s_part)[q * LANES + threadIdx.x]);
-      __stcg(reinterpret_cast<float4*>(o.partials + ((int64_t)f * o.n_chunks + c) * dim) + threadIdx.x, tot);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&o.tickets[f], 1) == used_chunks - 1);
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      // the chunk partials: fetched in parallel, added in chunk order
-      for (int base = 0; base < used_chunks; base += G) {
-        const int q = base + grp;
-        if (q < used_chunks)
-          reinterpret_cast<float4*>(s_part)[grp * LANES + lane] =
-              __ldcg(reinterpret_cast<const float4*>(o.partials + ((int64_t)f * o.n_chunks + q) * dim) + lane);
-        __syncthreads();
-        if (threadIdx.x < LANES) {
-          if (base == 0) tot = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int m = min(G, used_chunks - base);
-          for (int q2 = 0; q2 < m; ++q2) f4_acc(tot, reinterpret_cast<float4*>(s_part)[q2 * LANES + threadIdx.x]);
-        }
-        __syncthreads();
-      }
-      if (threadIdx.x < LANES) {
-        RowRegs r = load_row(a, row, threadIdx.x);
-        apply_row_vec(a, row, threadIdx.x, tot, 0, r);
-        if (threadIdx.x == 0) o.tickets[f] = 0;
-      }
-    }
-  } else {
-    for (int col = 0; col < dim; ++col) {
-      float g = 0.f;
-      for (int e = s0 + threadIdx.x; e < s1; e += 256) {
-        const int64_t l = (int64_t)sl.seg_begin + e;
-        if (o.rows[l] < 0) continue;
-        float coef = a.weights ? a.weights[l] : 1.0f;
-        if (a.seg_scale) coef = __fmul_rn(coef, a.seg_scale[l]);
-        g = __fadd_rn(g, __fmul_rn(gbuf[(int64_t)e * sl.out_stride + sl.out_col + col], coef));
-      }
-      s_part[threadIdx.x] = g;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float tot = 0.f;
-        for (int q = 0; q < 256; ++q) tot = __fadd_rn(tot, s_part[q]);
-        __stcg(o.partials + ((int64_t)f * o.n_chunks + c) * dim + col, tot);
-      }
-      __syncthreads();
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&o.tickets[f], 1) == used_chunks - 1);
-    __syncthreads();
-    if (s_last && (int)threadIdx.x < dim) {
-      __threadfence();
-      float tot = 0.f;
-      for (int q = 0; q < used_chunks; ++q)
-        tot = __fadd_rn(tot, __ldcg(o.partials + ((int64_t)f * o.n_chunks + q) * dim + threadIdx.x));
-      apply_scalar(a, row, (int)threadIdx.x, tot, 0);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) o.tickets[f] = 0;
-  }
-}
-
-inline size_t bk_reduce_smem(int n_slots, int cap, int threads) {
-  return ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15) + (size_t)cap * 8 + (((size_t)(cap + 1) * 2 + 15) & ~(size_t)15) +
-         (size_t)max(kStageF4, threads) * 16 + (size_t)(cap / bk::kCoopRun + 2) * 4 + 64;
-}
-
-struct BkSmem {
-  uint64_t* pairs;
-  uint16_t* start;
-  float4* stage;
-  float4* part;
-  int* coop;
-  int* ncoop;
-};
-__device__ __forceinline__ BkSmem bk_carve(unsigned char* s_raw, int n_slots, int cap, int threads) {
-  BkSmem m;
-  unsigned char* p = s_raw + ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15);
-  m.pairs = reinterpret_cast<uint64_t*>(p); p += (size_t)cap * 8;
-  m.start = reinterpret_cast<uint16_t*>(p); p += ((size_t)(cap + 1) * 2 + 15) & ~(size_t)15;
-  m.stage = reinterpret_cast<float4*>(p); p += (size_t)max(kStageF4, threads) * 16;
-  m.part = m.stage;   // the tree partials of the long runs are done with before the staging starts
-  m.coop = reinterpret_cast<int*>(p); p += (size_t)(cap / bk::kCoopRun + 1) * 4;
-  m.ncoop = reinterpret_cast<int*>(p);
-  return m;
-}
-
-// normal buckets (<= kCap pairs).  LANES == 0: scalar rows of any dim.
-template <int LANES>
-__global__ void __launch_bounds__(bk::kThreads, ER_BK_MINB) bk_reduce_kernel(const __grid_constant__ BwdArgs a,
-                                                                 const __grid_constant__ BkArgs k,
-                                                                 const __grid_constant__ OneRowArgs o) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_warp[bk::kThreads / 32 + 1];
-  const int b = blockIdx.x;
-  if (b >= (1 << k.log2_nb)) {   // the CTAs behind the buckets: column sums of the one-row slots
-    one_row_cta<LANES>(a, o, b - (1 << k.log2_nb), reinterpret_cast<float*>(s_raw));
-    return;
-  }
+// one warp per bucket of <= bk::kWarpCap pairs
+static __global__ void __launch_bounds__(256) bk_sort_kernel(const __grid_constant__ BkArgs k) {
+  const int nb = 1 << k.log2_nb;
+  const int n_sort_ctas = nb >> 3;
+  // positions behind the last bucket hold no lookup: sentinel keys, the run kernels skip them
+  const int64_t total = k.w.boff[nb];
+  for (int64_t i = total + (int64_t)blockIdx.x * 256 + threadIdx.x; i < k.cap; i += (int64_t)n_sort_ctas * 256)
+    k.keys_out[i] = k.sentinel;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int n = k.w.bcnt[b];
-  if (n == 0 || n > bk::kCap) return;   // empty, or one of the big buckets (bk_reduce_big_kernel)
-  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
-  const BkSmem m = bk_carve(s_raw, a.n_slots, bk::kCap, bk::kThreads);
-  const int off = k.w.boff[b];
-  int P = 32;
-  while (P < n) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += bk::kThreads) m.pairs[i] = i < n ? k.w.pairs[off + i] : ~0ull;
-  __syncthreads();
-  bk::bitonic_sort<bk::kThreads>(m.pairs, P);
-  const int R = bk::run_starts<bk::kThreads, bk::kCap / bk::kThreads>(m.pairs, n, m.start, s_warp);
-  if constexpr (LANES > 0)
-    process_runs_vec<LANES, bk::kThreads>(a, sv, m.pairs, m.start, R, m.stage, m.part, m.coop, m.ncoop, -1);
-  else
-    process_runs_scalar<bk::kThreads>(a, sv, m.pairs, m.start, R, reinterpret_cast<float*>(m.stage),
-                                      reinterpret_cast<float*>(m.part), m.coop, m.ncoop, -1);
+  if (n == 0 || n > bk::kWarpCap) return;   // empty, or a bucket of bk_sort_big_kernel
+  const int64_t off = k.w.boff[b];
+  const int P = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
+  uint64_t x[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int q = r * 32 + lane;
+    x[r] = q < n ? k.w.pairs[off + q] : ~0ull;
+  }
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j == 64) {
+        cx(x[0], x[2], ((lane) & kk) == 0);          // i = lane (+32): bit 7 of i is clear for r = 0, 1
+        cx(x[1], x[3], ((lane + 32) & kk) == 0);
+      } else if (j == 32) {
+        cx(x[0], x[1], ((lane) & kk) == 0);
+        if (P > 64) cx(x[2], x[3], ((lane + 64) & kk) == 0);
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r * 32 < P) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, x[r], j);
+            const bool up = ((lane + 32 * r) & kk) == 0;
+            const bool keep_min = (lower == up);
+            const uint64_t mn = x[r] < other ? x[r] : other, mx = x[r] < other ? other : x[r];
+            x[r] = keep_min ? mn : mx;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int q = r * 32 + lane;
+    if (q < n) {
+      k.keys_out[off + q] = (uint32_t)(x[r] >> 32);
+      k.vals_out[off + q] = (uint32_t)x[r];
+    }
+  }
 }
 
 // One pass of a CTA-local stable LSD radix sort through global memory (oversized buckets only).
@@ -1147,27 +970,32 @@ __device__ __forceinline__ bool cta_radix_pass(const uint64_t* __restrict__ in, 
   return true;
 }
 
-// big buckets: a few CTAs (one per SM, kBigCap pairs of shared memory) walk the list of buckets above kCap
-template <int LANES>
-__global__ void __launch_bounds__(bk::kBigThreads) bk_reduce_big_kernel(const __grid_constant__ BwdArgs a,
-                                                                        const __grid_constant__ BkArgs k) {
+// buckets above bk::kWarpCap: a few CTAs (one per SM, kBigCap pairs of shared memory) walk their list
+static __global__ void __launch_bounds__(bk::kBigThreads) bk_sort_big_kernel(const __grid_constant__ BkArgs k) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_warp[bk::kBigThreads / 32 + 1];
-  __shared__ int s_flag;
   const int n_big = *k.w.n_big;
   if ((int)blockIdx.x >= n_big) return;
-  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
-  const BkSmem m = bk_carve(s_raw, a.n_slots, bk::kBigCap, bk::kBigThreads);
+  uint64_t* sp = reinterpret_cast<uint64_t*>(s_raw);
   for (int x = blockIdx.x; x < n_big; x += gridDim.x) {
     const int b = k.w.big_list[x];
     const int n = k.w.bcnt[b];
     const int64_t off = k.w.boff[b];
     uint64_t* gp = k.w.pairs + off;
-    bool sorted_in_global = false;
-    if (n > bk::kBigCap) {
-      // more than kBigCap lookups in one bucket (>= thousands of duplicates of one row): stable LSD radix sort of the
-      // 64-bit composites through global memory, digits that do not vary are skipped
-      int* s_wh = reinterpret_cast<int*>(m.pairs);
+    if (n <= bk::kBigCap) {
+      int P = 32;
+      while (P < n) P <<= 1;
+      for (int i = threadIdx.x; i < P; i += bk::kBigThreads) sp[i] = i < n ? gp[i] : ~0ull;
+      __syncthreads();
+      bk::bitonic_sort<bk::kBigThreads>(sp, P);
+      for (int i = threadIdx.x; i < n; i += bk::kBigThreads) {
+        k.keys_out[off + i] = (uint32_t)(sp[i] >> 32);
+        k.vals_out[off + i] = (uint32_t)sp[i];
+      }
+      __syncthreads();
+    } else {
+      // more pairs than a CTA can hold (thousands of duplicates of one row): stable LSD radix sort of the 64-bit
+      // composites through global memory, digits that do not vary are skipped
+      int* s_wh = reinterpret_cast<int*>(sp);
       int* s_cur = s_wh + 32 * 256;
       uint64_t* src = gp;
       uint64_t* dst = k.w.pairs_tmp + off;
@@ -1177,62 +1005,11 @@ __global__ void __launch_bounds__(bk::kBigThreads) bk_reduce_big_kernel(const __
         }
         __syncthreads();
       }
-      if (src != gp) {
-        for (int i = threadIdx.x; i < n; i += bk::kBigThreads) gp[i] = src[i];
+      for (int i = threadIdx.x; i < n; i += bk::kBigThreads) {
+        const uint64_t e = src[i];
+        k.keys_out[off + i] = (uint32_t)(e >> 32);
+        k.vals_out[off + i] = (uint32_t)e;
       }
-      __threadfence_block();
-      __syncthreads();
-      sorted_in_global = true;
-    }
-    int p = 0;
-    while (p < n) {
-      const int mwin = min(bk::kBigCap, n - p);
-      if (!sorted_in_global) {
-        int P = 32;
-        while (P < mwin) P <<= 1;
-        for (int i = threadIdx.x; i < P; i += bk::kBigThreads) m.pairs[i] = i < mwin ? gp[i] : ~0ull;
-        __syncthreads();
-        bk::bitonic_sort<bk::kBigThreads>(m.pairs, P);
-      } else {
-        for (int i = threadIdx.x; i < mwin; i += bk::kBigThreads) m.pairs[i] = gp[p + i];
-        __syncthreads();
-      }
-      int R = bk::run_starts<bk::kBigThreads, bk::kBigCap / bk::kBigThreads>(m.pairs, mwin, m.start, s_warp);
-      int advance = mwin;
-      if (sorted_in_global && p + mwin < n &&
-          (uint32_t)(m.pairs[mwin - 1] >> 32) == (uint32_t)(gp[p + mwin] >> 32)) {
-        // the last run of the window continues past it
-        if (R == 1) {   // the window is one run: find its end, queue it (len > kBigCap > kQueueRun)
-          const uint32_t key = (uint32_t)(m.pairs[0] >> 32);
-          int lo = p + mwin, hi = n;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((uint32_t)(gp[mid] >> 32) <= key) lo = mid + 1; else hi = mid;
-          }
-          if (threadIdx.x == 0) enqueue_run(a, off + p, lo - p);
-          p = lo;
-          __syncthreads();
-          continue;
-        }
-        advance = m.start[R - 1];
-        R -= 1;
-      }
-      // does any run of this window go to the hot-row kernel?  then its pairs must lie sorted in global memory
-      if (!sorted_in_global) {
-        if (threadIdx.x == 0) s_flag = 0;
-        __syncthreads();
-        for (int r = threadIdx.x; r < R; r += bk::kBigThreads)
-          if (m.start[r + 1] - m.start[r] > bk::kQueueRun) s_flag = 1;
-        __syncthreads();
-        if (s_flag)
-          for (int i = threadIdx.x; i < mwin; i += bk::kBigThreads) gp[i] = m.pairs[i];
-      }
-      if constexpr (LANES > 0)
-        process_runs_vec<LANES, bk::kBigThreads>(a, sv, m.pairs, m.start, R, m.stage, m.part, m.coop, m.ncoop, off + p);
-      else
-        process_runs_scalar<bk::kBigThreads>(a, sv, m.pairs, m.start, R, reinterpret_cast<float*>(m.stage),
-                                             reinterpret_cast<float*>(m.part), m.coop, m.ncoop, off + p);
-      p += advance;
       __syncthreads();
     }
   }
@@ -1310,11 +1087,12 @@ template <int LANES>
 static void launch_vec(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = slot_smem_bytes(a.n_slots);
   // one warp per 32 sorted positions, 8 warps per CTA
+  const unsigned grid = (unsigned)(a.main_ctas + a.or_chunks * a.n_slots);
   if constexpr (LANES <= 8) {
     const size_t smem_scan = ((smem + 15) & ~(size_t)15) + (size_t)8 * 32 * LANES * sizeof(float4);
-    bwd_scan_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem_scan, st>>>(a);
+    bwd_scan_vec_kernel<LANES><<<grid, 256, smem_scan, st>>>(a);
   } else {
-    bwd_runs_vec_kernel<LANES><<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
+    bwd_runs_vec_kernel<LANES><<<grid, 256, smem, st>>>(a);
   }
   constexpr int TPE = (LANES <= 8) ? 1 : LANES;
   const size_t smem_long = ((smem + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
@@ -1359,44 +1137,25 @@ static void bk_place(const int64_t* rows, int64_t cap, const int32_t* n_dev, int
   count_launches(2);
 }
 
-template <int LANES>
-static void bk_launch_reduce(const BwdArgs& a, const BwdWs& src, const int64_t* rows, bool one_row,
-                             float* one_row_partials, int32_t* tickets, cudaStream_t st) {
+// sort the placed buckets into keys_out / vals_out
+static void bk_launch_sort(const BwdWs& place, int64_t cap, int64_t n_rows, uint32_t* keys_out, uint32_t* vals_out,
+                           cudaStream_t st) {
   BkArgs k;
-  k.w = src.bk;
-  const int nb = bk::num_buckets(a.n);
+  k.w = place.bk;
+  const int nb = bk::num_buckets(cap);
   k.log2_nb = log2_of(nb);
-  const size_t smem = bk_reduce_smem(a.n_slots, bk::kCap, bk::kThreads);
-  const size_t smem_big = bk_reduce_smem(a.n_slots, bk::kBigCap, bk::kBigThreads);
+  k.keys_out = keys_out;
+  k.vals_out = vals_out;
+  k.cap = cap;
+  k.sentinel = (uint32_t)n_rows;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(bk_reduce_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)bk_reduce_smem(2048, bk::kCap, bk::kThreads));
-    // ~30 KB per CTA: without this the driver's default carve-out leaves room for two of them per SM
-    cudaFuncSetAttribute(bk_reduce_kernel<LANES>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         (int)cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(bk_reduce_big_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)bk_reduce_smem(2048, bk::kBigCap, bk::kBigThreads));
+    cudaFuncSetAttribute(bk_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::kBigCap * 8);
     attr = true;
   }
-  OneRowArgs o;
-  o.rows = rows;
-  o.partials = one_row_partials;
-  o.tickets = tickets;
-  // one-row slots are single-valued: their segment count is the batch size, the smallest of the plan
-  o.n_chunks = (int)ceil_div(ceil_div(a.n, (int64_t)a.n_slots), (int64_t)bk::kOneRowChunk);
-  const int extra = one_row ? a.n_slots * o.n_chunks : 0;
-  bk_reduce_kernel<LANES><<<nb + extra, bk::kThreads, smem, st>>>(a, k, o);
-  bk_reduce_big_kernel<LANES><<<kSmCount, bk::kBigThreads, smem_big, st>>>(a, k);
-  const size_t sl = slot_smem_bytes(a.n_slots);
-  if constexpr (LANES > 0) {
-    constexpr int TPE = (LANES <= 8) ? 1 : LANES;
-    const size_t smem_long = ((sl + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
-    bwd_long_vec_kernel<LANES, TPE><<<4 * kSmCount, 256, smem_long, st>>>(a);
-  } else {
-    bwd_long_scalar_kernel<<<4 * kSmCount, 256, sl, st>>>(a);
-  }
-  count_launches(3);
+  bk_sort_kernel<<<nb >> 3, 256, 0, st>>>(k);
+  bk_sort_big_kernel<<<kSmCount, bk::kBigThreads, (size_t)bk::kBigCap * 8, st>>>(k);
+  count_launches(2);
 }
 
 }  // namespace er
@@ -1478,6 +1237,7 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
     cudaMemsetAsync(w.counters, 0, bk::zero_call_bytes(), st);
   } else if (bucketed) {
     bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, one_row, w, true, st);
+    bk_launch_sort(w, n_lookups_cap, n_rows, w.keys, w.vals, st);
   } else {
     rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, st);
   }
@@ -1491,7 +1251,6 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   a.sentinel = (uint32_t)n_rows;
   a.keys = w.keys;
   a.vals = w.vals;
-  a.pairs = bucketed ? src.bk.pairs : nullptr;
   a.n = n_lookups_cap;
   a.weights = weights;
   a.seg_ids = seg_ids;
@@ -1517,6 +1276,12 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   a.run_done = w.run_done;
   a.chunk_list = w.chunk_list;
   a.partials = w.partials;
+  a.main_ctas = (int)ceil_div(n_lookups_cap, 256);
+  a.or_rows = rows;
+  a.or_partials = w.one_row_partials;
+  a.or_tickets = w.tickets;
+  // one-row slots are single-valued: their segment count is the batch size, the smallest of the plan
+  a.or_chunks = one_row ? (int)ceil_div(ceil_div(n_lookups_cap, (int64_t)n_slots), (int64_t)bk::kOneRowChunk) : 0;
   if (uniq_rows) {
     scan::exclusive_scan(HeadIn{w.keys, a.sentinel}, HeadOut{w.head_rank}, n_lookups_cap, n_uniq,
                          w.scan_ws, st);
@@ -1530,23 +1295,6 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   }
   if (uniq_grads) aligned = aligned && reinterpret_cast<uintptr_t>(uniq_grads) % 16 == 0;
   const bool vec_dim = (dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128);
-  if (bucketed) {
-    ER_REQUIRE(table != nullptr, "the bucketed path updates a table");
-    if (vec_dim && aligned) {
-      switch (dim / 4) {
-        case 1: bk_launch_reduce<1>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
-        case 2: bk_launch_reduce<2>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
-        case 4: bk_launch_reduce<4>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
-        case 8: bk_launch_reduce<8>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
-        case 16: bk_launch_reduce<16>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
-        default: bk_launch_reduce<32>(a, src, rows, one_row, w.one_row_partials, w.tickets, st); break;
-      }
-    } else {
-      bk_launch_reduce<0>(a, src, rows, one_row, w.one_row_partials, w.tickets, st);
-    }
-    ER_CUDA_LAUNCH_CHECK();
-    return ER_OK;
-  }
   if (vec_dim && aligned) {
     switch (dim / 4) {
       case 1: launch_vec<1>(a, st); break;
@@ -1558,10 +1306,13 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
     }
   } else {
     const size_t smem = slot_smem_bytes(n_slots);
-    if (dim == 1)
-      bwd_scan_d1_kernel<<<(unsigned)ceil_div(a.n, 256), 256, smem, st>>>(a);
-    else
-      bwd_runs_scalar_kernel<<<(unsigned)ceil_div(a.n * dim, 256), 256, smem, st>>>(a);
+    if (dim == 1) {
+      a.main_ctas = (int)ceil_div(a.n, 256);
+      bwd_scan_d1_kernel<<<(unsigned)(a.main_ctas + a.or_chunks * a.n_slots), 256, smem, st>>>(a);
+    } else {
+      a.main_ctas = (int)ceil_div(a.n * dim, 256);
+      bwd_runs_scalar_kernel<<<(unsigned)(a.main_ctas + a.or_chunks * a.n_slots), 256, smem, st>>>(a);
+    }
     bwd_long_scalar_kernel<<<4 * kSmCount, 256, smem, st>>>(a);
     count_launches(2);
   }
@@ -1600,8 +1351,11 @@ extern "C" int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, con
   if (k7_radix_forced())
     rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, as_stream(stream));
   else
+  {
     bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, seg_ids == nullptr, w, false,
              as_stream(stream));
+    bk_launch_sort(w, n_lookups_cap, n_rows, w.keys, w.vals, as_stream(stream));
+  }
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

@@ -1,12 +1,13 @@
-"""GPU parity of the bucketed K7 (bucket_bwd.cuh: hash the lookups into buckets, sort each bucket in shared memory,
-sum the runs, fused row update) against the CPU oracle, through the C ABI.
+"""GPU parity of K7 on the bucketed dedup (bucket_bwd.cuh: hash the lookups into buckets by row, one warp sorts each
+bucket on (row, lookup) in registers, the run kernels sum and apply) against the CPU oracle, through the C ABI.
 
-Runs up to 48 lookups are summed in ascending lookup order = the oracle's order, so the post-step rows agree to the
-last bit there (only `__frsqrt_rn` vs `1/sqrtf` differs for Adagrad: <= 1 ulp); longer runs use a fixed tree (fp32
-reassociation, tolerance stated).  Covered: every dim class (vector 4..128, scalar 1 and 6), CSR with weights and
-mean / sqrtn scaling, dropped lookups, medium (49..1024), big-bucket (> 1024) and beyond-shared-memory (> 16384)
-duplicates of one row, one-row slots (ER_BUCKET_ONE_ROW), the presort + reuse split, clustered rows (identity ids),
-device-side lookup counts, and agreement with the radix engine (uniq_rows output) at the C2 size.
+Equal rows come out adjacent and in ascending lookup order, as from the radix sort, so the sums have the same fixed
+order as before: sequential for dim > 32, a fixed shuffle tree for dim <= 32 (last-ulp differences to the oracle's
+sequential order), chunked trees for hot rows (tolerance stated).  Covered: every dim class (vector 4..128, scalar 1
+and 6), CSR with weights and mean / sqrtn scaling, dropped lookups, duplicates of one row that overflow a warp's
+128 pairs (CTA sort), a CTA's 16384 pairs (global-memory radix fallback), one-row slots (ER_BUCKET_ONE_ROW), the
+presort + reuse split, clustered rows (identity ids), device-side lookup counts, and agreement with the radix engine
+(uniq_rows output) at the C2 size.
 """
 import numpy as np
 import pytest
@@ -94,8 +95,8 @@ def _check(got, want, long_rows=()):
   cold = np.ones(want[0].shape[0], bool)
   cold[list(long_rows)] = False
   for g, w_ in zip(got, want):
-    # short runs: same order of additions as the oracle
-    np.testing.assert_allclose(g[cold], w_[cold], rtol=2e-7, atol=2e-7)
+    # short runs: the oracle's order, or the fixed shuffle tree (dim <= 32): last-ulp differences
+    np.testing.assert_allclose(g[cold], w_[cold], rtol=2e-6, atol=2e-6)
     if long_rows:   # fixed-tree sums of hundreds..tens of thousands of N(0,1) gradients
       np.testing.assert_allclose(g[~cold], w_[~cold], rtol=2e-4, atol=2e-4)
 
@@ -106,10 +107,10 @@ def _check(got, want, long_rows=()):
 def test_bucketed_bwd_matches_the_oracle(kind, dim, with_csr):
   rng = np.random.default_rng(kind * 1000 + dim)
   B, F, V = 700, 3, 5000
-  hot = [(5, 300), (9, 70), (11, 49), (12, 48)]      # whole-CTA runs, and both sides of the kCoopRun boundary
+  hot = [(5, 300), (9, 70), (11, 65), (12, 64)]      # hot-row kernel runs, and both sides of its 64-lookup boundary
   c = _case(kind, dim, rng, V, B, F, with_csr=with_csr, hot=hot)
   got, want = _run(kind, dim, c, B, F, with_csr)
-  _check(got, want, long_rows=[5, 9, 11])
+  _check(got, want, long_rows=[5, 9, 11, 12])
   # untouched rows did not move at all
   touched = np.unique(c['rows'][c['rows'] >= 0])
   mask = np.ones(V, bool)
@@ -119,8 +120,8 @@ def test_bucketed_bwd_matches_the_oracle(kind, dim, with_csr):
 
 @pytest.mark.parametrize('dim', [16, 1, 6])
 def test_big_buckets_and_beyond_shared_memory(dim):
-  """2000 duplicates of one row (big-bucket kernel, in-CTA tree), 6000 of another (queued to the multi-CTA hot-row
-  kernel) and 20000 of a third (more than the 16384 pairs a CTA can hold: global-memory radix fallback)."""
+  """2000 and 6000 duplicates of one row (buckets sorted by a CTA in shared memory) and 20000 of a third (more than
+  the 16384 pairs a CTA can hold: global-memory radix fallback)."""
   rng = np.random.default_rng(dim)
   B, F, V = 12000, 4, 200000
   hot = [(17, 2000), (123456, 6000), (99, 20000)]
@@ -150,7 +151,7 @@ def test_clustered_rows_and_device_side_counts():
   c = _case(_lib.OPT_LAZY_ADAM, 16, rng, V, B, F, with_csr=True, clustered=True)
   got, want = _run(_lib.OPT_LAZY_ADAM, 16, c, B, F, True)
   runs = np.bincount(c['rows'][c['rows'] >= 0])
-  _check(got, want, long_rows=list(np.flatnonzero(runs > 48)))
+  _check(got, want, long_rows=list(np.flatnonzero(runs > 32)))
 
 
 def test_presort_then_two_tables_equals_fresh_calls():
