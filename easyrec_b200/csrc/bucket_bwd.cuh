@@ -28,17 +28,22 @@ namespace er {
 namespace bk {
 
 constexpr int kWarpCap = 128;     // pairs a warp sorts in registers (4 per lane)
+constexpr int kCap = 1024;        // pairs a 256-thread CTA sorts in shared memory (medium buckets)
+constexpr int kThreads = 256;
 constexpr int kBigCap = 16384;    // pairs a big-bucket CTA sorts in shared memory (128 KB)
 constexpr int kBigThreads = 1024;
+constexpr int kCoopRun = 48;      // CTA paths: longer runs are summed by the whole CTA
+constexpr int kQueueRun = 4096;   // big buckets: longer runs go to the multi-CTA hot-row kernel
 constexpr int kTile = 2048;       // lookups per CTA of the count / place passes
 constexpr int kTileThreads = 512;
 constexpr int kMaxBuckets = 8192;
 constexpr int kOneRowChunk = 512; // samples per CTA of the one-row column sum
 
-// about 50-80 lookups per bucket: a warp sorts 64 pairs with two registers per lane
-inline int num_buckets(int64_t n) {
+// warp mode: about 50-80 lookups per bucket (a warp sorts 64 pairs with two registers per lane);
+// CTA mode (rows a warp cannot stage: dim > 32, odd dims): about 200-300 per bucket
+inline int num_buckets(int64_t n, bool warp_mode) {
   int nb = 64;
-  while (nb < kMaxBuckets && (int64_t)nb * 80 < n) nb <<= 1;
+  while (nb < kMaxBuckets && (int64_t)nb * (warp_mode ? 80 : 320) < n) nb <<= 1;
   return nb;
 }
 
@@ -53,7 +58,8 @@ struct Ws {
   int32_t* bcur;        // [NB] placement cursors
   int32_t* boff;        // [NB + 1] exclusive offsets
   int32_t* big_list;    // [NB] buckets with more than kCap pairs
-  int32_t* n_big;       // [1] (+ padding)
+  int32_t* med_list;    // [NB] buckets with (warp_cap, kCap] pairs
+  int32_t* n_big;       // [0] big buckets, [1] medium buckets (+ padding)
 };
 
 inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -65,7 +71,7 @@ constexpr size_t kTicketBytes = 2048 * 4;
 inline size_t zero_place_bytes() { return 2 * kCntBytes + 256; }
 inline size_t zero_call_bytes() { return 256 + kTicketBytes; }
 inline size_t ws_bytes(int64_t n) {
-  return 2 * a256((size_t)n * 8) + zero_place_bytes() + zero_call_bytes() + 2 * kCntBytes + 256;
+  return 2 * a256((size_t)n * 8) + zero_place_bytes() + zero_call_bytes() + 3 * kCntBytes + 256;
 }
 // p: 256-byte aligned.  *counters / *tickets receive the per-call zero block.
 inline Ws carve(char* p, int64_t n, int32_t** counters, int32_t** tickets, char** end) {
@@ -79,6 +85,7 @@ inline Ws carve(char* p, int64_t n, int32_t** counters, int32_t** tickets, char*
   *tickets = reinterpret_cast<int32_t*>(p); p += kTicketBytes;
   w.boff = reinterpret_cast<int32_t*>(p); p += kCntBytes;
   w.big_list = reinterpret_cast<int32_t*>(p); p += kCntBytes;
+  w.med_list = reinterpret_cast<int32_t*>(p); p += kCntBytes;
   *end = p;
   return w;
 }
@@ -92,6 +99,7 @@ struct PlaceArgs {
   const er_slot_t* slots; // to skip ER_BUCKET_ONE_ROW slots (NULL: none)
   int n_slots;
   int log2_nb;
+  int warp_cap;           // buckets up to this size are sorted by a warp (0: CTA mode, every bucket is "medium")
   Ws w;
 };
 
@@ -194,7 +202,10 @@ static __global__ void __launch_bounds__(kTileThreads) bk_place_kernel(const __g
       s_base[b] = ex;
       if (blockIdx.x == 0) {
         a.w.boff[b] = ex;
-        if (loc[u] > kWarpCap) a.w.big_list[atomicAdd(a.w.n_big, 1)] = b;
+        if (loc[u] > kCap)
+          a.w.big_list[atomicAdd(&a.w.n_big[0], 1)] = b;
+        else if (loc[u] > a.warp_cap)
+          a.w.med_list[atomicAdd(&a.w.n_big[1], 1)] = b;
       }
       ex += loc[u];
     }
@@ -245,6 +256,43 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* s, int P) {
       __syncthreads();
     }
   }
+}
+
+// run starts of the sorted pairs s[0, n): s_start[r] = first index of run r, s_start[R] = n.  Returns R.
+// ITEMS consecutive elements per thread (THREADS * ITEMS >= n).
+template <int THREADS, int ITEMS, typename IdxT>
+__device__ __forceinline__ int run_starts(const uint64_t* s, int n, IdxT* s_start, int* s_warp /*[THREADS/32 + 1]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i0 = threadIdx.x * ITEMS;
+  unsigned heads = 0;
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < ITEMS; ++u) {
+    const int i = i0 + u;
+    const bool h = i < n && (i == 0 || (uint32_t)(s[i] >> 32) != (uint32_t)(s[i - 1] >> 32));
+    heads |= (h ? 1u : 0u) << u;
+    cnt += h;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+  for (int ww = 0; ww < THREADS / 32; ++ww) {
+    if (ww < wid) woff += s_warp[ww];
+    total += s_warp[ww];
+  }
+  int r = woff + incl - cnt;
+#pragma unroll
+  for (int u = 0; u < ITEMS; ++u)
+    if ((heads >> u) & 1u) s_start[r++] = (IdxT)(i0 + u);
+  if (threadIdx.x == 0) s_start[total] = (IdxT)n;
+  __syncthreads();
+  return total;
 }
 
 }  // namespace bk

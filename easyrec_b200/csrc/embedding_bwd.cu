@@ -52,6 +52,7 @@ struct BwdArgs {
   uint32_t sentinel;  // == n_rows
   const uint32_t* keys;
   const uint32_t* vals;
+  const uint64_t* pairs;  // bucketed engine: sorted (row << 32 | lookup) pairs of the queued hot rows
   int64_t n;  // sorted pairs (== n_lookups_cap)
   const float* weights;
   const int32_t* seg_ids;
@@ -84,7 +85,7 @@ __device__ __forceinline__ const float* grad_src(const BwdArgs& a, const SlotVie
                                                  float* coef) {
   const int32_t s = a.seg_ids ? a.seg_ids[l] : (int32_t)l;
   const SlotLite sl = slot_lite(sv, slot_of(sv, s));
-  float c = a.weights ? a.weights[l] : 1.0f;
+  float c = (a.weights && !slot_unit_weights(sl)) ? a.weights[l] : 1.0f;
   if (a.seg_scale) c = __fmul_rn(c, a.seg_scale[s]);
   *coef = c;
   return a.gbufs.p[sl.misc & 0xff] + (int64_t)(s - sl.seg_begin) * sl.out_stride + sl.out_col;
@@ -586,8 +587,12 @@ __global__ void __launch_bounds__(256) bwd_scan_vec_kernel(const __grid_constant
   }
 }
 
-__device__ __forceinline__ uint32_t key_at(const BwdArgs& a, int64_t i) { return a.keys[i]; }
-__device__ __forceinline__ uint32_t val_at(const BwdArgs& a, int64_t i) { return a.vals[i]; }
+__device__ __forceinline__ uint32_t key_at(const BwdArgs& a, int64_t i) {
+  return a.pairs ? (uint32_t)(a.pairs[i] >> 32) : a.keys[i];
+}
+__device__ __forceinline__ uint32_t val_at(const BwdArgs& a, int64_t i) {
+  return a.pairs ? (uint32_t)a.pairs[i] : a.vals[i];
+}
 
 // ---- hot rows, vector: one CTA per chunk of a run; TPE threads share one lookup (TPE = 1 for
 // dim <= 32: a thread moves a whole gradient row) -----------------------------------------------
@@ -846,46 +851,272 @@ __global__ void __launch_bounds__(256) bwd_scan_d1_kernel(const __grid_constant_
 // ascending lookup order - what the run kernels above consume.  One WARP per bucket sorts in registers (bitonic
 // network over 32-wide shuffles, no shared memory, no block barriers); the rare bigger buckets go to one CTA each.
 // =====================================================================================================
+#ifndef ER_BK_MINB
+#define ER_BK_MINB 4   // resident CTAs per SM the register allocation of the fused kernel aims for
+#endif
+
 struct BkArgs {
   bk::Ws w;
   int log2_nb;
-  uint32_t* keys_out;
-  uint32_t* vals_out;
-  int64_t cap;
-  uint32_t sentinel;
+  int warp_ctas;   // CTAs of the warp role (one warp per bucket), 0 in CTA mode
+  int med_ctas;    // CTAs of the medium role (they walk med_list)
 };
+
+__device__ __forceinline__ void enqueue_run(const BwdArgs& a, int64_t start, int len) {
+  const int nch = (len + kChunk - 1) / kChunk;
+  const int q = atomicAdd(&a.counters[0], 1);
+  const int c0 = atomicAdd(&a.counters[1], nch);
+  a.long_list[q] = make_int4((int)start, len, c0, nch);
+  a.run_done[q] = 0;
+  for (int c = 0; c < nch; ++c) a.chunk_list[c0 + c] = make_int2(q, c);
+}
+
+// Sum entries [j0, j1) of the sorted pairs `sp` (shared memory) for one row, sequentially in lookup order.
+template <int LANES>
+__device__ __forceinline__ float4 sum_entries(const BwdArgs& a, const SlotView& sv, const uint64_t* sp, int j0, int j1,
+                                              int lane) {
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = j0; j < j1; j += kBatch) {
+    float4 gv[kBatch];
+    float c[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (j + u < j1) {
+        const float* src = grad_src(a, sv, (uint32_t)sp[j + u], &c[u]);
+        gv[u] = reinterpret_cast<const float4*>(src)[lane];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (j + u < j1) f4_fma_sep(g, gv[u], c[u]);
+  }
+  return g;
+}
+
+constexpr int kStageF4 = 1024;   // float4 slots of the gradient staging buffer (16 KB)
+constexpr uint32_t kDonePos = 0xFFFFFFFFu;
+
+template <typename IdxT>
+__device__ __forceinline__ bool run_is_long(const IdxT* s_start, int r) {
+  return (int)s_start[r + 1] - (int)s_start[r] > bk::kCoopRun;
+}
+
+// Runs [0, R) of the sorted window sp[0, s_start[R]).
+//  1. runs longer than kCoopRun: the whole CTA sums them straight from global memory with a fixed two-level tree
+//     (or, queue_base >= 0 and longer than kQueueRun, hands them to the multi-CTA hot-row kernel - their pairs lie
+//     sorted in global memory at queue_base + index); their entries are then marked done;
+//  2. everything else in chunks: ALL threads stage the chunk's gradient rows (already multiplied by their
+//     coefficients) in shared memory - every load of the chunk is in flight at once, no per-row serial chain - then
+//     each lane group walks its runs r = grp, grp + G, ... adding the staged rows in lookup order and applies the
+//     optimizer; the next run's table row is requested before the current update is computed.
+template <int LANES, int THREADS, typename IdxT>
+__device__ __forceinline__ void process_runs_vec(const BwdArgs& a, const SlotView& sv, uint64_t* sp,
+                                                 const IdxT* s_start, int R, float4* s_stage, float4* s_part,
+                                                 int* s_coop, int* s_ncoop, int64_t queue_base) {
+  constexpr int G = THREADS / LANES;
+  constexpr int S_ENT = kStageF4 / LANES;
+  const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  if (threadIdx.x == 0) *s_ncoop = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += THREADS)
+    if (run_is_long(s_start, r)) s_coop[atomicAdd(s_ncoop, 1)] = r;
+  __syncthreads();
+  const int nco = *s_ncoop;
+  for (int c = 0; c < nco; ++c) {
+    const int r = s_coop[c];
+    const int st = s_start[r], en = s_start[r + 1], len = en - st;
+    if (queue_base >= 0 && len > bk::kQueueRun) {
+      if (threadIdx.x == 0) enqueue_run(a, queue_base + st, len);
+    } else {
+      // fixed two-level tree: G consecutive sub-ranges summed in lookup order, then added in sub-range order
+      const int chunk = (len + G - 1) / G;
+      const int j0 = st + grp * chunk, j1 = min(en, j0 + chunk);
+      const float4 g = sum_entries<LANES>(a, sv, sp, j0, j1, lane);
+      s_part[grp * LANES + lane] = g;
+      __syncthreads();
+      if (threadIdx.x < LANES) {
+        const uint32_t key = (uint32_t)(sp[st] >> 32);
+        RowRegs row = load_row(a, key, threadIdx.x);
+        const int used = (len + chunk - 1) / chunk;
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < used; ++q) f4_acc(tot, s_part[q * LANES + threadIdx.x]);
+        apply_row_vec(a, key, threadIdx.x, tot, 0, row);
+      }
+    }
+    __syncthreads();
+    for (int i = st + threadIdx.x; i < en; i += THREADS) sp[i] |= (uint64_t)kDonePos;
+  }
+  __syncthreads();
+  // ---- staged chunks ----
+  const int n = s_start[R];
+  int r = grp;
+  while (r < R && run_is_long(s_start, r)) r += G;
+  RowRegs row;
+  row.w = row.s0 = row.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < R) row = load_row(a, (uint32_t)(sp[s_start[r]] >> 32), lane);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = 0; c0 < n; c0 += S_ENT) {
+    const int c1 = min(n, c0 + S_ENT);
+    for (int q = threadIdx.x; q < (c1 - c0) * LANES; q += THREADS) {
+      const int e = q / LANES;
+      const uint32_t pos = (uint32_t)sp[c0 + e];
+      if (pos != kDonePos) {
+        float coef;
+        const float* src = grad_src(a, sv, pos, &coef);
+        s_stage[q] = f4_scale1(reinterpret_cast<const float4*>(src)[q % LANES], coef);
+      }
+    }
+    __syncthreads();
+    while (r < R && (int)s_start[r] < c1) {
+      const int st = s_start[r], en = s_start[r + 1];
+      const int lo = max(st, c0), hi = min(en, c1);
+      for (int i = lo; i < hi; ++i) f4_acc(acc, s_stage[(i - c0) * LANES + lane]);
+      if (en > c1) break;   // the run continues in the next chunk
+      const uint32_t key = (uint32_t)(sp[st] >> 32);
+      int rn = r + G;
+      while (rn < R && run_is_long(s_start, rn)) rn += G;
+      RowRegs nxt;
+      nxt.w = nxt.s0 = nxt.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rn < R) nxt = load_row(a, (uint32_t)(sp[s_start[rn]] >> 32), lane);
+      apply_row_vec(a, key, lane, acc, 0, row);
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      row = nxt;
+      r = rn;
+    }
+    __syncthreads();
+  }
+}
+
+// any dim: one thread per (run, column), same two phases; the staging buffer holds kStageF4 * 4 floats
+template <int THREADS, typename IdxT>
+__device__ __forceinline__ void process_runs_scalar(const BwdArgs& a, const SlotView& sv, uint64_t* sp,
+                                                    const IdxT* s_start, int R, float* s_stagef, float* s_partf,
+                                                    int* s_coop, int* s_ncoop, int64_t queue_base) {
+  const int dim = a.dim;
+  if (threadIdx.x == 0) *s_ncoop = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += THREADS)
+    if (run_is_long(s_start, r)) s_coop[atomicAdd(s_ncoop, 1)] = r;
+  __syncthreads();
+  const int nco = *s_ncoop;
+  for (int cc = 0; cc < nco; ++cc) {
+    const int r = s_coop[cc];
+    const int st = s_start[r], en = s_start[r + 1], len = en - st;
+    if (queue_base >= 0 && len > bk::kQueueRun) {
+      if (threadIdx.x == 0) enqueue_run(a, queue_base + st, len);
+    } else {
+      const int chunk = (len + THREADS - 1) / THREADS;
+      const int j0 = st + threadIdx.x * chunk, j1 = min(en, j0 + chunk);
+      const int used = (len + chunk - 1) / chunk;
+      for (int c = 0; c < dim; ++c) {
+        float g = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          float coef;
+          const float* src = grad_src(a, sv, (uint32_t)sp[j], &coef);
+          g = __fadd_rn(g, __fmul_rn(src[c], coef));
+        }
+        s_partf[threadIdx.x] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float tot = 0.f;
+          for (int q = 0; q < used; ++q) tot = __fadd_rn(tot, s_partf[q]);
+          apply_scalar(a, (uint32_t)(sp[st] >> 32), c, tot, 0);
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    for (int i = st + threadIdx.x; i < en; i += THREADS) sp[i] |= (uint64_t)kDonePos;
+  }
+  __syncthreads();
+  const int n = s_start[R];
+  const int S_ENT = max(1, (kStageF4 * 4) / dim);
+  const int total = R * dim;
+  int idx = threadIdx.x;
+  float acc = 0.f;
+  for (int c0 = 0; c0 < n; c0 += S_ENT) {
+    const int c1 = min(n, c0 + S_ENT);
+    for (int q = threadIdx.x; q < (c1 - c0) * dim; q += THREADS) {
+      const int e = q / dim;
+      const uint32_t pos = (uint32_t)sp[c0 + e];
+      if (pos != kDonePos) {
+        float coef;
+        const float* src = grad_src(a, sv, pos, &coef);
+        s_stagef[q] = __fmul_rn(src[q - e * dim], coef);
+      }
+    }
+    __syncthreads();
+    while (idx < total) {
+      const int r = idx / dim, c = idx - r * dim;
+      if (run_is_long(s_start, r)) {
+        idx += THREADS;
+        continue;
+      }
+      const int st = s_start[r], en = s_start[r + 1];
+      if (st >= c1) break;
+      const int lo = max(st, c0), hi = min(en, c1);
+      for (int i = lo; i < hi; ++i) acc = __fadd_rn(acc, s_stagef[(i - c0) * dim + c]);
+      if (en > c1) break;
+      apply_scalar(a, (uint32_t)(sp[st] >> 32), c, acc, 0);
+      acc = 0.f;
+      idx += THREADS;
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t bk_reduce_smem(int n_slots, int cap, int threads) {
+  return ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15) + (size_t)cap * 8 + (((size_t)(cap + 1) * 2 + 15) & ~(size_t)15) +
+         (size_t)max(kStageF4, threads) * 16 + (size_t)(cap / bk::kCoopRun + 2) * 4 + 64;
+}
+
+struct BkSmem {
+  uint64_t* pairs;
+  uint16_t* start;
+  float4* stage;
+  float4* part;
+  int* coop;
+  int* ncoop;
+};
+__device__ __forceinline__ BkSmem bk_carve(unsigned char* s_raw, int n_slots, int cap, int threads) {
+  BkSmem m;
+  unsigned char* p = s_raw + ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15);
+  m.pairs = reinterpret_cast<uint64_t*>(p); p += (size_t)cap * 8;
+  m.start = reinterpret_cast<uint16_t*>(p); p += ((size_t)(cap + 1) * 2 + 15) & ~(size_t)15;
+  m.stage = reinterpret_cast<float4*>(p); p += (size_t)max(kStageF4, threads) * 16;
+  m.part = m.stage;   // the tree partials of the long runs are done with before the staging starts
+  m.coop = reinterpret_cast<int*>(p); p += (size_t)(cap / bk::kCoopRun + 1) * 4;
+  m.ncoop = reinterpret_cast<int*>(p);
+  return m;
+}
 
 // compare-exchange of two registers of one lane (indices i < l = i | j of the network)
 __device__ __forceinline__ void cx(uint64_t& lo, uint64_t& hi, bool up) {
-  const uint64_t mn = lo < hi ? lo : hi, mx = lo < hi ? hi : lo;
-  lo = up ? mn : mx;
-  hi = up ? mx : mn;
+  if ((lo > hi) == up) {
+    const uint64_t t = lo;
+    lo = hi;
+    hi = t;
+  }
 }
 
-// one warp per bucket of <= bk::kWarpCap pairs
-static __global__ void __launch_bounds__(256) bk_sort_kernel(const __grid_constant__ BkArgs k) {
-  const int nb = 1 << k.log2_nb;
-  const int n_sort_ctas = nb >> 3;
-  // positions behind the last bucket hold no lookup: sentinel keys, the run kernels skip them
-  const int64_t total = k.w.boff[nb];
-  for (int64_t i = total + (int64_t)blockIdx.x * 256 + threadIdx.x; i < k.cap; i += (int64_t)n_sort_ctas * 256)
-    k.keys_out[i] = k.sentinel;
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int n = k.w.bcnt[b];
-  if (n == 0 || n > bk::kWarpCap) return;   // empty, or a bucket of bk_sort_big_kernel
-  const int64_t off = k.w.boff[b];
-  const int P = n <= 32 ? 32 : (n <= 64 ? 64 : 128);
-  uint64_t x[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int q = r * 32 + lane;
-    x[r] = q < n ? k.w.pairs[off + q] : ~0ull;
-  }
+// ---- warp role: one warp owns a bucket of <= kWarpCap pairs ---------------------------------------------------
+// The pairs are sorted in registers (bitonic network over 32-wide shuffles: no shared memory, no block barrier), then
+// consumed 32 at a time: all lanes stage the chunk's gradient rows (times their coefficients) in the warp's slice of
+// shared memory - every load of the chunk in flight at once - and the 32/LANES lane groups walk the chunk's runs,
+// adding the staged rows in lookup order (the order of a sequential CPU segment sum) and applying the optimizer.  A run
+// that crosses a chunk boundary hands its partial sum to the next chunk through a carry slot.
+template <int LANES>
+struct WarpSmem {
+  float4 stage[32 * LANES];
+  float4 carry[LANES];
+  uint32_t keys[32];
+};
+
+__device__ __forceinline__ void sort4(uint64_t (&x)[4], int P, int lane) {
   for (int kk = 2; kk <= P; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
       if (j == 64) {
-        cx(x[0], x[2], ((lane) & kk) == 0);          // i = lane (+32): bit 7 of i is clear for r = 0, 1
+        cx(x[0], x[2], ((lane) & kk) == 0);
         cx(x[1], x[3], ((lane + 32) & kk) == 0);
       } else if (j == 32) {
         cx(x[0], x[1], ((lane) & kk) == 0);
@@ -897,21 +1128,229 @@ static __global__ void __launch_bounds__(256) bk_sort_kernel(const __grid_consta
           if (r * 32 < P) {
             const uint64_t other = __shfl_xor_sync(0xffffffffu, x[r], j);
             const bool up = ((lane + 32 * r) & kk) == 0;
-            const bool keep_min = (lower == up);
-            const uint64_t mn = x[r] < other ? x[r] : other, mx = x[r] < other ? other : x[r];
-            x[r] = keep_min ? mn : mx;
+            // this lane keeps the smaller of the pair iff it holds the lower index of an ascending pair (or the
+            // higher index of a descending one): one 64-bit compare, one select
+            if ((x[r] > other) == (lower == up)) x[r] = other;
           }
         }
       }
     }
   }
+}
+
+template <int LANES>
+__device__ __forceinline__ void warp_bucket_vec(const BwdArgs& a, const SlotView& sv, const BkArgs& k, int b,
+                                                WarpSmem<LANES>* ws) {
+  constexpr int G = 32 / LANES;
+  const int lane = threadIdx.x & 31;
+  const int gi = lane / LANES, gl = lane % LANES;
+  const int n = k.w.bcnt[b];
+  if (n == 0 || n > bk::kWarpCap) return;   // empty, or a bucket of the medium / big CTAs
+  const int64_t off = k.w.boff[b];
+  uint64_t x[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int q = r * 32 + lane;
-    if (q < n) {
-      k.keys_out[off + q] = (uint32_t)(x[r] >> 32);
-      k.vals_out[off + q] = (uint32_t)x[r];
+    x[r] = q < n ? k.w.pairs[off + q] : ~0ull;
+  }
+  sort4(x, n <= 32 ? 32 : (n <= 64 ? 64 : 128), lane);
+  uint32_t carry_key = 0xFFFFFFFFu;   // no run is open
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (r * 32 >= n) break;
+    const uint32_t key = (uint32_t)(x[r] >> 32), pos = (uint32_t)x[r];
+    const int nv = min(32, n - r * 32);   // valid lanes are a prefix
+    const uint32_t next_first = (r < 3 && (r + 1) * 32 < n) ? __shfl_sync(0xffffffffu, (uint32_t)(x[r < 3 ? r + 1 : 3] >> 32), 0)
+                                                            : 0xFFFFFFFFu;
+    uint32_t prevk = __shfl_up_sync(0xffffffffu, key, 1);
+    if (lane == 0) prevk = carry_key;
+    const bool is_head = lane < nv && key != prevk;
+    const unsigned H = __ballot_sync(0xffffffffu, is_head);
+    const int nh = __popc(H);
+    ws->keys[lane] = key;
+    const float4 open_sum = ws->carry[gl];   // read before this chunk may overwrite it (ordered by the __syncwarp below)
+    // the table rows of this group's first two runs: requested first, they arrive under the gradient staging
+    RowRegs row0, row1;
+    row0.w = row0.s0 = row0.s1 = row1.w = row1.s0 = row1.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+      const unsigned h0 = __fns(H, 0, gi + 1), h1 = __fns(H, 0, gi + G + 1);
+      const uint32_t k0 = __shfl_sync(0xffffffffu, key, h0 & 31), k1 = __shfl_sync(0xffffffffu, key, h1 & 31);
+      if (gi < nh) row0 = load_row(a, k0, gl);
+      if (gi + G < nh) row1 = load_row(a, k1, gl);
     }
+    // stage the chunk: LANES lanes fetch one gradient row, G rows per step
+#pragma unroll
+    for (int t = 0; t < LANES; ++t) {
+      const int e = t * G + gi;
+      const uint32_t pe = __shfl_sync(0xffffffffu, pos, e);
+      if (e < nv) {
+        float coef;
+        const float* src = grad_src(a, sv, pe, &coef);
+        ws->stage[e * LANES + gl] = f4_scale1(reinterpret_cast<const float4*>(src)[gl], coef);
+      }
+    }
+    __syncwarp();
+    const uint32_t lastk = ws->keys[31];
+    const bool chunk_open = (nv == 32) && next_first == lastk;   // the chunk's last run goes on in the next chunk
+    // the entries in front of the first head continue the run the previous chunk left open
+    const int lead = nh ? (__ffs(H) - 1) : nv;
+    if (lead > 0 && gi == 0) {
+      float4 acc = open_sum;
+      for (int i = 0; i < lead; ++i) f4_acc(acc, ws->stage[i * LANES + gl]);
+      if (lead == 32 && chunk_open) {
+        ws->carry[gl] = acc;
+      } else {
+        RowRegs row = load_row(a, carry_key, gl);
+        apply_row_vec(a, carry_key, gl, acc, 0, row);
+      }
+    }
+    for (int q = gi; q < nh; q += G) {
+      const int h = __fns(H, 0, q + 1);
+      const unsigned rest = (h == 31) ? 0u : (H >> (h + 1)) << (h + 1);
+      const int e_end = rest ? (__ffs(rest) - 1) : nv;
+      const uint32_t kh = ws->keys[h];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = h; i < e_end; ++i) f4_acc(acc, ws->stage[i * LANES + gl]);
+      if (e_end == 32 && chunk_open) {
+        ws->carry[gl] = acc;
+      } else {
+        RowRegs row = (q == gi) ? row0 : (q == gi + G) ? row1 : load_row(a, kh, gl);
+        apply_row_vec(a, kh, gl, acc, 0, row);
+      }
+    }
+    carry_key = chunk_open ? lastk : 0xFFFFFFFFu;
+    __syncwarp();
+  }
+}
+
+// dim == 1 (wide tables): a lane per run, the staged values are single floats
+struct WarpSmem1 {
+  float stage[32];
+  float carry;
+  uint32_t keys[32];
+};
+
+__device__ __forceinline__ void warp_bucket_d1(const BwdArgs& a, const SlotView& sv, const BkArgs& k, int b,
+                                               WarpSmem1* ws) {
+  const int lane = threadIdx.x & 31;
+  const int n = k.w.bcnt[b];
+  if (n == 0 || n > bk::kWarpCap) return;
+  const int64_t off = k.w.boff[b];
+  uint64_t x[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int q = r * 32 + lane;
+    x[r] = q < n ? k.w.pairs[off + q] : ~0ull;
+  }
+  sort4(x, n <= 32 ? 32 : (n <= 64 ? 64 : 128), lane);
+  uint32_t carry_key = 0xFFFFFFFFu;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (r * 32 >= n) break;
+    const uint32_t key = (uint32_t)(x[r] >> 32), pos = (uint32_t)x[r];
+    const int nv = min(32, n - r * 32);
+    const uint32_t next_first = (r < 3 && (r + 1) * 32 < n) ? __shfl_sync(0xffffffffu, (uint32_t)(x[r < 3 ? r + 1 : 3] >> 32), 0)
+                                                            : 0xFFFFFFFFu;
+    uint32_t prevk = __shfl_up_sync(0xffffffffu, key, 1);
+    if (lane == 0) prevk = carry_key;
+    const bool is_head = lane < nv && key != prevk;
+    const unsigned H = __ballot_sync(0xffffffffu, is_head);
+    const int nh = __popc(H);
+    ws->keys[lane] = key;
+    const float open_sum = ws->carry;   // read before this chunk may overwrite it
+    if (lane < nv) {
+      float coef;
+      const float* src = grad_src(a, sv, pos, &coef);
+      ws->stage[lane] = __fmul_rn(src[0], coef);
+    }
+    __syncwarp();
+    const uint32_t lastk = ws->keys[31];
+    const bool chunk_open = (nv == 32) && next_first == lastk;
+    const int lead = nh ? (__ffs(H) - 1) : nv;
+    if (lead > 0 && lane == 31) {   // (lane 31 never owns a head run of its own beyond the 32nd: see below)
+      float acc = open_sum;
+      for (int i = 0; i < lead; ++i) acc = __fadd_rn(acc, ws->stage[i]);
+      if (lead == 32 && chunk_open)
+        ws->carry = acc;
+      else
+        apply_scalar(a, carry_key, 0, acc, 0);
+    }
+    if (lane < nh && !(lead > 0 && lane == 31)) {
+      const int h = __fns(H, 0, lane + 1);
+      const unsigned rest = (h == 31) ? 0u : (H >> (h + 1)) << (h + 1);
+      const int e_end = rest ? (__ffs(rest) - 1) : nv;
+      float acc = 0.f;
+      for (int i = h; i < e_end; ++i) acc = __fadd_rn(acc, ws->stage[i]);
+      if (e_end == 32 && chunk_open)
+        ws->carry = acc;
+      else
+        apply_scalar(a, ws->keys[h], 0, acc, 0);
+    }
+    carry_key = chunk_open ? lastk : 0xFFFFFFFFu;
+    __syncwarp();
+  }
+}
+
+constexpr bool warp_mode_lanes(int lanes) { return lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8; }
+
+template <int LANES>
+inline size_t bk_fused_smem(int n_slots, bool warp_mode) {
+  size_t warp_bytes = 0;
+  if (warp_mode) {
+    if constexpr (LANES > 0)
+      warp_bytes = ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15) + 8 * sizeof(WarpSmem<(LANES > 0 && LANES <= 8) ? LANES : 1>);
+    else
+      warp_bytes = ((slot_smem_bytes(n_slots) + 15) & ~(size_t)15) + 8 * sizeof(WarpSmem1);
+  }
+  const size_t med = bk_reduce_smem(n_slots, bk::kCap, bk::kThreads);
+  return warp_bytes > med ? warp_bytes : med;
+}
+
+// One launch, three roles by block index:
+//   [0, warp_ctas)                       8 warps, one bucket each (vector rows up to dim 32, and dim 1)
+//   [warp_ctas, warp_ctas + med_ctas)    a CTA sorts a medium bucket (warp_cap < n <= kCap) in shared memory
+//   behind them                          column sums of the one-row slots
+template <int LANES>
+__global__ void __launch_bounds__(bk::kThreads, ER_BK_MINB) bk_fused_kernel(const __grid_constant__ BwdArgs a,
+                                                                const __grid_constant__ BkArgs k) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_warp[bk::kThreads / 32 + 1];
+  // (block order = scheduling order; measured at C2: the many short warp CTAs first, the few long-running ones -
+  //  hot medium buckets, one-row column sums - behind them is ~15% faster than the other way round)
+  const int bid = blockIdx.x;
+  if (bid >= k.warp_ctas + k.med_ctas) {
+    one_row_cta<LANES>(a, bid - k.warp_ctas - k.med_ctas);
+    return;
+  }
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  if (bid < k.warp_ctas) {
+    unsigned char* p = s_raw + ((slot_smem_bytes(a.n_slots) + 15) & ~(size_t)15);
+    const int b = bid * 8 + (threadIdx.x >> 5);
+    if constexpr (LANES > 0 && LANES <= 8) {
+      warp_bucket_vec<LANES>(a, sv, k, b, reinterpret_cast<WarpSmem<LANES>*>(p) + (threadIdx.x >> 5));
+    } else if constexpr (LANES == 0) {
+      warp_bucket_d1(a, sv, k, b, reinterpret_cast<WarpSmem1*>(p) + (threadIdx.x >> 5));
+    }
+    return;
+  }
+  const BkSmem m = bk_carve(s_raw, a.n_slots, bk::kCap, bk::kThreads);
+  const int n_med = k.w.n_big[1];
+  for (int xi = bid - k.warp_ctas; xi < n_med; xi += k.med_ctas) {
+    const int b = k.w.med_list[xi];
+    const int n = k.w.bcnt[b];
+    const int off = k.w.boff[b];
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += bk::kThreads) m.pairs[i] = i < n ? k.w.pairs[off + i] : ~0ull;
+    __syncthreads();
+    bk::bitonic_sort<bk::kThreads>(m.pairs, P);
+    const int R = bk::run_starts<bk::kThreads, bk::kCap / bk::kThreads>(m.pairs, n, m.start, s_warp);
+    if constexpr (LANES > 0)
+      process_runs_vec<LANES, bk::kThreads>(a, sv, m.pairs, m.start, R, m.stage, m.part, m.coop, m.ncoop, -1);
+    else
+      process_runs_scalar<bk::kThreads>(a, sv, m.pairs, m.start, R, reinterpret_cast<float*>(m.stage),
+                                        reinterpret_cast<float*>(m.part), m.coop, m.ncoop, -1);
+    __syncthreads();
   }
 }
 
@@ -970,32 +1409,27 @@ __device__ __forceinline__ bool cta_radix_pass(const uint64_t* __restrict__ in, 
   return true;
 }
 
-// buckets above bk::kWarpCap: a few CTAs (one per SM, kBigCap pairs of shared memory) walk their list
-static __global__ void __launch_bounds__(bk::kBigThreads) bk_sort_big_kernel(const __grid_constant__ BkArgs k) {
+// big buckets: a few CTAs (one per SM, kBigCap pairs of shared memory) walk the list of buckets above kCap
+template <int LANES>
+__global__ void __launch_bounds__(bk::kBigThreads) bk_reduce_big_kernel(const __grid_constant__ BwdArgs a,
+                                                                        const __grid_constant__ BkArgs k) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  const int n_big = *k.w.n_big;
+  __shared__ int s_warp[bk::kBigThreads / 32 + 1];
+  __shared__ int s_flag;
+  const int n_big = k.w.n_big[0];
   if ((int)blockIdx.x >= n_big) return;
-  uint64_t* sp = reinterpret_cast<uint64_t*>(s_raw);
+  const SlotView sv = load_slots(s_raw, a.slots, a.n_slots);
+  const BkSmem m = bk_carve(s_raw, a.n_slots, bk::kBigCap, bk::kBigThreads);
   for (int x = blockIdx.x; x < n_big; x += gridDim.x) {
     const int b = k.w.big_list[x];
     const int n = k.w.bcnt[b];
     const int64_t off = k.w.boff[b];
     uint64_t* gp = k.w.pairs + off;
-    if (n <= bk::kBigCap) {
-      int P = 32;
-      while (P < n) P <<= 1;
-      for (int i = threadIdx.x; i < P; i += bk::kBigThreads) sp[i] = i < n ? gp[i] : ~0ull;
-      __syncthreads();
-      bk::bitonic_sort<bk::kBigThreads>(sp, P);
-      for (int i = threadIdx.x; i < n; i += bk::kBigThreads) {
-        k.keys_out[off + i] = (uint32_t)(sp[i] >> 32);
-        k.vals_out[off + i] = (uint32_t)sp[i];
-      }
-      __syncthreads();
-    } else {
-      // more pairs than a CTA can hold (thousands of duplicates of one row): stable LSD radix sort of the 64-bit
-      // composites through global memory, digits that do not vary are skipped
-      int* s_wh = reinterpret_cast<int*>(sp);
+    bool sorted_in_global = false;
+    if (n > bk::kBigCap) {
+      // more than kBigCap lookups in one bucket (>= thousands of duplicates of one row): stable LSD radix sort of the
+      // 64-bit composites through global memory, digits that do not vary are skipped
+      int* s_wh = reinterpret_cast<int*>(m.pairs);
       int* s_cur = s_wh + 32 * 256;
       uint64_t* src = gp;
       uint64_t* dst = k.w.pairs_tmp + off;
@@ -1005,11 +1439,62 @@ static __global__ void __launch_bounds__(bk::kBigThreads) bk_sort_big_kernel(con
         }
         __syncthreads();
       }
-      for (int i = threadIdx.x; i < n; i += bk::kBigThreads) {
-        const uint64_t e = src[i];
-        k.keys_out[off + i] = (uint32_t)(e >> 32);
-        k.vals_out[off + i] = (uint32_t)e;
+      if (src != gp) {
+        for (int i = threadIdx.x; i < n; i += bk::kBigThreads) gp[i] = src[i];
       }
+      __threadfence_block();
+      __syncthreads();
+      sorted_in_global = true;
+    }
+    int p = 0;
+    while (p < n) {
+      const int mwin = min(bk::kBigCap, n - p);
+      if (!sorted_in_global) {
+        int P = 32;
+        while (P < mwin) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += bk::kBigThreads) m.pairs[i] = i < mwin ? gp[i] : ~0ull;
+        __syncthreads();
+        bk::bitonic_sort<bk::kBigThreads>(m.pairs, P);
+      } else {
+        for (int i = threadIdx.x; i < mwin; i += bk::kBigThreads) m.pairs[i] = gp[p + i];
+        __syncthreads();
+      }
+      int R = bk::run_starts<bk::kBigThreads, bk::kBigCap / bk::kBigThreads>(m.pairs, mwin, m.start, s_warp);
+      int advance = mwin;
+      if (sorted_in_global && p + mwin < n &&
+          (uint32_t)(m.pairs[mwin - 1] >> 32) == (uint32_t)(gp[p + mwin] >> 32)) {
+        // the last run of the window continues past it
+        if (R == 1) {   // the window is one run: find its end, queue it (len > kBigCap > kQueueRun)
+          const uint32_t key = (uint32_t)(m.pairs[0] >> 32);
+          int lo = p + mwin, hi = n;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)(gp[mid] >> 32) <= key) lo = mid + 1; else hi = mid;
+          }
+          if (threadIdx.x == 0) enqueue_run(a, off + p, lo - p);
+          p = lo;
+          __syncthreads();
+          continue;
+        }
+        advance = m.start[R - 1];
+        R -= 1;
+      }
+      // does any run of this window go to the hot-row kernel?  then its pairs must lie sorted in global memory
+      if (!sorted_in_global) {
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        for (int r = threadIdx.x; r < R; r += bk::kBigThreads)
+          if (m.start[r + 1] - m.start[r] > bk::kQueueRun) s_flag = 1;
+        __syncthreads();
+        if (s_flag)
+          for (int i = threadIdx.x; i < mwin; i += bk::kBigThreads) gp[i] = m.pairs[i];
+      }
+      if constexpr (LANES > 0)
+        process_runs_vec<LANES, bk::kBigThreads>(a, sv, m.pairs, m.start, R, m.stage, m.part, m.coop, m.ncoop, off + p);
+      else
+        process_runs_scalar<bk::kBigThreads>(a, sv, m.pairs, m.start, R, reinterpret_cast<float*>(m.stage),
+                                             reinterpret_cast<float*>(m.part), m.coop, m.ncoop, off + p);
+      p += advance;
       __syncthreads();
     }
   }
@@ -1108,9 +1593,12 @@ static int log2_of(int v) {
 }
 
 // zero the placement state, count, place.  one_row: slots of mode ER_BUCKET_ONE_ROW are left out.
+// rows a warp can stage (vector rows up to dim 32, and the wide dim-1 tables) use one warp per small bucket
+static bool k7_warp_mode(int dim) { return dim == 1 || dim == 4 || dim == 8 || dim == 16 || dim == 32; }
+
 static void bk_place(const int64_t* rows, int64_t cap, const int32_t* n_dev, int64_t n_rows, const int32_t* seg_ids,
-                     const er_slot_t* slots, int n_slots, bool one_row, const BwdWs& w, bool zero_call_block,
-                     cudaStream_t st) {
+                     const er_slot_t* slots, int n_slots, bool one_row, bool warp_mode, const BwdWs& w,
+                     bool zero_call_block, cudaStream_t st) {
   bk::PlaceArgs pa;
   pa.rows = rows;
   pa.cap = cap;
@@ -1119,8 +1607,9 @@ static void bk_place(const int64_t* rows, int64_t cap, const int32_t* n_dev, int
   pa.seg_ids = seg_ids;
   pa.slots = one_row ? slots : nullptr;
   pa.n_slots = n_slots;
-  const int nb = bk::num_buckets(cap);
+  const int nb = bk::num_buckets(cap, warp_mode);
   pa.log2_nb = log2_of(nb);
+  pa.warp_cap = warp_mode ? bk::kWarpCap : 0;
   pa.w = w.bk;
   cudaMemsetAsync(w.bk.bcnt, 0, bk::zero_place_bytes() + (zero_call_block ? bk::zero_call_bytes() : 0), st);
   const size_t smem = bk::place_smem_bytes(n_slots, nb, pa.slots != nullptr);
@@ -1137,25 +1626,40 @@ static void bk_place(const int64_t* rows, int64_t cap, const int32_t* n_dev, int
   count_launches(2);
 }
 
-// sort the placed buckets into keys_out / vals_out
-static void bk_launch_sort(const BwdWs& place, int64_t cap, int64_t n_rows, uint32_t* keys_out, uint32_t* vals_out,
-                           cudaStream_t st) {
+// per-bucket sort + sums + row update over a placement (bk_place) made in `place_warp_mode`
+template <int LANES>
+static void bk_launch_fused(BwdArgs a, const BwdWs& place, bool place_warp_mode, cudaStream_t st) {
   BkArgs k;
   k.w = place.bk;
-  const int nb = bk::num_buckets(cap);
+  const int nb = bk::num_buckets(a.n, place_warp_mode);
   k.log2_nb = log2_of(nb);
-  k.keys_out = keys_out;
-  k.vals_out = vals_out;
-  k.cap = cap;
-  k.sentinel = (uint32_t)n_rows;
+  k.warp_ctas = place_warp_mode ? (nb >> 3) : 0;
+  k.med_ctas = place_warp_mode ? kSmCount : nb;
+  const size_t smem = bk_fused_smem<LANES>(a.n_slots, place_warp_mode);
+  const size_t smem_big = bk_reduce_smem(a.n_slots, bk::kBigCap, bk::kBigThreads);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(bk_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bk::kBigCap * 8);
+    cudaFuncSetAttribute(bk_fused_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)bk_fused_smem<LANES>(2048, true));
+    cudaFuncSetAttribute(bk_fused_kernel<LANES>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bk_reduce_big_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)bk_reduce_smem(2048, bk::kBigCap, bk::kBigThreads));
     attr = true;
   }
-  bk_sort_kernel<<<nb >> 3, 256, 0, st>>>(k);
-  bk_sort_big_kernel<<<kSmCount, bk::kBigThreads, (size_t)bk::kBigCap * 8, st>>>(k);
-  count_launches(2);
+  const int extra = a.or_chunks * a.n_slots;
+  a.main_ctas = k.warp_ctas + k.med_ctas;
+  bk_fused_kernel<LANES><<<k.warp_ctas + k.med_ctas + extra, bk::kThreads, smem, st>>>(a, k);
+  bk_reduce_big_kernel<LANES><<<kSmCount, bk::kBigThreads, smem_big, st>>>(a, k);
+  const size_t sl = slot_smem_bytes(a.n_slots);
+  if constexpr (LANES > 0) {
+    constexpr int TPE = (LANES <= 8) ? 1 : LANES;
+    const size_t smem_long = ((sl + 15) & ~(size_t)15) + (size_t)8 * LANES * sizeof(float4);
+    bwd_long_vec_kernel<LANES, TPE><<<4 * kSmCount, 256, smem_long, st>>>(a);
+  } else {
+    bwd_long_scalar_kernel<<<4 * kSmCount, 256, sl, st>>>(a);
+  }
+  count_launches(3);
 }
 
 }  // namespace er
@@ -1236,11 +1740,15 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
     w.vals = src.vals;
     cudaMemsetAsync(w.counters, 0, bk::zero_call_bytes(), st);
   } else if (bucketed) {
-    bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, one_row, w, true, st);
-    bk_launch_sort(w, n_lookups_cap, n_rows, w.keys, w.vals, st);
+    bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, one_row, k7_warp_mode(dim), w, true, st);
   } else {
     rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, st);
   }
+  // the mode the placement was made in: a table that reuses another table's placement follows it
+  const bool place_warp = k7_warp_mode(sorted_ws ? sorted_dim : dim);
+  if (bucketed && place_warp && !k7_warp_mode(dim))
+    return fail(ER_ERR_UNSUPPORTED, "er_embedding_bwd_reuse_sort: the placement was made for warp-sized buckets, "
+                                    "rows of this dim need CTA-sized ones (presort with this dim instead)");
 
   BwdArgs a;
   a.table = table;
@@ -1251,6 +1759,7 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   a.sentinel = (uint32_t)n_rows;
   a.keys = w.keys;
   a.vals = w.vals;
+  a.pairs = nullptr;
   a.n = n_lookups_cap;
   a.weights = weights;
   a.seg_ids = seg_ids;
@@ -1295,6 +1804,26 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   }
   if (uniq_grads) aligned = aligned && reinterpret_cast<uintptr_t>(uniq_grads) % 16 == 0;
   const bool vec_dim = (dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128);
+  if (bucketed) {
+    ER_REQUIRE(table != nullptr, "the bucketed path updates a table");
+    a.keys = nullptr;
+    a.vals = nullptr;
+    a.pairs = src.bk.pairs;
+    if (vec_dim && aligned) {
+      switch (dim / 4) {
+        case 1: bk_launch_fused<1>(a, src, place_warp, st); break;
+        case 2: bk_launch_fused<2>(a, src, place_warp, st); break;
+        case 4: bk_launch_fused<4>(a, src, place_warp, st); break;
+        case 8: bk_launch_fused<8>(a, src, place_warp, st); break;
+        case 16: bk_launch_fused<16>(a, src, place_warp, st); break;
+        default: bk_launch_fused<32>(a, src, place_warp, st); break;
+      }
+    } else {
+      bk_launch_fused<0>(a, src, place_warp, st);
+    }
+    ER_CUDA_LAUNCH_CHECK();
+    return ER_OK;
+  }
   if (vec_dim && aligned) {
     switch (dim / 4) {
       case 1: launch_vec<1>(a, st); break;
@@ -1351,11 +1880,8 @@ extern "C" int er_embedding_bwd_presort(const int64_t* rows, int64_t n_rows, con
   if (k7_radix_forced())
     rsort::sort_rows(rows, n_lookups_cap, n_dev, n_rows, w.keys, w.vals, w.sort_ws, w.counters, as_stream(stream));
   else
-  {
-    bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, seg_ids == nullptr, w, false,
-             as_stream(stream));
-    bk_launch_sort(w, n_lookups_cap, n_rows, w.keys, w.vals, as_stream(stream));
-  }
+    bk_place(rows, n_lookups_cap, n_dev, n_rows, seg_ids, slots, n_slots, seg_ids == nullptr, k7_warp_mode(dim), w,
+             false, as_stream(stream));
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256)
       const int64_t s = base + (int64_t)u * n_groups + g;
       if (s >= n_seg) continue;
       const SlotLite sl = slot_lite(sv, slot_of(sv, (int32_t)s));
-      const int comb = sl.misc >> 8;
+      const int comb = slot_comb(sl);
       float4 o = f4_zero();
       float scale = 0.f;
       const bool keep = r[u] >= 0 && (comb == ER_COMBINER_SUM || w[u] > 0.f);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256)
   constexpr int U = 4;
   for (int64_t s = g; s < n_seg; s += n_groups) {
     const SlotLite sl = slot_lite(sv, slot_of(sv, (int32_t)s));
-    const int comb = sl.misc >> 8;
+    const int comb = slot_comb(sl);
     int64_t b = row_ptr[s], e = row_ptr[s + 1];
     if (e > cap) e = cap;
     float4 acc = f4_zero();
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256)
     const int64_t s = (total < (1LL << 32)) ? (int64_t)fastdiv((uint32_t)t, ddiv) : t / dim;
     const int c = (int)(t - s * dim);
     const SlotLite sl = slot_lite(sv, slot_of(sv, (int32_t)s));
-    const int comb = sl.misc >> 8;
+    const int comb = slot_comb(sl);
     int64_t b = row_ptr ? row_ptr[s] : s, e = row_ptr ? row_ptr[s + 1] : s + 1;
     if (e > cap) e = cap;
     const bool is_sum = comb == ER_COMBINER_SUM;

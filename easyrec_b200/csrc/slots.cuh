@@ -62,7 +62,7 @@ __device__ __forceinline__ SlotView load_slots(void* smem, const er_slot_t* __re
     l.seg_begin = s.seg_begin;
     l.out_stride = s.out_stride;
     l.out_col = s.out_col;
-    l.misc = (s.out_buf & 0xff) | (s.combiner << 8);
+    l.misc = (s.out_buf & 0xff) | (s.combiner << 8);   // combiner incl. the ER_COMBINER_UNIT_WEIGHTS flag
     tab[i] = l;
     if (s.n_seg != nseg0 || s.seg_begin != i * nseg0) ok = 0;
   }
@@ -88,6 +88,9 @@ __device__ __forceinline__ int slot_of(const SlotView& v, int32_t s) {
   }
   return lo;
 }
+
+__device__ __forceinline__ int slot_comb(const SlotLite& l) { return (l.misc >> 8) & 0xf; }
+__device__ __forceinline__ bool slot_unit_weights(const SlotLite& l) { return (l.misc >> 12) & 1; }
 
 __device__ __forceinline__ SlotLite slot_lite(const SlotView& v, int f) {
   const int4 q = *reinterpret_cast<const int4*>(v.tab + f);

@@ -33,6 +33,9 @@ class Slot(object):
     self.combiner = combiner
     self.out_buf = out_buf        # which output matrix of the arena call
     self.n_seg_per_sample = n_seg_per_sample  # T for sequence slots (un-pooled [B,T,D])
+    # True: whatever weights array accompanies the call holds 1.0 for this slot's lookups (plain id / sequence slots
+    # next to raw-value slots): the backward skips the per-lookup weight read (ER_COMBINER_UNIT_WEIGHTS)
+    self.unit_weights = False
 
 
 class Arena(object):
@@ -133,7 +136,8 @@ class ArenaCall(object):
       stride = self.out_strides[s.out_buf]
       self.slot_cols.append(col)
       recs.append(dict(num_buckets=s.num_buckets, row_offset=off, seg_begin=seg, n_seg=n_seg,
-                       bucket_mode=s.bucket_mode, combiner=s.combiner, out_buf=s.out_buf,
+                       bucket_mode=s.bucket_mode,
+                       combiner=s.combiner | (_lib.COMBINER_UNIT_WEIGHTS if s.unit_weights else 0), out_buf=s.out_buf,
                        out_stride=stride, out_col=col, shard_n=arena.shard_n))
       seg += n_seg
     self.n_seg = seg
@@ -142,7 +146,7 @@ class ArenaCall(object):
     self.n_slots = len(recs)
     self.single_valued = single_valued
     self.max_lookups = self.n_seg if single_valued else int(max_lookups)
-    self.needs_scale = any(s.combiner != _lib.COMBINER_SUM for s in slots)
+    self.needs_scale = any((s.combiner & 0xf) != _lib.COMBINER_SUM for s in slots)
     self.ws = K.bwd_workspace(self.max_lookups, arena.device, arena.dim)
     self.seg_scale = (torch.empty(self.n_seg, dtype=torch.float32, device=arena.device)
                       if self.needs_scale else None)

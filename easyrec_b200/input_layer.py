@@ -190,6 +190,8 @@ class InputLayer(object):
       comb = _lib.COMBINER_SUM if (wide or f.kind == 'raw' or kind == 'seq') else _COMBINER[f.combiner]
       slot = E.Slot(out_key + '/' + fname, table, f.bucket_mode, f.num_buckets, comb, out_buf=out_key,
                     n_seg_per_sample=f.seq_len if kind == 'seq' else 1)
+      # id and sequence slots never carry per-lookup weights (raw-value and kv-weighted tag slots do)
+      slot.unit_weights = f.kind != 'raw' and kind in ('single', 'seq')
       if f.kind == 'raw':
         src = ('raw', self.raw_cols[fname][0])
       elif kind == 'seq':
@@ -348,7 +350,9 @@ class InputLayer(object):
       # arenas with the same row plan (DeepFM / Wide&Deep: the wide dim-1 and the deep tables) look up the
       # same rows tensor: the second K7 reuses the first one's radix sort.
       hit = sorted_by.get(id(rows))
-      src = (hit[0], hit[1]) if hit is not None and hit[2] == m.arena.n_rows else None
+      # (a placement made for warp-sized buckets serves only tables whose rows a warp can stage)
+      src = (hit[0], hit[1]) if (hit is not None and hit[2] == m.arena.n_rows and
+                                 (not K.k7_warp_mode(hit[1]) or K.k7_warp_mode(m.arena.dim))) else None
       if idx > 0 and src is not None and self._side is not None and cur is not None:
         # different arenas, sort already done: this update runs beside the first one on the side stream
         if not forked:

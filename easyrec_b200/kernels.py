@@ -215,6 +215,11 @@ def embedding_bwd(table, state0, state1, dim, rows, slots_dev, n_slots, n_seg, g
                            _p(n_uniq), _p(ws), ws.numel(), _stream()), 'er_embedding_bwd')
 
 
+def k7_warp_mode(dim):
+  """mirror of k7_warp_mode in csrc/embedding_bwd.cu: tables whose rows one warp can stage."""
+  return dim in (1, 4, 8, 16, 32)
+
+
 def embedding_bwd_presort(rows, n_rows, dim, ws, slots_dev, n_slots, seg_ids=None, row_ptr=None, n_seg=0):
   """The row-only half of K7's dedup (hashing the lookups into buckets), with the same rows / seg_ids / slots as the
   embedding_bwd it prepares: finish with embedding_bwd(..., sorted_from=(ws, dim))."""

@@ -67,7 +67,10 @@ typedef enum er_bucket_mode {
 typedef enum er_combiner {
   ER_COMBINER_SUM = 0,
   ER_COMBINER_MEAN = 1,
-  ER_COMBINER_SQRTN = 2
+  ER_COMBINER_SQRTN = 2,
+  /* flag, OR-ed into er_slot_t.combiner: every entry of weights[] that belongs to this slot is 1.0 (single-valued id
+   * slots of a call whose weights array exists only for other slots); the backward then skips the per-lookup read */
+  ER_COMBINER_UNIT_WEIGHTS = 16
 } er_combiner;
 
 /* One embedding slot = one (feature column, output position) pair; the

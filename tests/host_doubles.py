@@ -14,7 +14,8 @@ def _slots(slots_dev):
 
 
 def _seg_field(sl, field, n_seg):
-  return np.concatenate([np.full(int(s['n_seg']), s[field]) for s in sl])[:n_seg]
+  v = np.concatenate([np.full(int(s['n_seg']), s[field]) for s in sl])[:n_seg]
+  return v & 0xf if field == 'combiner' else v   # (the ER_COMBINER_UNIT_WEIGHTS flag is a hint for the kernels)
 
 
 def install_sparse(patch):
