@@ -1,26 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- samples/sec of one DeepFM training step on the fused sm_100a sparse path.
+"""bench.py -- samples/sec of the DeepFM Criteo-shape training step (BASELINE.json config 2) on the fused sm_100a
+sparse path, driven through the product surface: EasyRecEstimator(pipeline_config) built from a protobuf-text config.
 
-Contract: `python bench.py --gpus N --steps K --warmup W` (torchrun for N>1) prints ONE JSON
-line on rank 0.  A step = K1 hash/bucketize -> K2 gather+pool -> FM + MLPs -> sigmoid CE ->
-backward -> K7 dedup + fused adagrad row update -> dense optimizer, on one batch of the
-BASELINE.json config-2 shape (26 sparse + 13 dense, V rows x 16 fp32, batch 8192 per GPU).
+Contract: `python bench.py --gpus N --steps K --warmup W` (torchrun for N>1) prints ONE JSON line on rank 0.
+A step = K1 hash/bucketize -> K2 gather+pool -> FM + MLPs -> sigmoid CE -> backward -> K7 dedup + fused row update
+-> dense optimizer, on one batch of the config-2 shape (26 sparse + 13 dense, V rows x 16 fp32, batch 8192 per GPU;
+V = 10M, and 100M - the north-star size - when N = 8).
 
-  value     : samples/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e       : samples/s through Trainer.train_step with pinned HOST batches: H2D of ids/dense/
-              labels and D2H of the loss inside the timed region
-  roofline  : the dominant own HBM-bound kernel (K7 run-sum + row update, else K2 gather),
-              algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline: the CPU oracle port of the same step on a bounded sample (rank 0, N=1)
+  value        samples/s with the batches already resident in HBM (CUDA events, max over ranks), CUDA-graph replay
+  e2e          EasyRecEstimator.train(input_fn) over pinned HOST batches: a parsing thread, pinned double-buffered
+               H2D (readers.DeviceFeeder), the step, and a D2H read of the loss after every step, all inside the
+               timed region.  e2e.from_csv / e2e.from_parquet: the same through the CSV / Parquet readers over files
+               written by workloads.write_c2_files (host parsing included)
+  optimizers   the same device-resident step with lazy_adam_optimizer and adam_optimizer (tf.train.AdamOptimizer:
+               dense decay sweep over the whole table) - every optimizer runs CUDA-graph captured
+  lines        a second workload: C3 = DIN (batch 4096, two length-50 histories, 1M-row item table)
+  roofline     the dominant own HBM-bound kernel (K7 = er_embedding_bwd, else K2 = er_embedding_fwd): algorithmic
+               bytes / CUDA-event time, L2 flushed between launches, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the CPU oracle port of the same step on a bounded sample (rank 0, N = 1)
 
-`--impl reference` times the CPU oracle port (TensorFlow, hence the real reference, cannot be
-installed in this image: see DESIGN.md) with all host threads on the same workload.
+`--impl reference` times the CPU oracle port (TensorFlow, hence the real reference, cannot be installed in this
+image: DESIGN.md) with the host threads it runs fastest with, for exactly --steps / --warmup steps (capped at 64).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -41,11 +48,14 @@ def parse():
   ap.add_argument('--steps', type=int, default=2000)
   ap.add_argument('--warmup', type=int, default=50)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--vocab', type=int, default=10_000_000)
+  ap.add_argument('--vocab', type=int, default=0, help='table rows; 0 = 10M, 100M at 8 GPUs')
   ap.add_argument('--batch', type=int, default=BATCH)
+  ap.add_argument('--optimizer', default='adagrad_optimizer',
+                  choices=['adagrad_optimizer', 'lazy_adam_optimizer', 'adam_optimizer'])
   ap.add_argument('--uniform-ids', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-extras', action='store_true', help='skip the optimizer / file / C3 lines (quick runs)')
   ap.add_argument('--kernel-iters', type=int, default=30)
   return ap.parse_args()
 
@@ -54,12 +64,12 @@ def peaks():
   p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(p):
     d = json.load(open(p))
-    return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-  return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+    return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)', float(d.get('bf16_tflops', 2250.0))
+  return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)', 2250.0
 
 
 class ClockSampler(threading.Thread):
-  """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+  """nvidia-smi clocks + throttle reasons during the timed regions (B200_PROFILING.md)."""
 
   def __init__(self, index=0):
     super().__init__(daemon=True)
@@ -67,6 +77,7 @@ class ClockSampler(threading.Thread):
     self.rows = []
     self.stop_flag = False
     self.proc = None
+    self.t_mark = 0.0
 
   def run(self):
     q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
@@ -75,7 +86,7 @@ class ClockSampler(threading.Thread):
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
-           '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+           '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       for line in self.proc.stdout:
         self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
         if self.stop_flag:
@@ -84,12 +95,12 @@ class ClockSampler(threading.Thread):
       pass
 
   def mark(self):
-    """start of the timed region: samples taken before it (warm-up) only count if none falls inside"""
+    """start of the timed regions: samples taken before it (warm-up) only count if none falls inside"""
     self.t_mark = time.time()
 
   def finish(self):
-    t_end = time.time() + 0.06   # one more sampling period: the last line may still be in the pipe
-    while time.time() < t_end and not any(t >= getattr(self, 't_mark', 0.0) for t, _ in self.rows):
+    t_end = time.time() + 0.06
+    while time.time() < t_end and not any(t >= self.t_mark for t, _ in self.rows):
       time.sleep(0.01)
     self.stop_flag = True
     if self.proc is not None:
@@ -99,8 +110,7 @@ class ClockSampler(threading.Thread):
         pass
     sm, mx, reasons = [], 0.0, set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    t_mark = getattr(self, 't_mark', 0.0)
-    inside = [r for t, r in self.rows if t >= t_mark]
+    inside = [r for t, r in self.rows if t >= self.t_mark]
     for r in (inside or [r for _, r in self.rows]):
       try:
         sm.append(float(r[0]))
@@ -177,6 +187,13 @@ def make_cpu_state(V, seed=0):
           'emb_reg': 1e-5}
 
 
+def cpu_threads():
+  """threads for the oracle port: a quarter of the host's hardware threads, at least 8, at most 32 - where the
+  small per-step matrices stop scaling (more threads only add fork/join cost); the same rule on every box"""
+  n = os.cpu_count() or 1
+  return int(max(1, min(32, max(8, n // 4), n)))
+
+
 def run_cpu(args, steps, warmup, vocab):
   """CPU oracle port of the step; returns (samples/s, threads, seconds)."""
   from easyrec_b200 import workloads
@@ -184,35 +201,33 @@ def run_cpu(args, steps, warmup, vocab):
   B = args.batch
   state = make_cpu_state(vocab)
   batches = [workloads.criteo_batch(B, 1000 + i, uniform=args.uniform_ids) for i in range(4)]
-  # the port is given the thread count it runs fastest with on this host (more threads than the small
-  # per-step matrices can use only adds fork/join cost): one step per candidate, best kept
+  n = cpu_threads()
+  O.set_num_threads(n)
+  ctx = None
   try:
     from threadpoolctl import threadpool_limits
+    ctx = threadpool_limits(limits=n)
   except Exception:
-    threadpool_limits = None
-  n_all = max(O.num_threads(), os.cpu_count() or 1)
-  cands = sorted({n_all, max(1, n_all // 2), max(1, n_all // 4), min(n_all, 16), min(n_all, 8)}, reverse=True)
+    pass
   cpu_step_oracle(state, *batches[0], vocab, B)   # first touch of the tables
-  best, best_t = n_all, None
-  for n in cands:
-    O.set_num_threads(n)
-    ctx = threadpool_limits(limits=n) if threadpool_limits else None
-    t0 = time.perf_counter()
-    cpu_step_oracle(state, *batches[1], vocab, B)
-    t = time.perf_counter() - t0
-    if ctx is not None:
-      ctx.restore_original_limits() if hasattr(ctx, 'restore_original_limits') else ctx.unregister()
-    if best_t is None or t < best_t:
-      best, best_t = n, t
-  O.set_num_threads(best)
-  ctx = threadpool_limits(limits=best) if threadpool_limits else None
   for i in range(warmup):
     cpu_step_oracle(state, *batches[i % 4], vocab, B)
   t0 = time.perf_counter()
   for i in range(steps):
     cpu_step_oracle(state, *batches[i % 4], vocab, B)
   dt = time.perf_counter() - t0
-  return B * steps / dt, best, dt
+  del ctx
+  return B * steps / dt, n, dt
+
+
+def ncu_traffic(kernel_key):
+  """dram bytes per launch of a kernel from the committed ncu summary (profiles/r02_ncu_traffic.json), or None."""
+  p = os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')
+  if not os.path.exists(p):
+    return None, None
+  d = json.load(open(p))
+  v = d.get(kernel_key)
+  return (float(v['dram_bytes']), 'profiles/' + v.get('source', 'r02_ncu_traffic.json')) if v else (None, None)
 
 
 def main():
@@ -221,28 +236,32 @@ def main():
   world = int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
   B = args.batch
+  vocab = args.vocab or (100_000_000 if world >= 8 else 10_000_000)
+  opt_name = {'adagrad_optimizer': 'adagrad', 'lazy_adam_optimizer': 'lazy_adam', 'adam_optimizer': 'adam'}
   workload = 'deepfm_criteo_c2(26 sparse+13 dense, shared table V=%d x emb16 fp32, batch %d/GPU, %s ids)' % (
-      args.vocab, B, 'uniform' if args.uniform_ids else 'zipf1.05')
-  config = {'workload': workload, 'optimizer': 'adagrad(sparse rows fused in backward)+adagrad(dense)',
-            'l2_flush': 'none: table+accumulator %.1f GB >> 126 MB L2, ids rotate over 16 distinct batches'
-            % ((args.vocab + 13) * 17 * 4 * 2 / 1e9), 'parallelism': 'dp%d' % world}
+      vocab, B, 'uniform' if args.uniform_ids else 'zipf1.05')
+  config = {'workload': workload,
+            'optimizer': '%s(sparse rows fused in backward)+%s(dense)' % (opt_name[args.optimizer], opt_name[args.optimizer]),
+            'built_from': 'EasyRecEstimator(protobuf-text pipeline config: workloads.c2_config_text)',
+            'l2_flush': 'none in the step loop: table+optimizer state %.1f GB >> 126 MB L2, ids rotate over 16 distinct '
+                        'batches; the per-kernel roofline timings flush L2 (256 MB write) before every launch'
+            % ((vocab + 13) * 17 * 4 * 2 / 1e9), 'parallelism': 'dp%d' % world}
 
   if args.impl == 'reference':
     if rank != 0:
       return 0
-    # bounded sample: each "step" is one full batch-8192 training step on the CPU oracle port
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
-    v, threads, dt = run_cpu(args, steps, warm, args.vocab)
+    steps = max(1, min(args.steps, 64))
+    warm = max(0, min(args.warmup, 16))
+    v, threads, dt = run_cpu(args, steps, warm, min(vocab, 10_000_000))
     line = {'metric': METRIC, 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': 1000.0 * dt / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'impl': 'reference', 'config': config,
             'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d full steps of batch %d (CPU oracle: C sparse path with OpenMP + '
-                                       'numpy/BLAS dense, thread count picked as the fastest of all/half/quarter/16/8 '
-                                       'host threads); TensorFlow is not installable here so the TF graph itself is '
-                                       'not what runs' % (steps, B)},
+                             'sample': '%d full steps of batch %d after %d warm-up steps (CPU oracle: C sparse path with '
+                                       'OpenMP + numpy/BLAS dense, %d of %d host threads); TensorFlow is not installable '
+                                       'here so the TF graph itself is not what runs'
+                                       % (steps, B, warm, threads, os.cpu_count() or 1)},
             'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -250,8 +269,8 @@ def main():
 
   import torch
   import torch.distributed as dist
-  from easyrec_b200 import _lib, kernels as K, workloads
-  from easyrec_b200.trainer import Trainer
+  from easyrec_b200 import _lib, workloads
+  from easyrec_b200.estimator import EasyRecEstimator
   torch.backends.cuda.matmul.allow_tf32 = False
   torch.backends.cudnn.allow_tf32 = False
   torch.cuda.set_device(local_rank)
@@ -259,87 +278,200 @@ def main():
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device(dev))
   lib = _lib.load()
-
-  il, model = workloads.build_deepfm_criteo(B, args.vocab, dev, seed=20240)
-  trainer = Trainer(model, il, 'adagrad', lr=0.01, use_cuda_graph=not args.no_graph, world_size=world)
-  n_rot = 16
-  host = [workloads.criteo_batch(B, 20240 + rank * 1000 + i, uniform=args.uniform_ids) for i in range(n_rot)]
-  pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(), torch.from_numpy(c).pin_memory())
-            for a, b, c in host]
-  devb = [({'sparse_fea': a.to(dev), 'dense_fea': b.to(dev)}, c.to(dev)) for a, b, c in pinned]
+  graph = not args.no_graph
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
-  # ---- device-resident throughput -----------------------------------------------------
+  def max_over_ranks(ms):
+    if world > 1:
+      tms = torch.tensor([ms], device=dev)
+      dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+      return float(tms.item())
+    return ms
+
+  def build(optimizer, v=vocab, input_type='CSVInput'):
+    text = workloads.c2_config_text(v, B, optimizer=optimizer, lr=0.01, input_type=input_type)
+    return EasyRecEstimator(text, device=dev, seed=20240, use_cuda_graph=graph, world_size=world)
+
+  n_rot = 16
+  host = [workloads.criteo_batch(B, 20240 + rank * 1000 + i, uniform=args.uniform_ids) for i in range(n_rot)]
+  pinned = [({'sparse_fea': torch.from_numpy(a).pin_memory(), 'dense_fea': torch.from_numpy(b).pin_memory()},
+             torch.from_numpy(c).pin_memory()) for a, b, c in host]
+  devb = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in pinned]
+  W = max(args.warmup, 3)
+
+  def timed_resident(est, steps, warm):
+    """device-resident throughput: CUDA events around `steps` train_step calls"""
+    for i in range(warm):
+      est.trainer.train_step(*devb[i % n_rot])
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+      loss, _ = est.trainer.train_step(*devb[i % n_rot])
+    ev1.record()
+    barrier()
+    return max_over_ranks(ev0.elapsed_time(ev1)), float(loss)
+
+  def timed_train(est, input_fn, steps, warm):
+    """EasyRecEstimator.train end to end: reader thread -> pinned staging -> H2D -> step -> loss D2H, per step"""
+    est.train(input_fn, steps=warm, fetch_loss_every_step=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    est.train(input_fn, steps=steps, fetch_loss_every_step=True)
+    ev1.record()
+    barrier()
+    return max_over_ranks(ev0.elapsed_time(ev1))
+
+  # ---- headline: device-resident, then end to end through EasyRecEstimator.train ----------------------------
   sampler = ClockSampler(local_rank)   # started before the warm-up so nvidia-smi is already sampling
   if rank == 0:
     sampler.start()
-  for i in range(max(args.warmup, 3)):
-    trainer.train_step(*devb[i % n_rot])
-  barrier()
-  n0 = lib.er_launch_count()
-  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  est = build(args.optimizer)
+  il = est.input_layer
+  for i in range(W):
+    est.trainer.train_step(*devb[i % n_rot])
   barrier()
   sampler.mark()
-  ev0.record()
-  for i in range(args.steps):
-    loss, _ = trainer.train_step(*devb[i % n_rot])
-  ev1.record()
-  barrier()
-  ms = ev0.elapsed_time(ev1)
-  clocks = sampler.finish() if rank == 0 else None
-  if world > 1:
-    tms = torch.tensor([ms], device=dev)
-    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-  launches_host = lib.er_launch_count() - n0
-  per_step_launches = getattr(trainer, 'launches_per_step', None)
-  if per_step_launches is None:
-    per_step_launches = launches_host // max(args.steps, 1)
+  ms, final_loss = timed_resident(est, args.steps, 0)
   value = world * B * args.steps / (ms / 1000.0)
+  per_step_launches = getattr(est.trainer, 'launches_per_step', None)
+  if per_step_launches is None:   # eager run: count the launches of one step
+    n0 = lib.er_launch_count()
+    est.trainer.train_step(*devb[0])
+    per_step_launches = int(lib.er_launch_count() - n0)
 
-  # ---- end to end: pinned host batch -> H2D -> step -> loss D2H -------------------------
-  e2e_steps = args.steps
-  sfeat = {'sparse_fea': torch.empty_like(devb[0][0]['sparse_fea']),
-           'dense_fea': torch.empty_like(devb[0][0]['dense_fea'])}
-  slab = torch.empty_like(devb[0][1])
-  for i in range(3):
-    a, b, c = pinned[i % n_rot]
-    sfeat['sparse_fea'].copy_(a, non_blocking=True)
-    sfeat['dense_fea'].copy_(b, non_blocking=True)
-    slab.copy_(c, non_blocking=True)
-    float(trainer.train_step(sfeat, slab)[0])
-  barrier()
-  ev0.record()
-  for i in range(e2e_steps):
-    a, b, c = pinned[i % n_rot]
-    sfeat['sparse_fea'].copy_(a, non_blocking=True)
-    sfeat['dense_fea'].copy_(b, non_blocking=True)
-    slab.copy_(c, non_blocking=True)
-    loss, _ = trainer.train_step(sfeat, slab)
-    lv = float(loss)  # device -> host read of the step's loss
-  ev1.record()
-  barrier()
-  e2e_ms = ev0.elapsed_time(ev1)
-  if world > 1:
-    tms = torch.tensor([e2e_ms], device=dev)
-    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(tms.item())
-  e2e_value = world * B * e2e_steps / (e2e_ms / 1000.0)
-  h2d = pinned[0][0].numel() * 8 + pinned[0][1].numel() * 4 + pinned[0][2].numel() * 4
+  def mem_input_fn():
+    def gen():
+      i = 0
+      while True:
+        yield pinned[i % n_rot]
+        i += 1
+    return gen()
+
+  e2e_ms = timed_train(est, mem_input_fn, args.steps, 3)
+  clocks = sampler.finish() if rank == 0 else None
+  e2e_value = world * B * args.steps / (e2e_ms / 1000.0)
+  h2d = pinned[0][0]['sparse_fea'].numel() * 8 + pinned[0][0]['dense_fea'].numel() * 4 + pinned[0][1].numel() * 4
+  e2e = {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+         'ms_per_step': e2e_ms / args.steps,
+         'through': 'EasyRecEstimator.train(input_fn) - Prefetcher thread + pinned double-buffered DeviceFeeder, loss read '
+                    'back every step'}
 
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
     return 0
 
-  # ---- per-kernel roofline (own kernels, CUDA events on the launching stream) -----------
-  peak, peak_src = peaks()
+  extras = world == 1 and not args.no_extras
+  opt_lines, lines = [], []
+  roofline = None
+  if extras:
+    # ---- e2e from files: the CSV (native er_csv_parse) and Parquet (pyarrow) readers feed the same estimator -----
+    n_file = 16
+    tmp = tempfile.mkdtemp(prefix='er_bench_')
+    tsv, pq_path = workloads.write_c2_files(os.path.join(tmp, 'c2'), n_file, B, seed=20240, uniform=args.uniform_ids)
+    from easyrec_b200.input import readers
+    file_steps = min(args.steps, 200)
+    cfg = est._pipeline_config
+    ms_csv = timed_train(est, lambda: readers.make_input(cfg, il, tsv), file_steps, 3)
+    e2e['from_csv'] = {'value': B * file_steps / (ms_csv / 1000.0), 'unit': 'samples/s', 'steps': file_steps,
+                       'file_mb': os.path.getsize(tsv) / 1e6,
+                       'reader': 'CSVInput: native er_csv_parse, %d parser threads' % max(1, min(16, (os.cpu_count() or 1) // 2))}
+    # (the per-kernel roofline needs this estimator's arena: measured before the other estimators are built)
+    roofline = measure_roofline(args, est, devb, B, dev)
+    del est
+    torch.cuda.empty_cache()
+    est_pq = build(args.optimizer, input_type='ParquetInput')
+    for i in range(3):
+      est_pq.trainer.train_step(*devb[i % n_rot])
+    cfg_pq = est_pq._pipeline_config
+    ms_pq = timed_train(est_pq, lambda: readers.make_input(cfg_pq, est_pq.input_layer, pq_path), file_steps, 3)
+    e2e['from_parquet'] = {'value': B * file_steps / (ms_pq / 1000.0), 'unit': 'samples/s', 'steps': file_steps,
+                           'file_mb': os.path.getsize(pq_path) / 1e6, 'reader': 'ParquetInput: pyarrow row groups'}
+    del est_pq
+    torch.cuda.empty_cache()
+    # ---- the other optimizers of BASELINE.md C2, all CUDA-graph captured -----------------------------------------
+    o_steps, o_warm = min(args.steps, 200), min(W, 10)
+    for o in ('adagrad_optimizer', 'lazy_adam_optimizer', 'adam_optimizer'):
+      if o == args.optimizer:
+        opt_lines.append({'optimizer': o, 'value': value, 'ms_per_step': ms / args.steps, 'cuda_graph': graph,
+                          'gpu_launches_per_step': int(per_step_launches)})
+        continue
+      e = build(o)
+      m, _ = timed_resident(e, o_steps, o_warm + 3)
+      row = {'optimizer': o, 'value': B * o_steps / (m / 1000.0), 'ms_per_step': m / o_steps,
+             'cuda_graph': graph and e.trainer._graph is not None,
+             'gpu_launches_per_step': int(getattr(e.trainer, 'launches_per_step', 0) or 0)}
+      if o == 'adam_optimizer':
+        row['note'] = ('tf.train.AdamOptimizer semantics: every row of the table decays each step '
+                       '(er_adam_dense_sweep streams the %.1f GB of [w|m|v] rows)' % ((vocab + 13) * 17 * 12 / 1e9))
+      opt_lines.append(row)
+      del e
+      torch.cuda.empty_cache()
+    # ---- C3: DIN ----------------------------------------------------------------------------------------------
+    B3, T3 = 4096, 50
+    est3 = EasyRecEstimator(workloads.c3_config_text(B3, 1_000_000, T3), device=dev, seed=20240, use_cuda_graph=graph,
+                            default_seq_len=T3)
+    b3 = []
+    for i in range(8):
+      f, l = workloads.c3_batch(B3, T3, 777 + i)
+      b3.append(({'sparse_fea': f['sparse_fea'].to(dev), 'dense_fea': f['dense_fea'].to(dev),
+                  'seq_fea': {k: (a.to(dev), b.to(dev)) for k, (a, b) in f['seq_fea'].items()}}, l.to(dev)))
+    for i in range(o_warm + 3):
+      est3.trainer.train_step(*b3[i % 8])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(o_steps):
+      est3.trainer.train_step(*b3[i % 8])
+    ev1.record()
+    torch.cuda.synchronize()
+    m3 = ev0.elapsed_time(ev1)
+    lines.append({'workload': 'din_c3(MultiTowerDIN, batch %d, 2 histories x %d, item table 1M x 16, attention MLP '
+                              '[128,64,32,1])' % (B3, T3), 'value': B3 * o_steps / (m3 / 1000.0), 'unit': 'samples/s',
+                  'ms_per_step': m3 / o_steps, 'steps': o_steps, 'cuda_graph': graph and est3.trainer._graph is not None,
+                  'gpu_launches_per_step': int(getattr(est3.trainer, 'launches_per_step', 0) or 0)})
+    del est3
+    torch.cuda.empty_cache()
+  elif world == 1:
+    roofline = measure_roofline(args, est, devb, B, dev)
+
+  # ---- CPU baseline (oracle port) on a bounded sample ---------------------------------
+  cpu = None
+  if world == 1 and not args.no_cpu_baseline:
+    v, threads, dt = run_cpu(args, 8, 2, min(vocab, 10_000_000))
+    cpu = {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+           'sample': '8 full training steps of batch %d after 2 warm-up steps on the CPU oracle (C sparse path + numpy '
+                     'dense, %d of %d host threads), %.1f s' % (B, threads, os.cpu_count() or 1, dt)}
+
+  line = {'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+          'warmup': W, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+          'clocks': clocks, 'e2e': e2e,
+          'gpu_launches': int(per_step_launches * args.steps), 'gpu_launches_per_step': int(per_step_launches),
+          'cuda_graph': graph, 'roofline': roofline, 'cpu_baseline': cpu, 'optimizers': opt_lines, 'lines': lines,
+          'final_loss': final_loss}
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+  return 0
+
+
+def measure_roofline(args, est, devb, B, dev):
+  """per-kernel roofline of the estimator's own kernels: CUDA events on the launching stream, L2 flushed"""
+  import torch
+  from easyrec_b200 import _lib, kernels as K
+  peak, peak_src, bf16_peak = peaks()
+  il = est.input_layer
   call = il.calls[DIM]
   arena = il.arenas[DIM]
+  kind = arena.opt_kind
+  k_rw = {_lib.OPT_SGD: 2, _lib.OPT_ADAGRAD: 4}.get(kind, 6)
   F = N_SPARSE + N_DENSE
   L = S = F * B
   flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -354,12 +486,14 @@ def main():
     rows_list.append(rows.clone())
     w_list.append(w.clone())
     uniq.append(int(torch.unique(rows).numel()))
-  opt = K.make_opt(_lib.OPT_ADAGRAD, 0.01)
+  opt = K.make_opt(kind, 0.01)
   st = torch.cuda.current_stream()
 
-  def time_kernel(fn, iters):
+  def time_kernel(fn, iters, pre=None):
     tot = 0.0
     for it in range(iters):
+      if pre:
+        pre(it)
       flush.fill_(float(it))  # evict L2 between timed launches
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record(st)
@@ -374,11 +508,15 @@ def main():
                     weights=w_list[it % 4])
 
   def run_bwd(it):
-    K.embedding_bwd(arena.weight, arena.state0, None, DIM, rows_list[it % 4], call.slots_dev, call.n_slots,
+    K.embedding_bwd(arena.weight, arena.state0, arena.state1, DIM, rows_list[it % 4], call.slots_dev, call.n_slots,
                     call.n_seg, [gout], opt, call.ws, weights=w_list[it % 4])
 
-  def run_hash(it):
-    K.bucketize(devb[it % 4][0]['sparse_fea'], il.calls[DIM].slots_dev, 1, N_SPARSE * B)
+  def run_place(it):
+    K.embedding_bwd_presort(rows_list[it % 4], arena.n_rows, DIM, call.ws, call.slots_dev, call.n_slots)
+
+  def run_after_place(it):
+    K.embedding_bwd(arena.weight, arena.state0, arena.state1, DIM, rows_list[it % 4], call.slots_dev, call.n_slots,
+                    call.n_seg, [gout], opt, call.ws, weights=w_list[it % 4], sorted_from=(call.ws, DIM))
 
   for it in range(3):
     run_fwd(it)
@@ -386,29 +524,10 @@ def main():
   torch.cuda.synchronize()
   fwd_ms = time_kernel(run_fwd, args.kernel_iters)
   bwd_ms = time_kernel(run_bwd, args.kernel_iters)
-
-  # the two stages of K7 on their own: the dedup sort (L2-resident, latency-bound) and the HBM stage
-  def run_sort(it):
-    K.embedding_bwd_presort(rows_list[it % 4], arena.n_rows, DIM, call.ws, call.slots_dev, call.n_slots)
-
-  def run_after_sort(it):
-    K.embedding_bwd(arena.weight, arena.state0, None, DIM, rows_list[it % 4], call.slots_dev, call.n_slots,
-                    call.n_seg, [gout], opt, call.ws, weights=w_list[it % 4], sorted_from=(call.ws, DIM))
-
-  sort_ms = time_kernel(run_sort, args.kernel_iters)
-  tot = 0.0
-  for it in range(args.kernel_iters):   # sort untimed, then flush, then the timed HBM stage
-    run_sort(it)
-    flush.fill_(float(it))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    run_after_sort(it)
-    e1.record(st)
-    e1.synchronize()
-    tot += e0.elapsed_time(e1)
-  upd_ms = tot / args.kernel_iters
+  place_ms = time_kernel(run_place, args.kernel_iters)
+  upd_ms = time_kernel(run_after_place, args.kernel_iters, pre=run_place)
   U = float(np.mean(uniq))
-  fwd_bytes, bwd_bytes = algorithmic_bytes(L, S, U, DIM, 4)
+  fwd_bytes, bwd_bytes = algorithmic_bytes(L, S, U, DIM, k_rw)
   fwd_bytes += 4 * L  # per-lookup weights (13 raw slots carry values)
   bwd_bytes += 4 * L
   # dense-tower GEMM on the tensor cores: the largest layer of the step (forward 624 -> 256), timed alone
@@ -419,9 +538,6 @@ def main():
     K.gemm(gx_, gw_, out=gout_)
   gemm_ms = time_kernel(lambda it: K.gemm(gx_, gw_, out=gout_), args.kernel_iters)
   gemm_flop = 2.0 * B * F * DIM * 256
-  pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
-      os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
-  bf16_peak = float(pk.get('bf16_tflops', 2250.0))
   k_gemm = {'kernel': 'er_gemm (gemm_tf32x3_kernel, [8192 x 624] x [624 x 256])', 'bound': 'tensor',
             'achieved': gemm_flop / (gemm_ms * 1e-3) / 1e12, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'ms': gemm_ms,
             'algorithmic_flop': gemm_flop,
@@ -429,53 +545,33 @@ def main():
                     'work is 6x the algorithmic flop count against this bf16 peak'}
   k_gemm['frac'] = k_gemm['achieved'] / bf16_peak
   k_gemm['tensor_pipe_frac'] = 6.0 * k_gemm['frac']
+  if os.environ.get('ER_K7') == 'radix':
+    bwd_name = 'er_embedding_bwd (init_hist + 3 x scatter radix sort + bwd_scan_vec_kernel<4> + bwd_long_vec_kernel<4,1>)'
+  else:
+    bwd_name = ('er_embedding_bwd (memset + bk_count_kernel + bk_place_kernel + bk_fused_kernel<4> [warp-per-bucket sort, '
+                'staged sums, fused row update, one-row column sums] + bk_reduce_big_kernel<4> + bwd_long_vec_kernel<4,1>)')
   k_fwd = {'kernel': 'er_embedding_fwd (fwd_single_kernel<4,4>)', 'bound': 'hbm',
            'achieved': fwd_bytes / (fwd_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
            'ms': fwd_ms, 'algorithmic_bytes': fwd_bytes}
-  k_bwd = {'kernel': 'er_embedding_bwd (init_hist + 3 x scatter radix sort + bwd_scan_vec_kernel<4> + bwd_long_vec_kernel<4,1>)',
-           'bound': 'hbm', 'achieved': bwd_bytes / (bwd_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+  k_bwd = {'kernel': bwd_name, 'bound': 'hbm', 'achieved': bwd_bytes / (bwd_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
            'ms': bwd_ms, 'algorithmic_bytes': bwd_bytes, 'unique_rows': U}
-  k_upd = {'kernel': 'er_embedding_bwd after the sort (bwd_scan_vec_kernel<4> + bwd_long_vec_kernel<4,1>: segment '
-                     'sums + fused adagrad row update)', 'bound': 'hbm',
+  k_upd = {'kernel': 'er_embedding_bwd after the row-only placement (the part that needs the gradient: per-bucket sort, '
+                     'segment sums, fused row update)', 'bound': 'hbm',
            'achieved': (bwd_bytes - 8 * L) / (upd_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s', 'ms': upd_ms,
-           'algorithmic_bytes': bwd_bytes - 8 * L, 'sort_ms': sort_ms,
-           'note': 'the radix sort (sort_ms) depends only on the rows and runs on a side stream under the dense '
+           'algorithmic_bytes': bwd_bytes - 8 * L, 'placement_ms': place_ms,
+           'note': 'the placement (placement_ms) depends only on the rows and runs on a side stream under the dense '
                    'forward/backward inside the step'}
   for k in (k_fwd, k_bwd, k_upd):
     k['frac'] = k['achieved'] / peak
   dom = k_bwd if bwd_ms >= fwd_ms else k_fwd
-  roofline = {'bound': 'hbm', 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s', 'frac': dom['frac'],
-              # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the pipeline's largest launch
-              # (bwd_scan_vec_kernel<4>: 37.03 MB read + 0.07 MB written during the launch; the updated rows are
-              # written back from L2 after it) -- profiles/r01_ncu_bwd_scan_vec.txt; fwd_single_kernel: 23.4 MB
-              'traffic': 37.1e6 if dom is k_bwd else 23.5e6, 'traffic_source': 'profiles/r01_ncu_*.txt',
-              'kernel': dom['kernel'], 'peak_source': peak_src,
-              'kernels': [k_fwd, k_bwd, k_upd, k_gemm],
-              'random_64B_row_ceiling_gbs': 1000.0,
-              'ceiling_note': 'tools/microbench_gather.cu: independent random 64 B row reads reach 15.6 Grows/s '
-                              '(1.0 TB/s of rows) at 320K lookups on this B200, not the 6.57 TB/s copy peak'}
-
-  # ---- CPU baseline (oracle port) on a bounded sample ---------------------------------
-  cpu = None
-  if world == 1 and not args.no_cpu_baseline:
-    v, threads, dt = run_cpu(args, 3, 1, args.vocab)
-    cpu = {'value': v, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-           'sample': '3 full training steps of batch %d on the CPU oracle (C sparse path + numpy dense, fastest '
-                     'thread count of all/half/quarter/16/8), %.1f s' % (B, dt)}
-
-  line = {'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
-          'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-          'clocks': clocks,
-          'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                  'ms_per_step': e2e_ms / e2e_steps},
-          'gpu_launches': int(per_step_launches * args.steps), 'gpu_launches_per_step': int(per_step_launches),
-          'cuda_graph': not args.no_graph, 'roofline': roofline, 'cpu_baseline': cpu,
-          'final_loss': float(lv)}
-  print(json.dumps(line))
-  if world > 1:
-    dist.destroy_process_group()
-  return 0
+  traffic, traffic_src = ncu_traffic('er_embedding_bwd' if dom is k_bwd else 'er_embedding_fwd')
+  return {'bound': 'hbm', 'achieved': dom['achieved'], 'peak': peak, 'unit': 'GB/s', 'frac': dom['frac'],
+          'traffic': traffic, 'traffic_source': traffic_src,
+          'kernel': dom['kernel'], 'peak_source': peak_src,
+          'kernels': [k_fwd, k_bwd, k_upd, k_gemm],
+          'random_64B_row_ceiling_gbs': 1000.0,
+          'ceiling_note': 'tools/microbench_gather.cu: independent random 64 B row reads reach 15.6 Grows/s '
+                          '(1.0 TB/s of rows) at 320K lookups on this B200, not the 6.57 TB/s copy peak'}
 
 
 if __name__ == '__main__':

@@ -60,9 +60,12 @@ class EasyRecEstimator(object):
   def eval_config(self):
     return self._pipeline_config.eval_config
 
-  def train(self, input_fn, hooks=None, steps=None, max_steps=None, saving_listeners=None):
+  def train(self, input_fn, hooks=None, steps=None, max_steps=None, saving_listeners=None, fetch_loss_every_step=False):
     """input_fn() -> iterable of (features, labels) host batches.  Logs step/loss/steps-per-sec every
-    log_step_count_steps like LoggingTensorHook + StepCounterHook (easy_rec_estimator.py:384-396,455-458)."""
+    log_step_count_steps like LoggingTensorHook + StepCounterHook (easy_rec_estimator.py:384-396,455-458).
+    The batches reach the device through pinned, double-buffered staging (readers.DeviceFeeder) behind a parsing
+    thread (readers.Prefetcher).  fetch_loss_every_step: read the loss back to the host after every step (what a
+    per-step logging hook costs; bench.py's end-to-end number)."""
     limit = steps if steps is not None else (max_steps or self.train_config.num_steps or None)
     every = max(int(self.train_config.log_step_count_steps), 1)
     t0, n0 = time.time(), self.global_step
@@ -74,10 +77,13 @@ class EasyRecEstimator(object):
     epoch = 0
     while not done:
       seen = self.global_step
-      for feats, labels in readers.Prefetcher(input_fn(), depth=2):   # host parsing runs ahead of the device step
-        feats, labels = readers.to_device(feats, labels, self._device)
+      feeder = readers.DeviceFeeder(readers.Prefetcher(input_fn(), depth=2), self._device, depth=2)
+      self.last_feeder = feeder
+      for feats, labels in feeder:   # host parsing and the H2D copies run ahead of the device step
         loss, _ = self.trainer.train_step(feats, labels)
         self.global_step += 1
+        if fetch_loss_every_step:
+          self.last_loss_value = float(loss)
         if self.global_step % every == 0:
           dt = time.time() - t0
           logging.info('global_step = %d, loss = %.6f, global_step/sec = %.2f', self.global_step, float(loss),

@@ -155,7 +155,7 @@ class CSVInput(object):
     self.path = path
     assert engine in ('native', 'python')
     self.engine = engine
-    self.n_threads = n_threads or min(8, os.cpu_count() or 1)
+    self.n_threads = n_threads or max(1, min(16, (os.cpu_count() or 1) // 2))
     dc = pipeline_config.data_config
     self.sep = dc.separator or ','
     self.fields = [f.input_name for f in dc.input_fields]
@@ -744,7 +744,104 @@ class Prefetcher(object):
         yield item
     finally:
       stop.set()
+      try:                      # unblock a producer that waits for room in the queue
+        while True:
+          q.get_nowait()
+      except queue.Empty:
+        pass
       t.join(timeout=5.0)
+
+
+class DeviceFeeder(object):
+  """Host batches -> device batches through PINNED staging buffers, `depth` batches ahead of the consumer on a copy
+  stream of its own (double buffering at depth 2): while step i runs, batch i+1 is already crossing PCIe - the
+  `dataset.prefetch` + H2D of the reference input pipeline (input/input.py:1046-1051, input/load_parquet.py:139-317
+  feed the session the same way).  Per slot: pageable host tensor -> pinned buffer (a CPU memcpy) -> cudaMemcpyAsync on
+  the copy stream -> an event the compute stream waits on; a slot's device buffers are rewritten only after the
+  step that read them has been enqueued and has finished (event recorded when the consumer asks for the next batch).
+  On a CPU device it passes the batches through."""
+
+  def __init__(self, source, device, depth=2):
+    self.source = source
+    self.device = device
+    self.depth = max(int(depth), 1)
+    self.h2d_bytes = 0   # bytes copied host -> device so far (bench.py reports them per step)
+
+  class _Slot(object):
+    def __init__(self):
+      self.pinned = {}
+      self.dev = {}
+      self.ready = None
+      self.consumed = None
+
+  def _stage(self, slot, path, t, stream):
+    """one tensor: grow-only pinned + device buffers keyed by its place in the batch structure."""
+    n = t.numel()
+    dev_buf = slot.dev.get(path)
+    if dev_buf is None or dev_buf.numel() < n or dev_buf.dtype != t.dtype:
+      cap = max(n, 1) if dev_buf is None else max(n, 2 * dev_buf.numel())
+      slot.pinned[path] = torch.empty(cap, dtype=t.dtype, pin_memory=True)
+      slot.pinned_np = getattr(slot, 'pinned_np', {})
+      slot.pinned_np[path] = slot.pinned[path].numpy()
+      dev_buf = slot.dev[path] = torch.empty(cap, dtype=t.dtype, device=self.device)
+    dev = dev_buf[:n]
+    if t.is_pinned() and t.is_contiguous():
+      dev.copy_(t.reshape(-1), non_blocking=True)      # the reader already produced page-locked memory
+    else:
+      # one plain memcpy into the slot's page-locked buffer (numpy: torch's CPU copy forks its whole intra-op
+      # thread pool for a 2 MB tensor, 1.2 ms on a 128-thread host against 0.15 ms for the memcpy)
+      np.copyto(slot.pinned_np[path][:n], t.detach().reshape(-1).numpy())
+      dev.copy_(slot.pinned[path][:n], non_blocking=True)
+    self.h2d_bytes += n * t.element_size()
+    return dev.view(t.shape)
+
+  def _stage_batch(self, slot, feats, labels, stream):
+    if slot.ready is not None and not slot.ready.query():
+      slot.ready.synchronize()      # (the previous copy out of this slot's pinned buffers is normally long done)
+    with torch.cuda.stream(stream):
+      if slot.consumed is not None:
+        stream.wait_event(slot.consumed)
+      out = {}
+      for k, v in feats.items():
+        if isinstance(v, dict):
+          out[k] = {n: tuple(None if t is None else self._stage(slot, (k, n, i), t, stream) for i, t in enumerate(tup))
+                    for n, tup in v.items()}
+        else:
+          out[k] = self._stage(slot, (k,), v, stream)
+      lab = self._stage(slot, ('__labels',), labels, stream)
+      slot.ready = torch.cuda.Event()
+      slot.ready.record(stream)
+    slot.batch = (out, lab)
+
+  def __iter__(self):
+    if not str(self.device).startswith('cuda'):
+      for feats, labels in self.source:
+        yield feats, labels
+      return
+    import collections as _c
+    stream = torch.cuda.Stream(device=self.device)
+    ring = [self._Slot() for _ in range(self.depth)]
+    it = iter(self.source)
+    queue = _c.deque()
+    i = 0
+    for _ in range(self.depth):
+      nxt = next(it, None)
+      if nxt is None:
+        break
+      self._stage_batch(ring[i % self.depth], nxt[0], nxt[1], stream)
+      queue.append(ring[i % self.depth])
+      i += 1
+    while queue:
+      slot = queue.popleft()
+      torch.cuda.current_stream().wait_event(slot.ready)
+      yield slot.batch
+      # the consumer has enqueued the step that reads this slot: its buffers are free once that step is done
+      slot.consumed = torch.cuda.Event()
+      slot.consumed.record(torch.cuda.current_stream())
+      nxt = next(it, None)
+      if nxt is not None:
+        self._stage_batch(slot, nxt[0], nxt[1], stream)
+        queue.append(slot)
 
 
 def to_device(feats, labels, device):

@@ -116,6 +116,36 @@ class FlatDenseOptimizer(object):
                            torch.cuda.current_stream().cuda_stream), 'er_dense_apply')
 
 
+def _tree_clone(x):
+  """device copy of a batch structure: tensors inside dicts / tuples (seq_fea, tag_fea), None passed through."""
+  if x is None:
+    return None
+  if isinstance(x, dict):
+    return {k: _tree_clone(v) for k, v in x.items()}
+  if isinstance(x, (tuple, list)):
+    return tuple(_tree_clone(v) for v in x)
+  return x.clone()
+
+
+def _tree_copy(dst, src, path='features'):
+  """src -> the static buffers a captured graph reads; the shapes are part of the capture."""
+  if dst is None and src is None:
+    return
+  if isinstance(dst, dict):
+    for k in dst:
+      _tree_copy(dst[k], src[k], path + '.' + str(k))
+    return
+  if isinstance(dst, tuple):
+    for i, d in enumerate(dst):
+      _tree_copy(d, src[i], '%s[%d]' % (path, i))
+    return
+  if dst is None or src is None or dst.shape != src.shape:
+    raise _lib.ErError('%s: a CUDA-graph captured step needs batches of one fixed shape (got %s, captured %s); '
+                       'variable-length inputs (TagFeature lists) train with use_cuda_graph=False'
+                       % (path, None if src is None else tuple(src.shape), None if dst is None else tuple(dst.shape)))
+  dst.copy_(src, non_blocking=True)
+
+
 class Trainer(object):
 
   def __init__(self, model, input_layer, dense_optimizer='adagrad', lr=0.01, lr_fn=None,
@@ -203,8 +233,7 @@ class Trainer(object):
     if self._graph is None:
       self._capture(features, labels)
     else:
-      for k, v in features.items():
-        self._static[k].copy_(v, non_blocking=True)
+      _tree_copy(self._static_feats, features)
       self._static['__labels'].copy_(labels, non_blocking=True)
     if self._graph2 is not None:
       self._segment_pre(self._static_feats)
@@ -220,9 +249,8 @@ class Trainer(object):
     scalar of the optimizers - learning rate, Adam's beta powers, gradient scale - is read by the kernels from
     the device block `input_layer.hyper` that _set_hyper refreshes before each replay, so Adagrad, lazy Adam
     and tf.train.AdamOptimizer rows and any learning-rate schedule replay the same graph."""
-    self._static = {k: v.clone() for k, v in features.items()}
-    self._static['__labels'] = labels.clone()
-    feats = {k: self._static[k] for k in features}
+    feats = _tree_clone(features)
+    self._static = {'__labels': labels.clone()}
     self._static_feats = feats
     torch.cuda.synchronize()
     self._graph = torch.cuda.CUDAGraph()

@@ -64,3 +64,114 @@ def criteo_batch(batch_size, seed, zipf_alpha=1.05, uniform=False):
   dense = np.minimum(dense, np.array(CRITEO_MAX, np.float32))
   labels = (rng.uniform(size=batch_size) < 0.25).astype(np.float32)
   return ids, dense, labels
+
+
+# ---- the same workloads as pipeline configs (protobuf text): what EasyRecEstimator is handed ---------------------
+def c2_config_text(vocab, batch_size, optimizer='adagrad_optimizer', lr=0.01, input_type='CSVInput', model_dir='/tmp/er_c2',
+                   dnn=(256, 128, 64), final=(256, 128, 64)):
+  """C2 as a pipeline config in the reference's schema: the feature / model sections of
+  examples/configs/deepfm_on_criteo.config with the 26 id features sharing one `vocab`-row table (embedding_name
+  "embedding", as samples/model_config/dlrm_on_criteo_parquet_ep.config:319-324).  Columns: label, f1..f13, c1..c26
+  (TSV) / is_click, f1..f13, c1..c26 (Parquet, tools/criteo/convert_data.py:29-39)."""
+  label = 'is_click' if input_type.startswith('Parquet') else 'label'
+  fields = ['  input_fields { input_name: "%s" input_type: FLOAT }' % label]
+  feats = []
+  for i in range(13):
+    fields.append('  input_fields { input_name: "f%d" input_type: FLOAT }' % (i + 1))
+    feats.append('  features { input_names: "f%d" feature_type: RawFeature embedding_dim: 16 min_val: %r max_val: %r }'
+                 % (i + 1, CRITEO_MIN[i], CRITEO_MAX[i]))
+  for i in range(26):
+    fields.append('  input_fields { input_name: "c%d" input_type: INT64 }' % (i + 1))
+    feats.append('  features { input_names: "c%d" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: %d '
+                 'embedding_name: "embedding" }' % (i + 1, vocab))
+  names = ', '.join('"f%d"' % (i + 1) for i in range(13)) + ', ' + ', '.join('"c%d"' % (i + 1) for i in range(26))
+  text = '\n'.join([
+      'model_dir: "%s"' % model_dir,
+      'train_config { log_step_count_steps: 1000000',
+      '  optimizer_config { %s { learning_rate { constant_learning_rate { learning_rate: %r } } } } }' % (optimizer, lr),
+      'data_config { batch_size: %d input_type: %s separator: "\\t" label_fields: "%s"' % (batch_size, input_type, label),
+      '\n'.join(fields) + ' }',
+      'feature_config {', '\n'.join(feats) + ' }',
+      'model_config { model_class: "DeepFM"',
+      '  feature_groups { group_name: "deep" feature_names: [%s] wide_deep: DEEP }' % names,
+      '  feature_groups { group_name: "wide" feature_names: [%s] wide_deep: WIDE }' % names,
+      '  deepfm { dnn { hidden_units: %s } final_dnn { hidden_units: %s } l2_regularization: 1e-5 }' % (list(dnn), list(final)),
+      '  embedding_regularization: 1e-5 }', ''])
+  return text.encode()
+
+
+def c3_config_text(batch_size=4096, item_vocab=1_000_000, seq_len=50, optimizer='adagrad_optimizer', lr=0.01):
+  """C3: DIN, the shape of samples/model_config/din_on_taobao.config - user / item towers, two behaviour sequences
+  (item ids over `item_vocab`, categories over 10K) attended by their keys, attention MLP [128, 64, 32, 1]
+  (layers/sequence_feature_layer.py:158-165), final DNN [256, 128, 64]."""
+  seq = 'feature_type: SequenceFeature embedding_dim: 16 max_seq_len: %d separator: "|"' % seq_len
+  text = '\n'.join([
+      'train_config { log_step_count_steps: 1000000',
+      '  optimizer_config { %s { learning_rate { constant_learning_rate { learning_rate: %r } } } } }' % (optimizer, lr),
+      'data_config { batch_size: %d input_type: DummyInput label_fields: "clk"' % batch_size,
+      '  input_fields { input_name: "clk" input_type: FLOAT } input_fields { input_name: "user_id" input_type: INT64 }',
+      '  input_fields { input_name: "age" input_type: INT64 } input_fields { input_name: "item_id" input_type: INT64 }',
+      '  input_fields { input_name: "cate_id" input_type: INT64 } input_fields { input_name: "price" input_type: FLOAT }',
+      '  input_fields { input_name: "hist_items" input_type: STRING } input_fields { input_name: "hist_cates" input_type: STRING } }',
+      'feature_config {',
+      '  features { input_names: "user_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 1000000 }',
+      '  features { input_names: "age" feature_type: IdFeature embedding_dim: 16 num_buckets: 100 }',
+      '  features { input_names: "item_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: %d }' % item_vocab,
+      '  features { input_names: "cate_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 10000 }',
+      '  features { input_names: "price" feature_type: RawFeature embedding_dim: 16 min_val: 0.0 max_val: 1.0 }',
+      '  features { input_names: "hist_items" hash_bucket_size: %d %s }' % (item_vocab, seq),
+      '  features { input_names: "hist_cates" hash_bucket_size: 10000 %s } }' % seq,
+      'model_config { model_class: "MultiTowerDIN"',
+      '  feature_groups { group_name: "user" feature_names: ["user_id", "age"] wide_deep: DEEP }',
+      '  feature_groups { group_name: "item" feature_names: ["item_id", "cate_id", "price"] wide_deep: DEEP }',
+      '  seq_att_groups { group_name: "din" seq_att_map { key: "item_id" hist_seq: "hist_items" }',
+      '                   seq_att_map { key: "cate_id" hist_seq: "hist_cates" } }',
+      '  multi_tower { towers { input: "user" dnn { hidden_units: [128, 64] } } towers { input: "item" dnn { hidden_units: [128, 64] } }',
+      '                din_towers { input: "din" dnn { hidden_units: [128, 64, 32, 1] } } final_dnn { hidden_units: [256, 128, 64] }',
+      '                l2_regularization: 1e-5 }',
+      '  embedding_regularization: 1e-5 }', ''])
+  return text.encode()
+
+
+def c3_batch(batch_size, seq_len, seed, zipf_alpha=1.05):
+  """host batch in c3_config_text's InputLayer form: ids feature-major (user_id, age, item_id, cate_id), price,
+  histories padded to seq_len with lengths ~ U[1, seq_len], label Bernoulli(0.25)."""
+  rng = np.random.default_rng(seed)
+  B = batch_size
+
+  def z(n):
+    return (rng.zipf(zipf_alpha, n).astype(np.int64) - 1) % (2**40)
+  ids = np.concatenate([z(B), rng.integers(0, 100, B), z(B), z(B) % 100000]).astype(np.int64)
+  dense = rng.uniform(0, 1, (B, 1)).astype(np.float32)
+  lens = rng.integers(1, seq_len + 1, B).astype(np.int32)
+  seq = {'hist_items': (torch.from_numpy(z(B * seq_len).reshape(B, seq_len)), torch.from_numpy(lens)),
+         'hist_cates': (torch.from_numpy((z(B * seq_len) % 100000).reshape(B, seq_len)), torch.from_numpy(lens.copy()))}
+  labels = (rng.uniform(size=B) < 0.25).astype(np.float32)
+  return {'sparse_fea': torch.from_numpy(ids), 'dense_fea': torch.from_numpy(dense), 'seq_fea': seq}, torch.from_numpy(labels)
+
+
+def write_c2_files(prefix, n_batches, batch_size, seed=20240, uniform=False):
+  """The C2 batches of `criteo_batch` as a TSV and a Parquet file (same rows): returns (tsv path, parquet path)."""
+  import pyarrow as pa
+  import pyarrow.parquet as pq
+  ids, dense, labels = [], [], []
+  for i in range(n_batches):
+    x, d, l = criteo_batch(batch_size, seed + i, uniform=uniform)
+    ids.append(x.reshape(26, batch_size).T)
+    dense.append(d)
+    labels.append(l)
+  ids, dense, labels = np.concatenate(ids), np.concatenate(dense), np.concatenate(labels)
+  cols = [labels.astype(np.int64).astype(str)] + [np.char.mod('%.9g', dense[:, j]) for j in range(13)]
+  cols += [ids[:, j].astype(str) for j in range(26)]
+  lines = cols[0]
+  for c in cols[1:]:
+    lines = np.char.add(np.char.add(lines, '\t'), c)
+  with open(prefix + '.tsv', 'w') as f:
+    f.write('\n'.join(lines.tolist()) + '\n')
+  tab = {'is_click': labels.astype(np.int32)}
+  for j in range(13):
+    tab['f%d' % (j + 1)] = dense[:, j].astype(np.float32)
+  for j in range(26):
+    tab['c%d' % (j + 1)] = ids[:, j].astype(np.int64)
+  pq.write_table(pa.table(tab), prefix + '.parquet', row_group_size=batch_size)
+  return prefix + '.tsv', prefix + '.parquet'
