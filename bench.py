@@ -232,6 +232,9 @@ def ncu_traffic(kernel_key):
 
 def main():
   args = parse()
+  if os.environ.get('ER_BENCH_WATCHDOG'):   # dump every thread's Python stack if the run is still going after N seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ['ER_BENCH_WATCHDOG']), exit=True)
   rank = int(os.environ.get('RANK', 0))
   world = int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -362,10 +365,16 @@ def main():
          'through': 'EasyRecEstimator.train(input_fn) - Prefetcher thread + pinned double-buffered DeviceFeeder, loss read '
                     'back every step'}
 
-  if rank != 0:
+  def leave():
+    """multi-GPU exit: no destroy_process_group - it blocks while captured graphs still hold NCCL work"""
     if world > 1:
-      dist.destroy_process_group()
+      barrier()
+      sys.stdout.flush()
+      os._exit(0)
     return 0
+
+  if rank != 0:
+    return leave()
 
   extras = world == 1 and not args.no_extras
   opt_lines, lines = [], []
@@ -457,9 +466,7 @@ def main():
           'cuda_graph': graph, 'roofline': roofline, 'cpu_baseline': cpu, 'optimizers': opt_lines, 'lines': lines,
           'final_loss': final_loss}
   print(json.dumps(line))
-  if world > 1:
-    dist.destroy_process_group()
-  return 0
+  return leave()
 
 
 def measure_roofline(args, est, devb, B, dev):

@@ -19,6 +19,13 @@ from easyrec_b200 import embedding as E
 from easyrec_b200 import kernels as K
 
 
+import contextlib
+
+
+def _null():
+  return contextlib.nullcontext()
+
+
 class GlobalCall(object):
   """Slot plan of one arena call replicated for `world` ranks' gathered lookups."""
 
@@ -27,13 +34,16 @@ class GlobalCall(object):
     self.world = world
     recs = []
     base = call.slots_np
+    # (lookup == segment for the slots of a call without CSR lookups: the one-row shortcut applies)
+    call.single_one_row_ok = not getattr(call, 'has_csr', False)
     for r in range(world):
       for i in range(call.n_slots):
         s = base[i]
         rows_of_buf = call.out_rows(int(s['out_buf']))
         recs.append(dict(num_buckets=int(s['num_buckets']), row_offset=int(s['row_offset']),
                          seg_begin=int(s['seg_begin']) + r * call.n_seg, n_seg=int(s['n_seg']),
-                         # every rank's copy of a one-row slot reads the same table row: ordinary dedup here
+                         # one-row slots do not take part in the gathered dedup (their rows are gathered as -1): every
+                         # rank sums its own column block and the [n, dim] sums are all-reduced (OneRowPlan)
                          bucket_mode=(_lib.BUCKET_NONE if int(s['bucket_mode']) == _lib.BUCKET_ONE_ROW
                                       else int(s['bucket_mode'])), combiner=int(s['combiner']),
                          out_buf=int(s['out_buf']), out_stride=int(s['out_stride']),
@@ -52,6 +62,25 @@ class GlobalCall(object):
     self.seg_scale = None
     self.grads = [torch.empty(world * call.out_rows(i), st, dtype=torch.float32, device=dev)
                   for i, st in enumerate(call.out_strides)]
+    # one-row slots (RawFeature projections: B lookups of one table row per rank)
+    self.one_row = [(int(s['seg_begin']), int(s['n_seg']), int(s['out_buf']), int(s['out_col']), int(s['row_offset']))
+                    for s in base if int(s['bucket_mode']) == _lib.BUCKET_ONE_ROW and call.single_one_row_ok]
+    if self.one_row:
+      self.one_row_rows = torch.tensor([r[4] for r in self.one_row], dtype=torch.int64, device=dev)
+      self.one_row_sums = torch.zeros(len(self.one_row), call.arena.dim, dtype=torch.float32, device=dev)
+      mask = torch.zeros(call.max_lookups, dtype=torch.bool, device=dev)
+      for sb, ns, _, _, _ in self.one_row:
+        mask[sb:sb + ns] = True
+      self.one_row_mask = mask
+      self.rows_send = torch.empty(call.max_lookups, dtype=torch.int64, device=dev)
+      # the usual plan lists the raw features side by side: their blocks are ONE [B, n, dim] view of the gradient
+      # matrix and their weights one [n, B] view -> two launches for all of them
+      o = self.one_row
+      dim = call.arena.dim
+      self.one_row_block = None
+      if all(o[i][1] == o[0][1] and o[i][2] == o[0][2] and o[i][0] == o[0][0] + i * o[0][1] and
+             o[i][3] == o[0][3] + i * dim for i in range(len(o))):
+        self.one_row_block = (o[0][0], o[0][1], o[0][2], o[0][3], len(o))
 
 
 class DataParallel(object):
@@ -81,25 +110,28 @@ class DataParallel(object):
     self._pre = {}
     owners = {}
     todo = []
-    for dim, m, rows, w in il.precompute_rows(features):
-      g = self.gcalls[id(m)]
-      first = owners.get(id(rows))
-      if first is not None and first.call.arena.n_rows == m.arena.n_rows:
-        self._pre[id(m)] = (first, False)
-        continue
-      owners[id(rows)] = g
-      dist.all_gather_into_tensor(g.rows, rows)
-      if w is not None:
-        dist.all_gather_into_tensor(g.weights, w)
-      self._pre[id(m)] = (g, True)
-      todo.append(g)
-    if todo:
-      if self._side is None:
-        self._side = torch.cuda.Stream(device=todo[0].rows.device)
+    plans = il.precompute_rows(features)   # K1 on the step's stream
+    if self._side is None and plans:
+      self._side = torch.cuda.Stream(device=plans[0][2].device)
+    if plans:
       self._side.wait_stream(torch.cuda.current_stream())
-      with torch.cuda.stream(self._side):
-        for g in todo:
-          K.embedding_bwd_presort(g.rows, g.call.arena.n_rows, g.call.arena.dim, g.ws, g.slots_dev, g.n_slots)
+    # the all-gathers of the rows and the global placement run on a side stream: a parallel branch of the step
+    # (joined in join_presort) that sits under the lookup and the dense forward / backward
+    with torch.cuda.stream(self._side) if plans else _null():
+      for dim, m, rows, w in plans:
+        g = self.gcalls[id(m)]
+        first = owners.get(id(rows))
+        if first is not None and first.call.arena.n_rows == m.arena.n_rows:
+          self._pre[id(m)] = (first, False)
+          continue
+        owners[id(rows)] = g
+        dist.all_gather_into_tensor(g.rows, self._rows_to_send(g, rows))
+        if w is not None:
+          dist.all_gather_into_tensor(g.weights, w)
+        self._pre[id(m)] = (g, True)
+        todo.append(g)
+      for g in todo:
+        K.embedding_bwd_presort(g.rows, g.call.arena.n_rows, g.call.arena.dim, g.ws, g.slots_dev, g.n_slots)
 
   def sync_dense_grads(self):
     """sum over replicas in one bucket; the 1/world of hvd.allreduce(Average)
@@ -115,7 +147,7 @@ class DataParallel(object):
       owner, is_owner = pre
       g.rows_src = None if is_owner else owner
       g.presorted = True
-      self._gather_grads(g, call, outs)
+      self._gather_grads(g, call, outs, w)
       return g
     g.presorted = False
     # arenas with the same row plan (wide dim-1 next to the deep tables) were looked up with the SAME rows /
@@ -126,13 +158,41 @@ class DataParallel(object):
     else:
       g.rows_src = None
       self._rows_owner[id(rows)] = g
-      dist.all_gather_into_tensor(g.rows, rows)
+      dist.all_gather_into_tensor(g.rows, self._rows_to_send(g, rows))
       if w is not None:
         dist.all_gather_into_tensor(g.weights, w)
-    self._gather_grads(g, call, outs)
+    self._gather_grads(g, call, outs, w)
     return g
 
-  def _gather_grads(self, g, call, outs):
+  @staticmethod
+  def _rows_to_send(g, rows):
+    """this rank's rows with the lookups of one-row slots dropped (-1): those are reduced locally"""
+    if not g.one_row:
+      return rows
+    torch.where(g.one_row_mask[:rows.numel()], torch.full_like(rows, -1), rows, out=g.rows_send[:rows.numel()])
+    return g.rows_send[:rows.numel()]
+
+  def _gather_grads(self, g, call, outs, w=None):
+    if g.one_row:
+      # weighted column sums of this rank's one-row slots, summed over the replicas (mean: the 1/world is in the
+      # gradient scale of the row update)
+      dim = call.arena.dim
+      if g.one_row_block is not None and outs[g.one_row_block[2]].grad is not None:
+        sb, ns, buf, col, n = g.one_row_block
+        blk = outs[buf].grad[:, col:col + n * dim].reshape(ns, n, dim)
+        if w is not None:
+          blk = blk * w[sb:sb + n * ns].view(n, ns).t()[:, :, None]
+        torch.sum(blk, dim=0, out=g.one_row_sums)
+      else:
+        for i, (sb, ns, buf, col, _) in enumerate(g.one_row):
+          grad = outs[buf].grad
+          if grad is None:
+            g.one_row_sums[i].zero_()
+          elif w is not None:
+            torch.sum(grad[:, col:col + dim] * w[sb:sb + ns, None], dim=0, out=g.one_row_sums[i])
+          else:
+            torch.sum(grad[:, col:col + dim], dim=0, out=g.one_row_sums[i])
+      dist.all_reduce(g.one_row_sums, op=dist.ReduceOp.SUM)
     if call.seg_scale is not None:
       if g.seg_scale is None:
         g.seg_scale = torch.empty(g.n_seg, dtype=torch.float32, device=outs[0].device)
@@ -175,7 +235,10 @@ class DataParallel(object):
       K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, owner.rows, g.slots_dev, g.n_slots, g.n_seg,
                       g.grads, opt, g.ws, weights=owner.weights if w is not None else None,
                       seg_scale=g.seg_scale, sorted_from=sorted_from)
-      E.adam_dense_decay(a, owner.rows, opt)   # tf.train.AdamOptimizer: the rows nobody looked up decay too
+      if g.one_row:
+        K.sparse_apply(a.weight, a.state0, a.state1, a.dim, g.one_row_rows, g.one_row_sums, None, opt)
+      # tf.train.AdamOptimizer: the rows nobody looked up decay too
+      E.adam_dense_decay(a, owner.rows if not g.one_row else torch.cat([owner.rows, g.one_row_rows]), opt)
     if struct_scaled:
       opt.grad_scale = opt.grad_scale * self.world
 

@@ -128,6 +128,7 @@ class MergedCall(object):
     self._out_rows = [subcalls[si].call.out_rows(b) for si, b in self.buf_of]
     self.ws = K.bwd_workspace(lookups, arena.device, arena.dim)
     self.has_csr = any(sc.kind == 'tag' for sc in subcalls)
+    self.single_valued = not self.has_csr
     self.needs_scale = any(sc.call.needs_scale for sc in subcalls)
     dev = arena.device
     self.rows = torch.empty(lookups, dtype=torch.int64, device=dev) if len(subcalls) > 1 else None

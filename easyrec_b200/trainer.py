@@ -9,6 +9,7 @@ batch-8192 step: SURVEY.md section 8d); the learning rate lives in device memory
 does not need a re-capture.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -255,8 +256,14 @@ class Trainer(object):
     torch.cuda.synchronize()
     self._graph = torch.cuda.CUDAGraph()
     n0 = _lib.load().er_launch_count()
-    if self.dp is None:
-      with torch.cuda.graph(self._graph):
+    # Data parallel: the collectives (NCCL on the capture stream) are captured with the rest of the step - one
+    # graph per step.  capture_error_mode 'thread_local': NCCL's watchdog thread polls CUDA events while this
+    # thread captures, which the default global mode treats as a capture violation.  ER_DP_ONE_GRAPH=0 keeps the
+    # collectives eager between two captured segments.
+    one_graph = self.dp is None or os.environ.get('ER_DP_ONE_GRAPH', '1') == '1'
+    if one_graph:
+      kw = {} if self.dp is None else {'capture_error_mode': 'thread_local'}
+      with torch.cuda.graph(self._graph, **kw):
         self._loss, self._probs = self._step_body(feats, self._static['__labels'])
     else:
       self._segment_pre(feats)   # eager, before the capture: the captured lookup reuses these rows

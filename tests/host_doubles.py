@@ -87,6 +87,21 @@ def install_sparse(patch):
     if state1 is not None:
       state1.copy_(torch.from_numpy(b))
 
+  def sparse_apply(table, state0, state1, dim, uniq_rows, uniq_grads, n_uniq, opt, row_stride=None):
+    n = uniq_rows.numel() if n_uniq is None else int(n_uniq.reshape(-1)[0])
+    t = np.ascontiguousarray(table.numpy())
+    a = None if state0 is None else np.ascontiguousarray(state0.numpy())
+    b = None if state1 is None else np.ascontiguousarray(state1.numpy())
+    kind = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_LAZY_ADAM, 3: O.OPT_LAZY_ADAM}[int(opt.kind)]
+    O.embedding_bwd(t, a, b, uniq_rows.numpy()[:n], None, np.ascontiguousarray(uniq_grads.numpy()[:n]), kind, opt.lr,
+                    beta1=opt.beta1, beta2=opt.beta2, eps=opt.eps, beta1_power=opt.beta1_power,
+                    beta2_power=opt.beta2_power, grad_scale=opt.grad_scale)
+    table.copy_(torch.from_numpy(t))
+    if state0 is not None:
+      state0.copy_(torch.from_numpy(a))
+    if state1 is not None:
+      state1.copy_(torch.from_numpy(b))
+
   def mark_rows(rows, n_rows, touched, value, n_dev=None):
     r = rows.numpy()
     n = r.size if n_dev is None else min(int(n_dev.reshape(-1)[0]), r.size)
@@ -103,7 +118,8 @@ def install_sparse(patch):
     v[cold] = torch.from_numpy(vc)
     table[cold] = torch.from_numpy(table[cold].numpy() - (lr_t * mc) / (np.sqrt(vc) + f(opt.eps)))
   for name, fn in (('csr_from_lens', csr_from_lens), ('bucketize', bucketize), ('embedding_fwd', embedding_fwd),
-                   ('embedding_bwd', embedding_bwd), ('mark_rows', mark_rows), ('adam_dense_sweep', adam_dense_sweep)):
+                   ('embedding_bwd', embedding_bwd), ('mark_rows', mark_rows), ('adam_dense_sweep', adam_dense_sweep),
+                   ('sparse_apply', sparse_apply)):
     patch(K, name, fn)
 
 

@@ -3,7 +3,9 @@
 Checks: (1) replicas stay BIT-identical (tables, optimizer state, dense parameters) - K7 and the dense path
 are deterministic and every rank applies the same gathered update; (2) the early exchange (K1 + all-gather
 of rows + global dedup sort on a side stream before the step) gives exactly the same model as the plain
-exchange after the backward pass; (3) the same under CUDA-graph replay (replicas identical).  Skipped on boxes with fewer than 2 GPUs."""
+exchange after the backward pass; (3) CUDA-graph replay - collectives eager between two captured segments, and
+captured inside ONE graph per step (NCCL on the capture stream) - trains exactly the same model as the eager run
+(2 eager steps, capture, replays: every batch applied once).  Skipped on boxes with fewer than 2 GPUs."""
 import os
 import socket
 
@@ -48,18 +50,19 @@ def _worker(rank, port, ret):
   dist.init_process_group('nccl', rank=rank, world_size=WORLD, device_id=torch.device(dev))
   torch.backends.cuda.matmul.allow_tf32 = False
   results = {}
-  for name, (pre, graph) in {'plain': (False, False), 'early': (True, False), 'early_graph': (True, True)}.items():
-    loss, state = _train(rank, dev, pre, graph)
+  for name, (pre, graph, one) in {'plain': (False, False, '1'), 'early': (True, False, '1'),
+                                  'graph_two_segments': (True, True, '0'), 'graph_one': (True, True, '1')}.items():
+    os.environ['ER_DP_ONE_GRAPH'] = one
+    loss, state = _train(rank, dev, pre, graph, steps=6)
     assert loss == loss and abs(loss) < 10
     for t in state:   # replicas identical: max over ranks of |mine - rank0's| must be exactly 0
       ref = t.clone()
       dist.broadcast(ref, src=0)
       assert torch.equal(t, ref), '%s: replicas diverged' % name
     results[name] = state
-  for a, b in zip(results['plain'], results['early']):
-    assert torch.equal(a, b), 'early exchange changed the result'
-  # (graph capture warms up with two extra real steps on the first batch, so its model is not compared with
-  # the eager ones; its replicas were checked above)
+  for other in ('early', 'graph_two_segments', 'graph_one'):
+    for a, b in zip(results['plain'], results[other]):
+      assert torch.equal(a, b), '%s: a different model than the plain eager exchange' % other
   ret[rank] = True
   dist.destroy_process_group()
 
