@@ -262,8 +262,16 @@ def check_scope(pipeline_config):
     raise NotImplementedError('config is outside the hot-path scope: ' + '; '.join(bad))
 
 
+def embedding_parallel(pipeline_config):
+  """train_config.train_distribute: EmbeddingParallelStrategy (protos/train.proto; main.py / estimator
+  `embedding_parallel` property, model/easy_rec_estimator.py:97-153)."""
+  tc = pipeline_config.train_config
+  names = tc.DESCRIPTOR.fields_by_name['train_distribute'].enum_type.values_by_number
+  return names[tc.train_distribute].name == 'EmbeddingParallelStrategy'
+
+
 def build_model(pipeline_config, batch_size, device, generator=None, cpu_generator=None, world=1, rank=0,
-                default_seq_len=50):
+                default_seq_len=50, shard_tables=False):
   """Returns (input_layer, model, optimizer settings) for the config's model_class."""
   from easyrec_b200 import model as model_pkg
   check_scope(pipeline_config)
@@ -280,7 +288,8 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
     generator = cpu_generator   # tables initialised from the caller's seed on a host build too
   il = IL.InputLayer(specs, groups, batch_size, device, wide_output_dim=wide_dim,
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
-                     adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc))
+                     adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc),
+                     shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0)
   model = cls.from_config(mc, il, generator=cpu_generator).to(device)
   bind_task_labels(model, list(pipeline_config.data_config.label_fields))
   return il, model, opt

@@ -85,10 +85,21 @@ class GlobalCall(object):
 
 class DataParallel(object):
 
-  def __init__(self, input_layer, dense_opt, world):
-    """dense_opt: trainer.FlatDenseOptimizer -- its flat gradient buffer is the all-reduce bucket."""
+  def __init__(self, input_layer, dense_opt, world, sparse=True):
+    """dense_opt: trainer.FlatDenseOptimizer -- its flat gradient buffer is the all-reduce bucket.
+    sparse=False (EmbeddingParallel: the tables are row-sharded and exchange their own lookups, sharded.ShardedLookup):
+    only the dense gradients are averaged here."""
     self.input_layer = input_layer
     self.world = world
+    self.sparse = sparse
+    if not sparse:
+      self.dense_opt = dense_opt
+      dense_opt.grad_scale = 1.0 / world
+      self.gcalls = {}
+      self._pre = {}
+      self._side = None
+      self.prephase = False
+      return
     input_layer.presort_enabled = False   # K7 runs on the gathered global batch, sorted after the exchange
     self.dense_opt = dense_opt
     dense_opt.grad_scale = 1.0 / world  # mean over replicas, applied inside er_dense_apply
@@ -205,6 +216,8 @@ class DataParallel(object):
     """The collectives of one step (eager NCCL calls, kept OUTSIDE CUDA-graph capture): dense flat
     all-reduce + all-gather of every arena's K7 inputs."""
     self.sync_dense_grads()
+    if not self.sparse:
+      return
     self._rows_owner = {}
     for call, rows, w, outs, seg_ids in pending:
       if seg_ids is not None:
@@ -219,6 +232,9 @@ class DataParallel(object):
   def apply_sparse(self, pending, opt):
     """The same fused dedup + row update on every rank over the gathered global batch; gradients
     are scaled by 1/world (mean over replicas).  No collectives: CUDA-graph capturable."""
+    if not self.sparse:
+      self.input_layer.backward_update()   # sharded tables: all-to-all of the gradients + K7 on the owners
+      return
     # mean over replicas: a caller that keeps the step scalars in device memory (InputLayer.hyper) has folded
     # 1/world into them (replica_grad_scale); a plain er_opt_t is scaled here
     struct_scaled = not opt.hyper_dev

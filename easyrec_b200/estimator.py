@@ -25,16 +25,24 @@ auc = metrics.auc   # exact ROC AUC; the reference's tf.metrics.auc is a 200-thr
 class EasyRecEstimator(object):
 
   def __init__(self, pipeline_config, model_cls=None, run_config=None, params=None, device='cuda:0',
-               batch_size=None, use_cuda_graph=False, world_size=1, seed=20240, default_seq_len=50):
+               batch_size=None, use_cuda_graph=False, world_size=1, seed=20240, default_seq_len=50, rank=None,
+               embedding_parallel=None):
     if isinstance(pipeline_config, (str, bytes)):
       pipeline_config = config_util.get_configs_from_pipeline_file(pipeline_config)
     self._pipeline_config = pipeline_config
     self._device = device
     self._batch_size = batch_size or pipeline_config.data_config.batch_size
     gen = torch.Generator(device=device).manual_seed(seed) if str(device).startswith('cuda') else None
+    # EmbeddingParallel (row-sharded tables + all-to-all) when the config asks for it (train_distribute) or the
+    # caller does; otherwise world_size > 1 is data parallel over replicated tables
+    self._ep = (builder.embedding_parallel(pipeline_config) if embedding_parallel is None else bool(embedding_parallel)) \
+        and world_size > 1
+    if rank is None:
+      rank = int(os.environ.get('RANK', 0)) if world_size > 1 else 0
     self.input_layer, self.model, self._opt = builder.build_model(
         pipeline_config, self._batch_size, device, generator=gen,
-        cpu_generator=torch.Generator().manual_seed(seed), default_seq_len=default_seq_len)
+        cpu_generator=torch.Generator().manual_seed(seed), default_seq_len=default_seq_len, world=world_size, rank=rank,
+        shard_tables=self._ep)
     self.trainer = Trainer(self.model, self.input_layer, _DENSE_KIND[self._opt['kind']], lr_fn=self._opt['lr_fn'],
                            use_cuda_graph=use_cuda_graph, world_size=world_size, beta1=self._opt['beta1'],
                            beta2=self._opt['beta2'], adagrad_init=self._opt['acc0'])
@@ -44,6 +52,10 @@ class EasyRecEstimator(object):
     self.global_step = 0
 
   # -- properties of the reference estimator (easy_rec_estimator.py:97-153) --
+  @property
+  def embedding_parallel(self):
+    return self._ep
+
   @property
   def feature_configs(self):
     return config_util.get_feature_configs(self._pipeline_config)

@@ -312,11 +312,24 @@ class InputLayer(object):
     self.hyper = K.StepHyper(device)
     self.hyper.set(0.01, 0)
     self.opt_holder = {'opt': self.hyper.opt(embedding_optimizer)}
+    # EmbeddingParallel (train_distribute: EmbeddingParallelStrategy): the tables are row-sharded over shard_n ranks
+    # and every single-valued lookup goes through the all-to-all exchange of sharded.ShardedLookup
+    self.ep = shard_n > 1
+    if self.ep:
+      from easyrec_b200.sharded import ShardedLookup
+      for dim, subs in self.subcalls.items():
+        for sk, sc in subs.items():
+          if sc.kind != 'single':
+            raise NotImplementedError('EmbeddingParallel with %s features (group slots of kind %s): only single-valued id '
+                                      '/ raw slots are exchanged' % (sk[0], sc.kind))
+          sc.sharded = ShardedLookup(sc.call, shard_n, shard_rank)
+          self.merged[dim].sharded = sc.sharded
+      self._ep_scale = 1.0 / shard_n
     # embedding_learning_rate_multiplier: the reference multiplies the GRADIENT of every `embedding_weights`
     # variable by it (model/easy_rec_estimator.py:308-317 gradient_multipliers), before the optimizer rule
     self.emb_grad_mult = 1.0
     # 1/N of data-parallel replicas or of row-sharded tables (compat/optimizers.py:289-292,315-316)
-    self.replica_grad_scale = 1.0
+    self.replica_grad_scale = getattr(self, '_ep_scale', 1.0)
     self._pending = []
     self._rows_cache = {}
     self._presorted = {}
@@ -341,6 +354,11 @@ class InputLayer(object):
     """After loss.backward(): K7 for every arena looked up since the last call (dedup, segment
     sum and the fused optimizer row update).  The reference's counterpart is
     opt.apply_gradients on the tables' IndexedSlices (compat/optimizers.py:413-416)."""
+    if self.ep:
+      for m, rows, w, outs, seg_ids in self._pending:
+        m.sharded.backward_update(outs, self.opt_holder['opt'])
+      self._pending = []
+      return
     sorted_by = dict(self._presorted)   # id(rows tensor) -> (workspace, dim, n_rows) of the call that sorted it
     if self._presorted:
       torch.cuda.current_stream().wait_stream(self._side)   # join the early sorts
@@ -408,7 +426,7 @@ class InputLayer(object):
     """K7's radix sort needs only the looked-up rows: start it now on a side stream so it runs under the
     dense forward/backward instead of after it (joined in backward_update; captured as a fork/join)."""
     self._presorted = {}
-    if not (self.presort_enabled and torch.is_grad_enabled() and str(self.device).startswith('cuda')):
+    if not (self.presort_enabled and not self.ep and torch.is_grad_enabled() and str(self.device).startswith('cuda')):
       return
     todo = []
     for m, rows, w, outs, seg_ids in self._pending:
@@ -486,6 +504,13 @@ class InputLayer(object):
         key = (tuple((int(r['num_buckets']), int(r['row_offset']), int(r['seg_begin']), int(r['n_seg']),
                       int(r['bucket_mode']), int(r['shard_n'])) for r in call.slots_np), tuple(call.sources))
         sc.rows_key = key
+      if self.ep:
+        cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
+        outs = call.alloc_outputs()
+        rows = sc.sharded.forward(cids, w, outs)
+        for o in outs:
+          o.requires_grad_(True)
+        return rows, w, None, None, outs
       hit = self._rows_cache.get(key)
       if hit is None:
         cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)

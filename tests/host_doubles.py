@@ -38,10 +38,12 @@ def install_sparse(patch):
       live = np.arange(n) < total
       seg_of = np.where(live, seg_of, 0)
     per = lambda f: _seg_field(sl, f, n_seg)[seg_of]   # noqa: E731
-    r, _ = O.bucketize(ids.numpy(), per('bucket_mode'), per('num_buckets'), per('row_offset'))
+    r, own = O.bucketize(ids.numpy(), per('bucket_mode'), per('num_buckets'), per('row_offset'), shard_n=per('shard_n'))
     r = np.where(live, r, -1)
     out = rows if rows is not None else torch.empty_like(ids)
     out.copy_(torch.from_numpy(r))
+    if owner is not None:
+      owner.copy_(torch.from_numpy(np.where(live, own, -1).astype(np.int32)))
     return out
 
   def _csr(n_seg, rows, row_ptr):
@@ -55,7 +57,7 @@ def install_sparse(patch):
                                     weights=None if weights is None else weights.numpy())
     for s in sl:
       out = outs[int(s['out_buf'])].view(-1)
-      for k in range(int(s['n_seg'])):
+      for k in range(min(int(s['n_seg']), n_seg - int(s['seg_begin']))):   # (a call may use a prefix of its plan)
         o = k * int(s['out_stride']) + int(s['out_col'])
         out[o:o + dim] = torch.from_numpy(pooled[int(s['seg_begin']) + k])
     if seg_scale is not None:
@@ -68,9 +70,18 @@ def install_sparse(patch):
     gseg = np.zeros((n_seg, dim), np.float32)
     for s in sl:
       buf = grad_bufs[int(s['out_buf'])].reshape(-1).numpy()
-      for k in range(int(s['n_seg'])):
+      for k in range(min(int(s['n_seg']), n_seg - int(s['seg_begin']))):
         o = k * int(s['out_stride']) + int(s['out_col'])
         gseg[int(s['seg_begin']) + k] = buf[o:o + dim]
+    if table is None:   # emit only: the deduplicated gradient, sorted by row
+      nu, ur, ug = O.embedding_bwd(None, None, None, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()],
+                                   gseg, O.OPT_SGD, 0.0, weights=None if weights is None else weights.numpy(),
+                                   seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=opt.grad_scale,
+                                   want_uniq=True)
+      uniq_rows[:nu].copy_(torch.from_numpy(ur))
+      uniq_grads[:nu].copy_(torch.from_numpy(ug))
+      n_uniq.fill_(nu)
+      return
     t = np.ascontiguousarray(table.numpy())
     a = None if state0 is None else np.ascontiguousarray(state0.numpy())
     b = None if state1 is None else np.ascontiguousarray(state1.numpy())
