@@ -147,6 +147,8 @@ SIGNATURES = {
                              c_vp, c_sz, c_vp]),
     'er_mmoe_mix_fwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'er_mmoe_mix_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    'er_gram_fwd': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    'er_gram_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     'er_l2norm_fwd': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     'er_l2norm_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     'er_inbatch_softmax_ce': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),

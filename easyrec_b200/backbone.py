@@ -187,7 +187,7 @@ class FM(nn.Module):
 class DotInteraction(nn.Module):
   """DLRM dot interaction (layers/keras/interaction.py:47-128): features [B, F, D] -> all pairwise dot products
   of the lower triangle (with the diagonal when self_interaction), [B, F(F-1)/2] (or [B, F*F] with the upper
-  triangle zeroed when skip_gather).  One batched F x D x F product per sample: a library bmm (fp32)."""
+  triangle zeroed when skip_gather).  One F x D x F product per sample: the library's batched Gram kernel (er_gram_fwd)."""
 
   def __init__(self, params):
     super().__init__()
@@ -203,7 +203,7 @@ class DotInteraction(nn.Module):
   def forward(self, inputs):
     x = torch.stack(list(inputs), dim=1) if isinstance(inputs, (list, tuple)) else inputs
     n = x.shape[1]
-    xa = torch.bmm(x, x.transpose(1, 2)).reshape(x.shape[0], n * n)
+    xa = I.gram(x.contiguous()).reshape(x.shape[0], n * n)
     key = (n, x.device)
     if key not in self._idx:   # static gather indices (row-major lower triangle): no boolean-mask host sync
       keep = torch.tril(torch.ones(n, n, dtype=torch.bool), diagonal=0 if self.self_interaction else -1)

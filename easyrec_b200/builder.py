@@ -171,7 +171,7 @@ def optimizer_settings(pipeline_config):
               if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
 
 
-_RANK_CLASSES = ('DeepFM', 'DCN', 'MultiTowerDIN', 'RankModel')
+_RANK_CLASSES = ('DeepFM', 'DCN', 'DLRM', 'MultiTowerDIN', 'RankModel')
 
 
 def _is_repeated(fd):

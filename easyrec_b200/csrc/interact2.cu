@@ -486,3 +486,62 @@ extern "C" int er_inbatch_softmax_ce(const float* sim, const int64_t* item_ids, 
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }
+
+// ---- batched Gram matrices: DLRM / DotInteraction pairwise dot products -------------------------------------
+// out[b, i, j] = sum_k x[b, i, k] * x[b, j, k]   (model/dlrm.py:52-61 einsum 'bne,bme->bnm';
+// layers/keras/interaction.py:47-128).  n and d are small (tens): one thread per output element, the sample's
+// [n, d] block is read through L1; sequential sums (deterministic, the order of a CPU loop).
+namespace er {
+__global__ void __launch_bounds__(256)
+    gram_fwd_kernel(const float* __restrict__ x, int64_t batch, int n, int d, float* __restrict__ out) {
+  const int64_t total = batch * n * n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / (n * n);
+    const int ij = (int)(t - b * n * n);
+    const int i = ij / n, j = ij - i * n;
+    const float* xi = x + (b * n + i) * d;
+    const float* xj = x + (b * n + j) * d;
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = __fadd_rn(acc, __fmul_rn(xi[k], xj[k]));
+    out[t] = acc;
+  }
+}
+// gx[b, i, k] = sum_j (g[b, i, j] + g[b, j, i]) * x[b, j, k]
+__global__ void __launch_bounds__(256)
+    gram_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, int64_t batch, int n, int d,
+                    float* __restrict__ gx) {
+  const int64_t total = batch * n * d;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / (n * d);
+    const int ik = (int)(t - b * n * d);
+    const int i = ik / d, k = ik - i * d;
+    const float* gb = g + b * n * n;
+    const float* xb = x + b * n * d;
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j)
+      acc = __fadd_rn(acc, __fmul_rn(__fadd_rn(gb[i * n + j], gb[j * n + i]), xb[j * d + k]));
+    gx[t] = acc;
+  }
+}
+}  // namespace er
+
+extern "C" int er_gram_fwd(const float* x, int64_t batch, int32_t n, int32_t dim, float* out, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && out, "null argument");
+  ER_REQUIRE(batch > 0 && n > 0 && dim > 0 && n <= 4096, "bad shape");
+  gram_fwd_kernel<<<grid_for(batch * n * n, 256, 8), 256, 0, as_stream(stream)>>>(x, batch, n, dim, out);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_gram_bwd(const float* x, const float* g, int64_t batch, int32_t n, int32_t dim, float* gx,
+                           er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && g && gx, "null argument");
+  ER_REQUIRE(batch > 0 && n > 0 && dim > 0 && n <= 4096, "bad shape");
+  gram_bwd_kernel<<<grid_for(batch * n * dim, 256, 8), 256, 0, as_stream(stream)>>>(x, g, batch, n, dim, gx);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}

@@ -13,6 +13,7 @@ This is the host-side counterpart of `feature_column.input_layer` +
 643-715): same role, none of its graph.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -75,6 +76,9 @@ class Arena(object):
     k = (1 + n_state) if interleave else 1
     self.storage = torch.empty(self.n_rows, k * self.dim, dtype=torch.float32, device=self.device)
     w = self.storage[:, :self.dim]
+    plan_only = os.environ.get('ER_PLAN_ONLY') == '1'   # tests of the table PLAN: allocate, do not touch gigabytes
+    if plan_only:
+      init_fn = lambda t: None   # noqa: E731
     if init_fn is not None:
       init_fn(w)
     else:
@@ -90,7 +94,8 @@ class Arena(object):
     def state(i, fill):
       if interleave:
         v = self.storage[:, (1 + i) * self.dim:(2 + i) * self.dim]
-        v.fill_(fill)
+        if not plan_only:
+          v.fill_(fill)
         return v
       return torch.full((self.n_rows, self.dim), fill, dtype=torch.float32, device=self.device)
 

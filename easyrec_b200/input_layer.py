@@ -568,6 +568,34 @@ class InputLayer(object):
     outs = E.fused_lookup(call, rows, weights=weights, row_ptr=row_ptr)
     return rows, weights, row_ptr, seg_ids, outs
 
+  def has_group(self, group_name):
+    return group_name in self.group_layout or group_name in self.seq_layout
+
+  def __call__(self, features, group_name, is_combine=True, is_dict=False):
+    """The reference's call form (layers/input_layer.py:245-278; sequence groups: layers/seq_input_layer.py:34-124):
+
+      is_combine=True : (concat [B, sum D] in feature_group config order, [per-feature [B, D] ...][, {feature name: tensor}])
+      is_combine=False: (seq_features [(emb [B, T, D], len [B]) ...], plain concat, plain per-feature list)
+      a seq_att group : {'key', 'hist_seq_emb', 'hist_seq_len'} (SeqInputLayer)
+
+    Every group of one `features` dict comes out of ONE fused lookup per arena: the first call for a batch runs it, the
+    calls for the other groups of the same batch (same dict object) read its outputs."""
+    if not self.has_group(group_name):
+      raise AssertionError('invalid group_name[%s], list: %s' % (group_name, ','.join(
+          list(self.group_layout) + list(self.seq_layout))))
+    if getattr(self, '_last_features', None) is not features:
+      self._last_groups = self.lookup(features)
+      self._last_features = features
+    if group_name in self.seq_layout:
+      return self.seq_outputs[group_name]
+    concat, per_feature = self._last_groups[group_name]
+    if not is_combine:
+      return [], concat, per_feature
+    if is_dict:
+      names = [e[0] for e in self.group_layout[group_name]]
+      return concat, per_feature, dict(zip(names, per_feature))
+    return concat, per_feature
+
   def lookup(self, features):
     """Runs K1 + K2 for every arena; returns {group: (concat, [per-feature views])} and fills
     self.seq_outputs {seq group: {key, hist_seq_emb, hist_seq_len}}."""

@@ -1,7 +1,7 @@
 """Autograd wrappers of the fused interaction kernels (K4 DIN, K5 DCN cross, MMoE, DSSM pieces).
 
-Each Function is one or two calls into liber_b200.so per direction; the matmuls between them are
-library SGEMMs (torch.mm).  Reference code restated by the kernels:
+Each Function is one or two calls into liber_b200.so per direction; the matmuls between them run on the
+library's own tensor-core GEMM (er_gemm).  Reference code restated by the kernels:
   DIN    layers/sequence_feature_layer.py:150-189, model/multi_tower_din.py:62-97
   cross  model/dcn.py:32-45
   MMoE   layers/mmoe.py:53-83
@@ -10,7 +10,56 @@ library SGEMMs (torch.mm).  Reference code restated by the kernels:
 import torch
 
 from easyrec_b200 import _lib
+from easyrec_b200 import kernels as K
 from easyrec_b200.kernels import _p, _stream
+
+
+class _Gram(torch.autograd.Function):
+  """x [B, n, d] -> x x^T [B, n, n] (DLRM / DotInteraction pairwise dot products: model/dlrm.py:52-61,
+  layers/keras/interaction.py:47-128) on the library's own batched small-matrix kernel."""
+
+  @staticmethod
+  def forward(ctx, x):
+    x = _f32(x)
+    B, n, d = x.shape
+    out = torch.empty(B, n, n, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().er_gram_fwd(x.data_ptr(), B, n, d, out.data_ptr(), K._stream()), 'er_gram_fwd')
+    ctx.save_for_backward(x)
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    (x,) = ctx.saved_tensors
+    B, n, d = x.shape
+    g = _f32(g)
+    gx = torch.empty_like(x)
+    _lib.check(_lib.load().er_gram_bwd(x.data_ptr(), g.data_ptr(), B, n, d, gx.data_ptr(), K._stream()), 'er_gram_bwd')
+    return gx
+
+
+def gram(x):
+  return _Gram.apply(x)
+
+
+class _MatmulNT(torch.autograd.Function):
+  """u [B, H] x i [C, H] -> u i^T [B, C] (the in-batch similarity matrix of MatchModel, model/match_model.py:92-97)
+  on the tensor-core GEMM; the transposes are read in place (er_gemm's NT / TN forms)."""
+
+  @staticmethod
+  def forward(ctx, u, i):
+    u, i = K.gemm_ready(_f32(u)), K.gemm_ready(_f32(i))
+    ctx.save_for_backward(u, i)
+    return K.gemm(u, i.t())
+
+  @staticmethod
+  def backward(ctx, g):
+    u, i = ctx.saved_tensors
+    g = K.gemm_ready(_f32(g))
+    return K.gemm(g, i), K.gemm(g.t(), u)
+
+
+def matmul_nt(u, i):
+  return _MatmulNT.apply(u, i)
 
 
 def _f32(t):

@@ -64,7 +64,7 @@ class DSSM(RankModel):
     u, i = self.towers(features)
     self._ui = (u, i)
     temp = self.temperature if self.cosine else 1.0
-    sim = (u @ i.t() if self.listwise else (u * i).sum(dim=1, keepdim=True)) / temp
+    sim = (I.matmul_nt(u, i) if self.listwise else (u * i).sum(dim=1, keepdim=True)) / temp
     if self.scale_simi:
       sim = sim * self.sim_w.abs() + self.sim_b
     self._item_ids = features.get('item_ids')

@@ -449,6 +449,13 @@ int er_inbatch_softmax_ce(const float* sim, const int64_t* item_ids, const float
                           int64_t batch, int32_t n_cols, float inv_wsum, float* loss_rows,
                           float* probs_diag, float* g_sim, er_stream_t stream);
 
+/* ---- DLRM / DotInteraction pairwise dot products (model/dlrm.py:52-61 `einsum('bne,bme->bnm')`,
+ * layers/keras/interaction.py:47-128): out[b,i,j] = x[b,i,:].x[b,j,:] for x [B, n, dim] (contiguous);
+ * gx[b,i,:] = sum_j (g[b,i,j] + g[b,j,i]) * x[b,j,:].  Sequential sums: deterministic. */
+int er_gram_fwd(const float* x, int64_t batch, int32_t n, int32_t dim, float* out, er_stream_t stream);
+int er_gram_bwd(const float* x, const float* g, int64_t batch, int32_t n, int32_t dim, float* gx,
+                er_stream_t stream);
+
 /* ---- CSV input: text lines -> the column arrays of the packed batch (HOST function, HOST pointers) ----
  * Replaces tf.decode_csv + the per-field parsing of the CSV input path (input/csv_input.py:78-175,
  * input/input.py:537-675: ids stay int64 / string ids are fingerprinted, raw values become fp32, Tag /

@@ -239,6 +239,8 @@ def install_interactions(patch):
     diag = p[torch.arange(B), torch.arange(B)]
     w = torch.ones(B) if weights is None else weights
     return -(torch.log(diag + 1e-12) * w).mean() / w.mean(), diag.detach()
+  patch(I, 'gram', lambda x: torch.bmm(x, x.transpose(1, 2)))
+  patch(I, 'matmul_nt', lambda u, i: u @ i.t())
   patch(I, 'din_attention', din_attention)
   patch(I, 'cross_layer', lambda x0, xl, w, b: x0 * (xl * w).sum(1, keepdim=True) + b + xl)
   patch(I, 'mmoe_mix', lambda g, ex: (torch.softmax(g, dim=1)[:, :, None] * ex).sum(1))

@@ -95,7 +95,8 @@ def test_every_reference_sample_config_parses():
                                  'examples/configs/dlrm_backbone_on_criteo.config',
                                  'examples/configs/dlrm_senet_on_criteo.config',
                                  'examples/configs/wide_and_deep_backbone_on_movielens.config'])
-def test_baseline_model_families_build_from_unmodified_reference_configs(rel):
+def test_baseline_model_families_build_from_unmodified_reference_configs(rel, monkeypatch):
+  monkeypatch.setenv('ER_PLAN_ONLY', '1')   # the plan is what is checked: the 10M-row criteo tables are not randomised
   cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, rel))
   il, model, opt = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
   assert sum(p.numel() for p in model.parameters()) > 1000
@@ -387,13 +388,15 @@ def test_non_binary_task_towers_are_refused():
 
 
 @pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
-def test_no_model_or_optimizer_field_is_silently_dropped_for_configs_that_build():
+def test_no_model_or_optimizer_field_is_silently_dropped_for_configs_that_build(monkeypatch):
   """The subset schema skips fields it does not know.  For every reference sample config that BUILDS here, parse it
   with the reference's full schema as well and diff the set fields: anything under model_config, the optimizer, the
   label / input-field declarations that the subset dropped would mean training a different model in silence.
   (Control plane - export, kafka / odps inputs, extra eval metrics - may be dropped.)"""
   full = proto_loader.load_schema(sorted(glob.glob(os.path.join(REF, 'easy_rec/python/protos/*.proto'))),
                                   virtual_name='full_ref2.proto')
+  # (only the plan matters here: the 10M-row tables of the criteo configs are allocated but not randomised)
+  monkeypatch.setenv('ER_PLAN_ONLY', '1')
 
   def walk(msg, prefix, out):
     for fd, v in msg.ListFields():

@@ -144,3 +144,31 @@ def test_kernels_reproduce_the_reference_code_outputs():
     x = torch.tensor(c['x'], device=DEV)                    # [B, F, D]
     got = BB.DotInteraction({'self_interaction': c['self_interaction']})([x[:, i] for i in range(x.shape[1])])
     assert torch.allclose(got, torch.tensor(c['y'], device=DEV), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('B,n,d', [(64, 27, 16), (5, 3, 7), (8192, 27, 16), (130, 40, 32)])
+def test_gram_matches_bmm(B, n, d):
+  """DLRM / DotInteraction pairwise dot products (model/dlrm.py:52-61 einsum 'bne,bme->bnm') and their gradient"""
+  g = torch.Generator(device=DEV).manual_seed(B + n)
+  x = torch.randn(B, n, d, device=DEV, generator=g)
+  gout = torch.randn(B, n, n, device=DEV, generator=g)
+  y0, (gx0,) = _grads(lambda x: torch.einsum('bne,bme->bnm', x, x), [x], gout)
+  y1, (gx1,) = _grads(I.gram, [x], gout)
+  torch.testing.assert_close(y1, y0, **TOL)
+  torch.testing.assert_close(gx1, gx0, rtol=1e-4, atol=1e-4)
+  assert torch.equal(y1, y1.transpose(1, 2))   # same operands, same order of additions: exactly symmetric
+
+
+@pytest.mark.parametrize('B,C,H', [(512, 512, 32), (100, 260, 16), (4096, 4096, 32)])
+def test_in_batch_similarity_matmul_matches_torch(B, C, H):
+  """MatchModel's U I^T (model/match_model.py:92-97) on er_gemm (3xTF32): fp32-level accuracy, both gradients"""
+  torch.backends.cuda.matmul.allow_tf32 = False
+  g = torch.Generator(device=DEV).manual_seed(B)
+  u = torch.randn(B, H, device=DEV, generator=g)
+  i = torch.randn(C, H, device=DEV, generator=g)
+  gout = torch.randn(B, C, device=DEV, generator=g)
+  y0, (gu0, gi0) = _grads(lambda u, i: u.double() @ i.double().t(), [u, i], gout.double())
+  y1, (gu1, gi1) = _grads(I.matmul_nt, [u, i], gout)
+  torch.testing.assert_close(y1.double(), y0, rtol=1e-5, atol=2e-5)
+  torch.testing.assert_close(gu1.double(), gu0.double(), rtol=1e-5, atol=2e-4)
+  torch.testing.assert_close(gi1.double(), gi0.double(), rtol=1e-5, atol=2e-4)

@@ -50,6 +50,15 @@ model_config { model_class: "MultiTowerDIN"
   embedding_regularization: 1e-5 }
 '''
 
+DLRM_CFG = HEAD + FEATS.replace('features { input_names: "price" feature_type: RawFeature embedding_dim: 16 min_val: 0 max_val: 100 }',
+                                'features { input_names: "price" feature_type: RawFeature min_val: 0 max_val: 100 }') + '''
+model_config { model_class: "DLRM"
+  feature_groups { group_name: "sparse" feature_names: ["user_id", "age", "item_id", "cate"] wide_deep: DEEP }
+  feature_groups { group_name: "dense" feature_names: ["price"] wide_deep: DEEP }
+  dlrm { bot_dnn { hidden_units: [32, 16] } top_dnn { hidden_units: [64, 32] } arch_with_dense_feature: true l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
 BACKBONE_DCN_CFG = HEAD + FEATS + '''
 model_config { model_class: "RankModel"
   feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
@@ -168,7 +177,7 @@ def make_batch(seed, n_task=1):
   return feats, lab, (ids, dense, hist, lens)
 
 
-@pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1),
+@pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1), (DLRM_CFG, 1),
                                              (BACKBONE_DCN_CFG, 1), (BACKBONE_DLRM_CFG, 1), (BACKBONE_MTL_CFG, 2),
                                              (BACKBONE_MATCH_CFG, 1), (BACKBONE_WIRING_CFG, 1)])
 def test_models_from_pipeline_config_train(cfg_text, n_task):
