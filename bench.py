@@ -52,6 +52,11 @@ def parse():
   ap.add_argument('--batch', type=int, default=BATCH)
   ap.add_argument('--optimizer', default='adagrad_optimizer',
                   choices=['adagrad_optimizer', 'lazy_adam_optimizer', 'adam_optimizer'])
+  ap.add_argument('--workload', default='deepfm_c2', choices=['deepfm_c2', 'dssm_c4'],
+                  help='deepfm_c2 = the headline metric; dssm_c4 = BASELINE.json configs[3] (row-sharded item table)')
+  ap.add_argument('--parallelism', default='', choices=['', 'dp', 'ep'],
+                  help='N > 1: dp = replicated tables + row all-gather (default for deepfm_c2), ep = row-sharded tables + '
+                       'all-to-all (EmbeddingParallelStrategy; default for dssm_c4)')
   ap.add_argument('--uniform-ids', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -240,6 +245,8 @@ def main():
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
   B = args.batch
   vocab = args.vocab or (100_000_000 if world >= 8 else 10_000_000)
+  par = args.parallelism or ('ep' if args.workload == 'dssm_c4' else 'dp')
+  ep = world > 1 and par == 'ep'
   opt_name = {'adagrad_optimizer': 'adagrad', 'lazy_adam_optimizer': 'lazy_adam', 'adam_optimizer': 'adam'}
   workload = 'deepfm_criteo_c2(26 sparse+13 dense, shared table V=%d x emb16 fp32, batch %d/GPU, %s ids)' % (
       vocab, B, 'uniform' if args.uniform_ids else 'zipf1.05')
@@ -248,7 +255,7 @@ def main():
             'built_from': 'EasyRecEstimator(protobuf-text pipeline config: workloads.c2_config_text)',
             'l2_flush': 'none in the step loop: table+optimizer state %.1f GB >> 126 MB L2, ids rotate over 16 distinct '
                         'batches; the per-kernel roofline timings flush L2 (256 MB write) before every launch'
-            % ((vocab + 13) * 17 * 4 * 2 / 1e9), 'parallelism': 'dp%d' % world}
+            % ((vocab + 13) * 17 * 4 * 2 / 1e9), 'parallelism': '%s%d' % ('ep' if ep else 'dp', world)}
 
   if args.impl == 'reference':
     if rank != 0:
@@ -281,7 +288,7 @@ def main():
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device(dev))
   lib = _lib.load()
-  graph = not args.no_graph
+  graph = not args.no_graph and not ep   # the sharded exchange sizes its all-to-alls per batch on the host: eager
 
   def barrier():
     if world > 1:
@@ -297,7 +304,11 @@ def main():
 
   def build(optimizer, v=vocab, input_type='CSVInput'):
     text = workloads.c2_config_text(v, B, optimizer=optimizer, lr=0.01, input_type=input_type)
-    return EasyRecEstimator(text, device=dev, seed=20240, use_cuda_graph=graph, world_size=world)
+    return EasyRecEstimator(text, device=dev, seed=20240, use_cuda_graph=graph, world_size=world, rank=rank,
+                            embedding_parallel=ep)
+
+  if args.workload == 'dssm_c4':
+    return run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks)
 
   n_rot = 16
   host = [workloads.criteo_batch(B, 20240 + rank * 1000 + i, uniform=args.uniform_ids) for i in range(n_rot)]
@@ -373,6 +384,17 @@ def main():
       os._exit(0)
     return 0
 
+  replicas_identical = None
+  if world > 1:
+    # every replica must hold the same dense parameters (and, under dp, the same tables) after the timed steps
+    chk = [est.trainer.dense_opt.flat_p.double().sum()]
+    if not ep:
+      chk += [a.weight.double().sum() for a in il.arenas.values()]
+    chk = torch.stack(chk)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    replicas_identical = bool(torch.equal(lo, hi))
   if rank != 0:
     return leave()
 
@@ -428,7 +450,7 @@ def main():
                             default_seq_len=T3)
     b3 = []
     for i in range(8):
-      f, l = workloads.c3_batch(B3, T3, 777 + i)
+      f, l = workloads.c3_batch(B3, T3, 777 + i, 1_000_000)
       b3.append(({'sparse_fea': f['sparse_fea'].to(dev), 'dense_fea': f['dense_fea'].to(dev),
                   'seq_fea': {k: (a.to(dev), b.to(dev)) for k, (a, b) in f['seq_fea'].items()}}, l.to(dev)))
     for i in range(o_warm + 3):
@@ -463,10 +485,88 @@ def main():
           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
           'clocks': clocks, 'e2e': e2e,
           'gpu_launches': int(per_step_launches * args.steps), 'gpu_launches_per_step': int(per_step_launches),
-          'cuda_graph': graph, 'roofline': roofline, 'cpu_baseline': cpu, 'optimizers': opt_lines, 'lines': lines,
+          'cuda_graph': graph, 'replicas_identical': replicas_identical, 'roofline': roofline, 'cpu_baseline': cpu, 'optimizers': opt_lines, 'lines': lines,
           'final_loss': final_loss}
   print(json.dumps(line))
   return leave()
+
+
+def run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks):
+  """BASELINE.json configs[3]: DSSM two towers, in-batch negatives, the item table row-sharded over the ranks
+  (EmbeddingParallelStrategy: ids bucketed per owner, three all-to-alls per step, owner-side fused row update)."""
+  import torch
+  from easyrec_b200 import _lib, workloads
+  from easyrec_b200.estimator import EasyRecEstimator
+  B = args.batch if args.batch != BATCH else 4096
+  item_vocab = args.vocab or {1: 25_000_000, 2: 50_000_000, 4: 100_000_000}.get(world, 200_000_000)
+  est = EasyRecEstimator(workloads.c4_config_text(B, item_vocab, embedding_parallel=ep), device=dev, seed=20240,
+                         use_cuda_graph=graph, world_size=world, rank=rank, embedding_parallel=ep)
+  n_rot = 16
+  pinned = []
+  for i in range(n_rot):
+    f, l = workloads.c4_batch(B, 4040 + rank * 1000 + i)
+    pinned.append(({k: v.pin_memory() for k, v in f.items()}, l.pin_memory()))
+  devb = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in pinned]
+  W = max(args.warmup, 3)
+  steps = args.steps
+  sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0)))
+  if rank == 0:
+    sampler.start()
+  for i in range(W):
+    est.trainer.train_step(*devb[i % n_rot])
+  barrier()
+  sampler.mark()
+  lib = _lib.load()
+  n0 = lib.er_launch_count()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  for i in range(steps):
+    loss, _ = est.trainer.train_step(*devb[i % n_rot])
+  ev1.record()
+  barrier()
+  ms = max_over_ranks(ev0.elapsed_time(ev1))
+  launches = int(lib.er_launch_count() - n0)
+  if getattr(est.trainer, 'launches_per_step', None):
+    launches = int(est.trainer.launches_per_step) * steps
+
+  def input_fn():
+    def gen():
+      i = 0
+      while True:
+        yield pinned[i % n_rot]
+        i += 1
+    return gen()
+  est.train(input_fn, steps=3, fetch_loss_every_step=True)
+  barrier()
+  ev0.record()
+  est.train(input_fn, steps=steps, fetch_loss_every_step=True)
+  ev1.record()
+  barrier()
+  e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+  clocks = sampler.finish() if rank == 0 else None
+  if rank == 0:
+    h2d = sum(v.numel() * v.element_size() for v in pinned[0][0].values()) + pinned[0][1].numel() * 4
+    print(json.dumps({
+        'metric': 'samples/sec DSSM two-tower in-batch negatives (BASELINE.json configs[3])',
+        'value': world * B * steps / (ms / 1000.0), 'unit': 'samples/s', 'n_gpus': world, 'steps': steps, 'warmup': W,
+        'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'dssm_c4(user tower 5 ids, item tower 3 ids + price, towers [256,128,64,32], cosine, in-batch '
+                               'softmax; item table %d rows x emb16, batch %d/GPU, zipf1.05 ids)' % (item_vocab, B),
+                   'built_from': 'EasyRecEstimator(protobuf-text pipeline config: workloads.c4_config_text)',
+                   'parallelism': '%s%d' % ('ep' if ep else 'dp', world),
+                   'l2_flush': 'none: tables >> L2 and ids rotate over 16 distinct batches'},
+        'clocks': clocks,
+        'e2e': {'value': world * B * steps / (e2e_ms / 1000.0), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / steps,
+                'through': 'EasyRecEstimator.train(input_fn), loss read back every step'},
+        'gpu_launches': launches, 'gpu_launches_per_step': launches // steps, 'cuda_graph': bool(graph),
+        'roofline': None, 'cpu_baseline': None, 'final_loss': float(loss)}))
+  if world > 1:
+    barrier()
+    sys.stdout.flush()
+    os._exit(0)
+  return 0
 
 
 def measure_roofline(args, est, devb, B, dev):

@@ -133,9 +133,14 @@ def c3_config_text(batch_size=4096, item_vocab=1_000_000, seq_len=50, optimizer=
   return text.encode()
 
 
-def c3_batch(batch_size, seq_len, seed, zipf_alpha=1.05):
+def c3_batch(batch_size, seq_len, seed, vocab, cate_buckets=10000, zipf_alpha=1.05):
   """host batch in c3_config_text's InputLayer form: ids feature-major (user_id, age, item_id, cate_id), price,
-  histories padded to seq_len with lengths ~ U[1, seq_len], label Bernoulli(0.25)."""
+  histories padded to seq_len with lengths ~ U[1, seq_len], label Bernoulli(0.25).
+
+  The two histories are STRING fields with a hash_bucket_size in the config, so - like the file readers
+  (input/readers.py) - the batch carries them host-hashed: Fingerprint64(decimal text) % buckets, the same
+  rule the device applies to the INT64 id fields."""
+  from .input.readers import fingerprint_i64
   rng = np.random.default_rng(seed)
   B = batch_size
 
@@ -144,8 +149,11 @@ def c3_batch(batch_size, seq_len, seed, zipf_alpha=1.05):
   ids = np.concatenate([z(B), rng.integers(0, 100, B), z(B), z(B) % 100000]).astype(np.int64)
   dense = rng.uniform(0, 1, (B, 1)).astype(np.float32)
   lens = rng.integers(1, seq_len + 1, B).astype(np.int32)
-  seq = {'hist_items': (torch.from_numpy(z(B * seq_len).reshape(B, seq_len)), torch.from_numpy(lens)),
-         'hist_cates': (torch.from_numpy((z(B * seq_len) % 100000).reshape(B, seq_len)), torch.from_numpy(lens.copy()))}
+
+  def hashed(raw, buckets):
+    return (fingerprint_i64(raw) % np.uint64(buckets)).astype(np.int64).reshape(B, seq_len)
+  seq = {'hist_items': (torch.from_numpy(hashed(z(B * seq_len), vocab)), torch.from_numpy(lens)),
+         'hist_cates': (torch.from_numpy(hashed(z(B * seq_len) % 100000, cate_buckets)), torch.from_numpy(lens.copy()))}
   labels = (rng.uniform(size=B) < 0.25).astype(np.float32)
   return {'sparse_fea': torch.from_numpy(ids), 'dense_fea': torch.from_numpy(dense), 'seq_fea': seq}, torch.from_numpy(labels)
 
@@ -175,3 +183,55 @@ def write_c2_files(prefix, n_batches, batch_size, seed=20240, uniform=False):
     tab['c%d' % (j + 1)] = ids[:, j].astype(np.int64)
   pq.write_table(pa.table(tab), prefix + '.parquet', row_group_size=batch_size)
   return prefix + '.tsv', prefix + '.parquet'
+
+
+def c4_config_text(batch_size=4096, item_vocab=200_000_000, user_vocab=10_000_000, emb_dim=16, lr=0.01,
+                   embedding_parallel=True):
+  """C4 of BASELINE.json as a pipeline config: DSSM two towers (samples/model_config/dssm_on_taobao.config's shape:
+  user side = user id + 4 profile ids, item side = item id + category + brand + price), cosine similarity with
+  in-batch negatives (loss_type SOFTMAX_CROSS_ENTROPY, model/dssm.py + match_model.py:95-165), the item table
+  row-sharded (train_distribute: EmbeddingParallelStrategy)."""
+  return ('''
+train_config { log_step_count_steps: 1000000 %s
+  optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: %g } } } } }
+data_config { batch_size: %d input_type: DummyInput label_fields: "clk"
+  input_fields { input_name: "clk" input_type: FLOAT } input_fields { input_name: "user_id" input_type: INT64 }
+  input_fields { input_name: "age" input_type: INT64 } input_fields { input_name: "gender" input_type: INT64 }
+  input_fields { input_name: "city" input_type: INT64 } input_fields { input_name: "level" input_type: INT64 }
+  input_fields { input_name: "item_id" input_type: INT64 } input_fields { input_name: "cate_id" input_type: INT64 }
+  input_fields { input_name: "brand" input_type: INT64 } input_fields { input_name: "price" input_type: FLOAT } }
+feature_config {
+  features { input_names: "user_id" feature_type: IdFeature embedding_dim: %d hash_bucket_size: %d }
+  features { input_names: "age" feature_type: IdFeature embedding_dim: %d num_buckets: 100 }
+  features { input_names: "gender" feature_type: IdFeature embedding_dim: %d num_buckets: 3 }
+  features { input_names: "city" feature_type: IdFeature embedding_dim: %d hash_bucket_size: 10000 }
+  features { input_names: "level" feature_type: IdFeature embedding_dim: %d num_buckets: 10 }
+  features { input_names: "item_id" feature_type: IdFeature embedding_dim: %d hash_bucket_size: %d }
+  features { input_names: "cate_id" feature_type: IdFeature embedding_dim: %d hash_bucket_size: 10000 }
+  features { input_names: "brand" feature_type: IdFeature embedding_dim: %d hash_bucket_size: 1000000 }
+  features { input_names: "price" feature_type: RawFeature embedding_dim: %d min_val: 0.0 max_val: 1.0 } }
+model_config { model_class: "DSSM"
+  feature_groups { group_name: "user" feature_names: ["user_id", "age", "gender", "city", "level"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate_id", "brand", "price"] wide_deep: DEEP }
+  dssm { user_tower { id: "user_id" dnn { hidden_units: [256, 128, 64, 32] } }
+         item_tower { id: "item_id" dnn { hidden_units: [256, 128, 64, 32] } }
+         simi_func: COSINE temperature: 0.05 scale_simi: true l2_regularization: 1e-6 }
+  loss_type: SOFTMAX_CROSS_ENTROPY embedding_regularization: 5e-5 }
+''' % ('train_distribute: EmbeddingParallelStrategy' if embedding_parallel else '', lr, batch_size,
+       emb_dim, user_vocab, emb_dim, emb_dim, emb_dim, emb_dim, emb_dim, item_vocab, emb_dim, emb_dim, emb_dim)).encode()
+
+
+def c4_batch(batch_size, seed, zipf_alpha=1.05):
+  """host batch in c4_config_text's InputLayer form: ids feature-major (user_id, age, gender, city, level, item_id,
+  cate_id, brand), price; the label column is ignored by the in-batch softmax (every row is its own positive)."""
+  rng = np.random.default_rng(seed)
+  B = batch_size
+
+  def z(n):
+    return (rng.zipf(zipf_alpha, n).astype(np.int64) - 1) % (2**40)
+  item = z(B)
+  ids = np.concatenate([z(B), rng.integers(0, 100, B), rng.integers(0, 3, B), z(B) % 100000, rng.integers(0, 10, B),
+                        item, z(B) % 100000, z(B) % 10_000_000]).astype(np.int64)
+  dense = rng.uniform(0, 1, (B, 1)).astype(np.float32)
+  return {'sparse_fea': torch.from_numpy(ids), 'dense_fea': torch.from_numpy(dense),
+          'item_ids': torch.from_numpy(item.copy())}, torch.ones(B, dtype=torch.float32)

@@ -1,4 +1,6 @@
-"""GPU: end-to-end DeepFM parity against the CPU oracle on identical inputs and identical initial weights.
+"""GPU: end-to-end DeepFM parity against the CPU oracle on identical inputs and identical initial weights - at a small
+shape for ten steps, and at the real BASELINE.json config-2 shape (batch 8192, 26 + 13 features over a shared
+10M-row table, towers [256, 128, 64]) built from the pipeline-config text through EasyRecEstimator.
 
 BASELINE.md parity gates: bucket ids bit-exact; pooled embeddings <= 1e-6 abs; logits and loss <= 1e-4 abs
 (fp32); post-step touched rows <= 1e-6 abs after 1 and after 10 steps.
@@ -13,7 +15,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
-B, V, F, D = 512, 100003, 39, 16
+F, D = 39, 16
 LR, L2, EMB_REG = 0.01, 1e-5, 1e-5
 
 
@@ -33,7 +35,7 @@ def _oracle_params(model):
           'out_b': model.output.bias.detach().cpu().numpy().copy()}
 
 
-def _oracle_inputs(ids, dense):
+def _oracle_inputs(ids, dense, B, V):
   rows_id, _ = O.bucketize(ids, 0, V, 13)
   rows = np.concatenate([np.repeat(np.arange(13, dtype=np.int64), B), rows_id])
   mn = np.array(workloads.CRITEO_MIN, np.float32)
@@ -43,8 +45,8 @@ def _oracle_inputs(ids, dense):
   return rows, w
 
 
-def _oracle_step(st, ids, dense, labels):
-  rows, w = _oracle_inputs(ids, dense)
+def _oracle_step(st, ids, dense, labels, B, V):
+  rows, w = _oracle_inputs(ids, dense, B, V)
   rp = np.arange(F * B + 1, dtype=np.int32)
   deep_seg, _ = O.embedding_fwd(st['t16'], rows, rp, 0, weights=w)
   wide_seg, _ = O.embedding_fwd(st['t1'], rows, rp, 0, weights=w)
@@ -82,15 +84,44 @@ def _oracle_step(st, ids, dense, labels):
   return logits, ce + reg, deep
 
 
-def test_deepfm_logits_loss_and_ten_training_steps_match_oracle():
+def _resync_oracle(st, il, model, tr):
+  """Teacher forcing: load the device state (tables, accumulators, dense parameters and their adagrad accumulators)
+  into the oracle, so the NEXT step's logits / loss are compared on identical weights."""
+  a16, a1 = il.arenas[16], il.arenas[1]
+  st['t16'], st['a16'] = a16.weight.cpu().numpy().copy(), a16.state0.cpu().numpy().copy()
+  st['t1'], st['a1'] = a1.weight.cpu().numpy().copy(), a1.state0.cpu().numpy().copy()
+  st['params'] = _oracle_params(model)
+  opt = tr.dense_opt
+  s0 = opt.s0.cpu().numpy()
+  acc_of = {id(p): s0[off:off + n].reshape(tuple(p.shape)).copy() for p, (_, off, n) in zip(opt.params, opt.named_ranges())}
+  for tag, dnn in (('dnn', model.dnn), ('final', model.final_dnn)):
+    for i, lay in enumerate(dnn.layers):
+      st['acc'][(tag, i, 'W')] = acc_of[id(lay.kernel)]
+      st['acc'][(tag, i, 'gamma')] = acc_of[id(lay.gamma)]
+      st['acc'][(tag, i, 'beta')] = acc_of[id(lay.beta)]
+  st['acc']['oW'] = acc_of[id(model.output.kernel)]
+  st['acc']['ob'] = acc_of[id(model.output.bias)]
+
+
+@pytest.mark.parametrize('B,V,dnn,final,steps,via_config', [
+    (512, 100003, (64, 32), (32, 16), 10, False),
+    # BASELINE.json config 2 at its real shape, built the way a user builds it: EasyRecEstimator(pipeline config text)
+    (8192, 10_000_000, (256, 128, 64), (256, 128, 64), 3, True)])
+def test_deepfm_logits_loss_and_training_steps_match_oracle(B, V, dnn, final, steps, via_config):
   torch.backends.cuda.matmul.allow_tf32 = False
-  il, model = workloads.build_deepfm_criteo(B, V, DEV, dnn=(64, 32), final=(32, 16), l2_reg=L2, emb_reg=EMB_REG)
-  tr = Trainer(model, il, 'adagrad', lr=LR)
+  if via_config:
+    from easyrec_b200.estimator import EasyRecEstimator
+    est = EasyRecEstimator(workloads.c2_config_text(V, B, lr=LR, dnn=dnn, final=final), device=DEV, seed=20240)
+    il, model, tr = est.input_layer, est.model, est.trainer
+    assert type(model).__name__ == 'DeepFM' and il.arenas[16].n_rows == V + 13
+  else:
+    il, model = workloads.build_deepfm_criteo(B, V, DEV, dnn=dnn, final=final, l2_reg=L2, emb_reg=EMB_REG)
+    tr = Trainer(model, il, 'adagrad', lr=LR)
   a16, a1 = il.arenas[16], il.arenas[1]
   st = {'t16': a16.weight.cpu().numpy().copy(), 'a16': a16.state0.cpu().numpy().copy(),
         't1': a1.weight.cpu().numpy().copy(), 'a1': a1.state0.cpu().numpy().copy(),
         'params': _oracle_params(model), 'acc': {}}
-  for step in range(10):
+  for step in range(steps):
     ids, dense, labels = workloads.criteo_batch(B, 50 + step)
     feats = {'sparse_fea': torch.from_numpy(ids).to(DEV), 'dense_fea': torch.from_numpy(dense).to(DEV)}
     lab = torch.from_numpy(labels).to(DEV)
@@ -100,12 +131,12 @@ def test_deepfm_logits_loss_and_ten_training_steps_match_oracle():
       cids, w = il._gather_inputs(16, feats['sparse_fea'], dn)
       from easyrec_b200 import kernels as K
       rows = K.bucketize(cids, call.slots_dev, call.n_slots, call.n_seg).cpu().numpy()
-      want_rows, want_w = _oracle_inputs(ids, dense)
+      want_rows, want_w = _oracle_inputs(ids, dense, B, V)
       assert np.array_equal(rows, want_rows)
       np.testing.assert_allclose(w.cpu().numpy(), want_w, rtol=0, atol=1e-7)
     # forward of THIS step on the pre-step weights: logits/loss from train_step are pre-update
     loss, probs = tr.train_step(feats, lab)
-    o_logits, o_loss, o_deep = _oracle_step(st, ids, dense, labels)
+    o_logits, o_loss, o_deep = _oracle_step(st, ids, dense, labels, B, V)
     got_probs = probs.detach().cpu().numpy()
     want_probs = 1.0 / (1.0 + np.exp(-o_logits.astype(np.float64)))
     # logits within 1e-4  <=>  probabilities within 2.5e-5 (|d sigmoid| <= 1/4)
@@ -113,13 +144,13 @@ def test_deepfm_logits_loss_and_ten_training_steps_match_oracle():
     assert np.abs(got_logits - o_logits).max() < 1e-4, (step, np.abs(got_logits - o_logits).max())
     assert np.abs(got_probs - want_probs).max() < 2.5e-5
     assert abs(float(loss) - o_loss) < 1e-4, (step, float(loss), o_loss)
-    if step in (0, 9):
+    if step in (0, steps - 1):
       # End to end the upstream gradients themselves carry fp32 noise (batch-norm reductions over the batch
       # in a different order) and ReLU masks can flip for pre-activations within that noise, which changes one
       # sample's gradient discretely.  So: the bulk of the touched rows must agree to 1e-5, and no row may be
       # off by more than one full adagrad step of a unit gradient.  (With IDENTICAL upstream gradients the
       # post-step rows agree to 1e-6: tests/test_gpu_sparse.py::test_bwd_ten_steps_adagrad_tracks_oracle.)
-      touched = np.unique(_oracle_inputs(ids, dense)[0])
+      touched = np.unique(_oracle_inputs(ids, dense, B, V)[0])
       for got, want in ((a16.weight.cpu().numpy()[touched], st['t16'][touched]),
                         (a1.weight.cpu().numpy()[touched], st['t1'][touched]),
                         (a16.state0.cpu().numpy()[touched], st['a16'][touched])):
@@ -127,6 +158,14 @@ def test_deepfm_logits_loss_and_ten_training_steps_match_oracle():
         assert np.median(d) < 1e-6, np.median(d)
         assert (d > 1e-5).mean() < 0.02, (d > 1e-5).mean()
         assert d.max() < 5e-3, d.max()
+    if via_config and step + 1 < steps:
+      # At this shape (2M activations per 256-wide layer, six batch-normed layers) two fp32 evaluations of the SAME
+      # step already disagree after one update: the oracle against itself with the batch permuted gives rows off by
+      # 5e-5 after a step and logits off by 5e-3 one step later (tools/fp32_order_sensitivity.py,
+      # output recorded in its header) - a ReLU mask flipping on a pre-activation within an ulp of
+      # zero, amplified by the batch-norm chain.  So the multi-step gate here is per step on identical weights:
+      # forward within 1e-4, update by the row statistics above, then the oracle restarts from the device state.
+      _resync_oracle(st, il, model, tr)
   d = np.abs(a16.weight.cpu().numpy() - st['t16'])
   assert (d > 2e-5).mean() < 0.001 and d.max() < 5e-3
   # dense weights after ten adagrad steps

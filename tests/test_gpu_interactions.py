@@ -170,5 +170,6 @@ def test_in_batch_similarity_matmul_matches_torch(B, C, H):
   y0, (gu0, gi0) = _grads(lambda u, i: u.double() @ i.double().t(), [u, i], gout.double())
   y1, (gu1, gi1) = _grads(I.matmul_nt, [u, i], gout)
   torch.testing.assert_close(y1.double(), y0, rtol=1e-5, atol=2e-5)
-  torch.testing.assert_close(gu1.double(), gu0.double(), rtol=1e-5, atol=2e-4)
-  torch.testing.assert_close(gi1.double(), gi0.double(), rtol=1e-5, atol=2e-4)
+  # K = C (or B) products of N(0,1) pairs, |result| ~ sqrt(K): 3xTF32 with fp32 accumulation, <= ~1e-5 of that scale
+  torch.testing.assert_close(gu1.double(), gu0.double(), rtol=1e-5, atol=1e-5 * C ** 0.5 + 2e-4)
+  torch.testing.assert_close(gi1.double(), gi0.double(), rtol=1e-5, atol=1e-5 * B ** 0.5 + 2e-4)
