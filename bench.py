@@ -288,7 +288,7 @@ def main():
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device(dev))
   lib = _lib.load()
-  graph = not args.no_graph and not ep   # the sharded exchange sizes its all-to-alls per batch on the host: eager
+  graph = not args.no_graph
 
   def barrier():
     if world > 1:
@@ -384,6 +384,7 @@ def main():
       os._exit(0)
     return 0
 
+  il.check_exchange()   # row-sharded runs: no per-peer block of the exchange overflowed during the timed steps
   replicas_identical = None
   if world > 1:
     # every replica must hold the same dense parameters (and, under dp, the same tables) after the timed steps
@@ -543,6 +544,7 @@ def run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks):
   ev1.record()
   barrier()
   e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+  est.input_layer.check_exchange()
   clocks = sampler.finish() if rank == 0 else None
   if rank == 0:
     h2d = sum(v.numel() * v.element_size() for v in pinned[0][0].values()) + pinned[0][1].numel() * 4

@@ -70,6 +70,8 @@ SIGNATURES = {
                                  c_vp]),
     'er_bucketize': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32,
                              c_vp, c_vp, c_vp]),
+    'er_shard_group_workspace_bytes': (c_sz, [c_i64]),
+    'er_shard_group': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'er_fingerprint64_host': (ctypes.c_uint64, [ctypes.c_char_p, c_sz]),
     'er_csv_parse': (c_i32, [c_vp, c_sz, ctypes.c_char, ctypes.POINTER(ErCsvCol), c_i32, c_i64, c_i32,
                              ctypes.POINTER(c_i64), ctypes.POINTER(c_sz)]),

@@ -387,6 +387,14 @@ class InputLayer(object):
       cur.wait_stream(self._side)
     self._pending = []
 
+  def check_exchange(self):
+    """EmbeddingParallel: raise if a per-peer block of the fixed-capacity exchange overflowed since the last check
+    (reads one counter per arena back: call it outside the step loop, e.g. when the loss is logged)."""
+    if self.ep:
+      for subs in self.subcalls.values():
+        for sc in subs.values():
+          sc.sharded.check()
+
   def _rows_buf(self, key, call):
     """persistent output buffer of K1 per row plan (stable address: CUDA graphs, early exchange)."""
     buf = self._rows_bufs.get(key)
@@ -505,9 +513,14 @@ class InputLayer(object):
                       int(r['bucket_mode']), int(r['shard_n'])) for r in call.slots_np), tuple(call.sources))
         sc.rows_key = key
       if self.ep:
-        cids, w = self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
+        # arenas with the same row plan (the wide dim-1 tables next to the deep ones) share K1, the grouping and the
+        # id all-to-all of the first one; only their rows travel separately
+        hit = self._rows_cache.get(key)
+        cids, w = (None, hit[1]) if hit is not None else self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
         outs = call.alloc_outputs()
-        rows = sc.sharded.forward(cids, w, outs)
+        rows = sc.sharded.forward(cids, w, outs, group_from=hit[2] if hit is not None else None)
+        if hit is None:
+          self._rows_cache[key] = (rows, w, sc.sharded)
         for o in outs:
           o.requires_grad_(True)
         return rows, w, None, None, outs

@@ -100,6 +100,22 @@ def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=N
   return rows
 
 
+def shard_group_workspace(n_lookups, device):
+  return torch.empty(_lib.load().er_shard_group_workspace_bytes(int(n_lookups)), dtype=torch.uint8, device=device)
+
+
+def shard_group(rows, owner, world, cap_per_peer, send_rows, pos, counts, ws):
+  """K8 (er_shard_group): distinct (owner, row) pairs into fixed-capacity per-owner blocks; see include/er_b200.h."""
+  _chk(rows, torch.int64, 'rows')
+  _chk(owner, torch.int32, 'owner')
+  _chk(send_rows, torch.int64, 'send_rows')
+  _chk(pos, torch.int64, 'pos')
+  _chk(counts, torch.int32, 'counts')
+  assert send_rows.numel() == world * cap_per_peer and pos.numel() == rows.numel() and counts.numel() == world + 1
+  _lib.check(_lib.load().er_shard_group(_p(rows), _p(owner), rows.numel(), int(world), int(cap_per_peer), _p(send_rows),
+                                        _p(pos), _p(counts), _p(ws), ws.numel(), _stream()), 'er_shard_group')
+
+
 def embedding_fwd(table, dim, rows, slots_dev, n_slots, n_seg, out_bufs, weights=None,
                   row_ptr=None, seg_scale=None, row_stride=None):
   lib = _lib.load()

@@ -14,6 +14,9 @@ Shard rule (bit-exact with the reference): owner = row mod N, local row = row di
 Split sizes are data dependent, so (like Horovod's alltoall) the counts are exchanged first and read
 on the host; this path is therefore not CUDA-graph captured.  Single-valued slots only.
 """
+import os
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -130,100 +133,102 @@ class ShardedLookup(object):
   (Arena.shard_n > 1): what InputLayer runs instead of K1 + K2 when the pipeline asks for
   `train_distribute: EmbeddingParallelStrategy` (compat/feature_column/feature_column.py:248-357, 416-625).
 
-    forward : K1 (owner = row mod N, local row = row div N) -> unique (row, owner) pairs (the reference dedups before
-              it sends, feature_column.py:263) -> all_to_all(ids) -> K2 gather on the owner -> all_to_all(rows) ->
-              K2 again, pooling the received rows into the call's own output matrices (config-order concat)
-    backward: per-unique-id gradient rows (summed over the local duplicates on the requester, in lookup order) ->
-              all_to_all to the owners -> K7 on each owner, gradient scale 1/N (compat/optimizers.py:315-316)
+    forward : K1 (owner = row mod N, local row = row div N) -> K8 er_shard_group: distinct (owner, row) pairs in
+              fixed-capacity per-owner blocks (the reference dedups before it sends too, feature_column.py:263) ->
+              all_to_all(ids) -> K2 gather on the owner -> all_to_all(rows) -> K2 again, pooling the received rows
+              into the call's own output matrices (config-order concat)
+    backward: K7 with the plain SGD rule (lr = -1) sums the local duplicates of every position into the send buffer,
+              in lookup order -> all_to_all to the owners -> K7 on each owner (one contribution per source rank, summed
+              in rank order), gradient scale 1/N (compat/optimizers.py:315-316)
 
-  Split sizes are data dependent: counts are exchanged first and read on the host (what hvd.alltoall does), so this
-  path is not CUDA-graph captured.  Single-valued slots (the packed sparse_fea / raw projections)."""
+  Every buffer and every split size is fixed when the plan is built (`cap` ids per peer, -1 padded: a padded id
+  gathers a zero row and its gradient slot is dropped by K7), so nothing is read back on the host and the exchange
+  is captured in the step's CUDA graph with the rest.  A block that overflows loses lookups: counted on the device
+  (`overflow`), raised by check().  Single-valued slots (the packed sparse_fea / raw projections)."""
 
-  def __init__(self, call, world, rank):
+  def __init__(self, call, world, rank, slack=None):
     a = call.arena
     assert a.shard_n == world and a.shard_rank == rank
     self.call, self.world, self.rank = call, world, rank
     dev, D = a.device, a.dim
-    self.L = call.n_seg
+    self.L = L = call.n_seg
+    slack = float(os.environ.get('ER_EP_SLACK', '1.25')) if slack is None else slack
+    self.cap = cap = min(L, (int(np.ceil(slack * L / world)) + 256 + 255) // 256 * 256)
+    self.n_ex = n_ex = world * cap
     recs = []
-    for r in call.slots_np:   # pools the RECEIVED rows (a [U, dim] "table" indexed by position) into the call's layout
-      recs.append(dict(num_buckets=self.L, row_offset=0, seg_begin=int(r['seg_begin']), n_seg=int(r['n_seg']),
-                       bucket_mode=_lib.BUCKET_NONE, combiner=int(r['combiner']) & 0xf, out_buf=int(r['out_buf']),
+    for r in call.slots_np:   # pools the RECEIVED rows (a [N*cap, dim] "table" indexed by position) into the call's layout
+      recs.append(dict(num_buckets=n_ex, row_offset=0, seg_begin=int(r['seg_begin']), n_seg=int(r['n_seg']),
+                       bucket_mode=_lib.BUCKET_NONE, combiner=int(r['combiner']), out_buf=int(r['out_buf']),
                        out_stride=int(r['out_stride']), out_col=int(r['out_col']), shard_n=1))
     self.pool_slots_np = K.make_slots(recs)
     self.pool_slots = K.slots_to_device(self.pool_slots_np, dev)
-    self.cap = max(4 * self.L, 1024)
-    own = [dict(num_buckets=a.n_rows, row_offset=0, seg_begin=0, n_seg=self.cap, bucket_mode=_lib.BUCKET_NONE,
-                combiner=_lib.COMBINER_SUM, out_buf=0, out_stride=D, out_col=0, shard_n=1)]
+    own = [dict(num_buckets=a.n_rows, row_offset=0, seg_begin=0, n_seg=n_ex, bucket_mode=_lib.BUCKET_NONE,
+                combiner=_lib.COMBINER_SUM | _lib.COMBINER_UNIT_WEIGHTS, out_buf=0, out_stride=D, out_col=0, shard_n=1)]
     self.owner_slots = K.slots_to_device(K.make_slots(own), dev)
-    self.owner_ws = K.bwd_workspace(self.cap, dev, D)
-    self.pool_ws = K.bwd_workspace(self.L, dev, D)
-    self._ctx = None
+    self.owner_ws = K.bwd_workspace(n_ex, dev, D)
+    self.pool_ws = K.bwd_workspace(L, dev, D)
+    f32, i64 = torch.float32, torch.int64
+    self.owner = torch.empty(L, dtype=torch.int32, device=dev)
+    self.rows_local = torch.empty(L, dtype=i64, device=dev)
+    self.send_rows = torch.empty(n_ex, dtype=i64, device=dev)
+    self.recv_rows = torch.empty(n_ex, dtype=i64, device=dev)
+    self.pos = torch.empty(L, dtype=i64, device=dev)
+    self.counts = torch.zeros(world + 1, dtype=torch.int32, device=dev)
+    self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    self.group_ws = K.shard_group_workspace(L, dev)
+    self.send_emb = torch.empty(n_ex, D, dtype=f32, device=dev)
+    self.recv_emb = torch.empty(n_ex, D, dtype=f32, device=dev)
+    self.send_g = torch.empty(n_ex, D, dtype=f32, device=dev)
+    self.recv_g = torch.empty(n_ex, D, dtype=f32, device=dev)
+    self.sum_opt = K.make_opt(_lib.OPT_SGD, -1.0)   # w - (-1) * sum(g) on a zeroed buffer = the summed gradient
+    self._grouped = None   # the ShardedLookup whose pos / recv_rows this step's exchange uses (self or a sharer)
+    self._weights = None
 
-  def forward(self, ids, weights, outs):
-    """ids int64 [L] in the call's slot order; writes the pooled rows into `outs` (the call's output matrices)."""
+  def forward(self, ids, weights, outs, group_from=None):
+    """ids int64 [L] in the call's slot order; writes the pooled rows into `outs` (the call's output matrices).
+    group_from: another ShardedLookup of the SAME row plan that already ran forward() this step (the wide dim-1 arena
+    next to the deep one): its positions and received ids are reused, only the rows travel."""
     call, N, D = self.call, self.world, self.call.arena.dim
-    dev = ids.device
-    owner = torch.empty(self.L, dtype=torch.int32, device=dev)
-    rows_local = K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, owner=owner)
-    # unique (owner, local row) pairs, grouped by owner: key = owner * n_local_rows + local row
-    n_loc = call.arena.n_rows
-    key = torch.where(owner < 0, torch.full_like(rows_local, -1), owner.to(torch.int64) * n_loc + rows_local)
-    uniq, inverse = torch.unique(key, sorted=True, return_inverse=True)
-    if uniq.numel() and int(uniq[0]) < 0:     # the dropped lookups (-1) sort first: no position
-      uniq = uniq[1:]
-      inverse = inverse - 1
-    u_owner = torch.div(uniq, n_loc, rounding_mode='floor')
-    send_rows = (uniq - u_owner * n_loc).contiguous()
-    send_counts = torch.bincount(u_owner, minlength=N)
-    recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts)
-    sc, rc = send_counts.tolist(), recv_counts.tolist()   # host sync, as hvd.alltoall does
-    n_send, n_recv = sum(sc), sum(rc)
-    if n_recv > self.cap:
-      raise _lib.ErError('received %d ids > capacity %d of the owner-side plan' % (n_recv, self.cap))
-    recv_rows = torch.empty(n_recv, dtype=torch.int64, device=dev)
-    dist.all_to_all_single(recv_rows, send_rows, rc, sc)
-    send_emb = torch.empty(max(n_recv, 1), D, dtype=torch.float32, device=dev)
-    if n_recv:
-      K.embedding_fwd(call.arena.weight, D, recv_rows, self.owner_slots, 1, n_recv, [send_emb])
-    recv_emb = torch.empty(max(n_send, 1), D, dtype=torch.float32, device=dev)
-    dist.all_to_all_single(recv_emb[:n_send], send_emb[:n_recv], sc, rc)
-    pos = inverse.to(torch.int64).contiguous()    # lookup -> its id's position in recv_emb (-1: dropped)
-    K.embedding_fwd(recv_emb, D, pos, self.pool_slots, call.n_slots, self.L, outs, weights=weights,
+    g = group_from or self
+    if group_from is None:
+      K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local, owner=self.owner)
+      K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
+      self.overflow += self.counts[N:]
+      dist.all_to_all_single(self.recv_rows, self.send_rows)
+    else:
+      assert g.L == self.L and g.cap == self.cap and g.call.arena.n_rows == call.arena.n_rows
+    K.embedding_fwd(call.arena.weight, D, g.recv_rows, self.owner_slots, 1, self.n_ex, [self.send_emb])
+    dist.all_to_all_single(self.recv_emb, self.send_emb)
+    K.embedding_fwd(self.recv_emb, D, g.pos, self.pool_slots, call.n_slots, self.L, outs, weights=weights,
                     seg_scale=call.seg_scale)
-    self._ctx = (pos, n_send, sc, rc, recv_rows, weights)
-    return rows_local
+    self._grouped, self._weights = g, weights
+    return g.rows_local
 
   def backward_update(self, outs, opt):
-    """each unique id's gradient row (local duplicates summed first) goes to its owner, which dedups across the
+    """each distinct id's gradient row (local duplicates summed first) goes to its owner, which dedups across the
     ranks and applies the fused row update."""
-    pos, n_send, sc, rc, recv_rows, weights = self._ctx
+    g, weights = self._grouped, self._weights
     call, N, D = self.call, self.world, self.call.arena.dim
-    dev = pos.device
     gbufs = [(o.grad if o.grad is not None else torch.zeros_like(o)).contiguous() for o in outs]
-    send_g = torch.zeros(max(n_send, 1), D, dtype=torch.float32, device=dev)
-    if n_send:
-      # K7 in "emit only" form over the pooling plan: rows = positions, so uniq_grads[p] is the summed gradient of
-      # the p-th unique id (positions are dense 0..n_send-1 and come out sorted)
-      ur = torch.empty(self.L, dtype=torch.int64, device=dev)
-      ug = torch.empty(self.L, D, dtype=torch.float32, device=dev)
-      nu = torch.zeros(1, dtype=torch.int32, device=dev)
-      K.embedding_bwd(None, None, None, D, pos, self.pool_slots, call.n_slots, self.L, gbufs,
-                      K.make_opt(_lib.OPT_SGD, 0.0), self.pool_ws, weights=weights, seg_scale=call.seg_scale,
-                      uniq_rows=ur, uniq_grads=ug, n_uniq=nu, n_rows=max(n_send, 1))
-      send_g = ug[:n_send]
-    n_recv = sum(rc)
-    recv_g = torch.empty(max(n_recv, 1), D, dtype=torch.float32, device=dev)
-    dist.all_to_all_single(recv_g[:n_recv], send_g[:n_send].contiguous(), rc, sc)
+    self.send_g.zero_()
+    K.embedding_bwd(self.send_g, None, None, D, g.pos, self.pool_slots, call.n_slots, self.L, gbufs, self.sum_opt,
+                    self.pool_ws, weights=weights, seg_scale=call.seg_scale, n_rows=self.n_ex)
+    dist.all_to_all_single(self.recv_g, self.send_g)
     a = call.arena
-    if n_recv:
-      struct_scaled = not opt.hyper_dev   # a device-resident grad_scale already carries the 1/N
-      if struct_scaled:
-        opt.grad_scale = opt.grad_scale / N
-      K.embedding_bwd(a.weight, a.state0, a.state1, D, recv_rows, self.owner_slots, 1, n_recv, [recv_g], opt,
-                      self.owner_ws, n_rows=a.n_rows)
-      if struct_scaled:
-        opt.grad_scale = opt.grad_scale * N
-    E.adam_dense_decay(a, recv_rows if n_recv else None, opt)
-    self._ctx = None
+    struct_scaled = not opt.hyper_dev   # a device-resident grad_scale already carries the 1/N
+    if struct_scaled:
+      opt.grad_scale = opt.grad_scale / N
+    K.embedding_bwd(a.weight, a.state0, a.state1, D, g.recv_rows, self.owner_slots, 1, self.n_ex, [self.recv_g], opt,
+                    self.owner_ws, n_rows=a.n_rows)
+    if struct_scaled:
+      opt.grad_scale = opt.grad_scale * N
+    E.adam_dense_decay(a, g.recv_rows, opt)
+    self._grouped = None
+
+  def check(self):
+    """Raises if any step since the last check lost lookups to a full per-peer block (host sync)."""
+    lost = int(self.overflow.item())
+    if lost:
+      self.overflow.zero_()
+      raise _lib.ErError('row-sharded exchange: %d lookups exceeded the per-peer capacity %d (x%d peers, %d lookups per '
+                         'step); raise ER_EP_SLACK' % (lost, self.cap, self.world, self.L))

@@ -167,9 +167,6 @@ class Trainer(object):
       from easyrec_b200.distributed import DataParallel
       ep = bool(getattr(input_layer, 'ep', False))
       self.dp = DataParallel(input_layer, self.dense_opt, world_size, sparse=not ep)
-      if ep and use_cuda_graph:
-        raise _lib.ErError('EmbeddingParallel exchanges data-dependent all-to-all splits through the host: it runs '
-                           'with use_cuda_graph=False')
     self.step = 0
     self.use_cuda_graph = use_cuda_graph
     # the first steps of a graph-mode run execute eagerly as ordinary training steps (allocator pools, lazily

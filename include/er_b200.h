@@ -156,6 +156,24 @@ int er_bucketize(const int64_t* ids, const int32_t* seg_ids,
                  const er_slot_t* slots, int32_t n_slots, int64_t* rows,
                  int32_t* owner, er_stream_t stream);
 
+/* ---- K8: index bucketing of the row-sharded lookup --------------------
+ * Replaces the Unique + dynamic_partition + host-read split sizes of
+ * embedding_parallel_lookup (compat/feature_column/feature_column.py:258-303).
+ * rows / owner: er_bucketize's outputs under shard_n = world.  Distinct
+ * (owner, row) pairs are grouped by owner into FIXED-capacity blocks, so the
+ * all-to-alls that follow use equal splits and need no host round trip:
+ *   send_rows[o*cap_per_peer + k] = k-th distinct row owned by rank o, -1 padding
+ *   pos[l]    = o*cap_per_peer + k for lookup l (-1: dropped lookup)
+ *   counts[o] = distinct rows owned by o; counts[world] = lookups lost because a
+ *               block overflowed (the caller must treat > 0 as an error)
+ * The k a row receives is not deterministic; no sum depends on it (see
+ * csrc/shard_group.cu).  ws: er_shard_group_workspace_bytes(n_lookups). */
+size_t er_shard_group_workspace_bytes(int64_t n_lookups);
+int er_shard_group(const int64_t* rows, const int32_t* owner, int64_t n_lookups,
+                   int32_t world, int64_t cap_per_peer, int64_t* send_rows,
+                   int64_t* pos, int32_t* counts, void* ws, size_t ws_bytes,
+                   er_stream_t stream);
+
 /* Scalar helpers used by tests and by host-side plan code (host pointers). */
 uint64_t er_fingerprint64_host(const char* s, size_t len);
 

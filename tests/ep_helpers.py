@@ -84,4 +84,5 @@ def run(make_estimator, dev, rank, world, steps=4, atol=2e-6):
   d = float((dp.trainer.dense_opt.flat_p - ep.trainer.dense_opt.flat_p).abs().max())
   assert d < 1e-5, 'dense parameters differ by %g' % d
   assert losses[-1][0] != losses[0][0]
+  ep.input_layer.check_exchange()   # no per-peer block of the fixed-capacity exchange overflowed
   return worst

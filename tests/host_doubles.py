@@ -128,9 +128,36 @@ def install_sparse(patch):
     m[cold] = torch.from_numpy(mc)
     v[cold] = torch.from_numpy(vc)
     table[cold] = torch.from_numpy(table[cold].numpy() - (lr_t * mc) / (np.sqrt(vc) + f(opt.eps)))
+  def shard_group_workspace(n_lookups, device):
+    return torch.empty(16, dtype=torch.uint8)
+
+  def shard_group(rows, owner, world, cap, send_rows, pos, counts, ws):
+    """er_shard_group: distinct (owner, row) pairs in first-occurrence order (the kernel's order is arbitrary)"""
+    r, o = rows.numpy(), owner.numpy()
+    send = np.full(world * cap, -1, np.int64)
+    p = np.full(r.size, -1, np.int64)
+    cnt = np.zeros(world + 1, np.int32)
+    seen = {}
+    for l in range(r.size):
+      if r[l] < 0 or o[l] < 0:
+        continue
+      key = (int(o[l]), int(r[l]))
+      if key not in seen:
+        k = int(cnt[o[l]])
+        cnt[o[l]] += 1
+        seen[key] = o[l] * cap + k if k < cap else -1
+        if k < cap:
+          send[o[l] * cap + k] = r[l]
+      p[l] = seen[key]
+      if p[l] < 0:
+        cnt[world] += 1
+    send_rows.copy_(torch.from_numpy(send))
+    pos.copy_(torch.from_numpy(p))
+    counts.copy_(torch.from_numpy(cnt))
   for name, fn in (('csr_from_lens', csr_from_lens), ('bucketize', bucketize), ('embedding_fwd', embedding_fwd),
                    ('embedding_bwd', embedding_bwd), ('mark_rows', mark_rows), ('adam_dense_sweep', adam_dense_sweep),
-                   ('sparse_apply', sparse_apply)):
+                   ('sparse_apply', sparse_apply), ('shard_group', shard_group),
+                   ('shard_group_workspace', shard_group_workspace)):
     patch(K, name, fn)
 
 
