@@ -259,7 +259,11 @@ __device__ __forceinline__ void one_row_cta(const BwdArgs& a, int cta) {
   const int used_chunks = (sl.n_seg + bk::kOneRowChunk - 1) / bk::kOneRowChunk;
   if (s0 >= sl.n_seg) return;
   const float* gbuf = a.gbufs.p[sl.out_buf];
-  const uint32_t row = (uint32_t)sl.row_offset;
+  // every lookup of a one-row slot resolves to the same row: K1 writes slot.row_offset for all of them, and the
+  // row-sharded exchange (sharded.ShardedLookup) the position of that one row in its send buffer
+  const int64_t row64 = a.or_rows[sl.seg_begin];
+  if (row64 < 0) return;
+  const uint32_t row = (uint32_t)row64;
   if constexpr (LANES > 0) {
     const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);

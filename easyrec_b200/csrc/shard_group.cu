@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(256) insert_kernel(Args a) {
     const unsigned long long key = ((unsigned long long)o << 48) | (unsigned long long)r;
     uint32_t h = mix(key) & a.mask;
     for (;;) {
-      const unsigned long long old = atomicCAS(a.keys + h, kEmpty, key);
+      // hot ids (one-row tables, the head of a Zipf distribution) are looked up thousands of times per batch: a
+      // plain read finds their entry without queueing on the atomic unit
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a.keys + h);
+      if (old == kEmpty) old = atomicCAS(a.keys + h, kEmpty, key);
       if (old == kEmpty) {
         const int32_t k = atomicAdd(a.counts + o, 1);
         int32_t p = -1;

@@ -157,8 +157,10 @@ class ShardedLookup(object):
     self.n_ex = n_ex = world * cap
     recs = []
     for r in call.slots_np:   # pools the RECEIVED rows (a [N*cap, dim] "table" indexed by position) into the call's layout
+      # a one-row table is one position: its lookups stay out of the requester's dedup (weighted column sum instead)
+      mode = _lib.BUCKET_ONE_ROW if int(r['bucket_mode']) == _lib.BUCKET_ONE_ROW else _lib.BUCKET_NONE
       recs.append(dict(num_buckets=n_ex, row_offset=0, seg_begin=int(r['seg_begin']), n_seg=int(r['n_seg']),
-                       bucket_mode=_lib.BUCKET_NONE, combiner=int(r['combiner']), out_buf=int(r['out_buf']),
+                       bucket_mode=mode, combiner=int(r['combiner']), out_buf=int(r['out_buf']),
                        out_stride=int(r['out_stride']), out_col=int(r['out_col']), shard_n=1))
     self.pool_slots_np = K.make_slots(recs)
     self.pool_slots = K.slots_to_device(self.pool_slots_np, dev)
@@ -183,6 +185,8 @@ class ShardedLookup(object):
     self.sum_opt = K.make_opt(_lib.OPT_SGD, -1.0)   # w - (-1) * sum(g) on a zeroed buffer = the summed gradient
     self._grouped = None   # the ShardedLookup whose pos / recv_rows this step's exchange uses (self or a sharer)
     self._weights = None
+    self._side = torch.cuda.Stream(device=dev) if str(dev).startswith('cuda') else None
+    self._presorted = False
 
   def forward(self, ids, weights, outs, group_from=None):
     """ids int64 [L] in the call's slot order; writes the pooled rows into `outs` (the call's output matrices).
@@ -195,6 +199,15 @@ class ShardedLookup(object):
       K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
       self.overflow += self.counts[N:]
       dist.all_to_all_single(self.recv_rows, self.send_rows)
+      self._presorted = False
+      if self._side is not None and torch.is_grad_enabled():
+        # the row-only halves of both K7s (requester: positions, owner: received rows) need no gradient: a parallel
+        # branch under the row exchange and the dense forward / backward, joined in backward_update
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+          K.embedding_bwd_presort(self.pos, self.n_ex, D, self.pool_ws, self.pool_slots, call.n_slots)
+          K.embedding_bwd_presort(self.recv_rows, call.arena.n_rows, D, self.owner_ws, self.owner_slots, 1)
+        self._presorted = True
     else:
       assert g.L == self.L and g.cap == self.cap and g.call.arena.n_rows == call.arena.n_rows
     K.embedding_fwd(call.arena.weight, D, g.recv_rows, self.owner_slots, 1, self.n_ex, [self.send_emb])
@@ -210,16 +223,20 @@ class ShardedLookup(object):
     g, weights = self._grouped, self._weights
     call, N, D = self.call, self.world, self.call.arena.dim
     gbufs = [(o.grad if o.grad is not None else torch.zeros_like(o)).contiguous() for o in outs]
+    pre = g._presorted and (g is self or (K.k7_warp_mode(D) or not K.k7_warp_mode(g.call.arena.dim)))
+    if pre:
+      torch.cuda.current_stream().wait_stream(g._side)
     self.send_g.zero_()
     K.embedding_bwd(self.send_g, None, None, D, g.pos, self.pool_slots, call.n_slots, self.L, gbufs, self.sum_opt,
-                    self.pool_ws, weights=weights, seg_scale=call.seg_scale, n_rows=self.n_ex)
+                    self.pool_ws, weights=weights, seg_scale=call.seg_scale, n_rows=self.n_ex,
+                    sorted_from=(g.pool_ws, g.call.arena.dim) if pre else None)
     dist.all_to_all_single(self.recv_g, self.send_g)
     a = call.arena
     struct_scaled = not opt.hyper_dev   # a device-resident grad_scale already carries the 1/N
     if struct_scaled:
       opt.grad_scale = opt.grad_scale / N
     K.embedding_bwd(a.weight, a.state0, a.state1, D, g.recv_rows, self.owner_slots, 1, self.n_ex, [self.recv_g], opt,
-                    self.owner_ws, n_rows=a.n_rows)
+                    self.owner_ws, n_rows=a.n_rows, sorted_from=(g.owner_ws, g.call.arena.dim) if pre else None)
     if struct_scaled:
       opt.grad_scale = opt.grad_scale * N
     E.adam_dense_decay(a, g.recv_rows, opt)

@@ -174,6 +174,7 @@ class Trainer(object):
     # executed and replayed from then on, so every batch is applied exactly once
     self.graph_warmup_steps = 2
     self._eager_steps = 0
+    self._warm_stream = None
     self._graph = None
     self._graph2 = None
     self._step_pending = []
@@ -227,8 +228,21 @@ class Trainer(object):
     """features/labels: device tensors.  Returns (loss [scalar tensor], probs [B])."""
     self.model.train()
     self._set_hyper()
-    if not self.use_cuda_graph or self._eager_steps < self.graph_warmup_steps:
+    if not self.use_cuda_graph:
       out = self._step_body(features, labels)
+      self.step += 1
+      return out
+    if self._eager_steps < self.graph_warmup_steps:
+      # the eager steps ahead of a capture run on a side stream, like the capture itself: autograd keys the gradient
+      # accumulation of a parameter to the stream it first ran on, and the legacy default stream may not take part
+      # in a capture (torch's own rule for whole-step capture: "warm up on a side stream")
+      cur = torch.cuda.current_stream()
+      if self._warm_stream is None:
+        self._warm_stream = torch.cuda.Stream(device=cur.device)
+      self._warm_stream.wait_stream(cur)
+      with torch.cuda.stream(self._warm_stream):
+        out = self._step_body(features, labels)
+      cur.wait_stream(self._warm_stream)
       self.step += 1
       self._eager_steps += 1
       return out

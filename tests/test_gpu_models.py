@@ -195,6 +195,27 @@ def test_models_from_pipeline_config_train(cfg_text, n_task):
   assert np.isfinite(float(tr.train_step(feats2, lab2)[0]))
 
 
+@pytest.mark.parametrize('cfg_text', [DSSM_CFG, MMOE_CFG])
+def test_step_replayed_from_a_cuda_graph_equals_the_eager_step(cfg_text):
+  """Models whose graphs hold plain torch ops on parameters (DSSM's similarity scale, the multi-task loss sum) capture
+  too: the eager steps ahead of the capture run on a side stream, as torch asks for whole-step capture."""
+  torch.backends.cuda.matmul.allow_tf32 = False
+  n_task = 2 if cfg_text is MMOE_CFG else 1
+  cfg = config_util.get_configs_from_pipeline_file(cfg_text.encode())
+  losses = []
+  for graph in (False, True):
+    il, model, opt = builder.build_model(cfg, B, DEV, generator=torch.Generator(device=DEV).manual_seed(1),
+                                         cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+    tr = Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'], use_cuda_graph=graph)
+    out = []
+    for k in range(6):
+      feats, lab, _ = make_batch(10 + k, n_task)
+      out.append(float(tr.train_step(feats, lab)[0]))
+    losses.append(out)
+    assert (not graph) or tr._graph is not None
+  np.testing.assert_allclose(losses[1], losses[0], rtol=0, atol=1e-6)
+
+
 def test_din_forward_matches_plain_torch_restatement():
   torch.backends.cuda.matmul.allow_tf32 = False
   cfg = config_util.get_configs_from_pipeline_file(DIN_CFG.encode())
