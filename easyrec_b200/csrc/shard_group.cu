@@ -44,34 +44,40 @@ struct Args {
 
 // pass 1: every lookup finds / claims its key's table entry; the claimer takes the next free position of the owner
 __global__ void __launch_bounds__(256) insert_kernel(Args a) {
-  for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < a.n; l += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = a.row[l];
-    const int32_t o = a.owner[l];
-    if (r < 0 || o < 0 || o >= a.world) {
-      a.pos[l] = -1;
-      continue;
-    }
+  const int lane = threadIdx.x & 31;
+  const int64_t n_pad = (a.n + 31) & ~(int64_t)31;   // whole warps run every iteration (warp-wide match below)
+  for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_pad; l += (int64_t)gridDim.x * blockDim.x) {
+    const bool in = l < a.n;
+    const int64_t r = in ? a.row[l] : -1;
+    const int32_t o = in ? a.owner[l] : -1;
+    const bool live = r >= 0 && o >= 0 && o < a.world;
     const unsigned long long key = ((unsigned long long)o << 48) | (unsigned long long)r;
-    uint32_t h = mix(key) & a.mask;
-    for (;;) {
-      // hot ids (one-row tables, the head of a Zipf distribution) are looked up thousands of times per batch: a
-      // plain read finds their entry without queueing on the atomic unit
-      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a.keys + h);
-      if (old == kEmpty) old = atomicCAS(a.keys + h, kEmpty, key);
-      if (old == kEmpty) {
-        const int32_t k = atomicAdd(a.counts + o, 1);
-        int32_t p = -1;
-        if (k < a.cap) {
-          p = (int32_t)(o * a.cap + k);
-          a.send_rows[p] = r;
+    // lookups of one slot are neighbours and hot ids (one-row tables, the head of a Zipf distribution) repeat
+    // thousands of times per batch: one lane per distinct key of the warp talks to the table, the rest copy its answer
+    const unsigned peers = __match_any_sync(0xffffffffu, live ? key : (kEmpty - (unsigned)lane));
+    const int leader = __ffs(peers) - 1;
+    uint32_t h = 0;
+    if (live && lane == leader) {
+      h = mix(key) & a.mask;
+      for (;;) {
+        unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a.keys + h);
+        if (old == kEmpty) old = atomicCAS(a.keys + h, kEmpty, key);
+        if (old == kEmpty) {
+          const int32_t k = atomicAdd(a.counts + o, 1);
+          int32_t p = -1;
+          if (k < a.cap) {
+            p = (int32_t)(o * a.cap + k);
+            a.send_rows[p] = r;
+          }
+          a.vals[h] = p;
+          break;
         }
-        a.vals[h] = p;
-        break;
+        if (old == key) break;
+        h = (h + 1) & a.mask;
       }
-      if (old == key) break;
-      h = (h + 1) & a.mask;
     }
-    a.pos[l] = h;   // resolved to the position by pass 2 (the claimer may not have written vals[h] yet)
+    h = __shfl_sync(0xffffffffu, h, leader);
+    if (in) a.pos[l] = live ? (int64_t)h : -1;   // resolved to the position by pass 2 (vals[h] may not be written yet)
   }
 }
 

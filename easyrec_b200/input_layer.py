@@ -317,12 +317,15 @@ class InputLayer(object):
     self.ep = shard_n > 1
     if self.ep:
       from easyrec_b200.sharded import ShardedLookup
+      exchanges = {}   # row plan -> the exchange its arenas share (ids once, rows in one packed all-to-all)
       for dim, subs in self.subcalls.items():
         for sk, sc in subs.items():
           if sc.kind != 'single':
             raise NotImplementedError('EmbeddingParallel with %s features (group slots of kind %s): only single-valued id '
                                       '/ raw slots are exchanged' % (sk[0], sc.kind))
-          sc.sharded = ShardedLookup(sc.call, shard_n, shard_rank)
+          key = self._rows_key(sc)
+          sc.sharded = ShardedLookup(sc.call, shard_n, shard_rank, exchange=exchanges.get(key))
+          exchanges.setdefault(key, sc.sharded.ex)
           self.merged[dim].sharded = sc.sharded
       self._ep_scale = 1.0 / shard_n
     # embedding_learning_rate_multiplier: the reference multiplies the GRADIENT of every `embedding_weights`
@@ -502,25 +505,30 @@ class InputLayer(object):
     return out_ids, out_w
 
   # ------------------------------------------------------------------
+  @staticmethod
+  def _rows_key(sc):
+    key = getattr(sc, 'rows_key', None)
+    if key is None:
+      call = sc.call
+      key = (tuple((int(r['num_buckets']), int(r['row_offset']), int(r['seg_begin']), int(r['n_seg']),
+                    int(r['bucket_mode']), int(r['shard_n'])) for r in call.slots_np), tuple(call.sources))
+      sc.rows_key = key
+    return key
+
   def _run_subcall(self, dim, sk, sc, features, dense_norm):
     """K1 + K2 of one uniform launch; returns (rows, weights, row_ptr, seg_ids, outs)."""
     call = sc.call
     B = self.batch_size
     if sc.kind == 'single':
-      key = getattr(sc, 'rows_key', None)
-      if key is None:   # arenas with the same row plan (wide dim-1 next to the deep tables) share K1's rows
-        key = (tuple((int(r['num_buckets']), int(r['row_offset']), int(r['seg_begin']), int(r['n_seg']),
-                      int(r['bucket_mode']), int(r['shard_n'])) for r in call.slots_np), tuple(call.sources))
-        sc.rows_key = key
+      key = self._rows_key(sc)   # arenas with the same row plan (wide dim-1 next to the deep tables) share K1's rows
       if self.ep:
-        # arenas with the same row plan (the wide dim-1 tables next to the deep ones) share K1, the grouping and the
-        # id all-to-all of the first one; only their rows travel separately
+        # ... and under EmbeddingParallel the whole exchange: the first arena of a row plan runs it for all of them
         hit = self._rows_cache.get(key)
         cids, w = (None, hit[1]) if hit is not None else self._gather_inputs(dim, features.get('sparse_fea'), dense_norm)
         outs = call.alloc_outputs()
-        rows = sc.sharded.forward(cids, w, outs, group_from=hit[2] if hit is not None else None)
+        rows = sc.sharded.forward(cids, w, outs)
         if hit is None:
-          self._rows_cache[key] = (rows, w, sc.sharded)
+          self._rows_cache[key] = (rows, w)
         for o in outs:
           o.requires_grad_(True)
         return rows, w, None, None, outs

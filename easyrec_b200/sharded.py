@@ -128,6 +128,90 @@ class ShardedArena(object):
     self._ctx = None
 
 
+class ShardedExchange(object):
+  """The part of the row-sharded lookup that arenas with the SAME row plan share (the wide dim-1 tables next to the deep
+  ones: same ids, same bucket rules, same owners): K1, K8, the id all-to-all, and ONE packed row exchange each way -
+  every member owns a column range of the `[N*cap, width]` send / receive matrices."""
+
+  def __init__(self, world, rank, device):
+    self.world, self.rank, self.device = world, rank, device
+    self.members = []
+    self.width = 0
+    self._built = False
+    self._active = []       # members that looked up this step, in call order
+    self._summed = 0        # members whose requester-side gradient sums are in send_g
+    self._side = torch.cuda.Stream(device=device) if str(device).startswith('cuda') else None
+    self._presorted = False
+
+  def add(self, member):
+    assert not self._built
+    if self.members:
+      m0 = self.members[0]
+      assert m0.L == member.L and m0.cap == member.cap and m0.call.arena.n_rows == member.call.arena.n_rows
+    member.col = self.width
+    self.width += (member.call.arena.dim + 3) // 4 * 4    # 16-byte aligned column blocks
+    self.members.append(member)
+
+  def build(self):
+    if self._built:
+      return
+    m0 = self.members[0]
+    dev, N = self.device, self.world
+    self.L, self.cap, self.n_ex = m0.L, m0.cap, m0.n_ex
+    f32, i64 = torch.float32, torch.int64
+    self.owner = torch.empty(self.L, dtype=torch.int32, device=dev)
+    self.rows_local = torch.empty(self.L, dtype=i64, device=dev)
+    self.send_rows = torch.empty(self.n_ex, dtype=i64, device=dev)
+    self.recv_rows = torch.empty(self.n_ex, dtype=i64, device=dev)
+    self.pos = torch.empty(self.L, dtype=i64, device=dev)
+    self.counts = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+    self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    self.group_ws = K.shard_group_workspace(self.L, dev)
+    shape = (self.n_ex, self.width)
+    self.send_emb, self.recv_emb = torch.zeros(shape, dtype=f32, device=dev), torch.zeros(shape, dtype=f32, device=dev)
+    self.send_g, self.recv_g = torch.zeros(shape, dtype=f32, device=dev), torch.zeros(shape, dtype=f32, device=dev)
+    for m in self.members:
+      m._plan(self)
+    self._built = True
+
+  def lookup(self, first, ids):
+    """K1 -> K8 -> all_to_all(ids) -> every member's K2 on the owner -> ONE all_to_all(rows)."""
+    N = self.world
+    call = first.call
+    K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local, owner=self.owner)
+    K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
+    self.overflow += self.counts[N:]
+    dist.all_to_all_single(self.recv_rows, self.send_rows)
+    self._presorted = False
+    if self._side is not None and torch.is_grad_enabled():
+      # the row-only halves of both K7s (requester: positions, owner: received rows) need no gradient: a parallel
+      # branch under the row exchange and the dense forward / backward, joined in the backward
+      m = max(self.members, key=lambda x: x.call.arena.dim)   # (a placement for wide rows serves the narrow tables too)
+      self._side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(self._side):
+        K.embedding_bwd_presort(self.pos, self.n_ex, m.call.arena.dim, m.pool_ws, m.pool_slots, m.call.n_slots)
+        K.embedding_bwd_presort(self.recv_rows, m.call.arena.n_rows, m.call.arena.dim, m.owner_ws, m.owner_slots, 1)
+      self._presorted = m
+    for m in self.members:
+      K.embedding_fwd(m.call.arena.weight, m.call.arena.dim, self.recv_rows, m.owner_slots, 1, self.n_ex, [self.send_emb])
+    dist.all_to_all_single(self.recv_emb, self.send_emb)
+    self._active, self._summed = [], 0
+
+  def sorted_from(self, member, which):
+    """(workspace, dim) of the early placement a member's K7 may reuse, or None."""
+    m = self._presorted
+    if not m or not (K.k7_warp_mode(member.call.arena.dim) or not K.k7_warp_mode(m.call.arena.dim)):
+      return None
+    return (m.pool_ws if which == 'pool' else m.owner_ws, m.call.arena.dim)
+
+  def check(self):
+    lost = int(self.overflow.item())
+    if lost:
+      self.overflow.zero_()
+      raise _lib.ErError('row-sharded exchange: %d lookups exceeded the per-peer capacity %d (x%d peers, %d lookups per '
+                         'step); raise ER_EP_SLACK' % (lost, self.cap, self.world, self.L))
+
+
 class ShardedLookup(object):
   """The exchange of `embedding_parallel_lookup` around ONE fused call of an InputLayer whose arenas are row-sharded
   (Arena.shard_n > 1): what InputLayer runs instead of K1 + K2 when the pipeline asks for
@@ -143,109 +227,91 @@ class ShardedLookup(object):
 
   Every buffer and every split size is fixed when the plan is built (`cap` ids per peer, -1 padded: a padded id
   gathers a zero row and its gradient slot is dropped by K7), so nothing is read back on the host and the exchange
-  is captured in the step's CUDA graph with the rest.  A block that overflows loses lookups: counted on the device
-  (`overflow`), raised by check().  Single-valued slots (the packed sparse_fea / raw projections)."""
+  is captured in the step's CUDA graph with the rest.  A block that overflows loses lookups: counted on the device,
+  raised by check().  Arenas with the same row plan share one ShardedExchange: ids travel once and the rows of all of
+  them in one packed all-to-all per direction.  Single-valued slots (the packed sparse_fea / raw projections)."""
 
-  def __init__(self, call, world, rank, slack=None):
+  def __init__(self, call, world, rank, exchange=None, slack=None):
     a = call.arena
     assert a.shard_n == world and a.shard_rank == rank
     self.call, self.world, self.rank = call, world, rank
-    dev, D = a.device, a.dim
     self.L = L = call.n_seg
     slack = float(os.environ.get('ER_EP_SLACK', '1.25')) if slack is None else slack
-    self.cap = cap = min(L, (int(np.ceil(slack * L / world)) + 256 + 255) // 256 * 256)
-    self.n_ex = n_ex = world * cap
+    # distinct rows this rank can ask one peer for: every lookup of the hashed / identity slots in the worst case
+    # (rows spread evenly over the owners, `slack` covers the imbalance), ONE row per one-row table
+    l_eff = sum(1 if int(r['bucket_mode']) == _lib.BUCKET_ONE_ROW else int(r['n_seg']) for r in call.slots_np)
+    self.cap = min(L, (int(np.ceil(slack * l_eff / world)) + 256 + 255) // 256 * 256)
+    self.n_ex = world * self.cap
+    self.sum_opt = K.make_opt(_lib.OPT_SGD, -1.0)   # w - (-1) * sum(g) on a zeroed buffer = the summed gradient
+    self._weights = None
+    self.ex = exchange or ShardedExchange(world, rank, a.device)
+    self.ex.add(self)
+
+  def _plan(self, ex):
+    """slot plans over the packed exchange matrices (called once by ShardedExchange.build)"""
+    call, a = self.call, self.call.arena
+    dev, D, W = a.device, a.dim, ex.width
     recs = []
     for r in call.slots_np:   # pools the RECEIVED rows (a [N*cap, dim] "table" indexed by position) into the call's layout
       # a one-row table is one position: its lookups stay out of the requester's dedup (weighted column sum instead)
       mode = _lib.BUCKET_ONE_ROW if int(r['bucket_mode']) == _lib.BUCKET_ONE_ROW else _lib.BUCKET_NONE
-      recs.append(dict(num_buckets=n_ex, row_offset=0, seg_begin=int(r['seg_begin']), n_seg=int(r['n_seg']),
+      recs.append(dict(num_buckets=self.n_ex, row_offset=0, seg_begin=int(r['seg_begin']), n_seg=int(r['n_seg']),
                        bucket_mode=mode, combiner=int(r['combiner']), out_buf=int(r['out_buf']),
                        out_stride=int(r['out_stride']), out_col=int(r['out_col']), shard_n=1))
     self.pool_slots_np = K.make_slots(recs)
     self.pool_slots = K.slots_to_device(self.pool_slots_np, dev)
-    own = [dict(num_buckets=a.n_rows, row_offset=0, seg_begin=0, n_seg=n_ex, bucket_mode=_lib.BUCKET_NONE,
-                combiner=_lib.COMBINER_SUM | _lib.COMBINER_UNIT_WEIGHTS, out_buf=0, out_stride=D, out_col=0, shard_n=1)]
+    own = [dict(num_buckets=a.n_rows, row_offset=0, seg_begin=0, n_seg=self.n_ex, bucket_mode=_lib.BUCKET_NONE,
+                combiner=_lib.COMBINER_SUM | _lib.COMBINER_UNIT_WEIGHTS, out_buf=0, out_stride=W, out_col=self.col,
+                shard_n=1)]
     self.owner_slots = K.slots_to_device(K.make_slots(own), dev)
-    self.owner_ws = K.bwd_workspace(n_ex, dev, D)
-    self.pool_ws = K.bwd_workspace(L, dev, D)
-    f32, i64 = torch.float32, torch.int64
-    self.owner = torch.empty(L, dtype=torch.int32, device=dev)
-    self.rows_local = torch.empty(L, dtype=i64, device=dev)
-    self.send_rows = torch.empty(n_ex, dtype=i64, device=dev)
-    self.recv_rows = torch.empty(n_ex, dtype=i64, device=dev)
-    self.pos = torch.empty(L, dtype=i64, device=dev)
-    self.counts = torch.zeros(world + 1, dtype=torch.int32, device=dev)
-    self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-    self.group_ws = K.shard_group_workspace(L, dev)
-    self.send_emb = torch.empty(n_ex, D, dtype=f32, device=dev)
-    self.recv_emb = torch.empty(n_ex, D, dtype=f32, device=dev)
-    self.send_g = torch.empty(n_ex, D, dtype=f32, device=dev)
-    self.recv_g = torch.empty(n_ex, D, dtype=f32, device=dev)
-    self.sum_opt = K.make_opt(_lib.OPT_SGD, -1.0)   # w - (-1) * sum(g) on a zeroed buffer = the summed gradient
-    self._grouped = None   # the ShardedLookup whose pos / recv_rows this step's exchange uses (self or a sharer)
-    self._weights = None
-    self._side = torch.cuda.Stream(device=dev) if str(dev).startswith('cuda') else None
-    self._presorted = False
+    self.owner_ws = K.bwd_workspace(self.n_ex, dev, D)
+    self.pool_ws = K.bwd_workspace(self.L, dev, D)
+    self.recv_view = ex.recv_emb[:, self.col:self.col + D]   # this arena's received rows: the pooling K2's "table"
+    self.sum_view = ex.send_g[:, self.col:self.col + D]      # ... and the requester-side gradient sums
 
-  def forward(self, ids, weights, outs, group_from=None):
-    """ids int64 [L] in the call's slot order; writes the pooled rows into `outs` (the call's output matrices).
-    group_from: another ShardedLookup of the SAME row plan that already ran forward() this step (the wide dim-1 arena
-    next to the deep one): its positions and received ids are reused, only the rows travel."""
-    call, N, D = self.call, self.world, self.call.arena.dim
-    g = group_from or self
-    if group_from is None:
-      K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local, owner=self.owner)
-      K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
-      self.overflow += self.counts[N:]
-      dist.all_to_all_single(self.recv_rows, self.send_rows)
-      self._presorted = False
-      if self._side is not None and torch.is_grad_enabled():
-        # the row-only halves of both K7s (requester: positions, owner: received rows) need no gradient: a parallel
-        # branch under the row exchange and the dense forward / backward, joined in backward_update
-        self._side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._side):
-          K.embedding_bwd_presort(self.pos, self.n_ex, D, self.pool_ws, self.pool_slots, call.n_slots)
-          K.embedding_bwd_presort(self.recv_rows, call.arena.n_rows, D, self.owner_ws, self.owner_slots, 1)
-        self._presorted = True
-    else:
-      assert g.L == self.L and g.cap == self.cap and g.call.arena.n_rows == call.arena.n_rows
-    K.embedding_fwd(call.arena.weight, D, g.recv_rows, self.owner_slots, 1, self.n_ex, [self.send_emb])
-    dist.all_to_all_single(self.recv_emb, self.send_emb)
-    K.embedding_fwd(self.recv_emb, D, g.pos, self.pool_slots, call.n_slots, self.L, outs, weights=weights,
+  def forward(self, ids, weights, outs):
+    """ids int64 [L] in the call's slot order (None for a member whose exchange already ran this step); writes the
+    pooled rows into `outs` (the call's output matrices)."""
+    ex, call = self.ex, self.call
+    ex.build()
+    if ids is not None:
+      ex.lookup(self, ids)
+    K.embedding_fwd(self.recv_view, call.arena.dim, ex.pos, self.pool_slots, call.n_slots, self.L, outs, weights=weights,
                     seg_scale=call.seg_scale)
-    self._grouped, self._weights = g, weights
-    return g.rows_local
+    self._weights = weights
+    ex._active.append(self)
+    return ex.rows_local
 
   def backward_update(self, outs, opt):
     """each distinct id's gradient row (local duplicates summed first) goes to its owner, which dedups across the
-    ranks and applies the fused row update."""
-    g, weights = self._grouped, self._weights
-    call, N, D = self.call, self.world, self.call.arena.dim
+    ranks and applies the fused row update.  The gradient rows of all arenas of the exchange travel together: the
+    last member to sum its gradients sends them and runs every owner-side update."""
+    ex, call, N, D = self.ex, self.call, self.world, self.call.arena.dim
     gbufs = [(o.grad if o.grad is not None else torch.zeros_like(o)).contiguous() for o in outs]
-    pre = g._presorted and (g is self or (K.k7_warp_mode(D) or not K.k7_warp_mode(g.call.arena.dim)))
-    if pre:
-      torch.cuda.current_stream().wait_stream(g._side)
-    self.send_g.zero_()
-    K.embedding_bwd(self.send_g, None, None, D, g.pos, self.pool_slots, call.n_slots, self.L, gbufs, self.sum_opt,
-                    self.pool_ws, weights=weights, seg_scale=call.seg_scale, n_rows=self.n_ex,
-                    sorted_from=(g.pool_ws, g.call.arena.dim) if pre else None)
-    dist.all_to_all_single(self.recv_g, self.send_g)
-    a = call.arena
+    if ex._summed == 0:
+      if ex._presorted:
+        torch.cuda.current_stream().wait_stream(ex._side)
+      ex.send_g.zero_()
+    K.embedding_bwd(self.sum_view, None, None, D, ex.pos, self.pool_slots, call.n_slots, self.L, gbufs, self.sum_opt,
+                    self.pool_ws, weights=self._weights, seg_scale=call.seg_scale, n_rows=self.n_ex,
+                    sorted_from=ex.sorted_from(self, 'pool'))
+    ex._summed += 1
+    if ex._summed < len(ex._active):
+      return
+    dist.all_to_all_single(ex.recv_g, ex.send_g)
     struct_scaled = not opt.hyper_dev   # a device-resident grad_scale already carries the 1/N
     if struct_scaled:
       opt.grad_scale = opt.grad_scale / N
-    K.embedding_bwd(a.weight, a.state0, a.state1, D, g.recv_rows, self.owner_slots, 1, self.n_ex, [self.recv_g], opt,
-                    self.owner_ws, n_rows=a.n_rows, sorted_from=(g.owner_ws, g.call.arena.dim) if pre else None)
+    for m in ex._active:
+      a = m.call.arena
+      K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, ex.recv_rows, m.owner_slots, 1, m.n_ex, [ex.recv_g], opt,
+                      m.owner_ws, n_rows=a.n_rows, sorted_from=ex.sorted_from(m, 'owner'))
+      E.adam_dense_decay(a, ex.recv_rows, opt)
     if struct_scaled:
       opt.grad_scale = opt.grad_scale * N
-    E.adam_dense_decay(a, g.recv_rows, opt)
-    self._grouped = None
+    ex._active, ex._summed = [], 0
 
   def check(self):
     """Raises if any step since the last check lost lookups to a full per-peer block (host sync)."""
-    lost = int(self.overflow.item())
-    if lost:
-      self.overflow.zero_()
-      raise _lib.ErError('row-sharded exchange: %d lookups exceeded the per-peer capacity %d (x%d peers, %d lookups per '
-                         'step); raise ER_EP_SLACK' % (lost, self.cap, self.world, self.L))
+    self.ex.build()
+    self.ex.check()
