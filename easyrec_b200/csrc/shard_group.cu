@@ -43,9 +43,15 @@ struct Args {
 };
 
 // pass 1: every lookup finds / claims its key's table entry; the claimer takes the next free position of the owner
+constexpr int kMaxAgg = 64;   // owners whose position counters a CTA aggregates in shared memory
+
 __global__ void __launch_bounds__(256) insert_kernel(Args a) {
+  __shared__ int s_cnt[kMaxAgg], s_base[kMaxAgg];
   const int lane = threadIdx.x & 31;
-  const int64_t n_pad = (a.n + 31) & ~(int64_t)31;   // whole warps run every iteration (warp-wide match below)
+  const bool agg = a.world <= kMaxAgg;
+  if (threadIdx.x < kMaxAgg) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t n_pad = (a.n + 255) & ~(int64_t)255;   // whole CTAs run every iteration (block-wide steps below)
   for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n_pad; l += (int64_t)gridDim.x * blockDim.x) {
     const bool in = l < a.n;
     const int64_t r = in ? a.row[l] : -1;
@@ -57,24 +63,41 @@ __global__ void __launch_bounds__(256) insert_kernel(Args a) {
     const unsigned peers = __match_any_sync(0xffffffffu, live ? key : (kEmpty - (unsigned)lane));
     const int leader = __ffs(peers) - 1;
     uint32_t h = 0;
+    bool won = false;
     if (live && lane == leader) {
       h = mix(key) & a.mask;
       for (;;) {
         unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a.keys + h);
         if (old == kEmpty) old = atomicCAS(a.keys + h, kEmpty, key);
         if (old == kEmpty) {
-          const int32_t k = atomicAdd(a.counts + o, 1);
-          int32_t p = -1;
-          if (k < a.cap) {
-            p = (int32_t)(o * a.cap + k);
-            a.send_rows[p] = r;
-          }
-          a.vals[h] = p;
+          won = true;
           break;
         }
         if (old == key) break;
         h = (h + 1) & a.mask;
       }
+    }
+    // the claimers take the next free positions of their owners: counted per CTA in shared memory, ONE global
+    // atomic per owner and CTA (with two owners, per-claim atomics on two addresses would serialise the kernel)
+    int k = 0;
+    if (won) k = agg ? atomicAdd(&s_cnt[o], 1) : atomicAdd(a.counts + o, 1);
+    if (agg) {
+      __syncthreads();
+      if ((int)threadIdx.x < a.world) {
+        const int c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(a.counts + threadIdx.x, c) : 0;
+        s_cnt[threadIdx.x] = 0;
+      }
+      __syncthreads();
+      if (won) k += s_base[o];
+    }
+    if (won) {
+      int32_t p = -1;
+      if (k < a.cap) {
+        p = (int32_t)(o * a.cap + k);
+        a.send_rows[p] = r;
+      }
+      a.vals[h] = p;
     }
     h = __shfl_sync(0xffffffffu, h, leader);
     if (in) a.pos[l] = live ? (int64_t)h : -1;   // resolved to the position by pass 2 (vals[h] may not be written yet)
