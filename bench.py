@@ -55,8 +55,8 @@ def parse():
   ap.add_argument('--workload', default='deepfm_c2', choices=['deepfm_c2', 'dssm_c4'],
                   help='deepfm_c2 = the headline metric; dssm_c4 = BASELINE.json configs[3] (row-sharded item table)')
   ap.add_argument('--parallelism', default='', choices=['', 'dp', 'ep'],
-                  help='N > 1: dp = replicated tables + row all-gather (default for deepfm_c2), ep = row-sharded tables + '
-                       'all-to-all (EmbeddingParallelStrategy; default for dssm_c4)')
+                  help='N > 1: ep = row-sharded tables + all-to-all (EmbeddingParallelStrategy; the default), dp = replicated '
+                       'tables + row all-gather')
   ap.add_argument('--uniform-ids', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -245,7 +245,7 @@ def main():
   local_rank = int(os.environ.get('LOCAL_RANK', 0))
   B = args.batch
   vocab = args.vocab or (100_000_000 if world >= 8 else 10_000_000)
-  par = args.parallelism or ('ep' if args.workload == 'dssm_c4' else 'dp')
+  par = args.parallelism or 'ep'   # N > 1: row-sharded tables scale (constant per-rank work); dp is kept as an option
   ep = world > 1 and par == 'ep'
   opt_name = {'adagrad_optimizer': 'adagrad', 'lazy_adam_optimizer': 'lazy_adam', 'adam_optimizer': 'adam'}
   workload = 'deepfm_criteo_c2(26 sparse+13 dense, shared table V=%d x emb16 fp32, batch %d/GPU, %s ids)' % (

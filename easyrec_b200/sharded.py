@@ -288,6 +288,9 @@ class ShardedLookup(object):
     last member to sum its gradients sends them and runs every owner-side update."""
     ex, call, N, D = self.ex, self.call, self.world, self.call.arena.dim
     gbufs = [(o.grad if o.grad is not None else torch.zeros_like(o)).contiguous() for o in outs]
+    if gbufs and gbufs[0].is_cuda:
+      for g in gbufs:   # (the trainer runs this backward on a side stream: the gradients were produced on the main one)
+        g.record_stream(torch.cuda.current_stream())
     if ex._summed == 0:
       if ex._presorted:
         torch.cuda.current_stream().wait_stream(ex._side)

@@ -167,6 +167,9 @@ class Trainer(object):
       from easyrec_b200.distributed import DataParallel
       ep = bool(getattr(input_layer, 'ep', False))
       self.dp = DataParallel(input_layer, self.dense_opt, world_size, sparse=not ep)
+    dev = str(getattr(input_layer, 'device', 'cpu'))
+    self._ep_side = torch.cuda.Stream(device=dev) if (self.dp is not None and not self.dp.sparse and
+                                                      dev.startswith('cuda')) else None
     self.step = 0
     self.use_cuda_graph = use_cuda_graph
     # the first steps of a graph-mode run execute eagerly as ordinary training steps (allocator pools, lazily
@@ -201,16 +204,26 @@ class Trainer(object):
 
   def _segment_exchange(self):
     if self.dp is not None:
+      if not self.dp.sparse and self._ep_side is not None:
+        # row-sharded tables: their backward (gradient sums, all-to-all to the owners, owner-side row update) is a
+        # parallel branch beside the dense all-reduce + dense optimizer; joined at the end of _segment_update
+        self._ep_side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._ep_side):
+          self.input_layer.backward_update()
       self.dp.exchange(self._step_pending)   # flat all-reduce + all-gather of K7 inputs
       self.dp.join_presort()
 
   def _segment_update(self, loss):
-    if self.dp is not None:
+    if self.dp is not None and not self.dp.sparse and self._ep_side is not None:
+      self.input_layer._pending = []
+    elif self.dp is not None:
       self.dp.apply_sparse(self._step_pending, self.input_layer.opt_holder['opt'])
       self.input_layer._pending = []
     else:
       self.input_layer.backward_update()   # K7: dedup + fused row update, on this thread/stream
     self.dense_opt.apply()                 # one launch: l2 + adagrad/adam over the flat buffer
+    if self.dp is not None and not self.dp.sparse and self._ep_side is not None:
+      torch.cuda.current_stream().wait_stream(self._ep_side)
     # reported loss = data loss + embedding regularisation (autograd) + dense l2 (from the apply)
     return loss + self.dense_opt.reg_loss[0]
 
