@@ -256,8 +256,6 @@ def check_scope(pipeline_config):
         bad.append('%s.dropout_ratio' % path)
       if kind == 'DNN' and m.activation not in ('tf.nn.relu', 'relu'):
         bad.append('%s.activation %r' % (path, m.activation))
-      if kind == 'DNN' and not m.use_bn:
-        bad.append('%s.use_bn false' % path)
   if bad:
     raise NotImplementedError('config is outside the hot-path scope: ' + '; '.join(bad))
 

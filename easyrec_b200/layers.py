@@ -171,6 +171,25 @@ class Dense(DenseLayer):
     super().__init__(n_in, n_out, use_bn=False, relu=False, generator=generator)
 
 
+class Units(list):
+  """hidden_units of a protos/dnn.proto DNN message together with its use_bn flag (slices keep the flag)."""
+  use_bn = True
+
+  def __getitem__(self, k):
+    v = list.__getitem__(self, k)
+    if isinstance(k, slice):
+      v = Units(v)
+      v.use_bn = self.use_bn
+    return v
+
+
+def units_of(dnn_config):
+  """DNN message -> Units (layers/dnn.py:50-87 reads hidden_units and use_bn from the same message)."""
+  u = Units(int(x) for x in dnn_config.hidden_units)
+  u.use_bn = bool(dnn_config.use_bn)
+  return u
+
+
 class DNN(nn.Module):
   """layers/dnn.py:50-87.  Inputs of rank 3 ([B, T, d], DIN attention) are flattened to rows, which
   is exactly what tf.layers.batch_normalization does on the last axis."""
@@ -178,6 +197,7 @@ class DNN(nn.Module):
   def __init__(self, n_in, hidden_units, use_bn=True, last_layer_no_activation=False,
                last_layer_no_batch_norm=False, generator=None):
     super().__init__()
+    use_bn = use_bn and getattr(hidden_units, 'use_bn', True)   # protos/dnn.proto use_bn (default true)
     self.layers = nn.ModuleList()
     n = len(hidden_units)
     for i, u in enumerate(hidden_units):

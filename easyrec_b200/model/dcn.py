@@ -18,8 +18,8 @@ class DCN(RankModel):
   @classmethod
   def from_config(cls, model_config, input_layer, generator=None):
     c = model_config.dcn
-    return cls(input_layer, c.deep_tower.input, list(c.deep_tower.dnn.hidden_units), c.cross_tower.cross_num,
-               list(c.final_dnn.hidden_units), l2_reg=c.l2_regularization,
+    return cls(input_layer, c.deep_tower.input, L.units_of(c.deep_tower.dnn), c.cross_tower.cross_num,
+               L.units_of(c.final_dnn), l2_reg=c.l2_regularization,
                embedding_reg=model_config.embedding_regularization, generator=generator)
 
   def __init__(self, input_layer, group, deep_units, cross_num, final_units, l2_reg=0.0, embedding_reg=0.0,

@@ -25,7 +25,7 @@ class DeepFM(nn.Module):
   @classmethod
   def from_config(cls, model_config, input_layer, generator=None):
     c = model_config.deepfm
-    return cls(input_layer, list(c.dnn.hidden_units), list(c.final_dnn.hidden_units),
+    return cls(input_layer, L.units_of(c.dnn), L.units_of(c.final_dnn),
                l2_reg=c.l2_regularization, embedding_reg=model_config.embedding_regularization,
                generator=generator)
 

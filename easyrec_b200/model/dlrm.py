@@ -20,7 +20,7 @@ class DLRM(RankModel):
     if model_config.WhichOneof('model') != 'dlrm':
       raise ValueError('invalid model config: %s' % model_config.WhichOneof('model'))
     c = model_config.dlrm
-    return cls(input_layer, list(c.bot_dnn.hidden_units), list(c.top_dnn.hidden_units), op=c.arch_interaction_op,
+    return cls(input_layer, L.units_of(c.bot_dnn), L.units_of(c.top_dnn), op=c.arch_interaction_op,
                itself=c.arch_interaction_itself, with_dense=c.arch_with_dense_feature, l2_reg=c.l2_regularization,
                embedding_reg=model_config.embedding_regularization, generator=generator)
 

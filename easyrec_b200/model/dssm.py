@@ -22,7 +22,7 @@ class DSSM(RankModel):
     loss_name = model_config.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[
         model_config.loss_type].name
     simi = c.DESCRIPTOR.fields_by_name['simi_func'].enum_type.values_by_number[c.simi_func].name
-    return cls(input_layer, list(c.user_tower.dnn.hidden_units), list(c.item_tower.dnn.hidden_units),
+    return cls(input_layer, L.units_of(c.user_tower.dnn), L.units_of(c.item_tower.dnn),
                cosine=(simi == 'COSINE'), temperature=c.temperature, scale_simi=c.scale_simi,
                listwise=(loss_name == 'SOFTMAX_CROSS_ENTROPY'), item_id=c.item_id or None,
                l2_reg=c.l2_regularization, embedding_reg=model_config.embedding_regularization,

@@ -18,10 +18,10 @@ class MMoE(RankModel):
   def from_config(cls, model_config, input_layer, generator=None):
     c = model_config.mmoe
     if c.HasField('expert_dnn'):
-      experts = [list(c.expert_dnn.hidden_units)] * c.num_expert
+      experts = [L.units_of(c.expert_dnn)] * c.num_expert
     else:
-      experts = [list(e.dnn.hidden_units) for e in c.experts]
-    towers = [(t.tower_name, t.label_name if t.HasField('label_name') else None, list(t.dnn.hidden_units) if t.HasField('dnn') else [], t.weight)
+      experts = [L.units_of(e.dnn) for e in c.experts]
+    towers = [(t.tower_name, t.label_name if t.HasField('label_name') else None, L.units_of(t.dnn) if t.HasField('dnn') else [], t.weight)
               for t in c.task_towers]
     group = model_config.feature_groups[0].group_name
     return cls(input_layer, group, experts, towers, l2_reg=c.l2_regularization,

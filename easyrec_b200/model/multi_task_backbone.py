@@ -40,7 +40,7 @@ class MultiTaskBackboneModel(RankModel):
     self.tower_dnn = nn.ModuleList()
     self.tower_out = nn.ModuleList()
     for t in towers:
-      units = list(t.dnn.hidden_units) if t.HasField('dnn') else []
+      units = L.units_of(t.dnn) if t.HasField('dnn') else []
       self.tower_dnn.append(L.DNN(d, units, generator=generator) if units else nn.Identity())
       self.tower_out.append(L.Dense(units[-1] if units else d, 1, generator))
     self.groups = sorted({inp.feature_group_name for b in model_config.backbone.blocks for inp in b.inputs

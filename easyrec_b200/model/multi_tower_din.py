@@ -21,8 +21,8 @@ class MultiTowerDIN(RankModel):
   @classmethod
   def from_config(cls, model_config, input_layer, generator=None):
     c = model_config.multi_tower
-    return cls(input_layer, [(t.input, list(t.dnn.hidden_units)) for t in c.towers],
-               [(t.input, list(t.dnn.hidden_units)) for t in c.din_towers], list(c.final_dnn.hidden_units),
+    return cls(input_layer, [(t.input, L.units_of(t.dnn)) for t in c.towers],
+               [(t.input, L.units_of(t.dnn)) for t in c.din_towers], L.units_of(c.final_dnn),
                l2_reg=c.l2_regularization, embedding_reg=model_config.embedding_regularization,
                generator=generator)
 

@@ -263,3 +263,28 @@ def test_beta_powers_are_fp32_products_like_the_tf_accumulators():
   h2.set(0.001, 37)                          # a restored run starts in the middle: same accumulators
   h.set(0.001, 37)
   assert (h2.b1p, h2.b2p) == (h.b1p, h.b2p)
+
+
+def test_dnn_use_bn_false_builds_plain_dense_relu_towers(dense_kernels):  # noqa: F811
+  """protos/dnn.proto `use_bn: false` (layers/dnn.py:62-70): dense + bias -> relu, no batch norm - per DNN message."""
+  text = workloads_c2(dnn_extra='use_bn: false')
+  cfg = config_util.get_configs_from_pipeline_file(text)
+  import os
+  os.environ['ER_PLAN_ONLY'] = '1'
+  try:
+    il, model, _ = builder.build_model(cfg, 32, 'cpu', cpu_generator=torch.Generator().manual_seed(1))
+  finally:
+    del os.environ['ER_PLAN_ONLY']
+  assert [l.use_bn for l in model.dnn.layers] == [False, False] and all(l.use_bn for l in model.final_dnn.layers)
+  assert not hasattr(model.dnn.layers[0], 'gamma') or model.dnn.layers[0].gamma is None
+  x = torch.randn(32, model.dnn.layers[0].kernel.shape[0])
+  want = x
+  for l in model.dnn.layers:
+    want = torch.relu(want @ l.kernel + l.bias)
+  torch.testing.assert_close(model.dnn(x), want, rtol=1e-5, atol=1e-6)
+
+
+def workloads_c2(dnn_extra=''):
+  from easyrec_b200 import workloads
+  text = workloads.c2_config_text(1000, 32, dnn=(16, 8), final=(8, 4)).decode()
+  return text.replace('dnn { hidden_units: [16, 8]', 'dnn { %s hidden_units: [16, 8]' % dnn_extra, 1).encode()
