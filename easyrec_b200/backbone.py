@@ -285,6 +285,19 @@ def _shape_of(x):
   return tuple(x.shape)
 
 
+def regularised_groups(backbone_config):
+  """feature groups whose looked-up outputs carry the embedding regulariser (layers/input_layer.py:369-375): the ones
+  read through InputLayer; the table of an `embedding_layer` block is a plain Keras Embedding without one."""
+  out = set()
+  for b in backbone_config.blocks:
+    if b.WhichOneof('layer') == 'embedding_layer':
+      continue
+    for inp in b.inputs:
+      if inp.WhichOneof('name') == 'feature_group_name':
+        out.add(inp.feature_group_name)
+  return sorted(out)
+
+
 class Backbone(nn.Module):
   """Backbone.__call__ + Package.call (backbone.py:215-348,482-510).  Layers are instantiated by a shape-only
   dry run on `meta` tensors, so construction needs no GPU and the optimizer sees every parameter."""
@@ -458,6 +471,13 @@ class Backbone(nn.Module):
         getter = lambda n: torch.stack(groups(n, True), dim=1)  # noqa: E731
       else:
         getter = lambda n: (groups(n), groups(n, True))  # noqa: E731
+      if which == 'embedding_layer':
+        # keras EmbeddingLayer over the bucketized features of one group (layers/keras/embedding.py:26-81,
+        # layers/backbone.py:314-318): the fused lookup has already produced the group in its concat layout
+        # (builder.embedding_layer_tables gave its features the block's width and their own tables)
+        name = block.inputs[0].feature_group_name
+        outputs[block.name] = groups(name) if block.embedding_layer.concat else groups(name, True)
+        continue
       x = self._block_input(block, outputs, getter)
       if which == 'input_layer':
         if any(0.0 < r < 1.0 for r in (ilc.dropout_rate, ilc.feature_dropout_rate)) or ilc.do_batch_norm or ilc.do_layer_norm:

@@ -279,6 +279,7 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   specs = feature_specs(pipeline_config, packed_mod=input_type_name(pipeline_config).startswith('Parquet'),
                         default_seq_len=default_seq_len)
   groups = feature_groups(mc)
+  specs, keras_tables = embedding_layer_tables(mc, specs)
   opt = optimizer_settings(pipeline_config)
   cls = model_pkg.get_model_class(mc.model_class)
   wide_dim = cls.wide_output_dim(mc)
@@ -287,10 +288,49 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   il = IL.InputLayer(specs, groups, batch_size, device, wide_output_dim=wide_dim,
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc),
-                     shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0)
+                     shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0,
+                     uniform_tables=keras_tables)
   model = cls.from_config(mc, il, generator=cpu_generator).to(device)
   bind_task_labels(model, list(pipeline_config.data_config.label_fields))
   return il, model, opt
+
+
+def embedding_layer_tables(model_config, specs):
+  """Backbone `embedding_layer` blocks (layers/backbone.py:93-101,314-318 + InputLayer.get_bucketized_features,
+  layers/input_layer.py:209-243 + keras EmbeddingLayer, layers/keras/embedding.py:26-81): the features of the block's
+  feature group are bucketized by their own rule (`string_to_hash_bucket_fast(v, vocab_f)` for hashed ids, numeric
+  inputs taken as already bucketized), offset by the vocabularies before them and looked up in ONE
+  `Embedding(sum vocab, embedding_dim)` of the block.  That is the arena layout of this path already: each feature
+  gets its own `vocab_f`-row table of the BLOCK's width (back to back in group order = the offsets), Keras' default
+  `uniform(-0.05, 0.05)` initialiser instead of the feature columns' truncated normal.
+
+  Returns (specs with those features re-dimensioned, {table name: 0.05})."""
+  if not model_config.HasField('backbone'):
+    return specs, {}
+  by_name = {s.name: i for i, s in enumerate(specs)}
+  groups = {g.group_name: list(g.feature_names) for g in model_config.feature_groups}
+  other_use = collections.Counter(n for g in model_config.feature_groups for n in g.feature_names)
+  specs, tables = list(specs), {}
+  blocks = list(model_config.backbone.blocks) + [b for p in model_config.backbone.packages for b in p.blocks]
+  for b in blocks:
+    if b.WhichOneof('layer') != 'embedding_layer':
+      continue
+    if len(b.inputs) != 1 or b.inputs[0].WhichOneof('name') != 'feature_group_name':
+      raise ValueError('embedding_layer block %s takes exactly one feature_group_name input' % b.name)
+    for n in groups[b.inputs[0].feature_group_name]:
+      sp = specs[by_name[n]]
+      if sp.kind != 'id':
+        # multi-valued inputs are densified with '' padding and the PADDING is looked up and pooled too
+        # (input_layer.py:232-235, embedding.py:9-23,60-78): not built
+        raise NotImplementedError('embedding_layer block %s: feature %s is a %s feature; only single-valued id / '
+                                  'bucketized features are exchanged through this block' % (b.name, n, sp.kind))
+      if other_use[n] > 1:
+        raise NotImplementedError('feature %s is read by embedding_layer block %s and by another feature group: it '
+                                  'would need two tables' % (n, b.name))
+      table = '%s/%s_embedding' % (b.name, n)
+      specs[by_name[n]] = sp._replace(embedding_dim=int(b.embedding_layer.embedding_dim), embedding_name=table)
+      tables[table] = 0.05
+  return specs, tables
 
 
 def bind_task_labels(model, label_fields):

@@ -21,6 +21,7 @@ backward is ONE dedup + fused row update over all of them, so a table shared by 
 (key + history of the same id space) gets one optimizer step from the summed gradient, as in TF.
 """
 import collections
+import os
 
 import numpy as np
 import torch
@@ -154,7 +155,7 @@ class InputLayer(object):
 
   def __init__(self, features, groups, batch_size, device, wide_output_dim=1,
                embedding_optimizer=_lib.OPT_ADAGRAD, shard_n=1, shard_rank=0, generator=None,
-               adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None):
+               adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None, uniform_tables=None):
     self.features = collections.OrderedDict((f.name, f) for f in features)
     self.groups = groups
     self.seq_att_groups = seq_att_groups or collections.OrderedDict()
@@ -252,6 +253,13 @@ class InputLayer(object):
             slot.bucket_mode = _lib.BUCKET_NONE
     for a in self.arenas.values():
       a.materialize(embedding_optimizer, generator=generator, adagrad_init=adagrad_init)
+      # tables of a backbone `embedding_layer` block: Keras Embedding's uniform(-limit, limit) initialiser
+      for tname, limit in (uniform_tables or {}).items():
+        if tname in a.tables and os.environ.get('ER_PLAN_ONLY') != '1':
+          off, local, _ = a.tables[tname]
+          rows = torch.empty(local, a.dim, dtype=torch.float32, device=device)
+          rows.uniform_(-limit, limit, generator=generator)
+          a.weight[off:off + local].copy_(rows)
     # ---- launches ---------------------------------------------------------------------
     self.calls = collections.OrderedDict()     # dim -> the single-valued ArenaCall (bench/tests)
     self.merged = collections.OrderedDict()    # dim -> MergedCall

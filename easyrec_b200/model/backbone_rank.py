@@ -6,7 +6,7 @@ import torch
 
 from easyrec_b200 import layers as L
 from easyrec_b200 import model as registry
-from easyrec_b200.backbone import Backbone
+from easyrec_b200.backbone import Backbone, regularised_groups
 from easyrec_b200.model.rank_model import RankModel
 
 
@@ -26,8 +26,7 @@ class BackboneRankModel(RankModel):
     self.l2_reg = model_config.model_params.l2_regularization if model_config.HasField('model_params') else 0.0
     self.embedding_reg = model_config.embedding_regularization
     self.output = L.Dense(self.backbone.out_dim, 1, generator) if self.backbone.out_dim != 1 else None
-    self.groups = sorted({inp.feature_group_name for b in model_config.backbone.blocks for inp in b.inputs
-                          if inp.WhichOneof('name') == 'feature_group_name'})
+    self.groups = regularised_groups(model_config.backbone)
 
   def forward(self, features):
     g = self.input_layer.lookup(features)

@@ -7,7 +7,7 @@ from torch import nn
 
 from easyrec_b200 import interactions as I
 from easyrec_b200 import model as registry
-from easyrec_b200.backbone import Backbone
+from easyrec_b200.backbone import Backbone, regularised_groups
 from easyrec_b200.model.dssm import DSSM
 
 
@@ -39,8 +39,7 @@ class MatchBackboneModel(DSSM):
     self.item_id = None
     self.l2_reg = mp.l2_regularization
     self.embedding_reg = model_config.embedding_regularization
-    self.groups = sorted({inp.feature_group_name for b in model_config.backbone.blocks for inp in b.inputs
-                          if inp.WhichOneof('name') == 'feature_group_name'})
+    self.groups = regularised_groups(model_config.backbone)
 
   def towers(self, features):
     g = self.input_layer.lookup(features)

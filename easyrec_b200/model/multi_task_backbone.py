@@ -7,7 +7,7 @@ from torch import nn
 from easyrec_b200 import embedding as E
 from easyrec_b200 import layers as L
 from easyrec_b200 import model as registry
-from easyrec_b200.backbone import Backbone
+from easyrec_b200.backbone import Backbone, regularised_groups
 from easyrec_b200.model.rank_model import RankModel
 
 
@@ -43,8 +43,7 @@ class MultiTaskBackboneModel(RankModel):
       units = L.units_of(t.dnn) if t.HasField('dnn') else []
       self.tower_dnn.append(L.DNN(d, units, generator=generator) if units else nn.Identity())
       self.tower_out.append(L.Dense(units[-1] if units else d, 1, generator))
-    self.groups = sorted({inp.feature_group_name for b in model_config.backbone.blocks for inp in b.inputs
-                          if inp.WhichOneof('name') == 'feature_group_name'})
+    self.groups = regularised_groups(model_config.backbone)
 
   def forward(self, features):
     g = self.input_layer.lookup(features)

@@ -73,6 +73,23 @@ model_config { model_class: "RankModel"
   embedding_regularization: 1e-5 }
 '''
 
+# a23: a backbone `embedding_layer` block (one Embedding(sum vocab, 12) over the bucketized ids of group "ids",
+# layers/keras/embedding.py + InputLayer.get_bucketized_features) next to an ordinary input_layer group
+BACKBONE_EMBLAYER_CFG = HEAD + FEATS + '''
+model_config { model_class: "RankModel"
+  feature_groups { group_name: "ids" feature_names: ["user_id", "age", "item_id", "cate"] wide_deep: DEEP }
+  feature_groups { group_name: "dense" feature_names: ["price"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "emb" inputs { feature_group_name: "ids" } embedding_layer { embedding_dim: 12 } }
+    blocks { name: "raw" inputs { feature_group_name: "dense" } input_layer { } }
+    blocks { name: "mlp" inputs { block_name: "emb" } inputs { block_name: "raw" }
+             keras_layer { class_name: "MLP" mlp { hidden_units: [64, 32] } } }
+    concat_blocks: ["mlp"]
+  }
+  model_params { l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+
 BACKBONE_DLRM_CFG = HEAD + FEATS + '''
 model_config { model_class: "RankModel"
   feature_groups { group_name: "sparse" feature_names: ["user_id", "age", "item_id", "cate"] wide_deep: DEEP }
@@ -179,7 +196,7 @@ def make_batch(seed, n_task=1):
 
 @pytest.mark.parametrize('cfg_text,n_task', [(DCN_CFG, 1), (DIN_CFG, 1), (MMOE_CFG, 2), (DSSM_CFG, 1), (DLRM_CFG, 1),
                                              (BACKBONE_DCN_CFG, 1), (BACKBONE_DLRM_CFG, 1), (BACKBONE_MTL_CFG, 2),
-                                             (BACKBONE_MATCH_CFG, 1), (BACKBONE_WIRING_CFG, 1)])
+                                             (BACKBONE_MATCH_CFG, 1), (BACKBONE_WIRING_CFG, 1), (BACKBONE_EMBLAYER_CFG, 1)])
 def test_models_from_pipeline_config_train(cfg_text, n_task):
   torch.backends.cuda.matmul.allow_tf32 = False
   cfg = config_util.get_configs_from_pipeline_file(cfg_text.encode())

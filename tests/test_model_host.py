@@ -170,7 +170,7 @@ def interaction_doubles(monkeypatch, dense_kernels):
 def _gpu_test_configs():
   import test_gpu_models as G
   names = ['DCN_CFG', 'DIN_CFG', 'MMOE_CFG', 'DSSM_CFG', 'DLRM_CFG', 'BACKBONE_DCN_CFG', 'BACKBONE_DLRM_CFG', 'BACKBONE_MTL_CFG',
-           'BACKBONE_MATCH_CFG', 'BACKBONE_WIRING_CFG']
+           'BACKBONE_MATCH_CFG', 'BACKBONE_WIRING_CFG', 'BACKBONE_EMBLAYER_CFG']
   return [(n, getattr(G, n)) for n in names]
 
 

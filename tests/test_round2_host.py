@@ -288,3 +288,40 @@ def workloads_c2(dnn_extra=''):
   from easyrec_b200 import workloads
   text = workloads.c2_config_text(1000, 32, dnn=(16, 8), final=(8, 4)).decode()
   return text.replace('dnn { hidden_units: [16, 8]', 'dnn { %s hidden_units: [16, 8]' % dnn_extra, 1).encode()
+
+
+def test_backbone_embedding_layer_block_is_one_offset_table_of_the_blocks_width(interaction_doubles):  # noqa: F811
+  """§8 a23 (layers/input_layer.py:209-243 + layers/keras/embedding.py:26-81): ids bucketized per feature, offset by the
+  vocabularies before them, ONE Embedding(sum vocab, block dim) with Keras' uniform(-0.05, 0.05) init, concat."""
+  import test_gpu_models as G
+  cfg = config_util.get_configs_from_pipeline_file(G.BACKBONE_EMBLAYER_CFG.encode())
+  B = 256
+  il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  a = il.arenas[12]                                   # the block's width, not the features' own embedding_dim 16
+  names = ['emb/user_id_embedding', 'emb/age_embedding', 'emb/item_id_embedding', 'emb/cate_embedding']
+  vocab = [1000, 10, 5000, 200]
+  assert list(a.tables) == names
+  off = 0
+  for n, v in zip(names, vocab):                      # offset += vocab, in feature-group order
+    assert a.tables[n] == (off, v, v)
+    off += v
+  W = a.weight.numpy()
+  assert np.abs(W).max() <= 0.05 and 0.02 < W.std() < 0.035   # uniform(-0.05, 0.05): std 0.0289
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64)),
+           'dense_fea': torch.from_numpy(rng.uniform(0, 100, (B, 1)).astype(np.float32))}
+  g = il.lookup(feats)
+  out = g['ids'][0].detach().numpy()
+  assert out.shape == (B, 48)
+  off = 0
+  for j, v in enumerate(vocab):
+    rows = O.bucketize(ids[j], 2 if j == 1 else 0, v, 0)[0]   # string_to_hash_bucket_fast(as_string(id), vocab) / as is
+    np.testing.assert_array_equal(out[:, 12 * j:12 * (j + 1)], W[off + rows])
+    off += v
+  # the Keras table carries no embedding regulariser; the input_layer group does
+  assert model.groups == ['dense']
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  lab = torch.from_numpy((rng.uniform(size=B) < 0.3).astype(np.float32))
+  losses = [float(tr.train_step(feats, lab)[0]) for _ in range(12)]
+  assert losses[-1] < losses[0] - 0.01
