@@ -70,6 +70,7 @@ SIGNATURES = {
                                  c_vp]),
     'er_bucketize': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32,
                              c_vp, c_vp, c_vp]),
+    'er_dropout': (c_i32, [c_vp, c_i64, ctypes.c_float, ctypes.c_uint64, c_vp, c_vp, c_vp]),
     'er_shard_group_workspace_bytes': (c_sz, [c_i64]),
     'er_shard_group': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'er_fingerprint64_host': (ctypes.c_uint64, [ctypes.c_char_p, c_sz]),

@@ -561,6 +561,41 @@ extern "C" int er_bias_bn_act_bwd(const float* z, const float* bias, const float
   return ER_OK;
 }
 
+// ---- dropout of DNN.__call__ (layers/dnn.py:77-82: tf.nn.dropout(x, keep_prob = 1 - ratio), training only) ----------
+// y = x * keep_mask / keep.  The mask is a counter-based function of (seed, step counter, element index): the backward
+// pass recomputes it instead of storing it, and the step counter is a DEVICE scalar, so a captured CUDA graph draws a
+// new mask on every replay (the host bumps the counter with one tiny device add after the backward).  TensorFlow's
+// own random stream cannot be reproduced; the contract is the distribution (Bernoulli(keep) per element, E[y] = x).
+namespace er {
+__device__ __forceinline__ uint32_t drop_bits(uint64_t seed, uint64_t ctr, uint64_t i) {
+  uint64_t z = seed + ctr * 0x9E3779B97F4A7C15ull + i * 0xD1B54A32D192ED03ull;   // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+__global__ void __launch_bounds__(256)
+    dropout_kernel(const float* __restrict__ x, int64_t n, uint32_t keep_thresh, float inv_keep, uint64_t seed,
+                   const int64_t* __restrict__ counter, float* __restrict__ y) {
+  const uint64_t ctr = (uint64_t)*counter;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = drop_bits(seed, ctr, (uint64_t)i) < keep_thresh ? x[i] * inv_keep : 0.f;
+}
+}  // namespace er
+
+extern "C" int er_dropout(const float* x, int64_t n, float rate, uint64_t seed, const int64_t* counter_dev, float* y,
+                          er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && y && counter_dev, "null argument");
+  ER_REQUIRE(n > 0 && rate >= 0.f && rate < 1.f, "rate must be in [0, 1)");
+  const double keep = 1.0 - (double)rate;
+  const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  dropout_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(x, n, thresh, (float)(1.0 / keep), seed, counter_dev, y);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
 // ---- dense optimizer: every dense parameter lives in ONE flat fp32 buffer (params, grads and
 // optimizer state are flat arrays with the same segment table), so the whole dense update of
 // optimize_loss -> opt.apply_gradients (compat/optimizers.py:413-416) is one launch:

@@ -100,6 +100,17 @@ def bucketize(ids, slots_dev, n_slots, n_seg, seg_ids=None, row_ptr=None, rows=N
   return rows
 
 
+def dropout(x, rate, seed, counter, out=None):
+  """er_dropout: x * Bernoulli(1 - rate) / (1 - rate), mask = f(seed, counter[0], index); counter: device int64 [1]."""
+  x = x.contiguous()
+  _chk(x, torch.float32, 'x')
+  _chk(counter, torch.int64, 'counter')
+  y = torch.empty_like(x) if out is None else out
+  _lib.check(_lib.load().er_dropout(_p(x), x.numel(), float(rate), int(seed) & (2**64 - 1), _p(counter), _p(y), _stream()),
+             'er_dropout')
+  return y
+
+
 def shard_group_workspace(n_lookups, device):
   return torch.empty(_lib.load().er_shard_group_workspace_bytes(int(n_lookups)), dtype=torch.uint8, device=device)
 

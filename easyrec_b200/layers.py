@@ -171,22 +171,73 @@ class Dense(DenseLayer):
     super().__init__(n_in, n_out, use_bn=False, relu=False, generator=generator)
 
 
+class _DropoutFn(torch.autograd.Function):
+  """y = x * mask / keep; the backward pass recomputes the mask from (seed, counter) - nothing is stored."""
+
+  @staticmethod
+  def forward(ctx, x, rate, seed, counter):
+    ctx.rate, ctx.seed, ctx.counter = rate, seed, counter
+    return K.dropout(x, rate, seed, counter)
+
+  @staticmethod
+  def backward(ctx, g):
+    return K.dropout(g, ctx.rate, ctx.seed, ctx.counter), None, None, None
+
+
+class Dropout(nn.Module):
+  """tf.nn.dropout(x, keep_prob = 1 - ratio) of DNN.__call__ (layers/dnn.py:77-82): training only.  The mask is a
+  counter-based function of (layer seed, step counter, element): the counter is a device scalar advanced once per
+  training step by a hook on the upstream gradient (a tiny device add, captured with the step), so a replayed CUDA
+  graph draws a fresh mask every step and forward / backward of one step agree."""
+  _next_seed = [0x5EED0001]
+
+  def __init__(self, rate):
+    super().__init__()
+    assert 0.0 <= rate < 1.0, 'invalid dropout_ratio: %.3f' % rate
+    self.rate = float(rate)
+    self.seed = Dropout._next_seed[0]
+    Dropout._next_seed[0] += 0x9E3779B1
+    self.register_buffer('counter', torch.zeros(1, dtype=torch.int64))
+
+  def forward(self, x):
+    if not self.training or self.rate == 0.0:
+      return x
+    if x.requires_grad:
+      # a hook on the INPUT's gradient runs after this layer's own backward has recomputed the mask: the moment to
+      # advance the counter for the next step
+      x.register_hook(self._advance)
+      return _DropoutFn.apply(x, self.rate, self.seed, self.counter)
+    y = K.dropout(x, self.rate, self.seed, self.counter)
+    self.counter.add_(1)
+    return y
+
+  def _advance(self, grad):
+    self.counter.add_(1)
+    return grad
+
+
 class Units(list):
-  """hidden_units of a protos/dnn.proto DNN message together with its use_bn flag (slices keep the flag)."""
+  """hidden_units of a protos/dnn.proto DNN message together with its use_bn flag and dropout_ratio list (slices
+  keep them)."""
   use_bn = True
+  dropout = ()
 
   def __getitem__(self, k):
     v = list.__getitem__(self, k)
     if isinstance(k, slice):
       v = Units(v)
       v.use_bn = self.use_bn
+      v.dropout = tuple(self.dropout[k])
     return v
 
 
 def units_of(dnn_config):
-  """DNN message -> Units (layers/dnn.py:50-87 reads hidden_units and use_bn from the same message)."""
+  """DNN message -> Units (layers/dnn.py:50-87 reads hidden_units, use_bn and dropout_ratio from the same message)."""
   u = Units(int(x) for x in dnn_config.hidden_units)
   u.use_bn = bool(dnn_config.use_bn)
+  u.dropout = tuple(float(r) for r in dnn_config.dropout_ratio)
+  if u.dropout and len(u.dropout) != len(u):
+    raise ValueError('dropout_ratio needs one entry per hidden layer (layers/dnn.py:78 indexes it by layer)')
   return u
 
 
@@ -198,12 +249,16 @@ class DNN(nn.Module):
                last_layer_no_batch_norm=False, generator=None):
     super().__init__()
     use_bn = use_bn and getattr(hidden_units, 'use_bn', True)   # protos/dnn.proto use_bn (default true)
+    drop = tuple(getattr(hidden_units, 'dropout', ()))
     self.layers = nn.ModuleList()
+    self.dropouts = nn.ModuleList()
     n = len(hidden_units)
     for i, u in enumerate(hidden_units):
       bn = use_bn and (i + 1 < n or not last_layer_no_batch_norm)
       act = i + 1 < n or not last_layer_no_activation
       self.layers.append(DenseLayer(n_in, u, bn, act, generator))
+      # dropout follows the activation of EVERY layer, the last one included (layers/dnn.py:77-82)
+      self.dropouts.append(Dropout(drop[i]) if drop and drop[i] > 0 else nn.Identity())
       n_in = u
     self.out_dim = n_in
 
@@ -211,8 +266,8 @@ class DNN(nn.Module):
     shape = x.shape
     if x.dim() == 3:
       x = x.reshape(-1, shape[-1])
-    for layer in self.layers:
-      x = layer(x)
+    for layer, drop in zip(self.layers, self.dropouts):
+      x = drop(layer(x))
     if len(shape) == 3:
       x = x.reshape(shape[0], shape[1], -1)
     return x

@@ -349,6 +349,13 @@ int er_bias_bn_act_bwd(const float* z, const float* bias, const float* gamma,
                        int32_t relu, float* gz, float* gbias, float* ggamma,
                        float* gbeta, void* ws, size_t ws_bytes, er_stream_t stream);
 
+/* tf.nn.dropout of DNN.__call__ (layers/dnn.py:77-82): y = x * mask / (1 - rate), mask ~ Bernoulli(1 - rate) per
+ * element, a counter-based function of (seed, *counter_dev, element index).  The backward pass is the SAME call on the
+ * upstream gradient (same seed, same counter value): the mask is recomputed, not stored.  counter_dev is a device
+ * int64 the caller advances once per step, so a captured graph draws a new mask on every replay. */
+int er_dropout(const float* x, int64_t n, float rate, uint64_t seed, const int64_t* counter_dev, float* y,
+               er_stream_t stream);
+
 /* Dense optimizer over ONE flat parameter buffer (dense apply_gradients,
  * compat/optimizers.py:413-416): g = grad*grad_scale + l2*w, then the adagrad / adam / sgd rule.
  * segs: DEVICE array describing the tensors inside the flat buffers; the step's rate comes from lr_dev

@@ -164,6 +164,17 @@ def install_sparse(patch):
 
 def install_dense(patch):
   """dense towers, loss, FM and the flat dense optimizer -> plain torch / the oracle's numpy."""
+  def dropout(x, rate, seed, counter, out=None):
+    g = torch.Generator().manual_seed((int(seed) + 1000003 * int(counter[0])) % (2**63))
+    keep = 1.0 - rate
+    mask = (torch.rand(x.shape, generator=g) < keep).to(x.dtype) / keep
+    y = x * mask
+    if out is not None:
+      out.copy_(y)
+      return out
+    return y
+  patch(K, 'dropout', dropout)
+
   def gemm(a, b, bias=None, out=None):
     r = a @ b
     if bias is not None:

@@ -285,14 +285,13 @@ def test_data_options_that_change_the_batches_or_the_loss_are_refused_and_header
 
 
 def test_tower_options_that_are_not_implemented_are_refused():
-  for new, word in ((b'dnn { hidden_units: [32, 16] dropout_ratio: [0.1, 0.1] }', 'dropout_ratio'),
-                    (b'dnn { hidden_units: [32, 16] activation: "dice" }', 'activation')):
+  for new, word in ((b'dnn { hidden_units: [32, 16] activation: "dice" }', 'activation'),):
     cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'dnn { hidden_units: [32, 16] }', new))
     with pytest.raises(NotImplementedError, match=word):
       builder.check_scope(cfg)
-  # use_bn: false is built (dense + bias -> relu per layer, layers/dnn.py:62-70)
-  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'dnn { hidden_units: [32, 16] }',
-                                                                b'dnn { hidden_units: [32, 16] use_bn: false }'))
+  # use_bn: false and dropout_ratio are built (dense + bias -> [bn] -> relu -> dropout per layer, layers/dnn.py:62-82)
+  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
+      b'dnn { hidden_units: [32, 16] }', b'dnn { hidden_units: [32, 16] use_bn: false dropout_ratio: [0.1, 0.1] }'))
   builder.check_scope(cfg)
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from easyrec_b200 import layers as L
+from easyrec_b200 import kernels as K, layers as L
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -188,3 +188,36 @@ def test_concat_cols_into_pitched_buffer_and_split_back():
   y.backward(gy)
   ref = torch.split(gy, [1, 16, 64], dim=1)
   assert all(torch.equal(l.grad, r) for l, r in zip(leaves, ref))
+
+
+def test_dropout_kernel_is_bernoulli_keep_scaled_and_its_backward_reuses_the_mask():
+  """er_dropout (layers/dnn.py:77-82 tf.nn.dropout): Bernoulli(keep) mask scaled by 1/keep, a function of (seed,
+  device counter, index) - the backward recomputes it; a captured graph redraws when the counter advances."""
+  from easyrec_b200 import layers as L
+  torch.manual_seed(0)
+  n, rate = 1 << 20, 0.3
+  x = torch.randn(n, device=DEV) + 3.0
+  ctr = torch.zeros(1, dtype=torch.int64, device=DEV)
+  y = K.dropout(x, rate, 1234, ctr)
+  kept = y != 0
+  assert abs(float(kept.float().mean()) - 0.7) < 3e-3                       # 5 sigma of a 1M-sample Bernoulli(0.7)
+  torch.testing.assert_close(y[kept], x[kept] / 0.7, rtol=1e-6, atol=0)
+  assert torch.equal(K.dropout(x, rate, 1234, ctr), y)                      # same (seed, counter): same mask
+  ctr.add_(1)
+  y2 = K.dropout(x, rate, 1234, ctr)
+  both = float(((y2 != 0) & kept).float().mean())
+  assert abs(both - 0.49) < 5e-3                                            # independent of the previous step's mask
+  assert abs(float(((K.dropout(x, rate, 99, ctr) != 0) & (y2 != 0)).float().mean()) - 0.49) < 5e-3   # and of other layers
+  # no run structure: neighbouring elements are independent
+  k = kept.float()
+  assert abs(float((k[1:] * k[:-1]).mean()) - 0.49) < 5e-3
+  # the layer: backward uses the forward's mask, then advances the counter
+  drop = L.Dropout(0.5).to(DEV).train()
+  xin = (torch.randn(4096, 64, device=DEV) + 2.0).requires_grad_(True)
+  h = xin * 1.0
+  out = drop(h)
+  out.sum().backward()
+  torch.testing.assert_close(xin.grad, (out != 0).float() * 2.0)
+  assert int(drop.counter[0]) == 1
+  drop.eval()
+  assert drop(h) is h

@@ -325,3 +325,29 @@ def test_backbone_embedding_layer_block_is_one_offset_table_of_the_blocks_width(
   lab = torch.from_numpy((rng.uniform(size=B) < 0.3).astype(np.float32))
   losses = [float(tr.train_step(feats, lab)[0]) for _ in range(12)]
   assert losses[-1] < losses[0] - 0.01
+
+
+def test_dnn_dropout_ratio_masks_in_training_only_and_redraws_every_step(dense_kernels):  # noqa: F811
+  """protos/dnn.proto dropout_ratio (layers/dnn.py:77-82): tf.nn.dropout after every layer's activation while training."""
+  text = workloads_c2(dnn_extra='dropout_ratio: [0.5, 0.25]')
+  cfg = config_util.get_configs_from_pipeline_file(text)
+  import os
+  os.environ['ER_PLAN_ONLY'] = '1'
+  try:
+    il, model, _ = builder.build_model(cfg, 32, 'cpu', cpu_generator=torch.Generator().manual_seed(1))
+  finally:
+    del os.environ['ER_PLAN_ONLY']
+  from easyrec_b200 import layers as L
+  assert [type(d).__name__ for d in model.dnn.dropouts] == ['Dropout', 'Dropout'] and model.dnn.dropouts[0].rate == 0.5
+  assert all(isinstance(d, torch.nn.Identity) for d in model.final_dnn.dropouts)
+  x = torch.randn(32, model.dnn.layers[0].kernel.shape[0])
+  model.train()
+  y1 = model.dnn(x)
+  (y1.sum()).backward()
+  y2 = model.dnn(x)
+  assert not torch.equal(y1, y2)                                   # the counter advanced with the backward pass
+  assert int(model.dnn.dropouts[1].counter[0]) == 1
+  zeros = float((y1 == 0).float().mean())
+  assert zeros > 0.25                                              # relu zeros + the 25 % of the last layer
+  model.eval()
+  assert torch.equal(model.dnn(x), model.dnn(x))                   # inference: identity
