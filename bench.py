@@ -317,15 +317,19 @@ def main():
   devb = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in pinned]
   W = max(args.warmup, 3)
 
+  def nxt(i, n):
+    """row-sharded runs name the next batch (its id exchange runs beside the current step); None on the last step"""
+    return devb[(i + 1) % n_rot][0] if (ep and i + 1 < n) else None
+
   def timed_resident(est, steps, warm):
     """device-resident throughput: CUDA events around `steps` train_step calls"""
     for i in range(warm):
-      est.trainer.train_step(*devb[i % n_rot])
+      est.trainer.train_step(*devb[i % n_rot], next_features=nxt(i, warm))
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(steps):
-      loss, _ = est.trainer.train_step(*devb[i % n_rot])
+      loss, _ = est.trainer.train_step(*devb[i % n_rot], next_features=nxt(i, steps))
     ev1.record()
     barrier()
     return max_over_ranks(ev0.elapsed_time(ev1)), float(loss)
@@ -348,7 +352,7 @@ def main():
   est = build(args.optimizer)
   il = est.input_layer
   for i in range(W):
-    est.trainer.train_step(*devb[i % n_rot])
+    est.trainer.train_step(*devb[i % n_rot], next_features=nxt(i, W))
   barrier()
   sampler.mark()
   ms, final_loss = timed_resident(est, args.steps, 0)
@@ -513,8 +517,10 @@ def run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks):
   sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0)))
   if rank == 0:
     sampler.start()
+  def nxt(i, n):
+    return devb[(i + 1) % n_rot][0] if (ep and i + 1 < n) else None
   for i in range(W):
-    est.trainer.train_step(*devb[i % n_rot])
+    est.trainer.train_step(*devb[i % n_rot], next_features=nxt(i, W))
   barrier()
   sampler.mark()
   lib = _lib.load()
@@ -522,7 +528,7 @@ def run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks):
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
   for i in range(steps):
-    loss, _ = est.trainer.train_step(*devb[i % n_rot])
+    loss, _ = est.trainer.train_step(*devb[i % n_rot], next_features=nxt(i, steps))
   ev1.record()
   barrier()
   ms = max_over_ranks(ev0.elapsed_time(ev1))

@@ -22,6 +22,20 @@ _DENSE_KIND = {'adagrad_optimizer': 'adagrad', 'adam_optimizer': 'adam', 'lazy_a
 auc = metrics.auc   # exact ROC AUC; the reference's tf.metrics.auc is a 200-threshold approximation of it
 
 
+def _with_next(batches, ahead, want_more):
+  """(features, labels, next batch or None): the next batch is drawn only when another step will follow, so no batch is
+  taken from the input and left untrained."""
+  it = iter(batches)
+  cur = next(it, None)
+  while cur is not None:
+    nxt = next(it, None) if (ahead and want_more()) else None
+    yield cur[0], cur[1], nxt
+    if ahead:
+      cur = nxt if nxt is not None else (next(it, None) if want_more() else None)
+    else:
+      cur = next(it, None)
+
+
 class EasyRecEstimator(object):
 
   def __init__(self, pipeline_config, model_cls=None, run_config=None, params=None, device='cuda:0',
@@ -89,10 +103,13 @@ class EasyRecEstimator(object):
     epoch = 0
     while not done:
       seen = self.global_step
-      feeder = readers.DeviceFeeder(readers.Prefetcher(input_fn(), depth=2), self._device, depth=2)
+      # row-sharded tables: train_step is told the NEXT batch, whose id exchange then runs beside the current step
+      ahead = 1 if self._ep else 0
+      feeder = readers.DeviceFeeder(readers.Prefetcher(input_fn(), depth=2), self._device, depth=2, lookahead=ahead)
       self.last_feeder = feeder
-      for feats, labels in feeder:   # host parsing and the H2D copies run ahead of the device step
-        loss, _ = self.trainer.train_step(feats, labels)
+      for feats, labels, nxt in _with_next(feeder, ahead, lambda: limit is None or self.global_step - n0 + 1 < limit):
+        # host parsing and the H2D copies run ahead of the device step
+        loss, _ = self.trainer.train_step(feats, labels, next_features=None if nxt is None else nxt[0])
         self.global_step += 1
         if fetch_loss_every_step:
           self.last_loss_value = float(loss)

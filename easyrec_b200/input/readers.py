@@ -761,10 +761,14 @@ class DeviceFeeder(object):
   step that read them has been enqueued and has finished (event recorded when the consumer asks for the next batch).
   On a CPU device it passes the batches through."""
 
-  def __init__(self, source, device, depth=2):
+  def __init__(self, source, device, depth=2, lookahead=0):
+    """lookahead: how many batches the consumer holds beyond the one it is training on (EasyRecEstimator.train names
+    the next batch to train_step so that its id exchange can run early): a slot is recycled only after the step that
+    reads it has been enqueued, i.e. `lookahead` requests later."""
     self.source = source
     self.device = device
-    self.depth = max(int(depth), 1)
+    self.lookahead = max(int(lookahead), 0)
+    self.depth = max(int(depth), 1) + self.lookahead
     self.h2d_bytes = 0   # bytes copied host -> device so far (bench.py reports them per step)
 
   class _Slot(object):
@@ -831,11 +835,16 @@ class DeviceFeeder(object):
       self._stage_batch(ring[i % self.depth], nxt[0], nxt[1], stream)
       queue.append(ring[i % self.depth])
       i += 1
+    held = _c.deque()
     while queue:
       slot = queue.popleft()
       torch.cuda.current_stream().wait_event(slot.ready)
       yield slot.batch
-      # the consumer has enqueued the step that reads this slot: its buffers are free once that step is done
+      held.append(slot)
+      if len(held) <= self.lookahead:
+        continue
+      # the consumer has enqueued the step that reads the oldest held slot: its buffers are free once that step is done
+      slot = held.popleft()
       slot.consumed = torch.cuda.Event()
       slot.consumed.record(torch.cuda.current_stream())
       nxt = next(it, None)

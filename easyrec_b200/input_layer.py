@@ -349,6 +349,7 @@ class InputLayer(object):
     self._preset_rows = {}
     self._rows_bufs = {}
     self._pos = {}
+    self._next_ids = {}
 
   # ------------------------------------------------------------------
   def set_optimizer_step(self, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
@@ -466,7 +467,44 @@ class InputLayer(object):
       return dense
     return (dense - self.raw_sub) / self.raw_range  # (x - min) / (max - min), input/input.py:638-640
 
-  def _gather_inputs(self, dim, ids, dense_norm):
+  def prefetch_exchange(self, next_features):
+    """EmbeddingParallel: start the id half of the NEXT batch's exchange (K1, K8, id all-to-all) beside the rest of
+    this step; the next lookup() promotes it instead of computing it on the critical path."""
+    if not self.ep:
+      return
+    done = set()
+    for dim, subs in self.subcalls.items():
+      for sk, sc in subs.items():
+        ex = sc.sharded.ex
+        if id(ex) in done:
+          continue
+        done.add(id(ex))
+        buf = self._next_ids.get(dim)
+        if buf is None:
+          buf = self._next_ids[dim] = torch.zeros_like(self.static_ids[dim])
+        cids, _ = self._gather_inputs(dim, next_features.get('sparse_fea'), None, ids_buf=buf, want_w=False)
+        ex.prefetch(ex.members[0], cids)
+
+  def _exchanges(self):
+    seen, out = set(), []
+    if self.ep:
+      for subs in self.subcalls.values():
+        for sc in subs.values():
+          if id(sc.sharded.ex) not in seen:
+            seen.add(id(sc.sharded.ex))
+            out.append(sc.sharded.ex)
+    return out
+
+  def join_prefetch(self):
+    for ex in self._exchanges():
+      ex.join_prefetch()
+
+  def prefetch_ready(self):
+    """True when every exchange holds a prefetched id exchange for the next lookup()."""
+    ex = self._exchanges()
+    return bool(ex) and all(e._have_next for e in ex)
+
+  def _gather_inputs(self, dim, ids, dense_norm, ids_buf=None, want_w=True):
     """ids int64 [n_id*B] feature-major -> (ids, weights) in the single-valued call's slot order.
 
     Two strided copies per arena (ids of the id slots, normalised values of the raw slots);
@@ -476,8 +514,8 @@ class InputLayer(object):
       return ids, None
     B = self.batch_size
     S = call.n_slots
-    out_ids = self.static_ids[dim]
-    out_w = self.static_w[dim]
+    out_ids = self.static_ids[dim] if ids_buf is None else ids_buf
+    out_w = self.static_w[dim] if want_w else None
     plan = self._gather_plan.get(dim)
     if plan is None:
       src = call.sources

@@ -141,7 +141,9 @@ class ShardedExchange(object):
     self._active = []       # members that looked up this step, in call order
     self._summed = 0        # members whose requester-side gradient sums are in send_g
     self._side = torch.cuda.Stream(device=device) if str(device).startswith('cuda') else None
+    self._pre = torch.cuda.Stream(device=device) if str(device).startswith('cuda') else None
     self._presorted = False
+    self._have_next = False   # K1 / K8 / id all-to-all of the NEXT batch already sit in the *_n buffers
 
   def add(self, member):
     assert not self._built
@@ -167,6 +169,15 @@ class ShardedExchange(object):
     self.counts = torch.zeros(N + 1, dtype=torch.int32, device=dev)
     self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     self.group_ws = K.shard_group_workspace(self.L, dev)
+    # the same for the batch AFTER this one (prefetch): ids need no table state, so their exchange runs a step ahead
+    self.owner_n = torch.empty(self.L, dtype=torch.int32, device=dev)
+    self.rows_local_n = torch.empty(self.L, dtype=i64, device=dev)
+    self.send_rows_n = torch.empty(self.n_ex, dtype=i64, device=dev)
+    self.recv_rows_n = torch.empty(self.n_ex, dtype=i64, device=dev)
+    self.pos_n = torch.empty(self.L, dtype=i64, device=dev)
+    self.ids_n = torch.empty(self.L, dtype=i64, device=dev)
+    self.counts_n = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+    self.mismatch = torch.zeros(1, dtype=i64, device=dev)
     shape = (self.n_ex, self.width)
     self.send_emb, self.recv_emb = torch.zeros(shape, dtype=f32, device=dev), torch.zeros(shape, dtype=f32, device=dev)
     self.send_g, self.recv_g = torch.zeros(shape, dtype=f32, device=dev), torch.zeros(shape, dtype=f32, device=dev)
@@ -174,14 +185,49 @@ class ShardedExchange(object):
       m._plan(self)
     self._built = True
 
+  def prefetch(self, first, ids_next):
+    """The id half of the NEXT batch's exchange (K1 -> K8 -> all_to_all(ids)), on a side stream beside this step's
+    dense backward: it reads no table, so it may run a whole step ahead.  lookup() of the next step then only
+    promotes the results.  ids_next must be the ids the next lookup() is called with (checked on the device)."""
+    self.build()
+    N = self.world
+    call = first.call
+    import contextlib
+    if self._pre is not None:
+      self._pre.wait_stream(torch.cuda.current_stream())
+    with (torch.cuda.stream(self._pre) if self._pre is not None else contextlib.nullcontext()):
+      self.ids_n.copy_(ids_next)
+      K.bucketize(self.ids_n, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local_n, owner=self.owner_n)
+      K.shard_group(self.rows_local_n, self.owner_n, N, self.cap, self.send_rows_n, self.pos_n, self.counts_n,
+                    self.group_ws)
+      self.overflow += self.counts_n[N:]
+      dist.all_to_all_single(self.recv_rows_n, self.send_rows_n)
+    self._have_next = True
+
+  def join_prefetch(self):
+    """the step's stream waits for the prefetch branch (a fork inside a capture must be joined before it ends)"""
+    if self._pre is not None:
+      torch.cuda.current_stream().wait_stream(self._pre)
+
   def lookup(self, first, ids):
     """K1 -> K8 -> all_to_all(ids) -> every member's K2 on the owner -> ONE all_to_all(rows)."""
     N = self.world
     call = first.call
-    K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local, owner=self.owner)
-    K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
-    self.overflow += self.counts[N:]
-    dist.all_to_all_single(self.recv_rows, self.send_rows)
+    if self._have_next:
+      # (inside a capture the prefetch being promoted ran in the PREVIOUS replay or eagerly before this one: ordered
+      # by the stream already, and a captured stream may not wait on work outside its capture)
+      if self._pre is not None and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.current_stream().wait_stream(self._pre)
+      self.mismatch += (self.ids_n != ids).sum()   # the prefetched batch must be the one looked up now
+      self.pos.copy_(self.pos_n)
+      self.recv_rows.copy_(self.recv_rows_n)
+      self.rows_local.copy_(self.rows_local_n)
+      self._have_next = False
+    else:
+      K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local, owner=self.owner)
+      K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
+      self.overflow += self.counts[N:]
+      dist.all_to_all_single(self.recv_rows, self.send_rows)
     self._presorted = False
     if self._side is not None and torch.is_grad_enabled():
       # the row-only halves of both K7s (requester: positions, owner: received rows) need no gradient: a parallel
@@ -205,6 +251,11 @@ class ShardedExchange(object):
     return (m.pool_ws if which == 'pool' else m.owner_ws, m.call.arena.dim)
 
   def check(self):
+    bad = int(self.mismatch.item())
+    if bad:
+      self.mismatch.zero_()
+      raise _lib.ErError('row-sharded exchange: the prefetched batch differed from the batch looked up in %d ids '
+                         '(train_step(next_features=...) must name the batch of the next call)' % bad)
     lost = int(self.overflow.item())
     if lost:
       self.overflow.zero_()

@@ -177,6 +177,9 @@ class Trainer(object):
     # executed and replayed from then on, so every batch is applied exactly once
     self.graph_warmup_steps = 2
     self._eager_steps = 0
+    self._prefetch_mode = False
+    self._stale_next = False
+    self._static_next = None
     self._warm_stream = None
     self._graph = None
     self._graph2 = None
@@ -191,10 +194,14 @@ class Trainer(object):
 
   # The step is three segments; only the middle one talks to other ranks, so with world > 1 the
   # CUDA graph is captured as two graphs around eager NCCL calls.
-  def _segment_compute(self, features, labels):
+  def _segment_compute(self, features, labels, next_features=None):
     """lookup -> model -> loss -> backward -> dense grads into the flat buffer."""
     self.dense_opt.zero_grad()
     logits = self.model(features)
+    if next_features is not None:
+      # row-sharded tables: the id half of the NEXT batch's exchange reads no table, so it runs beside this step's
+      # backward and the next lookup only promotes it (InputLayer.prefetch_exchange)
+      self.input_layer.prefetch_exchange(next_features)
     loss, probs = self.model.loss(logits, labels)
     with L.defer_dw_join():   # kernel-gradient GEMMs overlap the rest of the backward chain
       loss.backward()
@@ -231,18 +238,28 @@ class Trainer(object):
     if self.dp is not None:
       self.dp.pre_exchange(features)   # eager: K1 + all-gather of rows + global dedup sort on a side stream
 
-  def _step_body(self, features, labels):
+  def _step_body(self, features, labels, next_features=None):
     self._segment_pre(features)
-    loss, probs = self._segment_compute(features, labels)
+    loss, probs = self._segment_compute(features, labels, next_features)
     self._segment_exchange()
-    return self._segment_update(loss), probs
+    out = self._segment_update(loss), probs
+    if next_features is not None:
+      self.input_layer.join_prefetch()
+    return out
 
-  def train_step(self, features, labels):
-    """features/labels: device tensors.  Returns (loss [scalar tensor], probs [B])."""
+  def train_step(self, features, labels, next_features=None):
+    """features/labels: device tensors.  Returns (loss [scalar tensor], probs [B]).
+
+    next_features (EmbeddingParallel only, else ignored): the features of the batch the NEXT train_step call will be
+    given - its id exchange then runs beside this step instead of at the head of the next one.  A run that passes it
+    should pass it on every step but the last; the exchange verifies on the device that the batch it prefetched is the
+    one that arrives (InputLayer.check_exchange)."""
     self.model.train()
     self._set_hyper()
+    if not bool(getattr(self.input_layer, 'ep', False)):
+      next_features = None
     if not self.use_cuda_graph:
-      out = self._step_body(features, labels)
+      out = self._step_body(features, labels, next_features)
       self.step += 1
       return out
     if self._eager_steps < self.graph_warmup_steps:
@@ -254,16 +271,26 @@ class Trainer(object):
         self._warm_stream = torch.cuda.Stream(device=cur.device)
       self._warm_stream.wait_stream(cur)
       with torch.cuda.stream(self._warm_stream):
-        out = self._step_body(features, labels)
+        out = self._step_body(features, labels, next_features)
       cur.wait_stream(self._warm_stream)
       self.step += 1
       self._eager_steps += 1
       return out
     if self._graph is None:
-      self._capture(features, labels)
+      # row-sharded tables: the captured step always promotes a prefetched id exchange and prefetches the next one;
+      # a call that does not name its successor leaves the exchange "stale" and the next call runs it eagerly first
+      self._prefetch_mode = bool(getattr(self.input_layer, 'ep', False))
+      self._capture(features, labels, next_features)
     else:
       _tree_copy(self._static_feats, features)
       self._static['__labels'].copy_(labels, non_blocking=True)
+      if self._prefetch_mode and next_features is not None:
+        _tree_copy(self._static_next, next_features)
+    if self._prefetch_mode:
+      if self._stale_next:   # the previous call did not name this batch: its id exchange runs now, ahead of the replay
+        self.input_layer.prefetch_exchange(self._static_feats)
+        self.input_layer.join_prefetch()
+      self._stale_next = next_features is None
     if self._graph2 is not None:
       self._segment_pre(self._static_feats)
     self._graph.replay()
@@ -273,7 +300,7 @@ class Trainer(object):
     self.step += 1
     return self._loss, self._probs
 
-  def _capture(self, features, labels):
+  def _capture(self, features, labels, next_features=None):
     """Record one step into a CUDA graph (nothing executes here; train_step replays it).  Every step-varying
     scalar of the optimizers - learning rate, Adam's beta powers, gradient scale - is read by the kernels from
     the device block `input_layer.hyper` that _set_hyper refreshes before each replay, so Adagrad, lazy Adam
@@ -281,6 +308,12 @@ class Trainer(object):
     feats = _tree_clone(features)
     self._static = {'__labels': labels.clone()}
     self._static_feats = feats
+    self._static_next = _tree_clone(next_features if next_features is not None else features) \
+        if self._prefetch_mode else None
+    if self._prefetch_mode and not self.input_layer.prefetch_ready():
+      self.input_layer.prefetch_exchange(feats)   # eager: the captured lookup promotes a prefetched exchange
+      self.input_layer.join_prefetch()
+    self._stale_next = False
     torch.cuda.synchronize()
     self._graph = torch.cuda.CUDAGraph()
     n0 = _lib.load().er_launch_count()
@@ -292,7 +325,7 @@ class Trainer(object):
     if one_graph:
       kw = {} if self.dp is None else {'capture_error_mode': 'thread_local'}
       with torch.cuda.graph(self._graph, **kw):
-        self._loss, self._probs = self._step_body(feats, self._static['__labels'])
+        self._loss, self._probs = self._step_body(feats, self._static['__labels'], self._static_next)
     else:
       self._segment_pre(feats)   # eager, before the capture: the captured lookup reuses these rows
       with torch.cuda.graph(self._graph):

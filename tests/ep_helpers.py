@@ -62,7 +62,7 @@ def compare(dp_il, ep_il, rank, world, atol):
   return worst
 
 
-def run(make_estimator, dev, rank, world, steps=4, atol=2e-6):
+def run(make_estimator, dev, rank, world, steps=4, atol=2e-6, lookahead=False):
   """make_estimator(config bytes, embedding_parallel) -> EasyRecEstimator on `dev`"""
   dp = make_estimator(CFG_EP.replace(b'train_distribute: EmbeddingParallelStrategy', b''), False)
   ep = make_estimator(CFG_EP, None)
@@ -72,12 +72,16 @@ def run(make_estimator, dev, rank, world, steps=4, atol=2e-6):
   ep.model.load_state_dict(dp.model.state_dict())
   ep.trainer.dense_opt.flat_p.copy_(dp.trainer.dense_opt.flat_p)
   losses = []
+  batches = []
   for step in range(steps):
     f, l = batch(64, rank, step)
-    f = {k: v.to(dev) for k, v in f.items()}
-    l = l.to(dev)
+    batches.append(({k: v.to(dev) for k, v in f.items()}, l.to(dev)))
+  for step in range(steps):
+    f, l = batches[step]
     l_dp, _ = dp.trainer.train_step(f, l)
-    l_ep, _ = ep.trainer.train_step(f, l)
+    # lookahead: the trainer is told the next batch, whose id exchange then runs beside this step
+    nxt = batches[step + 1][0] if (lookahead and step + 1 < steps) else None
+    l_ep, _ = ep.trainer.train_step(f, l, next_features=nxt)
     losses.append((float(l_dp), float(l_ep)))
     assert abs(float(l_dp) - float(l_ep)) < 1e-5, losses
   worst = compare(dp.input_layer, ep.input_layer, rank, world, atol)

@@ -36,6 +36,8 @@ def _worker(rank, port, ret, world):
   def make(cfg, ep):
     return EasyRecEstimator(cfg, device='cpu', seed=5, world_size=world, rank=rank, embedding_parallel=ep)
   ret[rank] = ep_helpers.run(make, 'cpu', rank, world)
+  # ... and with the next batch's id exchange prefetched beside the current step (train_step(next_features=...))
+  ret[rank] = max(ret[rank], ep_helpers.run(make, 'cpu', rank, world, steps=5, lookahead=True))
   dist.destroy_process_group()
 
 

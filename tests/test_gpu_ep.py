@@ -40,6 +40,10 @@ def _worker(rank, port, ret):
   # replays), against the eager replicated model
   worst = ep_helpers.run(lambda cfg, ep: make(cfg, ep, graph=True), dev, rank, WORLD, steps=7, atol=5e-6)
   ret[rank] = max(ret[rank], worst)
+  # the id exchange of the next batch prefetched beside the current step: eager, and replayed from the graph
+  for graph in (False, True):
+    worst = ep_helpers.run(lambda cfg, ep: make(cfg, ep, graph=graph), dev, rank, WORLD, steps=8, atol=5e-6, lookahead=True)
+    ret[rank] = max(ret[rank], worst)
   dist.barrier()
   os._exit(0)
 

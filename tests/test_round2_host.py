@@ -351,3 +351,33 @@ def test_dnn_dropout_ratio_masks_in_training_only_and_redraws_every_step(dense_k
   assert zeros > 0.25                                              # relu zeros + the 25 % of the last layer
   model.eval()
   assert torch.equal(model.dnn(x), model.dnn(x))                   # inference: identity
+
+
+def test_lookahead_iteration_names_the_next_batch_and_never_draws_one_it_will_not_train():
+  from easyrec_b200.estimator import _with_next
+  drawn = []
+
+  def src(n):
+    for i in range(n):
+      drawn.append(i)
+      yield ('f%d' % i, 'l%d' % i)
+  # no lookahead: plain iteration
+  assert [(f, n) for f, _, n in _with_next(src(3), 0, lambda: True)] == [('f0', None), ('f1', None), ('f2', None)]
+  # lookahead with a step limit of 3 over a longer input: the 4th batch is never drawn
+  drawn.clear()
+  state = {'done': 0}
+  out = []
+  for f, l, nxt in _with_next(src(10), 1, lambda: state['done'] + 1 < 3):
+    out.append((f, None if nxt is None else nxt[0]))
+    state['done'] += 1
+    if state['done'] >= 3:
+      break
+  assert out == [('f0', 'f1'), ('f1', 'f2'), ('f2', None)] and drawn == [0, 1, 2]
+  # lookahead, input shorter than the limit: the last batch has no successor
+  drawn.clear()
+  state = {'done': 0}
+  out = []
+  for f, l, nxt in _with_next(src(2), 1, lambda: state['done'] + 1 < 100):
+    out.append((f, None if nxt is None else nxt[0]))
+    state['done'] += 1
+  assert out == [('f0', 'f1'), ('f1', None)]
