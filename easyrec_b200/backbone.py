@@ -103,9 +103,17 @@ class MLP(nn.Module):
       if act not in ('relu', '', 'linear', 'None'):
         raise NotImplementedError('MLP activation %r' % act)
     self.layers = nn.ModuleList()
+    self.dropouts = nn.ModuleList()
+    rates = [float(r) for r in conf.dropout_ratio]
     n = len(units)
     for i, u in enumerate(units):
       last = i + 1 == n
+      # Dropout(rate) after the layer's activation when 0 < rate < 1; layers beyond the list get none (blocks.py:56-67,
+      # 113-117)
+      rate = rates[i] if i < len(rates) else 0.0
+      if rate >= 1.0:
+        raise ValueError('invalid dropout_ratio: %.3f' % rate)
+      self.dropouts.append(L.Dropout(rate) if rate > 0.0 else nn.Identity())
       bn = conf.use_final_bn if last else conf.use_bn
       act = conf.final_activation if last else conf.activation
       lay = L.DenseLayer(n_in, u, bn, act == 'relu', generator)
@@ -122,8 +130,8 @@ class MLP(nn.Module):
   def forward(self, x):
     if isinstance(x, (list, tuple)):
       x = torch.cat(list(x), dim=-1)
-    for lay in self.layers:
-      x = lay(x)
+    for lay, drop in zip(self.layers, self.dropouts):
+      x = drop(lay(x))
     return x
 
 

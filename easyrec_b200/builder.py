@@ -252,8 +252,6 @@ def check_scope(pipeline_config):
         bad.append('%s: loss_type %s / num_class %d (task towers train with binary sigmoid cross entropy)'
                    % (path, lt, m.num_class))
     if kind in ('DNN', 'MLP'):
-      if kind == 'MLP' and any(r > 0 for r in m.dropout_ratio):
-        bad.append('%s.dropout_ratio' % path)
       if kind == 'DNN' and m.activation not in ('tf.nn.relu', 'relu'):
         bad.append('%s.activation %r' % (path, m.activation))
   if bad:

@@ -381,3 +381,29 @@ def test_lookahead_iteration_names_the_next_batch_and_never_draws_one_it_will_no
     out.append((f, None if nxt is None else nxt[0]))
     state['done'] += 1
   assert out == [('f0', 'f1'), ('f1', None)]
+
+
+def test_keras_mlp_block_dropout_ratio_follows_the_activation_of_the_listed_layers(dense_kernels):  # noqa: F811
+  """layers/keras/blocks.py:56-67,113-117: Dropout(rate) after a layer when 0 < rate < 1; layers past the list get none."""
+  from easyrec_b200 import backbone as BB
+  from easyrec_b200.config import config_util as cu
+  import test_gpu_models as G
+  text = G.BACKBONE_DCN_CFG.replace('mlp { hidden_units: [64, 32] }', 'mlp { hidden_units: [64, 32] dropout_ratio: [0.5] }')
+  cfg = cu.get_configs_from_pipeline_file(text.encode())
+  import os
+  os.environ['ER_PLAN_ONLY'] = '1'
+  try:
+    il, model, _ = builder.build_model(cfg, 64, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  finally:
+    del os.environ['ER_PLAN_ONLY']
+  mlp = [m for m in model.modules() if isinstance(m, BB.MLP) and len(m.layers) == 2 and m.layers[0].n_out == 64][0]
+  assert type(mlp.dropouts[0]).__name__ == 'Dropout' and mlp.dropouts[0].rate == 0.5
+  assert isinstance(mlp.dropouts[1], torch.nn.Identity)
+  x = torch.randn(64, mlp.layers[0].kernel.shape[0])
+  model.train()
+  a, b = mlp(x), mlp(x)
+  assert torch.equal(a, b)          # no backward in between: the same step, the same mask
+  a.sum().backward()
+  assert not torch.equal(mlp(x), a)
+  model.eval()
+  assert torch.equal(mlp(x), mlp(x))
