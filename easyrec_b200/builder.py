@@ -119,12 +119,19 @@ def input_type_name(pipeline_config):
   return dc.DESCRIPTOR.fields_by_name['input_type'].enum_type.values_by_number[dc.input_type].name
 
 
-def optimizer_settings(pipeline_config):
-  """builders/optimizer_builder.py:28-144: kind + constant / exponential-decay schedule."""
+def optimizer_settings(pipeline_config, index=0):
+  """builders/optimizer_builder.py:28-144: kind + constant / exponential-decay schedule of optimizer_config[index].
+  With TWO entries the first trains the embedding tables and the second every other variable
+  (model/easy_rec_estimator.py:216-232, EasyRecModel.get_grouped_vars model/easy_rec_model.py:446-467): the result
+  for index 0 then carries the second one's settings under 'dense'."""
   tc = pipeline_config.train_config
   if len(tc.optimizer_config) == 0:
     return dict(kind='adagrad_optimizer', lr_fn=lambda step: 0.01, beta1=0.9, beta2=0.999, acc0=0.1)
-  oc = tc.optimizer_config[0]
+  if index == 0 and len(tc.optimizer_config) == 2:
+    out = optimizer_settings(pipeline_config, index=-2)   # (-2 = entry 0 of two, without re-entering this branch)
+    out['dense'] = optimizer_settings(pipeline_config, index=1)
+    return out
+  oc = tc.optimizer_config[index]
   kind = oc.WhichOneof('optimizer')
   if kind is None:
     # builders/optimizer_builder.py:28-144 knows more optimizers (adam_async, ftrl, adamw, ...); only the ones with a
@@ -227,8 +234,9 @@ def check_scope(pipeline_config):
     bad.append('train_config.freeze_gradient')
   if tc.fine_tune_checkpoint:
     bad.append('train_config.fine_tune_checkpoint (TF checkpoints cannot be read here; use EasyRecEstimator.restore)')
-  if len(tc.optimizer_config) > 1:
-    bad.append('two optimizer_config entries (separate embedding / dense optimizers, easy_rec_model.py:446-467)')
+  if len(tc.optimizer_config) > 2:
+    bad.append('%d optimizer_config entries (one, or two = embedding + everything else, easy_rec_model.py:446-467)'
+               % len(tc.optimizer_config))
   if any(oc.use_moving_average for oc in tc.optimizer_config):
     bad.append('optimizer_config.use_moving_average')
   if mc.model_class in _RANK_CLASSES:

@@ -57,9 +57,15 @@ class EasyRecEstimator(object):
         pipeline_config, self._batch_size, device, generator=gen,
         cpu_generator=torch.Generator().manual_seed(seed), default_seq_len=default_seq_len, world=world_size, rank=rank,
         shard_tables=self._ep)
-    self.trainer = Trainer(self.model, self.input_layer, _DENSE_KIND[self._opt['kind']], lr_fn=self._opt['lr_fn'],
+    # one optimizer_config: tables and dense variables share kind / schedule; two: [0] trains the embedding tables
+    # (the fused row rule), [1] everything else (model/easy_rec_estimator.py:216-232)
+    dense = self._opt.get('dense')
+    d = dense or self._opt
+    self.trainer = Trainer(self.model, self.input_layer, _DENSE_KIND[d['kind']], lr_fn=self._opt['lr_fn'],
                            use_cuda_graph=use_cuda_graph, world_size=world_size, beta1=self._opt['beta1'],
-                           beta2=self._opt['beta2'], adagrad_init=self._opt['acc0'])
+                           beta2=self._opt['beta2'], adagrad_init=d['acc0'],
+                           dense_lr_fn=dense['lr_fn'] if dense else None,
+                           dense_betas=(dense['beta1'], dense['beta2']) if dense else None)
     # optimizer_config.embedding_learning_rate_multiplier: gradient multiplier of the embedding tables
     # (model/easy_rec_estimator.py:308-317)
     self.input_layer.emb_grad_mult = float(self._opt.get('emb_lr_mult', 1.0))

@@ -150,17 +150,23 @@ def _tree_copy(dst, src, path='features'):
 class Trainer(object):
 
   def __init__(self, model, input_layer, dense_optimizer='adagrad', lr=0.01, lr_fn=None,
-               use_cuda_graph=False, world_size=1, beta1=0.9, beta2=0.999, adagrad_init=0.1):
+               use_cuda_graph=False, world_size=1, beta1=0.9, beta2=0.999, adagrad_init=0.1, dense_lr_fn=None,
+               dense_betas=None):
     self.model = model
     self.input_layer = input_layer
     self.lr = lr
     self.lr_fn = lr_fn or (lambda step: lr)
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
     l2 = getattr(model, 'l2_of', None)
-    self.dense_opt = FlatDenseOptimizer(named, dense_optimizer, lr, l2_of=l2, beta1=beta1, beta2=beta2,
+    db1, db2 = dense_betas or (beta1, beta2)
+    self.dense_opt = FlatDenseOptimizer(named, dense_optimizer, lr, l2_of=l2, beta1=db1, beta2=db2,
                                         adagrad_init=adagrad_init)
     self.beta1, self.beta2 = beta1, beta2
-    self.dense_opt.hyper = input_layer.hyper   # one device block for both optimizers: one copy per step
+    # dense_lr_fn: a second optimizer_config for everything that is not an embedding table (easy_rec_model.py:446-467):
+    # its own schedule and beta powers in its own device block; otherwise one block serves both optimizers
+    self.dense_lr_fn = dense_lr_fn
+    if dense_lr_fn is None:
+      self.dense_opt.hyper = input_layer.hyper   # one device block for both optimizers: one copy per step
     self.world = world_size
     self.dp = None
     if world_size > 1:
@@ -191,6 +197,8 @@ class Trainer(object):
   def _set_hyper(self):
     lr = self.lr_fn(self.step)
     self.input_layer.set_optimizer_step(lr, self.step, beta1=self.beta1, beta2=self.beta2)
+    if self.dense_lr_fn is not None:
+      self.dense_opt.hyper.set(self.dense_lr_fn(self.step), self.step)
 
   # The step is three segments; only the middle one talks to other ranks, so with world > 1 the
   # CUDA graph is captured as two graphs around eager NCCL calls.

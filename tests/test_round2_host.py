@@ -407,3 +407,36 @@ def test_keras_mlp_block_dropout_ratio_follows_the_activation_of_the_listed_laye
   assert not torch.equal(mlp(x), a)
   model.eval()
   assert torch.equal(mlp(x), mlp(x))
+
+
+def test_two_optimizer_configs_train_tables_with_the_first_and_everything_else_with_the_second(dense_kernels):  # noqa: F811
+  """model/easy_rec_estimator.py:216-232 + EasyRecModel.get_grouped_vars (easy_rec_model.py:446-467): optimizer_config[0]
+  for the embedding tables, [1] for the other variables - kinds, schedules and Adam state apart."""
+  from easyrec_b200 import workloads
+  from easyrec_b200.estimator import EasyRecEstimator
+  text = workloads.c2_config_text(1000, 32, dnn=(16, 8), final=(8, 4)).decode()
+  one = 'optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.01 } } } }'
+  assert one in text
+  two = ('optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } '
+         'optimizer_config { adam_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.001 } } } }')
+  est = EasyRecEstimator(text.replace(one, two).encode(), device='cpu', seed=3)
+  il, tr = est.input_layer, est.trainer
+  assert il.arenas[16].opt_kind == _lib.OPT_ADAGRAD and il.arenas[16].state1 is None
+  assert tr.dense_opt.kind == _lib.OPT_ADAM_ROWS and tr.dense_opt.s1 is not None
+  assert tr.dense_opt.hyper is not il.hyper
+  ids, dense, labels = workloads.criteo_batch(32, 5)
+  feats = {'sparse_fea': torch.from_numpy(ids), 'dense_fea': torch.from_numpy(dense)}
+  w0 = il.arenas[16].weight.clone()
+  p0 = tr.dense_opt.flat_p.clone()
+  tr.train_step(feats, torch.from_numpy(labels))
+  assert abs(il.hyper.lr - 0.05) < 1e-9 and abs(tr.dense_opt.hyper.lr - 0.001) < 1e-9
+  # first Adam step moves every dense weight with a gradient by ~lr (|m/sqrt(v)| = 1 after bias correction)
+  dp = (tr.dense_opt.flat_p - p0).abs()
+  assert 0.0009 < float(dp[dp > 0].median()) < 0.0011
+  # the touched rows took an Adagrad step of the embedding rate: |dw| = 0.05 |g| / sqrt(0.1 + g^2) < 0.05
+  dw = (il.arenas[16].weight - w0).abs()
+  assert 0 < float(dw.max()) < 0.05
+  # three entries are refused
+  cfg = config_util.get_configs_from_pipeline_file(text.replace(one, two + ' ' + one).encode())
+  with pytest.raises(NotImplementedError, match='optimizer_config entries'):
+    builder.check_scope(cfg)
