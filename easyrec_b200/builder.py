@@ -210,8 +210,8 @@ def check_scope(pipeline_config):
   tc = pipeline_config.train_config
   bad = []
   dc = pipeline_config.data_config
-  if dc.HasField('sample_weight'):
-    bad.append('data_config.sample_weight (per-sample loss weights)')
+  if dc.HasField('sample_weight') and mc.model_class in ('DSSM', 'MatchModel'):
+    bad.append('data_config.sample_weight with a match model (the list-wise loss normalises by mean(w))')
   for g in mc.feature_groups:
     if len(g.sequence_features) > 0:
       bad.append('feature_groups[%s].sequence_features (target attention inside a plain group, '

@@ -163,6 +163,8 @@ class CSVInput(object):
                    .enum_type.values_by_number[f.input_type].name for f in dc.input_fields}
     self.defaults = {f.input_name: f.default_val for f in dc.input_fields}
     self.labels = list(dc.label_fields)
+    # data_config.sample_weight: a float field that weighs each sample's loss (input/input.py:140-141)
+    self.weight_field = dc.sample_weight if dc.HasField('sample_weight') else None
     self.batch_size = batch_size or input_layer.batch_size
     self.feature_inputs = {}
     self.hash_buckets = {}     # feature -> hash_bucket_size when its STRING field is hashed here, on the host
@@ -234,6 +236,8 @@ class CSVInput(object):
         raise ValueError('input field %r is used by features that need different parsings' % field)
     for l in self.labels:
       want(l, (_lib.CSV_F32, 0, b',', 0.0, 0))
+    if self.weight_field:
+      want(self.weight_field, (_lib.CSV_F32, 0, b',', 1.0, 0))
     def raw_spec(field):
       """a field read by a cross: raw Fingerprint64 of a STRING field / the integer of an INT field."""
       if self.ftypes[field] == 'STRING':
@@ -403,6 +407,8 @@ class CSVInput(object):
       feats['seq_fea'] = seq
     if tag:
       feats['tag_fea'] = tag
+    if self.weight_field:
+      feats['sample_weight'] = torch.from_numpy(cols[self.weight_field][0].copy())
     lab = np.stack([cols[l][0] for l in self.labels], 1)
     return feats, torch.from_numpy(lab if lab.shape[1] > 1 else lab[:, 0].copy())
 
@@ -483,6 +489,8 @@ class CSVInput(object):
       feats['seq_fea'] = seq
     if tag:
       feats['tag_fea'] = tag
+    if self.weight_field:
+      feats['sample_weight'] = torch.from_numpy(np.array([float(x or 1) for x in cols[self.weight_field]], np.float32))
     lab = np.stack([np.array([float(x or 0) for x in cols[l]], np.float32) for l in self.labels], 1)
     labels = torch.from_numpy(lab if lab.shape[1] > 1 else lab[:, 0])
     return feats, labels
@@ -508,6 +516,8 @@ class ParquetInput(object):
     self.il = input_layer
     self.paths = [path] if isinstance(path, str) else list(path)
     self.labels = list(pipeline_config.data_config.label_fields)
+    dc = pipeline_config.data_config
+    self.weight_field = dc.sample_weight if dc.HasField('sample_weight') else None
     self.batch_size = batch_size or input_layer.batch_size
     self.feature_inputs = {}
     for fc in config_util.get_feature_configs(pipeline_config):
@@ -600,6 +610,9 @@ class ParquetInput(object):
       feats['seq_fea'] = seq
     if tag:
       feats['tag_fea'] = tag
+    if self.weight_field:
+      feats['sample_weight'] = torch.from_numpy(
+          np.asarray(table.column(self.weight_field).to_numpy(zero_copy_only=False), np.float32).copy())
     lab = np.stack([np.asarray(table.column(l).to_numpy(zero_copy_only=False), np.float32) for l in self.labels], 1)
     labels = torch.from_numpy(lab if lab.shape[1] > 1 else lab[:, 0].copy())
     return feats, labels

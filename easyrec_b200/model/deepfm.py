@@ -93,6 +93,7 @@ class DeepFM(nn.Module):
       reg = reg + self.embedding_reg * 0.5 * (wide_sq + deep_sq)
     return reg
 
-  def loss(self, logits, labels):
-    ce, probs = E.sigmoid_cross_entropy(logits, labels)
+  def loss(self, logits, labels, sample_weight=None):
+    from easyrec_b200.model.rank_model import RankModel
+    ce, probs = RankModel.weighted_ce(logits, labels, sample_weight)
     return ce + self.regularization_loss(), probs

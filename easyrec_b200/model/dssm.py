@@ -70,6 +70,8 @@ class DSSM(RankModel):
     self._item_ids = features.get('item_ids')
     return sim if self.listwise else sim[:, 0]
 
+  accepts_sample_weight = False   # (the list-wise loss normalises by mean(w): not built)
+
   def loss(self, logits, labels):
     reg = self.embedding_reg_loss(self._emb_outputs)
     if not self.listwise:

@@ -61,14 +61,14 @@ class MMoE(RankModel):
       logits.append(out(dnn(mix))[:, 0])
     return torch.stack(logits, dim=1)  # [B, n_task]
 
-  def loss(self, logits, labels):
+  def loss(self, logits, labels, sample_weight=None):
     """labels [B, n_label] in data_config.label_fields order; tower t reads column label_cols[t] (its
     label_name, multi_task_model.py:114-122); multi_task_model.py:201-280: sum_t w_t * CE_t."""
     total = 0.0
     probs = []
     cols = getattr(self, 'label_cols', None) or list(range(len(self.task_weights)))
     for t, w in enumerate(self.task_weights):
-      ce, p = E.sigmoid_cross_entropy(logits[:, t].contiguous(), labels[:, cols[t]].contiguous())
+      ce, p = self.weighted_ce(logits[:, t].contiguous(), labels[:, cols[t]].contiguous(), sample_weight)
       total = total + w * ce
       probs.append(p)
     return total + self.embedding_reg_loss(self._emb_outputs), torch.stack(probs, dim=1)

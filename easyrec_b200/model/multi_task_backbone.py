@@ -57,12 +57,12 @@ class MultiTaskBackboneModel(RankModel):
     logits = [o(d(x))[:, 0] for x, d, o in zip(xs, self.tower_dnn, self.tower_out)]
     return torch.stack(logits, dim=1)   # [B, n_task]
 
-  def loss(self, logits, labels):
+  def loss(self, logits, labels, sample_weight=None):
     total = 0.0
     probs = []
     cols = getattr(self, 'label_cols', None) or list(range(len(self.task_weights)))
     for t, w in enumerate(self.task_weights):
-      ce, p = E.sigmoid_cross_entropy(logits[:, t].contiguous(), labels[:, cols[t]].contiguous())
+      ce, p = self.weighted_ce(logits[:, t].contiguous(), labels[:, cols[t]].contiguous(), sample_weight)
       total = total + w * ce
       probs.append(p)
     return total + self.embedding_reg_loss(self._emb_outputs), torch.stack(probs, dim=1)

@@ -28,6 +28,20 @@ class RankModel(nn.Module):
       return 0.0
     return self.embedding_reg * 0.5 * sum((t * t).sum() for t in tensors)
 
-  def loss(self, logits, labels):
-    ce, probs = E.sigmoid_cross_entropy(logits, labels)
+  accepts_sample_weight = True
+
+  @staticmethod
+  def weighted_ce(logits, labels, sample_weight=None):
+    """tf.losses.sigmoid_cross_entropy(labels, logits, weights=sample_weight) (model/rank_model.py:213-269,
+    builders/loss_builder.py:36-39), reduction SUM_BY_NONZERO_WEIGHTS: sum(w * ce) / count_nonzero(w).  The kernel
+    divides by the batch size, so the weights carry the ratio B / count_nonzero(w) (two tiny device ops)."""
+    w = None
+    if sample_weight is not None:
+      sw = sample_weight.to(torch.float32).reshape(-1)
+      nnz = (sw != 0).sum().clamp(min=1).to(torch.float32)
+      w = (sw * (float(sw.numel()) / nnz)).contiguous()
+    return E.sigmoid_cross_entropy(logits, labels, weights=w)
+
+  def loss(self, logits, labels, sample_weight=None):
+    ce, probs = self.weighted_ce(logits, labels, sample_weight)
     return ce + self.embedding_reg_loss(getattr(self, '_emb_outputs', ())), probs

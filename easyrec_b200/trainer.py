@@ -210,7 +210,11 @@ class Trainer(object):
       # row-sharded tables: the id half of the NEXT batch's exchange reads no table, so it runs beside this step's
       # backward and the next lookup only promotes it (InputLayer.prefetch_exchange)
       self.input_layer.prefetch_exchange(next_features)
-    loss, probs = self.model.loss(logits, labels)
+    sw = features.get('sample_weight') if isinstance(features, dict) else None
+    if sw is not None:   # data_config.sample_weight (input/input.py:140-141 -> EasyRecModel._sample_weight)
+      loss, probs = self.model.loss(logits, labels, sample_weight=sw)
+    else:
+      loss, probs = self.model.loss(logits, labels)
     with L.defer_dw_join():   # kernel-gradient GEMMs overlap the rest of the backward chain
       loss.backward()
     self.dense_opt.gather_grads()

@@ -212,8 +212,17 @@ def install_dense(patch):
     return gz, gz.sum(0), ggamma, gbeta
 
   def sigmoid_ce(logits, labels, weights=None, inv_count=None, want_grad=True):
-    loss, probs, g = O.sigmoid_ce(logits.detach().numpy(), labels.numpy())
-    return torch.tensor([loss], dtype=torch.float32), torch.from_numpy(probs), torch.from_numpy(g)
+    if weights is None and inv_count is None:
+      loss, probs, g = O.sigmoid_ce(logits.detach().numpy(), labels.numpy())
+      return torch.tensor([loss], dtype=torch.float32), torch.from_numpy(probs), torch.from_numpy(g)
+    # the kernel's contract: loss = sum(w * ce) * inv_count, g = w * (p - z) * inv_count
+    x, z = logits.detach().numpy().astype(np.float32), labels.numpy().astype(np.float32)
+    w = np.ones_like(x) if weights is None else weights.numpy().astype(np.float32)
+    inv = np.float32(1.0 / x.size if inv_count is None else inv_count)
+    ce = np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
+    p = (1.0 / (1.0 + np.exp(-x))).astype(np.float32)
+    return (torch.tensor([float((w * ce).sum(dtype=np.float32) * inv)], dtype=torch.float32), torch.from_numpy(p),
+            torch.from_numpy((w * (p - z) * inv).astype(np.float32)))
 
   def fm_fwd(x, n_field, dim, y=None):
     return torch.from_numpy(O.fm_fwd(np.ascontiguousarray(x.detach().numpy()[:, :n_field * dim]), n_field, dim))

@@ -268,7 +268,11 @@ def test_feature_options_that_change_the_looked_up_rows_are_refused():
 
 def test_data_options_that_change_the_batches_or_the_loss_are_refused_and_headers_are_skipped(tmp_path):
   from easyrec_b200.input import readers
+  # sample weights are built for the sigmoid-CE losses (tests/test_round2_host.py), refused for the list-wise match loss
   cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'label_fields: "label"', b'label_fields: "label" sample_weight: "F1"'))
+  builder.check_scope(cfg)
+  cfg = config_util.get_configs_from_pipeline_file(
+      MINI.replace(b'label_fields: "label"', b'label_fields: "label" sample_weight: "F1"').replace(b'model_class: "DeepFM"', b'model_class: "DSSM"'))
   with pytest.raises(NotImplementedError, match='sample_weight'):
     builder.check_scope(cfg)
   cfg = config_util.get_configs_from_pipeline_file(MINI.replace(

@@ -315,6 +315,19 @@ def test_fm_and_sigmoid_ce_parity():
   assert abs(float(loss.item()) - wl) < 1e-5
   np.testing.assert_allclose(probs.cpu().numpy(), wp, atol=1e-6)
   np.testing.assert_allclose(g.cpu().numpy(), wg, atol=1e-8, rtol=1e-5)
+  # sample weights (data_config.sample_weight -> tf.losses.sigmoid_cross_entropy(weights), SUM_BY_NONZERO_WEIGHTS):
+  # RankModel.weighted_ce hands the kernel w * B / count_nonzero(w); zero weights are real zeros in the gradient
+  from easyrec_b200.model.rank_model import RankModel
+  w = rng.uniform(0, 3, 8192).astype(np.float32)
+  w[rng.uniform(size=8192) < 0.2] = 0.0
+  tl = t(logits).requires_grad_(True)
+  loss, probs = RankModel.weighted_ce(tl, t(labels), t(w))
+  loss.backward()
+  wl, wp, wg = O.sigmoid_ce(logits, labels, weights=w)
+  assert abs(float(loss) - wl) < 2e-5 * max(1.0, abs(wl))
+  np.testing.assert_allclose(probs.cpu().numpy(), wp, atol=1e-6)
+  np.testing.assert_allclose(tl.grad.cpu().numpy(), wg, atol=1e-8, rtol=2e-5)
+  assert np.all(tl.grad.cpu().numpy()[w == 0] == 0)
 
 
 def test_fm_block_one_pass_matches_oracle():

@@ -440,3 +440,45 @@ def test_two_optimizer_configs_train_tables_with_the_first_and_everything_else_w
   cfg = config_util.get_configs_from_pipeline_file(text.replace(one, two + ' ' + one).encode())
   with pytest.raises(NotImplementedError, match='optimizer_config entries'):
     builder.check_scope(cfg)
+
+
+def test_sample_weight_field_weighs_the_loss_by_nonzero_weight_mean(tmp_path, dense_kernels):  # noqa: F811
+  """data_config.sample_weight (input/input.py:140-141) -> tf.losses.sigmoid_cross_entropy(weights=...)
+  (model/rank_model.py:213-269): sum(w * ce) / count_nonzero(w); a zero-weight sample moves no table row."""
+  from easyrec_b200.estimator import EasyRecEstimator
+  cfg_text = b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } }
+data_config { batch_size: 8 input_type: CSVInput separator: "," label_fields: "label" sample_weight: "w"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "w" input_type: FLOAT }
+  input_fields { input_name: "uid" input_type: INT64 } input_fields { input_name: "x" input_type: FLOAT } }
+feature_config {
+  features { input_names: "uid" feature_type: IdFeature embedding_dim: 4 num_buckets: 50 }
+  features { input_names: "x" feature_type: RawFeature embedding_dim: 4 min_val: 0.0 max_val: 4.0 } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["uid", "x"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["uid", "x"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [8] use_bn: false } final_dnn { hidden_units: [4] use_bn: false } } }
+'''
+  # (no batch norm: nothing couples the samples, so a zero-weight sample has a zero gradient)
+  rows = [(1, 2.0, 3, 1.0), (0, 0.0, 7, 2.0), (1, 0.5, 9, 3.0), (0, 1.0, 11, 0.5), (1, 0.0, 13, 1.5), (0, 3.0, 15, 2.5),
+          (1, 1.0, 17, 3.5), (0, 1.0, 19, 0.0)]
+  path = tmp_path / 'sw.csv'
+  path.write_text(''.join('%d,%g,%d,%g\n' % r for r in rows))
+  est = EasyRecEstimator(cfg_text, device='cpu', seed=3)
+  for engine in ('native', 'python'):
+    (feats, labels), = list(readers.CSVInput(est._pipeline_config, est.input_layer, str(path), engine=engine))
+    assert feats['sample_weight'].tolist() == [r[1] for r in rows]
+  il = est.input_layer
+  w0 = il.arenas[4].weight.clone()
+  est.model.train()
+  logits = est.model(feats).detach()
+  want_loss, _, _ = O.sigmoid_ce(logits.numpy(), labels.numpy(), weights=feats['sample_weight'].numpy())
+  il._pending = []
+  loss, _ = est.trainer.train_step(feats, labels)
+  reg = float(est.trainer.dense_opt.reg_loss[0])     # deepfm.l2_regularization defaults to 1e-4 (protos/deepfm.proto)
+  assert abs(float(loss) - reg - want_loss) < 1e-6
+  moved = ((il.arenas[4].weight - w0).abs().sum(1) > 0).nonzero().reshape(-1).tolist()
+  off = il.arenas[4].tables['uid_embedding'][0]
+  zero_w = [off + r[2] for r in rows if r[1] == 0.0]
+  live = [off + r[2] for r in rows if r[1] != 0.0]
+  assert all(r not in moved for r in zero_w) and all(r in moved for r in live)
