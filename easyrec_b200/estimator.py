@@ -134,6 +134,7 @@ class EasyRecEstimator(object):
   @torch.no_grad()
   def _forward_eval(self, feats):
     self.model.eval()
+    self.input_layer.drop_prefetch()   # (an id exchange prefetched for the next TRAINING batch is not this batch's)
     logits = self.model(feats)
     self.input_layer._pending = []
     self.input_layer._presorted = {}

@@ -499,6 +499,12 @@ class InputLayer(object):
     for ex in self._exchanges():
       ex.join_prefetch()
 
+  def drop_prefetch(self):
+    """forget any prefetched id exchange: the next lookup() computes its own (called after a graph replay, whose
+    captured promote / prefetch pair does not go through the Python-side flag)"""
+    for ex in self._exchanges():
+      ex._have_next = False
+
   def prefetch_ready(self):
     """True when every exchange holds a prefetched id exchange for the next lookup()."""
     ex = self._exchanges()

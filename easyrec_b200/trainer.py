@@ -306,6 +306,10 @@ class Trainer(object):
     if self._graph2 is not None:
       self._segment_pre(self._static_feats)
     self._graph.replay()
+    if self._prefetch_mode:
+      # the replay promoted and prefetched on its own; an EAGER lookup after it (evaluate / predict) must not take
+      # the graph's prefetched ids for its own
+      self.input_layer.drop_prefetch()
     if self._graph2 is not None:   # world > 1: collectives between the two captured segments
       self._segment_exchange()
       self._graph2.replay()
