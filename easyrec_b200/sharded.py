@@ -1,18 +1,20 @@
-"""Row-sharded embedding arena (model-parallel) with all-to-all over NCCL: the B200 counterpart of
+"""Row-sharded embedding tables (model parallel) with all-to-all over NCCL: the B200 counterpart of
 `embedding_parallel_lookup` (compat/feature_column/feature_column.py:248-357) and of the EP half of
 `optimize_loss` (compat/optimizers.py:294-345).
 
 Shard rule (bit-exact with the reference): owner = row mod N, local row = row div N, each worker holds
 (V + N - 1) // N rows of every table (feature_column.py:296,317,461-463); produced by er_bucketize.
 
-  forward : K1 (rows_local, owner) -> stable sort by owner (er_sort_rows) -> all_to_all(row ids)
-            -> K2 gather on the owner -> all_to_all(embedding rows) -> K2 again, now pooling the
-            received rows straight into the group's [B, sum D] layout
-  backward: per-lookup gradient rows -> all_to_all to the owners -> K7 (dedup + fused optimizer row
-            update) on each owner with grad_scale 1/N (optimizers.py:315-316)
+Two implementations live here:
 
-Split sizes are data dependent, so (like Horovod's alltoall) the counts are exchanged first and read
-on the host; this path is therefore not CUDA-graph captured.  Single-valued slots only.
+* `ShardedLookup` / `ShardedExchange` - the product path, what `InputLayer` runs for sharded arenas: distinct ids per
+  owner in FIXED-capacity blocks (K8 er_shard_group), equal-split all-to-alls, nothing read back on the host, the whole
+  exchange captured in the step's CUDA graph; arenas of one row plan share ids and one packed row exchange; the id half
+  can be prefetched a step ahead.
+* `ShardedArena` - round 1's stand-alone form with the reference's own data flow (sort by owner, counts exchanged and
+  read on the host like hvd.alltoall, per-lookup gradient rows): kept because it is pinned, lookup by lookup, to the
+  reference's `embedding_parallel_lookup` run (tests/golden/reference_lookup.json, tests/test_sharded_gloo.py,
+  tests/test_gpu_sharded.py).  Not CUDA-graph captured; single-valued slots only.
 """
 import os
 
