@@ -227,9 +227,6 @@ def check_scope(pipeline_config):
     bad.append('model_config.kd (knowledge distillation losses)')
   if mc.HasField('variational_dropout'):
     bad.append('model_config.variational_dropout')
-  if tc.gradient_clipping_by_norm > 0:
-    bad.append('train_config.gradient_clipping_by_norm (global-norm clipping needs every gradient, sparse rows included, '
-               'before any update: not available with the row update fused into the backward pass)')
   if len(tc.freeze_gradient) > 0:
     bad.append('train_config.freeze_gradient')
   if tc.fine_tune_checkpoint:

@@ -65,7 +65,8 @@ class EasyRecEstimator(object):
                            use_cuda_graph=use_cuda_graph, world_size=world_size, beta1=self._opt['beta1'],
                            beta2=self._opt['beta2'], adagrad_init=d['acc0'],
                            dense_lr_fn=dense['lr_fn'] if dense else None,
-                           dense_betas=(dense['beta1'], dense['beta2']) if dense else None)
+                           dense_betas=(dense['beta1'], dense['beta2']) if dense else None,
+                           clip_norm=max(float(pipeline_config.train_config.gradient_clipping_by_norm), 0.0))
     # optimizer_config.embedding_learning_rate_multiplier: gradient multiplier of the embedding tables
     # (model/easy_rec_estimator.py:308-317)
     self.input_layer.emb_grad_mult = float(self._opt.get('emb_lr_mult', 1.0))

@@ -350,6 +350,7 @@ class InputLayer(object):
     self._rows_bufs = {}
     self._pos = {}
     self._next_ids = {}
+    self._clip_state = {}
 
   # ------------------------------------------------------------------
   def set_optimizer_step(self, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
@@ -406,6 +407,41 @@ class InputLayer(object):
       for subs in self.subcalls.values():
         for sc in subs.values():
           sc.sharded.check()
+
+  def sparse_grad_sqnorm(self):
+    """sum over the tables of ||IndexedSlices.values||^2 as TF would build them after loss.backward(): the gradient of a
+    column's lookup is deduplicated PER COLUMN (embedding_lookup_sparse runs `unique` on its ids), columns that share a
+    table are concatenated, not merged (compat/optimizers.py:453-481 l2_loss(grad.values)).  K7 in emit form over
+    virtual rows `row + slot * n_rows` produces exactly those per-(column, row) sums; the embedding gradient multiplier
+    (model/easy_rec_estimator.py:308-317) is applied first, as optimize_loss does.  Returns a device scalar."""
+    total = torch.zeros((), dtype=torch.float32, device=self.device)
+    for m, rows, w, outs, seg_ids in self._pending:
+      if seg_ids is not None or rows.numel() != m.n_seg:
+        raise NotImplementedError('gradient_clipping_by_norm over multi-valued (tag / sequence) slots')
+      a = m.arena
+      st = self._clip_state.get(id(m))
+      if st is None:
+        if a.n_rows * m.n_slots >= 0xFFFFFFFF:
+          raise NotImplementedError('gradient_clipping_by_norm: %d rows x %d columns exceed the 32-bit row key' %
+                                    (a.n_rows, m.n_slots))
+        off = torch.zeros(m.n_seg, dtype=torch.int64)
+        for j, r in enumerate(m.slots_np):
+          off[int(r['seg_begin']):int(r['seg_begin']) + int(r['n_seg'])] = j * a.n_rows
+        st = dict(off=off.to(self.device), ws=K.bwd_workspace(m.n_seg, self.device, a.dim),
+                  ur=torch.empty(m.n_seg, dtype=torch.int64, device=self.device),
+                  ug=torch.empty(m.n_seg, a.dim, dtype=torch.float32, device=self.device),
+                  nu=torch.zeros(1, dtype=torch.int32, device=self.device),
+                  idx=torch.arange(m.n_seg, device=self.device, dtype=torch.int32))
+        self._clip_state[id(m)] = st
+      vr = torch.where(rows < 0, rows, rows + st['off'])
+      gbufs = [(o.grad if o.grad is not None else torch.zeros_like(o)).contiguous() for o in outs]
+      opt = K.make_opt(_lib.OPT_SGD, 0.0, grad_scale=float(self.emb_grad_mult))
+      K.embedding_bwd(None, None, None, a.dim, vr, m.slots_dev, m.n_slots, m.n_seg, gbufs, opt, st['ws'], weights=w,
+                      seg_scale=m.seg_scale, uniq_rows=st['ur'], uniq_grads=st['ug'], n_uniq=st['nu'],
+                      n_rows=a.n_rows * m.n_slots)
+      rowsq = (st['ug'] * st['ug']).sum(dim=1)
+      total = total + torch.where(st['idx'] < st['nu'], rowsq, torch.zeros_like(rowsq)).sum()
+    return total
 
   def _rows_buf(self, key, call):
     """persistent output buffer of K1 per row plan (stable address: CUDA graphs, early exchange)."""

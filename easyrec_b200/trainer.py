@@ -56,6 +56,16 @@ class FlatDenseOptimizer(object):
       segs[i]['lr_mult'] = 1.0
       off += (sizes[i] + 3) // 4 * 4
     self.segs_dev = torch.from_numpy(segs.view(np.uint8).reshape(-1).copy()).to(dev)
+    # global-norm clipping needs the regularisation gradient l2 * w BEFORE the update rule: l2 per element, and a
+    # copy of the segment table without l2 for the apply that follows (the gradient then already carries it)
+    l2_vec = np.zeros(total, np.float32)
+    for sg in segs:
+      l2_vec[int(sg['offset']):int(sg['offset']) + int(sg['n'])] = sg['l2']
+    self._l2_vec_np = l2_vec
+    self.l2_vec = None
+    nol2 = segs.copy()
+    nol2['l2'] = 0.0
+    self.segs_nol2_dev = torch.from_numpy(nol2.view(np.uint8).reshape(-1).copy()).to(dev)
     self.n_segs = len(sizes)
     self.max_n = max(sizes)
     self.kind = {'adagrad': _lib.OPT_ADAGRAD, 'adam': _lib.OPT_ADAM_ROWS, 'lazy_adam': _lib.OPT_ADAM_ROWS,
@@ -106,15 +116,27 @@ class FlatDenseOptimizer(object):
     if srcs:
       torch._foreach_copy_(dsts, srcs)
 
-  def apply(self):
+  def apply(self, l2_folded=False):
+    """l2_folded: the gradient buffer already holds g + l2 * w (fold_l2): apply without the regulariser."""
     lib = _lib.load()
     opt = self.hyper.opt(self.kind, self.eps, grad_scale=self.grad_scale)
-    self.reg_loss.zero_()
+    segs = self.segs_nol2_dev if l2_folded else self.segs_dev
+    if not l2_folded:
+      self.reg_loss.zero_()
     _lib.check(
         lib.er_dense_apply(self.flat_p.data_ptr(), self.flat_g.data_ptr(), K._p(self.s0), K._p(self.s1),
-                           self.segs_dev.data_ptr(), self.n_segs, self.max_n, ctypes.byref(opt),
-                           None, self.reg_loss.data_ptr(),
+                           segs.data_ptr(), self.n_segs, self.max_n, ctypes.byref(opt),
+                           None, None if l2_folded else self.reg_loss.data_ptr(),
                            torch.cuda.current_stream().cuda_stream), 'er_dense_apply')
+
+  def fold_l2(self):
+    """flat_g <- flat_g + l2 * w (the gradient of the kernel regularisers, which TF's loss carries) and
+    reg_loss <- sum l2/2 * w^2; returns sum(flat_g^2).  For global-norm clipping, which sees the FULL gradient."""
+    if self.l2_vec is None:
+      self.l2_vec = torch.from_numpy(self._l2_vec_np).to(self.flat_p.device)
+    self.reg_loss.copy_((0.5 * self.l2_vec * self.flat_p * self.flat_p).sum().reshape(1))
+    self.flat_g.addcmul_(self.l2_vec, self.flat_p)
+    return (self.flat_g * self.flat_g).sum()
 
 
 def _tree_clone(x):
@@ -151,7 +173,7 @@ class Trainer(object):
 
   def __init__(self, model, input_layer, dense_optimizer='adagrad', lr=0.01, lr_fn=None,
                use_cuda_graph=False, world_size=1, beta1=0.9, beta2=0.999, adagrad_init=0.1, dense_lr_fn=None,
-               dense_betas=None):
+               dense_betas=None, clip_norm=0.0):
     self.model = model
     self.input_layer = input_layer
     self.lr = lr
@@ -168,6 +190,12 @@ class Trainer(object):
     if dense_lr_fn is None:
       self.dense_opt.hyper = input_layer.hyper   # one device block for both optimizers: one copy per step
     self.world = world_size
+    # train_config.gradient_clipping_by_norm (> 0): global-norm clipping of all gradients before the updates
+    self.clip_norm = float(clip_norm or 0.0)
+    self.last_grad_norm = None
+    if self.clip_norm and world_size > 1:
+      raise NotImplementedError('gradient_clipping_by_norm with world_size > 1 (the norm of the reduced gradients, '
+                                'compat/optimizers.py:453-481)')
     self.dp = None
     if world_size > 1:
       from easyrec_b200.distributed import DataParallel
@@ -232,7 +260,26 @@ class Trainer(object):
       self.dp.exchange(self._step_pending)   # flat all-reduce + all-gather of K7 inputs
       self.dp.join_presort()
 
+  def _clip_by_global_norm(self):
+    """clip_ops.clip_by_global_norm over EVERY gradient, the tables' IndexedSlices included (compat/optimizers.py:
+    365-376, norm as _get_grad_norm :453-481): t <- t * clip / max(global_norm, clip).  Runs after the backward pass
+    and before any update: the sparse part is a K7 pass in emit form (deduplicated per column, like the IndexedSlices
+    TF builds), the factor lands in the device-resident gradient scale the fused row update reads and on the dense
+    gradient buffer.  Device-only: captured with the step."""
+    il, opt = self.input_layer, self.dense_opt
+    sq = il.sparse_grad_sqnorm() + opt.fold_l2()
+    norm = torch.sqrt(sq)
+    scale = self.clip_norm / torch.clamp(norm, min=self.clip_norm)
+    opt.flat_g.mul_(scale)
+    il.hyper.dev[_lib.HYPER_GRAD_SCALE:_lib.HYPER_GRAD_SCALE + 1].mul_(scale)
+    self.last_grad_norm = norm
+
   def _segment_update(self, loss):
+    if self.clip_norm:
+      self._clip_by_global_norm()
+      self.input_layer.backward_update()
+      self.dense_opt.apply(l2_folded=True)
+      return loss + self.dense_opt.reg_loss[0]
     if self.dp is not None and not self.dp.sparse and self._ep_side is not None:
       self.input_layer._pending = []
     elif self.dp is not None:

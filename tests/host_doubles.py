@@ -18,6 +18,19 @@ def _seg_field(sl, field, n_seg):
   return v & 0xf if field == 'combiner' else v   # (the ER_COMBINER_UNIT_WEIGHTS flag is a hint for the kernels)
 
 
+class _Hyper(object):
+  """the step scalars as the kernels see them: from er_opt_t.hyper_dev when set (float[4] = lr, beta1^t, beta2^t,
+  gradient scale - host memory in these CPU tests), else from the struct"""
+
+  def __init__(self, opt):
+    if opt.hyper_dev:
+      import ctypes
+      h = (ctypes.c_float * 4).from_address(opt.hyper_dev)
+      self.lr, self.beta1_power, self.beta2_power, self.grad_scale = float(h[0]), float(h[1]), float(h[2]), float(h[3])
+    else:
+      self.lr, self.beta1_power, self.beta2_power, self.grad_scale = opt.lr, opt.beta1_power, opt.beta2_power, opt.grad_scale
+
+
 def install_sparse(patch):
   """bucketize / csr_from_lens / embedding_fwd / embedding_bwd -> the CPU oracle."""
   def csr_from_lens(lens, cap, want_seg_ids=True):
@@ -76,7 +89,7 @@ def install_sparse(patch):
     if table is None:   # emit only: the deduplicated gradient, sorted by row
       nu, ur, ug = O.embedding_bwd(None, None, None, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()],
                                    gseg, O.OPT_SGD, 0.0, weights=None if weights is None else weights.numpy(),
-                                   seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=opt.grad_scale,
+                                   seg_scale=None if seg_scale is None else seg_scale.numpy(), grad_scale=_Hyper(opt).grad_scale,
                                    want_uniq=True)
       uniq_rows[:nu].copy_(torch.from_numpy(ur))
       uniq_grads[:nu].copy_(torch.from_numpy(ug))
@@ -89,9 +102,10 @@ def install_sparse(patch):
     # adam_dense_sweep double below
     kind = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_LAZY_ADAM, 3: O.OPT_LAZY_ADAM}[int(opt.kind)]
     O.embedding_bwd(t, a, b, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
-                    kind, opt.lr, weights=None if weights is None else weights.numpy(),
+                    kind, _Hyper(opt).lr, weights=None if weights is None else weights.numpy(),
                     seg_scale=None if seg_scale is None else seg_scale.numpy(), beta1=opt.beta1, beta2=opt.beta2,
-                    eps=opt.eps, beta1_power=opt.beta1_power, beta2_power=opt.beta2_power, grad_scale=opt.grad_scale)
+                    eps=opt.eps, beta1_power=_Hyper(opt).beta1_power, beta2_power=_Hyper(opt).beta2_power,
+                    grad_scale=_Hyper(opt).grad_scale)
     table.copy_(torch.from_numpy(t))
     if state0 is not None:
       state0.copy_(torch.from_numpy(a))
@@ -104,9 +118,9 @@ def install_sparse(patch):
     a = None if state0 is None else np.ascontiguousarray(state0.numpy())
     b = None if state1 is None else np.ascontiguousarray(state1.numpy())
     kind = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_LAZY_ADAM, 3: O.OPT_LAZY_ADAM}[int(opt.kind)]
-    O.embedding_bwd(t, a, b, uniq_rows.numpy()[:n], None, np.ascontiguousarray(uniq_grads.numpy()[:n]), kind, opt.lr,
-                    beta1=opt.beta1, beta2=opt.beta2, eps=opt.eps, beta1_power=opt.beta1_power,
-                    beta2_power=opt.beta2_power, grad_scale=opt.grad_scale)
+    O.embedding_bwd(t, a, b, uniq_rows.numpy()[:n], None, np.ascontiguousarray(uniq_grads.numpy()[:n]), kind, _Hyper(opt).lr,
+                    beta1=opt.beta1, beta2=opt.beta2, eps=opt.eps, beta1_power=_Hyper(opt).beta1_power,
+                    beta2_power=_Hyper(opt).beta2_power, grad_scale=_Hyper(opt).grad_scale)
     table.copy_(torch.from_numpy(t))
     if state0 is not None:
       state0.copy_(torch.from_numpy(a))
@@ -122,7 +136,7 @@ def install_sparse(patch):
   def adam_dense_sweep(table, m, v, dim, touched, opt, row_stride=None):
     f = np.float32
     cold = torch.from_numpy(touched.numpy() == 0) if touched is not None else torch.ones(table.shape[0], dtype=torch.bool)
-    lr_t = O.adam_lr_t(opt.lr, opt.beta1_power, opt.beta2_power)
+    lr_t = O.adam_lr_t(_Hyper(opt).lr, _Hyper(opt).beta1_power, _Hyper(opt).beta2_power)
     mc = (m[cold].numpy() * f(opt.beta1)).astype(np.float32)
     vc = (v[cold].numpy() * f(opt.beta2)).astype(np.float32)
     m[cold] = torch.from_numpy(mc)
@@ -238,9 +252,11 @@ def install_dense(patch):
       gx[:, :w] = g
     return gx
 
-  def apply(self):   # FlatDenseOptimizer.apply: l2 + TF Adagrad / Adam over the flat buffer
-    assert self.kind in (1, 3), 'this double implements the adagrad and adam rules'
-    segs = np.frombuffer(self.segs_dev.numpy().tobytes(), dtype=T._lib.DENSE_SEG_DTYPE)
+  def apply(self, l2_folded=False):   # FlatDenseOptimizer.apply: l2 + TF Adagrad / Adam / SGD over the flat buffer
+    assert self.kind in (0, 1, 3), 'this double implements the sgd, adagrad and adam rules'
+    segs = np.frombuffer((self.segs_nol2_dev if l2_folded else self.segs_dev).numpy().tobytes(),
+                         dtype=T._lib.DENSE_SEG_DTYPE)
+    keep_reg = self.reg_loss.clone()
     self.reg_loss.zero_()
     lr = float(self.lr_dev[0])
     for s in segs:
@@ -249,13 +265,17 @@ def install_dense(patch):
       if s['l2'] > 0:
         self.reg_loss += 0.5 * float(s['l2']) * (w * w).sum()
         g = g + float(s['l2']) * w
-      if self.kind == 1:
+      if self.kind == 0:
+        w -= lr * float(s['lr_mult']) * g
+      elif self.kind == 1:
         self.s0[o:o + n] += g * g
         w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
       else:   # ApplyAdam: m, v, var -= lr_t*m/(sqrt(v)+eps)
         self.s0[o:o + n] = self.b1 * self.s0[o:o + n] + (1 - self.b1) * g
         self.s1[o:o + n] = self.b2 * self.s1[o:o + n] + (1 - self.b2) * g * g
         w -= lr * float(s['lr_mult']) * self.s0[o:o + n] / (torch.sqrt(self.s1[o:o + n]) + self.eps)
+    if l2_folded:   # (the caller computed the regularisation loss when it folded l2 * w into the gradient)
+      self.reg_loss.copy_(keep_reg)
   for name, fn in (('gemm', gemm), ('gemm_ready', lambda t: t), ('gemm_bn', lambda *a, **k: None),
                    ('bias_bn_act_fwd', bias_bn_act_fwd), ('bias_bn_act_bwd', bias_bn_act_bwd),
                    ('dense_workspace', lambda b, u, d: torch.zeros(1, dtype=torch.uint8)), ('sigmoid_ce', sigmoid_ce),

@@ -161,3 +161,47 @@ def test_cuda_graph_run_equals_eager_run_for_every_optimizer(opt):
   for k in sd0:
     assert torch.equal(sd0[k], sd1[k]), k     # incl. batch-norm moving statistics: no double application
   assert l0[-1] != l0[0]
+
+
+def test_global_norm_clipping_on_the_kernels_eager_and_captured():
+  """train_config.gradient_clipping_by_norm through the real K7 (emit form over per-column virtual rows) and the
+  device-resident gradient scale: plain SGD makes every update linear in its gradient, so clipped = scale * unclipped
+  for every dense parameter and table row; the captured step follows the eager one."""
+  import sys, os
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  from test_round2_host import CLIP_CFG
+  from easyrec_b200.estimator import EasyRecEstimator
+  torch.backends.cuda.matmul.allow_tf32 = False
+  rng = np.random.default_rng(0)
+  B = 16
+  batches = []
+  for _ in range(5):
+    ids = np.stack([rng.integers(0, 6, B), rng.integers(0, 6, B), rng.integers(0, 1000, B)]).astype(np.int64)
+    batches.append(({'sparse_fea': torch.from_numpy(ids.reshape(-1)).to(DEV),
+                     'dense_fea': torch.from_numpy(rng.uniform(0, 2, (B, 1)).astype(np.float32)).to(DEV)},
+                    torch.from_numpy((rng.uniform(size=B) < 0.4).astype(np.float32)).to(DEV)))
+  plain = EasyRecEstimator(CLIP_CFG % b'', device=DEV, seed=11)
+  clip = EasyRecEstimator(CLIP_CFG % b'gradient_clipping_by_norm: 0.05', device=DEV, seed=11)
+  p0 = plain.trainer.dense_opt.flat_p.clone()
+  t0 = {d: a.weight.clone() for d, a in plain.input_layer.arenas.items()}
+  plain.trainer.train_step(*batches[0])
+  clip.trainer.train_step(*batches[0])
+  norm = float(clip.trainer.last_grad_norm)
+  assert norm > 0.05
+  scale = 0.05 / norm
+  torch.testing.assert_close(clip.trainer.dense_opt.flat_p - p0, (plain.trainer.dense_opt.flat_p - p0) * scale,
+                             rtol=2e-4, atol=2e-7)
+  for d, a in clip.input_layer.arenas.items():
+    want = (plain.input_layer.arenas[d].weight - t0[d]) * scale
+    assert float(want.abs().max()) > 1e-5
+    torch.testing.assert_close(a.weight - t0[d], want, rtol=2e-4, atol=2e-8)
+  # captured: the same five steps eager and from the graph (two eager steps, capture, replays)
+  runs = []
+  for graph in (False, True):
+    e = EasyRecEstimator(CLIP_CFG % b'gradient_clipping_by_norm: 0.05', device=DEV, seed=11, use_cuda_graph=graph)
+    losses = [float(e.trainer.train_step(*b)[0]) for b in batches]
+    runs.append((losses, e.trainer.dense_opt.flat_p.clone(), float(e.trainer.last_grad_norm)))
+    assert (not graph) or e.trainer._graph is not None
+  np.testing.assert_allclose(runs[1][0], runs[0][0], rtol=0, atol=1e-6)
+  torch.testing.assert_close(runs[1][1], runs[0][1], rtol=0, atol=1e-7)
+  assert abs(runs[1][2] - runs[0][2]) < 1e-5 * max(1.0, runs[0][2])

@@ -482,3 +482,80 @@ model_config { model_class: "DeepFM"
   zero_w = [off + r[2] for r in rows if r[1] == 0.0]
   live = [off + r[2] for r in rows if r[1] != 0.0]
   assert all(r not in moved for r in zero_w) and all(r in moved for r in live)
+
+
+CLIP_CFG = b'''
+train_config { %s
+  optimizer_config { momentum_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.5 } }
+                                          momentum_optimizer_value: 0.0 } } }
+data_config { batch_size: 16 input_type: DummyInput label_fields: "label" }
+feature_config {
+  features { input_names: "a" feature_type: IdFeature embedding_dim: 4 num_buckets: 6 embedding_name: "shared" }
+  features { input_names: "b" feature_type: IdFeature embedding_dim: 4 num_buckets: 6 embedding_name: "shared" }
+  features { input_names: "c" feature_type: IdFeature embedding_dim: 4 hash_bucket_size: 11 }
+  features { input_names: "x" feature_type: RawFeature embedding_dim: 4 min_val: 0.0 max_val: 2.0 } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["a", "b", "c", "x"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["a", "b", "c", "x"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [8] } final_dnn { hidden_units: [4] } l2_regularization: 1e-2 }
+  embedding_regularization: 1e-3 }
+'''
+
+
+def test_global_norm_clipping_scales_every_gradient_by_clip_over_the_tf_global_norm(dense_kernels):  # noqa: F811
+  """train_config.gradient_clipping_by_norm (compat/optimizers.py:365-376, 453-481): norm over the dense gradients
+  (regularisers included) and the tables' IndexedSlices, which TF deduplicates per COLUMN even when columns share a
+  table; every gradient is scaled by clip / max(norm, clip) before the update."""
+  from easyrec_b200.estimator import EasyRecEstimator
+  rng = np.random.default_rng(0)
+  B = 16
+  ids = np.stack([rng.integers(0, 6, B), rng.integers(0, 6, B), rng.integers(0, 1000, B)]).astype(np.int64)   # a, b collide
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1)), 'dense_fea': torch.from_numpy(rng.uniform(0, 2, (B, 1)).astype(np.float32))}
+  labels = torch.from_numpy((rng.uniform(size=B) < 0.4).astype(np.float32))
+  plain = EasyRecEstimator(CLIP_CFG % b'', device='cpu', seed=11)
+  clip = EasyRecEstimator(CLIP_CFG % b'gradient_clipping_by_norm: 0.05', device='cpu', seed=11)
+  assert clip.trainer.clip_norm == pytest.approx(0.05) and plain.trainer.clip_norm == 0.0
+  # -- the norm: an independent restatement from the per-lookup gradients of one backward pass
+  tr, il = clip.trainer, clip.input_layer
+  tr._set_hyper()
+  clip.model.train()
+  tr._segment_compute(feats, labels)
+  want_sq = 0.0
+  for m, rows, w, outs, seg_ids in il._pending:
+    a, D = m.arena, m.arena.dim
+    r = rows.numpy()
+    for sl in m.slots_np:                      # one IndexedSlices per column: unique rows of THAT column
+      g = outs[int(sl['out_buf'])].grad.numpy().reshape(-1, int(sl['out_stride']))[:, int(sl['out_col']):int(sl['out_col']) + D]
+      lo = int(sl['seg_begin'])
+      rr = r[lo:lo + int(sl['n_seg'])]
+      ww = np.ones(rr.size, np.float32) if w is None else w.numpy()[lo:lo + rr.size]
+      for u in np.unique(rr[rr >= 0]):
+        want_sq += float(((g[rr == u] * ww[rr == u, None]).sum(0).astype(np.float64) ** 2).sum())
+  opt = tr.dense_opt
+  l2 = torch.from_numpy(opt._l2_vec_np)
+  want_sq += float(((opt.flat_g + l2 * opt.flat_p).double() ** 2).sum())
+  got_sparse = float(il.sparse_grad_sqnorm())
+  got = float(torch.sqrt(torch.tensor(got_sparse) + ((opt.flat_g + l2 * opt.flat_p) ** 2).sum()))
+  assert got == pytest.approx(np.sqrt(want_sq), rel=1e-5)
+  il._pending = []
+  # -- the step: with plain SGD every update is linear in its gradient, so clipped = scale * unclipped everywhere
+  clip2 = EasyRecEstimator(CLIP_CFG % b'gradient_clipping_by_norm: 0.05', device='cpu', seed=11)
+  before_p = plain.trainer.dense_opt.flat_p.clone()
+  before_t = {d: a.weight.clone() for d, a in plain.input_layer.arenas.items()}
+  plain.trainer.train_step(feats, labels)
+  clip2.trainer.train_step(feats, labels)
+  norm = float(clip2.trainer.last_grad_norm)
+  assert norm == pytest.approx(np.sqrt(want_sq), rel=1e-5) and norm > 0.05
+  scale = 0.05 / norm
+  dp_plain = plain.trainer.dense_opt.flat_p - before_p
+  dp_clip = clip2.trainer.dense_opt.flat_p - before_p
+  torch.testing.assert_close(dp_clip, dp_plain * scale, rtol=1e-4, atol=2e-7)   # (differences of O(1) fp32 parameters)
+  assert float(dp_plain.abs().max()) > 1e-3
+  for d, a in clip2.input_layer.arenas.items():
+    dt_plain = plain.input_layer.arenas[d].weight - before_t[d]
+    torch.testing.assert_close(a.weight - before_t[d], dt_plain * scale, rtol=1e-4, atol=2e-8)
+    assert float(dt_plain.abs().max()) > 1e-4
+  # a clip above the norm leaves the step untouched
+  loose = EasyRecEstimator(CLIP_CFG % b'gradient_clipping_by_norm: 1000.0', device='cpu', seed=11)
+  loose.trainer.train_step(feats, labels)
+  torch.testing.assert_close(loose.trainer.dense_opt.flat_p, plain.trainer.dense_opt.flat_p, rtol=1e-6, atol=2e-7)
