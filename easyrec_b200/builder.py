@@ -240,8 +240,9 @@ def check_scope(pipeline_config):
     names = mc.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number
     if mc.num_class != 1:
       bad.append('num_class %d (only the binary head, num_class 1)' % mc.num_class)
-    if names[mc.loss_type].name != 'CLASSIFICATION':
-      bad.append('loss_type %s (rank models train with CLASSIFICATION = sigmoid cross entropy)' % names[mc.loss_type].name)
+    if names[mc.loss_type].name not in ('CLASSIFICATION', 'L2_LOSS', 'SIGMOID_L2_LOSS'):
+      bad.append('loss_type %s (rank models train with CLASSIFICATION = sigmoid cross entropy, L2_LOSS or SIGMOID_L2_LOSS)'
+                 % names[mc.loss_type].name)
     extra = [names[l.loss_type].name for l in mc.losses if names[l.loss_type].name != 'CLASSIFICATION' or l.weight != 1.0]
     if extra or len(mc.losses) > 1:
       bad.append('model_config.losses %s' % ([names[l.loss_type].name for l in mc.losses],))
@@ -294,6 +295,8 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                      shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0,
                      uniform_tables=keras_tables)
   model = cls.from_config(mc, il, generator=cpu_generator).to(device)
+  if mc.model_class in _RANK_CLASSES:
+    model.loss_type = mc.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[mc.loss_type].name
   bind_task_labels(model, list(pipeline_config.data_config.label_fields))
   return il, model, opt
 

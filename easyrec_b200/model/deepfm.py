@@ -95,5 +95,5 @@ class DeepFM(nn.Module):
 
   def loss(self, logits, labels, sample_weight=None):
     from easyrec_b200.model.rank_model import RankModel
-    ce, probs = RankModel.weighted_ce(logits, labels, sample_weight)
+    ce, probs = RankModel.data_loss(self, logits, labels, sample_weight)   # by model_config.loss_type
     return ce + self.regularization_loss(), probs

@@ -42,6 +42,26 @@ class RankModel(nn.Module):
       w = (sw * (float(sw.numel()) / nnz)).contiguous()
     return E.sigmoid_cross_entropy(logits, labels, weights=w)
 
+  loss_type = 'CLASSIFICATION'   # model_config.loss_type (set by builder.build_model)
+
+  def data_loss(self, logits, labels, sample_weight=None):
+    """(loss, predictions) of the single head by model_config.loss_type (model/rank_model.py:75-129, 213-269,
+    builders/loss_builder.py:36-55): CLASSIFICATION = sigmoid cross entropy, predictions `probs`; L2_LOSS /
+    SIGMOID_L2_LOSS = tf.losses.mean_squared_error(labels, y, weights) with y = logits / sigmoid(logits),
+    predictions `y`.  Both reduce by SUM_BY_NONZERO_WEIGHTS."""
+    lt = getattr(self, 'loss_type', 'CLASSIFICATION')
+    if lt == 'CLASSIFICATION':
+      return RankModel.weighted_ce(logits, labels, sample_weight)
+    if lt not in ('L2_LOSS', 'SIGMOID_L2_LOSS'):
+      raise NotImplementedError('loss_type %s' % lt)
+    y = torch.sigmoid(logits) if lt == 'SIGMOID_L2_LOSS' else logits
+    d = y - labels.to(y.dtype)
+    if sample_weight is None:
+      return (d * d).mean(), y.detach()
+    sw = sample_weight.to(torch.float32).reshape(-1)
+    nnz = (sw != 0).sum().clamp(min=1).to(torch.float32)
+    return (sw * d * d).sum() / nnz, y.detach()
+
   def loss(self, logits, labels, sample_weight=None):
-    ce, probs = self.weighted_ce(logits, labels, sample_weight)
+    ce, probs = self.data_loss(logits, labels, sample_weight)
     return ce + self.embedding_reg_loss(getattr(self, '_emb_outputs', ())), probs

@@ -559,3 +559,27 @@ def test_global_norm_clipping_scales_every_gradient_by_clip_over_the_tf_global_n
   loose = EasyRecEstimator(CLIP_CFG % b'gradient_clipping_by_norm: 1000.0', device='cpu', seed=11)
   loose.trainer.train_step(feats, labels)
   torch.testing.assert_close(loose.trainer.dense_opt.flat_p, plain.trainer.dense_opt.flat_p, rtol=1e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize('loss_type', ['L2_LOSS', 'SIGMOID_L2_LOSS'])
+def test_l2_loss_types_train_the_rank_head_as_a_regressor(loss_type, dense_kernels):  # noqa: F811
+  """model_config.loss_type L2_LOSS / SIGMOID_L2_LOSS (builders/loss_builder.py:52-55, model/rank_model.py:123-128):
+  mean squared error between the label and y = logits / sigmoid(logits); predictions are `y`."""
+  from easyrec_b200 import workloads
+  from easyrec_b200.estimator import EasyRecEstimator
+  text = workloads.c2_config_text(1000, 32, dnn=(16, 8), final=(8, 4)).decode()
+  text = text.replace('model_config { model_class: "DeepFM"', 'model_config { model_class: "DeepFM" loss_type: %s' % loss_type)
+  est = EasyRecEstimator(text.encode(), device='cpu', seed=3)
+  assert est.model.loss_type == loss_type
+  ids, dense, _ = workloads.criteo_batch(32, 5)
+  labels = torch.from_numpy(np.random.default_rng(1).uniform(0, 1, 32).astype(np.float32))
+  feats = {'sparse_fea': torch.from_numpy(ids), 'dense_fea': torch.from_numpy(dense)}
+  est.model.train()
+  logits = est.model(feats)
+  y = torch.sigmoid(logits) if loss_type == 'SIGMOID_L2_LOSS' else logits
+  loss, pred = est.model.loss(logits, labels)
+  want = ((y - labels) ** 2).mean() + est.model.regularization_loss()
+  assert abs(float(loss) - float(want)) < 1e-6 and torch.allclose(pred, y.detach())
+  est.input_layer._pending = []
+  losses = [float(est.trainer.train_step(feats, labels)[0]) for _ in range(30)]
+  assert losses[-1] < losses[0]
