@@ -234,7 +234,6 @@ def test_optimizers_without_a_fused_row_rule_are_refused():
 @pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
 @pytest.mark.parametrize('rel,why', [
     ('samples/model_config/multi_tower_backbone_on_taobao.config', 'losses'),           # F1-reweighted + pairwise
-    ('samples/model_config/deepfm_combo_on_avazu_reg.config', None),                    # ComboFeature comes first
     ('samples/model_config/deepfm_multi_cls_on_avazu_ctr.config', None),
     ('samples/model_config/wide_and_deep_two_opti.config', None),
     ('samples/model_config/taobao_fg_ev.config', 'ev_params')])
@@ -246,13 +245,24 @@ def test_configs_that_need_unimplemented_training_semantics_are_refused(rel, why
     assert why in str(e.value)
 
 
+@pytest.mark.skipif(not HAVE_REF, reason='reference checkout not mounted')
+def test_the_reference_regression_sample_builds_with_its_l2_loss():
+  cfg = config_util.get_configs_from_pipeline_file(os.path.join(REF, 'samples/model_config/deepfm_combo_on_avazu_reg.config'))
+  os.environ['ER_PLAN_ONLY'] = '1'
+  try:
+    _, model, _ = builder.build_model(cfg, 16, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  finally:
+    del os.environ['ER_PLAN_ONLY']
+  assert model.loss_type == 'L2_LOSS'
+
+
 def test_scope_check_names_every_offending_field():
   cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
-      b'embedding_regularization: 1e-5', b'embedding_regularization: 1e-5 num_class: 3 loss_type: L2_LOSS '
+      b'embedding_regularization: 1e-5', b'embedding_regularization: 1e-5 num_class: 3 loss_type: SOFTMAX_CROSS_ENTROPY '
       b'variational_dropout { } losses { loss_type: PAIR_WISE_LOSS }'))
   with pytest.raises(NotImplementedError) as e:
     builder.check_scope(cfg)
-  for word in ('num_class 3', 'L2_LOSS', 'variational_dropout', 'PAIR_WISE_LOSS'):
+  for word in ('num_class 3', 'SOFTMAX_CROSS_ENTROPY', 'variational_dropout', 'PAIR_WISE_LOSS'):
     assert word in str(e.value)
   builder.check_scope(config_util.get_configs_from_pipeline_file(MINI))   # the plain config passes
 
