@@ -178,7 +178,7 @@ def optimizer_settings(pipeline_config, index=0):
               if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
 
 
-_RANK_CLASSES = ('DeepFM', 'DCN', 'DLRM', 'MultiTowerDIN', 'RankModel')
+_RANK_CLASSES = ('DeepFM', 'DCN', 'DLRM', 'MultiTower', 'MultiTowerDIN', 'RankModel')
 
 
 def _is_repeated(fd):

@@ -70,3 +70,15 @@ class MultiTowerDIN(RankModel):
       feas.append(torch.cat([att, key], dim=1))
     self._emb_outputs = tuple(reg)
     return self.output(self.final_dnn(torch.cat(feas, dim=1)))[:, 0]
+
+
+@registry.register('MultiTower')
+class MultiTower(MultiTowerDIN):
+  """model/multi_tower.py:17-62: per tower batch_normalization -> DNN, concat, final DNN, dense(1) - MultiTowerDIN's
+  graph without the attention towers (it reads only `multi_tower.towers`; din / bst towers of the message are not its)."""
+
+  @classmethod
+  def from_config(cls, model_config, input_layer, generator=None):
+    c = model_config.multi_tower
+    return cls(input_layer, [(t.input, L.units_of(t.dnn)) for t in c.towers], [], L.units_of(c.final_dnn),
+               l2_reg=c.l2_regularization, embedding_reg=model_config.embedding_regularization, generator=generator)

@@ -583,3 +583,28 @@ def test_l2_loss_types_train_the_rank_head_as_a_regressor(loss_type, dense_kerne
   est.input_layer._pending = []
   losses = [float(est.trainer.train_step(feats, labels)[0]) for _ in range(30)]
   assert losses[-1] < losses[0]
+
+
+def test_multi_tower_model_class_trains_from_its_config(interaction_doubles):  # noqa: F811
+  """model_class MultiTower (model/multi_tower.py:17-62): batch-normed group -> DNN per tower, concat, final DNN."""
+  import test_gpu_models as G
+  text = G.HEAD + G.FEATS + '''
+model_config { model_class: "MultiTower"
+  feature_groups { group_name: "user" feature_names: ["user_id", "age"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate", "price"] wide_deep: DEEP }
+  multi_tower { towers { input: "user" dnn { hidden_units: [32, 16] } } towers { input: "item" dnn { hidden_units: [32, 16] } }
+                final_dnn { hidden_units: [32, 16] } l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+  cfg = config_util.get_configs_from_pipeline_file(text.encode())
+  B = 256
+  il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  assert type(model).__name__ == 'MultiTower' and len(model.din_dnn) == 0 and len(model.tower_dnn) == 2
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64)),
+           'dense_fea': torch.from_numpy(rng.uniform(0, 100, (B, 1)).astype(np.float32))}
+  lab = torch.from_numpy((rng.uniform(size=B) < 0.3).astype(np.float32))
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
+  assert losses[-1] < losses[0] - 0.01
