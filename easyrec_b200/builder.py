@@ -95,8 +95,22 @@ def feature_groups(model_config):
   groups = collections.OrderedDict()
   for g in model_config.feature_groups:
     wd = g.DESCRIPTOR.fields_by_name['wide_deep'].enum_type.values_by_number[g.wide_deep].name
-    groups[g.group_name] = dict(features=list(g.feature_names), wide=(wd == 'WIDE'))
+    seq = []
+    for sf in g.sequence_features:
+      # target attention inside the group (layers/input_layer.py:96-111 -> layers/sequence_feature_layer.py:190-249):
+      # seq_dnn defaults to [128, 64, 32, 1] (:226-230)
+      units = IL_units(sf.seq_dnn) if sf.HasField('seq_dnn') else IL_units(None)
+      seq.append(dict(name=sf.group_name, maps=[(list(m.key), list(m.hist_seq)) for m in sf.seq_att_map], units=units,
+                      need_key=bool(sf.need_key_feature)))
+    groups[g.group_name] = dict(features=list(g.feature_names), wide=(wd == 'WIDE'), seq=seq)
   return groups
+
+
+def IL_units(dnn_config):
+  from easyrec_b200 import layers as L
+  if dnn_config is None:
+    return L.Units([128, 64, 32, 1])
+  return L.units_of(dnn_config)
 
 
 def seq_att_groups(model_config):
@@ -213,9 +227,12 @@ def check_scope(pipeline_config):
   if dc.HasField('sample_weight') and mc.model_class in ('DSSM', 'MatchModel'):
     bad.append('data_config.sample_weight with a match model (the list-wise loss normalises by mean(w))')
   for g in mc.feature_groups:
-    if len(g.sequence_features) > 0:
-      bad.append('feature_groups[%s].sequence_features (target attention inside a plain group, '
-                 'layers/sequence_feature_layer.py; use seq_att_groups with MultiTowerDIN)' % g.group_name)
+    for sf in g.sequence_features:
+      what = [w for w, on in (('allow_key_transform', sf.allow_key_transform), ('transform_dnn', sf.transform_dnn),
+                              ('aux_hist_seq', any(len(m.aux_hist_seq) for m in sf.seq_att_map)),
+                              ('negative_sampler', g.negative_sampler)) if on]
+      if what:
+        bad.append('feature_groups[%s].sequence_features[%s]: %s' % (g.group_name, sf.group_name, ', '.join(what)))
     if g.negative_sampler:
       bad.append('feature_groups[%s].negative_sampler' % g.group_name)
     names = g.DESCRIPTOR.fields_by_name['wide_deep'].enum_type.values_by_number
@@ -293,8 +310,15 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc),
                      shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0,
-                     uniform_tables=keras_tables)
-  model = cls.from_config(mc, il, generator=cpu_generator).to(device)
+                     uniform_tables=keras_tables, dense_generator=cpu_generator)
+  model = cls.from_config(mc, il, generator=cpu_generator)
+  if il.attention_modules:
+    # the attention MLPs of in-group sequence_features are InputLayer's in the reference (sequence_feature_layer.py);
+    # their parameters train with the model's
+    import torch
+    model.input_attention = torch.nn.ModuleDict({k.replace('/', '__').replace('.', '_'): v
+                                                 for k, v in il.attention_modules.items()})
+  model = model.to(device)
   if mc.model_class in _RANK_CLASSES:
     model.loss_type = mc.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[mc.loss_type].name
   bind_task_labels(model, list(pipeline_config.data_config.label_fields))

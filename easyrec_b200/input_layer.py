@@ -155,7 +155,8 @@ class InputLayer(object):
 
   def __init__(self, features, groups, batch_size, device, wide_output_dim=1,
                embedding_optimizer=_lib.OPT_ADAGRAD, shard_n=1, shard_rank=0, generator=None,
-               adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None, uniform_tables=None):
+               adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None, uniform_tables=None,
+               dense_generator=None):
     self.features = collections.OrderedDict((f.name, f) for f in features)
     self.groups = groups
     self.seq_att_groups = seq_att_groups or collections.OrderedDict()
@@ -243,6 +244,47 @@ class InputLayer(object):
           add_slot(f.embedding_dim, sname + '/hist', h, table, 'seq')
           lay['hist'].append([h, f.embedding_dim, sname + '/hist', None])
       self.seq_layout[sname] = lay
+    # feature_groups[...].sequence_features: target attention INSIDE a group (layers/input_layer.py:96-111 ->
+    # SequenceFeatureLayer, layers/sequence_feature_layer.py:190-249 -> SeqInputLayer with scope_name = the group's):
+    # a key that is a feature of the same group reuses the group's own embedding output (seq_input_layer.py:63-75);
+    # histories live in the group's scope; the attended vector (+ the key) is appended to the group's concat
+    self.attention_modules = collections.OrderedDict()
+    for gname, g in groups.items():
+      for sub in g.get('seq') or []:
+        if g.get('wide'):
+          raise NotImplementedError('sequence_features in the wide group %s' % gname)
+        from easyrec_b200 import layers as L
+        sname = '%s/%s' % (gname, sub['name'])
+        lay = dict(key=[], hist=[], T=None)
+        for keys, hists in sub['maps']:
+          for k in keys:
+            f = self.features[k]
+            own = [e for e in self.group_layout[gname] if e[0] == k and e[1] == 'emb']
+            if own:
+              if own[0][4] != gname:
+                raise NotImplementedError('sequence_features key %s is a multi-valued feature of group %s' % (k, gname))
+              lay['key'].append([k, own[0][3], gname, None])       # the column is filled in with the group's slot
+            else:
+              table = f.embedding_name or '%s/%s_embedding' % (gname, k)
+              add_slot(f.embedding_dim, sname + '/key', k, table, 'single')
+              lay['key'].append([k, f.embedding_dim, sname + '/key', None])
+          for h in hists:
+            f = self.features[h]
+            assert f.kind == 'seq', '%s must be a SequenceFeature' % h
+            assert lay['T'] in (None, f.seq_len), 'hist_seq features of one group must share seq_len'
+            lay['T'] = f.seq_len
+            table = f.embedding_name or '%s/%s_embedding' % (gname, h)
+            add_slot(f.embedding_dim, sname + '/hist', h, table, 'seq')
+            lay['hist'].append([h, f.embedding_dim, sname + '/hist', None])
+        dk, dh = sum(e[1] for e in lay['key']), sum(e[1] for e in lay['hist'])
+        if dk != dh:
+          raise NotImplementedError('sequence_features %s: key width %d != history width %d (allow_key_transform)'
+                                    % (sname, dk, dh))
+        self.seq_layout[sname] = lay
+        need_key = bool(sub.get('need_key', True))
+        self.group_layout[gname].append(['seq_fea/' + sub['name'], 'att', dh + (dk if need_key else 0), None, sname, need_key])
+        self.attention_modules[sname] = L.DNN(4 * dh, sub['units'], last_layer_no_activation=True,
+                                              last_layer_no_batch_norm=True, generator=dense_generator)
     # ER_BUCKET_ONE_ROW promises that no other slot of the arena reads the table (a raw feature listed in two groups
     # of the same width breaks that): such slots go through the ordinary dedup
     for dim, subs in self.subcalls.items():
@@ -755,13 +797,32 @@ class InputLayer(object):
         self._pending.append((m, m.rows, m.weights if any_w else None, all_outs,
                               m.seg_ids if m.has_csr else None))
     self._presort()
+    self.seq_outputs = {}
+    B = self.batch_size
+    for sname, lay in self.seq_layout.items():
+      keys = [outs_by_key[(d, ok)][:, c:c + d] for (_, d, ok, c) in lay['key']]
+      hists = [outs_by_key[(d, ok)][:, c:c + d].reshape(B, lay['T'], d) for (_, d, ok, c) in lay['hist']]
+      lens = features['seq_fea'][lay['hist'][0][0]][1]
+      self.seq_outputs[sname] = dict(
+          key=keys[0] if len(keys) == 1 else torch.cat(keys, dim=-1),
+          hist_seq_emb=hists[0] if len(hists) == 1 else torch.cat(hists, dim=-1),
+          hist_seq_len=lens)
     out = {}
     for gname, layout in self.group_layout.items():
-      per_feature, mats, kinds = [], {}, []
+      per_feature, mats, kinds, reg = [], {}, [], None
       for (fname, kind, width, dim, out_key, col) in layout:
         if kind == 'dense':
           c0, c1 = self.raw_cols[fname]
           v = dense_norm[:, c0:c1]
+        elif kind == 'att':
+          # target attention over the group's sequence_features (sequence_feature_layer.py:123-189): softmax of the
+          # masked attention-MLP scores over the history, [attended history | key] (need_key_feature)
+          from easyrec_b200 import interactions as I
+          so = self.seq_outputs[out_key]
+          key = so['key'].contiguous()
+          att = I.din_attention(key, so['hist_seq_emb'].contiguous(), so['hist_seq_len'], self.attention_modules[out_key])
+          v = torch.cat([att, key], dim=1) if col else att
+          reg = (reg or []) + [so['hist_seq_emb']]
         else:
           mat = outs_by_key[(dim, out_key)]
           mats[(dim, out_key)] = mat
@@ -774,15 +835,9 @@ class InputLayer(object):
         concat = mat if mat.shape[1] == width else mat[:, :width]
       else:
         concat = torch.cat(per_feature, dim=1)
+      if reg is not None:
+        # the embedding regulariser covers what was LOOKED UP (the group's columns and the histories,
+        # input_layer.py:369-375, sequence_feature_layer.py:215-217), not the attended vectors appended to the concat
+        concat._er_reg = [v for v, k in zip(per_feature, kinds) if k == 'emb'] + reg
       out[gname] = (concat, per_feature)
-    self.seq_outputs = {}
-    B = self.batch_size
-    for sname, lay in self.seq_layout.items():
-      keys = [outs_by_key[(d, ok)][:, c:c + d] for (_, d, ok, c) in lay['key']]
-      hists = [outs_by_key[(d, ok)][:, c:c + d].reshape(B, lay['T'], d) for (_, d, ok, c) in lay['hist']]
-      lens = features['seq_fea'][lay['hist'][0][0]][1]
-      self.seq_outputs[sname] = dict(
-          key=keys[0] if len(keys) == 1 else torch.cat(keys, dim=-1),
-          hist_seq_emb=hists[0] if len(hists) == 1 else torch.cat(hists, dim=-1),
-          hist_seq_len=lens)
     return out

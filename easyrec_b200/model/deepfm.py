@@ -32,6 +32,9 @@ class DeepFM(nn.Module):
   def __init__(self, input_layer, dnn_units, final_units, l2_reg=0.0, embedding_reg=0.0,
                generator=None):
     super().__init__()
+    for gname in ('wide', 'deep'):
+      if any(e[1] == 'att' for e in input_layer.group_layout.get(gname, [])):
+        raise NotImplementedError('DeepFM over a group with sequence_features (the FM fields must share one width)')
     self.input_layer = input_layer
     deep_layout = input_layer.group_layout['deep']
     self.n_field = len(deep_layout)

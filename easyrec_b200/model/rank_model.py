@@ -26,7 +26,9 @@ class RankModel(nn.Module):
     (layers/input_layer.py:369-375, compat/regularizers.py): scale * sum(x^2) / 2."""
     if self.embedding_reg <= 0 or not tensors:
       return 0.0
-    return self.embedding_reg * 0.5 * sum((t * t).sum() for t in tensors)
+    # (a group that carries in-group target attention names the looked-up tensors it is made of: `_er_reg`)
+    flat = [r for t in tensors for r in getattr(t, '_er_reg', [t])]
+    return self.embedding_reg * 0.5 * sum((t * t).sum() for t in flat)
 
   accepts_sample_weight = True
 

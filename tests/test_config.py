@@ -383,14 +383,16 @@ def test_reference_avazu_combo_config_reads_synthetic_lines(tmp_path):
   assert kinds == {'ComboFeature', 'RawFeature', 'IdFeature'}
 
 
-def test_in_group_sequence_features_are_refused():
-  """feature_groups { sequence_features { ... } } asks for target attention inside a plain group
-  (layers/sequence_feature_layer.py); building the model without it would train something else."""
-  cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
-      b'feature_names: "C1" wide_deep: DEEP', b'feature_names: "C1" wide_deep: DEEP sequence_features { group_name: "s" '
-      b'seq_att_map { key: "C1" hist_seq: "C1" } }'))
-  with pytest.raises(NotImplementedError, match='sequence_features'):
-    builder.check_scope(cfg)
+def test_in_group_sequence_feature_options_that_are_not_built_are_refused():
+  """feature_groups { sequence_features { ... } } = target attention inside a plain group (built:
+  tests/test_round2_host.py); its key-transform / auxiliary-history / negative-sampler variants would train
+  something else and are refused."""
+  for extra in (b'allow_key_transform: true', b'transform_dnn: true'):
+    cfg = config_util.get_configs_from_pipeline_file(MINI.replace(
+        b'feature_names: "C1" wide_deep: DEEP', b'feature_names: "C1" wide_deep: DEEP sequence_features { group_name: "s" '
+        b'seq_att_map { key: "C1" hist_seq: "C1" } ' + extra + b' }'))
+    with pytest.raises(NotImplementedError, match='sequence_features'):
+      builder.check_scope(cfg)
 
 
 def test_non_binary_task_towers_are_refused():

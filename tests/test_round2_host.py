@@ -608,3 +608,60 @@ model_config { model_class: "MultiTower"
   tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
   losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
   assert losses[-1] < losses[0] - 0.01
+
+
+def test_in_group_sequence_features_append_target_attention_to_the_group(interaction_doubles):  # noqa: F811
+  """feature_groups[...].sequence_features (layers/input_layer.py:96-111, layers/sequence_feature_layer.py:123-249):
+  the key reuses the group's own embedding of that feature, the history lives in the group's scope (or the shared
+  embedding_name), [attended history | key] is appended to the group's concat, the regulariser sees what was looked up."""
+  import test_gpu_models as G
+  feats_cfg = G.FEATS.replace('features { input_names: "item_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 5000 }',
+                              'features { input_names: "item_id" feature_type: IdFeature embedding_dim: 16 hash_bucket_size: 5000 embedding_name: "item" }')
+  feats_cfg = feats_cfg.replace('hash_bucket_size: 5000 max_seq_len: 20', 'hash_bucket_size: 5000 max_seq_len: 20 embedding_name: "item"')
+  text = G.HEAD + feats_cfg + '''
+model_config { model_class: "MultiTower"
+  feature_groups { group_name: "user" feature_names: ["user_id", "age"] wide_deep: DEEP }
+  feature_groups { group_name: "item" feature_names: ["item_id", "cate", "price"] wide_deep: DEEP
+                   sequence_features { group_name: "seq" seq_att_map { key: "item_id" hist_seq: "hist_items" }
+                                       seq_dnn { hidden_units: [8, 1] } } }
+  multi_tower { towers { input: "user" dnn { hidden_units: [32, 16] } } towers { input: "item" dnn { hidden_units: [32, 16] } }
+                final_dnn { hidden_units: [32, 16] } l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+  cfg = config_util.get_configs_from_pipeline_file(text.encode())
+  B = 256
+  il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  assert [e[1] for e in il.group_layout['item']] == ['emb', 'emb', 'emb', 'att'] and il.group_layout['item'][-1][2] == 32
+  assert 'item' in il.arenas[16].tables and 'item_id_embedding' not in il.arenas[16].tables   # key and history share it
+  assert sorted(dict(model.named_parameters())) != [] and any(n.startswith('input_attention.') for n, _ in model.named_parameters())
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  T_ = 20
+  hist = rng.integers(0, 10**6, (B, T_)).astype(np.int64)
+  lens = rng.integers(0, T_ + 1, B).astype(np.int32)
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64)),
+           'dense_fea': torch.from_numpy(rng.uniform(0, 100, (B, 1)).astype(np.float32)),
+           'seq_fea': {'hist_items': (torch.from_numpy(hist), torch.from_numpy(lens))}}
+  model.train()
+  g = il.lookup(feats)
+  concat, per = g['item']
+  assert concat.shape == (B, 16 * 3 + 32) and len(per) == 4
+  W = il.arenas[16].weight.detach().numpy()
+  off = il.arenas[16].tables['item'][0]
+  key = W[off + O.bucketize(ids[2], 0, 5000, 0)[0]]
+  np.testing.assert_array_equal(concat[:, :16].detach().numpy(), key)                # the group's own item_id column
+  np.testing.assert_array_equal(concat[:, 64:80].detach().numpy(), key)              # ... is the attention's key
+  hrows = O.bucketize(hist.reshape(-1), 0, 5000, 0)[0].reshape(B, T_)
+  he = W[off + hrows] * (np.arange(T_)[None, :] < lens[:, None])[:, :, None]
+  dnn = il.attention_modules['item/seq']
+  layers = [dict(W=l.kernel.detach().numpy(), b=l.bias.detach().numpy(),
+                 **(dict(gamma=l.gamma.detach().numpy(), beta=l.beta.detach().numpy()) if l.use_bn else {})) for l in dnn.layers]
+  want = O.din_attention(key, he.astype(np.float32), lens, layers)
+  np.testing.assert_allclose(concat[:, 48:64].detach().numpy(), want, rtol=1e-4, atol=1e-6)
+  assert len(concat._er_reg) == 4     # three looked-up columns + the history
+  il._pending = []
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  lab = torch.from_numpy((rng.uniform(size=B) < 0.3).astype(np.float32))
+  p0 = dnn.layers[0].kernel.detach().clone()
+  losses = [float(tr.train_step(feats, lab)[0]) for _ in range(12)]
+  assert losses[-1] < losses[0] - 0.01 and not torch.equal(dnn.layers[0].kernel.detach(), p0)   # the attention MLP trains
