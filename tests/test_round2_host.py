@@ -665,3 +665,43 @@ model_config { model_class: "MultiTower"
   p0 = dnn.layers[0].kernel.detach().clone()
   losses = [float(tr.train_step(feats, lab)[0]) for _ in range(12)]
   assert losses[-1] < losses[0] - 0.01 and not torch.equal(dnn.layers[0].kernel.detach(), p0)   # the attention MLP trains
+
+
+def test_dbmtl_and_simple_multi_task_train_from_their_configs(interaction_doubles):  # noqa: F811
+  """model_class DBMTL (model/dbmtl.py:44-121: bottom DNN, MMoE experts, tower DNNs, relation DNNs over the towers a
+  task depends on) and SimpleMultiTask (model/simple_multi_task.py:38-55), composed from the same layers as MMoE."""
+  import test_gpu_models as G
+  head = G.HEAD.replace('label_fields: "clk"', 'label_fields: ["clk", "buy"]')
+  group = 'feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }'
+  dbmtl = head + G.FEATS + '''
+model_config { model_class: "DBMTL" %s
+  dbmtl { bottom_dnn { hidden_units: [64] } expert_dnn { hidden_units: [32] } num_expert: 3
+          task_towers { tower_name: "ctr" label_name: "clk" loss_type: CLASSIFICATION dnn { hidden_units: [16] }
+                        relation_dnn { hidden_units: [8] } weight: 1.0 }
+          task_towers { tower_name: "cvr" label_name: "buy" loss_type: CLASSIFICATION dnn { hidden_units: [16] }
+                        relation_tower_names: ["ctr"] relation_dnn { hidden_units: [8] } weight: 0.5 }
+          l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+''' % group
+  smt = head + G.FEATS + '''
+model_config { model_class: "SimpleMultiTask" %s
+  simple_multi_task { task_towers { tower_name: "ctr" label_name: "clk" dnn { hidden_units: [32, 16] } weight: 1.0 }
+                      task_towers { tower_name: "cvr" label_name: "buy" dnn { hidden_units: [32, 16] } weight: 1.0 }
+                      l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+''' % group
+  B = 256
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64)),
+           'dense_fea': torch.from_numpy(rng.uniform(0, 100, (B, 1)).astype(np.float32))}
+  lab = torch.from_numpy((rng.uniform(size=(B, 2)) < 0.3).astype(np.float32))
+  for text, name in ((dbmtl, 'DBMTL'), (smt, 'SimpleMultiTask')):
+    cfg = config_util.get_configs_from_pipeline_file(text.encode())
+    il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+    assert type(model).__name__ == name and model.label_cols == [0, 1]
+    if name == 'DBMTL':
+      assert model.relations == [[], [0]] and model.relation_dnn[1].layers[0].kernel.shape[0] == 16 + 8
+    tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+    losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
+    assert losses[-1] < losses[0] - 0.01, (name, losses)
