@@ -192,7 +192,7 @@ def optimizer_settings(pipeline_config, index=0):
               if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
 
 
-_RANK_CLASSES = ('DeepFM', 'DCN', 'DLRM', 'MultiTower', 'MultiTowerDIN', 'RankModel')
+_RANK_CLASSES = ('DeepFM', 'DCN', 'DLRM', 'FM', 'MultiTower', 'MultiTowerDIN', 'RankModel', 'WideAndDeep')
 
 
 def _is_repeated(fd):
@@ -248,6 +248,8 @@ def check_scope(pipeline_config):
     bad.append('train_config.freeze_gradient')
   if tc.fine_tune_checkpoint:
     bad.append('train_config.fine_tune_checkpoint (TF checkpoints cannot be read here; use EasyRecEstimator.restore)')
+  if len(tc.optimizer_config) == 2 and mc.model_class == 'WideAndDeep':
+    bad.append('two optimizer_config entries with WideAndDeep (wide variables / the rest, wide_and_deep.py:82-110)')
   if len(tc.optimizer_config) > 2:
     bad.append('%d optimizer_config entries (one, or two = embedding + everything else, easy_rec_model.py:446-467)'
                % len(tc.optimizer_config))

@@ -705,3 +705,45 @@ model_config { model_class: "SimpleMultiTask" %s
     tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
     losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
     assert losses[-1] < losses[0] - 0.01, (name, losses)
+
+
+def test_wide_and_deep_and_fm_model_classes_match_their_formulas(interaction_doubles):  # noqa: F811
+  """model/wide_and_deep.py:44-80 (with and without final_dnn) and model/fm.py:43-62 on the shared wide / deep groups."""
+  import test_gpu_models as G
+  feats_cfg = G.FEATS.replace('features { input_names: "price" feature_type: RawFeature embedding_dim: 16 min_val: 0 max_val: 100 }\n', '')
+  groups = ('feature_groups { group_name: "deep" feature_names: ["user_id", "age", "item_id", "cate"] wide_deep: DEEP }\n'
+            '  feature_groups { group_name: "wide" feature_names: ["user_id", "item_id", "cate"] wide_deep: WIDE }')
+  B = 256
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64))}
+  lab = torch.from_numpy((rng.uniform(size=B) < 0.3).astype(np.float32))
+  cases = (('WideAndDeep', 'wide_and_deep { wide_output_dim: 4 dnn { hidden_units: [32, 16] } final_dnn { hidden_units: [8] } l2_regularization: 1e-5 }'),
+           ('WideAndDeep', 'wide_and_deep { wide_output_dim: 4 dnn { hidden_units: [32, 16] } l2_regularization: 1e-5 }'),
+           ('FM', 'fm { l2_regularization: 1e-5 }'))
+  for name, body in cases:
+    text = G.HEAD + feats_cfg + 'model_config { model_class: "%s"\n  %s\n  %s\n  embedding_regularization: 1e-5 }' % (name, groups, body)
+    cfg = config_util.get_configs_from_pipeline_file(text.encode())
+    il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+    model.train()
+    logits = model(feats).detach()
+    g = il.lookup(feats)
+    wide, deep = g['wide'][0].detach(), g['deep'][0].detach()
+    il._pending = []
+    if name == 'FM':
+      assert wide.shape == (B, 3)                                       # wide_output_dim = num_class = 1
+      v = deep.reshape(B, 4, 16)
+      second = 0.5 * ((v.sum(1) ** 2) - (v ** 2).sum(1)).sum(1)
+      torch.testing.assert_close(logits, wide.sum(1) + second + model.fm_bias.detach()[0], rtol=1e-5, atol=1e-6)
+    elif 'final_dnn' in body:
+      assert wide.shape == (B, 12)                                      # 3 features x wide_output_dim 4
+      wide_fea = wide.reshape(B, 3, 4).sum(1)
+      want = model.output(model.final_dnn(torch.cat([wide_fea, model.dnn(deep)], 1)))[:, 0].detach()
+      torch.testing.assert_close(logits, want, rtol=1e-5, atol=1e-6)
+    else:
+      assert wide.shape == (B, 3)                                       # no final_dnn: the wide sum is the logit's other half
+      want = (model.output(model.dnn(deep))[:, 0] + wide.sum(1)).detach()
+      torch.testing.assert_close(logits, want, rtol=1e-5, atol=1e-6)
+    tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+    losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
+    assert losses[-1] < losses[0] - 0.005, (name, losses)
