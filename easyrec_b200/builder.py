@@ -273,9 +273,9 @@ def check_scope(pipeline_config):
         bad.append('%s.losses (per-tower loss list)' % path)
       if m.HasField('task_space_indicator_label'):
         bad.append('%s.task_space_indicator_label (in / out of task-space sample weights)' % path)
-      if lt != 'CLASSIFICATION' or m.num_class != 1:
-        bad.append('%s: loss_type %s / num_class %d (task towers train with binary sigmoid cross entropy)'
-                   % (path, lt, m.num_class))
+      if lt not in ('CLASSIFICATION', 'L2_LOSS', 'SIGMOID_L2_LOSS') or m.num_class != 1:
+        bad.append('%s: loss_type %s / num_class %d (task towers train one output with sigmoid cross entropy or an '
+                   'L2 loss)' % (path, lt, m.num_class))
     if kind in ('DNN', 'MLP'):
       if kind == 'DNN' and m.activation not in ('tf.nn.relu', 'relu'):
         bad.append('%s.activation %r' % (path, m.activation))
@@ -324,7 +324,20 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   if mc.model_class in _RANK_CLASSES:
     model.loss_type = mc.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[mc.loss_type].name
   bind_task_labels(model, list(pipeline_config.data_config.label_fields))
+  towers = task_towers_of(mc)
+  if towers and hasattr(model, 'task_weights') and len(towers) == len(model.task_weights):
+    model.task_loss_types = [t.DESCRIPTOR.fields_by_name['loss_type'].enum_type.values_by_number[t.loss_type].name
+                             for t in towers]
   return il, model, opt
+
+
+def task_towers_of(model_config):
+  """the task tower messages of a multi-task model_config, in config order (mmoe / dbmtl / simple_multi_task /
+  backbone model_params)"""
+  which = model_config.WhichOneof('model')
+  if which is None:
+    return []
+  return list(getattr(getattr(model_config, which), 'task_towers', []))
 
 
 def embedding_layer_tables(model_config, specs):

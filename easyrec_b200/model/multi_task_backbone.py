@@ -62,7 +62,8 @@ class MultiTaskBackboneModel(RankModel):
     probs = []
     cols = getattr(self, 'label_cols', None) or list(range(len(self.task_weights)))
     for t, w in enumerate(self.task_weights):
-      ce, p = self.weighted_ce(logits[:, t].contiguous(), labels[:, cols[t]].contiguous(), sample_weight)
+      lt = (getattr(self, 'task_loss_types', None) or ['CLASSIFICATION'] * len(self.task_weights))[t]
+      ce, p = self.data_loss(logits[:, t].contiguous(), labels[:, cols[t]].contiguous(), sample_weight, loss_type=lt)
       total = total + w * ce
       probs.append(p)
     return total + self.embedding_reg_loss(self._emb_outputs), torch.stack(probs, dim=1)

@@ -46,12 +46,12 @@ class RankModel(nn.Module):
 
   loss_type = 'CLASSIFICATION'   # model_config.loss_type (set by builder.build_model)
 
-  def data_loss(self, logits, labels, sample_weight=None):
-    """(loss, predictions) of the single head by model_config.loss_type (model/rank_model.py:75-129, 213-269,
-    builders/loss_builder.py:36-55): CLASSIFICATION = sigmoid cross entropy, predictions `probs`; L2_LOSS /
-    SIGMOID_L2_LOSS = tf.losses.mean_squared_error(labels, y, weights) with y = logits / sigmoid(logits),
-    predictions `y`.  Both reduce by SUM_BY_NONZERO_WEIGHTS."""
-    lt = getattr(self, 'loss_type', 'CLASSIFICATION')
+  def data_loss(self, logits, labels, sample_weight=None, loss_type=None):
+    """(loss, predictions) of one binary head by its loss_type - model_config.loss_type, or the task tower's
+    (model/rank_model.py:75-129, 213-269, builders/loss_builder.py:36-55): CLASSIFICATION = sigmoid cross entropy,
+    predictions `probs`; L2_LOSS / SIGMOID_L2_LOSS = tf.losses.mean_squared_error(labels, y, weights) with
+    y = logits / sigmoid(logits), predictions `y`.  Both reduce by SUM_BY_NONZERO_WEIGHTS."""
+    lt = loss_type or getattr(self, 'loss_type', 'CLASSIFICATION')
     if lt == 'CLASSIFICATION':
       return RankModel.weighted_ce(logits, labels, sample_weight)
     if lt not in ('L2_LOSS', 'SIGMOID_L2_LOSS'):

@@ -400,7 +400,9 @@ def test_non_binary_task_towers_are_refused():
   sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
   import test_gpu_models as G
   cfg = config_util.get_configs_from_pipeline_file(G.MMOE_CFG.replace('loss_type: CLASSIFICATION weight: 0.5', 'loss_type: L2_LOSS weight: 0.5').encode())
-  with pytest.raises(NotImplementedError, match='L2_LOSS'):
+  builder.check_scope(cfg)    # a tower may be a regressor (L2_LOSS / SIGMOID_L2_LOSS on its one output)
+  cfg = config_util.get_configs_from_pipeline_file(G.MMOE_CFG.replace('loss_type: CLASSIFICATION weight: 0.5', 'loss_type: PAIR_WISE_LOSS weight: 0.5').encode())
+  with pytest.raises(NotImplementedError, match='PAIR_WISE_LOSS'):
     builder.check_scope(cfg)
   builder.check_scope(config_util.get_configs_from_pipeline_file(G.MMOE_CFG.encode()))
 

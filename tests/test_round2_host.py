@@ -747,3 +747,34 @@ def test_wide_and_deep_and_fm_model_classes_match_their_formulas(interaction_dou
     tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
     losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
     assert losses[-1] < losses[0] - 0.005, (name, losses)
+
+
+def test_a_task_tower_with_an_l2_loss_type_is_trained_as_a_regressor(interaction_doubles):  # noqa: F811
+  """TaskTower.loss_type (protos/tower.proto, model/multi_task_model.py:201-280): per tower CLASSIFICATION or an L2 loss."""
+  import test_gpu_models as G
+  text = G.MMOE_CFG.replace('loss_type: CLASSIFICATION weight: 0.5', 'loss_type: L2_LOSS weight: 0.5')
+  assert text != G.MMOE_CFG
+  cfg = config_util.get_configs_from_pipeline_file(text.encode())
+  B = G.B
+  il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  assert sorted(model.task_loss_types) == ['CLASSIFICATION', 'L2_LOSS']
+  t_l2 = model.task_loss_types.index('L2_LOSS')
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64)),
+           'dense_fea': torch.from_numpy(rng.uniform(0, 100, (B, 1)).astype(np.float32))}
+  labels = torch.from_numpy(rng.uniform(0, 1, (B, 2)).astype(np.float32))
+  model.train()
+  logits = model(feats)
+  loss, preds = model.loss(logits, labels)
+  cols = model.label_cols
+  want = 0.0
+  for t, w in enumerate(model.task_weights):
+    x, z = logits[:, t], labels[:, cols[t]]
+    if t == t_l2:
+      want = want + w * ((x - z) ** 2).mean()
+    else:
+      want = want + w * torch.nn.functional.binary_cross_entropy_with_logits(x, z)
+  want = want + model.embedding_reg_loss(model._emb_outputs)
+  assert abs(float(loss) - float(want)) < 1e-5
+  torch.testing.assert_close(preds[:, t_l2], logits[:, t_l2].detach())     # a regressor predicts y = its output
