@@ -1,5 +1,5 @@
-"""DBMTL and SimpleMultiTask (reference: easy_rec/python/model/dbmtl.py:17-121, model/simple_multi_task.py:17-56,
-model/multi_task_model.py): multi-task heads over the 'all' group, composed from the same fused DNN layers and the
+"""DBMTL, SimpleMultiTask and PLE (reference: easy_rec/python/model/dbmtl.py:17-121, model/simple_multi_task.py:17-56,
+model/ple.py:17-128, model/multi_task_model.py): multi-task heads over the 'all' group, composed from the same fused DNN layers and the
 MMoE mixture kernel as MMoE; the loss is MMoE's (sum_t weight_t * sigmoid CE on the tower's label)."""
 import torch
 from torch import nn
@@ -111,3 +111,63 @@ class DBMTL(MMoE):
       rel.append(r)
       logits.append(out(r)[:, 0])
     return torch.stack(logits, dim=1)
+
+
+@registry.register('PLE')
+class PLE(MMoE):
+  """Progressive layered extraction (ple.py:36-128): per extraction network, `expert_num_per_task` experts per task on
+  that task's features and `share_num` shared experts on the shared features; a task's gate (softmax(dense(task
+  features)) over [its experts | shared experts], the MMoE mixture kernel) gives its next features, the shared gate
+  (over every expert) the next shared features - dropped in the last network; then tower DNN -> dense(1) per task."""
+
+  @classmethod
+  def from_config(cls, model_config, input_layer, generator=None):
+    c = model_config.ple
+    nets = [dict(per_task=int(n.expert_num_per_task), share=int(n.share_num), task_units=L.units_of(n.task_expert_net),
+                 share_units=L.units_of(n.share_expert_net)) for n in c.extraction_networks]
+    return cls(input_layer, model_config.feature_groups[0].group_name, _towers(c.task_towers), nets,
+               [L.units_of(t.dnn) for t in c.task_towers], l2_reg=c.l2_regularization,
+               embedding_reg=model_config.embedding_regularization, generator=generator)
+
+  def __init__(self, input_layer, group, towers, nets, tower_units, l2_reg=0.0, embedding_reg=0.0, generator=None):
+    nn.Module.__init__(self)
+    self.input_layer, self.group = input_layer, group
+    self.in_dim = d = sum(e[2] for e in input_layer.group_layout[group])
+    self.tower_names = [t[0] for t in towers]
+    self.label_names = [t[1] for t in towers]
+    self.task_weights = [t[2] for t in towers]
+    n_task = len(towers)
+    self.nets = nn.ModuleList()
+    d_task, d_share = [d] * n_task, d
+    for li, n in enumerate(nets):
+      last = li + 1 == len(nets)
+      net = nn.Module()
+      net.share = nn.ModuleList([L.DNN(d_share, n['share_units'], generator=generator) for _ in range(n['share'])])
+      net.task = nn.ModuleList([nn.ModuleList([L.DNN(d_task[t], n['task_units'], generator=generator)
+                                               for _ in range(n['per_task'])]) for t in range(n_task)])
+      h = net.task[0][0].out_dim
+      if n['share'] and net.share[0].out_dim != h:
+        raise ValueError('PLE: task_expert_net and share_expert_net must end in the same width (their outputs are mixed)')
+      net.task_gate = nn.ModuleList([L.Dense(d_task[t], n['per_task'] + n['share'], generator) for t in range(n_task)])
+      net.share_gate = None if last else L.Dense(d_share, n_task * n['per_task'] + n['share'], generator)
+      self.nets.append(net)
+      d_task, d_share = [h] * n_task, h
+    self.tower_dnn = nn.ModuleList([L.DNN(d_task[t], u, generator=generator) for t, u in enumerate(tower_units)])
+    self.tower_out = nn.ModuleList([L.Dense(dnn.out_dim, 1, generator) for dnn in self.tower_dnn])
+    self.l2_reg, self.embedding_reg = l2_reg, embedding_reg
+
+  def forward(self, features):
+    x, _ = self.input_layer.lookup(features)[self.group]
+    self._emb_outputs = (x,)
+    x = x.contiguous()
+    task_fea, share_fea = [x] * len(self.tower_names), x
+    for net in self.nets:
+      shared = [e(share_fea) for e in net.share]
+      own = [[e(task_fea[t]) for e in net.task[t]] for t in range(len(task_fea))]
+      nxt = [I.mmoe_mix(net.task_gate[t](task_fea[t]), torch.stack(own[t] + shared, dim=1)) for t in range(len(task_fea))]
+      if net.share_gate is not None:
+        every = [e for o in own for e in o] + shared
+        share_fea = I.mmoe_mix(net.share_gate(share_fea), torch.stack(every, dim=1))
+      task_fea = nxt
+    return torch.stack([out(dnn(task_fea[t]))[:, 0] for t, (dnn, out) in enumerate(zip(self.tower_dnn, self.tower_out))],
+                       dim=1)

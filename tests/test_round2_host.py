@@ -778,3 +778,36 @@ def test_a_task_tower_with_an_l2_loss_type_is_trained_as_a_regressor(interaction
   want = want + model.embedding_reg_loss(model._emb_outputs)
   assert abs(float(loss) - float(want)) < 1e-5
   torch.testing.assert_close(preds[:, t_l2], logits[:, t_l2].detach())     # a regressor predicts y = its output
+
+
+def test_ple_model_class_trains_and_its_gates_mix_own_and_shared_experts(interaction_doubles):  # noqa: F811
+  """model_class PLE (model/ple.py:36-128): two extraction networks, the last one without a shared gate."""
+  import test_gpu_models as G
+  head = G.HEAD.replace('label_fields: "clk"', 'label_fields: ["clk", "buy"]')
+  text = head + G.FEATS + '''
+model_config { model_class: "PLE"
+  feature_groups { group_name: "all" feature_names: ["user_id", "age", "item_id", "cate", "price"] wide_deep: DEEP }
+  ple { extraction_networks { network_name: "l1" expert_num_per_task: 2 share_num: 2
+                              task_expert_net { hidden_units: [32] } share_expert_net { hidden_units: [32] } }
+        extraction_networks { network_name: "l2" expert_num_per_task: 1 share_num: 1
+                              task_expert_net { hidden_units: [16] } share_expert_net { hidden_units: [16] } }
+        task_towers { tower_name: "ctr" label_name: "clk" dnn { hidden_units: [8] } weight: 1.0 }
+        task_towers { tower_name: "cvr" label_name: "buy" dnn { hidden_units: [8] } weight: 1.0 }
+        l2_regularization: 1e-5 }
+  embedding_regularization: 1e-5 }
+'''
+  cfg = config_util.get_configs_from_pipeline_file(text.encode())
+  B = 256
+  il, model, opt = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(1), default_seq_len=20)
+  assert type(model).__name__ == 'PLE' and len(model.nets) == 2
+  n1, n2 = model.nets
+  assert n1.task_gate[0].kernel.shape[1] == 4 and n1.share_gate.kernel.shape[1] == 6      # 2 own + 2 shared; all 4 + 2 shared
+  assert n2.share_gate is None and n2.task_gate[1].kernel.shape == (32, 2)
+  rng = np.random.default_rng(0)
+  ids = np.stack([rng.integers(0, 10**6, B), rng.integers(0, 10, B), rng.integers(0, 10**6, B), rng.integers(0, 500, B)])
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1).astype(np.int64)),
+           'dense_fea': torch.from_numpy(rng.uniform(0, 100, (B, 1)).astype(np.float32))}
+  lab = torch.from_numpy((rng.uniform(size=(B, 2)) < 0.3).astype(np.float32))
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
+  assert losses[-1] < losses[0] - 0.01, losses
