@@ -99,10 +99,13 @@ class MLP(nn.Module):
     assert units, 'MLP takes at least one hidden unit'
     if conf.use_bn_after_activation:
       raise NotImplementedError('MLP.use_bn_after_activation')
-    for act in (conf.activation, conf.final_activation):
-      if act not in ('relu', '', 'linear', 'None'):
-        raise NotImplementedError('MLP activation %r' % act)
+    # activation / final_activation by name (layers/keras/activation.py:97-110 -> utils/activation.py:get_activation);
+    # dice carries its own batch norm and learned alpha and is not built
+    # (a pb-message MLP reads the proto default 'relu' for an unset final_activation: Parameter.get_or_default returns a
+    # non-empty string field as is, layers/utils.py:224-227)
+    kinds = [L.activation_kind(conf.activation), L.activation_kind(conf.final_activation)]
     self.layers = nn.ModuleList()
+    self.acts = nn.ModuleList()
     self.dropouts = nn.ModuleList()
     rates = [float(r) for r in conf.dropout_ratio]
     n = len(units)
@@ -115,8 +118,9 @@ class MLP(nn.Module):
         raise ValueError('invalid dropout_ratio: %.3f' % rate)
       self.dropouts.append(L.Dropout(rate) if rate > 0.0 else nn.Identity())
       bn = conf.use_final_bn if last else conf.use_bn
-      act = conf.final_activation if last else conf.activation
-      lay = L.DenseLayer(n_in, u, bn, act == 'relu', generator)
+      kind = kinds[1] if last else kinds[0]
+      lay = L.DenseLayer(n_in, u, bn, kind == 'relu', generator)
+      self.acts.append(L.Activation(kind) if kind not in (None, 'relu') else nn.Identity())
       lim = math.sqrt(6.0 / n_in)   # he_uniform
       with torch.no_grad():
         lay.kernel.uniform_(-lim, lim, generator=generator)
@@ -130,8 +134,8 @@ class MLP(nn.Module):
   def forward(self, x):
     if isinstance(x, (list, tuple)):
       x = torch.cat(list(x), dim=-1)
-    for lay, drop in zip(self.layers, self.dropouts):
-      x = drop(lay(x))
+    for lay, act, drop in zip(self.layers, self.acts, self.dropouts):
+      x = drop(act(lay(x)))
     return x
 
 

@@ -277,8 +277,12 @@ def check_scope(pipeline_config):
         bad.append('%s: loss_type %s / num_class %d (task towers train one output with sigmoid cross entropy or an '
                    'L2 loss)' % (path, lt, m.num_class))
     if kind in ('DNN', 'MLP'):
-      if kind == 'DNN' and m.activation not in ('tf.nn.relu', 'relu'):
-        bad.append('%s.activation %r' % (path, m.activation))
+      from easyrec_b200 import layers as L
+      for act in ([m.activation] if kind == 'DNN' else [m.activation, m.final_activation]):
+        try:
+          L.activation_kind(act)
+        except NotImplementedError as e:
+          bad.append('%s: %s' % (path, e))
   if bad:
     raise NotImplementedError('config is outside the hot-path scope: ' + '; '.join(bad))
 

@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "elementwise.cuh"
 
 namespace er {
 
@@ -592,6 +593,72 @@ extern "C" int er_dropout(const float* x, int64_t n, float rate, uint64_t seed, 
   const uint32_t thresh = keep >= 1.0 ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
   dropout_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(x, n, thresh, (float)(1.0 / keep), seed, counter_dev, y);
   count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+// ---- the non-relu activations of get_activation (utils/activation.py:66-118; DNN.__call__ layers/dnn.py:70-73, keras
+// MLP layers/keras/blocks.py:82) --------------------------------------------------------------------------------------
+// ReLU stays fused in the bias / batch-norm epilogue above; a layer configured with another stateless activation runs
+// that epilogue in its linear form and this elementwise pass on top.  The backward pass recomputes the derivative from
+// the pre-activation x (kept for the batch-norm backward anyway), in the branch conventions of TF's gradient kernels
+// (EluGrad / SeluGrad / LeakyReluGrad take the negative branch for x < 0 resp. x <= 0).
+namespace er {
+template <int KIND>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = act_value<KIND>(x[i]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+    act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, int64_t n, float* __restrict__ gx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    gx[i] = gy[i] * act_slope<KIND>(x[i]);
+}
+
+template <int KIND>
+static void act_launch(const float* x, const float* gy, int64_t n, float* out, cudaStream_t st) {
+  const int grid = grid_for(n, 256 * 4, 8);
+  if (gy)
+    act_bwd_kernel<KIND><<<grid, 256, 0, st>>>(x, gy, n, out);
+  else
+    act_fwd_kernel<KIND><<<grid, 256, 0, st>>>(x, n, out);
+}
+
+static int act_dispatch(const float* x, const float* gy, int64_t n, int kind, float* out, er_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  switch (kind) {
+    case ER_ACT_GELU: act_launch<ER_ACT_GELU>(x, gy, n, out, st); break;
+    case ER_ACT_LEAKY_RELU: act_launch<ER_ACT_LEAKY_RELU>(x, gy, n, out, st); break;
+    case ER_ACT_ELU: act_launch<ER_ACT_ELU>(x, gy, n, out, st); break;
+    case ER_ACT_SELU: act_launch<ER_ACT_SELU>(x, gy, n, out, st); break;
+    case ER_ACT_TANH: act_launch<ER_ACT_TANH>(x, gy, n, out, st); break;
+    case ER_ACT_SWISH: act_launch<ER_ACT_SWISH>(x, gy, n, out, st); break;
+    case ER_ACT_SIGMOID: act_launch<ER_ACT_SIGMOID>(x, gy, n, out, st); break;
+    default: return fail(ER_ERR_INVALID_ARG, "er_act: unknown activation kind");
+  }
+  count_launches(1);
+  return ER_OK;
+}
+}  // namespace er
+
+extern "C" int er_act_fwd(const float* x, int64_t n, int kind, float* y, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && y, "null argument");
+  ER_REQUIRE(n > 0, "n must be positive");
+  int rc = act_dispatch(x, nullptr, n, kind, y, stream);
+  if (rc != ER_OK) return rc;
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_act_bwd(const float* x, const float* gy, int64_t n, int kind, float* gx, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && gy && gx, "null argument");
+  ER_REQUIRE(n > 0, "n must be positive");
+  int rc = act_dispatch(x, gy, n, kind, gx, stream);
+  if (rc != ER_OK) return rc;
   ER_CUDA_LAUNCH_CHECK();
   return ER_OK;
 }

@@ -161,8 +161,17 @@ class EasyRecEstimator(object):
     return out
 
   def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
+    """One pass over input_fn() (or `steps` batches) -> {metric name: value, 'global_step'} for eval_config.metrics_set
+    (no metrics_set: auc).  The streaming metrics (auc at AUC.num_thresholds thresholds as tf.metrics.auc computes it,
+    max_f1, the mean / root-mean errors; every task tower of a multi-task model under '<metric>_<tower_name>') are
+    accumulated on the device, batch by batch (metrics.MetricSet over er_auc_hist); the grouped AUCs gauc / session_auc
+    are computed on the host over the collected predictions, as the reference's py_func does (core/metrics.py:59-106).
+    `auc_exact` is the exact ROC AUC of the single binary head (what the thresholded `auc` approximates)."""
+    heads = metrics.heads_of(self.model)
+    mset = metrics.MetricSet(self.eval_config.metrics_set, heads, self._device)
+    single = len(heads) == 1 and heads[0][0] == '' and heads[0][1] == 'CLASSIFICATION'
     labels_all, probs_all = [], []
-    groups = self._group_fields()
+    groups = self._group_fields() if single else []
     keys_all = [[] for _ in groups]
     B = self.input_layer.batch_size
     n = 0
@@ -171,16 +180,20 @@ class EasyRecEstimator(object):
         keys_all[k].append(feats['sparse_fea'][pos * B:(pos + 1) * B].cpu().numpy())
       feats, labels = readers.to_device(feats, labels, self._device)
       logits = self._forward_eval(feats)
-      if logits.dim() == 1:
-        probs_all.append(torch.sigmoid(logits).cpu().numpy())
-        labels_all.append(labels.cpu().numpy())
+      if heads:
+        mset.update(logits, labels)
+      if single:
+        probs_all.append(torch.sigmoid(logits))
+        labels_all.append(labels)
       n += 1
       if steps is not None and n >= steps:
         break
     out = {'global_step': self.global_step}
+    if n and heads:
+      out.update(mset.result())
     if probs_all:
-      lab, prob = np.concatenate(labels_all), np.concatenate(probs_all)
-      out['auc'] = metrics.auc(lab, prob)
+      lab, prob = torch.cat(labels_all).cpu().numpy(), torch.cat(probs_all).cpu().numpy()
+      out['auc_exact'] = metrics.auc(lab, prob)
       for (which, _, reduction), keys in zip(groups, keys_all):
         out[which] = float(metrics.gauc(lab, prob, np.concatenate(keys), reduction))
     return out

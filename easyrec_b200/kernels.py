@@ -111,6 +111,44 @@ def dropout(x, rate, seed, counter, out=None):
   return y
 
 
+ACT_KINDS = {'gelu': _lib.ACT_GELU, 'leaky_relu': _lib.ACT_LEAKY_RELU, 'prelu': _lib.ACT_LEAKY_RELU, 'elu': _lib.ACT_ELU,
+             'selu': _lib.ACT_SELU, 'tanh': _lib.ACT_TANH, 'swish': _lib.ACT_SWISH, 'sigmoid': _lib.ACT_SIGMOID}
+
+
+def act_fwd(x, kind):
+  """er_act_fwd: y = f(x), f one of the stateless non-relu activations of utils/activation.py:get_activation."""
+  x = x.contiguous()
+  _chk(x, torch.float32, 'x')
+  y = torch.empty_like(x)
+  _lib.check(_lib.load().er_act_fwd(_p(x), x.numel(), int(kind), _p(y), _stream()), 'er_act_fwd')
+  return y
+
+
+def act_bwd(x, gy, kind):
+  """er_act_bwd: gx = gy * f'(x), the derivative recomputed from the pre-activation."""
+  x, gy = x.contiguous(), gy.contiguous()
+  _chk(x, torch.float32, 'x')
+  _chk(gy, torch.float32, 'gy')
+  assert x.numel() == gy.numel()
+  gx = torch.empty_like(x)
+  _lib.check(_lib.load().er_act_bwd(_p(x), _p(gy), x.numel(), int(kind), _p(gx), _stream()), 'er_act_bwd')
+  return gx
+
+
+def auc_hist(probs, labels, thresholds, hist):
+  """er_auc_hist: one batch into the uint64 confusion histograms behind tf.metrics.auc / max_f1 (hist: int64 tensor of
+  2 * (T + 1) counters reinterpreted as uint64; they never approach 2^63)."""
+  probs, labels = probs.contiguous().view(-1), labels.contiguous().view(-1)
+  _chk(probs, torch.float32, 'probs')
+  _chk(labels, torch.float32, 'labels')
+  _chk(thresholds, torch.float32, 'thresholds')
+  _chk(hist, torch.int64, 'hist')
+  assert probs.numel() == labels.numel() and hist.numel() == 2 * (thresholds.numel() + 1)
+  _lib.check(_lib.load().er_auc_hist(_p(probs), _p(labels), probs.numel(), _p(thresholds), thresholds.numel(), _p(hist),
+                                     _stream()), 'er_auc_hist')
+  return hist
+
+
 def shard_group_workspace(n_lookups, device):
   return torch.empty(_lib.load().er_shard_group_workspace_bytes(int(n_lookups)), dtype=torch.uint8, device=device)
 

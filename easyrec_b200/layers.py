@@ -216,17 +216,68 @@ class Dropout(nn.Module):
     return grad
 
 
+def activation_kind(name):
+  """activation string of a DNN / MLP config -> None (linear), 'relu' (fused in the dense epilogue) or an er_act_*
+  kind.  Names as utils/activation.py:66-118 resolves them: case-insensitive short names, or a `tf.nn.<fn>` /
+  `tf.<fn>` path (load_by_path); 'prelu' without arguments is tf.nn.leaky_relu there (:98-101)."""
+  if name is None:
+    return None
+  n = str(name).strip().lower()
+  for prefix in ('tf.nn.', 'tf.math.', 'tf.keras.activations.', 'tf.'):
+    if n.startswith(prefix):
+      n = n[len(prefix):]
+      break
+  if n in ('', 'linear', 'none'):
+    return None
+  if n == 'relu':
+    return 'relu'
+  if n in K.ACT_KINDS:
+    return K.ACT_KINDS[n]
+  raise NotImplementedError('activation %r (built: relu, linear, %s)' % (name, ', '.join(sorted(K.ACT_KINDS))))
+
+
+class _ActFn(torch.autograd.Function):
+  """y = f(x); the backward pass recomputes f'(x) from the saved pre-activation (er_act_bwd)."""
+
+  @staticmethod
+  def forward(ctx, x, kind):
+    x = x.contiguous()
+    ctx.kind = kind
+    ctx.save_for_backward(x)
+    return K.act_fwd(x, kind)
+
+  @staticmethod
+  def backward(ctx, gy):
+    (x,) = ctx.saved_tensors
+    return K.act_bwd(x, gy.contiguous(), ctx.kind), None
+
+
+class Activation(nn.Module):
+  """one of the stateless non-relu activations of get_activation (utils/activation.py:66-118) on top of a layer whose
+  dense / batch-norm epilogue ran in its linear form (layers/dnn.py:70-73, layers/keras/blocks.py:82)."""
+
+  def __init__(self, kind):
+    super().__init__()
+    assert isinstance(kind, int) and kind > 0
+    self.kind = kind
+
+  def forward(self, x):
+    return _ActFn.apply(x, self.kind)
+
+
 class Units(list):
   """hidden_units of a protos/dnn.proto DNN message together with its use_bn flag and dropout_ratio list (slices
   keep them)."""
   use_bn = True
   dropout = ()
+  activation = 'relu'
 
   def __getitem__(self, k):
     v = list.__getitem__(self, k)
     if isinstance(k, slice):
       v = Units(v)
       v.use_bn = self.use_bn
+      v.activation = self.activation
       v.dropout = tuple(self.dropout[k])
     return v
 
@@ -235,6 +286,8 @@ def units_of(dnn_config):
   """DNN message -> Units (layers/dnn.py:50-87 reads hidden_units, use_bn and dropout_ratio from the same message)."""
   u = Units(int(x) for x in dnn_config.hidden_units)
   u.use_bn = bool(dnn_config.use_bn)
+  u.activation = dnn_config.activation   # 'tf.nn.relu' by default (protos/dnn.proto:11)
+  activation_kind(u.activation)          # (unknown names are refused where the config is read)
   u.dropout = tuple(float(r) for r in dnn_config.dropout_ratio)
   if u.dropout and len(u.dropout) != len(u):
     raise ValueError('dropout_ratio needs one entry per hidden layer (layers/dnn.py:78 indexes it by layer)')
@@ -250,13 +303,17 @@ class DNN(nn.Module):
     super().__init__()
     use_bn = use_bn and getattr(hidden_units, 'use_bn', True)   # protos/dnn.proto use_bn (default true)
     drop = tuple(getattr(hidden_units, 'dropout', ()))
+    kind = activation_kind(getattr(hidden_units, 'activation', 'relu'))
     self.layers = nn.ModuleList()
+    self.acts = nn.ModuleList()
     self.dropouts = nn.ModuleList()
     n = len(hidden_units)
     for i, u in enumerate(hidden_units):
       bn = use_bn and (i + 1 < n or not last_layer_no_batch_norm)
       act = i + 1 < n or not last_layer_no_activation
-      self.layers.append(DenseLayer(n_in, u, bn, act, generator))
+      # relu rides in the dense / batch-norm epilogue; any other activation is an elementwise pass over its linear form
+      self.layers.append(DenseLayer(n_in, u, bn, act and kind == 'relu', generator))
+      self.acts.append(Activation(kind) if act and kind not in (None, 'relu') else nn.Identity())
       # dropout follows the activation of EVERY layer, the last one included (layers/dnn.py:77-82)
       self.dropouts.append(Dropout(drop[i]) if drop and drop[i] > 0 else nn.Identity())
       n_in = u
@@ -266,8 +323,8 @@ class DNN(nn.Module):
     shape = x.shape
     if x.dim() == 3:
       x = x.reshape(-1, shape[-1])
-    for layer, drop in zip(self.layers, self.dropouts):
-      x = drop(layer(x))
+    for layer, act, drop in zip(self.layers, self.acts, self.dropouts):
+      x = drop(act(layer(x)))
     if len(shape) == 3:
       x = x.reshape(shape[0], shape[1], -1)
     return x

@@ -108,24 +108,17 @@ class _Bound(EasyRecModel):
     return d
 
   def build_metric_graph(self, eval_config):
-    """metrics of eval_config.metrics_set on the bound batch (auc: exact ROC AUC; the reference's tf.metrics.auc
-    is a 200-threshold streaming approximation of it)."""
-    if not self._prediction_dict:
+    """eval_config.metrics_set on the bound batch, by the reference's streaming definitions (metrics.MetricSet: auc =
+    tf.metrics.auc at AUC.num_thresholds thresholds, max_f1, the mean / root-mean errors; '<metric>_<tower_name>' per
+    task tower).  The estimator keeps one MetricSet over a whole evaluate() pass; this call evaluates it on one batch."""
+    if self._logits is None:
       self.build_predict_graph()
     out = {}
-    kinds = [m.WhichOneof('metric') for m in eval_config.metrics_set] if eval_config is not None else ['auc']
-    lab = self._labels
-    for kind in kinds or ['auc']:
-      if kind != 'auc' or lab is None:
-        continue
-      towers = self._towers()
-      if towers and 'probs_' + towers[0] in self._prediction_dict:
-        cols = getattr(self, 'label_cols', None) or list(range(len(towers)))
-        for t, name in enumerate(towers):
-          out['auc_' + name] = M.auc(lab[:, cols[t]].detach().cpu().numpy(),
-                                     self._prediction_dict['probs_' + name].detach().cpu().numpy())
-      elif self._prediction_dict['probs'].dim() == 1:
-        out['auc'] = M.auc(lab.detach().cpu().numpy(), self._prediction_dict['probs'].detach().cpu().numpy())
+    heads = M.heads_of(self)
+    if self._labels is not None and heads:
+      mset = M.MetricSet(eval_config.metrics_set if eval_config is not None else [], heads, self._logits.device)
+      mset.update(self._logits, self._labels)
+      out = mset.result()
     self._metric_dict = out
     return out
 

@@ -356,6 +356,31 @@ int er_bias_bn_act_bwd(const float* z, const float* bias, const float* gamma,
 int er_dropout(const float* x, int64_t n, float rate, uint64_t seed, const int64_t* counter_dev, float* y,
                er_stream_t stream);
 
+/* The stateless non-relu activations of get_activation (utils/activation.py:66-118), applied by DNN.__call__
+ * (layers/dnn.py:70-73) and the keras MLP block (layers/keras/blocks.py:82) after the dense / batch-norm stage:
+ * y = f(x) elementwise; the backward pass recomputes f'(x) from the pre-activation: gx = gy * f'(x).  relu stays fused
+ * in er_bias_bn_act_*; 'linear' is no call at all; dice (learned alpha over a batch norm) is not built. */
+enum {
+  ER_ACT_GELU = 1,       /* x * 0.5 * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  (activation.py:46-60) */
+  ER_ACT_LEAKY_RELU = 2, /* tf.nn.leaky_relu, alpha 0.2 (also 'prelu' without arguments, activation.py:98-101) */
+  ER_ACT_ELU = 3,
+  ER_ACT_SELU = 4,
+  ER_ACT_TANH = 5,
+  ER_ACT_SWISH = 6,      /* x * sigmoid(x) */
+  ER_ACT_SIGMOID = 7
+};
+int er_act_fwd(const float* x, int64_t n, int kind, float* y, er_stream_t stream);
+int er_act_bwd(const float* x, const float* gy, int64_t n, int kind, float* gx, er_stream_t stream);
+
+/* One batch into the accumulators of tf.metrics.auc (model/rank_model.py:360-373; eval.proto AUC.num_thresholds,
+ * default 200) and max_f1 (core/metrics.py:25-56).  thresholds: DEVICE float32[n_thresholds], ascending (TF's list:
+ * -1e-7, (i + 1) / (T - 1) for i < T - 2, 1 + 1e-7).  hist: DEVICE uint64[2 * (n_thresholds + 1)], zeroed by the caller
+ * before the first batch; hist[k] counts the negatives and hist[n_thresholds + 1 + k] the positives (int64(label) != 0)
+ * whose prediction exceeds exactly k thresholds, so tp[i] = sum_{k > i} pos[k], fp[i] = sum_{k > i} neg[k].  Integer
+ * counters: exact and independent of the order of the batches. */
+int er_auc_hist(const float* probs, const float* labels, int64_t n, const float* thresholds, int32_t n_thresholds,
+                uint64_t* hist, er_stream_t stream);
+
 /* Dense optimizer over ONE flat parameter buffer (dense apply_gradients,
  * compat/optimizers.py:413-416): g = grad*grad_scale + l2*w, then the adagrad / adam / sgd rule.
  * segs: DEVICE array describing the tensors inside the flat buffers; the step's rate comes from lr_dev

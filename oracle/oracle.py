@@ -377,3 +377,97 @@ def inbatch_softmax_ce(sim, item_ids=None, weights=None):
   hit = probs[np.arange(B), np.arange(B)]
   loss = -np.mean(np.log(hit + np.float32(1e-12)) * w, dtype=np.float32) / np.mean(w, dtype=np.float32)
   return np.float32(loss), probs
+
+
+# ---- stateless activations of get_activation (utils/activation.py:46-118) --------------------------------------------
+_SELU_SCALE, _SELU_ALPHA = 1.0507009873554804934193349852946, 1.6732632423543772848170429916717
+
+
+def activation(x, name):
+  """float64 evaluation of `name`(x) as utils/activation.py:66-118 resolves it (gelu is the reference's own tanh form,
+  :46-60; leaky_relu / prelu-without-arguments = tf.nn.leaky_relu, alpha 0.2; swish = x * sigmoid(x), :63-65)."""
+  x = np.asarray(x, np.float64)
+  if name == 'gelu':
+    return x * 0.5 * (1.0 + np.tanh(np.sqrt(2 / np.pi) * (x + 0.044715 * x ** 3)))
+  if name in ('leaky_relu', 'prelu'):
+    return np.maximum(0.2 * x, x)
+  if name == 'elu':
+    return np.where(x < 0, np.expm1(x), x)
+  if name == 'selu':
+    return np.where(x < 0, _SELU_SCALE * _SELU_ALPHA * np.expm1(x), _SELU_SCALE * x)
+  if name == 'tanh':
+    return np.tanh(x)
+  if name == 'swish':
+    return x / (1.0 + np.exp(-x))
+  if name == 'sigmoid':
+    return 1.0 / (1.0 + np.exp(-x))
+  if name == 'relu':
+    return np.maximum(x, 0.0)
+  raise ValueError(name)
+
+
+def activation_grad(x, name):
+  """d activation / dx in float64 (TF's gradient kernels take the negative branch of elu / selu for x < 0 and of
+  leaky_relu for x <= 0)."""
+  x = np.asarray(x, np.float64)
+  if name == 'gelu':
+    c = np.sqrt(2 / np.pi)
+    t = np.tanh(c * (x + 0.044715 * x ** 3))
+    return 0.5 * (1.0 + t) + 0.5 * x * (1.0 - t * t) * c * (1.0 + 3 * 0.044715 * x * x)
+  if name in ('leaky_relu', 'prelu'):
+    return np.where(x > 0, 1.0, 0.2)
+  if name == 'elu':
+    return np.where(x < 0, np.exp(x), 1.0)
+  if name == 'selu':
+    return np.where(x < 0, _SELU_SCALE * _SELU_ALPHA * np.exp(x), _SELU_SCALE)
+  if name == 'tanh':
+    return 1.0 - np.tanh(x) ** 2
+  s = 1.0 / (1.0 + np.exp(-x))
+  if name == 'swish':
+    return s * (1.0 + x * (1.0 - s))
+  if name == 'sigmoid':
+    return s * (1.0 - s)
+  if name == 'relu':
+    return (x > 0).astype(np.float64)
+  raise ValueError(name)
+
+
+# ---- tf.metrics.auc / max_f1 (model/rank_model.py:360-373, core/metrics.py:25-56) -------------------------------------
+def tf_thresholds(num_thresholds=200):
+  """the threshold list of tf.metrics.auc and of core/metrics.py:33-38, as the float32 constants the graph compares
+  float32 predictions with."""
+  kepsilon = 1e-7
+  t = [(i + 1) * 1.0 / (num_thresholds - 1) for i in range(num_thresholds - 2)]
+  return np.array([0.0 - kepsilon] + t + [1.0 + kepsilon], np.float32)
+
+
+def confusion_at_thresholds(labels, probs, num_thresholds=200):
+  """tp, fn, tn, fp [T] by the definition: label & (pred > thr[i]) counted sample by sample (TF tiles the predictions
+  against the thresholds, metrics_impl._confusion_matrix_at_thresholds); labels go through tf.to_int64 then bool."""
+  thr = tf_thresholds(num_thresholds)
+  lab = np.asarray(labels).reshape(-1).astype(np.int64) != 0
+  p = np.asarray(probs, np.float32).reshape(-1)
+  above = p[None, :] > thr[:, None]
+  tp = (above & lab[None, :]).sum(1)
+  fp = (above & ~lab[None, :]).sum(1)
+  return tp, lab.sum() - tp, (~lab).sum() - fp, fp
+
+
+def auc_tf(labels, probs, num_thresholds=200):
+  """tf.metrics.auc(curve='ROC', summation_method='trapezoidal'): float32 accumulators, rec = (tp + 1e-6) /
+  (tp + fn + 1e-6), fp_rate = fp / (fp + tn + 1e-6), sum((x[:-1] - x[1:]) * (y[:-1] + y[1:]) / 2)."""
+  tp, fn, tn, fp = [a.astype(np.float32) for a in confusion_at_thresholds(labels, probs, num_thresholds)]
+  eps = np.float32(1e-6)
+  y = (tp + eps) / (tp + fn + eps)
+  x = fp / (fp + tn + eps)
+  return float(np.sum((x[:-1] - x[1:]) * ((y[:-1] + y[1:]) / np.float32(2.0)), dtype=np.float32))
+
+
+def max_f1(labels, probs):
+  """core/metrics.py:25-56: max over the 200 thresholds of 2 p r / (p + r + 1e-12), p = tp / (tp + fp), r = tp / (tp + fn)
+  (tf.metrics.precision / recall: 0 when the denominator is 0)."""
+  tp, fn, tn, fp = [a.astype(np.float32) for a in confusion_at_thresholds(labels, probs, 200)]
+  with np.errstate(divide='ignore', invalid='ignore'):
+    prec = np.where(tp + fp > 0, tp / (tp + fp), np.float32(0))
+    rec = np.where(tp + fn > 0, tp / (tp + fn), np.float32(0))
+  return float(np.max(2 * prec * rec / (prec + rec + np.float32(1e-12))))

@@ -189,6 +189,26 @@ def install_dense(patch):
     return y
   patch(K, 'dropout', dropout)
 
+  names = {v: k for k, v in K.ACT_KINDS.items() if k != 'prelu'}
+
+  def act_fwd(x, kind):
+    return torch.from_numpy(O.activation(x.detach().numpy(), names[kind]).astype(np.float32))
+
+  def act_bwd(x, gy, kind):
+    return torch.from_numpy((gy.detach().numpy().astype(np.float64) *
+                             O.activation_grad(x.detach().numpy(), names[kind])).astype(np.float32))
+
+  def auc_hist(probs, labels, thresholds, hist):
+    # k = number of thresholds strictly below the prediction; negatives in the first T + 1 bins, positives after
+    T = thresholds.numel()
+    p, lab = probs.detach().reshape(-1).numpy(), labels.detach().reshape(-1).numpy().astype(np.int64) != 0
+    k = np.where(np.isnan(p), 0, np.searchsorted(thresholds.numpy(), p, side='left'))   # (a NaN exceeds no threshold)
+    hist += torch.from_numpy(np.bincount(k + lab * (T + 1), minlength=2 * (T + 1)).astype(np.int64))
+    return hist
+  patch(K, 'act_fwd', act_fwd)
+  patch(K, 'act_bwd', act_bwd)
+  patch(K, 'auc_hist', auc_hist)
+
   def gemm(a, b, bias=None, out=None):
     r = a @ b
     if bias is not None:

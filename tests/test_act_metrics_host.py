@@ -1,0 +1,274 @@
+"""CPU: the non-relu activations (utils/activation.py:66-118) and the streaming evaluation metrics
+(model/rank_model.py:334-496, core/metrics.py:25-56) - oracle restatements against known answers and independent
+implementations, and the host logic around the kernels (layers.DNN / keras MLP activation wiring, metrics.MetricSet,
+EasyRecEstimator.evaluate) with kernel doubles."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import host_doubles
+from easyrec_b200 import builder, kernels as K, layers as L, metrics as M
+from easyrec_b200.config import config_util, proto_loader
+from oracle import oracle as O
+
+
+@pytest.fixture
+def doubles(monkeypatch):
+  host_doubles.install_all(monkeypatch.setattr)
+
+
+TORCH_ACT = {
+    'gelu': lambda x: F.gelu(x, approximate='tanh'), 'leaky_relu': lambda x: F.leaky_relu(x, 0.2), 'elu': F.elu,
+    'selu': F.selu, 'tanh': torch.tanh, 'swish': F.silu, 'sigmoid': torch.sigmoid}
+
+
+def test_oracle_activations_known_answers():
+  # closed forms at x = 1 / -1 (gelu: the tanh form the reference defines itself, activation.py:46-60)
+  assert O.activation(1.0, 'gelu') == pytest.approx(0.8411919906082768, abs=1e-12)
+  assert O.activation(-1.0, 'gelu') == pytest.approx(-0.15880800939172324, abs=1e-12)
+  assert O.activation(-1.0, 'leaky_relu') == pytest.approx(-0.2) and O.activation(2.0, 'prelu') == 2.0
+  assert O.activation(-1.0, 'elu') == pytest.approx(np.expm1(-1.0))
+  assert O.activation(-1.0, 'selu') == pytest.approx(-1.1113307378125625, abs=1e-12)
+  assert O.activation(1.0, 'selu') == pytest.approx(1.0507009873554805, abs=1e-15)
+  assert O.activation(1.0, 'swish') == pytest.approx(0.7310585786300049, abs=1e-12)
+  assert O.activation(0.5, 'tanh') == pytest.approx(np.tanh(0.5)) and O.activation(0.0, 'sigmoid') == 0.5
+
+
+@pytest.mark.parametrize('name', sorted(TORCH_ACT))
+def test_oracle_activations_match_torch_values_and_gradients(name):
+  rng = np.random.default_rng(1)
+  x = np.concatenate([rng.normal(0, 2, 4000), [0.0, -0.0, 1e-8, -1e-8, 20.0, -20.0]])
+  xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+  y = TORCH_ACT[name](xt)
+  y.sum().backward()
+  np.testing.assert_allclose(O.activation(x, name), y.detach().numpy(), rtol=1e-12, atol=1e-14)
+  g = O.activation_grad(x, name)
+  nz = x != 0   # (at exactly 0 the one-sided conventions differ between frameworks: TF's are restated, not torch's)
+  np.testing.assert_allclose(g[nz], xt.grad.numpy()[nz], rtol=1e-10, atol=1e-13)
+  # TF's gradient kernels at 0: EluGrad / SeluGrad take the positive branch for out >= 0, LeakyReluGrad alpha for x <= 0
+  at0 = {'elu': 1.0, 'selu': 1.0507009873554805, 'leaky_relu': 0.2}.get(name)
+  if at0 is not None:
+    assert O.activation_grad(0.0, name) == pytest.approx(at0)
+
+
+def test_activation_names_resolve_like_get_activation():
+  assert L.activation_kind('tf.nn.relu') == 'relu' and L.activation_kind('relu') == 'relu'
+  assert L.activation_kind('') is None and L.activation_kind('linear') is None and L.activation_kind(None) is None
+  assert L.activation_kind('tf.nn.tanh') == K.ACT_KINDS['tanh'] == L.activation_kind('Tanh')
+  assert L.activation_kind('prelu') == L.activation_kind('tf.nn.leaky_relu') == K.ACT_KINDS['leaky_relu']
+  assert L.activation_kind('gelu') == K.ACT_KINDS['gelu'] and L.activation_kind('tf.nn.swish') == K.ACT_KINDS['swish']
+  with pytest.raises(NotImplementedError):
+    L.activation_kind('dice')
+
+
+@pytest.mark.parametrize('name', ['gelu', 'selu', 'tanh'])
+def test_dnn_with_a_configured_activation_trains_like_plain_torch(doubles, name):
+  """layers.DNN built from a DNN message with `activation` set: the dense / batch-norm stage runs linear, the
+  activation is the elementwise pass on top, dropout-free; forward and every gradient equal plain torch autograd."""
+  msg = proto_loader.default_schema().DNN()
+  msg.hidden_units.extend([12, 6])
+  msg.activation = name
+  units = L.units_of(msg)
+  assert units.activation == name and units[:-1].activation == name
+  g = torch.Generator().manual_seed(0)
+  dnn = L.DNN(9, units, generator=g)
+  dnn.train()
+  x = torch.randn(32, 9, generator=g, requires_grad=True)
+  y = dnn(x)
+  gy = torch.randn(y.shape, generator=g)
+  y.backward(gy)
+  # plain torch restatement on the same parameters
+  xr = x.detach().clone().requires_grad_(True)
+  h = xr
+  params = []
+  for lay in dnn.layers:
+    W, b = lay.kernel.detach().clone().requires_grad_(True), lay.bias.detach().clone().requires_grad_(True)
+    ga, be = lay.gamma.detach().clone().requires_grad_(True), lay.beta.detach().clone().requires_grad_(True)
+    params.append((lay, W, b, ga, be))
+    z = h @ W + b
+    mu, var = z.mean(0), ((z - z.mean(0)) ** 2).mean(0)
+    h = TORCH_ACT[name]((z - mu) / torch.sqrt(var + 1e-3) * ga + be)
+  h.backward(gy)
+  assert torch.allclose(y, h, atol=1e-5)
+  assert torch.allclose(x.grad, xr.grad, atol=1e-4)
+  for lay, W, b, ga, be in params:
+    assert torch.allclose(lay.kernel.grad, W.grad, atol=1e-4) and torch.allclose(lay.gamma.grad, ga.grad, atol=1e-4)
+
+
+CFG_ACT = b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } }
+eval_config { metrics_set { auc { num_thresholds: 500 } } metrics_set { max_f1 {} } metrics_set { mean_squared_error {} }
+  metrics_set { mean_absolute_error {} } metrics_set { root_mean_squared_error {} } }
+data_config { batch_size: 256 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "a" input_type: INT64 }
+  input_fields { input_name: "b" input_type: INT64 } }
+feature_config {
+  features { input_names: "a" feature_type: IdFeature embedding_dim: 8 num_buckets: 50 }
+  features { input_names: "b" feature_type: IdFeature embedding_dim: 8 num_buckets: 50 } }
+model_config { model_class: "MultiTower"
+  feature_groups { group_name: "g" feature_names: ["a", "b"] wide_deep: DEEP }
+  multi_tower { towers { input: "g" dnn { hidden_units: [16] activation: "ACT" } }
+                final_dnn { hidden_units: [8] activation: "tf.nn.tanh" } l2_regularization: 1e-6 } }
+'''
+
+
+def _batches(n, B, seed):
+  rng = np.random.default_rng(seed)
+  for _ in range(n):
+    a, b = rng.integers(0, 50, B), rng.integers(0, 50, B)
+    lab = ((a + b) % 2 == 0).astype(np.float32)
+    yield {'sparse_fea': torch.from_numpy(np.concatenate([a, b]).astype(np.int64)),
+           'dense_fea': torch.zeros(B, 0)}, torch.from_numpy(lab)
+
+
+@pytest.mark.parametrize('act', ['gelu', 'swish'])
+def test_config_with_activations_trains_and_evaluates_streaming_metrics(doubles, act):
+  from easyrec_b200.estimator import EasyRecEstimator
+  est = EasyRecEstimator(CFG_ACT.replace(b'ACT', act.encode()), device='cpu', seed=3)
+  tower = est.model.tower_dnn[0]
+  assert isinstance(tower.acts[0], L.Activation) and tower.acts[0].kind == K.ACT_KINDS[act]
+  assert est.model.final_dnn.acts[0].kind == K.ACT_KINDS['tanh'] and not tower.layers[0].relu
+  first = est.train(lambda: _batches(1, 256, 0), steps=1)
+  last = est.train(lambda: _batches(150, 256, 1), steps=150)
+  assert last < first - 0.1, (first, last)
+  # evaluate: the streaming metrics against the oracle's definitions over the same predictions
+  ev = est.evaluate(lambda: _batches(6, 256, 99))
+  logits, labels = [], []
+  for f, l in _batches(6, 256, 99):
+    logits.append(est._forward_eval(f).numpy())
+    labels.append(l.numpy())
+  logits, labels = np.concatenate(logits), np.concatenate(labels)
+  probs = 1.0 / (1.0 + np.exp(-logits.astype(np.float64)))
+  assert ev['auc'] == pytest.approx(O.auc_tf(labels, probs.astype(np.float32), 500), abs=2e-6)
+  assert ev['max_f1'] == pytest.approx(O.max_f1(labels, logits), abs=1e-6)
+  assert ev['mean_squared_error'] == pytest.approx(np.mean((labels - probs) ** 2), rel=1e-5)
+  assert ev['mean_absolute_error'] == pytest.approx(np.mean(np.abs(labels - probs)), rel=1e-5)
+  assert ev['root_mean_squared_error'] == pytest.approx(np.sqrt(np.mean((labels - probs) ** 2)), rel=1e-5)
+  assert abs(ev['auc'] - ev['auc_exact']) < 5e-3 and ev['auc_exact'] > 0.9
+
+
+def test_dice_and_unknown_activations_are_refused_by_the_scope_check():
+  cfg = config_util.get_configs_from_pipeline_file(CFG_ACT.replace(b'ACT', b'dice'))
+  with pytest.raises(NotImplementedError, match='dice'):
+    builder.check_scope(cfg)
+
+
+# ---- tf.metrics.auc / max_f1 ---------------------------------------------------------------------------------------
+def test_oracle_auc_reproduces_tensorflows_own_test_values():
+  """tensorflow/python/kernel_tests/metrics_test.py, AUCTest (values recalled from the TF source tree, TF is not
+  installable here): testAllCorrect 1, testSomeCorrect 0.5, testAllIncorrect 0, testZeroTruePositivesAndFalseNegatives-
+  GivesOneAUC 1 - all with the default 200 thresholds."""
+  assert O.auc_tf([0, 1, 1, 0], [0, 1, 1, 0]) == pytest.approx(1.0, abs=1e-6)
+  assert O.auc_tf([0, 1, 1, 0], [1, 0, 1, 0]) == pytest.approx(0.5, abs=1e-6)
+  assert O.auc_tf([1, 0, 0, 1], [0, 1, 1, 0]) == pytest.approx(0.0, abs=1e-5)
+  assert O.auc_tf(np.zeros(4), np.zeros(4)) == pytest.approx(1.0, abs=1e-6)
+  t = O.tf_thresholds(200)
+  assert t.dtype == np.float32 and len(t) == 200 and t[0] < 0 < t[1] and t[-2] < 1 < t[-1]
+  assert t[1] == np.float32(1.0 / 199) and np.all(np.diff(t) > 0)
+
+
+def test_thresholded_auc_approaches_the_exact_auc():
+  rng = np.random.default_rng(5)
+  lab = rng.random(50000) < 0.3
+  p = np.clip(rng.normal(0.4 + 0.25 * lab, 0.2), 0, 1).astype(np.float32)
+  exact = M.auc(lab, p)
+  assert abs(O.auc_tf(lab, p, 200) - exact) < 1e-3
+  assert abs(O.auc_tf(lab, p, 2000) - exact) < 1e-4
+
+
+@pytest.mark.parametrize('T', [2, 200, 4095])
+def test_streaming_confusion_counts_equal_the_definition(doubles, T):
+  rng = np.random.default_rng(T)
+  thr = O.tf_thresholds(T)
+  assert np.array_equal(M.tf_thresholds(T), thr)
+  # predictions sitting exactly on thresholds, outside [0, 1], NaN; labels that truncate to 0 (0.5) and to 1 (1.7)
+  p = np.concatenate([rng.random(5000).astype(np.float32), thr[rng.integers(0, T, 500)],
+                      np.array([0.0, 1.0, -0.5, 1.5, np.nan], np.float32)])
+  lab = rng.choice(np.array([0.0, 1.0, 0.5, 1.7, -1.0], np.float32), p.size)
+  acc = M.ConfusionAtThresholds(T, 'cpu')
+  order = rng.permutation(p.size)
+  for part in np.array_split(order, 7):   # any batching, any order: integer counters
+    acc.update(torch.from_numpy(p[part]), torch.from_numpy(lab[part]))
+  want = O.confusion_at_thresholds(lab, p, T)
+  for got, w in zip(acc.counts(), want):
+    assert np.array_equal(got, w.astype(np.float32))
+  assert acc.auc() == pytest.approx(O.auc_tf(lab, p, T), abs=1e-6)
+  if T == 200:
+    assert acc.max_f1() == pytest.approx(O.max_f1(lab, p), abs=1e-7)
+  with pytest.raises(ValueError):
+    M.tf_thresholds(4096)
+
+
+def test_metric_set_over_task_towers_uses_each_towers_label_and_loss_type(doubles):
+  schema = proto_loader.default_schema()
+  ms = []
+  for kind in ('auc', 'mean_squared_error'):
+    m = schema.EvalMetrics()
+    getattr(m, kind).SetInParent()
+    ms.append(m)
+  heads = [('_ctr', 'CLASSIFICATION', 1), ('_cvr', 'CLASSIFICATION', 0)]
+  mset = M.MetricSet(ms, heads, 'cpu')
+  rng = np.random.default_rng(0)
+  logits = torch.from_numpy(rng.normal(size=(4000, 2)).astype(np.float32))
+  labels = torch.from_numpy((rng.random((4000, 2)) < 0.4).astype(np.float32))
+  for i in range(0, 4000, 1000):
+    mset.update(logits[i:i + 1000], labels[i:i + 1000])
+  out = mset.result()
+  probs = torch.sigmoid(logits).numpy()
+  assert sorted(out) == ['auc_ctr', 'auc_cvr', 'mean_squared_error_ctr', 'mean_squared_error_cvr']
+  assert out['auc_ctr'] == pytest.approx(O.auc_tf(labels[:, 1].numpy(), probs[:, 0]), abs=1e-6)
+  assert out['auc_cvr'] == pytest.approx(O.auc_tf(labels[:, 0].numpy(), probs[:, 1]), abs=1e-6)
+  assert out['mean_squared_error_cvr'] == pytest.approx(np.mean((labels[:, 0].numpy() - probs[:, 1]) ** 2), rel=1e-5)
+  # an L2 head reads `y` = the logits and has no auc
+  reg = M.MetricSet(ms[1:], [('', 'L2_LOSS', None)], 'cpu')
+  reg.update(logits[:, 0], labels[:, 0])
+  assert reg.result()['mean_squared_error'] == pytest.approx(np.mean((labels[:, 0].numpy() - logits[:, 0].numpy()) ** 2), rel=1e-5)
+  with pytest.raises(ValueError):
+    M.MetricSet(ms[:1], [('', 'L2_LOSS', None)], 'cpu')
+
+
+# ---- the kernels' own source, compiled for the CPU ------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def native(tmp_path_factory):
+  """easyrec_b200/csrc/elementwise.cuh (the formulas the kernels are built from) compiled by g++ into a scratch .so"""
+  import ctypes
+  import os
+  import subprocess
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  so = str(tmp_path_factory.mktemp('native') / 'elementwise_host.so')
+  subprocess.check_call(['g++', '-O2', '-shared', '-fPIC', '-x', 'c++', '-I', os.path.join(root, 'include'),
+                         '-I', os.path.join(root, 'easyrec_b200', 'csrc'),
+                         os.path.join(root, 'tests', 'native', 'elementwise_host.cpp'), '-o', so])
+  return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize('name', sorted(TORCH_ACT))
+def test_kernel_source_activation_formulas_match_the_oracle(native, name):
+  import ctypes
+  rng = np.random.default_rng(2)
+  x = np.concatenate([rng.normal(0, 3, 20000), np.linspace(-30, 30, 2001), [0.0, -0.0, 88.0, -88.0, 1e-20]]).astype(np.float32)
+  y, g = np.empty_like(x), np.empty_like(x)
+  vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+  assert native.host_act(K.ACT_KINDS[name], vp(x), ctypes.c_long(x.size), vp(y), vp(g)) == 0
+  want, want_g = O.activation(x, name), O.activation_grad(x, name)
+  np.testing.assert_allclose(y, want, rtol=2e-6, atol=1e-7)
+  np.testing.assert_allclose(g, want_g, rtol=4e-6, atol=1e-6)   # (1 - tanh^2 cancels in fp32 where the slope vanishes)
+  assert np.isfinite(y).all() and np.isfinite(g).all()
+
+
+@pytest.mark.parametrize('T', [2, 200, 4095])
+def test_kernel_source_threshold_binning_matches_the_definition(native, T):
+  import ctypes
+  rng = np.random.default_rng(T + 1)
+  thr = O.tf_thresholds(T)
+  p = np.concatenate([rng.random(20000).astype(np.float32), thr, np.nextafter(thr, np.float32(2)), np.nextafter(thr, np.float32(-1)),
+                      np.array([0.0, 1.0, -3.0, 7.0, np.nan, np.inf, -np.inf], np.float32)])
+  lab = rng.choice(np.array([0.0, 1.0, 0.5, 1.7, -1.0, -0.5], np.float32), p.size)
+  hist = np.zeros(2 * (T + 1), np.uint64)
+  vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+  native.host_auc_hist(vp(p), vp(lab), ctypes.c_long(p.size), vp(thr), T, vp(hist))
+  neg, pos = np.cumsum(hist[:T + 1].astype(np.int64)), np.cumsum(hist[T + 1:].astype(np.int64))
+  tp, fn, tn, fp = O.confusion_at_thresholds(lab, p, T)
+  assert np.array_equal(pos[-1] - pos[:T], tp) and np.array_equal(neg[-1] - neg[:T], fp)
+  assert pos[-1] == tp[0] + fn[0] and neg[-1] == fp[0] + tn[0]

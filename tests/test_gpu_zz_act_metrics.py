@@ -1,0 +1,95 @@
+"""GPU: er_act_fwd / er_act_bwd (the non-relu activations of utils/activation.py:66-118) and er_auc_hist (the
+confusion accumulators of tf.metrics.auc / max_f1, model/rank_model.py:360-373, core/metrics.py:25-56) against the
+oracle, through the C ABI.  Tolerances: activation values 2e-6 relative / 1e-6 absolute, gradients 1e-5 / 2e-5, against the
+float64 oracle (fp32 transcendental functions); the histograms are integers and must match exactly."""
+import numpy as np
+import pytest
+import torch
+
+from easyrec_b200 import kernels as K, layers as L, metrics as M
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+NAMES = ['gelu', 'leaky_relu', 'elu', 'selu', 'tanh', 'swish', 'sigmoid']
+
+
+@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('n', [1, 255, 1000003])
+def test_activation_forward_and_backward_match_the_oracle(name, n):
+  rng = np.random.default_rng(n)
+  x = rng.normal(0, 3, n).astype(np.float32)
+  x[:min(n, 5)] = np.array([0.0, -0.0, 30.0, -30.0, 1e-20], np.float32)[:min(n, 5)]
+  gy = rng.normal(size=n).astype(np.float32)
+  xd, gd = torch.from_numpy(x).to(DEV), torch.from_numpy(gy).to(DEV)
+  kind = K.ACT_KINDS[name]
+  y = K.act_fwd(xd, kind).cpu().numpy()
+  gx = K.act_bwd(xd, gd, kind).cpu().numpy()
+  np.testing.assert_allclose(y, O.activation(x, name), rtol=2e-6, atol=1e-6)
+  np.testing.assert_allclose(gx, gy.astype(np.float64) * O.activation_grad(x, name), rtol=1e-5, atol=2e-5)   # (|gy| up to 5; 1 - tanh^2 cancels in fp32 where the slope vanishes)
+
+
+def test_dnn_with_gelu_matches_plain_torch():
+  torch.backends.cuda.matmul.allow_tf32 = False
+  g = torch.Generator().manual_seed(1)
+  units = L.Units([64, 32])
+  units.activation = 'gelu'
+  dnn = L.DNN(48, units, generator=g).to(DEV)
+  dnn.train()
+  x = torch.randn(512, 48, generator=g).to(DEV).requires_grad_(True)
+  y = dnn(x)
+  gy = torch.randn(512, 32, generator=g).to(DEV)
+  y.backward(gy)
+  xr = x.detach().double().requires_grad_(True)
+  h = xr
+  for lay in dnn.layers:
+    z = h @ lay.kernel.detach().double() + lay.bias.detach().double()
+    mu, var = z.mean(0), ((z - z.mean(0)) ** 2).mean(0)
+    h = torch.nn.functional.gelu((z - mu) / torch.sqrt(var + 1e-3) * lay.gamma.detach().double() + lay.beta.detach().double(),
+                                 approximate='tanh')
+  h.backward(gy.double())
+  assert float((y.double() - h).abs().max()) < 2e-5
+  assert float((x.grad.double() - xr.grad).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize('T', [2, 200, 4095])
+def test_auc_histograms_are_exact(T):
+  rng = np.random.default_rng(T)
+  thr = O.tf_thresholds(T)
+  acc = M.ConfusionAtThresholds(T, DEV)
+  ps, ls = [], []
+  for n in (1, 8192, 100003):   # several batches accumulate into the same device counters
+    p = rng.random(n).astype(np.float32)
+    k = min(n, 300)
+    p[:k] = thr[rng.integers(0, T, k)]                       # predictions sitting exactly on thresholds
+    if n > 10:
+      p[-6:] = np.array([0.0, 1.0, -3.0, 7.0, np.nan, np.inf], np.float32)
+    lab = rng.choice(np.array([0.0, 1.0, 0.5, 1.7, -1.0], np.float32), n)
+    acc.update(torch.from_numpy(p).to(DEV), torch.from_numpy(lab).to(DEV))
+    ps.append(p)
+    ls.append(lab)
+  p, lab = np.concatenate(ps), np.concatenate(ls)
+  for got, want in zip(acc.counts(), O.confusion_at_thresholds(lab, p, T)):
+    assert np.array_equal(got, want.astype(np.float32))
+  assert acc.auc() == pytest.approx(O.auc_tf(lab, p, T), abs=1e-6)
+  if T == 200:
+    assert acc.max_f1() == pytest.approx(O.max_f1(lab, p), abs=1e-7)
+
+
+def test_tensorflows_auc_known_answers_on_the_device():
+  """tensorflow/python/kernel_tests/metrics_test.py AUCTest (recalled): all correct 1, some correct 0.5, all wrong 0."""
+  for labels, preds, want in (([0, 1, 1, 0], [0, 1, 1, 0], 1.0), ([0, 1, 1, 0], [1, 0, 1, 0], 0.5),
+                              ([1, 0, 0, 1], [0, 1, 1, 0], 0.0), ([0, 0, 0, 0], [0, 0, 0, 0], 1.0)):
+    acc = M.ConfusionAtThresholds(200, DEV)
+    acc.update(torch.tensor(preds, dtype=torch.float32, device=DEV), torch.tensor(labels, dtype=torch.float32, device=DEV))
+    assert acc.auc() == pytest.approx(want, abs=1e-5)
+
+
+def test_invalid_metric_arguments_fail_loudly():
+  from easyrec_b200 import _lib
+  p = torch.zeros(4, device=DEV)
+  thr = torch.zeros(5000, device=DEV)
+  with pytest.raises((_lib.ErError, AssertionError)):
+    K.auc_hist(p, p, thr, torch.zeros(2 * 5001, dtype=torch.int64, device=DEV))
+  with pytest.raises(_lib.ErError):
+    K.act_fwd(p, 99)
