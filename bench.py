@@ -377,8 +377,9 @@ def main():
   h2d = pinned[0][0]['sparse_fea'].numel() * 8 + pinned[0][0]['dense_fea'].numel() * 4 + pinned[0][1].numel() * 4
   e2e = {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
          'ms_per_step': e2e_ms / args.steps,
-         'through': 'EasyRecEstimator.train(input_fn) - Prefetcher thread + pinned double-buffered DeviceFeeder, loss read '
-                    'back every step'}
+         'through': 'EasyRecEstimator.train(input_fn) - Prefetcher thread + pinned double-buffered DeviceFeeder; the loss '
+                    'of every step is read back through pinned slots one step behind the device (the last one before '
+                    'train() returns)'}
 
   def leave():
     """multi-GPU exit: no destroy_process_group - it blocks while captured graphs still hold NCCL work"""

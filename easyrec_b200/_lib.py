@@ -60,7 +60,7 @@ class ErCsvCol(ctypes.Structure):
 
 
 ER_OK, ER_ERR_INVALID_ARG, ER_ERR_WORKSPACE, ER_ERR_CUDA, ER_ERR_UNSUPPORTED = range(5)
-CSV_SKIP, CSV_I64, CSV_F32, CSV_HASH, CSV_I64_LIST, CSV_F32_VEC, CSV_HASH_LIST, CSV_I64_KV_LIST, CSV_HASH_KV_LIST = range(9)
+CSV_SKIP, CSV_I64, CSV_F32, CSV_HASH, CSV_I64_LIST, CSV_F32_VEC, CSV_HASH_LIST, CSV_I64_KV_LIST, CSV_HASH_KV_LIST, CSV_F32_LIST = range(10)
 
 # name -> (restype, argtypes); must list every symbol include/er_b200.h declares
 SIGNATURES = {
@@ -73,6 +73,9 @@ SIGNATURES = {
     'er_bucketize': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32,
                              c_vp, c_vp, c_vp]),
     'er_dropout': (c_i32, [c_vp, c_i64, ctypes.c_float, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    'er_gemm_small_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64]),
+    'er_gemm_small': (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_sz,
+                              c_vp]),
     'er_act_fwd': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'er_act_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     'er_auc_hist': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),

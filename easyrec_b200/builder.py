@@ -28,10 +28,8 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     unsupported = [w for w, on in (
         ('vocab_file / vocab_list (vocabulary lookup)', fc.HasField('vocab_file') or len(fc.vocab_list) > 0),
         ('kv_separator on a feature that is not a TagFeature', fc.HasField('kv_separator') and ftype_name(fc) != 'TagFeature'),
-        ('a separate weight input (second input_names entry of a TagFeature)',
-         ftype_name(fc) == 'TagFeature' and len(fc.input_names) > 1),
         ('seq_multi_sep (multi-valued sequence steps)', fc.HasField('seq_multi_sep')),
-        ('normalizer_fn', fc.HasField('normalizer_fn')),
+        ('normalizer_fn on a feature that is not a RawFeature', fc.HasField('normalizer_fn') and ftype_name(fc) != 'RawFeature'),
         ('shared_names', len(fc.shared_names) > 0),
         ('sub_feature_type RawFeature', fc.HasField('sub_feature_type') and fc.sub_feature_type != fc.IdFeature)) if on]
     if unsupported:
@@ -317,6 +315,14 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc),
                      shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0,
                      uniform_tables=keras_tables, dense_generator=cpu_generator)
+  # RawFeature.normalizer_fn: applied to the min-max normalised value on the device (input/input.py:642-646); the
+  # readers apply the same function on the host to raw features they bucketize themselves (readers.bucketize_raw)
+  from easyrec_b200 import normalizer
+  for fc in config_util.get_feature_configs(pipeline_config):
+    if fc.HasField('normalizer_fn') and ftype_name(fc) == 'RawFeature':
+      name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+      if name in il.raw_cols:
+        il.raw_normalizers[name] = normalizer.load(fc.normalizer_fn, 'torch')
   model = cls.from_config(mc, il, generator=cpu_generator)
   if il.attention_modules:
     # the attention MLPs of in-group sequence_features are InputLayer's in the reference (sequence_feature_layer.py);

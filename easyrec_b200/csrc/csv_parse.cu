@@ -20,7 +20,9 @@ namespace er {
 namespace {
 
 inline bool is_kv(int kind) { return kind == ER_CSV_I64_KV_LIST || kind == ER_CSV_HASH_KV_LIST; }
-inline bool is_list(int kind) { return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST || is_kv(kind); }
+inline bool is_list(int kind) {
+  return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST || kind == ER_CSV_F32_LIST || is_kv(kind);
+}
 
 struct Span {
   const char* p;
@@ -156,7 +158,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
   ER_REQUIRE(n_cols > 0 && max_rows >= 0, "bad n_cols / max_rows");
   for (int c = 0; c < n_cols; ++c) {
     const er_csv_col_t& k = cols[c];
-    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_HASH_KV_LIST, "unknown column kind");
+    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_F32_LIST, "unknown column kind");
     ER_REQUIRE(k.kind == ER_CSV_SKIP || k.out, "column without an output array");
     ER_REQUIRE(!is_list(k.kind) || (k.lens && k.list_cap >= 0), "list column needs lens and list_cap");
     ER_REQUIRE(!is_kv(k.kind) || (k.weights && k.kv_sep), "key:weight list column needs weights and kv_sep");
@@ -218,7 +220,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
     const er_csv_col_t& k = cols[errs[t].col];
     return fail(ER_ERR_INVALID_ARG, "er_csv_parse: line " + std::to_string(errs[t].row + 1) + ", field " +
                                         std::to_string(errs[t].col + 1) + " is not a valid " +
-                                        (k.kind == ER_CSV_F32 || k.kind == ER_CSV_F32_VEC ? "float"
+                                        (k.kind == ER_CSV_F32 || k.kind == ER_CSV_F32_VEC || k.kind == ER_CSV_F32_LIST ? "float"
                                          : is_kv(k.kind)                                  ? "key:weight list"
                                                                                           : "integer"));
   };
@@ -273,6 +275,7 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
         case ER_CSV_HASH_LIST:
         case ER_CSV_I64_KV_LIST:
         case ER_CSV_HASH_KV_LIST:
+        case ER_CSV_F32_LIST:
         case ER_CSV_I64_LIST: {   // count the non-empty tokens
           int32_t cnt = 0;
           const char* p = s.p;
@@ -317,10 +320,24 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
     for (int c = 0; c < n_cols; ++c) {
       const er_csv_col_t& k = cols[c];
       if (!is_list(k.kind)) continue;
-      int64_t* o = (int64_t*)k.out + offs[c][r];
       int32_t left = k.lens[r];
       const char* p = f[c].p;
       const char* e = p + f[c].n;
+      if (k.kind == ER_CSV_F32_LIST) {             // a ragged float list (the weight input of a TagFeature)
+        float* of = (float*)k.out + offs[c][r];
+        while (p < e && left > 0) {
+          const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
+          const char* fe = q ? q : e;
+          if (fe > p) {
+            if (!parse_f32(Span{p, (size_t)(fe - p)}, of)) return c;
+            ++of;
+            --left;
+          }
+          p = fe + 1;
+        }
+        continue;
+      }
+      int64_t* o = (int64_t*)k.out + offs[c][r];
       while (p < e && left > 0) {
         const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
         const char* fe = q ? q : e;

@@ -1,5 +1,5 @@
 // K4 DIN target attention, K5 DCN cross, MMoE mixture, DSSM similarity pieces.
-// The matmuls inside these blocks (attention MLP, towers, U.I^T) are plain library SGEMMs; what is
+// The matmuls inside these blocks (attention MLP, towers, U.I^T) are er_gemm calls (gemm.cu); what is
 // here is everything around them, fused so that the [B,T,4D] / [B,E,H] intermediates are produced
 // and consumed in one pass each.  One warp per sample: T <= a few hundred, D <= 128.
 //   DIN   : layers/sequence_feature_layer.py:150-189, model/multi_tower_din.py:62-97

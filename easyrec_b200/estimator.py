@@ -36,6 +36,51 @@ def _with_next(batches, ahead, want_more):
       cur = next(it, None)
 
 
+class _LossReader(object):
+  """Every step's loss read back to the host without stalling the device: right after step k is enqueued its loss
+  (a device scalar the next step will overwrite) is copied into one of two PINNED host slots on the step's stream and
+  an event is recorded; the value is consumed one step later, while step k + 1 already runs.  The host thus works one
+  step ahead of the device - batch hand-off, the copies into the step's static buffers and the next launch overlap
+  the running step - and still reads every step's result (what a per-step LoggingTensorHook costs the reference,
+  easy_rec_estimator.py:384-396, is a sync per step).  flush() returns the newest value (blocks for the last step).
+  On a CPU device it reads the value directly."""
+
+  def __init__(self, device):
+    self.cuda = str(device).startswith('cuda')
+    self.k = 0
+    self.value = None
+    if self.cuda:
+      self.buf = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+      self.ev = [torch.cuda.Event() for _ in range(2)]
+      self.pending = [False, False]
+
+  def _take(self, j):
+    if self.pending[j]:
+      self.ev[j].synchronize()
+      self.value = float(self.buf[j][0])
+      self.pending[j] = False
+
+  def push(self, loss):
+    """enqueue the read of this step's loss; returns the newest value already on the host (the previous step's)"""
+    if not self.cuda:
+      self.value = float(loss)
+      return self.value
+    j = self.k & 1
+    self._take(j)                      # (slot reuse: its value was consumed two steps ago, normally a no-op)
+    self.buf[j].copy_(loss.detach().reshape(1), non_blocking=True)
+    self.ev[j].record()
+    self.pending[j] = True
+    self.k += 1
+    self._take(j ^ 1)                  # the previous step's loss: its step has (nearly) finished
+    return self.value
+
+  def flush(self):
+    if self.cuda:
+      self._take(self.k & 1)           # older slot first, the newest value wins
+      self._take((self.k & 1) ^ 1)
+    return self.value
+
+
 class EasyRecEstimator(object):
 
   def __init__(self, pipeline_config, model_cls=None, run_config=None, params=None, device='cuda:0',
@@ -97,8 +142,10 @@ class EasyRecEstimator(object):
     """input_fn() -> iterable of (features, labels) host batches.  Logs step/loss/steps-per-sec every
     log_step_count_steps like LoggingTensorHook + StepCounterHook (easy_rec_estimator.py:384-396,455-458).
     The batches reach the device through pinned, double-buffered staging (readers.DeviceFeeder) behind a parsing
-    thread (readers.Prefetcher).  fetch_loss_every_step: read the loss back to the host after every step (what a
-    per-step logging hook costs; bench.py's end-to-end number)."""
+    thread (readers.Prefetcher).  fetch_loss_every_step: read the loss of EVERY step back to the host (what a per-step
+    logging hook costs; bench.py's end-to-end number) - through pinned slots, one step behind the device
+    (_LossReader), so the host prepares step k + 1 while step k runs; `last_loss_value` is the newest value read and,
+    when train() returns, the last step's."""
     limit = steps if steps is not None else (max_steps or self.train_config.num_steps or None)
     every = max(int(self.train_config.log_step_count_steps), 1)
     t0, n0 = time.time(), self.global_step
@@ -108,6 +155,7 @@ class EasyRecEstimator(object):
     epochs = int(self._pipeline_config.data_config.num_epochs)
     done = False
     epoch = 0
+    reader = _LossReader(self._device) if fetch_loss_every_step else None
     while not done:
       seen = self.global_step
       # row-sharded tables: train_step is told the NEXT batch, whose id exchange then runs beside the current step
@@ -118,8 +166,8 @@ class EasyRecEstimator(object):
         # host parsing and the H2D copies run ahead of the device step
         loss, _ = self.trainer.train_step(feats, labels, next_features=None if nxt is None else nxt[0])
         self.global_step += 1
-        if fetch_loss_every_step:
-          self.last_loss_value = float(loss)
+        if reader is not None:
+          self.last_loss_value = reader.push(loss)
         if self.global_step % every == 0:
           dt = time.time() - t0
           logging.info('global_step = %d, loss = %.6f, global_step/sec = %.2f', self.global_step, float(loss),
@@ -130,6 +178,9 @@ class EasyRecEstimator(object):
       epoch += 1
       if limit is None or self.global_step == seen or (epochs > 0 and epoch >= epochs):
         done = True
+    if reader is not None and loss is not None:
+      self.last_loss_value = reader.flush()      # the last step's loss: every step's result has reached the host
+      return self.last_loss_value
     return None if loss is None else float(loss)
 
   @torch.no_grad()

@@ -25,13 +25,22 @@ def bucketize_raw(x, fc):
   (bucketized_column, feature_column_v2.py:2866-2870)."""
   from easyrec_b200 import builder
   x = np.asarray(x, np.float32)
-  if fc.max_val > fc.min_val:
-    x = (x - np.float32(fc.min_val)) / np.float32(fc.max_val - fc.min_val)
+  x = _normalized_raw(x, fc)
   bounds = np.asarray(builder.raw_boundaries(fc), np.float32)
   return np.searchsorted(bounds, x, side='right').astype(np.int64)
 
 
-_LIST_KINDS = (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST, _lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST)
+def _normalized_raw(x, fc):
+  """(x - min) / (max - min) when max > min, then RawFeature.normalizer_fn (input/input.py:638-646), float32"""
+  if fc.max_val > fc.min_val:
+    x = (x - np.float32(fc.min_val)) / np.float32(fc.max_val - fc.min_val)
+  if getattr(fc, 'normalizer_fn', ''):
+    from easyrec_b200 import normalizer
+    x = normalizer.load(fc.normalizer_fn, 'numpy')(x)
+  return x
+
+
+_LIST_KINDS = (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST, _lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST, _lib.CSV_F32_LIST)
 FP_EMPTY = 0x9ae16a3b2f90404f       # Fingerprint64('')
 CROSS_HASH_KEY = 0xDECAFCAFFE       # sparse_ops._DEFAULT_HASH_KEY, what crossed_column(hash_key=None) uses
 
@@ -99,6 +108,29 @@ def _bucketized_features(pipeline_config, input_layer):
     if ftype == 'RawFeature' and builder.raw_boundaries(fc) is not None and name in input_layer.features:
       out[name] = fc     # a single-valued id slot (raw_input_dim 1) or a fixed-length tag slot (raw_input_dim k)
   return out
+
+
+def _tag_weight_inputs(pipeline_config):
+  """TagFeature with a second input_names entry: that field holds the per-tag weights, split by the feature's own
+  separator (input/input.py:477-497) -> {feature name: weight field}."""
+  out = {}
+  for fc in config_util.get_feature_configs(pipeline_config):
+    if len(fc.input_names) > 1 and fc.DESCRIPTOR.fields_by_name['feature_type'].enum_type.values_by_number[
+        fc.feature_type].name == 'TagFeature':
+      name = fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]
+      if fc.HasField('kv_separator'):
+        raise ValueError('Tag Feature Error, Cannot set kv_separator and multi input_names in one feature config. '
+                         'Feature: %s.' % fc.input_names[0])
+      out[name] = fc.input_names[1]
+  return out
+
+
+def _check_tag_weights(name, lens, wlens):
+  """the weight field must hold one value per tag (input/input.py:490-494 asserts equal sizes; the two SparseTensors
+  must then share their indices)"""
+  if not np.array_equal(lens, wlens):
+    raise ValueError('TagFeature Error: The size of %s not equal to the size of its weight input. Please check the input.'
+                     % name)
 
 
 class DummyInput(object):
@@ -171,6 +203,7 @@ class CSVInput(object):
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
     self.combos = _combo_features(pipeline_config, input_layer)
     self.kv_seps = {}          # TagFeature -> kv_separator: tokens are `id<kv>weight` (input/input.py:447-458)
+    self.tag_weights = _tag_weight_inputs(pipeline_config)   # TagFeature -> the field that holds its weights
     # fields a cross reads: parsed to raw fingerprints (STRING) or integers (INT), every consumer derives from those
     self.cross_fields = set(f for fields, _ in self.combos.values() for f in fields)
     for fc in config_util.get_feature_configs(pipeline_config):
@@ -276,6 +309,8 @@ class CSVInput(object):
         else:
           kind = _lib.CSV_HASH_LIST if nb else _lib.CSV_I64_LIST
         want(src, (kind, f.seq_len if f.kind == 'seq' else 0, sep.encode(), self.kv_seps.get(f.name, ''), nb))
+        if f.kind == 'tag' and f.name in self.tag_weights:
+          want(self.tag_weights[f.name], (_lib.CSV_F32_LIST, 0, sep.encode(), 0.0, 0))
     return plan
 
   def _parse(self, data, size, plan, list_cap):
@@ -303,7 +338,7 @@ class CSVInput(object):
         out[name] = (np.empty((B, width), np.float32),)
       elif kind in _LIST_KINDS:
         cap = B * width if width else list_cap
-        out[name] = (np.empty(cap, np.int64), np.empty(B, np.int32))
+        out[name] = (np.empty(cap, np.float32 if kind == _lib.CSV_F32_LIST else np.int64), np.empty(B, np.int32))
         c.lens = out[name][1].ctypes.data
         c.list_cap = cap
         if kind in (_lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST):
@@ -401,8 +436,11 @@ class CSVInput(object):
         arr[np.repeat(np.arange(B), lens), np.arange(vals.size) - np.repeat(starts, lens)] = vals
         seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(lens))
       else:
-        tag[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens),
-                       torch.from_numpy(got[2].copy()) if len(got) > 2 else None)
+        w = got[2] if len(got) > 2 else None
+        if f.name in self.tag_weights:
+          w, wlens = cols[self.tag_weights[f.name]]
+          _check_tag_weights(f.name, lens, wlens)
+        tag[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens), None if w is None else torch.from_numpy(w.copy()))
     if seq:
       feats['seq_fea'] = seq
     if tag:
@@ -484,6 +522,10 @@ class CSVInput(object):
           w = torch.from_numpy(np.array([float(p_[1]) for p_ in pairs], np.float32))
         else:
           flat = np.array([self._token(t, f.name) for ts in toks for t in ts], np.int64)
+        if f.name in self.tag_weights:   # the weights come from their own field, split by the same separator
+          wt = [[t for t in x.split(sep) if t != ''] for x in cols[self.tag_weights[f.name]]]
+          _check_tag_weights(f.name, lens, np.array([len(ts) for ts in wt], np.int32))
+          w = torch.from_numpy(np.array([float(t) for ts in wt for t in ts], np.float32))
         tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), w)
     if seq:
       feats['seq_fea'] = seq
@@ -527,6 +569,7 @@ class ParquetInput(object):
         raise NotImplementedError('feature %s: kv_separator needs text tokens; Parquet columns carry ids only' % name)
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
     self.combos = _combo_features(pipeline_config, input_layer)
+    self.tag_weights = _tag_weight_inputs(pipeline_config)   # TagFeature -> the (list) column that holds its weights
 
   @staticmethod
   def _column(col):
@@ -605,7 +648,12 @@ class ParquetInput(object):
           arr[i, :keep[i]] = vals[start[i]:start[i] + keep[i]]
         seq[f.name] = (torch.from_numpy(arr), torch.from_numpy(keep.astype(np.int32)))
       else:
-        tag[f.name] = (torch.from_numpy(vals), torch.from_numpy(lens), None)
+        w = None
+        if f.name in self.tag_weights:   # a second list column of the same shape (input/input.py:498-501)
+          wv, wl = self._column(table.column(self.tag_weights[f.name]))
+          _check_tag_weights(f.name, lens, np.ones(n, np.int32) if wl is None else wl)
+          w = torch.from_numpy(np.array(wv, np.float32))
+        tag[f.name] = (torch.from_numpy(vals), torch.from_numpy(lens), w)
     if seq:
       feats['seq_fea'] = seq
     if tag:

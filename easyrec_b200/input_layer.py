@@ -355,6 +355,7 @@ class InputLayer(object):
     mx = [self.features[n].max_val for n in self.raw_names for _ in range(self.features[n].raw_input_dim)]
     rng = np.array(mx, np.float32) - np.array(mn, np.float32)
     self.raw_has_range = bool((rng > 0).any())
+    self.raw_normalizers = collections.OrderedDict()   # feature -> normalizer_fn (set by builder.build_model)
     self.raw_range = torch.tensor(np.where(rng > 0, rng, 1.0), dtype=torch.float32, device=device)
     self.raw_sub = torch.tensor(np.where(rng > 0, np.array(mn, np.float32), 0.0),
                                 dtype=torch.float32, device=device)
@@ -541,9 +542,15 @@ class InputLayer(object):
         K.embedding_bwd_presort(rows, m.arena.n_rows, m.arena.dim, m.ws, m.slots_dev, m.n_slots, seg_ids=sids)
 
   def normalize_dense(self, dense):
-    if not self.raw_has_range:
-      return dense
-    return (dense - self.raw_sub) / self.raw_range  # (x - min) / (max - min), input/input.py:638-640
+    if self.raw_has_range:
+      dense = (dense - self.raw_sub) / self.raw_range  # (x - min) / (max - min), input/input.py:638-640
+    if self.raw_normalizers:
+      # RawFeature.normalizer_fn on the normalised value (input/input.py:642-646), feature by feature
+      dense = dense.clone() if not self.raw_has_range else dense
+      for name, fn in self.raw_normalizers.items():
+        c0, c1 = self.raw_cols[name]
+        dense[:, c0:c1] = fn(dense[:, c0:c1])
+    return dense
 
   def prefetch_exchange(self, next_features):
     """EmbeddingParallel: start the id half of the NEXT batch's exchange (K1, K8, id all-to-all) beside the rest of

@@ -539,14 +539,9 @@ def gemm(a, b, bias=None, out=None):
   Kb, N = b.shape
   assert Ka == Kb, (a.shape, b.shape)
   if N < 8 or Ka < 8 or M < 8:
-    # vector-sized problems (the [64 -> 1] logit head): library GEMV, a 128x128 tensor-core tile is idle
-    r = torch.mm(a, b)
-    if bias is not None:
-      r += bias
-    if out is not None:
-      out.copy_(r)
-      return out
-    return r
+    # vector-sized problems (MMoE gates [d -> num_expert], their dX and dW): er_gemm_small on the CUDA cores, operands
+    # read through their strides (transposed views in place); a 128x128 tensor-core tile would be all padding
+    return gemm_small(a, b, bias, out)
   a, lda, a_unit = _gemm_operand(a, 'a')      # a_unit == 1: k contiguous -> K-major
   b, ldb, b_unit = _gemm_operand(b, 'b')      # b_unit == 1: n contiguous -> MN-major
   if out is None:
@@ -562,6 +557,32 @@ def gemm(a, b, bias=None, out=None):
       _gemm_ws[key] = ws
   _lib.check(lib.er_gemm(_p(a), lda, 0 if a_unit else 1, _p(b), ldb, 1 if b_unit else 0, _p(bias), _p(out),
                          out.stride(0), M, N, Ka, _p(ws), 0 if ws is None else ws.numel(), _stream()), 'er_gemm')
+  return out
+
+
+def gemm_small(a, b, bias=None, out=None):
+  """er_gemm_small: out[M,N] = a[M,K] @ b[K,N] (+ bias) for vector-sized shapes; any strides."""
+  lib = _lib.load()
+  M, Ka = a.shape
+  _, N = b.shape
+  for t, name in ((a, 'a'), (b, 'b')):
+    if not t.is_cuda or t.dtype != torch.float32:
+      raise _lib.ErError('%s must be a CUDA fp32 matrix (no CPU fallback)' % name)
+  _chk(bias, torch.float32, 'bias')
+  if out is None:
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+  assert out.shape == (M, N) and out.stride(1) == 1 and out.is_cuda and out.dtype == torch.float32
+  nbytes = lib.er_gemm_small_workspace_bytes(M, N, Ka)
+  ws = None
+  if nbytes:
+    key = (a.device, torch.cuda.current_stream().cuda_stream, 'small')
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+      ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+      _gemm_ws[key] = ws
+  _lib.check(lib.er_gemm_small(_p(a), a.stride(0), a.stride(1), _p(b), b.stride(0), b.stride(1), _p(bias), _p(out),
+                               out.stride(0), M, N, Ka, _p(ws), 0 if ws is None else ws.numel(), _stream()),
+             'er_gemm_small')
   return out
 
 

@@ -414,6 +414,17 @@ int er_gemm(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int
             int32_t b_mn_major, const float* bias, float* C, int64_t ldc, int64_t M, int64_t N,
             int64_t K, void* ws, size_t ws_bytes, er_stream_t stream);
 
+/* Vector-sized dense layers: C[M,N] = A(M,K).B(K,N) (+ bias[n]) when one of M, N, K is below 8 - the MMoE gate
+ * layers dense(x) -> [B, num_expert] (layers/mmoe.py:66-72) with their dX and dW - where a 128 x 128 tensor-core tile
+ * would be almost all padding.  CUDA cores, fp32 FMA in k order; A(m,k) = A[m*sa_m + k*sa_k], B(k,n) = B[k*sb_k +
+ * n*sb_n] (any strides, in floats: transposed views are read in place).  A long K over few outputs (the dW form, K =
+ * batch) is cut into slices whose partials go to ws (er_gemm_small_workspace_bytes, 0 when unsplit) and are summed in
+ * slice order: deterministic. */
+size_t er_gemm_small_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int er_gemm_small(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n,
+                  const float* bias, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* ws, size_t ws_bytes,
+                  er_stream_t stream);
+
 /* Dense + batch-norm training forward: the GEMM also produces the batch statistics of its output
  * columns (per-tile Welford partials merged in tile order by the last CTA of each column tile:
  * deterministic, no extra pass over z).  On return (stream order) save_mean[n] = mean(z[:,n]) + bias[n],
@@ -525,7 +536,10 @@ enum {
   ER_CSV_HASH_LIST = 6, /* like ER_CSV_I64_LIST, every token fingerprinted (string Tag / Sequence tokens) */
   ER_CSV_I64_KV_LIST = 7,  /* tokens `key<kv_sep>weight` (TagFeature kv_separator, input/input.py:447-458): integer
                               keys to out, fp32 weights to `weights` at the same positions */
-  ER_CSV_HASH_KV_LIST = 8  /* the same with fingerprinted string keys */
+  ER_CSV_HASH_KV_LIST = 8, /* the same with fingerprinted string keys */
+  ER_CSV_F32_LIST = 9      /* out float[list_cap] + lens int32[max_rows]: inner_sep-separated floats, empty tokens
+                            * skipped - the weight input of a TagFeature (its second input_names entry,
+                            * input/input.py:477-497) */
 };
 typedef struct {
   int32_t kind;

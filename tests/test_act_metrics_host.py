@@ -272,3 +272,120 @@ def test_kernel_source_threshold_binning_matches_the_definition(native, T):
   tp, fn, tn, fp = O.confusion_at_thresholds(lab, p, T)
   assert np.array_equal(pos[-1] - pos[:T], tp) and np.array_equal(neg[-1] - neg[:T], fp)
   assert pos[-1] == tp[0] + fn[0] and neg[-1] == fp[0] + tn[0]
+
+
+# ---- RawFeature.normalizer_fn (input/input.py:133-137, 642-646) -----------------------------------------------------
+CFG_NORM = b'''
+data_config { batch_size: 4 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "a" input_type: FLOAT }
+  input_fields { input_name: "b" input_type: FLOAT } input_fields { input_name: "c" input_type: FLOAT } }
+feature_config {
+  features { input_names: "a" feature_type: RawFeature embedding_dim: 4 min_val: 0.0 max_val: 10.0
+             normalizer_fn: "lambda x: tf.math.log1p(tf.maximum(x, 0.0))" }
+  features { input_names: "b" feature_type: RawFeature embedding_dim: 4 normalizer_fn: "tf.math.sqrt" }
+  features { input_names: "c" feature_type: RawFeature embedding_dim: 4 boundaries: [0.5, 1.0, 1.5]
+             normalizer_fn: "tf.math.log1p" } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["a", "b", "c"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["c"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [8] } final_dnn { hidden_units: [4] } } }
+'''
+
+
+def test_raw_feature_normalizer_fn_on_the_device_matrix_and_in_the_host_bucketizer(doubles, tmp_path):
+  from easyrec_b200 import normalizer
+  from easyrec_b200.input import readers
+  cfg = config_util.get_configs_from_pipeline_file(CFG_NORM)
+  il, _, _ = builder.build_model(cfg, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert sorted(il.raw_normalizers) == ['a', 'b']          # `c` is bucketized by the reader, with its normalizer
+  a, b, c = [5.0, -2.0, 10.0, 0.0], [4.0, 0.25, 9.0, 0.0], [0.1, 0.7, 2.0, 5.0]
+  open(tmp_path / 'n.csv', 'w').write(''.join('1,%g,%g,%g\n' % r for r in zip(a, b, c)))
+  (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 'n.csv')))
+  # host: log1p(c) against the boundaries -> bucket ids of the `c` slot (the last single-valued slot)
+  want_c = np.searchsorted(np.array([0.5, 1.0, 1.5], np.float32), np.log1p(np.array(c, np.float32)), side='right')
+  assert feats['sparse_fea'].tolist() == want_c.tolist()
+  # device side: the dense matrix after min-max and the normalizers
+  dn = il.normalize_dense(feats['dense_fea'])
+  np.testing.assert_allclose(dn[:, 0].numpy(), np.log1p(np.maximum(np.array(a, np.float32) / 10.0, 0.0)), rtol=1e-6)
+  np.testing.assert_allclose(dn[:, 1].numpy(), np.sqrt(np.array(b, np.float32)), rtol=1e-6)
+  assert feats['dense_fea'][:, 1].tolist() == b             # the reader's batch itself is left untouched
+  # ... and they reach the projection: out = normalised value * the one-row table
+  out = il.lookup(feats)['deep'][0]
+  t = il.arenas[4]
+  off_a = t.tables[[k for k in t.tables if k.endswith('a_embedding') or '/a' in k][0]][0]
+  np.testing.assert_allclose(out[:, :4].detach().numpy(), dn[:, :1].numpy() * t.weight[off_a:off_a + 1].numpy(), rtol=1e-5, atol=1e-7)
+  # both backends of one expression agree; unknown tf calls are refused, not guessed
+  f_np, f_t = normalizer.load('lambda x: tf.clip_by_value(x * 2.0, 0.0, 1.0)', 'numpy'), \
+      normalizer.load('lambda x: tf.clip_by_value(x * 2.0, 0.0, 1.0)', 'torch')
+  x = np.linspace(-1, 1, 9).astype(np.float32)
+  assert np.array_equal(f_np(x), f_t(torch.from_numpy(x)).numpy())
+  with pytest.raises(NotImplementedError):
+    normalizer.load('tf.signal.fft', 'numpy')
+
+
+# ---- er_gemm_small (vector-sized dense layers: MMoE gates, their dX and dW) -------------------------------------------
+@pytest.mark.parametrize('M,N,K,form', [(8192, 4, 256, 'fwd'), (8192, 256, 4, 'dx'), (256, 4, 8192, 'dw'), (3, 5, 7, 'fwd'),
+                                        (1000, 7, 33, 'fwd'), (33, 7, 1000, 'dw'), (5, 300, 2, 'dx'), (64, 3, 511, 'dw'),
+                                        (64, 3, 512, 'dw')])
+def test_kernel_source_small_gemm_reads_strided_operands_and_sums_slices_in_order(native, M, N, K, form):
+  """small_gemm.cuh compiled for the CPU, driven with the strides kernels.gemm_small passes for the three forms of a
+  dense layer: forward (X row-major, W row-major), dX (dY, W^T as a transposed VIEW), dW (X^T as a view, dY)."""
+  import ctypes
+  rng = np.random.default_rng(M + N + K)
+  if form == 'fwd':
+    a = torch.from_numpy(rng.normal(size=(M, K + 3)).astype(np.float32))[:, :K]      # a pitched view
+    b = torch.from_numpy(rng.normal(size=(K, N)).astype(np.float32))
+  elif form == 'dx':
+    a = torch.from_numpy(rng.normal(size=(M, K)).astype(np.float32))
+    b = torch.from_numpy(rng.normal(size=(N, K)).astype(np.float32)).t()             # W^T read in place
+  else:
+    a = torch.from_numpy(rng.normal(size=(K, M)).astype(np.float32)).t()             # X^T read in place
+    b = torch.from_numpy(rng.normal(size=(K, N)).astype(np.float32))
+  bias = torch.from_numpy(rng.normal(size=N).astype(np.float32)) if form == 'fwd' else None
+  out = torch.full((M, N + 2), float('nan'))
+  L = ctypes.c_long
+  native.host_gemm_small.restype = ctypes.c_long
+  n_slice = native.host_gemm_small(
+      ctypes.c_void_p(a.data_ptr()), L(a.stride(0)), L(a.stride(1)), ctypes.c_void_p(b.data_ptr()), L(b.stride(0)),
+      L(b.stride(1)), ctypes.c_void_p(bias.data_ptr() if bias is not None else None), ctypes.c_void_p(out.data_ptr()),
+      L(out.stride(0)), L(M), L(N), L(K))
+  want = a.double() @ b.double() + (bias.double() if bias is not None else 0.0)
+  scale = float(np.sqrt(K))
+  assert float((out[:, :N].double() - want).abs().max()) < 2e-6 * scale + 1e-6
+  assert torch.isnan(out[:, N:]).all()                       # nothing written beyond the N columns of a pitched output
+  assert (n_slice > 1) == (K >= 512 and form == 'dw')         # only the long-K / few-output form is cut into slices
+  from easyrec_b200 import _lib
+  ws = _lib.load().er_gemm_small_workspace_bytes(M, N, K)
+  assert ws == (n_slice * M * N * 4 if n_slice > 1 else 0)    # the library sizes the workspace for the same slicing
+
+
+# ---- EasyRecEstimator.train(fetch_loss_every_step=True): the pipelined loss read ----------------------------------
+def test_loss_reader_returns_every_steps_loss_one_step_behind_and_the_last_on_flush():
+  from easyrec_b200 import estimator as E
+
+  class FakeEvent(object):
+    def __init__(self):
+      self.recorded = self.synced = 0
+
+    def record(self):
+      self.recorded += 1
+
+    def synchronize(self):
+      assert self.recorded > self.synced     # never waits for an event that was not recorded since its last use
+      self.synced = self.recorded
+
+  r = E._LossReader('cpu')
+  assert r.push(torch.tensor(0.5)) == 0.5 and r.flush() == 0.5      # host device: read directly
+  r = E._LossReader.__new__(E._LossReader)                          # the CUDA branch over stand-in buffers / events
+  r.cuda, r.k, r.value = True, 0, None
+  r.buf = [torch.empty(1), torch.empty(1)]
+  r.ev = [FakeEvent(), FakeEvent()]
+  r.pending = [False, False]
+  static = torch.zeros(())                                          # the graph's loss output: overwritten every step
+  seen = []
+  for k in range(7):
+    static.fill_(10.0 + k)
+    seen.append(r.push(static))
+  assert seen == [None, 10.0, 11.0, 12.0, 13.0, 14.0, 15.0]          # one step behind, nothing skipped
+  assert r.flush() == 16.0 and r.flush() == 16.0                    # the last step's value; idempotent
+  assert [e.recorded for e in r.ev] == [4, 3] and [e.synced for e in r.ev] == [4, 3]

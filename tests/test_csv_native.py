@@ -341,3 +341,61 @@ model_config { model_class: "DeepFM"
   open(tmp_path / 'bad.csv', 'w').write('1,3:0.5|7,cat=1\n0,,\n1,,\n')
   with pytest.raises(_lib.ErError, match='line 1, field 2 is not a valid key:weight list'):
     list(readers.CSVInput(cfg, il, str(tmp_path / 'bad.csv')))
+
+
+def test_tag_weights_from_a_second_input_field(tmp_path):
+  """TagFeature with two input_names (input/input.py:477-501): the second field holds the per-tag weights, split by
+  the feature's own separator; it must hold one weight per tag.  Both parser engines, a Parquet list column, and the
+  same batch as the `id:weight` spelling of the same data (kv_separator)."""
+  head = b'''
+data_config { batch_size: 3 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "tags" input_type: STRING }
+  input_fields { input_name: "wts" input_type: STRING } }
+feature_config {
+  features { input_names: ["tags", "wts"] feature_type: TagFeature embedding_dim: 8 num_buckets: 100 separator: "|" combiner: "mean" } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: ["tags"] wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["tags"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [16] } final_dnn { hidden_units: [8] } } }
+'''
+  cfg = config_util.get_configs_from_pipeline_file(head)
+  il, _, _ = builder.build_model(cfg, 3, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 'w.csv', 'w').write('1,3|7,0.5|2\n0,,\n1,99||5|,1e-1|-3\n')
+  got = {}
+  for engine in ('native', 'python'):
+    (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 'w.csv'), engine=engine))
+    ids, lens, w = feats['tag_fea']['tags']
+    assert ids.tolist() == [3, 7, 99, 5] and lens.tolist() == [2, 0, 2] and w.dtype == torch.float32
+    assert w.tolist() == pytest.approx([0.5, 2.0, 0.1, -3.0])
+    got[engine] = w
+  assert torch.equal(got['native'], got['python'])
+  # the kv spelling of the same data gives the same batch
+  kv = config_util.get_configs_from_pipeline_file(
+      head.replace(b'input_names: ["tags", "wts"]', b'input_names: "tags" kv_separator: ":"'))
+  il2, _, _ = builder.build_model(kv, 3, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 'kv.csv', 'w').write('1,3:0.5|7:2,\n0,,\n1,99:1e-1|5:-3,\n')
+  (f2, _), = list(readers.CSVInput(kv, il2, str(tmp_path / 'kv.csv')))
+  for a, b in zip(f2['tag_fea']['tags'], (ids, lens, w)):
+    assert torch.equal(a, b)
+  # one weight per tag, row by row
+  open(tmp_path / 'bad.csv', 'w').write('1,3|7,0.5\n0,,\n1,9,1|2\n')
+  for engine in ('native', 'python'):
+    with pytest.raises(ValueError, match='TagFeature Error: The size of tags'):
+      list(readers.CSVInput(cfg, il, str(tmp_path / 'bad.csv'), engine=engine))
+  open(tmp_path / 'nan.csv', 'w').write('1,3|7,0.5|x\n0,,\n1,,\n')
+  with pytest.raises(_lib.ErError, match='line 1, field 3 is not a valid float'):
+    list(readers.CSVInput(cfg, il, str(tmp_path / 'nan.csv')))
+  # kv_separator together with a weight field is the reference's own assertion (input/input.py:443-445)
+  both = config_util.get_configs_from_pipeline_file(head.replace(b'separator: "|"', b'separator: "|" kv_separator: ":"'))
+  with pytest.raises(ValueError, match='Cannot set kv_separator and multi input_names'):
+    readers.CSVInput(both, il, str(tmp_path / 'w.csv'))
+  # Parquet: a float list column beside the id list column
+  import pyarrow as pa
+  import pyarrow.parquet as pq
+  pq.write_table(pa.table({'label': pa.array([1.0, 0.0, 1.0], pa.float32()),
+                           'tags': pa.array([[3, 7], [], [99, 5]], pa.list_(pa.int64())),
+                           'wts': pa.array([[0.5, 2.0], [], [0.1, -3.0]], pa.list_(pa.float32()))}),
+                 str(tmp_path / 'w.parquet'))
+  (fp, _), = list(readers.ParquetInput(cfg, il, str(tmp_path / 'w.parquet')))
+  for a, b in zip(fp['tag_fea']['tags'], (ids, lens, w)):
+    assert torch.equal(a, b)

@@ -93,3 +93,50 @@ def test_invalid_metric_arguments_fail_loudly():
     K.auc_hist(p, p, thr, torch.zeros(2 * 5001, dtype=torch.int64, device=DEV))
   with pytest.raises(_lib.ErError):
     K.act_fwd(p, 99)
+
+
+@pytest.mark.parametrize('M,N,K,form', [(8192, 4, 256, 'fwd'), (8192, 256, 4, 'dx'), (256, 4, 8192, 'dw'), (3, 5, 7, 'fwd'),
+                                        (1000, 7, 33, 'fwd'), (33, 7, 1000, 'dw'), (16384, 3, 96, 'fwd'), (96, 3, 16384, 'dw')])
+def test_small_gemm_matches_float64(M, N, K, form):
+  """er_gemm_small through kernels.gemm (what the MMoE gate layers call): forward with bias, dX over W^T and dW over X^T
+  read in place; against a float64 product, tolerance 2e-6 * sqrt(K) (fp32 FMA chain)."""
+  rng = np.random.default_rng(M + N + K)
+  if form == 'fwd':
+    a = torch.from_numpy(rng.normal(size=(M, K + 4)).astype(np.float32)).to(DEV)[:, :K]
+    b = torch.from_numpy(rng.normal(size=(K, N)).astype(np.float32)).to(DEV)
+  elif form == 'dx':
+    a = torch.from_numpy(rng.normal(size=(M, K)).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rng.normal(size=(N, K)).astype(np.float32)).to(DEV).t()
+  else:
+    a = torch.from_numpy(rng.normal(size=(K, M)).astype(np.float32)).to(DEV).t()
+    b = torch.from_numpy(rng.normal(size=(K, N)).astype(np.float32)).to(DEV)
+  bias = torch.from_numpy(rng.normal(size=N).astype(np.float32)).to(DEV) if form == 'fwd' else None
+  assert min(M, N, K) < 8
+  got = K_gemm(a, b, bias)
+  want = a.double() @ b.double() + (bias.double() if bias is not None else 0.0)
+  assert float((got.double() - want).abs().max()) < 2e-6 * np.sqrt(K) + 1e-6
+  again = K_gemm(a, b, bias)
+  assert torch.equal(got, again)                              # deterministic: slices summed in order, no atomics
+  out = torch.full((M, N + 4), float('nan'), device=DEV)
+  K_gemm(a, b, bias, out=out[:, :N])
+  assert torch.equal(out[:, :N], got) and torch.isnan(out[:, N:]).all()
+
+
+def K_gemm(a, b, bias=None, out=None):
+  return K.gemm(a, b, bias=bias, out=out)
+
+
+def test_mmoe_gate_sized_dense_layer_trains_like_float64():
+  """a [d -> 4] dense layer (an MMoE gate): forward, dX and dW all take the vector-sized path"""
+  g = torch.Generator().manual_seed(2)
+  lay = L.Dense(96, 4, generator=g).to(DEV)
+  x = torch.randn(4096, 96, generator=g).to(DEV).requires_grad_(True)
+  y = lay(x)
+  gy = torch.randn(4096, 4, generator=g).to(DEV)
+  y.backward(gy)
+  xd = x.detach().double().requires_grad_(True)
+  W = lay.kernel.detach().double().requires_grad_(True)
+  (xd @ W + lay.bias.detach().double()).backward(gy.double())
+  assert float((y.double() - (xd @ W + lay.bias.detach().double())).abs().max()) < 1e-5
+  assert float((x.grad.double() - xd.grad).abs().max()) < 1e-5
+  assert float((lay.kernel.grad.double() - W.grad).abs().max()) < 2e-4
