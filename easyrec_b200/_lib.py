@@ -56,11 +56,13 @@ class ErCsvCol(ctypes.Structure):
   """er_csv_col_t."""
   _fields_ = [('kind', c_i32), ('width', c_i32), ('inner_sep', ctypes.c_char), ('kv_sep', ctypes.c_char), ('pad_', ctypes.c_char * 6),
               ('default_i64', c_i64), ('default_f32', c_f32), ('pad2_', c_i32), ('default_str', ctypes.c_char_p),
-              ('out', c_vp), ('lens', c_vp), ('list_cap', c_i64), ('n_vals', c_i64), ('hash_mod', ctypes.c_uint64), ('weights', c_vp)]
+              ('out', c_vp), ('lens', c_vp), ('list_cap', c_i64), ('n_vals', c_i64), ('hash_mod', ctypes.c_uint64), ('weights', c_vp),
+              ('step_lens', c_vp)]
 
 
 ER_OK, ER_ERR_INVALID_ARG, ER_ERR_WORKSPACE, ER_ERR_CUDA, ER_ERR_UNSUPPORTED = range(5)
-CSV_SKIP, CSV_I64, CSV_F32, CSV_HASH, CSV_I64_LIST, CSV_F32_VEC, CSV_HASH_LIST, CSV_I64_KV_LIST, CSV_HASH_KV_LIST, CSV_F32_LIST = range(10)
+CSV_SKIP, CSV_I64, CSV_F32, CSV_HASH, CSV_I64_LIST, CSV_F32_VEC, CSV_HASH_LIST, CSV_I64_KV_LIST, CSV_HASH_KV_LIST, CSV_F32_LIST, \
+    CSV_I64_STEP_LIST, CSV_HASH_STEP_LIST = range(12)
 
 # name -> (restype, argtypes); must list every symbol include/er_b200.h declares
 SIGNATURES = {

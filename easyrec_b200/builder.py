@@ -28,7 +28,7 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
     unsupported = [w for w, on in (
         ('vocab_file / vocab_list (vocabulary lookup)', fc.HasField('vocab_file') or len(fc.vocab_list) > 0),
         ('kv_separator on a feature that is not a TagFeature', fc.HasField('kv_separator') and ftype_name(fc) != 'TagFeature'),
-        ('seq_multi_sep (multi-valued sequence steps)', fc.HasField('seq_multi_sep')),
+        ('seq_multi_sep on a feature that is not a SequenceFeature', fc.HasField('seq_multi_sep') and ftype_name(fc) != 'SequenceFeature'),
         ('normalizer_fn on a feature that is not a RawFeature', fc.HasField('normalizer_fn') and ftype_name(fc) != 'RawFeature'),
         ('shared_names', len(fc.shared_names) > 0),
         ('sub_feature_type RawFeature', fc.HasField('sub_feature_type') and fc.sub_feature_type != fc.IdFeature)) if on]
@@ -314,7 +314,10 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                      embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc),
                      shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0,
-                     uniform_tables=keras_tables, dense_generator=cpu_generator)
+                     uniform_tables=keras_tables, dense_generator=cpu_generator,
+                     multi_valued_seq=[(fc.feature_name if fc.HasField('feature_name') else fc.input_names[0])
+                                       for fc in config_util.get_feature_configs(pipeline_config)
+                                       if fc.HasField('seq_multi_sep')])
   # RawFeature.normalizer_fn: applied to the min-max normalised value on the device (input/input.py:642-646); the
   # readers apply the same function on the host to raw features they bucketize themselves (readers.bucketize_raw)
   from easyrec_b200 import normalizer

@@ -20,8 +20,9 @@ namespace er {
 namespace {
 
 inline bool is_kv(int kind) { return kind == ER_CSV_I64_KV_LIST || kind == ER_CSV_HASH_KV_LIST; }
+inline bool is_steps(int kind) { return kind == ER_CSV_I64_STEP_LIST || kind == ER_CSV_HASH_STEP_LIST; }
 inline bool is_list(int kind) {
-  return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST || kind == ER_CSV_F32_LIST || is_kv(kind);
+  return kind == ER_CSV_I64_LIST || kind == ER_CSV_HASH_LIST || kind == ER_CSV_F32_LIST || is_kv(kind) || is_steps(kind);
 }
 
 struct Span {
@@ -158,7 +159,8 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
   ER_REQUIRE(n_cols > 0 && max_rows >= 0, "bad n_cols / max_rows");
   for (int c = 0; c < n_cols; ++c) {
     const er_csv_col_t& k = cols[c];
-    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_F32_LIST, "unknown column kind");
+    ER_REQUIRE(k.kind >= ER_CSV_SKIP && k.kind <= ER_CSV_HASH_STEP_LIST, "unknown column kind");
+    ER_REQUIRE(!is_steps(k.kind) || (k.step_lens && k.width > 0 && k.kv_sep), "step-list column needs step_lens, width and the value separator");
     ER_REQUIRE(k.kind == ER_CSV_SKIP || k.out, "column without an output array");
     ER_REQUIRE(!is_list(k.kind) || (k.lens && k.list_cap >= 0), "list column needs lens and list_cap");
     ER_REQUIRE(!is_kv(k.kind) || (k.weights && k.kv_sep), "key:weight list column needs weights and kv_sep");
@@ -272,6 +274,32 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
           if (!s.n) o[0] = k.default_f32;
           break;
         }
+        case ER_CSV_I64_STEP_LIST:
+        case ER_CSV_HASH_STEP_LIST: {   // steps split by inner_sep, the values of a step by kv_sep; empty tokens dropped
+          int32_t* sl = k.step_lens + r * k.width;
+          for (int j = 0; j < k.width; ++j) sl[j] = 0;
+          int32_t steps = 0;
+          const char* p = s.p;
+          const char* e = s.p + s.n;
+          while (p < e && steps < k.width) {   // keep the FIRST width steps
+            const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
+            const char* fe = q ? q : e;
+            if (fe > p) {
+              int32_t cnt = 0;
+              const char* vp = p;
+              while (vp < fe) {
+                const char* vq = (const char*)std::memchr(vp, k.kv_sep, (size_t)(fe - vp));
+                const char* ve = vq ? vq : fe;
+                cnt += ve > vp;
+                vp = ve + 1;
+              }
+              sl[steps++] = cnt;
+            }
+            p = fe + 1;
+          }
+          k.lens[r] = steps;
+          break;
+        }
         case ER_CSV_HASH_LIST:
         case ER_CSV_I64_KV_LIST:
         case ER_CSV_HASH_KV_LIST:
@@ -308,7 +336,11 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
     int64_t acc = 0;
     for (int64_t r = 0; r < rows; ++r) {
       offs[c][r] = acc;
-      acc += k.lens[r];
+      if (is_steps(k.kind)) {
+        for (int j = 0; j < k.lens[r]; ++j) acc += k.step_lens[r * k.width + j];
+      } else {
+        acc += k.lens[r];
+      }
     }
     offs[c][rows] = acc;
     k.n_vals = acc;
@@ -323,6 +355,32 @@ extern "C" int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t*
       int32_t left = k.lens[r];
       const char* p = f[c].p;
       const char* e = p + f[c].n;
+      if (is_steps(k.kind)) {                      // the values of the first lens[r] non-empty steps, step by step
+        int64_t* ov = (int64_t*)k.out + offs[c][r];
+        int32_t steps = 0;
+        while (p < e && steps < left) {
+          const char* q = (const char*)std::memchr(p, k.inner_sep, (size_t)(e - p));
+          const char* fe = q ? q : e;
+          if (fe > p) {
+            const char* vp = p;
+            while (vp < fe) {
+              const char* vq = (const char*)std::memchr(vp, k.kv_sep, (size_t)(fe - vp));
+              const char* ve = vq ? vq : fe;
+              if (ve > vp) {
+                if (k.kind == ER_CSV_HASH_STEP_LIST)
+                  *ov = hashed(k, vp, (size_t)(ve - vp));
+                else if (!parse_i64(Span{vp, (size_t)(ve - vp)}, ov))
+                  return c;
+                ++ov;
+              }
+              vp = ve + 1;
+            }
+            ++steps;
+          }
+          p = fe + 1;
+        }
+        continue;
+      }
       if (k.kind == ER_CSV_F32_LIST) {             // a ragged float list (the weight input of a TagFeature)
         float* of = (float*)k.out + offs[c][r];
         while (p < e && left > 0) {

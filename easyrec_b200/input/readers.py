@@ -40,7 +40,8 @@ def _normalized_raw(x, fc):
   return x
 
 
-_LIST_KINDS = (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST, _lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST, _lib.CSV_F32_LIST)
+_STEP_KINDS = (_lib.CSV_I64_STEP_LIST, _lib.CSV_HASH_STEP_LIST)
+_LIST_KINDS = (_lib.CSV_I64_LIST, _lib.CSV_HASH_LIST, _lib.CSV_I64_KV_LIST, _lib.CSV_HASH_KV_LIST, _lib.CSV_F32_LIST) + _STEP_KINDS
 FP_EMPTY = 0x9ae16a3b2f90404f       # Fingerprint64('')
 CROSS_HASH_KEY = 0xDECAFCAFFE       # sparse_ops._DEFAULT_HASH_KEY, what crossed_column(hash_key=None) uses
 
@@ -204,6 +205,9 @@ class CSVInput(object):
     self.combos = _combo_features(pipeline_config, input_layer)
     self.kv_seps = {}          # TagFeature -> kv_separator: tokens are `id<kv>weight` (input/input.py:447-458)
     self.tag_weights = _tag_weight_inputs(pipeline_config)   # TagFeature -> the field that holds its weights
+    # SequenceFeature -> seq_multi_sep: every step is a list of values (input/input.py:686-700)
+    self.multi_seps = {(fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]): fc.seq_multi_sep
+                       for fc in config_util.get_feature_configs(pipeline_config) if fc.HasField('seq_multi_sep')}
     # fields a cross reads: parsed to raw fingerprints (STRING) or integers (INT), every consumer derives from those
     self.cross_fields = set(f for fields, _ in self.combos.values() for f in fields)
     for fc in config_util.get_feature_configs(pipeline_config):
@@ -304,6 +308,10 @@ class CSVInput(object):
       elif f.kind in ('seq', 'tag'):
         src, sep = self.feature_inputs[f.name]
         nb = self.hash_buckets.get(f.name, 0)
+        if f.kind == 'seq' and f.name in self.multi_seps:
+          want(src, (_lib.CSV_HASH_STEP_LIST if nb else _lib.CSV_I64_STEP_LIST, f.seq_len, sep.encode(),
+                     self.multi_seps[f.name], nb))
+          continue
         if f.name in self.kv_seps:
           kind = _lib.CSV_HASH_KV_LIST if nb else _lib.CSV_I64_KV_LIST
         else:
@@ -336,6 +344,12 @@ class CSVInput(object):
       elif kind == _lib.CSV_F32_VEC:
         c.default_f32 = default
         out[name] = (np.empty((B, width), np.float32),)
+      elif kind in _STEP_KINDS:
+        out[name] = (np.empty(list_cap, np.int64), np.empty(B, np.int32), np.empty(B * width, np.int32))
+        c.lens = out[name][1].ctypes.data
+        c.step_lens = out[name][2].ctypes.data
+        c.list_cap = list_cap
+        c.kv_sep = default.encode()       # the plan's default slot carries the separator of the values of a step
       elif kind in _LIST_KINDS:
         cap = B * width if width else list_cap
         out[name] = (np.empty(cap, np.float32 if kind == _lib.CSV_F32_LIST else np.int64), np.empty(B, np.int32))
@@ -354,7 +368,9 @@ class CSVInput(object):
       return None
     _lib.check(st, 'er_csv_parse')
     for i, name in enumerate(self.fields):
-      if cols[i].kind in _LIST_KINDS:
+      if cols[i].kind in _STEP_KINDS:
+        out[name] = (out[name][0][:cols[i].n_vals], out[name][1], out[name][2])
+      elif cols[i].kind in _LIST_KINDS:
         out[name] = (out[name][0][:cols[i].n_vals], out[name][1]) + tuple(w[:cols[i].n_vals] for w in out[name][2:])
     return n_rows.value, consumed.value, out
 
@@ -430,7 +446,9 @@ class CSVInput(object):
         continue
       got = cols[self.feature_inputs[f.name][0]]
       vals, lens = got[0], got[1]
-      if f.kind == 'seq':
+      if f.kind == 'seq' and f.name in self.multi_seps:
+        seq[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens), torch.from_numpy(got[2]))
+      elif f.kind == 'seq':
         arr = np.zeros((B, f.seq_len), np.int64)
         starts = np.cumsum(lens) - lens
         arr[np.repeat(np.arange(B), lens), np.arange(vals.size) - np.repeat(starts, lens)] = vals
@@ -502,7 +520,20 @@ class CSVInput(object):
         tag[f.name] = (torch.from_numpy(v), torch.from_numpy(l), None)
         continue
       toks = [[t for t in x.split(sep) if t != ''] for x in cols[src]]
-      if f.kind == 'seq':
+      if f.kind == 'seq' and f.name in self.multi_seps:
+        # every step token is itself a list: (values of all steps back to back, steps per sample, values per step)
+        T, ms = f.seq_len, self.multi_seps[f.name]
+        flat, lens, step_lens = [], np.zeros(len(rows), np.int32), np.zeros((len(rows), T), np.int32)
+        for i, ts in enumerate(toks):
+          ts = ts[:T]  # keep the FIRST max_seq_len steps (utils/shape_utils.py:393-410)
+          lens[i] = len(ts)
+          for j, t in enumerate(ts):
+            vs = [v for v in t.split(ms) if v != '']
+            step_lens[i, j] = len(vs)
+            flat.extend(self._token(v, f.name) for v in vs)
+        seq[f.name] = (torch.from_numpy(np.array(flat, np.int64)), torch.from_numpy(lens),
+                       torch.from_numpy(step_lens.reshape(-1)))
+      elif f.kind == 'seq':
         T = f.seq_len
         arr = np.zeros((len(rows), T), np.int64)
         lens = np.zeros(len(rows), np.int32)
@@ -570,6 +601,10 @@ class ParquetInput(object):
     self.bucketized = _bucketized_features(pipeline_config, input_layer)
     self.combos = _combo_features(pipeline_config, input_layer)
     self.tag_weights = _tag_weight_inputs(pipeline_config)   # TagFeature -> the (list) column that holds its weights
+    for fc in config_util.get_feature_configs(pipeline_config):
+      if fc.HasField('seq_multi_sep'):
+        raise NotImplementedError('feature %s: seq_multi_sep splits text steps; a Parquet column would need nested lists'
+                                  % fc.input_names[0])
 
   @staticmethod
   def _column(col):

@@ -128,7 +128,7 @@ class MergedCall(object):
     self.out_strides = [subcalls[si].call.out_strides[b] for si, b in self.buf_of]
     self._out_rows = [subcalls[si].call.out_rows(b) for si, b in self.buf_of]
     self.ws = K.bwd_workspace(lookups, arena.device, arena.dim)
-    self.has_csr = any(sc.kind == 'tag' for sc in subcalls)
+    self.has_csr = any(sc.kind in ('tag', 'mseq') for sc in subcalls)
     self.single_valued = not self.has_csr
     self.needs_scale = any(sc.call.needs_scale for sc in subcalls)
     dev = arena.device
@@ -156,8 +156,12 @@ class InputLayer(object):
   def __init__(self, features, groups, batch_size, device, wide_output_dim=1,
                embedding_optimizer=_lib.OPT_ADAGRAD, shard_n=1, shard_rank=0, generator=None,
                adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None, uniform_tables=None,
-               dense_generator=None):
+               dense_generator=None, multi_valued_seq=()):
     self.features = collections.OrderedDict((f.name, f) for f in features)
+    # SequenceFeatures with seq_multi_sep: every step holds a LIST of values, pooled per step by the feature's
+    # combiner (input/input.py:686-700 builds the 3-D SparseTensor; pinned by test/embed_test.py:88-151) - a CSR slot
+    # with one segment per (sample, step) instead of one id per step
+    self.multi_valued_seq = set(multi_valued_seq)
     self.groups = groups
     self.seq_att_groups = seq_att_groups or collections.OrderedDict()
     self.batch_size = batch_size
@@ -182,7 +186,10 @@ class InputLayer(object):
       f = self.features[fname]
       arena = self.arenas.setdefault(dim, E.Arena(dim, device, shard_n, shard_rank))
       arena.add_table(table, f.num_buckets)
-      if kind == 'seq':
+      if kind == 'seq' and fname in self.multi_valued_seq:
+        kind = 'mseq'
+        sk, nseg = ('mseq', f.seq_len), B * f.seq_len
+      elif kind == 'seq':
         sk, nseg = ('seq', f.seq_len), B * f.seq_len
       elif kind == 'tag':
         sk, nseg = ('tag',), B
@@ -192,12 +199,12 @@ class InputLayer(object):
       sc = subs.setdefault(sk, _SubCall(sk[0], nseg))
       comb = _lib.COMBINER_SUM if (wide or f.kind == 'raw' or kind == 'seq') else _COMBINER[f.combiner]
       slot = E.Slot(out_key + '/' + fname, table, f.bucket_mode, f.num_buckets, comb, out_buf=out_key,
-                    n_seg_per_sample=f.seq_len if kind == 'seq' else 1)
+                    n_seg_per_sample=f.seq_len if kind in ('seq', 'mseq') else 1)
       # id and sequence slots never carry per-lookup weights (raw-value and kv-weighted tag slots do)
-      slot.unit_weights = f.kind != 'raw' and kind in ('single', 'seq')
+      slot.unit_weights = f.kind != 'raw' and kind in ('single', 'seq', 'mseq')
       if f.kind == 'raw':
         src = ('raw', self.raw_cols[fname][0])
-      elif kind == 'seq':
+      elif kind in ('seq', 'mseq'):
         src = ('seq', fname)
       elif kind == 'tag':
         src = ('tag', fname)
@@ -323,6 +330,9 @@ class InputLayer(object):
           slots.append(slot)
         if sc.kind == 'tag':
           cap = max_tag_lookups or 8 * B * len(slots)
+          sc.call = E.ArenaCall(self.arenas[dim], slots, B, widths, single_valued=False, max_lookups=cap)
+        elif sc.kind == 'mseq':
+          cap = max_tag_lookups or 4 * B * sk[1] * len(slots)     # room for 4 values per step on average
           sc.call = E.ArenaCall(self.arenas[dim], slots, B, widths, single_valued=False, max_lookups=cap)
         else:
           sc.call = E.ArenaCall(self.arenas[dim], slots, B, widths, single_valued=True)
@@ -699,7 +709,12 @@ class InputLayer(object):
     ids_list, lens_list, w_list = [], [], []
     any_w = False
     for _, fname, _, _ in sc.items:
-      ids, lens, w = features['tag_fea'][fname]
+      if sc.kind == 'mseq':
+        # (values of every step back to back, steps per sample, values per (sample, step) - 0 beyond the length)
+        ids, _, lens = features['seq_fea'][fname]
+        w = None
+      else:
+        ids, lens, w = features['tag_fea'][fname]
       ids_list.append(ids)
       lens_list.append(lens)
       w_list.append(w)

@@ -537,9 +537,14 @@ enum {
   ER_CSV_I64_KV_LIST = 7,  /* tokens `key<kv_sep>weight` (TagFeature kv_separator, input/input.py:447-458): integer
                               keys to out, fp32 weights to `weights` at the same positions */
   ER_CSV_HASH_KV_LIST = 8, /* the same with fingerprinted string keys */
-  ER_CSV_F32_LIST = 9      /* out float[list_cap] + lens int32[max_rows]: inner_sep-separated floats, empty tokens
+  ER_CSV_F32_LIST = 9,     /* out float[list_cap] + lens int32[max_rows]: inner_sep-separated floats, empty tokens
                             * skipped - the weight input of a TagFeature (its second input_names entry,
                             * input/input.py:477-497) */
+  ER_CSV_I64_STEP_LIST = 10, /* SequenceFeature with seq_multi_sep (input/input.py:686-700): steps separated by
+                            * inner_sep, the values of one step by kv_sep.  out int64[list_cap] = the values of all
+                            * steps back to back, lens[r] = steps of line r (the first `width` non-empty ones),
+                            * step_lens int32[max_rows * width] = values per step (0 beyond lens[r]) */
+  ER_CSV_HASH_STEP_LIST = 11 /* the same with fingerprinted string values */
 };
 typedef struct {
   int32_t kind;
@@ -557,6 +562,7 @@ typedef struct {
   int64_t n_vals;          /* written by the call: values stored for a list column */
   uint64_t hash_mod;       /* ER_CSV_HASH / ER_CSV_HASH_LIST: 0 = raw fingerprints, else the hash_bucket_size */
   float* weights;          /* *_KV_LIST: float[list_cap] */
+  int32_t* step_lens;      /* *_STEP_LIST: int32[max_rows * width] */
 } er_csv_col_t;
 int er_csv_parse(const char* buf, size_t len, char sep, er_csv_col_t* cols, int32_t n_cols,
                  int64_t max_rows, int32_t n_threads, int64_t* n_rows, size_t* consumed);

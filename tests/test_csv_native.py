@@ -399,3 +399,61 @@ model_config { model_class: "DeepFM"
   (fp, _), = list(readers.ParquetInput(cfg, il, str(tmp_path / 'w.parquet')))
   for a, b in zip(fp['tag_fea']['tags'], (ids, lens, w)):
     assert torch.equal(a, b)
+
+
+def test_multi_valued_sequence_steps_seq_multi_sep(tmp_path):
+  """SequenceFeature with seq_multi_sep (input/input.py:686-700; the lookup pinned by test/embed_test.py:88-151): every
+  step holds a list of values pooled by the feature's combiner.  Both parser engines give (values of all steps back to
+  back, steps per sample, values per step); through InputLayer with oracle-backed kernels each step's vector is the
+  mean of its rows - embed_test's own table and expected output."""
+  import host_doubles
+  cfg = config_util.get_configs_from_pipeline_file(b'''
+data_config { batch_size: 2 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "key" input_type: INT64 }
+  input_fields { input_name: "clk" input_type: STRING } input_fields { input_name: "sclk" input_type: STRING } }
+feature_config {
+  features { input_names: "key" feature_type: IdFeature embedding_dim: 2 num_buckets: 6 embedding_name: "t" }
+  features { input_names: "clk" feature_type: SequenceFeature embedding_dim: 2 num_buckets: 6 embedding_name: "t"
+             separator: "|" seq_multi_sep: "#" combiner: "mean" max_seq_len: 4 }
+  features { input_names: "sclk" feature_type: SequenceFeature embedding_dim: 2 hash_bucket_size: 11
+             separator: "|" seq_multi_sep: "#" combiner: "sum" max_seq_len: 2 } }
+model_config { model_class: "MultiTowerDIN"
+  seq_att_groups { group_name: "din" seq_att_map { key: "key" hist_seq: "clk" } }
+  feature_groups { group_name: "u" feature_names: ["key"] wide_deep: DEEP }
+  multi_tower { towers { input: "u" dnn { hidden_units: [4] } } din_towers { input: "din" dnn { hidden_units: [4, 1] } }
+                final_dnn { hidden_units: [4] } } }
+''')
+  il, _, _ = builder.build_model(cfg, 2, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert il.multi_valued_seq == {'clk', 'sclk'}
+  # embed_test.py:88-151: ids '0#1|1#2|2#3|3#4' / '4#5|5' ... with table [[1,2],[3,4],...]: step means [2,3],[4,5],...
+  open(tmp_path / 's.csv', 'w').write('1,0,0#1|1#2||2#3|3#4|4#5,a#b|c|d\n0,3,4#5|#|5,\n')
+  got = {}
+  for engine in ('native', 'python'):
+    (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 's.csv'), engine=engine))
+    ids, lens, step_lens = feats['seq_fea']['clk']
+    assert ids.tolist() == [0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5]            # the first max_seq_len = 4 non-empty steps
+    assert lens.tolist() == [4, 3] and step_lens.tolist() == [2, 2, 2, 2, 2, 0, 1, 0]   # '#' alone: a step without values
+    sid, slens, ssteps = feats['seq_fea']['sclk']
+    from oracle import oracle as O
+    assert sid.tolist() == [O.fingerprint64(x) % 11 for x in ('a', 'b', 'c')] and slens.tolist() == [2, 0]
+    assert ssteps.tolist() == [2, 1, 0, 0]
+    got[engine] = feats
+  for a, b in zip(got['native']['seq_fea']['clk'], got['python']['seq_fea']['clk']):
+    assert torch.equal(a, b) and a.dtype == b.dtype
+  # through the input layer: [B, T, D] with per-step means, zero vectors beyond the length
+  import pytest as _pytest
+  mp = _pytest.MonkeyPatch()
+  try:
+    host_doubles.install_sparse(mp.setattr)
+    t = il.arenas[2]
+    off, n, _ = t.tables['t']
+    with torch.no_grad():
+      t.weight[off:off + 6].copy_(torch.tensor([[1., 2.], [3., 4.], [5., 6.], [7., 8.], [9., 10.], [11., 12.]]))
+    il.lookup(got['native'])
+    so = il.seq_outputs['din']
+    assert so['hist_seq_len'].tolist() == [4, 3]
+    want = torch.tensor([[[2., 3.], [4., 5.], [6., 7.], [8., 9.]], [[10., 11.], [0., 0.], [11., 12.], [0., 0.]]])
+    assert torch.allclose(so['hist_seq_emb'], want)
+    assert torch.equal(so['key'], torch.tensor([[1., 2.], [7., 8.]]))
+  finally:
+    mp.undo()

@@ -140,3 +140,45 @@ def test_mmoe_gate_sized_dense_layer_trains_like_float64():
   assert float((y.double() - (xd @ W + lay.bias.detach().double())).abs().max()) < 1e-5
   assert float((x.grad.double() - xd.grad).abs().max()) < 1e-5
   assert float((lay.kernel.grad.double() - W.grad).abs().max()) < 2e-4
+
+
+def test_multi_valued_sequence_steps_on_the_kernels(tmp_path):
+  """SequenceFeature with seq_multi_sep through InputLayer on the GPU: test/embed_test.py:88-151's table and expected
+  per-step means ([[2,3],[4,5],...]), then one eager training step (CSR backward over (sample, step) segments)."""
+  from easyrec_b200 import builder
+  from easyrec_b200.config import config_util
+  from easyrec_b200.input import readers
+  from easyrec_b200.trainer import Trainer
+  cfg = config_util.get_configs_from_pipeline_file(b'''
+data_config { batch_size: 2 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "key" input_type: INT64 }
+  input_fields { input_name: "clk" input_type: STRING } }
+feature_config {
+  features { input_names: "key" feature_type: IdFeature embedding_dim: 2 num_buckets: 6 embedding_name: "t" }
+  features { input_names: "clk" feature_type: SequenceFeature embedding_dim: 2 num_buckets: 6 embedding_name: "t"
+             separator: "|" seq_multi_sep: "#" combiner: "mean" max_seq_len: 4 } }
+model_config { model_class: "MultiTowerDIN"
+  seq_att_groups { group_name: "din" seq_att_map { key: "key" hist_seq: "clk" } }
+  feature_groups { group_name: "u" feature_names: ["key"] wide_deep: DEEP }
+  multi_tower { towers { input: "u" dnn { hidden_units: [4] } } din_towers { input: "din" dnn { hidden_units: [4, 1] } }
+                final_dnn { hidden_units: [4] } } }
+''')
+  il, model, _ = builder.build_model(cfg, 2, DEV, cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 's.csv', 'w').write('1,0,0#1|1#2||2#3|3#4|4#5\n0,3,4#5|#|5\n')
+  (feats, labels), = list(readers.CSVInput(cfg, il, str(tmp_path / 's.csv')))
+  feats, labels = readers.to_device(feats, labels, DEV)
+  t = il.arenas[2]
+  off, n, _ = t.tables['t']
+  with torch.no_grad():
+    t.weight[off:off + 6].copy_(torch.tensor([[1., 2.], [3., 4.], [5., 6.], [7., 8.], [9., 10.], [11., 12.]], device=DEV))
+  il.lookup(feats)
+  so = il.seq_outputs['din']
+  want = torch.tensor([[[2., 3.], [4., 5.], [6., 7.], [8., 9.]], [[10., 11.], [0., 0.], [11., 12.], [0., 0.]]], device=DEV)
+  assert torch.allclose(so['hist_seq_emb'], want, atol=1e-6) and so['hist_seq_len'].tolist() == [4, 3]
+  il._pending = []
+  before = t.weight[off:off + 6].clone()
+  tr = Trainer(model, il, 'adagrad', lr=0.1)
+  loss, _ = tr.train_step(feats, labels)
+  assert np.isfinite(float(loss))
+  changed = (t.weight[off:off + 6] != before).any(1)
+  assert int(changed.sum()) >= 3                 # the rows of the keys and of the attended histories moved
