@@ -4,6 +4,7 @@
 // CUDA cores, fp32 FMA chains in index order (deterministic).  The cell function below is the whole arithmetic: the
 // kernels (small_gemm.cu) only map threads to (output element, k-slice); tests/native/ compiles it for the CPU.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #ifdef __CUDACC__
