@@ -321,10 +321,11 @@ class CSVInput(object):
           want(self.tag_weights[f.name], (_lib.CSV_F32_LIST, 0, sep.encode(), 0.0, 0))
     return plan
 
-  def _parse(self, data, size, plan, list_cap):
-    """one er_csv_parse call on `size` bytes at `data` (address or bytes) for up to batch_size lines
+  def _parse(self, data, size, plan, list_cap, n_batches=1):
+    """one er_csv_parse call on `size` bytes at `data` (address or bytes) for up to n_batches * batch_size lines
     -> (n_rows, consumed, {field: arrays}), or None when a list column needs a larger array."""
-    B = self.batch_size
+    B = self.batch_size * n_batches
+    list_cap = list_cap * n_batches
     cols = (_lib.ErCsvCol * len(self.fields))()
     out, keep = {}, []
     for i, name in enumerate(self.fields):
@@ -374,12 +375,35 @@ class CSVInput(object):
         out[name] = (out[name][0][:cols[i].n_vals], out[name][1]) + tuple(w[:cols[i].n_vals] for w in out[name][2:])
     return n_rows.value, consumed.value, out
 
+  @staticmethod
+  def _slice_chunk(cols, plan, k, B):
+    """batch k of a chunk parsed in one call: row ranges of the scalar / vector columns, value ranges of the list
+    columns (by the running sum of their per-row counts)."""
+    out = {}
+    for name, arrs in cols.items():
+      kind, width = plan[name][0], plan[name][1]
+      if kind in _STEP_KINDS:
+        vals, lens, steps = arrs
+        per_row = steps.reshape(-1, width).sum(1)
+        lo, hi = int(per_row[:k * B].sum()), int(per_row[:(k + 1) * B].sum())
+        out[name] = (vals[lo:hi], lens[k * B:(k + 1) * B], steps[k * B * width:(k + 1) * B * width])
+      elif kind in _LIST_KINDS:
+        lens = arrs[1]
+        lo, hi = int(lens[:k * B].sum()), int(lens[:(k + 1) * B].sum())
+        out[name] = (arrs[0][lo:hi], lens[k * B:(k + 1) * B]) + tuple(w[lo:hi] for w in arrs[2:])
+      else:
+        out[name] = (arrs[0][k * B:(k + 1) * B],)
+    return out
+
   def _batches_native(self):
-    """the file is memory-mapped and parsed in place, batch_size lines per call."""
+    """the file is memory-mapped and parsed in place; one er_csv_parse call takes a CHUNK of several batches (about
+    32K lines) so that the parser's threads are started once per chunk, not once per batch, and have enough lines each;
+    the last, short chunk of the file is parsed batch by batch."""
     import mmap
     B = self.batch_size
     plan = self._column_plan()
     list_cap = 16 * B
+    chunk = max(1, 32768 // B)
     if os.path.getsize(self.path) == 0:
       return
     with open(self.path, 'rb') as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
@@ -388,6 +412,17 @@ class CSVInput(object):
         base, size, off = view.ctypes.data, view.size, 0
         if self.cfg.data_config.with_header:      # the first line names the columns (csv_input.py:139-145)
           off = mm.find(b'\n') + 1 or size
+        while chunk > 1:
+          res = self._parse(base + off, size - off, plan, list_cap, n_batches=chunk)
+          if res is None:          # a list column outgrew its array
+            list_cap *= 4
+            continue
+          n_rows, consumed, cols = res
+          if n_rows < chunk * B:   # the end of the file is inside this chunk: batch by batch from here
+            break
+          off += consumed
+          for k in range(chunk):
+            yield self._pack_columns(self._slice_chunk(cols, plan, k, B))
         while True:
           res = self._parse(base + off, size - off, plan, list_cap)
           if res is None:          # a list column outgrew its array

@@ -457,3 +457,31 @@ model_config { model_class: "MultiTowerDIN"
     assert torch.equal(so['key'], torch.tensor([[1., 2.], [7., 8.]]))
   finally:
     mp.undo()
+
+
+@pytest.mark.parametrize('last_newline', [True, False])
+def test_chunked_native_parsing_equals_batch_by_batch(tmp_path, last_newline, monkeypatch):
+  """the native engine parses about 32K lines per er_csv_parse call and slices the batches out of the chunk (scalar
+  rows, list values by running sums, weights, sequence steps); the end of the file falls back to one batch per call.
+  Every batch equals the pure-python engine's, across two whole chunks, the short remainder and a last line without
+  a newline that completes a batch."""
+  cfg = config_util.get_configs_from_pipeline_file(CFG)
+  B = 512
+  il, _, _ = builder.build_model(cfg, B, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  chunk = 32768 // B
+  n = 2 * chunk * B + 3 * B + (0 if not last_newline else 100)   # without the last newline the final line completes a batch
+  path = str(tmp_path / 'big.csv')
+  _file(path, n, np.random.default_rng(11), last_newline=last_newline)
+  calls = []
+  real = readers.CSVInput._parse
+
+  def spy(self, data, size, plan, list_cap, n_batches=1):
+    calls.append(n_batches)
+    return real(self, data, size, plan, list_cap, n_batches)
+  monkeypatch.setattr(readers.CSVInput, '_parse', spy)
+  native = list(readers.CSVInput(cfg, il, path, n_threads=4))
+  assert calls.count(chunk) >= 3 and calls.count(1) >= 3        # two full chunks + the short one, then batch by batch
+  python = list(readers.CSVInput(cfg, il, path, engine='python'))
+  assert len(native) == len(python) == 2 * chunk + 3
+  for a, b in zip(native, python):
+    _same(a, b)
