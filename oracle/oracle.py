@@ -471,3 +471,14 @@ def max_f1(labels, probs):
     prec = np.where(tp + fp > 0, tp / (tp + fp), np.float32(0))
     rec = np.where(tp + fn > 0, tp / (tp + fn), np.float32(0))
   return float(np.max(2 * prec * rec / (prec + rec + np.float32(1e-12))))
+
+
+def dice(x, alphas, eps=1e-9):
+  """utils/activation.py:13-43 (training): p = sigmoid(batch_norm(x) without centre / scale, epsilon 1e-9, batch
+  statistics with the biased variance); alphas * (1 - p) * x + p * x.  Not built in the product (refused by the scope
+  check); restated here against the reference function's own output (tests/golden/reference_activations.json)."""
+  x = np.asarray(x, np.float32)
+  mu = x.mean(0, dtype=np.float32)
+  var = ((x - mu) ** 2).mean(0, dtype=np.float32)
+  p = 1.0 / (1.0 + np.exp(-((x - mu) / np.sqrt(var + np.float32(eps)))))
+  return (np.asarray(alphas, np.float32) * (1.0 - p) * x + p * x).astype(np.float32)

@@ -389,3 +389,40 @@ def test_loss_reader_returns_every_steps_loss_one_step_behind_and_the_last_on_fl
   assert seen == [None, 10.0, 11.0, 12.0, 13.0, 14.0, 15.0]          # one step behind, nothing skipped
   assert r.flush() == 16.0 and r.flush() == 16.0                    # the last step's value; idempotent
   assert [e.recorded for e in r.ev] == [4, 3] and [e.synced for e in r.ev] == [4, 3]
+
+
+# ---- the reference's own activation code, executed (tests/golden/make_activation_golden.py) ---------------------------
+def _act_gold():
+  import json
+  import os
+  return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_activations.json')))
+
+
+def test_activations_reproduce_the_reference_functions_executed(native):
+  """gelu / swish / dice as utils/activation.py computes them (function bodies run on a numpy shim): the oracle, and
+  the kernels' own source compiled for the CPU, give the same values."""
+  import ctypes
+  g = _act_gold()
+  x = np.array(g['x'], np.float32)
+  for name in ('gelu', 'swish'):
+    want = np.array(g['cases'][name]['y'], np.float32)
+    np.testing.assert_allclose(O.activation(x, name), want, rtol=2e-6, atol=1e-7)
+    y, s = np.empty_like(x), np.empty_like(x)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    assert native.host_act(K.ACT_KINDS[name], vp(x), ctypes.c_long(x.size), vp(y), vp(s)) == 0
+    np.testing.assert_allclose(y, want, rtol=2e-6, atol=1e-7)
+  d = g['cases']['dice']
+  np.testing.assert_allclose(O.dice(d['x'], d['alphas']), np.array(d['y'], np.float32), rtol=1e-5, atol=1e-6)
+
+
+def test_activation_names_follow_get_activation_executed():
+  """the config string -> function map recorded by running the reference's get_activation: every name it resolves to a
+  stateless function resolves here to the same one; 'linear' / '' mean no activation."""
+  tf_name = {'relu': 'tf.nn.relu', K.ACT_KINDS['gelu']: 'gelu', K.ACT_KINDS['leaky_relu']: 'tf.nn.leaky_relu',
+             K.ACT_KINDS['elu']: 'tf.nn.elu', K.ACT_KINDS['selu']: 'tf.nn.selu', K.ACT_KINDS['tanh']: 'tf.tanh',
+             K.ACT_KINDS['swish']: 'tf.nn.swish', K.ACT_KINDS['sigmoid']: 'tf.nn.sigmoid', None: None}
+  for s, fn in _act_gold()['cases']['get_activation']['map'].items():
+    got = tf_name[L.activation_kind(s)]
+    if fn is not None and fn.startswith('load_by_path('):       # a dotted path: the function it names
+      fn = fn[len('load_by_path('):-1].replace('tf.nn.tanh', 'tf.tanh')
+    assert got == fn, (s, got, fn)
