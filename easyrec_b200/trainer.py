@@ -116,10 +116,11 @@ class FlatDenseOptimizer(object):
     if srcs:
       torch._foreach_copy_(dsts, srcs)
 
-  def apply(self, l2_folded=False):
-    """l2_folded: the gradient buffer already holds g + l2 * w (fold_l2): apply without the regulariser."""
+  def apply(self, l2_folded=False, grad_scale=None):
+    """l2_folded: the gradient buffer already holds g + l2 * w (fold_l2): apply without the regulariser.
+    grad_scale: instead of self.grad_scale (a buffer that was already averaged over the replicas)."""
     lib = _lib.load()
-    opt = self.hyper.opt(self.kind, self.eps, grad_scale=self.grad_scale)
+    opt = self.hyper.opt(self.kind, self.eps, grad_scale=self.grad_scale if grad_scale is None else grad_scale)
     segs = self.segs_nol2_dev if l2_folded else self.segs_dev
     if not l2_folded:
       self.reg_loss.zero_()
@@ -193,13 +194,14 @@ class Trainer(object):
     # train_config.gradient_clipping_by_norm (> 0): global-norm clipping of all gradients before the updates
     self.clip_norm = float(clip_norm or 0.0)
     self.last_grad_norm = None
-    if self.clip_norm and world_size > 1:
-      raise NotImplementedError('gradient_clipping_by_norm with world_size > 1 (the norm of the reduced gradients, '
-                                'compat/optimizers.py:453-481)')
     self.dp = None
     if world_size > 1:
       from easyrec_b200.distributed import DataParallel
       ep = bool(getattr(input_layer, 'ep', False))
+      if self.clip_norm and ep:
+        # (row-sharded tables: the owners would have to hold their update until the norm of every shard's received
+        # gradients has been reduced, compat/optimizers.py:453-470 part_norms - the sharded backward is one fused branch)
+        raise NotImplementedError('gradient_clipping_by_norm with row-sharded tables (EmbeddingParallel)')
       self.dp = DataParallel(input_layer, self.dense_opt, world_size, sparse=not ep)
     dev = str(getattr(input_layer, 'device', 'cpu'))
     self._ep_side = torch.cuda.Stream(device=dev) if (self.dp is not None and not self.dp.sparse and
@@ -267,7 +269,19 @@ class Trainer(object):
     TF builds), the factor lands in the device-resident gradient scale the fused row update reads and on the dense
     gradient buffer.  Device-only: captured with the step."""
     il, opt = self.input_layer, self.dense_opt
-    sq = il.sparse_grad_sqnorm() + opt.fold_l2()
+    if self.dp is not None:
+      # data parallel over replicated tables (compat/optimizers.py:285-293 then :365-376): the norm is taken over the
+      # REDUCED gradients - the dense ones averaged (the flat buffer holds their sum after the all-reduce), every
+      # table's IndexedSlices all-gathered and divided by N, i.e. each rank's per-column slices side by side: the
+      # local sums of squares add up over the ranks, over N^2.  One scalar all-reduce; replicas get the same factor.
+      n = float(self.world)
+      sparse_sq = il.sparse_grad_sqnorm().reshape(1)
+      import torch.distributed as dist
+      dist.all_reduce(sparse_sq, op=dist.ReduceOp.SUM)
+      opt.flat_g.mul_(1.0 / n)
+      sq = sparse_sq[0] / (n * n) + opt.fold_l2()
+    else:
+      sq = il.sparse_grad_sqnorm() + opt.fold_l2()
     norm = torch.sqrt(sq)
     scale = self.clip_norm / torch.clamp(norm, min=self.clip_norm)
     opt.flat_g.mul_(scale)
@@ -277,8 +291,15 @@ class Trainer(object):
   def _segment_update(self, loss):
     if self.clip_norm:
       self._clip_by_global_norm()
-      self.input_layer.backward_update()
-      self.dense_opt.apply(l2_folded=True)
+      if self.dp is not None:
+        # the gathered K7 reads the clip factor from the device-resident gradient scale (x 1/N, replica_grad_scale);
+        # the dense buffer already holds the averaged, regularised, clipped gradient
+        self.dp.apply_sparse(self._step_pending, self.input_layer.opt_holder['opt'])
+        self.input_layer._pending = []
+        self.dense_opt.apply(l2_folded=True, grad_scale=1.0)
+      else:
+        self.input_layer.backward_update()
+        self.dense_opt.apply(l2_folded=True)
       return loss + self.dense_opt.reg_loss[0]
     if self.dp is not None and not self.dp.sparse and self._ep_side is not None:
       self.input_layer._pending = []

@@ -272,7 +272,8 @@ def install_dense(patch):
       gx[:, :w] = g
     return gx
 
-  def apply(self, l2_folded=False):   # FlatDenseOptimizer.apply: l2 + TF Adagrad / Adam / SGD over the flat buffer
+  def apply(self, l2_folded=False, grad_scale=None):   # FlatDenseOptimizer.apply: l2 + TF Adagrad / Adam / SGD over the flat buffer
+    scale = self.grad_scale if grad_scale is None else grad_scale
     assert self.kind in (0, 1, 3), 'this double implements the sgd, adagrad and adam rules'
     segs = np.frombuffer((self.segs_nol2_dev if l2_folded else self.segs_dev).numpy().tobytes(),
                          dtype=T._lib.DENSE_SEG_DTYPE)
@@ -281,7 +282,7 @@ def install_dense(patch):
     lr = float(self.lr_dev[0])
     for s in segs:
       o, n = int(s['offset']), int(s['n'])
-      w, g = self.flat_p[o:o + n], self.flat_g[o:o + n] * self.grad_scale
+      w, g = self.flat_p[o:o + n], self.flat_g[o:o + n] * scale
       if s['l2'] > 0:
         self.reg_loss += 0.5 * float(s['l2']) * (w * w).sum()
         g = g + float(s['l2']) * w
