@@ -453,6 +453,26 @@ class InputLayer(object):
       cur.wait_stream(self._side)
     self._pending = []
 
+  def ep_hold_updates(self, on=True):
+    """EmbeddingParallel + global-norm clipping: backward_update() stops after the gradient all-to-all; the owners
+    update in ep_apply_held() once the clip factor is in the gradient scale."""
+    for ex in self._exchanges():
+      ex.hold = bool(on)
+
+  def ep_recv_sqnorm(self):
+    """sum of squares of the gradient rows this rank RECEIVED as an owner: one entry per (source rank, distinct row) -
+    the IndexedSlices.values of the sharded tables as the reference's backward through hvd.alltoall builds them
+    (compat/optimizers.py:453-470 part_norms), times the embedding gradient multiplier squared."""
+    total = torch.zeros((), dtype=torch.float32, device=self.device)
+    for ex in self._exchanges():
+      total = total + (ex.recv_g * ex.recv_g).sum()
+    return total * float(self.emb_grad_mult) ** 2
+
+  def ep_apply_held(self):
+    for ex in self._exchanges():
+      if ex.members:
+        ex.members[0].apply_held()
+
   def check_exchange(self):
     """EmbeddingParallel: raise if a per-peer block of the fixed-capacity exchange overflowed since the last check
     (reads one counter per arena back: call it outside the step loop, e.g. when the loss is logged)."""

@@ -146,6 +146,10 @@ class ShardedExchange(object):
     self._pre = torch.cuda.Stream(device=device) if str(device).startswith('cuda') else None
     self._presorted = False
     self._have_next = False   # K1 / K8 / id all-to-all of the NEXT batch already sit in the *_n buffers
+    # global-norm clipping: the owners hold their row update after the gradient exchange until the norm of every
+    # rank's received gradients is known (ShardedLookup.apply_held)
+    self.hold = False
+    self._held = None
 
   def add(self, member):
     assert not self._built
@@ -355,6 +359,20 @@ class ShardedLookup(object):
     if ex._summed < len(ex._active):
       return
     dist.all_to_all_single(ex.recv_g, ex.send_g)
+    if ex.hold:
+      ex._held = opt
+      return
+    self._owner_update(opt)
+
+  def apply_held(self):
+    """the owner-side updates of a held exchange (after the clip factor went into the gradient scale)"""
+    ex = self.ex
+    if ex._held is not None:
+      opt, ex._held = ex._held, None
+      self._owner_update(opt)
+
+  def _owner_update(self, opt):
+    ex, N = self.ex, self.world
     struct_scaled = not opt.hyper_dev   # a device-resident grad_scale already carries the 1/N
     if struct_scaled:
       opt.grad_scale = opt.grad_scale / N

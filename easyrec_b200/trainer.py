@@ -199,9 +199,9 @@ class Trainer(object):
       from easyrec_b200.distributed import DataParallel
       ep = bool(getattr(input_layer, 'ep', False))
       if self.clip_norm and ep:
-        # (row-sharded tables: the owners would have to hold their update until the norm of every shard's received
-        # gradients has been reduced, compat/optimizers.py:453-470 part_norms - the sharded backward is one fused branch)
-        raise NotImplementedError('gradient_clipping_by_norm with row-sharded tables (EmbeddingParallel)')
+        # row-sharded tables: the owners hold their update after the gradient all-to-all until the norm of every
+        # shard's received gradients has been reduced (compat/optimizers.py:453-470 part_norms)
+        input_layer.ep_hold_updates(True)
       self.dp = DataParallel(input_layer, self.dense_opt, world_size, sparse=not ep)
     dev = str(getattr(input_layer, 'device', 'cpu'))
     self._ep_side = torch.cuda.Stream(device=dev) if (self.dp is not None and not self.dp.sparse and
@@ -275,7 +275,9 @@ class Trainer(object):
       # table's IndexedSlices all-gathered and divided by N, i.e. each rank's per-column slices side by side: the
       # local sums of squares add up over the ranks, over N^2.  One scalar all-reduce; replicas get the same factor.
       n = float(self.world)
-      sparse_sq = il.sparse_grad_sqnorm().reshape(1)
+      # (row-sharded tables: what each owner received - one entry per source rank and distinct row, summed over all
+      # columns of the call, as the reference's single `unique` before the exchange gives it, feature_column.py:263)
+      sparse_sq = (il.sparse_grad_sqnorm() if self.dp.sparse else il.ep_recv_sqnorm()).reshape(1)
       import torch.distributed as dist
       dist.all_reduce(sparse_sq, op=dist.ReduceOp.SUM)
       opt.flat_g.mul_(1.0 / n)
@@ -290,8 +292,18 @@ class Trainer(object):
 
   def _segment_update(self, loss):
     if self.clip_norm:
+      ep = self.dp is not None and not self.dp.sparse
+      if ep:
+        if self._ep_side is not None:
+          torch.cuda.current_stream().wait_stream(self._ep_side)   # the gradient exchange of _segment_exchange
+        else:
+          self.input_layer.backward_update()   # (host build) gradient sums + all-to-all; the owners hold their update
       self._clip_by_global_norm()
-      if self.dp is not None:
+      if ep:
+        self.input_layer.ep_apply_held()       # owner-side K7 with the clipped, 1/N-scaled gradient scale
+        self.input_layer._pending = []
+        self.dense_opt.apply(l2_folded=True, grad_scale=1.0)
+      elif self.dp is not None:
         # the gathered K7 reads the clip factor from the device-resident gradient scale (x 1/N, replica_grad_scale);
         # the dense buffer already holds the averaged, regularised, clipped gradient
         self.dp.apply_sparse(self._step_pending, self.input_layer.opt_holder['opt'])
