@@ -62,6 +62,11 @@ class GlobalCall(object):
     self.seg_scale = None
     self.grads = [torch.empty(world * call.out_rows(i), st, dtype=torch.float32, device=dev)
                   for i, st in enumerate(call.out_strides)]
+    # multi-valued (CSR) slots: every lookup names its segment; rank r's segments follow rank r-1's in the gathered plan
+    self.seg_ids = self.seg_off = None
+    if getattr(call, 'has_csr', False):
+      self.seg_ids = torch.empty(self.max_lookups, dtype=torch.int32, device=dev)
+      self.seg_off = (torch.arange(world, dtype=torch.int32, device=dev) * call.n_seg).repeat_interleave(call.max_lookups)
     # one-row slots (RawFeature projections: B lookups of one table row per rank)
     self.one_row = [(int(s['seg_begin']), int(s['n_seg']), int(s['out_buf']), int(s['out_col']), int(s['row_offset']))
                     for s in base if int(s['bucket_mode']) == _lib.BUCKET_ONE_ROW and call.single_one_row_ok]
@@ -149,10 +154,14 @@ class DataParallel(object):
     (compat/optimizers.py:289-292) is folded into the dense apply's grad_scale."""
     dist.all_reduce(self.dense_opt.flat_g, op=dist.ReduceOp.SUM)
 
-  def gather_sparse(self, call, rows, w, outs):
-    """all-gather one arena call's K7 inputs (rows, weights, segment scales, upstream gradients)
-    into the GlobalCall buffers; returns the GlobalCall."""
+  def gather_sparse(self, call, rows, w, outs, seg_ids=None):
+    """all-gather one arena call's K7 inputs (rows, weights, segment scales, upstream gradients; for a call with
+    multi-valued slots also the segment of every lookup) into the GlobalCall buffers; returns the GlobalCall."""
     g = self.gcalls[id(call)]
+    if seg_ids is not None:
+      # (lookups past a rank's real count carry row -1 and are dropped by K7 whatever segment they name)
+      dist.all_gather_into_tensor(g.seg_ids, seg_ids.contiguous())
+      g.seg_ids.add_(g.seg_off)
     pre = self._pre.get(id(call))
     if pre is not None:   # rows / weights were gathered (and their sort started) before the step
       owner, is_owner = pre
@@ -220,9 +229,7 @@ class DataParallel(object):
       return
     self._rows_owner = {}
     for call, rows, w, outs, seg_ids in pending:
-      if seg_ids is not None:
-        raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
-      self.gather_sparse(call, rows, w, outs)
+      self.gather_sparse(call, rows, w, outs, seg_ids)
 
   def join_presort(self):
     """main stream waits for the early global sorts (call before apply_sparse / its graph replay)."""
@@ -250,7 +257,7 @@ class DataParallel(object):
         sorted_from = (owner.ws, owner.call.arena.dim)
       K.embedding_bwd(a.weight, a.state0, a.state1, a.dim, owner.rows, g.slots_dev, g.n_slots, g.n_seg,
                       g.grads, opt, g.ws, weights=owner.weights if w is not None else None,
-                      seg_scale=g.seg_scale, sorted_from=sorted_from)
+                      seg_ids=g.seg_ids if seg_ids is not None else None, seg_scale=g.seg_scale, sorted_from=sorted_from)
       if g.one_row:
         K.sparse_apply(a.weight, a.state0, a.state1, a.dim, g.one_row_rows, g.one_row_sums, None, opt)
       # tf.train.AdamOptimizer: the rows nobody looked up decay too
@@ -262,8 +269,6 @@ class DataParallel(object):
     il = self.input_layer
     self._rows_owner = {}
     for call, rows, w, outs, seg_ids in il._pending:
-      if seg_ids is not None:
-        raise NotImplementedError('data-parallel K7 over multi-valued (CSR) slots')
-      self.gather_sparse(call, rows, w, outs)
+      self.gather_sparse(call, rows, w, outs, seg_ids)
     self.apply_sparse(il._pending, opt)
     il._pending = []
