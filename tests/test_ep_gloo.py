@@ -1,4 +1,4 @@
-"""CPU, world 2 over gloo, kernels replaced by the oracle-backed doubles: EmbeddingParallel through the product surface
+"""CPU, world 2 and 8 over gloo, kernels replaced by the oracle-backed doubles: EmbeddingParallel through the product surface
 (EasyRecEstimator with train_distribute: EmbeddingParallelStrategy -> row-sharded arenas, ShardedLookup all-to-all
 around every lookup, gradient rows to the owners, 1/N gradient scale, dense all-reduce) trains the same model as
 replicated data parallel on the same per-rank batches (compat/feature_column/feature_column.py:248-357,
@@ -42,7 +42,7 @@ def _worker(rank, port, ret, world):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('world', [2, 4])
+@pytest.mark.parametrize('world', [2, 8])   # (8 = the scaling bench's largest run: 8 owners, per-peer blocks, rank-major sums)
 def test_embedding_parallel_equals_replicated_data_parallel_gloo(world):
   mgr = mp.Manager()
   ret = mgr.dict()
