@@ -118,8 +118,7 @@ def _batches(n, B, seed):
   for _ in range(n):
     a, b = rng.integers(0, 50, B), rng.integers(0, 50, B)
     lab = ((a + b) % 2 == 0).astype(np.float32)
-    yield {'sparse_fea': torch.from_numpy(np.concatenate([a, b]).astype(np.int64)),
-           'dense_fea': torch.zeros(B, 0)}, torch.from_numpy(lab)
+    yield {'sparse_fea': torch.from_numpy(np.concatenate([a, b]).astype(np.int64))}, torch.from_numpy(lab)
 
 
 @pytest.mark.parametrize('act', ['gelu', 'swish'])
@@ -326,7 +325,7 @@ def test_raw_feature_normalizer_fn_on_the_device_matrix_and_in_the_host_bucketiz
 # ---- er_gemm_small (vector-sized dense layers: MMoE gates, their dX and dW) -------------------------------------------
 @pytest.mark.parametrize('M,N,K,form', [(8192, 4, 256, 'fwd'), (8192, 256, 4, 'dx'), (256, 4, 8192, 'dw'), (3, 5, 7, 'fwd'),
                                         (1000, 7, 33, 'fwd'), (33, 7, 1000, 'dw'), (5, 300, 2, 'dx'), (64, 3, 511, 'dw'),
-                                        (64, 3, 512, 'dw')])
+                                        (64, 3, 512, 'dw'), (16384, 3, 96, 'fwd'), (96, 3, 16384, 'dw')])
 def test_kernel_source_small_gemm_reads_strided_operands_and_sums_slices_in_order(native, M, N, K, form):
   """small_gemm.cuh compiled for the CPU, driven with the strides kernels.gemm_small passes for the three forms of a
   dense layer: forward (X row-major, W row-major), dX (dY, W^T as a transposed VIEW), dW (X^T as a view, dY)."""

@@ -182,3 +182,21 @@ model_config { model_class: "MultiTowerDIN"
   assert np.isfinite(float(loss))
   changed = (t.weight[off:off + 6] != before).any(1)
   assert int(changed.sum()) >= 3                 # the rows of the keys and of the attended histories moved
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_pipelined_loss_read_returns_every_steps_loss(graph):
+  """EasyRecEstimator.train(fetch_loss_every_step=True): the losses travel through pinned slots one step behind the
+  device; the value train() returns (and last_loss_value) is the LAST step's, equal to a run that synchronises once at the
+  end; evaluate() then runs the streaming metrics on the device."""
+  from test_act_metrics_host import CFG_ACT, _batches
+  from easyrec_b200.estimator import EasyRecEstimator
+  cfg = CFG_ACT.replace(b'ACT', b'gelu')
+  a = EasyRecEstimator(cfg, device=DEV, seed=3, use_cuda_graph=graph)
+  b = EasyRecEstimator(cfg, device=DEV, seed=3, use_cuda_graph=graph)
+  la = a.train(lambda: _batches(9, 256, 1), steps=9, fetch_loss_every_step=True)
+  lb = b.train(lambda: _batches(9, 256, 1), steps=9)
+  assert la == pytest.approx(lb, rel=1e-6) and a.last_loss_value == la and a.global_step == b.global_step == 9
+  ev = a.evaluate(lambda: _batches(4, 256, 99))
+  assert 0.0 <= ev['auc'] <= 1.0 and abs(ev['auc'] - ev['auc_exact']) < 5e-3
+  assert ev['max_f1'] > 0.0 and ev['root_mean_squared_error'] == pytest.approx(np.sqrt(ev['mean_squared_error']), rel=1e-6)
