@@ -81,6 +81,18 @@ def _replay(g):
   np.testing.assert_allclose(1.0 * 0.99 + d['var'] * 0.01, g['dense_moving_var'], rtol=1e-4, atol=1e-6)
 
 
+  # activations and their gradients (dumps made before these were added do not carry them)
+  if 'act_x' in g:
+    for name in ('leaky_relu', 'elu', 'selu', 'tanh', 'sigmoid', 'swish', 'gelu'):
+      np.testing.assert_allclose(O.activation(g['act_x'], name), g['act_%s' % name], rtol=2e-6, atol=1e-6, err_msg=name)
+      np.testing.assert_allclose(O.activation_grad(g['act_x'], name), g['act_%s_grad' % name], rtol=1e-5, atol=2e-6,
+                                 err_msg=name + ' gradient')
+  # tf.metrics.auc streamed over batches
+  if 'auc_labels' in g:
+    for T in (200, 500):
+      assert abs(O.auc_tf(g['auc_labels'], g['auc_preds'], T) - float(g['auc_%d' % T])) < 2e-6
+
+
 @pytest.mark.skipif(not os.path.exists(PATH), reason='no TensorFlow dump (tools/dump_tf_golden.py needs a box with TF)')
 def test_oracle_matches_the_tensorflow_dump():
   _replay(dict(np.load(PATH, allow_pickle=False)))
@@ -124,4 +136,11 @@ def test_replay_plumbing_on_a_self_made_dump():
     g['dense_' + k] = d[k]
   g['dense_moving_mean'] = d['mean'] * 0.01
   g['dense_moving_var'] = 0.99 + d['var'] * 0.01
+  g['act_x'] = rng.normal(0, 2, 64).astype(np.float32)
+  for name in ('leaky_relu', 'elu', 'selu', 'tanh', 'sigmoid', 'swish', 'gelu'):
+    g['act_%s' % name], g['act_%s_grad' % name] = O.activation(g['act_x'], name), O.activation_grad(g['act_x'], name)
+  g['auc_labels'] = (rng.uniform(size=500) < 0.3).astype(np.float32)
+  g['auc_preds'] = rng.uniform(size=500).astype(np.float32)
+  for T in (200, 500):
+    g['auc_%d' % T] = O.auc_tf(g['auc_labels'], g['auc_preds'], T)
   _replay(g)

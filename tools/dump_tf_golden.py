@@ -2,7 +2,7 @@
 
 The reference's path is a TF graph; the pieces EasyRec does not implement itself - StringToHashBucketFast / AsString,
 safe_embedding_lookup_sparse, SparseApplyAdagrad, the sparse applies of tf.train.AdamOptimizer and of EasyRec's lazy
-AdamOptimizerS, layers.dense + batch_normalization, losses.sigmoid_cross_entropy - are restated by `oracle/` and marked
+AdamOptimizerS, layers.dense + batch_normalization, losses.sigmoid_cross_entropy, the tf.nn activations, tf.metrics.auc - are restated by `oracle/` and marked
 "parity unpinned vs TF" in DESIGN.md §4 where no frozen TF test value exists.  TensorFlow is not installable in the build
 container (no network) nor on the GPU box, so this script is for any machine that HAS it (TF 1.15 or 2.x):
 
@@ -111,6 +111,30 @@ def main(out_path):
     out['dense_moving_mean'] = sess.run(params['d0/bn/moving_mean:0'])
     out['dense_moving_var'] = sess.run(params['d0/bn/moving_variance:0'])
   out['dense_x'], out['dense_labels'] = x, labels
+
+  # ---- activations (tf.nn.* as utils/activation.py:get_activation resolves them) with gradients ----------------------
+  ax = np.concatenate([rng.normal(0, 2.5, 2048), [0.0, -0.0, 1e-6, -1e-6, 20.0, -20.0]]).astype(np.float32)
+  acts = {'leaky_relu': tf.nn.leaky_relu, 'elu': tf.nn.elu, 'selu': tf.nn.selu, 'tanh': tf.tanh, 'sigmoid': tf.nn.sigmoid,
+          'swish': tf.nn.swish, 'gelu': lambda t: t * 0.5 * (1.0 + tf.tanh(np.sqrt(2 / np.pi) * (t + 0.044715 * tf.pow(t, 3))))}
+  with tf1.Session(graph=tf.Graph()) as sess:
+    t = tf1.placeholder(tf.float32, [None])
+    for name, fn in acts.items():
+      y = fn(t)
+      out['act_%s' % name], out['act_%s_grad' % name] = sess.run([y, tf.gradients(tf.reduce_sum(y), t)[0]], {t: ax})
+  out['act_x'] = ax
+
+  # ---- tf.metrics.auc at several num_thresholds, streamed over batches (model/rank_model.py:360-373) -----------------
+  mlab = (rng.uniform(size=6000) < 0.3).astype(np.float32)
+  mpred = np.clip(rng.normal(0.4 + 0.25 * mlab, 0.2), 0, 1).astype(np.float32)
+  for T in (200, 500):
+    with tf1.Session(graph=tf.Graph()) as sess:
+      tl, tp = tf1.placeholder(tf.float32, [None]), tf1.placeholder(tf.float32, [None])
+      val, upd = tf1.metrics.auc(tf.cast(tl, tf.int64), tp, num_thresholds=T)
+      sess.run(tf1.local_variables_initializer())
+      for k in range(0, 6000, 1000):
+        sess.run(upd, {tl: mlab[k:k + 1000], tp: mpred[k:k + 1000]})
+      out['auc_%d' % T] = sess.run(val)
+  out['auc_labels'], out['auc_preds'] = mlab, mpred
 
   np.savez_compressed(out_path, **out)
   print('wrote %s (%d arrays) from TensorFlow %s' % (out_path, len(out), tf.__version__))
