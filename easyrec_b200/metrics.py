@@ -140,13 +140,18 @@ class MetricSet(object):
   def __init__(self, metrics_set, heads, device):
     self.heads = list(heads)
     self.acc = []   # (key, kind, head index, accumulator)
-    kinds = [(m.WhichOneof('metric'), m) for m in metrics_set] or [('auc', None)]
+    kinds = [(m.WhichOneof('metric'), m) for m in metrics_set]
+    default = not kinds
+    if default:   # no metrics_set: auc for the binary heads (a regression head has no default metric)
+      kinds = [('auc', None)]
     for which, m in kinds:
       if which not in self.STREAMING:
         continue
       for h, (suffix, loss_type, _) in enumerate(self.heads):
         binary = loss_type == 'CLASSIFICATION'
         if which in ('auc', 'max_f1'):
+          if not binary and default:
+            continue
           if not binary:
             raise ValueError('%s needs a binary classification head (loss_type %s)' % (which, loss_type))
           T = int(m.auc.num_thresholds) if (which == 'auc' and m is not None) else 200
