@@ -43,6 +43,12 @@ extern "C" int er_auc_hist(const float* probs, const float* labels, int64_t n, c
   ER_REQUIRE(n > 0, "n must be positive");
   ER_REQUIRE(n_thresholds >= 2 && n_thresholds <= 4095, "num_thresholds must be in [2, 4095]");
   const size_t smem = (size_t)n_thresholds * sizeof(float) + 2 * (size_t)(n_thresholds + 1) * sizeof(unsigned int);
+  static bool attr = false;   // (up to 48 KB at 4095 thresholds: opt in explicitly, the default limit sits right there)
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(auc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return fail(ER_ERR_CUDA, std::string("er_auc_hist: ") + cudaGetErrorString(e));
+    attr = true;
+  }
   const int grid = grid_for(n, 256 * 8, 2);
   auc_hist_kernel<<<grid, 256, smem, as_stream(stream)>>>(probs, labels, n, thresholds, (int)n_thresholds,
                                                           reinterpret_cast<unsigned long long*>(hist));
