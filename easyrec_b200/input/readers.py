@@ -154,7 +154,13 @@ class DummyInput(object):
       feats['dense_fea'] = torch.from_numpy(rng.uniform(0, 1, (B, il.n_dense)).astype(np.float32))
     seq, tag = {}, {}
     for f in il.features.values():
-      if f.kind == 'seq':
+      if f.kind == 'seq' and f.name in getattr(il, 'multi_valued_seq', ()):
+        # seq_multi_sep: (values of all steps back to back, steps per sample, values per (sample, step))
+        lens = rng.integers(1, f.seq_len + 1, B).astype(np.int32)
+        steps = np.where(np.arange(f.seq_len)[None, :] < lens[:, None], rng.integers(1, 4, (B, f.seq_len)), 0).astype(np.int32)
+        seq[f.name] = (torch.from_numpy(rng.integers(0, 2**40, int(steps.sum()), dtype=np.int64)), torch.from_numpy(lens),
+                       torch.from_numpy(steps.reshape(-1)))
+      elif f.kind == 'seq':
         lens = rng.integers(1, f.seq_len + 1, B).astype(np.int32)
         seq[f.name] = (torch.from_numpy(rng.integers(0, 2**40, (B, f.seq_len), dtype=np.int64)),
                        torch.from_numpy(lens))
