@@ -317,7 +317,11 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                      uniform_tables=keras_tables, dense_generator=cpu_generator,
                      multi_valued_seq=[(fc.feature_name if fc.HasField('feature_name') else fc.input_names[0])
                                        for fc in config_util.get_feature_configs(pipeline_config)
-                                       if fc.HasField('seq_multi_sep')])
+                                       if fc.HasField('seq_multi_sep')],
+                     seq_combiners={(fc.feature_name if fc.HasField('feature_name') else fc.input_names[0]):
+                                    fc.sequence_combiner.WhichOneof('combiner')
+                                    for fc in config_util.get_feature_configs(pipeline_config)
+                                    if fc.HasField('sequence_combiner')})
   # RawFeature.normalizer_fn: applied to the min-max normalised value on the device (input/input.py:642-646); the
   # readers apply the same function on the host to raw features they bucketize themselves (readers.bucketize_raw)
   from easyrec_b200 import normalizer

@@ -156,12 +156,15 @@ class InputLayer(object):
   def __init__(self, features, groups, batch_size, device, wide_output_dim=1,
                embedding_optimizer=_lib.OPT_ADAGRAD, shard_n=1, shard_rank=0, generator=None,
                adagrad_init=0.1, seq_att_groups=None, max_tag_lookups=None, uniform_tables=None,
-               dense_generator=None, multi_valued_seq=()):
+               dense_generator=None, multi_valued_seq=(), seq_combiners=None):
     self.features = collections.OrderedDict((f.name, f) for f in features)
     # SequenceFeatures with seq_multi_sep: every step holds a LIST of values, pooled per step by the feature's
     # combiner (input/input.py:686-700 builds the 3-D SparseTensor; pinned by test/embed_test.py:88-151) - a CSR slot
     # with one segment per (sample, step) instead of one id per step
     self.multi_valued_seq = set(multi_valued_seq)
+    # SequenceFeatures of a PLAIN feature group carry a sequence_combiner (layers/input_layer.py:312-347): 'attention' =
+    # softmax over the steps of a learned linear score (dense(units=1, no bias)), masked beyond the length, weighted sum
+    self.seq_combiners = dict(seq_combiners or {})
     self.groups = groups
     self.seq_att_groups = seq_att_groups or collections.OrderedDict()
     self.batch_size = batch_size
@@ -212,8 +215,11 @@ class InputLayer(object):
         src = ('id', self.sparse_names.index(fname))
       sc.items.append((out_key, fname, slot, src))
 
+    self.attention_modules = collections.OrderedDict()
+    self.seqc_order = {}      # group -> names of its sequence-combiner features in config order
     for gname, g in groups.items():
       layout = []
+      seqc = []
       wide = bool(g.get('wide'))
       for fname in g['features']:
         f = self.features[fname]
@@ -222,8 +228,21 @@ class InputLayer(object):
           layout.append((fname, 'dense', f.raw_input_dim, None, None, None))
           continue
         if f.kind == 'seq':
-          raise NotImplementedError('SequenceFeature %s in a plain group needs a sequence_combiner; '
-                                    'put it in seq_att_groups (DIN)' % fname)
+          if self.seq_combiners.get(fname) != 'attention' or wide or fname in self.multi_valued_seq:
+            raise NotImplementedError('SequenceFeature %s in a plain group needs a sequence_combiner { attention } '
+                                      '(or put it in seq_att_groups / sequence_features)' % fname)
+          # un-pooled [B*T, D] rows in a matrix of their own; pooled in lookup() by the attention combiner.  In the
+          # concat these features follow the plain ones in NAME order, in the per-feature list in config order
+          # (input_layer.py:312, 364-367)
+          table = f.embedding_name or fname + '_embedding'
+          out_key = '%s#seqc/%s' % (gname, fname)
+          add_slot(dim, out_key, fname, table, 'seq')
+          seqc.append([fname, 'seqc', dim, dim, out_key, None])
+          from easyrec_b200 import layers as L
+          att = L.Dense(dim, 1, generator=dense_generator)
+          att.bias.requires_grad_(False)       # tf.layers.dense(units=1, use_bias=False, name='attention')
+          self.attention_modules[out_key] = att
+          continue
         table = (f.embedding_name or fname + '_embedding') + ('_wide' if wide else '')
         kind = 'tag' if f.kind == 'tag' else 'single'
         # one output matrix per (group, launch kind): the single-valued and the CSR launch of a mixed group
@@ -231,7 +250,8 @@ class InputLayer(object):
         out_key = gname if kind == 'single' else gname + '#tag'
         add_slot(dim, out_key, fname, table, kind, wide=wide)
         layout.append([fname, 'emb', dim, dim, out_key, None])
-      self.group_layout[gname] = layout
+      self.seqc_order[gname] = [e[0] for e in seqc]
+      self.group_layout[gname] = layout + sorted(seqc, key=lambda e: e[0])
     for sname, maps in self.seq_att_groups.items():
       lay = dict(key=[], hist=[], T=None)
       for keys, hists in maps:
@@ -255,7 +275,6 @@ class InputLayer(object):
     # SequenceFeatureLayer, layers/sequence_feature_layer.py:190-249 -> SeqInputLayer with scope_name = the group's):
     # a key that is a feature of the same group reuses the group's own embedding output (seq_input_layer.py:63-75);
     # histories live in the group's scope; the attended vector (+ the key) is appended to the group's concat
-    self.attention_modules = collections.OrderedDict()
     for gname, g in groups.items():
       for sub in g.get('seq') or []:
         if g.get('wide'):
@@ -340,7 +359,7 @@ class InputLayer(object):
           col = sc.call.slot_cols[i]
           for lay in list(self.group_layout.values()):
             for e in lay:
-              if e[1] == 'emb' and e[0] == fname and e[4] == out_key and e[5] is None:
+              if e[1] in ('emb', 'seqc') and e[0] == fname and e[4] == out_key and e[5] is None:
                 e[5] = col
           for lay in self.seq_layout.values():
             for part in ('key', 'hist'):
@@ -856,6 +875,16 @@ class InputLayer(object):
         if kind == 'dense':
           c0, c1 = self.raw_cols[fname]
           v = dense_norm[:, c0:c1]
+        elif kind == 'seqc':
+          # sequence_combiner { attention } (input_layer.py:323-339): logits = dense(seq, 1, no bias), positions beyond
+          # the length masked with -2^32 + 1, softmax over the steps, weighted sum of the step embeddings
+          from easyrec_b200 import interactions as I
+          mat = outs_by_key[(dim, out_key)]
+          T = self.features[fname].seq_len
+          seq = mat[:, col:col + width].reshape(B, T, width).contiguous()
+          scores = self.attention_modules[out_key](seq.reshape(B * T, width)).reshape(B, T)
+          v = I.din_pool(scores.contiguous(), seq, features['seq_fea'][fname][1])
+          reg = (reg or []) + [seq]           # embedding_reg_lst takes the un-pooled sequence (input_layer.py:316)
         elif kind == 'att':
           # target attention over the group's sequence_features (sequence_feature_layer.py:123-189): softmax of the
           # masked attention-MLP scores over the history, [attended history | key] (need_key_feature)
@@ -881,5 +910,10 @@ class InputLayer(object):
         # the embedding regulariser covers what was LOOKED UP (the group's columns and the histories,
         # input_layer.py:369-375, sequence_feature_layer.py:215-217), not the attended vectors appended to the concat
         concat._er_reg = [v for v, k in zip(per_feature, kinds) if k == 'emb'] + reg
+      order = self.seqc_order.get(gname)
+      if order and len(order) > 1:
+        # the per-feature list keeps the sequence-combiner features in config order (the concat has them by name)
+        by_name = {e[0]: v for e, v in zip(layout, per_feature) if e[1] == 'seqc'}
+        per_feature = [v for e, v in zip(layout, per_feature) if e[1] != 'seqc'] + [by_name[n] for n in order]
       out[gname] = (concat, per_feature)
     return out

@@ -117,6 +117,12 @@ class _DinPool(torch.autograd.Function):
     return gs, gk, None
 
 
+def din_pool(scores, keys, lens):
+  """softmax over the first lens[b] steps of scores [B,T] (the rest masked with -2^32 + 1), weighted sum of keys [B,T,D]
+  -> [B,D]: the pooling half of target attention, and the `attention` sequence_combiner (layers/input_layer.py:323-339)."""
+  return _DinPool.apply(scores, keys, lens)
+
+
 def din_attention(query, keys, lens, attention_mlp):
   """query [B,D], keys [B,T,D], lens int32 [B]; attention_mlp maps [B,T,4D] -> [B,T,1].
   Returns [B,D] (the caller concatenates the query: multi_tower_din.py:96)."""

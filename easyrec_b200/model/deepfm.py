@@ -39,7 +39,8 @@ class DeepFM(nn.Module):
     deep_layout = input_layer.group_layout['deep']
     self.n_field = len(deep_layout)
     self.dim = deep_layout[0][2]
-    assert all(e[2] == self.dim and e[1] == 'emb' for e in deep_layout), \
+    # (a SequenceFeature pooled by its sequence_combiner is one more field of the same width, input_layer.py:312-347)
+    assert all(e[2] == self.dim and e[1] in ('emb', 'seqc') for e in deep_layout), \
         'FM needs every deep feature embedded with the same dim'
     self.deep_width = self.n_field * self.dim
     self.dnn = L.DNN(self.deep_width, dnn_units, generator=generator)
@@ -62,7 +63,8 @@ class DeepFM(nn.Module):
     else:
       wide_fea = wide.sum(dim=1, keepdim=True)
     self._deep_sumsq = None
-    if deep.shape[1] == self.deep_width and K.fm_block_ok(self.n_field, self.dim) and deep.is_cuda:
+    if deep.shape[1] == self.deep_width and K.fm_block_ok(self.n_field, self.dim) and deep.is_cuda and \
+        not hasattr(deep, '_er_reg'):
       # FM, the tower input and the regulariser's sum of squares from one pass; one merged gradient back
       fm_fea, deep_in, self._deep_sumsq = E.fm_block(deep, self.n_field, self.dim)
     else:
@@ -91,7 +93,11 @@ class DeepFM(nn.Module):
     # launch: see l2_of() and trainer.FlatDenseOptimizer
     if self.embedding_reg > 0:
       wide, deep = self._emb_outputs
-      deep_sq = self._deep_sumsq[0] if self._deep_sumsq is not None else (deep * deep).sum()
+      if hasattr(deep, '_er_reg'):
+        # sequence-combiner fields: the regulariser covers their un-pooled step embeddings (input_layer.py:316, 369-375)
+        deep_sq = sum((t * t).sum() for t in deep._er_reg)
+      else:
+        deep_sq = self._deep_sumsq[0] if self._deep_sumsq is not None else (deep * deep).sum()
       wide_sq = self._wide_sumsq[0] if self._wide_sumsq is not None else (wide * wide).sum()
       reg = reg + self.embedding_reg * 0.5 * (wide_sq + deep_sq)
     return reg

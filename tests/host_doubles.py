@@ -327,6 +327,12 @@ def install_interactions(patch):
     diag = p[torch.arange(B), torch.arange(B)]
     w = torch.ones(B) if weights is None else weights
     return -(torch.log(diag + 1e-12) * w).mean() / w.mean(), diag.detach()
+  def din_pool(scores, keys, lens):
+    T = keys.shape[1]
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    p = torch.softmax(torch.where(mask, scores, torch.full_like(scores, -2.0**32 + 1)), dim=1)
+    return (p[:, :, None] * keys).sum(1)
+  patch(I, 'din_pool', din_pool)
   patch(I, 'gram', lambda x: torch.bmm(x, x.transpose(1, 2)))
   patch(I, 'matmul_nt', lambda u, i: u @ i.t())
   patch(I, 'din_attention', din_attention)

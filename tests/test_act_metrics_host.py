@@ -425,3 +425,86 @@ def test_activation_names_follow_get_activation_executed():
     if fn is not None and fn.startswith('load_by_path('):       # a dotted path: the function it names
       fn = fn[len('load_by_path('):-1].replace('tf.nn.tanh', 'tf.tanh')
     assert got == fn, (s, got, fn)
+
+
+# ---- sequence_combiner { attention } of a SequenceFeature in a plain feature group (layers/input_layer.py:312-347) ---------
+CFG_SEQC = b'''
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.1 } } } } }
+data_config { batch_size: 4 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "u" input_type: INT64 }
+  input_fields { input_name: "zz" input_type: STRING } input_fields { input_name: "aa" input_type: STRING } }
+feature_config {
+  features { input_names: "zz" feature_type: SequenceFeature embedding_dim: 4 num_buckets: 9 separator: "|" max_seq_len: 3
+             sequence_combiner { attention {} } }
+  features { input_names: "u" feature_type: IdFeature embedding_dim: 4 num_buckets: 9 }
+  features { input_names: "aa" feature_type: SequenceFeature embedding_dim: 4 num_buckets: 9 separator: "|" max_seq_len: 3
+             sequence_combiner { attention {} } embedding_name: "zz_embedding" } }
+model_config { model_class: "MultiTower"
+  feature_groups { group_name: "g" feature_names: ["zz", "u", "aa"] wide_deep: DEEP }
+  multi_tower { towers { input: "g" dnn { hidden_units: [8] } } final_dnn { hidden_units: [4] } }
+  embedding_regularization: 1e-3 }
+'''
+
+
+def seqc_expected(il, feats):
+  """numpy restatement of the group: plain features in config order, then the sequence-combiner features by NAME"""
+  t = il.arenas[4]
+  B = il.batch_size
+
+  def rows(table, ids):
+    off = t.tables[table][0]
+    return t.weight[off:off + 9].detach().cpu().numpy()[ids]
+  u = rows('u_embedding', feats['sparse_fea'].cpu().numpy())
+  pooled, unpooled = {}, {}
+  for name, table in (('aa', 'zz_embedding'), ('zz', 'zz_embedding')):
+    ids, lens = [x.cpu().numpy() for x in feats['seq_fea'][name]]
+    emb = rows(table, ids)                                       # [B, T, D]
+    emb = emb * (np.arange(3)[None, :, None] < lens[:, None, None])   # steps beyond the length look up nothing
+    w = il.attention_modules['g#seqc/' + name].kernel.detach().cpu().numpy()[:, 0]
+    logit = emb @ w
+    logit = np.where(np.arange(3)[None, :] < lens[:, None], logit, np.float32(-2.0 ** 32 + 1))
+    p = np.exp(logit - logit.max(1, keepdims=True))
+    p = p / p.sum(1, keepdims=True)
+    pooled[name], unpooled[name] = (p[:, :, None] * emb).sum(1), emb
+  return u, pooled, unpooled
+
+
+def seqc_batch():
+  return {'sparse_fea': torch.tensor([1, 5, 0, 8]),
+          'seq_fea': {'zz': (torch.tensor([[1, 2, 3], [4, 0, 0], [7, 7, 0], [2, 5, 8]]), torch.tensor([3, 1, 2, 3], dtype=torch.int32)),
+                      'aa': (torch.tensor([[8, 0, 0], [3, 3, 3], [1, 6, 0], [0, 0, 0]]), torch.tensor([1, 3, 2, 1], dtype=torch.int32))}}, \
+      torch.tensor([1.0, 0.0, 0.0, 1.0])
+
+
+def test_attention_sequence_combiner_in_a_plain_group(doubles):
+  cfg = config_util.get_configs_from_pipeline_file(CFG_SEQC)
+  il, model, _ = builder.build_model(cfg, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(2))
+  assert [e[0] for e in il.group_layout['g']] == ['u', 'aa', 'zz']          # concat: plain features, then by name
+  assert il.seqc_order['g'] == ['zz', 'aa']                                  # per-feature list: config order
+  with torch.no_grad():
+    for m in il.attention_modules.values():
+      m.kernel.copy_(torch.randn(m.kernel.shape, generator=torch.Generator().manual_seed(5)))
+      assert not m.bias.requires_grad and float(m.bias.abs().sum()) == 0.0   # use_bias=False
+  feats, labels = seqc_batch()
+  concat, per_feature = il.lookup(feats)['g']
+  u, pooled, unpooled = seqc_expected(il, feats)
+  np.testing.assert_allclose(concat.detach().numpy(), np.concatenate([u, pooled['aa'], pooled['zz']], 1), rtol=1e-5, atol=1e-6)
+  for got, want in zip(per_feature, (u, pooled['zz'], pooled['aa'])):
+    np.testing.assert_allclose(got.detach().numpy(), want, rtol=1e-5, atol=1e-6)
+  # the embedding regulariser covers the looked-up tensors: u and the UN-POOLED sequences
+  reg = concat._er_reg
+  assert len(reg) == 3 and sorted(tuple(r.shape) for r in reg) == [(4, 3, 4), (4, 3, 4), (4, 4)]
+  want_sq = (u ** 2).sum() + (unpooled['aa'] ** 2).sum() + (unpooled['zz'] ** 2).sum()
+  assert float(sum((r * r).sum() for r in reg)) == pytest.approx(float(want_sq), rel=1e-5)
+  il._pending = []
+  # ... and the whole thing trains: table rows, attention vectors and towers move, the loss falls
+  from easyrec_b200.estimator import EasyRecEstimator
+  est = EasyRecEstimator(CFG_SEQC, device='cpu', seed=2)
+  w0 = [m.kernel.detach().clone() for m in est.input_layer.attention_modules.values()]
+  losses = [float(est.trainer.train_step(feats, labels)[0]) for _ in range(30)]
+  assert losses[-1] < losses[0] - 0.05
+  assert all(float((m.kernel - w).abs().max()) > 0 for m, w in zip(est.input_layer.attention_modules.values(), w0))
+  # text_cnn (or a missing combiner) stays refused
+  bad = config_util.get_configs_from_pipeline_file(CFG_SEQC.replace(b'sequence_combiner { attention {} } }', b'}', 1))
+  with pytest.raises(NotImplementedError, match='sequence_combiner'):
+    builder.build_model(bad, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(2))

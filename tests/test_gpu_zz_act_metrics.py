@@ -200,3 +200,33 @@ def test_pipelined_loss_read_returns_every_steps_loss(graph):
   ev = a.evaluate(lambda: _batches(4, 256, 99))
   assert 0.0 <= ev['auc'] <= 1.0 and abs(ev['auc'] - ev['auc_exact']) < 5e-3
   assert ev['max_f1'] > 0.0 and ev['root_mean_squared_error'] == pytest.approx(np.sqrt(ev['mean_squared_error']), rel=1e-6)
+
+
+def test_attention_sequence_combiner_on_the_kernels():
+  """sequence_combiner { attention } of SequenceFeatures in a plain group (layers/input_layer.py:312-347) through the real
+  lookup, er_dense1 and er_din_pool kernels, against the numpy restatement of tests/test_act_metrics_host.py; then one
+  training step moves the attention vectors and the table."""
+  from test_act_metrics_host import CFG_SEQC, seqc_batch, seqc_expected
+  from easyrec_b200 import builder
+  from easyrec_b200.config import config_util
+  from easyrec_b200.input import readers
+  from easyrec_b200.trainer import Trainer
+  cfg = config_util.get_configs_from_pipeline_file(CFG_SEQC)
+  il, model, _ = builder.build_model(cfg, 4, DEV, cpu_generator=torch.Generator().manual_seed(2))
+  with torch.no_grad():
+    for m in il.attention_modules.values():
+      m.kernel.copy_(torch.randn(m.kernel.shape, generator=torch.Generator().manual_seed(5)).to(DEV))
+  feats, labels = seqc_batch()
+  feats, labels = readers.to_device(feats, labels, DEV)
+  concat, per_feature = il.lookup(feats)['g']
+  u, pooled, _ = seqc_expected(il, feats)
+  np.testing.assert_allclose(concat.detach().cpu().numpy(), np.concatenate([u, pooled['aa'], pooled['zz']], 1), rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(per_feature[1].detach().cpu().numpy(), pooled['zz'], rtol=1e-5, atol=1e-6)
+  il._pending = []
+  w0 = [m.kernel.detach().clone() for m in il.attention_modules.values()]
+  t0 = il.arenas[4].weight.clone()
+  tr = Trainer(model, il, 'adagrad', lr=0.1)
+  loss, _ = tr.train_step(feats, labels)
+  assert np.isfinite(float(loss))
+  assert all(float((m.kernel - w).abs().max()) > 0 for m, w in zip(il.attention_modules.values(), w0))
+  assert float((il.arenas[4].weight - t0).abs().max()) > 0
