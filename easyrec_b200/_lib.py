@@ -31,7 +31,7 @@ assert DENSE_SEG_DTYPE.itemsize == 24
 BUCKET_FARM_DECIMAL, BUCKET_MOD, BUCKET_IDENTITY, BUCKET_NONE, BUCKET_ONE_ROW = 0, 1, 2, 3, 4
 COMBINER_SUM, COMBINER_MEAN, COMBINER_SQRTN = 0, 1, 2
 COMBINER_UNIT_WEIGHTS = 16   # flag OR-ed into er_slot_t.combiner: the slot's weights[] entries are all 1.0
-OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM, OPT_ADAM_ROWS = 0, 1, 2, 3
+OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM, OPT_ADAM_ROWS, OPT_MOMENTUM = 0, 1, 2, 3, 4
 # er_act_*: the stateless non-relu activations of utils/activation.py:get_activation
 ACT_GELU, ACT_LEAKY_RELU, ACT_ELU, ACT_SELU, ACT_TANH, ACT_SWISH, ACT_SIGMOID = 1, 2, 3, 4, 5, 6, 7
 MAX_BUFS = 8

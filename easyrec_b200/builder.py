@@ -150,10 +150,9 @@ def optimizer_settings(pipeline_config, index=0):
     # fused row rule on this path are accepted
     raise ValueError('unsupported optimizer in train_config.optimizer_config (have: %s)' % sorted(_OPT_KIND))
   o = getattr(oc, kind)
-  if kind == 'momentum_optimizer' and o.momentum_optimizer_value != 0:
-    # the fused row rule keeps no momentum accumulator: plain SGD is only the same optimizer at momentum 0
-    raise ValueError('momentum_optimizer with momentum_optimizer_value %g is not supported (only 0 = SGD)'
-                     % o.momentum_optimizer_value)
+  momentum = float(o.momentum_optimizer_value) if kind == 'momentum_optimizer' else 0.0
+  if kind == 'momentum_optimizer' and (momentum < 0 or getattr(o, 'use_nesterov', False)):
+    raise ValueError('momentum_optimizer: momentum_optimizer_value %g / use_nesterov are not supported' % momentum)
   lr = o.learning_rate
   which = lr.WhichOneof('learning_rate')
   if which == 'exponential_decay_learning_rate':
@@ -184,7 +183,10 @@ def optimizer_settings(pipeline_config, index=0):
     # builders/optimizer_builder.py:145-215 also knows manual_step / cosine / poly / transformer schedules;
     # they are outside the hot-path scope: refuse instead of training with a made-up rate.
     raise ValueError('unsupported learning_rate schedule: %r' % which)
-  return dict(kind=kind, lr_fn=lr_fn, beta1=getattr(o, 'beta1', 0.9), beta2=getattr(o, 'beta2', 0.999),
+  # tf.train.MomentumOptimizer(momentum > 0) keeps one accumulator per variable (builders/optimizer_builder.py:91-97);
+  # the value travels where Adam's beta1 does (er_opt_t.beta1); momentum 0 is plain SGD, no state
+  return dict(kind=kind, lr_fn=lr_fn, beta1=momentum if momentum > 0 else getattr(o, 'beta1', 0.9),
+              beta2=getattr(o, 'beta2', 0.999), momentum=momentum,
               acc0=getattr(o, 'initial_accumulator_value', 0.1),
               emb_lr_mult=oc.embedding_learning_rate_multiplier
               if oc.HasField('embedding_learning_rate_multiplier') else 1.0)
@@ -311,7 +313,8 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   if generator is None and not str(device).startswith('cuda'):
     generator = cpu_generator   # tables initialised from the caller's seed on a host build too
   il = IL.InputLayer(specs, groups, batch_size, device, wide_output_dim=wide_dim,
-                     embedding_optimizer=_OPT_KIND[opt['kind']], generator=generator,
+                     embedding_optimizer=(_lib.OPT_MOMENTUM if opt.get('momentum', 0.0) > 0 else _OPT_KIND[opt['kind']]),
+                     generator=generator,
                      adagrad_init=opt['acc0'], seq_att_groups=seq_att_groups(mc),
                      shard_n=world if (shard_tables and world > 1) else 1, shard_rank=rank if shard_tables else 0,
                      uniform_tables=keras_tables, dense_generator=cpu_generator,

@@ -19,7 +19,7 @@ import torch
 from easyrec_b200 import _lib
 
 _SLOTS = {_lib.OPT_SGD: (), _lib.OPT_ADAGRAD: ('Adagrad',), _lib.OPT_LAZY_ADAM: ('Adam', 'Adam_1'),
-          _lib.OPT_ADAM_ROWS: ('Adam', 'Adam_1')}
+          _lib.OPT_ADAM_ROWS: ('Adam', 'Adam_1'), _lib.OPT_MOMENTUM: ('Momentum',)}
 
 
 def variable_name(table, scope='input_layer', slot=None):

@@ -730,6 +730,10 @@ __global__ void __launch_bounds__(256)
       s0[j] = m;
       s1[j] = v;
       w -= lr * m / (sqrtf(v) + opt.eps);
+    } else if (opt.kind == ER_OPT_MOMENTUM) {   // ApplyMomentum: accum = accum * momentum + g ; var -= lr * accum
+      const float a = __fadd_rn(__fmul_rn(s0[j], opt.beta1), gr);
+      s0[j] = a;
+      w -= lr * a;
     } else {
       w -= lr * gr;
     }

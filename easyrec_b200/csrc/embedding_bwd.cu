@@ -128,6 +128,13 @@ __device__ __forceinline__ void upd_one(const BwdArgs& a, const Hyper& h, float 
       w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-h.lr_t, s0), __fadd_rn(__fsqrt_rn(s1), a.opt.eps)));
       break;
     }
+    case ER_OPT_MOMENTUM: {
+      // tf.train.MomentumOptimizer (ApplyMomentum / SparseApplyMomentum, use_nesterov false):
+      // accum = accum * momentum + g ; var -= lr * accum   (momentum rides in opt.beta1)
+      s0 = __fadd_rn(__fmul_rn(s0, a.opt.beta1), g);
+      w = __fsub_rn(w, __fmul_rn(h.lr, s0));
+      break;
+    }
     default:  // SGD
       w = __fsub_rn(w, __fmul_rn(h.lr, g));
   }
@@ -1714,7 +1721,7 @@ static int embedding_bwd_impl(float* table, float* state0, float* state1, int64_
   ER_REQUIRE(!row_ptr || seg_ids, "CSR input needs seg_ids (er_csr_from_lens)");
   if (table) {
     const int k = opt->kind;
-    ER_REQUIRE(k == ER_OPT_SGD || k == ER_OPT_ADAGRAD || k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS,
+    ER_REQUIRE(k == ER_OPT_SGD || k == ER_OPT_ADAGRAD || k == ER_OPT_LAZY_ADAM || k == ER_OPT_ADAM_ROWS || k == ER_OPT_MOMENTUM,
                "unknown optimizer kind");
     ER_REQUIRE(k == ER_OPT_SGD || state0, "optimizer state0 missing");
     ER_REQUIRE((k != ER_OPT_LAZY_ADAM && k != ER_OPT_ADAM_ROWS) || state1, "adam needs state1 (v)");

@@ -72,7 +72,7 @@ class Arena(object):
     read-modify-writes per second on B200 (tools/microbench_gather.cu), while the forward gather of
     the 64 B weight half costs the same as from a dense [V, 16] table."""
     assert self.n_rows > 0
-    n_state = {_lib.OPT_SGD: 0, _lib.OPT_ADAGRAD: 1}.get(opt_kind, 2)
+    n_state = {_lib.OPT_SGD: 0, _lib.OPT_ADAGRAD: 1, _lib.OPT_MOMENTUM: 1}.get(opt_kind, 2)
     k = (1 + n_state) if interleave else 1
     self.storage = torch.empty(self.n_rows, k * self.dim, dtype=torch.float32, device=self.device)
     w = self.storage[:, :self.dim]
@@ -102,6 +102,8 @@ class Arena(object):
     self.state0 = self.state1 = None
     if opt_kind == _lib.OPT_ADAGRAD:
       self.state0 = state(0, adagrad_init)
+    elif opt_kind == _lib.OPT_MOMENTUM:
+      self.state0 = state(0, 0.0)      # the momentum accumulator (slot 'Momentum', zeros)
     elif opt_kind in (_lib.OPT_LAZY_ADAM, _lib.OPT_ADAM_ROWS):
       self.state0 = state(0, 0.0)
       self.state1 = state(1, 0.0)

@@ -106,7 +106,8 @@ class EasyRecEstimator(object):
     # (the fused row rule), [1] everything else (model/easy_rec_estimator.py:216-232)
     dense = self._opt.get('dense')
     d = dense or self._opt
-    self.trainer = Trainer(self.model, self.input_layer, _DENSE_KIND[d['kind']], lr_fn=self._opt['lr_fn'],
+    dense_kind = 'momentum' if (d['kind'] == 'momentum_optimizer' and d.get('momentum', 0.0) > 0) else _DENSE_KIND[d['kind']]
+    self.trainer = Trainer(self.model, self.input_layer, dense_kind, lr_fn=self._opt['lr_fn'],
                            use_cuda_graph=use_cuda_graph, world_size=world_size, beta1=self._opt['beta1'],
                            beta2=self._opt['beta2'], adagrad_init=d['acc0'],
                            dense_lr_fn=dense['lr_fn'] if dense else None,

@@ -69,10 +69,12 @@ class FlatDenseOptimizer(object):
     self.n_segs = len(sizes)
     self.max_n = max(sizes)
     self.kind = {'adagrad': _lib.OPT_ADAGRAD, 'adam': _lib.OPT_ADAM_ROWS, 'lazy_adam': _lib.OPT_ADAM_ROWS,
-                 'sgd': _lib.OPT_SGD}[kind]
+                 'sgd': _lib.OPT_SGD, 'momentum': _lib.OPT_MOMENTUM}[kind]
     self.s0 = self.s1 = None
     if self.kind == _lib.OPT_ADAGRAD:
       self.s0 = torch.full((total,), adagrad_init, dtype=torch.float32, device=dev)
+    elif self.kind == _lib.OPT_MOMENTUM:
+      self.s0 = torch.zeros(total, dtype=torch.float32, device=dev)   # accum; the momentum itself is beta1
     elif self.kind == _lib.OPT_ADAM_ROWS:
       self.s0 = torch.zeros(total, dtype=torch.float32, device=dev)
       self.s1 = torch.zeros(total, dtype=torch.float32, device=dev)

@@ -96,11 +96,16 @@ typedef enum er_opt_kind {
   ER_OPT_SGD = 0,
   ER_OPT_ADAGRAD = 1,   /* tf.train.AdagradOptimizer sparse apply            */
   ER_OPT_LAZY_ADAM = 2, /* compat/adam_s.py:185-213                          */
-  ER_OPT_ADAM_ROWS = 3  /* tf.train.AdamOptimizer (builders/optimizer_builder.py:61-66):
+  ER_OPT_ADAM_ROWS = 3, /* tf.train.AdamOptimizer (builders/optimizer_builder.py:61-66):
                            touched rows take the same row rule as lazy Adam in
                            er_embedding_bwd; every other row decays in
                            er_adam_dense_sweep (behaviour documented at
                            compat/adam_s.py:74-81)                            */
+  ER_OPT_MOMENTUM = 4   /* tf.train.MomentumOptimizer (builders/optimizer_builder.py:91-97,
+                           momentum_optimizer_value > 0): accum = accum * momentum + g,
+                           var -= lr * accum on the touched rows (SparseApplyMomentum);
+                           one state array (accum, starts at 0); momentum travels in
+                           er_opt_t.beta1                                        */
 } er_opt_kind;
 
 /* Step-varying hyper-parameters in DEVICE memory (er_opt_t.hyper_dev): the kernels read them at run

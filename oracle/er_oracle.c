@@ -325,6 +325,13 @@ int64_t oracle_embedding_bwd(float* table, float* s0, float* s1, int32_t dim, in
           s1[off + c] = vp;
           float step = (-lr_t * mp) / (sqrtf(vp) + eps);
           table[off + c] = table[off + c] + step;
+        } else if (kind == 4) {   /* tf.train.MomentumOptimizer, use_nesterov false (momentum in beta1):
+                                     accum = accum * momentum + g ; var -= lr * accum */
+          float acc = s0[off + c] * beta1;
+          acc = acc + gg;
+          s0[off + c] = acc;
+          float step = lr * acc;
+          table[off + c] = table[off + c] - step;
         } else {
           float step = lr * gg;
           table[off + c] = table[off + c] - step;

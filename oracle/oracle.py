@@ -109,6 +109,7 @@ def embedding_fwd(table, rows, row_ptr, combiner, weights=None):
 
 
 OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM = 0, 1, 2
+OPT_MOMENTUM = 4   # tf.train.MomentumOptimizer: accum = accum * momentum + g, var -= lr * accum (momentum passed as beta1)
 
 
 def embedding_bwd(table, s0, s1, rows, seg_of, gseg, kind, lr, weights=None, seg_scale=None,

@@ -100,7 +100,7 @@ def install_sparse(patch):
     b = None if state1 is None else np.ascontiguousarray(state1.numpy())
     # the row rule of tf.train.AdamOptimizer on touched rows is the lazy rule (kind 3 -> 2); its dense decay is the
     # adam_dense_sweep double below
-    kind = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_LAZY_ADAM, 3: O.OPT_LAZY_ADAM}[int(opt.kind)]
+    kind = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_LAZY_ADAM, 3: O.OPT_LAZY_ADAM, 4: O.OPT_MOMENTUM}[int(opt.kind)]
     O.embedding_bwd(t, a, b, rows.numpy(), None if seg_ids is None else seg_ids.numpy()[:rows.numel()], gseg,
                     kind, _Hyper(opt).lr, weights=None if weights is None else weights.numpy(),
                     seg_scale=None if seg_scale is None else seg_scale.numpy(), beta1=opt.beta1, beta2=opt.beta2,
@@ -274,7 +274,7 @@ def install_dense(patch):
 
   def apply(self, l2_folded=False, grad_scale=None):   # FlatDenseOptimizer.apply: l2 + TF Adagrad / Adam / SGD over the flat buffer
     scale = self.grad_scale if grad_scale is None else grad_scale
-    assert self.kind in (0, 1, 3), 'this double implements the sgd, adagrad and adam rules'
+    assert self.kind in (0, 1, 3, 4), 'this double implements the sgd, adagrad, adam and momentum rules'
     segs = np.frombuffer((self.segs_nol2_dev if l2_folded else self.segs_dev).numpy().tobytes(),
                          dtype=T._lib.DENSE_SEG_DTYPE)
     keep_reg = self.reg_loss.clone()
@@ -291,6 +291,9 @@ def install_dense(patch):
       elif self.kind == 1:
         self.s0[o:o + n] += g * g
         w -= lr * float(s['lr_mult']) * g / torch.sqrt(self.s0[o:o + n])
+      elif self.kind == 4:   # ApplyMomentum: accum = accum * momentum + g ; var -= lr * accum
+        self.s0[o:o + n] = self.s0[o:o + n] * self.b1 + g
+        w -= lr * float(s['lr_mult']) * self.s0[o:o + n]
       else:   # ApplyAdam: m, v, var -= lr_t*m/(sqrt(v)+eps)
         self.s0[o:o + n] = self.b1 * self.s0[o:o + n] + (1 - self.b1) * g
         self.s1[o:o + n] = self.b2 * self.s1[o:o + n] + (1 - self.b2) * g * g

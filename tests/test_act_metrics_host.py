@@ -508,3 +508,72 @@ def test_attention_sequence_combiner_in_a_plain_group(doubles):
   bad = config_util.get_configs_from_pipeline_file(CFG_SEQC.replace(b'sequence_combiner { attention {} } }', b'}', 1))
   with pytest.raises(NotImplementedError, match='sequence_combiner'):
     builder.build_model(bad, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(2))
+
+
+# ---- momentum_optimizer with momentum > 0 (builders/optimizer_builder.py:54-59 -> tf.train.MomentumOptimizer) -----------
+def test_oracle_momentum_rule_reproduces_tensorflows_own_test_values():
+  """tensorflow/python/training/momentum_test.py testBasic (recalled): lr 2.0, momentum 0.9, grads 0.1 / 0.01 -
+  var0 [1, 2] -> [0.8, 1.8] -> 1 - 0.1*2 - (0.9*0.1 + 0.1)*2; var1 [3, 4] -> 3 - 0.01*2 - (0.9*0.01 + 0.01)*2."""
+  table = np.array([[1.0, 2.0], [3.0, 4.0]], np.float32)
+  acc = np.zeros_like(table)
+  g = np.array([[0.1, 0.1], [0.01, 0.01]], np.float32)
+  rows, seg = np.array([0, 1], np.int64), np.arange(2, dtype=np.int32)
+  O.embedding_bwd(table, acc, None, rows, seg, g, O.OPT_MOMENTUM, 2.0, beta1=0.9)
+  np.testing.assert_allclose(table, [[0.8, 1.8], [2.98, 3.98]], rtol=1e-6)
+  np.testing.assert_allclose(acc, g, rtol=1e-7)
+  O.embedding_bwd(table, acc, None, rows, seg, g, O.OPT_MOMENTUM, 2.0, beta1=0.9)
+  np.testing.assert_allclose(table, [[1.0 - 0.2 - 0.38, 2.0 - 0.2 - 0.38], [3.0 - 0.02 - 0.038, 4.0 - 0.02 - 0.038]], rtol=1e-6)
+  np.testing.assert_allclose(acc, [[0.19, 0.19], [0.019, 0.019]], rtol=1e-6)
+  # sparse apply: duplicates are summed first, rows without a gradient keep weight AND accumulator
+  table = np.arange(8, dtype=np.float32).reshape(4, 2)
+  acc = np.full((4, 2), 0.5, np.float32)
+  O.embedding_bwd(table, acc, None, np.array([2, 0, 2], np.int64), np.arange(3, dtype=np.int32),
+                  np.array([[1, 1], [2, 2], [3, 3]], np.float32), O.OPT_MOMENTUM, 0.1, beta1=0.5)
+  np.testing.assert_allclose(acc, [[2.25, 2.25], [0.5, 0.5], [4.25, 4.25], [0.5, 0.5]])
+  np.testing.assert_allclose(table, [[0 - 0.225, 1 - 0.225], [2, 3], [4 - 0.425, 5 - 0.425], [6, 7]], rtol=1e-6)
+
+
+def test_momentum_optimizer_config_trains_tables_and_towers_with_the_accumulator_rule(doubles):
+  from test_round2_host import CLIP_CFG
+  from easyrec_b200 import _lib
+  from easyrec_b200.estimator import EasyRecEstimator
+  cfg = (CLIP_CFG % b'').replace(b'momentum_optimizer_value: 0.0', b'momentum_optimizer_value: 0.9')
+  est = EasyRecEstimator(cfg, device='cpu', seed=11)
+  il, tr = est.input_layer, est.trainer
+  assert all(a.opt_kind == _lib.OPT_MOMENTUM and a.state0 is not None and a.state1 is None for a in il.arenas.values())
+  assert tr.dense_opt.kind == _lib.OPT_MOMENTUM and float(tr.dense_opt.s0.abs().sum()) == 0.0
+  rng = np.random.default_rng(0)
+  B = 16
+  ids = np.stack([rng.integers(0, 6, B), rng.integers(0, 6, B), rng.integers(0, 1000, B)]).astype(np.int64)
+  feats = {'sparse_fea': torch.from_numpy(ids.reshape(-1)), 'dense_fea': torch.from_numpy(rng.uniform(0, 2, (B, 1)).astype(np.float32))}
+  labels = torch.from_numpy((rng.uniform(size=B) < 0.4).astype(np.float32))
+  # plain SGD twin with the same initial weights: its per-step update IS lr * g, the gradient the momentum run sees at
+  # step 1; at step 1 both runs therefore move identically (accum = g), and the accumulators equal update / lr
+  sgd = EasyRecEstimator(CLIP_CFG % b'', device='cpu', seed=11)
+  p0 = tr.dense_opt.flat_p.clone()
+  t0 = {d: a.weight.clone() for d, a in il.arenas.items()}
+  tr.train_step(feats, labels)
+  sgd.trainer.train_step(feats, labels)
+  torch.testing.assert_close(tr.dense_opt.flat_p, sgd.trainer.dense_opt.flat_p, rtol=1e-6, atol=1e-7)
+  torch.testing.assert_close(tr.dense_opt.s0, (p0 - tr.dense_opt.flat_p) / 0.5, rtol=1e-4, atol=1e-6)
+  seen_untouched = False
+  for d, a in il.arenas.items():
+    torch.testing.assert_close(a.weight, sgd.input_layer.arenas[d].weight, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(a.state0, (t0[d] - a.weight) / 0.5, rtol=1e-4, atol=1e-6)
+    untouched = (a.weight == t0[d]).all(1)
+    seen_untouched = seen_untouched or bool(untouched.any())
+    assert float(a.state0[untouched].abs().sum()) == 0.0                 # rows without a gradient: no state
+  # step 2 on the same batch: var -= lr * (0.9 * accum + g2), i.e. further than the SGD twin by lr * 0.9 * accum
+  acc1 = {d: a.state0.clone() for d, a in il.arenas.items()}
+  w1 = {d: a.weight.clone() for d, a in il.arenas.items()}
+  sgd.model.load_state_dict(est.model.state_dict())     # (same weights before step 2 -> same gradient g2)
+  for d, a in il.arenas.items():
+    sgd.input_layer.arenas[d].weight.copy_(a.weight)
+  sgd.trainer.dense_opt.flat_p.copy_(tr.dense_opt.flat_p)
+  tr.train_step(feats, labels)
+  sgd.trainer.train_step(feats, labels)
+  for d, a in il.arenas.items():
+    g2 = (w1[d] - sgd.input_layer.arenas[d].weight) / 0.5
+    touched = (g2 != 0).any(1)
+    torch.testing.assert_close(a.state0[touched], (acc1[d] * 0.9 + g2)[touched], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(a.weight[touched], (w1[d] - 0.5 * (acc1[d] * 0.9 + g2))[touched], rtol=1e-5, atol=1e-6)

@@ -223,9 +223,10 @@ def test_reference_criteo_config_reads_kaggle_format_lines(tmp_path):
 def test_optimizers_without_a_fused_row_rule_are_refused():
   base = b'train_config { optimizer_config { %s { learning_rate { constant_learning_rate { learning_rate: 0.1 } } %s } } }'
   ok = config_util.get_configs_from_pipeline_file(base % (b'momentum_optimizer', b'momentum_optimizer_value: 0.0'))
-  assert builder.optimizer_settings(ok)['kind'] == 'momentum_optimizer'
-  with pytest.raises(ValueError, match='momentum'):
-    builder.optimizer_settings(config_util.get_configs_from_pipeline_file(base % (b'momentum_optimizer', b'')))  # default 0.9
+  assert builder.optimizer_settings(ok)['kind'] == 'momentum_optimizer' and builder.optimizer_settings(ok)['momentum'] == 0.0
+  # momentum > 0 (the proto default is 0.9) keeps an accumulator per row / parameter: built (ER_OPT_MOMENTUM)
+  mom = builder.optimizer_settings(config_util.get_configs_from_pipeline_file(base % (b'momentum_optimizer', b'')))
+  assert mom['momentum'] == pytest.approx(0.9) and mom['beta1'] == pytest.approx(0.9)
   with pytest.raises(ValueError, match='unsupported optimizer'):
     builder.optimizer_settings(config_util.get_configs_from_pipeline_file(
         b'train_config { optimizer_config { ftrl_optimizer { } } }'))

@@ -230,3 +230,55 @@ def test_attention_sequence_combiner_on_the_kernels():
   assert np.isfinite(float(loss))
   assert all(float((m.kernel - w).abs().max()) > 0 for m, w in zip(il.attention_modules.values(), w0))
   assert float((il.arenas[4].weight - t0).abs().max()) > 0
+
+
+@pytest.mark.parametrize('dim', [16, 6, 1])
+def test_momentum_row_rule_and_dense_apply_track_the_oracle(dim):
+  """momentum_optimizer with momentum > 0 (tf.train.MomentumOptimizer): K7's fused row update with the accumulator
+  rule against the oracle over three steps (duplicated rows, dropped lookups, rows that appear only once keep their
+  accumulator afterwards), and the flat dense apply against numpy."""
+  from easyrec_b200 import _lib, embedding as E
+  rng = np.random.default_rng(dim)
+  V, B, F = 2000, 160, 3
+  arena = E.Arena(dim, DEV)
+  arena.add_table('t', V)
+  arena.materialize(_lib.OPT_MOMENTUM, generator=torch.Generator(device=DEV).manual_seed(1))
+  assert arena.state0 is not None and arena.state1 is None and float(arena.state0.abs().sum()) == 0.0
+  table = arena.weight.cpu().numpy().copy()
+  acc = np.zeros((V, dim), np.float32)
+  stride = F * dim
+  recs = [dict(num_buckets=V, row_offset=0, seg_begin=f * B, n_seg=B, bucket_mode=3, combiner=0, out_buf=0,
+               out_stride=stride, out_col=f * dim) for f in range(F)]
+  sd = K.slots_to_device(K.make_slots(recs), DEV)
+  pad = (4 - stride % 4) % 4 if dim % 4 == 0 else 0
+  ws = K.bwd_workspace(B * F, DEV, dim)
+  hyper = K.StepHyper(DEV, 0.9, 0.999)     # beta1 carries the momentum
+  for step in range(3):
+    rows = rng.integers(0, V if step == 0 else 50, B * F).astype(np.int64)
+    rows[rng.integers(0, B * F, 5)] = -1
+    gout = rng.normal(0, 0.1, (B, stride + pad)).astype(np.float32)
+    lr = 0.05 * (0.8 ** step)
+    hyper.set(lr, step, grad_scale=0.5)
+    opt = hyper.opt(_lib.OPT_MOMENTUM)
+    K.embedding_bwd(arena.weight, arena.state0, None, dim, torch.from_numpy(rows).to(DEV), sd, F, B * F,
+                    [torch.from_numpy(gout).to(DEV)], opt, ws)
+    gseg = np.concatenate([gout[:, f * dim:(f + 1) * dim] for f in range(F)], 0)
+    O.embedding_bwd(table, acc, None, rows, np.arange(B * F, dtype=np.int32), gseg, O.OPT_MOMENTUM, lr, beta1=0.9,
+                    grad_scale=0.5)
+    np.testing.assert_allclose(arena.weight.cpu().numpy(), table, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(arena.state0.cpu().numpy(), acc, rtol=0, atol=1e-6)
+  # dense apply: one flat buffer, l2 folded in by the kernel
+  import torch.nn as nn
+  from easyrec_b200.trainer import FlatDenseOptimizer
+  p = nn.Parameter(torch.from_numpy(rng.normal(size=(37, 5)).astype(np.float32)).to(DEV))
+  fo = FlatDenseOptimizer([('w/kernel', p)], 'momentum', lr=0.1, beta1=0.9, l2_of=lambda n, q: 0.01)
+  w, a = p.detach().cpu().numpy().copy(), np.zeros((37, 5), np.float32)
+  for step in range(3):
+    g = rng.normal(size=(37, 5)).astype(np.float32)
+    fo.grad_views[0].copy_(torch.from_numpy(g).to(DEV))
+    fo.hyper.set(0.1, step)
+    fo.apply()
+    gg = g + np.float32(0.01) * w
+    a = a * np.float32(0.9) + gg
+    w = w - np.float32(0.1) * a
+    np.testing.assert_allclose(p.detach().cpu().numpy(), w, rtol=1e-5, atol=1e-6)
