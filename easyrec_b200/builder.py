@@ -30,7 +30,6 @@ def feature_specs(pipeline_config, packed_mod=False, default_seq_len=50):
         ('kv_separator on a feature that is not a TagFeature', fc.HasField('kv_separator') and ftype_name(fc) != 'TagFeature'),
         ('seq_multi_sep on a feature that is not a SequenceFeature', fc.HasField('seq_multi_sep') and ftype_name(fc) != 'SequenceFeature'),
         ('normalizer_fn on a feature that is not a RawFeature', fc.HasField('normalizer_fn') and ftype_name(fc) != 'RawFeature'),
-        ('shared_names', len(fc.shared_names) > 0),
         ('sub_feature_type RawFeature', fc.HasField('sub_feature_type') and fc.sub_feature_type != fc.IdFeature)) if on]
     if unsupported:
       raise NotImplementedError('feature %s: %s is outside the hot-path scope' % (name, ', '.join(unsupported)))

@@ -30,7 +30,60 @@ def get_configs_from_pipeline_file(pipeline_config_path, schema=None):
   schema = schema or proto_loader.default_schema()
   cfg = schema.EasyRecConfig()
   text_format.Merge(text, cfg, allow_unknown_field=not _is_full_schema(schema))
-  return cfg
+  return auto_expand_share_feature_configs(cfg)
+
+
+def auto_expand_names(input_name):
+  """field[1-3] -> [field1, field2, field3]  (utils/config_util.py:116-135)."""
+  m = re.match(r'([a-zA-Z_]+)\[([0-9]+)-([0-9]+)\]', input_name)
+  if m:
+    return ['%s%d' % (m.group(1), t) for t in range(int(m.group(2)), int(m.group(3)) + 1)]
+  return [input_name]
+
+
+def auto_expand_share_feature_configs(pipeline_config):
+  """utils/config_util.py:81-113: a FeatureConfig with `shared_names` stands for one more feature per shared name - a
+  copy of the config (without its own input_names and shared_names) reading that input; the copies are appended to the
+  feature list, the original keeps its own input.  Patterns in shared_names expand when
+  data_config.auto_expand_input_fields is set."""
+  feats = pipeline_config.feature_configs if len(pipeline_config.feature_configs) > 0 else pipeline_config.feature_config.features
+  expand = bool(getattr(pipeline_config.data_config, 'auto_expand_input_fields', False))
+  new = []
+  for fc in list(feats):
+    if len(fc.shared_names) == 0:
+      continue
+    names = []
+    for n in fc.shared_names:
+      names.extend(auto_expand_names(n) if expand else [n])
+    del fc.shared_names[:]
+    for n in names:
+      c = type(fc)()
+      c.CopyFrom(fc)
+      del c.input_names[:]
+      c.input_names.append(n)
+      new.append(c)
+  for c in new:
+    feats.add().CopyFrom(c)
+  # data_config.input_fields named by a pattern stand for one field per expanded name (input/input.py:62-75)
+  dc = pipeline_config.data_config
+  if expand and any(len(auto_expand_names(f.input_name)) > 1 for f in dc.input_fields):
+    fields = [type(f)() for f in dc.input_fields]
+    for dst, src in zip(fields, dc.input_fields):
+      dst.CopyFrom(src)
+    del dc.input_fields[:]
+    for f in fields:
+      for n in auto_expand_names(f.input_name):
+        g = dc.input_fields.add()
+        g.CopyFrom(f)
+        g.input_name = n
+  # feature_groups name their features with the same patterns: FeatureGroup._auto_expand_feature_name always expands
+  # them (feature_column/feature_group.py:46-60)
+  for g in pipeline_config.model_config.feature_groups:
+    names = [x for n in g.feature_names for x in auto_expand_names(n)]
+    if names != list(g.feature_names):
+      del g.feature_names[:]
+      g.feature_names.extend(names)
+  return pipeline_config
 
 
 def unknown_fields(pipeline_config_path, schema=None):

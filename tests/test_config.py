@@ -446,3 +446,28 @@ def test_no_model_or_optimizer_field_is_silently_dropped_for_configs_that_build(
       dropped[os.path.basename(p)] = bad
   assert built >= 40
   assert not dropped, dropped
+
+
+def test_shared_names_and_name_patterns_expand_like_the_reference():
+  """utils/config_util.py:81-135 auto_expand_share_feature_configs / auto_expand_names and
+  feature_column/feature_group.py:46-60: a FeatureConfig with shared_names stands for one more feature per shared name
+  (same settings, its own input), and `field[1-3]` in a feature group names field1, field2, field3."""
+  cfg = config_util.get_configs_from_pipeline_file(b"""
+data_config { batch_size: 8 input_type: CSVInput label_fields: "label" auto_expand_input_fields: true
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "field1" input_type: INT64 }
+  input_fields { input_name: "field2" input_type: INT64 } input_fields { input_name: "field3" input_type: INT64 } }
+feature_config { features { input_names: "field1" shared_names: "field[2-3]" feature_type: IdFeature embedding_dim: 8
+                            hash_bucket_size: 100 embedding_name: "shared" } }
+model_config { model_class: "DeepFM"
+  feature_groups { group_name: "deep" feature_names: "field[1-3]" wide_deep: DEEP }
+  feature_groups { group_name: "wide" feature_names: ["field1", "field[2-3]"] wide_deep: WIDE }
+  deepfm { dnn { hidden_units: [8] } final_dnn { hidden_units: [4] } } }
+""")
+  feats = config_util.get_feature_configs(cfg)
+  assert [list(f.input_names) for f in feats] == [['field1'], ['field2'], ['field3']]
+  assert all(len(f.shared_names) == 0 and f.embedding_name == 'shared' and f.hash_bucket_size == 100 for f in feats)
+  assert list(cfg.model_config.feature_groups[0].feature_names) == ['field1', 'field2', 'field3']
+  assert list(cfg.model_config.feature_groups[1].feature_names) == ['field1', 'field2', 'field3']
+  assert config_util.auto_expand_names('c[9-11]') == ['c9', 'c10', 'c11'] and config_util.auto_expand_names('plain') == ['plain']
+  il, _, _ = builder.build_model(cfg, 8, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  assert il.sparse_names == ['field1', 'field2', 'field3'] and list(il.arenas[8].tables) == ['shared']
