@@ -11,3 +11,5 @@ for k in bk_fused_kernel fwd_single_kernel bk_place_kernel gemm_tf32x3_kernel; d
       -o gpurun_out/r02_$k $B > gpurun_out/ncu_$k.log 2>&1
 done
 ls -la gpurun_out/r02_*.ncu-rep
+# kernels added after round 2's lease: event timings (no graph, L2 flushed between launches)
+timeout 300 python tools/bench_small_kernels.py > gpurun_out/r02_small_kernels.txt 2>&1
