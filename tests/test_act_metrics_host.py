@@ -577,3 +577,20 @@ def test_momentum_optimizer_config_trains_tables_and_towers_with_the_accumulator
     touched = (g2 != 0).any(1)
     torch.testing.assert_close(a.state0[touched], (acc1[d] * 0.9 + g2)[touched], rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(a.weight[touched], (w1[d] - 0.5 * (acc1[d] * 0.9 + g2))[touched], rtol=1e-5, atol=1e-6)
+
+
+# ---- the reference's own metric tests (easy_rec/python/test/eval_metric_test.py) --------------------------------------
+def test_reference_eval_metric_known_answers(doubles):
+  """test_max_f1 (:21-33): labels [1,0,0,1], predictions [0.9,0.8,0.7,0.6] -> 2/3; test_gauc / test_session_auc
+  (:46-103): two users fed in two updates -> 0.5833333 / 0.5925926 / 0.6 by reduction; all-negative labels -> 0."""
+  lab, pred = np.array([1, 0, 0, 1], np.float32), np.array([0.9, 0.8, 0.7, 0.6], np.float32)
+  assert O.max_f1(lab, pred) == pytest.approx(2.0 / 3, abs=1e-6)
+  acc = M.ConfusionAtThresholds(200, 'cpu')
+  acc.update(torch.from_numpy(pred), torch.from_numpy(lab))
+  assert acc.max_f1() == pytest.approx(2.0 / 3, abs=1e-6)
+  labels = np.array([1, 0, 1, 1, 0, 1, 0, 0, 1])
+  probs = np.array([0.9, 0.8, 0.7, 0.6, 0.5, 0.9, 0.8, 0.7, 0.6], np.float32)
+  uids = np.array([1, 1, 1, 1, 1, 2, 2, 2, 2])
+  for reduction, want in (('mean', 0.5833333), ('mean_by_sample_num', 0.5925926), ('mean_by_positive_num', 0.6)):
+    assert float(M.gauc(labels, probs, uids, reduction)) == pytest.approx(want, abs=1e-6)
+  assert float(M.gauc(np.zeros(4), pred, np.ones(4))) == 0.0

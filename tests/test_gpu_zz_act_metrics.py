@@ -85,6 +85,13 @@ def test_tensorflows_auc_known_answers_on_the_device():
     assert acc.auc() == pytest.approx(want, abs=1e-5)
 
 
+def test_reference_max_f1_known_answer_on_the_device():
+  """easy_rec/python/test/eval_metric_test.py:21-33: labels [1,0,0,1], predictions [0.9,0.8,0.7,0.6] -> 2/3"""
+  acc = M.ConfusionAtThresholds(200, DEV)
+  acc.update(torch.tensor([0.9, 0.8, 0.7, 0.6], device=DEV), torch.tensor([1.0, 0.0, 0.0, 1.0], device=DEV))
+  assert acc.max_f1() == pytest.approx(2.0 / 3, abs=1e-6)
+
+
 def test_invalid_metric_arguments_fail_loudly():
   from easyrec_b200 import _lib
   p = torch.zeros(4, device=DEV)
