@@ -485,3 +485,50 @@ def test_chunked_native_parsing_equals_batch_by_batch(tmp_path, last_newline, mo
   assert len(native) == len(python) == 2 * chunk + 3
   for a, b in zip(native, python):
     _same(a, b)
+
+
+def test_embed_test_seq_multi_embed_verbatim(tmp_path):
+  """easy_rec/python/test/embed_test.py:88-151 with its own separators (control characters \\x03 between steps, \\x04
+  between the values of a step), table and inputs: '0^D1^C1^D2' and '1^D3^C2^D4^D3^C0' -> hist[0] = [[2,3],[4,5]],
+  hist[1] = [[5,6],[7,8],[1,2]], lengths 2 and 3 - through the native parser and the input layer (oracle-backed kernels)."""
+  import host_doubles
+  cfg = config_util.get_configs_from_pipeline_file(
+      b'data_config { batch_size: 2 input_type: CSVInput separator: "," label_fields: "clk"\n'
+      b'  input_fields { input_name: "clk" input_type: INT32 default_val: "0" }\n'
+      b'  input_fields { input_name: "key" input_type: INT64 }\n'
+      b'  input_fields { input_name: "field1" input_type: STRING default_val: "0" } }\n'
+      b'feature_config {\n'
+      b'  features { input_names: "key" feature_type: IdFeature embedding_dim: 2 num_buckets: 5 embedding_name: "field1_embedding" }\n'
+      b'  features { input_names: "field1" feature_type: SequenceFeature separator: "\x03" seq_multi_sep: "\x04"\n'
+      b'             embedding_dim: 2 num_buckets: 5 combiner: "mean" max_seq_len: 3 } }\n'
+      b'model_config { model_class: "MultiTowerDIN"\n'
+      b'  seq_att_groups { group_name: "din" seq_att_map { key: "key" hist_seq: "field1" } }\n'
+      b'  feature_groups { group_name: "u" feature_names: ["key"] wide_deep: DEEP }\n'
+      b'  multi_tower { towers { input: "u" dnn { hidden_units: [4] } } din_towers { input: "din" dnn { hidden_units: [4, 1] } }\n'
+      b'                final_dnn { hidden_units: [4] } } }\n')
+  fc = config_util.get_feature_configs(cfg)[1]
+  assert fc.separator == '\x03' and fc.seq_multi_sep == '\x04'
+  il, _, _ = builder.build_model(cfg, 2, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  open(tmp_path / 'e.csv', 'wb').write(b'0,0,0\x041\x031\x042\n0,1,1\x043\x032\x044\x043\x030\n')
+  import pytest as _pytest
+  mp = _pytest.MonkeyPatch()
+  try:
+    host_doubles.install_sparse(mp.setattr)
+    for engine in ('native', 'python'):
+      (feats, _), = list(readers.CSVInput(cfg, il, str(tmp_path / 'e.csv'), engine=engine))
+      ids, lens, steps = feats['seq_fea']['field1']
+      assert ids.tolist() == [0, 1, 1, 2, 1, 3, 2, 4, 3, 0] and lens.tolist() == [2, 3] and steps.tolist() == [2, 2, 0, 2, 3, 1]
+      t = il.arenas[2]
+      hist_tables = [n for n in t.tables if 'field1' in n]
+      assert hist_tables, list(t.tables)
+      with torch.no_grad():
+        for n in hist_tables:     # (the history's table lives in the sequence group's own variable scope)
+          off = t.tables[n][0]
+          t.weight[off:off + 5].copy_(torch.tensor([[1., 2.], [3., 4.], [5., 6.], [7., 8.], [9., 10.]]))
+      il.lookup(feats)
+      so = il.seq_outputs['din']
+      want = torch.tensor([[[2., 3.], [4., 5.], [0., 0.]], [[5., 6.], [7., 8.], [1., 2.]]])
+      assert torch.allclose(so['hist_seq_emb'], want) and so['hist_seq_len'].tolist() == [2, 3]
+      il._pending = []
+  finally:
+    mp.undo()
