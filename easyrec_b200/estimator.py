@@ -50,9 +50,13 @@ class _LossReader(object):
     self.k = 0
     self.value = None
     if self.cuda:
-      self.buf = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-      self.ev = [torch.cuda.Event() for _ in range(2)]
-      self.pending = [False, False]
+      try:
+        self.buf = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.ev = [torch.cuda.Event() for _ in range(2)]
+        self.pending = [False, False]
+      except RuntimeError as e:   # no page-locked memory to be had: read every loss with a synchronisation instead
+        logging.warning('loss reader falls back to synchronous reads: %s', e)
+        self.cuda = False
 
   def _take(self, j):
     if self.pending[j]:
