@@ -67,26 +67,22 @@ def _batch(cfg_bytes, B, lines, tmp):
   return feats, labels
 
 
-def _worker(rank, port, ret, world, tmp):
-  os.environ['MASTER_ADDR'] = '127.0.0.1'
-  os.environ['MASTER_PORT'] = str(port)
+def _worker(rank, port, ret, world, tmp, cuda=False):
   sys.path.insert(0, HERE)
-  dist.init_process_group('gloo', rank=rank, world_size=world)
-  import host_doubles
-  host_doubles.install_all()
-  torch.use_deterministic_algorithms(True)
-  torch.utils.deterministic.fill_uninitialized_memory = True
+  from test_dp_clip_gloo import _setup
+  dev = _setup(rank, port, world, cuda)
   from easyrec_b200.estimator import EasyRecEstimator
+  from easyrec_b200.input import readers
   B = 12
   parts = [_lines(B, 50 + r) for r in range(world)]
-  dp = EasyRecEstimator(CFG % B, device='cpu', seed=3, world_size=world, rank=rank, embedding_parallel=False)
-  one = EasyRecEstimator(CFG % (B * world), device='cpu', seed=3)          # the same model on the concatenated batch
+  dp = EasyRecEstimator(CFG % B, device=dev, seed=3, world_size=world, rank=rank, embedding_parallel=False)
+  one = EasyRecEstimator(CFG % (B * world), device=dev, seed=3)          # the same model on the concatenated batch
   for d, a in dp.input_layer.arenas.items():
     one.input_layer.arenas[d].storage.copy_(a.storage)
   one.model.load_state_dict(dp.model.state_dict())
   one.trainer.dense_opt.flat_p.copy_(dp.trainer.dense_opt.flat_p)
-  mine = _batch(CFG % B, B, parts[rank], tmp)
-  whole = _batch(CFG % (B * world), B * world, sum(parts, []), tmp)
+  mine = readers.to_device(*_batch(CFG % B, B, parts[rank], tmp), dev)
+  whole = readers.to_device(*_batch(CFG % (B * world), B * world, sum(parts, []), tmp), dev)
   for step in range(3):
     dp.trainer.train_step(*mine)
     one.trainer.train_step(*whole)
@@ -96,6 +92,9 @@ def _worker(rank, port, ret, world, tmp):
   dworst = float((dp.trainer.dense_opt.flat_p - one.trainer.dense_opt.flat_p).abs().max())
   ret[rank] = (worst, dworst, float(sum(a.storage.double().sum() for a in dp.input_layer.arenas.values())),
                float(dp.trainer.dense_opt.flat_p.double().sum()))
+  if cuda:
+    dist.barrier()
+    os._exit(0)
   dist.destroy_process_group()
 
 
