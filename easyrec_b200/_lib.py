@@ -78,6 +78,8 @@ SIGNATURES = {
     'er_gemm_small_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64]),
     'er_gemm_small': (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_sz,
                               c_vp]),
+    'er_dice_fwd': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'er_dice_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'er_act_fwd': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'er_act_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     'er_auc_hist': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),

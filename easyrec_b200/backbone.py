@@ -100,7 +100,6 @@ class MLP(nn.Module):
     if conf.use_bn_after_activation:
       raise NotImplementedError('MLP.use_bn_after_activation')
     # activation / final_activation by name (layers/keras/activation.py:97-110 -> utils/activation.py:get_activation);
-    # dice carries its own batch norm and learned alpha and is not built
     # (a pb-message MLP reads the proto default 'relu' for an unset final_activation: Parameter.get_or_default returns a
     # non-empty string field as is, layers/utils.py:224-227)
     kinds = [L.activation_kind(conf.activation), L.activation_kind(conf.final_activation)]
@@ -120,7 +119,7 @@ class MLP(nn.Module):
       bn = conf.use_final_bn if last else conf.use_bn
       kind = kinds[1] if last else kinds[0]
       lay = L.DenseLayer(n_in, u, bn, kind == 'relu', generator)
-      self.acts.append(L.Activation(kind) if kind not in (None, 'relu') else nn.Identity())
+      self.acts.append(L._act_module(kind, u))
       lim = math.sqrt(6.0 / n_in)   # he_uniform
       with torch.no_grad():
         lay.kernel.uniform_(-lim, lim, generator=generator)

@@ -643,6 +643,47 @@ static int act_dispatch(const float* x, const float* gy, int64_t n, int kind, fl
 }
 }  // namespace er
 
+namespace er {
+__global__ void __launch_bounds__(256)
+    dice_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xn, const float* __restrict__ alpha,
+                    int64_t n, int units, float* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = dice_value(x[i], xn[i], alpha[i % units]);
+}
+__global__ void __launch_bounds__(256)
+    dice_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xn, const float* __restrict__ alpha,
+                    const float* __restrict__ gy, int64_t n, int units, float* __restrict__ gx_direct,
+                    float* __restrict__ gxn, float* __restrict__ galpha_terms) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dice_grads(x[i], xn[i], alpha[i % units], gy[i], gx_direct + i, gxn + i, galpha_terms + i);
+}
+}  // namespace er
+
+extern "C" int er_dice_fwd(const float* x, const float* xn, const float* alpha, int64_t batch, int32_t units, float* y,
+                           er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && xn && alpha && y, "null argument");
+  ER_REQUIRE(batch > 0 && units > 0, "bad shape");
+  const int64_t n = batch * units;
+  dice_fwd_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, as_stream(stream)>>>(x, xn, alpha, n, (int)units, y);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
+extern "C" int er_dice_bwd(const float* x, const float* xn, const float* alpha, const float* gy, int64_t batch,
+                           int32_t units, float* gx_direct, float* gxn, float* galpha_terms, er_stream_t stream) {
+  using namespace er;
+  ER_REQUIRE(x && xn && alpha && gy && gx_direct && gxn && galpha_terms, "null argument");
+  ER_REQUIRE(batch > 0 && units > 0, "bad shape");
+  const int64_t n = batch * units;
+  dice_bwd_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, as_stream(stream)>>>(x, xn, alpha, gy, n, (int)units, gx_direct, gxn,
+                                                                        galpha_terms);
+  count_launches(1);
+  ER_CUDA_LAUNCH_CHECK();
+  return ER_OK;
+}
+
 extern "C" int er_act_fwd(const float* x, int64_t n, int kind, float* y, er_stream_t stream) {
   using namespace er;
   ER_REQUIRE(x && y, "null argument");

@@ -52,6 +52,22 @@ ER_HD float act_slope(float x) {
 }
 
 
+// ---- dice (utils/activation.py:13-43, layers/keras/activation.py:24-73): the data-adaptive activation of DIN ------------
+// p = sigmoid(xn), xn = batch_norm(x) without centre / scale (epsilon 1e-9);  y = alpha * (1 - p) * x + p * x.
+// The normalisation itself runs on the batch-norm kernels; these are the gate and its three gradient terms.
+ER_HD float dice_value(float x, float xn, float alpha) {
+  const float p = 1.0f / (1.0f + expf(-xn));
+  return alpha * (1.0f - p) * x + p * x;
+}
+// gx_direct: through the explicit x factors; gxn: into the normalised input (continues through the batch-norm
+// backward); galpha: this element's term of d/d alpha[c] (summed over the rows by the caller)
+ER_HD void dice_grads(float x, float xn, float alpha, float gy, float* gx_direct, float* gxn, float* galpha) {
+  const float p = 1.0f / (1.0f + expf(-xn));
+  *gx_direct = gy * (alpha * (1.0f - p) + p);
+  *gxn = gy * x * (1.0f - alpha) * p * (1.0f - p);
+  *galpha = gy * x * (1.0f - p);
+}
+
 // ---- tf.metrics.auc (model/rank_model.py:360-373) -------------------------------------------------------------------
 // bin of a prediction = number of thresholds strictly below it (math_ops.greater(pred, thr)); thr ascending; a NaN
 // prediction exceeds none.

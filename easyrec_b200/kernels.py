@@ -135,6 +135,26 @@ def act_bwd(x, gy, kind):
   return gx
 
 
+def dice_fwd(x, xn, alpha):
+  """er_dice_fwd: alpha * (1 - sigmoid(xn)) * x + sigmoid(xn) * x over [batch, units]."""
+  for t, nm in ((x, 'x'), (xn, 'xn'), (alpha, 'alpha')):
+    _chk(t, torch.float32, nm)
+  y = torch.empty_like(x)
+  _lib.check(_lib.load().er_dice_fwd(_p(x), _p(xn), _p(alpha), x.shape[0], x.shape[1], _p(y), _stream()), 'er_dice_fwd')
+  return y
+
+
+def dice_bwd(x, xn, alpha, gy):
+  """er_dice_bwd -> (gx_direct, gxn, galpha_terms), each [batch, units]."""
+  gy = gy.contiguous()
+  for t, nm in ((x, 'x'), (xn, 'xn'), (alpha, 'alpha'), (gy, 'gy')):
+    _chk(t, torch.float32, nm)
+  gd, gn, ga = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+  _lib.check(_lib.load().er_dice_bwd(_p(x), _p(xn), _p(alpha), _p(gy), x.shape[0], x.shape[1], _p(gd), _p(gn), _p(ga),
+                                     _stream()), 'er_dice_bwd')
+  return gd, gn, ga
+
+
 def auc_hist(probs, labels, thresholds, hist):
   """er_auc_hist: one batch into the uint64 confusion histograms behind tf.metrics.auc / max_f1 (hist: int64 tensor of
   2 * (T + 1) counters reinterpreted as uint64; they never approach 2^63)."""

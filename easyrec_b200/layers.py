@@ -231,9 +231,20 @@ def activation_kind(name):
     return None
   if n == 'relu':
     return 'relu'
+  if n == 'dice':
+    return 'dice'
   if n in K.ACT_KINDS:
     return K.ACT_KINDS[n]
-  raise NotImplementedError('activation %r (built: relu, linear, %s)' % (name, ', '.join(sorted(K.ACT_KINDS))))
+  raise NotImplementedError('activation %r (built: relu, linear, dice, %s)' % (name, ', '.join(sorted(K.ACT_KINDS))))
+
+
+def _act_module(kind, units):
+  """the module that follows a layer's (linear) dense / batch-norm stage: nothing for relu (fused there) and linear"""
+  if kind in (None, 'relu'):
+    return nn.Identity()
+  if kind == 'dice':
+    return Dice(units)
+  return Activation(kind)
 
 
 class _ActFn(torch.autograd.Function):
@@ -263,6 +274,58 @@ class Activation(nn.Module):
 
   def forward(self, x):
     return _ActFn.apply(x, self.kind)
+
+
+DICE_EPS = 1e-9
+
+
+class _DiceFn(torch.autograd.Function):
+  """y = alpha (1 - p) x + p x, p = sigmoid(batch_norm(x)) - the normalisation on the batch-norm kernels (unit gamma, zero
+  beta, epsilon 1e-9), the gate and its gradient terms on er_dice_*; d alpha is a column sum of the per-element terms."""
+
+  @staticmethod
+  def forward(ctx, x, alpha, ones, zeros, moving_mean, moving_var, training, ws):
+    x = x.contiguous()
+    xn, mean, rstd = K.bias_bn_act_fwd(x, None, ones, zeros, moving_mean, moving_var, DICE_EPS, BN_MOMENTUM, training,
+                                       False, ws)
+    ctx.ws = ws
+    ctx.save_for_backward(x, xn, alpha, ones, mean, rstd)
+    return K.dice_fwd(x, xn, alpha.contiguous())
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, xn, alpha, ones, mean, rstd = ctx.saved_tensors
+    gd, gn, ga = K.dice_bwd(x, xn, alpha.contiguous(), gy.contiguous())
+    gz, _, _, _ = K.bias_bn_act_bwd(x, None, ones, xn, gn, mean, rstd, False, ctx.ws)
+    return gd + gz, ga.sum(dim=0), None, None, None, None, None, None
+
+
+class Dice(nn.Module):
+  """dice(x) = alphas * (1 - p) * x + p * x, p = sigmoid(batch_normalization(x, center=False, scale=False, epsilon=1e-9))
+  (utils/activation.py:13-43; keras layers/keras/activation.py:24-73): alphas start at 0, the normalisation keeps its own
+  moving statistics (momentum 0.99) for evaluation."""
+
+  def __init__(self, units):
+    super().__init__()
+    self.units = units
+    self.alphas = nn.Parameter(torch.zeros(units))
+    self.register_buffer('ones', torch.ones(units))
+    self.register_buffer('zeros', torch.zeros(units))
+    self.register_buffer('moving_mean', torch.zeros(units))
+    self.register_buffer('moving_var', torch.ones(units))
+    self._ws = None
+    self._ws_batch = -1
+
+  def forward(self, x):
+    if self._ws is None or self._ws_batch != x.shape[0] or self._ws.device != x.device:
+      self._ws = K.dense_workspace(x.shape[0], self.units, x.device)
+      self._ws_batch = x.shape[0]
+    if self.training:
+      return _DiceFn.apply(x, self.alphas, self.ones, self.zeros, self.moving_mean, self.moving_var, True, self._ws)
+    x = x.contiguous()
+    xn, _, _ = K.bias_bn_act_fwd(x, None, self.ones, self.zeros, self.moving_mean, self.moving_var, DICE_EPS, BN_MOMENTUM,
+                                 False, False, self._ws)
+    return K.dice_fwd(x, xn, self.alphas.detach().contiguous())
 
 
 class Units(list):
@@ -313,7 +376,7 @@ class DNN(nn.Module):
       act = i + 1 < n or not last_layer_no_activation
       # relu rides in the dense / batch-norm epilogue; any other activation is an elementwise pass over its linear form
       self.layers.append(DenseLayer(n_in, u, bn, act and kind == 'relu', generator))
-      self.acts.append(Activation(kind) if act and kind not in (None, 'relu') else nn.Identity())
+      self.acts.append(_act_module(kind, u) if act else nn.Identity())
       # dropout follows the activation of EVERY layer, the last one included (layers/dnn.py:77-82)
       self.dropouts.append(Dropout(drop[i]) if drop and drop[i] > 0 else nn.Identity())
       n_in = u

@@ -364,7 +364,7 @@ int er_dropout(const float* x, int64_t n, float rate, uint64_t seed, const int64
 /* The stateless non-relu activations of get_activation (utils/activation.py:66-118), applied by DNN.__call__
  * (layers/dnn.py:70-73) and the keras MLP block (layers/keras/blocks.py:82) after the dense / batch-norm stage:
  * y = f(x) elementwise; the backward pass recomputes f'(x) from the pre-activation: gx = gy * f'(x).  relu stays fused
- * in er_bias_bn_act_*; 'linear' is no call at all; dice (learned alpha over a batch norm) is not built. */
+ * in er_bias_bn_act_*; 'linear' is no call at all; dice (learned alpha over a batch norm): er_dice_* below. */
 enum {
   ER_ACT_GELU = 1,       /* x * 0.5 * (1 + tanh(sqrt(2/pi) * (x + 0.044715 x^3)))  (activation.py:46-60) */
   ER_ACT_LEAKY_RELU = 2, /* tf.nn.leaky_relu, alpha 0.2 (also 'prelu' without arguments, activation.py:98-101) */
@@ -376,6 +376,17 @@ enum {
 };
 int er_act_fwd(const float* x, int64_t n, int kind, float* y, er_stream_t stream);
 int er_act_bwd(const float* x, const float* gy, int64_t n, int kind, float* gx, er_stream_t stream);
+
+/* dice (utils/activation.py:13-43; layers/keras/activation.py:24-73), the data-adaptive activation of DIN:
+ * y = alpha[c] * (1 - p) * x + p * x with p = sigmoid(xn), xn = batch_norm(x) WITHOUT centre / scale and epsilon 1e-9
+ * (the caller runs it with er_bias_bn_act_fwd on unit gamma / zero beta; moving statistics, momentum 0.99).  x, xn, y:
+ * [batch, units]; alpha [units].  Backward: gx_direct = gy * (alpha (1 - p) + p), gxn = gy * x * (1 - alpha) * p (1 - p)
+ * (the caller continues it through er_bias_bn_act_bwd and adds the result to gx_direct), galpha_terms[b, c] = gy * x *
+ * (1 - p) (summed over b by the caller). */
+int er_dice_fwd(const float* x, const float* xn, const float* alpha, int64_t batch, int32_t units, float* y,
+                er_stream_t stream);
+int er_dice_bwd(const float* x, const float* xn, const float* alpha, const float* gy, int64_t batch, int32_t units,
+                float* gx_direct, float* gxn, float* galpha_terms, er_stream_t stream);
 
 /* One batch into the accumulators of tf.metrics.auc (model/rank_model.py:360-373; eval.proto AUC.num_thresholds,
  * default 200) and max_f1 (core/metrics.py:25-56).  thresholds: DEVICE float32[n_thresholds], ascending (TF's list:

@@ -205,6 +205,15 @@ def install_dense(patch):
     k = np.where(np.isnan(p), 0, np.searchsorted(thresholds.numpy(), p, side='left'))   # (a NaN exceeds no threshold)
     hist += torch.from_numpy(np.bincount(k + lab * (T + 1), minlength=2 * (T + 1)).astype(np.int64))
     return hist
+  def dice_fwd(x, xn, alpha):
+    p = torch.sigmoid(xn)
+    return alpha * (1.0 - p) * x + p * x
+
+  def dice_bwd(x, xn, alpha, gy):
+    p = torch.sigmoid(xn)
+    return gy * (alpha * (1.0 - p) + p), gy * x * (1.0 - alpha) * p * (1.0 - p), gy * x * (1.0 - p)
+  patch(K, 'dice_fwd', dice_fwd)
+  patch(K, 'dice_bwd', dice_bwd)
   patch(K, 'act_fwd', act_fwd)
   patch(K, 'act_bwd', act_bwd)
   patch(K, 'auc_hist', auc_hist)

@@ -57,3 +57,11 @@ extern "C" long host_gemm_small(const float* A, long sa_m, long sa_k, const floa
   for (long o = 0; o < n_out; ++o) C[(o / N) * ldc + o % N] = er::small_gemm_reduce(part.data(), n_out, n_slice, o, bias, N);
   return n_slice;
 }
+
+// dice gate: value and the three gradient terms, out = [4][n]
+extern "C" void host_dice(const float* x, const float* xn, const float* alpha, const float* gy, long n, float* out) {
+  for (long i = 0; i < n; ++i) {
+    out[i] = er::dice_value(x[i], xn[i], alpha[i]);
+    er::dice_grads(x[i], xn[i], alpha[i], gy[i], out + n + i, out + 2 * n + i, out + 3 * n + i);
+  }
+}

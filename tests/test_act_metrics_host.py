@@ -58,8 +58,9 @@ def test_activation_names_resolve_like_get_activation():
   assert L.activation_kind('tf.nn.tanh') == K.ACT_KINDS['tanh'] == L.activation_kind('Tanh')
   assert L.activation_kind('prelu') == L.activation_kind('tf.nn.leaky_relu') == K.ACT_KINDS['leaky_relu']
   assert L.activation_kind('gelu') == K.ACT_KINDS['gelu'] and L.activation_kind('tf.nn.swish') == K.ACT_KINDS['swish']
+  assert L.activation_kind('dice') == L.activation_kind('Dice') == 'dice'
   with pytest.raises(NotImplementedError):
-    L.activation_kind('dice')
+    L.activation_kind('softmax')
 
 
 @pytest.mark.parametrize('name', ['gelu', 'selu', 'tanh'])
@@ -147,10 +148,65 @@ def test_config_with_activations_trains_and_evaluates_streaming_metrics(doubles,
   assert abs(ev['auc'] - ev['auc_exact']) < 5e-3 and ev['auc_exact'] > 0.9
 
 
-def test_dice_and_unknown_activations_are_refused_by_the_scope_check():
-  cfg = config_util.get_configs_from_pipeline_file(CFG_ACT.replace(b'ACT', b'dice'))
-  with pytest.raises(NotImplementedError, match='dice'):
+def test_unknown_activations_are_refused_by_the_scope_check():
+  cfg = config_util.get_configs_from_pipeline_file(CFG_ACT.replace(b'ACT', b'softmax'))
+  with pytest.raises(NotImplementedError, match='softmax'):
     builder.check_scope(cfg)
+  builder.check_scope(config_util.get_configs_from_pipeline_file(CFG_ACT.replace(b'ACT', b'dice')))
+
+
+def test_dice_reproduces_the_reference_function_and_its_gradients(doubles, native):
+  """layers.Dice against utils/activation.py:dice executed (tests/golden/reference_activations.json), its backward
+  against torch autograd of the restatement, the moving statistics it keeps for evaluation, and the kernels' own gate
+  formulas (elementwise.cuh compiled for the CPU) against the same numbers."""
+  import ctypes
+  d = _act_gold()['cases']['dice']
+  x = torch.tensor(d['x'], dtype=torch.float32)
+  alphas = torch.tensor(d['alphas'], dtype=torch.float32)
+  m = L.Dice(3)
+  with torch.no_grad():
+    m.alphas.copy_(alphas)
+  m.train()
+  xi = x.clone().requires_grad_(True)
+  y = m(xi)
+  np.testing.assert_allclose(y.detach().numpy(), np.array(d['y'], np.float32), rtol=1e-5, atol=1e-6)
+  gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(0))
+  y.backward(gy)
+  xr = x.clone().requires_grad_(True)
+  ar = alphas.clone().requires_grad_(True)
+  mu, var = xr.mean(0), ((xr - xr.mean(0)) ** 2).mean(0)
+  p = torch.sigmoid((xr - mu) / torch.sqrt(var + 1e-9))
+  (ar * (1 - p) * xr + p * xr).backward(gy)
+  assert torch.allclose(xi.grad, xr.grad, atol=1e-5) and torch.allclose(m.alphas.grad, ar.grad, atol=1e-5)
+  # moving statistics (momentum 0.99) feed the evaluation mode
+  np.testing.assert_allclose(m.moving_mean.numpy(), 0.01 * x.mean(0).numpy(), rtol=1e-5, atol=1e-7)
+  m.eval()
+  pe = torch.sigmoid((x - m.moving_mean) / torch.sqrt(m.moving_var + 1e-9))
+  assert torch.allclose(m(x), alphas * (1 - pe) * x + pe * x, atol=1e-6)
+  # the kernel source's gate given xn: same value, same three gradient terms
+  xn = ((x - x.mean(0)) / torch.sqrt(((x - x.mean(0)) ** 2).mean(0) + 1e-9)).numpy().astype(np.float32)
+  xv, al = x.numpy().reshape(-1), np.tile(alphas.numpy(), x.shape[0])
+  out = np.empty((4, xv.size), np.float32)
+  vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+  gyv = gy.numpy().reshape(-1).copy()
+  native.host_dice(vp(xv.copy()), vp(xn.reshape(-1).copy()), vp(al.copy()), vp(gyv), ctypes.c_long(xv.size), vp(out))
+  np.testing.assert_allclose(out[0].reshape(x.shape), np.array(d['y'], np.float32), rtol=1e-5, atol=1e-6)
+  pn = 1.0 / (1.0 + np.exp(-xn.reshape(-1).astype(np.float64)))
+  np.testing.assert_allclose(out[1], gyv * (al * (1 - pn) + pn), rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(out[2], gyv * xv * (1 - al) * pn * (1 - pn), rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(out[3], gyv * xv * (1 - pn), rtol=1e-5, atol=1e-6)
+
+
+def test_config_with_dice_trains(doubles):
+  from easyrec_b200.estimator import EasyRecEstimator
+  est = EasyRecEstimator(CFG_ACT.replace(b'ACT', b'dice'), device='cpu', seed=3)
+  dice = est.model.tower_dnn[0].acts[0]
+  assert isinstance(dice, L.Dice) and dice.units == 16 and 'tower_dnn.0.acts.0.alphas' in dict(est.model.named_parameters())
+  first = est.train(lambda: _batches(1, 256, 0), steps=1)
+  last = est.train(lambda: _batches(150, 256, 1), steps=150)
+  assert last < first - 0.1 and float(dice.alphas.abs().max()) > 0      # the alphas are trained with the towers
+  ev = est.evaluate(lambda: _batches(4, 256, 99))
+  assert ev['auc_exact'] > 0.9
 
 
 # ---- tf.metrics.auc / max_f1 ---------------------------------------------------------------------------------------

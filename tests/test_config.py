@@ -300,7 +300,7 @@ def test_data_options_that_change_the_batches_or_the_loss_are_refused_and_header
 
 
 def test_tower_options_that_are_not_implemented_are_refused():
-  for new, word in ((b'dnn { hidden_units: [32, 16] activation: "dice" }', 'activation'),):
+  for new, word in ((b'dnn { hidden_units: [32, 16] activation: "softmax" }', 'activation'),):
     cfg = config_util.get_configs_from_pipeline_file(MINI.replace(b'dnn { hidden_units: [32, 16] }', new))
     with pytest.raises(NotImplementedError, match=word):
       builder.check_scope(cfg)

@@ -289,3 +289,41 @@ def test_momentum_row_rule_and_dense_apply_track_the_oracle(dim):
     a = a * np.float32(0.9) + gg
     w = w - np.float32(0.1) * a
     np.testing.assert_allclose(p.detach().cpu().numpy(), w, rtol=1e-5, atol=1e-6)
+
+
+def test_dice_on_the_kernels_matches_the_reference_function_and_torch_autograd():
+  """layers.Dice (er_bias_bn_act_* with unit gamma / zero beta at epsilon 1e-9 + er_dice_fwd / er_dice_bwd) against the
+  output of utils/activation.py:dice executed (tests/golden/reference_activations.json) and, on a larger matrix, against
+  torch autograd of the restatement (values, dx, d alpha)."""
+  import json
+  import os
+  g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_activations.json')))
+  d = g['cases']['dice']
+  m = L.Dice(3).to(DEV)
+  with torch.no_grad():
+    m.alphas.copy_(torch.tensor(d['alphas'], device=DEV))
+  m.train()
+  y = m(torch.tensor(d['x'], dtype=torch.float32, device=DEV))
+  np.testing.assert_allclose(y.detach().cpu().numpy(), np.array(d['y'], np.float32), rtol=1e-5, atol=2e-6)
+  gen = torch.Generator().manual_seed(4)
+  B, C = 4099, 36
+  x = (torch.randn(B, C, generator=gen) * 1.5 + 0.3).to(DEV)
+  al = (torch.rand(C, generator=gen) - 0.5).to(DEV)
+  gy = torch.randn(B, C, generator=gen).to(DEV)
+  m = L.Dice(C).to(DEV)
+  with torch.no_grad():
+    m.alphas.copy_(al)
+  m.train()
+  xi = x.clone().requires_grad_(True)
+  out = m(xi)
+  out.backward(gy)
+  xr = x.double().clone().requires_grad_(True)
+  ar = al.double().clone().requires_grad_(True)
+  mu, var = xr.mean(0), ((xr - xr.mean(0)) ** 2).mean(0)
+  p = torch.sigmoid((xr - mu) / torch.sqrt(var + 1e-9))
+  ref = ar * (1 - p) * xr + p * xr
+  ref.backward(gy.double())
+  assert float((out.double() - ref).abs().max()) < 2e-5
+  assert float((xi.grad.double() - xr.grad).abs().max()) < 5e-5
+  assert float((m.alphas.grad.double() - ar.grad).abs().max()) < 2e-3      # a sum of 4099 terms of size ~1
+  np.testing.assert_allclose(m.moving_mean.cpu().numpy(), 0.01 * x.mean(0).cpu().numpy(), rtol=1e-4, atol=1e-6)
