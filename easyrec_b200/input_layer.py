@@ -400,9 +400,21 @@ class InputLayer(object):
       exchanges = {}   # row plan -> the exchange its arenas share (ids once, rows in one packed all-to-all)
       for dim, subs in self.subcalls.items():
         for sk, sc in subs.items():
+          if sc.kind == 'seq':
+            raise NotImplementedError('EmbeddingParallel with single-valued SequenceFeature slots (DIN histories): those '
+                                      'models run as replicas; id / raw / tag / multi-valued sequence slots are exchanged')
           if sc.kind != 'single':
-            raise NotImplementedError('EmbeddingParallel with %s features (group slots of kind %s): only single-valued id '
-                                      '/ raw slots are exchanged' % (sk[0], sc.kind))
+            # multi-valued slots (the ragged forms of embedding_parallel_lookup): an exchange of their own.  The owner
+            # applies one row update per exchange, so a table must not be read by slots of two different launches
+            mine = set(slot.table for _, _, slot, _ in sc.items)
+            for sk2, sc2 in subs.items():
+              if sc2 is not sc and mine & set(slot.table for _, _, slot, _ in sc2.items):
+                raise NotImplementedError('EmbeddingParallel: table(s) %s are shared by single- and multi-valued features'
+                                          % sorted(mine & set(slot.table for _, _, slot, _ in sc2.items)))
+            sc.sharded = ShardedLookup(sc.call, shard_n, shard_rank)
+            if len(subs) == 1:
+              self.merged[dim].sharded = sc.sharded
+            continue
           key = self._rows_key(sc)
           sc.sharded = ShardedLookup(sc.call, shard_n, shard_rank, exchange=exchanges.get(key))
           exchanges.setdefault(key, sc.sharded.ex)
@@ -609,6 +621,8 @@ class InputLayer(object):
     done = set()
     for dim, subs in self.subcalls.items():
       for sk, sc in subs.items():
+        if sc.kind != 'single':
+          continue                 # (variable-length inputs: their id exchange runs with the lookup)
         ex = sc.sharded.ex
         if id(ex) in done:
           continue
@@ -774,6 +788,13 @@ class InputLayer(object):
     ids_cap = torch.zeros(cap, dtype=torch.int64, device=self.device)
     ids_cap[:L].copy_(ids)
     row_ptr, seg_ids = K.csr_from_lens(lens.contiguous(), cap)
+    if self.ep:
+      # row-sharded tables: K1 (owner, local row) -> K8 -> all-to-alls -> pooling of the received rows by the same CSR
+      outs = call.alloc_outputs()
+      rows = sc.sharded.forward(ids_cap, weights, outs, row_ptr=row_ptr, seg_ids=seg_ids)
+      for o in outs:
+        o.requires_grad_(True)
+      return rows, weights, row_ptr, seg_ids, outs
     rows = torch.full((cap,), -1, dtype=torch.int64, device=self.device)
     K.bucketize(ids_cap, call.slots_dev, call.n_slots, call.n_seg, seg_ids=seg_ids, row_ptr=row_ptr,
                 rows=rows)
@@ -826,7 +847,11 @@ class InputLayer(object):
         for (d, k), (skk, j) in self.out_index.items():
           if d == dim and skk == sk:
             outs_by_key[(dim, k)] = outs[j]
-      if len(parts) == 1:
+      if self.ep and len(parts) > 1:
+        # row-sharded tables: every launch has its own exchange and its own owner-side update (disjoint tables)
+        for sc, rows, w, seg_ids, outs in parts:
+          self._pending.append((sc, rows, w, outs, seg_ids))
+      elif len(parts) == 1:
         sc, rows, w, seg_ids, outs = parts[0]
         self._pending.append((m, rows, w, outs, seg_ids))
       else:

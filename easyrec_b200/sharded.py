@@ -215,10 +215,14 @@ class ShardedExchange(object):
     if self._pre is not None:
       torch.cuda.current_stream().wait_stream(self._pre)
 
-  def lookup(self, first, ids):
+  def lookup(self, first, ids, seg_ids=None, row_ptr=None):
     """K1 -> K8 -> all_to_all(ids) -> every member's K2 on the owner -> ONE all_to_all(rows)."""
     N = self.world
     call = first.call
+    if seg_ids is not None:
+      # multi-valued slots: K1 writes the real lookups only; the padding of the fixed-capacity arrays asks for nothing
+      self.rows_local.fill_(-1)
+      self.owner.fill_(-1)
     if self._have_next:
       # (inside a capture the prefetch being promoted ran in the PREVIOUS replay or eagerly before this one: ordered
       # by the stream already, and a captured stream may not wait on work outside its capture)
@@ -230,12 +234,13 @@ class ShardedExchange(object):
       self.rows_local.copy_(self.rows_local_n)
       self._have_next = False
     else:
-      K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, rows=self.rows_local, owner=self.owner)
+      K.bucketize(ids, call.slots_dev, call.n_slots, call.n_seg, seg_ids=seg_ids, row_ptr=row_ptr, rows=self.rows_local,
+                  owner=self.owner)
       K.shard_group(self.rows_local, self.owner, N, self.cap, self.send_rows, self.pos, self.counts, self.group_ws)
       self.overflow += self.counts[N:]
       dist.all_to_all_single(self.recv_rows, self.send_rows)
     self._presorted = False
-    if self._side is not None and torch.is_grad_enabled():
+    if self._side is not None and torch.is_grad_enabled() and seg_ids is None:
       # the row-only halves of both K7s (requester: positions, owner: received rows) need no gradient: a parallel
       # branch under the row exchange and the dense forward / backward, joined in the backward
       m = max(self.members, key=lambda x: x.call.arena.dim)   # (a placement for wide rows serves the narrow tables too)
@@ -292,11 +297,16 @@ class ShardedLookup(object):
     a = call.arena
     assert a.shard_n == world and a.shard_rank == rank
     self.call, self.world, self.rank = call, world, rank
-    self.L = L = call.n_seg
+    # lookups of one call: one per segment for single-valued slots, the call's lookup capacity for multi-valued (CSR)
+    # slots - TagFeatures, multi-valued sequence steps (the ragged forms of embedding_parallel_lookup,
+    # feature_column.py:248-357 `ragged_ids / ragged_lens`)
+    self.csr = not call.single_valued
+    self.L = L = call.max_lookups
     slack = float(os.environ.get('ER_EP_SLACK', '1.25')) if slack is None else slack
     # distinct rows this rank can ask one peer for: every lookup of the hashed / identity slots in the worst case
     # (rows spread evenly over the owners, `slack` covers the imbalance), ONE row per one-row table
-    l_eff = sum(1 if int(r['bucket_mode']) == _lib.BUCKET_ONE_ROW else int(r['n_seg']) for r in call.slots_np)
+    l_eff = L if self.csr else sum(1 if int(r['bucket_mode']) == _lib.BUCKET_ONE_ROW else int(r['n_seg'])
+                                   for r in call.slots_np)
     self.cap = min(L, (int(np.ceil(slack * l_eff / world)) + 256 + 255) // 256 * 256)
     self.n_ex = world * self.cap
     self.sum_opt = K.make_opt(_lib.OPT_SGD, -1.0)   # w - (-1) * sum(g) on a zeroed buffer = the summed gradient
@@ -326,16 +336,19 @@ class ShardedLookup(object):
     self.recv_view = ex.recv_emb[:, self.col:self.col + D]   # this arena's received rows: the pooling K2's "table"
     self.sum_view = ex.send_g[:, self.col:self.col + D]      # ... and the requester-side gradient sums
 
-  def forward(self, ids, weights, outs):
+  def forward(self, ids, weights, outs, row_ptr=None, seg_ids=None):
     """ids int64 [L] in the call's slot order (None for a member whose exchange already ran this step); writes the
-    pooled rows into `outs` (the call's output matrices)."""
+    pooled rows into `outs` (the call's output matrices).  Multi-valued slots: ids padded to the lookup capacity,
+    row_ptr int32 [n_seg + 1] and seg_ids int32 [L] of the CSR (lookups beyond row_ptr[-1] are ignored)."""
     ex, call = self.ex, self.call
     ex.build()
+    assert (row_ptr is not None) == self.csr
     if ids is not None:
-      ex.lookup(self, ids)
-    K.embedding_fwd(self.recv_view, call.arena.dim, ex.pos, self.pool_slots, call.n_slots, self.L, outs, weights=weights,
-                    seg_scale=call.seg_scale)
+      ex.lookup(self, ids, seg_ids=seg_ids, row_ptr=row_ptr)
+    K.embedding_fwd(self.recv_view, call.arena.dim, ex.pos, self.pool_slots, call.n_slots, call.n_seg, outs, weights=weights,
+                    row_ptr=row_ptr, seg_scale=call.seg_scale)
     self._weights = weights
+    self._seg_ids = seg_ids
     ex._active.append(self)
     return ex.rows_local
 
@@ -352,9 +365,9 @@ class ShardedLookup(object):
       if ex._presorted:
         torch.cuda.current_stream().wait_stream(ex._side)
       ex.send_g.zero_()
-    K.embedding_bwd(self.sum_view, None, None, D, ex.pos, self.pool_slots, call.n_slots, self.L, gbufs, self.sum_opt,
-                    self.pool_ws, weights=self._weights, seg_scale=call.seg_scale, n_rows=self.n_ex,
-                    sorted_from=ex.sorted_from(self, 'pool'))
+    K.embedding_bwd(self.sum_view, None, None, D, ex.pos, self.pool_slots, call.n_slots, call.n_seg, gbufs, self.sum_opt,
+                    self.pool_ws, weights=self._weights, seg_ids=getattr(self, '_seg_ids', None), seg_scale=call.seg_scale,
+                    n_rows=self.n_ex, sorted_from=ex.sorted_from(self, 'pool'))
     ex._summed += 1
     if ex._summed < len(ex._active):
       return

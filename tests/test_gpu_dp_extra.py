@@ -1,6 +1,7 @@
 """2 GPUs over NCCL, real kernels: the multi-GPU additions whose host logic the gloo tests cover on the CPU -
 global-norm clipping under data parallel and with row-sharded tables (tests/test_dp_clip_gloo.py) and data parallel over
-multi-valued tag slots (tests/test_dp_tags_gloo.py) - run by the same worker functions on cuda devices.  Skipped on boxes
+multi-valued tag slots (tests/test_dp_tags_gloo.py), row-sharded tables with tag / multi-valued sequence slots
+(tests/test_ep_tags_gloo.py) - run by the same worker functions on cuda devices.  Skipped on boxes
 with fewer than 2 GPUs."""
 import os
 import sys
@@ -46,3 +47,9 @@ def test_data_parallel_over_tag_slots_on_2_gpus(tmp_path):
   for worst, dworst, _, _ in ret.values():
     assert worst < 5e-6 and dworst < 5e-6, ret
   assert len(set(v[2:] for v in ret.values())) == 1, ret
+
+
+@pytest.mark.timeout(400)
+def test_embedding_parallel_over_tag_slots_on_2_gpus(tmp_path):
+  from test_ep_tags_gloo import _worker
+  _spawn(_worker, str(tmp_path))
