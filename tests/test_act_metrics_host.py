@@ -406,7 +406,7 @@ def test_kernel_source_small_gemm_reads_strided_operands_and_sums_slices_in_orde
       L(out.stride(0)), L(M), L(N), L(K))
   want = a.double() @ b.double() + (bias.double() if bias is not None else 0.0)
   scale = float(np.sqrt(K))
-  assert float((out[:, :N].double() - want).abs().max()) < 2e-6 * scale + 1e-6
+  assert float((out[:, :N].double() - want).abs().max()) < 6e-6 * scale + 2e-6
   assert torch.isnan(out[:, N:]).all()                       # nothing written beyond the N columns of a pitched output
   assert (n_slice > 1) == (K >= 512 and form == 'dw')         # only the long-K / few-output form is cut into slices
   from easyrec_b200 import _lib
