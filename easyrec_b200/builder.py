@@ -305,7 +305,7 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
   specs = feature_specs(pipeline_config, packed_mod=input_type_name(pipeline_config).startswith('Parquet'),
                         default_seq_len=default_seq_len)
   groups = feature_groups(mc)
-  specs, keras_tables = embedding_layer_tables(mc, specs)
+  specs, keras_tables, pad_tags = embedding_layer_tables(mc, specs)
   opt = optimizer_settings(pipeline_config)
   cls = model_pkg.get_model_class(mc.model_class)
   wide_dim = cls.wide_output_dim(mc)
@@ -324,6 +324,7 @@ def build_model(pipeline_config, batch_size, device, generator=None, cpu_generat
                                     fc.sequence_combiner.WhichOneof('combiner')
                                     for fc in config_util.get_feature_configs(pipeline_config)
                                     if fc.HasField('sequence_combiner')})
+  il.pad_tags = pad_tags   # tag features of a backbone `embedding_layer` block: the readers pad them with the bucket of ''
   # RawFeature.normalizer_fn: applied to the min-max normalised value on the device (input/input.py:642-646); the
   # readers apply the same function on the host to raw features they bucketize themselves (readers.bucketize_raw)
   from easyrec_b200 import normalizer
@@ -368,13 +369,19 @@ def embedding_layer_tables(model_config, specs):
   gets its own `vocab_f`-row table of the BLOCK's width (back to back in group order = the offsets), Keras' default
   `uniform(-0.05, 0.05)` initialiser instead of the feature columns' truncated normal.
 
-  Returns (specs with those features re-dimensioned, {table name: 0.05})."""
+  A TagFeature (string tokens hashed on the host) takes part the way the reference treats it: the ragged tags are
+  densified with '' PADDING up to the longest list of the batch, the padding is hashed and looked up like a tag, and the
+  step axis is pooled by the block's `combiner` - 'weight' (default): mean over all positions when the feature has no
+  weights, sum(w e) / sum(w) with kv weights (padding weighs 0); 'mean'; 'sum' (input_layer.py:232-235,
+  embedding.py:9-23, 60-78).  The readers pad such features (pad_tags: feature -> bucket of ''); 'max' / 'min' are refused.
+
+  Returns (specs with those features re-dimensioned, {table name: 0.05}, {tag feature: pad bucket})."""
   if not model_config.HasField('backbone'):
-    return specs, {}
+    return specs, {}, {}
   by_name = {s.name: i for i, s in enumerate(specs)}
   groups = {g.group_name: list(g.feature_names) for g in model_config.feature_groups}
   other_use = collections.Counter(n for g in model_config.feature_groups for n in g.feature_names)
-  specs, tables = list(specs), {}
+  specs, tables, pad_tags = list(specs), {}, {}
   blocks = list(model_config.backbone.blocks) + [b for p in model_config.backbone.packages for b in p.blocks]
   for b in blocks:
     if b.WhichOneof('layer') != 'embedding_layer':
@@ -383,18 +390,28 @@ def embedding_layer_tables(model_config, specs):
       raise ValueError('embedding_layer block %s takes exactly one feature_group_name input' % b.name)
     for n in groups[b.inputs[0].feature_group_name]:
       sp = specs[by_name[n]]
-      if sp.kind != 'id':
-        # multi-valued inputs are densified with '' padding and the PADDING is looked up and pooled too
-        # (input_layer.py:232-235, embedding.py:9-23,60-78): not built
-        raise NotImplementedError('embedding_layer block %s: feature %s is a %s feature; only single-valued id / '
-                                  'bucketized features are exchanged through this block' % (b.name, n, sp.kind))
+      if sp.kind not in ('id', 'tag'):
+        raise NotImplementedError('embedding_layer block %s: feature %s is a %s feature; id / bucketized / tag features '
+                                  'go through this block' % (b.name, n, sp.kind))
       if other_use[n] > 1:
         raise NotImplementedError('feature %s is read by embedding_layer block %s and by another feature group: it '
                                   'would need two tables' % (n, b.name))
       table = '%s/%s_embedding' % (b.name, n)
-      specs[by_name[n]] = sp._replace(embedding_dim=int(b.embedding_layer.embedding_dim), embedding_name=table)
+      extra = {}
+      if sp.kind == 'tag':
+        comb = b.embedding_layer.combiner
+        if comb not in ('weight', 'mean', 'sum'):
+          raise NotImplementedError('embedding_layer block %s: combiner %r over a tag feature' % (b.name, comb))
+        if sp.bucket_mode != _lib.BUCKET_IDENTITY or sp.num_buckets <= 0:
+          # (the block hashes the densified STRING tags itself, '' included; integer tags cannot be densified with '')
+          raise NotImplementedError('embedding_layer block %s: tag feature %s must be a STRING field with a '
+                                    'hash_bucket_size' % (b.name, n))
+        extra = dict(combiner='sum' if comb == 'sum' else 'mean')
+        # (bucket of the '' padding, whether kv weights count: a callable combiner ignores them, embedding.py:11-12)
+        pad_tags[n] = (int(_lib.fingerprint64('') % sp.num_buckets), comb == 'weight')
+      specs[by_name[n]] = sp._replace(embedding_dim=int(b.embedding_layer.embedding_dim), embedding_name=table, **extra)
       tables[table] = 0.05
-  return specs, tables
+  return specs, tables, pad_tags
 
 
 def bind_task_labels(model, label_fields):

@@ -126,6 +126,31 @@ def _tag_weight_inputs(pipeline_config):
   return out
 
 
+def _pad_tags(il, name, ids, lens, w):
+  """tag feature of a backbone `embedding_layer` block: the reference densifies the ragged tags with '' up to the longest
+  list of the BATCH and looks the padding up too (layers/input_layer.py:232-235); weights of the padding are 0.
+  (ids, lens, w) numpy -> padded (ids, lens, w); a batch without any tag stays empty (embedding.py:69-72: zeros)."""
+  entry = getattr(il, 'pad_tags', {}).get(name)
+  if entry is None:
+    return ids, lens, w
+  pad, use_weights = entry
+  if not use_weights:
+    w = None                      # combiner mean / sum: reduce over the padded axis, weights unused (embedding.py:11-12)
+  n = int(lens.max()) if lens.size else 0
+  if n == 0 or bool((lens == n).all()):
+    return ids, lens, w
+  B = lens.size
+  out = np.full((B, n), pad, np.int64)
+  mask = np.arange(n)[None, :] < lens[:, None]
+  out[mask] = ids
+  wp = None
+  if w is not None:
+    wp = np.zeros((B, n), np.float32)
+    wp[mask] = w
+    wp = wp.reshape(-1)
+  return out.reshape(-1), np.full(B, n, np.int32), wp
+
+
 def _check_tag_weights(name, lens, wlens):
   """the weight field must hold one value per tag (input/input.py:490-494 asserts equal sizes; the two SparseTensors
   must then share their indices)"""
@@ -499,6 +524,7 @@ class CSVInput(object):
         if f.name in self.tag_weights:
           w, wlens = cols[self.tag_weights[f.name]]
           _check_tag_weights(f.name, lens, wlens)
+        vals, lens, w = _pad_tags(il, f.name, vals, lens, w)
         tag[f.name] = (torch.from_numpy(vals.copy()), torch.from_numpy(lens), None if w is None else torch.from_numpy(w.copy()))
     if seq:
       feats['seq_fea'] = seq
@@ -598,7 +624,8 @@ class CSVInput(object):
           wt = [[t for t in x.split(sep) if t != ''] for x in cols[self.tag_weights[f.name]]]
           _check_tag_weights(f.name, lens, np.array([len(ts) for ts in wt], np.int32))
           w = torch.from_numpy(np.array([float(t) for ts in wt for t in ts], np.float32))
-        tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), w)
+        flat, lens, wn = _pad_tags(il, f.name, flat, lens, None if w is None else w.numpy())
+        tag[f.name] = (torch.from_numpy(flat), torch.from_numpy(lens), None if wn is None else torch.from_numpy(wn))
     if seq:
       feats['seq_fea'] = seq
     if tag:
@@ -729,6 +756,8 @@ class ParquetInput(object):
           wv, wl = self._column(table.column(self.tag_weights[f.name]))
           _check_tag_weights(f.name, lens, np.ones(n, np.int32) if wl is None else wl)
           w = torch.from_numpy(np.array(wv, np.float32))
+        if f.name in getattr(il, 'pad_tags', {}):
+          raise NotImplementedError('tag feature %s of an embedding_layer block: string tags come from text inputs' % f.name)
         tag[f.name] = (torch.from_numpy(vals), torch.from_numpy(lens), w)
     if seq:
       feats['seq_fea'] = seq

@@ -811,3 +811,64 @@ model_config { model_class: "PLE"
   tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
   losses = [float(tr.train_step(feats, lab)[0]) for _ in range(15)]
   assert losses[-1] < losses[0] - 0.01, losses
+
+
+def test_backbone_embedding_layer_block_pools_padded_tag_features(interaction_doubles, tmp_path):  # noqa: F811
+  """§8 a23, multi-valued inputs (layers/input_layer.py:232-235 + layers/keras/embedding.py:9-23, 60-78): the ragged tags
+  are densified with '' up to the longest list of the batch, the PADDING is hashed and looked up too, and the positions are
+  pooled by the block's combiner - 'weight' without weights = mean over ALL positions, with kv weights sum(w e)/sum(w)."""
+  from easyrec_b200.input import readers
+  text = b"""
+train_config { optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.05 } } } } }
+data_config { batch_size: 4 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "u" input_type: INT64 }
+  input_fields { input_name: "tags" input_type: STRING } input_fields { input_name: "kv" input_type: STRING } }
+feature_config {
+  features { input_names: "u" feature_type: IdFeature embedding_dim: 8 hash_bucket_size: 50 }
+  features { input_names: "tags" feature_type: TagFeature embedding_dim: 8 hash_bucket_size: 31 separator: "|" }
+  features { input_names: "kv" feature_type: TagFeature embedding_dim: 8 hash_bucket_size: 17 separator: "|" kv_separator: ":" } }
+model_config { model_class: "RankModel"
+  feature_groups { group_name: "ids" feature_names: ["u", "tags", "kv"] wide_deep: DEEP }
+  backbone {
+    blocks { name: "emb" inputs { feature_group_name: "ids" } embedding_layer { embedding_dim: 6 } }
+    blocks { name: "mlp" inputs { block_name: "emb" } keras_layer { class_name: "MLP" mlp { hidden_units: [8] } } }
+    concat_blocks: ["mlp"] } }
+"""
+  cfg = config_util.get_configs_from_pipeline_file(text)
+  il, model, opt = builder.build_model(cfg, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(1))
+  pad_t, pad_k = O.fingerprint64('') % 31, O.fingerprint64('') % 17
+  assert il.pad_tags == {'tags': (pad_t, True), 'kv': (pad_k, True)}
+  a = il.arenas[6]
+  assert list(a.tables) == ['emb/u_embedding', 'emb/tags_embedding', 'emb/kv_embedding']    # offsets in group order
+  open(tmp_path / 't.csv', 'w').write('1,7,a|b|c,x:2|y:0.5\n0,8,,z:1\n1,9,d,\n0,7,e|f,x:1|z:3\n')
+  for engine in ('native', 'python'):
+    (feats, labels), = list(readers.CSVInput(cfg, il, str(tmp_path / 't.csv'), engine=engine))
+    ids, lens, w = feats['tag_fea']['tags']
+    h = lambda s, nb: O.fingerprint64(s) % nb   # noqa: E731
+    assert lens.tolist() == [3, 3, 3, 3] and w is None                       # padded to the batch's longest list
+    assert ids.tolist() == [h('a', 31), h('b', 31), h('c', 31), pad_t, pad_t, pad_t, h('d', 31), pad_t, pad_t,
+                            h('e', 31), h('f', 31), pad_t]
+    ids_k, lens_k, w_k = feats['tag_fea']['kv']
+    assert lens_k.tolist() == [2, 2, 2, 2] and w_k.tolist() == [2.0, 0.5, 1.0, 0.0, 0.0, 0.0, 1.0, 3.0]
+    out = il.lookup(feats)['ids'][0].detach().numpy()
+    W = a.weight.detach().numpy()
+    o_t, o_k = a.tables['emb/tags_embedding'][0], a.tables['emb/kv_embedding'][0]
+    want_tags = W[o_t + ids.numpy().reshape(4, 3)].mean(1)                    # 'weight' without weights: mean incl. padding
+    np.testing.assert_allclose(out[:, 6:12], want_tags, rtol=1e-5, atol=1e-7)
+    wk = w_k.numpy().reshape(4, 2)
+    rows_k = W[o_k + ids_k.numpy().reshape(4, 2)]
+    with np.errstate(invalid='ignore', divide='ignore'):
+      want_kv = (rows_k * wk[:, :, None]).sum(1) / wk.sum(1, keepdims=True)
+    want_kv[2] = 0.0   # a sample without tags: the reference divides 0 by 0 there (NaN); this path gives the zero vector
+    np.testing.assert_allclose(out[:, 12:18], want_kv, rtol=1e-5, atol=1e-7)
+    il._pending = []
+  tr = T.Trainer(model, il, 'adagrad', lr_fn=opt['lr_fn'])
+  feats, labels = list(readers.CSVInput(cfg, il, str(tmp_path / 't.csv')))[0]
+  losses = [float(tr.train_step(feats, labels)[0]) for _ in range(20)]
+  assert losses[-1] < losses[0] - 0.01
+  # the padding row itself is trained (it is looked up like a tag)
+  assert float((a.weight[a.tables['emb/tags_embedding'][0] + pad_t]).abs().sum()) > 0
+  bad = config_util.get_configs_from_pipeline_file(text.replace(b'embedding_layer { embedding_dim: 6 }',
+                                                                b'embedding_layer { embedding_dim: 6 combiner: "max" }'))
+  with pytest.raises(NotImplementedError, match='combiner'):
+    builder.build_model(bad, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(1))
