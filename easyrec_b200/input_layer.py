@@ -520,28 +520,32 @@ class InputLayer(object):
     (model/easy_rec_estimator.py:308-317) is applied first, as optimize_loss does.  Returns a device scalar."""
     total = torch.zeros((), dtype=torch.float32, device=self.device)
     for m, rows, w, outs, seg_ids in self._pending:
-      if seg_ids is not None or rows.numel() != m.n_seg:
-        raise NotImplementedError('gradient_clipping_by_norm over multi-valued (tag / sequence) slots')
+      if seg_ids is None and rows.numel() != m.n_seg:
+        raise NotImplementedError('gradient_clipping_by_norm: a call whose lookups are not its segments needs seg_ids')
       a = m.arena
+      n_l = rows.numel()          # lookups: one per segment for single-valued slots, the lookup capacity for CSR slots
       st = self._clip_state.get(id(m))
       if st is None:
         if a.n_rows * m.n_slots >= 0xFFFFFFFF:
           raise NotImplementedError('gradient_clipping_by_norm: %d rows x %d columns exceed the 32-bit row key' %
                                     (a.n_rows, m.n_slots))
-        off = torch.zeros(m.n_seg, dtype=torch.int64)
+        off = torch.zeros(m.n_seg, dtype=torch.int64)      # per SEGMENT: the virtual-row offset of its column (slot)
         for j, r in enumerate(m.slots_np):
           off[int(r['seg_begin']):int(r['seg_begin']) + int(r['n_seg'])] = j * a.n_rows
-        st = dict(off=off.to(self.device), ws=K.bwd_workspace(m.n_seg, self.device, a.dim),
-                  ur=torch.empty(m.n_seg, dtype=torch.int64, device=self.device),
-                  ug=torch.empty(m.n_seg, a.dim, dtype=torch.float32, device=self.device),
+        st = dict(off=off.to(self.device), ws=K.bwd_workspace(n_l, self.device, a.dim),
+                  ur=torch.empty(n_l, dtype=torch.int64, device=self.device),
+                  ug=torch.empty(n_l, a.dim, dtype=torch.float32, device=self.device),
                   nu=torch.zeros(1, dtype=torch.int32, device=self.device),
-                  idx=torch.arange(m.n_seg, device=self.device, dtype=torch.int32))
+                  idx=torch.arange(n_l, device=self.device, dtype=torch.int32))
         self._clip_state[id(m)] = st
-      vr = torch.where(rows < 0, rows, rows + st['off'])
+      # multi-valued slots: every lookup takes the offset of ITS segment's column (the segment ids of the unused tail of
+      # the fixed-capacity arrays are undefined: clamped, their rows are -1 anyway)
+      off = st['off'] if seg_ids is None else st['off'][seg_ids[:n_l].clamp(0, m.n_seg - 1).long()]
+      vr = torch.where(rows < 0, rows, rows + off)
       gbufs = [(o.grad if o.grad is not None else torch.zeros_like(o)).contiguous() for o in outs]
       opt = K.make_opt(_lib.OPT_SGD, 0.0, grad_scale=float(self.emb_grad_mult))
       K.embedding_bwd(None, None, None, a.dim, vr, m.slots_dev, m.n_slots, m.n_seg, gbufs, opt, st['ws'], weights=w,
-                      seg_scale=m.seg_scale, uniq_rows=st['ur'], uniq_grads=st['ug'], n_uniq=st['nu'],
+                      seg_ids=seg_ids, seg_scale=m.seg_scale, uniq_rows=st['ur'], uniq_grads=st['ug'], n_uniq=st['nu'],
                       n_rows=a.n_rows * m.n_slots)
       rowsq = (st['ug'] * st['ug']).sum(dim=1)
       total = total + torch.where(st['idx'] < st['nu'], rowsq, torch.zeros_like(rowsq)).sum()

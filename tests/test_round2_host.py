@@ -872,3 +872,65 @@ model_config { model_class: "RankModel"
                                                                 b'embedding_layer { embedding_dim: 6 combiner: "max" }'))
   with pytest.raises(NotImplementedError, match='combiner'):
     builder.build_model(bad, 4, 'cpu', cpu_generator=torch.Generator().manual_seed(1))
+
+
+def test_global_norm_clipping_over_tag_slots(dense_kernels, tmp_path):  # noqa: F811
+  """gradient_clipping_by_norm with multi-valued (CSR) slots: the IndexedSlices of a tag column hold one row per distinct
+  tag of the column, summed over its lookups with their weights and the combiner's per-sample scale."""
+  from easyrec_b200.estimator import EasyRecEstimator
+  from easyrec_b200.input import readers
+  text = b"""
+train_config { %s
+  optimizer_config { momentum_optimizer { learning_rate { constant_learning_rate { learning_rate: 0.5 } }
+                                          momentum_optimizer_value: 0.0 } } }
+data_config { batch_size: 6 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "a" input_type: INT64 }
+  input_fields { input_name: "t" input_type: STRING } input_fields { input_name: "s" input_type: STRING } }
+feature_config {
+  features { input_names: "a" feature_type: IdFeature embedding_dim: 4 num_buckets: 7 embedding_name: "e" }
+  features { input_names: "t" feature_type: TagFeature embedding_dim: 4 num_buckets: 7 embedding_name: "e" separator: "|"
+             kv_separator: ":" combiner: "mean" }
+  features { input_names: "s" feature_type: TagFeature embedding_dim: 4 hash_bucket_size: 9 separator: "|" combiner: "sum" } }
+model_config { model_class: "MultiTower"
+  feature_groups { group_name: "g" feature_names: ["a", "t", "s"] wide_deep: DEEP }
+  multi_tower { towers { input: "g" dnn { hidden_units: [8] } } final_dnn { hidden_units: [4] } l2_regularization: 1e-2 } }
+"""
+  open(tmp_path / 'c.csv', 'w').write('1,1,1:0.5|2:2|1:1,x|y\n0,2,,x\n1,1,3:1,\n0,6,2:1|2:3,y|y|z\n1,0,5:2,w\n0,3,1:1|4:1,x|w\n')
+  plain = EasyRecEstimator(text % b'', device='cpu', seed=4)
+  clip = EasyRecEstimator(text % b'gradient_clipping_by_norm: 0.02', device='cpu', seed=4)
+  probe = EasyRecEstimator(text % b'', device='cpu', seed=4)
+  (feats, labels), = list(readers.CSVInput(plain._pipeline_config, plain.input_layer, str(tmp_path / 'c.csv')))
+  # -- the norm, restated lookup by lookup
+  tr, il = probe.trainer, probe.input_layer
+  tr._set_hyper()
+  probe.model.train()
+  tr._segment_compute(feats, labels)
+  want_sq = 0.0
+  for m, rows, w, outs, seg_ids in il._pending:
+    D = m.arena.dim
+    r = rows.numpy()
+    seg = np.arange(r.size) if seg_ids is None else seg_ids.numpy()[:r.size]
+    scale = np.ones(m.n_seg, np.float32) if m.seg_scale is None else m.seg_scale.numpy()
+    ww = np.ones(r.size, np.float32) if w is None else w.numpy()
+    for j, sl in enumerate(m.slots_np):
+      lo, n = int(sl['seg_begin']), int(sl['n_seg'])
+      g = outs[int(sl['out_buf'])].grad.numpy().reshape(-1, int(sl['out_stride']))[:, int(sl['out_col']):int(sl['out_col']) + D]
+      mine = (r >= 0) & (seg >= lo) & (seg < lo + n)
+      for u in np.unique(r[mine]):
+        ls = np.flatnonzero(mine & (r == u))
+        want_sq += float(((g[seg[ls] - lo] * (ww[ls] * scale[seg[ls]])[:, None]).sum(0).astype(np.float64) ** 2).sum())
+  assert any(s is not None for _, _, _, _, s in il._pending)       # the call really holds CSR slots
+  got_sparse = float(il.sparse_grad_sqnorm())
+  assert got_sparse == pytest.approx(want_sq, rel=1e-5) and want_sq > 0
+  il._pending = []
+  # -- the step: SGD, clipped = scale * unclipped on the table and the towers
+  p0 = plain.trainer.dense_opt.flat_p.clone()
+  t0 = {d: a.weight.clone() for d, a in plain.input_layer.arenas.items()}
+  plain.trainer.train_step(feats, labels)
+  clip.trainer.train_step(feats, labels)
+  norm = float(clip.trainer.last_grad_norm)
+  assert norm > 0.02
+  sc = 0.02 / norm
+  torch.testing.assert_close(clip.trainer.dense_opt.flat_p - p0, (plain.trainer.dense_opt.flat_p - p0) * sc, rtol=1e-4, atol=2e-7)
+  for d, a in clip.input_layer.arenas.items():
+    torch.testing.assert_close(a.weight - t0[d], (plain.input_layer.arenas[d].weight - t0[d]) * sc, rtol=1e-4, atol=2e-8)
