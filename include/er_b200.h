@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ER_B200_ABI_VERSION 2
+#define ER_B200_ABI_VERSION 3
 
 typedef void* er_stream_t; /* cudaStream_t */
 

@@ -25,7 +25,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_abi_version_and_struct_layout():
   lib = _lib.load()
-  assert lib.er_abi_version() == _lib.ABI_VERSION == 2
+  assert lib.er_abi_version() == _lib.ABI_VERSION == 3
   assert _lib.SLOT_DTYPE.itemsize == 48
   assert ctypes.sizeof(_lib.ErOpt) == 40 and _lib.ErOpt.hyper_dev.offset == 32
 
