@@ -52,7 +52,7 @@ def parse():
   ap.add_argument('--batch', type=int, default=BATCH)
   ap.add_argument('--optimizer', default='adagrad_optimizer',
                   choices=['adagrad_optimizer', 'lazy_adam_optimizer', 'adam_optimizer'])
-  ap.add_argument('--workload', default='deepfm_c2', choices=['deepfm_c2', 'dssm_c4'],
+  ap.add_argument('--workload', default='deepfm_c2', choices=['deepfm_c2', 'dssm_c4', 'mmoe_c5'],
                   help='deepfm_c2 = the headline metric; dssm_c4 = BASELINE.json configs[3] (row-sharded item table)')
   ap.add_argument('--parallelism', default='', choices=['', 'dp', 'ep'],
                   help='N > 1: ep = row-sharded tables + all-to-all (EmbeddingParallelStrategy; the default), dp = replicated '
@@ -307,7 +307,7 @@ def main():
     return EasyRecEstimator(text, device=dev, seed=20240, use_cuda_graph=graph, world_size=world, rank=rank,
                             embedding_parallel=ep)
 
-  if args.workload == 'dssm_c4':
+  if args.workload in ('dssm_c4', 'mmoe_c5'):
     return run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks)
 
   n_rot = 16
@@ -503,14 +503,31 @@ def run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks):
   import torch
   from easyrec_b200 import _lib, workloads
   from easyrec_b200.estimator import EasyRecEstimator
-  B = args.batch if args.batch != BATCH else 4096
-  item_vocab = args.vocab or {1: 25_000_000, 2: 50_000_000, 4: 100_000_000}.get(world, 200_000_000)
-  est = EasyRecEstimator(workloads.c4_config_text(B, item_vocab, embedding_parallel=ep), device=dev, seed=20240,
-                         use_cuda_graph=graph, world_size=world, rank=rank, embedding_parallel=ep)
+  c5 = args.workload == 'mmoe_c5'
+  if c5:
+    # BASELINE.json configs[4]: 3-task MMoE over a DCN-style backbone, 40 id slots on one 100M x 32 table (12.5M rows per
+    # rank at 8 GPUs; smaller worlds take the same rows per rank), batch 16384 per GPU
+    B = args.batch if args.batch != BATCH else 16384
+    item_vocab = args.vocab or 12_500_000 * world
+    text = workloads.c5_config_text(B, item_vocab, embedding_parallel=ep)
+    make_batch = lambda seed: workloads.c5_batch(B, seed)   # noqa: E731
+    metric = 'samples/sec MMoE-3task over a DCN backbone (BASELINE.json configs[4])'
+    wl = ('mmoe_c5(40 id slots on one shared table %d rows x emb32, deep MLP [256,128] + 3 Cross layers, 4 experts '
+          '[128,64], 3 towers [64]; batch %d/GPU, zipf1.05 ids)' % (item_vocab, B))
+  else:
+    B = args.batch if args.batch != BATCH else 4096
+    item_vocab = args.vocab or {1: 25_000_000, 2: 50_000_000, 4: 100_000_000}.get(world, 200_000_000)
+    text = workloads.c4_config_text(B, item_vocab, embedding_parallel=ep)
+    make_batch = lambda seed: workloads.c4_batch(B, seed)   # noqa: E731
+    metric = 'samples/sec DSSM two-tower in-batch negatives (BASELINE.json configs[3])'
+    wl = ('dssm_c4(user tower 5 ids, item tower 3 ids + price, towers [256,128,64,32], cosine, in-batch '
+          'softmax; item table %d rows x emb16, batch %d/GPU, zipf1.05 ids)' % (item_vocab, B))
+  est = EasyRecEstimator(text, device=dev, seed=20240, use_cuda_graph=graph, world_size=world, rank=rank,
+                         embedding_parallel=ep)
   n_rot = 16
   pinned = []
   for i in range(n_rot):
-    f, l = workloads.c4_batch(B, 4040 + rank * 1000 + i)
+    f, l = make_batch(4040 + rank * 1000 + i)
     pinned.append(({k: v.pin_memory() for k, v in f.items()}, l.pin_memory()))
   devb = [({k: v.to(dev) for k, v in f.items()}, l.to(dev)) for f, l in pinned]
   W = max(args.warmup, 3)
@@ -556,19 +573,18 @@ def run_c4(args, rank, world, dev, ep, graph, barrier, max_over_ranks):
   if rank == 0:
     h2d = sum(v.numel() * v.element_size() for v in pinned[0][0].values()) + pinned[0][1].numel() * 4
     print(json.dumps({
-        'metric': 'samples/sec DSSM two-tower in-batch negatives (BASELINE.json configs[3])',
+        'metric': metric,
         'value': world * B * steps / (ms / 1000.0), 'unit': 'samples/s', 'n_gpus': world, 'steps': steps, 'warmup': W,
         'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'dssm_c4(user tower 5 ids, item tower 3 ids + price, towers [256,128,64,32], cosine, in-batch '
-                               'softmax; item table %d rows x emb16, batch %d/GPU, zipf1.05 ids)' % (item_vocab, B),
-                   'built_from': 'EasyRecEstimator(protobuf-text pipeline config: workloads.c4_config_text)',
+        'config': {'workload': wl,
+                   'built_from': 'EasyRecEstimator(protobuf-text pipeline config: workloads.%s_config_text)' % ('c5' if c5 else 'c4'),
                    'parallelism': '%s%d' % ('ep' if ep else 'dp', world),
                    'l2_flush': 'none: tables >> L2 and ids rotate over 16 distinct batches'},
         'clocks': clocks,
         'e2e': {'value': world * B * steps / (e2e_ms / 1000.0), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / steps,
-                'through': 'EasyRecEstimator.train(input_fn), loss read back every step'},
+                'through': 'EasyRecEstimator.train(input_fn), the loss of every step read back (pinned slots, one step behind)'},
         'gpu_launches': launches, 'gpu_launches_per_step': launches // steps, 'cuda_graph': bool(graph),
         'roofline': None, 'cpu_baseline': None, 'final_loss': float(loss)}))
   if world > 1:

@@ -235,3 +235,49 @@ def c4_batch(batch_size, seed, zipf_alpha=1.05):
   dense = rng.uniform(0, 1, (B, 1)).astype(np.float32)
   return {'sparse_fea': torch.from_numpy(ids), 'dense_fea': torch.from_numpy(dense),
           'item_ids': torch.from_numpy(item.copy())}, torch.ones(B, dtype=torch.float32)
+
+
+def c5_config_text(batch_size=16384, vocab=100_000_000, n_feat=40, emb_dim=32, lr=0.02, embedding_parallel=True):
+  """C5 of BASELINE.json as a pipeline config: 3-task MMoE over a DCN-style backbone (deep MLP next to three Cross
+  layers on the same input, samples/model_config/dcn_backbone_on_taobao.config + mmoe_backbone_on_taobao.config), `n_feat`
+  id slots over ONE shared `vocab` x `emb_dim` table (as dlrm_on_criteo_parquet_ep.config:319-324 shares its table),
+  row-sharded (train_distribute: EmbeddingParallelStrategy), three binary labels."""
+  feats = '\n'.join('  features { input_names: "c%d" feature_type: IdFeature embedding_dim: %d hash_bucket_size: %d '
+                    'embedding_name: "shared" }' % (i, emb_dim, vocab) for i in range(n_feat))
+  fields = ' '.join('input_fields { input_name: "c%d" input_type: INT64 }' % i for i in range(n_feat))
+  names = ', '.join('"c%d"' % i for i in range(n_feat))
+  return ('''
+train_config { log_step_count_steps: 1000000 %s
+  optimizer_config { adagrad_optimizer { learning_rate { constant_learning_rate { learning_rate: %g } } } } }
+data_config { batch_size: %d input_type: DummyInput label_fields: ["l0", "l1", "l2"]
+  input_fields { input_name: "l0" input_type: FLOAT } input_fields { input_name: "l1" input_type: FLOAT }
+  input_fields { input_name: "l2" input_type: FLOAT } %s }
+feature_config {
+%s
+}
+model_config { model_class: "MultiTaskModel"
+  feature_groups { group_name: "all" feature_names: [%s] wide_deep: DEEP }
+  backbone {
+    blocks { name: "deep" inputs { feature_group_name: "all" } keras_layer { class_name: "MLP" mlp { hidden_units: [256, 128] } } }
+    blocks { name: "cross" inputs { feature_group_name: "all" input_fn: "lambda x: [x, x]" }
+             recurrent { num_steps: 3 fixed_input_index: 0 keras_layer { class_name: "Cross" } } }
+    blocks { name: "both" inputs { block_name: "deep" } inputs { block_name: "cross" } merge_inputs_into_list: true
+             keras_layer { class_name: "Concatenate" } }
+    blocks { name: "mmoe" inputs { block_name: "both" }
+             keras_layer { class_name: "MMoE" mmoe { num_task: 3 num_expert: 4 expert_mlp { hidden_units: [128, 64] } } } }
+  }
+  model_params { l2_regularization: 1e-6
+    task_towers { tower_name: "t0" label_name: "l0" mlp { hidden_units: [64] } }
+    task_towers { tower_name: "t1" label_name: "l1" mlp { hidden_units: [64] } }
+    task_towers { tower_name: "t2" label_name: "l2" mlp { hidden_units: [64] } } }
+  embedding_regularization: 1e-6 }
+''' % ('train_distribute: EmbeddingParallelStrategy' if embedding_parallel else '', lr, batch_size, fields, feats,
+       names)).encode()
+
+
+def c5_batch(batch_size, seed, n_feat=40, zipf_alpha=1.05):
+  """host batch in c5_config_text's InputLayer form: `n_feat` id columns feature-major, three Bernoulli labels"""
+  rng = np.random.default_rng(seed)
+  ids = (rng.zipf(zipf_alpha, n_feat * batch_size).astype(np.int64) - 1) % (2**40)
+  labels = (rng.uniform(size=(batch_size, 3)) < 0.25).astype(np.float32)
+  return {'sparse_fea': torch.from_numpy(ids)}, torch.from_numpy(labels)

@@ -934,3 +934,20 @@ model_config { model_class: "MultiTower"
   torch.testing.assert_close(clip.trainer.dense_opt.flat_p - p0, (plain.trainer.dense_opt.flat_p - p0) * sc, rtol=1e-4, atol=2e-7)
   for d, a in clip.input_layer.arenas.items():
     torch.testing.assert_close(a.weight - t0[d], (plain.input_layer.arenas[d].weight - t0[d]) * sc, rtol=1e-4, atol=2e-8)
+
+
+def test_c5_workload_config_builds_and_trains_with_kernel_doubles(interaction_doubles):  # noqa: F811
+  """bench.py --workload mmoe_c5 (BASELINE.json configs[4]): the pipeline config text and the batch generator of
+  easyrec_b200.workloads at a small size - MultiTaskModel over the Cross + MLP backbone, MMoE with 4 experts (the gate
+  layers are the vector-sized GEMMs of er_gemm_small), three towers bound to their labels."""
+  from easyrec_b200 import workloads
+  from easyrec_b200.estimator import EasyRecEstimator
+  est = EasyRecEstimator(workloads.c5_config_text(64, 5000, n_feat=6, embedding_parallel=False), device='cpu', seed=2)
+  assert est.model.tower_names == ['t0', 't1', 't2'] and est.model.label_cols == [0, 1, 2]
+  assert list(est.input_layer.arenas[32].tables) == ['shared'] and est.input_layer.arenas[32].n_rows == 5000
+  feats, labels = workloads.c5_batch(64, 1, n_feat=6)
+  assert feats['sparse_fea'].numel() == 6 * 64 and labels.shape == (64, 3)
+  losses = [float(est.trainer.train_step(feats, labels)[0]) for _ in range(15)]
+  assert np.isfinite(losses).all() and losses[-1] < losses[0]
+  ev = est.evaluate(lambda: [(feats, labels)])
+  assert sorted(k for k in ev if k.startswith('auc')) == ['auc_t0', 'auc_t1', 'auc_t2']
