@@ -532,3 +532,66 @@ def test_embed_test_seq_multi_embed_verbatim(tmp_path):
       il._pending = []
   finally:
     mp.undo()
+
+
+def test_native_and_python_engines_agree_on_random_step_lists_and_weight_fields(tmp_path):
+  """randomised lines for the nested kinds added last (SequenceFeature seq_multi_sep: ER_CSV_*_STEP_LIST; TagFeature
+  weights in their own field: ER_CSV_F32_LIST): empty fields, empty steps, leading / trailing / doubled separators, more
+  steps than max_seq_len, string and integer values, \\r\\n - batch by batch the native parser must equal the
+  pure-python restatement (and must not touch memory it does not own: the arrays are exactly sized)."""
+  cfg = config_util.get_configs_from_pipeline_file(b"""
+data_config { batch_size: 32 input_type: CSVInput separator: "," label_fields: "label"
+  input_fields { input_name: "label" input_type: FLOAT } input_fields { input_name: "key" input_type: INT64 }
+  input_fields { input_name: "iseq" input_type: STRING } input_fields { input_name: "sseq" input_type: STRING }
+  input_fields { input_name: "tags" input_type: STRING } input_fields { input_name: "wts" input_type: STRING } }
+feature_config {
+  features { input_names: "key" feature_type: IdFeature embedding_dim: 4 num_buckets: 50 }
+  features { input_names: "iseq" feature_type: SequenceFeature embedding_dim: 4 num_buckets: 50 separator: "|" seq_multi_sep: "#"
+             combiner: "mean" max_seq_len: 5 }
+  features { input_names: "sseq" feature_type: SequenceFeature embedding_dim: 4 hash_bucket_size: 37 separator: ";" seq_multi_sep: "^"
+             combiner: "sum" max_seq_len: 3 }
+  features { input_names: ["tags", "wts"] feature_type: TagFeature embedding_dim: 4 hash_bucket_size: 29 separator: "|" combiner: "mean" } }
+model_config { model_class: "MultiTowerDIN"
+  seq_att_groups { group_name: "d1" seq_att_map { key: "key" hist_seq: "iseq" } }
+  seq_att_groups { group_name: "d2" seq_att_map { key: "key" hist_seq: "sseq" } }
+  feature_groups { group_name: "u" feature_names: ["key", "tags"] wide_deep: DEEP }
+  multi_tower { towers { input: "u" dnn { hidden_units: [4] } } din_towers { input: "d1" dnn { hidden_units: [4, 1] } }
+                din_towers { input: "d2" dnn { hidden_units: [4, 1] } } final_dnn { hidden_units: [4] } } }
+""")
+  il, _, _ = builder.build_model(cfg, 32, 'cpu', cpu_generator=torch.Generator().manual_seed(0))
+  rng = np.random.default_rng(123)
+
+  def nested(outer, inner, val, max_steps):
+    steps = []
+    for _ in range(rng.integers(0, max_steps + 1)):
+      vals = [val() for _ in range(rng.integers(0, 4))]
+      tok = inner.join(vals)
+      if rng.random() < 0.2:
+        tok = inner + tok               # leading / doubled inner separators
+      if rng.random() < 0.2:
+        tok = tok + inner
+      steps.append(tok)
+    s = outer.join(steps)
+    if rng.random() < 0.15:
+      s = outer + s + outer
+    return s
+  lines = []
+  for _ in range(32 * 9 + 7):
+    n_tag = rng.integers(0, 5)
+    tags = '|'.join('t%d' % rng.integers(0, 40) for _ in range(n_tag))
+    wts = '|'.join('%.3g' % rng.uniform(-1, 3) for _ in range(n_tag))
+    if n_tag and rng.random() < 0.2:
+      tags, wts = tags + '|', '|' + wts        # empty tokens are skipped on both sides
+    lines.append('%d,%d,%s,%s,%s,%s' % (rng.integers(0, 2), rng.integers(0, 50),
+                                       nested('|', '#', lambda: str(rng.integers(0, 50)), 8),
+                                       nested(';', '^', lambda: 'w%d' % rng.integers(0, 99), 5), tags, wts))
+  path = str(tmp_path / 'r.csv')
+  open(path, 'w', newline='').write('\r\n'.join(lines) + '\r\n')
+  for threads in (1, 5):
+    native = list(readers.CSVInput(cfg, il, path, n_threads=threads))
+    python = list(readers.CSVInput(cfg, il, path, engine='python'))
+    assert len(native) == len(python) == 9
+    for a, b in zip(native, python):
+      _same(a, b)
+  lens = torch.cat([f['seq_fea']['iseq'][1] for f, _ in native])
+  assert int(lens.max()) == 5 and int(lens.min()) == 0          # truncated to max_seq_len; empty histories occur
